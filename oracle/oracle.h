@@ -1,0 +1,44 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orb_oracle.cc header).  C interface of the CPU restatement.
+#pragma once
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OrcKeyPoint {  // cv::KeyPoint fields the reference fills (src/ORBextractor.cc:784-800)
+  float x, y, size, angle, response;
+  int32_t octave;
+} OrcKeyPoint;
+
+void orc_sincosf(float x, float* s, float* c);
+float orc_fast_atan2(float y, float x);
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
+void orc_fast_score_map(const uint8_t* img, int w, int h, int stride, uint8_t* out, int ostride);
+int orc_fast_detect(const uint8_t* img, int w, int h, int stride, int th, int* xs, int* ys, int* resp, int cap);
+void orc_gauss7_kernel(int k[7]);
+void orc_gaussian_blur7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
+
+void* orc_orb_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh);
+void orc_orb_destroy(void* h);
+void orc_orb_tables(void* h, float* scale, float* invScale, float* sigma2, float* invSigma2, int* quota, int* umax);
+int orc_orb_extract(void* h, const uint8_t* img, int w, int hgt, int stride, const int* lapping, OrcKeyPoint* kps,
+                    uint8_t* desc, int cap, int* n_mono);
+int orc_orb_level_size(void* h, int level, int* w, int* hgt);
+void orc_orb_get_level(void* h, int level, uint8_t* out);
+int orc_orb_get_candidates(void* h, int level, int* xyr, int cap);
+int orc_quadtree(const int* xyr, int n, int W, int H, int N, int* picked, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
+void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist);
+void orc_hamming_csr(const uint8_t* q, const uint8_t* t, const int32_t* row_ptr, const int32_t* cand, int nrows,
+                     int32_t* best_dist, int32_t* best_idx, int32_t* second_dist, int32_t* second_idx);
+#ifdef __cplusplus
+}
+#endif

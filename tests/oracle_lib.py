@@ -1,0 +1,178 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE ONLY (parity checker / CPU baseline)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "liboracle.so")
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO):
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+class OrcKeyPoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")])
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        L = _lib
+        u8p, i32p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_float)
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_sincosf.argtypes = [C.c_float, f32p, f32p]
+        L.orc_orb_create.restype = C.c_void_p
+        L.orc_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_orb_destroy.argtypes = [C.c_void_p]
+        L.orc_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, i32p]
+        L.orc_orb_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
+        L.orc_orb_get_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_orb_get_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_orb_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        for name in ("orc_resize_linear_u8", "orc_fast_score_map", "orc_fast_detect", "orc_gaussian_blur7_u8",
+                     "orc_quadtree", "orc_gauss7_kernel", "orc_descriptor_distance", "orc_hamming_knn2",
+                     "orc_hamming_csr"):
+            getattr(L, name).argtypes = None
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), C.c_int(src.shape[1]), C.c_int(src.shape[0]), C.c_int(src.strides[0]), _p(dst),
+                               C.c_int(dw), C.c_int(dh), C.c_int(dw))
+    return dst
+
+
+def fast_score_map(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().orc_fast_score_map(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(img.strides[0]), _p(out),
+                             C.c_int(img.shape[1]))
+    return out
+
+
+def fast_detect(img, th):
+    """cv::FAST(img, th, nms=True) -> (n,3) int array of (x, y, response), raster order."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    cap = max(16, img.shape[0] * img.shape[1] // 4)
+    xs, ys, rs = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().orc_fast_detect(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(img.strides[0]),
+                              C.c_int(th), _p(xs), _p(ys), _p(rs), C.c_int(cap))
+    return np.stack([xs[:n], ys[:n], rs[:n]], 1)
+
+
+def gaussian_blur7(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().orc_gaussian_blur7_u8(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(img.strides[0]), _p(out),
+                                C.c_int(img.shape[1]))
+    return out
+
+
+def gauss7_kernel():
+    k = np.empty(7, np.int32)
+    lib().orc_gauss7_kernel(_p(k))
+    return k
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(C.c_float(y), C.c_float(x))
+
+
+def sincosf(x):
+    s, c = C.c_float(), C.c_float()
+    lib().orc_sincosf(C.c_float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def quadtree(xyr, W, H, N):
+    xyr = np.ascontiguousarray(xyr, np.int32)
+    out = np.empty(max(len(xyr), 1), np.int32)
+    n = lib().orc_quadtree(_p(xyr), C.c_int(len(xyr)), C.c_int(W), C.c_int(H), C.c_int(N), _p(out), C.c_int(len(out)))
+    return out[:n]
+
+
+class OrbOracle:
+    """Mirror of ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)."""
+
+    def __init__(self, nfeatures=1200, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.h = lib().orc_orb_create(nfeatures, scale, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_orb_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sc, isc, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        q, um = np.empty(n, np.int32), np.empty(16, np.int32)
+        lib().orc_orb_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(q), _p(um))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, quota=q, umax=um)
+
+    def extract(self, img, lapping=None, cap=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = cap or 8192
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        mono = C.c_int32(0)
+        lap = None if lapping is None else _p(np.asarray(lapping, np.int32))
+        self._keep = lapping
+        n = lib().orc_orb_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], lap, _p(kps), _p(desc),
+                                  cap, C.byref(mono))
+        if n < 0:
+            return n, None, None, 0
+        return n, kps[:n].copy(), desc[:n].copy(), mono.value
+
+    def level(self, l):
+        w, h = C.c_int32(), C.c_int32()
+        lib().orc_orb_level_size(self.h, l, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        lib().orc_orb_get_level(self.h, l, _p(out))
+        return out
+
+    def candidates(self, l):
+        cap = 1 << 16
+        out = np.empty((cap, 3), np.int32)
+        n = lib().orc_orb_get_candidates(self.h, l, _p(out), cap)
+        return out[:n].copy()
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def hamming_knn2(q, t):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.empty((len(q), 2), np.int32); dist = np.empty((len(q), 2), np.int32)
+    lib().orc_hamming_knn2(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), _p(idx), _p(dist))
+    return idx, dist
+
+
+def hamming_csr(q, t, row_ptr, cand):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    row_ptr = np.ascontiguousarray(row_ptr, np.int32); cand = np.ascontiguousarray(cand, np.int32)
+    n = len(row_ptr) - 1
+    o = [np.empty(n, np.int32) for _ in range(4)]
+    lib().orc_hamming_csr(_p(q), _p(t), _p(row_ptr), _p(cand), C.c_int(n), *[_p(x) for x in o])
+    return o  # best_dist, best_idx, second_dist, second_idx
