@@ -1,0 +1,116 @@
+/* vieo_b200.h — C ABI of the B200-native VIEO_SLAM hot path (libvieo_b200.so).
+ *
+ * Plain C: opaque handles, plain pointers and sizes, int status (0 = ok, <0 = VIEO_E_*), no
+ * exceptions, no torch / OpenCV / Eigen types.  Buffers are HOST pointers unless the function name
+ * ends in _dev, in which case every pointer is a device pointer on the handle's GPU and the call is
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ * A handle owns its device scratch and one CUDA stream and must not be used from two threads at
+ * once (the reference drives one ORBextractor per camera thread, src/Frame.cc:259-278).
+ * There is NO CPU fallback: every entry point fails with VIEO_E_CUDA if no sm_100 device is usable.
+ *
+ * Each entry point cites the reference interface (leavesnight/VIEO_SLAM @356e4a22) it replaces.
+ */
+#ifndef VIEO_B200_H
+#define VIEO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIEO_OK 0
+#define VIEO_E_ARG (-1)      /* bad argument / unsupported configuration */
+#define VIEO_E_CUDA (-2)     /* CUDA runtime error or no device; see vieo_last_error() */
+#define VIEO_E_CAPACITY (-3) /* caller buffer or handle capacity too small */
+#define VIEO_E_EMPTY (-4)    /* empty image: ORBextractor::operator() returns -1 (src/ORBextractor.cc:970) */
+
+const char* vieo_last_error(void); /* thread-local text of the last failure */
+int vieo_device_count(void);
+const char* vieo_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORB extractor — replaces ORBextractor (include/ORBextractor.h:27-80, src/ORBextractor.cc:391-1081).
+ * Fields of cv::KeyPoint the reference fills (src/ORBextractor.cc:784-800); class_id is unused. */
+typedef struct VieoKeyPoint {
+  float x, y;     /* level-0 pixel coordinates (pt *= mvScaleFactor[octave], :1036) */
+  float size;     /* (int)(31 * scale[octave]) */
+  float angle;    /* degrees, cv::fastAtan2 of the intensity centroid (:55-80) */
+  float response; /* FAST-9/16 score (cornerScore<16>) */
+  int32_t octave;
+} VieoKeyPoint;
+
+typedef struct VieoOrbConfig {
+  int32_t width, height;  /* fixed per handle (the reference re-derives sizes per call; cameras are fixed) */
+  int32_t nfeatures;      /* ORBextractor.nFeatures */
+  float scale_factor;     /* ORBextractor.scaleFactor */
+  int32_t nlevels;        /* ORBextractor.nLevels (<= 16) */
+  int32_t ini_th_fast;    /* ORBextractor.iniThFAST */
+  int32_t min_th_fast;    /* ORBextractor.minThFAST */
+  int32_t max_batch;      /* images in flight per call (cameras x frames); device scratch is sized for it */
+} VieoOrbConfig;
+
+typedef struct vieo_orb vieo_orb_t;
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:391-456). */
+int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out);
+void vieo_orb_destroy(vieo_orb_t* h);
+/* per-image keypoint capacity the handle can produce (sum over levels of quota+3) */
+int vieo_orb_max_keypoints(const vieo_orb_t* h);
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:47-57) plus the per-level feature quota and level sizes. Arrays of nlevels. */
+int vieo_orb_get_tables(const vieo_orb_t* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                        int32_t* quota, int32_t* level_w, int32_t* level_h);
+
+/* ORBextractor::operator() (src/ORBextractor.cc:968-1058) for one image.
+ *   img/stride  CV_8UC1 rows;  lapping  NULL or {x0,x1} (KB8 "lapping area", :1041-1057)
+ *   kps/desc    caller arrays of `cap` entries (desc = cap x 32 bytes)
+ *   n_mono      the reference's return value (monoIndex), may be NULL
+ *   pyr_host    NULL, or nlevels host pointers receiving tightly packed copies of the pyramid levels
+ *               (public mvImagePyramid contract, read by Frame::ComputeStereoMatches src/Frame.cc:536-557)
+ * Returns the number of keypoints (>= 0), VIEO_E_EMPTY for a NULL/0-sized image, or an error. */
+int vieo_orb_extract(vieo_orb_t* h, const uint8_t* img, int stride, const int32_t* lapping, VieoKeyPoint* kps,
+                     uint8_t* desc, int cap, int32_t* n_mono, uint8_t* const* pyr_host);
+
+/* Batched form: the per-camera std::threads of Frame::Frame (src/Frame.cc:259-278) collapsed into one
+ * call; also used to keep several frames in flight.  imgs = n_img images, `img_stride` bytes apart, rows
+ * `row_stride` bytes apart.  kps = [n_img][cap], desc = [n_img][cap][32], n_kp = [n_img].  Level order
+ * output (no lapping area). */
+int vieo_orb_extract_batch(vieo_orb_t* h, int n_img, const uint8_t* imgs, size_t img_stride, int row_stride,
+                           VieoKeyPoint* kps, uint8_t* desc, int cap, int32_t* n_kp);
+/* Same with device-resident input and output; asynchronous on `stream`. */
+int vieo_orb_extract_batch_dev(vieo_orb_t* h, int n_img, const uint8_t* imgs_dev, size_t img_stride, int row_stride,
+                               VieoKeyPoint* kps_dev, uint8_t* desc_dev, int cap, int32_t* n_kp_dev, void* stream);
+/* Stage introspection for parity tests (device scratch of the last call -> host).
+ * level pixels (tightly packed w*h), FAST candidates before the quadtree as (x, y, response) int32
+ * triples in the reference's visiting order (cell-major, raster inside a cell). */
+int vieo_orb_debug_level(vieo_orb_t* h, int img_index, int level, uint8_t* out);
+int vieo_orb_debug_candidates(vieo_orb_t* h, int img_index, int level, int32_t* xyr, int cap);
+/* number of kernel launches issued by the last extract call (bench.py's gpu_launches) */
+int vieo_orb_last_launches(const vieo_orb_t* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * 256-bit Hamming matching — replaces ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1645-1667),
+ * cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) in Frame::ComputeStereoFishEyeMatches (src/Frame.cc:620-628)
+ * and the best/second-best candidate loops of the guided searches (src/ORBmatcher.cc:286-315,
+ * 1396-1424; src/Frame.cc:506-523).  Descriptors are rows of 32 bytes. */
+
+/* knnMatch k=2: idx/dist are [nq][2], ascending distance, ties -> lowest train index; missing
+ * neighbours are idx -1 / dist INT32_MAX. */
+int vieo_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist, int device);
+/* n_pairs independent (query set, train set) pairs, device resident.  Pair p: q + p*q_stride (bytes),
+ * nq_dev[p] rows (<= max_nq); t likewise; idx/dist = [n_pairs][max_nq][2]. */
+int vieo_hamming_knn2_batch_dev(const uint8_t* q_dev, size_t q_stride, const int32_t* nq_dev, int max_nq,
+                                const uint8_t* t_dev, size_t t_stride, const int32_t* nt_dev, int max_nt,
+                                int n_pairs, int32_t* idx_dev, int32_t* dist_dev, void* stream);
+/* Candidate-list search: row r compares q row r with t rows cand[row_ptr[r] .. row_ptr[r+1]) in list
+ * order; strict '<' keeps the first of equal distances (the reference's loops).  Outputs per row: best
+ * and second-best distance (256 when absent) and their train indices (-1 when absent). */
+int vieo_hamming_csr(const uint8_t* q, const uint8_t* t, int nt, const int32_t* row_ptr, const int32_t* cand,
+                     int nrows, int32_t* best_dist, int32_t* best_idx, int32_t* second_dist, int32_t* second_idx,
+                     int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIEO_B200_H */

@@ -1,0 +1,190 @@
+"""ctypes binding of libvieo_b200.so (the C ABI in include/vieo_b200.h) with thin classes named after the
+reference's (ORBextractor, ORBmatcher, IMUPreintegrator, Optimizer).  Used by tests and bench.py; a C++
+caller uses vieo_slam_b200/host/*.h or the C ABI directly.  There is no fallback: if the library is missing
+or no B200 is present every call raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvieo_b200.so")
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")])
+
+
+class VieoError(RuntimeError):
+    pass
+
+
+class VieoOrbConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("nfeatures", C.c_int32), ("scale_factor", C.c_float),
+                ("nlevels", C.c_int32), ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
+                ("max_batch", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VieoError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.vieo_last_error.restype = C.c_char_p
+        L.vieo_version.restype = C.c_char_p
+        L.vieo_orb_create.argtypes = [C.POINTER(VieoOrbConfig), i32, C.POINTER(vp)]
+        L.vieo_orb_destroy.argtypes = [vp]
+        L.vieo_orb_destroy.restype = None
+        L.vieo_orb_max_keypoints.argtypes = [vp]
+        L.vieo_orb_get_tables.argtypes = [vp] * 8
+        L.vieo_orb_extract.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp, vp]
+        L.vieo_orb_extract_batch.argtypes = [vp, i32, vp, sz, i32, vp, vp, i32, vp]
+        L.vieo_orb_extract_batch_dev.argtypes = [vp, i32, vp, sz, i32, vp, vp, i32, vp, vp]
+        L.vieo_orb_debug_level.argtypes = [vp, i32, i32, vp]
+        L.vieo_orb_debug_candidates.argtypes = [vp, i32, i32, vp, i32]
+        L.vieo_orb_last_launches.argtypes = [vp]
+        L.vieo_hamming_knn2.argtypes = [vp, i32, vp, i32, vp, vp, i32]
+        L.vieo_hamming_knn2_batch_dev.argtypes = [vp, sz, vp, i32, vp, sz, vp, i32, i32, vp, vp, vp]
+        L.vieo_hamming_csr.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise VieoError(f"vieo_b200 error {rc}: {lib().vieo_last_error().decode()}")
+    return rc
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class ORBextractor:
+    """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) (include/ORBextractor.h:31) for a
+    fixed image size; `max_batch` images (cameras x frames) can be extracted per call."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, width, height, max_batch=2, device=0):
+        self.cfg = VieoOrbConfig(width, height, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_batch)
+        self._h = C.c_void_p()
+        _check(lib().vieo_orb_create(C.byref(self.cfg), device, C.byref(self._h)))
+        self.nlevels = nlevels
+        self.width, self.height = width, height
+        self.cap = lib().vieo_orb_max_keypoints(self._h)
+        t = [np.empty(nlevels, np.float32) for _ in range(4)] + [np.empty(nlevels, np.int32) for _ in range(3)]
+        _check(lib().vieo_orb_get_tables(self._h, *[_p(x) for x in t]))
+        (self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2, self.quota,
+         self.level_w, self.level_h) = t
+        self.mvImagePyramid = []
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            lib().vieo_orb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return float(self.cfg.scale_factor)
+
+    def GetScaleFactors(self):
+        return self.mvScaleFactor
+
+    def GetInverseScaleFactors(self):
+        return self.mvInvScaleFactor
+
+    def GetScaleSigmaSquares(self):
+        return self.mvLevelSigma2
+
+    def GetInverseScaleSigmaSquares(self):
+        return self.mvInvLevelSigma2
+
+    def __call__(self, image, mask=None, pvLappingArea=None, want_pyramid=False):
+        """operator(): returns (ret, keypoints[KP_DTYPE], descriptors[n,32]); ret = monoIndex or -1 (empty image)."""
+        if image is None or image.size == 0:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 only (src/ORBextractor.cc:973)"
+        assert image.shape == (self.height, self.width)
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        kps = np.empty(self.cap, KP_DTYPE)
+        desc = np.empty((self.cap, 32), np.uint8)
+        mono = C.c_int32(0)
+        lap = None if pvLappingArea is None else np.asarray(pvLappingArea, np.int32)
+        pyr = None
+        if want_pyramid:
+            self.mvImagePyramid = [np.empty((int(h), int(w)), np.uint8) for w, h in zip(self.level_w, self.level_h)]
+            pyr = (C.c_void_p * self.nlevels)(*[x.ctypes.data for x in self.mvImagePyramid])
+        n = _check(lib().vieo_orb_extract(self._h, _p(image), image.strides[0], _p(lap), _p(kps), _p(desc), self.cap,
+                                          C.byref(mono), pyr))
+        return mono.value, kps[:n].copy(), desc[:n].copy()
+
+    def extract_batch(self, images):
+        """images: (n, H, W) u8 host array -> (kps[n,cap], desc[n,cap,32], n_kp[n])."""
+        images = np.ascontiguousarray(images, np.uint8)
+        n = images.shape[0]
+        kps = np.empty((n, self.cap), KP_DTYPE)
+        desc = np.empty((n, self.cap, 32), np.uint8)
+        nk = np.empty(n, np.int32)
+        _check(lib().vieo_orb_extract_batch(self._h, n, _p(images), images.strides[0], images.strides[1], _p(kps),
+                                            _p(desc), self.cap, _p(nk)))
+        return kps, desc, nk
+
+    def extract_batch_dev(self, imgs_ptr, n, img_stride, row_stride, kps_ptr, desc_ptr, cap, nkp_ptr, stream=0):
+        """All pointers are device addresses (ints); asynchronous on `stream`."""
+        _check(lib().vieo_orb_extract_batch_dev(self._h, n, imgs_ptr, img_stride, row_stride, kps_ptr, desc_ptr, cap,
+                                                nkp_ptr, stream))
+
+    def last_launches(self):
+        return lib().vieo_orb_last_launches(self._h)
+
+    def debug_level(self, img_index, level):
+        out = np.empty((int(self.level_h[level]), int(self.level_w[level])), np.uint8)
+        _check(lib().vieo_orb_debug_level(self._h, img_index, level, _p(out)))
+        return out
+
+    def debug_candidates(self, img_index, level):
+        cap = 1 << 17
+        out = np.empty((cap, 3), np.int32)
+        n = _check(lib().vieo_orb_debug_candidates(self._h, img_index, level, _p(out), cap))
+        return out[:n].copy()
+
+
+class ORBmatcher:
+    """The Hamming kernels behind ORBmatcher / Frame stereo association (include/ORBmatcher.h:18-113)."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30  # src/ORBmatcher.cc:20-22
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.mfNNratio, self.mbCheckOrientation, self.device = nnratio, checkOri, device
+
+    def knnMatch2(self, q, t):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) -> (idx[nq,2], dist[nq,2])."""
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        idx = np.empty((len(q), 2), np.int32)
+        dist = np.empty((len(q), 2), np.int32)
+        _check(lib().vieo_hamming_knn2(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist), self.device))
+        return idx, dist
+
+    def search_candidates(self, q, t, row_ptr, cand):
+        """Best / second-best over per-row candidate lists -> (best_dist, best_idx, second_dist, second_idx)."""
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        row_ptr = np.ascontiguousarray(row_ptr, np.int32)
+        cand = np.ascontiguousarray(cand, np.int32)
+        n = len(row_ptr) - 1
+        o = [np.empty(n, np.int32) for _ in range(4)]
+        _check(lib().vieo_hamming_csr(_p(q), _p(t), len(t), _p(row_ptr), _p(cand), n, *[_p(x) for x in o], self.device))
+        return o
+
+    def DescriptorDistance(self, a, b):
+        """ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1645) evaluated on the device."""
+        bd, _, _, _ = self.search_candidates(np.asarray(a).reshape(1, 32), np.asarray(b).reshape(1, 32), [0, 1], [0])
+        return int(bd[0])

@@ -1,0 +1,49 @@
+// Error reporting and device selection for libvieo_b200.so.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vieo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int use_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); libvieo_b200 has no CPU fallback",
+              e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    return VIEO_E_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (0..%d)", device, n - 1);
+    return VIEO_E_ARG;
+  }
+  VIEO_CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VIEO_CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return VIEO_E_CUDA;
+  }
+  return VIEO_OK;
+}
+
+}  // namespace vieo
+
+extern "C" {
+const char* vieo_last_error(void) { return vieo::g_err; }
+int vieo_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+const char* vieo_version(void) { return "vieo_b200 0.1.0 (sm_100a)"; }
+}

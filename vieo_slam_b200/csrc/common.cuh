@@ -1,0 +1,60 @@
+// Shared helpers for libvieo_b200.so (sm_100a only; no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/vieo_b200.h"
+
+namespace vieo {
+
+void set_error(const char* fmt, ...);
+
+#define VIEO_CK(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      vieo::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+      return VIEO_E_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define VIEO_ARG(cond, msg)                                   \
+  do {                                                        \
+    if (!(cond)) {                                            \
+      vieo::set_error("%s:%d %s", __FILE__, __LINE__, msg);   \
+      return VIEO_E_ARG;                                      \
+    }                                                         \
+  } while (0)
+
+// selects `device` and checks it is a Blackwell (sm_100) part; there is no other code path.
+int use_device(int device);
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// Exclusive scan of a[0..n) in shared memory, in place, by warp 0 of the block; returns total via *total.
+// Caller must __syncthreads() before (a written) and after (a read).
+__device__ __forceinline__ void warp0_excl_scan(int* a, int n, int* total) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+      int i = base + lane;
+      int v = i < n ? a[i] : 0;
+      int inc = warp_incl_scan(v, lane);
+      if (i < n) a[i] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) *total = carry;
+  }
+}
+
+}  // namespace vieo

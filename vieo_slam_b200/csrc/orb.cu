@@ -1,0 +1,1134 @@
+// ORB front-end on sm_100a: chained fixed-point pyramid, per-cell FAST-9/16 + NMS + threshold fallback,
+// data-parallel quadtree distribution, intensity-centroid orientation and Gaussian-blurred steered
+// rBRIEF — everything on the device, one fixed sequence of launches per batch of images.
+//
+// Reference behaviour reproduced (leavesnight/VIEO_SLAM @356e4a22): src/ORBextractor.cc:391-456 (tables),
+// :1060-1081 (pyramid, cv::resize INTER_LINEAR 8U fixed-point), :723-802 (cells, cv::FAST, fallback),
+// :467-721 (DistributeOctTree), :55-80 (IC_Angle, cv::fastAtan2), :1012-1024 + :83-127 (GaussianBlur 7x7
+// s=2 + computeOrbDescriptor), :968-1058 (operator()).  This is a new design, not a translation: see DESIGN.md.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vieo {
+
+constexpr int kMaxLevels = 16;
+constexpr int kBorder = 16;      // EDGE_THRESHOLD - 3
+constexpr int kHalfPatch = 15;
+constexpr int kFastThreads = 256;
+constexpr int kQtThreads = 512;
+constexpr int kDescWarps = 4;
+constexpr int kPR = 21;           // raw patch radius: 18 (rotated pattern reach) + 3 (7-tap blur)
+constexpr int kPW = 2 * kPR + 1;  // 43
+constexpr int kPWp = 44;          // padded row of the raw patch
+constexpr int kBW = 37;           // blurred window (+-18)
+constexpr int kBWp = 38;
+
+struct Cell {
+  int16_t level, x0, y0, cw, ch;  // cell image = [x0,x0+cw) x [y0,y0+ch) in level coordinates
+};
+
+struct OrbParams {  // passed by value to kernels
+  int nlevels;
+  int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+  size_t img_stride[kMaxLevels];  // bytes between images of a level (levels >= 1; level 0 may be external)
+  uint8_t* lvl[kMaxLevels];       // device base per level (lvl[0] = internal staging copy)
+  float scale[kMaxLevels];
+  float kp_size[kMaxLevels];
+  int quota[kMaxLevels];
+  int cell_begin[kMaxLevels + 1];
+  int n_cells;
+  int cell_cap;                // slots per cell
+  int key_begin[kMaxLevels + 1];  // per-image offsets into the dense key arrays (cell_begin * cell_cap)
+  int maxn[kMaxLevels];        // node capacity per level
+  int slot_begin[kMaxLevels + 1];  // per-image offsets into lvl_kp
+  int tile_w, tile_h;          // max cell dims (tile_w padded to 4)
+  int ini_th, min_th;
+  const Cell* cells;
+  const int4* rx[kMaxLevels];  // per dst x: {x0, x1, a0, a1}
+  const int4* ry[kMaxLevels];  // per dst y: {y0, y1, b0, b1}
+  uint32_t* cand;              // [img][n_cells][cell_cap] packed x | y<<12 | response<<24
+  int* cell_cnt;               // [img][n_cells]
+  uint32_t* keys;              // [img][key_begin[nlevels]]
+  uint16_t* knode;             // same shape
+  uint32_t* lvl_kp;            // [img][slot_begin[nlevels]] packed keypoints after the quadtree (list order)
+  int* lvl_cnt;                // [img][nlevels]
+};
+
+__constant__ int c_umax[kHalfPatch + 1];
+__device__ const int8_t d_pattern[1024] = {
+#include "../../data/orb_pattern_31.inc"
+};
+
+// ------------------------------------------------------------------------------------------------
+// Pyramid: level l from level l-1, all images of the batch in one launch.  4 pixels per thread.
+__global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src, size_t src_img_stride, int src_pitch,
+                                                uint8_t* __restrict__ dst, size_t dst_img_stride, int dst_pitch,
+                                                int dw, int dh, const int4* __restrict__ rx,
+                                                const int4* __restrict__ ry) {
+  const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x4 >= dw || y >= dh) return;
+  const uint8_t* s = src + blockIdx.z * src_img_stride;
+  const int4 fy = __ldg(ry + y);
+  const uint8_t* r0 = s + (size_t)fy.x * src_pitch;
+  const uint8_t* r1 = s + (size_t)fy.y * src_pitch;
+  uint32_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x4 + i;
+    if (x < dw) {
+      const int4 fx = __ldg(rx + x);
+      const int h0 = r0[fx.x] * fx.z + r0[fx.y] * fx.w;
+      const int h1 = r1[fx.x] * fx.z + r1[fx.y] * fx.w;
+      const int v = (((fy.z * (h0 >> 4)) >> 16) + ((fy.w * (h1 >> 4)) >> 16) + 2) >> 2;
+      out |= (uint32_t)(v & 0xff) << (8 * i);
+    }
+  }
+  *reinterpret_cast<uint32_t*>(dst + blockIdx.z * dst_img_stride + (size_t)y * dst_pitch + x4) = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST-9/16 arc score of one pixel: S = max(v - min_arcs(max9 p), max_arcs(min9 p) - v, 0) over the 16
+// contiguous 9-arcs of the radius-3 ring; equals cornerScore<16>()+1 for corners, and a pixel is a corner at
+// threshold t iff S > t.  Two ring pixels per register (u16x2 lanes: p[k] | p[k+8] << 16): the arc starting
+// at k+8 is the arc starting at k with the halves swapped, so one packed min/max tree (VIMNMX.U16x2) serves
+// both.  (A first formulation on signed differences v - p[k] was miscompiled by nvcc 12.9 for sm_100a —
+// tools/dev_fast_score_test.cu keeps it as V0 — so the tree runs on raw pixel values.)
+__device__ __forceinline__ int fast_score(const uint8_t* p, int pitch) {
+  const int v = p[0];
+  unsigned r[16];
+  r[0] = p[3 * pitch];
+  r[1] = p[3 * pitch + 1];
+  r[2] = p[2 * pitch + 2];
+  r[3] = p[pitch + 3];
+  r[4] = p[3];
+  r[5] = p[-pitch + 3];
+  r[6] = p[-2 * pitch + 2];
+  r[7] = p[-3 * pitch + 1];
+  r[8] = p[-3 * pitch];
+  r[9] = p[-3 * pitch - 1];
+  r[10] = p[-2 * pitch - 2];
+  r[11] = p[-pitch - 3];
+  r[12] = p[-3];
+  r[13] = p[pitch - 3];
+  r[14] = p[2 * pitch - 2];
+  r[15] = p[3 * pitch - 1];
+  unsigned X[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    X[k] = r[k] | (r[k + 8] << 16);
+    X[k + 8] = r[k + 8] | (r[k] << 16);
+  }
+  unsigned lo2[15], hi2[15], lo4[12], hi4[12];
+#pragma unroll
+  for (int j = 0; j < 15; ++j) {
+    lo2[j] = __vminu2(X[j], X[j + 1]);
+    hi2[j] = __vmaxu2(X[j], X[j + 1]);
+  }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    lo4[j] = __vminu2(lo2[j], lo2[j + 2]);
+    hi4[j] = __vmaxu2(hi2[j], hi2[j + 2]);
+  }
+  unsigned a = 0x00ff00ffu, b = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const unsigned lo9 = __vminu2(__vminu2(lo4[k], lo4[k + 4]), X[k + 8]);
+    const unsigned hi9 = __vmaxu2(__vmaxu2(hi4[k], hi4[k + 4]), X[k + 8]);
+    a = __vminu2(a, hi9);
+    b = __vmaxu2(b, lo9);
+  }
+  const int A = min(a & 0xffff, a >> 16), B = max(b & 0xffff, b >> 16);
+  return max(max(v - A, B - v), 0);
+}
+
+// One CTA per (cell, image): stage the cell image in shared memory, score every interior pixel, 3x3
+// strict NMS restricted to the cell interior (each cell is an independent cv::FAST call in the reference),
+// decide iniTh vs minTh from the post-NMS count, and write the survivors in raster order.
+__global__ void __launch_bounds__(kFastThreads) k_fast_cells(OrbParams P, const uint8_t* __restrict__ img0,
+                                                            size_t img0_stride, int img0_pitch) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Cell c = P.cells[blockIdx.x];
+  const int img = blockIdx.y;
+  const int tid = threadIdx.x;
+  const uint8_t* base;
+  int pitch;
+  if (c.level == 0) {
+    base = img0 + img * img0_stride;
+    pitch = img0_pitch;
+  } else {
+    base = P.lvl[c.level] + img * P.img_stride[c.level];
+    pitch = P.pitch[c.level];
+  }
+  const int TW = P.tile_w;
+  uint8_t* raw = smem;
+  const int iw = c.cw - 6, ih = c.ch - 6;
+  const int SW = P.tile_w;                  // score tile row (iw + 2 <= tile_w - 4)
+  uint8_t* sc = smem + P.tile_w * P.tile_h;  // (ih + 2) x SW with a zero ring
+  __shared__ int s_warp[kFastThreads / 32];
+
+  int* cnt_out = P.cell_cnt + (size_t)img * P.n_cells + blockIdx.x;
+  if (iw <= 0 || ih <= 0) {
+    if (tid == 0) *cnt_out = 0;
+    return;
+  }
+  for (int i = tid; i < c.cw * c.ch; i += kFastThreads) {
+    const int y = i / c.cw, x = i - y * c.cw;
+    raw[y * TW + x] = __ldg(base + (size_t)(c.y0 + y) * pitch + c.x0 + x);
+  }
+  for (int i = tid; i < (ih + 2) * SW; i += kFastThreads) sc[i] = 0;
+  __syncthreads();
+  const int npx = iw * ih;
+  for (int i = tid; i < npx; i += kFastThreads) {
+    const int y = i / iw, x = i - y * iw;
+    const int s = fast_score(raw + (y + 3) * TW + x + 3, TW);
+    sc[(y + 1) * SW + x + 1] = (uint8_t)(s > P.min_th ? s : 0);
+  }
+  __syncthreads();
+  // contiguous raster chunk per thread -> ordered compaction
+  const int per = (npx + kFastThreads - 1) / kFastThreads;  // <= 32 (checked at create)
+  const int beg = tid * per, end = min(beg + per, npx);
+  uint32_t mask_a = 0, mask_b = 0;
+  for (int i = beg; i < end; ++i) {
+    const int y = i / iw, x = i - y * iw;
+    const uint8_t* q = sc + (y + 1) * SW + x + 1;
+    const int s = q[0];
+    if (s == 0) continue;
+    const int m = max(max(max(q[-SW - 1], q[-SW]), max(q[-SW + 1], q[-1])),
+                      max(max(q[1], q[SW - 1]), max(q[SW], q[SW + 1])));
+    if (s > m) {
+      mask_b |= 1u << (i - beg);
+      if (s > P.ini_th) mask_a |= 1u << (i - beg);
+    }
+  }
+  const int total_a = __syncthreads_count(mask_a != 0);
+  const uint32_t mask = total_a > 0 ? mask_a : mask_b;
+  const int cnt = __popc(mask);
+  const int lane = tid & 31, wid = tid >> 5;
+  const int inc = warp_incl_scan(cnt, lane);
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  int off = inc - cnt;
+  int total = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < kFastThreads / 32; ++w2) {
+    if (w2 < wid) off += s_warp[w2];
+    total += s_warp[w2];
+  }
+  uint32_t* out = P.cand + ((size_t)img * P.n_cells + blockIdx.x) * P.cell_cap;
+  uint32_t m = mask;
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    const int i = beg + b;
+    const int y = i / iw, x = i - y * iw;
+    const int s = sc[(y + 1) * SW + x + 1];
+    out[off++] = (uint32_t)(c.x0 + 3 + x) | ((uint32_t)(c.y0 + 3 + y) << 12) | ((uint32_t)(s - 1) << 24);
+  }
+  if (tid == 0) *cnt_out = total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Quadtree distribution, one CTA per (level, image).  The reference's std::list algorithm
+// (src/ORBextractor.cc:518-721) restated as rounds of "count children per key" + prefix sums: the node
+// table is kept in LIST ORDER; a round replaces the processed nodes by their non-empty children
+// (pushed to the front in reverse creation order) and keeps the others behind them.  Keys never move:
+// each key carries the list position of its node, and the final pick is an atomicMax of
+// (response, first-in-order).  tools/quadtree_parallel_proto.py validates the formulation on CPU.
+struct QtSmem {
+  int16_t *x0[2], *x1[2], *y0[2], *y1[2];
+  int *cnt[2], *id[2];
+  uint8_t* flag[2];
+  int *cc, *cpos, *prank, *keptpos, *ord, *ta, *tb;
+};
+
+__device__ __forceinline__ int qt_quad(const QtSmem& S, int cur, int p, int kx, int ky) {
+  const int mx = S.x0[cur][p] + ((S.x1[cur][p] - S.x0[cur][p] + 1) >> 1);
+  const int my = S.y0[cur][p] + ((S.y1[cur][p] - S.y0[cur][p] + 1) >> 1);
+  return (kx >= mx ? 1 : 0) + (ky >= my ? 2 : 0);
+}
+
+__global__ void __launch_bounds__(kQtThreads) k_quadtree(OrbParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int level = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  const int MAXN = P.maxn[level];
+  const int N = P.quota[level];
+  QtSmem S;
+  {
+    uint8_t* p = smem;
+    auto take = [&](size_t bytes) {
+      uint8_t* r = p;
+      p += (bytes + 15) & ~size_t(15);
+      return r;
+    };
+    for (int b = 0; b < 2; ++b) {
+      S.cnt[b] = (int*)take(4 * MAXN);
+      S.id[b] = (int*)take(4 * MAXN);
+      S.x0[b] = (int16_t*)take(2 * MAXN);
+      S.x1[b] = (int16_t*)take(2 * MAXN);
+      S.y0[b] = (int16_t*)take(2 * MAXN);
+      S.y1[b] = (int16_t*)take(2 * MAXN);
+      S.flag[b] = take(MAXN);
+    }
+    S.cc = (int*)take(16 * MAXN);
+    S.cpos = (int*)take(16 * MAXN);
+    S.prank = (int*)take(4 * MAXN);
+    S.keptpos = (int*)take(4 * MAXN);
+    S.ord = (int*)take(4 * MAXN);
+    S.ta = (int*)take(4 * MAXN);
+    S.tb = (int*)take(4 * MAXN);
+  }
+  __shared__ int s_total, s_total2, s_nk, s_cut;
+  __shared__ int s_celloff[512];  // per-level cell count <= 512 (checked at create)
+
+  const int ncell = P.cell_begin[level + 1] - P.cell_begin[level];
+  const int* ccnt = P.cell_cnt + (size_t)img * P.n_cells + P.cell_begin[level];
+  uint32_t* keys = P.keys + (size_t)img * P.key_begin[P.nlevels] + P.key_begin[level];
+  uint16_t* knode = P.knode + (size_t)img * P.key_begin[P.nlevels] + P.key_begin[level];
+  uint32_t* out_kp = P.lvl_kp + (size_t)img * P.slot_begin[P.nlevels] + P.slot_begin[level];
+  int* out_cnt = P.lvl_cnt + (size_t)img * P.nlevels + level;
+
+  // ---- gather the cells' survivors into one dense, ordered key array
+  for (int i = tid; i < ncell; i += kQtThreads) s_celloff[i] = ccnt[i];
+  __syncthreads();
+  warp0_excl_scan(s_celloff, ncell, &s_nk);
+  __syncthreads();
+  const int nk = s_nk;
+  if (nk == 0) {
+    if (tid == 0) *out_cnt = 0;
+    return;
+  }
+  {
+    const uint32_t* cand = P.cand + ((size_t)img * P.n_cells + P.cell_begin[level]) * P.cell_cap;
+    const int wid = tid >> 5, lane = tid & 31;
+    for (int cidx = wid; cidx < ncell; cidx += kQtThreads / 32) {
+      const int n = ccnt[cidx], o = s_celloff[cidx];
+      for (int i = lane; i < n; i += 32) keys[o + i] = cand[(size_t)cidx * P.cell_cap + i];
+    }
+  }
+  // ---- root nodes (src/ORBextractor.cc:523-566)
+  const int W = P.w[level], H = P.h[level];
+  const int spanX = (W - kBorder) - kBorder, spanY = (H - kBorder) - kBorder;
+  const int nIni = (int)roundf((float)spanX / (float)spanY);
+  const float hX = (float)spanX / (float)nIni;
+  for (int i = tid; i < MAXN; i += kQtThreads) S.ta[i] = 0;
+  __syncthreads();
+  for (int k = tid; k < nk; k += kQtThreads) {
+    const uint32_t key = keys[k];
+    const int r = (int)((float)((int)(key & 0xfff) - kBorder) / hX);
+    knode[k] = (uint16_t)r;
+    atomicAdd(&S.ta[r], 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < nIni; i += kQtThreads) {
+    S.tb[i] = S.ta[i] > 0 ? 1 : 0;
+  }
+  __syncthreads();
+  warp0_excl_scan(S.tb, nIni, &s_total);
+  __syncthreads();
+  int n = s_total;
+  int cur = 0;
+  for (int i = tid; i < nIni; i += kQtThreads) {
+    if (S.ta[i] > 0) {
+      const int np = S.tb[i];
+      S.x0[0][np] = (int16_t)(int)(hX * (float)i);
+      S.x1[0][np] = (int16_t)(int)(hX * (float)(i + 1));
+      S.y0[0][np] = 0;
+      S.y1[0][np] = (int16_t)spanY;
+      S.cnt[0][np] = S.ta[i];
+      S.id[0][np] = i;
+      S.flag[0][np] = 0;
+    }
+    S.keptpos[i] = S.tb[i];
+  }
+  __syncthreads();
+  for (int k = tid; k < nk; k += kQtThreads) knode[k] = (uint16_t)S.keptpos[knode[k]];
+  int next_id = nIni;
+  bool phase_b = false;
+  __syncthreads();
+
+  for (int round = 0; round < 4096; ++round) {  // n grows every round or the loop ends; the cap is a safety net
+    const int prev = n;
+    int nproc;
+    // ---- choose the nodes to split this round and their processing order
+    if (!phase_b) {  // every node with >1 keys, in list order (:602-641)
+      for (int p = tid; p < n; p += kQtThreads) S.ta[p] = S.cnt[cur][p] > 1 ? 1 : 0;
+      __syncthreads();
+      warp0_excl_scan(S.ta, n, &s_total);
+      __syncthreads();
+      nproc = s_total;
+      for (int p = tid; p < n; p += kQtThreads) {
+        if (S.cnt[cur][p] > 1) {
+          S.prank[p] = S.ta[p];
+          S.ord[S.ta[p]] = p;
+        } else
+          S.prank[p] = -1;
+      }
+    } else {  // the children created last round with >1 keys, largest first, ties: latest created first (:644-652)
+      for (int p = tid; p < n; p += kQtThreads) S.ta[p] = S.flag[cur][p] ? 1 : 0;
+      __syncthreads();
+      warp0_excl_scan(S.ta, n, &s_total);
+      __syncthreads();
+      nproc = s_total;
+      for (int p = tid; p < n; p += kQtThreads) {
+        if (S.flag[cur][p]) S.tb[S.ta[p]] = p;  // compact list of expandable positions
+      }
+      __syncthreads();
+      for (int e = tid; e < nproc; e += kQtThreads) {
+        const int p = S.tb[e];
+        const int c = S.cnt[cur][p], idp = S.id[cur][p];
+        int r = 0;
+        for (int e2 = 0; e2 < nproc; ++e2) {
+          const int p2 = S.tb[e2];
+          const int c2 = S.cnt[cur][p2], id2 = S.id[cur][p2];
+          r += (c2 > c || (c2 == c && id2 > idp)) ? 1 : 0;
+        }
+        S.ord[r] = p;
+      }
+      __syncthreads();
+      for (int p = tid; p < n; p += kQtThreads) S.prank[p] = -1;
+      __syncthreads();
+      for (int r = tid; r < nproc; r += kQtThreads) S.prank[S.ord[r]] = r;
+    }
+    for (int i = tid; i < 4 * n; i += kQtThreads) S.cc[i] = 0;
+    __syncthreads();
+    if (nproc == 0) break;  // nothing split: list size unchanged -> finish (:664, :716)
+    // ---- children sizes
+    for (int k = tid; k < nk; k += kQtThreads) {
+      const int p = knode[k];
+      if (S.prank[p] >= 0) {
+        const uint32_t key = keys[k];
+        const int q = qt_quad(S, cur, p, (int)(key & 0xfff) - kBorder, (int)((key >> 12) & 0xfff) - kBorder);
+        atomicAdd(&S.cc[4 * p + q], 1);
+      }
+    }
+    __syncthreads();
+    if (phase_b) {  // stop splitting as soon as the list reaches N nodes (:713)
+      for (int r = tid; r < nproc; r += kQtThreads) {
+        const int p = S.ord[r];
+        S.ta[r] = (S.cc[4 * p] > 0) + (S.cc[4 * p + 1] > 0) + (S.cc[4 * p + 2] > 0) + (S.cc[4 * p + 3] > 0) - 1;
+      }
+      if (tid == 0) s_cut = nproc;
+      __syncthreads();
+      warp0_excl_scan(S.ta, nproc, &s_total);
+      __syncthreads();
+      for (int r = tid; r < nproc; r += kQtThreads) {
+        const int p = S.ord[r];
+        const int d = (S.cc[4 * p] > 0) + (S.cc[4 * p + 1] > 0) + (S.cc[4 * p + 2] > 0) + (S.cc[4 * p + 3] > 0) - 1;
+        const int after = n + S.ta[r] + d;
+        const int before = n + S.ta[r];
+        if (after >= N && before < N) s_cut = r + 1;  // unique: `after` is non-decreasing in r
+      }
+      __syncthreads();
+      const int cut = s_cut;
+      for (int r = cut + tid; r < nproc; r += kQtThreads) S.prank[S.ord[r]] = -1;
+      nproc = cut;
+      __syncthreads();
+    }
+    // ---- layout of the new list
+    for (int r = tid; r < nproc; r += kQtThreads) {
+      const int p = S.ord[r];
+      S.ta[r] = (S.cc[4 * p] > 0) + (S.cc[4 * p + 1] > 0) + (S.cc[4 * p + 2] > 0) + (S.cc[4 * p + 3] > 0);
+    }
+    for (int p = tid; p < n; p += kQtThreads) S.tb[p] = S.prank[p] < 0 ? 1 : 0;
+    __syncthreads();
+    warp0_excl_scan(S.ta, nproc, &s_total);
+    __syncthreads();
+    warp0_excl_scan(S.tb, n, &s_total2);
+    __syncthreads();
+    const int C = s_total, K = s_total2;
+    const int nxt = cur ^ 1;
+    for (int p = tid; p < n; p += kQtThreads) {
+      const int r = S.prank[p];
+      if (r < 0) {
+        const int np = C + S.tb[p];
+        S.x0[nxt][np] = S.x0[cur][p];
+        S.x1[nxt][np] = S.x1[cur][p];
+        S.y0[nxt][np] = S.y0[cur][p];
+        S.y1[nxt][np] = S.y1[cur][p];
+        S.cnt[nxt][np] = S.cnt[cur][p];
+        S.id[nxt][np] = S.id[cur][p];
+        S.flag[nxt][np] = 0;
+        S.keptpos[p] = np;
+      } else {
+        int c = S.ta[r];
+        const int ax0 = S.x0[cur][p], ax1 = S.x1[cur][p], ay0 = S.y0[cur][p], ay1 = S.y1[cur][p];
+        const int mx = ax0 + ((ax1 - ax0 + 1) >> 1), my = ay0 + ((ay1 - ay0 + 1) >> 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cq = S.cc[4 * p + q];
+          if (cq == 0) continue;
+          const int np = C - 1 - c;
+          S.x0[nxt][np] = (int16_t)((q & 1) ? mx : ax0);
+          S.x1[nxt][np] = (int16_t)((q & 1) ? ax1 : mx);
+          S.y0[nxt][np] = (int16_t)((q & 2) ? my : ay0);
+          S.y1[nxt][np] = (int16_t)((q & 2) ? ay1 : my);
+          S.cnt[nxt][np] = cq;
+          S.id[nxt][np] = next_id + c;
+          S.flag[nxt][np] = cq > 1 ? 1 : 0;
+          S.cpos[4 * p + q] = np;
+          ++c;
+        }
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < nk; k += kQtThreads) {
+      const int p = knode[k];
+      if (S.prank[p] >= 0) {
+        const uint32_t key = keys[k];
+        const int q = qt_quad(S, cur, p, (int)(key & 0xfff) - kBorder, (int)((key >> 12) & 0xfff) - kBorder);
+        knode[k] = (uint16_t)S.cpos[4 * p + q];
+      } else {
+        knode[k] = (uint16_t)S.keptpos[p];
+      }
+    }
+    n = C + K;
+    next_id += C;
+    cur = nxt;
+    __syncthreads();
+    if (n >= N || n == prev) break;
+    if (!phase_b) {  // would splitting every expandable child overshoot N?  then go largest-first (:669)
+      if (tid == 0) s_total = 0;
+      __syncthreads();
+      int mine = 0;
+      for (int p = tid; p < n; p += kQtThreads) mine += S.flag[cur][p];
+      if (mine) atomicAdd(&s_total, mine);
+      __syncthreads();
+      if (n + 3 * s_total > N) phase_b = true;
+      __syncthreads();
+    }
+  }
+  // ---- per node: highest response, first in candidate order (:702-718)
+  for (int p = tid; p < n; p += kQtThreads) S.ta[p] = 0;
+  __syncthreads();
+  for (int k = tid; k < nk; k += kQtThreads) {
+    const uint32_t key = keys[k];
+    atomicMax((unsigned int*)&S.ta[knode[k]], ((key >> 24) << 20) | (uint32_t)(0xFFFFF - k));
+  }
+  __syncthreads();
+  for (int p = tid; p < n; p += kQtThreads) {
+    const int k = 0xFFFFF - (int)((uint32_t)S.ta[p] & 0xFFFFF);
+    out_kp[p] = keys[k];
+  }
+  if (tid == 0) *out_cnt = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cv::fastAtan2 scalar path, fp32 with explicit rounding (the library is built with -fmad=false).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float s = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s,
+              p7 = -0.04432655554792128f * s;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = ay / (ax + 2.2204460492503131e-16f);
+    c2 = c * c;
+    a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  } else {
+    c = ax / (ay + 2.2204460492503131e-16f);
+    c2 = c * c;
+    a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  }
+  if (x < 0) a = 180.f - a;
+  if (y < 0) a = 360.f - a;
+  return a;
+}
+
+// glibc 2.39 sinf/cosf algorithm (double polynomial after pi/2 reduction) — the reference's
+// (float)cos(angle) / (float)sin(angle) at src/ORBextractor.cc:84-85 resolve to these.
+__device__ __forceinline__ float sc_poly(double x, double x2, int n, bool neg_cos) {
+  if ((n & 1) == 0) {
+    const double s1c = -0x1.555545995a603p-3, s2c = 0x1.1107605230bc4p-7, s3c = -0x1.994eb3774cf24p-13;
+    const double x3 = x * x2, s1 = s2c + x2 * s3c, x7 = x3 * x2, s = x + x3 * s1c;
+    return (float)(s + x7 * s1);
+  }
+  const double sg = neg_cos ? -1.0 : 1.0;
+  const double c0 = sg * 0x1p0, c1c = sg * -0x1.ffffffd0c621cp-2, c2c = sg * 0x1.55553e1068f19p-5,
+               c3c = sg * -0x1.6c087e89a359dp-10, c4c = sg * 0x1.99343027bf8c3p-16;
+  const double x4 = x2 * x2, c2 = c3c + x2 * c4c, c1 = c0 + x2 * c1c, x6 = x4 * x2, c = c1 + x4 * c2c;
+  return (float)(c + x6 * c2);
+}
+__device__ __forceinline__ void sincos_ref(float y, float* sn, float* cs) {
+  double x = (double)y;
+  const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ff;
+  if (top < ((__float_as_uint(0x1.921FB6p-1f) >> 20) & 0x7ff)) {
+    const double x2 = x * x;
+    if (top < ((__float_as_uint(0x1p-12f) >> 20) & 0x7ff)) {
+      *sn = y;
+      *cs = 1.0f;
+      return;
+    }
+    *sn = sc_poly(x, x2, 0, false);
+    *cs = sc_poly(x, x2, 1, false);
+    return;
+  }
+  const double r = x * 0x1.45F306DC9C883p+23;
+  const int n = ((int)r + 0x800000) >> 24;
+  x = x - (double)n * 0x1.921FB54442D18p0;
+  const int q = n & 3;
+  const double s = (q == 1 || q == 2) ? -1.0 : 1.0;
+  const bool neg = (n & 2) != 0;
+  *sn = sc_poly(x * s, x * x, n, neg);
+  *cs = sc_poly(x * s, x * x, n ^ 1, neg);
+}
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (p < 0) p = -p;
+  if (p >= n) p = 2 * n - 2 - p;
+  return p;
+}
+
+// One warp per keypoint: stage the 43x43 raw patch (REFLECT_101 at the image edge, as the blur of the
+// cloned level does), intensity-centroid angle on the raw pixels, separable 7-tap fixed-point blur
+// (exact integer accumulation, one final rounding — OpenCV's 8U GaussianBlur path) evaluated only where
+// the 512 steered samples land, then the 256 binary tests.  Also assembles the level-ordered output.
+__global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(OrbParams P, const uint8_t* __restrict__ img0,
+                                                                size_t img0_stride, int img0_pitch,
+                                                                VieoKeyPoint* __restrict__ kps,
+                                                                uint8_t* __restrict__ desc, int cap,
+                                                                int* __restrict__ n_kp) {
+  __shared__ __align__(16) uint8_t s_raw[kDescWarps][kPW * kPWp];
+  __shared__ __align__(16) uint16_t s_hb[kDescWarps][kPW * kBWp];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.y;
+  const int slot = blockIdx.x * kDescWarps + warp;
+  const int* lc = P.lvl_cnt + (size_t)img * P.nlevels;
+  int level = -1, j = 0, total = 0;
+  for (int l = 0; l < P.nlevels; ++l) {
+    const int c = lc[l];
+    if (level < 0 && slot < total + c) {
+      level = l;
+      j = slot - total;
+    }
+    total += c;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) n_kp[img] = min(total, cap);
+  if (level < 0 || slot >= cap) return;
+  const uint32_t key = P.lvl_kp[(size_t)img * P.slot_begin[P.nlevels] + P.slot_begin[level] + j];
+  const int kx = key & 0xfff, ky = (key >> 12) & 0xfff;
+  const uint8_t* base;
+  int pitch;
+  if (level == 0) {
+    base = img0 + img * img0_stride;
+    pitch = img0_pitch;
+  } else {
+    base = P.lvl[level] + img * P.img_stride[level];
+    pitch = P.pitch[level];
+  }
+  const int W = P.w[level], H = P.h[level];
+  uint8_t* raw = s_raw[warp];
+  uint16_t* hb = s_hb[warp];
+  for (int i = lane; i < kPW * kPW; i += 32) {
+    const int r = i / kPW, c = i - r * kPW;
+    const int gy = reflect101(ky - kPR + r, H), gx = reflect101(kx - kPR + c, W);
+    raw[r * kPWp + c] = __ldg(base + (size_t)gy * pitch + gx);
+  }
+  __syncwarp();
+  // intensity centroid over the radius-15 disc: lane = row v in [-15, 15]
+  int m10 = 0, m01 = 0;
+  if (lane < 2 * kHalfPatch + 1) {
+    const int v = lane - kHalfPatch;
+    const int d = c_umax[v < 0 ? -v : v];
+    const uint8_t* row = raw + (kPR + v) * kPWp + kPR;
+    int rs = 0;
+    for (int u = -d; u <= d; ++u) {
+      const int val = row[u];
+      m10 += u * val;
+      rs += val;
+    }
+    m01 = v * rs;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+  // horizontal pass, 8-fractional-bit kernel {18,34,48,56,48,34,18} (sum 256): exact in 16 bits
+  for (int i = lane; i < kPW * kBW; i += 32) {
+    const int r = i / kBW, c = i - r * kBW;
+    const uint8_t* s = raw + r * kPWp + c;
+    hb[r * kBWp + c] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+  }
+  __syncwarp();
+  float sn, cs;
+  sincos_ref(angle * (float)(3.14159265358979323846 / 180.f), &sn, &cs);
+  const int8_t* pat = d_pattern + lane * 32;
+  int byte = 0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    int v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float px = (float)pat[4 * t + 2 * e], py = (float)pat[4 * t + 2 * e + 1];
+      const int ry = __float2int_rn(px * sn + py * cs);
+      const int rx = __float2int_rn(px * cs - py * sn);
+      const uint16_t* h = hb + (ry + 18) * kBWp + rx + 18;
+      const uint32_t acc = 18u * (h[0] + h[6 * kBWp]) + 34u * (h[kBWp] + h[5 * kBWp]) +
+                           48u * (h[2 * kBWp] + h[4 * kBWp]) + 56u * h[3 * kBWp];
+      v[e] = (int)((acc + 32768u) >> 16);
+    }
+    byte |= (v[0] < v[1] ? 1 : 0) << t;
+  }
+  desc[((size_t)img * cap + slot) * 32 + lane] = (uint8_t)byte;
+  if (lane == 0) {
+    VieoKeyPoint k;
+    const float sc = P.scale[level];
+    k.x = level ? (float)kx * sc : (float)kx;
+    k.y = level ? (float)ky * sc : (float)ky;
+    k.size = P.kp_size[level];
+    k.angle = angle;
+    k.response = (float)(key >> 24);
+    k.octave = level;
+    kps[(size_t)img * cap + slot] = k;
+  }
+}
+
+}  // namespace vieo
+
+// =================================================================================================
+using namespace vieo;
+
+struct vieo_orb {
+  VieoOrbConfig cfg;
+  int device;
+  OrbParams P;
+  cudaStream_t stream;
+  float inv_scale[kMaxLevels], sigma2[kMaxLevels], inv_sigma2[kMaxLevels];
+  int cap_total;  // sum of maxn
+  size_t fast_smem, qt_smem;
+  std::vector<void*> allocs;
+  // staging for the host API
+  VieoKeyPoint* d_kps;
+  uint8_t* d_desc;
+  int* d_nkp;
+  void* h_pinned;  // pinned bounce for small D2H (counts)
+  int last_launches;
+  int last_n_img;
+  const uint8_t* last_img0;  // level-0 source of the last call (debug)
+  size_t last_img0_stride;
+  int last_img0_pitch;
+};
+
+namespace {
+
+inline int cv_roundf(float v) { return (int)nearbyintf(v); }
+
+template <class T>
+int dev_alloc(vieo_orb* h, T** p, size_t count) {
+  void* q = nullptr;
+  VIEO_CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return VIEO_OK;
+}
+
+template <class T>
+int dev_upload(vieo_orb* h, const T** p, const std::vector<T>& v) {
+  T* q;
+  int rc = dev_alloc(h, &q, v.size());
+  if (rc) return rc;
+  VIEO_CK(cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *p = q;
+  return VIEO_OK;
+}
+
+int orb_run(vieo_orb* h, int n_img, const uint8_t* img0, size_t img0_stride, int img0_pitch, VieoKeyPoint* kps,
+            uint8_t* desc, int cap, int* n_kp, cudaStream_t st) {
+  const OrbParams& P = h->P;
+  int launches = 0;
+  for (int l = 1; l < P.nlevels; ++l) {
+    const uint8_t* src = l == 1 ? img0 : P.lvl[l - 1];
+    const size_t sstride = l == 1 ? img0_stride : P.img_stride[l - 1];
+    const int spitch = l == 1 ? img0_pitch : P.pitch[l - 1];
+    dim3 grid((P.w[l] + 127) / 128, (P.h[l] + 7) / 8, n_img), block(32, 8);
+    k_resize<<<grid, block, 0, st>>>(src, sstride, spitch, P.lvl[l], P.img_stride[l], P.pitch[l], P.w[l], P.h[l],
+                                     P.rx[l], P.ry[l]);
+    ++launches;
+  }
+  k_fast_cells<<<dim3(P.n_cells, n_img), kFastThreads, h->fast_smem, st>>>(P, img0, img0_stride, img0_pitch);
+  k_quadtree<<<dim3(P.nlevels, n_img), kQtThreads, h->qt_smem, st>>>(P);
+  const int slots = std::min(cap, h->cap_total);
+  k_orient_desc<<<dim3((slots + kDescWarps - 1) / kDescWarps, n_img), kDescWarps * 32, 0, st>>>(
+      P, img0, img0_stride, img0_pitch, kps, desc, cap, n_kp);
+  launches += 3;
+  VIEO_CK(cudaGetLastError());
+  h->last_launches = launches;
+  h->last_n_img = n_img;
+  h->last_img0 = img0;
+  h->last_img0_stride = img0_stride;
+  h->last_img0_pitch = img0_pitch;
+  return VIEO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out) {
+  VIEO_ARG(cfg && out, "null argument");
+  VIEO_ARG(cfg->nlevels >= 1 && cfg->nlevels <= kMaxLevels, "nlevels must be in [1,16]");
+  VIEO_ARG(cfg->width >= 64 && cfg->height >= 64 && cfg->width < 4096 && cfg->height < 4096,
+           "image size must be in [64,4096)");
+  VIEO_ARG(cfg->nfeatures > 0 && cfg->scale_factor > 1.0f && cfg->max_batch >= 1, "bad nfeatures/scale/max_batch");
+  VIEO_ARG(cfg->min_th_fast >= 1 && cfg->ini_th_fast >= cfg->min_th_fast && cfg->ini_th_fast < 255,
+           "need 1 <= minThFAST <= iniThFAST < 255");
+  int rc = use_device(device);
+  if (rc) return rc;
+  vieo_orb* h = new vieo_orb();
+  h->cfg = *cfg;
+  h->device = device;
+  OrbParams& P = h->P;
+  memset(&P, 0, sizeof(P));
+  const int L = cfg->nlevels;
+  P.nlevels = L;
+  P.ini_th = cfg->ini_th_fast;
+  P.min_th = cfg->min_th_fast;
+  // scale tables and quotas: same arithmetic as src/ORBextractor.cc:397-431 (scaleFactor is a double member)
+  const double sf = (double)cfg->scale_factor;
+  P.scale[0] = 1.f;
+  h->sigma2[0] = 1.f;
+  for (int i = 1; i < L; ++i) {
+    P.scale[i] = (float)(P.scale[i - 1] * sf);
+    h->sigma2[i] = P.scale[i] * P.scale[i];
+  }
+  for (int i = 0; i < L; ++i) {
+    h->inv_scale[i] = 1.0f / P.scale[i];
+    h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+    P.kp_size[i] = (float)(int)(31 * P.scale[i]);
+  }
+  {
+    const float factor = (float)(1.0f / sf);
+    float per = (float)(cfg->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)L)));
+    int sum = 0;
+    for (int l = 0; l < L - 1; ++l) {
+      P.quota[l] = cv_roundf(per);
+      sum += P.quota[l];
+      per *= factor;
+    }
+    P.quota[L - 1] = std::max(cfg->nfeatures - sum, 0);
+  }
+  int umax[kHalfPatch + 1];
+  {
+    const int vmax = (int)floorf(kHalfPatch * sqrtf(2.f) / 2 + 1), vmin = (int)ceilf(kHalfPatch * sqrtf(2.f) / 2);
+    for (int v = 0; v <= vmax; ++v) umax[v] = (int)nearbyint(sqrt((double)kHalfPatch * kHalfPatch - v * v));
+    for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+      while (umax[v0] == umax[v0 + 1]) ++v0;
+      umax[v] = v0;
+      ++v0;
+    }
+  }
+  // levels, cells
+  std::vector<Cell> cells;
+  int max_cw = 0, max_ch = 0, max_npx = 0;
+  for (int l = 0; l < L; ++l) {
+    P.w[l] = cv_roundf((float)cfg->width * h->inv_scale[l]);
+    P.h[l] = cv_roundf((float)cfg->height * h->inv_scale[l]);
+    P.pitch[l] = (P.w[l] + 63) & ~63;
+    P.img_stride[l] = (size_t)P.pitch[l] * P.h[l];
+    P.cell_begin[l] = (int)cells.size();
+    const int maxBX = P.w[l] - kBorder, maxBY = P.h[l] - kBorder;
+    const float width = (float)(maxBX - kBorder), height = (float)(maxBY - kBorder);
+    const int nCols = (int)(width / 35.f), nRows = (int)(height / 35.f);
+    if (P.w[l] < 1 || P.h[l] < 1) {
+      set_error("level %d is empty (%dx%d)", l, P.w[l], P.h[l]);
+      delete h;
+      return VIEO_E_ARG;
+    }
+    if (nCols <= 0 || nRows <= 0) {  // level smaller than one 35-px cell: the reference's cell loops do not run
+      P.maxn[l] = 1;
+      continue;
+    }
+    const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
+    for (int i = 0; i < nRows; ++i) {
+      const float iniY = (float)(kBorder + i * hCell);
+      float maxY = iniY + hCell + 6;
+      if (iniY >= maxBY - 3) continue;
+      if (maxY > maxBY) maxY = (float)maxBY;
+      for (int j = 0; j < nCols; ++j) {
+        const float iniX = (float)(kBorder + j * wCell);
+        float maxX = iniX + wCell + 6;
+        if (iniX >= maxBX - 6) continue;
+        if (maxX > maxBX) maxX = (float)maxBX;
+        Cell c;
+        c.level = (int16_t)l;
+        c.x0 = (int16_t)iniX;
+        c.y0 = (int16_t)iniY;
+        c.cw = (int16_t)((int)maxX - (int)iniX);
+        c.ch = (int16_t)((int)maxY - (int)iniY);
+        cells.push_back(c);
+        max_cw = std::max<int>(max_cw, c.cw);
+        max_ch = std::max<int>(max_ch, c.ch);
+        max_npx = std::max(max_npx, std::max(0, c.cw - 6) * std::max(0, c.ch - 6));
+      }
+    }
+    const int spanX = maxBX - kBorder, spanY = maxBY - kBorder;
+    const int nIni = (int)roundf((float)spanX / (float)spanY);
+    if (nIni < 1) {
+      set_error("level %d: aspect ratio gives zero quadtree roots (the reference divides by zero here)", l);
+      delete h;
+      return VIEO_E_ARG;
+    }
+    P.maxn[l] = std::max(P.quota[l] + 3, 4 * nIni) + 1;
+  }
+  P.cell_begin[L] = (int)cells.size();
+  P.n_cells = (int)cells.size();
+  P.tile_w = (max_cw + 3) & ~3;
+  P.tile_h = max_ch;
+  P.cell_cap = ((max_cw - 6 + 1) / 2) * ((max_ch - 6 + 1) / 2);
+  bool ok = (max_npx + kFastThreads - 1) / kFastThreads <= 32;
+  for (int l = 0; l < L && ok; ++l) {
+    ok = (P.cell_begin[l + 1] - P.cell_begin[l]) <= 512 &&
+         (size_t)(P.cell_begin[l + 1] - P.cell_begin[l]) * P.cell_cap < (1u << 20) && P.maxn[l] < 65536;
+  }
+  if (!ok) {
+    set_error("unsupported geometry (cell grid / quota limits exceeded)");
+    delete h;
+    return VIEO_E_ARG;
+  }
+  P.slot_begin[0] = 0;
+  int max_maxn = 0;
+  for (int l = 0; l < L; ++l) {
+    P.key_begin[l] = P.cell_begin[l] * P.cell_cap;
+    P.slot_begin[l + 1] = P.slot_begin[l] + P.maxn[l];
+    max_maxn = std::max(max_maxn, P.maxn[l]);
+  }
+  P.key_begin[L] = P.n_cells * P.cell_cap;
+  h->cap_total = P.slot_begin[L];
+  h->fast_smem = (size_t)P.tile_w * P.tile_h + (size_t)P.tile_w * (P.tile_h - 6 + 2);
+  h->qt_smem = (size_t)max_maxn * (2 * (4 + 4 + 2 * 4 + 1) + 16 + 16 + 5 * 4) + 16 * 32;
+  if (h->qt_smem > 200 * 1024) {
+    set_error("per-level feature quota %d needs %zu B of shared memory for the quadtree (limit 200 KiB)", max_maxn,
+              h->qt_smem);
+    delete h;
+    return VIEO_E_ARG;
+  }
+
+#define ORB_TRY(expr)          \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_) {                 \
+      vieo_orb_destroy(h);     \
+      return rc_;              \
+    }                          \
+  } while (0)
+#define ORB_TRY_CUDA(call)                                                                         \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));              \
+      vieo_orb_destroy(h);                                                                         \
+      return VIEO_E_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+  ORB_TRY_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  ORB_TRY_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
+  const size_t B = cfg->max_batch;
+  for (int l = 0; l < L; ++l) ORB_TRY(dev_alloc(h, &P.lvl[l], B * P.img_stride[l] + 64));
+  ORB_TRY(dev_upload(h, &P.cells, cells));
+  // resize tables (cv::resize INTER_LINEAR 8U: 11-bit coefficients from float fx, see oracle + goldens)
+  for (int l = 1; l < L; ++l) {
+    const int sw = P.w[l - 1], sh = P.h[l - 1], dw = P.w[l], dh = P.h[l];
+    const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+    std::vector<int4> tx(dw), ty(dh);
+    for (int dx = 0; dx < dw; ++dx) {
+      float fx = (float)((dx + 0.5) * scale_x - 0.5);
+      int sx = (int)floorf(fx);
+      fx -= sx;
+      if (sx < 0) fx = 0, sx = 0;
+      if (sx >= sw - 1) fx = 0, sx = sw - 1;
+      tx[dx] = make_int4(sx, std::min(sx + 1, sw - 1), (short)cv_roundf((1.f - fx) * 2048.f),
+                         (short)cv_roundf(fx * 2048.f));
+    }
+    for (int dy = 0; dy < dh; ++dy) {
+      float fy = (float)((dy + 0.5) * scale_y - 0.5);
+      int sy = (int)floorf(fy);
+      fy -= sy;
+      ty[dy] = make_int4(std::min(std::max(sy, 0), sh - 1), std::min(std::max(sy + 1, 0), sh - 1),
+                         (short)cv_roundf((1.f - fy) * 2048.f), (short)cv_roundf(fy * 2048.f));
+    }
+    ORB_TRY(dev_upload(h, &P.rx[l], tx));
+    ORB_TRY(dev_upload(h, &P.ry[l], ty));
+  }
+  ORB_TRY(dev_alloc(h, &P.cand, B * P.n_cells * P.cell_cap));
+  ORB_TRY(dev_alloc(h, &P.cell_cnt, B * P.n_cells));
+  ORB_TRY(dev_alloc(h, &P.keys, B * P.key_begin[L]));
+  ORB_TRY(dev_alloc(h, &P.knode, B * P.key_begin[L]));
+  ORB_TRY(dev_alloc(h, &P.lvl_kp, B * P.slot_begin[L]));
+  ORB_TRY(dev_alloc(h, &P.lvl_cnt, B * L));
+  ORB_TRY(dev_alloc(h, &h->d_kps, B * h->cap_total));
+  ORB_TRY(dev_alloc(h, &h->d_desc, B * h->cap_total * 32));
+  ORB_TRY(dev_alloc(h, &h->d_nkp, B));
+  ORB_TRY_CUDA(cudaMallocHost(&h->h_pinned, sizeof(int) * B));
+  ORB_TRY_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
+  ORB_TRY_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qt_smem));
+  *out = h;
+  return VIEO_OK;
+}
+
+void vieo_orb_destroy(vieo_orb_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int vieo_orb_max_keypoints(const vieo_orb_t* h) { return h ? h->cap_total : VIEO_E_ARG; }
+
+int vieo_orb_get_tables(const vieo_orb_t* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                        int32_t* quota, int32_t* level_w, int32_t* level_h) {
+  VIEO_ARG(h, "null handle");
+  for (int l = 0; l < h->P.nlevels; ++l) {
+    if (scale) scale[l] = h->P.scale[l];
+    if (inv_scale) inv_scale[l] = h->inv_scale[l];
+    if (sigma2) sigma2[l] = h->sigma2[l];
+    if (inv_sigma2) inv_sigma2[l] = h->inv_sigma2[l];
+    if (quota) quota[l] = h->P.quota[l];
+    if (level_w) level_w[l] = h->P.w[l];
+    if (level_h) level_h[l] = h->P.h[l];
+  }
+  return VIEO_OK;
+}
+
+int vieo_orb_extract_batch_dev(vieo_orb_t* h, int n_img, const uint8_t* imgs_dev, size_t img_stride, int row_stride,
+                               VieoKeyPoint* kps_dev, uint8_t* desc_dev, int cap, int32_t* n_kp_dev, void* stream) {
+  VIEO_ARG(h && imgs_dev && kps_dev && desc_dev && n_kp_dev, "null argument");
+  VIEO_ARG(n_img >= 1 && n_img <= h->cfg.max_batch, "n_img exceeds max_batch");
+  VIEO_ARG(row_stride >= h->cfg.width && cap >= 1, "bad stride/cap");
+  VIEO_CK(cudaSetDevice(h->device));
+  return orb_run(h, n_img, imgs_dev, img_stride, row_stride, kps_dev, desc_dev, cap, n_kp_dev, (cudaStream_t)stream);
+}
+
+int vieo_orb_extract_batch(vieo_orb_t* h, int n_img, const uint8_t* imgs, size_t img_stride, int row_stride,
+                           VieoKeyPoint* kps, uint8_t* desc, int cap, int32_t* n_kp) {
+  VIEO_ARG(h && imgs && kps && desc && n_kp, "null argument");
+  VIEO_ARG(n_img >= 1 && n_img <= h->cfg.max_batch, "n_img exceeds max_batch");
+  VIEO_ARG(row_stride >= h->cfg.width && cap >= 1, "bad stride/cap");
+  VIEO_CK(cudaSetDevice(h->device));
+  const OrbParams& P = h->P;
+  const int dcap = std::min(cap, h->cap_total);
+  cudaStream_t st = h->stream;
+  if ((size_t)row_stride * h->cfg.height == img_stride && row_stride == P.pitch[0]) {
+    VIEO_CK(cudaMemcpyAsync(P.lvl[0], imgs, img_stride * n_img, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int i = 0; i < n_img; ++i)
+      VIEO_CK(cudaMemcpy2DAsync(P.lvl[0] + i * P.img_stride[0], P.pitch[0], imgs + i * img_stride, row_stride,
+                                h->cfg.width, h->cfg.height, cudaMemcpyHostToDevice, st));
+  }
+  int rc = orb_run(h, n_img, P.lvl[0], P.img_stride[0], P.pitch[0], h->d_kps, h->d_desc, dcap, h->d_nkp, st);
+  if (rc) return rc;
+  if (dcap == cap) {
+    VIEO_CK(cudaMemcpyAsync(kps, h->d_kps, sizeof(VieoKeyPoint) * (size_t)n_img * cap, cudaMemcpyDeviceToHost, st));
+    VIEO_CK(cudaMemcpyAsync(desc, h->d_desc, (size_t)32 * n_img * cap, cudaMemcpyDeviceToHost, st));
+  } else {
+    VIEO_CK(cudaMemcpy2DAsync(kps, sizeof(VieoKeyPoint) * (size_t)cap, h->d_kps, sizeof(VieoKeyPoint) * (size_t)dcap,
+                              sizeof(VieoKeyPoint) * (size_t)dcap, n_img, cudaMemcpyDeviceToHost, st));
+    VIEO_CK(cudaMemcpy2DAsync(desc, (size_t)32 * cap, h->d_desc, (size_t)32 * dcap, (size_t)32 * dcap, n_img,
+                              cudaMemcpyDeviceToHost, st));
+  }
+  VIEO_CK(cudaMemcpyAsync(n_kp, h->d_nkp, sizeof(int) * n_img, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaStreamSynchronize(st));
+  return VIEO_OK;
+}
+
+int vieo_orb_extract(vieo_orb_t* h, const uint8_t* img, int stride, const int32_t* lapping, VieoKeyPoint* kps,
+                     uint8_t* desc, int cap, int32_t* n_mono, uint8_t* const* pyr_host) {
+  VIEO_ARG(h, "null handle");
+  if (n_mono) *n_mono = 0;
+  if (!img || stride <= 0) return VIEO_E_EMPTY;
+  VIEO_ARG(kps && desc && cap >= 1, "null output");
+  const int W = h->cfg.width;
+  VIEO_ARG(stride >= W, "stride < width");
+  int n = 0;
+  const int full = h->cap_total;
+  std::vector<VieoKeyPoint> tk;
+  std::vector<uint8_t> td;
+  VieoKeyPoint* ok = kps;
+  uint8_t* od = desc;
+  const bool bounce = lapping != nullptr || cap < full;
+  if (bounce) {
+    tk.resize(full);
+    td.resize((size_t)full * 32);
+    ok = tk.data();
+    od = td.data();
+  }
+  int rc = vieo_orb_extract_batch(h, 1, img, (size_t)stride * h->cfg.height, stride, ok, od, bounce ? full : cap, &n);
+  if (rc) return rc;
+  if (bounce) {
+    if (n > cap) {
+      set_error("caller capacity %d < %d keypoints", cap, n);
+      return VIEO_E_CAPACITY;
+    }
+    if (lapping) {  // in-area keypoints fill from the back, the others from the front (src/ORBextractor.cc:1041-1052)
+      int mono = 0, stereo = n - 1;
+      for (int i = 0; i < n; ++i) {
+        const bool in = tk[i].x >= (float)lapping[0] && tk[i].x <= (float)lapping[1];
+        const int s = in ? stereo-- : mono++;
+        kps[s] = tk[i];
+        memcpy(desc + (size_t)s * 32, td.data() + (size_t)i * 32, 32);
+      }
+      if (n_mono) *n_mono = mono;
+    } else {
+      memcpy(kps, tk.data(), sizeof(VieoKeyPoint) * n);
+      memcpy(desc, td.data(), (size_t)32 * n);
+    }
+  }
+  if (pyr_host) {
+    for (int l = 0; l < h->P.nlevels; ++l)
+      if (pyr_host[l]) {
+        rc = vieo_orb_debug_level(h, 0, l, pyr_host[l]);
+        if (rc) return rc;
+      }
+  }
+  return n;
+}
+
+int vieo_orb_debug_level(vieo_orb_t* h, int img_index, int level, uint8_t* out) {
+  VIEO_ARG(h && out && level >= 0 && level < h->P.nlevels && img_index >= 0 && img_index < h->last_n_img,
+           "bad argument");
+  VIEO_CK(cudaSetDevice(h->device));
+  const OrbParams& P = h->P;
+  const uint8_t* src = level == 0 ? h->last_img0 + img_index * h->last_img0_stride
+                                  : P.lvl[level] + img_index * P.img_stride[level];
+  const int pitch = level == 0 ? h->last_img0_pitch : P.pitch[level];
+  VIEO_CK(cudaDeviceSynchronize());
+  VIEO_CK(cudaMemcpy2D(out, P.w[level], src, pitch, P.w[level], P.h[level], cudaMemcpyDeviceToHost));
+  return VIEO_OK;
+}
+
+int vieo_orb_debug_candidates(vieo_orb_t* h, int img_index, int level, int32_t* xyr, int cap) {
+  VIEO_ARG(h && level >= 0 && level < h->P.nlevels && img_index >= 0 && img_index < h->last_n_img, "bad argument");
+  VIEO_CK(cudaSetDevice(h->device));
+  const OrbParams& P = h->P;
+  const int nc = P.cell_begin[level + 1] - P.cell_begin[level];
+  std::vector<int> cnt(nc);
+  std::vector<uint32_t> cand((size_t)nc * P.cell_cap);
+  VIEO_CK(cudaDeviceSynchronize());
+  VIEO_CK(cudaMemcpy(cnt.data(), P.cell_cnt + (size_t)img_index * P.n_cells + P.cell_begin[level], sizeof(int) * nc,
+                     cudaMemcpyDeviceToHost));
+  VIEO_CK(cudaMemcpy(cand.data(), P.cand + ((size_t)img_index * P.n_cells + P.cell_begin[level]) * P.cell_cap,
+                     sizeof(uint32_t) * cand.size(), cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (int c = 0; c < nc; ++c)
+    for (int i = 0; i < cnt[c]; ++i, ++n) {
+      if (n < cap && xyr) {
+        const uint32_t k = cand[(size_t)c * P.cell_cap + i];
+        xyr[3 * n] = k & 0xfff;
+        xyr[3 * n + 1] = (k >> 12) & 0xfff;
+        xyr[3 * n + 2] = k >> 24;
+      }
+    }
+  return n;
+}
+
+int vieo_orb_last_launches(const vieo_orb_t* h) { return h ? h->last_launches : VIEO_E_ARG; }
+
+}  // extern "C"
