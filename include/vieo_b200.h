@@ -88,6 +88,12 @@ int vieo_orb_debug_level(vieo_orb_t* h, int img_index, int level, uint8_t* out);
 int vieo_orb_debug_candidates(vieo_orb_t* h, int img_index, int level, int32_t* xyr, int cap);
 /* number of kernel launches issued by the last extract call (bench.py's gpu_launches) */
 int vieo_orb_last_launches(const vieo_orb_t* h);
+/* Per-stage device timing with CUDA events on the launching stream (the reference's mlog::Timer stamps,
+ * common/mlog/log.h:109-155, moved to the device).  vieo_orb_profile(h,1) arms it; every following extract
+ * call records 5 events; vieo_orb_profile_read sums {pyramid, fast_cells, quadtree, orient_desc} ms over the
+ * calls since the last read (at most 1024) and rearms. */
+int vieo_orb_profile(vieo_orb_t* h, int enable);
+int vieo_orb_profile_read(vieo_orb_t* h, float stage_ms[4], int32_t* n_calls);
 
 /* ------------------------------------------------------------------------------------------------
  * 256-bit Hamming matching — replaces ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1645-1667),
@@ -99,16 +105,33 @@ int vieo_orb_last_launches(const vieo_orb_t* h);
  * neighbours are idx -1 / dist INT32_MAX. */
 int vieo_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist, int device);
 /* n_pairs independent (query set, train set) pairs, device resident.  Pair p: q + p*q_stride (bytes),
- * nq_dev[p] rows (<= max_nq); t likewise; idx/dist = [n_pairs][max_nq][2]. */
+ * nq_dev[p*count_stride] rows (<= max_nq); t likewise; idx/dist = [n_pairs][max_nq][2]. */
 int vieo_hamming_knn2_batch_dev(const uint8_t* q_dev, size_t q_stride, const int32_t* nq_dev, int max_nq,
                                 const uint8_t* t_dev, size_t t_stride, const int32_t* nt_dev, int max_nt,
-                                int n_pairs, int32_t* idx_dev, int32_t* dist_dev, void* stream);
+                                int count_stride, int n_pairs, int32_t* idx_dev, int32_t* dist_dev, void* stream);
 /* Candidate-list search: row r compares q row r with t rows cand[row_ptr[r] .. row_ptr[r+1]) in list
  * order; strict '<' keeps the first of equal distances (the reference's loops).  Outputs per row: best
  * and second-best distance (256 when absent) and their train indices (-1 when absent). */
 int vieo_hamming_csr(const uint8_t* q, const uint8_t* t, int nt, const int32_t* row_ptr, const int32_t* cand,
                      int nrows, int32_t* best_dist, int32_t* best_idx, int32_t* second_dist, int32_t* second_idx,
                      int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stereo front-end over HOST buffers — the hot work of the Frame::Frame stereo constructor
+ * (src/Frame.cc:218-316): ORBextractor::operator() for both cameras (:259-278) and the brute-force
+ * left->right knnMatch(k=2) of ComputeStereoFishEyeMatches (:620-628), for a batch of frames, with the
+ * host<->device copies pipelined against the kernels on independent streams.
+ *   imgs        [n_frames][2][height] rows of row_stride bytes (left, right), ideally pinned
+ *   kps/desc    [2*n_frames][cap] / [2*n_frames][cap][32], cap = vieo_frontend_max_keypoints()
+ *   n_kp        [2*n_frames]
+ *   match_idx / match_dist   [n_frames][cap][2]: for left keypoint i its two nearest right descriptors */
+typedef struct vieo_frontend vieo_frontend_t;
+int vieo_frontend_create(const VieoOrbConfig* cfg, int max_frames, int device, vieo_frontend_t** out);
+void vieo_frontend_destroy(vieo_frontend_t* f);
+int vieo_frontend_max_keypoints(const vieo_frontend_t* f);
+int vieo_frontend_last_launches(const vieo_frontend_t* f);
+int vieo_frontend_process(vieo_frontend_t* f, int n_frames, const uint8_t* imgs, int row_stride, VieoKeyPoint* kps,
+                          uint8_t* desc, int32_t* n_kp, int32_t* match_idx, int32_t* match_dist);
 
 #ifdef __cplusplus
 }

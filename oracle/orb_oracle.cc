@@ -168,69 +168,121 @@ void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8
 // FAST-9/16 arc score S(x,y) = max over the 16 contiguous 9-arcs of min(v - p_k), and of min(p_k - v)
 // (OpenCV features2d/fast_score.cpp cornerScore<16> returns max(th, S) - 1; a pixel is a corner at
 // threshold th iff S > th).  Output clamped to [0,255]; pixels closer than 3 to the border get 0.
+// Written on raw u8 values, S = max(v -sat min_arcs(max9 p), max_arcs(min9 p) -sat v), so that the x loop
+// auto-vectorises (vpminub/vpmaxub): this is what makes the CPU baseline a fair one.
+static inline uint8_t u8min(uint8_t a, uint8_t b) { return a < b ? a : b; }
+static inline uint8_t u8max(uint8_t a, uint8_t b) { return a > b ? a : b; }
+static void score_row(const uint8_t* __restrict c, int stride, int x0, int x1, uint8_t* __restrict out) {
+  const uint8_t* r[16] = {c + 3 * stride,     c + 3 * stride + 1, c + 2 * stride + 2, c + stride + 3,
+                          c + 3,              c - stride + 3,     c - 2 * stride + 2, c - 3 * stride + 1,
+                          c - 3 * stride,     c - 3 * stride - 1, c - 2 * stride - 2, c - stride - 3,
+                          c - 3,              c + stride - 3,     c + 2 * stride - 2, c + 3 * stride - 1};
+  for (int x = x0; x < x1; ++x) {
+    uint8_t d[16], lo2[16], hi2[16], lo4[16], hi4[16];
+    for (int k = 0; k < 16; ++k) d[k] = r[k][x];
+    for (int k = 0; k < 16; ++k) {
+      lo2[k] = u8min(d[k], d[(k + 1) & 15]);
+      hi2[k] = u8max(d[k], d[(k + 1) & 15]);
+    }
+    for (int k = 0; k < 16; ++k) {
+      lo4[k] = u8min(lo2[k], lo2[(k + 2) & 15]);
+      hi4[k] = u8max(hi2[k], hi2[(k + 2) & 15]);
+    }
+    uint8_t A = 255, B = 0;
+    for (int k = 0; k < 16; ++k) {
+      A = u8min(A, u8max(u8max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]));
+      B = u8max(B, u8min(u8min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]));
+    }
+    const uint8_t v = c[x];
+    const uint8_t s1 = v > A ? (uint8_t)(v - A) : (uint8_t)0, s2 = B > v ? (uint8_t)(B - v) : (uint8_t)0;
+    out[x] = u8max(s1, s2);
+  }
+}
 void orc_fast_score_map(const uint8_t* img, int w, int h, int stride, uint8_t* out, int ostride) {
-  static const int ox[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-  static const int oy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
   for (int y = 0; y < h; ++y) {
     uint8_t* o = out + (size_t)y * ostride;
-    if (y < 3 || y >= h - 3) {
+    if (y < 3 || y >= h - 3 || w < 7) {
       memset(o, 0, w);
       continue;
     }
-    for (int x = 0; x < w; ++x) {
-      if (x < 3 || x >= w - 3) {
-        o[x] = 0;
-        continue;
-      }
-      const uint8_t* p = img + (size_t)y * stride + x;
-      int v = p[0], d[25];
-      for (int k = 0; k < 16; ++k) d[k] = v - p[oy[k] * stride + ox[k]];
-      for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
-      int best = 0;
-      for (int k = 0; k < 16; ++k) {
-        int mn = d[k], mx = d[k];
-        for (int j = 1; j < 9; ++j) {
-          mn = std::min(mn, d[k + j]);
-          mx = std::max(mx, d[k + j]);
-        }
-        best = std::max(best, std::max(mn, -mx));
-      }
-      o[x] = (uint8_t)std::min(best, 255);
-    }
+    o[0] = o[1] = o[2] = o[w - 1] = o[w - 2] = o[w - 3] = 0;
+    score_row(img + (size_t)y * stride, stride, 3, w - 3, o);
   }
 }
 
-// cv::FAST(img, kps, th, nonmaxSuppression=true) semantics on one (cell) image, derived from the score
-// map: keep (x,y) iff S>th and S > S_n for the 8 neighbours inside the 3-px-inset interior
-// (OpenCV features2d/fast.cpp FAST_t<16>: scores of non-corners are 0 and NMS is strict).
-// Raster order; response = S-1.  Returns count (xs/ys/resp may be null).  Pinned against cv2.
+// cv::FAST(img, kps, th, nonmaxSuppression=true) on one (cell) image, OpenCV features2d/fast.cpp FAST_t<16>
+// structure: opposite-pair quick rejection, 9-contiguous test, cornerScore only for corners, then strict 3x3
+// NMS on the score rows (scores of non-corners are 0, the 3-px frame is never a corner).
+// Raster order; response = cornerScore = S-1.  Returns count (xs/ys/resp may be null).  Pinned against cv2.
+static inline int arc_score(const uint8_t* p, const int* off) {
+  int v = p[0], d[25];
+  for (int k = 0; k < 16; ++k) d[k] = v - p[off[k]];
+  for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
+  int best = 0;
+  for (int k = 0; k < 16; ++k) {
+    int mn = d[k], mx = d[k];
+    for (int j = 1; j < 9; ++j) {
+      mn = std::min(mn, d[k + j]);
+      mx = std::max(mx, d[k + j]);
+    }
+    best = std::max(best, std::max(mn, -mx));
+  }
+  return best;
+}
+static inline bool has9(uint32_t m) {  // 9 consecutive set bits in a circular 16-bit mask
+  uint32_t r = m | (m << 16);
+  r &= r >> 1;
+  r &= r >> 2;
+  r &= r >> 4;
+  r &= (m | (m << 16)) >> 8;
+  return r != 0;
+}
 int orc_fast_detect(const uint8_t* img, int w, int h, int stride, int th, int* xs, int* ys, int* resp, int cap) {
   if (w < 7 || h < 7) return 0;
-  std::vector<uint8_t> S((size_t)w * h);
-  orc_fast_score_map(img, w, h, stride, S.data(), w);
-  int n = 0;
-  for (int y = 3; y < h - 3; ++y)
+  static const int ox[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  static const int oy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  int off[16];
+  for (int k = 0; k < 16; ++k) off[k] = oy[k] * stride + ox[k];
+  std::vector<uint8_t> S((size_t)w * h, 0);  // corner scores (S-1 < 255), 0 elsewhere
+  for (int y = 3; y < h - 3; ++y) {
+    const uint8_t* row = img + (size_t)y * stride;
+    uint8_t* srow = S.data() + (size_t)y * w;
     for (int x = 3; x < w - 3; ++x) {
-      int s = S[(size_t)y * w + x];
-      if (s <= th) continue;
-      bool keep = true;
-      for (int dy = -1; dy <= 1 && keep; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          if (!dx && !dy) continue;
-          int sn = S[(size_t)(y + dy) * w + x + dx];  // border ring of S is 0
-          if (sn > th && sn >= s) {
-            keep = false;
-            break;
-          }
-        }
-      if (!keep) continue;
-      if (n < cap && xs) {
-        xs[n] = x;
-        ys[n] = y;
-        resp[n] = s - 1;
+      const uint8_t* p = row + x;
+      const int v = p[0], lo = v - th, hi = v + th;
+      // a 9-arc contains one pixel of every opposite pair
+      int a = p[off[0]], b = p[off[8]];
+      if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
+      a = p[off[4]], b = p[off[12]];
+      if (a >= lo && a <= hi && b >= lo && b <= hi) continue;
+      uint32_t mb = 0, md = 0;
+      for (int k = 0; k < 16; ++k) {
+        const int q = p[off[k]];
+        mb |= (uint32_t)(q > hi) << k;
+        md |= (uint32_t)(q < lo) << k;
       }
-      ++n;
+      if (!has9(mb) && !has9(md)) continue;
+      srow[x] = (uint8_t)std::min(arc_score(p, off) - 1, 255);
     }
+  }
+  int n = 0;
+  for (int y = 3; y < h - 3; ++y) {
+    const uint8_t* s1 = S.data() + (size_t)y * w;
+    const uint8_t *s0 = s1 - w, *s2 = s1 + w;
+    for (int x = 3; x < w - 3; ++x) {
+      const int s = s1[x];
+      if (!s) continue;
+      if (s > s0[x - 1] && s > s0[x] && s > s0[x + 1] && s > s1[x - 1] && s > s1[x + 1] && s > s2[x - 1] &&
+          s > s2[x] && s > s2[x + 1]) {
+        if (n < cap && xs) {
+          xs[n] = x;
+          ys[n] = y;
+          resp[n] = s;
+        }
+        ++n;
+      }
+    }
+  }
   return n;
 }
 
@@ -265,18 +317,25 @@ void orc_gaussian_blur7_u8(const uint8_t* src, int w, int h, int sstride, uint8_
   int k[7];
   orc_gauss7_kernel(k);
   std::vector<uint16_t> tmp((size_t)w * h);
-  for (int y = 0; y < h; ++y)
+  std::vector<uint8_t> line(w + 6);
+  for (int y = 0; y < h; ++y) {
+    for (int x = -3; x < w + 3; ++x) line[x + 3] = src[(size_t)y * sstride + reflect101(x, w)];
+    uint16_t* t = &tmp[(size_t)y * w];
+    const uint8_t* l = line.data();
+    for (int x = 0; x < w; ++x)
+      t[x] = (uint16_t)(k[0] * (l[x] + l[x + 6]) + k[1] * (l[x + 1] + l[x + 5]) + k[2] * (l[x + 2] + l[x + 4]) +
+                        k[3] * l[x + 3]);
+  }
+  for (int y = 0; y < h; ++y) {
+    const uint16_t* r[7];
+    for (int i = 0; i < 7; ++i) r[i] = &tmp[(size_t)reflect101(y + i - 3, h) * w];
+    uint8_t* d = dst + (size_t)y * dstride;
     for (int x = 0; x < w; ++x) {
-      int acc = 0;
-      for (int i = 0; i < 7; ++i) acc += k[i] * src[(size_t)y * sstride + reflect101(x + i - 3, w)];
-      tmp[(size_t)y * w + x] = (uint16_t)acc;
+      uint32_t acc = (uint32_t)k[0] * (r[0][x] + r[6][x]) + (uint32_t)k[1] * (r[1][x] + r[5][x]) +
+                     (uint32_t)k[2] * (r[2][x] + r[4][x]) + (uint32_t)k[3] * r[3][x];
+      d[x] = (uint8_t)((acc + 32768u) >> 16);
     }
-  for (int y = 0; y < h; ++y)
-    for (int x = 0; x < w; ++x) {
-      uint32_t acc = 0;
-      for (int i = 0; i < 7; ++i) acc += (uint32_t)k[i] * tmp[(size_t)reflect101(y + i - 3, h) * w + x];
-      dst[(size_t)y * dstride + x] = (uint8_t)((acc + 32768u) >> 16);
-    }
+  }
 }
 
 }  // extern "C"
@@ -301,6 +360,7 @@ struct OrbOracle {
   std::vector<int> lw, lh;
   std::vector<std::vector<uint8_t>> pyr;
   std::vector<std::vector<Cand>> cands;  // per level, pre-quadtree, cell-major raster order
+  std::vector<uint8_t> score;
 };
 
 // src/ORBextractor.cc:391-456
@@ -365,8 +425,12 @@ void build_pyramid(OrbOracle& o, const uint8_t* img, int w, int h, int stride) {
   }
 }
 
-// per-cell FAST with ini->min threshold fallback (src/ORBextractor.cc:738-779)
-void detect_level(const OrbOracle& o, int level, std::vector<Cand>& out) {
+// per-cell FAST with ini->min threshold fallback (src/ORBextractor.cc:738-779).  Each cell is an independent
+// cv::FAST call: corners only inside the cell's 3-px-inset interior and NMS blind to neighbouring cells.  S is a
+// function of the pixel neighbourhood only, so it is computed once per level and each cell applies
+// "S > th and S > S_n for the 8 neighbours inside my interior" — identical to running orc_fast_detect on
+// the cell image (tests compare both against per-cell cv2.FAST goldens).
+void detect_level(const OrbOracle& o, int level, std::vector<Cand>& out, std::vector<uint8_t>& S) {
   out.clear();
   const int W = o.lw[level], H = o.lh[level];
   const uint8_t* img = o.pyr[level].data();
@@ -375,7 +439,8 @@ void detect_level(const OrbOracle& o, int level, std::vector<Cand>& out) {
   const int nCols = (int)(width / 35.f), nRows = (int)(height / 35.f);
   if (nCols <= 0 || nRows <= 0) return;
   const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
-  std::vector<int> xs(4096), ys(4096), rs(4096);
+  S.resize((size_t)W * H);
+  orc_fast_score_map(img, W, H, W, S.data(), W);
   for (int i = 0; i < nRows; ++i) {
     const float iniY = (float)(minBY + i * hCell);
     float maxY = iniY + hCell + 6;
@@ -386,12 +451,32 @@ void detect_level(const OrbOracle& o, int level, std::vector<Cand>& out) {
       float maxX = iniX + wCell + 6;
       if (iniX >= maxBX - 6) continue;
       if (maxX > maxBX) maxX = (float)maxBX;
-      const int x0 = (int)iniX, y0 = (int)iniY, cw = (int)maxX - x0, ch = (int)maxY - y0;
-      const uint8_t* cell = img + (size_t)y0 * W + x0;
-      int n = orc_fast_detect(cell, cw, ch, W, o.iniTh, xs.data(), ys.data(), rs.data(), 4096);
-      if (n == 0) n = orc_fast_detect(cell, cw, ch, W, o.minTh, xs.data(), ys.data(), rs.data(), 4096);
-      for (int k = 0; k < n; ++k)
-        out.push_back({(float)(xs[k] + j * wCell), (float)(ys[k] + i * hCell), (float)rs[k]});
+      const int xa = (int)iniX + 3, xb = (int)maxX - 3, ya = (int)iniY + 3, yb = (int)maxY - 3;  // interior
+      const size_t first = out.size();
+      for (int pass = 0; pass < 2 && out.size() == first; ++pass) {
+        const int th = pass == 0 ? o.iniTh : o.minTh;
+        for (int y = ya; y < yb; ++y) {
+          const uint8_t* s1 = S.data() + (size_t)y * W;
+          for (int x = xa; x < xb; ++x) {
+            const int s = s1[x];
+            if (s <= th) continue;
+            bool keep = true;
+            for (int dy = -1; dy <= 1 && keep; ++dy) {
+              const int yy = y + dy;
+              if (yy < ya || yy >= yb) continue;
+              for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx;
+                if ((!dx && !dy) || xx < xa || xx >= xb) continue;
+                if (S[(size_t)yy * W + xx] >= s) {
+                  keep = false;
+                  break;
+                }
+              }
+            }
+            if (keep) out.push_back({(float)(x - minBX), (float)(y - minBY), (float)(s - 1)});
+          }
+        }
+      }
     }
   }
 }
@@ -602,7 +687,7 @@ int orc_orb_extract(void* h, const uint8_t* img, int w, int hgt, int stride, con
   std::vector<std::vector<OrcKeyPoint>> all(o.nlevels);
   std::vector<int> picked;
   for (int l = 0; l < o.nlevels; ++l) {
-    detect_level(o, l, o.cands[l]);
+    detect_level(o, l, o.cands[l], o.score);
     const int W = o.lw[l], H = o.lh[l];
     distribute_quadtree(o.cands[l], kBorder, W - kEdge + 3, kBorder, H - kEdge + 3, o.quota[l], picked);
     const int patch = (int)(31 * o.scale[l]);

@@ -103,3 +103,25 @@ def test_hamming_knn2_and_csr(api, goldens):
     for a, b, name in zip(got, ref, ("best_dist", "best_idx", "second_dist", "second_idx")):
         assert np.array_equal(a, b), name
     assert m.DescriptorDistance(q[0], t[0]) == O.descriptor_distance(q[0], t[0])
+
+
+def test_stereo_frontend_host_api(api):
+    """vieo_frontend_process (chunked, multi-stream, host buffers) == oracle per image and per pair."""
+    from vieo_slam_b200.synth import stereo_stream
+    F = 9  # 4 chunks of 3,3,3 frames (last chunk empty) -> exercises ragged chunking
+    imgs = stereo_stream(F, 77, dark_every=4).reshape(F, 2, 480, 752)
+    fe = api.StereoFrontend(1200, 1.2, 8, 20, 7, 752, 480, max_frames=F)
+    outs = fe.alloc_outputs(F)
+    kps, desc, nkp, midx, mdist = fe.process(imgs, outs)
+    ora = O.OrbOracle(1200, 1.2, 8, 20, 7)
+    for f in range(F):
+        d = []
+        for c in range(2):
+            n, okps, odesc, _ = ora.extract(imgs[f, c])
+            i = 2 * f + c
+            assert nkp[i] == n
+            assert kps[i, :n].tobytes() == okps.tobytes() and np.array_equal(desc[i, :n], odesc)
+            d.append(odesc)
+        oi, od = O.hamming_knn2(d[0], d[1])
+        assert np.array_equal(midx[f, :len(oi)], oi) and np.array_equal(mdist[f, :len(oi)], od)
+    assert fe.last_launches() == 3 * 11

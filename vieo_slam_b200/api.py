@@ -47,8 +47,16 @@ def lib():
         L.vieo_orb_debug_level.argtypes = [vp, i32, i32, vp]
         L.vieo_orb_debug_candidates.argtypes = [vp, i32, i32, vp, i32]
         L.vieo_orb_last_launches.argtypes = [vp]
+        L.vieo_orb_profile.argtypes = [vp, i32]
+        L.vieo_orb_profile_read.argtypes = [vp, vp, vp]
         L.vieo_hamming_knn2.argtypes = [vp, i32, vp, i32, vp, vp, i32]
-        L.vieo_hamming_knn2_batch_dev.argtypes = [vp, sz, vp, i32, vp, sz, vp, i32, i32, vp, vp, vp]
+        L.vieo_hamming_knn2_batch_dev.argtypes = [vp, sz, vp, i32, vp, sz, vp, i32, i32, i32, vp, vp, vp]
+        L.vieo_frontend_create.argtypes = [C.POINTER(VieoOrbConfig), i32, i32, C.POINTER(vp)]
+        L.vieo_frontend_destroy.argtypes = [vp]
+        L.vieo_frontend_destroy.restype = None
+        L.vieo_frontend_max_keypoints.argtypes = [vp]
+        L.vieo_frontend_last_launches.argtypes = [vp]
+        L.vieo_frontend_process.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp]
         L.vieo_hamming_csr.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32]
         _lib = L
     return _lib
@@ -145,6 +153,16 @@ class ORBextractor:
     def last_launches(self):
         return lib().vieo_orb_last_launches(self._h)
 
+    def profile(self, enable=True):
+        _check(lib().vieo_orb_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """-> (dict stage -> summed ms, number of profiled calls)"""
+        ms = np.zeros(4, np.float32)
+        n = C.c_int32(0)
+        _check(lib().vieo_orb_profile_read(self._h, _p(ms), C.byref(n)))
+        return dict(zip(("pyramid", "fast_cells", "quadtree", "orient_desc"), ms.tolist())), n.value
+
     def debug_level(self, img_index, level):
         out = np.empty((int(self.level_h[level]), int(self.level_w[level])), np.uint8)
         _check(lib().vieo_orb_debug_level(self._h, img_index, level, _p(out)))
@@ -188,3 +206,51 @@ class ORBmatcher:
         """ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1645) evaluated on the device."""
         bd, _, _, _ = self.search_candidates(np.asarray(a).reshape(1, 32), np.asarray(b).reshape(1, 32), [0, 1], [0])
         return int(bd[0])
+
+
+def hamming_knn2_batch_dev(q_ptr, q_stride, nq_ptr, max_nq, t_ptr, t_stride, nt_ptr, max_nt, count_stride, n_pairs,
+                           idx_ptr, dist_ptr, stream=0):
+    """Device-resident batched knnMatch(k=2); all pointers are device addresses."""
+    _check(lib().vieo_hamming_knn2_batch_dev(q_ptr, q_stride, nq_ptr, max_nq, t_ptr, t_stride, nt_ptr, max_nt,
+                                             count_stride, n_pairs, idx_ptr, dist_ptr, stream))
+
+
+class StereoFrontend:
+    """Frame::Frame stereo constructor hot path (src/Frame.cc:218-316) for a batch of frames with host buffers."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, width, height, max_frames, device=0):
+        cfg = VieoOrbConfig(width, height, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, 2)
+        self._h = C.c_void_p()
+        _check(lib().vieo_frontend_create(C.byref(cfg), max_frames, device, C.byref(self._h)))
+        self.cap = lib().vieo_frontend_max_keypoints(self._h)
+        self.width, self.height, self.max_frames = width, height, max_frames
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            lib().vieo_frontend_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def alloc_outputs(self, n_frames, pinned=False):
+        import torch
+        mk = (lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()) if pinned else \
+             (lambda shape, dt: torch.empty(shape, dtype=dt).numpy())
+        import torch as T
+        kps = mk((2 * n_frames, self.cap, 6), T.float32)
+        desc = mk((2 * n_frames, self.cap, 32), T.uint8)
+        nkp = mk((2 * n_frames,), T.int32)
+        midx = mk((n_frames, self.cap, 2), T.int32)
+        mdist = mk((n_frames, self.cap, 2), T.int32)
+        return kps, desc, nkp, midx, mdist
+
+    def process(self, imgs, outs):
+        """imgs: (n_frames, 2, H, W) u8 host (pinned for speed); outs from alloc_outputs()."""
+        n = imgs.shape[0]
+        kps, desc, nkp, midx, mdist = outs
+        _check(lib().vieo_frontend_process(self._h, n, _p(imgs), imgs.strides[2], _p(kps), _p(desc), _p(nkp), _p(midx),
+                                           _p(mdist)))
+        return kps.view(np.uint8).reshape(2 * n, self.cap, 24).view(KP_DTYPE).reshape(2 * n, self.cap), desc, nkp, midx, mdist
+
+    def last_launches(self):
+        return lib().vieo_frontend_last_launches(self._h)

@@ -31,12 +31,12 @@ __device__ __forceinline__ bool top2_less(int da, int ia, int db, int ib) {
 __global__ void __launch_bounds__(32 * kKnnWarps) k_knn2(const uint8_t* __restrict__ q, size_t q_stride,
                                                         const int* __restrict__ nq_p, int max_nq,
                                                         const uint8_t* __restrict__ t, size_t t_stride,
-                                                        const int* __restrict__ nt_p, int max_nt,
+                                                        const int* __restrict__ nt_p, int max_nt, int count_stride,
                                                         int* __restrict__ idx, int* __restrict__ dist) {
   __shared__ uint4 s_t[kKnnTile * 2];
   __shared__ Top2 s_m[kKnnWarps][32];
   const int pair = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nq = min(nq_p[pair], max_nq), nt = min(nt_p[pair], max_nt);
+  const int nq = min(nq_p[pair * count_stride], max_nq), nt = min(nt_p[pair * count_stride], max_nt);
   const int qi = blockIdx.x * 32 + lane;
   if (blockIdx.x * 32 >= nq) return;
   const uint4* qp = reinterpret_cast<const uint4*>(q + pair * q_stride);
@@ -135,12 +135,12 @@ extern "C" {
 
 int vieo_hamming_knn2_batch_dev(const uint8_t* q_dev, size_t q_stride, const int32_t* nq_dev, int max_nq,
                                 const uint8_t* t_dev, size_t t_stride, const int32_t* nt_dev, int max_nt,
-                                int n_pairs, int32_t* idx_dev, int32_t* dist_dev, void* stream) {
+                                int count_stride, int n_pairs, int32_t* idx_dev, int32_t* dist_dev, void* stream) {
   VIEO_ARG(q_dev && t_dev && nq_dev && nt_dev && idx_dev && dist_dev, "null argument");
   VIEO_ARG(max_nq >= 1 && max_nt >= 0 && n_pairs >= 1 && n_pairs <= 65535, "bad sizes");
   VIEO_ARG(((uintptr_t)q_dev | (uintptr_t)t_dev | q_stride | t_stride) % 16 == 0, "descriptors must be 16-byte aligned");
   k_knn2<<<dim3((max_nq + 31) / 32, n_pairs), 32 * kKnnWarps, 0, (cudaStream_t)stream>>>(
-      q_dev, q_stride, nq_dev, max_nq, t_dev, t_stride, nt_dev, max_nt, idx_dev, dist_dev);
+      q_dev, q_stride, nq_dev, max_nq, t_dev, t_stride, nt_dev, max_nt, count_stride, idx_dev, dist_dev);
   VIEO_CK(cudaGetLastError());
   return VIEO_OK;
 }
@@ -166,7 +166,7 @@ int vieo_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_
     step(cudaMemcpy(dn, hn, 8, cudaMemcpyHostToDevice));
   }
   if (e == cudaSuccess) {
-    rc = vieo_hamming_knn2_batch_dev(dq, 0, dn, nq, dt, 0, dn + 1, nt, 1, di, dd, nullptr);
+    rc = vieo_hamming_knn2_batch_dev(dq, 0, dn, nq, dt, 0, dn + 1, nt, 1, 1, di, dd, nullptr);
     if (rc == VIEO_OK) {
       step(cudaMemcpy(idx, di, (size_t)nq * 8, cudaMemcpyDeviceToHost));
       step(cudaMemcpy(dist, dd, (size_t)nq * 8, cudaMemcpyDeviceToHost));

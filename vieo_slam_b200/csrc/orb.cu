@@ -26,6 +26,7 @@ constexpr int kPW = 2 * kPR + 1;  // 43
 constexpr int kPWp = 44;          // padded row of the raw patch
 constexpr int kBW = 37;           // blurred window (+-18)
 constexpr int kBWp = 38;
+constexpr int kProfRing = 1024;    // profiled calls kept between vieo_orb_profile_read()s
 
 struct Cell {
   int16_t level, x0, y0, cw, ch;  // cell image = [x0,x0+cw) x [y0,y0+ch) in level coordinates
@@ -709,6 +710,10 @@ struct vieo_orb {
   int* d_nkp;
   void* h_pinned;  // pinned bounce for small D2H (counts)
   int last_launches;
+  // optional per-stage CUDA-event timing (bench.py's roofline): ring of 5 events per call
+  bool prof_on;
+  int prof_calls;
+  std::vector<cudaEvent_t> prof_ev;
   int last_n_img;
   const uint8_t* last_img0;  // level-0 source of the last call (debug)
   size_t last_img0_stride;
@@ -742,6 +747,15 @@ int orb_run(vieo_orb* h, int n_img, const uint8_t* img0, size_t img0_stride, int
             uint8_t* desc, int cap, int* n_kp, cudaStream_t st) {
   const OrbParams& P = h->P;
   int launches = 0;
+  cudaEvent_t* ev = nullptr;
+  if (h->prof_on && h->prof_calls < kProfRing) {
+    if (h->prof_ev.empty()) {
+      h->prof_ev.resize((size_t)kProfRing * 5);
+      for (auto& e : h->prof_ev) VIEO_CK(cudaEventCreate(&e));
+    }
+    ev = h->prof_ev.data() + (size_t)5 * h->prof_calls++;
+    VIEO_CK(cudaEventRecord(ev[0], st));
+  }
   for (int l = 1; l < P.nlevels; ++l) {
     const uint8_t* src = l == 1 ? img0 : P.lvl[l - 1];
     const size_t sstride = l == 1 ? img0_stride : P.img_stride[l - 1];
@@ -751,11 +765,15 @@ int orb_run(vieo_orb* h, int n_img, const uint8_t* img0, size_t img0_stride, int
                                      P.rx[l], P.ry[l]);
     ++launches;
   }
+  if (ev) VIEO_CK(cudaEventRecord(ev[1], st));
   k_fast_cells<<<dim3(P.n_cells, n_img), kFastThreads, h->fast_smem, st>>>(P, img0, img0_stride, img0_pitch);
+  if (ev) VIEO_CK(cudaEventRecord(ev[2], st));
   k_quadtree<<<dim3(P.nlevels, n_img), kQtThreads, h->qt_smem, st>>>(P);
+  if (ev) VIEO_CK(cudaEventRecord(ev[3], st));
   const int slots = std::min(cap, h->cap_total);
   k_orient_desc<<<dim3((slots + kDescWarps - 1) / kDescWarps, n_img), kDescWarps * 32, 0, st>>>(
       P, img0, img0_stride, img0_pitch, kps, desc, cap, n_kp);
+  if (ev) VIEO_CK(cudaEventRecord(ev[4], st));
   launches += 3;
   VIEO_CK(cudaGetLastError());
   h->last_launches = launches;
@@ -767,6 +785,35 @@ int orb_run(vieo_orb* h, int n_img, const uint8_t* img0, size_t img0_stride, int
 }
 
 }  // namespace
+
+// ---- internal hooks used by frontend.cu (same library) ----
+namespace vieo {
+int orb_enqueue_host(vieo_orb* h, int n_img, const uint8_t* imgs, size_t img_stride, int row_stride) {
+  const OrbParams& P = h->P;
+  cudaStream_t st = h->stream;
+  if ((size_t)row_stride * h->cfg.height == img_stride && row_stride == P.pitch[0]) {
+    VIEO_CK(cudaMemcpyAsync(P.lvl[0], imgs, img_stride * n_img, cudaMemcpyHostToDevice, st));
+  } else {
+    // one strided copy for the whole batch when images are back to back
+    if ((size_t)row_stride * h->cfg.height == img_stride) {
+      VIEO_CK(cudaMemcpy2DAsync(P.lvl[0], P.pitch[0], imgs, row_stride, h->cfg.width, (size_t)h->cfg.height * n_img,
+                                cudaMemcpyHostToDevice, st));
+    } else {
+      for (int i = 0; i < n_img; ++i)
+        VIEO_CK(cudaMemcpy2DAsync(P.lvl[0] + i * P.img_stride[0], P.pitch[0], imgs + i * img_stride, row_stride,
+                                  h->cfg.width, h->cfg.height, cudaMemcpyHostToDevice, st));
+    }
+  }
+  return orb_run(h, n_img, P.lvl[0], P.img_stride[0], P.pitch[0], h->d_kps, h->d_desc, h->cap_total, h->d_nkp, st);
+}
+void orb_dev_outputs(vieo_orb* h, VieoKeyPoint** kps, uint8_t** desc, int** nkp, int* cap, cudaStream_t* st) {
+  *kps = h->d_kps;
+  *desc = h->d_desc;
+  *nkp = h->d_nkp;
+  *cap = h->cap_total;
+  *st = h->stream;
+}
+}  // namespace vieo
 
 extern "C" {
 
@@ -975,6 +1022,7 @@ int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out) {
 void vieo_orb_destroy(vieo_orb_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1130,5 +1178,30 @@ int vieo_orb_debug_candidates(vieo_orb_t* h, int img_index, int level, int32_t* 
 }
 
 int vieo_orb_last_launches(const vieo_orb_t* h) { return h ? h->last_launches : VIEO_E_ARG; }
+
+int vieo_orb_profile(vieo_orb_t* h, int enable) {
+  VIEO_ARG(h, "null handle");
+  h->prof_on = enable != 0;
+  h->prof_calls = 0;
+  return VIEO_OK;
+}
+
+int vieo_orb_profile_read(vieo_orb_t* h, float stage_ms[4], int32_t* n_calls) {
+  VIEO_ARG(h && stage_ms, "null argument");
+  VIEO_CK(cudaSetDevice(h->device));
+  for (int i = 0; i < 4; ++i) stage_ms[i] = 0.f;
+  for (int c = 0; c < h->prof_calls; ++c) {
+    cudaEvent_t* ev = h->prof_ev.data() + (size_t)5 * c;
+    VIEO_CK(cudaEventSynchronize(ev[4]));
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0.f;
+      VIEO_CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      stage_ms[i] += ms;
+    }
+  }
+  if (n_calls) *n_calls = h->prof_calls;
+  h->prof_calls = 0;
+  return VIEO_OK;
+}
 
 }  // extern "C"
