@@ -117,6 +117,35 @@ int vieo_hamming_csr(const uint8_t* q, const uint8_t* t, int nt, const int32_t* 
                      int device);
 
 /* ------------------------------------------------------------------------------------------------
+ * On-manifold IMU pre-integration — replaces IMUPreIntegratorBase<IMUDataBase>::PreIntegration / update
+ * (src/Odom/OdomPreIntegrator.h:227-506) for a batch of intervals (one per frame pair / keyframe pair; the
+ * batched re-integration of IMUInitialization.cpp:648,1148,1422 is the same call).  Matrices are row-major. */
+typedef struct VieoImuNoise { /* IMUDataBase statics after SetParam (src/Odom/OdomData.h:41-56) */
+  double sigma_g, sigma_a, sigma_bg, sigma_ba; /* diagonal of mSigmag / mSigmaa / mSigmabg / mSigmaba */
+  double freq_ref;                             /* mFreqRef */
+  int32_t dt_cov_noise_fixed;                  /* mdt_cov_noise_fixed */
+  int32_t pad_;
+} VieoImuNoise;
+typedef struct VieoImuPreint { /* public members of IMUPreIntegratorBase (OdomPreIntegrator.h:108-150) */
+  double Rij[9], vij[3], pij[3];     /* mRij, mvij, mpij */
+  double SigmaPRV[81], SigmaPVR[81]; /* mSigmaijPRV (P,R,V order), mSigmaij (P,V,R order) */
+  double Jgp[9], Jap[9], Jgv[9], Jav[9], JgR[9]; /* mJgpij, mJapij, mJgvij, mJavij, mJgRij */
+  double dt;                         /* mdeltatij (0 = not pre-integrated) */
+  int32_t status;                    /* PreIntegration's return value: 0, or -1 for a sample gap > 1.5 s */
+  int32_t pad_;
+} VieoImuPreint;
+/* IMUDataBase::SetParam: sigma2 = squared {gyro, acc, gyro-bias, acc-bias} noise (src/Tracking.cc:744-748). */
+void vieo_imu_set_param(VieoImuNoise* nz, const double sigma2[4], int dt_cov_noise_fixed, double freq_ref);
+/* samples: rows {t, ax, ay, az, wx, wy, wz}; interval k integrates samples[seg_ptr[k] .. seg_ptr[k+1]) (the
+ * iterBegin/iterEnd list of the reference) over [ti_tj[2k], ti_tj[2k+1]] (reversed time allowed) with the
+ * linearisation biases bg_ba[6k..6k+6) = {bg, ba}.  An empty list leaves the identity state (dt = 0). */
+int vieo_imu_preint_batch(const double* samples, const int32_t* seg_ptr, const double* ti_tj, const double* bg_ba,
+                          const VieoImuNoise* noise, int n_intervals, VieoImuPreint* out, int device);
+int vieo_imu_preint_batch_dev(const double* samples_dev, const int32_t* seg_ptr_dev, const double* ti_tj_dev,
+                              const double* bg_ba_dev, const VieoImuNoise* noise, int n_intervals,
+                              VieoImuPreint* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stereo front-end over HOST buffers — the hot work of the Frame::Frame stereo constructor
  * (src/Frame.cc:218-316): ORBextractor::operator() for both cameras (:259-278) and the brute-force
  * left->right knnMatch(k=2) of ComputeStereoFishEyeMatches (:620-628), for a batch of frames, with the

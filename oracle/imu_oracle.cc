@@ -1,0 +1,383 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orb_oracle.cc header).  CPU restatement of the on-manifold IMU
+// pre-integrator: IMUPreIntegratorBase::PreIntegration / update (src/Odom/OdomPreIntegrator.h:227-506),
+// the SO(3) helpers of common/so3_extra.h:121-288 and IMUDataBase::SetParam (src/Odom/OdomData.h:41-56).
+// Eigen / Sophus are absent here ("parity unpinned" for their rounding): quaternion<->matrix conversions
+// follow Eigen 3.3.7's published formulas; the tests pin this file with closed-form constant-rate answers.
+#include <cmath>
+#include <cstring>
+
+#include "oracle.h"
+
+namespace {
+
+constexpr double kEps = 1e-5;  // SO3ex::SMALL_EPS
+
+struct M3 {
+  double m[9];  // row-major
+};
+inline M3 ident() { return {{1, 0, 0, 0, 1, 0, 0, 0, 1}}; }
+inline M3 mul(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += a.m[3 * i + k] * b.m[3 * k + j];
+      r.m[3 * i + j] = s;
+    }
+  return r;
+}
+inline M3 tr(const M3& a) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[3 * i + j] = a.m[3 * j + i];
+  return r;
+}
+inline M3 scale(const M3& a, double s) {
+  M3 r;
+  for (int i = 0; i < 9; ++i) r.m[i] = a.m[i] * s;
+  return r;
+}
+inline M3 add(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 9; ++i) r.m[i] = a.m[i] + b.m[i];
+  return r;
+}
+inline M3 sub(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 9; ++i) r.m[i] = a.m[i] - b.m[i];
+  return r;
+}
+inline M3 hat(const double w[3]) { return {{0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0}}; }
+inline void mulv(const M3& a, const double v[3], double out[3]) {
+  for (int i = 0; i < 3; ++i) out[i] = a.m[3 * i] * v[0] + a.m[3 * i + 1] * v[1] + a.m[3 * i + 2] * v[2];
+}
+
+struct Quat {
+  double w, x, y, z;
+};
+inline Quat qnormalized(Quat q) {
+  double n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+  if (n2 > 0) {
+    double n = std::sqrt(n2);
+    q.w /= n; q.x /= n; q.y /= n; q.z /= n;
+  }
+  return q;
+}
+// Eigen::Quaternion::toRotationMatrix
+inline M3 qmat(const Quat& q) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  return {{1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx,
+           1 - (txx + tyy)}};
+}
+// Eigen::Quaternion(Matrix3)
+inline Quat mquat(const M3& R) {
+  auto m = [&](int i, int j) { return R.m[3 * i + j]; };
+  double c[4];  // x y z w
+  double t = m(0, 0) + m(1, 1) + m(2, 2);
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    c[3] = 0.5 * t;
+    t = 0.5 / t;
+    c[0] = (m(2, 1) - m(1, 2)) * t;
+    c[1] = (m(0, 2) - m(2, 0)) * t;
+    c[2] = (m(1, 0) - m(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (m(1, 1) > m(0, 0)) i = 1;
+    if (m(2, 2) > m(i, i)) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+    c[i] = 0.5 * t;
+    t = 0.5 / t;
+    c[3] = (m(k, j) - m(j, k)) * t;
+    c[j] = (m(j, i) + m(i, j)) * t;
+    c[k] = (m(k, i) + m(i, k)) * t;
+  }
+  return {c[3], c[0], c[1], c[2]};
+}
+// SO3ex::exp (so3_extra.h:121-142) followed by the normalising constructor and .matrix()
+inline M3 so3_Exp(const double w[3]) {
+  const double theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  double imag, real;
+  if (theta < kEps) {
+    const double t2 = theta * theta;
+    imag = 0.5 - t2 / 48.;
+    real = 1.0 - t2 / 8.;
+  } else {
+    const double half = 0.5 * theta;
+    imag = std::sin(half) / theta;
+    real = std::cos(half);
+  }
+  return qmat(qnormalized({real, imag * w[0], imag * w[1], imag * w[2]}));
+}
+// SO3ex::JacobianR (so3_extra.h:255-270)
+inline M3 so3_Jr(const double w[3]) {
+  const double theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  if (theta < kEps) {
+    M3 O = hat(w), O2 = mul(O, O);
+    return add(sub(ident(), scale(O, 0.5)), scale(O2, 1. / 6.));
+  }
+  const double k[3] = {w[0] / theta, w[1] / theta, w[2] / theta};
+  M3 K = hat(k);
+  return add(sub(ident(), scale(K, (1 - std::cos(theta)) / theta)), scale(mul(K, K), 1 - std::sin(theta) / theta));
+}
+// SO3ex::normalizeRotationM (so3_extra.h:218-229)
+inline M3 normalize_rot(const M3& R) {
+  Quat q = mquat(R);
+  if (q.w < 0) {
+    q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z;
+  }
+  return qmat(qnormalized(q));
+}
+
+struct Preint {
+  M3 R, Jgp, Jap, Jgv, Jav, JgR;
+  double v[3], p[3], S_prv[81], S_pvr[81], dt;
+};
+void reset(Preint& s) {
+  memset(&s, 0, sizeof(s));
+  s.R = ident();
+}
+inline void set_block(double* A, int r, int c, const M3& b) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[9 * (r + i) + c + j] = b.m[3 * i + j];
+}
+// S <- A S A^T + Bg (sg I) Bg^T + Ba (sa I) Ba^T, Bg/Ba given as 9x3 row-major
+void propagate(double* S, const double* A, const double* Bg, const double* Ba, double sg, double sa) {
+  double T[81], N[81];
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 9; ++j) {
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += A[9 * i + k] * S[9 * k + j];
+      T[9 * i + j] = s;
+    }
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 9; ++j) {
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += T[9 * i + k] * A[9 * j + k];
+      N[9 * i + j] = s;
+    }
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 9; ++j) {
+      double g = 0, a = 0;
+      for (int k = 0; k < 3; ++k) {
+        g += (Bg[3 * i + k] * sg) * Bg[3 * j + k];
+        a += (Ba[3 * i + k] * sa) * Ba[3 * j + k];
+      }
+      S[9 * i + j] = N[9 * i + j] + g + a;
+    }
+}
+
+// IMUPreIntegratorBase::update (OdomPreIntegrator.h:432-506)
+void update(Preint& s, const double omega[3], const double acc[3], double dt, const OrcImuNoise& nz) {
+  const double dt2div2 = dt * dt / 2;
+  const double wdt[3] = {omega[0] * dt, omega[1] * dt, omega[2] * dt};
+  const M3 dR = so3_Exp(wdt), Jr = so3_Jr(wdt), skewa = hat(acc);
+  double sg, sa;
+  if (nz.dt_cov_noise_fixed) {
+    sg = nz.sigma_g;
+    sa = nz.sigma_a;
+  } else if (!nz.freq_ref || dt < 1.5 / nz.freq_ref) {
+    sg = nz.sigma_g / dt;
+    sa = nz.sigma_a / dt;
+  } else {
+    sg = nz.sigma_g * nz.freq_ref;
+    sa = nz.sigma_a * nz.freq_ref;
+  }
+  const M3 Rsk = mul(s.R, skewa);
+  const M3 nRsk_dt = scale(scale(Rsk, -1.0), dt), nRsk_dt2 = scale(scale(Rsk, -1.0), dt2div2);
+  const M3 dRt = tr(dR), Idt = scale(ident(), dt), Jrdt = scale(Jr, dt), Rdt = scale(s.R, dt), Rdt2 = scale(s.R, dt2div2);
+  double A[81], Bg[27], Ba[27];
+  // P-R-V ordering (:444-463)
+  memset(A, 0, sizeof(A)); memset(Bg, 0, sizeof(Bg)); memset(Ba, 0, sizeof(Ba));
+  for (int i = 0; i < 9; ++i) A[10 * i] = 1;
+  set_block(A, 3, 3, dRt);
+  set_block(A, 6, 3, nRsk_dt);
+  set_block(A, 0, 3, nRsk_dt2);
+  set_block(A, 0, 6, Idt);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      Bg[3 * (3 + i) + j] = Jrdt.m[3 * i + j];
+      Ba[3 * (6 + i) + j] = Rdt.m[3 * i + j];
+      Ba[3 * i + j] = Rdt2.m[3 * i + j];
+    }
+  propagate(s.S_prv, A, Bg, Ba, sg, sa);
+  // P-V-R ordering (:465-483)
+  memset(A, 0, sizeof(A)); memset(Bg, 0, sizeof(Bg)); memset(Ba, 0, sizeof(Ba));
+  for (int i = 0; i < 9; ++i) A[10 * i] = 1;
+  set_block(A, 6, 6, dRt);
+  set_block(A, 3, 6, nRsk_dt);
+  set_block(A, 0, 6, nRsk_dt2);
+  set_block(A, 0, 3, Idt);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      Bg[3 * (6 + i) + j] = Jrdt.m[3 * i + j];
+      Ba[3 * (3 + i) + j] = Rdt.m[3 * i + j];
+      Ba[3 * i + j] = Rdt2.m[3 * i + j];
+    }
+  propagate(s.S_pvr, A, Bg, Ba, sg, sa);
+  // bias Jacobians, P then V then R, all with the old delta-R (:488-493)
+  const M3 RskJgR = mul(Rsk, s.JgR);
+  s.Jap = add(s.Jap, sub(scale(s.Jav, dt), scale(s.R, dt2div2)));
+  s.Jgp = add(s.Jgp, sub(scale(s.Jgv, dt), scale(RskJgR, dt2div2)));
+  s.Jav = add(s.Jav, scale(scale(s.R, -1.0), dt));
+  s.Jgv = add(s.Jgv, scale(scale(RskJgR, -1.0), dt));
+  s.JgR = sub(mul(dRt, s.JgR), Jrdt);
+  // delta measurements (:497-503)
+  double a2[3] = {acc[0] * dt2div2, acc[1] * dt2div2, acc[2] * dt2div2}, a1[3] = {acc[0] * dt, acc[1] * dt, acc[2] * dt};
+  double Ra2[3], Ra1[3];
+  mulv(s.R, a2, Ra2);
+  mulv(s.R, a1, Ra1);
+  for (int i = 0; i < 3; ++i) s.p[i] += s.v[i] * dt + Ra2[i];
+  for (int i = 0; i < 3; ++i) s.v[i] += Ra1[i];
+  s.R = normalize_rot(mul(s.R, dR));
+  s.dt += dt;
+}
+
+}  // namespace
+
+extern "C" {
+
+// IMUDataBase::SetParam (src/Odom/OdomData.h:41-56): sigma2 = squared {gyro, acc, bias-gyro, bias-acc} noise
+void orc_imu_set_param(OrcImuNoise* nz, const double sigma2[4], int dt_cov_noise_fixed, double freq_ref) {
+  nz->sigma_g = sigma2[0];
+  nz->sigma_a = sigma2[1];
+  nz->sigma_bg = sigma2[2];
+  nz->sigma_ba = sigma2[3];
+  nz->dt_cov_noise_fixed = dt_cov_noise_fixed;
+  if (dt_cov_noise_fixed && freq_ref) {
+    nz->freq_ref = 0;
+    nz->sigma_g *= freq_ref;
+    nz->sigma_a *= freq_ref;
+  } else
+    nz->freq_ref = freq_ref;
+}
+
+// PreIntegration over samples[0..n) = rows {t, ax, ay, az, wx, wy, wz} (the std::list in the reference).
+// Returns 0, or -1 for a gap > 1.5 s (delta-t reset to 0, OdomPreIntegrator.h:289-293).  n == 0 leaves the
+// state untouched, as the reference does for an empty list.
+int orc_imu_preintegrate(const double* smp, int n, double ti, double tj, const double bg[3], const double ba[3],
+                         const OrcImuNoise* nz, OrcImuPreint* out) {
+  Preint s;
+  reset(s);
+  int status = 0;
+  auto T = [&](int i) { return smp[7 * i]; };
+  if (n > 0) {
+    const int END = n;
+    const bool back = ti > tj;
+    double tmin = ti, tmax = tj;
+    if (back) std::swap(tmin, tmax);
+    int start = 0, stop = END;
+    for (int j = 0; j != END && T(j) <= tmin; start = j++) {
+    }
+    for (int j = END; j != 0;) {
+      stop = j--;
+      if (T(j) >= tmax) continue;
+      break;
+    }
+    if (back) {
+      if (stop == END) --stop;
+      std::swap(start, stop);
+      if (T(stop) > tmin) stop = END;  // reference asserts stop == begin here
+    }
+    for (int j = start; j != stop;) {
+      const int jm1 = j;
+      if (back) {
+        if (j == 0) j = stop; else --j;
+      } else
+        ++j;
+      const double tj_1 = jm1 == start ? ti : T(jm1);
+      const double tjj = j == stop ? tj : T(j);
+      double dt = tjj - tj_1;
+      if (dt == 0) continue;
+      if (std::fabs(dt) > 1.5) {
+        s.dt = 0;
+        status = -1;
+        break;
+      }
+      double a0[3], w0[3], a1[3], w1[3], t1;  // imu (j-1) and imu_now (j)
+      memcpy(a0, smp + 7 * jm1 + 1, 24);
+      memcpy(w0, smp + 7 * jm1 + 4, 24);
+      if (j != END) {
+        memcpy(a1, smp + 7 * j + 1, 24);
+        memcpy(w1, smp + 7 * j + 4, 24);
+        t1 = T(j);
+      } else {
+        memcpy(a1, a0, 24);
+        memcpy(w1, w0, 24);
+        t1 = T(jm1);
+      }
+      if (j != END) {
+        if (j == stop) {
+          const double d = T(j) - tj;
+          if (back ? d < 0 : d > 0) {
+            const double rat = d / (T(j) - T(jm1));
+            for (int k = 0; k < 3; ++k) {
+              w1[k] = rat * w0[k] + (1 - rat) * w1[k];
+              a1[k] = rat * a0[k] + (1 - rat) * a1[k];
+            }
+          }
+        }
+        if (jm1 == start) {
+          const double d = ti - T(jm1);
+          if (back ? d < 0 : d > 0) {
+            const double rat = d / (T(j) - T(jm1));
+            for (int k = 0; k < 3; ++k) {
+              w0[k] = (1 - rat) * w0[k] + rat * w1[k];
+              a0[k] = (1 - rat) * a0[k] + rat * a1[k];
+            }
+          }
+        }
+      }
+      auto minus = [](const double x[3], const double b[3], double o[3]) {
+        for (int k = 0; k < 3; ++k) o[k] = x[k] - b[k];
+      };
+      double om[3], ac[3];
+      if (jm1 == start) {
+        const double dc = T(jm1) - ti;
+        if (back ? dc < 0 : dc > 0) {
+          minus(w0, bg, om);
+          minus(a0, ba, ac);
+          update(s, om, ac, dc, *nz);
+          dt -= dc;
+          if (!dt) continue;
+        }
+      }
+      double dcs = 0;
+      if (j == stop) {
+        dcs = tj - t1;
+        if (back ? dcs < 0 : dcs > 0) dt -= dcs;
+      }
+      double wm[3], am[3];
+      for (int k = 0; k < 3; ++k) {
+        wm[k] = (w1[k] + w0[k]) / 2;
+        am[k] = (a1[k] + a0[k]) / 2;
+      }
+      minus(wm, bg, om);
+      minus(am, ba, ac);
+      update(s, om, ac, dt, *nz);
+      if (back ? dcs < 0 : dcs > 0) {
+        minus(w1, bg, om);
+        minus(a1, ba, ac);
+        update(s, om, ac, dcs, *nz);
+      }
+    }
+  }
+  memcpy(out->Rij, s.R.m, 72);
+  memcpy(out->vij, s.v, 24);
+  memcpy(out->pij, s.p, 24);
+  memcpy(out->SigmaPRV, s.S_prv, 648);
+  memcpy(out->SigmaPVR, s.S_pvr, 648);
+  memcpy(out->Jgp, s.Jgp.m, 72);
+  memcpy(out->Jap, s.Jap.m, 72);
+  memcpy(out->Jgv, s.Jgv.m, 72);
+  memcpy(out->Jav, s.Jav.m, 72);
+  memcpy(out->JgR, s.JgR.m, 72);
+  out->dt = s.dt;
+  out->status = status;
+  return status;
+}
+
+}  // extern "C"

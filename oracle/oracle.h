@@ -42,3 +42,28 @@ void orc_hamming_csr(const uint8_t* q, const uint8_t* t, const int32_t* row_ptr,
 #ifdef __cplusplus
 }
 #endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* IMU pre-integration (imu_oracle.cc).  Matrices row-major. */
+typedef struct OrcImuNoise {
+  double sigma_g, sigma_a, sigma_bg, sigma_ba; /* diagonal entries of mSigmag/mSigmaa/mSigmabg/mSigmaba after SetParam */
+  double freq_ref;
+  int32_t dt_cov_noise_fixed;
+  int32_t pad_;
+} OrcImuNoise;
+typedef struct OrcImuPreint { /* public members of IMUPreIntegratorBase (OdomPreIntegrator.h:108-150) */
+  double Rij[9], vij[3], pij[3];
+  double SigmaPRV[81], SigmaPVR[81];
+  double Jgp[9], Jap[9], Jgv[9], Jav[9], JgR[9];
+  double dt;
+  int32_t status;
+  int32_t pad_;
+} OrcImuPreint;
+void orc_imu_set_param(OrcImuNoise* nz, const double sigma2[4], int dt_cov_noise_fixed, double freq_ref);
+int orc_imu_preintegrate(const double* smp, int n, double ti, double tj, const double bg[3], const double ba[3],
+                         const OrcImuNoise* nz, OrcImuPreint* out);
+#ifdef __cplusplus
+}
+#endif

@@ -176,3 +176,36 @@ def hamming_csr(q, t, row_ptr, cand):
     o = [np.empty(n, np.int32) for _ in range(4)]
     lib().orc_hamming_csr(_p(q), _p(t), _p(row_ptr), _p(cand), C.c_int(n), *[_p(x) for x in o])
     return o  # best_dist, best_idx, second_dist, second_idx
+
+
+# ---------------------------------------------------------------- IMU pre-integration
+class OrcImuNoise(C.Structure):
+    _fields_ = [("sigma_g", C.c_double), ("sigma_a", C.c_double), ("sigma_bg", C.c_double), ("sigma_ba", C.c_double),
+                ("freq_ref", C.c_double), ("dt_cov_noise_fixed", C.c_int32), ("pad_", C.c_int32)]
+
+
+PREINT_DTYPE = np.dtype([("Rij", "f8", (3, 3)), ("vij", "f8", 3), ("pij", "f8", 3), ("SigmaPRV", "f8", (9, 9)),
+                         ("SigmaPVR", "f8", (9, 9)), ("Jgp", "f8", (3, 3)), ("Jap", "f8", (3, 3)), ("Jgv", "f8", (3, 3)),
+                         ("Jav", "f8", (3, 3)), ("JgR", "f8", (3, 3)), ("dt", "f8"), ("status", "i4"), ("pad_", "i4")])
+
+EUROC_IMU_SIGMA = (1.6968e-4, 2.0e-3, 1.9393e-5, 3.0e-3)  # Examples/Stereo/EuRoC/EuRoC_VIO.yaml:13-18
+
+
+def imu_noise(sigma=EUROC_IMU_SIGMA, dt_cov_noise_fixed=1, freq_ref=200.0):
+    """IMUDataBase::SetParam with the caller-side squaring of src/Tracking.cc:744-745."""
+    nz = OrcImuNoise()
+    s2 = (C.c_double * 4)(*[s * s for s in sigma])
+    lib().orc_imu_set_param(C.byref(nz), s2, dt_cov_noise_fixed, C.c_double(freq_ref))
+    return nz
+
+
+def imu_preintegrate(samples, ti, tj, bg, ba, nz):
+    """samples: (n,7) rows {t, ax, ay, az, wx, wy, wz} -> PREINT_DTYPE record"""
+    L = lib()
+    L.orc_imu_preintegrate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    samples = np.ascontiguousarray(samples, np.float64).reshape(-1, 7)
+    bg = np.ascontiguousarray(bg, np.float64); ba = np.ascontiguousarray(ba, np.float64)
+    out = np.zeros(1, PREINT_DTYPE)
+    L.orc_imu_preintegrate(_p(samples), len(samples), ti, tj, _p(bg), _p(ba), C.byref(nz), _p(out))
+    return out[0]

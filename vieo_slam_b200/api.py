@@ -58,6 +58,10 @@ def lib():
         L.vieo_frontend_last_launches.argtypes = [vp]
         L.vieo_frontend_process.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp]
         L.vieo_hamming_csr.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32]
+        L.vieo_imu_set_param.argtypes = [vp, vp, i32, C.c_double]
+        L.vieo_imu_set_param.restype = None
+        L.vieo_imu_preint_batch.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32]
+        L.vieo_imu_preint_batch_dev.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
         _lib = L
     return _lib
 
@@ -254,3 +258,42 @@ class StereoFrontend:
 
     def last_launches(self):
         return lib().vieo_frontend_last_launches(self._h)
+
+
+# ---------------------------------------------------------------- IMU pre-integration
+class VieoImuNoise(C.Structure):
+    _fields_ = [("sigma_g", C.c_double), ("sigma_a", C.c_double), ("sigma_bg", C.c_double), ("sigma_ba", C.c_double),
+                ("freq_ref", C.c_double), ("dt_cov_noise_fixed", C.c_int32), ("pad_", C.c_int32)]
+
+
+PREINT_DTYPE = np.dtype([("Rij", "f8", (3, 3)), ("vij", "f8", 3), ("pij", "f8", 3), ("SigmaPRV", "f8", (9, 9)),
+                         ("SigmaPVR", "f8", (9, 9)), ("Jgp", "f8", (3, 3)), ("Jap", "f8", (3, 3)), ("Jgv", "f8", (3, 3)),
+                         ("Jav", "f8", (3, 3)), ("JgR", "f8", (3, 3)), ("dt", "f8"), ("status", "i4"), ("pad_", "i4")])
+
+EUROC_IMU_SIGMA = (1.6968e-4, 2.0e-3, 1.9393e-5, 3.0e-3)  # Examples/Stereo/EuRoC/EuRoC_VIO.yaml:13-18
+
+
+class IMUPreintegrator:
+    """IMUPreIntegratorBase (src/Odom/OdomPreIntegrator.h:108-223) for batches of intervals."""
+
+    def __init__(self, sigma=EUROC_IMU_SIGMA, dt_cov_noise_fixed=1, freq_ref=200.0, device=0):
+        """sigma = IMU.sigma {gyro, acc, gyro-bias, acc-bias}; squared here as src/Tracking.cc:744-745 does."""
+        self.noise = VieoImuNoise()
+        s2 = (C.c_double * 4)(*[x * x for x in sigma])
+        lib().vieo_imu_set_param(C.byref(self.noise), s2, dt_cov_noise_fixed, freq_ref)
+        self.device = device
+
+    def PreIntegration(self, samples, ti, tj, bg, ba):
+        """One interval: samples (n,7) rows {t, a, w}.  -> PREINT_DTYPE record (status mirrors the return value)."""
+        return self.preintegrate_batch(samples, [0, len(samples)], [[ti, tj]], [np.r_[bg, ba]])[0]
+
+    def preintegrate_batch(self, samples, seg_ptr, ti_tj, bg_ba):
+        samples = np.ascontiguousarray(samples, np.float64).reshape(-1, 7)
+        seg_ptr = np.ascontiguousarray(seg_ptr, np.int32)
+        ti_tj = np.ascontiguousarray(ti_tj, np.float64).reshape(-1, 2)
+        bg_ba = np.ascontiguousarray(bg_ba, np.float64).reshape(-1, 6)
+        n = len(seg_ptr) - 1
+        out = np.zeros(n, PREINT_DTYPE)
+        _check(lib().vieo_imu_preint_batch(_p(samples), _p(seg_ptr), _p(ti_tj), _p(bg_ba), C.byref(self.noise), n,
+                                           _p(out), self.device))
+        return out

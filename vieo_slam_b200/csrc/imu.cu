@@ -1,0 +1,330 @@
+// On-manifold IMU pre-integration on sm_100a — replaces IMUPreIntegratorBase::PreIntegration / update
+// (src/Odom/OdomPreIntegrator.h:227-506).  One warp per interval [t_i, t_j]: the sample recurrence is
+// sequential, so lane 0 carries the small state (dR, dv, dp, five 3x3 bias Jacobians) while all 32 lanes share
+// the two 9x9 covariance propagations (P-R-V and P-V-R orderings) held in shared memory.  fp64 throughout;
+// latency-bound by construction: batches of intervals fill the machine.
+#include <vector>
+
+#include "common.cuh"
+#include "so3.cuh"
+
+namespace vieo {
+
+constexpr int kImuWarps = 4;
+
+struct ImuWarpSmem {
+  double S[2][81];   // covariances: [0] = P-R-V, [1] = P-V-R
+  double T[2][81];
+  double A[2][81];
+  double Bg[2][27], Ba[2][27];
+  double sg, sa;
+};
+
+// all lanes: S <- A S A^T + Bg (sg I) Bg^T + Ba (sa I) Ba^T for both orderings
+__device__ __forceinline__ void imu_propagate(ImuWarpSmem& W, int lane) {
+  for (int e = lane; e < 162; e += 32) {
+    const int o = e / 81, ij = e - 81 * o, i = ij / 9, j = ij - 9 * i;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s += W.A[o][9 * i + k] * W.S[o][9 * k + j];
+    W.T[o][ij] = s;
+  }
+  __syncwarp();
+  for (int e = lane; e < 162; e += 32) {
+    const int o = e / 81, ij = e - 81 * o, i = ij / 9, j = ij - 9 * i;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s += W.T[o][9 * i + k] * W.A[o][9 * j + k];
+    double g = 0, a = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      g += (W.Bg[o][3 * i + k] * W.sg) * W.Bg[o][3 * j + k];
+      a += (W.Ba[o][3 * i + k] * W.sa) * W.Ba[o][3 * j + k];
+    }
+    W.S[o][ij] = s + g + a;
+  }
+  __syncwarp();
+}
+
+struct ImuState {  // lane 0 only
+  Mat3 R, Jgp, Jap, Jgv, Jav, JgR;
+  Vec3 v, p;
+  double dt;
+};
+
+__device__ __forceinline__ void put_block(double* A, int r, int c, const Mat3& b) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A[9 * (r + i) + c + j] = b.m[3 * i + j];
+}
+__device__ __forceinline__ void put_rows(double* B, int r, const Mat3& b) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) B[3 * (r + i) + j] = b.m[3 * i + j];
+}
+
+// IMUPreIntegratorBase::update (OdomPreIntegrator.h:432-506)
+__device__ void imu_update(ImuState& s, ImuWarpSmem& W, int lane, Vec3 omega, Vec3 acc, double dt,
+                           const VieoImuNoise& nz) {
+  for (int e = lane; e < 162; e += 32) {
+    const int o = e / 81, ij = e - 81 * o;
+    W.A[o][ij] = (ij % 10 == 0) ? 1.0 : 0.0;
+  }
+  for (int e = lane; e < 54; e += 32) {
+    (&W.Bg[0][0])[e] = 0.0;
+    (&W.Ba[0][0])[e] = 0.0;
+  }
+  __syncwarp();
+  const double dt2div2 = dt * dt / 2;
+  Mat3 dRt, Jrdt;
+  if (lane == 0) {
+    const Vec3 wdt = v3_scale(omega, dt);
+    const Mat3 dR = so3_Exp(wdt), Jr = so3_Jr(wdt), skewa = m3_hat(acc);
+    double sg, sa;
+    if (nz.dt_cov_noise_fixed) {
+      sg = nz.sigma_g;
+      sa = nz.sigma_a;
+    } else if (!nz.freq_ref || dt < 1.5 / nz.freq_ref) {
+      sg = nz.sigma_g / dt;
+      sa = nz.sigma_a / dt;
+    } else {
+      sg = nz.sigma_g * nz.freq_ref;
+      sa = nz.sigma_a * nz.freq_ref;
+    }
+    W.sg = sg;
+    W.sa = sa;
+    const Mat3 Rsk = m3_mul(s.R, skewa), nRsk = m3_scale(Rsk, -1.0);
+    const Mat3 nRsk_dt = m3_scale(nRsk, dt), nRsk_dt2 = m3_scale(nRsk, dt2div2);
+    dRt = m3_t(dR);
+    Jrdt = m3_scale(Jr, dt);
+    const Mat3 Idt = m3_scale(m3_identity(), dt), Rdt = m3_scale(s.R, dt), Rdt2 = m3_scale(s.R, dt2div2);
+    // P-R-V (:444-452)
+    put_block(W.A[0], 3, 3, dRt);
+    put_block(W.A[0], 6, 3, nRsk_dt);
+    put_block(W.A[0], 0, 3, nRsk_dt2);
+    put_block(W.A[0], 0, 6, Idt);
+    put_rows(W.Bg[0], 3, Jrdt);
+    put_rows(W.Ba[0], 6, Rdt);
+    put_rows(W.Ba[0], 0, Rdt2);
+    // P-V-R (:465-474)
+    put_block(W.A[1], 6, 6, dRt);
+    put_block(W.A[1], 3, 6, nRsk_dt);
+    put_block(W.A[1], 0, 6, nRsk_dt2);
+    put_block(W.A[1], 0, 3, Idt);
+    put_rows(W.Bg[1], 6, Jrdt);
+    put_rows(W.Ba[1], 3, Rdt);
+    put_rows(W.Ba[1], 0, Rdt2);
+    // bias Jacobians: P, then V, then R, all with the old delta-R (:488-493)
+    const Mat3 RskJgR = m3_mul(Rsk, s.JgR);
+    s.Jap = m3_add(s.Jap, m3_sub(m3_scale(s.Jav, dt), m3_scale(s.R, dt2div2)));
+    s.Jgp = m3_add(s.Jgp, m3_sub(m3_scale(s.Jgv, dt), m3_scale(RskJgR, dt2div2)));
+    s.Jav = m3_add(s.Jav, m3_scale(m3_scale(s.R, -1.0), dt));
+    s.Jgv = m3_add(s.Jgv, m3_scale(m3_scale(RskJgR, -1.0), dt));
+    s.JgR = m3_sub(m3_mul(dRt, s.JgR), Jrdt);
+    // delta measurements (:497-503)
+    const Vec3 Ra2 = m3_mulv(s.R, v3_scale(acc, dt2div2)), Ra1 = m3_mulv(s.R, v3_scale(acc, dt));
+    s.p = {s.p.x + (s.v.x * dt + Ra2.x), s.p.y + (s.v.y * dt + Ra2.y), s.p.z + (s.v.z * dt + Ra2.z)};
+    s.v = v3_add(s.v, Ra1);
+    s.R = so3_normalize(m3_mul(s.R, dR));
+    s.dt += dt;
+  }
+  __syncwarp();
+  imu_propagate(W, lane);
+}
+
+__global__ void __launch_bounds__(kImuWarps * 32) k_imu_preint(const double* __restrict__ smp,
+                                                              const int* __restrict__ seg_ptr,
+                                                              const double* __restrict__ ti_tj,
+                                                              const double* __restrict__ bg_ba, VieoImuNoise nz,
+                                                              int n_int, VieoImuPreint* __restrict__ out) {
+  __shared__ ImuWarpSmem s_w[kImuWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int it = blockIdx.x * kImuWarps + warp;
+  if (it >= n_int) return;
+  ImuWarpSmem& W = s_w[warp];
+  for (int e = lane; e < 162; e += 32) (&W.S[0][0])[e] = 0.0;
+  __syncwarp();
+  ImuState s;
+  s.R = m3_identity();
+  s.Jgp = s.Jap = s.Jgv = s.Jav = s.JgR = m3_zero();
+  s.v = s.p = {0, 0, 0};
+  s.dt = 0;
+  const double* S = smp + 7 * (size_t)seg_ptr[it];
+  const int n = seg_ptr[it + 1] - seg_ptr[it];
+  const double ti = ti_tj[2 * it], tj = ti_tj[2 * it + 1];
+  const Vec3 bg = {bg_ba[6 * it], bg_ba[6 * it + 1], bg_ba[6 * it + 2]};
+  const Vec3 ba = {bg_ba[6 * it + 3], bg_ba[6 * it + 4], bg_ba[6 * it + 5]};
+  int status = 0;
+  if (n > 0) {
+    // sample window selection (OdomPreIntegrator.h:237-262); END = one past the last sample
+    const int END = n;
+    const bool back = ti > tj;
+    const double tmin = back ? tj : ti, tmax = back ? ti : tj;
+    int start = 0, stop = END;
+    for (int j = 0; j != END && S[7 * j] <= tmin; start = j++) {
+    }
+    for (int j = END; j != 0;) {
+      stop = j--;
+      if (S[7 * j] >= tmax) continue;
+      break;
+    }
+    if (back) {
+      if (stop == END) --stop;
+      const int t = start;
+      start = stop;
+      stop = t;
+      if (S[7 * stop] > tmin) stop = END;
+    }
+    for (int j = start; j != stop;) {
+      const int jm1 = j;
+      if (back) {
+        if (j == 0) j = stop; else --j;
+      } else
+        ++j;
+      const double tj_1 = jm1 == start ? ti : S[7 * jm1];
+      const double tjj = j == stop ? tj : S[7 * j];
+      double dt = tjj - tj_1;
+      if (dt == 0) continue;
+      if (fabs(dt) > 1.5) {  // "CheckIMU!!!" (:289-293)
+        s.dt = 0;
+        status = -1;
+        break;
+      }
+      Vec3 a0 = {S[7 * jm1 + 1], S[7 * jm1 + 2], S[7 * jm1 + 3]}, w0 = {S[7 * jm1 + 4], S[7 * jm1 + 5], S[7 * jm1 + 6]};
+      Vec3 a1 = a0, w1 = w0;
+      double t1 = S[7 * jm1];
+      if (j != END) {
+        a1 = {S[7 * j + 1], S[7 * j + 2], S[7 * j + 3]};
+        w1 = {S[7 * j + 4], S[7 * j + 5], S[7 * j + 6]};
+        t1 = S[7 * j];
+        if (j == stop) {  // interpolate the last sample back to t_j (:301-311)
+          const double d = S[7 * j] - tj;
+          if (back ? d < 0 : d > 0) {
+            const double rat = d / (S[7 * j] - S[7 * jm1]);
+            w1 = v3_add(v3_scale(w0, rat), v3_scale(w1, 1 - rat));
+            a1 = v3_add(v3_scale(a0, rat), v3_scale(a1, 1 - rat));
+          }
+        }
+        if (jm1 == start) {  // interpolate the first sample forward to t_i (:312-326)
+          const double d = ti - S[7 * jm1];
+          if (back ? d < 0 : d > 0) {
+            const double rat = d / (S[7 * j] - S[7 * jm1]);
+            w0 = v3_add(v3_scale(w0, 1 - rat), v3_scale(w1, rat));
+            a0 = v3_add(v3_scale(a0, 1 - rat), v3_scale(a1, rat));
+          }
+        }
+      }
+      if (jm1 == start) {  // first sample later than t_i: hold it over the gap (:403-410)
+        const double dc = S[7 * jm1] - ti;
+        if (back ? dc < 0 : dc > 0) {
+          imu_update(s, W, lane, v3_sub(w0, bg), v3_sub(a0, ba), dc, nz);
+          dt -= dc;
+          if (!dt) continue;
+        }
+      }
+      double dcs = 0;
+      if (j == stop) {
+        dcs = tj - t1;
+        if (back ? dcs < 0 : dcs > 0) dt -= dcs;
+      }
+      const Vec3 wm = v3_scale(v3_add(w1, w0), 0.5), am = v3_scale(v3_add(a1, a0), 0.5);  // mid-point (:419)
+      imu_update(s, W, lane, v3_sub(wm, bg), v3_sub(am, ba), dt, nz);
+      if (back ? dcs < 0 : dcs > 0) imu_update(s, W, lane, v3_sub(w1, bg), v3_sub(a1, ba), dcs, nz);
+    }
+  }
+  VieoImuPreint& o = out[it];
+  for (int e = lane; e < 81; e += 32) {
+    o.SigmaPRV[e] = W.S[0][e];
+    o.SigmaPVR[e] = W.S[1][e];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      o.Rij[e] = s.R.m[e];
+      o.Jgp[e] = s.Jgp.m[e];
+      o.Jap[e] = s.Jap.m[e];
+      o.Jgv[e] = s.Jgv.m[e];
+      o.Jav[e] = s.Jav.m[e];
+      o.JgR[e] = s.JgR.m[e];
+    }
+    o.vij[0] = s.v.x; o.vij[1] = s.v.y; o.vij[2] = s.v.z;
+    o.pij[0] = s.p.x; o.pij[1] = s.p.y; o.pij[2] = s.p.z;
+    o.dt = s.dt;
+    o.status = status;
+    o.pad_ = 0;
+  }
+}
+
+}  // namespace vieo
+
+using namespace vieo;
+
+extern "C" {
+
+void vieo_imu_set_param(VieoImuNoise* nz, const double sigma2[4], int dt_cov_noise_fixed, double freq_ref) {
+  nz->sigma_g = sigma2[0];
+  nz->sigma_a = sigma2[1];
+  nz->sigma_bg = sigma2[2];
+  nz->sigma_ba = sigma2[3];
+  nz->dt_cov_noise_fixed = dt_cov_noise_fixed;
+  nz->pad_ = 0;
+  if (dt_cov_noise_fixed && freq_ref) {
+    nz->freq_ref = 0;
+    nz->sigma_g *= freq_ref;
+    nz->sigma_a *= freq_ref;
+  } else
+    nz->freq_ref = freq_ref;
+}
+
+int vieo_imu_preint_batch_dev(const double* samples_dev, const int32_t* seg_ptr_dev, const double* ti_tj_dev,
+                              const double* bg_ba_dev, const VieoImuNoise* noise, int n_intervals,
+                              VieoImuPreint* out_dev, void* stream) {
+  VIEO_ARG(noise && n_intervals >= 0, "bad argument");
+  if (n_intervals == 0) return VIEO_OK;
+  VIEO_ARG(samples_dev && seg_ptr_dev && ti_tj_dev && bg_ba_dev && out_dev, "null argument");
+  k_imu_preint<<<(n_intervals + kImuWarps - 1) / kImuWarps, kImuWarps * 32, 0, (cudaStream_t)stream>>>(
+      samples_dev, seg_ptr_dev, ti_tj_dev, bg_ba_dev, *noise, n_intervals, out_dev);
+  VIEO_CK(cudaGetLastError());
+  return VIEO_OK;
+}
+
+int vieo_imu_preint_batch(const double* samples, const int32_t* seg_ptr, const double* ti_tj, const double* bg_ba,
+                          const VieoImuNoise* noise, int n_intervals, VieoImuPreint* out, int device) {
+  VIEO_ARG(noise && n_intervals >= 0 && seg_ptr, "bad argument");
+  if (n_intervals == 0) return VIEO_OK;
+  VIEO_ARG(ti_tj && bg_ba && out, "null argument");
+  const int n_s = seg_ptr[n_intervals];
+  VIEO_ARG(n_s >= 0 && (n_s == 0 || samples), "bad sample list");
+  int rc = use_device(device);
+  if (rc) return rc;
+  double *d_s = nullptr, *d_t = nullptr, *d_b = nullptr;
+  int* d_p = nullptr;
+  VieoImuPreint* d_o = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  step(cudaMalloc(&d_s, sizeof(double) * 7 * std::max(n_s, 1)));
+  step(cudaMalloc(&d_p, sizeof(int) * (n_intervals + 1)));
+  step(cudaMalloc(&d_t, sizeof(double) * 2 * n_intervals));
+  step(cudaMalloc(&d_b, sizeof(double) * 6 * n_intervals));
+  step(cudaMalloc(&d_o, sizeof(VieoImuPreint) * n_intervals));
+  if (e == cudaSuccess) {
+    if (n_s) step(cudaMemcpy(d_s, samples, sizeof(double) * 7 * n_s, cudaMemcpyHostToDevice));
+    step(cudaMemcpy(d_p, seg_ptr, sizeof(int) * (n_intervals + 1), cudaMemcpyHostToDevice));
+    step(cudaMemcpy(d_t, ti_tj, sizeof(double) * 2 * n_intervals, cudaMemcpyHostToDevice));
+    step(cudaMemcpy(d_b, bg_ba, sizeof(double) * 6 * n_intervals, cudaMemcpyHostToDevice));
+  }
+  if (e == cudaSuccess) {
+    rc = vieo_imu_preint_batch_dev(d_s, d_p, d_t, d_b, noise, n_intervals, d_o, nullptr);
+    if (rc == VIEO_OK) step(cudaMemcpy(out, d_o, sizeof(VieoImuPreint) * n_intervals, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_s); cudaFree(d_p); cudaFree(d_t); cudaFree(d_b); cudaFree(d_o);
+  if (e != cudaSuccess) {
+    set_error("vieo_imu_preint_batch: %s", cudaGetErrorString(e));
+    return VIEO_E_CUDA;
+  }
+  return rc;
+}
+
+}  // extern "C"
