@@ -1,0 +1,1180 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orb_oracle.cc header).  CPU restatement of the bundle-adjustment path:
+//   edges       src/Odom/g2otypes.h:321-541 (EdgeReproject), :725-884 (EdgeNavStateI), g2otypes.cpp:14-124
+//               (EdgeNavStateBias, EdgeNavStatePriorPVRBias), NavState::IncSmall (src/Odom/NavState.h:47-82),
+//               pinhole projection rounded to float (common/camera_models/camera_pinhole.h:70-106)
+//   solver      g2o semantics: active set (sparse_optimizer.cpp:199-267), Levenberg-Marquardt
+//               (optimization_algorithm_levenberg.cpp:61-189), Huber with float delta^2 (robust_kernel_impl.cpp:65-91,
+//               base_edge.h:96-102), Schur complement (block_solver.hpp:353-486)
+//   drivers     Optimizer::PoseOptimization visual (src/Optimizer.cc:1611-1874) and IMU/PVR incl. the kExactRobust
+//               marginal prior (include/Optimizer.h:126-816), LocalBundleAdjustmentNavStatePRV (src/Optimizer.cc:21-769)
+// Eigen is absent here: LDLT / inverse() / JacobiSVD are restated as Cholesky / Gauss-Jordan ("parity unpinned" for
+// their rounding; the tests pin this file with numeric Jacobians, a scipy solve of the full normal equations and
+// closed-form cases).
+#include "ba_oracle.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "so3_oracle.h"
+
+namespace {
+using namespace orc;
+
+struct NS {
+  double p[3];
+  Quat q;
+  double v[3], bg[3], ba[3], dbg[3], dba[3];
+};
+NS from_c(const OrcNavState& s) {
+  NS n;
+  memcpy(n.p, s.p, 24);
+  n.q = {s.q[0], s.q[1], s.q[2], s.q[3]};
+  memcpy(n.v, s.v, 24); memcpy(n.bg, s.bg, 24); memcpy(n.ba, s.ba, 24); memcpy(n.dbg, s.dbg, 24); memcpy(n.dba, s.dba, 24);
+  return n;
+}
+void to_c(const NS& n, OrcNavState* s) {
+  memcpy(s->p, n.p, 24);
+  s->q[0] = n.q.w; s->q[1] = n.q.x; s->q[2] = n.q.y; s->q[3] = n.q.z;
+  memcpy(s->v, n.v, 24); memcpy(s->bg, n.bg, 24); memcpy(s->ba, n.ba, 24); memcpy(s->dbg, n.dbg, 24); memcpy(s->dba, n.dba, 24);
+}
+struct Cam {
+  float fx, fy, cx, cy, bf;
+  M3 Rcb;
+  double tcb[3];
+};
+Cam cam_from_c(const OrcCamera& c) {
+  Cam k;
+  k.fx = c.fx; k.fy = c.fy; k.cx = c.cx; k.cy = c.cy; k.bf = c.bf;
+  memcpy(k.Rcb.m, c.Rcb, 72);
+  memcpy(k.tcb, c.tcb, 24);
+  return k;
+}
+
+// ---- NavState::IncSmall (NavState.h:47-82), USE_P_PLUS_RDP ----------------------------------------------------
+void inc_pr(NS& s, const double* d) {
+  const M3 R = qmat(s.q);
+  double Rd[3];
+  mulv(R, d, Rd);
+  for (int i = 0; i < 3; ++i) s.p[i] += Rd[i];
+  s.q = qnormalized(qmul(s.q, so3_exp_q(d + 3)));
+}
+void inc_pvr(NS& s, const double* d) {
+  const M3 R = qmat(s.q);
+  double Rd[3];
+  mulv(R, d, Rd);
+  for (int i = 0; i < 3; ++i) s.p[i] += Rd[i];
+  for (int i = 0; i < 3; ++i) s.v[i] += d[3 + i];
+  s.q = qnormalized(qmul(s.q, so3_exp_q(d + 6)));
+}
+void inc_v(NS& s, const double* d) {
+  for (int i = 0; i < 3; ++i) s.v[i] += d[i];
+}
+void inc_bias(NS& s, const double* d) {
+  for (int i = 0; i < 3; ++i) s.dbg[i] += d[i];
+  for (int i = 0; i < 3; ++i) s.dba[i] += d[3 + i];
+}
+
+// ---- EdgeReproject (g2otypes.h:338-541), NV = 2 ---------------------------------------------------------------
+// e = obs - pi(Rcw Xw + tcw), pi rounded to float (camera_pinhole.h:81-82); returns depth (GetDepth, :431-436)
+double reproj_error(const Cam& c, const NS& s, const double Xw[3], const float obs[3], bool stereo, double e[3]) {
+  const M3 Rwb = qmat(s.q), Rcw = mul(c.Rcb, tr(Rwb));
+  double t[3], Pc[3];
+  mulv(Rcw, s.p, t);
+  for (int i = 0; i < 3; ++i) t[i] = -t[i] + c.tcb[i];
+  mulv(Rcw, Xw, Pc);
+  for (int i = 0; i < 3; ++i) Pc[i] += t[i];
+  const double invz = 1. / Pc[2];
+  const float u = (float)((double)c.fx * Pc[0] * invz + c.cx), v = (float)((double)c.fy * Pc[1] * invz + c.cy);
+  e[0] = (double)obs[0] - (double)u;
+  e[1] = (double)obs[1] - (double)v;
+  e[2] = stereo ? (double)obs[2] - ((double)u - (double)c.bf / Pc[2]) : 0.0;
+  // GetDepth: Rcw.row(2) * wX + tcw(2)
+  return Rcw.m[6] * Xw[0] + Rcw.m[7] * Xw[1] + Rcw.m[8] * Xw[2] + t[2];
+}
+// Jp (de/d dp), Jr (de/d dphi), JX (de/dX): rows 0..DE-1 of 3x3 row-major blocks
+void reproj_jac(const Cam& c, const NS& s, const double Xw[3], bool stereo, double Jp[9], double Jr[9], double JX[9]) {
+  const M3 Rwb = qmat(s.q), Rcw = mul(c.Rcb, tr(Rwb));
+  double t[3], Pc[3];
+  mulv(Rcw, s.p, t);
+  for (int i = 0; i < 3; ++i) t[i] = -t[i] + c.tcb[i];
+  mulv(Rcw, Xw, Pc);
+  for (int i = 0; i < 3; ++i) Pc[i] += t[i];
+  const double invz = 1 / Pc[2], invz_2 = invz * invz;
+  M3 Jproj = {{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+  Jproj.m[0] = -((double)c.fx * invz);
+  Jproj.m[2] = -(-(double)c.fx * Pc[0] * invz_2);
+  Jproj.m[4] = -((double)c.fy * invz);
+  Jproj.m[5] = -(-(double)c.fy * Pc[1] * invz_2);
+  if (stereo) {
+    Jproj.m[6] = Jproj.m[0];
+    Jproj.m[7] = Jproj.m[1];
+    Jproj.m[8] = Jproj.m[2] - (double)c.bf * invz_2;
+  }
+  const M3 JdP = mul(Jproj, scale(c.Rcb, -1.0));
+  double d[3] = {Xw[0] - s.p[0], Xw[1] - s.p[1], Xw[2] - s.p[2]}, Paux[3];
+  mulv(tr(Rwb), d, Paux);
+  const M3 JdR = mul(mul(Jproj, c.Rcb), hat(Paux));
+  const M3 JdX = mul(Jproj, Rcw);
+  memcpy(Jp, JdP.m, 72);
+  memcpy(Jr, JdR.m, 72);
+  memcpy(JX, JdX.m, 72);
+}
+
+// ---- EdgeNavStateI<NV> (g2otypes.h:725-884).  prv = true: residual / column order P,R,V (NV=5), else P,V,R (NV=3)
+void navstate_error(const NS& si, const NS& sj, const OrcImuPreint& m, const double gw[3], bool prv, double e[9]) {
+  const M3 RiT = tr(qmat(si.q));
+  const int idR = prv ? 3 : 6, idV = 9 - idR;
+  const double dt = m.dt;
+  double a[3], b[3];
+  for (int k = 0; k < 3; ++k) a[k] = sj.p[k] - si.p[k] - si.v[k] * dt - gw[k] * (dt * dt / 2);
+  mulv(RiT, a, b);
+  M3 Jgp, Jap, Jgv, Jav, JgR;
+  memcpy(Jgp.m, m.Jgp, 72); memcpy(Jap.m, m.Jap, 72); memcpy(Jgv.m, m.Jgv, 72); memcpy(Jav.m, m.Jav, 72); memcpy(JgR.m, m.JgR, 72);
+  double t1[3], t2[3];
+  mulv(Jgp, si.dbg, t1);
+  mulv(Jap, si.dba, t2);
+  for (int k = 0; k < 3; ++k) e[k] = b[k] - (m.pij[k] + t1[k] + t2[k]);
+  // eR = Log((dRij Exp(JgR dbg))^-1 * (Ri^-1 Rj))
+  M3 Rij;
+  memcpy(Rij.m, m.Rij, 72);
+  double w[3];
+  mulv(JgR, si.dbg, w);
+  const Quat qm = qnormalized(qmul(qnormalized(mquat(Rij)), so3_exp_q(w)));
+  const Quat qij = qnormalized(qmul(qconj(si.q), sj.q));
+  so3_log_q(qnormalized(qmul(qconj(qm), qij)), e + idR);
+  for (int k = 0; k < 3; ++k) a[k] = sj.v[k] - si.v[k] - gw[k] * dt;
+  mulv(RiT, a, b);
+  mulv(Jgv, si.dbg, t1);
+  mulv(Jav, si.dba, t2);
+  for (int k = 0; k < 3; ++k) e[idV + k] = b[k] - (m.vij[k] + t1[k] + t2[k]);
+}
+inline void setb(double* A, int ld, int r, int c, const M3& b) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[ld * (r + i) + c + j] = b.m[3 * i + j];
+}
+// Ji, Jj: 9x9 (state columns in residual order), Jb: 9x6.  `e` must hold the current error (eR is read from it).
+void navstate_jac(const NS& si, const NS& sj, const OrcImuPreint& m, const double gw[3], bool prv, const double e[9],
+                  double Ji[81], double Jj[81], double Jb[54]) {
+  const M3 Ri = qmat(si.q), RiT = tr(Ri), Rj = qmat(sj.q);
+  const int idR = prv ? 3 : 6, idV = 9 - idR;
+  const double dt = m.dt;
+  memset(Ji, 0, 81 * 8); memset(Jj, 0, 81 * 8); memset(Jb, 0, 54 * 8);
+  M3 Jgp, Jap, Jgv, Jav, JgR;
+  memcpy(Jgp.m, m.Jgp, 72); memcpy(Jap.m, m.Jap, 72); memcpy(Jgv.m, m.Jgv, 72); memcpy(Jav.m, m.Jav, 72); memcpy(JgR.m, m.JgR, 72);
+  double a[3], b[3];
+  for (int k = 0; k < 3; ++k) a[k] = sj.p[k] - si.p[k] - si.v[k] * dt - gw[k] * (dt * dt / 2);
+  mulv(RiT, a, b);
+  setb(Ji, 9, 0, idR, hat(b));
+  setb(Ji, 9, 0, 0, scale(ident(), -1.0));
+  setb(Ji, 9, 0, idV, scale(scale(RiT, -1.0), dt));
+  setb(Jb, 6, 0, 0, scale(Jgp, -1.0));
+  setb(Jb, 6, 0, 3, scale(Jap, -1.0));
+  setb(Jj, 9, 0, 0, mul(RiT, Rj));
+  for (int k = 0; k < 3; ++k) a[k] = sj.v[k] - si.v[k] - gw[k] * dt;
+  mulv(RiT, a, b);
+  setb(Ji, 9, idV, idR, hat(b));
+  setb(Ji, 9, idV, idV, scale(RiT, -1.0));
+  setb(Jb, 6, idV, 0, scale(Jgv, -1.0));
+  setb(Jb, 6, idV, 3, scale(Jav, -1.0));
+  setb(Jj, 9, idV, idV, RiT);
+  const double* eR = e + idR;
+  const M3 Jrinv = so3_JrInv(eR);
+  // -Jrinv * (Rj^-1 Ri).matrix()
+  const M3 RjTRi = qmat(qnormalized(qmul(qconj(sj.q), si.q)));
+  setb(Ji, 9, idR, idR, scale(mul(Jrinv, RjTRi), -1.0));
+  double neR[3] = {-eR[0], -eR[1], -eR[2]}, w[3];
+  mulv(JgR, si.dbg, w);
+  const M3 T = mul(mul(mul(scale(Jrinv, -1.0), so3_Exp(neR)), so3_Jr(w)), JgR);
+  setb(Jb, 6, idR, 0, T);
+  setb(Jj, 9, idR, idR, Jrinv);
+}
+
+// ---- EdgeNavStatePriorPVRBias (g2otypes.cpp:84-124): order P V R bg ba ----------------------------------------
+void prior_error(const NS& s, const NS& sb, const NS& pr, double e[15]) {
+  const Quat qbar_inv = qconj(pr.q);
+  const M3 Rbw = qmat(qbar_inv);
+  double d[3] = {s.p[0] - pr.p[0], s.p[1] - pr.p[1], s.p[2] - pr.p[2]};
+  mulv(Rbw, d, e);
+  for (int k = 0; k < 3; ++k) e[3 + k] = s.v[k] - pr.v[k];
+  so3_log_q(qnormalized(qmul(qbar_inv, s.q)), e + 6);
+  for (int k = 0; k < 3; ++k) e[9 + k] = sb.bg[k] + sb.dbg[k] - (pr.bg[k] + pr.dbg[k]);
+  for (int k = 0; k < 3; ++k) e[12 + k] = sb.ba[k] + sb.dba[k] - (pr.ba[k] + pr.dba[k]);
+}
+void prior_jac(const NS& s, const NS& pr, const double e[15], double Jpvr[135], double Jb[90]) {
+  memset(Jpvr, 0, 135 * 8);
+  memset(Jb, 0, 90 * 8);
+  setb(Jpvr, 9, 0, 0, mul(tr(qmat(pr.q)), qmat(s.q)));
+  setb(Jpvr, 9, 3, 3, ident());
+  setb(Jpvr, 9, 6, 6, so3_JrInv(e + 6));
+  setb(Jb, 6, 9, 0, ident());
+  setb(Jb, 6, 12, 3, ident());
+}
+
+// ---- small dense linear algebra --------------------------------------------------------------------------------
+// Gauss-Jordan inverse with partial pivoting (stands in for Eigen's inverse() / JacobiSVD pseudo-inverse without clamping)
+bool inverse(const double* A, int n, double* Ai) {
+  std::vector<double> M(A, A + n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) Ai[i * n + j] = i == j;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(M[r * n + c]) > std::fabs(M[piv * n + c])) piv = r;
+    if (M[piv * n + c] == 0) return false;
+    if (piv != c)
+      for (int j = 0; j < n; ++j) {
+        std::swap(M[piv * n + j], M[c * n + j]);
+        std::swap(Ai[piv * n + j], Ai[c * n + j]);
+      }
+    const double d = 1.0 / M[c * n + c];
+    for (int j = 0; j < n; ++j) {
+      M[c * n + j] *= d;
+      Ai[c * n + j] *= d;
+    }
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = M[r * n + c];
+      if (f == 0) continue;
+      for (int j = 0; j < n; ++j) {
+        M[r * n + j] -= f * M[c * n + j];
+        Ai[r * n + j] -= f * Ai[c * n + j];
+      }
+    }
+  }
+  return true;
+}
+// 3x3 inverse by cofactors (Eigen's fixed-size inverse, block_solver.hpp:389)
+void inv3(const double* D, double* I) {
+  const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
+  const double det = D[0] * c00 + D[1] * c01 + D[2] * c02, id = 1.0 / det;
+  I[0] = c00 * id; I[1] = (D[2] * D[7] - D[1] * D[8]) * id; I[2] = (D[1] * D[5] - D[2] * D[4]) * id;
+  I[3] = c01 * id; I[4] = (D[0] * D[8] - D[2] * D[6]) * id; I[5] = (D[2] * D[3] - D[0] * D[5]) * id;
+  I[6] = c02 * id; I[7] = (D[1] * D[6] - D[0] * D[7]) * id; I[8] = (D[0] * D[4] - D[1] * D[3]) * id;
+}
+// Cholesky solve A x = b (A symmetric, full storage); false when a pivot is not positive (LDLT::isPositive)
+bool chol_solve(std::vector<double>& A, int n, const double* b, double* x) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[j * n + j];
+    for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
+    if (!(d > 0) || !std::isfinite(d)) return false;
+    d = std::sqrt(d);
+    A[j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[i * n + j];
+      for (int k = 0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = s / d;
+    }
+  }
+  std::vector<double> y(n);
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= A[i * n + k] * y[k];
+    y[i] = s / A[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < n; ++k) s -= A[k * n + i] * x[k];
+    x[i] = s / A[i * n + i];
+  }
+  return true;
+}
+
+// ---- RobustKernelHuber (robust_kernel_impl.cpp:65-91): delta double, delta^2 stored as float -----------------------
+struct Huber {
+  bool on = false;
+  double delta = 0;
+  float dsqr = 0;
+  void set(double d) {
+    on = true;
+    delta = d;
+    dsqr = (float)(d * d);
+  }
+  void rho(double e, double r[2]) const {
+    if (!on || e <= (double)dsqr) {
+      r[0] = e;
+      r[1] = 1.;
+    } else {
+      const double sq = std::sqrt(e);
+      r[0] = 2 * sq * delta - (double)dsqr;
+      r[1] = delta / sq;
+    }
+  }
+};
+
+// ================================================================================================================
+// Graph engine.  A "state" carries up to three vertices: slot 0 = PR(6) or PVR(9), slot 1 = V(3) (PR-V-B layout
+// only), slot 2 = Bias(6).  Hessian index order = states in the given order, slots ascending (the reference's vertex
+// ids 3k, 3k+1, 3k+2 resp. 0..3; sparse_optimizer.cpp:166-190), marginalised points after.
+struct DenseEdge {  // IMU / bias / prior factors
+  int type;         // 0 IMU, 1 bias, 2 prior (PVR-Bias)
+  int si, sj;       // states (prior: si only)
+  const OrcImuPreint* pre = nullptr;
+  NS prior;
+  int D;
+  std::vector<double> info;  // D x D
+  Huber rk;
+  double err[15];
+  double chi2 = 0;
+};
+struct VisEdge {
+  int s, p;
+  float obs[3];
+  double w;  // invSigma2
+  bool stereo, close;
+  int level;
+  Huber rk;
+  double err[3];
+  double chi2 = 0;
+};
+
+struct Graph {
+  bool pvr;  // slot 0 is PVR(9) (pose optimisation) instead of PR(6)
+  Cam cam;
+  double gw[3];
+  std::vector<NS> st;
+  std::vector<uint8_t> fix0, has_vb, fix_vb;  // per state
+  std::vector<double> X;                      // points
+  bool points_free = false;
+  std::vector<VisEdge> vis;
+  std::vector<DenseEdge> den;
+  volatile const bool* stop = nullptr;
+  // index mapping
+  std::vector<int> off0, off1, off2;
+  int np = 0;
+  std::vector<uint8_t> vis_active, den_active, pt_active;
+  // system
+  std::vector<double> H, b, x, Hll, bl, W, xl;  // H np x np, W per visual edge [d0][3]
+  // LM
+  double lambda = 0, ni = 2, user_lambda = 0;
+  int nBad = 0;
+  int total_iters = 0;
+  std::vector<NS> st_bak;
+  std::vector<double> X_bak;
+
+  int d0() const { return pvr ? 9 : 6; }
+
+  void initialize() {  // initializeOptimization(0) + buildIndexMapping
+    const int K = (int)st.size();
+    off0.assign(K, -1); off1.assign(K, -1); off2.assign(K, -1);
+    np = 0;
+    for (int k = 0; k < K; ++k) {
+      if (!fix0[k]) { off0[k] = np; np += d0(); }
+      if (has_vb[k] && !fix_vb[k]) {
+        if (!pvr) { off1[k] = np; np += 3; }
+        off2[k] = np; np += 6;
+      }
+    }
+    vis_active.assign(vis.size(), 0);
+    pt_active.assign(X.size() / 3, 0);
+    for (size_t i = 0; i < vis.size(); ++i) {
+      const VisEdge& e = vis[i];
+      const bool anyfree = off0[e.s] >= 0 || points_free;
+      vis_active[i] = e.level == 0 && anyfree;
+      if (vis_active[i] && points_free) pt_active[e.p] = 1;
+    }
+    den_active.assign(den.size(), 0);
+    for (size_t i = 0; i < den.size(); ++i) {
+      const DenseEdge& e = den[i];
+      bool anyfree = false;
+      if (e.type == 0) anyfree = off0[e.si] >= 0 || off0[e.sj] >= 0 || off1[e.si] >= 0 || off1[e.sj] >= 0 || off2[e.si] >= 0;
+      if (e.type == 1) anyfree = off2[e.si] >= 0 || off2[e.sj] >= 0;
+      if (e.type == 2) anyfree = off0[e.si] >= 0 || off2[e.si] >= 0;
+      den_active[i] = anyfree;
+    }
+  }
+  void vis_error(VisEdge& e) {
+    reproj_error(cam, st[e.s], &X[3 * e.p], e.obs, e.stereo, e.err);
+    double c = 0;
+    for (int k = 0; k < (e.stereo ? 3 : 2); ++k) c += e.err[k] * (e.w * e.err[k]);
+    e.chi2 = c;
+  }
+  double vis_depth(const VisEdge& e) {
+    double t[3];
+    return reproj_error(cam, st[e.s], &X[3 * e.p], e.obs, e.stereo, t);
+  }
+  void den_error(DenseEdge& e) {
+    if (e.type == 0) navstate_error(st[e.si], st[e.sj], *e.pre, gw, !pvr, e.err);
+    if (e.type == 1) {
+      const NS &a = st[e.si], &c = st[e.sj];
+      for (int k = 0; k < 3; ++k) e.err[k] = (c.bg[k] + c.dbg[k]) - (a.bg[k] + a.dbg[k]);
+      for (int k = 0; k < 3; ++k) e.err[3 + k] = (c.ba[k] + c.dba[k]) - (a.ba[k] + a.dba[k]);
+    }
+    if (e.type == 2) prior_error(st[e.si], st[e.si], e.prior, e.err);
+    double c = 0;
+    for (int i = 0; i < e.D; ++i) {
+      double s = 0;
+      for (int j = 0; j < e.D; ++j) s += e.info[i * e.D + j] * e.err[j];
+      c += e.err[i] * s;
+    }
+    e.chi2 = c;
+  }
+  void compute_active_errors() {
+    for (size_t i = 0; i < vis.size(); ++i)
+      if (vis_active[i]) vis_error(vis[i]);
+    for (size_t i = 0; i < den.size(); ++i)
+      if (den_active[i]) den_error(den[i]);
+  }
+  double active_robust_chi2() const {
+    double chi = 0, r[2];
+    for (size_t i = 0; i < den.size(); ++i)
+      if (den_active[i]) {
+        den[i].rk.rho(den[i].chi2, r);
+        chi += r[0];
+      }
+    for (size_t i = 0; i < vis.size(); ++i)
+      if (vis_active[i]) {
+        vis[i].rk.rho(vis[i].chi2, r);
+        chi += r[0];
+      }
+    return chi;
+  }
+  // H[oa.., ob..] += Ja^T (w Omega) Jb ; b[oa] += Ja^T (-w Omega e) for every pair of free vertex blocks
+  struct Blk {
+    int off, dim;
+    const double* J;  // D x ld, columns [c0, c0+dim)
+    int ld, c0;
+  };
+  void add_dense(const DenseEdge& e, const std::vector<Blk>& blks) {
+    double r[2];
+    e.rk.rho(e.chi2, r);
+    const int D = e.D;
+    std::vector<double> Om(D * D), oe(D);
+    for (int i = 0; i < D * D; ++i) Om[i] = r[1] * e.info[i];
+    for (int i = 0; i < D; ++i) {
+      double s = 0;
+      for (int j = 0; j < D; ++j) s += e.info[i * D + j] * e.err[j];
+      oe[i] = -s * r[1];
+    }
+    for (const Blk& A : blks) {
+      if (A.off < 0) continue;
+      std::vector<double> AtO(A.dim * D);
+      for (int a = 0; a < A.dim; ++a)
+        for (int j = 0; j < D; ++j) {
+          double s = 0;
+          for (int i = 0; i < D; ++i) s += A.J[i * A.ld + A.c0 + a] * Om[i * D + j];
+          AtO[a * D + j] = s;
+        }
+      for (int a = 0; a < A.dim; ++a) {
+        double s = 0;
+        for (int i = 0; i < D; ++i) s += A.J[i * A.ld + A.c0 + a] * oe[i];
+        b[A.off + a] += s;
+      }
+      for (const Blk& B : blks) {
+        if (B.off < 0) continue;
+        for (int a = 0; a < A.dim; ++a)
+          for (int c = 0; c < B.dim; ++c) {
+            double s = 0;
+            for (int j = 0; j < D; ++j) s += AtO[a * D + j] * B.J[j * B.ld + B.c0 + c];
+            H[(A.off + a) * np + B.off + c] += s;
+          }
+      }
+    }
+  }
+  std::vector<Blk> dense_blocks(const DenseEdge& e, double* Ji, double* Jj, double* Jb) {
+    std::vector<Blk> blks;
+    if (e.type == 0) {
+      navstate_jac(st[e.si], st[e.sj], *e.pre, gw, !pvr, e.err, Ji, Jj, Jb);
+      if (pvr) {
+        blks = {{off0[e.si], 9, Ji, 9, 0}, {off0[e.sj], 9, Jj, 9, 0}, {off2[e.si], 6, Jb, 6, 0}};
+      } else {
+        blks = {{off0[e.si], 6, Ji, 9, 0}, {off0[e.sj], 6, Jj, 9, 0}, {off1[e.si], 3, Ji, 9, 6},
+                {off1[e.sj], 3, Jj, 9, 6}, {off2[e.si], 6, Jb, 6, 0}};
+      }
+    } else if (e.type == 1) {
+      for (int i = 0; i < 36; ++i) Ji[i] = Jj[i] = 0;
+      for (int i = 0; i < 6; ++i) {
+        Ji[7 * i] = -1;
+        Jj[7 * i] = 1;
+      }
+      blks = {{off2[e.si], 6, Ji, 6, 0}, {off2[e.sj], 6, Jj, 6, 0}};
+    } else {
+      prior_jac(st[e.si], e.prior, e.err, Ji, Jb);
+      blks = {{off0[e.si], 9, Ji, 9, 0}, {off2[e.si], 6, Jb, 6, 0}};
+    }
+    return blks;
+  }
+  void build_system() {
+    const int P = (int)X.size() / 3, dv = d0();
+    H.assign((size_t)np * np, 0.0);
+    b.assign(np, 0.0);
+    if (points_free) {
+      Hll.assign((size_t)P * 9, 0.0);
+      bl.assign((size_t)P * 3, 0.0);
+      W.assign(vis.size() * (size_t)dv * 3, 0.0);
+    }
+    double Ji[135], Jj[81], Jb[90];
+    for (size_t i = 0; i < den.size(); ++i)
+      if (den_active[i]) add_dense(den[i], dense_blocks(den[i], Ji, Jj, Jb));
+    for (size_t i = 0; i < vis.size(); ++i) {
+      if (!vis_active[i]) continue;
+      const VisEdge& e = vis[i];
+      const int DE = e.stereo ? 3 : 2;
+      double Jp[9], Jr[9], JX[9], r[2];
+      reproj_jac(cam, st[e.s], &X[3 * e.p], e.stereo, Jp, Jr, JX);
+      e.rk.rho(e.chi2, r);
+      const double w = r[1] * e.w;
+      double J[3][9];  // pose Jacobian DE x dv: dp | (dv) | dphi
+      memset(J, 0, sizeof(J));
+      for (int k = 0; k < DE; ++k)
+        for (int c = 0; c < 3; ++c) {
+          J[k][c] = Jp[3 * k + c];
+          J[k][dv - 3 + c] = Jr[3 * k + c];
+        }
+      double oe[3];
+      for (int k = 0; k < DE; ++k) oe[k] = -(e.w * e.err[k]) * r[1];
+      const int o = off0[e.s];
+      if (o >= 0) {
+        for (int a = 0; a < dv; ++a) {
+          double s = 0;
+          for (int k = 0; k < DE; ++k) s += J[k][a] * oe[k];
+          b[o + a] += s;
+          for (int c = 0; c < dv; ++c) {
+            double h = 0;
+            for (int k = 0; k < DE; ++k) h += (J[k][a] * w) * J[k][c];
+            H[(size_t)(o + a) * np + o + c] += h;
+          }
+        }
+      }
+      if (points_free) {
+        double* Hl = &Hll[(size_t)9 * e.p];
+        double* bp = &bl[(size_t)3 * e.p];
+        for (int a = 0; a < 3; ++a) {
+          double s = 0;
+          for (int k = 0; k < DE; ++k) s += JX[3 * k + a] * oe[k];
+          bp[a] += s;
+          for (int c = 0; c < 3; ++c) {
+            double h = 0;
+            for (int k = 0; k < DE; ++k) h += (JX[3 * k + a] * w) * JX[3 * k + c];
+            Hl[3 * a + c] += h;
+          }
+        }
+        if (o >= 0) {
+          double* Wp = &W[i * (size_t)dv * 3];
+          for (int a = 0; a < dv; ++a)
+            for (int c = 0; c < 3; ++c) {
+              double h = 0;
+              for (int k = 0; k < DE; ++k) h += (J[k][a] * w) * JX[3 * k + c];
+              Wp[3 * a + c] = h;
+            }
+        }
+      }
+    }
+  }
+  double lambda_init() const {
+    if (user_lambda > 0) return user_lambda;
+    double mx = 0;
+    for (int i = 0; i < np; ++i) mx = std::max(std::fabs(H[(size_t)i * np + i]), mx);
+    if (points_free)
+      for (size_t p = 0; p < pt_active.size(); ++p)
+        if (pt_active[p])
+          for (int k = 0; k < 3; ++k) mx = std::max(std::fabs(Hll[9 * p + 4 * k]), mx);
+    return 1e-5 * mx;
+  }
+  // (H + lambda I) x = b, with the Schur complement over the free points (block_solver.hpp:353-486)
+  bool solve_system() {
+    const int P = (int)X.size() / 3, dv = d0();
+    std::vector<double> S(H);
+    for (int i = 0; i < np; ++i) S[(size_t)i * np + i] += lambda;
+    std::vector<double> bs(b);
+    std::vector<double> Dinv;
+    if (points_free) {
+      Dinv.assign((size_t)P * 9, 0.0);
+      xl.assign((size_t)P * 3, 0.0);
+      // edges are sorted by point: walk each point's range
+      size_t i0 = 0;
+      while (i0 < vis.size()) {
+        size_t i1 = i0;
+        const int p = vis[i0].p;
+        while (i1 < vis.size() && vis[i1].p == p) ++i1;
+        if (pt_active[p]) {
+          double D[9];
+          memcpy(D, &Hll[(size_t)9 * p], 72);
+          D[0] += lambda; D[4] += lambda; D[8] += lambda;
+          double* Di = &Dinv[(size_t)9 * p];
+          inv3(D, Di);
+          double db[3];
+          for (int a = 0; a < 3; ++a) db[a] = Di[3 * a] * bl[3 * p] + Di[3 * a + 1] * bl[3 * p + 1] + Di[3 * a + 2] * bl[3 * p + 2];
+          for (size_t a = i0; a < i1; ++a) {
+            if (!vis_active[a] || off0[vis[a].s] < 0) continue;
+            const double* Wa = &W[a * (size_t)dv * 3];
+            const int oa = off0[vis[a].s];
+            double WD[27];
+            for (int r = 0; r < dv; ++r)
+              for (int c = 0; c < 3; ++c) WD[3 * r + c] = Wa[3 * r] * Di[c] + Wa[3 * r + 1] * Di[3 + c] + Wa[3 * r + 2] * Di[6 + c];
+            for (int r = 0; r < dv; ++r) bs[oa + r] -= Wa[3 * r] * db[0] + Wa[3 * r + 1] * db[1] + Wa[3 * r + 2] * db[2];
+            for (size_t c2 = i0; c2 < i1; ++c2) {
+              if (!vis_active[c2] || off0[vis[c2].s] < 0) continue;
+              const double* Wb = &W[c2 * (size_t)dv * 3];
+              const int ob = off0[vis[c2].s];
+              for (int r = 0; r < dv; ++r)
+                for (int c = 0; c < dv; ++c)
+                  S[(size_t)(oa + r) * np + ob + c] -= WD[3 * r] * Wb[3 * c] + WD[3 * r + 1] * Wb[3 * c + 1] + WD[3 * r + 2] * Wb[3 * c + 2];
+            }
+          }
+        }
+        i0 = i1;
+      }
+    }
+    if ((int)x.size() != np) x.assign(np, 0.0);
+    bool ok = np == 0 ? true : chol_solve(S, np, bs.data(), x.data());
+    if (!ok) return false;
+    if (points_free) {
+      size_t i0 = 0;
+      while (i0 < vis.size()) {
+        size_t i1 = i0;
+        const int p = vis[i0].p;
+        while (i1 < vis.size() && vis[i1].p == p) ++i1;
+        if (pt_active[p]) {
+          double c[3] = {bl[3 * p], bl[3 * p + 1], bl[3 * p + 2]};
+          for (size_t a = i0; a < i1; ++a) {
+            if (!vis_active[a] || off0[vis[a].s] < 0) continue;
+            const double* Wa = &W[a * (size_t)dv * 3];
+            const int oa = off0[vis[a].s];
+            for (int k = 0; k < 3; ++k)
+              for (int r = 0; r < dv; ++r) c[k] -= Wa[3 * r + k] * x[oa + r];
+          }
+          const double* Di = &Dinv[(size_t)9 * p];
+          for (int a = 0; a < 3; ++a) xl[3 * p + a] = Di[3 * a] * c[0] + Di[3 * a + 1] * c[1] + Di[3 * a + 2] * c[2];
+        }
+        i0 = i1;
+      }
+    }
+    return true;
+  }
+  void apply_update() {
+    for (size_t k = 0; k < st.size(); ++k) {
+      if (off0[k] >= 0) {
+        if (pvr) inc_pvr(st[k], &x[off0[k]]);
+        else inc_pr(st[k], &x[off0[k]]);
+      }
+      if (off1[k] >= 0) inc_v(st[k], &x[off1[k]]);
+      if (off2[k] >= 0) inc_bias(st[k], &x[off2[k]]);
+    }
+    if (points_free)
+      for (size_t p = 0; p < pt_active.size(); ++p)
+        if (pt_active[p])
+          for (int k = 0; k < 3; ++k) X[3 * p + k] += xl[3 * p + k];
+  }
+  double compute_scale() const {
+    double s = 0;
+    for (int j = 0; j < np; ++j) s += x[j] * (lambda * x[j] + b[j]);
+    if (points_free)
+      for (size_t p = 0; p < pt_active.size(); ++p)
+        if (pt_active[p])
+          for (int k = 0; k < 3; ++k) s += xl[3 * p + k] * (lambda * xl[3 * p + k] + bl[3 * p + k]);
+    return s;
+  }
+  bool terminate() const { return stop && *stop; }
+  // OptimizationAlgorithmLevenberg::solve: 0 OK, 1 Terminate
+  int lm_iteration(int iteration) {
+    compute_active_errors();
+    double currentChi = active_robust_chi2();
+    double tempChi = currentChi;
+    const double iniChi = currentChi;
+    build_system();
+    if (iteration == 0) {
+      lambda = lambda_init();
+      ni = 2;
+      nBad = 0;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      st_bak = st;
+      X_bak = X;
+      const bool ok2 = solve_system();
+      if ((int)x.size() != np) x.assign(np, 0.0);
+      if (points_free && xl.size() != X.size()) xl.assign(X.size(), 0.0);
+      apply_update();
+      compute_active_errors();
+      tempChi = active_robust_chi2();
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = compute_scale();
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        const double sf = std::max(1. / 3., alpha);
+        lambda *= sf;
+        ni = 2;
+        currentChi = tempChi;
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        st = st_bak;
+        X = X_bak;
+      }
+      qmax++;
+    } while (rho < 0 && qmax < 10 && !terminate());
+    if (qmax == 10 || rho == 0) return 1;
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+    else nBad = 0;
+    if (nBad >= 3) return 1;
+    return 0;
+  }
+  int optimize(int iterations) {
+    int n = 0;
+    bool ok = true;
+    x.assign(np, 0.0);
+    for (int i = 0; i < iterations && !terminate() && ok; ++i) {
+      ok = lm_iteration(i) == 0;
+      ++n;
+      ++total_iters;
+    }
+    return n;
+  }
+};
+
+
+// Sigma^-1 (IMUPreIntegratorBase::GetProcessedInfoij / InfoijPRV, OdomPreIntegrator.h:119-138)
+std::vector<double> info_from_sigma(const double* S) {
+  std::vector<double> I(81);
+  if (!inverse(S, 9, I.data())) std::fill(I.begin(), I.end(), std::numeric_limits<double>::quiet_NaN());
+  return I;
+}
+
+// J^T (w Omega) J' for the explicit marginal (g2otypes.h:36-254)
+void jtoj(const double* Ja, int lda, int ca, int na, const double* Om, int D, double w, const double* Jb, int ldb, int cb,
+          int nb, double* out, int ldo, int r0, int c0, bool add) {
+  for (int a = 0; a < na; ++a)
+    for (int c = 0; c < nb; ++c) {
+      double s = 0;
+      for (int i = 0; i < D; ++i) {
+        double t = 0;
+        for (int j = 0; j < D; ++j) t += (w * Om[i * D + j]) * Jb[j * ldb + cb + c];
+        s += Ja[i * lda + ca + a] * t;
+      }
+      if (add) out[(r0 + a) * ldo + c0 + c] += s;
+      else out[(r0 + a) * ldo + c0 + c] = s;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_inverse(const double* A, int n, double* Ainv) { return inverse(A, n, Ainv) ? 0 : -1; }
+
+void orc_edge_reproject(const OrcCamera* cam, const OrcNavState* ns, const double Xw[3], const float obs[3], int stereo,
+                        double e[3], double* J_pose, double* J_point, double* depth) {
+  const Cam c = cam_from_c(*cam);
+  const NS s = from_c(*ns);
+  const double d = reproj_error(c, s, Xw, obs, stereo != 0, e);
+  if (depth) *depth = d;
+  if (J_pose || J_point) {
+    double Jp[9], Jr[9], JX[9];
+    reproj_jac(c, s, Xw, stereo != 0, Jp, Jr, JX);
+    if (J_pose)
+      for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j) {
+          J_pose[6 * k + j] = Jp[3 * k + j];
+          J_pose[6 * k + 3 + j] = Jr[3 * k + j];
+        }
+    if (J_point) memcpy(J_point, JX, 72);
+  }
+}
+
+void orc_edge_navstate(const OrcNavState* nsi, const OrcNavState* nsj, const OrcImuPreint* pre, const double gw[3],
+                       int order, double e[9], double* Ji, double* Jj, double* Jb) {
+  const NS a = from_c(*nsi), b = from_c(*nsj);
+  navstate_error(a, b, *pre, gw, order == 1, e);
+  if (Ji && Jj && Jb) navstate_jac(a, b, *pre, gw, order == 1, e, Ji, Jj, Jb);
+}
+
+void orc_navstate_oplus(OrcNavState* ns, int kind, const double* dx) {
+  NS s = from_c(*ns);
+  if (kind == 0) inc_pr(s, dx);
+  if (kind == 1) inc_pvr(s, dx);
+  if (kind == 2) inc_v(s, dx);
+  if (kind == 3) inc_bias(s, dx);
+  to_c(s, ns);
+}
+
+void orc_edge_prior_pvr(const OrcNavState* ns, const OrcNavState* prior, double e[15], double* Jpvr) {
+  const NS s = from_c(*ns), p = from_c(*prior);
+  prior_error(s, s, p, e);
+  if (Jpvr) {
+    double Jb[90];
+    prior_jac(s, p, e, Jpvr, Jb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Optimizer::PoseOptimization — mode 0: src/Optimizer.cc:1611-1874, mode 1: include/Optimizer.h:208-816
+int orc_pose_optimization(const OrcPoseOptProblem* pb, const OrcCamera* cam, const double* Xw, const float* obs,
+                          const float* inv_sigma2, const uint8_t* flags, OrcPoseOptResult* res, uint8_t* outlier,
+                          double* chi2_out) {
+  memset(res, 0, sizeof(*res));
+  res->cur = pb->cur;
+  res->last = pb->last;
+  const int E = pb->edge_end - pb->edge_begin;
+  const bool imu_mode = pb->mode == 1;
+  const bool fixed_last = !pb->last_has_prior;
+  Graph g;
+  g.pvr = imu_mode;
+  g.cam = cam_from_c(*cam);
+  memcpy(g.gw, pb->gw, 24);
+  const NS nsj0 = from_c(pb->cur), nsl0 = from_c(pb->last);
+  g.st = {nsj0};
+  g.fix0 = {0};
+  g.has_vb = {(uint8_t)imu_mode};
+  g.fix_vb = {0};
+  if (imu_mode) {
+    g.st.push_back(nsl0);
+    g.fix0.push_back(fixed_last);
+    g.has_vb.push_back(1);
+    g.fix_vb.push_back(fixed_last);
+  }
+  bool bodom_edge = false;
+  int i_imu = -1, i_bias = -1, i_prior = -1;
+  if (imu_mode) {
+    if (pb->preint.dt != 0) {
+      bodom_edge = true;
+      DenseEdge e;
+      e.type = 0; e.si = 1; e.sj = 0; e.pre = &pb->preint; e.D = 9;
+      e.info = info_from_sigma(pb->preint.SigmaPVR);
+      if (fixed_last) {
+        for (double& v : e.info) v *= 1e-2;
+        e.rk.set(std::sqrt(16.919));
+      }
+      i_imu = (int)g.den.size();
+      g.den.push_back(e);
+    }
+    {
+      DenseEdge e;
+      e.type = 1; e.si = 1; e.sj = 0; e.D = 6;
+      e.info.assign(36, 0.0);
+      const double dtij = pb->preint.dt != 0 ? pb->preint.dt : pb->dt_frames;
+      for (int k = 0; k < 6; ++k) {
+        const double w = (k < 3 ? pb->inv_sigma_bg2 : pb->inv_sigma_ba2) / dtij;
+        e.info[7 * k] = fixed_last ? w * 1e-2 : w;
+      }
+      if (fixed_last) e.rk.set(std::sqrt(12.592));
+      i_bias = (int)g.den.size();
+      g.den.push_back(e);
+    }
+    if (!fixed_last) {
+      DenseEdge e;
+      e.type = 2; e.si = 1; e.sj = 1; e.D = 15;
+      e.prior = from_c(pb->prior);
+      e.info.assign(pb->prior_info, pb->prior_info + 225);
+      e.rk.set(std::sqrt(25.0));
+      i_prior = (int)g.den.size();
+      g.den.push_back(e);
+    }
+  }
+  const float deltaMono = (float)std::sqrt(5.991), deltaStereo = (float)std::sqrt(7.815);
+  g.X.resize((size_t)3 * E);
+  g.vis.resize(E);
+  for (int i = 0; i < E; ++i) {
+    const int gi = pb->edge_begin + i;
+    memcpy(&g.X[3 * i], Xw + 3 * gi, 24);
+    VisEdge& e = g.vis[i];
+    e.s = 0; e.p = i;
+    memcpy(e.obs, obs + 3 * gi, 12);
+    e.w = (double)inv_sigma2[gi];
+    e.stereo = flags[gi] & ORC_EDGE_STEREO;
+    e.close = flags[gi] & ORC_EDGE_CLOSE;
+    e.level = 0;
+    e.rk.set(e.stereo ? (double)deltaStereo : (double)deltaMono);
+    outlier[gi] = 0;
+    chi2_out[gi] = 0;
+  }
+  const int nInitial = E;
+  res->n_initial = nInitial;
+  if (nInitial < 3 && !(imu_mode && pb->no_mps)) {
+    res->n_inliers = 0;
+    return 0;
+  }
+  const float chi2Mono = 5.991f, chi2Stereo = 7.815f;
+  const size_t n_edges_total = g.vis.size() + g.den.size();
+  int nBad = 0;
+  for (int it = 0; it < 4; ++it) {
+    if (!imu_mode || !bodom_edge) {
+      g.st[0] = nsj0;
+      if (imu_mode && !fixed_last) g.st[1] = nsl0;
+    }
+    g.initialize();
+    g.optimize(10);
+    const float chi2close = 1.5 * chi2Mono;
+    nBad = 0;
+    for (int i = 0; i < E; ++i) {
+      VisEdge& e = g.vis[i];
+      const int gi = pb->edge_begin + i;
+      if (imu_mode || outlier[gi]) g.vis_error(e);
+      const float chi2 = (float)e.chi2;
+      bool bad;
+      if (e.stereo) bad = chi2 > chi2Stereo;
+      else if (imu_mode) bad = chi2 > (e.close ? chi2close : chi2Mono) || !(g.vis_depth(e) > 0.);
+      else bad = chi2 > chi2Mono;
+      outlier[gi] = bad;
+      e.level = bad ? 1 : 0;
+      nBad += bad;
+      if (it == 2) e.rk.on = false;
+    }
+    if (n_edges_total < 10) break;
+  }
+  if (imu_mode && nInitial - nBad < 30) {  // rescue pass (include/Optimizer.h:619-648)
+    nBad = 0;
+    for (int i = 0; i < E; ++i) {
+      VisEdge& e = g.vis[i];
+      const int gi = pb->edge_begin + i;
+      g.vis_error(e);
+      if (e.chi2 < (e.stereo ? (double)24.f : (double)18.f)) {
+        e.level = 0;
+        outlier[gi] = 0;
+      } else
+        nBad++;
+    }
+  }
+  for (int i = 0; i < E; ++i) chi2_out[pb->edge_begin + i] = g.vis[i].chi2;
+  to_c(g.st[0], &res->cur);
+  if (imu_mode) to_c(g.st[1], &res->last);
+  res->n_inliers = nInitial - nBad;
+  res->iterations = g.total_iters;
+  res->lambda_final = g.lambda;
+  res->chi2_final = g.active_robust_chi2();
+  if (imu_mode && pb->compute_marg) {
+    // kExactRobust: recompute errors, re-linearise every edge at the final estimate (include/Optimizer.h:126-206, 671-728)
+    if (i_imu >= 0) g.den_error(g.den[i_imu]);
+    g.den_error(g.den[i_bias]);
+    double C[225];
+    memset(C, 0, sizeof(C));
+    double Ji[81], Jj[81], Jb[54], r[2];
+    const DenseEdge* eI = i_imu >= 0 ? &g.den[i_imu] : nullptr;
+    const DenseEdge& eB = g.den[i_bias];
+    double wI = 1;
+    if (eI) {
+      navstate_jac(g.st[1], g.st[0], *eI->pre, g.gw, false, eI->err, Ji, Jj, Jb);
+      eI->rk.rho(eI->chi2, r);
+      wI = r[1];
+      jtoj(Jj, 9, 0, 9, eI->info.data(), 9, wI, Jj, 9, 0, 9, C, 15, 0, 0, false);
+    }
+    eB.rk.rho(eB.chi2, r);
+    const double wB = r[1];
+    for (int k = 0; k < 6; ++k) C[(9 + k) * 15 + 9 + k] = wB * eB.info[7 * k];  // Xj^T (w Omega) Xj, Xj = I
+    for (int i = 0; i < E; ++i) {
+      VisEdge& e = g.vis[i];
+      if (e.level) continue;
+      double Jp[9], Jr[9], JX[9];
+      reproj_jac(g.cam, g.st[0], &g.X[3 * e.p], e.stereo, Jp, Jr, JX);
+      e.rk.rho(e.chi2, r);
+      const double w = r[1] * e.w;
+      const int DE = e.stereo ? 3 : 2;
+      double J[3][9];
+      memset(J, 0, sizeof(J));
+      for (int k = 0; k < DE; ++k)
+        for (int c = 0; c < 3; ++c) {
+          J[k][c] = Jp[3 * k + c];
+          J[k][6 + c] = Jr[3 * k + c];
+        }
+      for (int a = 0; a < 9; ++a)
+        for (int c = 0; c < 9; ++c) {
+          double s = 0;
+          for (int k = 0; k < DE; ++k) s += J[k][a] * (w * J[k][c]);
+          C[a * 15 + c] += s;
+        }
+    }
+    if (!fixed_last) {
+      DenseEdge& eP = g.den[i_prior];
+      g.den_error(eP);
+      double CL[225], CCL[225];
+      memset(CL, 0, sizeof(CL));
+      memset(CCL, 0, sizeof(CCL));
+      if (eI) {
+        jtoj(Ji, 9, 0, 9, eI->info.data(), 9, wI, Ji, 9, 0, 9, CL, 15, 0, 0, false);
+        jtoj(Ji, 9, 0, 9, eI->info.data(), 9, wI, Jb, 6, 0, 6, CL, 15, 0, 9, false);
+        jtoj(Jb, 6, 0, 6, eI->info.data(), 9, wI, Jb, 6, 0, 6, CL, 15, 9, 9, false);
+        for (int a = 0; a < 9; ++a)
+          for (int c = 0; c < 6; ++c) CL[(9 + c) * 15 + a] = CL[a * 15 + 9 + c];
+      }
+      for (int k = 0; k < 6; ++k) CL[(9 + k) * 15 + 9 + k] += wB * eB.info[7 * k];  // Xi^T (w Omega) Xi, Xi = -I
+      double Jpp[135], Jpb[90];
+      prior_jac(g.st[1], eP.prior, eP.err, Jpp, Jpb);
+      eP.rk.rho(eP.chi2, r);
+      const double wP = r[1];
+      jtoj(Jpp, 9, 0, 9, eP.info.data(), 15, wP, Jpp, 9, 0, 9, CL, 15, 0, 0, true);
+      jtoj(Jpb, 6, 0, 6, eP.info.data(), 15, wP, Jpb, 6, 0, 6, CL, 15, 9, 9, true);
+      jtoj(Jpp, 9, 0, 9, eP.info.data(), 15, wP, Jpb, 6, 0, 6, CL, 15, 0, 9, true);
+      for (int a = 0; a < 9; ++a)
+        for (int c = 0; c < 6; ++c) CL[(9 + c) * 15 + a] = CL[a * 15 + 9 + c];
+      if (eI) {
+        jtoj(Jj, 9, 0, 9, eI->info.data(), 9, wI, Ji, 9, 0, 9, CCL, 15, 0, 0, false);
+        jtoj(Jj, 9, 0, 9, eI->info.data(), 9, wI, Jb, 6, 0, 6, CCL, 15, 0, 9, false);
+      }
+      for (int k = 0; k < 6; ++k) CCL[(9 + k) * 15 + 9 + k] = -(wB * eB.info[7 * k]);  // Xj^T (w Omega) Xi = -w Omega
+      double Cinv[225], T[225];
+      if (!inverse(CL, 15, Cinv))
+        for (double& v : Cinv) v = std::numeric_limits<double>::quiet_NaN();
+      for (int a = 0; a < 15; ++a)
+        for (int c = 0; c < 15; ++c) {
+          double s = 0;
+          for (int k = 0; k < 15; ++k) s += CCL[a * 15 + k] * Cinv[k * 15 + c];
+          T[a * 15 + c] = s;
+        }
+      for (int a = 0; a < 15; ++a)
+        for (int c = 0; c < 15; ++c) {
+          double s = 0;
+          for (int k = 0; k < 15; ++k) s += T[a * 15 + k] * CCL[c * 15 + k];
+          C[a * 15 + c] -= s;
+        }
+    }
+    memcpy(res->marg_cov_inv, C, sizeof(C));
+    res->prior_set = 1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Optimizer::LocalBundleAdjustmentNavStatePRV (src/Optimizer.cc:133-666): optimiser set-up to the err/err_end guard
+}  // extern "C"
+namespace {
+// Graph of Optimizer::LocalBundleAdjustmentNavStatePRV (src/Optimizer.cc:133-520): vertices, IMU + bias edges, visual edges
+bool build_lba_graph(const OrcBaProblem* pb, const OrcCamera* cam, Graph& g, int optit[2]) {
+  g.pvr = false;
+  g.cam = cam_from_c(*cam);
+  memcpy(g.gw, pb->gw, 24);
+  g.points_free = true;
+  if (pb->visual_only) { optit[0] = 5; optit[1] = 10; }
+  else if (pb->large) { optit[0] = 2; optit[1] = 2; g.user_lambda = 1e-2; }
+  else { optit[0] = 4; optit[1] = 6; g.user_lambda = 1e0; }
+  const int K = pb->n_states, P = pb->n_points, E = pb->n_edges;
+  g.st.resize(K); g.fix0.resize(K); g.has_vb.resize(K); g.fix_vb.resize(K);
+  bool anyfree = false;
+  for (int k = 0; k < K; ++k) {
+    g.st[k] = from_c(pb->states[k]);
+    g.fix0[k] = pb->state_flags[k] & 1;
+    g.has_vb[k] = (pb->state_flags[k] & 2) && !pb->visual_only;
+    g.fix_vb[k] = (pb->state_flags[k] & 4) != 0;
+    anyfree |= !g.fix0[k];
+  }
+  if (!anyfree) return false;
+  const float thHuberPRV = (float)std::sqrt(16.919), thHuberBias = (float)std::sqrt(12.592);
+  for (int m = 0; m < (pb->visual_only ? 0 : pb->n_imu); ++m) {
+    const int i = pb->imu_i[m], j = pb->imu_j[m];
+    const bool bfixedkf = g.fix0[i];
+    const OrcImuPreint& pre = pb->preint[m];
+    if (pre.dt != 0) {
+      DenseEdge e;
+      e.type = 0; e.si = i; e.sj = j; e.pre = &pre; e.D = 9;
+      e.info = info_from_sigma(pre.SigmaPRV);
+      if (bfixedkf || pb->rec_init) {
+        if (bfixedkf) for (double& v : e.info) v *= 1e-2;
+        e.rk.set((double)thHuberPRV);
+      }
+      g.den.push_back(e);
+    }
+    DenseEdge e;
+    e.type = 1; e.si = i; e.sj = j; e.D = 6;
+    double dtij = pre.dt != 0 ? pre.dt : pb->imu_dt_kf[m];
+    if (dtij <= (double)1e-6f) dtij = 15;
+    e.info.assign(36, 0.0);
+    for (int k = 0; k < 6; ++k) {
+      const double w = (k < 3 ? pb->inv_sigma_bg2 : pb->inv_sigma_ba2) / dtij;
+      e.info[7 * k] = bfixedkf ? w * 1e-2 : w;
+    }
+    if (bfixedkf || pb->rec_init) e.rk.set((double)thHuberBias);
+    g.den.push_back(e);
+  }
+  g.X.assign(pb->points, pb->points + (size_t)3 * P);
+  const float chi2Mono = 5.991f;
+  const float thHuberMono = std::sqrt(chi2Mono), thHuberStereo = (float)std::sqrt(7.815);
+  g.vis.resize(E);
+  for (int i = 0; i < E; ++i) {
+    VisEdge& e = g.vis[i];
+    e.s = pb->edge_state[i]; e.p = pb->edge_point[i];
+    memcpy(e.obs, pb->obs + 3 * i, 12);
+    e.w = (double)pb->inv_sigma2[i];
+    e.stereo = pb->edge_flags[i] & ORC_EDGE_STEREO;
+    e.close = pb->edge_flags[i] & ORC_EDGE_CLOSE;
+    e.level = (pb->edge_flags[i] & ORC_EDGE_LEVEL1) ? 1 : 0;
+    if (!(pb->edge_flags[i] & ORC_EDGE_NOKERNEL)) e.rk.set(e.stereo ? (double)thHuberStereo : (double)thHuberMono);
+  }
+  return true;
+}
+}  // namespace
+extern "C" {
+
+// One damped Gauss-Newton step of the LBA graph at the input estimate (build + Schur solve with the given lambda):
+// x_pose [np] in Hessian index order, x_points [P][3].  For the tests' cross-check against a dense solve of the
+// full normal equations.  Returns np.
+int orc_ba_debug_step(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, double* x_pose, double* x_points,
+                      double* chi2) {
+  Graph g;
+  int optit[2];
+  if (!build_lba_graph(pb, cam, g, optit)) return -1;
+  g.initialize();
+  g.compute_active_errors();
+  if (chi2) *chi2 = g.active_robust_chi2();
+  g.build_system();
+  g.lambda = lambda;
+  if (!g.solve_system()) return -2;
+  memcpy(x_pose, g.x.data(), g.np * 8);
+  memcpy(x_points, g.xl.data(), g.xl.size() * 8);
+  return g.np;
+}
+
+int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* states_out, double* points_out,
+                     double* edge_chi2, uint8_t* erase, OrcBaResult* res) {
+  memset(res, 0, sizeof(*res));
+  const int K = pb->n_states, P = pb->n_points, E = pb->n_edges;
+  for (int k = 0; k < K; ++k) states_out[k] = pb->states[k];
+  memcpy(points_out, pb->points, (size_t)P * 24);
+  memset(erase, 0, E);
+  Graph g;
+  int optit[2];
+  if (!build_lba_graph(pb, cam, g, optit)) return 0;
+  const float chi2Mono = 5.991f;
+  // GraphOperator::Chi2LargeSetLevel (g2o_graph_operator.h:23-40), rat 100
+  static const float chi2_sig5[4] = {0, 3.841f, 5.991f, 7.815f};
+  for (VisEdge& e : g.vis) {
+    g.vis_error(e);
+    if (e.chi2 > (double)(100.f * chi2_sig5[e.stereo ? 3 : 2])) e.level = 1;
+  }
+  g.initialize();
+  g.compute_active_errors();
+  const float err = (float)g.active_robust_chi2();
+  res->err0 = err;
+  res->iterations[0] = g.optimize(optit[0]);
+  {  // bDoMore
+    for (VisEdge& e : g.vis) {
+      bool bad;
+      if (e.stereo) bad = e.chi2 > 7.815 || !(g.vis_depth(e) > 0.);
+      else bad = e.chi2 > (e.close ? 1.5 * chi2Mono : (double)chi2Mono) || !(g.vis_depth(e) > 0.);
+      if (bad) e.level = 1;
+      e.rk.on = false;
+    }
+    g.initialize();
+    res->iterations[1] = g.optimize(optit[1]);
+  }
+  const float err_end = (float)g.active_robust_chi2();
+  res->err_end = err_end;
+  res->lambda_final = g.lambda;
+  for (int i = 0; i < E; ++i) edge_chi2[i] = g.vis[i].chi2;
+  if ((2 * err < err_end || std::isnan(err) || std::isnan(err_end)) && !pb->large) {
+    res->accepted = 0;
+    return 0;
+  }
+  res->accepted = 1;
+  int n_erase = 0;
+  for (int i = 0; i < E; ++i) {
+    VisEdge& e = g.vis[i];
+    bool bad;
+    if (e.stereo) bad = e.chi2 > 7.815 || !(g.vis_depth(e) > 0.);
+    else bad = e.chi2 > (e.close ? 1.5 * chi2Mono : (double)chi2Mono) || !(g.vis_depth(e) > 0.);
+    erase[i] = bad;
+    n_erase += bad;
+  }
+  res->n_erase = n_erase;
+  for (int k = 0; k < K; ++k) to_c(g.st[k], &states_out[k]);
+  memcpy(points_out, g.X.data(), (size_t)P * 24);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orb_oracle.cc header).  C interface of the CPU restatement of the
+// bundle-adjustment path: edges of src/Odom/g2otypes.h / g2otypes.cpp, the g2o Levenberg-Marquardt + Schur solver
+// semantics (optimizer/g2o/g2o/core) and the drivers Optimizer::PoseOptimization (visual and IMU/PVR) and
+// Optimizer::LocalBundleAdjustmentNavStatePRV / GlobalBundleAdjustmentNavStatePRV.  Layouts are identical to
+// include/vieo_b200.h so the parity tests feed both sides the same bytes.
+#pragma once
+#include <stdint.h>
+
+#include "oracle.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OrcNavState { /* NavState (src/Odom/NavState.h:17-36) */
+  double p[3];           /* mpwb */
+  double q[4];           /* mRwb unit quaternion (w, x, y, z) */
+  double v[3];           /* mvwb */
+  double bg[3], ba[3];   /* mbg, mba (frozen linearisation point) */
+  double dbg[3], dba[3]; /* mdbg, mdba (optimised) */
+} OrcNavState;
+
+typedef struct OrcCamera { /* pinhole intrinsics are float in the reference (camera_pinhole.h:70-83) */
+  float fx, fy, cx, cy, bf;
+  float pad_[3];
+  double Rcb[9], tcb[3]; /* Frame::meigRcb / meigtcb */
+} OrcCamera;
+
+/* Flags of a visual edge */
+#define ORC_EDGE_STEREO 1 /* 3-dim EdgeReproject*Stereo, else 2-dim */
+#define ORC_EDGE_CLOSE 2  /* track_depth_ < max(10, mThDepth): 1.5x chi2 gate */
+#define ORC_EDGE_LEVEL1 4 /* level 1 (outlier) */
+#define ORC_EDGE_NOKERNEL 8
+
+typedef struct OrcPoseOptProblem {
+  OrcNavState cur, last, prior; /* pFrame->mNavState, pLastKF->GetNavState(), pLastKF->mNavStatePrior */
+  OrcImuPreint preint;          /* pFrame->GetIMUPreInt() (dt == 0: no IMU edge) */
+  double prior_info[225];       /* pLastKF->mMargCovInv (row-major, order P V R bg ba) */
+  double gw[3];                 /* gravity in world */
+  double inv_sigma_bg2, inv_sigma_ba2; /* IMUDataBase::mInvSigmabg2 / mInvSigmaba2 */
+  double dt_frames;             /* pFrame->ftimestamp_ - pLastKF->ftimestamp_ */
+  int32_t mode;                 /* 0: visual, PR vertex (src/Optimizer.cc:1611); 1: IMU, PVR vertex (include/Optimizer.h:208) */
+  int32_t last_has_prior;       /* pLastKF->mbPrior -> last frame's vertices are free */
+  int32_t compute_marg;         /* bComputeMarg */
+  int32_t no_mps;               /* bNoMPs */
+  int32_t edge_begin, edge_end; /* this frame's range in the edge arrays */
+} OrcPoseOptProblem;
+
+typedef struct OrcPoseOptResult {
+  OrcNavState cur;          /* optimised pFrame->mNavState */
+  OrcNavState last;         /* optimised last-frame state (only meaningful when it was free) */
+  double marg_cov_inv[225]; /* pFrame->mMargCovInv when compute_marg */
+  double chi2_final;        /* activeRobustChi2 of the last optimize() */
+  double lambda_final;
+  int32_t n_inliers;        /* return value */
+  int32_t n_initial;
+  int32_t iterations;       /* total LM iterations run */
+  int32_t prior_set;        /* mbPrior after the call */
+} OrcPoseOptResult;
+
+/* One frame.  Edge arrays (global; the problem names its range):
+ *   Xw [E][3] map point positions (MapPoint::GetWorldPos cast to double), obs [E][3] (ul, vl, ur) as float,
+ *   inv_sigma2 [E], flags [E] (STEREO, CLOSE).  Outputs: outlier [E] (mvbOutlier), chi2 [E] last e->chi2(). */
+int orc_pose_optimization(const OrcPoseOptProblem* pb, const OrcCamera* cam, const double* Xw, const float* obs,
+                          const float* inv_sigma2, const uint8_t* flags, OrcPoseOptResult* res, uint8_t* outlier,
+                          double* chi2);
+
+/* ---- local / global BA (PR-V-Bias vertices per keyframe, marginalised points) ------------------------------- */
+typedef struct OrcBaProblem {
+  int32_t n_states;  /* keyframes: local first (ascending id), then fixed */
+  int32_t n_points, n_edges, n_imu;
+  const OrcNavState* states;
+  const uint8_t* state_flags; /* bit0: PR fixed, bit1: has V+Bias vertices, bit2: V/Bias fixed */
+  const double* points;       /* [P][3] */
+  const int32_t* edge_state;  /* [E] */
+  const int32_t* edge_point;  /* [E]  edges sorted by point */
+  const float* obs;           /* [E][3] */
+  const float* inv_sigma2;    /* [E] */
+  const uint8_t* edge_flags;  /* [E] STEREO | CLOSE | LEVEL1 */
+  /* inertial factors between consecutive keyframes */
+  const int32_t* imu_i;       /* [n_imu] state index of KF0 */
+  const int32_t* imu_j;       /* [n_imu] state index of KF1 */
+  const OrcImuPreint* preint; /* [n_imu] (dt == 0: only the bias edge) */
+  const double* imu_dt_kf;    /* [n_imu] pKF1->ftimestamp_ - pKF0->ftimestamp_ */
+  double gw[3];
+  double inv_sigma_bg2, inv_sigma_ba2;
+  int32_t large;    /* bLarge */
+  int32_t rec_init; /* bRecInit */
+  int32_t visual_only; /* LocalBundleAdjustment (PR vertices only, src/Optimizer.cc:1876) */
+  int32_t pad_;
+} OrcBaProblem;
+
+typedef struct OrcBaResult {
+  double err0, err_end; /* activeRobustChi2 before / after (src/Optimizer.cc:539, 652) */
+  double lambda_final;
+  int32_t iterations[2];
+  int32_t accepted; /* 0 when the "FAIL LOCAL-INERTIAL BA" guard rejected the result */
+  int32_t n_erase;
+} OrcBaResult;
+
+/* Optimizer::LocalBundleAdjustmentNavStatePRV from "Setup optimizer" to before the write-back.
+ * Outputs: states_out [n_states], points_out [P][3], edge_chi2 [E], erase [E] (1 = vToErase entry). */
+int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* states_out, double* points_out,
+                     double* edge_chi2, uint8_t* erase, OrcBaResult* res);
+
+/* One damped Gauss-Newton step (build + Schur solve at the given lambda) at the input estimate, for the tests'
+ * cross-check against a dense solve of the full normal equations.  Returns the pose dimension np or < 0. */
+int orc_ba_debug_step(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, double* x_pose, double* x_points,
+                      double* chi2);
+
+/* ---- building blocks exposed for the tests -------------------------------------------------------------------- */
+/* EdgeReproject<DE,DV,2> error and Jacobians (g2otypes.h:400-541): e[3], J_pose[3][6] (dp, dphi), J_point[3][3] */
+void orc_edge_reproject(const OrcCamera* cam, const OrcNavState* ns, const double Xw[3], const float obs[3], int stereo,
+                        double e[3], double* J_pose, double* J_point, double* depth);
+/* EdgeNavStateI<NV> (g2otypes.h:725-884): order 0 = PVR (NV=3), 1 = PRV (NV=5).  e[9], Ji[9][9], Jj[9][9], Jb[9][6]
+ * with the 9 state columns in the same order as the residual. */
+void orc_edge_navstate(const OrcNavState* nsi, const OrcNavState* nsj, const OrcImuPreint* pre, const double gw[3],
+                       int order, double e[9], double* Ji, double* Jj, double* Jb);
+/* NavState::IncSmall variants: kind 0 = PR(6), 1 = PVR(9), 2 = V(3), 3 = Bias(6) */
+void orc_navstate_oplus(OrcNavState* ns, int kind, const double* dx);
+void orc_edge_prior_pvr(const OrcNavState* ns, const OrcNavState* prior, double e[15], double* Jpvr /*15x9*/);
+int orc_inverse(const double* A, int n, double* Ainv);
+#ifdef __cplusplus
+}
+#endif

@@ -209,3 +209,121 @@ def imu_preintegrate(samples, ti, tj, bg, ba, nz):
     out = np.zeros(1, PREINT_DTYPE)
     L.orc_imu_preintegrate(_p(samples), len(samples), ti, tj, _p(bg), _p(ba), C.byref(nz), _p(out))
     return out[0]
+
+
+# ---------------------------------------------------------------- bundle adjustment (oracle/ba_oracle.cc)
+import sys as _sys  # noqa: E402
+_sys.path.insert(0, _ROOT)
+from vieo_slam_b200.layouts import (BA_RESULT_DTYPE, CAMERA_DTYPE, NAVSTATE_DTYPE, POSEOPT_PROBLEM_DTYPE,  # noqa: E402,F401
+                                    POSEOPT_RESULT_DTYPE)
+
+
+class OrcBaProblem(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("n_imu", C.c_int32),
+                ("states", C.c_void_p), ("state_flags", C.c_void_p), ("points", C.c_void_p), ("edge_state", C.c_void_p),
+                ("edge_point", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p), ("edge_flags", C.c_void_p),
+                ("imu_i", C.c_void_p), ("imu_j", C.c_void_p), ("preint", C.c_void_p), ("imu_dt_kf", C.c_void_p),
+                ("gw", C.c_double * 3), ("inv_sigma_bg2", C.c_double), ("inv_sigma_ba2", C.c_double),
+                ("large", C.c_int32), ("rec_init", C.c_int32), ("visual_only", C.c_int32), ("pad_", C.c_int32)]
+
+
+def ba_problem_struct(d, large=False, rec_init=False, visual_only=False, cls=OrcBaProblem):
+    """dict from synth.make_lba_problem -> (ctypes struct, keepalive list)."""
+    keep = {k: np.ascontiguousarray(d[k]) for k in ("states", "state_flags", "points", "edge_state", "edge_point", "obs",
+                                                    "inv_sigma2", "edge_flags", "imu_i", "imu_j", "preint", "imu_dt_kf")}
+    pb = cls()
+    pb.n_states, pb.n_points, pb.n_edges, pb.n_imu = len(keep["states"]), len(keep["points"]), len(keep["edge_state"]), len(keep["imu_i"])
+    for k, a in keep.items():
+        setattr(pb, k, a.ctypes.data)
+    pb.gw = (C.c_double * 3)(*d["gw"])
+    pb.inv_sigma_bg2, pb.inv_sigma_ba2 = d["inv_sigma_bg2"], d["inv_sigma_ba2"]
+    pb.large, pb.rec_init, pb.visual_only = int(large), int(rec_init), int(visual_only)
+    return pb, keep
+
+
+def pose_optimization(pbs, cam, Xw, obs, inv_sigma2, flags):
+    """Run orc_pose_optimization on every problem of `pbs` -> (results, outlier u8 [E], chi2 f64 [E])."""
+    L = lib()
+    L.orc_pose_optimization.argtypes = [C.c_void_p] * 9
+    pbs = np.ascontiguousarray(pbs); cam = np.ascontiguousarray(cam)
+    Xw = np.ascontiguousarray(Xw, np.float64); obs = np.ascontiguousarray(obs, np.float32)
+    inv_sigma2 = np.ascontiguousarray(inv_sigma2, np.float32); flags = np.ascontiguousarray(flags, np.uint8)
+    res = np.zeros(len(pbs), POSEOPT_RESULT_DTYPE)
+    outlier = np.zeros(len(flags), np.uint8); chi2 = np.zeros(len(flags), np.float64)
+    for k in range(len(pbs)):
+        L.orc_pose_optimization(pbs[k:k + 1].ctypes.data, cam.ctypes.data, _p(Xw), _p(obs), _p(inv_sigma2), _p(flags),
+                                res[k:k + 1].ctypes.data, _p(outlier), _p(chi2))
+    return res, outlier, chi2
+
+
+def local_ba_prv(d, cam, **kw):
+    L = lib()
+    L.orc_local_ba_prv.argtypes = [C.c_void_p] * 7
+    pb, keep = ba_problem_struct(d, **kw)
+    cam = np.ascontiguousarray(cam)
+    st = np.zeros(pb.n_states, NAVSTATE_DTYPE); pts = np.zeros((pb.n_points, 3)); chi2 = np.zeros(pb.n_edges)
+    erase = np.zeros(pb.n_edges, np.uint8); res = np.zeros(1, BA_RESULT_DTYPE)
+    L.orc_local_ba_prv(C.byref(pb), cam.ctypes.data, _p(st), _p(pts), _p(chi2), _p(erase), _p(res))
+    return dict(states=st, points=pts, edge_chi2=chi2, erase=erase, res=res[0])
+
+
+def ba_debug_step(d, cam, lam, **kw):
+    L = lib()
+    L.orc_ba_debug_step.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    pb, keep = ba_problem_struct(d, **kw)
+    cam = np.ascontiguousarray(cam)
+    xp = np.zeros(15 * pb.n_states); xl = np.zeros((pb.n_points, 3)); chi2 = np.zeros(1)
+    n = L.orc_ba_debug_step(C.byref(pb), cam.ctypes.data, lam, _p(xp), _p(xl), _p(chi2))
+    assert n >= 0, n
+    return xp[:n], xl, chi2[0]
+
+
+def edge_reproject(cam, ns, Xw, obs, stereo):
+    L = lib()
+    L.orc_edge_reproject.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    cam = np.ascontiguousarray(cam); ns = np.ascontiguousarray(ns)
+    Xw = np.ascontiguousarray(Xw, np.float64); obs = np.ascontiguousarray(obs, np.float32)
+    e = np.zeros(3); Jp = np.zeros((3, 6)); JX = np.zeros((3, 3)); d = np.zeros(1)
+    L.orc_edge_reproject(cam.ctypes.data, ns.ctypes.data, _p(Xw), _p(obs), int(stereo), _p(e), _p(Jp), _p(JX), _p(d))
+    return e, Jp, JX, d[0]
+
+
+def edge_navstate(nsi, nsj, pre, gw, order):
+    L = lib()
+    L.orc_edge_navstate.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4
+    nsi = np.ascontiguousarray(nsi); nsj = np.ascontiguousarray(nsj); pre = np.ascontiguousarray(pre)
+    gw = np.ascontiguousarray(gw, np.float64)
+    e = np.zeros(9); Ji = np.zeros((9, 9)); Jj = np.zeros((9, 9)); Jb = np.zeros((9, 6))
+    L.orc_edge_navstate(nsi.ctypes.data, nsj.ctypes.data, pre.ctypes.data, _p(gw), order, _p(e), _p(Ji), _p(Jj), _p(Jb))
+    return e, Ji, Jj, Jb
+
+
+def navstate_oplus(ns, kind, dx):
+    L = lib()
+    L.orc_navstate_oplus.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    out = np.array(ns, dtype=NAVSTATE_DTYPE).reshape(1).copy()
+    dx = np.ascontiguousarray(dx, np.float64)
+    L.orc_navstate_oplus(out.ctypes.data, kind, _p(dx))
+    return out[0]
+
+
+def edge_prior_pvr(ns, prior):
+    L = lib()
+    L.orc_edge_prior_pvr.argtypes = [C.c_void_p] * 4
+    ns = np.ascontiguousarray(ns); prior = np.ascontiguousarray(prior)
+    e = np.zeros(15); J = np.zeros((15, 9))
+    L.orc_edge_prior_pvr(ns.ctypes.data, prior.ctypes.data, _p(e), _p(J))
+    return e, J
+
+
+def imu_preintegrate_frames(seq, idx, nz):
+    """PREINT records for consecutive entries of frame-index list idx (record 0 is the identity state)."""
+    out = np.zeros(len(idx), PREINT_DTYPE)
+    out["Rij"] = np.eye(3); out["JgR"] = 0
+    imu, t = seq["imu"], seq["times"]
+    for k in range(1, len(idx)):
+        ti, tj = t[idx[k - 1]], t[idx[k]]
+        lo = max(np.searchsorted(imu[:, 0], ti, "right") - 1, 0)
+        hi = min(np.searchsorted(imu[:, 0], tj, "left") + 1, len(imu))
+        out[k] = imu_preintegrate(imu[lo:hi], ti, tj, seq["truth"][idx[k - 1]]["bg"], seq["truth"][idx[k - 1]]["ba"], nz)
+    return out

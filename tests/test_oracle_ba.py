@@ -1,0 +1,277 @@
+"""CPU tests pinning oracle/ba_oracle.cc (the reference's own tests hold no vectors for this path):
+analytic Jacobians against g2o's central-difference recipe (base_multi_edge.hpp:67-107), the Schur solve against a
+numpy dense solve of the full normal equations, closed-form / convergence properties of the drivers."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from vieo_slam_b200 import synth
+from vieo_slam_b200.layouts import EDGE_STEREO, NAVSTATE_DTYPE
+
+
+@pytest.fixture(scope="module")
+def seq():
+    s = synth.vio_sequence(5, 60)
+    s["pre"] = O.imu_preintegrate_frames(s, list(range(60)), O.imu_noise())
+    return s
+
+
+def test_reproject_jacobians_numeric():
+    cam = synth.euroc_camera()
+    r = np.random.default_rng(1)
+    seq = synth.vio_sequence(3, 4)
+    ns = seq["truth"][2]
+    X = synth.landmarks_in_view(cam, ns, 8, r)
+    for i in range(8):
+        for stereo in (0, 1):
+            obs = np.array([100, 200, 90], np.float32)
+            e, Jp, JX, depth = O.edge_reproject(cam, ns, X[i], obs, stereo)
+            assert depth > 0
+            # the projection is rounded to float (camera_pinhole.h:81-82): numeric differences need a coarse step
+            d = 2e-3
+            Jn = np.zeros((3, 6)); JXn = np.zeros((3, 3))
+            for c in range(6):
+                dx = np.zeros(6); dx[c] = d
+                ep = O.edge_reproject(cam, O.navstate_oplus(ns, 0, dx), X[i], obs, stereo)[0]
+                em = O.edge_reproject(cam, O.navstate_oplus(ns, 0, -dx), X[i], obs, stereo)[0]
+                Jn[:, c] = (ep - em) / (2 * d)
+            for c in range(3):
+                dx = np.zeros(3); dx[c] = d
+                JXn[:, c] = (O.edge_reproject(cam, ns, X[i] + dx, obs, stereo)[0] - O.edge_reproject(cam, ns, X[i] - dx, obs, stereo)[0]) / (2 * d)
+            rows = 3 if stereo else 2
+            assert np.allclose(Jp[:rows], Jn[:rows], rtol=2e-3, atol=0.15), (Jp, Jn)
+            assert np.allclose(JX[:rows], JXn[:rows], rtol=2e-3, atol=0.15)
+            if not stereo:
+                assert e[2] == 0 and np.all(Jp[2] == 0)
+
+
+def test_reproject_float_rounding_and_stereo_row():
+    cam = synth.euroc_camera()
+    ns = np.zeros(1, NAVSTATE_DTYPE)[0]; ns["q"] = [1, 0, 0, 0]
+    # body at the origin: Pc = Rcb X + tcb
+    X = np.array([0.3, -0.2, 4.0])
+    Pc = cam["Rcb"] @ X + cam["tcb"]
+    u = np.float32(np.float64(cam["fx"]) * Pc[0] / Pc[2] + np.float64(cam["cx"]))
+    obs = np.array([10.25, 20.5, 5.75], np.float32)
+    e = O.edge_reproject(cam, ns, X, obs, 1)[0]
+    assert abs(e[0] - (10.25 - float(u))) < 1e-12          # exact float pixel, not the double projection
+    assert abs(e[2] - (5.75 - (float(u) - float(cam["bf"]) / Pc[2]))) < 1e-9
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_navstate_edge_jacobians_numeric(seq, order):
+    r = np.random.default_rng(2)
+    i, j = 10, 11
+    nsi = synth.perturb_state(seq["truth"][i], r); nsj = synth.perturb_state(seq["truth"][j], r)
+    nsi["dbg"] = r.normal(0, 1e-3, 3); nsi["dba"] = r.normal(0, 1e-2, 3)
+    pre = seq["pre"][j]
+    gw = synth.GRAVITY_W
+    e, Ji, Jj, Jb = O.edge_navstate(nsi, nsj, pre, gw, order)
+    kind = 1 if order == 0 else None
+    d = 1e-6
+
+    def err(a, b):
+        return O.edge_navstate(a, b, pre, gw, order)[0]
+
+    def plus(ns, col, s):
+        # column order of Ji/Jj == residual order: PVR (P,V,R) for order 0, PRV (P,R,V) for order 1
+        dx9 = np.zeros(9); dx9[col] = s
+        if order == 0:
+            return O.navstate_oplus(ns, 1, dx9)
+        out = O.navstate_oplus(ns, 0, dx9[:6])
+        return O.navstate_oplus(out, 2, dx9[6:])
+    for c in range(9):
+        ni = (err(plus(nsi, c, d), nsj) - err(plus(nsi, c, -d), nsj)) / (2 * d)
+        nj = (err(nsi, plus(nsj, c, d)) - err(nsi, plus(nsj, c, -d))) / (2 * d)
+        assert np.allclose(Ji[:, c], ni, rtol=1e-5, atol=2e-5), (c, Ji[:, c], ni)
+        assert np.allclose(Jj[:, c], nj, rtol=1e-5, atol=2e-5), (c, Jj[:, c], nj)
+    for c in range(6):
+        dx = np.zeros(6); dx[c] = d
+        nb = (err(O.navstate_oplus(nsi, 3, dx), nsj) - err(O.navstate_oplus(nsi, 3, -dx), nsj)) / (2 * d)
+        # the bias columns are the first-order model of the reference (Forster eq. 44): exact for p, v; approximate for R
+        assert np.allclose(Jb[:, c], nb, rtol=1e-3, atol=1e-4), (c, Jb[:, c], nb)
+
+
+def test_navstate_residual_near_zero_at_truth():
+    s = synth.vio_sequence(9, 30, noisy_imu=False)
+    pre = O.imu_preintegrate_frames(s, list(range(30)), O.imu_noise())
+    for j in (5, 17, 29):
+        for order in (0, 1):
+            e = O.edge_navstate(s["truth"][j - 1], s["truth"][j], pre[j], synth.GRAVITY_W, order)[0]
+            assert np.abs(e).max() < 2e-4, e  # mid-point integration error only
+
+
+def test_prior_edge(seq):
+    r = np.random.default_rng(3)
+    pr = seq["truth"][7]
+    ns = synth.perturb_state(pr, r, dbg=0, dba=0)
+    ns["dbg"] = [1e-3, 0, 0]
+    e, J = O.edge_prior_pvr(ns, pr)
+    R0 = synth.R_from_quat(pr["q"]); R1 = synth.R_from_quat(ns["q"])
+    assert np.allclose(e[:3], R0.T @ (ns["p"] - pr["p"]), atol=1e-12)
+    assert np.allclose(e[3:6], ns["v"] - pr["v"], atol=1e-15)
+    assert np.allclose(e[6:9], synth.so3_log(R0.T @ R1), atol=1e-9)
+    assert np.allclose(e[9:12], [1e-3, 0, 0]) and np.allclose(e[12:], 0)
+    d = 1e-6
+    for c in range(9):
+        dx = np.zeros(9); dx[c] = d
+        n = (O.edge_prior_pvr(O.navstate_oplus(ns, 1, dx), pr)[0] - O.edge_prior_pvr(O.navstate_oplus(ns, 1, -dx), pr)[0]) / (2 * d)
+        assert np.allclose(J[:, c], n, atol=1e-6)
+
+
+def test_oplus_conventions():
+    ns = np.zeros(1, NAVSTATE_DTYPE)[0]
+    ns["q"] = synth.quat_from_R(synth.so3_exp(np.array([0.3, -0.2, 0.5]))); ns["p"] = [1, 2, 3]
+    R = synth.R_from_quat(ns["q"])
+    dx = np.array([0.1, -0.2, 0.05, 0.01, 0.02, -0.03])
+    o = O.navstate_oplus(ns, 0, dx)
+    assert np.allclose(o["p"], ns["p"] + R @ dx[:3], atol=1e-14)          # p <- p + R dp (USE_P_PLUS_RDP)
+    assert np.allclose(synth.R_from_quat(o["q"]), R @ synth.so3_exp(dx[3:]), atol=1e-12)  # R <- R Exp(dphi)
+    o = O.navstate_oplus(ns, 1, np.r_[dx[:3], [1, 2, 3], dx[3:]])
+    assert np.allclose(o["v"], [1, 2, 3]) and np.allclose(synth.R_from_quat(o["q"]), R @ synth.so3_exp(dx[3:]), atol=1e-12)
+    o = O.navstate_oplus(ns, 3, np.arange(6.0))
+    assert np.allclose(o["dbg"], [0, 1, 2]) and np.allclose(o["dba"], [3, 4, 5]) and np.all(o["bg"] == 0)
+
+
+def test_pose_optimization_imu_converges(seq):
+    cam = synth.euroc_camera()
+    pbs, X, obs, w, fl = synth.make_pose_problems(seq, seq["pre"], cam, n_points=400, seed=1)
+    pbs = pbs[:10]
+    res, outl, chi2 = O.pose_optimization(pbs, cam, X, obs, w, fl)
+    for k in range(len(pbs)):
+        tru = seq["truth"][k + 1]
+        assert np.linalg.norm(res[k]["cur"]["p"] - tru["p"]) < 0.012
+        assert 0.7 * 400 < res[k]["n_inliers"] < 0.92 * 400
+        assert res[k]["n_inliers"] == 400 - outl[k * 400:(k + 1) * 400].sum()
+        M = res[k]["marg_cov_inv"]
+        assert res[k]["prior_set"] == 1 and np.allclose(M, M.T, rtol=1e-9, atol=1e-6 * np.abs(M).max())
+        assert np.linalg.eigvalsh((M + M.T) / 2).min() > -1e-6 * np.abs(M).max()
+        assert np.all(M[:9, 9:] == 0)  # fixed last frame: PVR and bias blocks decouple (include/Optimizer.h:135-138)
+
+
+def test_pose_optimization_visual_mode_and_few_points(seq):
+    cam = synth.euroc_camera()
+    pbs, X, obs, w, fl = synth.make_pose_problems(seq, seq["pre"], cam, n_points=300, seed=2, mode=0, compute_marg=False)
+    res, outl, _ = O.pose_optimization(pbs[:4], cam, X, obs, w, fl)
+    for k in range(4):
+        assert np.linalg.norm(res[k]["cur"]["p"] - seq["truth"][k + 1]["p"]) < 0.015
+        assert np.array_equal(res[k]["cur"]["v"], pbs[k]["cur"]["v"])  # PR vertex: velocity untouched
+    pb = pbs[:1].copy(); pb["edge_end"] = pb["edge_begin"] + 2    # < 3 correspondences -> return 0 (src/Optimizer.cc:1787)
+    res, _, _ = O.pose_optimization(pb, cam, X, obs, w, fl)
+    assert res[0]["n_inliers"] == 0 and res[0]["iterations"] == 0
+
+
+def test_pose_optimization_free_last_frame_prior(seq):
+    cam = synth.euroc_camera()
+    pbs, X, obs, w, fl = synth.make_pose_problems(seq, seq["pre"], cam, n_points=350, seed=3, chain_prior=True)
+    res, _, _ = O.pose_optimization(pbs[1:2], cam, X, obs, w, fl)  # k = 2: last frame free with a 15-dim prior
+    assert pbs[1]["last_has_prior"] == 1
+    M = res[0]["marg_cov_inv"]
+    assert np.isfinite(M).all() and np.abs(M[:9, 9:]).max() > 0  # Schur over the last frame couples PVR and bias
+    assert np.linalg.norm(res[0]["cur"]["p"] - seq["truth"][2]["p"]) < 0.012
+    assert not np.array_equal(res[0]["last"]["p"], pbs[1]["last"]["p"])
+
+
+def _lba(seq, **kw):
+    cam = synth.euroc_camera()
+    kf = list(range(0, 60, 3))
+    pre = O.imu_preintegrate_frames(seq, kf, O.imu_noise())
+    return cam, synth.make_lba_problem(seq, pre, kf, cam, n_local=8, n_fixed=6, n_points=300, seed=4, **kw)
+
+
+def test_schur_step_matches_dense_normal_equations(seq):
+    """F3: the oracle's Schur-complement solve equals a numpy solve of the full (poses + points) system assembled
+    independently from the per-edge Jacobians."""
+    cam, d = _lba(seq)
+    lam = 1.0
+    xp, xl, chi2 = O.ba_debug_step(d, cam, lam)
+    K, P = len(d["states"]), len(d["points"])
+    off = {}; n = 0
+    for k in range(K):
+        f = d["state_flags"][k]
+        if not f & 1:
+            off[(k, 0)] = n; n += 6
+        if f & 2 and not f & 4:
+            off[(k, 1)] = n; n += 3
+            off[(k, 2)] = n; n += 6
+    assert n == len(xp)
+    N = n + 3 * P
+    H = np.zeros((N, N)); b = np.zeros(N)
+
+    def huber(c, delta):
+        d2 = float(np.float32(delta * delta))
+        return 1.0 if c <= d2 else delta / np.sqrt(c)
+    dm, ds = float(np.float32(np.sqrt(np.float32(5.991)))), float(np.float32(np.sqrt(7.815)))
+    for i in range(len(d["edge_state"])):
+        s, p = d["edge_state"][i], d["edge_point"][i]
+        st = bool(d["edge_flags"][i] & EDGE_STEREO)
+        e, Jp, JX, _ = O.edge_reproject(cam, d["states"][s], d["points"][p], d["obs"][i], st)
+        rows = 3 if st else 2
+        w = float(d["inv_sigma2"][i]); c = w * (e[:rows] ** 2).sum()
+        w *= huber(c, ds if st else dm)
+        blocks = [(n + 3 * p, JX[:rows])]
+        if (s, 0) in off:
+            blocks.append((off[(s, 0)], Jp[:rows]))
+        for oa, Ja in blocks:
+            b[oa:oa + Ja.shape[1]] -= Ja.T @ (w * e[:rows])
+            for ob, Jb_ in blocks:
+                H[oa:oa + Ja.shape[1], ob:ob + Jb_.shape[1]] += Ja.T @ (w * Jb_)
+    for m in range(len(d["imu_i"])):
+        i, j = d["imu_i"][m], d["imu_j"][m]
+        pre = d["preint"][m]
+        fixed = bool(d["state_flags"][i] & 1)
+        e, Ji, Jj, Jb = O.edge_navstate(d["states"][i], d["states"][j], pre, d["gw"], 1)
+        info = np.linalg.inv(pre["SigmaPRV"]) * (1e-2 if fixed else 1.0)
+        c = e @ info @ e
+        wI = huber(c, float(np.float32(np.sqrt(16.919)))) if fixed else 1.0
+        blocks = [((i, 0), Ji[:, :6]), ((j, 0), Jj[:, :6]), ((i, 1), Ji[:, 6:]), ((j, 1), Jj[:, 6:]), ((i, 2), Jb)]
+        blocks = [(off[k], J) for k, J in blocks if k in off]
+        for oa, Ja in blocks:
+            b[oa:oa + Ja.shape[1]] -= Ja.T @ (wI * info @ e)
+            for ob, Jb_ in blocks:
+                H[oa:oa + Ja.shape[1], ob:ob + Jb_.shape[1]] += Ja.T @ (wI * info) @ Jb_
+        si, sj = d["states"][i], d["states"][j]
+        eb = np.r_[sj["bg"] + sj["dbg"] - si["bg"] - si["dbg"], sj["ba"] + sj["dba"] - si["ba"] - si["dba"]]
+        ib = np.diag([d["inv_sigma_bg2"]] * 3 + [d["inv_sigma_ba2"]] * 3) / pre["dt"] * (1e-2 if fixed else 1.0)
+        wb = huber(eb @ ib @ eb, float(np.float32(np.sqrt(12.592)))) if fixed else 1.0
+        blocks = [(off[k], J) for k, J in (((i, 2), -np.eye(6)), ((j, 2), np.eye(6))) if k in off]
+        for oa, Ja in blocks:
+            b[oa:oa + 6] -= Ja.T @ (wb * ib @ eb)
+            for ob, Jb_ in blocks:
+                H[oa:oa + 6, ob:ob + 6] += Ja.T @ (wb * ib) @ Jb_
+    x = np.linalg.solve(H + lam * np.eye(N), b)
+    assert np.allclose(xp, x[:n], rtol=1e-7, atol=1e-10)
+    assert np.allclose(xl.ravel(), x[n:], rtol=1e-7, atol=1e-10)
+
+
+def test_local_ba_prv_converges(seq):
+    cam, d = _lba(seq)
+    out = O.local_ba_prv(d, cam)
+    res = out["res"]
+    assert res["accepted"] == 1 and res["err_end"] < res["err0"]
+    assert tuple(res["iterations"]) == (4, 6) or res["iterations"][0] <= 4
+    # fixed keyframes untouched, local ones moved towards the truth
+    kf = list(range(0, 60, 3))
+    nk = len(kf); local = list(range(nk - 8, nk))
+    err_in = [np.linalg.norm(d["states"][s]["p"] - seq["truth"][kf[k]]["p"]) for s, k in enumerate(local)]
+    err_out = [np.linalg.norm(out["states"][s]["p"] - seq["truth"][kf[k]]["p"]) for s, k in enumerate(local)]
+    assert np.mean(err_out) < 0.5 * np.mean(err_in)
+    for s in range(8, len(d["states"])):
+        assert out["states"][s].tobytes() == d["states"][s].tobytes()
+    assert 0.01 < out["erase"].mean() < 0.15  # ~5 % outlier observations flagged for ErasePairObs
+
+
+def test_local_ba_large_and_visual_only(seq):
+    cam, d = _lba(seq)
+    a = O.local_ba_prv(d, cam, large=True)["res"]
+    assert a["accepted"] == 1 and max(a["iterations"]) <= 2
+    v = O.local_ba_prv(d, cam, visual_only=True)
+    assert v["res"]["err_end"] < v["res"]["err0"]
+    assert np.array_equal(v["states"]["v"], d["states"]["v"])  # PR-only vertices: velocities and biases untouched
+
+
+def test_all_fixed_returns_untouched(seq):
+    cam, d = _lba(seq)
+    d = dict(d); d["state_flags"] = d["state_flags"] | 1
+    out = O.local_ba_prv(d, cam)
+    assert out["states"].tobytes() == d["states"].tobytes() and out["res"]["iterations"][0] == 0

@@ -1,0 +1,32 @@
+"""numpy dtypes of the C-ABI structs in include/vieo_b200.h (the oracle uses byte-identical layouts)."""
+import numpy as np
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")])
+
+PREINT_DTYPE = np.dtype([("Rij", "f8", (3, 3)), ("vij", "f8", 3), ("pij", "f8", 3), ("SigmaPRV", "f8", (9, 9)),
+                         ("SigmaPVR", "f8", (9, 9)), ("Jgp", "f8", (3, 3)), ("Jap", "f8", (3, 3)), ("Jgv", "f8", (3, 3)),
+                         ("Jav", "f8", (3, 3)), ("JgR", "f8", (3, 3)), ("dt", "f8"), ("status", "i4"), ("pad_", "i4")])
+
+# NavState (src/Odom/NavState.h:17-36): q = (w, x, y, z)
+NAVSTATE_DTYPE = np.dtype([("p", "f8", 3), ("q", "f8", 4), ("v", "f8", 3), ("bg", "f8", 3), ("ba", "f8", 3),
+                           ("dbg", "f8", 3), ("dba", "f8", 3)])
+
+CAMERA_DTYPE = np.dtype([("fx", "f4"), ("fy", "f4"), ("cx", "f4"), ("cy", "f4"), ("bf", "f4"), ("pad_", "f4", 3),
+                         ("Rcb", "f8", (3, 3)), ("tcb", "f8", 3)])
+
+EDGE_STEREO, EDGE_CLOSE, EDGE_LEVEL1, EDGE_NOKERNEL = 1, 2, 4, 8
+
+POSEOPT_PROBLEM_DTYPE = np.dtype([("cur", NAVSTATE_DTYPE), ("last", NAVSTATE_DTYPE), ("prior", NAVSTATE_DTYPE),
+                                  ("preint", PREINT_DTYPE), ("prior_info", "f8", (15, 15)), ("gw", "f8", 3),
+                                  ("inv_sigma_bg2", "f8"), ("inv_sigma_ba2", "f8"), ("dt_frames", "f8"),
+                                  ("mode", "i4"), ("last_has_prior", "i4"), ("compute_marg", "i4"), ("no_mps", "i4"),
+                                  ("edge_begin", "i4"), ("edge_end", "i4")])
+
+POSEOPT_RESULT_DTYPE = np.dtype([("cur", NAVSTATE_DTYPE), ("last", NAVSTATE_DTYPE), ("marg_cov_inv", "f8", (15, 15)),
+                                 ("chi2_final", "f8"), ("lambda_final", "f8"), ("n_inliers", "i4"), ("n_initial", "i4"),
+                                 ("iterations", "i4"), ("prior_set", "i4")])
+
+BA_RESULT_DTYPE = np.dtype([("err0", "f8"), ("err_end", "f8"), ("lambda_final", "f8"), ("iterations", "i4", 2),
+                            ("accepted", "i4"), ("n_erase", "i4")])
+
+assert NAVSTATE_DTYPE.itemsize == 22 * 8 and CAMERA_DTYPE.itemsize == 32 + 96

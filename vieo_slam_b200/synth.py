@@ -40,3 +40,286 @@ def stereo_stream(n_frames, seed, w=752, h=480, max_disp=40, dark_every=0):
         out[2 * f] = L
         out[2 * f + 1] = R
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Synthetic visual-inertial sequences and BA problems: smooth 6-DoF trajectory,
+# 200 Hz IMU with EuRoC noise (Examples/Stereo/EuRoC/EuRoC_VIO.yaml:13-18), pinhole stereo observations
+# quantised to float like cv::KeyPoint.  All numpy, seeded.
+from .layouts import (CAMERA_DTYPE, EDGE_CLOSE, EDGE_STEREO, NAVSTATE_DTYPE, POSEOPT_PROBLEM_DTYPE)  # noqa: E402
+
+EUROC_IMU_SIGMA = (1.6968e-4, 2.0e-3, 1.9393e-5, 3.0e-3)
+# Camera.Tbc of EuRoC_VIO.yaml:24-28 (body <- camera)
+EUROC_TBC = np.array([[0.0148655429818, -0.999880929698, 0.00414029679422, -0.0216401454975],
+                      [0.999557249008, 0.0149672133247, 0.025715529948, -0.064676986768],
+                      [-0.0257744366974, 0.00375618835797, 0.999660727178, 0.00981073058949],
+                      [0, 0, 0, 1.0]])
+GRAVITY_W = np.array([0.0, 0.0, -9.81])
+
+
+def hat(w):
+    return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0.0]])
+
+
+def so3_exp(w):
+    th = np.linalg.norm(w)
+    K = hat(w)
+    if th < 1e-9:
+        return np.eye(3) + K + 0.5 * K @ K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+
+
+def so3_log(R):
+    c = np.clip((np.trace(R) - 1) / 2, -1, 1)
+    th = np.arccos(c)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2
+    return w if th < 1e-9 else w * th / np.sin(th)
+
+
+def quat_from_R(R):
+    """(w, x, y, z), w >= 0"""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        q = np.zeros(4)
+        q[0] = (R[k, j] - R[j, k]) / s
+        q[1 + i] = 0.25 * s
+        q[1 + j] = (R[j, i] + R[i, j]) / s
+        q[1 + k] = (R[k, i] + R[i, k]) / s
+    q /= np.linalg.norm(q)
+    return q if q[0] >= 0 else -q
+
+
+def R_from_quat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def euroc_camera():
+    cam = np.zeros(1, CAMERA_DTYPE)[0]
+    cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"] = EUROC["fx"], EUROC["fy"], EUROC["cx"], EUROC["cy"], EUROC["bf"]
+    Tbc = EUROC_TBC.astype(np.float32).astype(np.float64)  # Camera.Tbc is read into CV_32F (src/Tracking.cc:704-732)
+    Rcb = Tbc[:3, :3].T
+    cam["Rcb"] = Rcb
+    cam["tcb"] = -Rcb @ Tbc[:3, 3]
+    return cam
+
+
+class Trajectory:
+    """Smooth body trajectory in a ~6x6x3 m room: p(t) sums of sinusoids, R(t) = Exp(theta(t))."""
+
+    def __init__(self, seed, speed=1.0, rot=0.5):
+        r = np.random.default_rng(seed)
+        self.A = np.array([2.0, 2.0, 0.6]) * r.uniform(0.6, 1.0, 3)
+        self.w = speed * r.uniform(0.25, 0.5, 3)
+        self.ph = r.uniform(0, 2 * np.pi, 3)
+        self.B = rot * r.uniform(0.3, 0.6, 3)
+        self.u = r.uniform(0.2, 0.45, 3)
+        self.qh = r.uniform(0, 2 * np.pi, 3)
+
+    def p(self, t):
+        return self.A * np.sin(self.w * t + self.ph)
+
+    def v(self, t):
+        return self.A * self.w * np.cos(self.w * t + self.ph)
+
+    def acc(self, t):
+        return -self.A * self.w ** 2 * np.sin(self.w * t + self.ph)
+
+    def R(self, t):
+        return so3_exp(self.B * np.sin(self.u * t + self.qh))
+
+    def omega(self, t, h=1e-5):
+        return so3_log(self.R(t - h).T @ self.R(t + h)) / (2 * h)
+
+
+def vio_sequence(seed, n_frames, frame_rate=20.0, imu_rate=200.0, speed=1.0, rot=0.5, noisy_imu=True):
+    """Returns dict(times[n], truth NAVSTATE[n], imu (m,7) rows {t, a, w}, bg, ba, traj)."""
+    traj = Trajectory(seed, speed, rot)
+    r = np.random.default_rng(seed + 7)
+    times = np.arange(n_frames) / frame_rate
+    m = int(np.ceil(times[-1] * imu_rate)) + 3
+    ti = np.arange(m) / imu_rate
+    bg = r.normal(0, 2e-3, 3)
+    ba = r.normal(0, 2e-2, 3)
+    imu = np.zeros((m, 7))
+    imu[:, 0] = ti
+    sg, sa = EUROC_IMU_SIGMA[0] * np.sqrt(imu_rate), EUROC_IMU_SIGMA[1] * np.sqrt(imu_rate)
+    for k, t in enumerate(ti):
+        R = traj.R(t)
+        imu[k, 1:4] = R.T @ (traj.acc(t) - GRAVITY_W) + ba
+        imu[k, 4:7] = traj.omega(t) + bg
+    if noisy_imu:
+        imu[:, 1:4] += r.normal(0, sa, (m, 3))
+        imu[:, 4:7] += r.normal(0, sg, (m, 3))
+    truth = np.zeros(n_frames, NAVSTATE_DTYPE)
+    for k, t in enumerate(times):
+        truth[k]["p"] = traj.p(t)
+        truth[k]["q"] = quat_from_R(traj.R(t))
+        truth[k]["v"] = traj.v(t)
+        truth[k]["bg"] = bg
+        truth[k]["ba"] = ba
+    return dict(times=times, truth=truth, imu=imu, bg=bg, ba=ba, traj=traj, seed=seed)
+
+
+def perturb_state(ns, r, dp=0.01, drot=np.deg2rad(0.3), dv=0.02, dbg=1e-3, dba=1e-2):
+    out = ns.copy()
+    out["p"] = ns["p"] + r.normal(0, dp, 3)
+    out["q"] = quat_from_R(R_from_quat(ns["q"]) @ so3_exp(r.normal(0, drot, 3)))
+    out["v"] = ns["v"] + r.normal(0, dv, 3)
+    out["bg"] = ns["bg"] + r.normal(0, dbg, 3)
+    out["ba"] = ns["ba"] + r.normal(0, dba, 3)
+    return out
+
+
+def project(cam, ns, X):
+    """Pinhole stereo projection of world points X (n,3) through body state ns: (u, v, ur, z)."""
+    Rwb = R_from_quat(ns["q"])
+    Rcw = cam["Rcb"] @ Rwb.T
+    tcw = -Rcw @ ns["p"] + cam["tcb"]
+    Pc = X @ Rcw.T + tcw
+    z = Pc[:, 2]
+    u = cam["fx"] * Pc[:, 0] / z + cam["cx"]
+    v = cam["fy"] * Pc[:, 1] / z + cam["cy"]
+    return u, v, u - cam["bf"] / z, z
+
+
+def landmarks_in_view(cam, ns, n, r, zmin=0.8, zmax=9.0):
+    """n world points visible from state ns (uniform in the image, depth uniform in [zmin, zmax])."""
+    u = r.uniform(20, EUROC["w"] - 20, n)
+    v = r.uniform(20, EUROC["h"] - 20, n)
+    z = r.uniform(zmin, zmax, n)
+    Pc = np.stack([(u - cam["cx"]) / cam["fx"] * z, (v - cam["cy"]) / cam["fy"] * z, z], 1)
+    Rwb = R_from_quat(ns["q"])
+    Rcw = cam["Rcb"] @ Rwb.T
+    tcw = -Rcw @ ns["p"] + cam["tcb"]
+    return (Pc - tcw) @ Rcw  # Rcw^T (Pc - tcw)
+
+
+def inv_level_sigma2(nlevels=8, scale=1.2):
+    s = np.ones(nlevels, np.float32)
+    for i in range(1, nlevels):
+        s[i] = s[i - 1] * np.float32(scale)
+    return (np.float32(1.0) / (s * s)).astype(np.float32), s
+
+
+def make_observations(cam, ns, X, r, outlier_frac=0.15, stereo_frac=0.7, th_depth=35.0):
+    """Noisy float keypoint observations of X from ns: obs (n,3) f32 (ur = -1 for mono), inv_sigma2 f32, flags u8."""
+    n = len(X)
+    inv_s2, scl = inv_level_sigma2()
+    u, v, ur, z = project(cam, ns, X)
+    octave = r.integers(0, 8, n)
+    sig = scl[octave].astype(np.float64)
+    obs = np.stack([u + r.normal(0, 1, n) * sig, v + r.normal(0, 1, n) * sig, ur + r.normal(0, 1, n) * sig], 1)
+    out = r.random(n) < outlier_frac
+    obs[out, :2] += r.uniform(-20, 20, (int(out.sum()), 2))
+    obs[out, 2] = obs[out, 0] - (u - ur)[out] + r.uniform(-10, 10, int(out.sum()))
+    stereo = r.random(n) < stereo_frac
+    obs[~stereo, 2] = -1.0
+    flags = np.where(stereo, EDGE_STEREO, 0).astype(np.uint8)
+    thd = max(10.0, cam["bf"] / cam["fx"] * th_depth)
+    flags |= np.where(z < thd, EDGE_CLOSE, 0).astype(np.uint8)
+    return obs.astype(np.float32), inv_s2[octave], flags, out
+
+
+def make_pose_problems(seq, preints, cam, n_points=450, seed=0, mode=1, compute_marg=True, chain_prior=False,
+                       outlier_frac=0.15):
+    """One PoseOptimization problem per consecutive frame pair (k-1 -> k).  preints[k] = pre-integration over
+    (t_{k-1}, t_k] (PREINT record; dt == 0 -> no IMU edge).  Returns (problems, Xw, obs, inv_sigma2, flags)."""
+    r = np.random.default_rng(seed + 1000)
+    n = len(seq["times"])
+    pbs = np.zeros(n - 1, POSEOPT_PROBLEM_DTYPE)
+    Xs, Os, Ws, Fs = [], [], [], []
+    e0 = 0
+    sig = EUROC_IMU_SIGMA
+    for k in range(1, n):
+        pb = pbs[k - 1]
+        tru, last = seq["truth"][k], seq["truth"][k - 1]
+        pb["cur"] = perturb_state(tru, r, dbg=0, dba=0)
+        pb["last"] = perturb_state(last, r, dp=0.002, drot=np.deg2rad(0.05), dv=0.005, dbg=0, dba=0)
+        pb["prior"] = pb["last"]
+        pb["preint"] = preints[k]
+        A = r.normal(0, 1, (15, 15))
+        pb["prior_info"] = A @ A.T * 10 + np.diag([1e4] * 3 + [1e3] * 3 + [1e5] * 3 + [1e6] * 3 + [1e4] * 3)
+        pb["gw"] = GRAVITY_W
+        pb["inv_sigma_bg2"] = 1.0 / sig[2] ** 2
+        pb["inv_sigma_ba2"] = 1.0 / sig[3] ** 2
+        pb["dt_frames"] = seq["times"][k] - seq["times"][k - 1]
+        pb["mode"] = mode
+        pb["last_has_prior"] = int(chain_prior and k % 2 == 0)
+        pb["compute_marg"] = int(compute_marg)
+        X = landmarks_in_view(cam, tru, n_points, r)
+        obs, w, fl, _ = make_observations(cam, tru, X, r, outlier_frac)
+        Xf = X.astype(np.float32).astype(np.float64)  # MapPoint positions are float (include/MapPoint.h:52)
+        pb["edge_begin"], pb["edge_end"] = e0, e0 + n_points
+        e0 += n_points
+        Xs.append(Xf); Os.append(obs); Ws.append(w); Fs.append(fl)
+    return pbs, np.concatenate(Xs), np.concatenate(Os), np.concatenate(Ws), np.concatenate(Fs)
+
+
+def make_lba_problem(seq, preints_kf, kf_idx, cam, n_local=10, n_fixed=20, n_points=1500, obs_per_point=(4, 8), seed=0,
+                     outlier_frac=0.05):
+    """A LocalBundleAdjustmentNavStatePRV window over keyframes kf_idx (frame indices, ascending): the last n_local
+    are free, the one before is the fixed 'previous' KF (with V/Bias vertices), `n_fixed` earlier ones are
+    covisible fixed KFs (PR only).  preints_kf[i] = pre-integration from kf_idx[i-1] to kf_idx[i].
+    Returns dict of arrays laid out as the C ABI wants (edges sorted by point)."""
+    r = np.random.default_rng(seed + 2000)
+    kf_idx = np.asarray(kf_idx)
+    nk = len(kf_idx)
+    n_local = min(n_local, nk)
+    local = list(range(nk - n_local, nk))
+    prev = [nk - n_local - 1] if nk - n_local - 1 >= 0 else []
+    fixed = list(range(max(0, nk - n_local - 1 - n_fixed), nk - n_local - 1))
+    order = local + prev + fixed  # states: local first (ascending id), then fixed (reference adds lFixedCameras after)
+    states = np.zeros(len(order), NAVSTATE_DTYPE)
+    sflags = np.zeros(len(order), np.uint8)
+    for s, k in enumerate(order):
+        tru = seq["truth"][kf_idx[k]]
+        if k in local:
+            states[s] = perturb_state(tru, r)
+            states[s]["dbg"] = 0
+            sflags[s] = 2
+        else:
+            states[s] = perturb_state(tru, r, dp=0.002, drot=np.deg2rad(0.05), dv=0.005, dbg=1e-4, dba=1e-3)
+            sflags[s] = 1 | (2 | 4 if k in prev else 0)
+    pos_of = {k: s for s, k in enumerate(order)}
+    imu_i, imu_j, pre, dtk = [], [], [], []
+    for k in local:
+        if k - 1 in pos_of and k - 1 >= 0 and (k - 1 in local or k - 1 in prev):
+            imu_i.append(pos_of[k - 1]); imu_j.append(pos_of[k]); pre.append(preints_kf[k])
+            dtk.append(seq["times"][kf_idx[k]] - seq["times"][kf_idx[k - 1]])
+    # points: seen from a random local KF, then observed by a run of neighbouring KFs
+    es, ep, eo, ew, ef = [], [], [], [], []
+    X_all = []
+    p = 0
+    while p < n_points:
+        k0 = int(r.choice(local))
+        X = landmarks_in_view(cam, seq["truth"][kf_idx[k0]], 1, r)
+        nobs = int(r.integers(obs_per_point[0], obs_per_point[1] + 1))
+        cands = [k for k in range(k0 - nobs, k0 + nobs + 1) if k in pos_of]
+        seen = []
+        for k in cands:
+            u, v, ur, z = project(cam, seq["truth"][kf_idx[k]], X)
+            if z[0] > 0.3 and 0 < u[0] < EUROC["w"] and 0 < v[0] < EUROC["h"]:
+                seen.append(k)
+        if len(seen) < 2:
+            continue
+        seen = sorted(seen, key=lambda k: abs(k - k0))[:nobs]
+        for k in sorted(seen, key=lambda k: pos_of[k]):
+            obs, w, fl, _ = make_observations(cam, seq["truth"][kf_idx[k]], X, r, outlier_frac)
+            es.append(pos_of[k]); ep.append(p); eo.append(obs[0]); ew.append(w[0]); ef.append(fl[0])
+        X_all.append(X[0] + r.normal(0, 0.02, 3))
+        p += 1
+    return dict(states=states, state_flags=sflags, points=np.asarray(X_all, np.float32).astype(np.float64),
+                edge_state=np.asarray(es, np.int32), edge_point=np.asarray(ep, np.int32),
+                obs=np.asarray(eo, np.float32), inv_sigma2=np.asarray(ew, np.float32),
+                edge_flags=np.asarray(ef, np.uint8), imu_i=np.asarray(imu_i, np.int32), imu_j=np.asarray(imu_j, np.int32),
+                preint=np.asarray(pre), imu_dt_kf=np.asarray(dtk, np.float64), gw=GRAVITY_W.copy(),
+                inv_sigma_bg2=1.0 / EUROC_IMU_SIGMA[2] ** 2, inv_sigma_ba2=1.0 / EUROC_IMU_SIGMA[3] ** 2)
