@@ -146,6 +146,65 @@ int vieo_imu_preint_batch_dev(const double* samples_dev, const int32_t* seg_ptr_
                               VieoImuPreint* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Bundle adjustment — replaces the g2o graphs behind Optimizer::PoseOptimization (src/Optimizer.cc:1611-1874
+ * visual / PR vertex; include/Optimizer.h:208-816 IMU / PVR vertex incl. the marginal prior) and
+ * Optimizer::LocalBundleAdjustmentNavStatePRV / LocalBundleAdjustment (src/Optimizer.cc:21-769, 1876-2307):
+ * per-edge residual + Jacobian evaluation (src/Odom/g2otypes.h:321-541, 725-884; g2otypes.cpp:14-124), Huber
+ * weighting, the Levenberg-Marquardt loop and Schur complement of the vendored g2o
+ * (optimizer/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-189, block_solver.hpp:353-604). */
+typedef struct VieoNavState { /* NavState (src/Odom/NavState.h:17-36) */
+  double p[3];           /* mpwb */
+  double q[4];           /* mRwb unit quaternion (w, x, y, z) */
+  double v[3];           /* mvwb */
+  double bg[3], ba[3];   /* mbg, mba: frozen linearisation point */
+  double dbg[3], dba[3]; /* mdbg, mdba: optimised deltas */
+} VieoNavState;
+typedef struct VieoCamera { /* camm::PinholeCamera parameters (float, camera_pinhole.h:70-83) + Frame::meigRcb/meigtcb */
+  float fx, fy, cx, cy, bf;
+  float pad_[3];
+  double Rcb[9], tcb[3];
+} VieoCamera;
+/* visual edge flags */
+#define VIEO_EDGE_STEREO 1   /* EdgeReproject*Stereo (ul, vl, ur), else the 2-dim mono edge */
+#define VIEO_EDGE_CLOSE 2    /* track_depth_ < max(10, mThDepth): 1.5x chi2 gate (include/Optimizer.h:554,568) */
+#define VIEO_EDGE_LEVEL1 4   /* edge starts at level 1 (far-point guard, src/Optimizer.cc:514-518) */
+#define VIEO_EDGE_NOKERNEL 8 /* no Huber kernel */
+
+typedef struct VieoPoseOptProblem {
+  VieoNavState cur, last, prior; /* pFrame->mNavState, pLastKF->GetNavState(), pLastKF->mNavStatePrior */
+  VieoImuPreint preint;          /* pFrame->GetIMUPreInt(); dt == 0: no IMU edge */
+  double prior_info[225];        /* pLastKF->mMargCovInv, row-major, order P V R bg ba */
+  double gw[3];                  /* gravity in the world frame */
+  double inv_sigma_bg2, inv_sigma_ba2; /* IMUDataBase::mInvSigmabg2 / mInvSigmaba2 */
+  double dt_frames;              /* pFrame->ftimestamp_ - pLastKF->ftimestamp_ */
+  int32_t mode;                  /* 0: PoseOptimization(Frame*, Frame*) visual; 1: the IMU template (PVR vertex) */
+  int32_t last_has_prior;        /* pLastKF->mbPrior: last frame's vertices are free, 15-dim prior edge added */
+  int32_t compute_marg;          /* bComputeMarg */
+  int32_t no_mps;                /* bNoMPs */
+  int32_t edge_begin, edge_end;  /* this frame's range in the shared edge arrays */
+} VieoPoseOptProblem;
+typedef struct VieoPoseOptResult {
+  VieoNavState cur;          /* optimised pFrame->mNavState */
+  VieoNavState last;         /* optimised last-frame state when it was free */
+  double marg_cov_inv[225];  /* pFrame->mMargCovInv (compute_marg) */
+  double chi2_final;         /* activeRobustChi2 after the last optimize() */
+  double lambda_final;
+  int32_t n_inliers;         /* the reference's return value */
+  int32_t n_initial;         /* nInitialCorrespondences */
+  int32_t iterations;        /* LM iterations run in total */
+  int32_t prior_set;         /* pFrame->mbPrior after the call */
+} VieoPoseOptResult;
+/* A batch of independent frames, one thread block each, the whole 4 x optimize(10) schedule on the device.
+ *   Xw [E][3] f64 map points, obs [E][3] f32 (ul, vl, ur), inv_sigma2 [E] f32, flags [E] u8 (STEREO | CLOSE)
+ *   outputs: res [n], outlier [E] u8 (pFrame->mvbOutlier), chi2 [E] f64 (last e->chi2()) */
+int vieo_pose_opt_batch(const VieoPoseOptProblem* pbs, int n, const VieoCamera* cam, const double* Xw, const float* obs,
+                        const float* inv_sigma2, const uint8_t* flags, int n_edges, VieoPoseOptResult* res,
+                        uint8_t* outlier, double* chi2, int device);
+int vieo_pose_opt_batch_dev(const VieoPoseOptProblem* pbs_dev, int n, const VieoCamera* cam_dev, const double* Xw_dev,
+                            const float* obs_dev, const float* inv_sigma2_dev, const uint8_t* flags_dev,
+                            VieoPoseOptResult* res_dev, uint8_t* outlier_dev, double* chi2_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stereo front-end over HOST buffers — the hot work of the Frame::Frame stereo constructor
  * (src/Frame.cc:218-316): ORBextractor::operator() for both cameras (:259-278) and the brute-force
  * left->right knnMatch(k=2) of ComputeStereoFishEyeMatches (:620-628), for a batch of frames, with the

@@ -939,6 +939,7 @@ int orc_pose_optimization(const OrcPoseOptProblem* pb, const OrcCamera* cam, con
   res->n_inliers = nInitial - nBad;
   res->iterations = g.total_iters;
   res->lambda_final = g.lambda;
+  g.initialize();  // chi2_final: robust chi2 of the final level-0 set with the stored errors
   res->chi2_final = g.active_robust_chi2();
   if (imu_mode && pb->compute_marg) {
     // kExactRobust: recompute errors, re-linearise every edge at the final estimate (include/Optimizer.h:126-206, 671-728)

@@ -62,6 +62,8 @@ def lib():
         L.vieo_imu_set_param.restype = None
         L.vieo_imu_preint_batch.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32]
         L.vieo_imu_preint_batch_dev.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
+        L.vieo_pose_opt_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32]
+        L.vieo_pose_opt_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -297,3 +299,36 @@ class IMUPreintegrator:
         _check(lib().vieo_imu_preint_batch(_p(samples), _p(seg_ptr), _p(ti_tj), _p(bg_ba), C.byref(self.noise), n,
                                            _p(out), self.device))
         return out
+
+
+# ---------------------------------------------------------------- bundle adjustment
+from .layouts import (BA_RESULT_DTYPE, CAMERA_DTYPE, NAVSTATE_DTYPE, POSEOPT_PROBLEM_DTYPE,  # noqa: E402,F401
+                      POSEOPT_RESULT_DTYPE)
+
+
+class Optimizer:
+    """Static surface of the reference's Optimizer (include/Optimizer.h:46-121) over flattened problems."""
+
+    @staticmethod
+    def PoseOptimizationBatch(pbs, cam, Xw, obs, inv_sigma2, flags, device=0):
+        """A batch of Optimizer::PoseOptimization calls (visual or IMU/PVR, per problem `mode`).
+        -> (results POSEOPT_RESULT_DTYPE[n], outlier u8[E], chi2 f64[E])"""
+        pbs = np.ascontiguousarray(pbs, POSEOPT_PROBLEM_DTYPE)
+        cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
+        Xw = np.ascontiguousarray(Xw, np.float64).reshape(-1, 3)
+        obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3)
+        inv_sigma2 = np.ascontiguousarray(inv_sigma2, np.float32)
+        flags = np.ascontiguousarray(flags, np.uint8)
+        E = len(flags)
+        assert len(Xw) == E and len(obs) == E and len(inv_sigma2) == E
+        res = np.zeros(len(pbs), POSEOPT_RESULT_DTYPE)
+        outlier = np.zeros(E, np.uint8)
+        chi2 = np.zeros(E, np.float64)
+        _check(lib().vieo_pose_opt_batch(_p(pbs), len(pbs), _p(cam), _p(Xw), _p(obs), _p(inv_sigma2), _p(flags), E,
+                                         _p(res), _p(outlier), _p(chi2), device))
+        return res, outlier, chi2
+
+    @staticmethod
+    def pose_opt_batch_dev(pbs_ptr, n, cam_ptr, Xw_ptr, obs_ptr, w_ptr, flags_ptr, res_ptr, outlier_ptr, chi2_ptr, stream=0):
+        _check(lib().vieo_pose_opt_batch_dev(pbs_ptr, n, cam_ptr, Xw_ptr, obs_ptr, w_ptr, flags_ptr, res_ptr, outlier_ptr,
+                                             chi2_ptr, stream))
