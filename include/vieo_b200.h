@@ -204,6 +204,66 @@ int vieo_pose_opt_batch_dev(const VieoPoseOptProblem* pbs_dev, int n, const Vieo
                             const float* obs_dev, const float* inv_sigma2_dev, const uint8_t* flags_dev,
                             VieoPoseOptResult* res_dev, uint8_t* outlier_dev, double* chi2_dev, void* stream);
 
+/* ---- local bundle adjustment: PR-V-Bias vertices per keyframe, marginalised map points --------------------
+ * The flattened graph of Optimizer::LocalBundleAdjustmentNavStatePRV (src/Optimizer.cc:133-520).  Keyframes
+ * ("states") come local-first in ascending id (the reference's vertex ids 3k, 3k+1, 3k+2), then the fixed ones.
+ * Visual edges must be sorted by point index (they are created point by point, :367-520). */
+typedef struct VieoBaProblem {
+  int32_t n_states, n_points, n_edges, n_imu;
+  const VieoNavState* states;
+  const uint8_t* state_flags; /* bit0: PR vertex fixed; bit1: has V and Bias vertices; bit2: V / Bias fixed */
+  const double* points;       /* [P][3] MapPoint::GetWorldPos cast to double */
+  const int32_t* edge_state;  /* [E] keyframe of the observation */
+  const int32_t* edge_point;  /* [E] ascending */
+  const float* obs;           /* [E][3] (ul, vl, ur) kpUn.pt / vuright_ */
+  const float* inv_sigma2;    /* [E] vinvlevelsigma2_[octave] */
+  const uint8_t* edge_flags;  /* [E] VIEO_EDGE_* */
+  const int32_t* imu_i;       /* [n_imu] state of pKF0 (previous keyframe) */
+  const int32_t* imu_j;       /* [n_imu] state of pKF1 */
+  const VieoImuPreint* preint;/* [n_imu] pKF1->GetIMUPreInt(); dt == 0: bias edge only */
+  const double* imu_dt_kf;    /* [n_imu] pKF1->ftimestamp_ - pKF0->ftimestamp_ */
+  double gw[3];
+  double inv_sigma_bg2, inv_sigma_ba2;
+  int32_t large;       /* bLarge */
+  int32_t rec_init;    /* bRecInit */
+  int32_t visual_only; /* Optimizer::LocalBundleAdjustment: PR vertices only, no inertial edges */
+  int32_t pad_;
+} VieoBaProblem;
+typedef struct VieoBaResult {
+  double err0, err_end; /* activeRobustChi2 before / after (src/Optimizer.cc:539, 652), rounded to float like the reference */
+  double lambda_final;
+  int32_t iterations[2]; /* LM iterations of the two optimize() stages */
+  int32_t accepted;      /* 0: the "FAIL LOCAL-INERTIAL BA" guard (:663-666) rejected the result, nothing to write back */
+  int32_t n_erase;
+} VieoBaResult;
+typedef struct vieo_ba vieo_ba_t;
+int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, int device, vieo_ba_t** out);
+void vieo_ba_destroy(vieo_ba_t* h);
+/* Sharding over GPUs: each rank holds a subset of the points with all their edges, the keyframe states
+ * replicated, the inertial edges on rank 0.  `allreduce` sums `count` doubles at device pointer `buf` in place over
+ * all ranks, ordered on `stream` (the host wraps ncclAllReduce / torch.distributed.all_reduce).  NULL: single GPU. */
+typedef int (*vieo_allreduce_fn)(void* ctx, double* buf_dev, size_t count, void* stream);
+int vieo_ba_set_sharding(vieo_ba_t* h, int rank, int world, vieo_allreduce_fn allreduce, void* ctx);
+void* vieo_ba_stream(vieo_ba_t* h);
+/* The whole reference routine from "Setup optimizer" to the err/err_end guard on the flattened problem: Chi2LargeSetLevel,
+ * optimize(optit[0]), inlier re-classification + kernel removal, optimize(optit[1]), outlier list.
+ *   stop      pbStopFlag (mbAbortBA), polled before optimising and every LM iteration; may be NULL
+ *   outputs   states_out [n_states], points_out [P][3], edge_chi2 [E], erase [E] (1 = ErasePairObs candidate) */
+int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, const volatile uint8_t* stop,
+                      VieoNavState* states_out, double* points_out, double* edge_chi2, uint8_t* erase, VieoBaResult* res);
+/* Building blocks (what `optimizer.optimize(n)` and friends do), for callers that keep the policy on their side. */
+int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam);
+int vieo_ba_chi2_large_set_level(vieo_ba_t* h, float rat);           /* GraphOperator::Chi2LargeSetLevel */
+int vieo_ba_active_robust_chi2(vieo_ba_t* h, int recompute, double* chi2); /* [computeActiveErrors +] activeRobustChi2 */
+int vieo_ba_optimize(vieo_ba_t* h, int iterations, double lambda_init, const volatile uint8_t* stop); /* -> iterations run */
+int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host /* nullable [E] */); /* chi2 / depth gates -> level 1 */
+int vieo_ba_get(vieo_ba_t* h, VieoNavState* states_out, double* points_out, double* edge_chi2);
+/* One damped Gauss-Newton step at the current estimate without applying it: x_pose [np] (Hessian index order),
+ * x_points [P][3]; returns np.  H_out (np x np, nullable) / b_out receive the pose block of the normal equations
+ * (vieo_ba_get_hessian_blocks of SURVEY.md 8b). */
+int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_points, double* H_out, double* b_out);
+int vieo_ba_last_launches(const vieo_ba_t* h);
+
 /* ------------------------------------------------------------------------------------------------
  * Stereo front-end over HOST buffers — the hot work of the Frame::Frame stereo constructor
  * (src/Frame.cc:218-316): ORBextractor::operator() for both cameras (:259-278) and the brute-force

@@ -72,3 +72,84 @@ def test_pose_optimization_deterministic(seq):
     a = api.Optimizer.PoseOptimizationBatch(pbs, cam, X, obs, w, fl)
     b = api.Optimizer.PoseOptimizationBatch(pbs, cam, X, obs, w, fl)
     assert a[0].tobytes() == b[0].tobytes() and a[2].tobytes() == b[2].tobytes()
+
+
+# ---------------------------------------------------------------- local BA
+def _lba(seq, n_local=8, n_fixed=6, n_points=400, seed=4, step=3, **kw):
+    cam = synth.euroc_camera()
+    kf = list(range(0, len(seq["times"]), step))
+    pre = O.imu_preintegrate_frames(seq, kf, O.imu_noise())
+    return cam, synth.make_lba_problem(seq, pre, kf, cam, n_local=n_local, n_fixed=n_fixed, n_points=n_points, seed=seed, **kw)
+
+
+def test_lba_single_step_matches_oracle(seq):
+    import vieo_slam_b200.api as api
+    cam, d = _lba(seq)
+    ba = api.BundleAdjuster()
+    ba.set_problem(d, cam)
+    for lam in (1.0, 1e-2):
+        xp, xl, H, b = ba.debug_step(lam)
+        oxp, oxl, _ = O.ba_debug_step(d, cam, lam)
+        assert len(xp) == len(oxp)
+        assert np.abs(xp - oxp).max() <= 1e-9 * max(1.0, np.abs(oxp).max()), np.abs(xp - oxp).max()
+        assert np.abs(xl - oxl).max() <= 1e-9 * max(1.0, np.abs(oxl).max())
+        assert np.allclose(H, H.T, rtol=0, atol=1e-9 * np.abs(H).max())
+
+
+def _cmp_lba(out, ref):
+    r, o = out["res"], ref["res"]
+    assert r["accepted"] == o["accepted"]
+    assert abs(r["err0"] - o["err0"]) <= 1e-6 * abs(o["err0"])
+    assert abs(r["err_end"] - o["err_end"]) <= 1e-6 * abs(o["err_end"]), (r["err_end"], o["err_end"])
+    assert np.array_equal(out["erase"], ref["erase"])
+    for f in ("p", "q", "v", "dbg", "dba"):
+        assert np.abs(out["states"][f] - ref["states"][f]).max() < 1e-7, f   # << 1 mm
+    assert np.abs(out["points"] - ref["points"]).max() < 1e-6
+    sc = np.maximum(np.abs(ref["edge_chi2"]), 1.0)
+    assert (np.abs(out["edge_chi2"] - ref["edge_chi2"]) / sc).max() < 1e-6
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(large=True), dict(visual_only=True), dict(rec_init=True)])
+def test_local_ba_matches_oracle(seq, kw):
+    import vieo_slam_b200.api as api
+    cam, d = _lba(seq)
+    ba = api.BundleAdjuster()
+    out = ba.LocalBundleAdjustmentNavStatePRV(d, cam, **kw)
+    ref = O.local_ba_prv(d, cam, **kw)
+    _cmp_lba(out, ref)
+    assert out["res"]["err_end"] < out["res"]["err0"]
+    assert ba.last_launches() > 0
+
+
+def test_local_ba_v203_sized_window():
+    """BASELINE configs[2]-shaped window: N_local = 10, 20 fixed keyframes, 1500 points, ~9k edges."""
+    import vieo_slam_b200.api as api
+    s = synth.vio_sequence(203, 160, speed=1.5, rot=1.0)
+    cam, d = _lba(s, n_local=10, n_fixed=20, n_points=1500, seed=203, step=4)
+    ba = api.BundleAdjuster()
+    out = ba.LocalBundleAdjustmentNavStatePRV(d, cam)
+    ref = O.local_ba_prv(d, cam)
+    _cmp_lba(out, ref)
+    again = ba.LocalBundleAdjustmentNavStatePRV(d, cam)
+    assert again["states"].tobytes() == out["states"].tobytes() and again["points"].tobytes() == out["points"].tobytes()
+
+
+def test_local_ba_edge_cases(seq):
+    import vieo_slam_b200.api as api
+    cam, d = _lba(seq, n_points=120)
+    ba = api.BundleAdjuster()
+    allfixed = dict(d); allfixed["state_flags"] = d["state_flags"] | 1
+    out = ba.LocalBundleAdjustmentNavStatePRV(allfixed, cam)
+    assert out["states"].tobytes() == d["states"].tobytes() and out["res"]["iterations"][0] == 0
+    stop = np.ones(1, np.uint8)   # mbAbortBA already set: return before optimising, nothing written
+    out = ba.LocalBundleAdjustmentNavStatePRV(d, cam, stop=stop)
+    assert out["states"].tobytes() == d["states"].tobytes() and out["res"]["accepted"] == 0
+    # a point whose edges all start at level 1 (far-point guard) is left alone
+    far = dict(d); fl = d["edge_flags"].copy(); fl[d["edge_point"] == 0] |= 4; far["edge_flags"] = fl
+    out = ba.LocalBundleAdjustmentNavStatePRV(far, cam)
+    ref = O.local_ba_prv(far, cam)
+    _cmp_lba(out, ref)
+    assert np.array_equal(out["points"][0], d["points"][0])
+    small = api.BundleAdjuster(max_states=4, max_points=16, max_edges=64, max_imu=4)
+    with pytest.raises(api.VieoError):
+        small.LocalBundleAdjustmentNavStatePRV(d, cam)

@@ -64,6 +64,21 @@ def lib():
         L.vieo_imu_preint_batch_dev.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
         L.vieo_pose_opt_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32]
         L.vieo_pose_opt_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.vieo_ba_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
+        L.vieo_ba_destroy.argtypes = [vp]
+        L.vieo_ba_destroy.restype = None
+        L.vieo_ba_set_sharding.argtypes = [vp, i32, i32, vp, vp]
+        L.vieo_ba_stream.argtypes = [vp]
+        L.vieo_ba_stream.restype = vp
+        L.vieo_local_ba_prv.argtypes = [vp] * 9
+        L.vieo_ba_set_problem.argtypes = [vp, vp, vp]
+        L.vieo_ba_chi2_large_set_level.argtypes = [vp, C.c_float]
+        L.vieo_ba_active_robust_chi2.argtypes = [vp, i32, vp]
+        L.vieo_ba_optimize.argtypes = [vp, i32, C.c_double, vp]
+        L.vieo_ba_reclassify.argtypes = [vp, i32, vp]
+        L.vieo_ba_get.argtypes = [vp, vp, vp, vp]
+        L.vieo_ba_debug_step.argtypes = [vp, C.c_double, vp, vp, vp, vp]
+        L.vieo_ba_last_launches.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -332,3 +347,102 @@ class Optimizer:
     def pose_opt_batch_dev(pbs_ptr, n, cam_ptr, Xw_ptr, obs_ptr, w_ptr, flags_ptr, res_ptr, outlier_ptr, chi2_ptr, stream=0):
         _check(lib().vieo_pose_opt_batch_dev(pbs_ptr, n, cam_ptr, Xw_ptr, obs_ptr, w_ptr, flags_ptr, res_ptr, outlier_ptr,
                                              chi2_ptr, stream))
+
+
+class VieoBaProblem(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("n_imu", C.c_int32),
+                ("states", C.c_void_p), ("state_flags", C.c_void_p), ("points", C.c_void_p), ("edge_state", C.c_void_p),
+                ("edge_point", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p), ("edge_flags", C.c_void_p),
+                ("imu_i", C.c_void_p), ("imu_j", C.c_void_p), ("preint", C.c_void_p), ("imu_dt_kf", C.c_void_p),
+                ("gw", C.c_double * 3), ("inv_sigma_bg2", C.c_double), ("inv_sigma_ba2", C.c_double),
+                ("large", C.c_int32), ("rec_init", C.c_int32), ("visual_only", C.c_int32), ("pad_", C.c_int32)]
+
+
+_BA_ARRAYS = (("states", NAVSTATE_DTYPE), ("state_flags", np.uint8), ("points", np.float64), ("edge_state", np.int32),
+              ("edge_point", np.int32), ("obs", np.float32), ("inv_sigma2", np.float32), ("edge_flags", np.uint8),
+              ("imu_i", np.int32), ("imu_j", np.int32), ("preint", PREINT_DTYPE), ("imu_dt_kf", np.float64))
+
+
+def ba_problem(d, large=False, rec_init=False, visual_only=False):
+    """dict of arrays (synth.make_lba_problem layout) -> (VieoBaProblem, keepalive dict)"""
+    keep = {k: np.ascontiguousarray(d[k], dt) for k, dt in _BA_ARRAYS}
+    pb = VieoBaProblem()
+    pb.n_states, pb.n_points, pb.n_edges, pb.n_imu = len(keep["states"]), len(keep["points"]), len(keep["edge_state"]), len(keep["imu_i"])
+    for k, a in keep.items():
+        setattr(pb, k, a.ctypes.data)
+    pb.gw = (C.c_double * 3)(*d["gw"])
+    pb.inv_sigma_bg2, pb.inv_sigma_ba2 = d["inv_sigma_bg2"], d["inv_sigma_ba2"]
+    pb.large, pb.rec_init, pb.visual_only = int(large), int(rec_init), int(visual_only)
+    return pb, keep
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class BundleAdjuster:
+    """Device engine behind Optimizer::LocalBundleAdjustmentNavStatePRV / LocalBundleAdjustment (vieo_ba_* ABI)."""
+
+    def __init__(self, max_states=256, max_points=8192, max_edges=65536, max_imu=64, device=0):
+        self._h = C.c_void_p()
+        _check(lib().vieo_ba_create(max_states, max_points, max_edges, max_imu, device, C.byref(self._h)))
+        self._cb = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            lib().vieo_ba_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def stream(self):
+        return lib().vieo_ba_stream(self._h)
+
+    def set_sharding(self, rank, world, allreduce):
+        """allreduce(dev_ptr:int, count:int, stream:int) sums `count` fp64 in place over the ranks (e.g. NCCL)."""
+        def cb(ctx, buf, count, stream):
+            try:
+                allreduce(buf, count, stream)
+                return 0
+            except Exception:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._cb = ALLREDUCE_FN(cb) if allreduce else None
+        _check(lib().vieo_ba_set_sharding(self._h, rank, world, C.cast(self._cb, C.c_void_p) if self._cb else None, None))
+
+    def LocalBundleAdjustmentNavStatePRV(self, d, cam, large=False, rec_init=False, visual_only=False, stop=None):
+        pb, keep = ba_problem(d, large, rec_init, visual_only)
+        cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
+        st = np.zeros(pb.n_states, NAVSTATE_DTYPE); pts = np.zeros((pb.n_points, 3)); chi2 = np.zeros(pb.n_edges)
+        erase = np.zeros(pb.n_edges, np.uint8); res = np.zeros(1, BA_RESULT_DTYPE)
+        _check(lib().vieo_local_ba_prv(self._h, C.byref(pb), _p(cam), _p(stop), _p(st), _p(pts), _p(chi2), _p(erase), _p(res)))
+        return dict(states=st, points=pts, edge_chi2=chi2, erase=erase, res=res[0])
+
+    def set_problem(self, d, cam, **kw):
+        pb, keep = ba_problem(d, **kw)
+        cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
+        _check(lib().vieo_ba_set_problem(self._h, C.byref(pb), _p(cam)))
+        self._n = (pb.n_states, pb.n_points, pb.n_edges)
+
+    def debug_step(self, lam):
+        K, P, E = self._n
+        xp = np.zeros(15 * K); xl = np.zeros((P, 3)); H = np.zeros((15 * K) ** 2); b = np.zeros(15 * K)
+        n = _check(lib().vieo_ba_debug_step(self._h, lam, _p(xp), _p(xl), _p(H), _p(b)))
+        return xp[:n], xl, H[:n * n].reshape(n, n), b[:n]
+
+    def optimize(self, iterations, lambda_init=0.0):
+        return _check(lib().vieo_ba_optimize(self._h, iterations, lambda_init, None))
+
+    def active_robust_chi2(self, recompute=True):
+        c = C.c_double(0)
+        _check(lib().vieo_ba_active_robust_chi2(self._h, int(recompute), C.byref(c)))
+        return c.value
+
+    def get(self):
+        K, P, E = self._n
+        st = np.zeros(K, NAVSTATE_DTYPE); pts = np.zeros((P, 3)); chi2 = np.zeros(E)
+        _check(lib().vieo_ba_get(self._h, _p(st), _p(pts), _p(chi2)))
+        return st, pts, chi2
+
+    def last_launches(self):
+        return lib().vieo_ba_last_launches(self._h)
