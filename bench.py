@@ -34,8 +34,9 @@ FAST_BYTES_PER_IMAGE = LEVEL_PX + 700 * 4  # k_fast_cells: every level pixel onc
 
 
 def workload_name(frames):
-    return (f"EuRoC MH05 stereo-VIO 1200 feats (configs[1]), synthetic 752x480 stereo, batches of {frames} frames: "
-            "ORBextractor x2 + stereo knnMatch")
+    return (f"EuRoC MH05 stereo-VIO 1200 feats (configs[1]), synthetic 752x480 stereo + 200 Hz IMU, batches of {frames} frames: "
+            "ORBextractor x2 + stereo knnMatch + IMU pre-integration + 2x PoseOptimization (PVR) per frame, "
+            "LocalBundleAdjustmentNavStatePRV every 8th frame")
 
 
 def peaks():
@@ -85,71 +86,167 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_frames_per_s(images, threads, log=None):
-    """Oracle front-end over `images` (n_frames,2,H,W): ORB per camera + stereo knn2, `threads` workers."""
+# Workload: BASELINE.json configs[1] as SURVEY.md 8d restates it.  Per stereo frame: ORBextractor x2 + stereo knnMatch,
+# one IMU pre-integration (10 samples at 200 Hz / 20 fps), two PoseOptimization calls (TrackWithMotionModel with ~350
+# matches, TrackLocalMap with ~550; IMU/PVR vertex, 15 % outliers, 70 % stereo); every LBA_EVERY-th frame is a keyframe
+# and triggers one LocalBundleAdjustmentNavStatePRV window (N_local = 10, 20 fixed keyframes, 1500 points).
+LBA_EVERY = 8
+POSE_POINTS = (350, 550)
+LBA_SHAPE = dict(n_local=10, n_fixed=20, n_points=1500)
+
+
+def make_tracking_inputs(seed, F, preint_fn):
+    """F frames of tracking-thread inputs: IMU segments + 2F PoseOptimization problems (numpy, C-ABI layouts)."""
+    from vieo_slam_b200 import synth
+    seq = synth.vio_sequence(seed, F + 1, speed=1.5, rot=1.0)
+    imu, t = seq["imu"], seq["times"]
+    seg, smp, tt, bb = [0], [], [], []
+    for k in range(1, F + 1):
+        lo = max(np.searchsorted(imu[:, 0], t[k - 1], "right") - 1, 0)
+        hi = min(np.searchsorted(imu[:, 0], t[k], "left") + 1, len(imu))
+        smp.append(imu[lo:hi]); seg.append(seg[-1] + hi - lo); tt.append((t[k - 1], t[k]))
+        bb.append(np.r_[seq["truth"][k - 1]["bg"], seq["truth"][k - 1]["ba"]])
+    imu_in = (np.ascontiguousarray(np.vstack(smp)), np.asarray(seg, np.int32), np.asarray(tt), np.asarray(bb))
+    pre = preint_fn(*imu_in)
+    pre = np.concatenate([pre[:1], pre])  # make_pose_problems indexes preints by frame
+    cam = synth.euroc_camera()
+    sets = [synth.make_pose_problems(seq, pre, cam, n_points=n, seed=seed + i, compute_marg=True, chain_prior=(i == 0))
+            for i, n in enumerate(POSE_POINTS)]
+    # concatenate the two PoseOptimization calls of every frame into one batch of 2F problems
+    pbs = np.concatenate([sets[0][0], sets[1][0]])
+    off = len(sets[0][1])
+    pbs["edge_begin"][F:] += off
+    pbs["edge_end"][F:] += off
+    arrays = [np.concatenate([sets[0][i], sets[1][i]]) for i in range(1, 5)]
+    return dict(imu=imu_in, pbs=pbs, cam=cam, Xw=arrays[0], obs=arrays[1], w=arrays[2], flags=arrays[3], seq=seq)
+
+
+def make_lba_windows(seed, n, preint_fn):
+    from vieo_slam_b200 import synth
+    out = []
+    for i in range(n):
+        seq = synth.vio_sequence(seed + 31 * i, 130, speed=1.5, rot=1.0)
+        kf = list(range(0, 130, 4))
+        imu, t = seq["imu"], seq["times"]
+        seg, smp, tt, bb = [0], [], [], []
+        for k in range(1, len(kf)):
+            lo = max(np.searchsorted(imu[:, 0], t[kf[k - 1]], "right") - 1, 0)
+            hi = min(np.searchsorted(imu[:, 0], t[kf[k]], "left") + 1, len(imu))
+            smp.append(imu[lo:hi]); seg.append(seg[-1] + hi - lo); tt.append((t[kf[k - 1]], t[kf[k]]))
+            bb.append(np.r_[seq["truth"][kf[k - 1]]["bg"], seq["truth"][kf[k - 1]]["ba"]])
+        pre = preint_fn(np.vstack(smp), np.asarray(seg, np.int32), np.asarray(tt), np.asarray(bb))
+        pre = np.concatenate([pre[:1], pre])
+        out.append(synth.make_lba_problem(seq, pre, kf, synth.euroc_camera(), seed=seed + i, **LBA_SHAPE))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
+    return O
+
+
+def oracle_preint_fn():
+    O = _oracle()
+    nz = O.imu_noise()
+
+    def fn(samples, seg, tt, bb):
+        out = np.zeros(len(seg) - 1, O.PREINT_DTYPE)
+        for k in range(len(seg) - 1):
+            out[k] = O.imu_preintegrate(samples[seg[k]:seg[k + 1]], tt[k][0], tt[k][1], bb[k][:3], bb[k][3:], nz)
+        return out
+    return fn
+
+
+def cpu_pipeline(images, trk, lbas, threads_like_reference=True, workers=None):
+    """The reference's CPU path (oracle port) over `images` (n,2,H,W): per frame extraction on one thread per camera,
+    stereo knn + IMU pre-integration + 2x PoseOptimization on the tracking thread; LocalBA windows on the LocalMapping
+    thread (src/Frame.cc:259-278, src/Tracking.cc, src/LocalMapping.cc).  With threads_like_reference=False frames are
+    instead spread over `workers` threads (all host cores).  Returns (frames/s, seconds)."""
+    O = _oracle()
+    from concurrent.futures import ThreadPoolExecutor
     n = images.shape[0]
+    nz = O.imu_noise()
+    cam = trk["cam"]
+    F = len(trk["pbs"]) // 2
     tl = threading.local()
 
-    def work(f):
+    def orb():
         if not hasattr(tl, "orb"):
             tl.orb = O.OrbOracle(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"])
-        _, _, dl, _ = tl.orb.extract(images[f, 0])
-        _, _, dr, _ = tl.orb.extract(images[f, 1])
-        O.hamming_knn2(dl, dr)
+        return tl.orb
 
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(work, range(min(threads, n))))  # warm: build per-thread oracles
+    def tracking(f, dl, dr):
+        O.hamming_knn2(dl, dr)
+        k = f % F
+        smp, seg, tt, bb = trk["imu"]
+        O.imu_preintegrate(smp[seg[k]:seg[k + 1]], tt[k][0], tt[k][1], bb[k][:3], bb[k][3:], nz)
+        for j in (k, F + k):
+            O.pose_optimization(trk["pbs"][j:j + 1], cam, trk["Xw"], trk["obs"], trk["w"], trk["flags"])
+
+    def lba_thread(count):
+        for i in range(count):
+            O.local_ba_prv(lbas[i % len(lbas)], cam)
+
+    n_lba = n // LBA_EVERY
+    if threads_like_reference:
+        with ThreadPoolExecutor(2) as cams, ThreadPoolExecutor(1) as lm:
+            orbs = [O.OrbOracle(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"])
+                    for _ in range(2)]
+            a = cams.submit(lambda: orbs[0].extract(images[0, 0])); b = cams.submit(lambda: orbs[1].extract(images[0, 1]))
+            a.result(); b.result()
+            t0 = time.perf_counter()
+            fut = lm.submit(lba_thread, n_lba)
+            for f in range(n):
+                a = cams.submit(lambda f=f: orbs[0].extract(images[f, 0]))
+                b = cams.submit(lambda f=f: orbs[1].extract(images[f, 1]))
+                tracking(f, a.result()[2], b.result()[2])
+            fut.result()
+            dt = time.perf_counter() - t0
+        return n / dt, dt
+
+    def work(f):
+        _, _, dl, _ = orb().extract(images[f, 0])
+        _, _, dr, _ = orb().extract(images[f, 1])
+        tracking(f, dl, dr)
+        if f % LBA_EVERY == LBA_EVERY - 1:
+            O.local_ba_prv(lbas[(f // LBA_EVERY) % len(lbas)], cam)
+
+    with ThreadPoolExecutor(workers) as ex:
+        list(ex.map(lambda f: orb().extract(images[f % n, 0]), range(workers)))  # warm: per-thread oracles
         t0 = time.perf_counter()
         list(ex.map(work, range(n)))
         dt = time.perf_counter() - t0
     return n / dt, dt
 
 
-def cpu_reference_threads_like_reference(images):
-    """The reference's own threading for one frame: one thread per camera for extraction (src/Frame.cc:259-278),
-    matching on the tracking thread; frames strictly sequential."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    from concurrent.futures import ThreadPoolExecutor
-    orbs = [O.OrbOracle(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"])
-            for _ in range(2)]
-    with ThreadPoolExecutor(2) as ex:
-        def frame(f):
-            a = ex.submit(lambda: orbs[0].extract(images[f, 0]))
-            b = ex.submit(lambda: orbs[1].extract(images[f, 1]))
-            O.hamming_knn2(a.result()[2], b.result()[2])
-        frame(0)
-        t0 = time.perf_counter()
-        for f in range(images.shape[0]):
-            frame(f)
-        dt = time.perf_counter() - t0
-    return images.shape[0] / dt, dt
-
-
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = max(2 * cores, 8)
+    frames = max(2 * cores, 2 * LBA_EVERY)
+    frames -= frames % LBA_EVERY
     imgs = stereo_stream(frames, 505, dark_every=16).reshape(frames, 2, H, W)
-    for _ in range(args.warmup):
-        cpu_frames_per_s(imgs[: max(cores, 2)], cores)
+    pre = oracle_preint_fn()
+    trk = make_tracking_inputs(505, frames, pre)
+    lbas = make_lba_windows(203, 2, pre)
+    for _ in range(min(args.warmup, 1)):
+        cpu_pipeline(imgs[:cores], trk, lbas, False, cores)
     tot_t, tot_f = 0.0, 0
     for _ in range(args.steps):
-        _, dt = cpu_frames_per_s(imgs, cores)
+        _, dt = cpu_pipeline(imgs, trk, lbas, False, cores)
         tot_t += dt
         tot_f += frames
     v = tot_f / tot_t
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(frames), "frames_per_step": frames,
-                       "note": "CPU oracle port of the reference path (reference needs OpenCV/Eigen: unbuildable offline)"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
+            "config": {"workload": workload_name(frames), "frames_per_step": frames, "lba_every": LBA_EVERY,
+                       "note": "CPU oracle port of the reference path (the reference needs OpenCV/Eigen/Sophus: unbuildable offline)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{frames} synthetic stereo frames per step, one worker thread per core"},
+                             "sample": f"{frames} synthetic stereo frames per step (+{frames // LBA_EVERY} LocalBA windows), "
+                                       "frames spread over one worker thread per core"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -159,6 +256,7 @@ def run_reference(args, rank, world):
 def run_gpu(args, rank, world, local_rank):
     import torch
     import vieo_slam_b200.api as api
+    from concurrent.futures import ThreadPoolExecutor
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
@@ -172,11 +270,15 @@ def run_gpu(args, rank, world, local_rank):
     F = args.frames
     pool = args.pool
     n_img = 2 * F
+    n_lba = F // LBA_EVERY if args.lba else 0
     orb = api.ORBextractor(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"], W, H,
                            max_batch=n_img, device=local_rank)
     cap = orb.cap
+    pre_gpu = api.IMUPreintegrator(device=local_rank)
     # synthetic MH05-shaped stream: `pool` distinct batches so the per-step input (pool*F*722 KB > L2) is not cache resident
     host = stereo_stream(F * pool, 505 + rank, dark_every=16).reshape(pool, F, 2, H, W)
+    trk = make_tracking_inputs(505 + rank, F, pre_gpu.preintegrate_batch)
+    lbas = make_lba_windows(203 + rank, max(1, min(args.lba_windows, max(n_lba, 1))), pre_gpu.preintegrate_batch) if n_lba else []
     host_t = torch.from_numpy(host).pin_memory()
     dev_imgs = host_t.to(dev, non_blocking=True)
     kps = torch.empty((n_img, cap, 6), dtype=torch.float32, device=dev)
@@ -184,19 +286,53 @@ def run_gpu(args, rank, world, local_rank):
     nkp = torch.empty((n_img,), dtype=torch.int32, device=dev)
     midx = torch.empty((F, cap, 2), dtype=torch.int32, device=dev)
     mdist = torch.empty((F, cap, 2), dtype=torch.int32, device=dev)
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    smp, seg, tt, bb = trk["imu"]
+    d_smp, d_seg, d_tt, d_bb = to_dev(smp), to_dev(seg), to_dev(tt), to_dev(bb)
+    d_pre = torch.empty(F * api.PREINT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_pbs, d_cam = to_dev(trk["pbs"]), to_dev(np.asarray(trk["cam"]).reshape(1))
+    d_Xw, d_obs, d_w, d_fl = to_dev(trk["Xw"]), to_dev(trk["obs"]), to_dev(trk["w"]), to_dev(trk["flags"])
+    n_pb, n_edges = len(trk["pbs"]), len(trk["flags"])
+    d_res = torch.empty(n_pb * api.POSEOPT_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_outl = torch.empty(n_edges, dtype=torch.uint8, device=dev)
+    d_chi = torch.empty(n_edges, dtype=torch.float64, device=dev)
+    n_workers = max(1, min(args.lba_workers, n_lba)) if n_lba else 0
+    bas = [api.BundleAdjuster(max_states=64, max_points=2048, max_edges=16384, max_imu=16, device=local_rank)
+           for _ in range(n_workers)]
+    lba_pool = ThreadPoolExecutor(n_workers) if n_workers else None
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream().cuda_stream
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+
+    def lba_job(wk, i0):
+        for i in range(i0, n_lba, n_workers):
+            out = bas[wk].LocalBundleAdjustmentNavStatePRV(lbas[i % len(lbas)], trk["cam"])
+            assert out["res"]["accepted"] == 1
+        return bas[wk].last_launches()
 
     def step(i):
+        futs = [lba_pool.submit(lba_job, wk, wk) for wk in range(n_workers)]
         imgs = dev_imgs[i % pool]
-        orb.extract_batch_dev(imgs.data_ptr(), n_img, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), stream)
+        s = main.cuda_stream
+        orb.extract_batch_dev(imgs.data_ptr(), n_img, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), s)
         api.hamming_knn2_batch_dev(desc.data_ptr(), 2 * cap * 32, nkp.data_ptr(), cap, desc.data_ptr() + cap * 32,
-                                   2 * cap * 32, nkp.data_ptr() + 4, cap, 2, F, midx.data_ptr(), mdist.data_ptr(), stream)
+                                   2 * cap * 32, nkp.data_ptr() + 4, cap, 2, F, midx.data_ptr(), mdist.data_ptr(), s)
+        s2 = side.cuda_stream
+        pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(), d_bb.data_ptr(), F,
+                                       d_pre.data_ptr(), s2)
+        api.Optimizer.pose_opt_batch_dev(d_pbs.data_ptr(), n_pb, d_cam.data_ptr(), d_Xw.data_ptr(), d_obs.data_ptr(),
+                                         d_w.data_ptr(), d_fl.data_ptr(), d_res.data_ptr(), d_outl.data_ptr(),
+                                         d_chi.data_ptr(), s2)
+        main.wait_stream(side)
+        return sum(f.result() for f in futs)
 
-    launches_per_step = None
+    ba_launches = 0
     for i in range(args.warmup):
-        step(i)
-    launches_per_step = orb.last_launches() + 1
+        side.wait_stream(main)
+        ba_launches = step(i)
+    launches_per_step = orb.last_launches() + 1 + 2 + ba_launches
     torch.cuda.synchronize()
     if dist_on:
         dist.barrier()
@@ -207,8 +343,9 @@ def run_gpu(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
+    side.wait_stream(main)
     for i in range(args.steps):
-        step(args.warmup + i)
+        step(args.warmup + i)   # joins the LocalBA workers (their calls are synchronous) before returning
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -223,28 +360,71 @@ def run_gpu(args, rank, world, local_rank):
     ms_max = float(t.item())
     value = world * F * args.steps / (ms_max / 1e3)
 
-    # ---- e2e: host buffers through the C-ABI front-end call, copies inside the timed region
+    # stage times in isolation (CUDA events, device-resident), for the report
+    def time_it(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    s = main.cuda_stream
+    iso = {
+        "imu_preint": time_it(lambda: pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(),
+                                                                     d_bb.data_ptr(), F, d_pre.data_ptr(), s)),
+        "pose_opt_x2": time_it(lambda: api.Optimizer.pose_opt_batch_dev(d_pbs.data_ptr(), n_pb, d_cam.data_ptr(),
+                                                                        d_Xw.data_ptr(), d_obs.data_ptr(), d_w.data_ptr(),
+                                                                        d_fl.data_ptr(), d_res.data_ptr(), d_outl.data_ptr(),
+                                                                        d_chi.data_ptr(), s)),
+    }
+    if n_lba:
+        t0 = time.perf_counter()
+        for _ in range(3):
+            bas[0].LocalBundleAdjustmentNavStatePRV(lbas[0], trk["cam"])
+        iso["local_ba_window_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+
+    # ---- e2e: host buffers through the host-buffer C-ABI calls, copies inside the timed region; threads as in the
+    # reference: front-end, tracking (IMU + PoseOptimization), LocalMapping workers
     fe = api.StereoFrontend(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"], W, H,
                             max_frames=F, device=local_rank)
     outs = fe.alloc_outputs(F, pinned=True)
     host_np = host_t.numpy()
+    trk_pool = ThreadPoolExecutor(1)
+
+    def tracking_host():
+        pre_gpu.preintegrate_batch(*trk["imu"])
+        r = api.Optimizer.PoseOptimizationBatch(trk["pbs"], trk["cam"], trk["Xw"], trk["obs"], trk["w"], trk["flags"],
+                                                device=local_rank)
+        return int(r[0]["n_inliers"][0])
+
+    def e2e_step(i):
+        futs = [lba_pool.submit(lba_job, wk, wk) for wk in range(n_workers)]
+        ft = trk_pool.submit(tracking_host)
+        res = fe.process(host_np[i % pool], outs)
+        _ = int(res[2][0]) + ft.result()
+        for f in futs:
+            f.result()
+
     for i in range(max(3, args.warmup)):
-        fe.process(host_np[i % pool], outs)
+        e2e_step(i)
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        res = fe.process(host_np[(args.warmup + i) % pool], outs)
-        _ = int(res[2][0])  # read a result on the host
+        e2e_step(args.warmup + i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if dist_on:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * F * args.steps / float(t.item())
-    h2d = F * 2 * H * W
-    d2h = sum(int(o.nbytes) for o in outs)
+    lba_bytes = sum(int(np.asarray(v).nbytes) for v in lbas[0].values() if hasattr(v, "nbytes")) if lbas else 0
+    trk_in = sum(int(np.asarray(a).nbytes) for a in trk["imu"]) + sum(int(trk[k].nbytes) for k in ("pbs", "Xw", "obs", "w", "flags"))
+    h2d = F * 2 * H * W + trk_in + n_lba * lba_bytes
+    d2h = (sum(int(o.nbytes) for o in outs) + F * api.PREINT_DTYPE.itemsize + n_pb * api.POSEOPT_RESULT_DTYPE.itemsize
+           + 9 * n_edges + n_lba * (64 * 176 + 2048 * 24 + 16384 * 9))
 
     if rank != 0:
         if dist_on:
@@ -263,16 +443,19 @@ def run_gpu(args, rank, world, local_rank):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
-    # ---- CPU baseline: the oracle threaded like the reference (1 thread per camera), bounded sample
-    cpu_frames = args.cpu_frames
-    cpu_v, cpu_dt = cpu_reference_threads_like_reference(host[0, :cpu_frames])
+    # ---- CPU baseline: the oracle threaded like the reference, bounded sample
+    cpu_frames = args.cpu_frames - args.cpu_frames % LBA_EVERY
+    cpu_lbas = make_lba_windows(203, 1, oracle_preint_fn()) if not lbas else lbas
+    cpu_v, cpu_dt = cpu_pipeline(host[0, :cpu_frames], trk, cpu_lbas, True)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
+        "dtype": "u8+f64", "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_step_per_gpu": F, "image": f"{W}x{H}", "nfeatures": 1200,
                    "levels": 8, "cache": f"inputs rotate over {pool} batches ({pool * F * 2 * H * W / 1e6:.0f} MB > 126 MB L2)",
-                   "stages": ["orb_extract_x2", "stereo_knn2"]},
+                   "stages": ["orb_extract_x2", "stereo_knn2", "imu_preint", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
+                   "pose_opt_points": list(POSE_POINTS), "lba_every": LBA_EVERY if n_lba else 0, "lba_window": LBA_SHAPE,
+                   "lba_workers": n_workers, "isolated_stage_ms": iso},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches_per_step * args.steps,
@@ -281,9 +464,10 @@ def run_gpu(args, rank, world, local_rank):
                      "alg_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
                      "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
                      "orb_pipeline_GBps": ORB_BYTES_PER_IMAGE * n_img * ncalls / (sum(stage_ms.values()) / 1e3) / 1e9},
-        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 2, "kind": "port",
-                         "sample": f"{cpu_frames} stereo frames of the same stream, one thread per camera like "
-                                   f"src/Frame.cc:259-278 ({os.cpu_count()} host cores available)"},
+        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 3, "kind": "port",
+                         "sample": f"{cpu_frames} stereo frames of the same stream + {cpu_frames // LBA_EVERY} LocalBA windows; "
+                                   f"one thread per camera (src/Frame.cc:259-278), one tracking thread, one LocalMapping thread "
+                                   f"({os.cpu_count()} host cores available)"},
     }
     print(json.dumps(line))
     if dist_on:
@@ -299,6 +483,9 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
     ap.add_argument("--pool", type=int, default=4, help="distinct input batches rotated through")
     ap.add_argument("--cpu-frames", type=int, default=24)
+    ap.add_argument("--lba", type=int, default=1, help="0: leave LocalBA out of the step")
+    ap.add_argument("--lba-workers", type=int, default=4, help="host threads (one BA handle + stream each) running LocalBA windows")
+    ap.add_argument("--lba-windows", type=int, default=3, help="distinct LocalBA problems generated")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

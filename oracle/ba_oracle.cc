@@ -575,10 +575,12 @@ struct Graph {
     return 1e-5 * mx;
   }
   // (H + lambda I) x = b, with the Schur complement over the free points (block_solver.hpp:353-486)
+  double lambda_pose = -1;            // sharded form: lambda on the pose diagonal (rank 0: lambda, others: 0); < 0: = lambda
+  std::vector<double> S_out, bs_out;  // reduced camera system of the last solve_system() (before factorisation)
   bool solve_system() {
     const int P = (int)X.size() / 3, dv = d0();
     std::vector<double> S(H);
-    for (int i = 0; i < np; ++i) S[(size_t)i * np + i] += lambda;
+    for (int i = 0; i < np; ++i) S[(size_t)i * np + i] += lambda_pose >= 0 ? lambda_pose : lambda;
     std::vector<double> bs(b);
     std::vector<double> Dinv;
     if (points_free) {
@@ -620,6 +622,8 @@ struct Graph {
       }
     }
     if ((int)x.size() != np) x.assign(np, 0.0);
+    S_out = S;
+    bs_out = bs;
     bool ok = np == 0 ? true : chol_solve(S, np, bs.data(), x.data());
     if (!ok) return false;
     if (points_free) {
@@ -1118,6 +1122,26 @@ int orc_ba_debug_step(const OrcBaProblem* pb, const OrcCamera* cam, double lambd
   if (!g.solve_system()) return -2;
   memcpy(x_pose, g.x.data(), g.np * 8);
   memcpy(x_points, g.xl.data(), g.xl.size() * 8);
+  return g.np;
+}
+
+// Reduced camera system [S | bschur] and pose rhs b of a (partial) problem: lambda is added to the point blocks always
+// and to the pose diagonal only when lambda_on_poses (rank 0 of a landmark-sharded run).  Returns np.
+int orc_ba_debug_system(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, int lambda_on_poses, double* S,
+                        double* bs, double* b, double* chi2) {
+  Graph g;
+  int optit[2];
+  if (!build_lba_graph(pb, cam, g, optit)) return -1;
+  g.initialize();
+  g.compute_active_errors();
+  if (chi2) *chi2 = g.active_robust_chi2();
+  g.build_system();
+  g.lambda = lambda;
+  g.lambda_pose = lambda_on_poses ? lambda : 0.0;
+  g.solve_system();
+  memcpy(S, g.S_out.data(), g.S_out.size() * 8);
+  memcpy(bs, g.bs_out.data(), g.bs_out.size() * 8);
+  memcpy(b, g.b.data(), g.b.size() * 8);
   return g.np;
 }
 

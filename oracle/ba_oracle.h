@@ -107,6 +107,10 @@ int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* 
 int orc_ba_debug_step(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, double* x_pose, double* x_points,
                       double* chi2);
 
+/* Reduced camera system of a (partial) problem for the sharding tests: S [np*np], bs [np], b [np]. */
+int orc_ba_debug_system(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, int lambda_on_poses, double* S,
+                        double* bs, double* b, double* chi2);
+
 /* ---- building blocks exposed for the tests -------------------------------------------------------------------- */
 /* EdgeReproject<DE,DV,2> error and Jacobians (g2otypes.h:400-541): e[3], J_pose[3][6] (dp, dphi), J_point[3][3] */
 void orc_edge_reproject(const OrcCamera* cam, const OrcNavState* ns, const double Xw[3], const float obs[3], int stereo,

@@ -327,3 +327,15 @@ def imu_preintegrate_frames(seq, idx, nz):
         hi = min(np.searchsorted(imu[:, 0], tj, "left") + 1, len(imu))
         out[k] = imu_preintegrate(imu[lo:hi], ti, tj, seq["truth"][idx[k - 1]]["bg"], seq["truth"][idx[k - 1]]["ba"], nz)
     return out
+
+
+def ba_debug_system(d, cam, lam, lambda_on_poses=True, **kw):
+    L = lib()
+    L.orc_ba_debug_system.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int] + [C.c_void_p] * 4
+    pb, keep = ba_problem_struct(d, **kw)
+    cam = np.ascontiguousarray(cam)
+    n = 15 * pb.n_states
+    S = np.zeros(n * n); bs = np.zeros(n); b = np.zeros(n); chi2 = np.zeros(1)
+    m = L.orc_ba_debug_system(C.byref(pb), cam.ctypes.data, lam, int(lambda_on_poses), _p(S), _p(bs), _p(b), _p(chi2))
+    assert m >= 0, m
+    return S[:m * m].reshape(m, m), bs[:m], b[:m], chi2[0]

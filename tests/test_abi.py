@@ -47,3 +47,29 @@ def test_product_does_not_import_oracle():
                 if re.search(r"oracle_lib|liboracle|oracle/|orc_", s):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_cpp_host_shims_compile_and_link(tmp_path):
+    """vieo_slam_b200/host/vieo_shims.hpp (the reference-facing C++ class surfaces) builds against the C ABI."""
+    import subprocess
+    exe = tmp_path / "shimcheck"
+    libdir = os.path.join(ROOT, "vieo_slam_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", os.path.join(ROOT, "tools", "host_shim_check.cc"), "-o",
+                           str(exe), "-L", libdir, "-lvieo_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "sm_100a" in out.stdout
+
+
+def test_no_cpu_fallback_in_ba_entry_points():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    import vieo_slam_b200.api as api
+    from vieo_slam_b200 import synth
+    with pytest.raises(api.VieoError):
+        api.BundleAdjuster()
+    pbs = np.zeros(1, api.POSEOPT_PROBLEM_DTYPE)
+    with pytest.raises(api.VieoError):
+        api.Optimizer.PoseOptimizationBatch(pbs, synth.euroc_camera(), np.zeros((0, 3)), np.zeros((0, 3), np.float32),
+                                            np.zeros(0, np.float32), np.zeros(0, np.uint8))

@@ -1,0 +1,15 @@
+// Compile/link check of the C++ host shims against libvieo_b200.so (no GPU calls): g++ -std=c++17 ... -lvieo_b200
+#include <cstdio>
+
+#include "../vieo_slam_b200/host/vieo_shims.hpp"
+int main() {
+  using namespace VIEO_SLAM_B200;
+  ORBextractor* e = nullptr;
+  (void)e;
+  ORBmatcher m(0.6f, true);
+  IMUPreintegrator p;
+  const double s2[4] = {1e-8, 4e-6, 1e-10, 9e-6};
+  IMUPreintegrator::SetParam(s2, 1, 200.0);
+  std::printf("%s %d %g %zu\n", vieo_version(), ORBmatcher::TH_HIGH, IMUPreintegrator::Noise().sigma_g, sizeof(p));
+  return (IMUPreintegrator::Noise().freq_ref == 0 && m.mbCheckOrientation) ? 0 : 1;
+}

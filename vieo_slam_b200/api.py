@@ -315,6 +315,11 @@ class IMUPreintegrator:
                                            _p(out), self.device))
         return out
 
+    def preintegrate_batch_dev(self, samples_ptr, seg_ptr, ti_tj_ptr, bg_ba_ptr, n, out_ptr, stream=0):
+        """Device-resident form; all pointers are device addresses."""
+        _check(lib().vieo_imu_preint_batch_dev(samples_ptr, seg_ptr, ti_tj_ptr, bg_ba_ptr, C.byref(self.noise), n,
+                                               out_ptr, stream))
+
 
 # ---------------------------------------------------------------- bundle adjustment
 from .layouts import (BA_RESULT_DTYPE, CAMERA_DTYPE, NAVSTATE_DTYPE, POSEOPT_PROBLEM_DTYPE,  # noqa: E402,F401

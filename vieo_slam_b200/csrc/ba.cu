@@ -1146,9 +1146,19 @@ int vieo_ba_active_robust_chi2(vieo_ba_t* h, int recompute, double* chi2) {
       const double d = (lvl[i] & 2) ? 0.0 : ((fl[i] & VIEO_EDGE_STEREO) ? h->ds : h->dm);
       tot += rho0(d, c[i]);
     }
+    if (h->allreduce && h->world > 1) {  // partial sums of the ranks' own edges
+      h->h_ctl[7] = tot;
+      BA_CK(cudaMemcpyAsync(h->d_ctl + 7, h->h_ctl + 7, 8, cudaMemcpyHostToDevice, h->st));
+      if (h->allreduce(h->ar_ctx, h->d_ctl + 7, 1, (void*)h->st)) return VIEO_E_CUDA;
+      BA_CK(cudaMemcpyAsync(h->h_ctl + 7, h->d_ctl + 7, 8, cudaMemcpyDeviceToHost, h->st));
+      BA_CK(cudaStreamSynchronize(h->st));
+      tot = h->h_ctl[7];
+    }
     *chi2 = tot;
     return VIEO_OK;
   }
+  if (h->allreduce && h->world > 1)
+    if (h->allreduce(h->ar_ctx, h->d_ctl + 6, 1, (void*)h->st)) return VIEO_E_CUDA;
   BA_CK(cudaMemcpyAsync(h->h_ctl + 6, h->d_ctl + 6, 8, cudaMemcpyDeviceToHost, h->st));
   BA_CK(cudaStreamSynchronize(h->st));
   *chi2 = h->h_ctl[6];

@@ -36,6 +36,35 @@ int use_device(int device) {
   return VIEO_OK;
 }
 
+void* CallScratch::get(int slot, size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  if (cap[slot] >= bytes) return buf[slot];
+  if (buf[slot]) cudaFree(buf[slot]);
+  buf[slot] = nullptr;
+  cap[slot] = 0;
+  const size_t want = bytes + bytes / 2;
+  if (cudaMalloc(&buf[slot], want) != cudaSuccess) {
+    set_error("out of device memory (%zu bytes of call scratch)", want);
+    return nullptr;
+  }
+  cap[slot] = want;
+  return buf[slot];
+}
+
+CallScratch* call_scratch(int device) {
+  static thread_local CallScratch pool[16];
+  if (device < 0 || device >= 16) return nullptr;
+  CallScratch& c = pool[device];
+  if (c.device != device) {
+    if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("cannot create a stream on device %d", device);
+      return nullptr;
+    }
+    c.device = device;
+  }
+  return &c;
+}
+
 }  // namespace vieo
 
 extern "C" {

@@ -31,6 +31,18 @@ void set_error(const char* fmt, ...);
 // selects `device` and checks it is a Blackwell (sm_100) part; there is no other code path.
 int use_device(int device);
 
+// Per-thread, per-device staging for the host-buffer entry points (vieo_imu_preint_batch, vieo_pose_opt_batch): a
+// private non-blocking stream and device buffers that grow on demand and are reused by later calls, so a call costs
+// copies + kernels, not cudaMalloc/cudaFree.  Slots are independent buffers; get() returns nullptr on failure.
+struct CallScratch {
+  int device = -1;
+  cudaStream_t st = nullptr;
+  void* buf[12] = {};
+  size_t cap[12] = {};
+  void* get(int slot, size_t bytes);
+};
+CallScratch* call_scratch(int device);
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {

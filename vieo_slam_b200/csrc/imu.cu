@@ -299,32 +299,24 @@ int vieo_imu_preint_batch(const double* samples, const int32_t* seg_ptr, const d
   VIEO_ARG(n_s >= 0 && (n_s == 0 || samples), "bad sample list");
   int rc = use_device(device);
   if (rc) return rc;
-  double *d_s = nullptr, *d_t = nullptr, *d_b = nullptr;
-  int* d_p = nullptr;
-  VieoImuPreint* d_o = nullptr;
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  step(cudaMalloc(&d_s, sizeof(double) * 7 * std::max(n_s, 1)));
-  step(cudaMalloc(&d_p, sizeof(int) * (n_intervals + 1)));
-  step(cudaMalloc(&d_t, sizeof(double) * 2 * n_intervals));
-  step(cudaMalloc(&d_b, sizeof(double) * 6 * n_intervals));
-  step(cudaMalloc(&d_o, sizeof(VieoImuPreint) * n_intervals));
-  if (e == cudaSuccess) {
-    if (n_s) step(cudaMemcpy(d_s, samples, sizeof(double) * 7 * n_s, cudaMemcpyHostToDevice));
-    step(cudaMemcpy(d_p, seg_ptr, sizeof(int) * (n_intervals + 1), cudaMemcpyHostToDevice));
-    step(cudaMemcpy(d_t, ti_tj, sizeof(double) * 2 * n_intervals, cudaMemcpyHostToDevice));
-    step(cudaMemcpy(d_b, bg_ba, sizeof(double) * 6 * n_intervals, cudaMemcpyHostToDevice));
-  }
-  if (e == cudaSuccess) {
-    rc = vieo_imu_preint_batch_dev(d_s, d_p, d_t, d_b, noise, n_intervals, d_o, nullptr);
-    if (rc == VIEO_OK) step(cudaMemcpy(out, d_o, sizeof(VieoImuPreint) * n_intervals, cudaMemcpyDeviceToHost));
-  }
-  cudaFree(d_s); cudaFree(d_p); cudaFree(d_t); cudaFree(d_b); cudaFree(d_o);
-  if (e != cudaSuccess) {
-    set_error("vieo_imu_preint_batch: %s", cudaGetErrorString(e));
-    return VIEO_E_CUDA;
-  }
-  return rc;
+  CallScratch* cs = call_scratch(device);
+  if (!cs) return VIEO_E_CUDA;
+  double* d_s = (double*)cs->get(0, sizeof(double) * 7 * std::max(n_s, 1));
+  int* d_p = (int*)cs->get(1, sizeof(int) * (n_intervals + 1));
+  double* d_t = (double*)cs->get(2, sizeof(double) * 2 * n_intervals);
+  double* d_b = (double*)cs->get(3, sizeof(double) * 6 * n_intervals);
+  VieoImuPreint* d_o = (VieoImuPreint*)cs->get(4, sizeof(VieoImuPreint) * n_intervals);
+  if (!d_s || !d_p || !d_t || !d_b || !d_o) return VIEO_E_CUDA;
+  cudaStream_t st = cs->st;
+  if (n_s) VIEO_CK(cudaMemcpyAsync(d_s, samples, sizeof(double) * 7 * n_s, cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaMemcpyAsync(d_p, seg_ptr, sizeof(int) * (n_intervals + 1), cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaMemcpyAsync(d_t, ti_tj, sizeof(double) * 2 * n_intervals, cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaMemcpyAsync(d_b, bg_ba, sizeof(double) * 6 * n_intervals, cudaMemcpyHostToDevice, st));
+  rc = vieo_imu_preint_batch_dev(d_s, d_p, d_t, d_b, noise, n_intervals, d_o, st);
+  if (rc) return rc;
+  VIEO_CK(cudaMemcpyAsync(out, d_o, sizeof(VieoImuPreint) * n_intervals, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaStreamSynchronize(st));
+  return VIEO_OK;
 }
 
 }  // extern "C"

@@ -706,51 +706,42 @@ int vieo_pose_opt_batch(const VieoPoseOptProblem* pbs, int n, const VieoCamera* 
   }
   int rc = use_device(device);
   if (rc) return rc;
-  void *d_pb = nullptr, *d_cam = nullptr, *d_X = nullptr, *d_o = nullptr, *d_w = nullptr, *d_f = nullptr, *d_r = nullptr,
-       *d_out = nullptr, *d_chi = nullptr;
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  CallScratch* cs = call_scratch(device);
+  if (!cs) return VIEO_E_CUDA;
   const size_t ne = std::max(n_edges, 1);
-  step(cudaMalloc(&d_pb, sizeof(VieoPoseOptProblem) * n));
-  step(cudaMalloc(&d_cam, sizeof(VieoCamera)));
-  step(cudaMalloc(&d_X, 24 * ne));
-  step(cudaMalloc(&d_o, 12 * ne));
-  step(cudaMalloc(&d_w, 4 * ne));
-  step(cudaMalloc(&d_f, ne));
-  step(cudaMalloc(&d_r, sizeof(VieoPoseOptResult) * n));
-  step(cudaMalloc(&d_out, ne));
-  step(cudaMalloc(&d_chi, 8 * ne));
-  if (e == cudaSuccess) {
-    step(cudaMemcpy(d_pb, pbs, sizeof(VieoPoseOptProblem) * n, cudaMemcpyHostToDevice));
-    step(cudaMemcpy(d_cam, cam, sizeof(VieoCamera), cudaMemcpyHostToDevice));
-    if (n_edges) {
-      step(cudaMemcpy(d_X, Xw, 24 * ne, cudaMemcpyHostToDevice));
-      step(cudaMemcpy(d_o, obs, 12 * ne, cudaMemcpyHostToDevice));
-      step(cudaMemcpy(d_w, inv_sigma2, 4 * ne, cudaMemcpyHostToDevice));
-      step(cudaMemcpy(d_f, flags, ne, cudaMemcpyHostToDevice));
-    }
-    step(cudaMemset(d_out, 0, ne));
-    step(cudaMemset(d_chi, 0, 8 * ne));
+  void* d_pb = cs->get(0, sizeof(VieoPoseOptProblem) * n);
+  void* d_cam = cs->get(1, sizeof(VieoCamera));
+  void* d_X = cs->get(2, 24 * ne);
+  void* d_o = cs->get(3, 12 * ne);
+  void* d_w = cs->get(4, 4 * ne);
+  void* d_f = cs->get(5, ne);
+  void* d_r = cs->get(6, sizeof(VieoPoseOptResult) * n);
+  void* d_out = cs->get(7, ne);
+  void* d_chi = cs->get(8, 8 * ne);
+  if (!d_pb || !d_cam || !d_X || !d_o || !d_w || !d_f || !d_r || !d_out || !d_chi) return VIEO_E_CUDA;
+  cudaStream_t st = cs->st;
+  VIEO_CK(cudaMemcpyAsync(d_pb, pbs, sizeof(VieoPoseOptProblem) * n, cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaMemcpyAsync(d_cam, cam, sizeof(VieoCamera), cudaMemcpyHostToDevice, st));
+  if (n_edges) {
+    VIEO_CK(cudaMemcpyAsync(d_X, Xw, 24 * ne, cudaMemcpyHostToDevice, st));
+    VIEO_CK(cudaMemcpyAsync(d_o, obs, 12 * ne, cudaMemcpyHostToDevice, st));
+    VIEO_CK(cudaMemcpyAsync(d_w, inv_sigma2, 4 * ne, cudaMemcpyHostToDevice, st));
+    VIEO_CK(cudaMemcpyAsync(d_f, flags, ne, cudaMemcpyHostToDevice, st));
   }
-  if (e == cudaSuccess) {
-    rc = vieo_pose_opt_batch_dev((const VieoPoseOptProblem*)d_pb, n, (const VieoCamera*)d_cam, (const double*)d_X,
-                                 (const float*)d_o, (const float*)d_w, (const uint8_t*)d_f, (VieoPoseOptResult*)d_r,
-                                 (uint8_t*)d_out, (double*)d_chi, nullptr);
-    if (rc == VIEO_OK) {
-      step(cudaMemcpy(res, d_r, sizeof(VieoPoseOptResult) * n, cudaMemcpyDeviceToHost));
-      if (n_edges) {
-        step(cudaMemcpy(outlier, d_out, ne, cudaMemcpyDeviceToHost));
-        step(cudaMemcpy(chi2, d_chi, 8 * ne, cudaMemcpyDeviceToHost));
-      }
-    }
+  // edges not covered by any problem's range read back as 0 (the scratch buffers are reused across calls)
+  VIEO_CK(cudaMemsetAsync(d_out, 0, ne, st));
+  VIEO_CK(cudaMemsetAsync(d_chi, 0, 8 * ne, st));
+  rc = vieo_pose_opt_batch_dev((const VieoPoseOptProblem*)d_pb, n, (const VieoCamera*)d_cam, (const double*)d_X,
+                               (const float*)d_o, (const float*)d_w, (const uint8_t*)d_f, (VieoPoseOptResult*)d_r,
+                               (uint8_t*)d_out, (double*)d_chi, st);
+  if (rc) return rc;
+  VIEO_CK(cudaMemcpyAsync(res, d_r, sizeof(VieoPoseOptResult) * n, cudaMemcpyDeviceToHost, st));
+  if (n_edges) {
+    VIEO_CK(cudaMemcpyAsync(outlier, d_out, ne, cudaMemcpyDeviceToHost, st));
+    VIEO_CK(cudaMemcpyAsync(chi2, d_chi, 8 * ne, cudaMemcpyDeviceToHost, st));
   }
-  cudaFree(d_pb); cudaFree(d_cam); cudaFree(d_X); cudaFree(d_o); cudaFree(d_w); cudaFree(d_f); cudaFree(d_r);
-  cudaFree(d_out); cudaFree(d_chi);
-  if (e != cudaSuccess) {
-    set_error("vieo_pose_opt_batch: %s", cudaGetErrorString(e));
-    return VIEO_E_CUDA;
-  }
-  return rc;
+  VIEO_CK(cudaStreamSynchronize(st));
+  return VIEO_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,217 @@
+// C++ host shims with the reference's class surfaces over the C ABI of libvieo_b200.so (include/vieo_b200.h).
+// A VIEO_SLAM build replaces the bodies of src/ORBextractor.cc, ORBmatcher::DescriptorDistance, the knnMatch call of
+// Frame::ComputeStereoFishEyeMatches, IMUPreIntegratorBase::PreIntegration and the optimizer.optimize() sections of
+// src/Optimizer.cc / include/Optimizer.h with these (INTEGRATION.md shows the exact edits).  No CPU fallback: every
+// call throws std::runtime_error with vieo_last_error() when the library reports a failure.
+#pragma once
+#include <list>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vieo_b200.h"
+#include "cv_compat.h"
+
+namespace VIEO_SLAM_B200 {
+
+inline void vieo_check(int rc, const char* what) {
+  if (rc < 0) throw std::runtime_error(std::string(what) + ": " + vieo_last_error());
+}
+
+// ORBextractor (include/ORBextractor.h:27-80).  One instance per camera, driven by one thread at a time
+// (src/Frame.cc:259-278); the image size is fixed at the first call (cameras do not change size).
+class ORBextractor {
+ public:
+  ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device = 0)
+      : cfg_{0, 0, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, 1}, device_(device) {}
+  ~ORBextractor() { vieo_orb_destroy(h_); }
+  ORBextractor(const ORBextractor&) = delete;
+  ORBextractor& operator=(const ORBextractor&) = delete;
+
+  // Returns monoIndex, or -1 for an empty image (src/ORBextractor.cc:968-1058).  `mask` is ignored like upstream.
+  int operator()(cv::InputArray image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& keypoints,
+                 cv::OutputArray descriptors, const std::vector<int>* pvLappingArea = nullptr) {
+    if (image.empty()) return -1;
+    ensure(image.cols, image.rows);
+    std::vector<uint8_t*> pyr(cfg_.nlevels);
+    for (int l = 0; l < cfg_.nlevels; ++l) {
+      mvImagePyramid[l].create(level_h_[l], level_w_[l]);
+      pyr[l] = mvImagePyramid[l].data;
+    }
+    const int32_t* lap = (pvLappingArea && pvLappingArea->size() >= 2) ? pvLappingArea->data() : nullptr;
+    int32_t mono = 0;
+    kp_.resize(cap_);
+    desc_.resize((size_t)cap_ * 32);
+    const int n = vieo_orb_extract(h_, image.data, (int)image.step, lap, kp_.data(), desc_.data(), cap_, &mono, pyr.data());
+    if (n == VIEO_E_EMPTY) return -1;
+    vieo_check(n, "vieo_orb_extract");
+    keypoints.resize(n);
+    for (int i = 0; i < n; ++i) {
+      cv::KeyPoint& k = keypoints[i];
+      k.pt.x = kp_[i].x; k.pt.y = kp_[i].y; k.size = kp_[i].size; k.angle = kp_[i].angle;
+      k.response = kp_[i].response; k.octave = kp_[i].octave; k.class_id = -1;
+    }
+    descriptors.create(n, 32);
+    if (n) std::memcpy(descriptors.data, desc_.data(), (size_t)n * 32);
+    return mono;
+  }
+  int GetLevels() const { return cfg_.nlevels; }
+  float GetScaleFactor() const { return cfg_.scale_factor; }
+  const std::vector<float>& GetScaleFactors() { tables(); return mvScaleFactor; }
+  const std::vector<float>& GetInverseScaleFactors() { tables(); return mvInvScaleFactor; }
+  const std::vector<float>& GetScaleSigmaSquares() { tables(); return mvLevelSigma2; }
+  const std::vector<float>& GetInverseScaleSigmaSquares() { tables(); return mvInvLevelSigma2; }
+  std::vector<cv::Mat> mvImagePyramid;  // public in the reference; read by Frame::ComputeStereoMatches
+
+ private:
+  void ensure(int w, int h) {
+    if (h_ && (w != cfg_.width || h != cfg_.height)) {
+      vieo_orb_destroy(h_);
+      h_ = nullptr;
+    }
+    if (h_) return;
+    cfg_.width = w; cfg_.height = h;
+    vieo_check(vieo_orb_create(&cfg_, device_, &h_), "vieo_orb_create");
+    cap_ = vieo_orb_max_keypoints(h_);
+    tables();
+    mvImagePyramid.resize(cfg_.nlevels);
+  }
+  void tables() {
+    // scale tables do not depend on the image size; a 64x64 probe handle serves the getters before the first frame
+    const int n = cfg_.nlevels;
+    if ((int)mvScaleFactor.size() == n && (h_ == nullptr || !level_w_.empty())) return;
+    vieo_orb_t* t = h_;
+    VieoOrbConfig c = cfg_;
+    if (!t) {
+      c.width = c.height = 256;
+      vieo_check(vieo_orb_create(&c, device_, &t), "vieo_orb_create");
+    }
+    mvScaleFactor.resize(n); mvInvScaleFactor.resize(n); mvLevelSigma2.resize(n); mvInvLevelSigma2.resize(n);
+    std::vector<int32_t> quota(n), lw(n), lh(n);
+    vieo_check(vieo_orb_get_tables(t, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                                   mvInvLevelSigma2.data(), quota.data(), lw.data(), lh.data()), "vieo_orb_get_tables");
+    if (t == h_) { level_w_ = lw; level_h_ = lh; } else vieo_orb_destroy(t);
+  }
+  VieoOrbConfig cfg_;
+  int device_, cap_ = 0;
+  vieo_orb_t* h_ = nullptr;
+  std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+  std::vector<int32_t> level_w_, level_h_;
+  std::vector<VieoKeyPoint> kp_;
+  std::vector<uint8_t> desc_;
+};
+
+// The Hamming kernels behind ORBmatcher (include/ORBmatcher.h:18-113) and the BFMatcher call of src/Frame.cc:620-628
+struct DMatch2 {
+  int32_t idx[2], dist[2];
+};
+class ORBmatcher {
+ public:
+  static constexpr int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30;  // src/ORBmatcher.cc:20-22
+  explicit ORBmatcher(float nnratio = 0.6f, bool checkOri = true, int device = 0)
+      : mfNNratio(nnratio), mbCheckOrientation(checkOri), device_(device) {}
+  // cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, k = 2)
+  std::vector<DMatch2> knnMatch2(const cv::Mat& q, const cv::Mat& t) const {
+    std::vector<int32_t> idx((size_t)2 * q.rows), dist((size_t)2 * q.rows);
+    vieo_check(vieo_hamming_knn2(q.data, q.rows, t.data, t.rows, idx.data(), dist.data(), device_), "vieo_hamming_knn2");
+    std::vector<DMatch2> out(q.rows);
+    for (int i = 0; i < q.rows; ++i) out[i] = {{idx[2 * i], idx[2 * i + 1]}, {dist[2 * i], dist[2 * i + 1]}};
+    return out;
+  }
+  // best / second-best over candidate lists (the inner loops of SearchByProjection & co.), CSR rows
+  void SearchCandidates(const cv::Mat& q, const cv::Mat& t, const std::vector<int32_t>& row_ptr,
+                        const std::vector<int32_t>& cand, std::vector<int32_t>& best, std::vector<int32_t>& best_idx,
+                        std::vector<int32_t>& second, std::vector<int32_t>& second_idx) const {
+    const int n = (int)row_ptr.size() - 1;
+    best.resize(n); best_idx.resize(n); second.resize(n); second_idx.resize(n);
+    vieo_check(vieo_hamming_csr(q.data, t.data, t.rows, row_ptr.data(), cand.data(), n, best.data(), best_idx.data(),
+                                second.data(), second_idx.data(), device_), "vieo_hamming_csr");
+  }
+  float mfNNratio;
+  bool mbCheckOrientation;
+
+ private:
+  int device_;
+};
+
+// IMUPreIntegratorBase<IMUDataBase> (src/Odom/OdomPreIntegrator.h:108-223): public members kept, PreIntegration on
+// the device.  Sample = {t, a, w}.
+struct IMUSample {
+  double t, a[3], w[3];
+};
+class IMUPreintegrator {
+ public:
+  double mRij[9], mvij[3], mpij[3], mSigmaijPRV[81], mSigmaij[81], mJgpij[9], mJapij[9], mJgvij[9], mJavij[9], mJgRij[9];
+  double mdeltatij = 0;
+  static VieoImuNoise& Noise() {
+    static VieoImuNoise nz = {};
+    return nz;
+  }
+  // IMUDataBase::SetParam (src/Odom/OdomData.h:41-56)
+  static void SetParam(const double sigma2[4], int dt_cov_noise_fixed, double freq_ref) {
+    vieo_imu_set_param(&Noise(), sigma2, dt_cov_noise_fixed, freq_ref);
+  }
+  template <class It>
+  int PreIntegration(double ti, double tj, const double bg[3], const double ba[3], It iterBegin, It iterEnd, int device = 0) {
+    std::vector<double> smp;
+    for (It it = iterBegin; it != iterEnd; ++it) {
+      smp.push_back(it->t);
+      smp.insert(smp.end(), it->a, it->a + 3);
+      smp.insert(smp.end(), it->w, it->w + 3);
+    }
+    const int32_t seg[2] = {0, (int32_t)(smp.size() / 7)};
+    const double tt[2] = {ti, tj}, bb[6] = {bg[0], bg[1], bg[2], ba[0], ba[1], ba[2]};
+    VieoImuPreint o;
+    vieo_check(vieo_imu_preint_batch(smp.data(), seg, tt, bb, &Noise(), 1, &o, device), "vieo_imu_preint_batch");
+    std::memcpy(mRij, o.Rij, 72); std::memcpy(mvij, o.vij, 24); std::memcpy(mpij, o.pij, 24);
+    std::memcpy(mSigmaijPRV, o.SigmaPRV, 648); std::memcpy(mSigmaij, o.SigmaPVR, 648);
+    std::memcpy(mJgpij, o.Jgp, 72); std::memcpy(mJapij, o.Jap, 72); std::memcpy(mJgvij, o.Jgv, 72);
+    std::memcpy(mJavij, o.Jav, 72); std::memcpy(mJgRij, o.JgR, 72);
+    mdeltatij = o.dt;
+    return o.status;
+  }
+};
+
+// Optimizer (include/Optimizer.h:46-121): the flattened forms the reference's static methods call after collecting
+// the graph (INTEGRATION.md lists the Frame / KeyFrame / MapPoint fields each array comes from).
+struct Optimizer {
+  // PoseOptimization(Frame*, Frame*) / PoseOptimization<KF>(Frame*, KF*, gw, bComputeMarg, bNoMPs): one frame
+  static int PoseOptimization(VieoPoseOptProblem& pb, const VieoCamera& cam, const std::vector<double>& Xw,
+                              const std::vector<float>& obs, const std::vector<float>& inv_sigma2,
+                              const std::vector<uint8_t>& flags, VieoPoseOptResult& res, std::vector<uint8_t>& mvbOutlier,
+                              int device = 0) {
+    const int E = (int)flags.size();
+    pb.edge_begin = 0;
+    pb.edge_end = E;
+    mvbOutlier.assign(E, 0);
+    std::vector<double> chi2(E);
+    vieo_check(vieo_pose_opt_batch(&pb, 1, &cam, Xw.data(), obs.data(), inv_sigma2.data(), flags.data(), E, &res,
+                                   mvbOutlier.data(), chi2.data(), device), "vieo_pose_opt_batch");
+    return res.n_inliers;
+  }
+};
+
+// LocalBundleAdjustmentNavStatePRV engine: long-lived (LocalMapping thread), reused across windows
+class LocalBA {
+ public:
+  explicit LocalBA(int max_states = 256, int max_points = 16384, int max_edges = 131072, int max_imu = 64, int device = 0) {
+    vieo_check(vieo_ba_create(max_states, max_points, max_edges, max_imu, device, &h_), "vieo_ba_create");
+  }
+  ~LocalBA() { vieo_ba_destroy(h_); }
+  LocalBA(const LocalBA&) = delete;
+  LocalBA& operator=(const LocalBA&) = delete;
+  // pbStopFlag is the reference's bool* (mbAbortBA); outputs sized by the caller
+  int Run(const VieoBaProblem& pb, const VieoCamera& cam, const bool* pbStopFlag, VieoNavState* states_out,
+          double* points_out, double* edge_chi2, uint8_t* erase, VieoBaResult& res) {
+    static_assert(sizeof(bool) == 1, "bool* is polled as a byte");
+    int rc = vieo_local_ba_prv(h_, &pb, &cam, reinterpret_cast<const volatile uint8_t*>(pbStopFlag), states_out, points_out,
+                               edge_chi2, erase, &res);
+    vieo_check(rc, "vieo_local_ba_prv");
+    return rc;
+  }
+
+ private:
+  vieo_ba_t* h_ = nullptr;
+};
+
+}  // namespace VIEO_SLAM_B200
