@@ -39,8 +39,9 @@ struct BaDense {  // one inertial (EdgeNavStatePRV) or bias random-walk (EdgeNav
 };
 struct BaDenseWork {
   double J[9 * 24];  // IMU: [Ji(PR) | Jj(PR) | Ji(V) | Jj(V) | Jb], 9 x 24 row-major
-  double Om[81], oe[9], err[9];
-  double chi2, r1;
+  double AtO[216];   // J^T (rho' Omega), 24 x 9
+  double oe[9], err[9];
+  double chi2, r1, rho0;
 };
 
 __global__ void k_ba_campose(CamK cam, const VieoNavState* __restrict__ st, int K, CamPose* __restrict__ cp) {
@@ -122,12 +123,12 @@ __global__ void __launch_bounds__(128) k_ba_dense_errors(const BaDense* __restri
     W.chi2 = c;
     double r0;
     huber_rho(d.delta, c, r0, W.r1);
-    W.oe[8] = r0;  // parked until the sum below (oe is rewritten by k_ba_dense_build)
+    W.rho0 = r0;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0;
-    for (int k = 0; k < n_den; ++k) tot += wk[k].oe[8];
+    for (int k = 0; k < n_den; ++k) tot += wk[k].rho0;
     for (int k = 0; k < n_partial; ++k) tot += partial[k];
     *out = tot;
     if (scale_out) {
@@ -138,181 +139,131 @@ __global__ void __launch_bounds__(128) k_ba_dense_errors(const BaDense* __restri
   }
 }
 
-// One warp per map point: linearise its edges, reduce Hll / bl by shuffles, store W (Hpl) and A (Hpp part) per edge.
-__global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(
-    CamK cam, const CamPose* __restrict__ cp, const double* __restrict__ X, const int* __restrict__ pt_ptr, int P,
-    const int* __restrict__ es, const float* __restrict__ obs, const float* __restrict__ w,
-    const uint8_t* __restrict__ flags, const uint8_t* __restrict__ lvl, const uint8_t* __restrict__ sfix,
-    const double* __restrict__ chi2, double dm, double ds, double* __restrict__ Wb, double* __restrict__ Ab,
-    double* __restrict__ Hll, double* __restrict__ bl, uint8_t* __restrict__ pt_active) {
-  const int p = blockIdx.x * kBaWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (p >= P) return;
-  const int i0 = pt_ptr[p], i1 = pt_ptr[p + 1];
-  const Vec3 Xp = ld3(X + 3 * (size_t)p);
-  double acc[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0;
-  bool any = false;
-  for (int i = i0 + lane; i < i1; i += 32) {
-    double* Wi = Wb + 18 * (size_t)i;
-    double* Ai = Ab + 27 * (size_t)i;
-    if (lvl[i] & 1) {
-      for (int k = 0; k < 18; ++k) Wi[k] = 0;
-      for (int k = 0; k < 27; ++k) Ai[k] = 0;
-      continue;
-    }
-    any = true;
-    const bool stereo = flags[i] & VIEO_EDGE_STEREO;
-    const int DE = stereo ? 3 : 2;
-    const int s = es[i];
-    double e[3];
-    reproj_error(cam, cp[s], Xp, obs + 3 * (size_t)i, stereo, e);
-    Mat3 Jp, Jr, JX;
-    reproj_jac(cam, cp[s], Xp, stereo, Jp, Jr, JX);
-    double r0, r1;
-    huber_rho(edge_huber_delta(flags[i], lvl[i], dm, ds), chi2[i], r0, r1);
-    const double wi = (double)w[i], ww = r1 * wi;
-    double oe[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) oe[k] = -(wi * e[k]) * r1;
-    double J[3][6];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        J[k][c] = Jp.m[3 * k + c];
-        J[k][3 + c] = Jr.m[3 * k + c];
-      }
-    // point block: Hll (upper 6) and bl
-    int q = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      double sb = 0;
-      for (int k = 0; k < DE; ++k) sb += JX.m[3 * k + a] * oe[k];
-      acc[6 + a] += sb;
-#pragma unroll
-      for (int c = a; c < 3; ++c) {
-        double h = 0;
-        for (int k = 0; k < DE; ++k) h += (JX.m[3 * k + a] * ww) * JX.m[3 * k + c];
-        acc[q++] += h;
-      }
-    }
-    if (!sfix[s]) {
-      q = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        double sb = 0;
-        for (int k = 0; k < DE; ++k) sb += J[k][a] * oe[k];
-        Ai[21 + a] = sb;
-#pragma unroll
-        for (int c = a; c < 6; ++c) {
-          double h = 0;
-          for (int k = 0; k < DE; ++k) h += (J[k][a] * ww) * J[k][c];
-          Ai[q++] = h;
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          double h = 0;
-          for (int k = 0; k < DE; ++k) h += (J[k][a] * ww) * JX.m[3 * k + c];
-          Wi[3 * a + c] = h;
-        }
-      }
-    } else {
-      for (int k = 0; k < 18; ++k) Wi[k] = 0;
-      for (int k = 0; k < 27; ++k) Ai[k] = 0;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 9; ++k)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-  any = __any_sync(0xffffffffu, any);
-  if (lane == 0) {
-    double* H = Hll + 9 * (size_t)p;
-    H[0] = acc[0]; H[1] = acc[1]; H[2] = acc[2];
-    H[3] = acc[1]; H[4] = acc[3]; H[5] = acc[4];
-    H[6] = acc[2]; H[7] = acc[4]; H[8] = acc[5];
-    bl[3 * (size_t)p] = acc[6]; bl[3 * (size_t)p + 1] = acc[7]; bl[3 * (size_t)p + 2] = acc[8];
-    pt_active[p] = any;
-  }
+// EdgeNavStatePRV Jacobians written straight into the edge's 9 x 24 strip [Ji(PR) | Jj(PR) | Ji(V) | Jj(V) | Jb]
+// (same arithmetic as navstate_jac with prv = true)
+template <class Pre>
+__device__ void navstate_jac24(const NavS& si, const NavS& sj, const Pre& m, const Vec3& gw, const double e[9], double* J) {
+  const Mat3 RiT = m3_t(q_matrix(si.q)), Rj = q_matrix(sj.q);
+  const double dt = m.dt;
+  for (int i = 0; i < 216; ++i) J[i] = 0;
+  const Mat3 JgR = ld_m3(m.JgR);
+  // column bases: Ji P 0, R 3, V 12; Jj P 6, R 9, V 15; Jb 18
+  Vec3 a = {sj.p.x - si.p.x - si.v.x * dt - gw.x * (dt * dt / 2), sj.p.y - si.p.y - si.v.y * dt - gw.y * (dt * dt / 2),
+            sj.p.z - si.p.z - si.v.z * dt - gw.z * (dt * dt / 2)};
+  Vec3 b = m3_mulv(RiT, a);
+  setb(J, 24, 0, 3, m3_hat(b));
+  setb(J, 24, 0, 0, m3_scale(m3_identity(), -1.0));
+  setb(J, 24, 0, 12, m3_scale(m3_scale(RiT, -1.0), dt));
+  setb(J, 24, 0, 18, m3_scale(ld_m3(m.Jgp), -1.0));
+  setb(J, 24, 0, 21, m3_scale(ld_m3(m.Jap), -1.0));
+  setb(J, 24, 0, 6, m3_mul(RiT, Rj));
+  a = {sj.v.x - si.v.x - gw.x * dt, sj.v.y - si.v.y - gw.y * dt, sj.v.z - si.v.z - gw.z * dt};
+  b = m3_mulv(RiT, a);
+  setb(J, 24, 6, 3, m3_hat(b));
+  setb(J, 24, 6, 12, m3_scale(RiT, -1.0));
+  setb(J, 24, 6, 18, m3_scale(ld_m3(m.Jgv), -1.0));
+  setb(J, 24, 6, 21, m3_scale(ld_m3(m.Jav), -1.0));
+  setb(J, 24, 6, 15, RiT);
+  const Vec3 eR = ld3(e + 3);
+  const Mat3 Jrinv = so3_JrInv(eR);
+  const Mat3 RjTRi = q_matrix(q_normalized(q_mul(q_conj(sj.q), si.q)));
+  setb(J, 24, 3, 3, m3_scale(m3_mul(Jrinv, RjTRi), -1.0));
+  const Vec3 w = m3_mulv(JgR, si.dbg);
+  const Mat3 Tm = m3_mul(m3_mul(m3_mul(m3_scale(Jrinv, -1.0), so3_Exp({-eR.x, -eR.y, -eR.z})), so3_Jr(w)), JgR);
+  setb(J, 24, 3, 18, Tm);
+  setb(J, 24, 3, 9, Jrinv);
 }
 
-// One block (128 threads) per free keyframe: fixed-order sum of its edges' A blocks -> 6x6 diagonal block + rhs
-__global__ void __launch_bounds__(128) k_ba_pose_reduce(const int* __restrict__ free_state, const int* __restrict__ off0,
-                                                        const int* __restrict__ ps_ptr, const int* __restrict__ ps_edges,
-                                                        const double* __restrict__ Ab, int np, double* __restrict__ H,
-                                                        double* __restrict__ b) {
-  __shared__ double s_w[4][27];
-  const int f = blockIdx.x, k = free_state[f], o = off0[k];
-  double acc[27];
-#pragma unroll
-  for (int q = 0; q < 27; ++q) acc[q] = 0;
-  for (int t = ps_ptr[f] + threadIdx.x; t < ps_ptr[f + 1]; t += 128) {
-    const double* Ai = Ab + 27 * (size_t)ps_edges[t];
-#pragma unroll
-    for (int q = 0; q < 27; ++q) acc[q] += Ai[q];
+// Inertial and bias edges (one block).  Phase 0: zero H / b.  Phase 1 (one thread per edge): residual and, for IMU
+// edges, the Jacobian strip.  Phase 2 (all threads): Omega e, then chi2 / Huber weight per edge, then J^T (rho' Omega)
+// for every IMU edge.  Phase 3: the block walks the edges in order and adds (J^T rho' Omega) J to the mapped positions
+// of H / b (consecutive edges share keyframes, so the order is fixed and serial; every sum runs in the oracle's order).
+__device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const VieoNavState* __restrict__ st,
+                               const VieoImuPreint* __restrict__ pre, Vec3 gw, BaDenseWork* __restrict__ wk,
+                               const int* __restrict__ off0, const int* __restrict__ off1, const int* __restrict__ off2,
+                               int np, double* __restrict__ H, double* __restrict__ b, double* __restrict__ chi_dense) {
+  const int T = blockDim.x;
+  // the pre-integrations' fields the edges read (61 doubles each) staged in shared memory: the residual / Jacobian
+  // code is one long dependent chain per thread, global-memory latency on every field would dominate it
+  constexpr int kStage = 32;
+  __shared__ VieoImuPreintLite s_pre[kStage];
+  for (int t = threadIdx.x; t < n_den * 61; t += T) {
+    const int m = t / 61, e = t % 61;
+    if (m >= kStage || den[m].type != 0) continue;
+    const VieoImuPreint& P = pre[den[m].pre];
+    VieoImuPreintLite& Q = s_pre[m];
+    if (e < 9) Q.Rij[e] = P.Rij[e];
+    else if (e < 12) Q.vij[e - 9] = P.vij[e - 9];
+    else if (e < 15) Q.pij[e - 12] = P.pij[e - 12];
+    else if (e < 24) Q.Jgp[e - 15] = P.Jgp[e - 15];
+    else if (e < 33) Q.Jap[e - 24] = P.Jap[e - 24];
+    else if (e < 42) Q.Jgv[e - 33] = P.Jgv[e - 33];
+    else if (e < 51) Q.Jav[e - 42] = P.Jav[e - 42];
+    else if (e < 60) Q.JgR[e - 51] = P.JgR[e - 51];
+    else Q.dt = P.dt;
   }
-#pragma unroll
-  for (int q = 0; q < 27; ++q)
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], s);
-  if ((threadIdx.x & 31) == 0)
-#pragma unroll
-    for (int q = 0; q < 27; ++q) s_w[threadIdx.x >> 5][q] = acc[q];
   __syncthreads();
-  if (threadIdx.x < 27) {
-    const double v = ((s_w[0][threadIdx.x] + s_w[1][threadIdx.x]) + s_w[2][threadIdx.x]) + s_w[3][threadIdx.x];
-    s_w[0][threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int q = 0;
-    for (int a = 0; a < 6; ++a) {
-      b[o + a] = s_w[0][21 + a];
-      for (int c = a; c < 6; ++c) {
-        const double h = s_w[0][q++];
-        H[(size_t)(o + a) * np + o + c] = h;
-        H[(size_t)(o + c) * np + o + a] = h;
-      }
-    }
-  }
-}
-
-// Inertial and bias edges into Hpp / b.  Phase 1: one thread per edge builds its Jacobian strip and weighted
-// information; phase 2: the block walks the edges in order and adds J^T (rho' Omega) J to the mapped positions.
-__global__ void __launch_bounds__(256) k_ba_dense_build(const BaDense* __restrict__ den, int n_den,
-                                                        const VieoNavState* __restrict__ st,
-                                                        const VieoImuPreint* __restrict__ pre, Vec3 gw,
-                                                        BaDenseWork* __restrict__ wk, const int* __restrict__ off0,
-                                                        const int* __restrict__ off1, const int* __restrict__ off2, int np,
-                                                        double* __restrict__ H, double* __restrict__ b) {
-  for (int m = threadIdx.x; m < n_den; m += 256) {
+  for (int m = threadIdx.x; m < n_den; m += T) {
     const BaDense& d = den[m];
-    if (d.type != 0) continue;
     BaDenseWork& W = wk[m];
     const NavS a = ns_load(st[d.si]), c = ns_load(st[d.sj]);
-    double Ji[81], Jj[81], Jb[54];
-    navstate_jac(a, c, pre[d.pre], gw, true, W.err, Ji, Jj, Jb);
-    for (int i = 0; i < 9; ++i) {
-      for (int k = 0; k < 6; ++k) {
-        W.J[i * 24 + k] = Ji[i * 9 + k];
-        W.J[i * 24 + 6 + k] = Jj[i * 9 + k];
-        W.J[i * 24 + 18 + k] = Jb[i * 6 + k];
+    if (d.type == 0) {
+      if (m < kStage) {
+        navstate_error(a, c, s_pre[m], gw, true, W.err);
+        navstate_jac24(a, c, s_pre[m], gw, W.err, W.J);
+      } else {
+        navstate_error(a, c, pre[d.pre], gw, true, W.err);
+        navstate_jac24(a, c, pre[d.pre], gw, W.err, W.J);
       }
-      for (int k = 0; k < 3; ++k) {
-        W.J[i * 24 + 12 + k] = Ji[i * 9 + 6 + k];
-        W.J[i * 24 + 15 + k] = Jj[i * 9 + 6 + k];
-      }
-    }
-    for (int i = 0; i < 81; ++i) W.Om[i] = W.r1 * d.info[i];
-    for (int i = 0; i < 9; ++i) {
-      double s = 0;
-      for (int j = 0; j < 9; ++j) s += d.info[i * 9 + j] * W.err[j];
-      W.oe[i] = -s * W.r1;
+    } else {
+      W.err[0] = (c.bg.x + c.dbg.x) - (a.bg.x + a.dbg.x);
+      W.err[1] = (c.bg.y + c.dbg.y) - (a.bg.y + a.dbg.y);
+      W.err[2] = (c.bg.z + c.dbg.z) - (a.bg.z + a.dbg.z);
+      W.err[3] = (c.ba.x + c.dba.x) - (a.ba.x + a.dba.x);
+      W.err[4] = (c.ba.y + c.dba.y) - (a.ba.y + a.dba.y);
+      W.err[5] = (c.ba.z + c.dba.z) - (a.ba.z + a.dba.z);
     }
   }
+  for (int t = threadIdx.x; t < np * np; t += T) H[t] = 0;
+  for (int t = threadIdx.x; t < np; t += T) b[t] = 0;
   __syncthreads();
-  __threadfence_block();
+  // Omega e (row i of edge m)
+  for (int t = threadIdx.x; t < n_den * 9; t += T) {
+    const int m = t / 9, i = t % 9;
+    const BaDense& d = den[m];
+    double q = 0;
+    if (d.type == 0)
+      for (int j = 0; j < 9; ++j) q += d.info[i * 9 + j] * wk[m].err[j];
+    else if (i < 6)
+      q = d.info[i] * wk[m].err[i];
+    wk[m].oe[i] = q;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < n_den; m += T) {
+    BaDenseWork& W = wk[m];
+    const int D = den[m].type == 0 ? 9 : 6;
+    double chi = 0;
+    for (int i = 0; i < D; ++i) chi += W.err[i] * W.oe[i];
+    W.chi2 = chi;
+    huber_rho(den[m].delta, chi, W.rho0, W.r1);
+  }
+  __syncthreads();
+  // AtO[a][j] = sum_i J[i][a] (r1 Omega[i][j]) for IMU edges; oe <- -(Omega e) r1
+  for (int t = threadIdx.x; t < n_den * 216; t += T) {
+    const int m = t / 216, e = t % 216, a = e / 9, j = e % 9;
+    const BaDense& d = den[m];
+    if (d.type != 0) continue;
+    const BaDenseWork& W = wk[m];
+    double q = 0;
+    for (int i = 0; i < 9; ++i) q += W.J[i * 24 + a] * (W.r1 * d.info[i * 9 + j]);
+    wk[m].AtO[e] = q;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_den * 9; t += T) {
+    const int m = t / 9, i = t % 9;
+    wk[m].oe[i] = -wk[m].oe[i] * wk[m].r1;
+  }
+  __syncthreads();
   for (int m = 0; m < n_den; ++m) {
     const BaDense& d = den[m];
     const BaDenseWork& W = wk[m];
@@ -323,31 +274,27 @@ __global__ void __launch_bounds__(256) k_ba_dense_build(const BaDense* __restric
         int blk = lc < 6 ? 0 : lc < 12 ? 1 : lc < 15 ? 2 : lc < 18 ? 3 : 4;
         return offs[blk] < 0 ? -1 : offs[blk] + (lc - base[blk]);
       };
-      for (int t = threadIdx.x; t < 24 * 25; t += 256) {
+      for (int t = threadIdx.x; t < 24 * 25; t += T) {
         const int r = t / 25, c = t % 25;
         const int gr = gcol(r);
         if (gr < 0) continue;
         if (c == 24) {
-          double s = 0;
-          for (int i = 0; i < 9; ++i) s += W.J[i * 24 + r] * W.oe[i];
-          b[gr] += s;
+          double sum = 0;
+          for (int i = 0; i < 9; ++i) sum += W.J[i * 24 + r] * W.oe[i];
+          b[gr] += sum;
           continue;
         }
         const int gc = gcol(c);
         if (gc < 0) continue;
-        double s = 0;
-        for (int j = 0; j < 9; ++j) {
-          double a = 0;
-          for (int i = 0; i < 9; ++i) a += W.J[i * 24 + r] * W.Om[i * 9 + j];
-          s += a * W.J[j * 24 + c];
-        }
-        H[(size_t)gr * np + gc] += s;
+        double sum = 0;
+        for (int j = 0; j < 9; ++j) sum += W.AtO[r * 9 + j] * W.J[j * 24 + c];
+        H[(size_t)gr * np + gc] += sum;
       }
     } else {
       const int oi = off2[d.si], oj = off2[d.sj];
       if (threadIdx.x < 6) {
         const int k = threadIdx.x;
-        const double om = W.r1 * d.info[k], oe = -(d.info[k] * W.err[k]) * W.r1;
+        const double om = W.r1 * d.info[k], oe = W.oe[k];
         if (oj >= 0) {
           H[(size_t)(oj + k) * np + oj + k] += om;
           b[oj + k] += oe;
@@ -363,6 +310,230 @@ __global__ void __launch_bounds__(256) k_ba_dense_build(const BaDense* __restric
       }
     }
     __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int m = 0; m < n_den; ++m) tot += wk[m].rho0;
+    *chi_dense = tot;
+  }
+}
+
+// computeActiveErrors + linearizeOplus + constructQuadraticForm of the visual edges, one warp per map point: each lane
+// evaluates one reprojection edge (residual, chi2, Huber weight, Jacobians), the 3x3 Hll / bl are reduced with warp
+// shuffles, W (Hpl) and A (the edge's Hpp / b part) are stored per edge.  The extra last block does the inertial edges.
+struct BaLinArgs {
+  CamK cam;
+  const CamPose* cp;
+  const double* X;
+  const int* pt_ptr;
+  int P;
+  const int* es;
+  const float* obs;
+  const float* w;
+  const uint8_t* flags;
+  const uint8_t* lvl;
+  const uint8_t* sfix;
+  double dm, ds;
+  double *chi2, *Wb, *Ab, *Hll, *bl, *partial;
+  uint8_t* pt_active;
+  // dense block
+  const BaDense* den;
+  int n_den;
+  const VieoNavState* st;
+  const VieoImuPreint* pre;
+  Vec3 gw;
+  BaDenseWork* wk;
+  const int *off0, *off1, *off2;
+  int np;
+  double *H, *b, *chi_dense;
+};
+__global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaLinArgs a) {
+  __shared__ double s_chi[kBaWarps];
+  if (blockIdx.x == gridDim.x - 1) {
+    ba_dense_block(a.den, a.n_den, a.st, a.pre, a.gw, a.wk, a.off0, a.off1, a.off2, a.np, a.H, a.b, a.chi_dense);
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * kBaWarps + warp;
+  double acc[9], rsum = 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0;
+  bool any = false;
+  if (p < a.P) {
+    const int i0 = a.pt_ptr[p], i1 = a.pt_ptr[p + 1];
+    const Vec3 Xp = ld3(a.X + 3 * (size_t)p);
+    for (int i = i0 + lane; i < i1; i += 32) {
+      double* Wi = a.Wb + 18 * (size_t)i;
+      double* Ai = a.Ab + 27 * (size_t)i;
+      if (a.lvl[i] & 1) {
+        for (int k = 0; k < 18; ++k) Wi[k] = 0;
+        for (int k = 0; k < 27; ++k) Ai[k] = 0;
+        continue;
+      }
+      any = true;
+      const bool stereo = a.flags[i] & VIEO_EDGE_STEREO;
+      const int DE = stereo ? 3 : 2;
+      const int s = a.es[i];
+      double e[3];
+      reproj_error(a.cam, a.cp[s], Xp, a.obs + 3 * (size_t)i, stereo, e);
+      const double wi = (double)a.w[i];
+      double c = 0;
+      for (int k = 0; k < DE; ++k) c += e[k] * (wi * e[k]);
+      a.chi2[i] = c;
+      Mat3 Jp, Jr, JX;
+      reproj_jac(a.cam, a.cp[s], Xp, stereo, Jp, Jr, JX);
+      double r0, r1;
+      huber_rho(edge_huber_delta(a.flags[i], a.lvl[i], a.dm, a.ds), c, r0, r1);
+      rsum += r0;
+      const double ww = r1 * wi;
+      double oe[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) oe[k] = -(wi * e[k]) * r1;
+      double J[3][6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          J[k][cc] = Jp.m[3 * k + cc];
+          J[k][3 + cc] = Jr.m[3 * k + cc];
+        }
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        double sb = 0;
+        for (int k = 0; k < DE; ++k) sb += JX.m[3 * k + r] * oe[k];
+        acc[6 + r] += sb;
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc) {
+          double hh = 0;
+          for (int k = 0; k < DE; ++k) hh += (JX.m[3 * k + r] * ww) * JX.m[3 * k + cc];
+          acc[q++] += hh;
+        }
+      }
+      if (!a.sfix[s]) {
+        q = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double sb = 0;
+          for (int k = 0; k < DE; ++k) sb += J[k][r] * oe[k];
+          Ai[21 + r] = sb;
+#pragma unroll
+          for (int cc = r; cc < 6; ++cc) {
+            double hh = 0;
+            for (int k = 0; k < DE; ++k) hh += (J[k][r] * ww) * J[k][cc];
+            Ai[q++] = hh;
+          }
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            double hh = 0;
+            for (int k = 0; k < DE; ++k) hh += (J[k][r] * ww) * JX.m[3 * k + cc];
+            Wi[3 * r + cc] = hh;
+          }
+        }
+      } else {
+        for (int k = 0; k < 18; ++k) Wi[k] = 0;
+        for (int k = 0; k < 27; ++k) Ai[k] = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) {
+    s_chi[warp] = rsum;
+    if (p < a.P) {
+      double* H = a.Hll + 9 * (size_t)p;
+      H[0] = acc[0]; H[1] = acc[1]; H[2] = acc[2];
+      H[3] = acc[1]; H[4] = acc[3]; H[5] = acc[4];
+      H[6] = acc[2]; H[7] = acc[4]; H[8] = acc[5];
+      a.bl[3 * (size_t)p] = acc[6]; a.bl[3 * (size_t)p + 1] = acc[7]; a.bl[3 * (size_t)p + 2] = acc[8];
+      a.pt_active[p] = any;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int k = 0; k < kBaWarps; ++k) t += s_chi[k];
+    a.partial[blockIdx.x] = t;
+  }
+}
+
+// One block (256 threads) per free keyframe: fixed-order sum of its edges' A blocks, added to the 6x6 diagonal block
+// and rhs (the inertial part is already there).  Block 0 also totals the robust chi2 (dense edges first, then the
+// visual partial sums in block order) and the landmark part of the gain-ratio denominator of the last solve.
+__global__ void __launch_bounds__(256) k_ba_pose_reduce(const int* __restrict__ free_state, const int* __restrict__ off0,
+                                                        const int* __restrict__ ps_ptr, const int* __restrict__ ps_edges,
+                                                        const double* __restrict__ Ab, int np, double* __restrict__ H,
+                                                        double* __restrict__ b, const double* __restrict__ partial,
+                                                        int n_partial, const double* __restrict__ chi_dense,
+                                                        const double* __restrict__ scale_part, int n_scale,
+                                                        double* __restrict__ out2) {
+  __shared__ double s_w[8][27];
+  __shared__ double s_s[256];
+  const int f = blockIdx.x, k = free_state[f], o = off0[k];
+  double acc[27];
+#pragma unroll
+  for (int q = 0; q < 27; ++q) acc[q] = 0;
+  for (int t = ps_ptr[f] + threadIdx.x; t < ps_ptr[f + 1]; t += 256) {
+    const double* Ai = Ab + 27 * (size_t)ps_edges[t];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc[q] += Ai[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 27; ++q)
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], s);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int q = 0; q < 27; ++q) s_w[threadIdx.x >> 5][q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double v = 0;
+    for (int w = 0; w < 8; ++w) v += s_w[w][threadIdx.x];
+    s_w[0][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int q = 0;
+    for (int a = 0; a < 6; ++a) {
+      b[o + a] += s_w[0][21 + a];
+      for (int c = a; c < 6; ++c) {
+        const double h = s_w[0][q++];
+        H[(size_t)(o + a) * np + o + c] += h;
+        if (c != a) H[(size_t)(o + c) * np + o + a] += h;
+      }
+    }
+  }
+  if (f != 0) return;
+  double sc = 0;
+  for (int t = threadIdx.x; t < n_scale; t += 256) sc += scale_part[t];
+  s_s[threadIdx.x] = sc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) s_s[threadIdx.x] += s_s[threadIdx.x + st];
+    __syncthreads();
+  }
+  const double scale_total = s_s[0];
+  __syncthreads();
+  // robust chi2: dense edges first, then the per-block partial sums in block order (chunks of 256 staged in smem)
+  double tot = *chi_dense;
+  for (int base = 0; base < n_partial; base += 256) {
+    const int t = base + threadIdx.x;
+    s_s[threadIdx.x] = t < n_partial ? partial[t] : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int m = min(256, n_partial - base);
+      for (int q = 0; q < m; ++q) tot += s_s[q];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out2[0] = tot;
+    out2[1] = scale_total;
   }
 }
 
@@ -384,87 +555,87 @@ __global__ void k_ba_maxdiag(const double* __restrict__ H, int np, const double*
   if (threadIdx.x == 0) *out = s[0];
 }
 
-// Dinv = (Hll + lambda I)^-1 (cofactor inverse like Eigen's fixed 3x3, block_solver.hpp:389), db = Dinv bl
-__global__ void k_ba_point_inv(const double* __restrict__ Hll, const double* __restrict__ bl,
-                               const uint8_t* __restrict__ pt_active, int P, double lambda, double* __restrict__ Dinv,
-                               double* __restrict__ db) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  double* I = Dinv + 9 * (size_t)p;
+// Start of a solve: Dinv = (Hll + lambda I)^-1 (cofactor inverse like Eigen's fixed 3x3, block_solver.hpp:389),
+// db = Dinv bl; S = H + lambda_pose I, bschur = b, sys.b = b
+__global__ void k_ba_prep_solve(const double* __restrict__ Hll, const double* __restrict__ bl,
+                                const uint8_t* __restrict__ pt_active, int P, double lambda, double* __restrict__ Dinv,
+                                double* __restrict__ db, const double* __restrict__ H, const double* __restrict__ b, int np,
+                                double lambda_pose, double* __restrict__ S, double* __restrict__ bs,
+                                double* __restrict__ bsys) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t < (size_t)np * np) {
+    const int r = t / np, c = t % np;
+    S[t] = H[t] + (r == c ? lambda_pose : 0.0);
+  }
+  if (t < (size_t)np) {
+    bs[t] = b[t];
+    bsys[t] = b[t];
+  }
+  if (t >= (size_t)P) return;
+  const size_t p = t;
+  double* I = Dinv + 9 * p;
   if (!pt_active[p]) {
     for (int k = 0; k < 9; ++k) I[k] = 0;
-    db[3 * (size_t)p] = db[3 * (size_t)p + 1] = db[3 * (size_t)p + 2] = 0;
+    db[3 * p] = db[3 * p + 1] = db[3 * p + 2] = 0;
     return;
   }
   double D[9];
-  for (int k = 0; k < 9; ++k) D[k] = Hll[9 * (size_t)p + k];
+  for (int k = 0; k < 9; ++k) D[k] = Hll[9 * p + k];
   D[0] += lambda; D[4] += lambda; D[8] += lambda;
   const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
   const double det = D[0] * c00 + D[1] * c01 + D[2] * c02, id = 1.0 / det;
   I[0] = c00 * id; I[1] = (D[2] * D[7] - D[1] * D[8]) * id; I[2] = (D[1] * D[5] - D[2] * D[4]) * id;
   I[3] = c01 * id; I[4] = (D[0] * D[8] - D[2] * D[6]) * id; I[5] = (D[2] * D[3] - D[0] * D[5]) * id;
   I[6] = c02 * id; I[7] = (D[1] * D[6] - D[0] * D[7]) * id; I[8] = (D[0] * D[4] - D[1] * D[3]) * id;
-  const double* bb = bl + 3 * (size_t)p;
-  for (int a = 0; a < 3; ++a) db[3 * (size_t)p + a] = I[3 * a] * bb[0] + I[3 * a + 1] * bb[1] + I[3 * a + 2] * bb[2];
+  const double* bb = bl + 3 * p;
+  for (int a = 0; a < 3; ++a) db[3 * p + a] = I[3 * a] * bb[0] + I[3 * a + 1] * bb[1] + I[3 * a + 2] * bb[2];
 }
 
-// S = H + lambda I, bschur = b
-__global__ void k_ba_copy_sys(const double* __restrict__ H, const double* __restrict__ b, int np, double lambda,
-                              double* __restrict__ S, double* __restrict__ bs) {
-  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (t < (size_t)np * np) {
-    const int r = t / np, c = t % np;
-    S[t] = H[t] + (r == c ? lambda : 0.0);
-  }
-  if (t < (size_t)np) bs[t] = b[t];
-}
-
-// Schur complement, one block per free keyframe (6 rows of S): for every edge a of the keyframe (fixed chunks per
-// warp, in list order) and every edge c of a's point: acc[row][6*prcol(c) + col] += (W_a Dinv) W_c^T; the warps'
-// accumulators are summed in warp order and subtracted from S.  bschur -= W_a db.
+// Schur complement.  Block (f, s): chunk s of free keyframe f's edge list.  Each warp walks its edges in order; for
+// edge a and every edge c of a's point, lane (r, slot) adds row r of (W_a Dinv) W_c^T to the warp's accumulator tile
+// [6][6*nfree + 1] in shared memory (last column: W_a db).  The warps' tiles are summed in warp order into
+// part[f][s]; k_ba_schur_reduce then sums the chunks in order and subtracts from S / bschur.  No atomics.
+constexpr int kSchurSplit = 8;
 __global__ void __launch_bounds__(kBaWarps * 32) k_ba_schur(
-    const int* __restrict__ free_state, const int* __restrict__ off0, const int* __restrict__ prcol,
-    const int* __restrict__ free_off, int nfree, const int* __restrict__ ps_ptr, const int* __restrict__ ps_edges,
+    const int* __restrict__ prcol, int nfree, const int* __restrict__ ps_ptr, const int* __restrict__ ps_edges,
     const int* __restrict__ es, const int* __restrict__ ep, const int* __restrict__ pt_ptr, const double* __restrict__ Wb,
-    const double* __restrict__ Dinv, const double* __restrict__ db, int serial_lanes, int np, double* __restrict__ S,
-    double* __restrict__ bs) {
-  extern __shared__ double s_acc[];  // [kBaWarps][6][6 * nfree + 1]
-  const int ld = 6 * nfree + 1;      // last column: W_a db
-  const int f = blockIdx.x, o = off0[free_state[f]];
+    const double* __restrict__ Dinv, const double* __restrict__ db, int serial_lanes, double* __restrict__ part) {
+  extern __shared__ double s_acc[];  // [kBaWarps][6][ld]
+  const int ld = 6 * nfree + 1;
+  const int f = blockIdx.x, sp = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* acc = s_acc + (size_t)warp * 6 * ld;
   for (int t = lane; t < 6 * ld; t += 32) acc[t] = 0;
   __syncwarp();
   const int t0 = ps_ptr[f], t1 = ps_ptr[f + 1];
-  const int chunk = (t1 - t0 + kBaWarps - 1) / kBaWarps;
-  const int a0 = t0 + warp * chunk, a1 = min(a0 + chunk, t1);
+  const int per_blk = (t1 - t0 + kSchurSplit - 1) / kSchurSplit;
+  const int b0 = t0 + sp * per_blk, b1 = min(b0 + per_blk, t1);
+  const int per_warp = (max(b1 - b0, 0) + kBaWarps - 1) / kBaWarps;
+  const int a0 = b0 + warp * per_warp, a1 = min(a0 + per_warp, b1);
+  const int r = lane % 6, slot = lane / 6;  // lanes 30, 31 idle in the tile update
   for (int t = a0; t < a1; ++t) {
     const int a = ps_edges[t];
     const int p = ep[a];
-    const double* Wa = Wb + 18 * (size_t)a;
+    const double* Wa = Wb + 18 * (size_t)a + 3 * r;
     const double* Di = Dinv + 9 * (size_t)p;
-    double WD[18];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) WD[3 * r + c] = Wa[3 * r] * Di[c] + Wa[3 * r + 1] * Di[3 + c] + Wa[3 * r + 2] * Di[6 + c];
+    const double w0 = Wa[0], w1 = Wa[1], w2 = Wa[2];
+    const double d0 = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
+    const double d1 = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
+    const double d2 = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
     if (lane < 6) {
       const double* d = db + 3 * (size_t)p;
-      acc[lane * ld + 6 * nfree] += Wa[3 * lane] * d[0] + Wa[3 * lane + 1] * d[1] + Wa[3 * lane + 2] * d[2];
+      acc[r * ld + 6 * nfree] += w0 * d[0] + w1 * d[1] + w2 * d[2];
     }
     const int c0 = pt_ptr[p], c1 = pt_ptr[p + 1];
-    for (int cb = c0; cb < c1; cb += 32) {
-      const int c = cb + lane;
-      const int col = c < c1 ? prcol[es[c]] : -1;
-      for (int turn = 0; turn < (serial_lanes ? 32 : 1); ++turn) {
-        if (col >= 0 && (!serial_lanes || turn == lane)) {
+    for (int cb = c0; cb < c1; cb += 5) {
+      const int c = cb + slot;
+      const int col = (slot < 5 && c < c1) ? prcol[es[c]] : -1;
+      for (int turn = 0; turn < (serial_lanes ? 5 : 1); ++turn) {
+        if (col >= 0 && (!serial_lanes || turn == slot)) {
           const double* Wc = Wb + 18 * (size_t)c;
-          double* dst = acc + 6 * col;
+          double* dst = acc + r * ld + 6 * col;
 #pragma unroll
-          for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int cc = 0; cc < 6; ++cc)
-              dst[r * ld + cc] += WD[3 * r] * Wc[3 * cc] + WD[3 * r + 1] * Wc[3 * cc + 1] + WD[3 * r + 2] * Wc[3 * cc + 2];
+          for (int cc = 0; cc < 6; ++cc) dst[cc] += d0 * Wc[3 * cc] + d1 * Wc[3 * cc + 1] + d2 * Wc[3 * cc + 2];
         }
         if (serial_lanes) __syncwarp();
       }
@@ -472,135 +643,199 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_schur(
     __syncwarp();
   }
   __syncthreads();
+  double* out = part + ((size_t)f * kSchurSplit + sp) * 6 * ld;
   for (int t = threadIdx.x; t < 6 * ld; t += kBaWarps * 32) {
     double s = 0;
     for (int w = 0; w < kBaWarps; ++w) s += s_acc[(size_t)w * 6 * ld + t];
+    out[t] = s;
+  }
+}
+__global__ void __launch_bounds__(256) k_ba_schur_reduce(const int* __restrict__ free_state, const int* __restrict__ off0,
+                                                         const int* __restrict__ free_off, int nfree,
+                                                         const double* __restrict__ part, int np, double* __restrict__ S,
+                                                         double* __restrict__ bs) {
+  const int ld = 6 * nfree + 1;
+  const int f = blockIdx.x, o = off0[free_state[f]];
+  const double* in = part + (size_t)f * kSchurSplit * 6 * ld;
+  for (int t = threadIdx.x; t < 6 * ld; t += 256) {
+    double s = 0;
+    for (int sp = 0; sp < kSchurSplit; ++sp) s += in[(size_t)sp * 6 * ld + t];
     const int r = t / ld, c = t % ld;
     if (c == 6 * nfree) bs[o + r] -= s;
     else S[(size_t)(o + r) * np + free_off[c / 6] + c % 6] -= s;
   }
 }
 
-// Dense Cholesky (lower, in place) of S (n x n, row-major, global memory) and solve S x = bs by one block.
-// ok = 0 when a pivot is not positive (LinearSolverDense: LDLT::isPositive, linear_solver_dense.h:107-112).
-__global__ void __launch_bounds__(1024) k_ba_chol(double* __restrict__ A, const double* __restrict__ rhs, int n,
-                                                  double* __restrict__ x, double* __restrict__ y, int* __restrict__ ok) {
-  __shared__ double s_d;
-  __shared__ int s_ok;
+// Dense Cholesky of S (n x n) + solve S x = rhs by one block.  The lower triangle is staged in shared memory when it
+// fits (in_smem), else factorised in place in global memory.  Right-looking with panels of kCholNB columns; columns
+// are kept unnormalised (s_ij = a_ij - sum l l, so a_ik -= s_ij s_kj / s_jj) and scaled by 1/sqrt(s_jj) at the end:
+// one barrier per column inside a panel (cheap: one row per thread) and one rank-NB update of the trailing block per
+// panel.  ok = 0 when a pivot is not positive (LinearSolverDense: LDLT::isPositive, linear_solver_dense.h:107-112).
+constexpr int kCholNB = 8;
+constexpr int kCholThreads = 1024;
+__global__ void __launch_bounds__(kCholThreads) k_ba_chol(double* __restrict__ Ag, const double* __restrict__ rhs, int n,
+                                                          int in_smem, double* __restrict__ x_out, int* __restrict__ ok) {
+  extern __shared__ double sh[];
+  __shared__ double s_inv[kCholNB];
+  __shared__ int s_good;
   const int T = blockDim.x, t = threadIdx.x;
-  if (t == 0) s_ok = 1;
+  double* diag = sh;       // n: 1 / sqrt(s_jj)
+  double* y = sh + n;      // n
+  double* x = sh + 2 * n;  // n
+  double* A = in_smem ? sh + 3 * n : Ag;
+  const int ld = in_smem ? (n | 1) : n;
+  if (in_smem) {
+    for (int i = t >> 5; i < n; i += T >> 5)
+      for (int k = t & 31; k <= i; k += 32) A[i * ld + k] = Ag[(size_t)i * n + k];
+  }
+  for (int i = t; i < n; i += T) y[i] = rhs[i];
+  if (t == 0) s_good = 1;
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    if (t == 0) {
-      const double d = A[(size_t)j * n + j];
-      if (!(d > 0) || !isfinite(d)) s_ok = 0;
-      s_d = sqrt(d);
-      A[(size_t)j * n + j] = s_d;
+  const int nw = T >> 5, wp = t >> 5, ln = t & 31;
+  for (int j0 = 0; j0 < n; j0 += kCholNB) {
+    const int nb = min(kCholNB, n - j0), jend = j0 + nb;
+    // panel: one thread per row below the pivot, columns restricted to the panel
+    for (int j = j0; j < jend; ++j) {
+      const double sjj = A[(size_t)j * ld + j];
+      if (t == 0) {
+        if (!(sjj > 0) || !isfinite(sjj)) s_good = 0;
+        s_inv[j - j0] = 1.0 / sjj;
+      }
+      const double inv = 1.0 / sjj;
+      for (int i = j + 1 + t; i < n; i += T) {
+        const double f = A[(size_t)i * ld + j] * inv;
+        const int kmax = min(i, jend - 1);
+        for (int k = j + 1; k <= kmax; ++k) A[(size_t)i * ld + k] -= f * A[(size_t)k * ld + j];
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (!s_ok) break;
-    const double d = s_d;
-    for (int i = j + 1 + t; i < n; i += T) A[(size_t)i * n + j] /= d;
-    __syncthreads();
-    // trailing update of the lower triangle: A[i][k] -= A[i][j] A[k][j], j < k <= i
-    const int m = n - j - 1;
-    for (int e = t; e < m * m; e += T) {
-      const int i = j + 1 + e / m, k = j + 1 + e % m;
-      if (k <= i) A[(size_t)i * n + k] -= A[(size_t)i * n + j] * A[(size_t)k * n + j];
+    if (!s_good) break;
+    // trailing block: A[i][k] -= sum_c (s_ic / s_cc) s_kc for k >= jend, rows by warp, lanes along the row
+    for (int i = jend + wp; i < n; i += nw) {
+      double f[kCholNB];
+#pragma unroll
+      for (int c = 0; c < kCholNB; ++c) f[c] = c < nb ? A[(size_t)i * ld + j0 + c] * s_inv[c] : 0.0;
+      for (int k = jend + ln; k <= i; k += 32) {
+        double acc = A[(size_t)i * ld + k];
+        const double* Ak = A + (size_t)k * ld + j0;
+#pragma unroll
+        for (int c = 0; c < kCholNB; ++c)
+          if (c < nb) acc -= f[c] * Ak[c];
+        A[(size_t)i * ld + k] = acc;
+      }
     }
     __syncthreads();
   }
-  if (t == 0) *ok = s_ok;
-  if (!s_ok) return;
-  // forward / backward substitution, one warp: lanes split the dot products
+  const bool good = s_good != 0;
+  if (t == 0) *ok = good ? 1 : 0;
+  if (!good) return;
+  for (int j = t; j < n; j += T) diag[j] = 1.0 / sqrt(A[(size_t)j * ld + j]);
+  __syncthreads();
+  // l_ij = s_ij / sqrt(s_jj)
+  for (int i = wp; i < n; i += nw)
+    for (int k = ln; k < i; k += 32) A[(size_t)i * ld + k] *= diag[k];
+  __syncthreads();
   if (t < 32) {
     for (int i = 0; i < n; ++i) {
       double s = 0;
-      for (int k = t; k < i; k += 32) s += A[(size_t)i * n + k] * y[k];
+      for (int k = t; k < i; k += 32) s += A[(size_t)i * ld + k] * y[k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (t == 0) y[i] = (rhs[i] - s) / A[(size_t)i * n + i];
+      if (t == 0) y[i] = (y[i] - s) * diag[i];
       __syncwarp();
     }
     for (int i = n - 1; i >= 0; --i) {
       double s = 0;
-      for (int k = i + 1 + t; k < n; k += 32) s += A[(size_t)k * n + i] * x[k];
+      for (int k = i + 1 + t; k < n; k += 32) s += A[(size_t)k * ld + i] * x[k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (t == 0) x[i] = (y[i] - s) / A[(size_t)i * n + i];
+      if (t == 0) x[i] = (y[i] - s) * diag[i];
       __syncwarp();
     }
+    for (int i = t; i < n; i += 32) x_out[i] = x[i];
   }
 }
 
-// One warp per point: xl = Dinv (bl - sum_a W_a^T xp), X += xl (apply != 0), landmark part of computeScale
-__global__ void __launch_bounds__(kBaWarps * 32) k_ba_backsub(const int* __restrict__ pt_ptr, int P,
-                                                             const int* __restrict__ es, const int* __restrict__ off0,
-                                                             const double* __restrict__ Wb, const double* __restrict__ Dinv,
-                                                             const double* __restrict__ bl,
-                                                             const uint8_t* __restrict__ pt_active,
-                                                             const double* __restrict__ x, const int* __restrict__ ok,
-                                                             double lambda, int apply, double* __restrict__ X,
-                                                             double* __restrict__ xl_out, double* __restrict__ scale_part) {
-  const int p = blockIdx.x * kBaWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (p >= P) return;
-  if (!pt_active[p] || !*ok) {
-    if (lane == 0) {
-      scale_part[p] = 0;
-      if (xl_out && !*ok) xl_out[3 * (size_t)p] = xl_out[3 * (size_t)p + 1] = xl_out[3 * (size_t)p + 2] = 0;
+// One warp per point: xl = Dinv (bl - sum_a W_a^T xp), X += xl (apply != 0), landmark part of computeScale.
+// The extra last block applies the keyframe updates (NavState::IncSmall), refreshes the camera poses and computes the
+// pose part of computeScale.
+struct BaBackArgs {
+  const int* pt_ptr;
+  int P;
+  const int* es;
+  const int *off0, *off1, *off2;
+  const double *Wb, *Dinv, *bl;
+  const uint8_t* pt_active;
+  const double* x;
+  const int* ok;
+  double lambda;
+  int apply;
+  double *X, *xl_out, *scale_part;
+  VieoNavState* st;
+  int K;
+  CamK cam;
+  CamPose* cp;
+  const double* b;
+  int np;
+  double* scale_pose;
+};
+__global__ void __launch_bounds__(kBaWarps * 32) k_ba_backsub(BaBackArgs a) {
+  if (blockIdx.x == gridDim.x - 1) {
+    const bool ok = *a.ok != 0;
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
+      NavS s = ns_load(a.st[k]);
+      if (a.apply && ok && (a.off0[k] >= 0 || a.off1[k] >= 0 || a.off2[k] >= 0)) {
+        if (a.off0[k] >= 0) ns_inc_pr(s, a.x + a.off0[k]);
+        if (a.off1[k] >= 0) ns_inc_v(s, a.x + a.off1[k]);
+        if (a.off2[k] >= 0) ns_inc_bias(s, a.x + a.off2[k]);
+        ns_store(s, a.st[k]);
+      }
+      a.cp[k] = cam_pose(a.cam, s);
     }
-    if (!pt_active[p] && lane == 0 && xl_out) xl_out[3 * (size_t)p] = xl_out[3 * (size_t)p + 1] = xl_out[3 * (size_t)p + 2] = 0;
+    if (threadIdx.x == 0) {
+      double s = 0;
+      if (ok)
+        for (int j = 0; j < a.np; ++j) s += a.x[j] * (a.lambda * a.x[j] + a.b[j]);
+      *a.scale_pose = s;
+    }
+    return;
+  }
+  const int p = blockIdx.x * kBaWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= a.P) return;
+  const bool ok = *a.ok != 0;
+  if (!a.pt_active[p] || !ok) {
+    if (lane == 0) {
+      a.scale_part[p] = 0;
+      if (a.xl_out) a.xl_out[3 * (size_t)p] = a.xl_out[3 * (size_t)p + 1] = a.xl_out[3 * (size_t)p + 2] = 0;
+    }
     return;
   }
   double c[3] = {0, 0, 0};
-  for (int i = pt_ptr[p] + lane; i < pt_ptr[p + 1]; i += 32) {
-    const int o = off0[es[i]];
+  for (int i = a.pt_ptr[p] + lane; i < a.pt_ptr[p + 1]; i += 32) {
+    const int o = a.off0[a.es[i]];
     if (o < 0) continue;
-    const double* Wi = Wb + 18 * (size_t)i;
+    const double* Wi = a.Wb + 18 * (size_t)i;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int r = 0; r < 6; ++r) c[k] += Wi[3 * r + k] * x[o + r];
+      for (int r = 0; r < 6; ++r) c[k] += Wi[3 * r + k] * a.x[o + r];
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
   if (lane == 0) {
-    const double* bb = bl + 3 * (size_t)p;
-    const double* Di = Dinv + 9 * (size_t)p;
+    const double* bb = a.bl + 3 * (size_t)p;
+    const double* Di = a.Dinv + 9 * (size_t)p;
     const double cc[3] = {bb[0] - c[0], bb[1] - c[1], bb[2] - c[2]};
     double s = 0;
-    for (int a = 0; a < 3; ++a) {
-      const double xl = Di[3 * a] * cc[0] + Di[3 * a + 1] * cc[1] + Di[3 * a + 2] * cc[2];
-      if (apply) X[3 * (size_t)p + a] += xl;
-      if (xl_out) xl_out[3 * (size_t)p + a] = xl;
-      s += xl * (lambda * xl + bb[a]);
+    for (int q = 0; q < 3; ++q) {
+      const double xl = Di[3 * q] * cc[0] + Di[3 * q + 1] * cc[1] + Di[3 * q + 2] * cc[2];
+      if (a.apply) a.X[3 * (size_t)p + q] += xl;
+      if (a.xl_out) a.xl_out[3 * (size_t)p + q] = xl;
+      s += xl * (a.lambda * xl + bb[q]);
     }
-    scale_part[p] = s;
-  }
-}
-
-// oplus on the keyframe vertices (NavState::IncSmall) + pose part of computeScale
-__global__ void k_ba_update_states(VieoNavState* __restrict__ st, int K, const int* __restrict__ off0,
-                                   const int* __restrict__ off1, const int* __restrict__ off2,
-                                   const double* __restrict__ x, const double* __restrict__ b, int np, double lambda,
-                                   const int* __restrict__ ok, double* __restrict__ scale_pose) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < K && *ok) {
-    if (off0[k] >= 0 || off1[k] >= 0 || off2[k] >= 0) {
-      NavS s = ns_load(st[k]);
-      if (off0[k] >= 0) ns_inc_pr(s, x + off0[k]);
-      if (off1[k] >= 0) ns_inc_v(s, x + off1[k]);
-      if (off2[k] >= 0) ns_inc_bias(s, x + off2[k]);
-      ns_store(s, st[k]);
-    }
-  }
-  if (k == 0) {
-    double s = 0;
-    if (*ok)
-      for (int j = 0; j < np; ++j) s += x[j] * (lambda * x[j] + b[j]);
-    *scale_pose = s;
+    a.scale_part[p] = s;
   }
 }
 
@@ -639,7 +874,7 @@ struct vieo_ba {
   int device = 0;
   cudaStream_t st = nullptr;
   int capK = 0, capP = 0, capE = 0, capM = 0;
-  int K = 0, P = 0, E = 0, M = 0, np = 0, nfree = 0, n_den = 0, n_part = 0;
+  int K = 0, P = 0, E = 0, M = 0, np = 0, nfree = 0, n_den = 0, n_part = 0, n_pblk = 0;
   bool points_free = true, has_dup = false;
   int rank = 0, world = 1;
   vieo_allreduce_fn allreduce = nullptr;
@@ -647,34 +882,40 @@ struct vieo_ba {
   CamK cam;
   Vec3 gw;
   double dm = 0, ds = 0;
-  // device
+  // device.  Two linearisation sets (W, Hll, bl, pt_active, H, b, chi total): `cur` belongs to the current estimate,
+  // the other one receives the speculative linearisation at the trial estimate (accepted: swap; rejected: keep).
+  int cur = 0;
   VieoNavState *d_st = nullptr, *d_st_bak = nullptr;
   CamPose* d_cp = nullptr;
-  double *d_X = nullptr, *d_X_bak = nullptr, *d_chi2 = nullptr, *d_W = nullptr, *d_A = nullptr, *d_Hll = nullptr,
-         *d_bl = nullptr, *d_Dinv = nullptr, *d_db = nullptr, *d_H = nullptr, *d_sys = nullptr, *d_x = nullptr,
-         *d_y = nullptr, *d_xl = nullptr, *d_partial = nullptr, *d_scale_part = nullptr, *d_ctl = nullptr;
+  double *d_X = nullptr, *d_X_bak = nullptr, *d_chi2 = nullptr, *d_A = nullptr, *d_Dinv = nullptr, *d_db = nullptr,
+         *d_sys = nullptr, *d_x = nullptr, *d_xl = nullptr, *d_partial = nullptr, *d_scale_part = nullptr,
+         *d_ctl = nullptr, *d_part = nullptr;
+  double *d_W[2] = {}, *d_Hll[2] = {}, *d_bl[2] = {}, *d_H[2] = {}, *d_b[2] = {};
+  uint8_t* d_pt_active[2] = {};
+  size_t part_cap = 0;
   int *d_es = nullptr, *d_ep = nullptr, *d_pt_ptr = nullptr, *d_off0 = nullptr, *d_off1 = nullptr, *d_off2 = nullptr,
       *d_prcol = nullptr, *d_free_state = nullptr, *d_free_off = nullptr, *d_ps_ptr = nullptr, *d_ps_edges = nullptr,
       *d_ok = nullptr;
   float *d_obs = nullptr, *d_w = nullptr;
-  uint8_t *d_flags = nullptr, *d_lvl = nullptr, *d_sfix = nullptr, *d_pt_active = nullptr, *d_bad = nullptr;
+  uint8_t *d_flags = nullptr, *d_lvl = nullptr, *d_sfix = nullptr, *d_bad = nullptr;
   VieoImuPreint* d_pre = nullptr;
   BaDense* d_den = nullptr;
   BaDenseWork* d_wk = nullptr;
   double* h_ctl = nullptr;  // pinned
-  // host mirrors
   std::vector<int> off0, off1, off2;
   // LM state (OptimizationAlgorithmLevenberg members)
   double lambda = 0, ni = 2;
   int nBad = 0;
   int launches = 0;
-  // sys layout
+  // sys = [S | bschur | b]: what the sharded form all-reduces once per LM trial
   double* S() { return d_sys; }
   double* bs() { return d_sys + (size_t)np * np; }
   double* b() { return d_sys + (size_t)np * np + np; }
-  double* chi_cur() { return d_sys + (size_t)np * np + 2 * np; }
-  size_t sys_count() const { return (size_t)np * np + 2 * np + 1; }
+  size_t sys_count() const { return (size_t)np * np + 2 * np; }
 };
+// d_ctl (device doubles): [3] pose part of computeScale, [4] max diagonal, [5..7] stand-alone error sums,
+// [8] dense-edge chi2 of the last linearisation, [10] robust chi2 of the last linearisation, [11] landmark part of
+// computeScale of the last solve ([10..11] are all-reduced together when sharded)
 
 namespace {
 
@@ -730,8 +971,8 @@ int ba_campose(vieo_ba* h) {
   return VIEO_OK;
 }
 
-// computeActiveErrors (+ every edge when all) and the robust chi2 into *d_out; scale parts summed when asked
-int ba_errors(vieo_ba* h, int all, double* d_out, bool with_scale) {
+// stand-alone computeActiveErrors (+ every edge when all) and the robust chi2 into *d_out (used outside the LM loop)
+int ba_errors(vieo_ba* h, int all, double* d_out) {
   ba_campose(h);
   if (h->E > 0) {
     k_ba_errors<<<h->n_part, 256, 0, h->st>>>(h->cam, h->d_cp, h->d_X, h->d_es, h->d_ep, h->d_obs, h->d_w, h->d_flags,
@@ -739,58 +980,58 @@ int ba_errors(vieo_ba* h, int all, double* d_out, bool with_scale) {
                                               h->d_chi2, h->d_partial);
     h->launches++;
   }
-  k_ba_dense_errors<<<1, 128, 0, h->st>>>(
-      h->d_den, h->n_den, h->d_st, h->d_pre, h->gw, h->d_wk, h->d_partial, h->E > 0 ? h->n_part : 0, d_out,
-      h->d_scale_part, with_scale ? h->P : 0, with_scale ? h->d_ctl + 2 : nullptr);
+  k_ba_dense_errors<<<1, 128, 0, h->st>>>(h->d_den, h->n_den, h->d_st, h->d_pre, h->gw, h->d_wk, h->d_partial,
+                                          h->E > 0 ? h->n_part : 0, d_out, nullptr, 0, nullptr);
   h->launches++;
   BA_CK(cudaGetLastError());
   return VIEO_OK;
 }
 
-// buildSystem: H (np x np), b, Hll, bl, W
-int ba_build(vieo_ba* h) {
-  const int np = h->np;
-  BA_CK(cudaMemsetAsync(h->d_H, 0, sizeof(double) * std::max<size_t>((size_t)np * np, 1), h->st));
-  BA_CK(cudaMemsetAsync(h->b(), 0, sizeof(double) * std::max(np, 1), h->st));
-  if (h->P > 0) {
-    k_ba_linearize<<<(h->P + kBaWarps - 1) / kBaWarps, kBaWarps * 32, 0, h->st>>>(
-        h->cam, h->d_cp, h->d_X, h->d_pt_ptr, h->P, h->d_es, h->d_obs, h->d_w, h->d_flags, h->d_lvl, h->d_sfix, h->d_chi2,
-        h->dm, h->ds, h->d_W, h->d_A, h->d_Hll, h->d_bl, h->d_pt_active);
-    h->launches++;
-  }
+// computeActiveErrors + buildSystem at the current estimate into linearisation set `set`; leaves the robust chi2 in
+// d_ctl[10] and the landmark part of the previous solve's gain-ratio denominator in d_ctl[11]
+int ba_linearize(vieo_ba* h, int set) {
+  BaLinArgs a;
+  a.cam = h->cam; a.cp = h->d_cp; a.X = h->d_X; a.pt_ptr = h->d_pt_ptr; a.P = h->P; a.es = h->d_es; a.obs = h->d_obs;
+  a.w = h->d_w; a.flags = h->d_flags; a.lvl = h->d_lvl; a.sfix = h->d_sfix; a.dm = h->dm; a.ds = h->ds;
+  a.chi2 = h->d_chi2; a.Wb = h->d_W[set]; a.Ab = h->d_A; a.Hll = h->d_Hll[set]; a.bl = h->d_bl[set];
+  a.partial = h->d_partial; a.pt_active = h->d_pt_active[set];
+  a.den = h->d_den; a.n_den = h->n_den; a.st = h->d_st; a.pre = h->d_pre; a.gw = h->gw; a.wk = h->d_wk;
+  a.off0 = h->d_off0; a.off1 = h->d_off1; a.off2 = h->d_off2; a.np = h->np; a.H = h->d_H[set]; a.b = h->d_b[set];
+  a.chi_dense = h->d_ctl + 8;
+  k_ba_linearize<<<h->n_pblk + 1, kBaWarps * 32, 0, h->st>>>(a);
+  h->launches++;
   if (h->nfree > 0) {
-    k_ba_pose_reduce<<<h->nfree, 128, 0, h->st>>>(h->d_free_state, h->d_off0, h->d_ps_ptr, h->d_ps_edges, h->d_A, np, h->d_H,
-                                                  h->b());
-    h->launches++;
-  }
-  if (h->n_den > 0) {
-    k_ba_dense_build<<<1, 256, 0, h->st>>>(h->d_den, h->n_den, h->d_st, h->d_pre, h->gw, h->d_wk, h->d_off0, h->d_off1,
-                                           h->d_off2, np, h->d_H, h->b());
+    k_ba_pose_reduce<<<h->nfree, 256, 0, h->st>>>(h->d_free_state, h->d_off0, h->d_ps_ptr, h->d_ps_edges, h->d_A, h->np,
+                                                  h->d_H[set], h->d_b[set], h->d_partial, h->n_pblk, h->d_ctl + 8,
+                                                  h->d_scale_part, h->P, h->d_ctl + 10);
     h->launches++;
   }
   BA_CK(cudaGetLastError());
+  if (h->allreduce && h->world > 1)
+    if (h->allreduce(h->ar_ctx, h->d_ctl + 10, 2, (void*)h->st)) {
+      vieo::set_error("allreduce callback failed");
+      return VIEO_E_CUDA;
+    }
   return VIEO_OK;
 }
 
-// (H + lambda I) x = b through the Schur complement; apply: update the estimate
-int ba_solve(vieo_ba* h, double lambda, int apply, double* xl_out) {
+// (H + lambda I) x = b through the Schur complement on linearisation set `set`; apply: update the estimate
+int ba_solve(vieo_ba* h, int set, double lambda, int apply, double* xl_out) {
   const int np = h->np;
-  if (h->P > 0) {
-    k_ba_point_inv<<<(h->P + 127) / 128, 128, 0, h->st>>>(h->d_Hll, h->d_bl, h->d_pt_active, h->P, lambda, h->d_Dinv,
-                                                          h->d_db);
-    h->launches++;
-  }
-  const size_t nn = std::max<size_t>((size_t)np * np, np);
-  // sharded: lambda is added once (rank 0); the all-reduce sums the partial systems
-  k_ba_copy_sys<<<(unsigned)((nn + 255) / 256), 256, 0, h->st>>>(h->d_H, h->b(), np, h->rank == 0 ? lambda : 0.0, h->S(),
-                                                                h->bs());
+  const size_t nn = std::max<size_t>(std::max<size_t>((size_t)np * np, np), (size_t)h->P);
+  // sharded: lambda enters the pose diagonal once (rank 0); the all-reduce sums the partial systems
+  k_ba_prep_solve<<<(unsigned)((nn + 255) / 256), 256, 0, h->st>>>(h->d_Hll[set], h->d_bl[set], h->d_pt_active[set], h->P, lambda,
+                                                                  h->d_Dinv, h->d_db, h->d_H[set], h->d_b[set], np,
+                                                                  h->rank == 0 ? lambda : 0.0, h->S(), h->bs(), h->b());
   h->launches++;
   if (h->nfree > 0 && h->E > 0) {
     const size_t smem = sizeof(double) * kBaWarps * 6 * (6 * (size_t)h->nfree + 1);
-    k_ba_schur<<<h->nfree, kBaWarps * 32, smem, h->st>>>(h->d_free_state, h->d_off0, h->d_prcol, h->d_free_off, h->nfree,
-                                                         h->d_ps_ptr, h->d_ps_edges, h->d_es, h->d_ep, h->d_pt_ptr, h->d_W,
-                                                         h->d_Dinv, h->d_db, h->has_dup ? 1 : 0, np, h->S(), h->bs());
-    h->launches++;
+    k_ba_schur<<<dim3(h->nfree, kSchurSplit), kBaWarps * 32, smem, h->st>>>(h->d_prcol, h->nfree, h->d_ps_ptr, h->d_ps_edges,
+                                                                          h->d_es, h->d_ep, h->d_pt_ptr, h->d_W[set], h->d_Dinv,
+                                                                          h->d_db, h->has_dup ? 1 : 0, h->d_part);
+    k_ba_schur_reduce<<<h->nfree, 256, 0, h->st>>>(h->d_free_state, h->d_off0, h->d_free_off, h->nfree, h->d_part, np, h->S(),
+                                                   h->bs());
+    h->launches += 2;
   }
   if (h->allreduce && h->world > 1) {
     int rc = h->allreduce(h->ar_ctx, h->d_sys, h->sys_count(), (void*)h->st);
@@ -799,46 +1040,43 @@ int ba_solve(vieo_ba* h, double lambda, int apply, double* xl_out) {
       return VIEO_E_CUDA;
     }
   }
-  k_ba_chol<<<1, 1024, 0, h->st>>>(h->S(), h->bs(), np, h->d_x, h->d_y, h->d_ok);
+  const size_t tri = sizeof(double) * ((size_t)np * (np | 1) + 3 * (size_t)np);
+  const int in_smem = tri <= 220 * 1024;
+  const size_t chol_smem = in_smem ? tri : sizeof(double) * 3 * (size_t)np;
+  k_ba_chol<<<1, kCholThreads, chol_smem, h->st>>>(h->S(), h->bs(), np, in_smem, h->d_x, h->d_ok);
   h->launches++;
-  if (h->P > 0) {
-    k_ba_backsub<<<(h->P + kBaWarps - 1) / kBaWarps, kBaWarps * 32, 0, h->st>>>(
-        h->d_pt_ptr, h->P, h->d_es, h->d_off0, h->d_W, h->d_Dinv, h->d_bl, h->d_pt_active, h->d_x, h->d_ok, lambda, apply,
-        h->d_X, xl_out, h->d_scale_part);
-    h->launches++;
-  }
-  if (apply) {
-    k_ba_update_states<<<(h->K + 127) / 128, 128, 0, h->st>>>(h->d_st, h->K, h->d_off0, h->d_off1, h->d_off2, h->d_x, h->b(),
-                                                              np, lambda, h->d_ok, h->d_ctl + 3);
-    h->launches++;
-  }
+  BaBackArgs a;
+  a.pt_ptr = h->d_pt_ptr; a.P = h->P; a.es = h->d_es; a.off0 = h->d_off0; a.off1 = h->d_off1; a.off2 = h->d_off2;
+  a.Wb = h->d_W[set]; a.Dinv = h->d_Dinv; a.bl = h->d_bl[set]; a.pt_active = h->d_pt_active[set]; a.x = h->d_x; a.ok = h->d_ok;
+  a.lambda = lambda; a.apply = apply; a.X = h->d_X; a.xl_out = xl_out; a.scale_part = h->d_scale_part; a.st = h->d_st;
+  a.K = h->K; a.cam = h->cam; a.cp = h->d_cp; a.b = h->b(); a.np = np; a.scale_pose = h->d_ctl + 3;
+  k_ba_backsub<<<h->n_pblk + 1, kBaWarps * 32, 0, h->st>>>(a);
+  h->launches++;
   BA_CK(cudaGetLastError());
   return VIEO_OK;
 }
 
 int ba_read_ctl(vieo_ba* h) {
-  // ctl: [0] currentChi (copy of sys tail), [1] tempChi, [2] landmark scale, [3] pose scale, [4] maxdiag
-  BA_CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->st));
-  BA_CK(cudaMemcpyAsync(h->h_ctl + 8, h->chi_cur(), sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  BA_CK(cudaMemcpyAsync(h->h_ctl + 9, h->d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  BA_CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->st));
+  BA_CK(cudaMemcpyAsync(h->h_ctl + 12, h->d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   BA_CK(cudaStreamSynchronize(h->st));
   return VIEO_OK;
 }
 
-// OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-166): 0 OK, 1 Terminate, <0 error
-int ba_lm_iteration(vieo_ba* h, int iteration, double user_lambda, const volatile uint8_t* stop) {
+// OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-166): 0 OK, 1 Terminate, <0 error.
+// chi_cur: robust chi2 of the current estimate (linearisation set h->cur is valid for it) — g2o recomputes it at the
+// start of every iteration; here it is carried over from the accepted trial, which evaluated the same state.
+int ba_lm_iteration(vieo_ba* h, int iteration, double user_lambda, const volatile uint8_t* stop, double& chi_cur) {
   int rc;
-  if ((rc = ba_errors(h, 0, h->chi_cur(), false))) return rc;
-  if ((rc = ba_build(h))) return rc;
   if (iteration == 0) {
     if (user_lambda > 0) h->lambda = user_lambda;
     else {
-      k_ba_maxdiag<<<1, 256, 0, h->st>>>(h->d_H, h->np, h->d_Hll, h->d_pt_active, h->P, h->d_ctl + 4);
-      h->launches++;
       if (h->allreduce && h->world > 1) {
         vieo::set_error("sharded BA needs an explicit initial lambda");
         return VIEO_E_ARG;
       }
+      k_ba_maxdiag<<<1, 256, 0, h->st>>>(h->d_H[h->cur], h->np, h->d_Hll[h->cur], h->d_pt_active[h->cur], h->P, h->d_ctl + 4);
+      h->launches++;
       BA_CK(cudaMemcpyAsync(h->h_ctl + 4, h->d_ctl + 4, sizeof(double), cudaMemcpyDeviceToHost, h->st));
       BA_CK(cudaStreamSynchronize(h->st));
       h->lambda = 1e-5 * h->h_ctl[4];
@@ -846,24 +1084,21 @@ int ba_lm_iteration(vieo_ba* h, int iteration, double user_lambda, const volatil
     h->ni = 2;
     h->nBad = 0;
   }
-  double currentChi = 0, iniChi = 0, rho = 0;
+  double currentChi = chi_cur;
+  const double iniChi = chi_cur;
+  double rho = 0;
   int qmax = 0;
-  const bool sharded = h->allreduce && h->world > 1;
   do {
     BA_CK(cudaMemcpyAsync(h->d_st_bak, h->d_st, sizeof(VieoNavState) * h->K, cudaMemcpyDeviceToDevice, h->st));
     if (h->P) BA_CK(cudaMemcpyAsync(h->d_X_bak, h->d_X, sizeof(double) * 3 * h->P, cudaMemcpyDeviceToDevice, h->st));
-    if ((rc = ba_solve(h, h->lambda, 1, nullptr))) return rc;
-    if ((rc = ba_errors(h, 0, h->d_ctl + 1, true))) return rc;
-    if (sharded) {  // [tempChi, landmark scale] partial sums
-      if (h->allreduce(h->ar_ctx, h->d_ctl + 1, 2, (void*)h->st)) return VIEO_E_CUDA;
-    }
+    if ((rc = ba_solve(h, h->cur, h->lambda, 1, nullptr))) return rc;
+    if ((rc = ba_linearize(h, 1 - h->cur))) return rc;  // errors at the trial estimate + speculative build
     if ((rc = ba_read_ctl(h))) return rc;
-    if (qmax == 0) currentChi = iniChi = h->h_ctl[8];
-    const int ok2 = *(int*)(h->h_ctl + 9);
-    double tempChi = h->h_ctl[1];
+    const int ok2 = *(int*)(h->h_ctl + 12);
+    double tempChi = h->h_ctl[10];
     if (!ok2) tempChi = std::numeric_limits<double>::max();
     rho = currentChi - tempChi;
-    double scale = h->h_ctl[3] + h->h_ctl[2];
+    double scale = h->h_ctl[3] + h->h_ctl[11];
     scale += 1e-3;
     rho /= scale;
     if (rho > 0 && std::isfinite(tempChi)) {
@@ -872,6 +1107,7 @@ int ba_lm_iteration(vieo_ba* h, int iteration, double user_lambda, const volatil
       h->lambda *= std::max(1. / 3., alpha);
       h->ni = 2;
       currentChi = tempChi;
+      h->cur = 1 - h->cur;  // the speculative linearisation is the current one now
     } else {
       h->lambda *= h->ni;
       h->ni *= 2;
@@ -880,6 +1116,7 @@ int ba_lm_iteration(vieo_ba* h, int iteration, double user_lambda, const volatil
     }
     qmax++;
   } while (rho < 0 && qmax < 10 && !(stop && *stop));
+  chi_cur = currentChi;
   if (qmax == 10 || rho == 0) return 1;
   if ((iniChi - currentChi) * 1e3 < iniChi) h->nBad++;
   else h->nBad = 0;
@@ -888,11 +1125,12 @@ int ba_lm_iteration(vieo_ba* h, int iteration, double user_lambda, const volatil
 }
 
 void ba_free(vieo_ba* h) {
-  void* ptrs[] = {h->d_st, h->d_st_bak, h->d_cp, h->d_X, h->d_X_bak, h->d_chi2, h->d_W, h->d_A, h->d_Hll, h->d_bl, h->d_Dinv,
-                  h->d_db, h->d_H, h->d_sys, h->d_x, h->d_y, h->d_xl, h->d_partial, h->d_scale_part, h->d_ctl, h->d_es,
-                  h->d_ep, h->d_pt_ptr, h->d_off0, h->d_off1, h->d_off2, h->d_prcol, h->d_free_state, h->d_free_off,
-                  h->d_ps_ptr, h->d_ps_edges, h->d_ok, h->d_obs, h->d_w, h->d_flags, h->d_lvl, h->d_sfix, h->d_pt_active,
-                  h->d_bad, h->d_pre, h->d_den, h->d_wk};
+  void* ptrs[] = {h->d_st, h->d_st_bak, h->d_cp, h->d_X, h->d_X_bak, h->d_chi2, h->d_A, h->d_Dinv, h->d_db, h->d_sys, h->d_x,
+                  h->d_xl, h->d_partial, h->d_scale_part, h->d_ctl, h->d_part, h->d_W[0], h->d_W[1], h->d_Hll[0], h->d_Hll[1],
+                  h->d_bl[0], h->d_bl[1], h->d_H[0], h->d_H[1], h->d_b[0], h->d_b[1], h->d_pt_active[0], h->d_pt_active[1],
+                  h->d_es, h->d_ep, h->d_pt_ptr, h->d_off0, h->d_off1, h->d_off2, h->d_prcol, h->d_free_state, h->d_free_off,
+                  h->d_ps_ptr, h->d_ps_edges, h->d_ok, h->d_obs, h->d_w, h->d_flags, h->d_lvl, h->d_sfix, h->d_bad, h->d_pre,
+                  h->d_den, h->d_wk};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -916,15 +1154,18 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   step(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   step(dalloc(&h->d_st, K)); step(dalloc(&h->d_st_bak, K)); step(dalloc(&h->d_cp, K));
   step(dalloc(&h->d_X, 3 * P)); step(dalloc(&h->d_X_bak, 3 * P)); step(dalloc(&h->d_chi2, E));
-  step(dalloc(&h->d_W, 18 * E)); step(dalloc(&h->d_A, 27 * E)); step(dalloc(&h->d_Hll, 9 * P)); step(dalloc(&h->d_bl, 3 * P));
-  step(dalloc(&h->d_Dinv, 9 * P)); step(dalloc(&h->d_db, 3 * P)); step(dalloc(&h->d_H, NP * NP));
-  step(dalloc(&h->d_sys, NP * NP + 2 * NP + 8)); step(dalloc(&h->d_x, NP)); step(dalloc(&h->d_y, NP));
-  step(dalloc(&h->d_xl, 3 * P)); step(dalloc(&h->d_partial, (E + 255) / 256 + 1)); step(dalloc(&h->d_scale_part, P));
+  step(dalloc(&h->d_A, 27 * E)); step(dalloc(&h->d_Dinv, 9 * P)); step(dalloc(&h->d_db, 3 * P));
+  for (int s = 0; s < 2; ++s) {
+    step(dalloc(&h->d_W[s], 18 * E)); step(dalloc(&h->d_Hll[s], 9 * P)); step(dalloc(&h->d_bl[s], 3 * P));
+    step(dalloc(&h->d_H[s], NP * NP)); step(dalloc(&h->d_b[s], NP)); step(dalloc(&h->d_pt_active[s], P));
+  }
+  step(dalloc(&h->d_sys, NP * NP + 2 * NP + 8)); step(dalloc(&h->d_x, NP));
+  step(dalloc(&h->d_xl, 3 * P)); step(dalloc(&h->d_partial, std::max((E + 255) / 256, P / kBaWarps + 1) + 2)); step(dalloc(&h->d_scale_part, P));
   step(dalloc(&h->d_ctl, 16)); step(dalloc(&h->d_es, E)); step(dalloc(&h->d_ep, E)); step(dalloc(&h->d_pt_ptr, P + 1));
   step(dalloc(&h->d_off0, K)); step(dalloc(&h->d_off1, K)); step(dalloc(&h->d_off2, K)); step(dalloc(&h->d_prcol, K));
   step(dalloc(&h->d_free_state, K)); step(dalloc(&h->d_free_off, K)); step(dalloc(&h->d_ps_ptr, K + 1));
   step(dalloc(&h->d_ps_edges, E)); step(dalloc(&h->d_ok, 4)); step(dalloc(&h->d_obs, 3 * E)); step(dalloc(&h->d_w, E));
-  step(dalloc(&h->d_flags, E)); step(dalloc(&h->d_lvl, E)); step(dalloc(&h->d_sfix, K)); step(dalloc(&h->d_pt_active, P));
+  step(dalloc(&h->d_flags, E)); step(dalloc(&h->d_lvl, E)); step(dalloc(&h->d_sfix, K));
   step(dalloc(&h->d_bad, E)); step(dalloc(&h->d_pre, M)); step(dalloc(&h->d_den, 2 * M)); step(dalloc(&h->d_wk, 2 * M));
   step(cudaMallocHost((void**)&h->h_ctl, sizeof(double) * 16));
   if (e != cudaSuccess) {
@@ -968,6 +1209,8 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   h->launches = 0;
   h->points_free = true;
   h->n_part = (E + 255) / 256;
+  h->n_pblk = (P + kBaWarps - 1) / kBaWarps;
+  h->cur = 0;
   // camera
   h->cam.fx = (double)cam->fx; h->cam.fy = (double)cam->fy; h->cam.cx = (double)cam->cx; h->cam.cy = (double)cam->cy;
   h->cam.bf = (double)cam->bf;
@@ -1095,6 +1338,19 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
     return VIEO_E_CAPACITY;
   }
   if (smem > 48 * 1024) BA_CK(cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t part_need = (size_t)h->nfree * kSchurSplit * 6 * (6 * (size_t)h->nfree + 1);
+  if (part_need > h->part_cap) {
+    if (h->d_part) cudaFree(h->d_part);
+    h->d_part = nullptr;
+    h->part_cap = 0;
+    BA_CK(dalloc(&h->d_part, part_need));
+    h->part_cap = part_need;
+  }
+  const size_t tri = sizeof(double) * ((size_t)np * (np | 1) + 3 * (size_t)np);
+  BA_CK(cudaFuncSetAttribute(k_ba_chol, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(tri <= 220 * 1024 ? std::max<size_t>(tri, 48 * 1024) : 48 * 1024)));
+  BA_CK(cudaMemsetAsync(h->d_scale_part, 0, 8 * (size_t)std::max(P, 1), h->st));
+  BA_CK(cudaStreamSynchronize(h->st));
   h->lambda = 0; h->ni = 2; h->nBad = 0;
   return VIEO_OK;
 }
@@ -1102,7 +1358,7 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
 int vieo_ba_chi2_large_set_level(vieo_ba_t* h, float rat) {
   VIEO_ARG(h, "null handle");
   BA_CK(cudaSetDevice(h->device));
-  int rc = ba_errors(h, 1, h->d_ctl + 5, false);
+  int rc = ba_errors(h, 1, h->d_ctl + 5);
   if (rc) return rc;
   if (h->E > 0) {
     k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->d_cp, h->d_X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
@@ -1117,7 +1373,7 @@ int vieo_ba_active_robust_chi2(vieo_ba_t* h, int recompute, double* chi2) {
   VIEO_ARG(h && chi2, "null argument");
   BA_CK(cudaSetDevice(h->device));
   if (recompute) {
-    int rc = ba_errors(h, 0, h->d_ctl + 6, false);
+    int rc = ba_errors(h, 0, h->d_ctl + 6);
     if (rc) return rc;
   } else {
     // activeRobustChi2 over the stored errors of the current active set (levels may have changed since)
@@ -1168,12 +1424,18 @@ int vieo_ba_active_robust_chi2(vieo_ba_t* h, int recompute, double* chi2) {
 int vieo_ba_optimize(vieo_ba_t* h, int iterations, double lambda_init, const volatile uint8_t* stop) {
   VIEO_ARG(h && iterations >= 0, "bad argument");
   BA_CK(cudaSetDevice(h->device));
-  if (h->np == 0) return 0;
+  if (h->np == 0 || iterations == 0) return 0;
+  if (stop && *stop) return 0;
   BA_CK(cudaMemsetAsync(h->d_x, 0, 8 * (size_t)h->np, h->st));
+  // levels / kernels may have changed since the last call: fresh errors + linearisation at the current estimate
+  int rc = ba_campose(h);
+  if ((rc = ba_linearize(h, h->cur))) return rc;
+  if ((rc = ba_read_ctl(h))) return rc;
+  double chi_cur = h->h_ctl[10];
   int n = 0;
   bool ok = true;
   for (int i = 0; i < iterations && !(stop && *stop) && ok; ++i) {
-    const int r = ba_lm_iteration(h, i, lambda_init, stop);
+    const int r = ba_lm_iteration(h, i, lambda_init, stop, chi_cur);
     if (r < 0) return r;
     ok = r == 0;
     ++n;
@@ -1211,17 +1473,16 @@ int vieo_ba_get(vieo_ba_t* h, VieoNavState* states_out, double* points_out, doub
 int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_points, double* H_out, double* b_out) {
   VIEO_ARG(h && x_pose, "null argument");
   BA_CK(cudaSetDevice(h->device));
-  int rc;
-  if ((rc = ba_errors(h, 0, h->chi_cur(), false))) return rc;
-  if ((rc = ba_build(h))) return rc;
-  if ((rc = ba_solve(h, lambda, 0, h->d_xl))) return rc;
+  int rc = ba_campose(h);
+  if ((rc = ba_linearize(h, h->cur))) return rc;
+  if ((rc = ba_solve(h, h->cur, lambda, 0, h->d_xl))) return rc;
   BA_CK(cudaMemcpyAsync(x_pose, h->d_x, 8 * (size_t)h->np, cudaMemcpyDeviceToHost, h->st));
   if (x_points && h->P) BA_CK(cudaMemcpyAsync(x_points, h->d_xl, 24 * (size_t)h->P, cudaMemcpyDeviceToHost, h->st));
-  if (H_out) BA_CK(cudaMemcpyAsync(H_out, h->d_H, 8 * (size_t)h->np * h->np, cudaMemcpyDeviceToHost, h->st));
-  if (b_out) BA_CK(cudaMemcpyAsync(b_out, h->b(), 8 * (size_t)h->np, cudaMemcpyDeviceToHost, h->st));
-  BA_CK(cudaMemcpyAsync(h->h_ctl + 9, h->d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  if (H_out) BA_CK(cudaMemcpyAsync(H_out, h->d_H[h->cur], 8 * (size_t)h->np * h->np, cudaMemcpyDeviceToHost, h->st));
+  if (b_out) BA_CK(cudaMemcpyAsync(b_out, h->d_b[h->cur], 8 * (size_t)h->np, cudaMemcpyDeviceToHost, h->st));
+  BA_CK(cudaMemcpyAsync(h->h_ctl + 12, h->d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   BA_CK(cudaStreamSynchronize(h->st));
-  if (!*(int*)(h->h_ctl + 9)) {
+  if (!*(int*)(h->h_ctl + 12)) {
     set_error("vieo_ba_debug_step: reduced camera system is not positive definite");
     return VIEO_E_ARG;
   }

@@ -144,8 +144,12 @@ __device__ __forceinline__ Mat3 ld_m3(const double* a) {
   for (int i = 0; i < 9; ++i) r.m[i] = a[i];
   return r;
 }
-__device__ inline void navstate_error(const NavS& si, const NavS& sj, const VieoImuPreint& m, const Vec3& gw, bool prv,
-                                      double e[9]) {
+// the fields of VieoImuPreint the edges read, without the two 9x9 covariances (for staging in shared memory)
+struct VieoImuPreintLite {
+  double Rij[9], vij[3], pij[3], Jgp[9], Jap[9], Jgv[9], Jav[9], JgR[9], dt;
+};
+template <class Pre>
+__device__ inline void navstate_error(const NavS& si, const NavS& sj, const Pre& m, const Vec3& gw, bool prv, double e[9]) {
   const Mat3 RiT = m3_t(q_matrix(si.q));
   const int idR = prv ? 3 : 6, idV = 9 - idR;
   const double dt = m.dt;
@@ -176,7 +180,8 @@ __device__ __forceinline__ void setb(double* A, int ld, int r, int c, const Mat3
     for (int j = 0; j < 3; ++j) A[ld * (r + i) + c + j] = b.m[3 * i + j];
 }
 // Ji, Jj: 9x9 row-major (state columns in residual order), Jb: 9x6; e = current error
-__device__ inline void navstate_jac(const NavS& si, const NavS& sj, const VieoImuPreint& m, const Vec3& gw, bool prv,
+template <class Pre>
+__device__ inline void navstate_jac(const NavS& si, const NavS& sj, const Pre& m, const Vec3& gw, bool prv,
                                     const double e[9], double* Ji, double* Jj, double* Jb) {
   const Mat3 RiT = m3_t(q_matrix(si.q)), Rj = q_matrix(sj.q);
   const int idR = prv ? 3 : 6, idV = 9 - idR;

@@ -5,35 +5,63 @@
 //           kExactRobust marginal prior                                include/Optimizer.h:126-816
 // One thread block per frame runs the reference's whole schedule — 4 rounds x optimize(10) of g2o's
 // Levenberg-Marquardt (optimization_algorithm_levenberg.cpp:61-189), inlier re-classification between rounds,
-// rescue pass, marginalisation — without leaving the SM: the visual edges are evaluated one per thread and reduced
-// with warp shuffles in a fixed order (deterministic), the <= 30-dim normal equations live in shared memory.
-// Batched over frames (grid = number of frames) this is the throughput form of the tracking thread's hot loop.
+// rescue pass, marginalisation — without leaving the SM.  Batched over frames (grid = number of frames) this is the
+// throughput form of the tracking thread's hot loop.
+//
+// Inside a block the work of one LM trial is laid out to keep the dependent fp64 chain short:
+//   * evaluate(): warps 0..5 take the visual edges (one edge per thread: residual, chi2, Huber weight, Jacobian,
+//     28 partial sums reduced with warp shuffles in a fixed order); warp 7 lane 0 does the inertial edge (residual +
+//     9x24 Jacobian strip), warp 6 lane 0 the bias-walk and prior edges — concurrently.  Then all threads form
+//     Omega e, J^T (rho' Omega) and finally every entry of H / b (<= 30 x 30) in a fixed summation order.
+//   * evaluate() at the trial estimate IS the next iteration's linearisation when the trial is accepted (g2o recomputes
+//     the same numbers): H / b are double-buffered in shared memory, a rejected trial simply keeps the old set.
+//   * the <= 30-dim Cholesky and the triangular solves run on warp 0 with lanes over matrix entries.
 #include <algorithm>
 
 #include "ba_edges.cuh"
 
 namespace vieo {
 
+#ifdef VIEO_PROF
+__device__ long long g_po_prof[16];
+#define PO_T(var) const long long var = clock64()
+#define PO_ACC(slot, t0, t1) \
+  if (blockIdx.x == 0) atomicAdd((unsigned long long*)&g_po_prof[slot], (unsigned long long)((t1) - (t0)))
+#else
+#define PO_T(var)
+#define PO_ACC(slot, t0, t1)
+#endif
+
 constexpr int kPoThreads = 256;
 constexpr int kPoWarps = kPoThreads / 32;
+constexpr int kPoVisWarps = 6;    // warps 0..5: visual edges; warp 6: bias + prior edges; warp 7: inertial edge
 constexpr int kPoN = 30;          // largest system: cur PVR 9 + bias 6 + last PVR 9 + bias 6
 constexpr int kPoMaxEdges = 4096; // per frame (the reference has N <= nfeatures + a few per camera)
 
+struct PoLin {  // one linearisation: normal equations + robust chi2
+  double H[kPoN * kPoN], b[kPoN];
+  double chi;
+};
 struct PoSmem {
-  double H[kPoN * kPoN], S[kPoN * kPoN];
-  double b[kPoN], x[kPoN], y[kPoN];
+  PoLin lin[2];
+  double S[kPoN * kPoN];
+  double x[kPoN], y[kPoN];
   double red[kPoWarps][32];
   double tot[32];
-  double Ji[135], Jj[81], Jb[90], Om[225], AtO[15 * 15], oe[15];
+  double Jimu[9 * 24];   // [Ji (last PVR) | Jj (frame PVR) | Jb (last bias)]
+  double Jpri[15 * 15];  // [Jpvr 15x9 | Jb 15x6]
+  double AtOimu[24 * 9], AtOpri[15 * 15];
+  double oe_imu[9], oe_pri[15], oe_bias[6];
   double info_imu[81], info_prior[225], info_bias[6];
   double err_imu[9], err_bias[6], err_prior[15];
-  double chi2_imu, chi2_bias, chi2_prior;
+  double chi2_imu, chi2_bias, chi2_prior, r1_imu, r1_bias, r1_prior, rho_imu, rho_bias, rho_prior;
   double C[225], CL[225], CCL[225];
   NavS st[2], bak[2], ini[2];
   CamPose cp;
-  double lambda, ni, currentChi, tempChi;
-  int nBad, ctl, total_iters, nbad_edges;
-  uint8_t eflag[kPoMaxEdges];  // bit0: level 1, bit1: kernel removed, bit2: outlier
+  VieoImuPreintLite pre;  // the frame's pre-integration staged once (the Sigma blocks are left out)
+  double lambda, ni;
+  int nBad, ok, total_iters, cur;
+  uint8_t eflag[kPoMaxEdges];  // bit0: level 1, bit1: kernel removed
 };
 
 struct PoCtx {
@@ -46,14 +74,15 @@ struct PoCtx {
   double* chi2;
   int E, n, dv;
   bool imu_mode, fixed_last, has_imu;
-  double delta_mono, delta_stereo;
+  double delta_mono, delta_stereo, delta_imu, delta_bias, delta_prior;
   Vec3 gw;
+  NavS prior;
 };
 
-// block-wide sum of `nv` doubles per thread (v[0..nv)), fixed order: lanes by xor tree, warps 0..7 in sequence.
-// Result in sm.tot[0..nv) (valid for all threads after the call).
+// sum of NV doubles per thread over the first `nwarps` warps, fixed order: lanes by xor tree, then warps in sequence.
+// Every thread of the block must call it (two barriers); result in sm.tot[0..NV).
 template <int NV>
-__device__ __forceinline__ void block_sum(PoSmem& sm, double (&v)[NV]) {
+__device__ __forceinline__ void block_sum(PoSmem& sm, double (&v)[NV], int nwarps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -62,15 +91,14 @@ __device__ __forceinline__ void block_sum(PoSmem& sm, double (&v)[NV]) {
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     v[k] = a;
   }
-  __syncthreads();
-  if (lane == 0) {
+  if (lane == 0 && warp < nwarps) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) sm.red[warp][k] = v[k];
   }
   __syncthreads();
   if (threadIdx.x < NV) {
     double a = 0;
-    for (int w = 0; w < kPoWarps; ++w) a += sm.red[w][threadIdx.x];
+    for (int w = 0; w < nwarps; ++w) a += sm.red[w][threadIdx.x];
     sm.tot[threadIdx.x] = a;
   }
   __syncthreads();
@@ -91,265 +119,359 @@ __device__ __forceinline__ double vis_chi2(const PoCtx& c, const PoSmem& sm, int
   return chi;
 }
 
-// errors + chi2 of the IMU / bias / prior edges (thread 0)
-__device__ void dense_errors(const PoCtx& c, PoSmem& sm, const NavS& prior) {
-  auto chi = [](const double* info, const double* e, int D) {
-    double s = 0;
-    for (int i = 0; i < D; ++i) {
-      double t = 0;
-      for (int j = 0; j < D; ++j) t += info[i * D + j] * e[j];
-      s += e[i] * t;
-    }
-    return s;
-  };
-  if (c.has_imu) {
-    navstate_error(sm.st[1], sm.st[0], c.pb->preint, c.gw, false, sm.err_imu);
-    sm.chi2_imu = chi(sm.info_imu, sm.err_imu, 9);
+// EdgeNavStatePVR Jacobians straight into the 9 x 24 strip [Ji | Jj | Jb] (same arithmetic as navstate_jac, prv = false)
+template <class Pre>
+__device__ void navstate_jac_pvr24(const NavS& si, const NavS& sj, const Pre& m, const Vec3& gw, const double e[9],
+                                   double* J) {
+  const Mat3 RiT = m3_t(q_matrix(si.q)), Rj = q_matrix(sj.q);
+  const double dt = m.dt;
+  for (int i = 0; i < 216; ++i) J[i] = 0;
+  const Mat3 JgR = ld_m3(m.JgR);
+  // rows / state columns in P, V, R order; column bases: Ji 0, Jj 9, Jb 18
+  Vec3 a = {sj.p.x - si.p.x - si.v.x * dt - gw.x * (dt * dt / 2), sj.p.y - si.p.y - si.v.y * dt - gw.y * (dt * dt / 2),
+            sj.p.z - si.p.z - si.v.z * dt - gw.z * (dt * dt / 2)};
+  Vec3 b = m3_mulv(RiT, a);
+  setb(J, 24, 0, 6, m3_hat(b));
+  setb(J, 24, 0, 0, m3_scale(m3_identity(), -1.0));
+  setb(J, 24, 0, 3, m3_scale(m3_scale(RiT, -1.0), dt));
+  setb(J, 24, 0, 18, m3_scale(ld_m3(m.Jgp), -1.0));
+  setb(J, 24, 0, 21, m3_scale(ld_m3(m.Jap), -1.0));
+  setb(J, 24, 0, 9, m3_mul(RiT, Rj));
+  a = {sj.v.x - si.v.x - gw.x * dt, sj.v.y - si.v.y - gw.y * dt, sj.v.z - si.v.z - gw.z * dt};
+  b = m3_mulv(RiT, a);
+  setb(J, 24, 3, 6, m3_hat(b));
+  setb(J, 24, 3, 3, m3_scale(RiT, -1.0));
+  setb(J, 24, 3, 18, m3_scale(ld_m3(m.Jgv), -1.0));
+  setb(J, 24, 3, 21, m3_scale(ld_m3(m.Jav), -1.0));
+  setb(J, 24, 3, 12, RiT);
+  const Vec3 eR = ld3(e + 6);
+  const Mat3 Jrinv = so3_JrInv(eR);
+  const Mat3 RjTRi = q_matrix(q_normalized(q_mul(q_conj(sj.q), si.q)));
+  setb(J, 24, 6, 6, m3_scale(m3_mul(Jrinv, RjTRi), -1.0));
+  const Vec3 w = m3_mulv(JgR, si.dbg);
+  const Mat3 Tm = m3_mul(m3_mul(m3_mul(m3_scale(Jrinv, -1.0), so3_Exp({-eR.x, -eR.y, -eR.z})), so3_Jr(w)), JgR);
+  setb(J, 24, 6, 18, Tm);
+  setb(J, 24, 6, 15, Jrinv);
+}
+
+__device__ __forceinline__ void bias_error(PoSmem& sm) {
+  const NavS &a = sm.st[1], &d = sm.st[0];
+  sm.err_bias[0] = (d.bg.x + d.dbg.x) - (a.bg.x + a.dbg.x);
+  sm.err_bias[1] = (d.bg.y + d.dbg.y) - (a.bg.y + a.dbg.y);
+  sm.err_bias[2] = (d.bg.z + d.dbg.z) - (a.bg.z + a.dbg.z);
+  sm.err_bias[3] = (d.ba.x + d.dba.x) - (a.ba.x + a.dba.x);
+  sm.err_bias[4] = (d.ba.y + d.dba.y) - (a.ba.y + a.dba.y);
+  sm.err_bias[5] = (d.ba.z + d.dba.z) - (a.ba.z + a.dba.z);
+}
+// [Jpvr 15x9 | Jb 15x6] of the prior edge (ld 15) at the current estimate; err_prior must be current
+__device__ __forceinline__ void prior_jac15(const PoCtx& c, PoSmem& sm) {
+  for (int i = 0; i < 225; ++i) sm.Jpri[i] = 0;
+  setb(sm.Jpri, 15, 0, 0, m3_mul(m3_t(q_matrix(c.prior.q)), q_matrix(sm.st[1].q)));
+  setb(sm.Jpri, 15, 3, 3, m3_identity());
+  setb(sm.Jpri, 15, 6, 6, so3_JrInv(ld3(sm.err_prior + 6)));
+  setb(sm.Jpri, 15, 9, 9, m3_identity());
+  setb(sm.Jpri, 15, 12, 12, m3_identity());
+}
+
+// Omega e, chi2 and Huber weights of the inertial / bias / prior edges from the residuals in shared memory.
+// All threads call it (contains barriers); the residuals must be visible (barrier before).
+__device__ void dense_chi2(const PoCtx& c, PoSmem& sm) {
+  const int t = threadIdx.x;
+  if (t < 9) {
+    double q = 0;
+    if (c.has_imu)
+      for (int j = 0; j < 9; ++j) q += sm.info_imu[t * 9 + j] * sm.err_imu[j];
+    sm.oe_imu[t] = q;
+  } else if (t >= 32 && t < 47) {
+    double q = 0;
+    if (!c.fixed_last)
+      for (int j = 0; j < 15; ++j) q += sm.info_prior[(t - 32) * 15 + j] * sm.err_prior[j];
+    sm.oe_pri[t - 32] = q;
+  } else if (t >= 64 && t < 70) {
+    sm.oe_bias[t - 64] = sm.info_bias[t - 64] * sm.err_bias[t - 64];
   }
-  {
-    const NavS &a = sm.st[1], &d = sm.st[0];
-    sm.err_bias[0] = (d.bg.x + d.dbg.x) - (a.bg.x + a.dbg.x);
-    sm.err_bias[1] = (d.bg.y + d.dbg.y) - (a.bg.y + a.dbg.y);
-    sm.err_bias[2] = (d.bg.z + d.dbg.z) - (a.bg.z + a.dbg.z);
-    sm.err_bias[3] = (d.ba.x + d.dba.x) - (a.ba.x + a.dba.x);
-    sm.err_bias[4] = (d.ba.y + d.dba.y) - (a.ba.y + a.dba.y);
-    sm.err_bias[5] = (d.ba.z + d.dba.z) - (a.ba.z + a.dba.z);
+  __syncthreads();
+  if (t == 0) {
     double s = 0;
-    for (int i = 0; i < 6; ++i) s += sm.err_bias[i] * (sm.info_bias[i] * sm.err_bias[i]);
+    for (int i = 0; i < 9; ++i) s += sm.err_imu[i] * sm.oe_imu[i];
+    sm.chi2_imu = c.has_imu ? s : 0.0;
+    huber_rho(c.delta_imu, sm.chi2_imu, sm.rho_imu, sm.r1_imu);
+  } else if (t == 32) {
+    double s = 0;
+    for (int i = 0; i < 15; ++i) s += sm.err_prior[i] * sm.oe_pri[i];
+    sm.chi2_prior = c.fixed_last ? 0.0 : s;
+    huber_rho(c.delta_prior, sm.chi2_prior, sm.rho_prior, sm.r1_prior);
+  } else if (t == 64) {
+    double s = 0;
+    for (int i = 0; i < 6; ++i) s += sm.err_bias[i] * sm.oe_bias[i];
     sm.chi2_bias = s;
-  }
-  if (!c.fixed_last) {
-    prior_error(sm.st[1], prior, sm.err_prior);
-    sm.chi2_prior = chi(sm.info_prior, sm.err_prior, 15);
-  }
-}
-
-// H[oa.., ob..] += Ja^T (r1 info) Jb, b[oa..] += Ja^T (-r1 info e)   (BaseMultiEdge::constructQuadraticForm)
-struct PoBlk {
-  int off, dim;
-  const double* J;
-  int ld, c0;
-};
-__device__ void add_dense(PoSmem& sm, int n, int D, const double* info, const double* err, double r1, const PoBlk* blks,
-                          int nb) {
-  for (int i = 0; i < D * D; ++i) sm.Om[i] = r1 * info[i];
-  for (int i = 0; i < D; ++i) {
-    double s = 0;
-    for (int j = 0; j < D; ++j) s += info[i * D + j] * err[j];
-    sm.oe[i] = -s * r1;
-  }
-  for (int ia = 0; ia < nb; ++ia) {
-    const PoBlk& A = blks[ia];
-    if (A.off < 0) continue;
-    for (int a = 0; a < A.dim; ++a)
-      for (int j = 0; j < D; ++j) {
-        double s = 0;
-        for (int i = 0; i < D; ++i) s += A.J[i * A.ld + A.c0 + a] * sm.Om[i * D + j];
-        sm.AtO[a * D + j] = s;
-      }
-    for (int a = 0; a < A.dim; ++a) {
-      double s = 0;
-      for (int i = 0; i < D; ++i) s += A.J[i * A.ld + A.c0 + a] * sm.oe[i];
-      sm.b[A.off + a] += s;
-    }
-    for (int ib = 0; ib < nb; ++ib) {
-      const PoBlk& B = blks[ib];
-      if (B.off < 0) continue;
-      for (int a = 0; a < A.dim; ++a)
-        for (int cc = 0; cc < B.dim; ++cc) {
-          double s = 0;
-          for (int j = 0; j < D; ++j) s += sm.AtO[a * D + j] * B.J[j * B.ld + B.c0 + cc];
-          sm.H[(A.off + a) * n + B.off + cc] += s;
-        }
-    }
-  }
-}
-
-// Cholesky solve (H + lambda I) x = b in shared memory by one thread; false when a pivot is not positive
-__device__ bool chol_solve(PoSmem& sm, int n) {
-  double* A = sm.S;
-  for (int i = 0; i < n * n; ++i) A[i] = sm.H[i];
-  for (int i = 0; i < n; ++i) A[i * n + i] += sm.lambda;
-  for (int j = 0; j < n; ++j) {
-    double d = A[j * n + j];
-    for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
-    if (!(d > 0) || !isfinite(d)) return false;
-    d = sqrt(d);
-    A[j * n + j] = d;
-    for (int i = j + 1; i < n; ++i) {
-      double s = A[i * n + j];
-      for (int k = 0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
-      A[i * n + j] = s / d;
-    }
-  }
-  for (int i = 0; i < n; ++i) {
-    double s = sm.b[i];
-    for (int k = 0; k < i; ++k) s -= A[i * n + k] * sm.y[k];
-    sm.y[i] = s / A[i * n + i];
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = sm.y[i];
-    for (int k = i + 1; k < n; ++k) s -= A[k * n + i] * sm.x[k];
-    sm.x[i] = s / A[i * n + i];
-  }
-  return true;
-}
-
-// computeActiveErrors + activeRobustChi2: visual edges in parallel (chi2 stored per edge), dense edges by thread 0.
-// Returns the robust chi2 to every thread.
-__device__ double active_errors(const PoCtx& c, PoSmem& sm, const NavS& prior) {
-  if (threadIdx.x == 0) {
-    sm.cp = cam_pose(c.cam, sm.st[0]);
-    if (c.imu_mode) dense_errors(c, sm, prior);
+    huber_rho(c.delta_bias, s, sm.rho_bias, sm.r1_bias);
   }
   __syncthreads();
-  double acc[1] = {0.0};
-  for (int i = threadIdx.x; i < c.E; i += kPoThreads) {
-    if (sm.eflag[i] & 1) continue;
-    double e[3];
-    const double chi = vis_chi2(c, sm, i, e);
-    c.chi2[i] = chi;
-    double r0, r1;
-    huber_rho(edge_delta(c, sm, i), chi, r0, r1);
-    acc[0] += r0;
-  }
-  block_sum<1>(sm, acc);
-  double total = 0;
+}
+__device__ __forceinline__ double dense_rho_sum(const PoCtx& c, const PoSmem& sm) {
+  double tot = 0;
   if (c.imu_mode) {
-    double r0, r1;
-    if (c.has_imu) {
-      huber_rho(c.fixed_last ? sqrt(16.919) : 0.0, sm.chi2_imu, r0, r1);
-      total += r0;
-    }
-    huber_rho(c.fixed_last ? sqrt(12.592) : 0.0, sm.chi2_bias, r0, r1);
-    total += r0;
-    if (!c.fixed_last) {
-      huber_rho(sqrt(25.0), sm.chi2_prior, r0, r1);
-      total += r0;
-    }
+    if (c.has_imu) tot += sm.rho_imu;
+    tot += sm.rho_bias;
+    if (!c.fixed_last) tot += sm.rho_prior;
   }
-  return total + sm.tot[0];
+  return tot;
 }
 
-// buildSystem: H, b at the current estimate with the errors of the last active_errors()
-__device__ void build_system(const PoCtx& c, PoSmem& sm, const NavS& prior) {
-  const int n = c.n, dv = c.dv;
-  for (int i = threadIdx.x; i < n * n; i += kPoThreads) sm.H[i] = 0;
-  if (threadIdx.x < n) sm.b[threadIdx.x] = 0;
-  __syncthreads();
-  if (threadIdx.x == 0 && c.imu_mode) {
-    double r0, r1;
-    const int oL = c.fixed_last ? -1 : 15, oLb = c.fixed_last ? -1 : 24;
-    if (c.has_imu) {
-      navstate_jac(sm.st[1], sm.st[0], c.pb->preint, c.gw, false, sm.err_imu, sm.Ji, sm.Jj, sm.Jb);
-      huber_rho(c.fixed_last ? sqrt(16.919) : 0.0, sm.chi2_imu, r0, r1);
-      const PoBlk blks[3] = {{oL, 9, sm.Ji, 9, 0}, {0, 9, sm.Jj, 9, 0}, {oLb, 6, sm.Jb, 6, 0}};
-      add_dense(sm, n, 9, sm.info_imu, sm.err_imu, r1, blks, 3);
-    }
-    {
-      huber_rho(c.fixed_last ? sqrt(12.592) : 0.0, sm.chi2_bias, r0, r1);
-      // J_i = -I (last bias), J_j = +I (frame bias), diagonal information
-      for (int k = 0; k < 6; ++k) {
-        const double om = r1 * sm.info_bias[k];
-        const double oe = -(sm.info_bias[k] * sm.err_bias[k]) * r1;
-        sm.H[(9 + k) * n + 9 + k] += om;
-        sm.b[9 + k] += oe;
-        if (oLb >= 0) {
-          sm.H[(oLb + k) * n + oLb + k] += om;
-          sm.b[oLb + k] += -oe;
-          sm.H[(oLb + k) * n + 9 + k] += -om;
-          sm.H[(9 + k) * n + oLb + k] += -om;
+// computeActiveErrors + buildSystem at the current estimate into sm.lin[set]; chi2 per visual edge stored in c.chi2.
+// sm.cp must hold the camera pose of the current estimate.  All threads call it.
+__device__ void evaluate(const PoCtx& c, PoSmem& sm, int set) {
+  const int n = c.n, dv = c.dv, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PoLin& L = sm.lin[set];
+  double acc[28];
+#pragma unroll
+  for (int k = 0; k < 28; ++k) acc[k] = 0;
+  PO_T(t_a);
+  if (warp < kPoVisWarps) {
+    for (int i = threadIdx.x; i < c.E; i += kPoVisWarps * 32) {
+      if (sm.eflag[i] & 1) continue;
+      const bool stereo = c.flags[i] & VIEO_EDGE_STEREO;
+      const int DE = stereo ? 3 : 2;
+      const Vec3 X = ld3(c.Xw + 3 * (size_t)i);
+      double e[3];
+      reproj_error(c.cam, sm.cp, X, c.obs + 3 * (size_t)i, stereo, e);
+      const double wi = (double)c.w[i];
+      double chi = 0;
+      for (int k = 0; k < DE; ++k) chi += e[k] * (wi * e[k]);
+      c.chi2[i] = chi;
+      double r0, r1;
+      huber_rho(edge_delta(c, sm, i), chi, r0, r1);
+      acc[27] += r0;
+      Mat3 Jp, Jr, JX;
+      reproj_jac(c.cam, sm.cp, X, stereo, Jp, Jr, JX);
+      const double w = r1 * wi;
+      double J[3][6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          J[k][cc] = Jp.m[3 * k + cc];
+          J[k][3 + cc] = Jr.m[3 * k + cc];
+        }
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double s = 0;
+        for (int k = 0; k < DE; ++k) s += J[k][a] * (-(wi * e[k]) * r1);
+        acc[21 + a] += s;
+#pragma unroll
+        for (int cc = a; cc < 6; ++cc) {
+          double h = 0;
+          for (int k = 0; k < DE; ++k) h += (J[k][a] * w) * J[k][cc];
+          acc[q++] += h;
         }
       }
     }
-    if (!c.fixed_last) {
-      prior_jac(sm.st[1], prior, sm.err_prior, sm.Ji, sm.Jb);
-      huber_rho(sqrt(25.0), sm.chi2_prior, r0, r1);
-      const PoBlk blks[2] = {{15, 9, sm.Ji, 9, 0}, {24, 6, sm.Jb, 6, 0}};
-      add_dense(sm, n, 15, sm.info_prior, sm.err_prior, r1, blks, 2);
-    }
-  }
-  // visual edges: 6 non-zero pose columns (dp, dphi) -> 21 upper-triangle entries + 6 rhs
-  double acc[27];
-#pragma unroll
-  for (int k = 0; k < 27; ++k) acc[k] = 0;
-  for (int i = threadIdx.x; i < c.E; i += kPoThreads) {
-    if (sm.eflag[i] & 1) continue;
-    const bool stereo = c.flags[i] & VIEO_EDGE_STEREO;
-    const int DE = stereo ? 3 : 2;
-    const Vec3 X = ld3(c.Xw + 3 * (size_t)i);
-    double e[3];
-    reproj_error(c.cam, sm.cp, X, c.obs + 3 * (size_t)i, stereo, e);
-    Mat3 Jp, Jr, JX;
-    reproj_jac(c.cam, sm.cp, X, stereo, Jp, Jr, JX);
-    double r0, r1;
-    huber_rho(edge_delta(c, sm, i), c.chi2[i], r0, r1);
-    const double wi = (double)c.w[i], w = r1 * wi;
-    double J[3][6];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int cc = 0; cc < 3; ++cc) {
-        J[k][cc] = Jp.m[3 * k + cc];
-        J[k][3 + cc] = Jr.m[3 * k + cc];
+  } else if (c.imu_mode && lane == 0) {
+    if (warp == 7) {
+      if (c.has_imu) {
+        navstate_error(sm.st[1], sm.st[0], sm.pre, c.gw, false, sm.err_imu);
+        navstate_jac_pvr24(sm.st[1], sm.st[0], sm.pre, c.gw, sm.err_imu, sm.Jimu);
       }
-    int q = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double s = 0;
-      for (int k = 0; k < DE; ++k) s += J[k][a] * (-(wi * e[k]) * r1);
-      acc[21 + a] += s;
-#pragma unroll
-      for (int cc = a; cc < 6; ++cc) {
-        double h = 0;
-        for (int k = 0; k < DE; ++k) h += (J[k][a] * w) * J[k][cc];
-        acc[q++] += h;
+    } else {
+      bias_error(sm);
+      if (!c.fixed_last) {
+        prior_error(sm.st[1], c.prior, sm.err_prior);
+        prior_jac15(c, sm);
       }
     }
   }
-  block_sum<27>(sm, acc);
-  if (threadIdx.x == 0) {
-    int q = 0;
-    for (int a = 0; a < 6; ++a) {
-      const int ra = a < 3 ? a : dv - 6 + a;
-      sm.b[ra] += sm.tot[21 + a];
-      for (int cc = a; cc < 6; ++cc) {
-        const int rc = cc < 3 ? cc : dv - 6 + cc;
-        const double h = sm.tot[q++];
-        sm.H[ra * n + rc] += h;
-        if (rc != ra) sm.H[rc * n + ra] += h;
+  PO_T(t_b);
+  if (threadIdx.x == 0) PO_ACC(0, t_a, t_b);        // visual edges, thread 0
+  if (threadIdx.x == 224) PO_ACC(1, t_a, t_b);      // inertial edge, warp 7 lane 0
+  if (threadIdx.x == 192) PO_ACC(2, t_a, t_b);      // bias + prior, warp 6 lane 0
+  block_sum<28>(sm, acc, kPoVisWarps);  // its barriers also publish the dense residuals / Jacobians
+  PO_T(t_c);
+  if (threadIdx.x == 0) PO_ACC(3, t_b, t_c);        // wait + reduction
+  if (c.imu_mode) {
+    dense_chi2(c, sm);
+    // J^T (rho' Omega): AtO[a][j] = sum_i J[i][a] (r1 Omega[i][j])
+    for (int t = threadIdx.x; t < 216 + 225; t += kPoThreads) {
+      if (t < 216) {
+        if (!c.has_imu) continue;
+        const int a = t / 9, j = t % 9;
+        double q = 0;
+        for (int i = 0; i < 9; ++i) q += sm.Jimu[i * 24 + a] * (sm.r1_imu * sm.info_imu[i * 9 + j]);
+        sm.AtOimu[t] = q;
+      } else {
+        if (c.fixed_last) continue;
+        const int u = t - 216, a = u / 15, j = u % 15;
+        double q = 0;
+        for (int i = 0; i < 15; ++i) q += sm.Jpri[i * 15 + a] * (sm.r1_prior * sm.info_prior[i * 15 + j]);
+        sm.AtOpri[u] = q;
       }
     }
+    // oe <- -(Omega e) rho'
+    if (threadIdx.x < 9) sm.oe_imu[threadIdx.x] = -sm.oe_imu[threadIdx.x] * sm.r1_imu;
+    else if (threadIdx.x >= 32 && threadIdx.x < 47) sm.oe_pri[threadIdx.x - 32] = -sm.oe_pri[threadIdx.x - 32] * sm.r1_prior;
+    else if (threadIdx.x >= 64 && threadIdx.x < 70) sm.oe_bias[threadIdx.x - 64] = -sm.oe_bias[threadIdx.x - 64] * sm.r1_bias;
+    __syncthreads();
   }
+  PO_T(t_d);
+  if (threadIdx.x == 0) PO_ACC(4, t_c, t_d);        // Omega e, chi2, AtO
+  // every entry of H (b in the extra column) in a fixed order: inertial, bias, prior, visual.
+  // Hessian index order: frame PVR/PR 0.., frame bias 9..14, last PVR 15..23, last bias 24..29
+  for (int t = threadIdx.x; t < n * (n + 1); t += kPoThreads) {
+    const int r = t / (n + 1), cc = t % (n + 1);
+    const bool rhs = cc == n;
+    double h = 0;
+    if (c.imu_mode) {
+      // local column of the inertial strip: frame PVR -> 9.., last PVR -> 0.., last bias -> 18.., frame bias: none
+      auto imu_col = [](int g) { return g < 9 ? 9 + g : g < 15 ? -1 : g < 24 ? g - 15 : 18 + (g - 24); };
+      if (c.has_imu) {
+        const int lr = imu_col(r);
+        if (lr >= 0) {
+          if (rhs) {
+            double s = 0;
+            for (int i = 0; i < 9; ++i) s += sm.Jimu[i * 24 + lr] * sm.oe_imu[i];
+            h += s;
+          } else {
+            const int lc = imu_col(cc);
+            if (lc >= 0) {
+              double s = 0;
+              for (int j = 0; j < 9; ++j) s += sm.AtOimu[lr * 9 + j] * sm.Jimu[j * 24 + lc];
+              h += s;
+            }
+          }
+        }
+      }
+      {  // bias walk: J_i = -I on the last bias (24..29), J_j = +I on the frame bias (9..14)
+        const int kr = (r >= 9 && r < 15) ? r - 9 : (r >= 24 ? r - 24 : -1);
+        if (kr >= 0) {
+          const double sgn_r = r < 15 ? 1.0 : -1.0;
+          if (rhs) h += sgn_r * sm.oe_bias[kr];
+          else {
+            const int kc = (cc >= 9 && cc < 15) ? cc - 9 : (cc >= 24 ? cc - 24 : -1);
+            if (kc == kr) h += (sgn_r * (cc < 15 ? 1.0 : -1.0)) * (sm.r1_bias * sm.info_bias[kr]);
+          }
+        }
+      }
+      if (!c.fixed_last && r >= 15) {  // prior: last PVR 15..23 -> 0..8, last bias 24..29 -> 9..14
+        const int lr = r - 15;
+        if (rhs) {
+          double s = 0;
+          for (int i = 0; i < 15; ++i) s += sm.Jpri[i * 15 + lr] * sm.oe_pri[i];
+          h += s;
+        } else if (cc >= 15) {
+          const int lc = cc - 15;
+          double s = 0;
+          for (int j = 0; j < 15; ++j) s += sm.AtOpri[lr * 15 + j] * sm.Jpri[j * 15 + lc];
+          h += s;
+        }
+      }
+    }
+    // visual block: pose columns (dp 0..2, dphi dv-3..dv-1) of the frame vertex
+    const int va = r < 3 ? r : (r >= dv - 3 && r < dv ? r - (dv - 6) : -1);
+    if (va >= 0) {
+      if (rhs) h += sm.tot[21 + va];
+      else {
+        const int vc = cc < 3 ? cc : (cc >= dv - 3 && cc < dv ? cc - (dv - 6) : -1);
+        if (vc >= 0) {
+          const int lo = min(va, vc), hi = max(va, vc);
+          h += sm.tot[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];  // upper-triangle packing of the 6x6 block
+        }
+      }
+    }
+    if (rhs) L.b[r] = h;
+    else L.H[r * n + cc] = h;
+  }
+  if (threadIdx.x == 0) L.chi = dense_rho_sum(c, sm) + sm.tot[27];
   __syncthreads();
+  PO_T(t_e);
+  if (threadIdx.x == 0) {
+    PO_ACC(5, t_d, t_e);                            // H / b entries
+    PO_ACC(6, t_a, t_e);                            // evaluate total
+    PO_ACC(7, 0, 1);                                // evaluate calls
+  }
+}
+
+// (H + lambda I) x = b by warp 0 (n <= 30 <= 32: lane i owns row i).  Column-oriented Cholesky and substitutions with
+// one reciprocal square root per column instead of divisions.  Sets sm.ok (LDLT::isPositive).  Other warps wait at
+// the caller's barrier.
+__device__ void solve_system(PoSmem& sm, const PoLin& L, int n) {
+  if (threadIdx.x >= 32) return;
+  const int i = threadIdx.x;
+  double* A = sm.S;
+  for (int t = i; t < n * n; t += 32) A[t] = L.H[t] + ((t / n == t % n) ? sm.lambda : 0.0);
+  __syncwarp();
+  bool good = true;
+  for (int j = 0; j < n; ++j) {
+    const double d2 = A[j * n + j];
+    if (!(d2 > 0) || !isfinite(d2)) {
+      good = false;
+      break;
+    }
+    const double rd = rsqrt(d2);
+    __syncwarp();
+    if (i == j) A[j * n + j] = d2 * rd;  // sqrt(d2)
+    double f = 0;
+    if (i > j && i < n) {
+      f = A[i * n + j] * rd;
+      A[i * n + j] = f;
+    }
+    __syncwarp();
+    if (i > j && i < n)
+      for (int k = j + 1; k <= i; ++k) A[i * n + k] -= f * A[k * n + j];
+    __syncwarp();
+  }
+  if (i == 0) sm.ok = good ? 1 : 0;
+  if (!good) return;
+  // forward: L y = b; backward: L^T x = y.  Lane i carries entry i; the pivot entry is broadcast every step.
+  const double rdi = i < n ? 1.0 / A[i * n + i] : 0.0;
+  double yi = i < n ? L.b[i] : 0.0;
+  for (int j = 0; j < n; ++j) {
+    const double yj = __shfl_sync(0xffffffffu, yi * rdi, j);
+    if (i == j) yi = yj;
+    else if (i > j && i < n) yi -= A[i * n + j] * yj;
+  }
+  double xi = yi;
+  for (int j = n - 1; j >= 0; --j) {
+    const double xj = __shfl_sync(0xffffffffu, xi * rdi, j);
+    if (i == j) xi = xj;
+    else if (i < j) xi -= A[j * n + i] * xj;
+  }
+  if (i < n) {
+    sm.y[i] = yi;
+    sm.x[i] = xi;
+  }
 }
 
 __device__ void apply_update(const PoCtx& c, PoSmem& sm) {
   if (!c.imu_mode) {
     ns_inc_pr(sm.st[0], sm.x);
-    return;
+  } else {
+    ns_inc_pvr(sm.st[0], sm.x);
+    ns_inc_bias(sm.st[0], sm.x + 9);
+    if (!c.fixed_last) {
+      ns_inc_pvr(sm.st[1], sm.x + 15);
+      ns_inc_bias(sm.st[1], sm.x + 24);
+    }
   }
-  ns_inc_pvr(sm.st[0], sm.x);
-  ns_inc_bias(sm.st[0], sm.x + 9);
-  if (!c.fixed_last) {
-    ns_inc_pvr(sm.st[1], sm.x + 15);
-    ns_inc_bias(sm.st[1], sm.x + 24);
-  }
+  sm.cp = cam_pose(c.cam, sm.st[0]);
 }
 
 // SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg::solve inlined
-__device__ void optimize(const PoCtx& c, PoSmem& sm, const NavS& prior, int iterations) {
+__device__ void optimize(const PoCtx& c, PoSmem& sm, int iterations) {
   const int n = c.n;
   if (threadIdx.x < n) sm.x[threadIdx.x] = 0;
+  if (threadIdx.x == 0) sm.cp = cam_pose(c.cam, sm.st[0]);
+  __syncthreads();
+  int cur = 0;
+  evaluate(c, sm, cur);  // levels / kernels / estimate may have changed since the last call
   bool ok = true;
   for (int it = 0; it < iterations && ok; ++it) {
-    double currentChi = active_errors(c, sm, prior);
+    double currentChi = sm.lin[cur].chi;
     const double iniChi = currentChi;
-    build_system(c, sm, prior);
     if (threadIdx.x == 0) {
       if (it == 0) {  // computeLambdaInit: tau * max |diag(H)|
         double mx = 0;
-        for (int i = 0; i < n; ++i) mx = fmax(fabs(sm.H[i * n + i]), mx);
+        for (int i = 0; i < n; ++i) mx = fmax(fabs(sm.lin[cur].H[i * n + i]), mx);
         sm.lambda = 1e-5 * mx;
         sm.ni = 2;
         sm.nBad = 0;
@@ -360,18 +482,26 @@ __device__ void optimize(const PoCtx& c, PoSmem& sm, const NavS& prior, int iter
     int qmax = 0;
     do {
       __syncthreads();
+      PO_T(t_s0);
+      solve_system(sm, sm.lin[cur], n);
+      PO_T(t_s1);
       if (threadIdx.x == 0) {
         sm.bak[0] = sm.st[0];
         sm.bak[1] = sm.st[1];
-        sm.ctl = chol_solve(sm, n) ? 1 : 0;
-        apply_update(c, sm);
+        if (sm.ok) apply_update(c, sm);
+      }
+      PO_T(t_s2);
+      if (threadIdx.x == 0) {
+        PO_ACC(8, t_s0, t_s1);                      // Cholesky + solves
+        PO_ACC(9, t_s1, t_s2);                      // oplus + camera pose
       }
       __syncthreads();
-      double tempChi = active_errors(c, sm, prior);
-      if (!sm.ctl) tempChi = 1.7976931348623157e308;
+      evaluate(c, sm, 1 - cur);  // errors at the trial estimate + speculative linearisation
+      double tempChi = sm.lin[1 - cur].chi;
+      if (!sm.ok) tempChi = 1.7976931348623157e308;
       rho = currentChi - tempChi;
       double scale = 0;
-      for (int j = 0; j < n; ++j) scale += sm.x[j] * (sm.lambda * sm.x[j] + sm.b[j]);
+      for (int j = 0; j < n; ++j) scale += sm.x[j] * (sm.lambda * sm.x[j] + sm.lin[cur].b[j]);
       scale += 1e-3;
       rho /= scale;
       __syncthreads();  // every thread has read lambda / x before thread 0 changes them
@@ -383,12 +513,14 @@ __device__ void optimize(const PoCtx& c, PoSmem& sm, const NavS& prior, int iter
           sm.ni = 2;
         }
         currentChi = tempChi;
+        cur = 1 - cur;
       } else {
         if (threadIdx.x == 0) {
           sm.lambda *= sm.ni;
           sm.ni *= 2;
           sm.st[0] = sm.bak[0];
           sm.st[1] = sm.bak[1];
+          sm.cp = cam_pose(c.cam, sm.st[0]);
         }
       }
       qmax++;
@@ -437,8 +569,11 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
   c.n = c.imu_mode ? (c.fixed_last ? 15 : 30) : 6;
   c.delta_mono = (double)(float)sqrt(5.991);
   c.delta_stereo = (double)(float)sqrt(7.815);
+  c.delta_imu = c.fixed_last ? sqrt(16.919) : 0.0;   // USE_ZZH_IMU_EDGE_FEBA (include/Optimizer.h:293-303)
+  c.delta_bias = c.fixed_last ? sqrt(12.592) : 0.0;  // :326-333
+  c.delta_prior = sqrt(25.0);                        // :351
   c.gw = ld3(pb.gw);
-  const NavS prior = ns_load(pb.prior);
+  c.prior = ns_load(pb.prior);
   const int E = c.E;
 
   for (int i = threadIdx.x; i < E; i += kPoThreads) {
@@ -446,11 +581,28 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
     outl[i] = 0;
     c.chi2[i] = 0;
   }
+  if (threadIdx.x < 9) {
+    const int t = threadIdx.x;
+    sm.pre.Rij[t] = pb.preint.Rij[t]; sm.pre.Jgp[t] = pb.preint.Jgp[t]; sm.pre.Jap[t] = pb.preint.Jap[t];
+    sm.pre.Jgv[t] = pb.preint.Jgv[t]; sm.pre.Jav[t] = pb.preint.Jav[t]; sm.pre.JgR[t] = pb.preint.JgR[t];
+    if (t < 3) {
+      sm.pre.vij[t] = pb.preint.vij[t];
+      sm.pre.pij[t] = pb.preint.pij[t];
+    }
+    if (t == 0) sm.pre.dt = pb.preint.dt;
+  }
   if (threadIdx.x == 0) {
     sm.st[0] = sm.ini[0] = ns_load(pb.cur);
     sm.st[1] = sm.ini[1] = ns_load(pb.last);
     sm.total_iters = 0;
     sm.lambda = 0;
+    sm.ok = 1;
+    for (int i = 0; i < 9; ++i) sm.err_imu[i] = 0;
+    for (int i = 0; i < 15; ++i) sm.err_prior[i] = 0;
+    for (int i = 0; i < 6; ++i) sm.err_bias[i] = 0;
+    sm.chi2_imu = sm.chi2_bias = sm.chi2_prior = 0;
+    sm.rho_imu = sm.rho_bias = sm.rho_prior = 0;
+    sm.r1_imu = sm.r1_bias = sm.r1_prior = 1;
     if (c.imu_mode) {
       if (c.has_imu) {  // GetProcessedInfoij = mSigmaij.inverse() (OdomPreIntegrator.h:129-138), x 1e-2 when last is fixed
         for (int i = 0; i < 81; ++i) sm.S[i] = pb.preint.SigmaPVR[i];
@@ -492,9 +644,7 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
       }
     }
     __syncthreads();
-    optimize(c, sm, prior, 10);
-    if (threadIdx.x == 0) sm.cp = cam_pose(c.cam, sm.st[0]);
-    __syncthreads();
+    optimize(c, sm, 10);
     double bad[1] = {0};
     for (int i = threadIdx.x; i < E; i += kPoThreads) {
       double e[3], depth = 1;
@@ -510,7 +660,7 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
       sm.eflag[i] = f;
       bad[0] += isbad;
     }
-    block_sum<1>(sm, bad);
+    block_sum<1>(sm, bad, kPoWarps);
     nBad = (int)sm.tot[0];
     if (n_edges_total < 10) break;
   }
@@ -526,10 +676,10 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
       } else
         bad[0] += 1;
     }
-    block_sum<1>(sm, bad);
+    block_sum<1>(sm, bad, kPoWarps);
     nBad = (int)sm.tot[0];
   }
-  // activeRobustChi2 of the final active set with the stored errors
+  // activeRobustChi2 of the final level-0 set with the stored errors
   {
     double acc[1] = {0};
     for (int i = threadIdx.x; i < E; i += kPoThreads) {
@@ -538,18 +688,12 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
       huber_rho(edge_delta(c, sm, i), c.chi2[i], r0, r1);
       acc[0] += r0;
     }
-    block_sum<1>(sm, acc);
+    block_sum<1>(sm, acc, kPoWarps);
   }
   if (threadIdx.x == 0) {
     ns_store(sm.st[0], R.cur);
     ns_store(c.imu_mode ? sm.st[1] : sm.ini[1], R.last);
-    double tot = sm.tot[0], r0, r1;
-    if (c.imu_mode) {
-      if (c.has_imu) { huber_rho(c.fixed_last ? sqrt(16.919) : 0.0, sm.chi2_imu, r0, r1); tot += r0; }
-      huber_rho(c.fixed_last ? sqrt(12.592) : 0.0, sm.chi2_bias, r0, r1); tot += r0;
-      if (!c.fixed_last) { huber_rho(sqrt(25.0), sm.chi2_prior, r0, r1); tot += r0; }
-    }
-    R.chi2_final = tot;
+    R.chi2_final = sm.tot[0] + dense_rho_sum(c, sm);
     R.lambda_final = sm.lambda;
     R.n_inliers = nInitial - nBad;
     R.n_initial = nInitial;
@@ -561,21 +705,27 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
     return;
   }
   // ---- marginal prior, exact_mode = kExactRobust (include/Optimizer.h:126-206, 671-728) ----------------------
+  // errors of the inertial / bias / prior edges recomputed and every edge re-linearised at the final estimate
   __syncthreads();
-  double wI = 1, wB = 1;
-  if (threadIdx.x == 0) {
-    sm.cp = cam_pose(c.cam, sm.st[0]);
-    dense_errors(c, sm, prior);
-    for (int i = 0; i < 225; ++i) sm.C[i] = 0;
-    double r0;
-    if (c.has_imu) {
-      navstate_jac(sm.st[1], sm.st[0], pb.preint, c.gw, false, sm.err_imu, sm.Ji, sm.Jj, sm.Jb);
-      huber_rho(c.fixed_last ? sqrt(16.919) : 0.0, sm.chi2_imu, r0, wI);
-      jtoj(sm.Jj, 9, 0, 9, sm.info_imu, 9, wI, sm.Jj, 9, 0, 9, sm.C, 15, 0, 0, false);
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0 && warp == 7 && c.has_imu) {
+      navstate_error(sm.st[1], sm.st[0], sm.pre, c.gw, false, sm.err_imu);
+      navstate_jac_pvr24(sm.st[1], sm.st[0], sm.pre, c.gw, sm.err_imu, sm.Jimu);
     }
-    huber_rho(c.fixed_last ? sqrt(12.592) : 0.0, sm.chi2_bias, r0, wB);
-    for (int k = 0; k < 6; ++k) sm.C[(9 + k) * 15 + 9 + k] = wB * sm.info_bias[k];
+    if (lane == 0 && warp == 6) {
+      bias_error(sm);
+      if (!c.fixed_last) {
+        prior_error(sm.st[1], c.prior, sm.err_prior);
+        prior_jac15(c, sm);
+      }
+    }
+    if (threadIdx.x == 0) sm.cp = cam_pose(c.cam, sm.st[0]);
   }
+  __syncthreads();
+  dense_chi2(c, sm);
+  const double wI = sm.r1_imu, wB = sm.r1_bias, wP = sm.r1_prior;
+  for (int i = threadIdx.x; i < 225; i += kPoThreads) sm.C[i] = sm.CL[i] = sm.CCL[i] = 0;
   __syncthreads();
   {
     double acc[21];
@@ -608,9 +758,14 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
           acc[q++] += s;
         }
     }
-    block_sum<21>(sm, acc);
+    block_sum<21>(sm, acc, kPoWarps);
   }
   if (threadIdx.x == 0) {
+    const double* Ji = sm.Jimu;       // 9 x 24, columns 0..8
+    const double* Jj = sm.Jimu + 9;   // columns 9..17
+    const double* Jb = sm.Jimu + 18;  // columns 18..23
+    if (c.has_imu) jtoj(Jj, 24, 0, 9, sm.info_imu, 9, wI, Jj, 24, 0, 9, sm.C, 15, 0, 0, false);
+    for (int k = 0; k < 6; ++k) sm.C[(9 + k) * 15 + 9 + k] = wB * sm.info_bias[k];
     int q = 0;
     for (int a = 0; a < 6; ++a) {
       const int ra = a < 3 ? a : 3 + a;
@@ -622,31 +777,28 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
       }
     }
     if (!c.fixed_last) {
-      double r0, wP;
-      for (int i = 0; i < 225; ++i) sm.CL[i] = sm.CCL[i] = 0;
       if (c.has_imu) {
-        jtoj(sm.Ji, 9, 0, 9, sm.info_imu, 9, wI, sm.Ji, 9, 0, 9, sm.CL, 15, 0, 0, false);
-        jtoj(sm.Ji, 9, 0, 9, sm.info_imu, 9, wI, sm.Jb, 6, 0, 6, sm.CL, 15, 0, 9, false);
-        jtoj(sm.Jb, 6, 0, 6, sm.info_imu, 9, wI, sm.Jb, 6, 0, 6, sm.CL, 15, 9, 9, false);
+        jtoj(Ji, 24, 0, 9, sm.info_imu, 9, wI, Ji, 24, 0, 9, sm.CL, 15, 0, 0, false);
+        jtoj(Ji, 24, 0, 9, sm.info_imu, 9, wI, Jb, 24, 0, 6, sm.CL, 15, 0, 9, false);
+        jtoj(Jb, 24, 0, 6, sm.info_imu, 9, wI, Jb, 24, 0, 6, sm.CL, 15, 9, 9, false);
         for (int a = 0; a < 9; ++a)
           for (int cc = 0; cc < 6; ++cc) sm.CL[(9 + cc) * 15 + a] = sm.CL[a * 15 + 9 + cc];
-        jtoj(sm.Jj, 9, 0, 9, sm.info_imu, 9, wI, sm.Ji, 9, 0, 9, sm.CCL, 15, 0, 0, false);
-        jtoj(sm.Jj, 9, 0, 9, sm.info_imu, 9, wI, sm.Jb, 6, 0, 6, sm.CCL, 15, 0, 9, false);
+        jtoj(Jj, 24, 0, 9, sm.info_imu, 9, wI, Ji, 24, 0, 9, sm.CCL, 15, 0, 0, false);
+        jtoj(Jj, 24, 0, 9, sm.info_imu, 9, wI, Jb, 24, 0, 6, sm.CCL, 15, 0, 9, false);
       }
       for (int k = 0; k < 6; ++k) {
         sm.CL[(9 + k) * 15 + 9 + k] += wB * sm.info_bias[k];
         sm.CCL[(9 + k) * 15 + 9 + k] = -(wB * sm.info_bias[k]);
       }
-      // prior edge blocks: Ji <- 15x9, Jb <- 15x6 (the IMU Jacobians are no longer needed)
-      prior_jac(sm.st[1], prior, sm.err_prior, sm.Ji, sm.Jb);
-      huber_rho(sqrt(25.0), sm.chi2_prior, r0, wP);
-      jtoj(sm.Ji, 9, 0, 9, sm.info_prior, 15, wP, sm.Ji, 9, 0, 9, sm.CL, 15, 0, 0, true);
-      jtoj(sm.Jb, 6, 0, 6, sm.info_prior, 15, wP, sm.Jb, 6, 0, 6, sm.CL, 15, 9, 9, true);
-      jtoj(sm.Ji, 9, 0, 9, sm.info_prior, 15, wP, sm.Jb, 6, 0, 6, sm.CL, 15, 0, 9, true);
+      const double* Jpp = sm.Jpri;      // 15 x 15, columns 0..8
+      const double* Jpb = sm.Jpri + 9;  // columns 9..14
+      jtoj(Jpp, 15, 0, 9, sm.info_prior, 15, wP, Jpp, 15, 0, 9, sm.CL, 15, 0, 0, true);
+      jtoj(Jpb, 15, 0, 6, sm.info_prior, 15, wP, Jpb, 15, 0, 6, sm.CL, 15, 9, 9, true);
+      jtoj(Jpp, 15, 0, 9, sm.info_prior, 15, wP, Jpb, 15, 0, 6, sm.CL, 15, 0, 9, true);
       for (int a = 0; a < 9; ++a)
         for (int cc = 0; cc < 6; ++cc) sm.CL[(9 + cc) * 15 + a] = sm.CL[a * 15 + 9 + cc];
       // cov_inv -= E C^-1 E^T (JacobiSVD inverse without clamping in the reference, :709-728)
-      double* Cinv = sm.H;  // 225 <= 900
+      double* Cinv = sm.lin[0].H;  // 225 <= 900
       double* T = sm.S;
       if (!dense_inverse(sm.CL, 15, Cinv))
         for (int i = 0; i < 225; ++i) Cinv[i] = nan("");
@@ -673,6 +825,17 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
 using namespace vieo;
 
 extern "C" {
+
+#ifdef VIEO_PROF
+int vieo_debug_po_prof(long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, g_po_prof, sizeof(long long) * 16);
+  if (reset) {
+    long long z[16] = {};
+    cudaMemcpyToSymbol(g_po_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int vieo_pose_opt_batch_dev(const VieoPoseOptProblem* pbs_dev, int n, const VieoCamera* cam_dev, const double* Xw_dev,
                             const float* obs_dev, const float* inv_sigma2_dev, const uint8_t* flags_dev,
