@@ -1151,7 +1151,11 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   const size_t K = max_states, P = max_points, E = max_edges, M = max_imu, NP = 15 * K;
   cudaError_t e = cudaSuccess;
   auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  step(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  {  // the engine's kernels are tiny and latency-critical: let them overtake bulk work (front-end batches) on the device
+    int lo = 0, hi = 0;
+    step(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    step(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi));
+  }
   step(dalloc(&h->d_st, K)); step(dalloc(&h->d_st_bak, K)); step(dalloc(&h->d_cp, K));
   step(dalloc(&h->d_X, 3 * P)); step(dalloc(&h->d_X_bak, 3 * P)); step(dalloc(&h->d_chi2, E));
   step(dalloc(&h->d_A, 27 * E)); step(dalloc(&h->d_Dinv, 9 * P)); step(dalloc(&h->d_db, 3 * P));

@@ -15,8 +15,13 @@ void set_error(const char* fmt, ...) {
 }
 
 int use_device(int device) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
+  static int s_count = -1;  // cached once a device has been seen
+  int n = s_count;
+  cudaError_t e = cudaSuccess;
+  if (n <= 0) {
+    e = cudaGetDeviceCount(&n);
+    if (e == cudaSuccess && n > 0) s_count = n;
+  }
   if (e != cudaSuccess || n == 0) {
     set_error("no CUDA device available (%s); libvieo_b200 has no CPU fallback",
               e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
@@ -27,10 +32,26 @@ int use_device(int device) {
     return VIEO_E_ARG;
   }
   VIEO_CK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  VIEO_CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
-    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  // the architecture check is cached per device: cudaGetDeviceProperties costs about a millisecond per call
+  static int s_major[64], s_minor[64];
+  static bool s_known[64];
+  if (device >= 64 || !s_known[device]) {
+    int major = 0, minor = 0;
+    VIEO_CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    VIEO_CK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (device < 64) {
+      s_major[device] = major;
+      s_minor[device] = minor;
+      s_known[device] = true;
+    }
+    if (major != 10) {
+      set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, major, minor);
+      return VIEO_E_CUDA;
+    }
+    return VIEO_OK;
+  }
+  if (s_major[device] != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, s_major[device], s_minor[device]);
     return VIEO_E_CUDA;
   }
   return VIEO_OK;
