@@ -318,72 +318,87 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident optimiser state.  Every kernel of the LM trial reads its sizes and the current linearisation set from
+// here, so the trial sequence has constant launch parameters and is replayed as ONE CUDA graph launch per trial; the
+// Levenberg-Marquardt bookkeeping (gain ratio, lambda schedule, accept / restore, stop criteria) runs in k_ba_control.
+struct BaParams {
+  int K, P, E, np, nfree, n_den, n_pblk, has_dup;
+  int lambda_on_poses;  // sharded runs add lambda to the pose diagonal on rank 0 only
+  int cur;              // linearisation set (0/1) that belongs to the current estimate
+  int done;             // optimize() finished: trial kernels return immediately
+  int stop;             // host abort flag seen (pbStopFlag)
+  int iteration, iters_target, iters_done, qmax, nBad, ok;
+  double lambda, ni, user_lambda;
+  double chi_cur, ini_chi;   // activeRobustChi2 of the current estimate / at the start of the iteration
+  double pair[2];            // [robust chi2 of the last linearisation, landmark part of computeScale] (all-reduced when sharded)
+  double pscale, chi_dense;  // pose part of computeScale; dense-edge chi2 of the last linearisation
+  CamK cam;                  // camera, gravity and Huber deltas of the problem
+  Vec3 gw;
+  double dm, ds;
+};
+struct BaBuf {  // device pointers of one handle (constant for its lifetime)
+  BaParams* prm;
+  VieoNavState *st, *st_bak;
+  CamPose* cp;
+  double *X, *X_bak, *chi2, *A, *Dinv, *db, *S, *bs, *bsys, *x, *partial, *scale_part, *part;
+  double *W[2], *Hll[2], *bl[2], *H[2], *b[2];
+  uint8_t* pt_active[2];
+  const int *es, *ep, *pt_ptr, *off0, *off1, *off2, *prcol, *free_state, *free_off, *ps_ptr, *ps_edges;
+  const float *obs, *w;
+  const uint8_t *flags, *lvl, *sfix;
+  const VieoImuPreint* pre;
+  const BaDense* den;
+  BaDenseWork* wk;
+};
+
 // computeActiveErrors + linearizeOplus + constructQuadraticForm of the visual edges, one warp per map point: each lane
 // evaluates one reprojection edge (residual, chi2, Huber weight, Jacobians), the 3x3 Hll / bl are reduced with warp
 // shuffles, W (Hpl) and A (the edge's Hpp / b part) are stored per edge.  The extra last block does the inertial edges.
-struct BaLinArgs {
-  CamK cam;
-  const CamPose* cp;
-  const double* X;
-  const int* pt_ptr;
-  int P;
-  const int* es;
-  const float* obs;
-  const float* w;
-  const uint8_t* flags;
-  const uint8_t* lvl;
-  const uint8_t* sfix;
-  double dm, ds;
-  double *chi2, *Wb, *Ab, *Hll, *bl, *partial;
-  uint8_t* pt_active;
-  // dense block
-  const BaDense* den;
-  int n_den;
-  const VieoNavState* st;
-  const VieoImuPreint* pre;
-  Vec3 gw;
-  BaDenseWork* wk;
-  const int *off0, *off1, *off2;
-  int np;
-  double *H, *b, *chi_dense;
-};
-__global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaLinArgs a) {
+// into_other: write the set that does NOT belong to the current estimate (speculative linearisation of a trial).
+__global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaBuf B, int into_other) {
   __shared__ double s_chi[kBaWarps];
+  const BaParams& prm = *B.prm;
+  if (prm.done) return;
+  const int set = into_other ? 1 - prm.cur : prm.cur;
   if (blockIdx.x == gridDim.x - 1) {
-    ba_dense_block(a.den, a.n_den, a.st, a.pre, a.gw, a.wk, a.off0, a.off1, a.off2, a.np, a.H, a.b, a.chi_dense);
+    ba_dense_block(B.den, prm.n_den, B.st, B.pre, prm.gw, B.wk, B.off0, B.off1, B.off2, prm.np, B.H[set], B.b[set],
+                   &B.prm->chi_dense);
     return;
   }
+  if ((int)blockIdx.x >= prm.n_pblk) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * kBaWarps + warp;
+  double* Wb = B.W[set];
   double acc[9], rsum = 0;
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = 0;
   bool any = false;
-  if (p < a.P) {
-    const int i0 = a.pt_ptr[p], i1 = a.pt_ptr[p + 1];
-    const Vec3 Xp = ld3(a.X + 3 * (size_t)p);
+  if (p < prm.P) {
+    const int i0 = B.pt_ptr[p], i1 = B.pt_ptr[p + 1];
+    const Vec3 Xp = ld3(B.X + 3 * (size_t)p);
     for (int i = i0 + lane; i < i1; i += 32) {
-      double* Wi = a.Wb + 18 * (size_t)i;
-      double* Ai = a.Ab + 27 * (size_t)i;
-      if (a.lvl[i] & 1) {
+      double* Wi = Wb + 18 * (size_t)i;
+      double* Ai = B.A + 27 * (size_t)i;
+      if (B.lvl[i] & 1) {
         for (int k = 0; k < 18; ++k) Wi[k] = 0;
         for (int k = 0; k < 27; ++k) Ai[k] = 0;
         continue;
       }
       any = true;
-      const bool stereo = a.flags[i] & VIEO_EDGE_STEREO;
+      const bool stereo = B.flags[i] & VIEO_EDGE_STEREO;
       const int DE = stereo ? 3 : 2;
-      const int s = a.es[i];
+      const int s = B.es[i];
       double e[3];
-      reproj_error(a.cam, a.cp[s], Xp, a.obs + 3 * (size_t)i, stereo, e);
-      const double wi = (double)a.w[i];
+      reproj_error(prm.cam, B.cp[s], Xp, B.obs + 3 * (size_t)i, stereo, e);
+      const double wi = (double)B.w[i];
       double c = 0;
       for (int k = 0; k < DE; ++k) c += e[k] * (wi * e[k]);
-      a.chi2[i] = c;
+      B.chi2[i] = c;
       Mat3 Jp, Jr, JX;
-      reproj_jac(a.cam, a.cp[s], Xp, stereo, Jp, Jr, JX);
+      reproj_jac(prm.cam, B.cp[s], Xp, stereo, Jp, Jr, JX);
       double r0, r1;
-      huber_rho(edge_huber_delta(a.flags[i], a.lvl[i], a.dm, a.ds), c, r0, r1);
+      huber_rho(edge_huber_delta(B.flags[i], B.lvl[i], prm.dm, prm.ds), c, r0, r1);
       rsum += r0;
       const double ww = r1 * wi;
       double oe[3];
@@ -410,7 +425,7 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaLinArgs a) {
           acc[q++] += hh;
         }
       }
-      if (!a.sfix[s]) {
+      if (!B.sfix[s]) {
         q = 0;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
@@ -445,41 +460,42 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaLinArgs a) {
   any = __any_sync(0xffffffffu, any);
   if (lane == 0) {
     s_chi[warp] = rsum;
-    if (p < a.P) {
-      double* H = a.Hll + 9 * (size_t)p;
+    if (p < prm.P) {
+      double* H = B.Hll[set] + 9 * (size_t)p;
       H[0] = acc[0]; H[1] = acc[1]; H[2] = acc[2];
       H[3] = acc[1]; H[4] = acc[3]; H[5] = acc[4];
       H[6] = acc[2]; H[7] = acc[4]; H[8] = acc[5];
-      a.bl[3 * (size_t)p] = acc[6]; a.bl[3 * (size_t)p + 1] = acc[7]; a.bl[3 * (size_t)p + 2] = acc[8];
-      a.pt_active[p] = any;
+      double* bb = B.bl[set] + 3 * (size_t)p;
+      bb[0] = acc[6]; bb[1] = acc[7]; bb[2] = acc[8];
+      B.pt_active[set][p] = any;
     }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0;
     for (int k = 0; k < kBaWarps; ++k) t += s_chi[k];
-    a.partial[blockIdx.x] = t;
+    B.partial[blockIdx.x] = t;
   }
 }
 
 // One block (256 threads) per free keyframe: fixed-order sum of its edges' A blocks, added to the 6x6 diagonal block
 // and rhs (the inertial part is already there).  Block 0 also totals the robust chi2 (dense edges first, then the
 // visual partial sums in block order) and the landmark part of the gain-ratio denominator of the last solve.
-__global__ void __launch_bounds__(256) k_ba_pose_reduce(const int* __restrict__ free_state, const int* __restrict__ off0,
-                                                        const int* __restrict__ ps_ptr, const int* __restrict__ ps_edges,
-                                                        const double* __restrict__ Ab, int np, double* __restrict__ H,
-                                                        double* __restrict__ b, const double* __restrict__ partial,
-                                                        int n_partial, const double* __restrict__ chi_dense,
-                                                        const double* __restrict__ scale_part, int n_scale,
-                                                        double* __restrict__ out2) {
+__global__ void __launch_bounds__(256) k_ba_pose_reduce(BaBuf B, int into_other) {
   __shared__ double s_w[8][27];
   __shared__ double s_s[256];
-  const int f = blockIdx.x, k = free_state[f], o = off0[k];
+  const BaParams& prm = *B.prm;
+  if (prm.done || (int)blockIdx.x >= prm.nfree) return;
+  const int set = into_other ? 1 - prm.cur : prm.cur;
+  const int np = prm.np;
+  double* H = B.H[set];
+  double* b = B.b[set];
+  const int f = blockIdx.x, k = B.free_state[f], o = B.off0[k];
   double acc[27];
 #pragma unroll
   for (int q = 0; q < 27; ++q) acc[q] = 0;
-  for (int t = ps_ptr[f] + threadIdx.x; t < ps_ptr[f + 1]; t += 256) {
-    const double* Ai = Ab + 27 * (size_t)ps_edges[t];
+  for (int t = B.ps_ptr[f] + threadIdx.x; t < B.ps_ptr[f + 1]; t += 256) {
+    const double* Ai = B.A + 27 * (size_t)B.ps_edges[t];
 #pragma unroll
     for (int q = 0; q < 27; ++q) acc[q] += Ai[q];
   }
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(256) k_ba_pose_reduce(const int* __restrict__ 
   }
   if (f != 0) return;
   double sc = 0;
-  for (int t = threadIdx.x; t < n_scale; t += 256) sc += scale_part[t];
+  for (int t = threadIdx.x; t < prm.P; t += 256) sc += B.scale_part[t];
   s_s[threadIdx.x] = sc;
   __syncthreads();
   for (int st = 128; st > 0; st >>= 1) {
@@ -520,27 +536,26 @@ __global__ void __launch_bounds__(256) k_ba_pose_reduce(const int* __restrict__ 
   const double scale_total = s_s[0];
   __syncthreads();
   // robust chi2: dense edges first, then the per-block partial sums in block order (chunks of 256 staged in smem)
-  double tot = *chi_dense;
-  for (int base = 0; base < n_partial; base += 256) {
+  double tot = prm.chi_dense;
+  for (int base = 0; base < prm.n_pblk; base += 256) {
     const int t = base + threadIdx.x;
-    s_s[threadIdx.x] = t < n_partial ? partial[t] : 0.0;
+    s_s[threadIdx.x] = t < prm.n_pblk ? B.partial[t] : 0.0;
     __syncthreads();
     if (threadIdx.x == 0) {
-      const int m = min(256, n_partial - base);
+      const int m = min(256, prm.n_pblk - base);
       for (int q = 0; q < m; ++q) tot += s_s[q];
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    out2[0] = tot;
-    out2[1] = scale_total;
+    B.prm->pair[0] = tot;
+    B.prm->pair[1] = scale_total;
   }
 }
 
-// max |diag| of Hpp and of the active Hll (computeLambdaInit)
-__global__ void k_ba_maxdiag(const double* __restrict__ H, int np, const double* __restrict__ Hll,
-                             const uint8_t* __restrict__ pt_active, int P, double* __restrict__ out) {
-  __shared__ double s[256];
+// max |diag| of Hpp and of the active Hll (computeLambdaInit), by one block of 256 threads
+__device__ double ba_maxdiag(const double* __restrict__ H, int np, const double* __restrict__ Hll,
+                             const uint8_t* __restrict__ pt_active, int P, double* s) {
   double mx = 0;
   for (int i = threadIdx.x; i < np; i += 256) mx = fmax(mx, fabs(H[(size_t)i * np + i]));
   for (int p = threadIdx.x; p < P; p += 256)
@@ -552,43 +567,116 @@ __global__ void k_ba_maxdiag(const double* __restrict__ H, int np, const double*
     if (threadIdx.x < o) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + o]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = s[0];
+  return s[0];
+}
+
+// Levenberg-Marquardt bookkeeping on the device (OptimizationAlgorithmLevenberg::solve, :83-166; SparseOptimizer::
+// optimize loop, sparse_optimizer.cpp:376-414).  mode 0: after the initial linearisation of an optimize() call;
+// mode 1: after a trial (solve + update + linearisation at the trial estimate).
+__global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode) {
+  __shared__ double s[256];
+  __shared__ int s_restore;
+  BaParams& prm = *B.prm;
+  if (prm.done) return;
+  if (mode == 0) {
+    double lam = prm.user_lambda;
+    if (!(lam > 0)) lam = 1e-5 * ba_maxdiag(B.H[prm.cur], prm.np, B.Hll[prm.cur], B.pt_active[prm.cur], prm.P, s);
+    if (threadIdx.x == 0) {
+      prm.chi_cur = prm.ini_chi = prm.pair[0];
+      prm.lambda = lam;
+      prm.ni = 2;
+      prm.nBad = 0;
+      prm.iteration = 0;
+      prm.iters_done = 0;
+      prm.qmax = 0;
+      if (prm.iters_target <= 0 || prm.stop) prm.done = 1;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    double tempChi = prm.pair[0];
+    if (!prm.ok) tempChi = 1.7976931348623157e308;
+    double rho = prm.chi_cur - tempChi;
+    double scale = prm.pscale + prm.pair[1];
+    scale += 1e-3;
+    rho /= scale;
+    int restore = 0;
+    if (rho > 0 && isfinite(tempChi)) {
+      double alpha = 1. - pow((2 * rho - 1), 3);
+      alpha = fmin(alpha, 2. / 3.);
+      prm.lambda *= fmax(1. / 3., alpha);
+      prm.ni = 2;
+      prm.chi_cur = tempChi;
+      prm.cur = 1 - prm.cur;  // the speculative linearisation is the current one now
+    } else {
+      prm.lambda *= prm.ni;
+      prm.ni *= 2;
+      restore = 1;
+    }
+    prm.qmax++;
+    const bool more_trials = rho < 0 && prm.qmax < 10 && !prm.stop;
+    if (!more_trials) {
+      prm.iters_done++;
+      bool terminate = prm.qmax == 10 || rho == 0;
+      if (!terminate) {
+        if ((prm.ini_chi - prm.chi_cur) * 1e3 < prm.ini_chi) prm.nBad++;
+        else prm.nBad = 0;
+        if (prm.nBad >= 3) terminate = true;
+      }
+      prm.iteration++;
+      if (terminate || prm.iteration >= prm.iters_target || prm.stop) prm.done = 1;
+      else {
+        prm.ini_chi = prm.chi_cur;
+        prm.qmax = 0;
+      }
+    }
+    s_restore = restore;
+  }
+  __syncthreads();
+  if (s_restore) {  // pop(): back to the estimate before the trial
+    const int nS = prm.K * (int)(sizeof(VieoNavState) / sizeof(double)), nX = 3 * prm.P;
+    const double* sb = reinterpret_cast<const double*>(B.st_bak);
+    double* sd = reinterpret_cast<double*>(B.st);
+    for (int t = threadIdx.x; t < nS; t += 256) sd[t] = sb[t];
+    for (int t = threadIdx.x; t < nX; t += 256) B.X[t] = B.X_bak[t];
+  }
 }
 
 // Start of a solve: Dinv = (Hll + lambda I)^-1 (cofactor inverse like Eigen's fixed 3x3, block_solver.hpp:389),
 // db = Dinv bl; S = H + lambda_pose I, bschur = b, sys.b = b
-__global__ void k_ba_prep_solve(const double* __restrict__ Hll, const double* __restrict__ bl,
-                                const uint8_t* __restrict__ pt_active, int P, double lambda, double* __restrict__ Dinv,
-                                double* __restrict__ db, const double* __restrict__ H, const double* __restrict__ b, int np,
-                                double lambda_pose, double* __restrict__ S, double* __restrict__ bs,
-                                double* __restrict__ bsys) {
+__global__ void k_ba_prep_solve(BaBuf B, double lambda_arg, int use_arg) {
+  const BaParams& prm = *B.prm;
+  if (prm.done && !use_arg) return;
+  const int np = prm.np, P = prm.P, set = prm.cur;
+  const double lambda = use_arg ? lambda_arg : prm.lambda;
+  const double lambda_pose = prm.lambda_on_poses ? lambda : 0.0;
   const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t < (size_t)np * np) {
     const int r = t / np, c = t % np;
-    S[t] = H[t] + (r == c ? lambda_pose : 0.0);
+    B.S[t] = B.H[set][t] + (r == c ? lambda_pose : 0.0);
   }
   if (t < (size_t)np) {
-    bs[t] = b[t];
-    bsys[t] = b[t];
+    B.bs[t] = B.b[set][t];
+    B.bsys[t] = B.b[set][t];
   }
   if (t >= (size_t)P) return;
   const size_t p = t;
-  double* I = Dinv + 9 * p;
-  if (!pt_active[p]) {
+  double* I = B.Dinv + 9 * p;
+  if (!B.pt_active[set][p]) {
     for (int k = 0; k < 9; ++k) I[k] = 0;
-    db[3 * p] = db[3 * p + 1] = db[3 * p + 2] = 0;
+    B.db[3 * p] = B.db[3 * p + 1] = B.db[3 * p + 2] = 0;
     return;
   }
   double D[9];
-  for (int k = 0; k < 9; ++k) D[k] = Hll[9 * p + k];
+  for (int k = 0; k < 9; ++k) D[k] = B.Hll[set][9 * p + k];
   D[0] += lambda; D[4] += lambda; D[8] += lambda;
   const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
   const double det = D[0] * c00 + D[1] * c01 + D[2] * c02, id = 1.0 / det;
   I[0] = c00 * id; I[1] = (D[2] * D[7] - D[1] * D[8]) * id; I[2] = (D[1] * D[5] - D[2] * D[4]) * id;
   I[3] = c01 * id; I[4] = (D[0] * D[8] - D[2] * D[6]) * id; I[5] = (D[2] * D[3] - D[0] * D[5]) * id;
   I[6] = c02 * id; I[7] = (D[1] * D[6] - D[0] * D[7]) * id; I[8] = (D[0] * D[4] - D[1] * D[3]) * id;
-  const double* bb = bl + 3 * p;
-  for (int a = 0; a < 3; ++a) db[3 * p + a] = I[3 * a] * bb[0] + I[3 * a + 1] * bb[1] + I[3 * a + 2] * bb[2];
+  const double* bb = B.bl[set] + 3 * p;
+  for (int a = 0; a < 3; ++a) B.db[3 * p + a] = I[3 * a] * bb[0] + I[3 * a + 1] * bb[1] + I[3 * a + 2] * bb[2];
 }
 
 // Schur complement.  Block (f, s): chunk s of free keyframe f's edge list.  Each warp walks its edges in order; for
@@ -596,40 +684,43 @@ __global__ void k_ba_prep_solve(const double* __restrict__ Hll, const double* __
 // [6][6*nfree + 1] in shared memory (last column: W_a db).  The warps' tiles are summed in warp order into
 // part[f][s]; k_ba_schur_reduce then sums the chunks in order and subtracts from S / bschur.  No atomics.
 constexpr int kSchurSplit = 8;
-__global__ void __launch_bounds__(kBaWarps * 32) k_ba_schur(
-    const int* __restrict__ prcol, int nfree, const int* __restrict__ ps_ptr, const int* __restrict__ ps_edges,
-    const int* __restrict__ es, const int* __restrict__ ep, const int* __restrict__ pt_ptr, const double* __restrict__ Wb,
-    const double* __restrict__ Dinv, const double* __restrict__ db, int serial_lanes, double* __restrict__ part) {
+constexpr int kSchurMaxFree = 48;  // shared-memory tile of the trial graph is sized for this many free keyframes
+__global__ void __launch_bounds__(kBaWarps * 32) k_ba_schur(BaBuf B, int force) {
   extern __shared__ double s_acc[];  // [kBaWarps][6][ld]
+  const BaParams& prm = *B.prm;
+  if ((prm.done && !force) || (int)blockIdx.x >= prm.nfree || prm.E == 0) return;
+  const int nfree = prm.nfree;
   const int ld = 6 * nfree + 1;
   const int f = blockIdx.x, sp = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* Wb = B.W[prm.cur];
   double* acc = s_acc + (size_t)warp * 6 * ld;
   for (int t = lane; t < 6 * ld; t += 32) acc[t] = 0;
   __syncwarp();
-  const int t0 = ps_ptr[f], t1 = ps_ptr[f + 1];
+  const int t0 = B.ps_ptr[f], t1 = B.ps_ptr[f + 1];
   const int per_blk = (t1 - t0 + kSchurSplit - 1) / kSchurSplit;
   const int b0 = t0 + sp * per_blk, b1 = min(b0 + per_blk, t1);
   const int per_warp = (max(b1 - b0, 0) + kBaWarps - 1) / kBaWarps;
   const int a0 = b0 + warp * per_warp, a1 = min(a0 + per_warp, b1);
   const int r = lane % 6, slot = lane / 6;  // lanes 30, 31 idle in the tile update
+  const int serial_lanes = prm.has_dup;
   for (int t = a0; t < a1; ++t) {
-    const int a = ps_edges[t];
-    const int p = ep[a];
+    const int a = B.ps_edges[t];
+    const int p = B.ep[a];
     const double* Wa = Wb + 18 * (size_t)a + 3 * r;
-    const double* Di = Dinv + 9 * (size_t)p;
+    const double* Di = B.Dinv + 9 * (size_t)p;
     const double w0 = Wa[0], w1 = Wa[1], w2 = Wa[2];
     const double d0 = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
     const double d1 = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
     const double d2 = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
     if (lane < 6) {
-      const double* d = db + 3 * (size_t)p;
+      const double* d = B.db + 3 * (size_t)p;
       acc[r * ld + 6 * nfree] += w0 * d[0] + w1 * d[1] + w2 * d[2];
     }
-    const int c0 = pt_ptr[p], c1 = pt_ptr[p + 1];
+    const int c0 = B.pt_ptr[p], c1 = B.pt_ptr[p + 1];
     for (int cb = c0; cb < c1; cb += 5) {
       const int c = cb + slot;
-      const int col = (slot < 5 && c < c1) ? prcol[es[c]] : -1;
+      const int col = (slot < 5 && c < c1) ? B.prcol[B.es[c]] : -1;
       for (int turn = 0; turn < (serial_lanes ? 5 : 1); ++turn) {
         if (col >= 0 && (!serial_lanes || turn == slot)) {
           const double* Wc = Wb + 18 * (size_t)c;
@@ -643,45 +734,53 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_schur(
     __syncwarp();
   }
   __syncthreads();
-  double* out = part + ((size_t)f * kSchurSplit + sp) * 6 * ld;
+  double* out = B.part + ((size_t)f * kSchurSplit + sp) * 6 * ld;
   for (int t = threadIdx.x; t < 6 * ld; t += kBaWarps * 32) {
     double s = 0;
     for (int w = 0; w < kBaWarps; ++w) s += s_acc[(size_t)w * 6 * ld + t];
     out[t] = s;
   }
 }
-__global__ void __launch_bounds__(256) k_ba_schur_reduce(const int* __restrict__ free_state, const int* __restrict__ off0,
-                                                         const int* __restrict__ free_off, int nfree,
-                                                         const double* __restrict__ part, int np, double* __restrict__ S,
-                                                         double* __restrict__ bs) {
+__global__ void __launch_bounds__(256) k_ba_schur_reduce(BaBuf B, int force) {
+  const BaParams& prm = *B.prm;
+  if ((prm.done && !force) || (int)blockIdx.x >= prm.nfree || prm.E == 0) return;
+  const int nfree = prm.nfree, np = prm.np;
   const int ld = 6 * nfree + 1;
-  const int f = blockIdx.x, o = off0[free_state[f]];
-  const double* in = part + (size_t)f * kSchurSplit * 6 * ld;
+  const int f = blockIdx.x, o = B.off0[B.free_state[f]];
+  const double* in = B.part + (size_t)f * kSchurSplit * 6 * ld;
   for (int t = threadIdx.x; t < 6 * ld; t += 256) {
     double s = 0;
     for (int sp = 0; sp < kSchurSplit; ++sp) s += in[(size_t)sp * 6 * ld + t];
     const int r = t / ld, c = t % ld;
-    if (c == 6 * nfree) bs[o + r] -= s;
-    else S[(size_t)(o + r) * np + free_off[c / 6] + c % 6] -= s;
+    if (c == 6 * nfree) B.bs[o + r] -= s;
+    else B.S[(size_t)(o + r) * np + B.free_off[c / 6] + c % 6] -= s;
   }
 }
 
 // Dense Cholesky of S (n x n) + solve S x = rhs by one block.  The lower triangle is staged in shared memory when it
-// fits (in_smem), else factorised in place in global memory.  Right-looking with panels of kCholNB columns; columns
-// are kept unnormalised (s_ij = a_ij - sum l l, so a_ik -= s_ij s_kj / s_jj) and scaled by 1/sqrt(s_jj) at the end:
-// one barrier per column inside a panel (cheap: one row per thread) and one rank-NB update of the trailing block per
-// panel.  ok = 0 when a pivot is not positive (LinearSolverDense: LDLT::isPositive, linear_solver_dense.h:107-112).
+// fits (n <= kCholSmemN), else factorised in place in global memory.  Right-looking with panels of kCholNB columns;
+// columns are kept unnormalised (s_ij = a_ij - sum l l, so a_ik -= s_ij s_kj / s_jj) and scaled by 1/sqrt(s_jj) at the
+// end: one barrier per column inside a panel (cheap: one row per thread) and one rank-NB update of the trailing block
+// per panel.  ok = 0 when a pivot is not positive (LinearSolverDense: LDLT::isPositive, linear_solver_dense.h:107-112).
 constexpr int kCholNB = 8;
 constexpr int kCholThreads = 1024;
-__global__ void __launch_bounds__(kCholThreads) k_ba_chol(double* __restrict__ Ag, const double* __restrict__ rhs, int n,
-                                                          int in_smem, double* __restrict__ x_out, int* __restrict__ ok) {
+constexpr int kCholSmemN = 165;
+constexpr size_t kCholSmemBytes = sizeof(double) * ((size_t)kCholSmemN * (kCholSmemN | 1) + 3 * kCholSmemN);
+__global__ void __launch_bounds__(kCholThreads) k_ba_chol(BaBuf B, int force) {
   extern __shared__ double sh[];
   __shared__ double s_inv[kCholNB];
   __shared__ int s_good;
+  BaParams& prm = *B.prm;
+  if (prm.done && !force) return;
+  const int n = prm.np;
+  const int in_smem = n <= kCholSmemN;
+  double* Ag = B.S;
+  const double* rhs = B.bs;
   const int T = blockDim.x, t = threadIdx.x;
-  double* diag = sh;       // n: 1 / sqrt(s_jj)
-  double* y = sh + n;      // n
-  double* x = sh + 2 * n;  // n
+  // scratch vectors: in shared memory when the matrix is (3n doubles), else in the tail of the sys buffer's bs copy
+  double* diag = in_smem ? sh : B.part;  // B.part is free between schur_reduce and the next schur
+  double* y = diag + n;
+  double* x = diag + 2 * n;
   double* A = in_smem ? sh + 3 * n : Ag;
   const int ld = in_smem ? (n | 1) : n;
   if (in_smem) {
@@ -694,23 +793,46 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_chol(double* __restrict__ A
   const int nw = T >> 5, wp = t >> 5, ln = t & 31;
   for (int j0 = 0; j0 < n; j0 += kCholNB) {
     const int nb = min(kCholNB, n - j0), jend = j0 + nb;
-    // panel: one thread per row below the pivot, columns restricted to the panel
-    for (int j = j0; j < jend; ++j) {
-      const double sjj = A[(size_t)j * ld + j];
-      if (t == 0) {
-        if (!(sjj > 0) || !isfinite(sjj)) s_good = 0;
-        s_inv[j - j0] = 1.0 / sjj;
+    // (1) the nb x nb diagonal block, warp 0, lane r = row j0 + r
+    if (wp == 0) {
+      for (int c = 0; c < nb; ++c) {
+        const double sjj = A[(size_t)(j0 + c) * ld + j0 + c];
+        const double inv = 1.0 / sjj;
+        if (ln == 0) {
+          if (!(sjj > 0) || !isfinite(sjj)) s_good = 0;
+          s_inv[c] = inv;
+        }
+        if (ln > c && ln < nb) {
+          double* Ar = A + (size_t)(j0 + ln) * ld + j0;
+          const double f = Ar[c] * inv;
+          for (int k = c + 1; k <= ln; ++k) Ar[k] -= f * A[(size_t)(j0 + k) * ld + j0 + c];
+        }
+        __syncwarp();
       }
-      const double inv = 1.0 / sjj;
-      for (int i = j + 1 + t; i < n; i += T) {
-        const double f = A[(size_t)i * ld + j] * inv;
-        const int kmax = min(i, jend - 1);
-        for (int k = j + 1; k <= kmax; ++k) A[(size_t)i * ld + k] -= f * A[(size_t)k * ld + j];
-      }
-      __syncthreads();
     }
+    __syncthreads();
     if (!s_good) break;
-    // trailing block: A[i][k] -= sum_c (s_ic / s_cc) s_kc for k >= jend, rows by warp, lanes along the row
+    // (2) rows below the panel: one thread per row eliminates its nb panel entries in registers (no barriers)
+    for (int i = jend + t; i < n; i += T) {
+      double* Ar = A + (size_t)i * ld + j0;
+      double r[kCholNB];
+#pragma unroll
+      for (int c = 0; c < kCholNB; ++c) r[c] = c < nb ? Ar[c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < kCholNB; ++c) {
+        if (c < nb) {
+          const double f = r[c] * s_inv[c];
+#pragma unroll
+          for (int k = c + 1; k < kCholNB; ++k)
+            if (k < nb) r[k] -= f * A[(size_t)(j0 + k) * ld + j0 + c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kCholNB; ++c)
+        if (c < nb) Ar[c] = r[c];
+    }
+    __syncthreads();
+    // (3) trailing block: A[i][k] -= sum_c (s_ic / s_cc) s_kc for k >= jend, rows by warp, lanes along the row
     for (int i = jend + wp; i < n; i += nw) {
       double f[kCholNB];
 #pragma unroll
@@ -727,7 +849,7 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_chol(double* __restrict__ A
     __syncthreads();
   }
   const bool good = s_good != 0;
-  if (t == 0) *ok = good ? 1 : 0;
+  if (t == 0) prm.ok = good ? 1 : 0;
   if (!good) return;
   for (int j = t; j < n; j += T) diag[j] = 1.0 / sqrt(A[(size_t)j * ld + j]);
   __syncthreads();
@@ -735,107 +857,125 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_chol(double* __restrict__ A
   for (int i = wp; i < n; i += nw)
     for (int k = ln; k < i; k += 32) A[(size_t)i * ld + k] *= diag[k];
   __syncthreads();
-  if (t < 32) {
-    for (int i = 0; i < n; ++i) {
-      double s = 0;
-      for (int k = t; k < i; k += 32) s += A[(size_t)i * ld + k] * y[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (t == 0) y[i] = (y[i] - s) * diag[i];
-      __syncwarp();
+  // forward substitution L y = b in blocks of 32 rows: warp 0 solves the 32 x 32 triangle with shuffles, then every
+  // remaining row subtracts the block's contribution
+  for (int b0 = 0; b0 < n; b0 += 32) {
+    const int bn = min(32, n - b0);
+    if (wp == 0) {
+      const int i = b0 + ln;
+      double yi = ln < bn ? y[i] : 0.0;
+      const double rd = ln < bn ? diag[i] : 0.0;
+      for (int j = 0; j < bn; ++j) {
+        const double yj = __shfl_sync(0xffffffffu, yi * rd, j);
+        if (ln == j) yi = yj;
+        else if (ln > j && ln < bn) yi -= A[(size_t)i * ld + b0 + j] * yj;
+      }
+      if (ln < bn) y[i] = yi;
     }
-    for (int i = n - 1; i >= 0; --i) {
-      double s = 0;
-      for (int k = i + 1 + t; k < n; k += 32) s += A[(size_t)k * ld + i] * x[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (t == 0) x[i] = (y[i] - s) * diag[i];
-      __syncwarp();
+    __syncthreads();
+    for (int i = b0 + bn + t; i < n; i += T) {
+      double acc = y[i];
+      const double* Ar = A + (size_t)i * ld + b0;
+      for (int j = 0; j < bn; ++j) acc -= Ar[j] * y[b0 + j];
+      y[i] = acc;
     }
-    for (int i = t; i < n; i += 32) x_out[i] = x[i];
+    __syncthreads();
   }
+  // backward substitution L^T x = y, blocks from the bottom
+  for (int b1 = n; b1 > 0; b1 -= 32) {
+    const int b0 = max(b1 - 32, 0), bn = b1 - b0;
+    if (wp == 0) {
+      const int i = b0 + ln;
+      double xi = ln < bn ? y[i] : 0.0;
+      const double rd = ln < bn ? diag[i] : 0.0;
+      for (int j = bn - 1; j >= 0; --j) {
+        const double xj = __shfl_sync(0xffffffffu, xi * rd, j);
+        if (ln == j) xi = xj;
+        else if (ln < j) xi -= A[(size_t)(b0 + j) * ld + i] * xj;
+      }
+      if (ln < bn) x[i] = xi;
+    }
+    __syncthreads();
+    for (int i = t; i < b0; i += T) {
+      double acc = y[i];
+      for (int j = 0; j < bn; ++j) acc -= A[(size_t)(b0 + j) * ld + i] * x[b0 + j];
+      y[i] = acc;
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < n; i += T) B.x[i] = x[i];
 }
 
-// One warp per point: xl = Dinv (bl - sum_a W_a^T xp), X += xl (apply != 0), landmark part of computeScale.
-// The extra last block applies the keyframe updates (NavState::IncSmall), refreshes the camera poses and computes the
-// pose part of computeScale.
-struct BaBackArgs {
-  const int* pt_ptr;
-  int P;
-  const int* es;
-  const int *off0, *off1, *off2;
-  const double *Wb, *Dinv, *bl;
-  const uint8_t* pt_active;
-  const double* x;
-  const int* ok;
-  double lambda;
-  int apply;
-  double *X, *xl_out, *scale_part;
-  VieoNavState* st;
-  int K;
-  CamK cam;
-  CamPose* cp;
-  const double* b;
-  int np;
-  double* scale_pose;
-};
-__global__ void __launch_bounds__(kBaWarps * 32) k_ba_backsub(BaBackArgs a) {
+// One warp per point: xl = Dinv (bl - sum_a W_a^T xp), X += xl (apply != 0), landmark part of computeScale; the
+// estimate before the update is kept in X_bak / st_bak (push()).  The extra last block applies the keyframe updates
+// (NavState::IncSmall), refreshes the camera poses and computes the pose part of computeScale.
+__global__ void __launch_bounds__(kBaWarps * 32) k_ba_backsub(BaBuf B, int apply, double lambda_arg, double* xl_out) {
+  BaParams& prm = *B.prm;
+  if (prm.done && apply) return;
+  const int set = prm.cur;
+  const double lambda = apply ? prm.lambda : lambda_arg;
+  const bool ok = prm.ok != 0;
   if (blockIdx.x == gridDim.x - 1) {
-    const bool ok = *a.ok != 0;
-    for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
-      NavS s = ns_load(a.st[k]);
-      if (a.apply && ok && (a.off0[k] >= 0 || a.off1[k] >= 0 || a.off2[k] >= 0)) {
-        if (a.off0[k] >= 0) ns_inc_pr(s, a.x + a.off0[k]);
-        if (a.off1[k] >= 0) ns_inc_v(s, a.x + a.off1[k]);
-        if (a.off2[k] >= 0) ns_inc_bias(s, a.x + a.off2[k]);
-        ns_store(s, a.st[k]);
+    for (int k = threadIdx.x; k < prm.K; k += blockDim.x) {
+      NavS s = ns_load(B.st[k]);
+      if (apply) {
+        B.st_bak[k] = B.st[k];
+        if (ok && (B.off0[k] >= 0 || B.off1[k] >= 0 || B.off2[k] >= 0)) {
+          if (B.off0[k] >= 0) ns_inc_pr(s, B.x + B.off0[k]);
+          if (B.off1[k] >= 0) ns_inc_v(s, B.x + B.off1[k]);
+          if (B.off2[k] >= 0) ns_inc_bias(s, B.x + B.off2[k]);
+          ns_store(s, B.st[k]);
+        }
       }
-      a.cp[k] = cam_pose(a.cam, s);
+      B.cp[k] = cam_pose(prm.cam, s);
     }
     if (threadIdx.x == 0) {
       double s = 0;
       if (ok)
-        for (int j = 0; j < a.np; ++j) s += a.x[j] * (a.lambda * a.x[j] + a.b[j]);
-      *a.scale_pose = s;
+        for (int j = 0; j < prm.np; ++j) s += B.x[j] * (lambda * B.x[j] + B.bsys[j]);
+      prm.pscale = s;
     }
     return;
   }
+  if ((int)blockIdx.x >= prm.n_pblk) return;
   const int p = blockIdx.x * kBaWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (p >= a.P) return;
-  const bool ok = *a.ok != 0;
-  if (!a.pt_active[p] || !ok) {
+  if (p >= prm.P) return;
+  if (apply && lane < 3) B.X_bak[3 * (size_t)p + lane] = B.X[3 * (size_t)p + lane];
+  if (!B.pt_active[set][p] || !ok) {
     if (lane == 0) {
-      a.scale_part[p] = 0;
-      if (a.xl_out) a.xl_out[3 * (size_t)p] = a.xl_out[3 * (size_t)p + 1] = a.xl_out[3 * (size_t)p + 2] = 0;
+      B.scale_part[p] = 0;
+      if (xl_out) xl_out[3 * (size_t)p] = xl_out[3 * (size_t)p + 1] = xl_out[3 * (size_t)p + 2] = 0;
     }
     return;
   }
+  const double* Wb = B.W[set];
   double c[3] = {0, 0, 0};
-  for (int i = a.pt_ptr[p] + lane; i < a.pt_ptr[p + 1]; i += 32) {
-    const int o = a.off0[a.es[i]];
+  for (int i = B.pt_ptr[p] + lane; i < B.pt_ptr[p + 1]; i += 32) {
+    const int o = B.off0[B.es[i]];
     if (o < 0) continue;
-    const double* Wi = a.Wb + 18 * (size_t)i;
+    const double* Wi = Wb + 18 * (size_t)i;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int r = 0; r < 6; ++r) c[k] += Wi[3 * r + k] * a.x[o + r];
+      for (int r = 0; r < 6; ++r) c[k] += Wi[3 * r + k] * B.x[o + r];
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+  __syncwarp();  // the X_bak copy above read X before lane 0 updates it
   if (lane == 0) {
-    const double* bb = a.bl + 3 * (size_t)p;
-    const double* Di = a.Dinv + 9 * (size_t)p;
+    const double* bb = B.bl[set] + 3 * (size_t)p;
+    const double* Di = B.Dinv + 9 * (size_t)p;
     const double cc[3] = {bb[0] - c[0], bb[1] - c[1], bb[2] - c[2]};
     double s = 0;
     for (int q = 0; q < 3; ++q) {
       const double xl = Di[3 * q] * cc[0] + Di[3 * q + 1] * cc[1] + Di[3 * q + 2] * cc[2];
-      if (a.apply) a.X[3 * (size_t)p + q] += xl;
-      if (a.xl_out) a.xl_out[3 * (size_t)p + q] = xl;
-      s += xl * (a.lambda * xl + bb[q]);
+      if (apply) B.X[3 * (size_t)p + q] += xl;
+      if (xl_out) xl_out[3 * (size_t)p + q] = xl;
+      s += xl * (lambda * xl + bb[q]);
     }
-    a.scale_part[p] = s;
+    B.scale_part[p] = s;
   }
 }
 
@@ -873,7 +1013,7 @@ using namespace vieo;
 struct vieo_ba {
   int device = 0;
   cudaStream_t st = nullptr;
-  int capK = 0, capP = 0, capE = 0, capM = 0;
+  int capK = 0, capP = 0, capE = 0, capM = 0, cap_pblk = 0, cap_free = 0;
   int K = 0, P = 0, E = 0, M = 0, np = 0, nfree = 0, n_den = 0, n_part = 0, n_pblk = 0;
   bool points_free = true, has_dup = false;
   int rank = 0, world = 1;
@@ -882,40 +1022,24 @@ struct vieo_ba {
   CamK cam;
   Vec3 gw;
   double dm = 0, ds = 0;
-  // device.  Two linearisation sets (W, Hll, bl, pt_active, H, b, chi total): `cur` belongs to the current estimate,
-  // the other one receives the speculative linearisation at the trial estimate (accepted: swap; rejected: keep).
-  int cur = 0;
-  VieoNavState *d_st = nullptr, *d_st_bak = nullptr;
-  CamPose* d_cp = nullptr;
-  double *d_X = nullptr, *d_X_bak = nullptr, *d_chi2 = nullptr, *d_A = nullptr, *d_Dinv = nullptr, *d_db = nullptr,
-         *d_sys = nullptr, *d_x = nullptr, *d_xl = nullptr, *d_partial = nullptr, *d_scale_part = nullptr,
-         *d_ctl = nullptr, *d_part = nullptr;
-  double *d_W[2] = {}, *d_Hll[2] = {}, *d_bl[2] = {}, *d_H[2] = {}, *d_b[2] = {};
-  uint8_t* d_pt_active[2] = {};
-  size_t part_cap = 0;
+  BaBuf B;                    // device pointers handed to the kernels by value
+  BaParams* h_prm = nullptr;  // pinned host mirror of B.prm
+  cudaGraphExec_t trial_graph = nullptr;
+  // buffers that are not part of BaBuf
+  double *d_sys = nullptr, *d_xl = nullptr, *d_ctl = nullptr;
+  uint8_t *d_lvl = nullptr, *d_bad = nullptr, *d_flags = nullptr, *d_sfix = nullptr;
   int *d_es = nullptr, *d_ep = nullptr, *d_pt_ptr = nullptr, *d_off0 = nullptr, *d_off1 = nullptr, *d_off2 = nullptr,
-      *d_prcol = nullptr, *d_free_state = nullptr, *d_free_off = nullptr, *d_ps_ptr = nullptr, *d_ps_edges = nullptr,
-      *d_ok = nullptr;
+      *d_prcol = nullptr, *d_free_state = nullptr, *d_free_off = nullptr, *d_ps_ptr = nullptr, *d_ps_edges = nullptr;
   float *d_obs = nullptr, *d_w = nullptr;
-  uint8_t *d_flags = nullptr, *d_lvl = nullptr, *d_sfix = nullptr, *d_bad = nullptr;
   VieoImuPreint* d_pre = nullptr;
   BaDense* d_den = nullptr;
-  BaDenseWork* d_wk = nullptr;
   double* h_ctl = nullptr;  // pinned
   std::vector<int> off0, off1, off2;
-  // LM state (OptimizationAlgorithmLevenberg members)
-  double lambda = 0, ni = 2;
-  int nBad = 0;
   int launches = 0;
-  // sys = [S | bschur | b]: what the sharded form all-reduces once per LM trial
-  double* S() { return d_sys; }
-  double* bs() { return d_sys + (size_t)np * np; }
-  double* b() { return d_sys + (size_t)np * np + np; }
-  size_t sys_count() const { return (size_t)np * np + 2 * np; }
+  size_t cap_np = 0;
+  // sys = [bschur (cap_np) | b (cap_np) | S (np x np)]: the prefix that the sharded form all-reduces once per LM trial
+  size_t sys_count() const { return 2 * cap_np + (size_t)np * np; }
 };
-// d_ctl (device doubles): [3] pose part of computeScale, [4] max diagonal, [5..7] stand-alone error sums,
-// [8] dense-edge chi2 of the last linearisation, [10] robust chi2 of the last linearisation, [11] landmark part of
-// computeScale of the last solve ([10..11] are all-reduced together when sharded)
 
 namespace {
 
@@ -965,8 +1089,10 @@ bool host_inverse(const double* A, int n, double* Ai) {
     }                                                                                    \
   } while (0)
 
+size_t schur_smem(int nfree) { return sizeof(double) * kBaWarps * 6 * (6 * (size_t)nfree + 1); }
+
 int ba_campose(vieo_ba* h) {
-  k_ba_campose<<<(h->K + 127) / 128, 128, 0, h->st>>>(h->cam, h->d_st, h->K, h->d_cp);
+  k_ba_campose<<<(h->K + 127) / 128, 128, 0, h->st>>>(h->cam, h->B.st, h->K, h->B.cp);
   h->launches++;
   return VIEO_OK;
 }
@@ -975,165 +1101,86 @@ int ba_campose(vieo_ba* h) {
 int ba_errors(vieo_ba* h, int all, double* d_out) {
   ba_campose(h);
   if (h->E > 0) {
-    k_ba_errors<<<h->n_part, 256, 0, h->st>>>(h->cam, h->d_cp, h->d_X, h->d_es, h->d_ep, h->d_obs, h->d_w, h->d_flags,
+    k_ba_errors<<<h->n_part, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_w, h->d_flags,
                                               h->d_lvl, h->d_sfix, h->points_free ? 1 : 0, h->E, all, h->dm, h->ds,
-                                              h->d_chi2, h->d_partial);
+                                              h->B.chi2, h->B.partial);
     h->launches++;
   }
-  k_ba_dense_errors<<<1, 128, 0, h->st>>>(h->d_den, h->n_den, h->d_st, h->d_pre, h->gw, h->d_wk, h->d_partial,
+  k_ba_dense_errors<<<1, 128, 0, h->st>>>(h->d_den, h->n_den, h->B.st, h->d_pre, h->gw, h->B.wk, h->B.partial,
                                           h->E > 0 ? h->n_part : 0, d_out, nullptr, 0, nullptr);
   h->launches++;
   BA_CK(cudaGetLastError());
   return VIEO_OK;
 }
 
-// computeActiveErrors + buildSystem at the current estimate into linearisation set `set`; leaves the robust chi2 in
-// d_ctl[10] and the landmark part of the previous solve's gain-ratio denominator in d_ctl[11]
-int ba_linearize(vieo_ba* h, int set) {
-  BaLinArgs a;
-  a.cam = h->cam; a.cp = h->d_cp; a.X = h->d_X; a.pt_ptr = h->d_pt_ptr; a.P = h->P; a.es = h->d_es; a.obs = h->d_obs;
-  a.w = h->d_w; a.flags = h->d_flags; a.lvl = h->d_lvl; a.sfix = h->d_sfix; a.dm = h->dm; a.ds = h->ds;
-  a.chi2 = h->d_chi2; a.Wb = h->d_W[set]; a.Ab = h->d_A; a.Hll = h->d_Hll[set]; a.bl = h->d_bl[set];
-  a.partial = h->d_partial; a.pt_active = h->d_pt_active[set];
-  a.den = h->d_den; a.n_den = h->n_den; a.st = h->d_st; a.pre = h->d_pre; a.gw = h->gw; a.wk = h->d_wk;
-  a.off0 = h->d_off0; a.off1 = h->d_off1; a.off2 = h->d_off2; a.np = h->np; a.H = h->d_H[set]; a.b = h->d_b[set];
-  a.chi_dense = h->d_ctl + 8;
-  k_ba_linearize<<<h->n_pblk + 1, kBaWarps * 32, 0, h->st>>>(a);
-  h->launches++;
-  if (h->nfree > 0) {
-    k_ba_pose_reduce<<<h->nfree, 256, 0, h->st>>>(h->d_free_state, h->d_off0, h->d_ps_ptr, h->d_ps_edges, h->d_A, h->np,
-                                                  h->d_H[set], h->d_b[set], h->d_partial, h->n_pblk, h->d_ctl + 8,
-                                                  h->d_scale_part, h->P, h->d_ctl + 10);
-    h->launches++;
+int ba_allreduce(vieo_ba* h, double* buf, size_t n) {
+  if (!(h->allreduce && h->world > 1)) return VIEO_OK;
+  if (h->allreduce(h->ar_ctx, buf, n, (void*)h->st)) {
+    vieo::set_error("allreduce callback failed");
+    return VIEO_E_CUDA;
   }
-  BA_CK(cudaGetLastError());
-  if (h->allreduce && h->world > 1)
-    if (h->allreduce(h->ar_ctx, h->d_ctl + 10, 2, (void*)h->st)) {
-      vieo::set_error("allreduce callback failed");
-      return VIEO_E_CUDA;
-    }
   return VIEO_OK;
 }
 
-// (H + lambda I) x = b through the Schur complement on linearisation set `set`; apply: update the estimate
-int ba_solve(vieo_ba* h, int set, double lambda, int apply, double* xl_out) {
-  const int np = h->np;
-  const size_t nn = std::max<size_t>(std::max<size_t>((size_t)np * np, np), (size_t)h->P);
-  // sharded: lambda enters the pose diagonal once (rank 0); the all-reduce sums the partial systems
-  k_ba_prep_solve<<<(unsigned)((nn + 255) / 256), 256, 0, h->st>>>(h->d_Hll[set], h->d_bl[set], h->d_pt_active[set], h->P, lambda,
-                                                                  h->d_Dinv, h->d_db, h->d_H[set], h->d_b[set], np,
-                                                                  h->rank == 0 ? lambda : 0.0, h->S(), h->bs(), h->b());
-  h->launches++;
-  if (h->nfree > 0 && h->E > 0) {
-    const size_t smem = sizeof(double) * kBaWarps * 6 * (6 * (size_t)h->nfree + 1);
-    k_ba_schur<<<dim3(h->nfree, kSchurSplit), kBaWarps * 32, smem, h->st>>>(h->d_prcol, h->nfree, h->d_ps_ptr, h->d_ps_edges,
-                                                                          h->d_es, h->d_ep, h->d_pt_ptr, h->d_W[set], h->d_Dinv,
-                                                                          h->d_db, h->has_dup ? 1 : 0, h->d_part);
-    k_ba_schur_reduce<<<h->nfree, 256, 0, h->st>>>(h->d_free_state, h->d_off0, h->d_free_off, h->nfree, h->d_part, np, h->S(),
-                                                   h->bs());
-    h->launches += 2;
-  }
-  if (h->allreduce && h->world > 1) {
-    int rc = h->allreduce(h->ar_ctx, h->d_sys, h->sys_count(), (void*)h->st);
-    if (rc) {
-      vieo::set_error("allreduce callback failed (%d)", rc);
-      return VIEO_E_CUDA;
-    }
-  }
-  const size_t tri = sizeof(double) * ((size_t)np * (np | 1) + 3 * (size_t)np);
-  const int in_smem = tri <= 220 * 1024;
-  const size_t chol_smem = in_smem ? tri : sizeof(double) * 3 * (size_t)np;
-  k_ba_chol<<<1, kCholThreads, chol_smem, h->st>>>(h->S(), h->bs(), np, in_smem, h->d_x, h->d_ok);
-  h->launches++;
-  BaBackArgs a;
-  a.pt_ptr = h->d_pt_ptr; a.P = h->P; a.es = h->d_es; a.off0 = h->d_off0; a.off1 = h->d_off1; a.off2 = h->d_off2;
-  a.Wb = h->d_W[set]; a.Dinv = h->d_Dinv; a.bl = h->d_bl[set]; a.pt_active = h->d_pt_active[set]; a.x = h->d_x; a.ok = h->d_ok;
-  a.lambda = lambda; a.apply = apply; a.X = h->d_X; a.xl_out = xl_out; a.scale_part = h->d_scale_part; a.st = h->d_st;
-  a.K = h->K; a.cam = h->cam; a.cp = h->d_cp; a.b = h->b(); a.np = np; a.scale_pose = h->d_ctl + 3;
-  k_ba_backsub<<<h->n_pblk + 1, kBaWarps * 32, 0, h->st>>>(a);
-  h->launches++;
-  BA_CK(cudaGetLastError());
+// computeActiveErrors + buildSystem at the current estimate; into_other: into the set that is not the current one
+int ba_enqueue_linearize(vieo_ba* h, int into_other, bool at_capacity) {
+  const int pblk = at_capacity ? h->cap_pblk : h->n_pblk, nf = at_capacity ? h->cap_free : h->nfree;
+  k_ba_linearize<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
+  k_ba_pose_reduce<<<std::max(nf, 1), 256, 0, h->st>>>(h->B, into_other);
+  h->launches += 2;
   return VIEO_OK;
 }
 
-int ba_read_ctl(vieo_ba* h) {
-  BA_CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->st));
-  BA_CK(cudaMemcpyAsync(h->h_ctl + 12, h->d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+// (H + lambda I) x = b through the Schur complement on the current set.  Trial form (force == 0): lambda from the
+// device state, estimate updated.  force == 1: explicit lambda, nothing applied (vieo_ba_debug_step).
+int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, double* xl_out) {
+  const int pblk = at_capacity ? h->cap_pblk : h->n_pblk, nf = at_capacity ? h->cap_free : h->nfree;
+  const size_t P = at_capacity ? (size_t)h->capP : (size_t)h->P;
+  const size_t npc = at_capacity ? 15 * (size_t)std::min(h->capK, kSchurMaxFree + 8) : (size_t)h->np;
+  const size_t nn = std::max<size_t>(std::max<size_t>(npc * npc, npc), std::max<size_t>(P, 1));
+  k_ba_prep_solve<<<(unsigned)((nn + 255) / 256), 256, 0, h->st>>>(h->B, lambda, force);
+  k_ba_schur<<<dim3(std::max(nf, 1), kSchurSplit), kBaWarps * 32, schur_smem(at_capacity ? h->cap_free : h->nfree), h->st>>>(h->B, force);
+  k_ba_schur_reduce<<<std::max(nf, 1), 256, 0, h->st>>>(h->B, force);
+  h->launches += 3;
+  if (!at_capacity) {
+    int rc = ba_allreduce(h, h->d_sys, h->sys_count());
+    if (rc) return rc;
+  }
+  k_ba_chol<<<1, kCholThreads, kCholSmemBytes, h->st>>>(h->B, force);
+  k_ba_backsub<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, force ? 0 : 1, lambda, xl_out);
+  h->launches += 2;
+  return VIEO_OK;
+}
+
+// one LM trial: solve + update + linearisation at the trial estimate + bookkeeping
+int ba_enqueue_trial(vieo_ba* h, bool at_capacity) {
+  int rc;
+  if ((rc = ba_enqueue_solve(h, at_capacity, 0, 0.0, nullptr))) return rc;
+  if ((rc = ba_enqueue_linearize(h, 1, at_capacity))) return rc;
+  if (!at_capacity && (rc = ba_allreduce(h, h->B.prm->pair, 2))) return rc;
+  k_ba_control<<<1, 256, 0, h->st>>>(h->B, 1);
+  h->launches++;
+  return VIEO_OK;
+}
+
+int ba_read_prm(vieo_ba* h) {
+  BA_CK(cudaMemcpyAsync(h->h_prm, h->B.prm, sizeof(BaParams), cudaMemcpyDeviceToHost, h->st));
   BA_CK(cudaStreamSynchronize(h->st));
   return VIEO_OK;
 }
 
-// OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-166): 0 OK, 1 Terminate, <0 error.
-// chi_cur: robust chi2 of the current estimate (linearisation set h->cur is valid for it) — g2o recomputes it at the
-// start of every iteration; here it is carried over from the accepted trial, which evaluated the same state.
-int ba_lm_iteration(vieo_ba* h, int iteration, double user_lambda, const volatile uint8_t* stop, double& chi_cur) {
-  int rc;
-  if (iteration == 0) {
-    if (user_lambda > 0) h->lambda = user_lambda;
-    else {
-      if (h->allreduce && h->world > 1) {
-        vieo::set_error("sharded BA needs an explicit initial lambda");
-        return VIEO_E_ARG;
-      }
-      k_ba_maxdiag<<<1, 256, 0, h->st>>>(h->d_H[h->cur], h->np, h->d_Hll[h->cur], h->d_pt_active[h->cur], h->P, h->d_ctl + 4);
-      h->launches++;
-      BA_CK(cudaMemcpyAsync(h->h_ctl + 4, h->d_ctl + 4, sizeof(double), cudaMemcpyDeviceToHost, h->st));
-      BA_CK(cudaStreamSynchronize(h->st));
-      h->lambda = 1e-5 * h->h_ctl[4];
-    }
-    h->ni = 2;
-    h->nBad = 0;
-  }
-  double currentChi = chi_cur;
-  const double iniChi = chi_cur;
-  double rho = 0;
-  int qmax = 0;
-  do {
-    BA_CK(cudaMemcpyAsync(h->d_st_bak, h->d_st, sizeof(VieoNavState) * h->K, cudaMemcpyDeviceToDevice, h->st));
-    if (h->P) BA_CK(cudaMemcpyAsync(h->d_X_bak, h->d_X, sizeof(double) * 3 * h->P, cudaMemcpyDeviceToDevice, h->st));
-    if ((rc = ba_solve(h, h->cur, h->lambda, 1, nullptr))) return rc;
-    if ((rc = ba_linearize(h, 1 - h->cur))) return rc;  // errors at the trial estimate + speculative build
-    if ((rc = ba_read_ctl(h))) return rc;
-    const int ok2 = *(int*)(h->h_ctl + 12);
-    double tempChi = h->h_ctl[10];
-    if (!ok2) tempChi = std::numeric_limits<double>::max();
-    rho = currentChi - tempChi;
-    double scale = h->h_ctl[3] + h->h_ctl[11];
-    scale += 1e-3;
-    rho /= scale;
-    if (rho > 0 && std::isfinite(tempChi)) {
-      double alpha = 1. - std::pow((2 * rho - 1), 3);
-      alpha = std::min(alpha, 2. / 3.);
-      h->lambda *= std::max(1. / 3., alpha);
-      h->ni = 2;
-      currentChi = tempChi;
-      h->cur = 1 - h->cur;  // the speculative linearisation is the current one now
-    } else {
-      h->lambda *= h->ni;
-      h->ni *= 2;
-      BA_CK(cudaMemcpyAsync(h->d_st, h->d_st_bak, sizeof(VieoNavState) * h->K, cudaMemcpyDeviceToDevice, h->st));
-      if (h->P) BA_CK(cudaMemcpyAsync(h->d_X, h->d_X_bak, sizeof(double) * 3 * h->P, cudaMemcpyDeviceToDevice, h->st));
-    }
-    qmax++;
-  } while (rho < 0 && qmax < 10 && !(stop && *stop));
-  chi_cur = currentChi;
-  if (qmax == 10 || rho == 0) return 1;
-  if ((iniChi - currentChi) * 1e3 < iniChi) h->nBad++;
-  else h->nBad = 0;
-  if (h->nBad >= 3) return 1;
-  return 0;
-}
-
 void ba_free(vieo_ba* h) {
-  void* ptrs[] = {h->d_st, h->d_st_bak, h->d_cp, h->d_X, h->d_X_bak, h->d_chi2, h->d_A, h->d_Dinv, h->d_db, h->d_sys, h->d_x,
-                  h->d_xl, h->d_partial, h->d_scale_part, h->d_ctl, h->d_part, h->d_W[0], h->d_W[1], h->d_Hll[0], h->d_Hll[1],
-                  h->d_bl[0], h->d_bl[1], h->d_H[0], h->d_H[1], h->d_b[0], h->d_b[1], h->d_pt_active[0], h->d_pt_active[1],
-                  h->d_es, h->d_ep, h->d_pt_ptr, h->d_off0, h->d_off1, h->d_off2, h->d_prcol, h->d_free_state, h->d_free_off,
-                  h->d_ps_ptr, h->d_ps_edges, h->d_ok, h->d_obs, h->d_w, h->d_flags, h->d_lvl, h->d_sfix, h->d_bad, h->d_pre,
-                  h->d_den, h->d_wk};
+  BaBuf& B = h->B;
+  void* ptrs[] = {B.prm, B.st, B.st_bak, B.cp, B.X, B.X_bak, B.chi2, B.A, B.Dinv, B.db, B.x, B.partial, B.scale_part, B.part,
+                  B.W[0], B.W[1], B.Hll[0], B.Hll[1], B.bl[0], B.bl[1], B.H[0], B.H[1], B.b[0], B.b[1], B.pt_active[0],
+                  B.pt_active[1], B.wk, h->d_sys, h->d_xl, h->d_ctl, h->d_lvl, h->d_bad, h->d_flags, h->d_sfix, h->d_es,
+                  h->d_ep, h->d_pt_ptr, h->d_off0, h->d_off1, h->d_off2, h->d_prcol, h->d_free_state, h->d_free_off,
+                  h->d_ps_ptr, h->d_ps_edges, h->d_obs, h->d_w, h->d_pre, h->d_den};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (h->trial_graph) cudaGraphExecDestroy(h->trial_graph);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->h_prm) cudaFreeHost(h->h_prm);
   if (h->st) cudaStreamDestroy(h->st);
 }
 
@@ -1146,9 +1193,14 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   int rc = use_device(device);
   if (rc) return rc;
   vieo_ba* h = new vieo_ba();
+  memset(&h->B, 0, sizeof(h->B));
   h->device = device;
   h->capK = max_states; h->capP = max_points; h->capE = max_edges; h->capM = max_imu;
-  const size_t K = max_states, P = max_points, E = max_edges, M = max_imu, NP = 15 * K;
+  h->cap_pblk = (max_points + kBaWarps - 1) / kBaWarps;
+  h->cap_free = std::min(max_states, kSchurMaxFree);
+  const size_t K = max_states, P = max_points, E = max_edges, M = max_imu;
+  const size_t NP = 15 * (size_t)std::min(max_states, kSchurMaxFree + 8);  // free keyframes (+ a few V/Bias-only) x 15
+  BaBuf& B = h->B;
   cudaError_t e = cudaSuccess;
   auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   {  // the engine's kernels are tiny and latency-critical: let them overtake bulk work (front-end batches) on the device
@@ -1156,22 +1208,51 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
     step(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     step(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi));
   }
-  step(dalloc(&h->d_st, K)); step(dalloc(&h->d_st_bak, K)); step(dalloc(&h->d_cp, K));
-  step(dalloc(&h->d_X, 3 * P)); step(dalloc(&h->d_X_bak, 3 * P)); step(dalloc(&h->d_chi2, E));
-  step(dalloc(&h->d_A, 27 * E)); step(dalloc(&h->d_Dinv, 9 * P)); step(dalloc(&h->d_db, 3 * P));
+  step(dalloc(&B.prm, 1));
+  step(dalloc(&B.st, K)); step(dalloc(&B.st_bak, K)); step(dalloc(&B.cp, K));
+  step(dalloc(&B.X, 3 * P)); step(dalloc(&B.X_bak, 3 * P)); step(dalloc(&B.chi2, E));
+  step(dalloc(&B.A, 27 * E)); step(dalloc(&B.Dinv, 9 * P)); step(dalloc(&B.db, 3 * P));
   for (int s = 0; s < 2; ++s) {
-    step(dalloc(&h->d_W[s], 18 * E)); step(dalloc(&h->d_Hll[s], 9 * P)); step(dalloc(&h->d_bl[s], 3 * P));
-    step(dalloc(&h->d_H[s], NP * NP)); step(dalloc(&h->d_b[s], NP)); step(dalloc(&h->d_pt_active[s], P));
+    step(dalloc(&B.W[s], 18 * E)); step(dalloc(&B.Hll[s], 9 * P)); step(dalloc(&B.bl[s], 3 * P));
+    step(dalloc(&B.H[s], NP * NP)); step(dalloc(&B.b[s], NP)); step(dalloc(&B.pt_active[s], P));
   }
-  step(dalloc(&h->d_sys, NP * NP + 2 * NP + 8)); step(dalloc(&h->d_x, NP));
-  step(dalloc(&h->d_xl, 3 * P)); step(dalloc(&h->d_partial, std::max((E + 255) / 256, P / kBaWarps + 1) + 2)); step(dalloc(&h->d_scale_part, P));
+  step(dalloc(&h->d_sys, NP * NP + 2 * NP + 8)); step(dalloc(&B.x, NP));
+  step(dalloc(&h->d_xl, 3 * P)); step(dalloc(&B.partial, std::max((E + 255) / 256, P / kBaWarps + 1) + 2));
+  step(dalloc(&B.scale_part, P));
+  step(dalloc(&B.part, (size_t)h->cap_free * kSchurSplit * 6 * (6 * (size_t)h->cap_free + 1)));
   step(dalloc(&h->d_ctl, 16)); step(dalloc(&h->d_es, E)); step(dalloc(&h->d_ep, E)); step(dalloc(&h->d_pt_ptr, P + 1));
   step(dalloc(&h->d_off0, K)); step(dalloc(&h->d_off1, K)); step(dalloc(&h->d_off2, K)); step(dalloc(&h->d_prcol, K));
   step(dalloc(&h->d_free_state, K)); step(dalloc(&h->d_free_off, K)); step(dalloc(&h->d_ps_ptr, K + 1));
-  step(dalloc(&h->d_ps_edges, E)); step(dalloc(&h->d_ok, 4)); step(dalloc(&h->d_obs, 3 * E)); step(dalloc(&h->d_w, E));
+  step(dalloc(&h->d_ps_edges, E)); step(dalloc(&h->d_obs, 3 * E)); step(dalloc(&h->d_w, E));
   step(dalloc(&h->d_flags, E)); step(dalloc(&h->d_lvl, E)); step(dalloc(&h->d_sfix, K));
-  step(dalloc(&h->d_bad, E)); step(dalloc(&h->d_pre, M)); step(dalloc(&h->d_den, 2 * M)); step(dalloc(&h->d_wk, 2 * M));
+  step(dalloc(&h->d_bad, E)); step(dalloc(&h->d_pre, M)); step(dalloc(&h->d_den, 2 * M)); step(dalloc(&B.wk, 2 * M));
   step(cudaMallocHost((void**)&h->h_ctl, sizeof(double) * 16));
+  step(cudaMallocHost((void**)&h->h_prm, sizeof(BaParams)));
+  if (e == cudaSuccess) {
+    h->cap_np = NP;
+    B.bs = h->d_sys; B.bsys = h->d_sys + NP; B.S = h->d_sys + 2 * NP;
+    B.es = h->d_es; B.ep = h->d_ep; B.pt_ptr = h->d_pt_ptr; B.off0 = h->d_off0; B.off1 = h->d_off1; B.off2 = h->d_off2;
+    B.prcol = h->d_prcol; B.free_state = h->d_free_state; B.free_off = h->d_free_off; B.ps_ptr = h->d_ps_ptr;
+    B.ps_edges = h->d_ps_edges; B.obs = h->d_obs; B.w = h->d_w; B.flags = h->d_flags; B.lvl = h->d_lvl; B.sfix = h->d_sfix;
+    B.pre = h->d_pre; B.den = h->d_den;
+    memset(h->h_prm, 0, sizeof(BaParams));
+    h->h_prm->done = 1;
+    step(cudaMemcpy(B.prm, h->h_prm, sizeof(BaParams), cudaMemcpyHostToDevice));
+    step(cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem(h->cap_free)));
+    step(cudaFuncSetAttribute(k_ba_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+  }
+  if (e == cudaSuccess) {
+    // the LM trial as one CUDA graph: constant launch parameters (capacity grids, sizes read from B.prm on the device)
+    cudaGraph_t g = nullptr;
+    step(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+    if (e == cudaSuccess) {
+      ba_enqueue_trial(h, true);
+      step(cudaStreamEndCapture(h->st, &g));
+      if (e == cudaSuccess) step(cudaGraphInstantiate(&h->trial_graph, g, 0));
+      if (g) cudaGraphDestroy(g);
+    }
+    h->launches = 0;
+  }
   if (e != cudaSuccess) {
     set_error("vieo_ba_create: %s", cudaGetErrorString(e));
     ba_free(h);
@@ -1214,7 +1295,6 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   h->points_free = true;
   h->n_part = (E + 255) / 256;
   h->n_pblk = (P + kBaWarps - 1) / kBaWarps;
-  h->cur = 0;
   // camera
   h->cam.fx = (double)cam->fx; h->cam.fy = (double)cam->fy; h->cam.cx = (double)cam->cx; h->cam.cy = (double)cam->cy;
   h->cam.bf = (double)cam->bf;
@@ -1311,8 +1391,8 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   std::vector<uint8_t> lvl(std::max(E, 1));
   for (int i = 0; i < E; ++i) lvl[i] = ((pb->edge_flags[i] & VIEO_EDGE_LEVEL1) ? 1 : 0) | ((pb->edge_flags[i] & VIEO_EDGE_NOKERNEL) ? 2 : 0);
   auto up = [&](void* d, const void* s, size_t n) { return n ? cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, h->st) : cudaSuccess; };
-  BA_CK(up(h->d_st, pb->states, sizeof(VieoNavState) * K));
-  BA_CK(up(h->d_X, pb->points, 24 * (size_t)P));
+  BA_CK(up(h->B.st, pb->states, sizeof(VieoNavState) * K));
+  BA_CK(up(h->B.X, pb->points, 24 * (size_t)P));
   BA_CK(up(h->d_es, pb->edge_state, 4 * (size_t)E));
   BA_CK(up(h->d_ep, pb->edge_point, 4 * (size_t)E));
   BA_CK(up(h->d_obs, pb->obs, 12 * (size_t)E));
@@ -1331,31 +1411,26 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   BA_CK(up(h->d_ps_edges, ps_edges.data(), 4 * (size_t)ps_ptr[h->nfree]));
   BA_CK(up(h->d_pre, pb->preint, sizeof(VieoImuPreint) * (size_t)M));
   BA_CK(up(h->d_den, den.data(), sizeof(BaDense) * den.size()));
-  BA_CK(cudaMemsetAsync(h->d_chi2, 0, 8 * (size_t)std::max(E, 1), h->st));
+  BA_CK(cudaMemsetAsync(h->B.chi2, 0, 8 * (size_t)std::max(E, 1), h->st));
   BA_CK(cudaMemsetAsync(h->d_ctl, 0, 8 * 16, h->st));
-  BA_CK(cudaMemsetAsync(h->d_x, 0, 8 * (size_t)std::max(np, 1), h->st));
-  BA_CK(cudaMemsetAsync(h->d_ok, 0, 16, h->st));
-  BA_CK(cudaStreamSynchronize(h->st));  // the host staging vectors die here
-  const size_t smem = sizeof(double) * kBaWarps * 6 * (6 * (size_t)h->nfree + 1);
-  if (smem > 200 * 1024) {
-    set_error("vieo_ba_set_problem: %d free keyframes exceed the Schur kernel's shared-memory tile", h->nfree);
+  BA_CK(cudaMemsetAsync(h->B.x, 0, 8 * (size_t)std::max(np, 1), h->st));
+  BA_CK(cudaMemsetAsync(h->B.scale_part, 0, 8 * (size_t)std::max(P, 1), h->st));
+  if (h->nfree > h->cap_free || (size_t)np > h->cap_np) {
+    set_error("vieo_ba_set_problem: %d free keyframes / %d pose dimensions exceed the engine's tile (%d / %zu)", h->nfree, np,
+              h->cap_free, h->cap_np);
     return VIEO_E_CAPACITY;
   }
-  if (smem > 48 * 1024) BA_CK(cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const size_t part_need = (size_t)h->nfree * kSchurSplit * 6 * (6 * (size_t)h->nfree + 1);
-  if (part_need > h->part_cap) {
-    if (h->d_part) cudaFree(h->d_part);
-    h->d_part = nullptr;
-    h->part_cap = 0;
-    BA_CK(dalloc(&h->d_part, part_need));
-    h->part_cap = part_need;
-  }
-  const size_t tri = sizeof(double) * ((size_t)np * (np | 1) + 3 * (size_t)np);
-  BA_CK(cudaFuncSetAttribute(k_ba_chol, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(tri <= 220 * 1024 ? std::max<size_t>(tri, 48 * 1024) : 48 * 1024)));
-  BA_CK(cudaMemsetAsync(h->d_scale_part, 0, 8 * (size_t)std::max(P, 1), h->st));
-  BA_CK(cudaStreamSynchronize(h->st));
-  h->lambda = 0; h->ni = 2; h->nBad = 0;
+  BaParams& q = *h->h_prm;
+  memset(&q, 0, sizeof(q));
+  q.K = K; q.P = P; q.E = E; q.np = np; q.nfree = h->nfree; q.n_den = h->n_den; q.n_pblk = h->n_pblk;
+  q.has_dup = h->has_dup ? 1 : 0;
+  q.lambda_on_poses = h->rank == 0 ? 1 : 0;
+  q.done = 1;
+  q.ok = 1;
+  q.ni = 2;
+  q.cam = h->cam; q.gw = h->gw; q.dm = h->dm; q.ds = h->ds;
+  BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
+  BA_CK(cudaStreamSynchronize(h->st));  // the host staging vectors die here
   return VIEO_OK;
 }
 
@@ -1365,8 +1440,8 @@ int vieo_ba_chi2_large_set_level(vieo_ba_t* h, float rat) {
   int rc = ba_errors(h, 1, h->d_ctl + 5);
   if (rc) return rc;
   if (h->E > 0) {
-    k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->d_cp, h->d_X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
-                                                         h->d_chi2, h->E, 0, rat, 1, 0, h->d_lvl, nullptr);
+    k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
+                                                         h->B.chi2, h->E, 0, rat, 1, 0, h->d_lvl, nullptr);
     h->launches++;
   }
   BA_CK(cudaGetLastError());
@@ -1386,12 +1461,12 @@ int vieo_ba_active_robust_chi2(vieo_ba_t* h, int recompute, double* chi2) {
     // the stored values, so do that on the host.
     std::vector<double> c(std::max(h->E, 1));
     std::vector<uint8_t> lvl(std::max(h->E, 1)), fl(std::max(h->E, 1));
-    BA_CK(cudaMemcpyAsync(c.data(), h->d_chi2, 8 * (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
+    BA_CK(cudaMemcpyAsync(c.data(), h->B.chi2, 8 * (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
     BA_CK(cudaMemcpyAsync(lvl.data(), h->d_lvl, (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
     BA_CK(cudaMemcpyAsync(fl.data(), h->d_flags, (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
     std::vector<BaDenseWork> wk(std::max(h->n_den, 1));
     std::vector<BaDense> den(std::max(h->n_den, 1));
-    BA_CK(cudaMemcpyAsync(wk.data(), h->d_wk, sizeof(BaDenseWork) * h->n_den, cudaMemcpyDeviceToHost, h->st));
+    BA_CK(cudaMemcpyAsync(wk.data(), h->B.wk, sizeof(BaDenseWork) * h->n_den, cudaMemcpyDeviceToHost, h->st));
     BA_CK(cudaMemcpyAsync(den.data(), h->d_den, sizeof(BaDense) * h->n_den, cudaMemcpyDeviceToHost, h->st));
     BA_CK(cudaStreamSynchronize(h->st));
     auto rho0 = [](double delta, double e) {
@@ -1430,21 +1505,45 @@ int vieo_ba_optimize(vieo_ba_t* h, int iterations, double lambda_init, const vol
   BA_CK(cudaSetDevice(h->device));
   if (h->np == 0 || iterations == 0) return 0;
   if (stop && *stop) return 0;
-  BA_CK(cudaMemsetAsync(h->d_x, 0, 8 * (size_t)h->np, h->st));
-  // levels / kernels may have changed since the last call: fresh errors + linearisation at the current estimate
-  int rc = ba_campose(h);
-  if ((rc = ba_linearize(h, h->cur))) return rc;
-  if ((rc = ba_read_ctl(h))) return rc;
-  double chi_cur = h->h_ctl[10];
-  int n = 0;
-  bool ok = true;
-  for (int i = 0; i < iterations && !(stop && *stop) && ok; ++i) {
-    const int r = ba_lm_iteration(h, i, lambda_init, stop, chi_cur);
-    if (r < 0) return r;
-    ok = r == 0;
-    ++n;
+  const bool sharded = h->allreduce && h->world > 1;
+  if (sharded && !(lambda_init > 0)) {
+    set_error("sharded BA needs an explicit initial lambda");
+    return VIEO_E_ARG;
   }
-  return n;
+  // optimize() state machine on the device: reset, then a fresh linearisation at the current estimate (levels / kernels
+  // may have changed since the last call)
+  BaParams& q = *h->h_prm;
+  q.cur = 0; q.done = 0; q.stop = 0; q.ok = 1;
+  q.iteration = 0; q.iters_target = iterations; q.iters_done = 0; q.qmax = 0; q.nBad = 0;
+  q.user_lambda = lambda_init;
+  BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
+  BA_CK(cudaMemsetAsync(h->B.x, 0, 8 * (size_t)h->np, h->st));
+  int rc = ba_campose(h);
+  if ((rc = ba_enqueue_linearize(h, 0, false))) return rc;
+  if ((rc = ba_allreduce(h, h->B.prm->pair, 2))) return rc;
+  k_ba_control<<<1, 256, 0, h->st>>>(h->B, 0);
+  h->launches++;
+  BA_CK(cudaGetLastError());
+  // trials are launched in small chunks (a finished optimize() turns the remaining ones into no-ops); the abort flag is
+  // polled between chunks (sparse_optimizer.cpp:376 polls it once per iteration)
+  const int kChunk = 3, kNodes = 8;
+  for (int guard = 0; guard < 10 * iterations + 4; guard += kChunk) {
+    for (int c = 0; c < kChunk; ++c) {
+      if (!sharded && h->trial_graph) {
+        BA_CK(cudaGraphLaunch(h->trial_graph, h->st));
+        h->launches += kNodes;
+      } else if ((rc = ba_enqueue_trial(h, false)))
+        return rc;
+    }
+    if ((rc = ba_read_prm(h))) return rc;
+    if (h->h_prm->done) break;
+    if (stop && *stop && !h->h_prm->stop) {
+      const int one = 1;
+      BA_CK(cudaMemcpyAsync(&h->B.prm->stop, &one, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    }
+  }
+  BA_CK(cudaGetLastError());
+  return h->h_prm->iters_done;
 }
 
 int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host) {
@@ -1452,8 +1551,8 @@ int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host) {
   BA_CK(cudaSetDevice(h->device));
   if (h->E == 0) return VIEO_OK;
   ba_campose(h);
-  k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->d_cp, h->d_X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
-                                                       h->d_chi2, h->E, 1, 0.f, bad_host ? 0 : 1, remove_kernels, h->d_lvl,
+  k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
+                                                       h->B.chi2, h->E, 1, 0.f, bad_host ? 0 : 1, remove_kernels, h->d_lvl,
                                                        h->d_bad);
   h->launches++;
   BA_CK(cudaGetLastError());
@@ -1467,9 +1566,9 @@ int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host) {
 int vieo_ba_get(vieo_ba_t* h, VieoNavState* states_out, double* points_out, double* edge_chi2) {
   VIEO_ARG(h, "null handle");
   BA_CK(cudaSetDevice(h->device));
-  if (states_out) BA_CK(cudaMemcpyAsync(states_out, h->d_st, sizeof(VieoNavState) * h->K, cudaMemcpyDeviceToHost, h->st));
-  if (points_out && h->P) BA_CK(cudaMemcpyAsync(points_out, h->d_X, 24 * (size_t)h->P, cudaMemcpyDeviceToHost, h->st));
-  if (edge_chi2 && h->E) BA_CK(cudaMemcpyAsync(edge_chi2, h->d_chi2, 8 * (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
+  if (states_out) BA_CK(cudaMemcpyAsync(states_out, h->B.st, sizeof(VieoNavState) * h->K, cudaMemcpyDeviceToHost, h->st));
+  if (points_out && h->P) BA_CK(cudaMemcpyAsync(points_out, h->B.X, 24 * (size_t)h->P, cudaMemcpyDeviceToHost, h->st));
+  if (edge_chi2 && h->E) BA_CK(cudaMemcpyAsync(edge_chi2, h->B.chi2, 8 * (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
   BA_CK(cudaStreamSynchronize(h->st));
   return VIEO_OK;
 }
@@ -1477,16 +1576,23 @@ int vieo_ba_get(vieo_ba_t* h, VieoNavState* states_out, double* points_out, doub
 int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_points, double* H_out, double* b_out) {
   VIEO_ARG(h && x_pose, "null argument");
   BA_CK(cudaSetDevice(h->device));
+  BaParams& q = *h->h_prm;
+  q.cur = 0; q.done = 0; q.stop = 0; q.ok = 1;
+  BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
   int rc = ba_campose(h);
-  if ((rc = ba_linearize(h, h->cur))) return rc;
-  if ((rc = ba_solve(h, h->cur, lambda, 0, h->d_xl))) return rc;
-  BA_CK(cudaMemcpyAsync(x_pose, h->d_x, 8 * (size_t)h->np, cudaMemcpyDeviceToHost, h->st));
+  if ((rc = ba_enqueue_linearize(h, 0, false))) return rc;
+  if ((rc = ba_enqueue_solve(h, false, 1, lambda, h->d_xl))) return rc;
+  BA_CK(cudaGetLastError());
+  BA_CK(cudaMemcpyAsync(x_pose, h->B.x, 8 * (size_t)h->np, cudaMemcpyDeviceToHost, h->st));
   if (x_points && h->P) BA_CK(cudaMemcpyAsync(x_points, h->d_xl, 24 * (size_t)h->P, cudaMemcpyDeviceToHost, h->st));
-  if (H_out) BA_CK(cudaMemcpyAsync(H_out, h->d_H[h->cur], 8 * (size_t)h->np * h->np, cudaMemcpyDeviceToHost, h->st));
-  if (b_out) BA_CK(cudaMemcpyAsync(b_out, h->d_b[h->cur], 8 * (size_t)h->np, cudaMemcpyDeviceToHost, h->st));
-  BA_CK(cudaMemcpyAsync(h->h_ctl + 12, h->d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  if (H_out) BA_CK(cudaMemcpyAsync(H_out, h->B.H[0], 8 * (size_t)h->np * h->np, cudaMemcpyDeviceToHost, h->st));
+  if (b_out) BA_CK(cudaMemcpyAsync(b_out, h->B.b[0], 8 * (size_t)h->np, cudaMemcpyDeviceToHost, h->st));
+  if ((rc = ba_read_prm(h))) return rc;
+  const int ok = h->h_prm->ok;
+  q.done = 1;
+  BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
   BA_CK(cudaStreamSynchronize(h->st));
-  if (!*(int*)(h->h_ctl + 12)) {
+  if (!ok) {
     set_error("vieo_ba_debug_step: reduced camera system is not positive definite");
     return VIEO_E_ARG;
   }
@@ -1531,7 +1637,7 @@ int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* c
   if ((rc = vieo_ba_active_robust_chi2(h, 0, &chi))) return rc;
   const float err_end = (float)chi;
   res->err_end = err_end;
-  res->lambda_final = h->lambda;
+  res->lambda_final = h->h_prm->lambda;
   if ((rc = vieo_ba_get(h, nullptr, nullptr, edge_chi2))) return rc;
   if ((2 * err < err_end || std::isnan(err) || std::isnan(err_end)) && !pb->large) {
     res->accepted = 0;  // "FAIL LOCAL-INERTIAL BA" (:663-666)
