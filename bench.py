@@ -484,7 +484,7 @@ def main():
     ap.add_argument("--pool", type=int, default=4, help="distinct input batches rotated through")
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--lba", type=int, default=1, help="0: leave LocalBA out of the step")
-    ap.add_argument("--lba-workers", type=int, default=8, help="host threads (one BA handle + stream each) running LocalBA windows")
+    ap.add_argument("--lba-workers", type=int, default=16, help="host threads (one BA handle + stream each) running LocalBA windows")
     ap.add_argument("--lba-windows", type=int, default=3, help="distinct LocalBA problems generated")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

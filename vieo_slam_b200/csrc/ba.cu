@@ -68,7 +68,12 @@ __global__ void __launch_bounds__(256) k_ba_errors(CamK cam, const CamPose* __re
   double r0 = 0;
   if (i < E) {
     const bool active = !(lvl[i] & 1) && (points_free || !sfix[es[i]]);
-    if (active || all) {
+    if (all == 2) {  // activeRobustChi2 over the stored errors
+      if (active) {
+        double r1;
+        huber_rho(edge_huber_delta(flags[i], lvl[i], dm, ds), chi2[i], r0, r1);
+      }
+    } else if (active || all) {
       const bool stereo = flags[i] & VIEO_EDGE_STEREO;
       double e[3];
       reproj_error(cam, cp[es[i]], ld3(X + 3 * (size_t)ep[i]), obs + 3 * (size_t)i, stereo, e);
@@ -99,7 +104,8 @@ __global__ void __launch_bounds__(128) k_ba_dense_errors(const BaDense* __restri
                                   const VieoImuPreint* __restrict__ pre, Vec3 gw, BaDenseWork* __restrict__ wk,
                                   const double* __restrict__ partial, int n_partial, double* __restrict__ out,
                                   const double* __restrict__ scale_part, int n_scale, double* __restrict__ scale_out) {
-  for (int m = threadIdx.x; m < n_den; m += blockDim.x) {
+  const bool sum_only = n_scale < 0;  // keep the stored errors (activeRobustChi2 without computeActiveErrors)
+  for (int m = threadIdx.x; m < n_den && !sum_only; m += blockDim.x) {
     const BaDense& d = den[m];
     BaDenseWork& W = wk[m];
     const NavS a = ns_load(st[d.si]), b = ns_load(st[d.sj]);
@@ -1034,6 +1040,8 @@ struct vieo_ba {
   VieoImuPreint* d_pre = nullptr;
   BaDense* d_den = nullptr;
   double* h_ctl = nullptr;  // pinned
+  uint8_t* h_stage = nullptr;  // pinned staging for the problem upload / result download (no pageable copies)
+  size_t stage_cap = 0, stage_used = 0;
   std::vector<int> off0, off1, off2;
   int launches = 0;
   size_t cap_np = 0;
@@ -1107,7 +1115,7 @@ int ba_errors(vieo_ba* h, int all, double* d_out) {
     h->launches++;
   }
   k_ba_dense_errors<<<1, 128, 0, h->st>>>(h->d_den, h->n_den, h->B.st, h->d_pre, h->gw, h->B.wk, h->B.partial,
-                                          h->E > 0 ? h->n_part : 0, d_out, nullptr, 0, nullptr);
+                                          h->E > 0 ? h->n_part : 0, d_out, nullptr, all == 2 ? -1 : 0, nullptr);
   h->launches++;
   BA_CK(cudaGetLastError());
   return VIEO_OK;
@@ -1181,6 +1189,7 @@ void ba_free(vieo_ba* h) {
   if (h->trial_graph) cudaGraphExecDestroy(h->trial_graph);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_prm) cudaFreeHost(h->h_prm);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->st) cudaStreamDestroy(h->st);
 }
 
@@ -1228,6 +1237,8 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   step(dalloc(&h->d_bad, E)); step(dalloc(&h->d_pre, M)); step(dalloc(&h->d_den, 2 * M)); step(dalloc(&B.wk, 2 * M));
   step(cudaMallocHost((void**)&h->h_ctl, sizeof(double) * 16));
   step(cudaMallocHost((void**)&h->h_prm, sizeof(BaParams)));
+  h->stage_cap = K * (sizeof(VieoNavState) + 64) + P * 32 + E * 40 + M * (sizeof(VieoImuPreint) + 2 * sizeof(BaDense)) + 4096;
+  step(cudaMallocHost((void**)&h->h_stage, h->stage_cap));
   if (e == cudaSuccess) {
     h->cap_np = NP;
     B.bs = h->d_sys; B.bsys = h->d_sys + NP; B.S = h->d_sys + 2 * NP;
@@ -1390,7 +1401,16 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   VIEO_ARG(h->n_den <= 1024, "too many inertial edges");
   std::vector<uint8_t> lvl(std::max(E, 1));
   for (int i = 0; i < E; ++i) lvl[i] = ((pb->edge_flags[i] & VIEO_EDGE_LEVEL1) ? 1 : 0) | ((pb->edge_flags[i] & VIEO_EDGE_NOKERNEL) ? 2 : 0);
-  auto up = [&](void* d, const void* s, size_t n) { return n ? cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, h->st) : cudaSuccess; };
+  // every array goes through the pinned staging buffer: asynchronous copies, no driver-side pageable staging
+  h->stage_used = 0;
+  auto up = [&](void* d, const void* s, size_t n) {
+    if (!n) return cudaSuccess;
+    const size_t o = (h->stage_used + 15) & ~(size_t)15;
+    if (o + n > h->stage_cap) return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, h->st);
+    memcpy(h->h_stage + o, s, n);
+    h->stage_used = o + n;
+    return cudaMemcpyAsync(d, h->h_stage + o, n, cudaMemcpyHostToDevice, h->st);
+  };
   BA_CK(up(h->B.st, pb->states, sizeof(VieoNavState) * K));
   BA_CK(up(h->B.X, pb->points, 24 * (size_t)P));
   BA_CK(up(h->d_es, pb->edge_state, 4 * (size_t)E));
@@ -1455,42 +1475,10 @@ int vieo_ba_active_robust_chi2(vieo_ba_t* h, int recompute, double* chi2) {
     int rc = ba_errors(h, 0, h->d_ctl + 6);
     if (rc) return rc;
   } else {
-    // activeRobustChi2 over the stored errors of the current active set (levels may have changed since)
-    // -> recompute the partial sums without touching chi2: run the error kernel in "sum only" fashion is not needed:
-    // the stored chi2 of active edges equals a recomputation unless the last LM trial was rejected; the reference sums
-    // the stored values, so do that on the host.
-    std::vector<double> c(std::max(h->E, 1));
-    std::vector<uint8_t> lvl(std::max(h->E, 1)), fl(std::max(h->E, 1));
-    BA_CK(cudaMemcpyAsync(c.data(), h->B.chi2, 8 * (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
-    BA_CK(cudaMemcpyAsync(lvl.data(), h->d_lvl, (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
-    BA_CK(cudaMemcpyAsync(fl.data(), h->d_flags, (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
-    std::vector<BaDenseWork> wk(std::max(h->n_den, 1));
-    std::vector<BaDense> den(std::max(h->n_den, 1));
-    BA_CK(cudaMemcpyAsync(wk.data(), h->B.wk, sizeof(BaDenseWork) * h->n_den, cudaMemcpyDeviceToHost, h->st));
-    BA_CK(cudaMemcpyAsync(den.data(), h->d_den, sizeof(BaDense) * h->n_den, cudaMemcpyDeviceToHost, h->st));
-    BA_CK(cudaStreamSynchronize(h->st));
-    auto rho0 = [](double delta, double e) {
-      const double dsqr = (double)(float)(delta * delta);
-      if (delta == 0 || e <= dsqr) return e;
-      return 2 * std::sqrt(e) * delta - dsqr;
-    };
-    double tot = 0;
-    for (int m = 0; m < h->n_den; ++m) tot += rho0(den[m].delta, wk[m].chi2);
-    for (int i = 0; i < h->E; ++i) {
-      if (lvl[i] & 1) continue;
-      const double d = (lvl[i] & 2) ? 0.0 : ((fl[i] & VIEO_EDGE_STEREO) ? h->ds : h->dm);
-      tot += rho0(d, c[i]);
-    }
-    if (h->allreduce && h->world > 1) {  // partial sums of the ranks' own edges
-      h->h_ctl[7] = tot;
-      BA_CK(cudaMemcpyAsync(h->d_ctl + 7, h->h_ctl + 7, 8, cudaMemcpyHostToDevice, h->st));
-      if (h->allreduce(h->ar_ctx, h->d_ctl + 7, 1, (void*)h->st)) return VIEO_E_CUDA;
-      BA_CK(cudaMemcpyAsync(h->h_ctl + 7, h->d_ctl + 7, 8, cudaMemcpyDeviceToHost, h->st));
-      BA_CK(cudaStreamSynchronize(h->st));
-      tot = h->h_ctl[7];
-    }
-    *chi2 = tot;
-    return VIEO_OK;
+    // activeRobustChi2 over the stored errors of the current active set (levels may have changed since the last
+    // evaluation; after a rejected last trial the stored errors are those of the rejected estimate, as in g2o)
+    int rc = ba_errors(h, 2, h->d_ctl + 6);
+    if (rc) return rc;
   }
   if (h->allreduce && h->world > 1)
     if (h->allreduce(h->ar_ctx, h->d_ctl + 6, 1, (void*)h->st)) return VIEO_E_CUDA;
@@ -1557,8 +1545,10 @@ int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host) {
   h->launches++;
   BA_CK(cudaGetLastError());
   if (bad_host) {
-    BA_CK(cudaMemcpyAsync(bad_host, h->d_bad, (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
+    const bool staged = (size_t)h->E <= h->stage_cap;
+    BA_CK(cudaMemcpyAsync(staged ? (void*)h->h_stage : (void*)bad_host, h->d_bad, (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
     BA_CK(cudaStreamSynchronize(h->st));
+    if (staged) memcpy(bad_host, h->h_stage, (size_t)h->E);
   }
   return VIEO_OK;
 }
@@ -1566,9 +1556,24 @@ int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host) {
 int vieo_ba_get(vieo_ba_t* h, VieoNavState* states_out, double* points_out, double* edge_chi2) {
   VIEO_ARG(h, "null handle");
   BA_CK(cudaSetDevice(h->device));
-  if (states_out) BA_CK(cudaMemcpyAsync(states_out, h->B.st, sizeof(VieoNavState) * h->K, cudaMemcpyDeviceToHost, h->st));
-  if (points_out && h->P) BA_CK(cudaMemcpyAsync(points_out, h->B.X, 24 * (size_t)h->P, cudaMemcpyDeviceToHost, h->st));
-  if (edge_chi2 && h->E) BA_CK(cudaMemcpyAsync(edge_chi2, h->B.chi2, 8 * (size_t)h->E, cudaMemcpyDeviceToHost, h->st));
+  const size_t ns = states_out ? sizeof(VieoNavState) * h->K : 0, nx = points_out ? 24 * (size_t)h->P : 0,
+               nc = edge_chi2 ? 8 * (size_t)h->E : 0;
+  if (ns + nx + nc + 64 <= h->stage_cap) {  // through pinned staging (the upload staging is no longer needed)
+    uint8_t* ps = h->h_stage;
+    uint8_t* px = ps + ((ns + 15) & ~(size_t)15);
+    uint8_t* pc = px + ((nx + 15) & ~(size_t)15);
+    if (ns) BA_CK(cudaMemcpyAsync(ps, h->B.st, ns, cudaMemcpyDeviceToHost, h->st));
+    if (nx) BA_CK(cudaMemcpyAsync(px, h->B.X, nx, cudaMemcpyDeviceToHost, h->st));
+    if (nc) BA_CK(cudaMemcpyAsync(pc, h->B.chi2, nc, cudaMemcpyDeviceToHost, h->st));
+    BA_CK(cudaStreamSynchronize(h->st));
+    if (ns) memcpy(states_out, ps, ns);
+    if (nx) memcpy(points_out, px, nx);
+    if (nc) memcpy(edge_chi2, pc, nc);
+    return VIEO_OK;
+  }
+  if (ns) BA_CK(cudaMemcpyAsync(states_out, h->B.st, ns, cudaMemcpyDeviceToHost, h->st));
+  if (nx) BA_CK(cudaMemcpyAsync(points_out, h->B.X, nx, cudaMemcpyDeviceToHost, h->st));
+  if (nc) BA_CK(cudaMemcpyAsync(edge_chi2, h->B.chi2, nc, cudaMemcpyDeviceToHost, h->st));
   BA_CK(cudaStreamSynchronize(h->st));
   return VIEO_OK;
 }
