@@ -93,69 +93,67 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 }
 
 // ------------------------------------------------------------------------------------------------
-// FAST-9/16 arc score of one pixel: S = max(v - min_arcs(max9 p), max_arcs(min9 p) - v, 0) over the 16
-// contiguous 9-arcs of the radius-3 ring; equals cornerScore<16>()+1 for corners, and a pixel is a corner at
-// threshold t iff S > t.  Two ring pixels per register (u16x2 lanes: p[k] | p[k+8] << 16): the arc starting
-// at k+8 is the arc starting at k with the halves swapped, so one packed min/max tree (VIMNMX.U16x2) serves
-// both.  (A first formulation on signed differences v - p[k] was miscompiled by nvcc 12.9 for sm_100a —
-// tools/dev_fast_score_test.cu keeps it as V0 — so the tree runs on raw pixel values.)
-__device__ __forceinline__ int fast_score(const uint8_t* p, int pitch) {
-  const int v = p[0];
-  unsigned r[16];
-  r[0] = p[3 * pitch];
-  r[1] = p[3 * pitch + 1];
-  r[2] = p[2 * pitch + 2];
-  r[3] = p[pitch + 3];
-  r[4] = p[3];
-  r[5] = p[-pitch + 3];
-  r[6] = p[-2 * pitch + 2];
-  r[7] = p[-3 * pitch + 1];
-  r[8] = p[-3 * pitch];
-  r[9] = p[-3 * pitch - 1];
-  r[10] = p[-2 * pitch - 2];
-  r[11] = p[-pitch - 3];
-  r[12] = p[-3];
-  r[13] = p[pitch - 3];
-  r[14] = p[2 * pitch - 2];
-  r[15] = p[3 * pitch - 1];
-  unsigned X[16];
+// FAST-9/16 arc score: S = max(v - min_arcs(max9 p), max_arcs(min9 p) - v, 0) over the 16 contiguous 9-arcs of the
+// radius-3 ring; equals cornerScore<16>()+1 for corners, and a pixel is a corner at threshold t iff S > t.
+// Four horizontally adjacent pixels per thread, one per byte lane of the u8x4 video instructions (VIMNMX.U8x4): the
+// ring pixel k of the four centres is an unaligned 4-byte window of the shared-memory tile, fetched as two aligned
+// words + a funnel shift.  Sliding-window min/max tree: 2-, 4-, 8-, 9-element windows, 16 arcs -> ~40 ops per pixel.
+__device__ __forceinline__ unsigned fast_score4(const uint8_t* row0, int pitch) {
+  // row0 = aligned address of the four centres; word_at(dy, j) = aligned word j (-1, 0, +1) of row dy
+  auto word = [&](int dy, int j) { return *reinterpret_cast<const unsigned*>(row0 + dy * pitch + 4 * j); };
+  auto win = [&](unsigned m1, unsigned z, unsigned p1, int dx) {  // bytes [dx, dx+4) relative to the centres
+    return dx == 0 ? z : dx > 0 ? __funnelshift_r(z, p1, 8 * dx) : __funnelshift_r(m1, z, 8 * (4 + dx));
+  };
+  unsigned R[16];
+  unsigned m, z, q;
+  m = word(3, -1); z = word(3, 0); q = word(3, 1);
+  R[15] = win(m, z, q, -1); R[0] = z; R[1] = win(m, z, q, 1);
+  m = word(2, -1); z = word(2, 0); q = word(2, 1);
+  R[14] = win(m, z, q, -2); R[2] = win(m, z, q, 2);
+  m = word(1, -1); z = word(1, 0); q = word(1, 1);
+  R[13] = win(m, z, q, -3); R[3] = win(m, z, q, 3);
+  m = word(0, -1); z = word(0, 0); q = word(0, 1);
+  const unsigned v = z;
+  R[12] = win(m, z, q, -3); R[4] = win(m, z, q, 3);
+  m = word(-1, -1); z = word(-1, 0); q = word(-1, 1);
+  R[11] = win(m, z, q, -3); R[5] = win(m, z, q, 3);
+  m = word(-2, -1); z = word(-2, 0); q = word(-2, 1);
+  R[10] = win(m, z, q, -2); R[6] = win(m, z, q, 2);
+  m = word(-3, -1); z = word(-3, 0); q = word(-3, 1);
+  R[9] = win(m, z, q, -1); R[8] = z; R[7] = win(m, z, q, 1);
+  unsigned lo[16], hi[16], t1[16], t2[16];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    X[k] = r[k] | (r[k + 8] << 16);
-    X[k + 8] = r[k + 8] | (r[k] << 16);
-  }
-  unsigned lo2[15], hi2[15], lo4[12], hi4[12];
-#pragma unroll
-  for (int j = 0; j < 15; ++j) {
-    lo2[j] = __vminu2(X[j], X[j + 1]);
-    hi2[j] = __vmaxu2(X[j], X[j + 1]);
+  for (int k = 0; k < 16; ++k) {  // windows of 2
+    lo[k] = __vminu4(R[k], R[(k + 1) & 15]);
+    hi[k] = __vmaxu4(R[k], R[(k + 1) & 15]);
   }
 #pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    lo4[j] = __vminu2(lo2[j], lo2[j + 2]);
-    hi4[j] = __vmaxu2(hi2[j], hi2[j + 2]);
+  for (int k = 0; k < 16; ++k) {  // windows of 4
+    t1[k] = __vminu4(lo[k], lo[(k + 2) & 15]);
+    t2[k] = __vmaxu4(hi[k], hi[(k + 2) & 15]);
   }
-  unsigned a = 0x00ff00ffu, b = 0;
+  unsigned a = 0xffffffffu, b = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const unsigned lo9 = __vminu2(__vminu2(lo4[k], lo4[k + 4]), X[k + 8]);
-    const unsigned hi9 = __vmaxu2(__vmaxu2(hi4[k], hi4[k + 4]), X[k + 8]);
-    a = __vminu2(a, hi9);
-    b = __vmaxu2(b, lo9);
+  for (int k = 0; k < 16; ++k) {  // windows of 8, then the 9th element; running min of maxima / max of minima
+    const unsigned lo9 = __vminu4(__vminu4(t1[k], t1[(k + 4) & 15]), R[(k + 8) & 15]);
+    const unsigned hi9 = __vmaxu4(__vmaxu4(t2[k], t2[(k + 4) & 15]), R[(k + 8) & 15]);
+    a = __vminu4(a, hi9);
+    b = __vmaxu4(b, lo9);
   }
-  const int A = min(a & 0xffff, a >> 16), B = max(b & 0xffff, b >> 16);
-  return max(max(v - A, B - v), 0);
+  return __vmaxu4(__vsubus4(v, a), __vsubus4(b, v));
 }
 
-// One CTA per (cell, image): stage the cell image in shared memory, score every interior pixel, 3x3
-// strict NMS restricted to the cell interior (each cell is an independent cv::FAST call in the reference),
-// decide iniTh vs minTh from the post-NMS count, and write the survivors in raster order.
+// One CTA per (cell, image): stage the cell image in shared memory, score every interior pixel (4 per thread), 3x3
+// strict NMS restricted to the cell interior (each cell is an independent cv::FAST call in the reference), decide
+// iniTh vs minTh from the post-NMS count, and write the survivors in raster order.
+// Tile layouts: raw row pitch TP = tile_w + 8, cell column x at byte 1 + x (interior column 3 -> aligned byte 4);
+// score row pitch TP, interior pixel (x, y) at row y + 1, byte 4 + x, with a zero ring around the interior.
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(OrbParams P, const uint8_t* __restrict__ img0,
                                                             size_t img0_stride, int img0_pitch) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Cell c = P.cells[blockIdx.x];
   const int img = blockIdx.y;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint8_t* base;
   int pitch;
   if (c.level == 0) {
@@ -165,11 +163,10 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(OrbParams P, const 
     base = P.lvl[c.level] + img * P.img_stride[c.level];
     pitch = P.pitch[c.level];
   }
-  const int TW = P.tile_w;
+  const int TP = P.tile_w + 8;
   uint8_t* raw = smem;
   const int iw = c.cw - 6, ih = c.ch - 6;
-  const int SW = P.tile_w;                  // score tile row (iw + 2 <= tile_w - 4)
-  uint8_t* sc = smem + P.tile_w * P.tile_h;  // (ih + 2) x SW with a zero ring
+  uint8_t* sc = smem + TP * P.tile_h;  // (ih + 2) rows
   __shared__ int s_warp[kFastThreads / 32];
 
   int* cnt_out = P.cell_cnt + (size_t)img * P.n_cells + blockIdx.x;
@@ -177,39 +174,50 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(OrbParams P, const 
     if (tid == 0) *cnt_out = 0;
     return;
   }
-  for (int i = tid; i < c.cw * c.ch; i += kFastThreads) {
-    const int y = i / c.cw, x = i - y * c.cw;
-    raw[y * TW + x] = __ldg(base + (size_t)(c.y0 + y) * pitch + c.x0 + x);
+  for (int y = wid; y < c.ch; y += kFastThreads / 32) {
+    const uint8_t* src = base + (size_t)(c.y0 + y) * pitch + c.x0;
+    for (int x = lane; x < c.cw; x += 32) raw[y * TP + 1 + x] = __ldg(src + x);
   }
-  for (int i = tid; i < (ih + 2) * SW; i += kFastThreads) sc[i] = 0;
+  for (int i = tid; i < (ih + 2) * (TP / 4); i += kFastThreads) reinterpret_cast<unsigned*>(sc)[i] = 0;
   __syncthreads();
-  const int npx = iw * ih;
-  for (int i = tid; i < npx; i += kFastThreads) {
-    const int y = i / iw, x = i - y * iw;
-    const int s = fast_score(raw + (y + 3) * TW + x + 3, TW);
-    sc[(y + 1) * SW + x + 1] = (uint8_t)(s > P.min_th ? s : 0);
+  const int ng = (iw + 3) >> 2;  // groups of 4 pixels per row
+  const unsigned th4 = (unsigned)P.min_th * 0x01010101u;
+  for (int i = tid; i < ng * ih; i += kFastThreads) {
+    const int y = i / ng, g = i - y * ng;
+    unsigned s4 = fast_score4(raw + (y + 3) * TP + 4 + 4 * g, TP);
+    s4 &= __vcmpgtu4(s4, th4);  // keep scores > minTh
+    const int rem = iw - 4 * g;
+    if (rem < 4) s4 &= 0xffffffffu >> (8 * (4 - rem));
+    *reinterpret_cast<unsigned*>(sc + (y + 1) * TP + 4 + 4 * g) = s4;
   }
   __syncthreads();
   // contiguous raster chunk per thread -> ordered compaction
+  const int npx = iw * ih;
   const int per = (npx + kFastThreads - 1) / kFastThreads;  // <= 32 (checked at create)
   const int beg = tid * per, end = min(beg + per, npx);
   uint32_t mask_a = 0, mask_b = 0;
-  for (int i = beg; i < end; ++i) {
-    const int y = i / iw, x = i - y * iw;
-    const uint8_t* q = sc + (y + 1) * SW + x + 1;
-    const int s = q[0];
-    if (s == 0) continue;
-    const int m = max(max(max(q[-SW - 1], q[-SW]), max(q[-SW + 1], q[-1])),
-                      max(max(q[1], q[SW - 1]), max(q[SW], q[SW + 1])));
-    if (s > m) {
-      mask_b |= 1u << (i - beg);
-      if (s > P.ini_th) mask_a |= 1u << (i - beg);
+  if (beg < end) {
+    int y = beg / iw, x = beg - y * iw;
+    for (int i = beg; i < end; ++i) {
+      const uint8_t* q = sc + (y + 1) * TP + 4 + x;
+      const int s = q[0];
+      if (s != 0) {
+        const int m = max(max(max(q[-TP - 1], q[-TP]), max(q[-TP + 1], q[-1])),
+                          max(max(q[1], q[TP - 1]), max(q[TP], q[TP + 1])));
+        if (s > m) {
+          mask_b |= 1u << (i - beg);
+          if (s > P.ini_th) mask_a |= 1u << (i - beg);
+        }
+      }
+      if (++x == iw) {
+        x = 0;
+        ++y;
+      }
     }
   }
   const int total_a = __syncthreads_count(mask_a != 0);
   const uint32_t mask = total_a > 0 ? mask_a : mask_b;
   const int cnt = __popc(mask);
-  const int lane = tid & 31, wid = tid >> 5;
   const int inc = warp_incl_scan(cnt, lane);
   if (lane == 31) s_warp[wid] = inc;
   __syncthreads();
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(OrbParams P, const 
     m &= m - 1;
     const int i = beg + b;
     const int y = i / iw, x = i - y * iw;
-    const int s = sc[(y + 1) * SW + x + 1];
+    const int s = sc[(y + 1) * TP + 4 + x];
     out[off++] = (uint32_t)(c.x0 + 3 + x) | ((uint32_t)(c.y0 + 3 + y) << 12) | ((uint32_t)(s - 1) << 24);
   }
   if (tid == 0) *cnt_out = total;
@@ -947,7 +955,7 @@ int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out) {
   }
   P.key_begin[L] = P.n_cells * P.cell_cap;
   h->cap_total = P.slot_begin[L];
-  h->fast_smem = (size_t)P.tile_w * P.tile_h + (size_t)P.tile_w * (P.tile_h - 6 + 2);
+  h->fast_smem = (size_t)(P.tile_w + 8) * P.tile_h + (size_t)(P.tile_w + 8) * (P.tile_h - 6 + 2);
   h->qt_smem = (size_t)max_maxn * (2 * (4 + 4 + 2 * 4 + 1) + 16 + 16 + 5 * 4) + 16 * 32;
   if (h->qt_smem > 200 * 1024) {
     set_error("per-level feature quota %d needs %zu B of shared memory for the quadtree (limit 200 KiB)", max_maxn,
