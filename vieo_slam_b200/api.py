@@ -111,8 +111,8 @@ class ORBextractor:
         self.mvImagePyramid = []
 
     def close(self):
-        if getattr(self, "_h", None) and self._h:
-            lib().vieo_orb_destroy(self._h)
+        if getattr(self, "_h", None) and self._h and _lib is not None:  # _lib is gone at interpreter shutdown
+            _lib.vieo_orb_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -247,8 +247,8 @@ class StereoFrontend:
         self.width, self.height, self.max_frames = width, height, max_frames
 
     def close(self):
-        if getattr(self, "_h", None) and self._h:
-            lib().vieo_frontend_destroy(self._h)
+        if getattr(self, "_h", None) and self._h and _lib is not None:
+            _lib.vieo_frontend_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -393,8 +393,8 @@ class BundleAdjuster:
         self._cb = None
 
     def close(self):
-        if getattr(self, "_h", None) and self._h:
-            lib().vieo_ba_destroy(self._h)
+        if getattr(self, "_h", None) and self._h and _lib is not None:
+            _lib.vieo_ba_destroy(self._h)
             self._h = None
 
     __del__ = close

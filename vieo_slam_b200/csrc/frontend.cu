@@ -4,6 +4,7 @@
 // independent streams (own ORB scratch each), so the H2D copy of one chunk overlaps the kernels of another
 // and the D2H of a third.  No CPU fallback.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -28,7 +29,8 @@ int vieo_frontend_create(const VieoOrbConfig* cfg, int max_frames, int device, v
   vieo_frontend* f = new vieo_frontend();
   f->device = device;
   f->max_frames = max_frames;
-  const int n_chunks = max_frames >= 8 ? 4 : 1;
+  int n_chunks = max_frames >= 8 ? 4 : 1;  // chunks on independent streams: copies of one overlap the kernels of another
+  if (const char* e = getenv("VIEO_FE_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), max_frames));
   f->chunk_frames = (max_frames + n_chunks - 1) / n_chunks;
   VieoOrbConfig c = *cfg;
   c.max_batch = 2 * f->chunk_frames;
