@@ -153,3 +153,17 @@ def test_local_ba_edge_cases(seq):
     small = api.BundleAdjuster(max_states=4, max_points=16, max_edges=64, max_imu=4)
     with pytest.raises(api.VieoError):
         small.LocalBundleAdjustmentNavStatePRV(d, cam)
+
+
+def test_local_ba_large_window_global_cholesky():
+    """bLarge window (25 free keyframes, 375 pose dimensions): the reduced camera system no longer fits the Cholesky
+    kernel's shared-memory tile and is factorised in global memory; Schur tile with 25 keyframe columns."""
+    import vieo_slam_b200.api as api
+    s = synth.vio_sequence(77, 200, speed=1.2, rot=0.8)
+    cam, d = _lba(s, n_local=25, n_fixed=10, n_points=900, seed=9, step=5)
+    assert (d["state_flags"] & 1 == 0).sum() == 25
+    ba = api.BundleAdjuster()
+    for kw in (dict(large=True), dict()):
+        out = ba.LocalBundleAdjustmentNavStatePRV(d, cam, **kw)
+        ref = O.local_ba_prv(d, cam, **kw)
+        _cmp_lba(out, ref)

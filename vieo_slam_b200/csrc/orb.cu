@@ -95,55 +95,69 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 // ------------------------------------------------------------------------------------------------
 // FAST-9/16 arc score: S = max(v - min_arcs(max9 p), max_arcs(min9 p) - v, 0) over the 16 contiguous 9-arcs of the
 // radius-3 ring; equals cornerScore<16>()+1 for corners, and a pixel is a corner at threshold t iff S > t.
-// Four horizontally adjacent pixels per thread, one per byte lane of the u8x4 video instructions (VIMNMX.U8x4): the
-// ring pixel k of the four centres is an unaligned 4-byte window of the shared-memory tile, fetched as two aligned
-// words + a funnel shift.  Sliding-window min/max tree: 2-, 4-, 8-, 9-element windows, 16 arcs -> ~40 ops per pixel.
-__device__ __forceinline__ unsigned fast_score4(const uint8_t* row0, int pitch) {
-  // row0 = aligned address of the four centres; word_at(dy, j) = aligned word j (-1, 0, +1) of row dy
-  auto word = [&](int dy, int j) { return *reinterpret_cast<const unsigned*>(row0 + dy * pitch + 4 * j); };
-  auto win = [&](unsigned m1, unsigned z, unsigned p1, int dx) {  // bytes [dx, dx+4) relative to the centres
-    return dx == 0 ? z : dx > 0 ? __funnelshift_r(z, p1, 8 * dx) : __funnelshift_r(m1, z, 8 * (4 + dx));
-  };
-  unsigned R[16];
-  unsigned m, z, q;
-  m = word(3, -1); z = word(3, 0); q = word(3, 1);
-  R[15] = win(m, z, q, -1); R[0] = z; R[1] = win(m, z, q, 1);
-  m = word(2, -1); z = word(2, 0); q = word(2, 1);
-  R[14] = win(m, z, q, -2); R[2] = win(m, z, q, 2);
-  m = word(1, -1); z = word(1, 0); q = word(1, 1);
-  R[13] = win(m, z, q, -3); R[3] = win(m, z, q, 3);
-  m = word(0, -1); z = word(0, 0); q = word(0, 1);
-  const unsigned v = z;
-  R[12] = win(m, z, q, -3); R[4] = win(m, z, q, 3);
-  m = word(-1, -1); z = word(-1, 0); q = word(-1, 1);
-  R[11] = win(m, z, q, -3); R[5] = win(m, z, q, 3);
-  m = word(-2, -1); z = word(-2, 0); q = word(-2, 1);
-  R[10] = win(m, z, q, -2); R[6] = win(m, z, q, 2);
-  m = word(-3, -1); z = word(-3, 0); q = word(-3, 1);
-  R[9] = win(m, z, q, -1); R[8] = z; R[7] = win(m, z, q, 1);
-  unsigned lo[16], hi[16], t1[16], t2[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {  // windows of 2
-    lo[k] = __vminu4(R[k], R[(k + 1) & 15]);
-    hi[k] = __vmaxu4(R[k], R[(k + 1) & 15]);
+// Two horizontally adjacent pixels per thread, one per 16-bit lane: sm_100a has native packed min/max only for
+// 16-bit lanes (VIMNMX.U16x2 and the 3-input VIMNMX3.U16x2; the u8x4 video intrinsics are emulated with ~10 LOP3/PRMT
+// each).  Ring pixel k of the two centres = two adjacent bytes of the shared-memory tile, cut out of three aligned
+// words per row with funnel shifts + one PRMT.  Sliding-window tree with 3-input ops: windows of 3, then 3+3+3 -> 9:
+// 64 VIMNMX3 for the 16 arcs of both pixels + 16 for the final min-of-max / max-of-min.
+__device__ __forceinline__ unsigned fast_score2(const uint8_t* rowc, int o8, int pitch) {
+  // rowc: aligned word that holds the first centre; o8 = 8 * (byte offset of that centre in the word) (0 or 16)
+#define VIEO_ROW3(dy)                                                          \
+  {                                                                            \
+    const unsigned* w_ = reinterpret_cast<const unsigned*>(rowc + (dy) * pitch); \
+    const unsigned wm_ = w_[-1], w0_ = w_[0], wp_ = w_[1];                      \
+    vm = __funnelshift_r(wm_, w0_, o8);                                         \
+    v0 = __funnelshift_r(w0_, wp_, o8);                                         \
+    vp = wp_ >> o8;                                                             \
   }
+  // bytes (dx, dx + 1) relative to the first centre -> 16-bit lanes
+#define VIEO_PICK(dx) \
+  (__byte_perm((dx) < 0 ? vm : v0, (dx) < 0 ? v0 : vp, ((dx) < 0 ? 4 + (dx) : (dx)) | ((((dx) < 0 ? 4 + (dx) : (dx)) + 1) << 8)) & 0x00ff00ffu)
+  unsigned R[16], vm, v0, vp;
+  VIEO_ROW3(3);
+  R[15] = VIEO_PICK(-1); R[0] = VIEO_PICK(0); R[1] = VIEO_PICK(1);
+  VIEO_ROW3(2);
+  R[14] = VIEO_PICK(-2); R[2] = VIEO_PICK(2);
+  VIEO_ROW3(1);
+  R[13] = VIEO_PICK(-3); R[3] = VIEO_PICK(3);
+  VIEO_ROW3(0);
+  const unsigned v = VIEO_PICK(0);
+  R[12] = VIEO_PICK(-3); R[4] = VIEO_PICK(3);
+  VIEO_ROW3(-1);
+  R[11] = VIEO_PICK(-3); R[5] = VIEO_PICK(3);
+  VIEO_ROW3(-2);
+  R[10] = VIEO_PICK(-2); R[6] = VIEO_PICK(2);
+  VIEO_ROW3(-3);
+  R[9] = VIEO_PICK(-1); R[8] = VIEO_PICK(0); R[7] = VIEO_PICK(1);
+#undef VIEO_ROW3
+#undef VIEO_PICK
+  unsigned lo3[16], hi3[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {  // windows of 4
-    t1[k] = __vminu4(lo[k], lo[(k + 2) & 15]);
-    t2[k] = __vmaxu4(hi[k], hi[(k + 2) & 15]);
+  for (int k = 0; k < 16; ++k) {
+    lo3[k] = __vimin3_u16x2(R[k], R[(k + 1) & 15], R[(k + 2) & 15]);
+    hi3[k] = __vimax3_u16x2(R[k], R[(k + 1) & 15], R[(k + 2) & 15]);
   }
-  unsigned a = 0xffffffffu, b = 0;
+  unsigned lo9[16], hi9[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {  // windows of 8, then the 9th element; running min of maxima / max of minima
-    const unsigned lo9 = __vminu4(__vminu4(t1[k], t1[(k + 4) & 15]), R[(k + 8) & 15]);
-    const unsigned hi9 = __vmaxu4(__vmaxu4(t2[k], t2[(k + 4) & 15]), R[(k + 8) & 15]);
-    a = __vminu4(a, hi9);
-    b = __vmaxu4(b, lo9);
+  for (int k = 0; k < 16; ++k) {
+    lo9[k] = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+    hi9[k] = __vimax3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
   }
-  return __vmaxu4(__vsubus4(v, a), __vsubus4(b, v));
+  unsigned a = __vimin3_u16x2(hi9[0], hi9[1], hi9[2]), b = __vimax3_u16x2(lo9[0], lo9[1], lo9[2]);
+#pragma unroll
+  for (int k = 3; k < 15; k += 2) {
+    a = __vimin3_u16x2(a, hi9[k], hi9[k + 1]);
+    b = __vimax3_u16x2(b, lo9[k], lo9[k + 1]);
+  }
+  a = __vminu2(a, hi9[15]);
+  b = __vmaxu2(b, lo9[15]);
+  // max(v - a, b - v, 0) per 16-bit lane; lanes hold values <= 255, so plain 32-bit arithmetic cannot borrow across
+  // lanes once the differences are clamped with max
+  const unsigned va = __vmaxu2(v, a) - a, bv = __vmaxu2(b, v) - v;  // max(v,a)-a = max(v-a,0)
+  return __vmaxu2(va, bv);
 }
 
-// One CTA per (cell, image): stage the cell image in shared memory, score every interior pixel (4 per thread), 3x3
+// One CTA per (cell, image): stage the cell image in shared memory, score every interior pixel (2 per thread), 3x3
 // strict NMS restricted to the cell interior (each cell is an independent cv::FAST call in the reference), decide
 // iniTh vs minTh from the post-NMS count, and write the survivors in raster order.
 // Tile layouts: raw row pitch TP = tile_w + 8, cell column x at byte 1 + x (interior column 3 -> aligned byte 4);
@@ -180,15 +194,15 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(OrbParams P, const 
   }
   for (int i = tid; i < (ih + 2) * (TP / 4); i += kFastThreads) reinterpret_cast<unsigned*>(sc)[i] = 0;
   __syncthreads();
-  const int ng = (iw + 3) >> 2;  // groups of 4 pixels per row
-  const unsigned th4 = (unsigned)P.min_th * 0x01010101u;
+  const int ng = (iw + 1) >> 1;  // pairs of pixels per row
   for (int i = tid; i < ng * ih; i += kFastThreads) {
     const int y = i / ng, g = i - y * ng;
-    unsigned s4 = fast_score4(raw + (y + 3) * TP + 4 + 4 * g, TP);
-    s4 &= __vcmpgtu4(s4, th4);  // keep scores > minTh
-    const int rem = iw - 4 * g;
-    if (rem < 4) s4 &= 0xffffffffu >> (8 * (4 - rem));
-    *reinterpret_cast<unsigned*>(sc + (y + 1) * TP + 4 + 4 * g) = s4;
+    const int col = 4 + 2 * g;  // byte column of the first centre in the tile row
+    const unsigned s2 = fast_score2(raw + (y + 3) * TP + (col & ~3), 8 * (col & 3), TP);
+    unsigned s0 = s2 & 0xffffu, s1 = s2 >> 16;
+    s0 = s0 > (unsigned)P.min_th ? s0 : 0u;  // keep scores > minTh
+    s1 = (s1 > (unsigned)P.min_th && 2 * g + 1 < iw) ? s1 : 0u;
+    *reinterpret_cast<uint16_t*>(sc + (y + 1) * TP + col) = (uint16_t)(s0 | (s1 << 8));
   }
   __syncthreads();
   // contiguous raster chunk per thread -> ordered compaction
