@@ -86,6 +86,15 @@ int vieo_orb_extract_batch_dev(vieo_orb_t* h, int n_img, const uint8_t* imgs_dev
  * triples in the reference's visiting order (cell-major, raster inside a cell). */
 int vieo_orb_debug_level(vieo_orb_t* h, int img_index, int level, uint8_t* out);
 int vieo_orb_debug_candidates(vieo_orb_t* h, int img_index, int level, int32_t* xyr, int cap);
+/* Rectified-stereo association — Frame::ComputeStereoMatches (src/Frame.cc:451-611) on the device-resident results of
+ * the LAST extract call of `h` (the pyramid levels it needs are still in the handle): images 2f / 2f+1 of that batch are
+ * the left / right view of frame f.  kps/desc/n_kp: that call's device outputs with `cap` slots per image.
+ *   bf = stereoinfo_.baseline_bf_[1], min_z = baseline_bf_[0] (= bf / fx)
+ * Outputs [n_frames][cap] indexed by left keypoint: uright (vuright_), depth (vdepth_) (-1: no match) and the block-search
+ * SAD of every match that passed the disparity checks (-1: none; matches dropped by the 2.1 x median filter keep it). */
+int vieo_orb_stereo_match_dev(vieo_orb_t* h, int n_frames, const VieoKeyPoint* kps_dev, const uint8_t* desc_dev,
+                              const int32_t* n_kp_dev, int cap, float bf, float min_z, float* uright_dev, float* depth_dev,
+                              int32_t* sad_dev, void* stream);
 /* number of kernel launches issued by the last extract call (bench.py's gpu_launches) */
 int vieo_orb_last_launches(const vieo_orb_t* h);
 /* Per-stage device timing with CUDA events on the launching stream (the reference's mlog::Timer stamps,
@@ -280,6 +289,11 @@ int vieo_frontend_max_keypoints(const vieo_frontend_t* f);
 int vieo_frontend_last_launches(const vieo_frontend_t* f);
 int vieo_frontend_process(vieo_frontend_t* f, int n_frames, const uint8_t* imgs, int row_stride, VieoKeyPoint* kps,
                           uint8_t* desc, int32_t* n_kp, int32_t* match_idx, int32_t* match_dist);
+/* Frame::ComputeStereoMatches (rectified configs, src/Frame.cc:451-611) for the frames of the last
+ * vieo_frontend_process call (their keypoints, descriptors and pyramids are still on the device).
+ * uright / depth / sad: [n_frames][cap] host arrays indexed by left keypoint. */
+int vieo_frontend_stereo_rectified(vieo_frontend_t* f, int n_frames, float bf, float min_z, float* uright, float* depth,
+                                   int32_t* sad);
 
 #ifdef __cplusplus
 }

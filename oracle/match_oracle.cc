@@ -2,6 +2,11 @@
 #include <cstdint>
 #include <cstring>
 #include <climits>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <utility>
+#include <vector>
 #include "oracle.h"
 
 extern "C" {
@@ -60,3 +65,116 @@ void orc_hamming_csr(const uint8_t* q, const uint8_t* t, const int32_t* row_ptr,
 }
 
 }  // extern "C"
+
+// Frame::ComputeStereoMatches (src/Frame.cc:451-611): rectified-stereo association.  Right keypoints are bucketed by
+// row band (+-2 scale), a left keypoint takes the arg-min Hamming (< TH_HIGH, strict '<' keeps the first) over the
+// candidates of its row with octave within +-1 and uR in [uL - maxD, uL - minD]; matches under (TH_HIGH+TH_LOW)/2 are
+// refined by an 11x11 L1 block search over +-5 px in the keypoint's pyramid level + parabola fit; finally matches whose
+// SAD exceeds 1.5 * 1.4 * median are dropped.  pyrL / pyrR: tightly packed level images (lw[l] x lh[l]).
+// Outputs per left keypoint: uright, depth (-1 = no match), sad (block distance, -1 = none).  Returns #matches kept.
+extern "C" int orc_stereo_matches(const OrcKeyPoint* kl, const uint8_t* dl, int nl, const OrcKeyPoint* kr, const uint8_t* dr,
+                                  int nr, const uint8_t* const* pyrL, const uint8_t* const* pyrR, const int* lw, const int* lh,
+                                  const float* scale, const float* inv_scale, float bf, float minZ, float* uright,
+                                  float* depth, int32_t* sad) {
+  const int thOrbDist = (100 + 50) / 2;
+  const int nRows = lh[0];
+  std::vector<std::vector<int>> rows(nRows);
+  for (int iR = 0; iR < nr; ++iR) {
+    const float kpY = kr[iR].y;
+    const float r = 2.0f * scale[kr[iR].octave];
+    const int maxr = (int)std::ceil(kpY + r), minr = (int)std::floor(kpY - r);
+    for (int yi = minr; yi <= maxr; ++yi)
+      if (yi >= 0 && yi < nRows) rows[yi].push_back(iR);  // (the reference indexes unchecked; keypoints stay 16 px inside)
+  }
+  const float minD = 0, maxD = bf / minZ;
+  std::vector<std::pair<int, int>> vDistIdx;
+  for (int iL = 0; iL < nl; ++iL) {
+    uright[iL] = -1.0f;
+    depth[iL] = -1.0f;
+    sad[iL] = -1;
+  }
+  for (int iL = 0; iL < nl; ++iL) {
+    const OrcKeyPoint& kpL = kl[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    if (row < 0 || row >= nRows) continue;
+    const std::vector<int>& cand = rows[row];
+    if (cand.empty()) continue;
+    const float minU = uL - maxD, maxU = uL - minD;
+    if (maxU < 0) continue;
+    int bestDist = 100;
+    int bestIdxR = 0;
+    for (int iR : cand) {
+      const OrcKeyPoint& kpR = kr[iR];
+      if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+      const float uR = kpR.x;
+      if (uR >= minU && uR <= maxU) {
+        const int dist = orc_descriptor_distance(dl + 32 * (size_t)iL, dr + 32 * (size_t)iR);
+        if (dist < bestDist) {
+          bestDist = dist;
+          bestIdxR = iR;
+        }
+      }
+    }
+    if (!(bestDist < thOrbDist)) continue;
+    const float uR0 = kr[bestIdxR].x;
+    const float scaleFactor = inv_scale[levelL];
+    const float scaleduL = std::round(kpL.x * scaleFactor);
+    const float scaledvL = std::round(kpL.y * scaleFactor);
+    const float scaleduR0 = std::round(uR0 * scaleFactor);
+    const int w = 5, L = 5;
+    const int W = lw[levelL];
+    const uint8_t* IL = pyrL[levelL];
+    const uint8_t* IR = pyrR[levelL];
+    const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+    const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+    if (iniu < 0 || endu >= W) continue;
+    int bestSad = INT_MAX, bestincR = 0;
+    float vDists[2 * 5 + 1];
+    const int cL = IL[(size_t)cv * W + cu];
+    for (int incR = -L; incR <= L; ++incR) {
+      const int cR = IR[(size_t)cv * W + cr + incR];
+      float dist = 0;  // cv::norm(IL, IR, NORM_L1) over float patches of integers: exact
+      for (int dy = -w; dy <= w; ++dy)
+        for (int dx = -w; dx <= w; ++dx) {
+          const int a = IL[(size_t)(cv + dy) * W + cu + dx] - cL;
+          const int b = IR[(size_t)(cv + dy) * W + cr + incR + dx] - cR;
+          dist += (float)std::abs(a - b);
+        }
+      if (dist < (float)bestSad) {
+        bestSad = (int)dist;
+        bestincR = incR;
+      }
+      vDists[L + incR] = dist;
+    }
+    if (bestincR == -L || bestincR == L) continue;
+    const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+    const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+    if (deltaR < -1 || deltaR > 1) continue;
+    float bestuR = scale[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+    float disparity = uL - bestuR;
+    if (disparity >= minD && disparity < maxD) {
+      if (disparity <= 0) {
+        disparity = 0.01f;
+        bestuR = uL - 0.01f;
+      }
+      depth[iL] = bf / disparity;
+      uright[iL] = bestuR;
+      sad[iL] = bestSad;
+      vDistIdx.emplace_back(bestSad, iL);
+    }
+  }
+  if (vDistIdx.empty()) return 0;
+  std::sort(vDistIdx.begin(), vDistIdx.end());
+  const float median = (float)vDistIdx[vDistIdx.size() / 2].first;
+  const float thDist = 1.5f * 1.4f * median;
+  int kept = (int)vDistIdx.size();
+  for (int i = (int)vDistIdx.size() - 1; i >= 0; --i) {
+    if ((float)vDistIdx[i].first < thDist) break;
+    uright[vDistIdx[i].second] = -1;
+    depth[vDistIdx[i].second] = -1;
+    --kept;
+  }
+  return kept;
+}

@@ -39,6 +39,10 @@ int orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
 void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist);
 void orc_hamming_csr(const uint8_t* q, const uint8_t* t, const int32_t* row_ptr, const int32_t* cand, int nrows,
                      int32_t* best_dist, int32_t* best_idx, int32_t* second_dist, int32_t* second_idx);
+int orc_stereo_matches(const OrcKeyPoint* kl, const uint8_t* dl, int nl, const OrcKeyPoint* kr, const uint8_t* dr, int nr,
+                       const uint8_t* const* pyrL, const uint8_t* const* pyrR, const int* lw, const int* lh,
+                       const float* scale, const float* inv_scale, float bf, float minZ, float* uright, float* depth,
+                       int32_t* sad);
 #ifdef __cplusplus
 }
 #endif

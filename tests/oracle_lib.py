@@ -339,3 +339,24 @@ def ba_debug_system(d, cam, lam, lambda_on_poses=True, **kw):
     m = L.orc_ba_debug_system(C.byref(pb), cam.ctypes.data, lam, int(lambda_on_poses), _p(S), _p(bs), _p(b), _p(chi2))
     assert m >= 0, m
     return S[:m * m].reshape(m, m), bs[:m], b[:m], chi2[0]
+
+
+def stereo_matches(orbL, kl, dl, orbR, kr, dr, bf, minZ):
+    """Frame::ComputeStereoMatches on two OrbOracle instances that have just extracted the left / right image
+    (their pyramids are read back).  -> (uright f32[nl], depth f32[nl], sad i32[nl], kept)"""
+    L = lib()
+    L.orc_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    n = orbL.nlevels
+    lvL = [orbL.level(l) for l in range(n)]
+    lvR = [orbR.level(l) for l in range(n)]
+    pl = (C.c_void_p * n)(*[a.ctypes.data for a in lvL]); pr = (C.c_void_p * n)(*[a.ctypes.data for a in lvR])
+    lw = np.array([a.shape[1] for a in lvL], np.int32); lh = np.array([a.shape[0] for a in lvL], np.int32)
+    tb = orbL.tables()
+    kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    ur = np.empty(len(kl), np.float32); dp = np.empty(len(kl), np.float32); sad = np.empty(len(kl), np.int32)
+    kept = L.orc_stereo_matches(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), pl, pr, _p(lw), _p(lh), _p(tb["scale"]),
+                                _p(tb["inv_scale"]), C.c_float(bf), C.c_float(minZ), _p(ur), _p(dp), _p(sad))
+    return ur, dp, sad, kept

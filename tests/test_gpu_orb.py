@@ -125,3 +125,24 @@ def test_stereo_frontend_host_api(api):
         oi, od = O.hamming_knn2(d[0], d[1])
         assert np.array_equal(midx[f, :len(oi)], oi) and np.array_equal(mdist[f, :len(oi)], od)
     assert fe.last_launches() == 3 * 11
+
+
+def test_rectified_stereo_matches_bit_exact(api):
+    """vieo_frontend_stereo_rectified (Frame::ComputeStereoMatches on the device) == oracle: uright / depth bit-exact,
+    SADs identical, same matches dropped by the median filter."""
+    from vieo_slam_b200.synth import EUROC, stereo_stream
+    F = 5
+    imgs = stereo_stream(F, 91, dark_every=3).reshape(F, 2, 480, 752)
+    fe = api.StereoFrontend(1200, 1.2, 8, 20, 7, 752, 480, max_frames=F)
+    outs = fe.alloc_outputs(F)
+    kps, desc, nkp, _, _ = fe.process(imgs, outs)
+    bf = np.float32(EUROC["bf"]); minZ = np.float32(bf / np.float32(EUROC["fx"]))
+    ur, dp, sad = fe.stereo_rectified(F, bf, minZ)
+    for f in range(F):
+        oL, oR = O.OrbOracle(1200, 1.2, 8, 20, 7), O.OrbOracle(1200, 1.2, 8, 20, 7)
+        nl, kl, dl, _ = oL.extract(imgs[f, 0]); nr, kr, dr, _ = oR.extract(imgs[f, 1])
+        our, odp, osad, kept = O.stereo_matches(oL, kl, dl, oR, kr, dr, bf, minZ)
+        assert kept > 100
+        assert np.array_equal(sad[f, :nl], osad)
+        assert ur[f, :nl].tobytes() == our.tobytes() and dp[f, :nl].tobytes() == odp.tobytes()
+        assert np.all(ur[f, nl:] == -1)

@@ -57,6 +57,8 @@ def lib():
         L.vieo_frontend_max_keypoints.argtypes = [vp]
         L.vieo_frontend_last_launches.argtypes = [vp]
         L.vieo_frontend_process.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp]
+        L.vieo_frontend_stereo_rectified.argtypes = [vp, i32, C.c_float, C.c_float, vp, vp, vp]
+        L.vieo_orb_stereo_match_dev.argtypes = [vp, i32, vp, vp, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp]
         L.vieo_hamming_csr.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32]
         L.vieo_imu_set_param.argtypes = [vp, vp, i32, C.c_double]
         L.vieo_imu_set_param.restype = None
@@ -171,6 +173,11 @@ class ORBextractor:
         _check(lib().vieo_orb_extract_batch_dev(self._h, n, imgs_ptr, img_stride, row_stride, kps_ptr, desc_ptr, cap,
                                                 nkp_ptr, stream))
 
+    def stereo_match_dev(self, n_frames, kps_ptr, desc_ptr, nkp_ptr, cap, bf, min_z, ur_ptr, depth_ptr, sad_ptr, stream=0):
+        """Device-resident Frame::ComputeStereoMatches over the last extract_batch_dev call (images 2f / 2f+1)."""
+        _check(lib().vieo_orb_stereo_match_dev(self._h, n_frames, kps_ptr, desc_ptr, nkp_ptr, cap, bf, min_z, ur_ptr,
+                                               depth_ptr, sad_ptr, stream))
+
     def last_launches(self):
         return lib().vieo_orb_last_launches(self._h)
 
@@ -272,6 +279,15 @@ class StereoFrontend:
         _check(lib().vieo_frontend_process(self._h, n, _p(imgs), imgs.strides[2], _p(kps), _p(desc), _p(nkp), _p(midx),
                                            _p(mdist)))
         return kps.view(np.uint8).reshape(2 * n, self.cap, 24).view(KP_DTYPE).reshape(2 * n, self.cap), desc, nkp, midx, mdist
+
+    def stereo_rectified(self, n_frames, bf, min_z):
+        """Frame::ComputeStereoMatches for the frames of the last process() call.
+        -> (uright f32[n,cap], depth f32[n,cap], sad i32[n,cap]) indexed by left keypoint (-1: no match)."""
+        ur = np.empty((n_frames, self.cap), np.float32)
+        dp = np.empty((n_frames, self.cap), np.float32)
+        sad = np.empty((n_frames, self.cap), np.int32)
+        _check(lib().vieo_frontend_stereo_rectified(self._h, n_frames, bf, min_z, _p(ur), _p(dp), _p(sad)))
+        return ur, dp, sad
 
     def last_launches(self):
         return lib().vieo_frontend_last_launches(self._h)

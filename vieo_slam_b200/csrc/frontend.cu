@@ -17,6 +17,9 @@ struct vieo_frontend {
   std::vector<vieo_orb_t*> orb;  // one per in-flight chunk
   std::vector<int32_t*> d_idx;   // [chunk_frames][cap][2]
   std::vector<int32_t*> d_dist;
+  std::vector<float*> d_ur;  // rectified-stereo outputs per chunk: [chunk_frames][cap] uright | depth, then sad
+  std::vector<int32_t*> d_sad;
+  int last_frames = 0;
   int launches;
 };
 
@@ -64,6 +67,8 @@ void vieo_frontend_destroy(vieo_frontend_t* f) {
   for (auto o : f->orb) vieo_orb_destroy(o);
   for (auto p : f->d_idx) cudaFree(p);
   for (auto p : f->d_dist) cudaFree(p);
+  for (auto p : f->d_ur) cudaFree(p);
+  for (auto p : f->d_sad) cudaFree(p);
   delete f;
 }
 
@@ -77,6 +82,7 @@ int vieo_frontend_process(vieo_frontend_t* f, int n_frames, const uint8_t* imgs,
   VIEO_CK(cudaSetDevice(f->device));
   const int cap = f->cap;
   f->launches = 0;
+  f->last_frames = n_frames;
   int chunk = 0;
   // image geometry from the first ORB handle
   int32_t lw[16], lh[16];
@@ -105,6 +111,52 @@ int vieo_frontend_process(vieo_frontend_t* f, int n_frames, const uint8_t* imgs,
                             cudaMemcpyDeviceToHost, st));
     VIEO_CK(cudaMemcpyAsync(match_dist + (size_t)2 * f0 * cap, f->d_dist[chunk], sizeof(int32_t) * 2 * nf * cap,
                             cudaMemcpyDeviceToHost, st));
+  }
+  for (int c = 0; c < chunk; ++c) {
+    VieoKeyPoint* dk; uint8_t* dd; int* dn; int ocap; cudaStream_t st;
+    orb_dev_outputs(f->orb[c], &dk, &dd, &dn, &ocap, &st);
+    VIEO_CK(cudaStreamSynchronize(st));
+  }
+  return VIEO_OK;
+}
+
+int vieo_frontend_stereo_rectified(vieo_frontend_t* f, int n_frames, float bf, float min_z, float* uright, float* depth,
+                                   int32_t* sad) {
+  VIEO_ARG(f && uright && depth && sad, "null argument");
+  VIEO_ARG(n_frames >= 1 && n_frames <= f->last_frames, "no processed frames to match");
+  VIEO_CK(cudaSetDevice(f->device));
+  const int cap = f->cap;
+  if (f->d_ur.empty()) {
+    for (size_t c = 0; c < f->orb.size(); ++c) {
+      float* a = nullptr;
+      int32_t* b = nullptr;
+      if (cudaMalloc(&a, sizeof(float) * 2 * cap * f->chunk_frames) != cudaSuccess ||
+          cudaMalloc(&b, sizeof(int32_t) * cap * f->chunk_frames) != cudaSuccess) {
+        set_error("vieo_frontend_stereo_rectified: out of device memory");
+        cudaFree(a);
+        return VIEO_E_CUDA;
+      }
+      f->d_ur.push_back(a);
+      f->d_sad.push_back(b);
+    }
+  }
+  int chunk = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += f->chunk_frames, ++chunk) {
+    const int nf = std::min(f->chunk_frames, n_frames - f0);
+    VieoKeyPoint* dk;
+    uint8_t* dd;
+    int* dn;
+    int ocap;
+    cudaStream_t st;
+    orb_dev_outputs(f->orb[chunk], &dk, &dd, &dn, &ocap, &st);
+    float* ur = f->d_ur[chunk];
+    float* dp = ur + (size_t)cap * f->chunk_frames;
+    int rc = vieo_orb_stereo_match_dev(f->orb[chunk], nf, dk, dd, dn, cap, bf, min_z, ur, dp, f->d_sad[chunk], st);
+    if (rc) return rc;
+    f->launches += 1;
+    VIEO_CK(cudaMemcpyAsync(uright + (size_t)f0 * cap, ur, sizeof(float) * nf * cap, cudaMemcpyDeviceToHost, st));
+    VIEO_CK(cudaMemcpyAsync(depth + (size_t)f0 * cap, dp, sizeof(float) * nf * cap, cudaMemcpyDeviceToHost, st));
+    VIEO_CK(cudaMemcpyAsync(sad + (size_t)f0 * cap, f->d_sad[chunk], sizeof(int32_t) * nf * cap, cudaMemcpyDeviceToHost, st));
   }
   for (int c = 0; c < chunk; ++c) {
     VieoKeyPoint* dk; uint8_t* dd; int* dn; int ocap; cudaStream_t st;

@@ -712,6 +712,177 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(OrbParams P, co
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rectified-stereo association, Frame::ComputeStereoMatches (src/Frame.cc:451-611).  One CTA per stereo frame (left
+// image 2f, right image 2f+1 of the batch).  A warp takes one left keypoint: lanes scan the right keypoints in index
+// order (row-band / octave / disparity-range predicate, 256-bit Hamming), the lexicographic (distance, index) minimum is
+// the reference's strict-'<' arg-min; matches under (TH_HIGH+TH_LOW)/2 are refined with the 11x11 L1 block search over
+// +-5 px in the keypoint's pyramid level (integer arithmetic, lanes over pixels) and the parabola fit.  The CTA then
+// applies the 1.5 * 1.4 * median(SAD) filter with a rank selection over the accepted matches.
+struct StereoLevels {
+  const uint8_t* base[kMaxLevels];
+  size_t img_stride[kMaxLevels];
+  int pitch[kMaxLevels], w[kMaxLevels];
+  float scale[kMaxLevels], inv_scale[kMaxLevels];
+};
+__global__ void __launch_bounds__(256) k_stereo_match(StereoLevels Lv, const VieoKeyPoint* __restrict__ kps,
+                                                      const uint8_t* __restrict__ desc, const int* __restrict__ nkp, int cap,
+                                                      int n_rows, float bf, float minZ, float* __restrict__ uright,
+                                                      float* __restrict__ depth, int* __restrict__ sad_out) {
+  extern __shared__ int s_sad[];  // [cap]
+  __shared__ int s_med;
+  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int iml = 2 * f, imr = 2 * f + 1;
+  const int nl = min(nkp[iml], cap), nr = min(nkp[imr], cap);
+  const VieoKeyPoint* KL = kps + (size_t)iml * cap;
+  const VieoKeyPoint* KR = kps + (size_t)imr * cap;
+  const uint8_t* DL = desc + (size_t)iml * cap * 32;
+  const uint8_t* DR = desc + (size_t)imr * cap * 32;
+  float* UR = uright + (size_t)f * cap;
+  float* DP = depth + (size_t)f * cap;
+  int* SD = sad_out + (size_t)f * cap;
+  const float minD = 0, maxD = bf / minZ;
+  for (int i = threadIdx.x; i < cap; i += 256) {
+    UR[i] = -1.0f;
+    DP[i] = -1.0f;
+    SD[i] = -1;
+    s_sad[i] = -1;
+  }
+  if (threadIdx.x == 0) s_med = 0;
+  __syncthreads();
+  for (int iL = warp; iL < nl; iL += 8) {
+    const VieoKeyPoint kpL = KL[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    const float minU = uL - maxD, maxU = uL - minD;
+    if (row < 0 || row >= n_rows || maxU < 0) continue;
+    uint32_t dl[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dl[k] = reinterpret_cast<const uint32_t*>(DL + 32 * (size_t)iL)[k];
+    int best = 100, bestIdx = 0x7fffffff;  // TH_HIGH
+    for (int iR = lane; iR < nr; iR += 32) {
+      const VieoKeyPoint kpR = KR[iR];
+      if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+      const float r = 2.0f * Lv.scale[kpR.octave];
+      const int maxr = (int)ceilf(kpR.y + r), minr = (int)floorf(kpR.y - r);
+      if (row < minr || row > maxr) continue;
+      if (!(kpR.x >= minU && kpR.x <= maxU)) continue;
+      const uint32_t* dr = reinterpret_cast<const uint32_t*>(DR + 32 * (size_t)iR);
+      int d = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d += __popc(dl[k] ^ dr[k]);
+      if (d < best) {  // lanes see ascending indices: strict '<' keeps the first
+        best = d;
+        bestIdx = iR;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
+      if (ob < best || (ob == best && oi < bestIdx)) {
+        best = ob;
+        bestIdx = oi;
+      }
+    }
+    if (!(best < 75)) continue;  // thOrbDist = (TH_HIGH + TH_LOW) / 2
+    const float uR0 = KR[bestIdx].x;
+    const float sf = Lv.inv_scale[levelL];
+    const float scaleduL = roundf(kpL.x * sf), scaledvL = roundf(kpL.y * sf), scaleduR0 = roundf(uR0 * sf);
+    const int w = 5, L = 5;
+    const int W = Lv.w[levelL];
+    const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+    if (iniu < 0 || endu >= W) continue;
+    const int pitch = Lv.pitch[levelL];
+    const uint8_t* IL = Lv.base[levelL] + (size_t)iml * Lv.img_stride[levelL];
+    const uint8_t* IR = Lv.base[levelL] + (size_t)imr * Lv.img_stride[levelL];
+    const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+    const int cL = IL[(size_t)cv * pitch + cu];
+    // the lane's pixels of the 11x11 left patch, centre subtracted
+    int a[4], py[4], px[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = lane + 32 * q;
+      py[q] = t / 11 - w;
+      px[q] = t % 11 - w;
+      a[q] = t < 121 ? (int)IL[(size_t)(cv + py[q]) * pitch + cu + px[q]] - cL : 0;
+    }
+    int bestSad = 0x7fffffff, bestinc = 0, dprev = 0, d1 = 0, d2 = 0, d3 = 0;
+    for (int inc = -L; inc <= L; ++inc) {
+      const int cR = IR[(size_t)cv * pitch + cr + inc];
+      int sum = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (lane + 32 * q < 121) sum += abs(a[q] - ((int)IR[(size_t)(cv + py[q]) * pitch + cr + inc + px[q]] - cR));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (sum < bestSad) {
+        bestSad = sum;
+        bestinc = inc;
+        d1 = dprev;
+        d2 = sum;
+        d3 = -1;  // filled by the next shift
+      } else if (inc == bestinc + 1)
+        d3 = sum;
+      dprev = sum;
+    }
+    if (bestinc == -L || bestinc == L) continue;
+    if (lane == 0) {
+      const float dist1 = (float)d1, dist2 = (float)d2, dist3 = (float)d3;
+      const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+      if (!(deltaR < -1 || deltaR > 1)) {
+        float bestuR = Lv.scale[levelL] * ((float)scaleduR0 + (float)bestinc + deltaR);
+        float disparity = uL - bestuR;
+        if (disparity >= minD && disparity < maxD) {
+          if (disparity <= 0) {
+            disparity = 0.01f;
+            bestuR = uL - 0.01f;
+          }
+          DP[iL] = bf / disparity;
+          UR[iL] = bestuR;
+          SD[iL] = bestSad;
+          s_sad[iL] = bestSad;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // median of the accepted SADs = element n/2 of the sorted (sad, index) list: the value v with
+  // #(sad < v) <= n/2 < #(sad <= v)
+  int n_acc = 0;
+  for (int i = threadIdx.x; i < nl; i += 256) n_acc += s_sad[i] >= 0;
+  __shared__ int s_cnt[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+  if (lane == 0) s_cnt[warp] = n_acc;
+  __syncthreads();
+  int total = 0;
+  for (int k = 0; k < 8; ++k) total += s_cnt[k];
+  if (total == 0) return;
+  const int rank = total / 2;
+  for (int i = threadIdx.x; i < nl; i += 256) {
+    const int v = s_sad[i];
+    if (v < 0) continue;
+    int less = 0, leq = 0;
+    for (int j = 0; j < nl; ++j) {
+      const int u = s_sad[j];
+      if (u < 0) continue;
+      less += u < v;
+      leq += u <= v;
+    }
+    if (less <= rank && rank < leq) s_med = v;  // every thread that qualifies writes the same value
+  }
+  __syncthreads();
+  const float thDist = 1.5f * 1.4f * (float)s_med;
+  for (int i = threadIdx.x; i < nl; i += 256) {
+    const int v = s_sad[i];
+    if (v >= 0 && !((float)v < thDist)) {
+      UR[i] = -1.0f;
+      DP[i] = -1.0f;
+    }
+  }
+}
+
 }  // namespace vieo
 
 // =================================================================================================
@@ -1201,6 +1372,38 @@ int vieo_orb_debug_candidates(vieo_orb_t* h, int img_index, int level, int32_t* 
       }
     }
   return n;
+}
+
+// Frame::ComputeStereoMatches over the device-resident results of the last extract call of `h` (its pyramid levels
+// are still in place): images 2f / 2f+1 are the left / right view of frame f.
+int vieo_orb_stereo_match_dev(vieo_orb_t* h, int n_frames, const VieoKeyPoint* kps_dev, const uint8_t* desc_dev,
+                              const int32_t* n_kp_dev, int cap, float bf, float min_z, float* uright_dev, float* depth_dev,
+                              int32_t* sad_dev, void* stream) {
+  VIEO_ARG(h && kps_dev && desc_dev && n_kp_dev && uright_dev && depth_dev && sad_dev, "null argument");
+  VIEO_ARG(n_frames >= 1 && 2 * n_frames <= h->last_n_img && cap >= 1 && bf > 0 && min_z > 0, "bad argument");
+  VIEO_CK(cudaSetDevice(h->device));
+  const OrbParams& P = h->P;
+  StereoLevels Lv;
+  for (int l = 0; l < P.nlevels; ++l) {
+    const bool ext = l == 0 && h->last_img0 != nullptr;
+    Lv.base[l] = ext ? h->last_img0 : P.lvl[l];
+    Lv.img_stride[l] = ext ? h->last_img0_stride : P.img_stride[l];
+    Lv.pitch[l] = ext ? h->last_img0_pitch : P.pitch[l];
+    Lv.w[l] = P.w[l];
+    Lv.scale[l] = P.scale[l];
+    Lv.inv_scale[l] = h->inv_scale[l];
+  }
+  const size_t smem = sizeof(int) * (size_t)cap;
+  VIEO_ARG(smem <= 96 * 1024, "cap too large for the stereo kernel");
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    VIEO_CK(cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  k_stereo_match<<<n_frames, 256, smem, (cudaStream_t)stream>>>(Lv, kps_dev, desc_dev, n_kp_dev, cap, P.h[0], bf, min_z,
+                                                                uright_dev, depth_dev, sad_dev);
+  VIEO_CK(cudaGetLastError());
+  return VIEO_OK;
 }
 
 int vieo_orb_last_launches(const vieo_orb_t* h) { return h ? h->last_launches : VIEO_E_ARG; }
