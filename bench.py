@@ -35,7 +35,7 @@ FAST_BYTES_PER_IMAGE = LEVEL_PX + 700 * 4  # k_fast_cells: every level pixel onc
 
 def workload_name(frames):
     return (f"EuRoC MH05 stereo-VIO 1200 feats (configs[1]), synthetic 752x480 stereo + 200 Hz IMU, batches of {frames} frames: "
-            "ORBextractor x2 + stereo knnMatch + IMU pre-integration + 2x PoseOptimization (PVR) per frame, "
+            "ORBextractor x2 + ComputeStereoMatches + IMU pre-integration + 2x PoseOptimization (PVR) per frame, "
             "LocalBundleAdjustmentNavStatePRV every 8th frame")
 
 
@@ -86,7 +86,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# Workload: BASELINE.json configs[1] as SURVEY.md 8d restates it.  Per stereo frame: ORBextractor x2 + stereo knnMatch,
+# Workload: BASELINE.json configs[1] as SURVEY.md 8d restates it.  Per stereo frame: ORBextractor x2 + ComputeStereoMatches,
 # one IMU pre-integration (10 samples at 200 Hz / 20 fps), two PoseOptimization calls (TrackWithMotionModel with ~350
 # matches, TrackLocalMap with ~550; IMU/PVR vertex, 15 % outliers, 70 % stereo); every LBA_EVERY-th frame is a keyframe
 # and triggers one LocalBundleAdjustmentNavStatePRV window (N_local = 10, 20 fixed keyframes, 1500 points).
@@ -177,8 +177,16 @@ def cpu_pipeline(images, trk, lbas, threads_like_reference=True, workers=None):
             tl.orb = O.OrbOracle(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"])
         return tl.orb
 
-    def tracking(f, dl, dr):
-        O.hamming_knn2(dl, dr)
+    def orb2():  # the right camera's extractor (its pyramid is read by the stereo matcher)
+        if not hasattr(tl, "orb2"):
+            tl.orb2 = O.OrbOracle(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"])
+        return tl.orb2
+
+    bf = np.float32(EUROC["bf"]); minz = np.float32(bf / np.float32(EUROC["fx"]))
+
+    def tracking(f, L, R):
+        # L / R = (oracle extractor that just ran on the view, keypoints, descriptors)
+        O.stereo_matches(L[0], L[1], L[2], R[0], R[1], R[2], bf, minz)
         k = f % F
         smp, seg, tt, bb = trk["imu"]
         O.imu_preintegrate(smp[seg[k]:seg[k + 1]], tt[k][0], tt[k][1], bb[k][:3], bb[k][3:], nz)
@@ -201,15 +209,17 @@ def cpu_pipeline(images, trk, lbas, threads_like_reference=True, workers=None):
             for f in range(n):
                 a = cams.submit(lambda f=f: orbs[0].extract(images[f, 0]))
                 b = cams.submit(lambda f=f: orbs[1].extract(images[f, 1]))
-                tracking(f, a.result()[2], b.result()[2])
+                ra, rb = a.result(), b.result()
+                tracking(f, (orbs[0], ra[1], ra[2]), (orbs[1], rb[1], rb[2]))
             fut.result()
             dt = time.perf_counter() - t0
         return n / dt, dt
 
     def work(f):
-        _, _, dl, _ = orb().extract(images[f, 0])
-        _, _, dr, _ = orb().extract(images[f, 1])
-        tracking(f, dl, dr)
+        oL, oR = orb(), orb2()
+        _, kl, dl, _ = oL.extract(images[f, 0])
+        _, kr, dr, _ = oR.extract(images[f, 1])
+        tracking(f, (oL, kl, dl), (oR, kr, dr))
         if f % LBA_EVERY == LBA_EVERY - 1:
             O.local_ba_prv(lbas[(f // LBA_EVERY) % len(lbas)], cam)
 
@@ -286,6 +296,10 @@ def run_gpu(args, rank, world, local_rank):
     nkp = torch.empty((n_img,), dtype=torch.int32, device=dev)
     midx = torch.empty((F, cap, 2), dtype=torch.int32, device=dev)
     mdist = torch.empty((F, cap, 2), dtype=torch.int32, device=dev)
+    s_ur = torch.empty((F, cap), dtype=torch.float32, device=dev)
+    s_dp = torch.empty((F, cap), dtype=torch.float32, device=dev)
+    s_sad = torch.empty((F, cap), dtype=torch.int32, device=dev)
+    BF = float(np.float32(EUROC["bf"])); MINZ = float(np.float32(EUROC["bf"]) / np.float32(EUROC["fx"]))
 
     def to_dev(a):
         return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
@@ -317,8 +331,8 @@ def run_gpu(args, rank, world, local_rank):
         imgs = dev_imgs[i % pool]
         s = main.cuda_stream
         orb.extract_batch_dev(imgs.data_ptr(), n_img, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), s)
-        api.hamming_knn2_batch_dev(desc.data_ptr(), 2 * cap * 32, nkp.data_ptr(), cap, desc.data_ptr() + cap * 32,
-                                   2 * cap * 32, nkp.data_ptr() + 4, cap, 2, F, midx.data_ptr(), mdist.data_ptr(), s)
+        orb.stereo_match_dev(F, kps.data_ptr(), desc.data_ptr(), nkp.data_ptr(), cap, BF, MINZ, s_ur.data_ptr(),
+                             s_dp.data_ptr(), s_sad.data_ptr(), s)
         s2 = side.cuda_stream
         pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(), d_bb.data_ptr(), F,
                                        d_pre.data_ptr(), s2)
@@ -332,7 +346,7 @@ def run_gpu(args, rank, world, local_rank):
     for i in range(args.warmup):
         side.wait_stream(main)
         ba_launches = step(i)
-    launches_per_step = orb.last_launches() + 1 + 2 + ba_launches
+    launches_per_step = orb.last_launches() + 1 + 2 + ba_launches  # extractor + stereo match + (imu, pose opt) + LocalBA
     torch.cuda.synchronize()
     if dist_on:
         dist.barrier()
@@ -402,7 +416,8 @@ def run_gpu(args, rank, world, local_rank):
         futs = [lba_pool.submit(lba_job, wk, wk) for wk in range(n_workers)]
         ft = trk_pool.submit(tracking_host)
         res = fe.process(host_np[i % pool], outs)
-        _ = int(res[2][0]) + ft.result()
+        st = fe.stereo_rectified(F, BF, MINZ)
+        _ = int(res[2][0]) + ft.result() + int(st[2][0, 0])
         for f in futs:
             f.result()
 
@@ -423,7 +438,7 @@ def run_gpu(args, rank, world, local_rank):
     lba_bytes = sum(int(np.asarray(v).nbytes) for v in lbas[0].values() if hasattr(v, "nbytes")) if lbas else 0
     trk_in = sum(int(np.asarray(a).nbytes) for a in trk["imu"]) + sum(int(trk[k].nbytes) for k in ("pbs", "Xw", "obs", "w", "flags"))
     h2d = F * 2 * H * W + trk_in + n_lba * lba_bytes
-    d2h = (sum(int(o.nbytes) for o in outs) + F * api.PREINT_DTYPE.itemsize + n_pb * api.POSEOPT_RESULT_DTYPE.itemsize
+    d2h = (sum(int(o.nbytes) for o in outs) + 3 * F * cap * 4 + F * api.PREINT_DTYPE.itemsize + n_pb * api.POSEOPT_RESULT_DTYPE.itemsize
            + 9 * n_edges + n_lba * (64 * 176 + 2048 * 24 + 16384 * 9))
 
     if rank != 0:
@@ -453,7 +468,7 @@ def run_gpu(args, rank, world, local_rank):
         "dtype": "u8+f64", "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_step_per_gpu": F, "image": f"{W}x{H}", "nfeatures": 1200,
                    "levels": 8, "cache": f"inputs rotate over {pool} batches ({pool * F * 2 * H * W / 1e6:.0f} MB > 126 MB L2)",
-                   "stages": ["orb_extract_x2", "stereo_knn2", "imu_preint", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
+                   "stages": ["orb_extract_x2", "stereo_matches_rectified", "imu_preint", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
                    "pose_opt_points": list(POSE_POINTS), "lba_every": LBA_EVERY if n_lba else 0, "lba_window": LBA_SHAPE,
                    "lba_workers": n_workers, "isolated_stage_ms": iso},
         "clocks": clocks,

@@ -168,9 +168,15 @@ typedef struct VieoNavState { /* NavState (src/Odom/NavState.h:17-36) */
   double bg[3], ba[3];   /* mbg, mba: frozen linearisation point */
   double dbg[3], dba[3]; /* mdbg, mdba: optimised deltas */
 } VieoNavState;
-typedef struct VieoCamera { /* camm::PinholeCamera parameters (float, camera_pinhole.h:70-83) + Frame::meigRcb/meigtcb */
+#define VIEO_CAM_PINHOLE 0 /* common/camera_models/camera_pinhole.h:70-106 */
+#define VIEO_CAM_RADTAN 1  /* camera_radtan.h:61-129: dist = {k1..k_num_k, p1, p2} */
+#define VIEO_CAM_KB8 2     /* camera_kb8.h:68-157: dist = {k1, k2, k3, k4} */
+typedef struct VieoCamera { /* camm::Camera parameters (all float in the reference) + Frame::meigRcb / meigtcb */
   float fx, fy, cx, cy, bf;
-  float pad_[3];
+  int32_t model;  /* VIEO_CAM_* */
+  int32_t num_k;  /* radtan: number of radial coefficients (2 or 3) */
+  float pad_;
+  float dist[8];
   double Rcb[9], tcb[3];
 } VieoCamera;
 /* visual edge flags */

@@ -43,12 +43,16 @@ void to_c(const NS& n, OrcNavState* s) {
 }
 struct Cam {
   float fx, fy, cx, cy, bf;
+  int model, num_k;
+  float dist[8];
   M3 Rcb;
   double tcb[3];
 };
 Cam cam_from_c(const OrcCamera& c) {
   Cam k;
   k.fx = c.fx; k.fy = c.fy; k.cx = c.cx; k.cy = c.cy; k.bf = c.bf;
+  k.model = c.model; k.num_k = c.num_k;
+  memcpy(k.dist, c.dist, sizeof(k.dist));
   memcpy(k.Rcb.m, c.Rcb, 72);
   memcpy(k.tcb, c.tcb, 24);
   return k;
@@ -78,6 +82,84 @@ void inc_bias(NS& s, const double* d) {
   for (int i = 0; i < 3; ++i) s.dba[i] += d[3 + i];
 }
 
+// ---- camera models: Project() rounded to float pixels + d(img)/d(p3d) --------------------------------------------
+// pinhole camera_pinhole.h:70-106, radtan camera_radtan.h:61-129, KB8 camera_kb8.h:68-157 (Jacobian formulas kept as
+// the reference writes them, including radtan's radial-derivative term that starts at k3)
+void cam_project(const Cam& c, const double P[3], float* u, float* v, double* J /*2x3 or null*/) {
+  const double fx = (double)c.fx, fy = (double)c.fy;
+  if (c.model == 1) {
+    const float* k = c.dist;
+    const float* p = k + c.num_k;
+    const double invz = 1 / P[2];
+    double x = P[0] * invz, y = P[1] * invz;
+    const double x2 = x * x, y2 = y * y, xy = x * y, r2 = x2 + y2;
+    double fd = 1, term_r = 1;
+    for (int i = 0; i < c.num_k; ++i) {
+      term_r *= r2;
+      fd += k[i] * term_r;
+    }
+    if (J) {
+      double fd2 = 0, coeff2 = 0;
+      term_r = 1;
+      for (int i = 2; i < c.num_k; ++i) {
+        coeff2 += 2;
+        fd2 += coeff2 * k[i] * term_r;
+        term_r *= r2;
+      }
+      const double du_dx = fx * invz * (fd + fd2 * x2 + 2 * (p[0] * y + 3 * p[1] * x));
+      const double du_dy = fx * invz * (fd2 * xy + 2 * (p[0] * x + p[1] * y));
+      const double du_dz = -(x * du_dx + y * du_dy);
+      const double dv_dx = du_dy * fy / fx;
+      const double dv_dy = fy * invz * (fd + fd2 * y2 + 2 * (p[1] * x + 3 * p[0] * y));
+      const double dv_dz = -(x * dv_dx + y * dv_dy);
+      J[0] = du_dx; J[1] = du_dy; J[2] = du_dz; J[3] = dv_dx; J[4] = dv_dy; J[5] = dv_dz;
+    }
+    const double xd = x * fd + 2 * p[0] * xy + p[1] * (r2 + 2 * x2);
+    const double yd = y * fd + 2 * p[1] * xy + p[0] * (r2 + 2 * y2);
+    *u = (float)(fx * xd * 1.0 + c.cx);
+    *v = (float)(fy * yd * 1.0 + c.cy);
+    return;
+  }
+  if (c.model == 2) {
+    const double x = P[0], y = P[1];
+    const double x2 = x * x, y2 = y * y, r2 = x2 + y2, r = std::sqrt(r2);
+    if (r > (double)1e-5f) {
+      const double k1 = c.dist[0], k2 = c.dist[1], k3 = c.dist[2], k4 = c.dist[3];
+      const double z = P[2];
+      const double theta = std::atan2(r, z), theta2 = theta * theta;
+      double thetad = k4 * theta2;
+      thetad += k3; thetad *= theta2; thetad += k2; thetad *= theta2; thetad += k1; thetad *= theta2; thetad += 1;
+      thetad *= theta;
+      const double mx = x * thetad / r, my = y * thetad / r;
+      *u = (float)(fx * mx * 1.0 + c.cx);
+      *v = (float)(fy * my * 1.0 + c.cy);
+      if (J) {
+        const double invr = 1. / r, d_r_d_x = x * invr, d_r_d_y = y * invr;
+        const double tmp = 1. / (z * z + r2);
+        const double d_thetad_x = d_r_d_x * z * tmp, d_thetad_y = d_r_d_y * z * tmp;
+        double dd = 9.0 * k4 * theta2;
+        dd += 7.0 * k3; dd *= theta2; dd += 5.0 * k2; dd *= theta2; dd += 3.0 * k1; dd *= theta2; dd += 1.0;
+        const double invr2 = invr * invr;
+        J[0] = fx * (x * r * dd * d_thetad_x + y2 * thetad / r) * invr2;
+        J[1] = fx * x * (dd * d_thetad_y * r - y * thetad / r) * invr2;
+        J[2] = -fx * x * dd * tmp;
+        J[3] = J[1] * fy / fx;
+        J[4] = fy * (y * r * dd * d_thetad_y + x2 * thetad / r) * invr2;
+        J[5] = -fy * y * dd * tmp;
+      }
+      return;
+    }
+  }
+  const double invz = 1. / P[2];
+  *u = (float)(fx * P[0] * invz + c.cx);
+  *v = (float)(fy * P[1] * invz + c.cy);
+  if (J) {
+    const double invz2 = invz * invz;
+    J[0] = fx * invz; J[1] = 0; J[2] = -fx * P[0] * invz2;
+    J[3] = 0; J[4] = fy * invz; J[5] = -fy * P[1] * invz2;
+  }
+}
+
 // ---- EdgeReproject (g2otypes.h:338-541), NV = 2 ---------------------------------------------------------------
 // e = obs - pi(Rcw Xw + tcw), pi rounded to float (camera_pinhole.h:81-82); returns depth (GetDepth, :431-436)
 double reproj_error(const Cam& c, const NS& s, const double Xw[3], const float obs[3], bool stereo, double e[3]) {
@@ -87,8 +169,8 @@ double reproj_error(const Cam& c, const NS& s, const double Xw[3], const float o
   for (int i = 0; i < 3; ++i) t[i] = -t[i] + c.tcb[i];
   mulv(Rcw, Xw, Pc);
   for (int i = 0; i < 3; ++i) Pc[i] += t[i];
-  const double invz = 1. / Pc[2];
-  const float u = (float)((double)c.fx * Pc[0] * invz + c.cx), v = (float)((double)c.fy * Pc[1] * invz + c.cy);
+  float u, v;
+  cam_project(c, Pc, &u, &v, nullptr);
   e[0] = (double)obs[0] - (double)u;
   e[1] = (double)obs[1] - (double)v;
   e[2] = stereo ? (double)obs[2] - ((double)u - (double)c.bf / Pc[2]) : 0.0;
@@ -105,10 +187,12 @@ void reproj_jac(const Cam& c, const NS& s, const double Xw[3], bool stereo, doub
   for (int i = 0; i < 3; ++i) Pc[i] += t[i];
   const double invz = 1 / Pc[2], invz_2 = invz * invz;
   M3 Jproj = {{0, 0, 0, 0, 0, 0, 0, 0, 0}};
-  Jproj.m[0] = -((double)c.fx * invz);
-  Jproj.m[2] = -(-(double)c.fx * Pc[0] * invz_2);
-  Jproj.m[4] = -((double)c.fy * invz);
-  Jproj.m[5] = -(-(double)c.fy * Pc[1] * invz_2);
+  {
+    float u, v;
+    double Jc[6];
+    cam_project(c, Pc, &u, &v, Jc);
+    for (int i = 0; i < 6; ++i) Jproj.m[i] = -Jc[i];
+  }
   if (stereo) {
     Jproj.m[6] = Jproj.m[0];
     Jproj.m[7] = Jproj.m[1];
@@ -1089,7 +1173,9 @@ bool build_lba_graph(const OrcBaProblem* pb, const OrcCamera* cam, Graph& g, int
   }
   g.X.assign(pb->points, pb->points + (size_t)3 * P);
   const float chi2Mono = 5.991f;
-  const float thHuberMono = std::sqrt(chi2Mono), thHuberStereo = (float)std::sqrt(7.815);
+  // src/Optimizer.cc:361-362 (PRV: sqrt of the float 5.991f) vs :2069-2070 (visual LocalBundleAdjustment: sqrt(5.991))
+  const float thHuberMono = pb->visual_only ? (float)std::sqrt(5.991) : std::sqrt(chi2Mono);
+  const float thHuberStereo = (float)std::sqrt(7.815);
   g.vis.resize(E);
   for (int i = 0; i < E; ++i) {
     VisEdge& e = g.vis[i];
@@ -1156,23 +1242,27 @@ int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* 
   int optit[2];
   if (!build_lba_graph(pb, cam, g, optit)) return 0;
   const float chi2Mono = 5.991f;
-  // GraphOperator::Chi2LargeSetLevel (g2o_graph_operator.h:23-40), rat 100
+  const bool vo = pb->visual_only != 0;  // Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1876-2307)
+  // GraphOperator::Chi2LargeSetLevel (g2o_graph_operator.h:23-40), rat 100 — PRV version only (src/Optimizer.cc:534-536)
   static const float chi2_sig5[4] = {0, 3.841f, 5.991f, 7.815f};
-  for (VisEdge& e : g.vis) {
-    g.vis_error(e);
-    if (e.chi2 > (double)(100.f * chi2_sig5[e.stereo ? 3 : 2])) e.level = 1;
-  }
+  if (!vo)
+    for (VisEdge& e : g.vis) {
+      g.vis_error(e);
+      if (e.chi2 > (double)(100.f * chi2_sig5[e.stereo ? 3 : 2])) e.level = 1;
+    }
   g.initialize();
   g.compute_active_errors();
   const float err = (float)g.active_robust_chi2();
   res->err0 = err;
   res->iterations[0] = g.optimize(optit[0]);
+  auto is_bad = [&](VisEdge& e) {
+    if (e.stereo) return e.chi2 > 7.815 || !(g.vis_depth(e) > 0.);
+    if (vo) return e.chi2 > 5.991 || !(g.vis_depth(e) > 0.);  // :2198, 2238: no "close point" relaxation
+    return e.chi2 > (e.close ? 1.5 * chi2Mono : (double)chi2Mono) || !(g.vis_depth(e) > 0.);
+  };
   {  // bDoMore
     for (VisEdge& e : g.vis) {
-      bool bad;
-      if (e.stereo) bad = e.chi2 > 7.815 || !(g.vis_depth(e) > 0.);
-      else bad = e.chi2 > (e.close ? 1.5 * chi2Mono : (double)chi2Mono) || !(g.vis_depth(e) > 0.);
-      if (bad) e.level = 1;
+      if (is_bad(e)) e.level = 1;
       e.rk.on = false;
     }
     g.initialize();
@@ -1182,17 +1272,15 @@ int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* 
   res->err_end = err_end;
   res->lambda_final = g.lambda;
   for (int i = 0; i < E; ++i) edge_chi2[i] = g.vis[i].chi2;
-  if ((2 * err < err_end || std::isnan(err) || std::isnan(err_end)) && !pb->large) {
+  // "FAIL LOCAL-INERTIAL BA" guard of the PRV version (:663-666); the visual version has none
+  if (!vo && (2 * err < err_end || std::isnan(err) || std::isnan(err_end)) && !pb->large) {
     res->accepted = 0;
     return 0;
   }
   res->accepted = 1;
   int n_erase = 0;
   for (int i = 0; i < E; ++i) {
-    VisEdge& e = g.vis[i];
-    bool bad;
-    if (e.stereo) bad = e.chi2 > 7.815 || !(g.vis_depth(e) > 0.);
-    else bad = e.chi2 > (e.close ? 1.5 * chi2Mono : (double)chi2Mono) || !(g.vis_depth(e) > 0.);
+    const bool bad = is_bad(g.vis[i]);
     erase[i] = bad;
     n_erase += bad;
   }

@@ -19,9 +19,12 @@ typedef struct OrcNavState { /* NavState (src/Odom/NavState.h:17-36) */
   double dbg[3], dba[3]; /* mdbg, mdba (optimised) */
 } OrcNavState;
 
-typedef struct OrcCamera { /* pinhole intrinsics are float in the reference (camera_pinhole.h:70-83) */
+typedef struct OrcCamera { /* intrinsics are float in the reference (camera_pinhole.h:70-83) */
   float fx, fy, cx, cy, bf;
-  float pad_[3];
+  int32_t model; /* 0 pinhole, 1 radtan (camera_radtan.h), 2 KB8 (camera_kb8.h) */
+  int32_t num_k; /* radtan: number of radial coefficients */
+  float pad_;
+  float dist[8]; /* radtan: k1..k_num_k, p1, p2; KB8: k1..k4 */
   double Rcb[9], tcb[3]; /* Frame::meigRcb / meigtcb */
 } OrcCamera;
 

@@ -47,6 +47,20 @@ def test_pose_optimization_matches_oracle(seq, mode, chain, npts):
     _cmp_pose(res, outl, chi2, ores, ooutl, ochi2, pbs)
 
 
+@pytest.mark.parametrize("model", ["radtan", "radtan3", "kb8"])
+def test_pose_optimization_lens_models(seq, model):
+    """EdgeReprojectPVR through camm::RadtanCamera / KB8Camera (camera_radtan.h:61-129, camera_kb8.h:68-157)."""
+    import vieo_slam_b200.api as api
+    cam = {"radtan": synth.radtan_camera(), "radtan3": synth.radtan_camera(k=(-0.28, 0.074, -0.01)),
+           "kb8": synth.kb8_camera()}[model]
+    pbs, X, obs, w, fl = synth.make_pose_problems(seq, seq["pre"], cam, n_points=350, seed=17)
+    pbs = pbs[:12]
+    res, outl, chi2 = api.Optimizer.PoseOptimizationBatch(pbs, cam, X, obs, w, fl)
+    ores, ooutl, ochi2 = O.pose_optimization(pbs, cam, X, obs, w, fl)
+    _cmp_pose(res, outl, chi2, ores, ooutl, ochi2, pbs)
+    assert res["n_inliers"].min() > 0.6 * 350
+
+
 def test_pose_optimization_edge_cases(seq):
     import vieo_slam_b200.api as api
     cam = synth.euroc_camera()
@@ -75,8 +89,8 @@ def test_pose_optimization_deterministic(seq):
 
 
 # ---------------------------------------------------------------- local BA
-def _lba(seq, n_local=8, n_fixed=6, n_points=400, seed=4, step=3, **kw):
-    cam = synth.euroc_camera()
+def _lba(seq, n_local=8, n_fixed=6, n_points=400, seed=4, step=3, cam=None, **kw):
+    cam = synth.euroc_camera() if cam is None else cam
     kf = list(range(0, len(seq["times"]), step))
     pre = O.imu_preintegrate_frames(seq, kf, O.imu_noise())
     return cam, synth.make_lba_problem(seq, pre, kf, cam, n_local=n_local, n_fixed=n_fixed, n_points=n_points, seed=seed, **kw)
@@ -119,6 +133,21 @@ def test_local_ba_matches_oracle(seq, kw):
     _cmp_lba(out, ref)
     assert out["res"]["err_end"] < out["res"]["err0"]
     assert ba.last_launches() > 0
+
+
+@pytest.mark.parametrize("model", ["radtan", "kb8"])
+@pytest.mark.parametrize("kw", [dict(), dict(visual_only=True)])
+def test_local_ba_lens_models(seq, model, kw):
+    import vieo_slam_b200.api as api
+    cam, d = _lba(seq, cam=synth.radtan_camera() if model == "radtan" else synth.kb8_camera())
+    ba = api.BundleAdjuster()
+    out = ba.LocalBundleAdjustmentNavStatePRV(d, cam, **kw)
+    ref = O.local_ba_prv(d, cam, **kw)
+    _cmp_lba(out, ref)
+    assert out["res"]["err_end"] < out["res"]["err0"]
+    wrong = cam.copy(); wrong["model"] = 7
+    with pytest.raises(api.VieoError):
+        ba.LocalBundleAdjustmentNavStatePRV(d, wrong)
 
 
 def test_local_ba_v203_sized_window():

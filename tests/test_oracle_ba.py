@@ -275,3 +275,96 @@ def test_all_fixed_returns_untouched(seq):
     d = dict(d); d["state_flags"] = d["state_flags"] | 1
     out = O.local_ba_prv(d, cam)
     assert out["states"].tobytes() == d["states"].tobytes() and out["res"]["iterations"][0] == 0
+
+
+# ---- camera models: radtan and KB8 next to pinhole ----------------------------------------------
+def _cam_points(cam, n, seed):
+    r = np.random.default_rng(seed)
+    ns = np.zeros(1, NAVSTATE_DTYPE)[0]; ns["q"] = [1, 0, 0, 0]
+    return ns, synth.landmarks_in_view(cam, ns, n, r, zmin=0.5, zmax=8.0)
+
+
+@pytest.mark.parametrize("model", ["radtan", "radtan3", "kb8"])
+def test_camera_models_projection_matches_cv2(model):
+    """Pins Project() of camera_radtan.h:61-129 / camera_kb8.h:68-157 against OpenCV's projectPoints (the reference
+    calibrations are OpenCV/Kalibr ones): the float pixel of the oracle equals cv2's double pixel rounded to float up
+    to one ulp-of-pixel."""
+    cv2 = pytest.importorskip("cv2")
+    cam = {"radtan": synth.radtan_camera(), "radtan3": synth.radtan_camera(k=(-0.28, 0.074, -0.01)),
+           "kb8": synth.kb8_camera(k=(-0.0135, 0.021, -0.03, 0.012))}[model]
+    ns, X = _cam_points(cam, 64, 3)
+    Pc = X @ cam["Rcb"].T + cam["tcb"]
+    K = np.array([[cam["fx"], 0, cam["cx"]], [0, cam["fy"], cam["cy"]], [0, 0, 1]], np.float64)
+    if model == "kb8":
+        ref = cv2.fisheye.projectPoints(Pc.reshape(-1, 1, 3), np.zeros(3), np.zeros(3), K, cam["dist"][:4].astype(np.float64))[0]
+    else:
+        nk = int(cam["num_k"])
+        d = cam["dist"].astype(np.float64)
+        dc = np.array([d[0], d[1], d[nk], d[nk + 1], d[2] if nk > 2 else 0.0])
+        ref = cv2.projectPoints(Pc.reshape(-1, 1, 3), np.zeros(3), np.zeros(3), K, dc)[0]
+    ref = ref.reshape(-1, 2)
+    for i in range(len(X)):
+        obs = np.zeros(3, np.float32)
+        e = O.edge_reproject(cam, ns, X[i], obs, 0)[0]
+        assert np.allclose(-e[:2], ref[i], rtol=0, atol=1e-4), (model, i, -e[:2], ref[i])
+    su, sv, _, _ = synth.project(cam, ns, X)
+    assert np.allclose(np.stack([su, sv], 1), ref, atol=1e-9)  # the generator's lens model is the same one
+
+
+@pytest.mark.parametrize("model", ["radtan_tangential", "kb8"])
+def test_camera_models_jacobians_numeric(model):
+    # radtan: the reference's d(img)/d(p3d) carries the radial derivative only from k3 on (camera_radtan.h:85-99), so it
+    # is exact for tangential-only distortion; KB8's is exact everywhere
+    cam = synth.radtan_camera(k=(0.0, 0.0), p=(2e-3, -1.5e-3)) if model != "kb8" else synth.kb8_camera(k=(-0.0135, 0.021, -0.03, 0.012))
+    ns, X = _cam_points(cam, 8, 5)
+    obs = np.array([100, 200, 90], np.float32)
+    d = 2e-3
+    for i in range(8):
+        for stereo in (0, 1):
+            e, Jp, JX, depth = O.edge_reproject(cam, ns, X[i], obs, stereo)
+            JXn = np.zeros((3, 3)); Jn = np.zeros((3, 6))
+            for c in range(3):
+                dx = np.zeros(3); dx[c] = d
+                JXn[:, c] = (O.edge_reproject(cam, ns, X[i] + dx, obs, stereo)[0] - O.edge_reproject(cam, ns, X[i] - dx, obs, stereo)[0]) / (2 * d)
+            for c in range(6):
+                dx = np.zeros(6); dx[c] = d
+                Jn[:, c] = (O.edge_reproject(cam, O.navstate_oplus(ns, 0, dx), X[i], obs, stereo)[0]
+                            - O.edge_reproject(cam, O.navstate_oplus(ns, 0, -dx), X[i], obs, stereo)[0]) / (2 * d)
+            rows = 3 if stereo else 2
+            assert np.allclose(JX[:rows], JXn[:rows], rtol=2e-3, atol=0.15), (model, JX, JXn)
+            assert np.allclose(Jp[:rows], Jn[:rows], rtol=2e-3, atol=0.15)
+
+
+def test_radtan_jacobian_is_the_references_formula():
+    """With radial coefficients the reference's Jacobian is NOT the exact derivative; the oracle must reproduce the
+    formula as written (camera_radtan.h:85-99), restated independently here in numpy."""
+    cam = synth.radtan_camera(k=(-0.28, 0.074, -0.01))
+    ns, X = _cam_points(cam, 6, 9)
+    k = cam["dist"][:3].astype(np.float64); p = cam["dist"][3:5].astype(np.float64)
+    fx, fy = float(cam["fx"]), float(cam["fy"])
+    for i in range(6):
+        Pc = cam["Rcb"] @ X[i] + cam["tcb"]
+        invz = 1 / Pc[2]; x = Pc[0] * invz; y = Pc[1] * invz; r2 = x * x + y * y
+        fd = 1 + k[0] * r2 + k[1] * r2 * r2 + k[2] * r2 ** 3
+        fd2 = 2 * k[2]
+        du_dx = fx * invz * (fd + fd2 * x * x + 2 * (p[0] * y + 3 * p[1] * x))
+        du_dy = fx * invz * (fd2 * x * y + 2 * (p[0] * x + p[1] * y))
+        dv_dx = du_dy * fy / fx
+        dv_dy = fy * invz * (fd + fd2 * y * y + 2 * (p[1] * x + 3 * p[0] * y))
+        J = np.array([[du_dx, du_dy, -(x * du_dx + y * du_dy)], [dv_dx, dv_dy, -(x * dv_dx + y * dv_dy)]])
+        JX = O.edge_reproject(cam, ns, X[i], np.zeros(3, np.float32), 0)[2]
+        assert np.allclose(JX[:2], -J @ cam["Rcb"], rtol=1e-9, atol=1e-9), np.abs(JX[:2] + J @ cam["Rcb"]).max()  # J_X = Jproj Rcw, Jproj = -d(img)/d(p3d)
+
+
+@pytest.mark.parametrize("model", ["radtan", "kb8"])
+def test_drivers_converge_with_lens_models(seq, model):
+    cam = synth.radtan_camera() if model == "radtan" else synth.kb8_camera()
+    pbs, Xw, obs, w, fl = synth.make_pose_problems(seq, seq["pre"], cam, n_points=300, seed=2)
+    pbs = pbs[:4]
+    res, outl, chi2 = O.pose_optimization(pbs, cam, Xw, obs, w, fl)
+    for k in range(len(pbs)):
+        assert np.linalg.norm(res[k]["cur"]["p"] - seq["truth"][k + 1]["p"]) < 0.02
+        assert 0.7 * 300 < res[k]["n_inliers"] < 0.93 * 300
+    # the same observations through the wrong (pinhole) model must fit visibly worse
+    res0, _, _ = O.pose_optimization(pbs, synth.euroc_camera(), Xw, obs, w, fl)
+    assert sum(r["n_inliers"] for r in res0) < sum(r["n_inliers"] for r in res)

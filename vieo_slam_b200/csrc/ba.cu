@@ -990,7 +990,8 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_backsub(BaBuf B, int apply
 __global__ void k_ba_classify(CamK cam, const CamPose* __restrict__ cp, const double* __restrict__ X,
                               const int* __restrict__ es, const int* __restrict__ ep, const float* __restrict__ obs,
                               const uint8_t* __restrict__ flags, const double* __restrict__ chi2, int E, int mode, float rat,
-                              int set_level, int remove_kernels, uint8_t* __restrict__ lvl, uint8_t* __restrict__ bad_out) {
+                              int set_level, int remove_kernels, int use_close, uint8_t* __restrict__ lvl,
+                              uint8_t* __restrict__ bad_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E) return;
   const bool stereo = flags[i] & VIEO_EDGE_STEREO;
@@ -1003,6 +1004,7 @@ __global__ void k_ba_classify(CamK cam, const CamPose* __restrict__ cp, const do
     const double depth = reproj_error(cam, cp[es[i]], ld3(X + 3 * (size_t)ep[i]), obs + 3 * (size_t)i, stereo, e);
     const float chi2Mono = 5.991f;
     if (stereo) bad = chi2[i] > 7.815 || !(depth > 0.);
+    else if (!use_close) bad = chi2[i] > 5.991 || !(depth > 0.);  // visual LocalBundleAdjustment (src/Optimizer.cc:2198)
     else bad = chi2[i] > ((flags[i] & VIEO_EDGE_CLOSE) ? 1.5 * chi2Mono : (double)chi2Mono) || !(depth > 0.);
   }
   uint8_t l = lvl[i];
@@ -1021,7 +1023,7 @@ struct vieo_ba {
   cudaStream_t st = nullptr;
   int capK = 0, capP = 0, capE = 0, capM = 0, cap_pblk = 0, cap_free = 0;
   int K = 0, P = 0, E = 0, M = 0, np = 0, nfree = 0, n_den = 0, n_part = 0, n_pblk = 0;
-  bool points_free = true, has_dup = false;
+  bool points_free = true, has_dup = false, visual_only = false;
   int rank = 0, world = 1;
   vieo_allreduce_fn allreduce = nullptr;
   void* ar_ctx = nullptr;
@@ -1307,13 +1309,13 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   h->n_part = (E + 255) / 256;
   h->n_pblk = (P + kBaWarps - 1) / kBaWarps;
   // camera
-  h->cam.fx = (double)cam->fx; h->cam.fy = (double)cam->fy; h->cam.cx = (double)cam->cx; h->cam.cy = (double)cam->cy;
-  h->cam.bf = (double)cam->bf;
-  for (int i = 0; i < 9; ++i) h->cam.Rcb.m[i] = cam->Rcb[i];
-  h->cam.tcb = {cam->tcb[0], cam->tcb[1], cam->tcb[2]};
+  cam_set(h->cam, *cam);
+  VIEO_ARG(cam->model >= 0 && cam->model <= 2 && cam->num_k >= 0 && cam->num_k <= 6, "unsupported camera model");
   h->gw = {pb->gw[0], pb->gw[1], pb->gw[2]};
   const float chi2Mono = 5.991f;
-  h->dm = (double)std::sqrt(chi2Mono);           // thHuberMono (src/Optimizer.cc:361)
+  h->visual_only = pb->visual_only != 0;
+  // thHuberMono: src/Optimizer.cc:361 (PRV: sqrt of the float 5.991f) vs :2069 (visual LocalBundleAdjustment: sqrt(5.991))
+  h->dm = h->visual_only ? (double)(float)std::sqrt(5.991) : (double)std::sqrt(chi2Mono);
   h->ds = (double)(float)std::sqrt(7.815);       // thHuberStereo
   // index mapping (sparse_optimizer.cpp:166-190): states in order, PR, V, Bias
   h->off0.assign(K, -1); h->off1.assign(K, -1); h->off2.assign(K, -1);
@@ -1461,7 +1463,7 @@ int vieo_ba_chi2_large_set_level(vieo_ba_t* h, float rat) {
   if (rc) return rc;
   if (h->E > 0) {
     k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
-                                                         h->B.chi2, h->E, 0, rat, 1, 0, h->d_lvl, nullptr);
+                                                         h->B.chi2, h->E, 0, rat, 1, 0, 1, h->d_lvl, nullptr);
     h->launches++;
   }
   BA_CK(cudaGetLastError());
@@ -1540,7 +1542,7 @@ int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host) {
   if (h->E == 0) return VIEO_OK;
   ba_campose(h);
   k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
-                                                       h->B.chi2, h->E, 1, 0.f, bad_host ? 0 : 1, remove_kernels, h->d_lvl,
+                                                       h->B.chi2, h->E, 1, 0.f, bad_host ? 0 : 1, remove_kernels, h->visual_only ? 0 : 1, h->d_lvl,
                                                        h->d_bad);
   h->launches++;
   BA_CK(cudaGetLastError());
@@ -1623,7 +1625,7 @@ int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* c
   int rc = vieo_ba_set_problem(h, pb, cam);
   if (rc) return rc;
   if (stop && *stop) return VIEO_OK;  // "Aborted OLBA" (:524-528)
-  if ((rc = vieo_ba_chi2_large_set_level(h, 100.f))) return rc;
+  if (!pb->visual_only && (rc = vieo_ba_chi2_large_set_level(h, 100.f))) return rc;  // PRV version only (:534-536)
   double chi = 0;
   if ((rc = vieo_ba_active_robust_chi2(h, 1, &chi))) return rc;
   const float err = (float)chi;
@@ -1644,7 +1646,7 @@ int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* c
   res->err_end = err_end;
   res->lambda_final = h->h_prm->lambda;
   if ((rc = vieo_ba_get(h, nullptr, nullptr, edge_chi2))) return rc;
-  if ((2 * err < err_end || std::isnan(err) || std::isnan(err_end)) && !pb->large) {
+  if (!pb->visual_only && (2 * err < err_end || std::isnan(err) || std::isnan(err_end)) && !pb->large) {
     res->accepted = 0;  // "FAIL LOCAL-INERTIAL BA" (:663-666)
     return VIEO_OK;
   }

@@ -83,12 +83,99 @@ struct CamPose {
 };
 struct CamK {
   double fx, fy, cx, cy, bf;  // float intrinsics promoted to double
+  int model, num_k;           // VIEO_CAM_*
+  double dist[8];             // float distortion coefficients promoted to double
   Mat3 Rcb;
   Vec3 tcb;
 };
+__host__ __device__ __forceinline__ void cam_set(CamK& k, const VieoCamera& c) {
+  k.fx = (double)c.fx; k.fy = (double)c.fy; k.cx = (double)c.cx; k.cy = (double)c.cy; k.bf = (double)c.bf;
+  k.model = c.model; k.num_k = c.num_k;
+  for (int i = 0; i < 8; ++i) k.dist[i] = (double)c.dist[i];
+  for (int i = 0; i < 9; ++i) k.Rcb.m[i] = c.Rcb[i];
+  k.tcb = {c.tcb[0], c.tcb[1], c.tcb[2]};
+}
+// Camera::Project rounded to float pixels and its 2x3 Jacobian (J may be null): pinhole camera_pinhole.h:70-106,
+// radtan camera_radtan.h:61-129, KB8 camera_kb8.h:68-157 — formulas as the reference writes them.
+__device__ __forceinline__ void cam_project(const CamK& c, const Vec3& P, float& u, float& v, double* J) {
+  if (c.model == VIEO_CAM_RADTAN) {
+    const double* k = c.dist;
+    const double* p = k + c.num_k;
+    const double invz = 1 / P.z;
+    const double x = P.x * invz, y = P.y * invz;
+    const double x2 = x * x, y2 = y * y, xy = x * y, r2 = x2 + y2;
+    double fd = 1, term_r = 1;
+    for (int i = 0; i < c.num_k; ++i) {
+      term_r *= r2;
+      fd += k[i] * term_r;
+    }
+    if (J) {
+      double fd2 = 0, coeff2 = 0;
+      term_r = 1;
+      for (int i = 2; i < c.num_k; ++i) {
+        coeff2 += 2;
+        fd2 += coeff2 * k[i] * term_r;
+        term_r *= r2;
+      }
+      const double du_dx = c.fx * invz * (fd + fd2 * x2 + 2 * (p[0] * y + 3 * p[1] * x));
+      const double du_dy = c.fx * invz * (fd2 * xy + 2 * (p[0] * x + p[1] * y));
+      const double du_dz = -(x * du_dx + y * du_dy);
+      const double dv_dx = du_dy * c.fy / c.fx;
+      const double dv_dy = c.fy * invz * (fd + fd2 * y2 + 2 * (p[1] * x + 3 * p[0] * y));
+      const double dv_dz = -(x * dv_dx + y * dv_dy);
+      J[0] = du_dx; J[1] = du_dy; J[2] = du_dz; J[3] = dv_dx; J[4] = dv_dy; J[5] = dv_dz;
+    }
+    const double xd = x * fd + 2 * p[0] * xy + p[1] * (r2 + 2 * x2);
+    const double yd = y * fd + 2 * p[1] * xy + p[0] * (r2 + 2 * y2);
+    u = (float)(c.fx * xd * 1.0 + c.cx);
+    v = (float)(c.fy * yd * 1.0 + c.cy);
+    return;
+  }
+  if (c.model == VIEO_CAM_KB8) {
+    const double x = P.x, y = P.y;
+    const double x2 = x * x, y2 = y * y, r2 = x2 + y2, r = sqrt(r2);
+    if (r > (double)1e-5f) {
+      const double k1 = c.dist[0], k2 = c.dist[1], k3 = c.dist[2], k4 = c.dist[3];
+      const double z = P.z;
+      const double theta = atan2(r, z), theta2 = theta * theta;
+      double thetad = k4 * theta2;
+      thetad += k3; thetad *= theta2; thetad += k2; thetad *= theta2; thetad += k1; thetad *= theta2; thetad += 1;
+      thetad *= theta;
+      const double mx = x * thetad / r, my = y * thetad / r;
+      u = (float)(c.fx * mx * 1.0 + c.cx);
+      v = (float)(c.fy * my * 1.0 + c.cy);
+      if (J) {
+        const double invr = 1. / r, d_r_d_x = x * invr, d_r_d_y = y * invr;
+        const double tmp = 1. / (z * z + r2);
+        const double d_thetad_x = d_r_d_x * z * tmp, d_thetad_y = d_r_d_y * z * tmp;
+        double dd = 9.0 * k4 * theta2;
+        dd += 7.0 * k3; dd *= theta2; dd += 5.0 * k2; dd *= theta2; dd += 3.0 * k1; dd *= theta2; dd += 1.0;
+        const double invr2 = invr * invr;
+        J[0] = c.fx * (x * r * dd * d_thetad_x + y2 * thetad / r) * invr2;
+        J[1] = c.fx * x * (dd * d_thetad_y * r - y * thetad / r) * invr2;
+        J[2] = -c.fx * x * dd * tmp;
+        J[3] = J[1] * c.fy / c.fx;
+        J[4] = c.fy * (y * r * dd * d_thetad_y + x2 * thetad / r) * invr2;
+        J[5] = -c.fy * y * dd * tmp;
+      }
+      return;
+    }
+  }
+  const double invz = 1. / P.z;
+  u = (float)(c.fx * P.x * invz + c.cx);
+  v = (float)(c.fy * P.y * invz + c.cy);
+  if (J) {
+    const double invz2 = invz * invz;
+    J[0] = c.fx * invz; J[1] = 0; J[2] = -c.fx * P.x * invz2;
+    J[3] = 0; J[4] = c.fy * invz; J[5] = -c.fy * P.y * invz2;
+  }
+}
 __device__ __forceinline__ CamK cam_load(const VieoCamera& c) {
   CamK k;
   k.fx = (double)c.fx; k.fy = (double)c.fy; k.cx = (double)c.cx; k.cy = (double)c.cy; k.bf = (double)c.bf;
+  k.model = c.model; k.num_k = c.num_k;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k.dist[i] = (double)c.dist[i];
 #pragma unroll
   for (int i = 0; i < 9; ++i) k.Rcb.m[i] = c.Rcb[i];
   k.tcb = ld3(c.tcb);
@@ -108,8 +195,8 @@ __device__ __forceinline__ double reproj_error(const CamK& c, const CamPose& P, 
                                                double e[3]) {
   Vec3 Pc = m3_mulv(P.Rcw, X);
   Pc = v3_add(Pc, P.tcw);
-  const double invz = 1. / Pc.z;
-  const float u = (float)(c.fx * Pc.x * invz + c.cx), v = (float)(c.fy * Pc.y * invz + c.cy);
+  float u, v;
+  cam_project(c, Pc, u, v, nullptr);
   e[0] = (double)obs[0] - (double)u;
   e[1] = (double)obs[1] - (double)v;
   e[2] = stereo ? (double)obs[2] - ((double)u - c.bf / Pc.z) : 0.0;
@@ -122,10 +209,13 @@ __device__ __forceinline__ void reproj_jac(const CamK& c, const CamPose& P, cons
   Pc = v3_add(Pc, P.tcw);
   const double invz = 1 / Pc.z, invz_2 = invz * invz;
   Mat3 Jproj = m3_zero();
-  Jproj.m[0] = -(c.fx * invz);
-  Jproj.m[2] = -(-c.fx * Pc.x * invz_2);
-  Jproj.m[4] = -(c.fy * invz);
-  Jproj.m[5] = -(-c.fy * Pc.y * invz_2);
+  {
+    float u, v;
+    double Jc[6];
+    cam_project(c, Pc, u, v, Jc);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Jproj.m[i] = -Jc[i];
+  }
   if (stereo) {
     Jproj.m[6] = Jproj.m[0];
     Jproj.m[7] = Jproj.m[1];

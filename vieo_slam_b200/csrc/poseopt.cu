@@ -860,6 +860,7 @@ int vieo_pose_opt_batch(const VieoPoseOptProblem* pbs, int n, const VieoCamera* 
   VIEO_ARG(n >= 0 && n_edges >= 0, "bad argument");
   if (n == 0) return VIEO_OK;
   VIEO_ARG(pbs && cam && res && (n_edges == 0 || (Xw && obs && inv_sigma2 && flags && outlier && chi2)), "null argument");
+  VIEO_ARG(cam->model >= 0 && cam->model <= 2 && cam->num_k >= 0 && cam->num_k <= 6, "unsupported camera model");
   for (int k = 0; k < n; ++k) {
     VIEO_ARG(pbs[k].edge_begin >= 0 && pbs[k].edge_end >= pbs[k].edge_begin && pbs[k].edge_end <= n_edges, "edge range");
     if (pbs[k].edge_end - pbs[k].edge_begin > kPoMaxEdges) {

@@ -11,8 +11,10 @@ PREINT_DTYPE = np.dtype([("Rij", "f8", (3, 3)), ("vij", "f8", 3), ("pij", "f8", 
 NAVSTATE_DTYPE = np.dtype([("p", "f8", 3), ("q", "f8", 4), ("v", "f8", 3), ("bg", "f8", 3), ("ba", "f8", 3),
                            ("dbg", "f8", 3), ("dba", "f8", 3)])
 
-CAMERA_DTYPE = np.dtype([("fx", "f4"), ("fy", "f4"), ("cx", "f4"), ("cy", "f4"), ("bf", "f4"), ("pad_", "f4", 3),
-                         ("Rcb", "f8", (3, 3)), ("tcb", "f8", 3)])
+# model: 0 pinhole, 1 radtan (dist = k1..k_numk, p1, p2), 2 KB8 (dist = k1..k4)
+CAMERA_DTYPE = np.dtype([("fx", "f4"), ("fy", "f4"), ("cx", "f4"), ("cy", "f4"), ("bf", "f4"), ("model", "i4"),
+                         ("num_k", "i4"), ("pad_", "f4"), ("dist", "f4", 8), ("Rcb", "f8", (3, 3)), ("tcb", "f8", 3)])
+CAM_PINHOLE, CAM_RADTAN, CAM_KB8 = 0, 1, 2
 
 EDGE_STEREO, EDGE_CLOSE, EDGE_LEVEL1, EDGE_NOKERNEL = 1, 2, 4, 8
 
@@ -29,4 +31,4 @@ POSEOPT_RESULT_DTYPE = np.dtype([("cur", NAVSTATE_DTYPE), ("last", NAVSTATE_DTYP
 BA_RESULT_DTYPE = np.dtype([("err0", "f8"), ("err_end", "f8"), ("lambda_final", "f8"), ("iterations", "i4", 2),
                             ("accepted", "i4"), ("n_erase", "i4")])
 
-assert NAVSTATE_DTYPE.itemsize == 22 * 8 and CAMERA_DTYPE.itemsize == 32 + 96
+assert NAVSTATE_DTYPE.itemsize == 22 * 8 and CAMERA_DTYPE.itemsize == 64 + 96

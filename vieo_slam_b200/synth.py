@@ -46,7 +46,8 @@ def stereo_stream(n_frames, seed, w=752, h=480, max_disp=40, dark_every=0):
 # Synthetic visual-inertial sequences and BA problems: smooth 6-DoF trajectory,
 # 200 Hz IMU with EuRoC noise (Examples/Stereo/EuRoC/EuRoC_VIO.yaml:13-18), pinhole stereo observations
 # quantised to float like cv::KeyPoint.  All numpy, seeded.
-from .layouts import (CAMERA_DTYPE, EDGE_CLOSE, EDGE_STEREO, NAVSTATE_DTYPE, POSEOPT_PROBLEM_DTYPE)  # noqa: E402
+from .layouts import (CAM_KB8, CAM_RADTAN, CAMERA_DTYPE, EDGE_CLOSE, EDGE_STEREO, NAVSTATE_DTYPE,  # noqa: E402
+                      POSEOPT_PROBLEM_DTYPE)
 
 EUROC_IMU_SIGMA = (1.6968e-4, 2.0e-3, 1.9393e-5, 3.0e-3)
 # Camera.Tbc of EuRoC_VIO.yaml:24-28 (body <- camera)
@@ -109,6 +110,23 @@ def euroc_camera():
     Rcb = Tbc[:3, :3].T
     cam["Rcb"] = Rcb
     cam["tcb"] = -Rcb @ Tbc[:3, 3]
+    return cam
+
+
+def radtan_camera(k=(-0.28340811, 0.07395907), p=(0.00019359, 1.76187114e-05)):
+    """EuRoC cam0 with its raw radial-tangential distortion (Examples/Stereo/EuRoC/EuRoC_dist*.yaml style)."""
+    cam = euroc_camera()
+    cam["model"], cam["num_k"] = CAM_RADTAN, len(k)
+    cam["dist"][:len(k)] = k
+    cam["dist"][len(k):len(k) + 2] = p
+    return cam
+
+
+def kb8_camera(k=(0.0034823894, 0.0007150348, -0.0020532361, 0.00020293673)):
+    """Kannala-Brandt fisheye with TUM-VI-like coefficients (Examples/Stereo/TUM_VI/TUM_VI_512_VIO.yaml)."""
+    cam = euroc_camera()
+    cam["model"] = CAM_KB8
+    cam["dist"][:4] = k
     return cam
 
 
@@ -179,15 +197,37 @@ def perturb_state(ns, r, dp=0.01, drot=np.deg2rad(0.3), dv=0.02, dbg=1e-3, dba=1
     return out
 
 
+def distort(cam, x, y):
+    """Normalised image-plane coordinates of camera-frame directions (x, y, 1)·z through the camera's lens model
+    (pinhole: identity; radtan camera_radtan.h:61-129; KB8 camera_kb8.h:68-157); x, y are Pc.x/Pc.z, Pc.y/Pc.z."""
+    model = int(cam["model"])
+    if model == CAM_RADTAN:
+        nk = int(cam["num_k"])
+        k = cam["dist"][:nk].astype(np.float64); p = cam["dist"][nk:nk + 2].astype(np.float64)
+        r2 = x * x + y * y
+        fd = 1 + sum(k[i] * r2 ** (i + 1) for i in range(nk))
+        return (x * fd + 2 * p[0] * x * y + p[1] * (r2 + 2 * x * x), y * fd + 2 * p[1] * x * y + p[0] * (r2 + 2 * y * y))
+    if model == CAM_KB8:
+        k1, k2, k3, k4 = cam["dist"][:4].astype(np.float64)
+        r = np.sqrt(x * x + y * y)
+        th = np.arctan(r)
+        t2 = th * th
+        thd = th * (1 + t2 * (k1 + t2 * (k2 + t2 * (k3 + t2 * k4))))
+        s = np.where(r > 1e-5, thd / np.maximum(r, 1e-300), 1.0)
+        return x * s, y * s
+    return x, y
+
+
 def project(cam, ns, X):
-    """Pinhole stereo projection of world points X (n,3) through body state ns: (u, v, ur, z)."""
+    """Stereo projection of world points X (n,3) through body state ns and the camera's lens model: (u, v, ur, z)."""
     Rwb = R_from_quat(ns["q"])
     Rcw = cam["Rcb"] @ Rwb.T
     tcw = -Rcw @ ns["p"] + cam["tcb"]
     Pc = X @ Rcw.T + tcw
     z = Pc[:, 2]
-    u = cam["fx"] * Pc[:, 0] / z + cam["cx"]
-    v = cam["fy"] * Pc[:, 1] / z + cam["cy"]
+    xd, yd = distort(cam, Pc[:, 0] / z, Pc[:, 1] / z)
+    u = cam["fx"] * xd + cam["cx"]
+    v = cam["fy"] * yd + cam["cy"]
     return u, v, u - cam["bf"] / z, z
 
 
