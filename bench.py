@@ -35,7 +35,8 @@ FAST_BYTES_PER_IMAGE = LEVEL_PX + 700 * 4  # k_fast_cells: every level pixel onc
 
 def workload_name(frames):
     return (f"EuRoC MH05 stereo-VIO 1200 feats (configs[1]), synthetic 752x480 stereo + 200 Hz IMU, batches of {frames} frames: "
-            "ORBextractor x2 + ComputeStereoMatches + IMU pre-integration + 2x PoseOptimization (PVR) per frame, "
+            "ORBextractor x2 + ComputeStereoMatches + IMU pre-integration + 2x SearchByProjection (last frame, local map) "
+            "+ 2x PoseOptimization (PVR) per frame, "
             "LocalBundleAdjustmentNavStatePRV every 8th frame")
 
 
@@ -92,6 +93,7 @@ class ClockSampler:
 # and triggers one LocalBundleAdjustmentNavStatePRV window (N_local = 10, 20 fixed keyframes, 1500 points).
 LBA_EVERY = 8
 POSE_POINTS = (350, 550)
+SBP_QUERIES = (700, 1500)   # map points searched per frame: last frame's / local map's in view
 LBA_SHAPE = dict(n_local=10, n_fixed=20, n_points=1500)
 
 
@@ -118,7 +120,12 @@ def make_tracking_inputs(seed, F, preint_fn):
     pbs["edge_begin"][F:] += off
     pbs["edge_end"][F:] += off
     arrays = [np.concatenate([sets[0][i], sets[1][i]]) for i in range(1, 5)]
-    return dict(imu=imu_in, pbs=pbs, cam=cam, Xw=arrays[0], obs=arrays[1], w=arrays[2], flags=arrays[3], seq=seq)
+    # the two guided searches of every frame: TrackWithMotionModel (last frame's map points, th = 7 for stereo,
+    # src/Tracking.cc:292-297) and TrackLocalMap (local map points in view, th = 1, :2367)
+    sbp = [synth.make_sbp_problem(seed + 7, n_frames=F, mode=synth.SBP_LAST_FRAME, n_kp=1200, n_q=SBP_QUERIES[0], th=7.0),
+           synth.make_sbp_problem(seed + 8, n_frames=F, mode=synth.SBP_LOCAL_MAP, n_kp=1200, n_q=SBP_QUERIES[1], th=1.0,
+                                  blocked_frac=0.3)]
+    return dict(imu=imu_in, pbs=pbs, cam=cam, Xw=arrays[0], obs=arrays[1], w=arrays[2], flags=arrays[3], seq=seq, sbp=sbp)
 
 
 def make_lba_windows(seed, n, preint_fn):
@@ -190,6 +197,8 @@ def cpu_pipeline(images, trk, lbas, threads_like_reference=True, workers=None):
         k = f % F
         smp, seg, tt, bb = trk["imu"]
         O.imu_preintegrate(smp[seg[k]:seg[k + 1]], tt[k][0], tt[k][1], bb[k][:3], bb[k][3:], nz)
+        for pb in trk["sbp"]:
+            O.search_by_projection(pb, frames=[k])
         for j in (k, F + k):
             O.pose_optimization(trk["pbs"][j:j + 1], cam, trk["Xw"], trk["obs"], trk["w"], trk["flags"])
 
@@ -312,6 +321,22 @@ def run_gpu(args, rank, world, local_rank):
     d_res = torch.empty(n_pb * api.POSEOPT_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d_outl = torch.empty(n_edges, dtype=torch.uint8, device=dev)
     d_chi = torch.empty(n_edges, dtype=torch.float64, device=dev)
+    sbp_dev = []
+    for pb in trk["sbp"]:
+        d = {k: to_dev(v) for k, v in pb.items() if isinstance(v, np.ndarray)}
+        q = api.VieoSbpQueries()
+        for name in ("Xw", "level", "angle", "proj", "viewcos", "depth", "desc", "flags"):
+            setattr(q, name, d["q_" + name].data_ptr())
+        nk, nq = len(pb["kps"]), len(pb["q_level"])
+        out = [torch.empty(n, dtype=torch.int32, device=dev) for n in (nk, nq, nq, F)]
+        scr = torch.empty(api.lib().vieo_sbp_scratch_bytes(nq), dtype=torch.uint8, device=dev)
+        sbp_dev.append((int(pb["mode"]), d, q, out, scr))
+
+    def sbp_enqueue(stream):
+        for mode, d, q, out, scr in sbp_dev:
+            api.sbp_batch_dev(mode, d["frames"].data_ptr(), F, d["kps"].data_ptr(), d["uright"].data_ptr(), d["desc"].data_ptr(),
+                              q, d["kp_blocked"].data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                              out[3].data_ptr(), scr.data_ptr(), scr.numel(), stream)
     n_workers = max(1, min(args.lba_workers, n_lba)) if n_lba else 0
     bas = [api.BundleAdjuster(max_states=64, max_points=2048, max_edges=16384, max_imu=16, device=local_rank)
            for _ in range(n_workers)]
@@ -336,6 +361,7 @@ def run_gpu(args, rank, world, local_rank):
         s2 = side.cuda_stream
         pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(), d_bb.data_ptr(), F,
                                        d_pre.data_ptr(), s2)
+        sbp_enqueue(s2)
         api.Optimizer.pose_opt_batch_dev(d_pbs.data_ptr(), n_pb, d_cam.data_ptr(), d_Xw.data_ptr(), d_obs.data_ptr(),
                                          d_w.data_ptr(), d_fl.data_ptr(), d_res.data_ptr(), d_outl.data_ptr(),
                                          d_chi.data_ptr(), s2)
@@ -346,7 +372,7 @@ def run_gpu(args, rank, world, local_rank):
     for i in range(args.warmup):
         side.wait_stream(main)
         ba_launches = step(i)
-    launches_per_step = orb.last_launches() + 1 + 2 + ba_launches  # extractor + stereo match + (imu, pose opt) + LocalBA
+    launches_per_step = orb.last_launches() + 1 + 2 + 2 + ba_launches  # extractor + stereo match + (imu, pose opt) + 2 guided searches + LocalBA
     torch.cuda.synchronize()
     if dist_on:
         dist.barrier()
@@ -392,6 +418,7 @@ def run_gpu(args, rank, world, local_rank):
                                                                         d_fl.data_ptr(), d_res.data_ptr(), d_outl.data_ptr(),
                                                                         d_chi.data_ptr(), s)),
     }
+    iso["search_by_projection_x2"] = time_it(lambda: sbp_enqueue(s))
     if n_lba:
         t0 = time.perf_counter()
         for _ in range(3):
@@ -405,12 +432,16 @@ def run_gpu(args, rank, world, local_rank):
     outs = fe.alloc_outputs(F, pinned=True)
     host_np = host_t.numpy()
     trk_pool = ThreadPoolExecutor(1)
+    matcher = api.ORBmatcher(0.8, True, device=local_rank)
 
     def tracking_host():
         pre_gpu.preintegrate_batch(*trk["imu"])
+        nm = 0
+        for pb in trk["sbp"]:
+            nm += int(matcher.SearchByProjection(pb)[3][0])
         r = api.Optimizer.PoseOptimizationBatch(trk["pbs"], trk["cam"], trk["Xw"], trk["obs"], trk["w"], trk["flags"],
                                                 device=local_rank)
-        return int(r[0]["n_inliers"][0])
+        return int(r[0]["n_inliers"][0]) + nm
 
     def e2e_step(i):
         futs = [lba_pool.submit(lba_job, wk, wk) for wk in range(n_workers)]
@@ -437,8 +468,10 @@ def run_gpu(args, rank, world, local_rank):
     e2e_value = world * F * args.steps / float(t.item())
     lba_bytes = sum(int(np.asarray(v).nbytes) for v in lbas[0].values() if hasattr(v, "nbytes")) if lbas else 0
     trk_in = sum(int(np.asarray(a).nbytes) for a in trk["imu"]) + sum(int(trk[k].nbytes) for k in ("pbs", "Xw", "obs", "w", "flags"))
-    h2d = F * 2 * H * W + trk_in + n_lba * lba_bytes
-    d2h = (sum(int(o.nbytes) for o in outs) + 3 * F * cap * 4 + F * api.PREINT_DTYPE.itemsize + n_pb * api.POSEOPT_RESULT_DTYPE.itemsize
+    sbp_in = sum(int(v.nbytes) for pb in trk["sbp"] for v in pb.values() if isinstance(v, np.ndarray))
+    sbp_out = sum(4 * (len(pb["kps"]) + 2 * len(pb["q_level"]) + F) for pb in trk["sbp"])
+    h2d = F * 2 * H * W + trk_in + sbp_in + n_lba * lba_bytes
+    d2h = (sum(int(o.nbytes) for o in outs) + 3 * F * cap * 4 + sbp_out + F * api.PREINT_DTYPE.itemsize + n_pb * api.POSEOPT_RESULT_DTYPE.itemsize
            + 9 * n_edges + n_lba * (64 * 176 + 2048 * 24 + 16384 * 9))
 
     if rank != 0:
@@ -468,8 +501,8 @@ def run_gpu(args, rank, world, local_rank):
         "dtype": "u8+f64", "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_step_per_gpu": F, "image": f"{W}x{H}", "nfeatures": 1200,
                    "levels": 8, "cache": f"inputs rotate over {pool} batches ({pool * F * 2 * H * W / 1e6:.0f} MB > 126 MB L2)",
-                   "stages": ["orb_extract_x2", "stereo_matches_rectified", "imu_preint", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
-                   "pose_opt_points": list(POSE_POINTS), "lba_every": LBA_EVERY if n_lba else 0, "lba_window": LBA_SHAPE,
+                   "stages": ["orb_extract_x2", "stereo_matches_rectified", "imu_preint", "search_by_projection_x2", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
+                   "pose_opt_points": list(POSE_POINTS), "sbp_queries": list(SBP_QUERIES), "lba_every": LBA_EVERY if n_lba else 0, "lba_window": LBA_SHAPE,
                    "lba_workers": n_workers, "isolated_stage_ms": iso},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

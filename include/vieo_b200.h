@@ -280,6 +280,54 @@ int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_po
 int vieo_ba_last_launches(const vieo_ba_t* h);
 
 /* ------------------------------------------------------------------------------------------------
+ * Guided searches of the tracking thread: ORBmatcher::SearchByProjection(Frame&, const Frame& last, th, bMono, th_far)
+ * (src/ORBmatcher.cc:1303-1467, VIEO_SBP_LAST_FRAME) and ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>, th,
+ * th_far) (:230-335, VIEO_SBP_LOCAL_MAP), including FrameBase::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid /
+ * IsInImage (src/FrameBase.cpp:95-174), the stereo ur gate, the Hamming arg-min (best / second best with the same-level
+ * ratio test), the greedy one-keypoint-one-point rule (a keypoint taken by a map point with Observations() > 0 is
+ * skipped by later points, :1400-1401 / :289-291) and the rotation-histogram check (:1445-1464, ComputeThreeMaxima
+ * :1608-1641).  Single pinhole camera (usedistort_ == false).  A batch holds n_frames independent current frames. */
+#define VIEO_SBP_LAST_FRAME 0
+#define VIEO_SBP_LOCAL_MAP 1
+#define VIEO_SBP_MAX_KEYPOINTS 4096
+typedef struct VieoSbpFrame {
+  int32_t kp_begin, n_kp;       /* this frame's keypoints in the keypoint arrays (n_kp <= VIEO_SBP_MAX_KEYPOINTS) */
+  int32_t q_begin, n_q;         /* this frame's queries = map points in the reference's loop order */
+  float minx, maxx, miny, maxy; /* FrameBase::gridinfo_.minmax_xy_ */
+  float grid_winv, grid_hinv;   /* gridinfo_.fgrids_widthinv_ / fgrids_heightinv_ (64 x 48 cells) */
+  float bf, b;                  /* stereoinfo_.baseline_bf_[1] / [0] */
+  float fx, fy, cx, cy;         /* mpCameras[0]->toK() cast to float */
+  float th, th_far;             /* window factor; th_far_pts (<= 0: off) */
+  float nn_ratio;               /* mfNNratio (LOCAL_MAP) */
+  int32_t mono, check_orientation, n_levels; /* bMono, mbCheckOrientation (LAST_FRAME) */
+  float scale[16];              /* scalepyrinfo_.vscalefactor_ */
+  double qcw[4], tcw[3];        /* CurrentFrame.GetTcwCst(): unit quaternion (w, x, y, z), translation (LAST_FRAME) */
+  double qlw[4], tlw[3];        /* LastFrame.GetTcwCst() (LAST_FRAME) */
+} VieoSbpFrame;
+typedef struct VieoSbpQueries { /* arrays over all queries of the batch; unused ones may be null */
+  const double* Xw;       /* [n][3] LAST_FRAME: MapPoint::GetWorldPos() cast to double */
+  const int32_t* level;   /* LAST_FRAME: LastFrame.mvKeys[i].octave; LOCAL_MAP: vtrack_scalelevel_ */
+  const float* angle;     /* LAST_FRAME: LastFrame.mvKeys[i].angle */
+  const float* proj;      /* [n][3] LOCAL_MAP: vtrack_proj_ (u, v, ur) left by Frame::isInFrustum */
+  const float* viewcos;   /* LOCAL_MAP: vtrack_viewcos_ */
+  const float* depth;     /* LOCAL_MAP: track_depth_ */
+  const uint8_t* desc;    /* [n][32] MapPoint::GetDescriptor(), 16-byte aligned */
+  const uint8_t* flags;   /* bit 0: Observations() > 0 */
+} VieoSbpQueries;
+/* Outputs: kp_match[keypoint] = frame-relative query that owns the keypoint at the end (AddMapPoint), -1 = untouched or
+ * erased by the rotation check; q_match / q_dist [query] = frame-relative keypoint the query took and its distance
+ * (-1 / 256) before the rotation check; n_matches[frame] = the reference's return value.  kp_blocked (nullable):
+ * keypoints that already hold a map point with Observations() > 0 on entry. */
+size_t vieo_sbp_scratch_bytes(int n_queries_total);
+int vieo_sbp_batch_dev(int mode, const VieoSbpFrame* frames_dev, int n_frames, const VieoKeyPoint* kps_dev,
+                       const float* uright_dev, const uint8_t* desc_dev, const VieoSbpQueries* q_of_dev_pointers,
+                       const uint8_t* kp_blocked_dev, int32_t* kp_match_dev, int32_t* q_match_dev, int32_t* q_dist_dev,
+                       int32_t* n_matches_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const VieoKeyPoint* kps, const float* uright,
+                   const uint8_t* desc, const VieoSbpQueries* q, const uint8_t* kp_blocked, int32_t* kp_match,
+                   int32_t* q_match, int32_t* q_dist, int32_t* n_matches, int device);
+
+/* ------------------------------------------------------------------------------------------------
  * Stereo front-end over HOST buffers — the hot work of the Frame::Frame stereo constructor
  * (src/Frame.cc:218-316): ORBextractor::operator() for both cameras (:259-278) and the brute-force
  * left->right knnMatch(k=2) of ComputeStereoFishEyeMatches (:620-628), for a batch of frames, with the

@@ -71,3 +71,33 @@ int orc_imu_preintegrate(const double* smp, int n, double ti, double tj, const d
 #ifdef __cplusplus
 }
 #endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* Guided searches of ORBmatcher (sbp_oracle.cc).  One current frame per call. */
+typedef struct OrcSbpFrame {
+  int32_t kp_begin, n_kp;       /* this frame's keypoints in the keypoint arrays */
+  int32_t q_begin, n_q;         /* this frame's queries (map points in the reference's loop order) */
+  float minx, maxx, miny, maxy; /* FrameBase::gridinfo_.minmax_xy_ */
+  float grid_winv, grid_hinv;   /* fgrids_widthinv_ / fgrids_heightinv_ */
+  float bf, b;                  /* stereoinfo_.baseline_bf_[1] / [0] */
+  float fx, fy, cx, cy;         /* mpCameras[0]->toK() cast to float */
+  float th, th_far;             /* window factor; th_far_pts (<= 0: off) */
+  float nn_ratio;               /* mfNNratio */
+  int32_t mono, check_orientation, n_levels;
+  float scale[16];              /* scalepyrinfo_.vscalefactor_ */
+  double qcw[4], tcw[3];        /* CurrentFrame.GetTcwCst(): unit quaternion (w, x, y, z) and translation */
+  double qlw[4], tlw[3];        /* LastFrame.GetTcwCst() */
+} OrcSbpFrame;
+int orc_sbp_last_frame(const OrcSbpFrame* f, const OrcKeyPoint* kps, const float* uright, const uint8_t* desc,
+                       const double* q_Xw, const int32_t* q_octave, const float* q_angle, const uint8_t* q_desc,
+                       const uint8_t* q_flags, const uint8_t* kp_blocked, int32_t* kp_match, int32_t* q_match,
+                       int32_t* q_dist);
+int orc_sbp_local_map(const OrcSbpFrame* f, const OrcKeyPoint* kps, const float* uright, const uint8_t* desc,
+                      const float* q_proj, const int32_t* q_level, const float* q_viewcos, const float* q_depth,
+                      const uint8_t* q_desc, const uint8_t* q_flags, const uint8_t* kp_blocked, int32_t* kp_match,
+                      int32_t* q_match, int32_t* q_dist);
+#ifdef __cplusplus
+}
+#endif

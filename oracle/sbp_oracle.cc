@@ -1,0 +1,242 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orb_oracle.cc header).  CPU restatement of the tracking thread's guided
+// searches: ORBmatcher::SearchByProjection(Frame&, const Frame& last, ...) (src/ORBmatcher.cc:1303-1467) and
+// ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>, ...) (:230-335) on top of FrameBase::AssignFeaturesToGrid /
+// GetFeaturesInArea / PosInGrid / IsInImage (src/FrameBase.cpp:95-174).  Single pinhole camera (rectified stereo /
+// monocular, usedistort_ == false).  parity unpinned by reference tests (there are none); pinned by brute-force
+// restatements in tests/test_oracle_sbp.py.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "oracle.h"
+
+namespace {
+constexpr int kCols = 64, kRows = 48;  // FRAME_GRID_COLS / FRAME_GRID_ROWS (include/FrameBase.h:224-225)
+constexpr int TH_HIGH = 100, HISTO_LENGTH = 30;
+
+struct Grid {
+  std::vector<std::vector<int>> cells;  // [ix * kRows + iy]
+  // FrameBase::AssignFeaturesToGrid + PosInGrid (src/FrameBase.cpp:143-170)
+  Grid(const OrcSbpFrame& f, const OrcKeyPoint* kps) : cells(kCols * kRows) {
+    for (int i = 0; i < f.n_kp; ++i) {
+      const int px = (int)std::round((kps[i].x - f.minx) * f.grid_winv);
+      const int py = (int)std::round((kps[i].y - f.miny) * f.grid_hinv);
+      if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
+      cells[px * kRows + py].push_back(i);
+    }
+  }
+};
+
+// FrameBase::GetFeaturesInArea (src/FrameBase.cpp:95-142)
+void features_in_area(const OrcSbpFrame& f, const Grid& g, const OrcKeyPoint* kps, float x, float y, float r, int minlevel,
+                      int maxlevel, std::vector<int>& out) {
+  out.clear();
+  const int min_cellx = std::max(0, (int)std::floor((x - f.minx - r) * f.grid_winv));
+  if (min_cellx >= kCols) return;
+  const int max_cellx = std::min(kCols - 1, (int)std::ceil((x - f.minx + r) * f.grid_winv));
+  if (max_cellx < 0) return;
+  const int min_celly = std::max(0, (int)std::floor((y - f.miny - r) * f.grid_hinv));
+  if (min_celly >= kRows) return;
+  const int max_celly = std::min(kRows - 1, (int)std::ceil((y - f.miny + r) * f.grid_hinv));
+  if (max_celly < 0) return;
+  const bool bchecklevel = (minlevel > 0) || (maxlevel >= 0);
+  for (int ix = min_cellx; ix <= max_cellx; ++ix)
+    for (int iy = min_celly; iy <= max_celly; ++iy)
+      for (int j : g.cells[ix * kRows + iy]) {
+        const OrcKeyPoint& kp = kps[j];
+        if (bchecklevel) {
+          if (kp.octave < minlevel) continue;
+          if (maxlevel >= 0)
+            if (kp.octave > maxlevel) continue;
+        }
+        const float distx = kp.x - x, disty = kp.y - y;
+        if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(j);
+      }
+}
+
+// Eigen::Quaternion::_transformVector as used by Sophus::SO3 * point: v + w * (2 q x v) + q x (2 q x v)
+void qrot(const double q[4], const double v[3], double o[3]) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  double uv[3] = {y * v[2] - z * v[1], z * v[0] - x * v[2], x * v[1] - y * v[0]};
+  for (int i = 0; i < 3; ++i) uv[i] += uv[i];
+  const double c[3] = {y * uv[2] - z * uv[1], z * uv[0] - x * uv[2], x * uv[1] - y * uv[0]};
+  for (int i = 0; i < 3; ++i) o[i] = v[i] + w * uv[i] + c[i];
+}
+
+int descriptor_distance(const uint8_t* a, const uint8_t* b) { return orc_descriptor_distance(a, b); }
+
+// ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1608-1641)
+void three_maxima(const int* cnt, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = cnt[i];
+    if (s > max1) {
+      max3 = max2; max2 = max1; max1 = s;
+      ind3 = ind2; ind2 = ind1; ind1 = i;
+    } else if (s > max2) {
+      max3 = max2; max2 = s;
+      ind3 = ind2; ind2 = i;
+    } else if (s > max3) {
+      max3 = s; ind3 = i;
+    }
+  }
+  if ((float)max2 < 0.1f * (float)max1) {
+    ind2 = -1; ind3 = -1;
+  } else if ((float)max3 < 0.1f * (float)max1) {
+    ind3 = -1;
+  }
+}
+}  // namespace
+
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono, th_far_pts).  Queries = the last frame's keypoints that hold a
+// map point and are not outliers, in keypoint order (the host filters, :1325-1327).  q_flags bit 0: the map point has
+// Observations() > 0, so the keypoint it takes is skipped by later queries (:1400-1401).  kp_blocked (nullable): keypoints
+// that already hold such a map point on entry.  Outputs: kp_match[n_kp] = query that owns the keypoint at the end (-1
+// none / erased by the rotation check), q_match / q_dist = keypoint chosen by each query (-1 / 256 when none) before the
+// rotation check.  Returns nmatches.
+extern "C" int orc_sbp_last_frame(const OrcSbpFrame* f, const OrcKeyPoint* kps, const float* uright, const uint8_t* desc,
+                                  const double* q_Xw, const int32_t* q_octave, const float* q_angle, const uint8_t* q_desc,
+                                  const uint8_t* q_flags, const uint8_t* kp_blocked, int32_t* kp_match, int32_t* q_match,
+                                  int32_t* q_dist) {
+  int nmatches = 0;
+  Grid grid(*f, kps);
+  std::vector<uint8_t> blocked(f->n_kp, 0);
+  for (int i = 0; i < f->n_kp; ++i) {
+    kp_match[i] = -1;
+    if (kp_blocked) blocked[i] = kp_blocked[i];
+  }
+  std::vector<std::vector<int>> rotHist(HISTO_LENGTH);
+  const float factor = 1.0f / HISTO_LENGTH;
+  // Tlrcr = Tlrw * Tcrw^-1: translation = Rl * (-(Rc^-1 tc)) + tl
+  double tz;
+  {
+    const double qci[4] = {f->qcw[0], -f->qcw[1], -f->qcw[2], -f->qcw[3]};
+    double a[3], b3[3];
+    qrot(qci, f->tcw, a);
+    for (int i = 0; i < 3; ++i) a[i] = -a[i];
+    qrot(f->qlw, a, b3);
+    tz = b3[2] + f->tlw[2];
+  }
+  const bool bForward = tz > (double)f->b && !f->mono;
+  const bool bBackward = -tz > (double)f->b && !f->mono;
+  std::vector<int> cand;
+  for (int i = 0; i < f->n_q; ++i) {
+    q_match[i] = -1;
+    q_dist[i] = 256;
+    double x3Dr[3];
+    qrot(f->qcw, q_Xw + 3 * (size_t)i, x3Dr);
+    for (int k = 0; k < 3; ++k) x3Dr[k] += f->tcw[k];
+    if (f->th_far > 0 && x3Dr[2] > (double)f->th_far) continue;
+    const float xc = (float)x3Dr[0], yc = (float)x3Dr[1];
+    const float invzc = (float)(1.0 / x3Dr[2]);
+    if (invzc < 0) continue;
+    // K (float) * (xc invzc, yc invzc, 1): Eigen's 3-term dot evaluates (a0 b0 + a1 b1) + a2 b2
+    const float xn = xc * invzc, yn = yc * invzc;
+    const float u = (f->fx * xn + 0.f * yn) + f->cx * 1.f;
+    const float v = (0.f * xn + f->fy * yn) + f->cy * 1.f;
+    if (!(u >= f->minx && u < f->maxx && v >= f->miny && v < f->maxy)) continue;
+    const int nLastOctave = q_octave[i];
+    const float radius = f->th * f->scale[nLastOctave];
+    if (bForward) features_in_area(*f, grid, kps, u, v, radius, 0, nLastOctave, cand);
+    else if (bBackward) features_in_area(*f, grid, kps, u, v, radius, nLastOctave, -1, cand);
+    else features_in_area(*f, grid, kps, u, v, radius, nLastOctave - 1, nLastOctave + 1, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (blocked[i2]) continue;
+      if (uright[i2] > 0) {
+        const float ur = u - f->bf * invzc;
+        const float er = std::fabs(ur - uright[i2]);
+        if (er > radius) continue;
+      }
+      const int dist = descriptor_distance(q_desc + 32 * (size_t)i, desc + 32 * (size_t)i2);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx2 = i2;
+      }
+    }
+    if (bestDist <= TH_HIGH) {
+      kp_match[bestIdx2] = i;  // AddMapPoint
+      if (q_flags[i] & 1) blocked[bestIdx2] = 1;
+      q_match[i] = bestIdx2;
+      q_dist[i] = bestDist;
+      nmatches++;
+      if (f->check_orientation) {
+        float rot = q_angle[i] - kps[bestIdx2].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(bestIdx2);
+      }
+    }
+  }
+  if (f->check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1, cnt[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; ++i) cnt[i] = (int)rotHist[i].size();
+    three_maxima(cnt, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int k : rotHist[i]) {
+          kp_match[k] = -1;  // EraseMapPointMatch
+          nmatches--;
+        }
+  }
+  return nmatches;
+}
+
+// SearchByProjection(F, vpMapPoints, th, th_far_pts).  Queries = the local map points that are in view (btrack_inview_,
+// not bad; the host filters, :244-248) with the tracking info Frame::isInFrustum left: q_proj = (u, v, ur),
+// q_level = predicted scale level, q_viewcos, q_depth = track_depth_.
+extern "C" int orc_sbp_local_map(const OrcSbpFrame* f, const OrcKeyPoint* kps, const float* uright, const uint8_t* desc,
+                                 const float* q_proj, const int32_t* q_level, const float* q_viewcos, const float* q_depth,
+                                 const uint8_t* q_desc, const uint8_t* q_flags, const uint8_t* kp_blocked, int32_t* kp_match,
+                                 int32_t* q_match, int32_t* q_dist) {
+  int nmatches = 0;
+  Grid grid(*f, kps);
+  std::vector<uint8_t> blocked(f->n_kp, 0);
+  for (int i = 0; i < f->n_kp; ++i) {
+    kp_match[i] = -1;
+    if (kp_blocked) blocked[i] = kp_blocked[i];
+  }
+  const bool bFactor = f->th != 1.0;
+  std::vector<int> cand;
+  for (int i = 0; i < f->n_q; ++i) {
+    q_match[i] = -1;
+    q_dist[i] = 256;
+    if (f->th_far > 0 && q_depth[i] > f->th_far) continue;
+    const int nPredictedLevel = q_level[i];
+    float r = q_viewcos[i] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos (:337-342), float vs double literal compare
+    if (bFactor) r *= f->th;
+    const float rs = r * f->scale[nPredictedLevel];
+    features_in_area(*f, grid, kps, q_proj[3 * i], q_proj[3 * i + 1], rs, nPredictedLevel - 1, nPredictedLevel, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int idx : cand) {
+      if (blocked[idx]) continue;
+      if (uright[idx] > 0) {
+        const float er = std::fabs(q_proj[3 * i + 2] - uright[idx]);
+        if (er > rs) continue;
+      }
+      const int dist = descriptor_distance(q_desc + 32 * (size_t)i, desc + 32 * (size_t)idx);
+      if (dist < bestDist) {
+        bestDist2 = bestDist;
+        bestDist = dist;
+        bestLevel2 = bestLevel;
+        bestLevel = kps[idx].octave;
+        bestIdx = idx;
+      } else if (dist < bestDist2) {
+        bestLevel2 = kps[idx].octave;
+        bestDist2 = dist;
+      }
+    }
+    if (bestDist <= TH_HIGH) {
+      if (bestLevel == bestLevel2 && (float)bestDist > f->nn_ratio * (float)bestDist2) continue;
+      kp_match[bestIdx] = i;
+      if (q_flags[i] & 1) blocked[bestIdx] = 1;
+      q_match[i] = bestIdx;
+      q_dist[i] = bestDist;
+      nmatches++;
+    }
+  }
+  return nmatches;
+}

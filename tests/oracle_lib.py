@@ -360,3 +360,33 @@ def stereo_matches(orbL, kl, dl, orbR, kr, dr, bf, minZ):
     kept = L.orc_stereo_matches(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), pl, pr, _p(lw), _p(lh), _p(tb["scale"]),
                                 _p(tb["inv_scale"]), C.c_float(bf), C.c_float(minZ), _p(ur), _p(dp), _p(sad))
     return ur, dp, sad, kept
+
+
+# ---- guided searches (oracle/sbp_oracle.cc) ----------------------------------------------------------------------------
+def search_by_projection(pb, frames=None):
+    """Runs the oracle over every frame of a synth.make_sbp_problem batch -> (kp_match, q_match, q_dist, n_matches)."""
+    L = lib()
+    for name in ("orc_sbp_last_frame", "orc_sbp_local_map"):
+        getattr(L, name).argtypes = None
+        getattr(L, name).restype = C.c_int
+    fr = pb["frames"]
+    kp_match = np.full(len(pb["kps"]), -9, np.int32)
+    q_match = np.full(len(pb["q_level"]), -9, np.int32); q_dist = np.full(len(pb["q_level"]), -9, np.int32)
+    nm = np.zeros(len(fr), np.int32)
+    vp = C.c_void_p
+
+    def at(a, i):
+        a = pb[a]
+        return vp(a.ctypes.data + i * a.strides[0])
+    for f in (range(len(fr)) if frames is None else frames):
+        kb, qb = int(fr[f]["kp_begin"]), int(fr[f]["q_begin"])
+        blk = at("kp_blocked", kb) if pb.get("kp_blocked") is not None else None
+        outs = (vp(kp_match.ctypes.data + 4 * kb), vp(q_match.ctypes.data + 4 * qb), vp(q_dist.ctypes.data + 4 * qb))
+        fp = vp(fr.ctypes.data + f * fr.strides[0])
+        if pb["mode"] == 0:
+            nm[f] = L.orc_sbp_last_frame(fp, at("kps", kb), at("uright", kb), at("desc", kb), at("q_Xw", qb), at("q_level", qb),
+                                         at("q_angle", qb), at("q_desc", qb), at("q_flags", qb), blk, *outs)
+        else:
+            nm[f] = L.orc_sbp_local_map(fp, at("kps", kb), at("uright", kb), at("desc", kb), at("q_proj", qb), at("q_level", qb),
+                                        at("q_viewcos", qb), at("q_depth", qb), at("q_desc", qb), at("q_flags", qb), blk, *outs)
+    return kp_match, q_match, q_dist, nm

@@ -23,6 +23,10 @@ class VieoOrbConfig(C.Structure):
                 ("max_batch", C.c_int32)]
 
 
+class VieoSbpQueries(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("Xw", "level", "angle", "proj", "viewcos", "depth", "desc", "flags")]
+
+
 _lib = None
 
 
@@ -51,6 +55,10 @@ def lib():
         L.vieo_orb_profile_read.argtypes = [vp, vp, vp]
         L.vieo_hamming_knn2.argtypes = [vp, i32, vp, i32, vp, vp, i32]
         L.vieo_hamming_knn2_batch_dev.argtypes = [vp, sz, vp, i32, vp, sz, vp, i32, i32, i32, vp, vp, vp]
+        L.vieo_sbp_scratch_bytes.argtypes = [i32]
+        L.vieo_sbp_scratch_bytes.restype = sz
+        L.vieo_sbp_batch.argtypes = [i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.vieo_sbp_batch_dev.argtypes = [i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
         L.vieo_frontend_create.argtypes = [C.POINTER(VieoOrbConfig), i32, i32, C.POINTER(vp)]
         L.vieo_frontend_destroy.argtypes = [vp]
         L.vieo_frontend_destroy.restype = None
@@ -203,12 +211,53 @@ class ORBextractor:
         return out[:n].copy()
 
 
+def sbp_batch_dev(mode, frames_ptr, n_frames, kps_ptr, ur_ptr, desc_ptr, queries, blocked_ptr, kp_match_ptr, q_match_ptr,
+                  q_dist_ptr, n_matches_ptr, scratch_ptr, scratch_bytes, stream=0):
+    """vieo_sbp_batch_dev: device-resident guided searches; `queries` is a VieoSbpQueries of device pointers."""
+    _check(lib().vieo_sbp_batch_dev(mode, frames_ptr, n_frames, kps_ptr, ur_ptr, desc_ptr, C.byref(queries), blocked_ptr,
+                                    kp_match_ptr, q_match_ptr, q_dist_ptr, n_matches_ptr, scratch_ptr, scratch_bytes, stream))
+
+
 class ORBmatcher:
     """The Hamming kernels behind ORBmatcher / Frame stereo association (include/ORBmatcher.h:18-113)."""
     TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30  # src/ORBmatcher.cc:20-22
 
     def __init__(self, nnratio=0.6, checkOri=True, device=0):
         self.mfNNratio, self.mbCheckOrientation, self.device = nnratio, checkOri, device
+
+    def SearchByProjection(self, pb):
+        """Batched ORBmatcher::SearchByProjection (src/ORBmatcher.cc:1303-1467 when pb["mode"] == SBP_LAST_FRAME, :230-335
+        when SBP_LOCAL_MAP) over the frames of a problem dict (see synth.make_sbp_problem for the arrays).  The matcher's
+        mfNNratio / mbCheckOrientation are written into every frame record.
+        Returns (kp_match, q_match, q_dist, n_matches)."""
+        fr = np.ascontiguousarray(pb["frames"]).copy()
+        fr["nn_ratio"] = self.mfNNratio
+        fr["check_orientation"] = int(self.mbCheckOrientation)
+        keep = []
+
+        def arr(k, dt):
+            a = pb.get(k)
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dt)
+            keep.append(a)
+            return a
+        q = VieoSbpQueries()
+        for name, key, dt in (("Xw", "q_Xw", np.float64), ("level", "q_level", np.int32), ("angle", "q_angle", np.float32),
+                              ("proj", "q_proj", np.float32), ("viewcos", "q_viewcos", np.float32),
+                              ("depth", "q_depth", np.float32), ("desc", "q_desc", np.uint8), ("flags", "q_flags", np.uint8)):
+            a = arr(key, dt)
+            setattr(q, name, a.ctypes.data if a is not None and a.size else None)
+        kps, ur, desc = arr("kps", KP_DTYPE), arr("uright", np.float32), arr("desc", np.uint8)
+        blk = arr("kp_blocked", np.uint8)
+        nq = len(pb["q_level"])
+        kp_match = np.full(len(kps), -9, np.int32)
+        q_match = np.full(nq, -9, np.int32); q_dist = np.full(nq, -9, np.int32)
+        nm = np.zeros(len(fr), np.int32)
+        _check(lib().vieo_sbp_batch(int(pb["mode"]), _p(fr), len(fr), _p(kps), _p(ur), _p(desc), C.byref(q),
+                                    _p(blk) if blk is not None else None, _p(kp_match), _p(q_match), _p(q_dist), _p(nm),
+                                    self.device))
+        return kp_match, q_match, q_dist, nm
 
     def knnMatch2(self, q, t):
         """cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) -> (idx[nq,2], dist[nq,2])."""

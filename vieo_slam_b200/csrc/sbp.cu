@@ -1,0 +1,512 @@
+// Guided searches of the tracking thread on the device: ORBmatcher::SearchByProjection(Frame&, const Frame& last, ...)
+// (src/ORBmatcher.cc:1303-1467) and ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>, ...) (:230-335) with the
+// frame grid of src/FrameBase.cpp:95-174.
+//
+// The reference loop is sequential in the map points: a keypoint taken by an earlier point (with Observations() > 0) is
+// skipped by every later one.  Only that claim step is order dependent, so the work is split:
+//   phase A  (whole CTA, one CTA per frame)  AssignFeaturesToGrid: counting sort of the keypoints into the 64 x 48 cells,
+//            cell lists ordered by keypoint index like the reference's push_back order; lists live in shared memory.
+//   phase B  (16 warps, one query per warp at a time)  projection (LAST_FRAME), GetFeaturesInArea in the reference's
+//            candidate order (ix-major, iy, insertion order), level band, window and stereo-ur gates, 256-bit Hamming
+//            distance of every surviving candidate -> compact per-query list (dist << 16 | keypoint) in HBM scratch.
+//   phase C  (warp 0)  walks the queries in order: masks the candidates whose keypoint is already claimed (bitmap in
+//            shared memory), arg-min / second-min by warp redux on (dist, position) keys (strict '<' of the reference ==
+//            lexicographic order), acceptance tests, claim.  Lists longer than kListCap fall back to a re-enumeration.
+//            LAST_FRAME then applies the rotation-histogram check.
+// No atomics in anything that decides an index: results are bit-reproducible and equal the oracle's.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace vieo;
+
+namespace {
+
+constexpr int kCols = 64, kRows = 48, kCells = kCols * kRows;
+constexpr int kMaxKp = VIEO_SBP_MAX_KEYPOINTS;
+constexpr int kSbpWarps = 16;
+constexpr int kListCap = 64;  // candidates kept per query in scratch (two per lane in phase C)
+constexpr int TH_HIGH = 100, HISTO_LENGTH = 30;
+
+struct SbpShared {
+  uint16_t cell_start[kCells + 1];
+  uint16_t cell_items[kMaxKp];
+  uint32_t blocked[kMaxKp / 32];
+  int cnt[kCells];  // phase A counters (reused as scan input)
+  int total;
+  int hist[HISTO_LENGTH];
+};
+
+struct Cand {  // one query's search window
+  float x, y, r;
+  int minlevel, maxlevel;
+  float ur;  // predicted right coordinate for the stereo gate
+};
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint8_t* __restrict__ b) {
+  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(b)), b1 = __ldg(reinterpret_cast<const uint4*>(b) + 1);
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+         __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// Eigen::Quaternion::_transformVector (Sophus::SO3d * point): v + w (2 q x v) + q x (2 q x v)
+__device__ __forceinline__ void qrot(const double* q, const double* v, double* o) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  double uv0 = y * v[2] - z * v[1], uv1 = z * v[0] - x * v[2], uv2 = x * v[1] - y * v[0];
+  uv0 += uv0; uv1 += uv1; uv2 += uv2;
+  const double c0 = y * uv2 - z * uv1, c1 = z * uv0 - x * uv2, c2 = x * uv1 - y * uv0;
+  o[0] = v[0] + w * uv0 + c0;
+  o[1] = v[1] + w * uv1 + c1;
+  o[2] = v[2] + w * uv2 + c2;
+}
+
+// GetFeaturesInArea (src/FrameBase.cpp:95-142), warp-cooperative.  Lanes take the window's cells in the reference's
+// order (32 per pass); sink(pos, kp) is called for every candidate that passes the level / window / ur gates, pos = its
+// rank in the reference's candidate order.  Returns the number of candidates (warp-uniform).
+template <class Sink>
+__device__ __forceinline__ int enumerate(const VieoSbpFrame& F, const SbpShared& S, const VieoKeyPoint* __restrict__ kps,
+                                         const float* __restrict__ uright, const Cand& c, int lane, Sink&& sink) {
+  const int min_cellx = max(0, (int)floorf((c.x - F.minx - c.r) * F.grid_winv));
+  if (min_cellx >= kCols) return 0;
+  const int max_cellx = min(kCols - 1, (int)ceilf((c.x - F.minx + c.r) * F.grid_winv));
+  if (max_cellx < 0) return 0;
+  const int min_celly = max(0, (int)floorf((c.y - F.miny - c.r) * F.grid_hinv));
+  if (min_celly >= kRows) return 0;
+  const int max_celly = min(kRows - 1, (int)ceilf((c.y - F.miny + c.r) * F.grid_hinv));
+  if (max_celly < 0) return 0;
+  const bool bchecklevel = (c.minlevel > 0) || (c.maxlevel >= 0);
+  const int ny = max_celly - min_celly + 1, ncell = (max_cellx - min_cellx + 1) * ny;
+  if (ncell <= 0) return 0;
+  auto passes = [&](int j) {
+    const VieoKeyPoint kp = kps[j];
+    if (bchecklevel) {
+      if (kp.octave < c.minlevel) return false;
+      if (c.maxlevel >= 0 && kp.octave > c.maxlevel) return false;
+    }
+    const float distx = kp.x - c.x, disty = kp.y - c.y;
+    if (!(fabsf(distx) < c.r && fabsf(disty) < c.r)) return false;
+    const float urj = uright[j];
+    if (urj > 0) {
+      const float er = fabsf(c.ur - urj);
+      if (er > c.r) return false;
+    }
+    return true;
+  };
+  int base = 0;
+  for (int c0 = 0; c0 < ncell; c0 += 32) {
+    const int ci = c0 + lane;
+    int s = 0, e = 0;
+    if (ci < ncell) {
+      const int cell = (min_cellx + ci / ny) * kRows + min_celly + ci % ny;
+      s = S.cell_start[cell];
+      e = S.cell_start[cell + 1];
+    }
+    int n = 0;
+    for (int k = s; k < e; ++k) n += passes(S.cell_items[k]) ? 1 : 0;
+    const int incl = warp_incl_scan(n, lane);
+    int pos = base + incl - n;
+    if (n > 0)
+      for (int k = s; k < e; ++k) {
+        const int j = S.cell_items[k];
+        if (passes(j)) sink(pos++, j);
+      }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  return base;
+}
+
+struct QueryIn {
+  const double* Xw;
+  const int32_t* level;
+  const float* angle;
+  const float* proj;
+  const float* viewcos;
+  const float* depth;
+  const uint8_t* desc;
+  const uint8_t* flags;
+};
+
+// window of query q (frame-relative qi = q - F.q_begin); false: the query is skipped before the search
+__device__ __forceinline__ bool make_window(int mode, const VieoSbpFrame& F, const QueryIn& Q, int q, bool fwd, bool bwd,
+                                            Cand& c) {
+  if (mode == VIEO_SBP_LAST_FRAME) {
+    double x3Dr[3];
+    qrot(F.qcw, Q.Xw + 3 * (size_t)q, x3Dr);
+    x3Dr[0] += F.tcw[0]; x3Dr[1] += F.tcw[1]; x3Dr[2] += F.tcw[2];
+    if (F.th_far > 0 && x3Dr[2] > (double)F.th_far) return false;
+    const float xc = (float)x3Dr[0], yc = (float)x3Dr[1];
+    const float invzc = (float)(1.0 / x3Dr[2]);
+    if (invzc < 0) return false;
+    const float xn = __fmul_rn(xc, invzc), yn = __fmul_rn(yc, invzc);
+    const float u = __fadd_rn(__fmul_rn(F.fx, xn), F.cx), v = __fadd_rn(__fmul_rn(F.fy, yn), F.cy);
+    if (!(u >= F.minx && u < F.maxx && v >= F.miny && v < F.maxy)) return false;
+    const int oct = Q.level[q];
+    c.x = u; c.y = v;
+    c.r = __fmul_rn(F.th, F.scale[oct]);
+    if (fwd) { c.minlevel = 0; c.maxlevel = oct; }
+    else if (bwd) { c.minlevel = oct; c.maxlevel = -1; }
+    else { c.minlevel = oct - 1; c.maxlevel = oct + 1; }
+    c.ur = __fsub_rn(u, __fmul_rn(F.bf, invzc));
+    return true;
+  }
+  if (F.th_far > 0 && Q.depth[q] > F.th_far) return false;
+  const int lvl = Q.level[q];
+  float r = (double)Q.viewcos[q] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos (:337-342)
+  if ((double)F.th != 1.0) r = __fmul_rn(r, F.th);
+  c.x = Q.proj[3 * (size_t)q]; c.y = Q.proj[3 * (size_t)q + 1];
+  c.r = __fmul_rn(r, F.scale[lvl]);
+  c.minlevel = lvl - 1; c.maxlevel = lvl;
+  c.ur = Q.proj[3 * (size_t)q + 2];
+  return true;
+}
+
+__global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpFrame* __restrict__ frames,
+                                                        const VieoKeyPoint* __restrict__ kps_all,
+                                                        const float* __restrict__ ur_all, const uint8_t* __restrict__ desc_all,
+                                                        QueryIn Q, const uint8_t* __restrict__ kp_blocked,
+                                                        int32_t* __restrict__ kp_match, int32_t* __restrict__ q_match,
+                                                        int32_t* __restrict__ q_dist, int32_t* __restrict__ n_matches,
+                                                        uint32_t* __restrict__ lists, int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SbpShared& S = *reinterpret_cast<SbpShared*>(smem_raw);
+  __shared__ VieoSbpFrame F;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
+  for (int i = tid; i < (int)(sizeof(VieoSbpFrame) / 4); i += T)
+    reinterpret_cast<uint32_t*>(&F)[i] = reinterpret_cast<const uint32_t*>(frames + f)[i];
+  for (int i = tid; i < kCells; i += T) S.cnt[i] = 0;
+  __syncthreads();
+  const int N = F.n_kp, nq = F.n_q;
+  if (N > kMaxKp || N < 0 || nq < 0) {
+    if (tid == 0) n_matches[f] = -1;
+    return;
+  }
+  const VieoKeyPoint* kps = kps_all + F.kp_begin;
+  const float* uright = ur_all + F.kp_begin;
+  const uint8_t* desc = desc_all + 32 * (size_t)F.kp_begin;
+  int32_t* kpm = kp_match + F.kp_begin;
+  // ---- phase A: AssignFeaturesToGrid / PosInGrid (src/FrameBase.cpp:143-170) ------------------------------------------
+  for (int i = tid; i < N; i += T) {
+    kpm[i] = -1;
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, F.minx), F.grid_winv));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, F.miny), F.grid_hinv));
+    if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
+    atomicAdd(&S.cnt[px * kRows + py], 1);
+  }
+  for (int i = tid; i < kMaxKp / 32; i += T) {
+    uint32_t m = 0;
+    if (kp_blocked)
+      for (int b = 0; b < 32; ++b) {
+        const int k = 32 * i + b;
+        if (k < N && kp_blocked[F.kp_begin + k]) m |= 1u << b;
+      }
+    S.blocked[i] = m;
+  }
+  __syncthreads();
+  warp0_excl_scan(S.cnt, kCells, &S.total);
+  __syncthreads();
+  for (int i = tid; i < kCells; i += T) S.cell_start[i] = (uint16_t)S.cnt[i];
+  if (tid == 0) S.cell_start[kCells] = (uint16_t)S.total;
+  __syncthreads();
+  // fill (unordered inside a cell), then order every cell's few entries by keypoint index = push_back order
+  for (int i = tid; i < N; i += T) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, F.minx), F.grid_winv));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, F.miny), F.grid_hinv));
+    if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
+    const int slot = atomicAdd(&S.cnt[px * kRows + py], 1);
+    S.cell_items[slot] = (uint16_t)i;
+  }
+  __syncthreads();
+  for (int cidx = tid; cidx < kCells; cidx += T) {
+    const int s = S.cell_start[cidx], e = S.cell_start[cidx + 1];
+    for (int a = s + 1; a < e; ++a) {
+      const uint16_t v = S.cell_items[a];
+      int b = a - 1;
+      while (b >= s && S.cell_items[b] > v) {
+        S.cell_items[b + 1] = S.cell_items[b];
+        --b;
+      }
+      S.cell_items[b + 1] = v;
+    }
+  }
+  __syncthreads();
+  // ---- frame constants ------------------------------------------------------------------------------------------------
+  bool fwd = false, bwd = false;
+  if (mode == VIEO_SBP_LAST_FRAME) {
+    // Tlrcr = Tlrw * Tcrw^-1: translation = Rl (-(Rc^-1 tc)) + tl (:1314-1319)
+    const double qci[4] = {F.qcw[0], -F.qcw[1], -F.qcw[2], -F.qcw[3]};
+    double a[3], b3[3];
+    qrot(qci, F.tcw, a);
+    a[0] = -a[0]; a[1] = -a[1]; a[2] = -a[2];
+    qrot(F.qlw, a, b3);
+    const double tz = b3[2] + F.tlw[2];
+    fwd = tz > (double)F.b && !F.mono;
+    bwd = -tz > (double)F.b && !F.mono;
+  }
+  uint32_t* flist = lists + (size_t)F.q_begin * kListCap;
+  int32_t* fcnt = counts + F.q_begin;
+  // ---- phase B: candidate lists -----------------------------------------------------------------------------------------
+  for (int qi = warp; qi < nq; qi += kSbpWarps) {
+    const int q = F.q_begin + qi;
+    Cand c;
+    int n = 0;
+    if (make_window(mode, F, Q, q, fwd, bwd, c)) {
+      const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q));
+      const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q) + 1);
+      uint32_t* L = flist + (size_t)qi * kListCap;
+      n = enumerate(F, S, kps, uright, c, lane, [&](int pos, int j) {
+        if (pos < kListCap) L[pos] = ((uint32_t)hamming256(d0, d1, desc + 32 * (size_t)j) << 16) | (uint32_t)j;
+      });
+    } else {
+      n = -1;  // skipped before the search
+    }
+    if (lane == 0) fcnt[qi] = n;
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  // ---- phase C: the sequential claim pass ---------------------------------------------------------------------------------
+  int nmatches = 0;
+  const float factor = 1.0f / HISTO_LENGTH;
+  for (int qi = 0; qi < nq; ++qi) {
+    const int q = F.q_begin + qi;
+    const int n = fcnt[qi];
+    uint32_t best = 0xffffffffu, second = 0xffffffffu;  // lane-local two smallest keys (dist << 16 | pos)
+    int idx_a = -1, idx_b = -1;                          // keypoints of the lane's two entries
+    if (n > 0 && n <= kListCap) {
+      const uint32_t* L = flist + (size_t)qi * kListCap;
+      if (lane < n) {
+        const uint32_t e = L[lane];
+        idx_a = (int)(e & 0xffffu);
+        if (!((S.blocked[idx_a >> 5] >> (idx_a & 31)) & 1u)) best = (e & 0xffff0000u) | (uint32_t)lane;
+      }
+      if (lane + 32 < n) {
+        const uint32_t e = L[lane + 32];
+        idx_b = (int)(e & 0xffffu);
+        if (!((S.blocked[idx_b >> 5] >> (idx_b & 31)) & 1u)) second = (e & 0xffff0000u) | (uint32_t)(lane + 32);
+      }
+      if (second < best) {
+        const uint32_t t = best; best = second; second = t;
+        const int ti = idx_a; idx_a = idx_b; idx_b = ti;
+      }
+    } else if (n > kListCap) {
+      // overflow: re-enumerate with the claim filter (same order, same keys)
+      Cand c;
+      make_window(mode, F, Q, q, fwd, bwd, c);
+      const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q));
+      const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q) + 1);
+      enumerate(F, S, kps, uright, c, lane, [&](int pos, int j) {
+        if ((S.blocked[j >> 5] >> (j & 31)) & 1u) return;
+        const uint32_t key = ((uint32_t)hamming256(d0, d1, desc + 32 * (size_t)j) << 16) | (uint32_t)pos;
+        if (key < best) {
+          second = best; idx_b = idx_a;
+          best = key; idx_a = j;
+        } else if (key < second) {
+          second = key; idx_b = j;
+        }
+      });
+    }
+    int take = -1, take_dist = 256;
+    if (n > 0) {
+      const uint32_t m1 = __reduce_min_sync(0xffffffffu, best);
+      if (m1 != 0xffffffffu) {
+        const int bestDist = (int)(m1 >> 16);
+        const int bestIdx = __reduce_max_sync(0xffffffffu, best == m1 ? idx_a : -1);
+        if (bestDist <= TH_HIGH) {
+          bool ok = true;
+          if (mode == VIEO_SBP_LOCAL_MAP) {
+            const uint32_t c2 = best == m1 ? second : best;
+            const uint32_t m2 = __reduce_min_sync(0xffffffffu, c2);
+            if (m2 != 0xffffffffu) {
+              const int i2 = __reduce_max_sync(0xffffffffu, c2 == m2 ? (best == m1 ? idx_b : idx_a) : -1);
+              const int bestDist2 = (int)(m2 >> 16);
+              if (kps[bestIdx].octave == kps[i2].octave && (float)bestDist > __fmul_rn(F.nn_ratio, (float)bestDist2)) ok = false;
+            }
+          }
+          if (ok) {
+            take = bestIdx;
+            take_dist = bestDist;
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      q_match[q] = take;
+      q_dist[q] = take_dist;
+      int bin = -1;
+      if (take >= 0) {
+        kpm[take] = qi;
+        if (Q.flags[q] & 1) S.blocked[take >> 5] |= 1u << (take & 31);
+        if (mode == VIEO_SBP_LAST_FRAME && F.check_orientation) {
+          float rot = __fsub_rn(Q.angle[q], kps[take].angle);
+          if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+          bin = (int)roundf(__fmul_rn(rot, factor));
+          if (bin == HISTO_LENGTH) bin = 0;
+        }
+      }
+      fcnt[qi] = bin;  // reused: rotation bin of an accepted query (-1 none)
+    }
+    nmatches += take >= 0;
+    __syncwarp();
+  }
+  // ---- rotation consistency (:1445-1464) ---------------------------------------------------------------------------------
+  if (mode == VIEO_SBP_LAST_FRAME && F.check_orientation) {
+    int h = 0;  // lane b < 30 counts bin b
+    for (int qi = 0; qi < nq; ++qi) h += (fcnt[qi] == lane) ? 1 : 0;
+    if (lane < HISTO_LENGTH) S.hist[lane] = h;
+    __syncwarp();
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    {
+      int max1 = 0, max2 = 0, max3 = 0;
+      for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = S.hist[i];
+        if (s > max1) {
+          max3 = max2; max2 = max1; max1 = s;
+          ind3 = ind2; ind2 = ind1; ind1 = i;
+        } else if (s > max2) {
+          max3 = max2; max2 = s;
+          ind3 = ind2; ind2 = i;
+        } else if (s > max3) {
+          max3 = s; ind3 = i;
+        }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) {
+        ind2 = -1; ind3 = -1;
+      } else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) {
+        ind3 = -1;
+      }
+    }
+    int erased = 0;
+    for (int qi = lane; qi < nq; qi += 32) {
+      const int bin = fcnt[qi];
+      if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3) {
+        kpm[q_match[F.q_begin + qi]] = -1;  // EraseMapPointMatch
+        ++erased;
+      }
+    }
+    erased = __reduce_add_sync(0xffffffffu, erased);
+    nmatches -= erased;
+  }
+  if (lane == 0) n_matches[f] = nmatches;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t vieo_sbp_scratch_bytes(int n_queries_total) {
+  return (size_t)std::max(n_queries_total, 1) * (kListCap + 1) * 4;
+}
+
+int vieo_sbp_batch_dev(int mode, const VieoSbpFrame* frames_dev, int n_frames, const VieoKeyPoint* kps_dev,
+                       const float* uright_dev, const uint8_t* desc_dev, const VieoSbpQueries* q, const uint8_t* kp_blocked_dev,
+                       int32_t* kp_match_dev, int32_t* q_match_dev, int32_t* q_dist_dev, int32_t* n_matches_dev,
+                       void* scratch_dev, size_t scratch_bytes, void* stream) {
+  VIEO_ARG(mode == VIEO_SBP_LAST_FRAME || mode == VIEO_SBP_LOCAL_MAP, "bad mode");
+  VIEO_ARG(n_frames >= 0, "bad argument");
+  if (n_frames == 0) return VIEO_OK;
+  VIEO_ARG(frames_dev && kps_dev && uright_dev && desc_dev && q && kp_match_dev && q_match_dev && q_dist_dev && n_matches_dev &&
+               scratch_dev, "null argument");
+  VIEO_ARG(q->desc && q->flags && q->level, "null query array");
+  if (mode == VIEO_SBP_LAST_FRAME) VIEO_ARG(q->Xw && q->angle, "null query array");
+  else VIEO_ARG(q->proj && q->viewcos && q->depth, "null query array");
+  VIEO_ARG(((uintptr_t)desc_dev | (uintptr_t)q->desc) % 16 == 0, "descriptors must be 16-byte aligned");
+  VIEO_ARG(scratch_bytes >= (size_t)(kListCap + 1) * 4, "scratch too small");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VIEO_CK(cudaFuncSetAttribute(k_sbp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SbpShared)));
+    attr_set = true;
+  }
+  // scratch = [counts (n_q_total) | lists (n_q_total x kListCap)]; the caller sized it with vieo_sbp_scratch_bytes
+  const size_t nq_total = scratch_bytes / ((size_t)(kListCap + 1) * 4);
+  int32_t* counts = (int32_t*)scratch_dev;
+  uint32_t* lists = (uint32_t*)scratch_dev + nq_total;
+  QueryIn Q{q->Xw, q->level, q->angle, q->proj, q->viewcos, q->depth, q->desc, q->flags};
+  k_sbp<<<n_frames, kSbpWarps * 32, sizeof(SbpShared), (cudaStream_t)stream>>>(
+      mode, frames_dev, kps_dev, uright_dev, desc_dev, Q, kp_blocked_dev, kp_match_dev, q_match_dev, q_dist_dev, n_matches_dev,
+      lists, counts);
+  VIEO_CK(cudaGetLastError());
+  return VIEO_OK;
+}
+
+int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const VieoKeyPoint* kps, const float* uright,
+                   const uint8_t* desc, const VieoSbpQueries* q, const uint8_t* kp_blocked, int32_t* kp_match, int32_t* q_match,
+                   int32_t* q_dist, int32_t* n_matches, int device) {
+  VIEO_ARG(mode == VIEO_SBP_LAST_FRAME || mode == VIEO_SBP_LOCAL_MAP, "bad mode");
+  VIEO_ARG(n_frames >= 0, "bad argument");
+  if (n_frames == 0) return VIEO_OK;
+  VIEO_ARG(frames && q && n_matches, "null argument");
+  size_t nk = 0, nq = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    VIEO_ARG(frames[f].n_kp >= 0 && frames[f].n_q >= 0 && frames[f].kp_begin >= 0 && frames[f].q_begin >= 0, "bad frame range");
+    if (frames[f].n_kp > kMaxKp) {
+      set_error("vieo_sbp_batch: frame %d has %d keypoints (max %d)", f, frames[f].n_kp, kMaxKp);
+      return VIEO_E_CAPACITY;
+    }
+    VIEO_ARG(frames[f].n_levels >= 1 && frames[f].n_levels <= 16, "bad pyramid depth");
+    nk = std::max(nk, (size_t)frames[f].kp_begin + frames[f].n_kp);
+    nq = std::max(nq, (size_t)frames[f].q_begin + frames[f].n_q);
+  }
+  VIEO_ARG(nk == 0 || (kps && uright && desc && kp_match), "null keypoint array");
+  VIEO_ARG(nq == 0 || (q->desc && q->flags && q->level && q_match && q_dist), "null query array");
+  if (mode == VIEO_SBP_LAST_FRAME) VIEO_ARG(nq == 0 || (q->Xw && q->angle), "null query array");
+  else VIEO_ARG(nq == 0 || (q->proj && q->viewcos && q->depth), "null query array");
+  for (size_t i = 0; i < nq; ++i)
+    VIEO_ARG(q->level[i] >= 0 && q->level[i] < 16, "query level out of range");
+  int rc = use_device(device);
+  if (rc) return rc;
+  CallScratch* cs = call_scratch(device);
+  VIEO_ARG(cs, "no call scratch");
+  const size_t nk1 = std::max<size_t>(nk, 1), nq1 = std::max<size_t>(nq, 1);
+  // one staging buffer: every array 16-byte aligned
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) / 16 * 16; return o; };
+  const size_t o_fr = take(sizeof(VieoSbpFrame) * n_frames), o_kp = take(sizeof(VieoKeyPoint) * nk1), o_ur = take(4 * nk1),
+               o_de = take(32 * nk1), o_bl = take(nk1), o_xw = take(24 * nq1), o_lv = take(4 * nq1), o_an = take(4 * nq1),
+               o_pr = take(12 * nq1), o_vc = take(4 * nq1), o_dp = take(4 * nq1), o_qd = take(32 * nq1), o_fl = take(nq1);
+  const size_t in_bytes = off;
+  const size_t o_km = take(4 * nk1), o_qm = take(4 * nq1), o_qs = take(4 * nq1), o_nm = take(4 * (size_t)n_frames);
+  const size_t io_bytes = off;
+  const size_t sc_bytes = vieo_sbp_scratch_bytes((int)nq1);
+  uint8_t* dbuf = (uint8_t*)cs->get(0, io_bytes);
+  void* dsc = cs->get(1, sc_bytes);
+  uint8_t* hbuf = nullptr;
+  VIEO_ARG(dbuf && dsc, "device allocation failed");
+  VIEO_CK(cudaMallocHost((void**)&hbuf, io_bytes));
+  auto put = [&](size_t o, const void* src, size_t bytes) { if (src && bytes) memcpy(hbuf + o, src, bytes); };
+  put(o_fr, frames, sizeof(VieoSbpFrame) * n_frames);
+  put(o_kp, kps, sizeof(VieoKeyPoint) * nk); put(o_ur, uright, 4 * nk); put(o_de, desc, 32 * nk);
+  put(o_bl, kp_blocked, nk);
+  put(o_lv, q->level, 4 * nq); put(o_qd, q->desc, 32 * nq); put(o_fl, q->flags, nq);
+  if (mode == VIEO_SBP_LAST_FRAME) { put(o_xw, q->Xw, 24 * nq); put(o_an, q->angle, 4 * nq); }
+  else { put(o_pr, q->proj, 12 * nq); put(o_vc, q->viewcos, 4 * nq); put(o_dp, q->depth, 4 * nq); }
+  cudaError_t e = cudaMemcpyAsync(dbuf, hbuf, in_bytes, cudaMemcpyHostToDevice, cs->st);
+  if (e == cudaSuccess) {
+    VieoSbpQueries dq{};
+    dq.Xw = (const double*)(dbuf + o_xw); dq.level = (const int32_t*)(dbuf + o_lv); dq.angle = (const float*)(dbuf + o_an);
+    dq.proj = (const float*)(dbuf + o_pr); dq.viewcos = (const float*)(dbuf + o_vc); dq.depth = (const float*)(dbuf + o_dp);
+    dq.desc = dbuf + o_qd; dq.flags = dbuf + o_fl;
+    rc = vieo_sbp_batch_dev(mode, (const VieoSbpFrame*)(dbuf + o_fr), n_frames, (const VieoKeyPoint*)(dbuf + o_kp),
+                            (const float*)(dbuf + o_ur), dbuf + o_de, &dq, kp_blocked ? dbuf + o_bl : nullptr,
+                            (int32_t*)(dbuf + o_km), (int32_t*)(dbuf + o_qm), (int32_t*)(dbuf + o_qs), (int32_t*)(dbuf + o_nm),
+                            dsc, sc_bytes, cs->st);
+    if (rc == VIEO_OK) {
+      e = cudaMemcpyAsync(hbuf + o_km, dbuf + o_km, io_bytes - o_km, cudaMemcpyDeviceToHost, cs->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(cs->st);
+    }
+  }
+  if (e == cudaSuccess && rc == VIEO_OK) {
+    if (nk) memcpy(kp_match, hbuf + o_km, 4 * nk);
+    if (nq) { memcpy(q_match, hbuf + o_qm, 4 * nq); memcpy(q_dist, hbuf + o_qs, 4 * nq); }
+    memcpy(n_matches, hbuf + o_nm, 4 * (size_t)n_frames);
+  }
+  cudaFreeHost(hbuf);
+  if (e != cudaSuccess) {
+    set_error("vieo_sbp_batch: %s", cudaGetErrorString(e));
+    return VIEO_E_CUDA;
+  }
+  return rc;
+}
+
+}  // extern "C"

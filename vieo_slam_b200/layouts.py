@@ -31,4 +31,13 @@ POSEOPT_RESULT_DTYPE = np.dtype([("cur", NAVSTATE_DTYPE), ("last", NAVSTATE_DTYP
 BA_RESULT_DTYPE = np.dtype([("err0", "f8"), ("err_end", "f8"), ("lambda_final", "f8"), ("iterations", "i4", 2),
                             ("accepted", "i4"), ("n_erase", "i4")])
 
+# VieoSbpFrame (include/vieo_b200.h): one current frame of a guided-search batch
+SBP_FRAME_DTYPE = np.dtype([("kp_begin", "i4"), ("n_kp", "i4"), ("q_begin", "i4"), ("n_q", "i4"), ("minx", "f4"), ("maxx", "f4"),
+                            ("miny", "f4"), ("maxy", "f4"), ("grid_winv", "f4"), ("grid_hinv", "f4"), ("bf", "f4"), ("b", "f4"),
+                            ("fx", "f4"), ("fy", "f4"), ("cx", "f4"), ("cy", "f4"), ("th", "f4"), ("th_far", "f4"),
+                            ("nn_ratio", "f4"), ("mono", "i4"), ("check_orientation", "i4"), ("n_levels", "i4"),
+                            ("scale", "f4", 16), ("qcw", "f8", 4), ("tcw", "f8", 3), ("qlw", "f8", 4), ("tlw", "f8", 3)])
+SBP_LAST_FRAME, SBP_LOCAL_MAP = 0, 1
+
+assert SBP_FRAME_DTYPE.itemsize == 88 + 64 + 112
 assert NAVSTATE_DTYPE.itemsize == 22 * 8 and CAMERA_DTYPE.itemsize == 64 + 96

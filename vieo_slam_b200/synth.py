@@ -363,3 +363,102 @@ def make_lba_problem(seq, preints_kf, kf_idx, cam, n_local=10, n_fixed=20, n_poi
                 edge_flags=np.asarray(ef, np.uint8), imu_i=np.asarray(imu_i, np.int32), imu_j=np.asarray(imu_j, np.int32),
                 preint=np.asarray(pre), imu_dt_kf=np.asarray(dtk, np.float64), gw=GRAVITY_W.copy(),
                 inv_sigma_bg2=1.0 / EUROC_IMU_SIGMA[2] ** 2, inv_sigma_ba2=1.0 / EUROC_IMU_SIGMA[3] ** 2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Guided-search problems: current frames with ~1200 keypoints on the 64 x 48 frame grid and the
+# map points of the last frame / the local map that project onto them.  Descriptors are random 256-bit strings; a true
+# match is its keypoint's descriptor with a few flipped bits, so Hamming arg-mins, ties and the one-keypoint-one-point
+# rule are all exercised.
+from .layouts import KP_DTYPE, SBP_FRAME_DTYPE, SBP_LAST_FRAME, SBP_LOCAL_MAP  # noqa: E402
+
+
+def _flip_bits(d, nflip, r):
+    out = d.copy()
+    for i in range(len(out)):
+        bits = r.choice(256, int(nflip[i]), replace=False)
+        for b in bits:
+            out[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return out
+
+
+def make_sbp_problem(seed, n_frames=2, mode=SBP_LAST_FRAME, n_kp=1200, n_q=700, th=15.0, motion="still", cluster=False,
+                     th_far=0.0, mono=False, blocked_frac=0.0):
+    """Batch of guided-search problems.  Returns dict(frames[SBP_FRAME_DTYPE], kps, uright, desc, q_* arrays, kp_blocked)."""
+    r = np.random.default_rng(seed)
+    cam = euroc_camera()
+    fx, fy, cx, cy, bf = (np.float32(EUROC[k]) for k in ("fx", "fy", "cx", "cy", "bf"))
+    W, H = EUROC["w"], EUROC["h"]
+    _, scl = inv_level_sigma2()
+    quota = np.array([261, 217, 181, 151, 126, 105, 87, 72], np.float64)
+    seq = vio_sequence(seed + 1, n_frames + 1, noisy_imu=False)
+    frames = np.zeros(n_frames, SBP_FRAME_DTYPE)
+    kps, urs, descs, blocked = [], [], [], []
+    qs = dict(Xw=[], level=[], angle=[], proj=[], viewcos=[], depth=[], desc=[], flags=[])
+    kb = qb = 0
+    for f in range(n_frames):
+        ns = seq["truth"][f + 1]
+        Rwb = R_from_quat(ns["q"])
+        Rcw = cam["Rcb"] @ Rwb.T
+        tcw = -Rcw @ ns["p"] + cam["tcb"]
+        nsl = seq["truth"][f]
+        Rlw = cam["Rcb"] @ R_from_quat(nsl["q"]).T
+        tlw = -Rlw @ nsl["p"] + cam["tcb"]
+        if motion == "forward":    # Tlrcr translation z = +0.5 m > baseline
+            tlw = Rlw @ Rcw.T @ tcw + np.array([0, 0, 0.5])
+        elif motion == "backward":
+            tlw = Rlw @ Rcw.T @ tcw - np.array([0, 0, 0.5])
+        else:
+            tlw = Rlw @ Rcw.T @ tcw   # same camera centre: neither forward nor backward
+        n = n_kp + int(r.integers(-40, 40))
+        kp = np.zeros(n, KP_DTYPE)
+        if cluster:
+            kp["x"] = r.uniform(300, 380, n).astype(np.float32); kp["y"] = r.uniform(200, 260, n).astype(np.float32)
+        else:
+            kp["x"] = r.uniform(16, W - 16, n).astype(np.float32); kp["y"] = r.uniform(16, H - 16, n).astype(np.float32)
+        kp["octave"] = r.choice(8, n, p=quota / quota.sum())
+        kp["angle"] = r.uniform(0, 360, n).astype(np.float32)
+        z = r.uniform(0.8, 12.0, n)
+        ur = (kp["x"] - bf / z.astype(np.float32)).astype(np.float32)
+        ur[r.random(n) > 0.7] = -1.0
+        d = r.integers(0, 256, (n, 32), dtype=np.uint8)
+        # queries: true matches, duplicates of true matches, strays
+        m_true = min(int(0.8 * n_q), n)
+        src = np.concatenate([r.choice(n, m_true, replace=False), r.choice(n, n_q - m_true, replace=True)])
+        r.shuffle(src)
+        stray = r.random(n_q) < 0.12
+        u = kp["x"][src].astype(np.float64) + r.normal(0, 1.5, n_q)
+        v = kp["y"][src].astype(np.float64) + r.normal(0, 1.5, n_q)
+        u[stray] = r.uniform(-40, W + 40, int(stray.sum())); v[stray] = r.uniform(-40, H + 40, int(stray.sum()))
+        zq = z[src] * r.uniform(0.97, 1.03, n_q)
+        zq[r.random(n_q) < 0.02] *= -1.0    # behind the camera
+        Pc = np.stack([(u - cx) / fx * zq, (v - cy) / fy * zq, zq], 1)
+        Xw = ((Pc - tcw) @ Rcw).astype(np.float32).astype(np.float64)   # MapPoint positions are float
+        qd = _flip_bits(d[src], np.where(stray, 128, r.integers(0, 70, n_q)), r)
+        lvl = np.clip(kp["octave"][src] + r.integers(-1, 2, n_q), 0, 7).astype(np.int32)
+        ang = (kp["angle"][src] + r.normal(0, 4, n_q) + np.where(r.random(n_q) < 0.15, r.uniform(0, 360, n_q), 0)) % 360
+        qs["Xw"].append(Xw); qs["level"].append(lvl); qs["angle"].append(ang.astype(np.float32))
+        uq = (u + r.normal(0, 0.5, n_q)).astype(np.float32); vq = (v + r.normal(0, 0.5, n_q)).astype(np.float32)
+        qs["proj"].append(np.stack([uq, vq, (uq - bf / np.abs(zq).astype(np.float32)).astype(np.float32)], 1))
+        qs["viewcos"].append(r.uniform(0.9, 1.0, n_q).astype(np.float32))
+        qs["depth"].append(np.abs(zq).astype(np.float32))
+        qs["desc"].append(qd); qs["flags"].append((r.random(n_q) < 0.9).astype(np.uint8))
+        kps.append(kp); urs.append(ur); descs.append(d)
+        blocked.append((r.random(n) < blocked_frac).astype(np.uint8))
+        F = frames[f]
+        F["kp_begin"], F["n_kp"], F["q_begin"], F["n_q"] = kb, n, qb, n_q
+        F["minx"], F["maxx"], F["miny"], F["maxy"] = 0.0, W, 0.0, H
+        F["grid_winv"] = np.float32(64) / (np.float32(W) - np.float32(0)); F["grid_hinv"] = np.float32(48) / (np.float32(H) - np.float32(0))
+        F["bf"], F["b"] = bf, bf / fx
+        F["fx"], F["fy"], F["cx"], F["cy"] = fx, fy, cx, cy
+        F["th"], F["th_far"], F["nn_ratio"] = th, th_far, 0.8
+        F["mono"], F["check_orientation"], F["n_levels"] = int(mono), 1, 8
+        F["scale"][:8] = scl
+        F["qcw"], F["tcw"] = quat_from_R(Rcw), tcw
+        F["qlw"], F["tlw"] = quat_from_R(Rlw), tlw
+        kb += n; qb += n_q
+    out = dict(frames=frames, kps=np.concatenate(kps), uright=np.concatenate(urs), desc=np.concatenate(descs),
+               kp_blocked=np.concatenate(blocked), mode=mode)
+    for k, v_ in qs.items():
+        out["q_" + k] = np.ascontiguousarray(np.concatenate(v_))
+    return out
