@@ -370,8 +370,8 @@ def search_by_projection(pb, frames=None):
         getattr(L, name).argtypes = None
         getattr(L, name).restype = C.c_int
     fr = pb["frames"]
-    kp_match = np.full(len(pb["kps"]), -9, np.int32)
-    q_match = np.full(len(pb["q_level"]), -9, np.int32); q_dist = np.full(len(pb["q_level"]), -9, np.int32)
+    kp_match = np.full(len(pb["kps"]), -1, np.int32)   # entries outside every frame's range stay -1
+    q_match = np.full(len(pb["q_level"]), -1, np.int32); q_dist = np.full(len(pb["q_level"]), -1, np.int32)
     nm = np.zeros(len(fr), np.int32)
     vp = C.c_void_p
 

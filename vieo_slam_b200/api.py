@@ -251,8 +251,8 @@ class ORBmatcher:
         kps, ur, desc = arr("kps", KP_DTYPE), arr("uright", np.float32), arr("desc", np.uint8)
         blk = arr("kp_blocked", np.uint8)
         nq = len(pb["q_level"])
-        kp_match = np.full(len(kps), -9, np.int32)
-        q_match = np.full(nq, -9, np.int32); q_dist = np.full(nq, -9, np.int32)
+        kp_match = np.full(len(kps), -1, np.int32)   # entries outside every frame's range stay -1
+        q_match = np.full(nq, -1, np.int32); q_dist = np.full(nq, -1, np.int32)
         nm = np.zeros(len(fr), np.int32)
         _check(lib().vieo_sbp_batch(int(pb["mode"]), _p(fr), len(fr), _p(kps), _p(ur), _p(desc), C.byref(q),
                                     _p(blk) if blk is not None else None, _p(kp_match), _p(q_match), _p(q_dist), _p(nm),

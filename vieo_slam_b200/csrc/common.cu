@@ -72,6 +72,21 @@ void* CallScratch::get(int slot, size_t bytes) {
   return buf[slot];
 }
 
+void* CallScratch::get_pinned(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  if (hcap >= bytes) return hbuf;
+  if (hbuf) cudaFreeHost(hbuf);
+  hbuf = nullptr;
+  hcap = 0;
+  const size_t want = bytes + bytes / 2;
+  if (cudaMallocHost(&hbuf, want) != cudaSuccess) {
+    set_error("out of pinned host memory (%zu bytes of call staging)", want);
+    return nullptr;
+  }
+  hcap = want;
+  return hbuf;
+}
+
 CallScratch* call_scratch(int device) {
   static thread_local CallScratch pool[16];
   if (device < 0 || device >= 16) return nullptr;

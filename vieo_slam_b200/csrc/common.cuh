@@ -40,6 +40,11 @@ struct CallScratch {
   void* buf[12] = {};
   size_t cap[12] = {};
   void* get(int slot, size_t bytes);
+  // pinned host staging (grows on demand, reused): cudaMallocHost / cudaFreeHost per call would cost milliseconds and
+  // cudaFreeHost synchronises the whole device
+  void* hbuf = nullptr;
+  size_t hcap = 0;
+  void* get_pinned(size_t bytes);
 };
 CallScratch* call_scratch(int device);
 

@@ -471,9 +471,8 @@ int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const Vie
   const size_t sc_bytes = vieo_sbp_scratch_bytes((int)nq1);
   uint8_t* dbuf = (uint8_t*)cs->get(0, io_bytes);
   void* dsc = cs->get(1, sc_bytes);
-  uint8_t* hbuf = nullptr;
-  VIEO_ARG(dbuf && dsc, "device allocation failed");
-  VIEO_CK(cudaMallocHost((void**)&hbuf, io_bytes));
+  uint8_t* hbuf = (uint8_t*)cs->get_pinned(io_bytes);
+  VIEO_ARG(dbuf && dsc && hbuf, "staging allocation failed");
   auto put = [&](size_t o, const void* src, size_t bytes) { if (src && bytes) memcpy(hbuf + o, src, bytes); };
   put(o_fr, frames, sizeof(VieoSbpFrame) * n_frames);
   put(o_kp, kps, sizeof(VieoKeyPoint) * nk); put(o_ur, uright, 4 * nk); put(o_de, desc, 32 * nk);
@@ -482,6 +481,8 @@ int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const Vie
   if (mode == VIEO_SBP_LAST_FRAME) { put(o_xw, q->Xw, 24 * nq); put(o_an, q->angle, 4 * nq); }
   else { put(o_pr, q->proj, 12 * nq); put(o_vc, q->viewcos, 4 * nq); put(o_dp, q->depth, 4 * nq); }
   cudaError_t e = cudaMemcpyAsync(dbuf, hbuf, in_bytes, cudaMemcpyHostToDevice, cs->st);
+  // keypoints / queries outside every frame's range read back as -1
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_km, 0xff, o_nm - o_km, cs->st);
   if (e == cudaSuccess) {
     VieoSbpQueries dq{};
     dq.Xw = (const double*)(dbuf + o_xw); dq.level = (const int32_t*)(dbuf + o_lv); dq.angle = (const float*)(dbuf + o_an);
@@ -501,7 +502,6 @@ int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const Vie
     if (nq) { memcpy(q_match, hbuf + o_qm, 4 * nq); memcpy(q_dist, hbuf + o_qs, 4 * nq); }
     memcpy(n_matches, hbuf + o_nm, 4 * (size_t)n_frames);
   }
-  cudaFreeHost(hbuf);
   if (e != cudaSuccess) {
     set_error("vieo_sbp_batch: %s", cudaGetErrorString(e));
     return VIEO_E_CUDA;
