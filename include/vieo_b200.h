@@ -242,7 +242,7 @@ typedef struct VieoBaProblem {
   int32_t large;       /* bLarge */
   int32_t rec_init;    /* bRecInit */
   int32_t visual_only; /* Optimizer::LocalBundleAdjustment: PR vertices only, no inertial edges */
-  int32_t pad_;
+  int32_t global_ba;   /* 0; vieo_global_ba_prv sets bit 0 (graph of GlobalBundleAdjustmentNavStatePRV) and bit 1 = bRobust */
 } VieoBaProblem;
 typedef struct VieoBaResult {
   double err0, err_end; /* activeRobustChi2 before / after (src/Optimizer.cc:539, 652), rounded to float like the reference */

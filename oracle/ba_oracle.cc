@@ -1145,18 +1145,21 @@ bool build_lba_graph(const OrcBaProblem* pb, const OrcCamera* cam, Graph& g, int
   }
   if (!anyfree) return false;
   const float thHuberPRV = (float)std::sqrt(16.919), thHuberBias = (float)std::sqrt(12.592);
+  // GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:903-983): information x 1e-2 where the previous keyframe's BIAS
+  // vertex is fixed, kernels on every inertial edge iff bRobust; the local BA keys both on a fixed previous keyframe
+  const bool global = pb->global_ba & 1, g_robust = pb->global_ba & 2;
+  if (global) g.user_lambda = 0;
   for (int m = 0; m < (pb->visual_only ? 0 : pb->n_imu); ++m) {
     const int i = pb->imu_i[m], j = pb->imu_j[m];
-    const bool bfixedkf = g.fix0[i];
+    const bool bfixedkf = global ? (!g.has_vb[i] || g.fix_vb[i]) : (bool)g.fix0[i];
+    const bool kernel = global ? g_robust : (bfixedkf || pb->rec_init);
     const OrcImuPreint& pre = pb->preint[m];
     if (pre.dt != 0) {
       DenseEdge e;
       e.type = 0; e.si = i; e.sj = j; e.pre = &pre; e.D = 9;
       e.info = info_from_sigma(pre.SigmaPRV);
-      if (bfixedkf || pb->rec_init) {
-        if (bfixedkf) for (double& v : e.info) v *= 1e-2;
-        e.rk.set((double)thHuberPRV);
-      }
+      if (bfixedkf) for (double& v : e.info) v *= 1e-2;
+      if (kernel) e.rk.set((double)thHuberPRV);
       g.den.push_back(e);
     }
     DenseEdge e;
@@ -1168,13 +1171,14 @@ bool build_lba_graph(const OrcBaProblem* pb, const OrcCamera* cam, Graph& g, int
       const double w = (k < 3 ? pb->inv_sigma_bg2 : pb->inv_sigma_ba2) / dtij;
       e.info[7 * k] = bfixedkf ? w * 1e-2 : w;
     }
-    if (bfixedkf || pb->rec_init) e.rk.set((double)thHuberBias);
+    if (kernel) e.rk.set((double)thHuberBias);
     g.den.push_back(e);
   }
   g.X.assign(pb->points, pb->points + (size_t)3 * P);
   const float chi2Mono = 5.991f;
   // src/Optimizer.cc:361-362 (PRV: sqrt of the float 5.991f) vs :2069-2070 (visual LocalBundleAdjustment: sqrt(5.991))
-  const float thHuberMono = pb->visual_only ? (float)std::sqrt(5.991) : std::sqrt(chi2Mono);
+  // global BA: thHuber2D = sqrt(5.99) (:1042)
+  const float thHuberMono = global ? (float)std::sqrt(5.99) : pb->visual_only ? (float)std::sqrt(5.991) : std::sqrt(chi2Mono);
   const float thHuberStereo = (float)std::sqrt(7.815);
   g.vis.resize(E);
   for (int i = 0; i < E; ++i) {
@@ -1185,12 +1189,44 @@ bool build_lba_graph(const OrcBaProblem* pb, const OrcCamera* cam, Graph& g, int
     e.stereo = pb->edge_flags[i] & ORC_EDGE_STEREO;
     e.close = pb->edge_flags[i] & ORC_EDGE_CLOSE;
     e.level = (pb->edge_flags[i] & ORC_EDGE_LEVEL1) ? 1 : 0;
-    if (!(pb->edge_flags[i] & ORC_EDGE_NOKERNEL)) e.rk.set(e.stereo ? (double)thHuberStereo : (double)thHuberMono);
+    if (!(pb->edge_flags[i] & ORC_EDGE_NOKERNEL) && !(global && !g_robust))
+      e.rk.set(e.stereo ? (double)thHuberStereo : (double)thHuberMono);
   }
   return true;
 }
 }  // namespace
 extern "C" {
+
+// Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342) with bScaleOpt = false and no IMU initiator:
+// one optimize(nIterations) from g2o's own initial lambda (1e-5 max diag), no level classification.
+int orc_global_ba_prv(const OrcBaProblem* pb_in, const OrcCamera* cam, int n_iterations, int robust, OrcNavState* states_out,
+                      double* points_out, double* edge_chi2, OrcBaResult* res) {
+  const int K = pb_in->n_states, P = pb_in->n_points, E = pb_in->n_edges;
+  memset(res, 0, sizeof(*res));
+  for (int k = 0; k < K; ++k) states_out[k] = pb_in->states[k];
+  if (points_out) memcpy(points_out, pb_in->points, sizeof(double) * 3 * (size_t)P);
+  OrcBaProblem pb = *pb_in;
+  pb.global_ba = 1 | (robust ? 2 : 0);
+  pb.large = 0; pb.rec_init = 0;
+  Graph g;
+  int optit[2];
+  if (!build_lba_graph(&pb, cam, g, optit)) return 0;
+  g.initialize();
+  if (g.np == 0) return 0;
+  g.compute_active_errors();
+  res->err0 = g.active_robust_chi2();
+  const int it = g.optimize(n_iterations);
+  res->iterations[0] = it;
+  g.compute_active_errors();
+  res->err_end = g.active_robust_chi2();
+  res->lambda_final = g.lambda;
+  res->accepted = 1;
+  if (edge_chi2)
+    for (int i = 0; i < E; ++i) edge_chi2[i] = g.vis[i].chi2;
+  for (int k = 0; k < K; ++k) to_c(g.st[k], &states_out[k]);
+  if (points_out) memcpy(points_out, g.X.data(), sizeof(double) * 3 * (size_t)P);
+  return it;
+}
 
 // One damped Gauss-Newton step of the LBA graph at the input estimate (build + Schur solve with the given lambda):
 // x_pose [np] in Hessian index order, x_points [P][3].  For the tests' cross-check against a dense solve of the

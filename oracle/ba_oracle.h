@@ -89,7 +89,7 @@ typedef struct OrcBaProblem {
   int32_t large;    /* bLarge */
   int32_t rec_init; /* bRecInit */
   int32_t visual_only; /* LocalBundleAdjustment (PR vertices only, src/Optimizer.cc:1876) */
-  int32_t pad_;
+  int32_t global_ba;   /* set by orc_global_ba_prv: bit 0 = GlobalBundleAdjustmentNavStatePRV graph, bit 1 = bRobust */
 } OrcBaProblem;
 
 typedef struct OrcBaResult {
@@ -104,6 +104,11 @@ typedef struct OrcBaResult {
  * Outputs: states_out [n_states], points_out [P][3], edge_chi2 [E], erase [E] (1 = vToErase entry). */
 int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* states_out, double* points_out,
                      double* edge_chi2, uint8_t* erase, OrcBaResult* res);
+
+/* Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342; bScaleOpt = false, no IMU initiator) from the
+ * vertex set-up to before the write-back.  Returns the LM iterations run. */
+int orc_global_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, int n_iterations, int robust, OrcNavState* states_out,
+                      double* points_out, double* edge_chi2, OrcBaResult* res);
 
 /* One damped Gauss-Newton step (build + Schur solve at the given lambda) at the input estimate, for the tests'
  * cross-check against a dense solve of the full normal equations.  Returns the pose dimension np or < 0. */

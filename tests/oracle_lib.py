@@ -224,7 +224,7 @@ class OrcBaProblem(C.Structure):
                 ("edge_point", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p), ("edge_flags", C.c_void_p),
                 ("imu_i", C.c_void_p), ("imu_j", C.c_void_p), ("preint", C.c_void_p), ("imu_dt_kf", C.c_void_p),
                 ("gw", C.c_double * 3), ("inv_sigma_bg2", C.c_double), ("inv_sigma_ba2", C.c_double),
-                ("large", C.c_int32), ("rec_init", C.c_int32), ("visual_only", C.c_int32), ("pad_", C.c_int32)]
+                ("large", C.c_int32), ("rec_init", C.c_int32), ("visual_only", C.c_int32), ("global_ba", C.c_int32)]
 
 
 def ba_problem_struct(d, large=False, rec_init=False, visual_only=False, cls=OrcBaProblem):
@@ -265,6 +265,18 @@ def local_ba_prv(d, cam, **kw):
     erase = np.zeros(pb.n_edges, np.uint8); res = np.zeros(1, BA_RESULT_DTYPE)
     L.orc_local_ba_prv(C.byref(pb), cam.ctypes.data, _p(st), _p(pts), _p(chi2), _p(erase), _p(res))
     return dict(states=st, points=pts, edge_chi2=chi2, erase=erase, res=res[0])
+
+
+def global_ba_prv(d, cam, n_iterations=10, robust=False):
+    pb, keep = ba_problem_struct(d)
+    L = lib()
+    cam = np.ascontiguousarray(cam)
+    st = np.zeros(len(d["states"]), NAVSTATE_DTYPE); pts = np.zeros((len(d["points"]), 3))
+    chi2 = np.zeros(len(d["edge_state"])); res = np.zeros(1, BA_RESULT_DTYPE)
+    L.orc_global_ba_prv.argtypes = None
+    it = L.orc_global_ba_prv(C.byref(pb), C.c_void_p(cam.ctypes.data), C.c_int(n_iterations), C.c_int(int(robust)), _p(st), _p(pts),
+                             _p(chi2), _p(res))
+    return dict(states=st, points=pts, edge_chi2=chi2, res=res[0], iterations=it)
 
 
 def ba_debug_step(d, cam, lam, **kw):

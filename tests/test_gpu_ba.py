@@ -196,3 +196,65 @@ def test_local_ba_large_window_global_cholesky():
         out = ba.LocalBundleAdjustmentNavStatePRV(d, cam, **kw)
         ref = O.local_ba_prv(d, cam, **kw)
         _cmp_lba(out, ref)
+
+
+# ---------------------------------------------------------------- global BA (dense multi-CTA reduced camera system)
+def _gba(n_kf, n_points, seed=3, **kw):
+    s = synth.vio_sequence(40 + seed, 4 * n_kf + 1, speed=1.0, rot=0.6)
+    kf = list(range(0, 4 * n_kf, 4))
+    pre = O.imu_preintegrate_frames(s, kf, O.imu_noise())
+    cam = synth.euroc_camera()
+    return s, kf, cam, synth.make_gba_problem(s, pre, kf, cam, n_points=n_points, seed=seed, **kw)
+
+
+@pytest.fixture(scope="module")
+def big_ba():
+    import vieo_slam_b200.api as api
+    return api.BundleAdjuster(max_states=448, max_points=32768, max_edges=400000, max_imu=448)
+
+
+def test_gba_single_step_matches_oracle(big_ba):
+    """One damped step through k_gba_schur + the blocked multi-CTA Cholesky (3 panels of 64 + a ragged one) against
+    the oracle's scalar Schur / Cholesky."""
+    _, _, cam, d = _gba(15, 400)
+    big_ba.set_problem(d, cam)
+    for lam in (1.0, 1e-3):
+        xp, xl, H, b = big_ba.debug_step(lam)
+        oxp, oxl, _ = O.ba_debug_step(d, cam, lam)
+        assert len(xp) == len(oxp) == 14 * 15
+        assert np.abs(xp - oxp).max() <= 1e-8 * max(1.0, np.abs(oxp).max()), np.abs(xp - oxp).max()
+        assert np.abs(xl - oxl).max() <= 1e-8 * max(1.0, np.abs(oxl).max())
+
+
+@pytest.mark.parametrize("robust,outl", [(False, 0.0), (True, 0.05)])
+def test_global_ba_matches_oracle(big_ba, robust, outl):
+    _, _, cam, d = _gba(40, 1500, seed=5, outlier_frac=outl)
+    out = big_ba.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=8, bRobust=robust)
+    ref = O.global_ba_prv(d, cam, n_iterations=8, robust=robust)
+    assert out["iterations"] == ref["iterations"]
+    for k in ("err0", "err_end"):
+        assert abs(out["res"][k] - ref["res"][k]) <= 1e-6 * abs(ref["res"][k]), (k, out["res"][k], ref["res"][k])
+    for f in ("p", "q", "v", "dbg", "dba"):
+        assert np.abs(out["states"][f] - ref["states"][f]).max() < 1e-7, f
+    assert np.abs(out["points"] - ref["points"]).max() < 1e-6
+    sc = np.maximum(np.abs(ref["edge_chi2"]), 1.0)
+    assert (np.abs(out["edge_chi2"] - ref["edge_chi2"]) / sc).max() < 1e-6
+    assert out["states"][0].tobytes() == d["states"][0].tobytes()
+
+
+def test_global_ba_config5_sized_properties(big_ba):
+    """BASELINE configs[4]-shaped map (400 keyframes, ~25k points, ~250k observations, 5985 pose dimensions): too large
+    for the scalar oracle, so size-independent properties: the cost falls monotonically to the noise floor, keyframe 0
+    stays put, the estimate lands on the ground truth, and a second run is bit-identical."""
+    s, kf, cam, d = _gba(400, 25000, seed=8)
+    assert len(d["edge_state"]) > 200000
+    out = big_ba.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=10, bRobust=False)
+    assert out["iterations"] >= 3
+    assert out["res"]["err_end"] < 0.02 * out["res"]["err0"]
+    assert out["states"][0].tobytes() == d["states"][0].tobytes()
+    err = max(np.linalg.norm(out["states"][k]["p"] - s["truth"][kf[k]]["p"]) for k in range(1, len(kf)))
+    assert err < 0.01, err
+    # chi2 per observation near its expectation (2 or 3 per edge, sigma-1 pixel noise)
+    assert 0.5 < out["res"]["err_end"] / (2.7 * len(d["edge_state"])) < 1.5
+    again = big_ba.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=10, bRobust=False)
+    assert again["states"].tobytes() == out["states"].tobytes() and again["points"].tobytes() == out["points"].tobytes()

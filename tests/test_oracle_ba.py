@@ -368,3 +368,36 @@ def test_drivers_converge_with_lens_models(seq, model):
     # the same observations through the wrong (pinhole) model must fit visibly worse
     res0, _, _ = O.pose_optimization(pbs, synth.euroc_camera(), Xw, obs, w, fl)
     assert sum(r["n_inliers"] for r in res0) < sum(r["n_inliers"] for r in res)
+
+
+# ---- global BA ------------------------------------------------------------------------------------
+def _gba(n_kf=12, n_points=300, seed=3, **kw):
+    s = synth.vio_sequence(40 + seed, 4 * n_kf + 1, speed=1.0, rot=0.6)
+    kf = list(range(0, 4 * n_kf, 4))
+    pre = O.imu_preintegrate_frames(s, kf, O.imu_noise())
+    cam = synth.euroc_camera()
+    return s, kf, cam, synth.make_gba_problem(s, pre, kf, cam, n_points=n_points, seed=seed, **kw)
+
+
+def test_global_ba_converges_and_keeps_keyframe0():
+    s, kf, cam, d = _gba()
+    assert d["state_flags"][0] == 7 and np.all(d["state_flags"][1:] == 2)
+    out = O.global_ba_prv(d, cam, n_iterations=10, robust=False)
+    assert out["iterations"] >= 3
+    assert out["res"]["err_end"] < 0.05 * out["res"]["err0"]
+    assert out["states"][0].tobytes() == d["states"][0].tobytes()       # keyframe 0: PR, V and Bias fixed
+    e0 = max(np.linalg.norm(d["states"][k]["p"] - s["truth"][kf[k]]["p"]) for k in range(1, len(kf)))
+    e1 = max(np.linalg.norm(out["states"][k]["p"] - s["truth"][kf[k]]["p"]) for k in range(1, len(kf)))
+    assert e1 < 0.5 * e0 and e1 < 0.01
+
+
+def test_global_ba_robust_flag_changes_kernels():
+    _, _, cam, d = _gba(outlier_frac=0.05)
+    a = O.global_ba_prv(d, cam, n_iterations=6, robust=True)
+    b = O.global_ba_prv(d, cam, n_iterations=6, robust=False)
+    # with outliers, the Huber cost is far below the plain quadratic one and the estimates differ
+    assert a["res"]["err0"] < 0.7 * b["res"]["err0"]
+    assert np.abs(a["states"]["p"] - b["states"]["p"]).max() > 1e-5
+    # global BA uses sqrt(5.99), not the local BA's sqrt(5.991f): a mono edge with chi2 between the two deltas^2 tells
+    c = O.local_ba_prv(d, cam)
+    assert c["res"]["err0"] != a["res"]["err0"]

@@ -81,6 +81,7 @@ def lib():
         L.vieo_ba_stream.argtypes = [vp]
         L.vieo_ba_stream.restype = vp
         L.vieo_local_ba_prv.argtypes = [vp] * 9
+        L.vieo_global_ba_prv.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
         L.vieo_ba_set_problem.argtypes = [vp, vp, vp]
         L.vieo_ba_chi2_large_set_level.argtypes = [vp, C.c_float]
         L.vieo_ba_active_robust_chi2.argtypes = [vp, i32, vp]
@@ -425,7 +426,7 @@ class VieoBaProblem(C.Structure):
                 ("edge_point", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p), ("edge_flags", C.c_void_p),
                 ("imu_i", C.c_void_p), ("imu_j", C.c_void_p), ("preint", C.c_void_p), ("imu_dt_kf", C.c_void_p),
                 ("gw", C.c_double * 3), ("inv_sigma_bg2", C.c_double), ("inv_sigma_ba2", C.c_double),
-                ("large", C.c_int32), ("rec_init", C.c_int32), ("visual_only", C.c_int32), ("pad_", C.c_int32)]
+                ("large", C.c_int32), ("rec_init", C.c_int32), ("visual_only", C.c_int32), ("global_ba", C.c_int32)]
 
 
 _BA_ARRAYS = (("states", NAVSTATE_DTYPE), ("state_flags", np.uint8), ("points", np.float64), ("edge_state", np.int32),
@@ -487,6 +488,18 @@ class BundleAdjuster:
         erase = np.zeros(pb.n_edges, np.uint8); res = np.zeros(1, BA_RESULT_DTYPE)
         _check(lib().vieo_local_ba_prv(self._h, C.byref(pb), _p(cam), _p(stop), _p(st), _p(pts), _p(chi2), _p(erase), _p(res)))
         return dict(states=st, points=pts, edge_chi2=chi2, erase=erase, res=res[0])
+
+    def GlobalBundleAdjustmentNavStatePRV(self, d, cam, nIterations=5, bRobust=True, stop=None):
+        """Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342; bScaleOpt = false) on the flattened
+        map; the handle must have been created with the map's capacity (max_states > 56 selects the dense multi-CTA
+        reduced-camera-system path)."""
+        pb, keep = ba_problem(d)
+        cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
+        st = np.zeros(pb.n_states, NAVSTATE_DTYPE); pts = np.zeros((pb.n_points, 3)); chi2 = np.zeros(pb.n_edges)
+        res = np.zeros(1, BA_RESULT_DTYPE)
+        it = _check(lib().vieo_global_ba_prv(self._h, C.byref(pb), _p(cam), int(nIterations), int(bRobust), _p(stop), _p(st),
+                                             _p(pts), _p(chi2), _p(res)))
+        return dict(states=st, points=pts, edge_chi2=chi2, res=res[0], iterations=it)
 
     def set_problem(self, d, cam, **kw):
         pb, keep = ba_problem(d, **kw)

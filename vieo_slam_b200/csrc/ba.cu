@@ -187,7 +187,8 @@ __device__ void navstate_jac24(const NavS& si, const NavS& sj, const Pre& m, con
 __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const VieoNavState* __restrict__ st,
                                const VieoImuPreint* __restrict__ pre, Vec3 gw, BaDenseWork* __restrict__ wk,
                                const int* __restrict__ off0, const int* __restrict__ off1, const int* __restrict__ off2,
-                               int np, double* __restrict__ H, double* __restrict__ b, double* __restrict__ chi_dense) {
+                               int np, double* __restrict__ H, double* __restrict__ b, double* __restrict__ chi_dense,
+                               bool zero_h = true) {
   const int T = blockDim.x;
   // the pre-integrations' fields the edges read (61 doubles each) staged in shared memory: the residual / Jacobian
   // code is one long dependent chain per thread, global-memory latency on every field would dominate it
@@ -230,7 +231,8 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
       W.err[5] = (c.ba.z + c.dba.z) - (a.ba.z + a.dba.z);
     }
   }
-  for (int t = threadIdx.x; t < np * np; t += T) H[t] = 0;
+  if (zero_h)
+    for (int t = threadIdx.x; t < np * np; t += T) H[t] = 0;
   for (int t = threadIdx.x; t < np; t += T) b[t] = 0;
   __syncthreads();
   // Omega e (row i of edge m)
@@ -330,6 +332,7 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
 // Levenberg-Marquardt bookkeeping (gain ratio, lambda schedule, accept / restore, stop criteria) runs in k_ba_control.
 struct BaParams {
   int K, P, E, np, nfree, n_den, n_pblk, has_dup;
+  int big;              // global-BA sized handle: H is zeroed by a memset node, multi-CTA Schur / Cholesky kernels
   int lambda_on_poses;  // sharded runs add lambda to the pose diagonal on rank 0 only
   int cur;              // linearisation set (0/1) that belongs to the current estimate
   int done;             // optimize() finished: trial kernels return immediately
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaBuf B, int int
   const int set = into_other ? 1 - prm.cur : prm.cur;
   if (blockIdx.x == gridDim.x - 1) {
     ba_dense_block(B.den, prm.n_den, B.st, B.pre, prm.gw, B.wk, B.off0, B.off1, B.off2, prm.np, B.H[set], B.b[set],
-                   &B.prm->chi_dense);
+                   &B.prm->chi_dense, !prm.big);
     return;
   }
   if ((int)blockIdx.x >= prm.n_pblk) return;
@@ -912,6 +915,273 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_chol(BaBuf B, int force) {
   for (int i = t; i < n; i += T) B.x[i] = x[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Global-BA sized systems (Optimizer::GlobalBundleAdjustmentNavStatePRV, src/Optimizer.cc:771-1342: every keyframe of
+// the map is free, np = 15 K reaches several thousand).  The reduced camera system stays DENSE in HBM (np = 6000 is
+// 288 MB of 180 GB): the reference's sparse LDLT exists to save CPU memory and flops this device does not lack.
+//
+// Schur complement, one CTA per free keyframe row: the CTA owns the 6 x (6 nfree + 1) row tile in shared memory and
+// walks the keyframe's edges in order; for edge a the whole CTA adds the (W_a Dinv) W_c^T blocks of the point's other
+// observations c (one thread per entry, distinct columns, no atomics), then the tile is subtracted from S / bschur.
+constexpr int kGbaSchurThreads = 512;
+__global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int force) {
+  extern __shared__ double s_tile[];  // [6][ld]
+  const BaParams& prm = *B.prm;
+  if ((prm.done && !force) || (int)blockIdx.x >= prm.nfree || prm.E == 0) return;
+  const int nfree = prm.nfree, np = prm.np, ld = 6 * nfree + 1;
+  const int f = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
+  const double* Wb = B.W[prm.cur];
+  for (int t = tid; t < 6 * ld; t += T) s_tile[t] = 0;
+  __syncthreads();
+  const int t0 = B.ps_ptr[f], t1 = B.ps_ptr[f + 1];
+  const int dup = prm.has_dup;
+  for (int t = t0; t < t1; ++t) {
+    const int a = B.ps_edges[t];
+    const int p = B.ep[a];
+    const int c0 = B.pt_ptr[p], nc = B.pt_ptr[p + 1] - c0;
+    const double* Di = B.Dinv + 9 * (size_t)p;
+    const double* Wa = Wb + 18 * (size_t)a;
+    if (tid < 6) {
+      const double* d = B.db + 3 * (size_t)p;
+      s_tile[tid * ld + 6 * nfree] += Wa[3 * tid] * d[0] + Wa[3 * tid + 1] * d[1] + Wa[3 * tid + 2] * d[2];
+    }
+    if (!dup) {
+      for (int e = tid; e < 36 * nc; e += T) {
+        const int c = c0 + e / 36, r = (e % 36) / 6, cc = e % 6;
+        const int col = B.prcol[B.es[c]];
+        if (col < 0) continue;
+        const double w0 = Wa[3 * r], w1 = Wa[3 * r + 1], w2 = Wa[3 * r + 2];
+        const double d0 = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
+        const double d1 = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
+        const double d2 = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
+        const double* Wc = Wb + 18 * (size_t)c + 3 * cc;
+        s_tile[r * ld + 6 * col + cc] += d0 * Wc[0] + d1 * Wc[1] + d2 * Wc[2];
+      }
+    } else {
+      // a point seen twice by one keyframe (multi-camera rigs): its observations may share a column, take them in turn
+      for (int c = c0; c < c0 + nc; ++c) {
+        const int col = B.prcol[B.es[c]];
+        if (col >= 0 && tid < 36) {
+          const int r = tid / 6, cc = tid % 6;
+          const double w0 = Wa[3 * r], w1 = Wa[3 * r + 1], w2 = Wa[3 * r + 2];
+          const double d0 = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
+          const double d1 = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
+          const double d2 = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
+          const double* Wc = Wb + 18 * (size_t)c + 3 * cc;
+          s_tile[r * ld + 6 * col + cc] += d0 * Wc[0] + d1 * Wc[1] + d2 * Wc[2];
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+  const int o = B.off0[B.free_state[f]];
+  for (int t = tid; t < 6 * ld; t += T) {
+    const int r = t / ld, c = t % ld;
+    if (c == 6 * nfree) B.bs[o + r] -= s_tile[t];
+    else B.S[(size_t)(o + r) * np + B.free_off[c / 6] + c % 6] -= s_tile[t];
+  }
+}
+
+// Blocked right-looking Cholesky of the dense reduced camera system over the whole device, panels of kGNB columns.
+// Per panel k: k_gchol_diag (one CTA) factorises the diagonal block, inverts the triangular factor and advances the
+// forward substitution (y_k = L_kk^-1 y_k); k_gchol_trsm (one CTA per 64 rows below) forms L_ik = A_ik L_kk^-T as a small
+// matrix product and updates y_i -= L_ik y_k; k_gchol_syrk (one CTA per 64 x 64 tile of the trailing lower triangle)
+// subtracts L_ik L_jk^T.  Back substitution walks the panels in reverse (k_gchol_back): x_k = L_kk^-T y_k, then every
+// earlier entry y_j -= L_kj^T x_k.  Products use explicit fma(): this factorisation is bound by the 1e-6 chi2 tolerance,
+// not by bit parity with the oracle's scalar Cholesky.  prm.ok = 0 when a pivot is not positive.
+constexpr int kGNB = 64;
+constexpr size_t kGcholSmem = sizeof(double) * 2 * kGNB * (kGNB + 4);
+__global__ void __launch_bounds__(256) k_gchol_diag(BaBuf B, double* __restrict__ Linv_all, double* __restrict__ yv, int k0,
+                                                    int force) {
+  extern __shared__ double s_gchol[];
+  double (*A)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol);
+  double (*Li)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol + kGNB * (kGNB + 1));
+  __shared__ double sy[kGNB];
+  __shared__ int s_good;
+  BaParams& prm = *B.prm;
+  if (prm.done && !force) return;
+  const int n = prm.np;
+  if (k0 >= n) return;
+  const int nb = min(kGNB, n - k0), t = threadIdx.x;
+  if (k0 == 0) {  // start of a solve: y = bschur
+    for (int i = t; i < n; i += 256) yv[i] = B.bs[i];
+  }
+  for (int e = t; e < kGNB * kGNB; e += 256) {
+    const int i = e / kGNB, j = e % kGNB;
+    A[i][j] = (i < nb && j <= i) ? B.S[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
+    Li[i][j] = 0;
+  }
+  if (t == 0) s_good = 1;
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (t == 0) {
+      const double d = A[j][j];
+      if (!(d > 0)) s_good = 0;
+      A[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    const double rd = 1.0 / A[j][j];
+    if (t > j && t < nb) A[t][j] *= rd;
+    __syncthreads();
+    // trailing update of the block: entries (i, k) with j < k <= i < nb
+    const int m = nb - j - 1;
+    for (int e = t; e < m * m; e += 256) {
+      const int i = j + 1 + e / m, k = j + 1 + e % m;
+      if (k <= i) A[i][k] = fma(-A[i][j], A[k][j], A[i][k]);
+    }
+    __syncthreads();
+  }
+  // inverse of the triangular factor, one column per thread (forward substitution on the unit vector)
+  if (t < kGNB) {
+    const int c = t;
+    Li[c][c] = 1.0 / A[c][c];
+    for (int i = c + 1; i < kGNB; ++i) {
+      double acc = 0;
+      for (int m = c; m < i; ++m) acc = fma(A[i][m], Li[m][c], acc);
+      Li[i][c] = -acc / A[i][i];
+    }
+  }
+  __syncthreads();
+  if (t < kGNB) {
+    double acc = 0;
+    if (t < nb)
+      for (int m = 0; m <= t; ++m) acc = fma(Li[t][m], yv[k0 + m], acc);
+    sy[t] = acc;
+  }
+  __syncthreads();
+  if (t < nb) yv[k0 + t] = sy[t];
+  for (int e = t; e < nb * nb; e += 256) {
+    const int i = e / nb, j = e % nb;
+    if (j <= i) B.S[(size_t)(k0 + i) * n + k0 + j] = A[i][j];
+  }
+  double* Lo = Linv_all + (size_t)(k0 / kGNB) * kGNB * kGNB;
+  for (int e = t; e < kGNB * kGNB; e += 256) Lo[e] = Li[e / kGNB][e % kGNB];
+  if (t == 0) {
+    if (k0 == 0) prm.ok = s_good;
+    else if (!s_good) prm.ok = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gchol_trsm(BaBuf B, const double* __restrict__ Linv_all, double* __restrict__ yv,
+                                                    int k0, int force) {
+  extern __shared__ double s_gchol[];
+  double (*As)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol);
+  double (*Ls)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol + kGNB * (kGNB + 1));
+  __shared__ double sy[kGNB];
+  const BaParams& prm = *B.prm;
+  if (prm.done && !force) return;
+  const int n = prm.np;
+  if (k0 >= n) return;
+  const int nb = min(kGNB, n - k0), t = threadIdx.x;
+  const int i0 = k0 + nb + kGNB * blockIdx.x;
+  if (i0 >= n) return;
+  const int nr = min(kGNB, n - i0);
+  const double* Li = Linv_all + (size_t)(k0 / kGNB) * kGNB * kGNB;
+  for (int e = t; e < kGNB * kGNB; e += 256) {
+    const int i = e / kGNB, j = e % kGNB;
+    As[i][j] = (i < nr && j < nb) ? B.S[(size_t)(i0 + i) * n + k0 + j] : 0.0;
+    Ls[i][j] = Li[e];
+  }
+  if (t < kGNB) sy[t] = t < nb ? yv[k0 + t] : 0.0;
+  __syncthreads();
+  // X[i][j] = sum_{m <= j} A[i][m] Linv[j][m]
+  for (int e = t; e < kGNB * kGNB; e += 256) {
+    const int i = e / kGNB, j = e % kGNB;
+    double acc = 0;
+    for (int m = 0; m <= j; ++m) acc = fma(As[i][m], Ls[j][m], acc);
+    if (i < nr && j < nb) B.S[(size_t)(i0 + i) * n + k0 + j] = acc;
+  }
+  __syncthreads();  // the block's own global writes are visible to it after the barrier
+  if (t < nr) {
+    double acc = yv[i0 + t];
+    const double* Xr = B.S + (size_t)(i0 + t) * n + k0;
+    for (int j = 0; j < nb; ++j) acc = fma(-Xr[j], sy[j], acc);
+    yv[i0 + t] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gchol_syrk(BaBuf B, int k0, int force) {
+  extern __shared__ double s_gchol[];
+  double (*At)[kGNB + 4] = reinterpret_cast<double (*)[kGNB + 4]>(s_gchol);                          // [m][row]
+  double (*Bt)[kGNB + 4] = reinterpret_cast<double (*)[kGNB + 4]>(s_gchol + kGNB * (kGNB + 4));      // [m][col]
+  const BaParams& prm = *B.prm;
+  if (prm.done && !force) return;
+  if (blockIdx.x > blockIdx.y) return;  // lower triangle of tiles only
+  const int n = prm.np;
+  if (k0 >= n) return;
+  const int nb = min(kGNB, n - k0), t = threadIdx.x;
+  const int i0 = k0 + nb + kGNB * blockIdx.y, j0 = k0 + nb + kGNB * blockIdx.x;
+  if (i0 >= n || j0 >= n) return;
+  for (int e = t; e < kGNB * kGNB; e += 256) {
+    const int r = e / kGNB, m = e % kGNB;
+    At[m][r] = (i0 + r < n && m < nb) ? B.S[(size_t)(i0 + r) * n + k0 + m] : 0.0;
+    Bt[m][r] = (j0 + r < n && m < nb) ? B.S[(size_t)(j0 + r) * n + k0 + m] : 0.0;
+  }
+  __syncthreads();
+  const int ty = t / 16, tx = t % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+  for (int m = 0; m < nb; ++m) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) av[a] = At[m][4 * ty + a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bv[b] = Bt[m][4 * tx + b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + 4 * ty + a;
+    if (i >= n) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = j0 + 4 * tx + b;
+      if (j < n && j <= i) B.S[(size_t)i * n + j] -= acc[a][b];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gchol_back(BaBuf B, const double* __restrict__ Linv_all, double* __restrict__ yv,
+                                                    int k0, int force) {
+  __shared__ double sx[kGNB];
+  const BaParams& prm = *B.prm;
+  if (prm.done && !force) return;
+  const int n = prm.np;
+  if (k0 >= n) return;
+  const int nb = min(kGNB, n - k0), t = threadIdx.x;
+  const double* Li = Linv_all + (size_t)(k0 / kGNB) * kGNB * kGNB;
+  if (t < kGNB) {  // x_k = Linv^T y_k
+    double acc = 0;
+    if (t < nb)
+      for (int m = t; m < nb; ++m) acc = fma(Li[m * kGNB + t], yv[k0 + m], acc);
+    sx[t] = acc;
+    if (blockIdx.x == 0 && t < nb) B.x[k0 + t] = acc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) return;  // block 0 only publishes x_k (its reads of y_k must not race with an update of y)
+  const int j = (blockIdx.x - 1) * 256 + t;
+  if (j >= k0) return;
+  double acc = yv[j];
+  for (int r = 0; r < nb; ++r) acc = fma(-B.S[(size_t)(k0 + r) * n + j], sx[r], acc);
+  yv[j] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_gba_zero_h(BaBuf B, int into_other) {
+  const BaParams& prm = *B.prm;
+  if (prm.done) return;
+  double2* H = reinterpret_cast<double2*>(B.H[into_other ? 1 - prm.cur : prm.cur]);
+  const size_t n2 = ((size_t)prm.np * prm.np + 1) / 2;  // the buffers are allocated with an even element count
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+    H[i] = make_double2(0.0, 0.0);
+}
+
 // One warp per point: xl = Dinv (bl - sum_a W_a^T xp), X += xl (apply != 0), landmark part of computeScale; the
 // estimate before the update is kept in X_bak / st_bak (push()).  The extra last block applies the keyframe updates
 // (NavState::IncSmall), refreshes the camera poses and computes the pose part of computeScale.
@@ -1024,6 +1294,8 @@ struct vieo_ba {
   int capK = 0, capP = 0, capE = 0, capM = 0, cap_pblk = 0, cap_free = 0;
   int K = 0, P = 0, E = 0, M = 0, np = 0, nfree = 0, n_den = 0, n_part = 0, n_pblk = 0;
   bool points_free = true, has_dup = false, visual_only = false;
+  bool big = false;  // global-BA sized handle (dense multi-CTA Schur / Cholesky path, no trial graph)
+  double *d_linv = nullptr, *d_yv = nullptr;
   int rank = 0, world = 1;
   vieo_allreduce_fn allreduce = nullptr;
   void* ar_ctx = nullptr;
@@ -1100,6 +1372,7 @@ bool host_inverse(const double* A, int n, double* Ai) {
   } while (0)
 
 size_t schur_smem(int nfree) { return sizeof(double) * kBaWarps * 6 * (6 * (size_t)nfree + 1); }
+size_t gba_schur_smem(int nfree) { return sizeof(double) * 6 * (6 * (size_t)nfree + 1); }
 
 int ba_campose(vieo_ba* h) {
   k_ba_campose<<<(h->K + 127) / 128, 128, 0, h->st>>>(h->cam, h->B.st, h->K, h->B.cp);
@@ -1135,6 +1408,10 @@ int ba_allreduce(vieo_ba* h, double* buf, size_t n) {
 // computeActiveErrors + buildSystem at the current estimate; into_other: into the set that is not the current one
 int ba_enqueue_linearize(vieo_ba* h, int into_other, bool at_capacity) {
   const int pblk = at_capacity ? h->cap_pblk : h->n_pblk, nf = at_capacity ? h->cap_free : h->nfree;
+  if (h->big) {  // the inertial block of k_ba_linearize cannot zero np^2 entries by itself
+    k_gba_zero_h<<<1184, 256, 0, h->st>>>(h->B, into_other);
+    h->launches++;
+  }
   k_ba_linearize<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
   k_ba_pose_reduce<<<std::max(nf, 1), 256, 0, h->st>>>(h->B, into_other);
   h->launches += 2;
@@ -1146,6 +1423,32 @@ int ba_enqueue_linearize(vieo_ba* h, int into_other, bool at_capacity) {
 int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, double* xl_out) {
   const int pblk = at_capacity ? h->cap_pblk : h->n_pblk, nf = at_capacity ? h->cap_free : h->nfree;
   const size_t P = at_capacity ? (size_t)h->capP : (size_t)h->P;
+  if (h->big) {
+    const int n = h->np;
+    const size_t nn = std::max<size_t>(std::max<size_t>((size_t)n * n, (size_t)n), std::max<size_t>(P, 1));
+    k_ba_prep_solve<<<(unsigned)((nn + 255) / 256), 256, 0, h->st>>>(h->B, lambda, force);
+    k_gba_schur<<<std::max(nf, 1), kGbaSchurThreads, gba_schur_smem(h->nfree), h->st>>>(h->B, force);
+    h->launches += 2;
+    int rc = ba_allreduce(h, h->d_sys, h->sys_count());
+    if (rc) return rc;
+    for (int k0 = 0; k0 < n; k0 += kGNB) {
+      const int k1 = std::min(k0 + kGNB, n), tiles = (n - k1 + kGNB - 1) / kGNB;
+      k_gchol_diag<<<1, 256, kGcholSmem, h->st>>>(h->B, h->d_linv, h->d_yv, k0, force);
+      h->launches++;
+      if (tiles > 0) {
+        k_gchol_trsm<<<tiles, 256, kGcholSmem, h->st>>>(h->B, h->d_linv, h->d_yv, k0, force);
+        k_gchol_syrk<<<dim3(tiles, tiles), 256, kGcholSmem, h->st>>>(h->B, k0, force);
+        h->launches += 2;
+      }
+    }
+    for (int k0 = ((n - 1) / kGNB) * kGNB; k0 >= 0; k0 -= kGNB) {
+      k_gchol_back<<<1 + (k0 + 255) / 256, 256, 0, h->st>>>(h->B, h->d_linv, h->d_yv, k0, force);
+      h->launches++;
+    }
+    k_ba_backsub<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, force ? 0 : 1, lambda, xl_out);
+    h->launches++;
+    return VIEO_OK;
+  }
   const size_t npc = at_capacity ? 15 * (size_t)std::min(h->capK, kSchurMaxFree + 8) : (size_t)h->np;
   const size_t nn = std::max<size_t>(std::max<size_t>(npc * npc, npc), std::max<size_t>(P, 1));
   k_ba_prep_solve<<<(unsigned)((nn + 255) / 256), 256, 0, h->st>>>(h->B, lambda, force);
@@ -1183,7 +1486,7 @@ void ba_free(vieo_ba* h) {
   BaBuf& B = h->B;
   void* ptrs[] = {B.prm, B.st, B.st_bak, B.cp, B.X, B.X_bak, B.chi2, B.A, B.Dinv, B.db, B.x, B.partial, B.scale_part, B.part,
                   B.W[0], B.W[1], B.Hll[0], B.Hll[1], B.bl[0], B.bl[1], B.H[0], B.H[1], B.b[0], B.b[1], B.pt_active[0],
-                  B.pt_active[1], B.wk, h->d_sys, h->d_xl, h->d_ctl, h->d_lvl, h->d_bad, h->d_flags, h->d_sfix, h->d_es,
+                  B.pt_active[1], B.wk, h->d_linv, h->d_yv, h->d_sys, h->d_xl, h->d_ctl, h->d_lvl, h->d_bad, h->d_flags, h->d_sfix, h->d_es,
                   h->d_ep, h->d_pt_ptr, h->d_off0, h->d_off1, h->d_off2, h->d_prcol, h->d_free_state, h->d_free_off,
                   h->d_ps_ptr, h->d_ps_edges, h->d_obs, h->d_w, h->d_pre, h->d_den};
   for (void* p : ptrs)
@@ -1208,9 +1511,16 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   h->device = device;
   h->capK = max_states; h->capP = max_points; h->capE = max_edges; h->capM = max_imu;
   h->cap_pblk = (max_points + kBaWarps - 1) / kBaWarps;
-  h->cap_free = std::min(max_states, kSchurMaxFree);
+  h->big = max_states > kSchurMaxFree + 8;
+  if (h->big && max_states > 768) {
+    set_error("vieo_ba_create: at most 768 keyframes (the Schur row tile of one keyframe must fit one SM's shared memory)");
+    delete h;
+    return VIEO_E_CAPACITY;
+  }
+  h->cap_free = h->big ? max_states : std::min(max_states, kSchurMaxFree);
   const size_t K = max_states, P = max_points, E = max_edges, M = max_imu;
-  const size_t NP = 15 * (size_t)std::min(max_states, kSchurMaxFree + 8);  // free keyframes (+ a few V/Bias-only) x 15
+  // free keyframes (+ a few V/Bias-only) x 15; even so that double2 stores cover H exactly
+  const size_t NP = 15 * (size_t)(h->big ? max_states + (max_states & 1) : std::min(max_states, kSchurMaxFree + 8));
   BaBuf& B = h->B;
   cudaError_t e = cudaSuccess;
   auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
@@ -1230,7 +1540,13 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   step(dalloc(&h->d_sys, NP * NP + 2 * NP + 8)); step(dalloc(&B.x, NP));
   step(dalloc(&h->d_xl, 3 * P)); step(dalloc(&B.partial, std::max((E + 255) / 256, P / kBaWarps + 1) + 2));
   step(dalloc(&B.scale_part, P));
-  step(dalloc(&B.part, (size_t)h->cap_free * kSchurSplit * 6 * (6 * (size_t)h->cap_free + 1)));
+  if (h->big) {
+    step(dalloc(&B.part, 16));
+    step(dalloc(&h->d_linv, (NP / kGNB + 1) * kGNB * kGNB));
+    step(dalloc(&h->d_yv, NP));
+  } else {
+    step(dalloc(&B.part, (size_t)h->cap_free * kSchurSplit * 6 * (6 * (size_t)h->cap_free + 1)));
+  }
   step(dalloc(&h->d_ctl, 16)); step(dalloc(&h->d_es, E)); step(dalloc(&h->d_ep, E)); step(dalloc(&h->d_pt_ptr, P + 1));
   step(dalloc(&h->d_off0, K)); step(dalloc(&h->d_off1, K)); step(dalloc(&h->d_off2, K)); step(dalloc(&h->d_prcol, K));
   step(dalloc(&h->d_free_state, K)); step(dalloc(&h->d_free_off, K)); step(dalloc(&h->d_ps_ptr, K + 1));
@@ -1251,10 +1567,17 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
     memset(h->h_prm, 0, sizeof(BaParams));
     h->h_prm->done = 1;
     step(cudaMemcpy(B.prm, h->h_prm, sizeof(BaParams), cudaMemcpyHostToDevice));
-    step(cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem(h->cap_free)));
-    step(cudaFuncSetAttribute(k_ba_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+    if (h->big) {
+      step(cudaFuncSetAttribute(k_gba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gba_schur_smem(h->cap_free)));
+      step(cudaFuncSetAttribute(k_gchol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcholSmem));
+      step(cudaFuncSetAttribute(k_gchol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcholSmem));
+      step(cudaFuncSetAttribute(k_gchol_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcholSmem));
+    } else {
+      step(cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem(h->cap_free)));
+      step(cudaFuncSetAttribute(k_ba_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+    }
   }
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && !h->big) {
     // the LM trial as one CUDA graph: constant launch parameters (capacity grids, sizes read from B.prm on the device)
     cudaGraph_t g = nullptr;
     step(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
@@ -1317,6 +1640,8 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   // thHuberMono: src/Optimizer.cc:361 (PRV: sqrt of the float 5.991f) vs :2069 (visual LocalBundleAdjustment: sqrt(5.991))
   h->dm = h->visual_only ? (double)(float)std::sqrt(5.991) : (double)std::sqrt(chi2Mono);
   h->ds = (double)(float)std::sqrt(7.815);       // thHuberStereo
+  const bool global = pb->global_ba & 1, g_robust = pb->global_ba & 2;
+  if (global) h->dm = (double)(float)std::sqrt(5.99);  // thHuber2D of the global BA (src/Optimizer.cc:1042)
   // index mapping (sparse_optimizer.cpp:166-190): states in order, PR, V, Bias
   h->off0.assign(K, -1); h->off1.assign(K, -1); h->off2.assign(K, -1);
   std::vector<int> prcol(K, -1), free_state, free_off;
@@ -1373,7 +1698,9 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   for (int m = 0; m < M; ++m) {
     const int i = pb->imu_i[m], j = pb->imu_j[m];
     VIEO_ARG(i >= 0 && i < K && j >= 0 && j < K, "imu state index out of range");
-    const bool bfixedkf = pb->state_flags[i] & 1;
+    // local BA: the previous KEYFRAME is fixed (src/Optimizer.cc:262-271); global BA: its BIAS vertex is (:955-958)
+    const bool bfixedkf = global ? (!(pb->state_flags[i] & 2) || (pb->state_flags[i] & 4)) : (pb->state_flags[i] & 1);
+    const bool kernel = global ? g_robust : (bfixedkf || pb->rec_init);
     const VieoImuPreint& pre = pb->preint[m];
     if (pre.dt != 0) {
       BaDense d;
@@ -1381,10 +1708,8 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
       d.type = 0; d.si = i; d.sj = j; d.pre = m;
       if (!host_inverse(pre.SigmaPRV, 9, d.info))
         for (double& v : d.info) v = std::numeric_limits<double>::quiet_NaN();
-      if (bfixedkf || pb->rec_init) {
-        if (bfixedkf) for (double& v : d.info) v *= 1e-2;
-        d.delta = (double)thPRV;
-      }
+      if (bfixedkf) for (double& v : d.info) v *= 1e-2;
+      if (kernel) d.delta = (double)thPRV;
       den.push_back(d);
     }
     BaDense d;
@@ -1396,13 +1721,14 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
       const double w = (k < 3 ? pb->inv_sigma_bg2 : pb->inv_sigma_ba2) / dtij;
       d.info[k] = bfixedkf ? w * 1e-2 : w;
     }
-    if (bfixedkf || pb->rec_init) d.delta = (double)thBias;
+    if (kernel) d.delta = (double)thBias;
     den.push_back(d);
   }
   h->n_den = (int)den.size();
-  VIEO_ARG(h->n_den <= 1024, "too many inertial edges");
+  VIEO_ARG(h->n_den <= 2 * h->capM, "too many inertial edges");
   std::vector<uint8_t> lvl(std::max(E, 1));
-  for (int i = 0; i < E; ++i) lvl[i] = ((pb->edge_flags[i] & VIEO_EDGE_LEVEL1) ? 1 : 0) | ((pb->edge_flags[i] & VIEO_EDGE_NOKERNEL) ? 2 : 0);
+  for (int i = 0; i < E; ++i)
+    lvl[i] = ((pb->edge_flags[i] & VIEO_EDGE_LEVEL1) ? 1 : 0) | (((pb->edge_flags[i] & VIEO_EDGE_NOKERNEL) || (global && !g_robust)) ? 2 : 0);
   // every array goes through the pinned staging buffer: asynchronous copies, no driver-side pageable staging
   h->stage_used = 0;
   auto up = [&](void* d, const void* s, size_t n) {
@@ -1446,6 +1772,7 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   memset(&q, 0, sizeof(q));
   q.K = K; q.P = P; q.E = E; q.np = np; q.nfree = h->nfree; q.n_den = h->n_den; q.n_pblk = h->n_pblk;
   q.has_dup = h->has_dup ? 1 : 0;
+  q.big = h->big ? 1 : 0;
   q.lambda_on_poses = h->rank == 0 ? 1 : 0;
   q.done = 1;
   q.ok = 1;
@@ -1604,6 +1931,39 @@ int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_po
     return VIEO_E_ARG;
   }
   return h->np;
+}
+
+// Optimizer::GlobalBundleAdjustmentNavStatePRV, src/Optimizer.cc:771-1342 (bScaleOpt = false, no IMU initiator), on the
+// flattened problem: one optimize(nIterations) with g2o's own initial lambda, no outlier pass.
+int vieo_global_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb_in, const VieoCamera* cam, int n_iterations, int robust,
+                       const volatile uint8_t* stop, VieoNavState* states_out, double* points_out, double* edge_chi2,
+                       VieoBaResult* res) {
+  VIEO_ARG(h && pb_in && cam && res && states_out, "null argument");
+  VIEO_ARG(!pb_in->visual_only, "the global BA of the visual-only system is not implemented");
+  memset(res, 0, sizeof(*res));
+  memcpy(states_out, pb_in->states, sizeof(VieoNavState) * pb_in->n_states);
+  if (points_out && pb_in->n_points) memcpy(points_out, pb_in->points, 24 * (size_t)pb_in->n_points);
+  VieoBaProblem pb = *pb_in;
+  pb.global_ba = 1 | (robust ? 2 : 0);
+  pb.large = 0; pb.rec_init = 0;
+  int rc = vieo_ba_set_problem(h, &pb, cam);
+  if (rc) return rc;
+  if (h->np == 0) return 0;  // bdimPoses == false (:1249)
+  double chi = 0;
+  if ((rc = vieo_ba_active_robust_chi2(h, 1, &chi))) return rc;
+  res->err0 = chi;
+  int it = 0;
+  if (!(stop && *stop)) {
+    it = vieo_ba_optimize(h, n_iterations, 0.0, stop);
+    if (it < 0) return it;
+  }
+  res->iterations[0] = it;
+  if ((rc = vieo_ba_active_robust_chi2(h, 1, &chi))) return rc;
+  res->err_end = chi;
+  res->lambda_final = h->h_prm->lambda;
+  res->accepted = 1;
+  if ((rc = vieo_ba_get(h, states_out, points_out, edge_chi2))) return rc;
+  return it;
 }
 
 // Optimizer::LocalBundleAdjustmentNavStatePRV, src/Optimizer.cc:133-700, on the flattened problem

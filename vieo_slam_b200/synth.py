@@ -365,6 +365,58 @@ def make_lba_problem(seq, preints_kf, kf_idx, cam, n_local=10, n_fixed=20, n_poi
                 inv_sigma_bg2=1.0 / EUROC_IMU_SIGMA[2] ** 2, inv_sigma_ba2=1.0 / EUROC_IMU_SIGMA[3] ** 2)
 
 
+def make_gba_problem(seq, preints_kf, kf_idx, cam, n_points=3000, obs_window=5, seed=0, loop_frac=0.1, outlier_frac=0.0):
+    """A GlobalBundleAdjustmentNavStatePRV problem (src/Optimizer.cc:771-1342) over every keyframe kf_idx of a sequence:
+    keyframe 0 fixed (PR, V, Bias), all others free with PR / V / Bias vertices; IMU + bias-walk factors between
+    consecutive keyframes; every point is observed by the keyframes within `obs_window` of the one that created it, and
+    a `loop_frac` share of the points additionally by far-away keyframes that happen to see them (loop closures: they
+    fill the reduced camera system off its band).  Vectorised: BASELINE configs[4] sizes (400 keyframes, 25k points,
+    250k observations) build in seconds.  Same dict layout as make_lba_problem."""
+    r = np.random.default_rng(seed + 4000)
+    kf_idx = np.asarray(kf_idx)
+    nk = len(kf_idx)
+    truth = [seq["truth"][i] for i in kf_idx]
+    states = np.zeros(nk, NAVSTATE_DTYPE)
+    sflags = np.full(nk, 2, np.uint8)
+    for k in range(nk):
+        states[k] = perturb_state(truth[k], r) if k else truth[k]
+        states[k]["dbg"] = 0
+    sflags[0] = 1 | 2 | 4
+    imu_i = np.arange(0, nk - 1, dtype=np.int32); imu_j = imu_i + 1
+    pre = np.asarray([preints_kf[k] for k in range(1, nk)])
+    dtk = np.asarray([seq["times"][kf_idx[k]] - seq["times"][kf_idx[k - 1]] for k in range(1, nk)], np.float64)
+    k0 = r.integers(0, nk, n_points)
+    X = np.zeros((n_points, 3))
+    for k in range(nk):
+        m = np.nonzero(k0 == k)[0]
+        if len(m):
+            X[m] = landmarks_in_view(cam, truth[k], len(m), r)
+    loop = r.random(n_points) < loop_frac
+    es, ep, eo, ew, ef = [], [], [], [], []
+    for k in range(nk):
+        u, v, ur, z = project(cam, truth[k], X)
+        vis = (z > 0.3) & (u > 0) & (u < EUROC["w"]) & (v > 0) & (v < EUROC["h"])
+        near = np.abs(k0 - k) <= obs_window
+        far = loop & (np.abs(k0 - k) > 4 * obs_window) & ((k0 + k) % 7 == 0)
+        m = np.nonzero(vis & (near | far))[0]
+        if not len(m):
+            continue
+        obs, w, fl, _ = make_observations(cam, truth[k], X[m], r, outlier_frac)
+        es.append(np.full(len(m), k, np.int32)); ep.append(m.astype(np.int32)); eo.append(obs); ew.append(w); ef.append(fl)
+    es, ep, eo, ew, ef = (np.concatenate(a) for a in (es, ep, eo, ew, ef))
+    cnt = np.bincount(ep, minlength=n_points)
+    keep_pt = cnt >= 2
+    remap = np.cumsum(keep_pt) - 1
+    ke = keep_pt[ep]
+    es, ep, eo, ew, ef = es[ke], remap[ep[ke]].astype(np.int32), eo[ke], ew[ke], ef[ke]
+    order = np.argsort(ep, kind="stable")   # by point, ascending keyframe inside a point
+    Xp = (X[keep_pt] + r.normal(0, 0.02, (int(keep_pt.sum()), 3))).astype(np.float32).astype(np.float64)
+    return dict(states=states, state_flags=sflags, points=Xp, edge_state=es[order], edge_point=ep[order],
+                obs=np.ascontiguousarray(eo[order]), inv_sigma2=ew[order], edge_flags=ef[order], imu_i=imu_i, imu_j=imu_j,
+                preint=pre, imu_dt_kf=dtk, gw=GRAVITY_W.copy(),
+                inv_sigma_bg2=1.0 / EUROC_IMU_SIGMA[2] ** 2, inv_sigma_ba2=1.0 / EUROC_IMU_SIGMA[3] ** 2)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # Guided-search problems (SURVEY.md §8a B2/B3): current frames with ~1200 keypoints on the 64 x 48 frame grid and the
 # map points of the last frame / the local map that project onto them.  Descriptors are random 256-bit strings; a true
