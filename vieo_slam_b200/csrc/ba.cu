@@ -34,6 +34,7 @@ constexpr int kBaWarps = 8;
 struct BaDense {  // one inertial (EdgeNavStatePRV) or bias random-walk (EdgeNavStateBias) factor
   int type;       // 0 IMU, 1 bias
   int si, sj, pre;
+  int color, pad_;  // big path: edges of one colour share no keyframe and are accumulated concurrently
   double delta;     // Huber delta, 0 = none
   double info[81];  // IMU: 9x9 information; bias: [0..6) diagonal
 };
@@ -180,6 +181,56 @@ __device__ void navstate_jac24(const NavS& si, const NavS& sj, const Pre& m, con
   setb(J, 24, 3, 9, Jrinv);
 }
 
+// accumulate one inertial / bias edge's (J^T rho' Omega) J block into H / b with the threads [t0, t0 + tn) of the block
+__device__ __forceinline__ void ba_dense_add_edge(const BaDense& d, const BaDenseWork& W, const int* __restrict__ off0,
+                                                  const int* __restrict__ off1, const int* __restrict__ off2, int np,
+                                                  double* __restrict__ H, double* __restrict__ b, int t0, int tn) {
+    const int tl = (int)threadIdx.x - t0;
+    if (tl < 0 || tl >= tn) return;
+    if (d.type == 0) {
+      const int offs[5] = {off0[d.si], off0[d.sj], off1[d.si], off1[d.sj], off2[d.si]};
+      const int base[6] = {0, 6, 12, 15, 18, 24};
+      auto gcol = [&](int lc) {
+        int blk = lc < 6 ? 0 : lc < 12 ? 1 : lc < 15 ? 2 : lc < 18 ? 3 : 4;
+        return offs[blk] < 0 ? -1 : offs[blk] + (lc - base[blk]);
+      };
+      for (int t = tl; t < 24 * 25; t += tn) {
+        const int r = t / 25, c = t % 25;
+        const int gr = gcol(r);
+        if (gr < 0) continue;
+        if (c == 24) {
+          double sum = 0;
+          for (int i = 0; i < 9; ++i) sum += W.J[i * 24 + r] * W.oe[i];
+          b[gr] += sum;
+          continue;
+        }
+        const int gc = gcol(c);
+        if (gc < 0) continue;
+        double sum = 0;
+        for (int j = 0; j < 9; ++j) sum += W.AtO[r * 9 + j] * W.J[j * 24 + c];
+        H[(size_t)gr * np + gc] += sum;
+      }
+    } else {
+      const int oi = off2[d.si], oj = off2[d.sj];
+      if (tl < 6) {
+        const int k = tl;
+        const double om = W.r1 * d.info[k], oe = W.oe[k];
+        if (oj >= 0) {
+          H[(size_t)(oj + k) * np + oj + k] += om;
+          b[oj + k] += oe;
+        }
+        if (oi >= 0) {
+          H[(size_t)(oi + k) * np + oi + k] += om;
+          b[oi + k] += -oe;
+          if (oj >= 0) {
+            H[(size_t)(oi + k) * np + oj + k] += -om;
+            H[(size_t)(oj + k) * np + oi + k] += -om;
+          }
+        }
+      }
+    }
+  }
+
 // Inertial and bias edges (one block).  Phase 0: zero H / b.  Phase 1 (one thread per edge): residual and, for IMU
 // edges, the Jacobian strip.  Phase 2 (all threads): Omega e, then chi2 / Huber weight per edge, then J^T (rho' Omega)
 // for every IMU edge.  Phase 3: the block walks the edges in order and adds (J^T rho' Omega) J to the mapped positions
@@ -188,7 +239,7 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
                                const VieoImuPreint* __restrict__ pre, Vec3 gw, BaDenseWork* __restrict__ wk,
                                const int* __restrict__ off0, const int* __restrict__ off1, const int* __restrict__ off2,
                                int np, double* __restrict__ H, double* __restrict__ b, double* __restrict__ chi_dense,
-                               bool zero_h = true) {
+                               bool eval_only = false) {
   const int T = blockDim.x;
   // the pre-integrations' fields the edges read (61 doubles each) staged in shared memory: the residual / Jacobian
   // code is one long dependent chain per thread, global-memory latency on every field would dominate it
@@ -231,9 +282,10 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
       W.err[5] = (c.ba.z + c.dba.z) - (a.ba.z + a.dba.z);
     }
   }
-  if (zero_h)
+  if (!eval_only) {
     for (int t = threadIdx.x; t < np * np; t += T) H[t] = 0;
-  for (int t = threadIdx.x; t < np; t += T) b[t] = 0;
+    for (int t = threadIdx.x; t < np; t += T) b[t] = 0;
+  }
   __syncthreads();
   // Omega e (row i of edge m)
   for (int t = threadIdx.x; t < n_den * 9; t += T) {
@@ -272,51 +324,10 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
     wk[m].oe[i] = -wk[m].oe[i] * wk[m].r1;
   }
   __syncthreads();
+  if (eval_only) return;  // global BA: accumulation by k_gba_dense_accum, one colour of edges per launch
+  // local windows: the block walks the edges in the oracle's order
   for (int m = 0; m < n_den; ++m) {
-    const BaDense& d = den[m];
-    const BaDenseWork& W = wk[m];
-    if (d.type == 0) {
-      const int offs[5] = {off0[d.si], off0[d.sj], off1[d.si], off1[d.sj], off2[d.si]};
-      const int base[6] = {0, 6, 12, 15, 18, 24};
-      auto gcol = [&](int lc) {
-        int blk = lc < 6 ? 0 : lc < 12 ? 1 : lc < 15 ? 2 : lc < 18 ? 3 : 4;
-        return offs[blk] < 0 ? -1 : offs[blk] + (lc - base[blk]);
-      };
-      for (int t = threadIdx.x; t < 24 * 25; t += T) {
-        const int r = t / 25, c = t % 25;
-        const int gr = gcol(r);
-        if (gr < 0) continue;
-        if (c == 24) {
-          double sum = 0;
-          for (int i = 0; i < 9; ++i) sum += W.J[i * 24 + r] * W.oe[i];
-          b[gr] += sum;
-          continue;
-        }
-        const int gc = gcol(c);
-        if (gc < 0) continue;
-        double sum = 0;
-        for (int j = 0; j < 9; ++j) sum += W.AtO[r * 9 + j] * W.J[j * 24 + c];
-        H[(size_t)gr * np + gc] += sum;
-      }
-    } else {
-      const int oi = off2[d.si], oj = off2[d.sj];
-      if (threadIdx.x < 6) {
-        const int k = threadIdx.x;
-        const double om = W.r1 * d.info[k], oe = W.oe[k];
-        if (oj >= 0) {
-          H[(size_t)(oj + k) * np + oj + k] += om;
-          b[oj + k] += oe;
-        }
-        if (oi >= 0) {
-          H[(size_t)(oi + k) * np + oi + k] += om;
-          b[oi + k] += -oe;
-          if (oj >= 0) {
-            H[(size_t)(oi + k) * np + oj + k] += -om;
-            H[(size_t)(oj + k) * np + oi + k] += -om;
-          }
-        }
-      }
-    }
+    ba_dense_add_edge(den[m], wk[m], off0, off1, off2, np, H, b, 0, T);
     __syncthreads();
   }
   if (threadIdx.x == 0) {
@@ -332,6 +343,8 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
 // Levenberg-Marquardt bookkeeping (gain ratio, lambda schedule, accept / restore, stop criteria) runs in k_ba_control.
 struct BaParams {
   int K, P, E, np, nfree, n_den, n_pblk, has_dup;
+  int n_colors;         // big path: colours of the inertial edges (see BaDense::color)
+  int rank, world;      // landmark sharding (1 = single GPU)
   int big;              // global-BA sized handle: H is zeroed by a memset node, multi-CTA Schur / Cholesky kernels
   int lambda_on_poses;  // sharded runs add lambda to the pose diagonal on rank 0 only
   int cur;              // linearisation set (0/1) that belongs to the current estimate
@@ -371,8 +384,9 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaBuf B, int int
   if (prm.done) return;
   const int set = into_other ? 1 - prm.cur : prm.cur;
   if (blockIdx.x == gridDim.x - 1) {
-    ba_dense_block(B.den, prm.n_den, B.st, B.pre, prm.gw, B.wk, B.off0, B.off1, B.off2, prm.np, B.H[set], B.b[set],
-                   &B.prm->chi_dense, !prm.big);
+    if (!prm.big)
+      ba_dense_block(B.den, prm.n_den, B.st, B.pre, prm.gw, B.wk, B.off0, B.off1, B.off2, prm.np, B.H[set], B.b[set],
+                     &B.prm->chi_dense);
     return;
   }
   if ((int)blockIdx.x >= prm.n_pblk) return;
@@ -579,6 +593,28 @@ __device__ double ba_maxdiag(const double* __restrict__ H, int np, const double*
   return s[0];
 }
 
+// Sharded computeLambdaInit: the pose diagonal is a sum over ranks and the landmark maximum a maximum over ranks, but the
+// exchange hook only sums.  Every rank writes [its part of diag(Hpp) | its landmark maximum in slot `rank`, zeros in the
+// other slots] into the (idle) S buffer; after one all-reduce, the maximum of the buffer is the global max |diagonal|.
+__global__ void __launch_bounds__(256) k_ba_diag_pack(BaBuf B) {
+  __shared__ double s[256];
+  const BaParams& prm = *B.prm;
+  if (prm.done) return;
+  const int np = prm.np, set = prm.cur;
+  for (int i = threadIdx.x; i < np; i += 256) B.S[i] = B.H[set][(size_t)i * np + i];
+  double mx = 0;
+  for (int p = threadIdx.x; p < prm.P; p += 256)
+    if (B.pt_active[set][p])
+      for (int k = 0; k < 3; ++k) mx = fmax(mx, fabs(B.Hll[set][9 * (size_t)p + 4 * k]));
+  s[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + o]);
+    __syncthreads();
+  }
+  for (int r = threadIdx.x; r < prm.world; r += 256) B.S[np + r] = r == prm.rank ? s[0] : 0.0;
+}
+
 // Levenberg-Marquardt bookkeeping on the device (OptimizationAlgorithmLevenberg::solve, :83-166; SparseOptimizer::
 // optimize loop, sparse_optimizer.cpp:376-414).  mode 0: after the initial linearisation of an optimize() call;
 // mode 1: after a trial (solve + update + linearisation at the trial estimate).
@@ -589,7 +625,17 @@ __global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode) {
   if (prm.done) return;
   if (mode == 0) {
     double lam = prm.user_lambda;
-    if (!(lam > 0)) lam = 1e-5 * ba_maxdiag(B.H[prm.cur], prm.np, B.Hll[prm.cur], B.pt_active[prm.cur], prm.P, s);
+    if (!(lam > 0) && prm.world > 1) {  // from the all-reduced k_ba_diag_pack buffer
+      double mx = 0;
+      for (int i = threadIdx.x; i < prm.np + prm.world; i += 256) mx = fmax(mx, fabs(B.S[i]));
+      s[threadIdx.x] = mx;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + o]);
+        __syncthreads();
+      }
+      lam = 1e-5 * s[0];
+    } else if (!(lam > 0)) lam = 1e-5 * ba_maxdiag(B.H[prm.cur], prm.np, B.Hll[prm.cur], B.pt_active[prm.cur], prm.P, s);
     if (threadIdx.x == 0) {
       prm.chi_cur = prm.ini_chi = prm.pair[0];
       prm.lambda = lam;
@@ -983,125 +1029,179 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
   }
 }
 
-// Blocked right-looking Cholesky of the dense reduced camera system over the whole device, panels of kGNB columns.
-// Per panel k: k_gchol_diag (one CTA) factorises the diagonal block, inverts the triangular factor and advances the
-// forward substitution (y_k = L_kk^-1 y_k); k_gchol_trsm (one CTA per 64 rows below) forms L_ik = A_ik L_kk^-T as a small
-// matrix product and updates y_i -= L_ik y_k; k_gchol_syrk (one CTA per 64 x 64 tile of the trailing lower triangle)
-// subtracts L_ik L_jk^T.  Back substitution walks the panels in reverse (k_gchol_back): x_k = L_kk^-T y_k, then every
-// earlier entry y_j -= L_kj^T x_k.  Products use explicit fma(): this factorisation is bound by the 1e-6 chi2 tolerance,
-// not by bit parity with the oracle's scalar Cholesky.  prm.ok = 0 when a pivot is not positive.
+// Blocked right-looking Cholesky of the dense reduced camera system over the whole device, panels of kGNB columns, with
+// a tile-level structure map: nz[i][j] says whether the 64 x 64 tile (i, j) of the lower triangle holds anything but
+// exact zeros (k_gchol_scan after the Schur complement; fill-in is propagated by k_gchol_syrk).  A tile of exact zeros
+// contributes exactly nothing, so skipping it changes no bit of the result, and a map whose covisibility is mostly a
+// band plus a few loop closures costs a fraction of the dense n^3 / 3.
+// Per panel k: k_gchol_diag (one CTA) factorises the diagonal block in four 16-column sub-panels and advances the
+// forward substitution (y_k = L_kk^-1 y_k); k_gchol_trsm (one CTA per 64 rows below, one thread per row) solves
+// L_ik L_kk^T = A_ik by substitution and updates y_i -= L_ik y_k; k_gchol_syrk (one CTA per tile of the trailing lower
+// triangle) subtracts L_ik L_jk^T.  Back substitution walks the panels in reverse (k_gchol_back): x_k = L_kk^-T y_k,
+// then every earlier entry y_j -= L_kj^T x_k.  Products use explicit fma(): this factorisation is bound by the 1e-6
+// chi2 tolerance, not by bit parity with the oracle's scalar Cholesky.  prm.ok = 0 when a pivot is not positive.
 constexpr int kGNB = 64;
+constexpr int kGSub = 16;
 constexpr size_t kGcholSmem = sizeof(double) * 2 * kGNB * (kGNB + 4);
-__global__ void __launch_bounds__(256) k_gchol_diag(BaBuf B, double* __restrict__ Linv_all, double* __restrict__ yv, int k0,
-                                                    int force) {
+
+__global__ void __launch_bounds__(256) k_gchol_scan(BaBuf B, uint8_t* __restrict__ nz, int ldt, int force) {
+  __shared__ int s_any;
+  const BaParams& prm = *B.prm;
+  if (prm.done && !force) return;
+  const int n = prm.np, ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti || ti * kGNB >= n) return;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  int any = 0;
+  for (int e = threadIdx.x; e < kGNB * kGNB; e += 256) {
+    const int i = ti * kGNB + e / kGNB, j = tj * kGNB + e % kGNB;
+    if (i < n && j <= i && B.S[(size_t)i * n + j] != 0.0) any = 1;
+  }
+  if (any) s_any = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) nz[ti * ldt + tj] = (uint8_t)(s_any || ti == tj);
+}
+
+__global__ void __launch_bounds__(256) k_gchol_diag(BaBuf B, double* __restrict__ yv, int k0, int force) {
   extern __shared__ double s_gchol[];
   double (*A)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol);
-  double (*Li)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol + kGNB * (kGNB + 1));
-  __shared__ double sy[kGNB];
+  __shared__ double sy[kGNB], rd[kGNB];  // rd = 1 / L_jj: fp64 division is a long instruction sequence, multiply instead
   __shared__ int s_good;
   BaParams& prm = *B.prm;
   if (prm.done && !force) return;
   const int n = prm.np;
   if (k0 >= n) return;
-  const int nb = min(kGNB, n - k0), t = threadIdx.x;
+  const int nb = min(kGNB, n - k0), t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (k0 == 0) {  // start of a solve: y = bschur
     for (int i = t; i < n; i += 256) yv[i] = B.bs[i];
   }
   for (int e = t; e < kGNB * kGNB; e += 256) {
     const int i = e / kGNB, j = e % kGNB;
     A[i][j] = (i < nb && j <= i) ? B.S[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
-    Li[i][j] = 0;
   }
   if (t == 0) s_good = 1;
   __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    if (t == 0) {
-      const double d = A[j][j];
-      if (!(d > 0)) s_good = 0;
-      A[j][j] = sqrt(d);
+  if (t < kGNB) sy[t] = t < nb ? yv[k0 + t] : 0.0;
+  for (int c0 = 0; c0 < kGNB; c0 += kGSub) {
+    // (1) the 16 x 16 diagonal sub-block, by warp 0 (lane = row)
+    if (warp == 0) {
+      for (int j = 0; j < kGSub; ++j) {
+        const double d = A[c0 + j][c0 + j];
+        if (lane == 0 && !(d > 0)) s_good = 0;
+        const double sq = sqrt(d), rs = 1.0 / sq;
+        __syncwarp();
+        double l = 0;
+        if (lane == j) {
+          A[c0 + j][c0 + j] = sq;
+          rd[c0 + j] = rs;
+        }
+        if (lane > j && lane < kGSub) {
+          l = A[c0 + lane][c0 + j] * rs;
+          A[c0 + lane][c0 + j] = l;
+        }
+        __syncwarp();
+        if (lane > j && lane < kGSub)
+          for (int k = j + 1; k <= lane; ++k) A[c0 + lane][c0 + k] = fma(-l, A[c0 + k][c0 + j], A[c0 + lane][c0 + k]);
+        __syncwarp();
+      }
     }
     __syncthreads();
-    const double rd = 1.0 / A[j][j];
-    if (t > j && t < nb) A[t][j] *= rd;
+    // (2) rows below the sub-block: X L^T = A by substitution, one thread per row
+    const int r0 = c0 + kGSub;
+    if (t < kGNB - r0) {
+      const int i = r0 + t;
+      for (int j = 0; j < kGSub; ++j) {
+        double acc = A[i][c0 + j];
+        for (int m = 0; m < j; ++m) acc = fma(-A[i][c0 + m], A[c0 + j][c0 + m], acc);
+        A[i][c0 + j] = acc * rd[c0 + j];
+      }
+    }
     __syncthreads();
-    // trailing update of the block: entries (i, k) with j < k <= i < nb
-    const int m = nb - j - 1;
+    // (3) rank-16 update of the trailing lower triangle
+    const int m = kGNB - r0;
     for (int e = t; e < m * m; e += 256) {
-      const int i = j + 1 + e / m, k = j + 1 + e % m;
-      if (k <= i) A[i][k] = fma(-A[i][j], A[k][j], A[i][k]);
+      const int i = r0 + e / m, k = r0 + e % m;
+      if (k > i) continue;
+      double acc = A[i][k];
+#pragma unroll
+      for (int q = 0; q < kGSub; ++q) acc = fma(-A[i][c0 + q], A[k][c0 + q], acc);
+      A[i][k] = acc;
     }
     __syncthreads();
   }
-  // inverse of the triangular factor, one column per thread (forward substitution on the unit vector)
-  if (t < kGNB) {
-    const int c = t;
-    Li[c][c] = 1.0 / A[c][c];
-    for (int i = c + 1; i < kGNB; ++i) {
-      double acc = 0;
-      for (int m = c; m < i; ++m) acc = fma(A[i][m], Li[m][c], acc);
-      Li[i][c] = -acc / A[i][i];
+  // forward substitution of the panel's right-hand side by warp 0 (lane holds rows lane and lane + 32)
+  if (warp == 0) {
+    double y0 = sy[lane], y1 = sy[lane + 32];
+    for (int j = 0; j < kGNB; ++j) {
+      double yj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31) * rd[j];
+      if (lane == j) y0 = yj;
+      if (lane + 32 == j) y1 = yj;
+      if (lane > j) y0 = fma(-A[lane][j], yj, y0);
+      if (lane + 32 > j) y1 = fma(-A[lane + 32][j], yj, y1);
     }
+    if (lane < nb) yv[k0 + lane] = y0;
+    if (lane + 32 < nb) yv[k0 + lane + 32] = y1;
   }
-  __syncthreads();
-  if (t < kGNB) {
-    double acc = 0;
-    if (t < nb)
-      for (int m = 0; m <= t; ++m) acc = fma(Li[t][m], yv[k0 + m], acc);
-    sy[t] = acc;
-  }
-  __syncthreads();
-  if (t < nb) yv[k0 + t] = sy[t];
   for (int e = t; e < nb * nb; e += 256) {
     const int i = e / nb, j = e % nb;
     if (j <= i) B.S[(size_t)(k0 + i) * n + k0 + j] = A[i][j];
   }
-  double* Lo = Linv_all + (size_t)(k0 / kGNB) * kGNB * kGNB;
-  for (int e = t; e < kGNB * kGNB; e += 256) Lo[e] = Li[e / kGNB][e % kGNB];
+  __syncthreads();
   if (t == 0) {
     if (k0 == 0) prm.ok = s_good;
     else if (!s_good) prm.ok = 0;
   }
 }
 
-__global__ void __launch_bounds__(256) k_gchol_trsm(BaBuf B, const double* __restrict__ Linv_all, double* __restrict__ yv,
+__global__ void __launch_bounds__(128) k_gchol_trsm(BaBuf B, const uint8_t* __restrict__ nz, int ldt, double* __restrict__ yv,
                                                     int k0, int force) {
   extern __shared__ double s_gchol[];
   double (*As)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol);
   double (*Ls)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol + kGNB * (kGNB + 1));
-  __shared__ double sy[kGNB];
+  __shared__ double sy[kGNB], rd[kGNB];
   const BaParams& prm = *B.prm;
   if (prm.done && !force) return;
   const int n = prm.np;
   if (k0 >= n) return;
-  const int nb = min(kGNB, n - k0), t = threadIdx.x;
+  const int nb = min(kGNB, n - k0), t = threadIdx.x, kt = k0 / kGNB;
   const int i0 = k0 + nb + kGNB * blockIdx.x;
   if (i0 >= n) return;
+  if (!nz[(kt + 1 + blockIdx.x) * ldt + kt]) return;  // a tile of zeros stays zero and leaves y alone
   const int nr = min(kGNB, n - i0);
-  const double* Li = Linv_all + (size_t)(k0 / kGNB) * kGNB * kGNB;
-  for (int e = t; e < kGNB * kGNB; e += 256) {
+  for (int e = t; e < kGNB * kGNB; e += 128) {
     const int i = e / kGNB, j = e % kGNB;
     As[i][j] = (i < nr && j < nb) ? B.S[(size_t)(i0 + i) * n + k0 + j] : 0.0;
-    Ls[i][j] = Li[e];
+    Ls[i][j] = (i < nb && j <= i) ? B.S[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
   }
-  if (t < kGNB) sy[t] = t < nb ? yv[k0 + t] : 0.0;
+  if (t < kGNB) {
+    sy[t] = t < nb ? yv[k0 + t] : 0.0;
+    rd[t] = t < nb ? 1.0 / B.S[(size_t)(k0 + t) * n + k0 + t] : 1.0;
+  }
   __syncthreads();
-  // X[i][j] = sum_{m <= j} A[i][m] Linv[j][m]
-  for (int e = t; e < kGNB * kGNB; e += 256) {
-    const int i = e / kGNB, j = e % kGNB;
-    double acc = 0;
-    for (int m = 0; m <= j; ++m) acc = fma(As[i][m], Ls[j][m], acc);
-    if (i < nr && j < nb) B.S[(size_t)(i0 + i) * n + k0 + j] = acc;
-  }
-  __syncthreads();  // the block's own global writes are visible to it after the barrier
   if (t < nr) {
-    double acc = yv[i0 + t];
-    const double* Xr = B.S + (size_t)(i0 + t) * n + k0;
-    for (int j = 0; j < nb; ++j) acc = fma(-Xr[j], sy[j], acc);
-    yv[i0 + t] = acc;
+    double dy = 0;
+    for (int j = 0; j < nb; ++j) {
+      double acc = As[t][j], acc2 = 0;
+      int m = 0;
+      for (; m + 1 < j; m += 2) {
+        acc = fma(-As[t][m], Ls[j][m], acc);
+        acc2 = fma(-As[t][m + 1], Ls[j][m + 1], acc2);
+      }
+      if (m < j) acc = fma(-As[t][m], Ls[j][m], acc);
+      acc = (acc + acc2) * rd[j];
+      As[t][j] = acc;
+      dy = fma(acc, sy[j], dy);
+    }
+    yv[i0 + t] -= dy;
+  }
+  __syncthreads();
+  for (int e = t; e < kGNB * kGNB; e += 128) {
+    const int i = e / kGNB, j = e % kGNB;
+    if (i < nr && j < nb) B.S[(size_t)(i0 + i) * n + k0 + j] = As[i][j];
   }
 }
 
-__global__ void __launch_bounds__(256) k_gchol_syrk(BaBuf B, int k0, int force) {
+__global__ void __launch_bounds__(256) k_gchol_syrk(BaBuf B, uint8_t* __restrict__ nz, int ldt, int k0, int force) {
   extern __shared__ double s_gchol[];
   double (*At)[kGNB + 4] = reinterpret_cast<double (*)[kGNB + 4]>(s_gchol);                          // [m][row]
   double (*Bt)[kGNB + 4] = reinterpret_cast<double (*)[kGNB + 4]>(s_gchol + kGNB * (kGNB + 4));      // [m][col]
@@ -1110,9 +1210,12 @@ __global__ void __launch_bounds__(256) k_gchol_syrk(BaBuf B, int k0, int force) 
   if (blockIdx.x > blockIdx.y) return;  // lower triangle of tiles only
   const int n = prm.np;
   if (k0 >= n) return;
-  const int nb = min(kGNB, n - k0), t = threadIdx.x;
+  const int nb = min(kGNB, n - k0), t = threadIdx.x, kt = k0 / kGNB;
+  const int ti = kt + 1 + blockIdx.y, tj = kt + 1 + blockIdx.x;
   const int i0 = k0 + nb + kGNB * blockIdx.y, j0 = k0 + nb + kGNB * blockIdx.x;
   if (i0 >= n || j0 >= n) return;
+  if (!nz[ti * ldt + kt] || !nz[tj * ldt + kt]) return;
+  if (t == 0) nz[ti * ldt + tj] = 1;  // fill-in
   for (int e = t; e < kGNB * kGNB; e += 256) {
     const int r = e / kGNB, m = e % kGNB;
     At[m][r] = (i0 + r < n && m < nb) ? B.S[(size_t)(i0 + r) * n + k0 + m] : 0.0;
@@ -1148,27 +1251,50 @@ __global__ void __launch_bounds__(256) k_gchol_syrk(BaBuf B, int k0, int force) 
   }
 }
 
-__global__ void __launch_bounds__(256) k_gchol_back(BaBuf B, const double* __restrict__ Linv_all, double* __restrict__ yv,
+__global__ void __launch_bounds__(256) k_gchol_back(BaBuf B, const uint8_t* __restrict__ nz, int ldt, double* __restrict__ yv,
                                                     int k0, int force) {
+  extern __shared__ double s_gchol[];
+  double (*Ls)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol);
   __shared__ double sx[kGNB];
   const BaParams& prm = *B.prm;
   if (prm.done && !force) return;
   const int n = prm.np;
   if (k0 >= n) return;
-  const int nb = min(kGNB, n - k0), t = threadIdx.x;
-  const double* Li = Linv_all + (size_t)(k0 / kGNB) * kGNB * kGNB;
-  if (t < kGNB) {  // x_k = Linv^T y_k
-    double acc = 0;
-    if (t < nb)
-      for (int m = t; m < nb; ++m) acc = fma(Li[m * kGNB + t], yv[k0 + m], acc);
-    sx[t] = acc;
-    if (blockIdx.x == 0 && t < nb) B.x[k0 + t] = acc;
+  const int nb = min(kGNB, n - k0), t = threadIdx.x, lane = t & 31, kt = k0 / kGNB;
+  // every block needs x_k; blocks > 0 whose four column tiles are all empty have nothing to update
+  if (blockIdx.x > 0) {
+    const int jt0 = (blockIdx.x - 1) * 4;
+    bool any = false;
+    for (int q = 0; q < 4; ++q) any |= (jt0 + q < kt) && nz[kt * ldt + jt0 + q];
+    if (!any) return;
+  }
+  for (int e = t; e < kGNB * kGNB; e += 256) {
+    const int i = e / kGNB, j = e % kGNB;
+    Ls[i][j] = (i < nb && j <= i) ? B.S[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
   }
   __syncthreads();
-  if (blockIdx.x == 0) return;  // block 0 only publishes x_k (its reads of y_k must not race with an update of y)
+  if (t < 32) {  // x_k = L_kk^-T y_k by back substitution (lane holds rows lane and lane + 32)
+    double x0 = lane < nb ? yv[k0 + lane] : 0.0, x1 = lane + 32 < nb ? yv[k0 + lane + 32] : 0.0;
+    for (int j = kGNB - 1; j >= 0; --j) {
+      const double xj = __shfl_sync(0xffffffffu, j < 32 ? x0 : x1, j & 31) * (1.0 / Ls[j][j]);
+      if (lane == j) x0 = xj;
+      if (lane + 32 == j) x1 = xj;
+      if (lane < j) x0 = fma(-Ls[j][lane], xj, x0);
+      if (lane + 32 < j) x1 = fma(-Ls[j][lane + 32], xj, x1);
+    }
+    sx[lane] = x0;
+    sx[lane + 32] = x1;
+    if (blockIdx.x == 0) {
+      if (lane < nb) B.x[k0 + lane] = x0;
+      if (lane + 32 < nb) B.x[k0 + lane + 32] = x1;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) return;
   const int j = (blockIdx.x - 1) * 256 + t;
-  if (j >= k0) return;
+  if (j >= k0 || !nz[kt * ldt + j / kGNB]) return;
   double acc = yv[j];
+#pragma unroll 8
   for (int r = 0; r < nb; ++r) acc = fma(-B.S[(size_t)(k0 + r) * n + j], sx[r], acc);
   yv[j] = acc;
 }
@@ -1180,6 +1306,34 @@ __global__ void __launch_bounds__(256) k_gba_zero_h(BaBuf B, int into_other) {
   const size_t n2 = ((size_t)prm.np * prm.np + 1) / 2;  // the buffers are allocated with an even element count
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
     H[i] = make_double2(0.0, 0.0);
+  double* b = B.b[into_other ? 1 - prm.cur : prm.cur];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < prm.np; i += gridDim.x * blockDim.x) b[i] = 0;
+}
+// Global BA: hundreds of inertial factors.  Residuals / Jacobians / J^T rho' Omega of eight edges per CTA ...
+constexpr int kGbaDenPerCta = 8;
+__global__ void __launch_bounds__(256) k_gba_dense_eval(BaBuf B, int into_other) {
+  const BaParams& prm = *B.prm;
+  if (prm.done) return;
+  const int m0 = blockIdx.x * kGbaDenPerCta;
+  if (m0 >= prm.n_den) return;
+  ba_dense_block(B.den + m0, min(kGbaDenPerCta, prm.n_den - m0), B.st, B.pre, prm.gw, B.wk + m0, B.off0, B.off1, B.off2, prm.np,
+                 nullptr, nullptr, nullptr, true);
+}
+// ... then the accumulation, one colour per launch and one CTA per edge: edges of a colour share no keyframe, colours run
+// one after the other, so every entry of H / b is summed in a fixed order without atomics.
+__global__ void __launch_bounds__(128) k_gba_dense_accum(BaBuf B, int into_other, int color) {
+  BaParams& prm = *B.prm;
+  if (prm.done) return;
+  const int m = blockIdx.x;
+  if (m >= prm.n_den) return;
+  const int set = into_other ? 1 - prm.cur : prm.cur;
+  if (color == 0 && m == 0 && threadIdx.x == 0) {
+    double tot = 0;
+    for (int k = 0; k < prm.n_den; ++k) tot += B.wk[k].rho0;
+    prm.chi_dense = tot;
+  }
+  if (B.den[m].color != color) return;
+  ba_dense_add_edge(B.den[m], B.wk[m], B.off0, B.off1, B.off2, prm.np, B.H[set], B.b[set], 0, 128);
 }
 
 // One warp per point: xl = Dinv (bl - sum_a W_a^T xp), X += xl (apply != 0), landmark part of computeScale; the
@@ -1292,10 +1446,11 @@ struct vieo_ba {
   int device = 0;
   cudaStream_t st = nullptr;
   int capK = 0, capP = 0, capE = 0, capM = 0, cap_pblk = 0, cap_free = 0;
-  int K = 0, P = 0, E = 0, M = 0, np = 0, nfree = 0, n_den = 0, n_part = 0, n_pblk = 0;
+  int K = 0, P = 0, E = 0, M = 0, np = 0, nfree = 0, n_den = 0, n_part = 0, n_pblk = 0, n_colors = 1;
   bool points_free = true, has_dup = false, visual_only = false;
   bool big = false;  // global-BA sized handle (dense multi-CTA Schur / Cholesky path, no trial graph)
-  double *d_linv = nullptr, *d_yv = nullptr;
+  double* d_yv = nullptr;
+  uint8_t* d_nz = nullptr;  // tile structure map of the dense Cholesky
   int rank = 0, world = 1;
   vieo_allreduce_fn allreduce = nullptr;
   void* ar_ctx = nullptr;
@@ -1408,9 +1563,18 @@ int ba_allreduce(vieo_ba* h, double* buf, size_t n) {
 // computeActiveErrors + buildSystem at the current estimate; into_other: into the set that is not the current one
 int ba_enqueue_linearize(vieo_ba* h, int into_other, bool at_capacity) {
   const int pblk = at_capacity ? h->cap_pblk : h->n_pblk, nf = at_capacity ? h->cap_free : h->nfree;
-  if (h->big) {  // the inertial block of k_ba_linearize cannot zero np^2 entries by itself
+  if (h->big) {  // one block cannot zero np^2 entries or walk hundreds of inertial factors: dedicated kernels
     k_gba_zero_h<<<1184, 256, 0, h->st>>>(h->B, into_other);
+    k_ba_linearize<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
+    h->launches += 2;
+    if (h->n_den > 0) {
+      k_gba_dense_eval<<<(h->n_den + kGbaDenPerCta - 1) / kGbaDenPerCta, 256, 0, h->st>>>(h->B, into_other);
+      for (int c = 0; c < h->n_colors; ++c) k_gba_dense_accum<<<h->n_den, 128, 0, h->st>>>(h->B, into_other, c);
+      h->launches += 1 + h->n_colors;
+    }
+    k_ba_pose_reduce<<<std::max(nf, 1), 256, 0, h->st>>>(h->B, into_other);
     h->launches++;
+    return VIEO_OK;
   }
   k_ba_linearize<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
   k_ba_pose_reduce<<<std::max(nf, 1), 256, 0, h->st>>>(h->B, into_other);
@@ -1431,18 +1595,21 @@ int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, dou
     h->launches += 2;
     int rc = ba_allreduce(h, h->d_sys, h->sys_count());
     if (rc) return rc;
+    const int T = (n + kGNB - 1) / kGNB;
+    k_gchol_scan<<<dim3(T, T), 256, 0, h->st>>>(h->B, h->d_nz, T, force);
+    h->launches++;
     for (int k0 = 0; k0 < n; k0 += kGNB) {
       const int k1 = std::min(k0 + kGNB, n), tiles = (n - k1 + kGNB - 1) / kGNB;
-      k_gchol_diag<<<1, 256, kGcholSmem, h->st>>>(h->B, h->d_linv, h->d_yv, k0, force);
+      k_gchol_diag<<<1, 256, kGcholSmem, h->st>>>(h->B, h->d_yv, k0, force);
       h->launches++;
       if (tiles > 0) {
-        k_gchol_trsm<<<tiles, 256, kGcholSmem, h->st>>>(h->B, h->d_linv, h->d_yv, k0, force);
-        k_gchol_syrk<<<dim3(tiles, tiles), 256, kGcholSmem, h->st>>>(h->B, k0, force);
+        k_gchol_trsm<<<tiles, 128, kGcholSmem, h->st>>>(h->B, h->d_nz, T, h->d_yv, k0, force);
+        k_gchol_syrk<<<dim3(tiles, tiles), 256, kGcholSmem, h->st>>>(h->B, h->d_nz, T, k0, force);
         h->launches += 2;
       }
     }
     for (int k0 = ((n - 1) / kGNB) * kGNB; k0 >= 0; k0 -= kGNB) {
-      k_gchol_back<<<1 + (k0 + 255) / 256, 256, 0, h->st>>>(h->B, h->d_linv, h->d_yv, k0, force);
+      k_gchol_back<<<1 + (k0 + 255) / 256, 256, kGcholSmem, h->st>>>(h->B, h->d_nz, T, h->d_yv, k0, force);
       h->launches++;
     }
     k_ba_backsub<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, force ? 0 : 1, lambda, xl_out);
@@ -1486,7 +1653,7 @@ void ba_free(vieo_ba* h) {
   BaBuf& B = h->B;
   void* ptrs[] = {B.prm, B.st, B.st_bak, B.cp, B.X, B.X_bak, B.chi2, B.A, B.Dinv, B.db, B.x, B.partial, B.scale_part, B.part,
                   B.W[0], B.W[1], B.Hll[0], B.Hll[1], B.bl[0], B.bl[1], B.H[0], B.H[1], B.b[0], B.b[1], B.pt_active[0],
-                  B.pt_active[1], B.wk, h->d_linv, h->d_yv, h->d_sys, h->d_xl, h->d_ctl, h->d_lvl, h->d_bad, h->d_flags, h->d_sfix, h->d_es,
+                  B.pt_active[1], B.wk, h->d_nz, h->d_yv, h->d_sys, h->d_xl, h->d_ctl, h->d_lvl, h->d_bad, h->d_flags, h->d_sfix, h->d_es,
                   h->d_ep, h->d_pt_ptr, h->d_off0, h->d_off1, h->d_off2, h->d_prcol, h->d_free_state, h->d_free_off,
                   h->d_ps_ptr, h->d_ps_edges, h->d_obs, h->d_w, h->d_pre, h->d_den};
   for (void* p : ptrs)
@@ -1542,7 +1709,7 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   step(dalloc(&B.scale_part, P));
   if (h->big) {
     step(dalloc(&B.part, 16));
-    step(dalloc(&h->d_linv, (NP / kGNB + 1) * kGNB * kGNB));
+    step(dalloc(&h->d_nz, (NP / kGNB + 1) * (NP / kGNB + 1)));
     step(dalloc(&h->d_yv, NP));
   } else {
     step(dalloc(&B.part, (size_t)h->cap_free * kSchurSplit * 6 * (6 * (size_t)h->cap_free + 1)));
@@ -1572,6 +1739,7 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
       step(cudaFuncSetAttribute(k_gchol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcholSmem));
       step(cudaFuncSetAttribute(k_gchol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcholSmem));
       step(cudaFuncSetAttribute(k_gchol_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcholSmem));
+      step(cudaFuncSetAttribute(k_gchol_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcholSmem));
     } else {
       step(cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem(h->cap_free)));
       step(cudaFuncSetAttribute(k_ba_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
@@ -1724,6 +1892,25 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
     if (kernel) d.delta = (double)thBias;
     den.push_back(d);
   }
+  // greedy colouring of the inertial edges by shared keyframes (a chain needs two colours)
+  int n_colors = 1;
+  {
+    std::vector<std::vector<int>> used(K);
+    for (BaDense& d : den) {
+      int c = 0;
+      for (;;) {
+        bool clash = false;
+        for (int k : {d.si, d.sj})
+          for (int u : used[k]) clash |= u == c;
+        if (!clash) break;
+        ++c;
+      }
+      d.color = c;
+      used[d.si].push_back(c);
+      used[d.sj].push_back(c);
+      n_colors = std::max(n_colors, c + 1);
+    }
+  }
   h->n_den = (int)den.size();
   VIEO_ARG(h->n_den <= 2 * h->capM, "too many inertial edges");
   std::vector<uint8_t> lvl(std::max(E, 1));
@@ -1773,6 +1960,10 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   q.K = K; q.P = P; q.E = E; q.np = np; q.nfree = h->nfree; q.n_den = h->n_den; q.n_pblk = h->n_pblk;
   q.has_dup = h->has_dup ? 1 : 0;
   q.big = h->big ? 1 : 0;
+  q.n_colors = n_colors;
+  h->n_colors = n_colors;
+  q.rank = h->rank;
+  q.world = (h->allreduce && h->world > 1) ? h->world : 1;
   q.lambda_on_poses = h->rank == 0 ? 1 : 0;
   q.done = 1;
   q.ok = 1;
@@ -1823,10 +2014,6 @@ int vieo_ba_optimize(vieo_ba_t* h, int iterations, double lambda_init, const vol
   if (h->np == 0 || iterations == 0) return 0;
   if (stop && *stop) return 0;
   const bool sharded = h->allreduce && h->world > 1;
-  if (sharded && !(lambda_init > 0)) {
-    set_error("sharded BA needs an explicit initial lambda");
-    return VIEO_E_ARG;
-  }
   // optimize() state machine on the device: reset, then a fresh linearisation at the current estimate (levels / kernels
   // may have changed since the last call)
   BaParams& q = *h->h_prm;
@@ -1838,6 +2025,11 @@ int vieo_ba_optimize(vieo_ba_t* h, int iterations, double lambda_init, const vol
   int rc = ba_campose(h);
   if ((rc = ba_enqueue_linearize(h, 0, false))) return rc;
   if ((rc = ba_allreduce(h, h->B.prm->pair, 2))) return rc;
+  if (sharded && !(lambda_init > 0)) {  // g2o's own initial lambda needs the global maximum of the diagonal
+    k_ba_diag_pack<<<1, 256, 0, h->st>>>(h->B);
+    h->launches++;
+    if ((rc = ba_allreduce(h, h->B.S, (size_t)h->np + h->world))) return rc;
+  }
   k_ba_control<<<1, 256, 0, h->st>>>(h->B, 0);
   h->launches++;
   BA_CK(cudaGetLastError());
