@@ -290,6 +290,10 @@ def run_gpu(args, rank, world, local_rank):
     pool = args.pool
     n_img = 2 * F
     n_lba = F // LBA_EVERY if args.lba else 0
+    # SM partition: the LocalBA streams own `ba_sms` SMs, front-end + tracking the rest (include/vieo_b200.h)
+    part = api.SmPartition(args.ba_sms, device=local_rank) if (args.ba_sms > 0 and n_lba) else None
+    if part:
+        part.bind(api.SM_FRONTEND)   # every handle / staging stream this thread creates from here on
     orb = api.ORBextractor(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"], W, H,
                            max_batch=n_img, device=local_rank)
     cap = orb.cap
@@ -338,12 +342,20 @@ def run_gpu(args, rank, world, local_rank):
                               q, d["kp_blocked"].data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                               out[3].data_ptr(), scr.data_ptr(), scr.numel(), stream)
     n_workers = max(1, min(args.lba_workers, n_lba)) if n_lba else 0
+    if part:
+        part.bind(api.SM_BA)
     bas = [api.BundleAdjuster(max_states=64, max_points=2048, max_edges=16384, max_imu=16, device=local_rank)
            for _ in range(n_workers)]
     lba_pool = ThreadPoolExecutor(n_workers) if n_workers else None
     torch.cuda.synchronize()
-    main = torch.cuda.current_stream()
-    side = torch.cuda.Stream()
+    if part:
+        part.bind(api.SM_FRONTEND)
+        main = torch.cuda.ExternalStream(part.stream(api.SM_FRONTEND), device=dev)
+        side = torch.cuda.ExternalStream(part.stream(api.SM_FRONTEND), device=dev)
+        torch.cuda.set_stream(main)
+    else:
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
 
     def lba_job(wk, i0):
         for i in range(i0, n_lba, n_workers):
@@ -432,6 +444,8 @@ def run_gpu(args, rank, world, local_rank):
     outs = fe.alloc_outputs(F, pinned=True)
     host_np = host_t.numpy()
     trk_pool = ThreadPoolExecutor(1)
+    if part:
+        trk_pool.submit(part.bind, api.SM_FRONTEND).result()   # the tracking thread's staging stream
     matcher = api.ORBmatcher(0.8, True, device=local_rank)
 
     def tracking_host():
@@ -503,7 +517,9 @@ def run_gpu(args, rank, world, local_rank):
                    "levels": 8, "cache": f"inputs rotate over {pool} batches ({pool * F * 2 * H * W / 1e6:.0f} MB > 126 MB L2)",
                    "stages": ["orb_extract_x2", "stereo_matches_rectified", "imu_preint", "search_by_projection_x2", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
                    "pose_opt_points": list(POSE_POINTS), "sbp_queries": list(SBP_QUERIES), "lba_every": LBA_EVERY if n_lba else 0, "lba_window": LBA_SHAPE,
-                   "lba_workers": n_workers, "isolated_stage_ms": iso},
+                   "lba_workers": n_workers,
+                   "sm_partition": {"ba": part.sms(api.SM_BA), "frontend_tracking": part.sms(api.SM_FRONTEND)} if part else None,
+                   "isolated_stage_ms": iso},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches_per_step * args.steps,
@@ -534,6 +550,7 @@ def main():
     ap.add_argument("--lba", type=int, default=1, help="0: leave LocalBA out of the step")
     ap.add_argument("--lba-workers", type=int, default=16, help="host threads (one BA handle + stream each) running LocalBA windows")
     ap.add_argument("--lba-windows", type=int, default=3, help="distinct LocalBA problems generated")
+    ap.add_argument("--ba-sms", type=int, default=0, help="SMs reserved for the LocalBA streams (CUDA green context); 0: no partition")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

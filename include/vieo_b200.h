@@ -253,6 +253,10 @@ typedef struct VieoBaResult {
 } VieoBaResult;
 typedef struct vieo_ba vieo_ba_t;
 int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, int device, vieo_ba_t** out);
+/* Handle for map-sized problems (vieo_global_ba_prv): every one of up to max_states (<= 768) keyframes may be free; the
+ * reduced camera system is kept dense in HBM and factorised by multi-CTA kernels.  vieo_ba_create handles keep at most 48
+ * free keyframes (local windows) and run an LM trial as one CUDA graph. */
+int vieo_ba_create_global(int max_states, int max_points, int max_edges, int max_imu, int device, vieo_ba_t** out);
 void vieo_ba_destroy(vieo_ba_t* h);
 /* Sharding over GPUs: each rank holds a subset of the points with all their edges, the keyframe states
  * replicated, the inertial edges on rank 0.  `allreduce` sums `count` doubles at device pointer `buf` in place over
@@ -278,6 +282,22 @@ int vieo_ba_get(vieo_ba_t* h, VieoNavState* states_out, double* points_out, doub
  * (vieo_ba_get_hessian_blocks of SURVEY.md 8b). */
 int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_points, double* H_out, double* b_out);
 int vieo_ba_last_launches(const vieo_ba_t* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * SM partitions (CUDA green contexts).  The reference runs Tracking, LocalMapping and LoopClosing on separate CPU
+ * threads (src/System.cc); here they share one device, and the BA engines' chains of tiny ordered kernels starve beside
+ * the front-end's saturating ones unless they own a few SMs.  A partition splits the device into `ba_sms` SMs for the
+ * BA streams (VIEO_SM_BA) and the rest for the front-end / tracking streams (VIEO_SM_FRONTEND).  Handles
+ * (vieo_orb_create, vieo_frontend_create, vieo_ba_create) and the per-thread staging streams of the host-buffer calls are
+ * created inside the partition the CALLING THREAD is bound to at that moment; unbound threads get ordinary streams. */
+#define VIEO_SM_FRONTEND 0
+#define VIEO_SM_BA 1
+typedef struct vieo_sm_partition vieo_sm_partition_t;
+int vieo_sm_partition_create(int device, int ba_sms, vieo_sm_partition_t** out);
+void vieo_sm_partition_destroy(vieo_sm_partition_t* p);
+int vieo_sm_partition_sms(const vieo_sm_partition_t* p, int which);
+int vieo_sm_partition_bind_thread(vieo_sm_partition_t* p, int which); /* p == NULL: unbind */
+void* vieo_sm_partition_stream(vieo_sm_partition_t* p, int which, int high_priority); /* a new stream for *_dev callers */
 
 /* ------------------------------------------------------------------------------------------------
  * Guided searches of the tracking thread: ORBmatcher::SearchByProjection(Frame&, const Frame& last, th, bMono, th_far)

@@ -210,7 +210,7 @@ def _gba(n_kf, n_points, seed=3, **kw):
 @pytest.fixture(scope="module")
 def big_ba():
     import vieo_slam_b200.api as api
-    return api.BundleAdjuster(max_states=448, max_points=32768, max_edges=400000, max_imu=448)
+    return api.BundleAdjuster(max_states=448, max_points=32768, max_edges=400000, max_imu=448, global_ba=True)
 
 
 def test_gba_single_step_matches_oracle(big_ba):

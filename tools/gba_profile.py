@@ -37,7 +37,7 @@ def problem(n_kf, n_pt, seed):
 
 cam, d = problem(n_kf, n_pt, 8)
 ba = api.BundleAdjuster(max_states=max(64, n_kf + 8), max_points=len(d["points"]) + 8, max_edges=len(d["edge_state"]) + 8,
-                        max_imu=n_kf + 8)
+                        max_imu=n_kf + 8, global_ba=True)
 ba.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=2, bRobust=False)   # warm-up
 for robust in (False, True):
     t0 = time.perf_counter()

@@ -41,7 +41,7 @@ def main():
     cam, d = problem(n_kf, n_pt, 8, api.IMUPreintegrator(device=local))
     part = sharding.shard_lba_problem(d, rank, world)
     caps = dict(max_states=n_kf + 8, max_points=len(d["points"]) + 8, max_edges=len(d["edge_state"]) + 8, max_imu=n_kf + 8)
-    ba = api.BundleAdjuster(device=local, **caps)
+    ba = api.BundleAdjuster(device=local, global_ba=True, **caps)
     sharding.install_allreduce(ba, rank, world)
     ba.GlobalBundleAdjustmentNavStatePRV(part, cam, nIterations=2, bRobust=False)  # warm-up (NCCL channels, allocations)
     torch.cuda.synchronize(); dist.barrier()
@@ -52,7 +52,7 @@ def main():
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     ok = True
     if rank == 0:
-        single = api.BundleAdjuster(device=local, **caps)
+        single = api.BundleAdjuster(device=local, global_ba=True, **caps)
         single.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=2, bRobust=False)
         t1 = time.perf_counter()
         ref = single.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=iters, bRobust=False)

@@ -55,6 +55,13 @@ def lib():
         L.vieo_orb_profile_read.argtypes = [vp, vp, vp]
         L.vieo_hamming_knn2.argtypes = [vp, i32, vp, i32, vp, vp, i32]
         L.vieo_hamming_knn2_batch_dev.argtypes = [vp, sz, vp, i32, vp, sz, vp, i32, i32, i32, vp, vp, vp]
+        L.vieo_sm_partition_create.argtypes = [i32, i32, C.POINTER(vp)]
+        L.vieo_sm_partition_destroy.argtypes = [vp]
+        L.vieo_sm_partition_destroy.restype = None
+        L.vieo_sm_partition_sms.argtypes = [vp, i32]
+        L.vieo_sm_partition_bind_thread.argtypes = [vp, i32]
+        L.vieo_sm_partition_stream.argtypes = [vp, i32, i32]
+        L.vieo_sm_partition_stream.restype = vp
         L.vieo_sbp_scratch_bytes.argtypes = [i32]
         L.vieo_sbp_scratch_bytes.restype = sz
         L.vieo_sbp_batch.argtypes = [i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
@@ -75,6 +82,7 @@ def lib():
         L.vieo_pose_opt_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32]
         L.vieo_pose_opt_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.vieo_ba_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
+        L.vieo_ba_create_global.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
         L.vieo_ba_destroy.argtypes = [vp]
         L.vieo_ba_destroy.restype = None
         L.vieo_ba_set_sharding.argtypes = [vp, i32, i32, vp, vp]
@@ -102,6 +110,46 @@ def _check(rc):
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+SM_FRONTEND, SM_BA = 0, 1
+
+
+class SmPartition:
+    """vieo_sm_partition_*: `ba_sms` SMs of the device for the bundle-adjustment streams, the rest for the front-end and
+    tracking streams (CUDA green contexts).  Handles and the calling thread's staging stream are created inside the
+    partition the thread is bound to: `with part.bound(SM_BA): ba = BundleAdjuster(...)`."""
+
+    def __init__(self, ba_sms=16, device=0):
+        self._h = C.c_void_p()
+        _check(lib().vieo_sm_partition_create(device, ba_sms, C.byref(self._h)))
+
+    def sms(self, which):
+        return lib().vieo_sm_partition_sms(self._h, which)
+
+    def bind(self, which):
+        _check(lib().vieo_sm_partition_bind_thread(self._h, which))
+
+    @staticmethod
+    def unbind():
+        _check(lib().vieo_sm_partition_bind_thread(None, 0))
+
+    def bound(self, which):
+        part = self
+
+        class _Ctx:
+            def __enter__(self):
+                part.bind(which)
+
+            def __exit__(self, *a):
+                SmPartition.unbind()
+        return _Ctx()
+
+    def stream(self, which, high_priority=False):
+        s = lib().vieo_sm_partition_stream(self._h, which, int(high_priority))
+        if not s:
+            raise VieoError("vieo_sm_partition_stream failed")
+        return s
 
 
 class ORBextractor:
@@ -453,9 +501,11 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 class BundleAdjuster:
     """Device engine behind Optimizer::LocalBundleAdjustmentNavStatePRV / LocalBundleAdjustment (vieo_ba_* ABI)."""
 
-    def __init__(self, max_states=256, max_points=8192, max_edges=65536, max_imu=64, device=0):
+    def __init__(self, max_states=256, max_points=8192, max_edges=65536, max_imu=64, device=0, global_ba=False):
+        """global_ba: a handle for map-sized problems (GlobalBundleAdjustmentNavStatePRV; dense multi-CTA solver)."""
         self._h = C.c_void_p()
-        _check(lib().vieo_ba_create(max_states, max_points, max_edges, max_imu, device, C.byref(self._h)))
+        create = lib().vieo_ba_create_global if global_ba else lib().vieo_ba_create
+        _check(create(max_states, max_points, max_edges, max_imu, device, C.byref(self._h)))
         self._cb = None
 
     def close(self):
@@ -491,8 +541,7 @@ class BundleAdjuster:
 
     def GlobalBundleAdjustmentNavStatePRV(self, d, cam, nIterations=5, bRobust=True, stop=None):
         """Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342; bScaleOpt = false) on the flattened
-        map; the handle must have been created with the map's capacity (max_states > 56 selects the dense multi-CTA
-        reduced-camera-system path)."""
+        map; the handle must have been created with global_ba=True."""
         pb, keep = ba_problem(d)
         cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
         st = np.zeros(pb.n_states, NAVSTATE_DTYPE); pts = np.zeros((pb.n_points, 3)); chi2 = np.zeros(pb.n_edges)

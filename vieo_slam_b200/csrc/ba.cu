@@ -1669,7 +1669,14 @@ void ba_free(vieo_ba* h) {
 
 extern "C" {
 
+static int ba_create_impl(int max_states, int max_points, int max_edges, int max_imu, int device, bool big, vieo_ba_t** out);
 int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, int device, vieo_ba_t** out) {
+  return ba_create_impl(max_states, max_points, max_edges, max_imu, device, false, out);
+}
+int vieo_ba_create_global(int max_states, int max_points, int max_edges, int max_imu, int device, vieo_ba_t** out) {
+  return ba_create_impl(max_states, max_points, max_edges, max_imu, device, true, out);
+}
+static int ba_create_impl(int max_states, int max_points, int max_edges, int max_imu, int device, bool big, vieo_ba_t** out) {
   VIEO_ARG(out && max_states > 0 && max_points >= 0 && max_edges >= 0 && max_imu >= 0, "bad argument");
   int rc = use_device(device);
   if (rc) return rc;
@@ -1678,7 +1685,7 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   h->device = device;
   h->capK = max_states; h->capP = max_points; h->capE = max_edges; h->capM = max_imu;
   h->cap_pblk = (max_points + kBaWarps - 1) / kBaWarps;
-  h->big = max_states > kSchurMaxFree + 8;
+  h->big = big;
   if (h->big && max_states > 768) {
     set_error("vieo_ba_create: at most 768 keyframes (the Schur row tile of one keyframe must fit one SM's shared memory)");
     delete h;
@@ -1691,11 +1698,9 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
   BaBuf& B = h->B;
   cudaError_t e = cudaSuccess;
   auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  {  // the engine's kernels are tiny and latency-critical: let them overtake bulk work (front-end batches) on the device
-    int lo = 0, hi = 0;
-    step(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    step(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi));
-  }
+  // the engine's kernels are tiny and latency-critical: highest stream priority, and inside the calling thread's SM
+  // partition when there is one (vieo_sm_partition_bind_thread)
+  step(make_stream(&h->st, true));
   step(dalloc(&B.prm, 1));
   step(dalloc(&B.st, K)); step(dalloc(&B.st_bak, K)); step(dalloc(&B.cp, K));
   step(dalloc(&B.X, 3 * P)); step(dalloc(&B.X_bak, 3 * P)); step(dalloc(&B.chi2, E));

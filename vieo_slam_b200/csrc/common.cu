@@ -87,12 +87,143 @@ void* CallScratch::get_pinned(size_t bytes) {
   return hbuf;
 }
 
+}  // namespace vieo
+
+// ---------------------------------------------------------------------------------------------------------------
+// SM partitions (CUDA green contexts).  The bundle-adjustment engines are chains of tiny, strictly ordered kernels
+// (an LM trial is eight launches of a few CTAs); on a device that the ORB front-end keeps full they are starved: a
+// stream priority only reorders CTAs that are waiting, it cannot free an SM, and the Cholesky CTA needs most of one
+// (measured on B200, tools/green_ctx_probe.cu: a 300-kernel chain takes 1.2 ms alone, 31 ms beside a saturating kernel
+// with priority streams, 1.3 ms with a 16-SM green context of its own).  A partition gives the BA streams `ba_sms` SMs
+// and the front-end / tracking streams the remaining ones.  Driver entry points are resolved through the runtime
+// (cudaGetDriverEntryPoint): no link-time dependency on libcuda.
+#include <cuda.h>
+struct vieo_sm_partition {
+  int device = 0;
+  CUgreenCtx ctx[2] = {nullptr, nullptr};  // [VIEO_SM_FRONTEND, VIEO_SM_BA]
+  int sms[2] = {0, 0};
+};
+namespace {
+struct DriverApi {
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int,
+                                        unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  bool ok = false;
+};
+const DriverApi& driver_api() {
+  static DriverApi api = [] {
+    DriverApi a;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    a.ok = get("cuDeviceGet", (void**)&a.DeviceGet) && get("cuDeviceGetDevResource", (void**)&a.DeviceGetDevResource) &&
+           get("cuDevSmResourceSplitByCount", (void**)&a.DevSmResourceSplitByCount) &&
+           get("cuDevResourceGenerateDesc", (void**)&a.DevResourceGenerateDesc) && get("cuGreenCtxCreate", (void**)&a.GreenCtxCreate) &&
+           get("cuGreenCtxDestroy", (void**)&a.GreenCtxDestroy) && get("cuGreenCtxStreamCreate", (void**)&a.GreenCtxStreamCreate);
+    return a;
+  }();
+  return api;
+}
+thread_local vieo_sm_partition* t_part = nullptr;
+thread_local int t_which = 0;
+}  // namespace
+
+namespace vieo {
+cudaError_t make_stream(cudaStream_t* st, bool high_priority) {
+  int lo = 0, hi = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (e != cudaSuccess) return e;
+  if (t_part && t_part->ctx[t_which]) {
+    CUstream s = nullptr;
+    if (driver_api().GreenCtxStreamCreate(&s, t_part->ctx[t_which], CU_STREAM_NON_BLOCKING, high_priority ? hi : 0) != CUDA_SUCCESS)
+      return cudaErrorUnknown;
+    *st = (cudaStream_t)s;
+    return cudaSuccess;
+  }
+  return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, high_priority ? hi : 0);
+}
+}  // namespace vieo
+
+extern "C" {
+int vieo_sm_partition_create(int device, int ba_sms, vieo_sm_partition_t** out) {
+  using namespace vieo;
+  VIEO_ARG(out && ba_sms > 0, "bad argument");
+  int rc = use_device(device);
+  if (rc) return rc;
+  VIEO_CK(cudaFree(0));
+  const DriverApi& D = driver_api();
+  if (!D.ok) {
+    set_error("vieo_sm_partition_create: the driver does not export the green-context API");
+    return VIEO_E_CUDA;
+  }
+  auto fail = [&](const char* what, CUresult r) {
+    set_error("vieo_sm_partition_create: %s failed (CUresult %d)", what, (int)r);
+    return VIEO_E_CUDA;
+  };
+  CUdevice dev;
+  CUresult r = D.DeviceGet(&dev, device);
+  if (r != CUDA_SUCCESS) return fail("cuDeviceGet", r);
+  CUdevResource all, grp[1], rest;
+  if ((r = D.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS) return fail("cuDeviceGetDevResource", r);
+  VIEO_ARG((unsigned)ba_sms < all.sm.smCount, "ba_sms must leave SMs for the front-end");
+  unsigned n = 1;
+  if ((r = D.DevSmResourceSplitByCount(grp, &n, &all, &rest, 0, (unsigned)ba_sms)) != CUDA_SUCCESS || n != 1)
+    return fail("cuDevSmResourceSplitByCount", r);
+  vieo_sm_partition* p = new vieo_sm_partition();
+  p->device = device;
+  CUdevResource* res[2] = {&rest, &grp[0]};
+  for (int w = 0; w < 2; ++w) {
+    CUdevResourceDesc desc;
+    if ((r = D.DevResourceGenerateDesc(&desc, res[w], 1)) != CUDA_SUCCESS ||
+        (r = D.GreenCtxCreate(&p->ctx[w], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) {
+      vieo_sm_partition_destroy(p);
+      return fail("cuGreenCtxCreate", r);
+    }
+    p->sms[w] = (int)res[w]->sm.smCount;
+  }
+  *out = p;
+  return VIEO_OK;
+}
+void vieo_sm_partition_destroy(vieo_sm_partition_t* p) {
+  if (!p) return;
+  if (t_part == p) t_part = nullptr;
+  for (int w = 0; w < 2; ++w)
+    if (p->ctx[w]) driver_api().GreenCtxDestroy(p->ctx[w]);
+  delete p;
+}
+int vieo_sm_partition_sms(const vieo_sm_partition_t* p, int which) { return p && (which == 0 || which == 1) ? p->sms[which] : 0; }
+int vieo_sm_partition_bind_thread(vieo_sm_partition_t* p, int which) {
+  using namespace vieo;
+  VIEO_ARG(which == VIEO_SM_FRONTEND || which == VIEO_SM_BA, "bad partition index");
+  t_part = p;
+  t_which = which;
+  return VIEO_OK;
+}
+void* vieo_sm_partition_stream(vieo_sm_partition_t* p, int which, int high_priority) {
+  if (!p || (which != 0 && which != 1)) return nullptr;
+  vieo_sm_partition* keep = t_part;
+  const int keep_w = t_which;
+  t_part = p; t_which = which;
+  cudaStream_t st = nullptr;
+  if (cudaSetDevice(p->device) != cudaSuccess || vieo::make_stream(&st, high_priority != 0) != cudaSuccess) st = nullptr;
+  t_part = keep; t_which = keep_w;
+  return (void*)st;
+}
+}  // extern "C"
+
+namespace vieo {
 CallScratch* call_scratch(int device) {
   static thread_local CallScratch pool[16];
   if (device < 0 || device >= 16) return nullptr;
   CallScratch& c = pool[device];
   if (c.device != device) {
-    if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) {
+    if (make_stream(&c.st, false) != cudaSuccess) {
       set_error("cannot create a stream on device %d", device);
       return nullptr;
     }

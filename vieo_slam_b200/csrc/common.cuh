@@ -48,6 +48,10 @@ struct CallScratch {
 };
 CallScratch* call_scratch(int device);
 
+// Stream for a handle / call scratch created by the calling thread: inside the SM partition the thread is bound to
+// (vieo_sm_partition_bind_thread), else an ordinary stream.  high_priority: the device's highest stream priority.
+cudaError_t make_stream(cudaStream_t* st, bool high_priority);
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {

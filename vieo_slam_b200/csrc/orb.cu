@@ -1165,7 +1165,7 @@ int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out) {
     }                                                                                              \
   } while (0)
 
-  ORB_TRY_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  ORB_TRY_CUDA(make_stream(&h->stream, false));
   ORB_TRY_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
   const size_t B = cfg->max_batch;
   for (int l = 0; l < L; ++l) ORB_TRY(dev_alloc(h, &P.lvl[l], B * P.img_stride[l] + 64));
