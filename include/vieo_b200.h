@@ -270,6 +270,16 @@ void* vieo_ba_stream(vieo_ba_t* h);
  *   outputs   states_out [n_states], points_out [P][3], edge_chi2 [E], erase [E] (1 = ErasePairObs candidate) */
 int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, const volatile uint8_t* stop,
                       VieoNavState* states_out, double* points_out, double* edge_chi2, uint8_t* erase, VieoBaResult* res);
+/* Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342; bScaleOpt = false, no IMU initiator): every
+ * keyframe carries PR / V / Bias vertices (keyframe 0: state_flags 1|2|4, the others 2), IMU + bias-walk edges between
+ * consecutive keyframes (information x 1e-2 where the previous bias vertex is fixed, :955-958, :979-983), reprojection
+ * edges of every map point, Huber kernels (sqrt(16.919), sqrt(12.592), sqrt(5.99) / sqrt(7.815), :903-904, :1042-1043)
+ * only when `robust`; one optimize(n_iterations) from g2o's own initial lambda; no outlier pass.  The handle must come
+ * from vieo_ba_create_global.  Returns the number of LM iterations run (>= 0) or an error; res->err0 / err_end =
+ * activeRobustChi2 before / after.  edge_chi2 may be NULL. */
+int vieo_global_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, int n_iterations, int robust,
+                       const volatile uint8_t* stop, VieoNavState* states_out, double* points_out, double* edge_chi2,
+                       VieoBaResult* res);
 /* Building blocks (what `optimizer.optimize(n)` and friends do), for callers that keep the policy on their side. */
 int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam);
 int vieo_ba_chi2_large_set_level(vieo_ba_t* h, float rat);           /* GraphOperator::Chi2LargeSetLevel */

@@ -8,6 +8,13 @@ int main() {
   (void)e;
   ORBmatcher m(0.6f, true);
   IMUPreintegrator p;
+  GlobalBA* g = nullptr;
+  SmPartition* sp = nullptr;
+  (void)g; (void)sp;
+  std::vector<VieoSbpFrame> no_frames;
+  std::vector<int32_t> a, b, c, d;
+  VieoSbpQueries q{};
+  if (m.SearchByProjection(VIEO_SBP_LAST_FRAME, no_frames, nullptr, nullptr, nullptr, q, nullptr, a, b, c, d) != 0) return 2;
   const double s2[4] = {1e-8, 4e-6, 1e-10, 9e-6};
   IMUPreintegrator::SetParam(s2, 1, 200.0);
   std::printf("%s %d %g %zu\n", vieo_version(), ORBmatcher::TH_HIGH, IMUPreintegrator::Noise().sigma_g, sizeof(p));

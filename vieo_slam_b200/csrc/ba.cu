@@ -2137,6 +2137,7 @@ int vieo_global_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb_in, const VieoCamer
                        VieoBaResult* res) {
   VIEO_ARG(h && pb_in && cam && res && states_out, "null argument");
   VIEO_ARG(!pb_in->visual_only, "the global BA of the visual-only system is not implemented");
+  VIEO_ARG(h->big, "vieo_global_ba_prv needs a handle from vieo_ba_create_global");
   memset(res, 0, sizeof(*res));
   memcpy(states_out, pb_in->states, sizeof(VieoNavState) * pb_in->n_states);
   if (points_out && pb_in->n_points) memcpy(points_out, pb_in->points, 24 * (size_t)pb_in->n_points);

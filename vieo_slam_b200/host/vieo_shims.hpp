@@ -4,6 +4,8 @@
 // src/Optimizer.cc / include/Optimizer.h with these (INTEGRATION.md shows the exact edits).  No CPU fallback: every
 // call throws std::runtime_error with vieo_last_error() when the library reports a failure.
 #pragma once
+#include <algorithm>
+#include <cstring>
 #include <list>
 #include <stdexcept>
 #include <string>
@@ -127,6 +129,28 @@ class ORBmatcher {
     vieo_check(vieo_hamming_csr(q.data, t.data, t.rows, row_ptr.data(), cand.data(), n, best.data(), best_idx.data(),
                                 second.data(), second_idx.data(), device_), "vieo_hamming_csr");
   }
+  // The tracking thread's SearchByProjection overloads on the flattened frame(s) (src/ORBmatcher.cc:230-335,
+  // 1303-1467; INTEGRATION.md 2b shows how Frame / MapPoint fields map onto the arrays).  mode = VIEO_SBP_LAST_FRAME or
+  // VIEO_SBP_LOCAL_MAP; the matcher's mfNNratio / mbCheckOrientation are written into every frame record.
+  // Returns the reference's nmatches summed over the frames; n_matches gets the per-frame values.
+  int SearchByProjection(int mode, std::vector<VieoSbpFrame>& frames, const VieoKeyPoint* keys_un, const float* vuright,
+                         const uint8_t* descriptors, const VieoSbpQueries& queries, const uint8_t* kp_blocked,
+                         std::vector<int32_t>& kp_match, std::vector<int32_t>& q_match, std::vector<int32_t>& q_dist,
+                         std::vector<int32_t>& n_matches) const {
+    size_t nk = 0, nq = 0;
+    for (VieoSbpFrame& f : frames) {
+      f.nn_ratio = mfNNratio;
+      f.check_orientation = mbCheckOrientation ? 1 : 0;
+      nk = std::max(nk, (size_t)f.kp_begin + f.n_kp);
+      nq = std::max(nq, (size_t)f.q_begin + f.n_q);
+    }
+    kp_match.assign(nk, -1); q_match.assign(nq, -1); q_dist.assign(nq, -1); n_matches.assign(frames.size(), 0);
+    vieo_check(vieo_sbp_batch(mode, frames.data(), (int)frames.size(), keys_un, vuright, descriptors, &queries, kp_blocked,
+                              kp_match.data(), q_match.data(), q_dist.data(), n_matches.data(), device_), "vieo_sbp_batch");
+    int total = 0;
+    for (int32_t n : n_matches) total += n;
+    return total;
+  }
   float mfNNratio;
   bool mbCheckOrientation;
 
@@ -212,6 +236,44 @@ class LocalBA {
 
  private:
   vieo_ba_t* h_ = nullptr;
+};
+
+// GlobalBundleAdjustmentNavStatePRV engine (src/Optimizer.cc:771-1342): a handle sized for the whole map
+class GlobalBA {
+ public:
+  explicit GlobalBA(int max_keyframes = 768, int max_points = 1 << 17, int max_edges = 1 << 21, int device = 0) {
+    vieo_check(vieo_ba_create_global(max_keyframes, max_points, max_edges, max_keyframes, device, &h_), "vieo_ba_create_global");
+  }
+  ~GlobalBA() { vieo_ba_destroy(h_); }
+  GlobalBA(const GlobalBA&) = delete;
+  GlobalBA& operator=(const GlobalBA&) = delete;
+  vieo_ba_t* handle() { return h_; }
+  // returns the LM iterations run; pbStopFlag is the reference's bool* (mbStopGBA)
+  int Run(const VieoBaProblem& pb, const VieoCamera& cam, int nIterations, bool bRobust, const bool* pbStopFlag,
+          VieoNavState* states_out, double* points_out, VieoBaResult& res) {
+    int rc = vieo_global_ba_prv(h_, &pb, &cam, nIterations, bRobust ? 1 : 0, reinterpret_cast<const volatile uint8_t*>(pbStopFlag),
+                                states_out, points_out, nullptr, &res);
+    vieo_check(rc, "vieo_global_ba_prv");
+    return rc;
+  }
+
+ private:
+  vieo_ba_t* h_ = nullptr;
+};
+
+// SM partition of one device between the front-end / tracking streams and the BA streams (CUDA green contexts); a
+// thread binds itself before it creates its handles (include/vieo_b200.h)
+class SmPartition {
+ public:
+  explicit SmPartition(int ba_sms, int device = 0) { vieo_check(vieo_sm_partition_create(device, ba_sms, &p_), "vieo_sm_partition_create"); }
+  ~SmPartition() { vieo_sm_partition_destroy(p_); }
+  SmPartition(const SmPartition&) = delete;
+  SmPartition& operator=(const SmPartition&) = delete;
+  void BindThisThread(int which) { vieo_check(vieo_sm_partition_bind_thread(p_, which), "vieo_sm_partition_bind_thread"); }
+  int SMs(int which) const { return vieo_sm_partition_sms(p_, which); }
+
+ private:
+  vieo_sm_partition_t* p_ = nullptr;
 };
 
 }  // namespace VIEO_SLAM_B200
