@@ -30,6 +30,7 @@
 namespace vieo {
 
 constexpr int kBaWarps = 8;
+constexpr int kLinPts = 4, kLinLanes = 32 / kLinPts;  // k_ba_linearize: map points per warp / lanes per point
 
 struct BaDense {  // one inertial (EdgeNavStatePRV) or bias random-walk (EdgeNavStateBias) factor
   int type;       // 0 IMU, 1 bias
@@ -390,8 +391,14 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaBuf B, int int
     return;
   }
   if ((int)blockIdx.x >= prm.n_pblk) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * kBaWarps + warp;
+  // a map point has ~6 observations: four points per warp, eight lanes each (a point with more edges takes more turns),
+  // so the blocks past ceil(P / 32) of the (warp-per-point sized) grid have nothing to do but report a zero chi2 part
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & (kLinLanes - 1);
+  if ((int)blockIdx.x * kBaWarps * kLinPts >= prm.P) {
+    if (threadIdx.x == 0) B.partial[blockIdx.x] = 0;
+    return;
+  }
+  const int p = (blockIdx.x * kBaWarps + warp) * kLinPts + lane / kLinLanes;
   double* Wb = B.W[set];
   double acc[9], rsum = 0;
 #pragma unroll
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaBuf B, int int
   if (p < prm.P) {
     const int i0 = B.pt_ptr[p], i1 = B.pt_ptr[p + 1];
     const Vec3 Xp = ld3(B.X + 3 * (size_t)p);
-    for (int i = i0 + lane; i < i1; i += 32) {
+    for (int i = i0 + sub; i < i1; i += kLinLanes) {
       double* Wi = Wb + 18 * (size_t)i;
       double* Ai = B.A + 27 * (size_t)i;
       if (B.lvl[i] & 1) {
@@ -477,12 +484,12 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaBuf B, int int
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    for (int o = kLinLanes / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
-  any = __any_sync(0xffffffffu, any);
-  if (lane == 0) {
-    s_chi[warp] = rsum;
+  any = ((__ballot_sync(0xffffffffu, any) >> (lane & ~(kLinLanes - 1))) & ((1u << kLinLanes) - 1)) != 0;
+  if (lane == 0) s_chi[warp] = rsum;
+  if (sub == 0) {
     if (p < prm.P) {
       double* H = B.Hll[set] + 9 * (size_t)p;
       H[0] = acc[0]; H[1] = acc[1]; H[2] = acc[2];
