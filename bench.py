@@ -20,6 +20,10 @@ import time
 
 import numpy as np
 
+# one stream per handle (extractors, front-end chunks, BA engines, staging): more hardware queues than the default 8, or
+# unrelated streams serialise on a shared queue; must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -544,7 +548,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=128, help="stereo frames per step per GPU")
     ap.add_argument("--pool", type=int, default=4, help="distinct input batches rotated through")
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--lba", type=int, default=1, help="0: leave LocalBA out of the step")

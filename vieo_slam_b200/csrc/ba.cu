@@ -23,6 +23,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "ba_edges.cuh"
@@ -352,6 +354,7 @@ struct BaParams {
   int done;             // optimize() finished: trial kernels return immediately
   int stop;             // host abort flag seen (pbStopFlag)
   int iteration, iters_target, iters_done, qmax, nBad, ok;
+  int trials;           // LM trials run by the current optimize()
   double lambda, ni, user_lambda;
   double chi_cur, ini_chi;   // activeRobustChi2 of the current estimate / at the start of the iteration
   double pair[2];            // [robust chi2 of the last linearisation, landmark part of computeScale] (all-reduced when sharded)
@@ -379,7 +382,7 @@ struct BaBuf {  // device pointers of one handle (constant for its lifetime)
 // evaluates one reprojection edge (residual, chi2, Huber weight, Jacobians), the 3x3 Hll / bl are reduced with warp
 // shuffles, W (Hpl) and A (the edge's Hpp / b part) are stored per edge.  The extra last block does the inertial edges.
 // into_other: write the set that does NOT belong to the current estimate (speculative linearisation of a trial).
-__global__ void __launch_bounds__(kBaWarps * 32) k_ba_linearize(BaBuf B, int into_other) {
+__global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize(BaBuf B, int into_other) {
   __shared__ double s_chi[kBaWarps];
   const BaParams& prm = *B.prm;
   if (prm.done) return;
@@ -625,11 +628,15 @@ __global__ void __launch_bounds__(256) k_ba_diag_pack(BaBuf B) {
 // Levenberg-Marquardt bookkeeping on the device (OptimizationAlgorithmLevenberg::solve, :83-166; SparseOptimizer::
 // optimize loop, sparse_optimizer.cpp:376-414).  mode 0: after the initial linearisation of an optimize() call;
 // mode 1: after a trial (solve + update + linearisation at the trial estimate).
-__global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode) {
+__global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode, cudaGraphConditionalHandle cond) {
   __shared__ double s[256];
   __shared__ int s_restore;
   BaParams& prm = *B.prm;
-  if (prm.done) return;
+  // cond != 0: this launch is the last node of the WHILE body of the optimize() graph; the loop goes on until done
+  if (prm.done) {
+    if (cond && threadIdx.x == 0) cudaGraphSetConditional(cond, 0);
+    return;
+  }
   if (mode == 0) {
     double lam = prm.user_lambda;
     if (!(lam > 0) && prm.world > 1) {  // from the all-reduced k_ba_diag_pack buffer
@@ -676,6 +683,7 @@ __global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode) {
       restore = 1;
     }
     prm.qmax++;
+    prm.trials++;
     const bool more_trials = rho < 0 && prm.qmax < 10 && !prm.stop;
     if (!more_trials) {
       prm.iters_done++;
@@ -693,6 +701,7 @@ __global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode) {
       }
     }
     s_restore = restore;
+    if (cond) cudaGraphSetConditional(cond, prm.done ? 0 : 1);
   }
   __syncthreads();
   if (s_restore) {  // pop(): back to the estimate before the trial
@@ -1467,6 +1476,10 @@ struct vieo_ba {
   BaBuf B;                    // device pointers handed to the kernels by value
   BaParams* h_prm = nullptr;  // pinned host mirror of B.prm
   cudaGraphExec_t trial_graph = nullptr;
+  // a whole optimize() as ONE launch: a WHILE conditional node whose body is the LM trial; k_ba_control keeps the loop
+  // alive until the device-side state machine is done (no host round trip per trial)
+  cudaGraphExec_t opt_graph = nullptr;
+  cudaStream_t st_ctl = nullptr;  // side stream for the abort flag while the optimize graph runs
   // buffers that are not part of BaBuf
   double *d_sys = nullptr, *d_xl = nullptr, *d_ctl = nullptr;
   uint8_t *d_lvl = nullptr, *d_bad = nullptr, *d_flags = nullptr, *d_sfix = nullptr;
@@ -1533,6 +1546,7 @@ bool host_inverse(const double* A, int n, double* Ai) {
     }                                                                                    \
   } while (0)
 
+constexpr int kNodesPerTrial = 8;  // kernels of one LM trial (ba_enqueue_trial)
 size_t schur_smem(int nfree) { return sizeof(double) * kBaWarps * 6 * (6 * (size_t)nfree + 1); }
 size_t gba_schur_smem(int nfree) { return sizeof(double) * 6 * (6 * (size_t)nfree + 1); }
 
@@ -1640,12 +1654,12 @@ int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, dou
 }
 
 // one LM trial: solve + update + linearisation at the trial estimate + bookkeeping
-int ba_enqueue_trial(vieo_ba* h, bool at_capacity) {
+int ba_enqueue_trial(vieo_ba* h, bool at_capacity, cudaGraphConditionalHandle cond = 0) {
   int rc;
   if ((rc = ba_enqueue_solve(h, at_capacity, 0, 0.0, nullptr))) return rc;
   if ((rc = ba_enqueue_linearize(h, 1, at_capacity))) return rc;
   if (!at_capacity && (rc = ba_allreduce(h, h->B.prm->pair, 2))) return rc;
-  k_ba_control<<<1, 256, 0, h->st>>>(h->B, 1);
+  k_ba_control<<<1, 256, 0, h->st>>>(h->B, 1, cond);
   h->launches++;
   return VIEO_OK;
 }
@@ -1666,6 +1680,8 @@ void ba_free(vieo_ba* h) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->trial_graph) cudaGraphExecDestroy(h->trial_graph);
+  if (h->opt_graph) cudaGraphExecDestroy(h->opt_graph);
+  if (h->st_ctl) cudaStreamDestroy(h->st_ctl);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_prm) cudaFreeHost(h->h_prm);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1766,6 +1782,39 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
       step(cudaStreamEndCapture(h->st, &g));
       if (e == cudaSuccess) step(cudaGraphInstantiate(&h->trial_graph, g, 0));
       if (g) cudaGraphDestroy(g);
+    }
+    // the optimize() graph; any failure here just leaves the chunked trial-graph loop in charge
+    if (e == cudaSuccess) {
+      cudaGraph_t og = nullptr, body = nullptr, tmp = nullptr;
+      cudaGraphConditionalHandle hc = 0;
+      bool ok = cudaGraphCreate(&og, 0) == cudaSuccess &&
+                cudaGraphConditionalHandleCreate(&hc, og, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+      if (ok) {
+        cudaGraphNodeParams np_ = {};
+        np_.type = cudaGraphNodeTypeConditional;
+        np_.conditional.handle = hc;
+        np_.conditional.type = cudaGraphCondTypeWhile;
+        np_.conditional.size = 1;
+        cudaGraphNode_t node;
+        ok = cudaGraphAddNode(&node, og, nullptr, 0, &np_) == cudaSuccess;
+        if (ok) body = np_.conditional.phGraph_out[0];
+      }
+      if (ok) ok = cudaStreamBeginCaptureToGraph(h->st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        ba_enqueue_trial(h, true, hc);
+        ok = cudaStreamEndCapture(h->st, &tmp) == cudaSuccess;
+      }
+      if (ok) ok = cudaGraphInstantiate(&h->opt_graph, og, 0) == cudaSuccess;
+      if (!ok) {
+        h->opt_graph = nullptr;
+        cudaGetLastError();
+      }
+      if (og) cudaGraphDestroy(og);
+      if (ok) ok = make_stream(&h->st_ctl, true) == cudaSuccess;
+      if (!ok && h->opt_graph) {
+        cudaGraphExecDestroy(h->opt_graph);
+        h->opt_graph = nullptr;
+      }
     }
     h->launches = 0;
   }
@@ -2030,7 +2079,7 @@ int vieo_ba_optimize(vieo_ba_t* h, int iterations, double lambda_init, const vol
   // may have changed since the last call)
   BaParams& q = *h->h_prm;
   q.cur = 0; q.done = 0; q.stop = 0; q.ok = 1;
-  q.iteration = 0; q.iters_target = iterations; q.iters_done = 0; q.qmax = 0; q.nBad = 0;
+  q.iteration = 0; q.iters_target = iterations; q.iters_done = 0; q.qmax = 0; q.nBad = 0; q.trials = 0;
   q.user_lambda = lambda_init;
   BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
   BA_CK(cudaMemsetAsync(h->B.x, 0, 8 * (size_t)h->np, h->st));
@@ -2042,12 +2091,34 @@ int vieo_ba_optimize(vieo_ba_t* h, int iterations, double lambda_init, const vol
     h->launches++;
     if ((rc = ba_allreduce(h, h->B.S, (size_t)h->np + h->world))) return rc;
   }
-  k_ba_control<<<1, 256, 0, h->st>>>(h->B, 0);
+  k_ba_control<<<1, 256, 0, h->st>>>(h->B, 0, 0);
   h->launches++;
   BA_CK(cudaGetLastError());
+  if (!sharded && h->opt_graph) {
+    // ONE launch for the whole optimize(): the graph's WHILE node repeats the trial until k_ba_control says done.  The
+    // caller's abort flag (pbStopFlag, polled once per iteration by sparse_optimizer.cpp:376) is forwarded through a side
+    // stream while the graph runs.
+    BA_CK(cudaGraphLaunch(h->opt_graph, h->st));
+    h->launches += kNodesPerTrial;
+    if (stop) {
+      bool sent = false;
+      while (cudaStreamQuery(h->st) == cudaErrorNotReady) {
+        if (*stop && !sent) {
+          static const int one = 1;
+          BA_CK(cudaMemcpyAsync(&h->B.prm->stop, &one, sizeof(int), cudaMemcpyHostToDevice, h->st_ctl));
+          sent = true;
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+      }
+    }
+    if ((rc = ba_read_prm(h))) return rc;
+    h->launches += kNodesPerTrial * std::max(h->h_prm->trials - 1, 0);
+    BA_CK(cudaGetLastError());
+    return h->h_prm->iters_done;
+  }
   // trials are launched in small chunks (a finished optimize() turns the remaining ones into no-ops); the abort flag is
   // polled between chunks (sparse_optimizer.cpp:376 polls it once per iteration)
-  const int kChunk = 3, kNodes = 8;
+  const int kChunk = 3, kNodes = kNodesPerTrial;
   for (int guard = 0; guard < 10 * iterations + 4; guard += kChunk) {
     for (int c = 0; c < kChunk; ++c) {
       if (!sharded && h->trial_graph) {

@@ -1,6 +1,8 @@
 // Error reporting and device selection for libvieo_b200.so.
 #include <stdarg.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vieo {
@@ -56,6 +58,12 @@ int use_device(int device) {
   }
   return VIEO_OK;
 }
+
+// Every handle owns a stream (one per camera extractor, per front-end chunk, per BA engine, per calling thread); with the
+// default of 8 hardware work queues unrelated streams alias onto one queue and serialise (measured on B200: 8 LocalBA
+// streams + front-end + tracking streams run 24 % faster with 32 queues).  The variable is read when the CUDA context is
+// created, so it is set when the library is loaded, unless the user chose a value.
+__attribute__((constructor)) static void vieo_more_hw_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 
 void* CallScratch::get(int slot, size_t bytes) {
   if (bytes == 0) bytes = 1;
