@@ -11,6 +11,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace vieo {
@@ -47,6 +49,7 @@ struct OrbParams {  // passed by value to kernels
   int maxn[kMaxLevels];        // node capacity per level
   int slot_begin[kMaxLevels + 1];  // per-image offsets into lvl_kp
   int tile_w, tile_h;          // max cell dims (tile_w padded to 4)
+  int tile_pitch;              // row pitch of the shared-memory cell tile (64 when the tile is TMA-staged)
   int ini_th, min_th;
   const Cell* cells;
   const int4* rx[kMaxLevels];  // per dst x: {x0, x1, a0, a1}
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 // words per row with funnel shifts + one PRMT.  Sliding-window tree with 3-input ops: windows of 3, then 3+3+3 -> 9:
 // 64 VIMNMX3 for the 16 arcs of both pixels + 16 for the final min-of-max / max-of-min.
 __device__ __forceinline__ unsigned fast_score2(const uint8_t* rowc, int o8, int pitch) {
-  // rowc: aligned word that holds the first centre; o8 = 8 * (byte offset of that centre in the word) (0 or 16)
+  // rowc: aligned word that holds the first centre; o8 = 8 * (byte offset of that centre in the word) (0, 8, 16 or 24)
 #define VIEO_ROW3(dy)                                                          \
   {                                                                            \
     const unsigned* w_ = reinterpret_cast<const unsigned*>(rowc + (dy) * pitch); \
@@ -157,14 +160,54 @@ __device__ __forceinline__ unsigned fast_score2(const uint8_t* rowc, int o8, int
   return __vmaxu2(va, bv);
 }
 
+// TMA staging of the cell tile: one tensor map per pyramid level over (x, y, image) with the level's 64-byte-multiple
+// pitch; a single thread issues one cp.async.bulk.tensor of a tile_pitch x tile_h box that lands in shared memory and
+// signals an mbarrier, while the other threads already clear the score tile.  The unit faults ("illegal instruction") when
+// the innermost coordinate is not a multiple of 16 bytes (measured on B200: tools/tma_probe2.cu), so the box starts at
+// x0 - 1 rounded down to 16 and the scorer reads the cell at the residual column offset.  Out-of-image parts of the
+// box are zero-filled by the unit.
+struct FastTmaps {
+  CUtensorMap m[kMaxLevels];
+};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_tile3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z,
+                                                uint32_t bytes) {
+  const uint32_t b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"((uint64_t)map), "r"(b), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  const uint32_t b = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "VIEO_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra VIEO_DONE_%=;\n"
+      "bra VIEO_WAIT_%=;\n"
+      "VIEO_DONE_%=:\n"
+      "}\n" ::"r"(b),
+      "r"(phase)
+      : "memory");
+}
+
 // One CTA per (cell, image): stage the cell image in shared memory, score every interior pixel (2 per thread), 3x3
 // strict NMS restricted to the cell interior (each cell is an independent cv::FAST call in the reference), decide
 // iniTh vs minTh from the post-NMS count, and write the survivors in raster order.
 // Tile layouts: raw row pitch TP = tile_w + 8, cell column x at byte 1 + x (interior column 3 -> aligned byte 4);
 // score row pitch TP, interior pixel (x, y) at row y + 1, byte 4 + x, with a zero ring around the interior.
+template <bool kTma>
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(OrbParams P, const uint8_t* __restrict__ img0,
-                                                            size_t img0_stride, int img0_pitch) {
-  extern __shared__ __align__(16) uint8_t smem[];
+                                                            size_t img0_stride, int img0_pitch,
+                                                            const __grid_constant__ FastTmaps tmaps) {
+  // no static shared memory in this kernel: the dynamic region then starts at offset 0 of the CTA's window, which gives
+  // the TMA destination (the raw tile, first in the region) its 128-byte alignment
+  extern __shared__ __align__(128) uint8_t fsmem[];
+  uint8_t* smem = fsmem;
   const Cell c = P.cells[blockIdx.x];
   const int img = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -177,28 +220,44 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(OrbParams P, const 
     base = P.lvl[c.level] + img * P.img_stride[c.level];
     pitch = P.pitch[c.level];
   }
-  const int TP = P.tile_w + 8;
+  const int TP = P.tile_pitch;
   uint8_t* raw = smem;
   const int iw = c.cw - 6, ih = c.ch - 6;
   uint8_t* sc = smem + TP * P.tile_h;  // (ih + 2) rows
-  __shared__ int s_warp[kFastThreads / 32];
+  uint8_t* tail = smem + ((2 * TP * P.tile_h + 15) & ~15);  // after the raw and score tiles
+  uint64_t& s_bar = *reinterpret_cast<uint64_t*>(tail);
+  int* s_warp = reinterpret_cast<int*>(tail + 16);
 
   int* cnt_out = P.cell_cnt + (size_t)img * P.n_cells + blockIdx.x;
   if (iw <= 0 || ih <= 0) {
     if (tid == 0) *cnt_out = 0;
     return;
   }
-  for (int y = wid; y < c.ch; y += kFastThreads / 32) {
-    const uint8_t* src = base + (size_t)(c.y0 + y) * pitch + c.x0;
-    for (int x = lane; x < c.cw; x += 32) raw[y * TP + 1 + x] = __ldg(src + x);
+  // tile byte (row y, column b) = level pixel (xs + b, y0 + y); cell column x sits at byte 1 + xoff + x
+  const int xs = kTma ? ((c.x0 - 1) & ~15) : c.x0 - 1, xoff = c.x0 - 1 - xs;
+  if (kTma) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tma_load_tile3d(raw, &tmaps.m[c.level], &s_bar, xs, c.y0, img, (uint32_t)(TP * P.tile_h));
+    }
+    for (int i = tid; i < (ih + 2) * (TP / 4); i += kFastThreads) reinterpret_cast<unsigned*>(sc)[i] = 0;
+    __syncthreads();        // the barrier is initialised (thread 0 passed it) before anybody polls it
+    mbar_wait(&s_bar, 0);
+  } else {
+    for (int y = wid; y < c.ch; y += kFastThreads / 32) {
+      const uint8_t* src = base + (size_t)(c.y0 + y) * pitch + c.x0;
+      for (int x = lane; x < c.cw; x += 32) raw[y * TP + 1 + x] = __ldg(src + x);
+    }
+    for (int i = tid; i < (ih + 2) * (TP / 4); i += kFastThreads) reinterpret_cast<unsigned*>(sc)[i] = 0;
+    __syncthreads();
   }
-  for (int i = tid; i < (ih + 2) * (TP / 4); i += kFastThreads) reinterpret_cast<unsigned*>(sc)[i] = 0;
-  __syncthreads();
   const int ng = (iw + 1) >> 1;  // pairs of pixels per row
   for (int i = tid; i < ng * ih; i += kFastThreads) {
     const int y = i / ng, g = i - y * ng;
-    const int col = 4 + 2 * g;  // byte column of the first centre in the tile row
-    const unsigned s2 = fast_score2(raw + (y + 3) * TP + (col & ~3), 8 * (col & 3), TP);
+    const int col = 4 + 2 * g;  // byte column of the first centre in the score row (and in the raw row when off == 0)
+    const int rc = col + xoff;
+    const unsigned s2 = fast_score2(raw + (y + 3) * TP + (rc & ~3), 8 * (rc & 3), TP);
     unsigned s0 = s2 & 0xffffu, s1 = s2 >> 16;
     s0 = s0 > (unsigned)P.min_th ? s0 : 0u;  // keep scores > minTh
     s1 = (s1 > (unsigned)P.min_th && 2 * g + 1 < iw) ? s1 : 0u;
@@ -896,6 +955,13 @@ struct vieo_orb {
   float inv_scale[kMaxLevels], sigma2[kMaxLevels], inv_sigma2[kMaxLevels];
   int cap_total;  // sum of maxn
   size_t fast_smem, qt_smem;
+  // TMA staging of the FAST cell tiles: tensor maps of the internal levels (encoded once) and of the level-0 source of
+  // the current call (re-encoded when it changes)
+  bool tma_ok;
+  FastTmaps tmaps;
+  const uint8_t* tm0_ptr;
+  size_t tm0_stride;
+  int tm0_pitch, tm0_n;
   std::vector<void*> allocs;
   // staging for the host API
   VieoKeyPoint* d_kps;
@@ -936,6 +1002,31 @@ int dev_upload(vieo_orb* h, const T** p, const std::vector<T>& v) {
   return VIEO_OK;
 }
 
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency): u8 tensor
+// (x: pitch bytes, y: rows, z: images), box tile_pitch x tile_h x 1, no swizzle, zero fill outside
+bool encode_level_map(CUtensorMap* map, const uint8_t* base, int pitch, int rows, size_t img_stride, int n_img, int box_w,
+                      int box_h) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeFn)f;
+  }();
+  if (!fn || pitch % 16 || img_stride % 16 || (uintptr_t)base % 16) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)std::max(n_img, 1)};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)img_stride};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int orb_run(vieo_orb* h, int n_img, const uint8_t* img0, size_t img0_stride, int img0_pitch, VieoKeyPoint* kps,
             uint8_t* desc, int cap, int* n_kp, cudaStream_t st) {
   const OrbParams& P = h->P;
@@ -959,7 +1050,15 @@ int orb_run(vieo_orb* h, int n_img, const uint8_t* img0, size_t img0_stride, int
     ++launches;
   }
   if (ev) VIEO_CK(cudaEventRecord(ev[1], st));
-  k_fast_cells<<<dim3(P.n_cells, n_img), kFastThreads, h->fast_smem, st>>>(P, img0, img0_stride, img0_pitch);
+  bool tma = h->tma_ok && ((uintptr_t)img0 % 16 == 0) && img0_pitch % 16 == 0 && img0_stride % 16 == 0;
+  if (tma && (h->tm0_ptr != img0 || h->tm0_stride != img0_stride || h->tm0_pitch != img0_pitch || h->tm0_n < n_img)) {
+    tma = encode_level_map(&h->tmaps.m[0], img0, img0_pitch, P.h[0], img0_stride, n_img, P.tile_pitch, P.tile_h);
+    h->tm0_ptr = tma ? img0 : nullptr; h->tm0_stride = img0_stride; h->tm0_pitch = img0_pitch; h->tm0_n = n_img;
+  }
+  if (tma)
+    k_fast_cells<true><<<dim3(P.n_cells, n_img), kFastThreads, h->fast_smem, st>>>(P, img0, img0_stride, img0_pitch, h->tmaps);
+  else
+    k_fast_cells<false><<<dim3(P.n_cells, n_img), kFastThreads, h->fast_smem, st>>>(P, img0, img0_stride, img0_pitch, h->tmaps);
   if (ev) VIEO_CK(cudaEventRecord(ev[2], st));
   k_quadtree<<<dim3(P.nlevels, n_img), kQtThreads, h->qt_smem, st>>>(P);
   if (ev) VIEO_CK(cudaEventRecord(ev[3], st));
@@ -1138,7 +1237,12 @@ int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out) {
   }
   P.key_begin[L] = P.n_cells * P.cell_cap;
   h->cap_total = P.slot_begin[L];
-  h->fast_smem = (size_t)(P.tile_w + 8) * P.tile_h + (size_t)(P.tile_w + 8) * (P.tile_h - 6 + 2);
+  // TMA wants box rows of a multiple of 16 bytes that start on a 16-byte boundary of the level row: tile rows hold the
+  // cell, the scorer's 8 bytes of slack and up to 15 bytes of alignment residue
+  h->tma_ok = P.tile_w + 24 <= 256 && P.tile_h <= 256;
+  P.tile_pitch = h->tma_ok ? ((P.tile_w + 24 + 15) & ~15) : P.tile_w + 8;
+  h->tm0_ptr = nullptr; h->tm0_stride = 0; h->tm0_pitch = 0; h->tm0_n = 0;
+  h->fast_smem = (((size_t)2 * P.tile_pitch * P.tile_h + 15) & ~(size_t)15) + 16 + 4 * (kFastThreads / 32);
   h->qt_smem = (size_t)max_maxn * (2 * (4 + 4 + 2 * 4 + 1) + 16 + 16 + 5 * 4) + 16 * 32;
   if (h->qt_smem > 200 * 1024) {
     set_error("per-level feature quota %d needs %zu B of shared memory for the quadtree (limit 200 KiB)", max_maxn,
@@ -1169,6 +1273,9 @@ int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out) {
   ORB_TRY_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
   const size_t B = cfg->max_batch;
   for (int l = 0; l < L; ++l) ORB_TRY(dev_alloc(h, &P.lvl[l], B * P.img_stride[l] + 64));
+  memset(&h->tmaps, 0, sizeof(h->tmaps));
+  for (int l = 1; l < L && h->tma_ok; ++l)
+    h->tma_ok = encode_level_map(&h->tmaps.m[l], P.lvl[l], P.pitch[l], P.h[l], P.img_stride[l], (int)B, P.tile_pitch, P.tile_h);
   ORB_TRY(dev_upload(h, &P.cells, cells));
   // resize tables (cv::resize INTER_LINEAR 8U: 11-bit coefficients from float fx, see oracle + goldens)
   for (int l = 1; l < L; ++l) {
@@ -1204,7 +1311,8 @@ int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out) {
   ORB_TRY(dev_alloc(h, &h->d_desc, B * h->cap_total * 32));
   ORB_TRY(dev_alloc(h, &h->d_nkp, B));
   ORB_TRY_CUDA(cudaMallocHost(&h->h_pinned, sizeof(int) * B));
-  ORB_TRY_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
+  ORB_TRY_CUDA(cudaFuncSetAttribute(k_fast_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
+  ORB_TRY_CUDA(cudaFuncSetAttribute(k_fast_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
   ORB_TRY_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qt_smem));
   *out = h;
   return VIEO_OK;
