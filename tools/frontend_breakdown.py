@@ -31,3 +31,12 @@ print("extract kernels (device-resident, one batch of %d images): %.3f ms" % (2 
 for nb in (8, 16, 32):
     o2 = api.ORBextractor(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"], W, H, max_batch=nb)
     print("  batch of %d images: %.3f ms" % (nb, t(lambda: o2.extract_batch_dev(dev.data_ptr(), nb, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), s))))
+# per-stage CUDA-event times of the extractor alone on the device (no other stream active)
+orb.profile(True)
+for _ in range(10):
+    orb.extract_batch_dev(dev.data_ptr(), 2 * F, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), s)
+torch.cuda.synchronize()
+stage_ms, ncalls = orb.profile_read()
+orb.profile(False)
+print("isolated stages, ms per batch of %d images:" % (2 * F), {k: round(v / max(ncalls, 1), 3) for k, v in stage_ms.items()},
+      "-> us per image:", {k: round(1e3 * v / max(ncalls, 1) / (2 * F), 2) for k, v in stage_ms.items()})

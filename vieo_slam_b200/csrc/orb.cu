@@ -705,10 +705,21 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(OrbParams P, co
   const int W = P.w[level], H = P.h[level];
   uint8_t* raw = s_raw[warp];
   uint16_t* hb = s_hb[warp];
-  for (int i = lane; i < kPW * kPW; i += 32) {
-    const int r = i / kPW, c = i - r * kPW;
-    const int gy = reflect101(ky - kPR + r, H), gx = reflect101(kx - kPR + c, W);
-    raw[r * kPWp + c] = __ldg(base + (size_t)gy * pitch + gx);
+  // rows of the patch, lanes along the row (two turns for the 43 columns); the reflection only exists at the image edge
+  if (kx >= kPR && kx + kPR < W && ky >= kPR && ky + kPR < H) {
+    const uint8_t* src = base + (size_t)(ky - kPR) * pitch + (kx - kPR);
+#pragma unroll 4
+    for (int r = 0; r < kPW; ++r) {
+      raw[r * kPWp + lane] = __ldg(src + (size_t)r * pitch + lane);
+      if (lane + 32 < kPW) raw[r * kPWp + lane + 32] = __ldg(src + (size_t)r * pitch + lane + 32);
+    }
+  } else {
+    const int gx0 = reflect101(kx - kPR + lane, W), gx1 = reflect101(kx - kPR + min(lane + 32, kPW - 1), W);
+    for (int r = 0; r < kPW; ++r) {
+      const uint8_t* src = base + (size_t)reflect101(ky - kPR + r, H) * pitch;
+      raw[r * kPWp + lane] = __ldg(src + gx0);
+      if (lane + 32 < kPW) raw[r * kPWp + lane + 32] = __ldg(src + gx1);
+    }
   }
   __syncwarp();
   // intensity centroid over the radius-15 disc: lane = row v in [-15, 15]
@@ -732,10 +743,14 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(OrbParams P, co
   }
   const float angle = fast_atan2_deg((float)m01, (float)m10);
   // horizontal pass, 8-fractional-bit kernel {18,34,48,56,48,34,18} (sum 256): exact in 16 bits
-  for (int i = lane; i < kPW * kBW; i += 32) {
-    const int r = i / kBW, c = i - r * kBW;
-    const uint8_t* s = raw + r * kPWp + c;
-    hb[r * kBWp + c] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+#pragma unroll 4
+  for (int r = 0; r < kPW; ++r) {
+    const uint8_t* s = raw + r * kPWp + lane;
+    hb[r * kBWp + lane] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+    if (lane + 32 < kBW) {
+      s += 32;
+      hb[r * kBWp + lane + 32] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+    }
   }
   __syncwarp();
   float sn, cs;
