@@ -39,7 +39,7 @@ FAST_BYTES_PER_IMAGE = LEVEL_PX + 700 * 4  # k_fast_cells: every level pixel onc
 
 def workload_name(frames):
     return (f"EuRoC MH05 stereo-VIO 1200 feats (configs[1]), synthetic 752x480 stereo + 200 Hz IMU, batches of {frames} frames: "
-            "ORBextractor x2 + ComputeStereoMatches + IMU pre-integration + 2x SearchByProjection (last frame, local map) "
+            "ORBextractor x2 + ComputeStereoMatches + IMU pre-integration + SearchByProjection (last frame) + isInFrustum + SearchByProjection (local map) "
             "+ 2x PoseOptimization (PVR) per frame, "
             "LocalBundleAdjustmentNavStatePRV every 8th frame")
 
@@ -97,7 +97,7 @@ class ClockSampler:
 # and triggers one LocalBundleAdjustmentNavStatePRV window (N_local = 10, 20 fixed keyframes, 1500 points).
 LBA_EVERY = 8
 POSE_POINTS = (350, 550)
-SBP_QUERIES = (700, 1500)   # map points searched per frame: last frame's / local map's in view
+SBP_QUERIES = (700, 2500)   # map points per frame: last frame's / local-map candidates tested by isInFrustum (~60 % in view)
 LBA_SHAPE = dict(n_local=10, n_fixed=20, n_points=1500)
 
 
@@ -127,8 +127,9 @@ def make_tracking_inputs(seed, F, preint_fn):
     # the two guided searches of every frame: TrackWithMotionModel (last frame's map points, th = 7 for stereo,
     # src/Tracking.cc:292-297) and TrackLocalMap (local map points in view, th = 1, :2367)
     sbp = [synth.make_sbp_problem(seed + 7, n_frames=F, mode=synth.SBP_LAST_FRAME, n_kp=1200, n_q=SBP_QUERIES[0], th=7.0),
-           synth.make_sbp_problem(seed + 8, n_frames=F, mode=synth.SBP_LOCAL_MAP, n_kp=1200, n_q=SBP_QUERIES[1], th=1.0,
-                                  blocked_frac=0.3)]
+           # SearchLocalPoints: Frame::isInFrustum over the candidates, then the search over those in view (:2308-2368)
+           synth.make_frustum_problem(seed + 8, n_frames=F, n_kp=1200, n_q=SBP_QUERIES[1], th=1.0, blocked_frac=0.3,
+                                      skip_frac=0.1)]
     return dict(imu=imu_in, pbs=pbs, cam=cam, Xw=arrays[0], obs=arrays[1], w=arrays[2], flags=arrays[3], seq=seq, sbp=sbp)
 
 
@@ -201,8 +202,8 @@ def cpu_pipeline(images, trk, lbas, threads_like_reference=True, workers=None):
         k = f % F
         smp, seg, tt, bb = trk["imu"]
         O.imu_preintegrate(smp[seg[k]:seg[k + 1]], tt[k][0], tt[k][1], bb[k][:3], bb[k][3:], nz)
-        for pb in trk["sbp"]:
-            O.search_by_projection(pb, frames=[k])
+        O.search_by_projection(trk["sbp"][0], frames=[k])
+        O.search_local_points(trk["sbp"][1], frames=[k])
         for j in (k, F + k):
             O.pose_optimization(trk["pbs"][j:j + 1], cam, trk["Xw"], trk["obs"], trk["w"], trk["flags"])
 
@@ -338,10 +339,27 @@ def run_gpu(args, rank, world, local_rank):
         nk, nq = len(pb["kps"]), len(pb["q_level"])
         out = [torch.empty(n, dtype=torch.int32, device=dev) for n in (nk, nq, nq, F)]
         scr = torch.empty(api.lib().vieo_sbp_scratch_bytes(nq), dtype=torch.uint8, device=dev)
-        sbp_dev.append((int(pb["mode"]), d, q, out, scr))
+        fr = None
+        if "frustum" in pb:
+            # the local-map search reads the tracking info k_frustum leaves in HBM
+            ff = np.ascontiguousarray(pb["frustum"], api.FRUSTUM_FRAME_DTYPE).copy()
+            for G in ff:
+                G["level_ratio"] = api.frustum_level_table(float(G["log_scale_factor"]), int(G["n_levels"]))
+            fr = dict(frames=to_dev(ff), inview=torch.empty(nq, dtype=torch.uint8, device=dev),
+                      proj=torch.empty(3 * nq, dtype=torch.float32, device=dev), level=torch.empty(nq, dtype=torch.int32, device=dev),
+                      viewcos=torch.empty(nq, dtype=torch.float32, device=dev), depth=torch.empty(nq, dtype=torch.float32, device=dev),
+                      n_inview=torch.empty(F, dtype=torch.int32, device=dev))
+            for name in ("proj", "level", "viewcos", "depth"):
+                setattr(q, name, fr[name].data_ptr())
+        sbp_dev.append((int(pb["mode"]), d, q, out, scr, fr))
 
     def sbp_enqueue(stream):
-        for mode, d, q, out, scr in sbp_dev:
+        for mode, d, q, out, scr, fr in sbp_dev:
+            if fr is not None:
+                api.frustum_batch_dev(fr["frames"].data_ptr(), F, d["p_wP"].data_ptr(), d["p_normal"].data_ptr(),
+                                      d["p_max_dist"].data_ptr(), d["p_min_dist"].data_ptr(), d["p_skip"].data_ptr(),
+                                      fr["inview"].data_ptr(), fr["proj"].data_ptr(), fr["level"].data_ptr(),
+                                      fr["viewcos"].data_ptr(), fr["depth"].data_ptr(), fr["n_inview"].data_ptr(), stream)
             api.sbp_batch_dev(mode, d["frames"].data_ptr(), F, d["kps"].data_ptr(), d["uright"].data_ptr(), d["desc"].data_ptr(),
                               q, d["kp_blocked"].data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                               out[3].data_ptr(), scr.data_ptr(), scr.numel(), stream)
@@ -455,8 +473,8 @@ def run_gpu(args, rank, world, local_rank):
     def tracking_host():
         pre_gpu.preintegrate_batch(*trk["imu"])
         nm = 0
-        for pb in trk["sbp"]:
-            nm += int(matcher.SearchByProjection(pb)[3][0])
+        nm += int(matcher.SearchByProjection(trk["sbp"][0])[3][0])
+        nm += int(matcher.SearchLocalPoints(trk["sbp"][1])[4][0])
         r = api.Optimizer.PoseOptimizationBatch(trk["pbs"], trk["cam"], trk["Xw"], trk["obs"], trk["w"], trk["flags"],
                                                 device=local_rank)
         return int(r[0]["n_inliers"][0]) + nm
@@ -486,8 +504,13 @@ def run_gpu(args, rank, world, local_rank):
     e2e_value = world * F * args.steps / float(t.item())
     lba_bytes = sum(int(np.asarray(v).nbytes) for v in lbas[0].values() if hasattr(v, "nbytes")) if lbas else 0
     trk_in = sum(int(np.asarray(a).nbytes) for a in trk["imu"]) + sum(int(trk[k].nbytes) for k in ("pbs", "Xw", "obs", "w", "flags"))
-    sbp_in = sum(int(v.nbytes) for pb in trk["sbp"] for v in pb.values() if isinstance(v, np.ndarray))
-    sbp_out = sum(4 * (len(pb["kps"]) + 2 * len(pb["q_level"]) + F) for pb in trk["sbp"])
+    # bytes the two host-buffer search calls stage: the last-frame search copies every array of its problem; the fused
+    # SearchLocalPoints copies the map-point arrays isInFrustum reads, not the projections (they are made on the device)
+    lm_keys = ("frames", "frustum", "p_wP", "p_normal", "p_max_dist", "p_min_dist", "p_skip", "q_desc", "q_flags", "kps",
+               "uright", "desc", "kp_blocked")
+    sbp_in = (sum(int(v.nbytes) for v in trk["sbp"][0].values() if isinstance(v, np.ndarray)) +
+              sum(int(trk["sbp"][1][k].nbytes) for k in lm_keys))
+    sbp_out = sum(4 * (len(pb["kps"]) + 2 * len(pb["q_level"]) + F) for pb in trk["sbp"]) + 25 * len(trk["sbp"][1]["q_level"]) + 4 * F
     h2d = F * 2 * H * W + trk_in + sbp_in + n_lba * lba_bytes
     d2h = (sum(int(o.nbytes) for o in outs) + 3 * F * cap * 4 + sbp_out + F * api.PREINT_DTYPE.itemsize + n_pb * api.POSEOPT_RESULT_DTYPE.itemsize
            + 9 * n_edges + n_lba * (64 * 176 + 2048 * 24 + 16384 * 9))
@@ -519,7 +542,7 @@ def run_gpu(args, rank, world, local_rank):
         "dtype": "u8+f64", "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_step_per_gpu": F, "image": f"{W}x{H}", "nfeatures": 1200,
                    "levels": 8, "cache": f"inputs rotate over {pool} batches ({pool * F * 2 * H * W / 1e6:.0f} MB > 126 MB L2)",
-                   "stages": ["orb_extract_x2", "stereo_matches_rectified", "imu_preint", "search_by_projection_x2", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
+                   "stages": ["orb_extract_x2", "stereo_matches_rectified", "imu_preint", "search_by_projection_last_frame", "is_in_frustum+search_by_projection_local_map", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
                    "pose_opt_points": list(POSE_POINTS), "sbp_queries": list(SBP_QUERIES), "lba_every": LBA_EVERY if n_lba else 0, "lba_window": LBA_SHAPE,
                    "lba_workers": n_workers,
                    "sm_partition": {"ba": part.sms(api.SM_BA), "frontend_tracking": part.sms(api.SM_FRONTEND)} if part else None,

@@ -125,6 +125,16 @@ int vieo_hamming_csr(const uint8_t* q, const uint8_t* t, int nt, const int32_t* 
                      int nrows, int32_t* best_dist, int32_t* best_idx, int32_t* second_dist, int32_t* second_idx,
                      int device);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:314-378) for a batch of map points: map
+ * point p owns the observed descriptors desc_pool[rows[k]], k in [ptr[p], ptr[p+1]) (rows nullable: desc_pool[k]) in the
+ * reference's vDescriptors order; all-pairs Hamming distances, per row the sorted entry at index int(0.5 * (N - 1)), first
+ * row with the least median wins.  best[p] = index into the point's list (-1: no observation, mDescriptor untouched),
+ * median[p] = that median.  desc_pool 16-byte aligned in the _dev form. */
+int vieo_distinctive_descriptors(const uint8_t* desc_pool, int n_pool, const int32_t* rows, const int32_t* ptr,
+                                 int n_points, int32_t* best, int32_t* median, int device);
+int vieo_distinctive_descriptors_dev(const uint8_t* desc_pool_dev, const int32_t* rows_dev, const int32_t* ptr_dev,
+                                     int n_points, int32_t* best_dev, int32_t* median_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * On-manifold IMU pre-integration — replaces IMUPreIntegratorBase<IMUDataBase>::PreIntegration / update
  * (src/Odom/OdomPreIntegrator.h:227-506) for a batch of intervals (one per frame pair / keyframe pair; the
@@ -153,6 +163,27 @@ int vieo_imu_preint_batch(const double* samples, const int32_t* seg_ptr, const d
 int vieo_imu_preint_batch_dev(const double* samples_dev, const int32_t* seg_ptr_dev, const double* ti_tj_dev,
                               const double* bg_ba_dev, const VieoImuNoise* noise, int n_intervals,
                               VieoImuPreint* out_dev, void* stream);
+
+/* Step 1 of the IMU initialiser — replaces Optimizer::OptimizeInitialGyroBias
+ * (include/Optimizer.h:819-892: EdgeGyrBias per consecutive keyframe pair, src/Odom/g2otypes.h:940-973, one Gauss-Newton
+ * iteration from a zero seed) and the re-integration of every keyframe interval with the new bias that follows it
+ * (src/Odom/IMUInitialization.cpp:606-648, IMUKeyFrameInit::ComputePreInt IMUInitialization.h:225-232): gyro-bias
+ * kernel -> pre-integration kernel on one stream, the bias never leaves the device in between.
+ *   pre  [n_kf]     keyframe i's pre-integration from keyframe i-1 (entry 0 and entries with dt == 0 are ignored)
+ *   Rwb  [n_kf][9]  Rwc_i * Rcb, row-major
+ *   use_info        bInfo: information = (SigmaPRV.block<3,3>(3,3))^-1, else identity
+ *   bg   [3]        in: the caller's bias; out: bias + estimate (untouched when there is no equation)
+ *   preint_out [n_kf] nullable: when given, interval i (samples[seg_ptr[i] .. seg_ptr[i+1]) over ti_tj[2i..2i+1]) is
+ *                   integrated again with {bg out, ba[3i..3i+3)} (ba nullable = zero); interval 0 is normally empty
+ * *num_equations = the reference's return value. */
+int vieo_imu_init_gyro_bias(const VieoImuPreint* pre, const double* Rwb, int n_kf, int use_info, double bg[3],
+                            int* num_equations, const double* samples, const int32_t* seg_ptr, const double* ti_tj,
+                            const double* ba, const VieoImuNoise* noise, VieoImuPreint* preint_out, int device);
+/* Device-pointer form of the gyro-bias step alone.  result_dev: 56 bytes {double dbg[3]; double bg[3]; int32
+ * num_equations; int32 solved}; bg_ba_out_dev (nullable) [n_kf][6] receives {bg + dbg, ba of bg_ba_in_dev (nullable: 0)}
+ * ready for vieo_imu_preint_batch_dev on the same stream. */
+int vieo_gyro_bias_init_dev(const VieoImuPreint* pre_dev, const double* Rwb_dev, int n_kf, int use_info, const double bg[3],
+                            const double* bg_ba_in_dev, double* bg_ba_out_dev, void* result_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bundle adjustment — replaces the g2o graphs behind Optimizer::PoseOptimization (src/Optimizer.cc:1611-1874
@@ -336,7 +367,8 @@ typedef struct VieoSbpFrame {
 } VieoSbpFrame;
 typedef struct VieoSbpQueries { /* arrays over all queries of the batch; unused ones may be null */
   const double* Xw;       /* [n][3] LAST_FRAME: MapPoint::GetWorldPos() cast to double */
-  const int32_t* level;   /* LAST_FRAME: LastFrame.mvKeys[i].octave; LOCAL_MAP: vtrack_scalelevel_ */
+  const int32_t* level;   /* LAST_FRAME: LastFrame.mvKeys[i].octave; LOCAL_MAP: vtrack_scalelevel_, -1 = !btrack_inview_
+                             (the query is skipped, src/ORBmatcher.cc:244) */
   const float* angle;     /* LAST_FRAME: LastFrame.mvKeys[i].angle */
   const float* proj;      /* [n][3] LOCAL_MAP: vtrack_proj_ (u, v, ur) left by Frame::isInFrustum */
   const float* viewcos;   /* LOCAL_MAP: vtrack_viewcos_ */
@@ -356,6 +388,47 @@ int vieo_sbp_batch_dev(int mode, const VieoSbpFrame* frames_dev, int n_frames, c
 int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const VieoKeyPoint* kps, const float* uright,
                    const uint8_t* desc, const VieoSbpQueries* q, const uint8_t* kp_blocked, int32_t* kp_match,
                    int32_t* q_match, int32_t* q_dist, int32_t* n_matches, int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame::isInFrustum (src/Frame.cc:335-416) with MapPoint::PredictScale (src/MapPoint.cc:491-509) for every candidate map
+ * point of a batch of frames, and Tracking::SearchLocalPoints' pair "visibility test -> SearchByProjection(F,
+ * vpMapPoints, th, th_far)" (src/Tracking.cc:2308-2368) as one call.  Single camera
+ * (mpCameras.size() == 1), usedistort_ == false; float arithmetic in Eigen's evaluation order. */
+typedef struct VieoFrustumFrame {
+  int32_t q_begin, n_q;         /* this frame's candidate map points in the point arrays */
+  float Rcw[9], tcw[3], Ow[3];  /* Tcw_ rotation (row-major), mtcw, mOw cast to float */
+  float fx, fy, cx, cy;         /* mpCameras[0]->toK() cast to float */
+  float minx, maxx, miny, maxy; /* gridinfo_.minmax_xy_ */
+  float bf;                     /* stereoinfo_.baseline_bf_[1] */
+  float cos_limit;              /* viewingCosLimit (0.5 in SearchLocalPoints) */
+  float log_scale_factor;       /* scalepyrinfo_.flogscalefactor_ */
+  int32_t n_levels;             /* scalepyrinfo_.vscalefactor_.size() (<= 16) */
+  float level_ratio[16];        /* vieo_frustum_level_table(log_scale_factor, n_levels): the host-buffer calls fill it,
+                                   *_dev callers fill it themselves */
+} VieoFrustumFrame;
+/* table[k] = the smallest float ratio for which ceil(logf(ratio) / log_scale_factor) >= k, found with the host libm's
+ * logf (the function the reference calls), so that counting thresholds on the device reproduces PredictScale exactly. */
+int vieo_frustum_level_table(float log_scale_factor, int n_levels, float table[16]);
+/* Per point: wP / normal [n][3] (GetWorldPos / GetNormal), max_dist / min_dist = mfMaxDistance / mfMinDistance (the 1.2 /
+ * 0.8 factors of Get*DistanceInvariance are applied here), skip (nullable) != 0: already matched in the frame or bad.
+ * Outputs per point: inview = btrack_inview_, proj [n][3] = (u, v, ur), level = vtrack_scalelevel_ (-1 when not in view),
+ * viewcos, depth = track_depth_; n_inview [n_frames] = nToMatch. */
+int vieo_frustum_batch_dev(const VieoFrustumFrame* frames_dev, int n_frames, const float* wP_dev, const float* normal_dev,
+                           const float* max_dist_dev, const float* min_dist_dev, const uint8_t* skip_dev,
+                           uint8_t* inview_dev, float* proj_dev, int32_t* level_dev, float* viewcos_dev, float* depth_dev,
+                           int32_t* n_inview_dev, void* stream);
+int vieo_frustum_batch(const VieoFrustumFrame* frames, int n_frames, const float* wP, const float* normal,
+                       const float* max_dist, const float* min_dist, const uint8_t* skip, uint8_t* inview, float* proj,
+                       int32_t* level, float* viewcos, float* depth, int32_t* n_inview, int device);
+/* Visibility test + local-map guided search on one stream; frames[f] and frustum[f] share q_begin / n_q, the search
+ * reads the tracking info the first kernel left in HBM.  Outputs of both halves as documented above / at
+ * vieo_sbp_batch. */
+int vieo_search_local_points(const VieoFrustumFrame* frustum, const VieoSbpFrame* frames, int n_frames, const float* wP,
+                             const float* normal, const float* max_dist, const float* min_dist, const uint8_t* skip,
+                             const uint8_t* q_desc, const uint8_t* q_flags, const VieoKeyPoint* kps, const float* uright,
+                             const uint8_t* desc, const uint8_t* kp_blocked, uint8_t* inview, float* proj, int32_t* level,
+                             float* viewcos, float* depth, int32_t* n_inview, int32_t* kp_match, int32_t* q_match,
+                             int32_t* q_dist, int32_t* n_matches, int device);
 
 /* ------------------------------------------------------------------------------------------------
  * Stereo front-end over HOST buffers — the hot work of the Frame::Frame stereo constructor

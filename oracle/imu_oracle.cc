@@ -260,4 +260,82 @@ int orc_imu_preintegrate(const double* smp, int n, double ti, double tj, const d
   return status;
 }
 
+// Optimizer::OptimizeInitialGyroBias (include/Optimizer.h:819-892) with EdgeGyrBias (src/Odom/g2otypes.h:940-973): one
+// Gauss-Newton iteration (OptimizationAlgorithmGaussNewton: errors -> buildSystem -> solve -> update, no damping) on a
+// 3-dim VertexGyrBias seeded with zero; one unary edge per keyframe i >= 1 whose pre-integration has dt != 0,
+// information = (SigmaPRV.block<3,3>(3,3))^-1 (bInfo) or identity.  pre[i] is keyframe i's pre-integration (pre[0] is
+// ignored), Rwb[i] = Rwc_i * Rcb row-major.  Output dbg = the vertex estimate (the caller adds it to bg); returns
+// num_equations.  parity unpinned for Eigen's 3x3 inverse() / LDLT rounding (restated: cofactor inverse, Cholesky).
+int orc_gyro_bias_init(const OrcImuPreint* pre, const double* Rwb, int n_kf, int use_info, double dbg[3]) {
+  using namespace orc;
+  double H[9] = {0}, b[3] = {0};
+  int num_equations = 0;
+  dbg[0] = dbg[1] = dbg[2] = 0;
+  for (int i = 1; i < n_kf; ++i) {
+    if (pre[i].dt == 0) continue;
+    ++num_equations;
+    M3 dR, JgR, Rwbi, Rwbj;
+    memcpy(dR.m, pre[i].Rij, 72);
+    memcpy(JgR.m, pre[i].JgR, 72);
+    memcpy(Rwbi.m, Rwb + 9 * (i - 1), 72);
+    memcpy(Rwbj.m, Rwb + 9 * i, 72);
+    const double bg[3] = {0, 0, 0};
+    double Jb[3];
+    mulv(JgR, bg, Jb);
+    // computeError: Log((deltaRij * Exp(JgRij * bg))^T * Rwbi^T * Rwbj)
+    const M3 dRbg = so3_Exp(Jb);
+    const M3 E = mul(mul(tr(mul(dR, dRbg)), tr(Rwbi)), Rwbj);
+    double e[3];
+    so3_log_q(qnormalized(mquat(E)), e);
+    // linearizeOplus: -JrInv(e) * Exp(-e) * Jr(JgRij * bg) * JgRij
+    const double ne[3] = {-e[0], -e[1], -e[2]};
+    const M3 J = scale(mul(mul(mul(so3_JrInv(e), so3_Exp(ne)), so3_Jr(Jb)), JgR), -1.0);
+    M3 W = ident();
+    if (use_info) {
+      // Matrix3d::inverse() of SigmaPRV(3:6, 3:6): cofactor formula
+      double a[9];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) a[3 * r + c] = pre[i].SigmaPRV[9 * (3 + r) + 3 + c];
+      const double c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+      const double det = a[0] * c00 + a[1] * c01 + a[2] * c02, id = 1.0 / det;
+      W = {{c00 * id, (a[2] * a[7] - a[1] * a[8]) * id, (a[1] * a[5] - a[2] * a[4]) * id,
+            c01 * id, (a[0] * a[8] - a[2] * a[6]) * id, (a[2] * a[3] - a[0] * a[5]) * id,
+            c02 * id, (a[1] * a[6] - a[0] * a[7]) * id, (a[0] * a[4] - a[1] * a[3]) * id}};
+    }
+    // constructQuadraticForm (base_unary_edge.hpp): H += J^T W J, b += -J^T W e
+    const M3 JtW = mul(tr(J), W);
+    const M3 JtWJ = mul(JtW, J);
+    double JtWe[3];
+    mulv(JtW, e, JtWe);
+    for (int k = 0; k < 9; ++k) H[k] += JtWJ.m[k];
+    for (int k = 0; k < 3; ++k) b[k] -= JtWe[k];
+  }
+  if (num_equations < 1) return num_equations;
+  // solve H x = b (3x3 SPD): Cholesky
+  double L[9] = {0};
+  for (int j = 0; j < 3; ++j) {
+    double d = H[3 * j + j];
+    for (int k = 0; k < j; ++k) d -= L[3 * j + k] * L[3 * j + k];
+    if (!(d > 0)) return num_equations;  // LDLT failure: the estimate stays zero
+    L[3 * j + j] = std::sqrt(d);
+    for (int r = j + 1; r < 3; ++r) {
+      double v = H[3 * r + j];
+      for (int k = 0; k < j; ++k) v -= L[3 * r + k] * L[3 * j + k];
+      L[3 * r + j] = v / L[3 * j + j];
+    }
+  }
+  double y[3];
+  for (int r = 0; r < 3; ++r) {
+    double v = b[r];
+    for (int k = 0; k < r; ++k) v -= L[3 * r + k] * y[k];
+    y[r] = v / L[3 * r + r];
+  }
+  for (int r = 2; r >= 0; --r) {
+    double v = y[r];
+    for (int k = r + 1; k < 3; ++k) v -= L[3 * k + r] * dbg[k];
+    dbg[r] = v / L[3 * r + r];
+  }
+  return num_equations;
+}
+
 }  // extern "C"

@@ -178,3 +178,38 @@ extern "C" int orc_stereo_matches(const OrcKeyPoint* kl, const uint8_t* dl, int 
   }
   return kept;
 }
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:314-378) for a batch of map points in CSR form: point p owns
+// the observed descriptors rows[ptr[p] .. ptr[p+1]) of desc_pool (rows == nullptr: the rows themselves, in order) in the
+// reference's vDescriptors order.  All-pairs Hamming distances, per row the sorted-distance entry at index
+// int(0.5 * (N - 1)), the first row with the least median wins.  best[p] = index into the point's list (-1: no
+// observations, the reference returns without touching mDescriptor), median[p] = that row's median.
+extern "C" void orc_distinctive_descriptors(const uint8_t* desc_pool, const int32_t* rows, const int32_t* ptr, int n_points,
+                                            int32_t* best, int32_t* median) {
+  std::vector<int> d, v;
+  for (int p = 0; p < n_points; ++p) {
+    const int b = ptr[p], N = ptr[p + 1] - b;
+    best[p] = -1;
+    median[p] = -1;
+    if (N <= 0) continue;
+    d.assign((size_t)N * N, 0);
+    for (int i = 0; i < N; ++i)
+      for (int j = i + 1; j < N; ++j) {
+        const int ri = rows ? rows[b + i] : b + i, rj = rows ? rows[b + j] : b + j;
+        d[(size_t)i * N + j] = d[(size_t)j * N + i] =
+            orc_descriptor_distance(desc_pool + 32 * (size_t)ri, desc_pool + 32 * (size_t)rj);
+      }
+    int BestMedian = INT32_MAX, BestIdx = 0;
+    for (int i = 0; i < N; ++i) {
+      v.assign(d.begin() + (size_t)i * N, d.begin() + (size_t)(i + 1) * N);
+      std::sort(v.begin(), v.end());
+      const int med = v[(size_t)(0.5 * (N - 1))];
+      if (med < BestMedian) {
+        BestMedian = med;
+        BestIdx = i;
+      }
+    }
+    best[p] = BestIdx;
+    median[p] = BestMedian;
+  }
+}

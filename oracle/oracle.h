@@ -36,6 +36,9 @@ int orc_quadtree(const int* xyr, int n, int W, int H, int N, int* picked, int ca
 extern "C" {
 #endif
 int orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
+/* MapPoint::ComputeDistinctiveDescriptors over a CSR batch of map points (match_oracle.cc) */
+void orc_distinctive_descriptors(const uint8_t* desc_pool, const int32_t* rows, const int32_t* ptr, int n_points,
+                                 int32_t* best, int32_t* median);
 void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist);
 void orc_hamming_csr(const uint8_t* q, const uint8_t* t, const int32_t* row_ptr, const int32_t* cand, int nrows,
                      int32_t* best_dist, int32_t* best_idx, int32_t* second_dist, int32_t* second_idx);
@@ -68,6 +71,8 @@ typedef struct OrcImuPreint { /* public members of IMUPreIntegratorBase (OdomPre
 void orc_imu_set_param(OrcImuNoise* nz, const double sigma2[4], int dt_cov_noise_fixed, double freq_ref);
 int orc_imu_preintegrate(const double* smp, int n, double ti, double tj, const double bg[3], const double ba[3],
                          const OrcImuNoise* nz, OrcImuPreint* out);
+/* Optimizer::OptimizeInitialGyroBias: pre [n_kf] (entry 0 ignored), Rwb [n_kf][9] -> dbg, returns num_equations */
+int orc_gyro_bias_init(const OrcImuPreint* pre, const double* Rwb, int n_kf, int use_info, double dbg[3]);
 #ifdef __cplusplus
 }
 #endif
@@ -98,6 +103,20 @@ int orc_sbp_local_map(const OrcSbpFrame* f, const OrcKeyPoint* kps, const float*
                       const float* q_proj, const int32_t* q_level, const float* q_viewcos, const float* q_depth,
                       const uint8_t* q_desc, const uint8_t* q_flags, const uint8_t* kp_blocked, int32_t* kp_match,
                       int32_t* q_match, int32_t* q_dist);
+/* Frame::isInFrustum + MapPoint::PredictScale (sbp_oracle.cc), single camera, usedistort_ == false. */
+typedef struct OrcFrustumFrame {
+  int32_t q_begin, n_q;         /* this frame's candidate map points in the point arrays */
+  float Rcw[9], tcw[3], Ow[3];  /* Tcw_ rotation (row-major), mtcw, mOw cast to float */
+  float fx, fy, cx, cy;         /* mpCameras[0]->toK() cast to float */
+  float minx, maxx, miny, maxy; /* gridinfo_.minmax_xy_ */
+  float bf;                     /* stereoinfo_.baseline_bf_[1] */
+  float cos_limit;              /* viewingCosLimit (0.5 in SearchLocalPoints) */
+  float log_scale_factor;       /* scalepyrinfo_.flogscalefactor_ */
+  int32_t n_levels;             /* scalepyrinfo_.vscalefactor_.size() */
+} OrcFrustumFrame;
+int orc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);
+int orc_is_in_frustum(const OrcFrustumFrame* f, int n, const float* wP, const float* Pn, const float* max_dist,
+                      const float* min_dist, uint8_t* inview, float* proj, int32_t* level, float* viewcos, float* depth);
 #ifdef __cplusplus
 }
 #endif

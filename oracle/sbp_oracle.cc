@@ -203,6 +203,7 @@ extern "C" int orc_sbp_local_map(const OrcSbpFrame* f, const OrcKeyPoint* kps, c
   for (int i = 0; i < f->n_q; ++i) {
     q_match[i] = -1;
     q_dist[i] = 256;
+    if (q_level[i] < 0) continue;  // !btrack_inview_ (:244): the level isInFrustum leaves for a point out of view is -1
     if (f->th_far > 0 && q_depth[i] > f->th_far) continue;
     const int nPredictedLevel = q_level[i];
     float r = q_viewcos[i] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos (:337-342), float vs double literal compare
@@ -239,4 +240,67 @@ extern "C" int orc_sbp_local_map(const OrcSbpFrame* f, const OrcKeyPoint* kps, c
     }
   }
   return nmatches;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Frame::isInFrustum (src/Frame.cc:335-416) + MapPoint::PredictScale (src/MapPoint.cc:491-509) for the single-camera
+// case (mpCameras.size() == 1: GetTcr() is the identity and GetTrc().translation() is zero, so Pc = Pcr and twc = mOw
+// exactly), usedistort_ == false.  Everything is float arithmetic.  Eigen 3.3's fixed-size products / dot / norm reduce a
+// 3-term sum with redux_novec_unroller, i.e. a0 + (a1 + a2); this file is compiled without FP contraction.  "parity
+// unpinned" for the last bit: the reference's own result depends on whether its compiler contracts to FMA.
+//   in : Rcw / tcw / Ow = Tcw_ rotation, mtcw, mOw cast to float; per point wP, normal Pn, mfMaxDistance, mfMinDistance
+//   out: inview (btrack_inview_), proj = (u, v, ur), level = vtrack_scalelevel_, viewcos, depth = track_depth_
+// Returns the number of points in view (what SearchLocalPoints counts in nToMatch, src/Tracking.cc:2341-2344).
+namespace {
+inline float sum3(float a0, float a1, float a2) { return a0 + (a1 + a2); }
+}  // namespace
+extern "C" int orc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels) {
+  const float ratio = max_distance / current_dist;
+  // log(float) resolves to the float overload; ceil(float); the int conversion of the reference is UB for inf / NaN,
+  // defined here as "largest level" (ratio = +inf) resp. 0 (NaN)
+  const float x = std::ceil(std::log(ratio) / log_scale_factor);
+  if (std::isnan(x)) return 0;
+  if (x < 0) return 0;
+  if (x >= (float)n_levels) return n_levels - 1;
+  return (int)x;
+}
+extern "C" int orc_is_in_frustum(const OrcFrustumFrame* f, int n, const float* wP, const float* Pn, const float* max_dist,
+                                 const float* min_dist, uint8_t* inview, float* proj, int32_t* level, float* viewcos,
+                                 float* depth) {
+  int n_in = 0;
+  for (int i = 0; i < n; ++i) {
+    inview[i] = 0;
+    level[i] = -1;
+    proj[3 * i] = proj[3 * i + 1] = proj[3 * i + 2] = 0;
+    viewcos[i] = 0;
+    depth[i] = 0;
+    const float* P = wP + 3 * i;
+    const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];  // MapPoint.cc:481-489
+    float Pc[3];
+    for (int r = 0; r < 3; ++r)
+      Pc[r] = sum3(f->Rcw[3 * r] * P[0], f->Rcw[3 * r + 1] * P[1], f->Rcw[3 * r + 2] * P[2]) + f->tcw[r];
+    const float PcZ = Pc[2];
+    if (PcZ < 0.0f) continue;
+    const float invz = 1.0f / PcZ;
+    const float xn = Pc[0] * invz, yn = Pc[1] * invz;
+    // K * (xn, yn, 1): row 0 = fx*xn + (0*yn + cx*1), row 1 = 0*xn + (fy*yn + cy*1)
+    const float u = sum3(f->fx * xn, 0.0f * yn, f->cx * 1.0f);
+    const float v = sum3(0.0f * xn, f->fy * yn, f->cy * 1.0f);
+    if (u < f->minx || u > f->maxx) continue;
+    if (v < f->miny || v > f->maxy) continue;
+    const float PO[3] = {P[0] - f->Ow[0], P[1] - f->Ow[1], P[2] - f->Ow[2]};
+    const float dist3D = std::sqrt(sum3(PO[0] * PO[0], PO[1] * PO[1], PO[2] * PO[2]));
+    if (dist3D < minDistance || dist3D > maxDistance) continue;
+    const float vc = sum3(PO[0] * Pn[3 * i], PO[1] * Pn[3 * i + 1], PO[2] * Pn[3 * i + 2]) / dist3D;
+    if (vc < f->cos_limit) continue;
+    level[i] = orc_predict_scale(max_dist[i], dist3D, f->log_scale_factor, f->n_levels);
+    proj[3 * i] = u;
+    proj[3 * i + 1] = v;
+    proj[3 * i + 2] = u - f->bf * invz;
+    viewcos[i] = vc;
+    depth[i] = dist3D;  // sum_depth / 1 camera
+    inview[i] = 1;
+    ++n_in;
+  }
+  return n_in;
 }

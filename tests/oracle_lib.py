@@ -402,3 +402,75 @@ def search_by_projection(pb, frames=None):
             nm[f] = L.orc_sbp_local_map(fp, at("kps", kb), at("uright", kb), at("desc", kb), at("q_proj", qb), at("q_level", qb),
                                         at("q_viewcos", qb), at("q_depth", qb), at("q_desc", qb), at("q_flags", qb), blk, *outs)
     return kp_match, q_match, q_dist, nm
+
+
+# ---- Frame::isInFrustum / MapPoint::PredictScale (oracle/sbp_oracle.cc) --------------------------------------------------
+def predict_scale(max_distance, current_dist, log_scale_factor, n_levels):
+    L = lib()
+    L.orc_predict_scale.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
+    return L.orc_predict_scale(max_distance, current_dist, log_scale_factor, n_levels)
+
+
+def is_in_frustum(pb, frames=None):
+    """Oracle over every frame of a synth.make_frustum_problem dict -> dict(inview, proj, level, viewcos, depth, n_inview);
+    points with p_skip set are left "not in view" (Tracking::SearchLocalPoints never tests them)."""
+    from vieo_slam_b200.layouts import ORC_FRUSTUM_FRAME_DTYPE
+    L = lib()
+    L.orc_is_in_frustum.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
+    ff = pb["frustum"]
+    n = len(pb["p_max_dist"])
+    out = dict(inview=np.zeros(n, np.uint8), proj=np.zeros((n, 3), np.float32), level=np.full(n, -1, np.int32),
+               viewcos=np.zeros(n, np.float32), depth=np.zeros(n, np.float32), n_inview=np.zeros(len(ff), np.int32))
+    skip = pb.get("p_skip")
+    for f in (range(len(ff)) if frames is None else frames):
+        of = np.zeros(1, ORC_FRUSTUM_FRAME_DTYPE)
+        for name in ORC_FRUSTUM_FRAME_DTYPE.names:
+            of[0][name] = ff[f][name]
+        b, m = int(ff[f]["q_begin"]), int(ff[f]["n_q"])
+        idx = np.arange(b, b + m)
+        if skip is not None:
+            idx = idx[skip[b:b + m] == 0]
+        if len(idx) == 0:
+            continue
+        a = [np.ascontiguousarray(pb[k][idx], np.float32) for k in ("p_wP", "p_normal", "p_max_dist", "p_min_dist")]
+        o = [np.zeros(len(idx), np.uint8), np.zeros((len(idx), 3), np.float32), np.zeros(len(idx), np.int32),
+             np.zeros(len(idx), np.float32), np.zeros(len(idx), np.float32)]
+        out["n_inview"][f] = L.orc_is_in_frustum(_p(of), len(idx), *[_p(x) for x in a], *[_p(x) for x in o])
+        for key, arr in zip(("inview", "proj", "level", "viewcos", "depth"), o):
+            out[key][idx] = arr
+    return out
+
+
+def search_local_points(pb, frames=None):
+    """isInFrustum then the local-map SearchByProjection of the oracle, the latter fed with what the former left."""
+    fo = is_in_frustum(pb, frames)
+    q = dict(pb)
+    q["mode"] = 1
+    q["q_proj"], q["q_level"], q["q_viewcos"], q["q_depth"] = fo["proj"], fo["level"], fo["viewcos"], fo["depth"]
+    return (fo,) + search_by_projection(q, frames)
+
+
+# ---- MapPoint::ComputeDistinctiveDescriptors (oracle/match_oracle.cc) ------------------------------------------------------
+def distinctive_descriptors(desc_pool, ptr, rows=None):
+    L = lib()
+    L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_distinctive_descriptors.restype = None
+    pool = np.ascontiguousarray(desc_pool, np.uint8).reshape(-1, 32)
+    ptr = np.ascontiguousarray(ptr, np.int32)
+    rows = None if rows is None else np.ascontiguousarray(rows, np.int32)
+    n = len(ptr) - 1
+    best = np.empty(n, np.int32); med = np.empty(n, np.int32)
+    L.orc_distinctive_descriptors(_p(pool), None if rows is None else _p(rows), _p(ptr), n, _p(best), _p(med))
+    return best, med
+
+
+# ---- Optimizer::OptimizeInitialGyroBias (oracle/imu_oracle.cc) -----------------------------------------------------------
+def gyro_bias_init(pre, Rwb, use_info=True):
+    """-> (num_equations, dbg)"""
+    L = lib()
+    L.orc_gyro_bias_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    pre = np.ascontiguousarray(pre, PREINT_DTYPE)
+    Rwb = np.ascontiguousarray(Rwb, np.float64).reshape(-1, 9)
+    dbg = np.zeros(3)
+    n = L.orc_gyro_bias_init(_p(pre), _p(Rwb), len(pre), int(use_info), _p(dbg))
+    return n, dbg

@@ -1,0 +1,140 @@
+"""GPU parity for the SURVEY.md 8(f) rows, through the C ABI, against the oracle:
+ * Frame::isInFrustum + MapPoint::PredictScale (k_frustum): bit-exact floats and levels;
+ * Tracking::SearchLocalPoints = visibility test + local-map SearchByProjection on one stream: bit-exact matches;
+ * MapPoint::ComputeDistinctiveDescriptors (k_distinctive): bit-exact index and median;
+ * Optimizer::OptimizeInitialGyroBias + re-integration (k_gyro_bias -> k_imu_preint): 1e-10 relative on the bias
+   (fp64; device sin/cos/atan differ from glibc's by an ulp), 1e-12 on the re-integrated states given the same bias."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from vieo_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FR_KEYS = ("inview", "level", "proj", "viewcos", "depth", "n_inview")
+
+
+def _same_frustum(got, ref):
+    """Bit-exact, except that a NaN only has to be a NaN on both sides (x86 and the GPU produce different payloads)."""
+    for k in FR_KEYS:
+        a, b = np.asarray(got[k]).ravel(), np.asarray(ref[k]).ravel()
+        if a.dtype.kind == "f":
+            na, nb = np.isnan(a), np.isnan(b)
+            assert np.array_equal(na, nb), (k, "NaN pattern")
+            a, b = a[~na], b[~nb]
+        assert a.tobytes() == b.tobytes(), (k, np.nonzero(a != b)[0][:10])
+
+
+@pytest.mark.parametrize("kw", [dict(n_frames=4, n_q=1500), dict(n_frames=1, n_q=20000, skip_frac=0.3),
+                                dict(n_frames=9, n_q=37, skip_frac=0.0)])
+def test_is_in_frustum_matches_oracle(kw):
+    import vieo_slam_b200.api as api
+    pb = synth.make_frustum_problem(41, **kw)
+    got = api.isInFrustum(pb)
+    ref = O.is_in_frustum(pb)
+    _same_frustum(got, ref)
+    assert got["n_inview"].sum() > 0.15 * len(pb["p_max_dist"])
+
+
+def test_is_in_frustum_edge_cases():
+    import vieo_slam_b200.api as api
+    pb = synth.make_frustum_problem(42, n_frames=3, n_q=400, skip_frac=0.0)
+    pb["p_skip"] = None
+    # degenerate points: on the camera plane (PcZ == 0 -> inf / NaN projection), at the camera centre (dist 0), zero
+    # invariance range, NaN coordinates
+    G = pb["frustum"][0]
+    b = int(G["q_begin"])
+    pb["p_wP"][b] = G["Ow"]
+    pb["p_min_dist"][b + 1] = 0; pb["p_max_dist"][b + 1] = 0
+    pb["p_wP"][b + 2] = np.nan
+    pb["p_max_dist"][b + 3] = np.inf
+    # an empty frame in the middle of the batch
+    pb["frustum"][1]["n_q"] = 0
+    got = api.isInFrustum(pb)
+    ref = O.is_in_frustum(pb)
+    _same_frustum(got, ref)
+    b1 = int(pb["frustum"][1]["q_begin"])
+    assert not got["inview"][b1:b1 + 400].any() and (got["level"][b1:b1 + 400] == -1).all()
+    # other pyramids (VR config: scale 2, 4 levels)
+    for f in pb["frustum"]:
+        f["log_scale_factor"] = np.log(np.float32(2.0)); f["n_levels"] = 4
+    pb["frames"]["n_levels"] = 4
+    _same_frustum(api.isInFrustum(pb), O.is_in_frustum(pb))
+    pb["frustum"][0]["log_scale_factor"] = -1.0
+    with pytest.raises(api.VieoError):
+        api.isInFrustum(pb)
+
+
+@pytest.mark.parametrize("kw", [dict(th=1.0, n_q=2500, blocked_frac=0.2), dict(th=3.0, th_far=8.0),
+                                dict(th=6.0, cluster=True, n_kp=1500, n_q=600)])
+def test_search_local_points_matches_oracle(kw):
+    import vieo_slam_b200.api as api
+    pb = synth.make_frustum_problem(43, n_frames=5, **kw)
+    pb["frames"]["nn_ratio"] = 0.8
+    fo, kp_match, q_match, q_dist, nm = api.ORBmatcher(0.8).SearchLocalPoints(pb)
+    rfo, rkp, rqm, rqd, rnm = O.search_local_points(pb)
+    _same_frustum(fo, rfo)
+    for a, b, name in ((kp_match, rkp, "kp_match"), (q_match, rqm, "q_match"), (q_dist, rqd, "q_dist"), (nm, rnm, "n")):
+        assert np.array_equal(a, b), (name, np.nonzero(a != b)[0][:10])
+    assert nm.min() > 20
+    assert (q_match[fo["inview"] == 0] == -1).all()
+    # the stand-alone search fed with the frustum outputs (level -1 = skipped query) gives the same answer
+    q = dict(pb); q["mode"] = 1
+    q["q_proj"], q["q_level"], q["q_viewcos"], q["q_depth"] = fo["proj"], fo["level"], fo["viewcos"], fo["depth"]
+    out = api.ORBmatcher(0.8).SearchByProjection(q)
+    assert np.array_equal(out[1], q_match) and np.array_equal(out[3], nm)
+
+
+def test_distinctive_descriptors_match_oracle():
+    import vieo_slam_b200.api as api
+    d = synth.make_distinctive_problem(51, n_points=3000, max_obs=40, long_lists=(64, 65, 255, 256, 257, 300, 700))
+    best, med = api.ORBmatcher().ComputeDistinctiveDescriptors(d["pool"], d["ptr"], d["rows"])
+    rb, rm = O.distinctive_descriptors(d["pool"], d["ptr"], d["rows"])
+    assert np.array_equal(best, rb) and np.array_equal(med, rm), np.nonzero((best != rb) | (med != rm))[0][:10]
+    assert (best == -1).sum() > 0
+    # without a row table
+    pool2 = np.ascontiguousarray(d["pool"][d["rows"]])
+    b2, m2 = api.ORBmatcher().ComputeDistinctiveDescriptors(pool2, d["ptr"])
+    assert np.array_equal(b2, rb) and np.array_equal(m2, rm)
+    # errors are reported: row outside the pool, descending lists
+    bad = d["rows"].copy(); bad[3] = len(d["pool"])
+    with pytest.raises(api.VieoError):
+        api.ORBmatcher().ComputeDistinctiveDescriptors(d["pool"], d["ptr"], bad)
+    with pytest.raises(api.VieoError):
+        api.ORBmatcher().ComputeDistinctiveDescriptors(d["pool"], [0, 5, 3], d["rows"])
+
+
+@pytest.mark.parametrize("use_info", [True, False])
+def test_initial_gyro_bias_and_reintegration(use_info):
+    import vieo_slam_b200.api as api
+    g = synth.make_gyro_bias_problem(61, n_kf=40, kf_gap=(1, 12))
+    nz = O.imu_noise()
+    imu = api.IMUPreintegrator()
+    n_kf = len(g["kf_idx"])
+    bias0 = np.zeros((n_kf, 6)); bias0[:, 3:] = g["seq"]["ba"]
+    pre = imu.preintegrate_batch(g["samples"], g["seg_ptr"], g["ti_tj"], bias0)
+    rng = np.random.default_rng(4)
+    Rwb = np.stack([R @ synth.so3_exp(rng.normal(0, 2e-3, 3)) for R in g["Rwb"]])
+    bg_in = np.array([1e-3, -2e-3, 5e-4])
+    neq, bg, re = imu.OptimizeInitialGyroBias(pre, Rwb, bg_in, bInfo=use_info, samples=g["samples"], seg_ptr=g["seg_ptr"],
+                                              ti_tj=g["ti_tj"], ba=bias0[:, 3:])
+    rn, dbg = O.gyro_bias_init(pre, Rwb, use_info)
+    assert neq == rn == n_kf - 1
+    assert np.abs(bg - (bg_in + dbg)).max() < 1e-10 * np.abs(dbg).max(), (bg - bg_in, dbg)
+    # every interval re-integrated with {bg, ba}: compare with the oracle at the SAME bias the device used
+    for k in range(1, n_kf):
+        ref = O.imu_preintegrate(g["samples"][g["seg_ptr"][k]:g["seg_ptr"][k + 1]], g["ti_tj"][k][0], g["ti_tj"][k][1], bg,
+                                 bias0[k, 3:], nz)
+        for f in ("Rij", "vij", "pij", "SigmaPRV", "JgR", "dt"):
+            a, b = np.asarray(re[k][f]), np.asarray(ref[f])
+            assert np.abs(a - b).max() <= 1e-12 * max(np.abs(b).max(), 1e-300), (k, f)
+    assert re[0]["dt"] == 0
+    # without the sample lists only the bias is estimated; a chain without equations leaves bg untouched
+    neq2, bg2, none = imu.OptimizeInitialGyroBias(pre, Rwb, bg_in, bInfo=use_info)
+    assert neq2 == neq and none is None and np.array_equal(bg2, bg)
+    neq3, bg3, _ = imu.OptimizeInitialGyroBias(pre[:1], Rwb[:1], bg_in)
+    assert neq3 == 0 and np.array_equal(bg3, bg_in)
+    # with exact rotations the step recovers the bias the gyro samples carry (first order)
+    _, bg4, _ = imu.OptimizeInitialGyroBias(pre, g["Rwb"], np.zeros(3), bInfo=use_info)
+    assert np.abs(bg4 - g["bg_true"]).max() < 3e-4

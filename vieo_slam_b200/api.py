@@ -10,6 +10,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvieo_b200.so")
 
+from .layouts import FRUSTUM_FRAME_DTYPE  # noqa: E402
+
 KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")])
 
 
@@ -66,6 +68,14 @@ def lib():
         L.vieo_sbp_scratch_bytes.restype = sz
         L.vieo_sbp_batch.argtypes = [i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
         L.vieo_sbp_batch_dev.argtypes = [i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+        L.vieo_frustum_level_table.argtypes = [C.c_float, i32, vp]
+        L.vieo_frustum_batch.argtypes = [vp, i32] + [vp] * 11 + [i32]
+        L.vieo_frustum_batch_dev.argtypes = [vp, i32] + [vp] * 12
+        L.vieo_search_local_points.argtypes = [vp, vp, i32] + [vp] * 21 + [i32]
+        L.vieo_distinctive_descriptors.argtypes = [vp, i32, vp, vp, i32, vp, vp, i32]
+        L.vieo_distinctive_descriptors_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+        L.vieo_imu_init_gyro_bias.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.vieo_gyro_bias_init_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
         L.vieo_frontend_create.argtypes = [C.POINTER(VieoOrbConfig), i32, i32, C.POINTER(vp)]
         L.vieo_frontend_destroy.argtypes = [vp]
         L.vieo_frontend_destroy.restype = None
@@ -267,6 +277,40 @@ def sbp_batch_dev(mode, frames_ptr, n_frames, kps_ptr, ur_ptr, desc_ptr, queries
                                     kp_match_ptr, q_match_ptr, q_dist_ptr, n_matches_ptr, scratch_ptr, scratch_bytes, stream))
 
 
+def frustum_batch_dev(frames_ptr, n_frames, wP_ptr, normal_ptr, max_dist_ptr, min_dist_ptr, skip_ptr, inview_ptr, proj_ptr,
+                      level_ptr, viewcos_ptr, depth_ptr, n_inview_ptr, stream=0):
+    """vieo_frustum_batch_dev: device-resident Frame::isInFrustum; the frames' level_ratio tables must be filled
+    (frustum_level_table)."""
+    _check(lib().vieo_frustum_batch_dev(frames_ptr, n_frames, wP_ptr, normal_ptr, max_dist_ptr, min_dist_ptr, skip_ptr,
+                                        inview_ptr, proj_ptr, level_ptr, viewcos_ptr, depth_ptr, n_inview_ptr, stream))
+
+
+def _frustum_outputs(nq, nf):
+    return dict(inview=np.zeros(nq, np.uint8), proj=np.zeros((nq, 3), np.float32), level=np.full(nq, -1, np.int32),
+                viewcos=np.zeros(nq, np.float32), depth=np.zeros(nq, np.float32), n_inview=np.zeros(nf, np.int32))
+
+
+def frustum_level_table(log_scale_factor, n_levels):
+    """vieo_frustum_level_table: smallest float ratio reaching each pyramid level under MapPoint::PredictScale."""
+    t = np.zeros(16, np.float32)
+    _check(lib().vieo_frustum_level_table(C.c_float(log_scale_factor), int(n_levels), _p(t)))
+    return t
+
+
+def isInFrustum(pb, device=0):
+    """Frame::isInFrustum (src/Frame.cc:335-416) + MapPoint::PredictScale for every candidate point of every frame of a
+    synth.make_frustum_problem dict -> dict(inview, proj, level, viewcos, depth, n_inview)."""
+    ff = np.ascontiguousarray(pb["frustum"], FRUSTUM_FRAME_DTYPE)
+    wP, Pn = np.ascontiguousarray(pb["p_wP"], np.float32), np.ascontiguousarray(pb["p_normal"], np.float32)
+    mx, mn = np.ascontiguousarray(pb["p_max_dist"], np.float32), np.ascontiguousarray(pb["p_min_dist"], np.float32)
+    skip = None if pb.get("p_skip") is None else np.ascontiguousarray(pb["p_skip"], np.uint8)
+    out = _frustum_outputs(len(mx), len(ff))
+    _check(lib().vieo_frustum_batch(_p(ff), len(ff), _p(wP), _p(Pn), _p(mx), _p(mn), _p(skip), _p(out["inview"]),
+                                    _p(out["proj"]), _p(out["level"]), _p(out["viewcos"]), _p(out["depth"]),
+                                    _p(out["n_inview"]), device))
+    return out
+
+
 class ORBmatcher:
     """The Hamming kernels behind ORBmatcher / Frame stereo association (include/ORBmatcher.h:18-113)."""
     TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30  # src/ORBmatcher.cc:20-22
@@ -327,6 +371,44 @@ class ORBmatcher:
         o = [np.empty(n, np.int32) for _ in range(4)]
         _check(lib().vieo_hamming_csr(_p(q), _p(t), len(t), _p(row_ptr), _p(cand), n, *[_p(x) for x in o], self.device))
         return o
+
+    def SearchLocalPoints(self, pb):
+        """Tracking::SearchLocalPoints (src/Tracking.cc:2308-2368): Frame::isInFrustum over every candidate local map point
+        followed by SearchByProjection(F, vpMapPoints, th, th_far) on the same stream (vieo_search_local_points).  `pb` is
+        a synth.make_frustum_problem dict that also carries the guided-search arrays.
+        Returns (frustum outputs dict, kp_match, q_match, q_dist, n_matches)."""
+        fr = np.ascontiguousarray(pb["frames"]).copy()
+        fr["nn_ratio"] = self.mfNNratio
+        fr["check_orientation"] = int(self.mbCheckOrientation)
+        ff = np.ascontiguousarray(pb["frustum"], FRUSTUM_FRAME_DTYPE)
+        a = {k: np.ascontiguousarray(pb[k], dt) for k, dt in (("p_wP", np.float32), ("p_normal", np.float32),
+                                                               ("p_max_dist", np.float32), ("p_min_dist", np.float32),
+                                                               ("q_desc", np.uint8), ("q_flags", np.uint8),
+                                                               ("kps", KP_DTYPE), ("uright", np.float32), ("desc", np.uint8))}
+        skip = None if pb.get("p_skip") is None else np.ascontiguousarray(pb["p_skip"], np.uint8)
+        blk = None if pb.get("kp_blocked") is None else np.ascontiguousarray(pb["kp_blocked"], np.uint8)
+        nq, nk = len(a["p_max_dist"]), len(a["kps"])
+        out = _frustum_outputs(nq, len(ff))
+        kp_match = np.full(nk, -1, np.int32)
+        q_match = np.full(nq, -1, np.int32); q_dist = np.full(nq, -1, np.int32)
+        nm = np.zeros(len(fr), np.int32)
+        _check(lib().vieo_search_local_points(_p(ff), _p(fr), len(fr), _p(a["p_wP"]), _p(a["p_normal"]), _p(a["p_max_dist"]),
+                                              _p(a["p_min_dist"]), _p(skip), _p(a["q_desc"]), _p(a["q_flags"]), _p(a["kps"]),
+                                              _p(a["uright"]), _p(a["desc"]), _p(blk), _p(out["inview"]), _p(out["proj"]),
+                                              _p(out["level"]), _p(out["viewcos"]), _p(out["depth"]), _p(out["n_inview"]),
+                                              _p(kp_match), _p(q_match), _p(q_dist), _p(nm), self.device))
+        return out, kp_match, q_match, q_dist, nm
+
+    def ComputeDistinctiveDescriptors(self, desc_pool, ptr, rows=None):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:314-378) for a CSR batch of map points.
+        -> (best index into each point's observation list or -1, that row's median distance)."""
+        pool = np.ascontiguousarray(desc_pool, np.uint8).reshape(-1, 32)
+        ptr = np.ascontiguousarray(ptr, np.int32)
+        rows = None if rows is None else np.ascontiguousarray(rows, np.int32)
+        n = len(ptr) - 1
+        best = np.empty(n, np.int32); med = np.empty(n, np.int32)
+        _check(lib().vieo_distinctive_descriptors(_p(pool), len(pool), _p(rows), _p(ptr), n, _p(best), _p(med), self.device))
+        return best, med
 
     def DescriptorDistance(self, a, b):
         """ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1645) evaluated on the device."""
@@ -428,6 +510,29 @@ class IMUPreintegrator:
         _check(lib().vieo_imu_preint_batch(_p(samples), _p(seg_ptr), _p(ti_tj), _p(bg_ba), C.byref(self.noise), n,
                                            _p(out), self.device))
         return out
+
+    def OptimizeInitialGyroBias(self, pre, Rwb, bg, bInfo=True, samples=None, seg_ptr=None, ti_tj=None, ba=None):
+        """Optimizer::OptimizeInitialGyroBias (include/Optimizer.h:819-892) on keyframe pre-integrations `pre`
+        (PREINT_DTYPE[n_kf], entry 0 ignored) and body rotations Rwb (n_kf, 3, 3); with the sample lists given, every
+        interval is re-integrated with the new bias on the same stream (IMUInitialization.cpp:640-648).
+        -> (num_equations, bg + estimate, re-integrated PREINT_DTYPE[n_kf] or None)"""
+        pre = np.ascontiguousarray(pre, PREINT_DTYPE)
+        Rwb = np.ascontiguousarray(Rwb, np.float64).reshape(-1, 9)
+        n = len(pre)
+        assert len(Rwb) == n
+        bg = np.array(bg, np.float64).reshape(3).copy()
+        neq = C.c_int32(0)
+        out = None
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, np.float64).reshape(-1, 7)
+            seg_ptr = np.ascontiguousarray(seg_ptr, np.int32)
+            ti_tj = np.ascontiguousarray(ti_tj, np.float64).reshape(-1, 2)
+            ba = None if ba is None else np.ascontiguousarray(ba, np.float64).reshape(-1, 3)
+            assert len(seg_ptr) == n + 1 and len(ti_tj) == n
+            out = np.zeros(n, PREINT_DTYPE)
+        _check(lib().vieo_imu_init_gyro_bias(_p(pre), _p(Rwb), n, int(bInfo), _p(bg), C.byref(neq), _p(samples), _p(seg_ptr),
+                                             _p(ti_tj), _p(ba), C.byref(self.noise), _p(out), self.device))
+        return neq.value, bg, out
 
     def preintegrate_batch_dev(self, samples_ptr, seg_ptr, ti_tj_ptr, bg_ba_ptr, n, out_ptr, stream=0):
         """Device-resident form; all pointers are device addresses."""

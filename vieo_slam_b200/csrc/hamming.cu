@@ -127,6 +127,93 @@ __global__ void __launch_bounds__(128) k_csr(const uint8_t* __restrict__ q, cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:314-378) for a batch of map points (LocalMapping calls it for
+// every point it created, fused or re-observed: src/LocalMapping.cc).  One warp per map point; for
+// row i the lanes hold the distances to observations lane, lane + 32, ... in registers (the first 256; a longer list —
+// not seen in practice — recomputes the rest inside the search) and the sorted-row entry at index (N - 1) / 2 is found
+// without sorting: bisection on the value v in [0, 256] of "count(d <= v) >= k + 1" with warp ballots.  The first row
+// with the least median wins, as in the reference's strict '<' scan.
+constexpr int kDdWarps = 4;
+constexpr int kDdChunks = 8;
+__device__ __forceinline__ int ham256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+         __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+__global__ void __launch_bounds__(kDdWarps * 32) k_distinctive(const uint8_t* __restrict__ pool,
+                                                              const int32_t* __restrict__ rows,
+                                                              const int32_t* __restrict__ ptr, int n_points,
+                                                              int32_t* __restrict__ best, int32_t* __restrict__ median) {
+  const int lane = threadIdx.x & 31, p = blockIdx.x * kDdWarps + (threadIdx.x >> 5);
+  if (p >= n_points) return;
+  const int b = ptr[p], N = ptr[p + 1] - b;
+  if (N <= 0) {
+    if (lane == 0) {
+      best[p] = -1;
+      median[p] = -1;
+    }
+    return;
+  }
+  auto row_of = [&](int j) { return rows ? rows[b + j] : b + j; };
+  auto load = [&](int j, uint4& d0, uint4& d1) {
+    const uint4* src = reinterpret_cast<const uint4*>(pool + 32 * (size_t)row_of(j));
+    d0 = __ldg(src);
+    d1 = __ldg(src + 1);
+  };
+  const int kth = (N - 1) >> 1;  // vDists[0.5 * (N - 1)]
+  const int chunks = min((N + 31) >> 5, kDdChunks);
+  uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;  // this lane's observation of chunk 0
+  if (lane < N) load(lane, m0, m1);
+  int best_med = INT_MAX, best_idx = 0;
+  for (int i = 0; i < N; ++i) {
+    uint4 a0, a1;
+    load(i, a0, a1);
+    int d[kDdChunks];
+#pragma unroll
+    for (int c = 0; c < kDdChunks; ++c) {
+      d[c] = 512;  // beyond any distance
+      const int j = lane + 32 * c;
+      if (c < chunks && j < N) {
+        if (c == 0) {
+          d[c] = ham256(a0, a1, m0, m1);
+        } else {
+          uint4 b0, b1;
+          load(j, b0, b1);
+          d[c] = ham256(a0, a1, b0, b1);
+        }
+      }
+    }
+    int lo = 0, hi = 256;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < kDdChunks; ++c)
+        if (c < chunks) cnt += __popc(__ballot_sync(0xffffffffu, d[c] <= mid));
+      if (N > 32 * kDdChunks) {
+        int extra = 0;
+        for (int j = 32 * kDdChunks + lane; j < N; j += 32) {
+          uint4 b0, b1;
+          load(j, b0, b1);
+          extra += ham256(a0, a1, b0, b1) <= mid ? 1 : 0;
+        }
+        cnt += __reduce_add_sync(0xffffffffu, extra);
+      }
+      if (cnt >= kth + 1) hi = mid;
+      else lo = mid + 1;
+    }
+    if (lo < best_med) {
+      best_med = lo;
+      best_idx = i;
+    }
+  }
+  if (lane == 0) {
+    best[p] = best_idx;
+    median[p] = best_med;
+  }
+}
+
 }  // namespace vieo
 
 using namespace vieo;
@@ -218,6 +305,52 @@ int vieo_hamming_csr(const uint8_t* q, const uint8_t* t, int nt, const int32_t* 
     set_error("vieo_hamming_csr: %s", cudaGetErrorString(e));
     return VIEO_E_CUDA;
   }
+  return VIEO_OK;
+}
+
+int vieo_distinctive_descriptors_dev(const uint8_t* desc_pool_dev, const int32_t* rows_dev, const int32_t* ptr_dev,
+                                     int n_points, int32_t* best_dev, int32_t* median_dev, void* stream) {
+  VIEO_ARG(n_points >= 0, "bad argument");
+  if (n_points == 0) return VIEO_OK;
+  VIEO_ARG(desc_pool_dev && ptr_dev && best_dev && median_dev, "null argument");
+  VIEO_ARG((uintptr_t)desc_pool_dev % 16 == 0, "descriptors must be 16-byte aligned");
+  k_distinctive<<<(n_points + kDdWarps - 1) / kDdWarps, kDdWarps * 32, 0, (cudaStream_t)stream>>>(
+      desc_pool_dev, rows_dev, ptr_dev, n_points, best_dev, median_dev);
+  VIEO_CK(cudaGetLastError());
+  return VIEO_OK;
+}
+
+int vieo_distinctive_descriptors(const uint8_t* desc_pool, int n_pool, const int32_t* rows, const int32_t* ptr,
+                                 int n_points, int32_t* best, int32_t* median, int device) {
+  VIEO_ARG(n_points >= 0 && n_pool >= 0, "bad argument");
+  if (n_points == 0) return VIEO_OK;
+  VIEO_ARG(ptr && best && median, "null argument");
+  const int n_obs = ptr[n_points];
+  VIEO_ARG(ptr[0] == 0 && n_obs >= 0 && (n_obs == 0 || desc_pool), "bad observation lists");
+  for (int p = 0; p < n_points; ++p) VIEO_ARG(ptr[p + 1] >= ptr[p], "observation lists must be ascending");
+  if (rows) {
+    for (int k = 0; k < n_obs; ++k) VIEO_ARG(rows[k] >= 0 && rows[k] < n_pool, "descriptor row out of range");
+  } else {
+    VIEO_ARG(n_obs <= n_pool, "descriptor row out of range");
+  }
+  int rc = use_device(device);
+  if (rc) return rc;
+  CallScratch* cs = call_scratch(device);
+  if (!cs) return VIEO_E_CUDA;
+  uint8_t* d_pool = (uint8_t*)cs->get(0, 32 * (size_t)std::max(n_pool, 1));
+  int32_t* d_rows = (int32_t*)cs->get(1, 4 * (size_t)std::max(n_obs, 1));
+  int32_t* d_ptr = (int32_t*)cs->get(2, 4 * (size_t)(n_points + 1));
+  int32_t* d_out = (int32_t*)cs->get(3, 8 * (size_t)n_points);
+  if (!d_pool || !d_rows || !d_ptr || !d_out) return VIEO_E_CUDA;
+  cudaStream_t st = cs->st;
+  if (n_pool) VIEO_CK(cudaMemcpyAsync(d_pool, desc_pool, 32 * (size_t)n_pool, cudaMemcpyHostToDevice, st));
+  if (rows && n_obs) VIEO_CK(cudaMemcpyAsync(d_rows, rows, 4 * (size_t)n_obs, cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaMemcpyAsync(d_ptr, ptr, 4 * (size_t)(n_points + 1), cudaMemcpyHostToDevice, st));
+  rc = vieo_distinctive_descriptors_dev(d_pool, rows ? d_rows : nullptr, d_ptr, n_points, d_out, d_out + n_points, st);
+  if (rc) return rc;
+  VIEO_CK(cudaMemcpyAsync(best, d_out, 4 * (size_t)n_points, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaMemcpyAsync(median, d_out + n_points, 4 * (size_t)n_points, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaStreamSynchronize(st));
   return VIEO_OK;
 }
 

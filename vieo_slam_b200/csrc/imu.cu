@@ -257,6 +257,134 @@ __global__ void __launch_bounds__(kImuWarps * 32) k_imu_preint(const double* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer::OptimizeInitialGyroBias (include/Optimizer.h:819-892) with EdgeGyrBias (src/Odom/g2otypes.h:940-973): one
+// Gauss-Newton iteration on the 3-dim gyro-bias vertex seeded with zero.  One CTA: a thread per keyframe pair evaluates
+// the residual Log((dRij Exp(JgR bg))^T Rwbi^T Rwbj) and its Jacobian at bg = 0, J^T W J / J^T W e are summed in a fixed
+// order (thread-strided partial sums, then a shared-memory tree), thread 0 solves the 3x3 system, and every thread then
+// writes the linearisation biases {bg + dbg, ba_i} of the re-integration that follows (IMUInitialization.cpp:640-648).
+constexpr int kGyroThreads = 256;
+struct GyroBiasOut {
+  double dbg[3];
+  double bg[3];
+  int32_t num_equations;
+  int32_t solved;
+};
+__global__ void __launch_bounds__(kGyroThreads) k_gyro_bias(const VieoImuPreint* __restrict__ pre,
+                                                            const double* __restrict__ Rwb, int n_kf, int use_info,
+                                                            double bg0x, double bg0y, double bg0z,
+                                                            const double* __restrict__ bg_ba_in,
+                                                            double* __restrict__ bg_ba_out, GyroBiasOut* __restrict__ out) {
+  __shared__ double red[kGyroThreads][13];
+  __shared__ double s_bg[3];
+  const int tid = threadIdx.x;
+  double acc[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) acc[k] = 0;
+  for (int i = 1 + tid; i < n_kf; i += kGyroThreads) {
+    const VieoImuPreint& P = pre[i];
+    if (P.dt == 0) continue;
+    Mat3 dR, JgR, Ri, Rj;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      dR.m[k] = P.Rij[k];
+      JgR.m[k] = P.JgR[k];
+      Ri.m[k] = Rwb[9 * (size_t)(i - 1) + k];
+      Rj.m[k] = Rwb[9 * (size_t)i + k];
+    }
+    const Vec3 Jb = m3_mulv(JgR, Vec3{0, 0, 0});
+    const Mat3 E = m3_mul(m3_mul(m3_t(m3_mul(dR, so3_Exp(Jb))), m3_t(Ri)), Rj);
+    const Vec3 e = so3_Log(E);
+    const Mat3 J = m3_scale(m3_mul(m3_mul(m3_mul(so3_JrInv(e), so3_Exp(Vec3{-e.x, -e.y, -e.z})), so3_Jr(Jb)), JgR), -1.0);
+    Mat3 W = m3_identity();
+    if (use_info) {
+      double a[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[3 * r + c] = P.SigmaPRV[9 * (3 + r) + 3 + c];
+      const double c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+      const double det = a[0] * c00 + a[1] * c01 + a[2] * c02, id = 1.0 / det;
+      W = {{c00 * id, (a[2] * a[7] - a[1] * a[8]) * id, (a[1] * a[5] - a[2] * a[4]) * id,
+            c01 * id, (a[0] * a[8] - a[2] * a[6]) * id, (a[2] * a[3] - a[0] * a[5]) * id,
+            c02 * id, (a[1] * a[6] - a[0] * a[7]) * id, (a[0] * a[4] - a[1] * a[3]) * id}};
+    }
+    const Mat3 JtW = m3_mul(m3_t(J), W);
+    const Mat3 JtWJ = m3_mul(JtW, J);
+    const Vec3 JtWe = m3_mulv(JtW, e);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] += JtWJ.m[k];
+    acc[9] -= JtWe.x;
+    acc[10] -= JtWe.y;
+    acc[11] -= JtWe.z;
+    acc[12] += 1.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 13; ++k) red[tid][k] = acc[k];
+  __syncthreads();
+  for (int s = kGyroThreads / 2; s > 0; s >>= 1) {
+    if (tid < s)
+#pragma unroll
+      for (int k = 0; k < 13; ++k) red[tid][k] += red[tid + s][k];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const double* H = red[0];
+    const double* b = red[0] + 9;
+    double x[3] = {0, 0, 0};
+    const int neq = (int)red[0][12];
+    int solved = 0;
+    if (neq >= 1) {
+      // 3x3 Cholesky (the reference: LinearSolverEigen's LDLT; an indefinite H leaves the estimate at zero)
+      double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      bool ok = true;
+      for (int j = 0; j < 3 && ok; ++j) {
+        double d = H[3 * j + j];
+        for (int k = 0; k < j; ++k) d -= L[3 * j + k] * L[3 * j + k];
+        if (!(d > 0)) {
+          ok = false;
+          break;
+        }
+        L[3 * j + j] = sqrt(d);
+        for (int r = j + 1; r < 3; ++r) {
+          double v = H[3 * r + j];
+          for (int k = 0; k < j; ++k) v -= L[3 * r + k] * L[3 * j + k];
+          L[3 * r + j] = v / L[3 * j + j];
+        }
+      }
+      if (ok) {
+        double y[3];
+        for (int r = 0; r < 3; ++r) {
+          double v = b[r];
+          for (int k = 0; k < r; ++k) v -= L[3 * r + k] * y[k];
+          y[r] = v / L[3 * r + r];
+        }
+        for (int r = 2; r >= 0; --r) {
+          double v = y[r];
+          for (int k = r + 1; k < 3; ++k) v -= L[3 * k + r] * x[k];
+          x[r] = v / L[3 * r + r];
+        }
+        solved = 1;
+      }
+    }
+    out->dbg[0] = x[0]; out->dbg[1] = x[1]; out->dbg[2] = x[2];
+    s_bg[0] = bg0x + x[0]; s_bg[1] = bg0y + x[1]; s_bg[2] = bg0z + x[2];
+    out->bg[0] = s_bg[0]; out->bg[1] = s_bg[1]; out->bg[2] = s_bg[2];
+    out->num_equations = neq;
+    out->solved = solved;
+  }
+  __syncthreads();
+  if (bg_ba_out)
+    for (int i = tid; i < n_kf; i += kGyroThreads) {
+      bg_ba_out[6 * (size_t)i + 0] = s_bg[0];
+      bg_ba_out[6 * (size_t)i + 1] = s_bg[1];
+      bg_ba_out[6 * (size_t)i + 2] = s_bg[2];
+#pragma unroll
+      for (int k = 3; k < 6; ++k) bg_ba_out[6 * (size_t)i + k] = bg_ba_in ? bg_ba_in[6 * (size_t)i + k] : 0.0;
+    }
+}
+
 }  // namespace vieo
 
 using namespace vieo;
@@ -316,6 +444,76 @@ int vieo_imu_preint_batch(const double* samples, const int32_t* seg_ptr, const d
   if (rc) return rc;
   VIEO_CK(cudaMemcpyAsync(out, d_o, sizeof(VieoImuPreint) * n_intervals, cudaMemcpyDeviceToHost, st));
   VIEO_CK(cudaStreamSynchronize(st));
+  return VIEO_OK;
+}
+
+int vieo_gyro_bias_init_dev(const VieoImuPreint* pre_dev, const double* Rwb_dev, int n_kf, int use_info, const double bg[3],
+                            const double* bg_ba_in_dev, double* bg_ba_out_dev, void* result_dev, void* stream) {
+  VIEO_ARG(n_kf >= 0 && bg && result_dev, "bad argument");
+  VIEO_ARG(n_kf == 0 || (pre_dev && Rwb_dev), "null argument");
+  k_gyro_bias<<<1, kGyroThreads, 0, (cudaStream_t)stream>>>(pre_dev, Rwb_dev, n_kf, use_info, bg[0], bg[1], bg[2], bg_ba_in_dev,
+                                                           bg_ba_out_dev, (GyroBiasOut*)result_dev);
+  VIEO_CK(cudaGetLastError());
+  return VIEO_OK;
+}
+
+int vieo_imu_init_gyro_bias(const VieoImuPreint* pre, const double* Rwb, int n_kf, int use_info, double bg[3],
+                            int* num_equations, const double* samples, const int32_t* seg_ptr, const double* ti_tj,
+                            const double* ba, const VieoImuNoise* noise, VieoImuPreint* preint_out, int device) {
+  VIEO_ARG(n_kf >= 0 && bg && num_equations, "bad argument");
+  *num_equations = 0;
+  if (n_kf == 0) return VIEO_OK;
+  VIEO_ARG(pre && Rwb, "null argument");
+  const bool reint = preint_out != nullptr;
+  int n_s = 0;
+  if (reint) {
+    VIEO_ARG(seg_ptr && ti_tj && noise, "re-integration needs the sample lists");
+    n_s = seg_ptr[n_kf];
+    VIEO_ARG(n_s >= 0 && (n_s == 0 || samples), "bad sample list");
+  }
+  int rc = use_device(device);
+  if (rc) return rc;
+  CallScratch* cs = call_scratch(device);
+  if (!cs) return VIEO_E_CUDA;
+  VieoImuPreint* d_pre = (VieoImuPreint*)cs->get(0, sizeof(VieoImuPreint) * n_kf);
+  double* d_R = (double*)cs->get(1, sizeof(double) * 9 * n_kf);
+  double* d_bi = (double*)cs->get(2, sizeof(double) * 6 * n_kf);
+  double* d_bo = (double*)cs->get(3, sizeof(double) * 6 * n_kf);
+  GyroBiasOut* d_res = (GyroBiasOut*)cs->get(4, sizeof(GyroBiasOut));
+  double* d_s = (double*)cs->get(5, sizeof(double) * 7 * std::max(n_s, 1));
+  int* d_p = (int*)cs->get(6, sizeof(int) * (n_kf + 1));
+  double* d_t = (double*)cs->get(7, sizeof(double) * 2 * n_kf);
+  VieoImuPreint* d_o = (VieoImuPreint*)cs->get(8, sizeof(VieoImuPreint) * n_kf);
+  if (!d_pre || !d_R || !d_bi || !d_bo || !d_res || !d_s || !d_p || !d_t || !d_o) return VIEO_E_CUDA;
+  cudaStream_t st = cs->st;
+  VIEO_CK(cudaMemcpyAsync(d_pre, pre, sizeof(VieoImuPreint) * n_kf, cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaMemcpyAsync(d_R, Rwb, sizeof(double) * 9 * n_kf, cudaMemcpyHostToDevice, st));
+  if (reint) {
+    // ba of the previous keyframe is kept (IMUInitialization.h:225-232); only bg changes
+    std::vector<double> bi(6 * (size_t)n_kf, 0.0);
+    if (ba)
+      for (int i = 0; i < n_kf; ++i)
+        for (int k = 0; k < 3; ++k) bi[6 * (size_t)i + 3 + k] = ba[3 * (size_t)i + k];
+    VIEO_CK(cudaMemcpyAsync(d_bi, bi.data(), sizeof(double) * 6 * n_kf, cudaMemcpyHostToDevice, st));
+    VIEO_CK(cudaStreamSynchronize(st));  // bi is a local
+    if (n_s) VIEO_CK(cudaMemcpyAsync(d_s, samples, sizeof(double) * 7 * n_s, cudaMemcpyHostToDevice, st));
+    VIEO_CK(cudaMemcpyAsync(d_p, seg_ptr, sizeof(int) * (n_kf + 1), cudaMemcpyHostToDevice, st));
+    VIEO_CK(cudaMemcpyAsync(d_t, ti_tj, sizeof(double) * 2 * n_kf, cudaMemcpyHostToDevice, st));
+  }
+  rc = vieo_gyro_bias_init_dev(d_pre, d_R, n_kf, use_info, bg, reint ? d_bi : nullptr, reint ? d_bo : nullptr, d_res, st);
+  if (rc) return rc;
+  if (reint) {
+    rc = vieo_imu_preint_batch_dev(d_s, d_p, d_t, d_bo, noise, n_kf, d_o, st);
+    if (rc) return rc;
+    VIEO_CK(cudaMemcpyAsync(preint_out, d_o, sizeof(VieoImuPreint) * n_kf, cudaMemcpyDeviceToHost, st));
+  }
+  GyroBiasOut res;
+  VIEO_CK(cudaMemcpyAsync(&res, d_res, sizeof(res), cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaStreamSynchronize(st));
+  *num_equations = res.num_equations;
+  if (res.num_equations >= 1) {  // the reference returns before bg += estimate when there is no equation
+    bg[0] = res.bg[0]; bg[1] = res.bg[1]; bg[2] = res.bg[2];
+  }
   return VIEO_OK;
 }
 

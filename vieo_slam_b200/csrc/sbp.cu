@@ -152,8 +152,9 @@ __device__ __forceinline__ bool make_window(int mode, const VieoSbpFrame& F, con
     c.ur = __fsub_rn(u, __fmul_rn(F.bf, invzc));
     return true;
   }
-  if (F.th_far > 0 && Q.depth[q] > F.th_far) return false;
   const int lvl = Q.level[q];
+  if (lvl < 0) return false;  // !btrack_inview_ (:244): the level k_frustum leaves for a point that is not in view
+  if (F.th_far > 0 && Q.depth[q] > F.th_far) return false;
   float r = (double)Q.viewcos[q] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos (:337-342)
   if ((double)F.th != 1.0) r = __fmul_rn(r, F.th);
   c.x = Q.proj[3 * (size_t)q]; c.y = Q.proj[3 * (size_t)q + 1];
@@ -453,7 +454,7 @@ int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const Vie
   if (mode == VIEO_SBP_LAST_FRAME) VIEO_ARG(nq == 0 || (q->Xw && q->angle), "null query array");
   else VIEO_ARG(nq == 0 || (q->proj && q->viewcos && q->depth), "null query array");
   for (size_t i = 0; i < nq; ++i)
-    VIEO_ARG(q->level[i] >= 0 && q->level[i] < 16, "query level out of range");
+    VIEO_ARG(q->level[i] >= (mode == VIEO_SBP_LOCAL_MAP ? -1 : 0) && q->level[i] < 16, "query level out of range");
   int rc = use_device(device);
   if (rc) return rc;
   CallScratch* cs = call_scratch(device);

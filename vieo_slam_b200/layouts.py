@@ -39,5 +39,14 @@ SBP_FRAME_DTYPE = np.dtype([("kp_begin", "i4"), ("n_kp", "i4"), ("q_begin", "i4"
                             ("scale", "f4", 16), ("qcw", "f8", 4), ("tcw", "f8", 3), ("qlw", "f8", 4), ("tlw", "f8", 3)])
 SBP_LAST_FRAME, SBP_LOCAL_MAP = 0, 1
 
+# VieoFrustumFrame (include/vieo_b200.h): one current frame of a Frame::isInFrustum batch; the oracle's OrcFrustumFrame is
+# the same record without the trailing level_ratio table
+_FRUSTUM_FIELDS = [("q_begin", "i4"), ("n_q", "i4"), ("Rcw", "f4", 9), ("tcw", "f4", 3), ("Ow", "f4", 3), ("fx", "f4"),
+                   ("fy", "f4"), ("cx", "f4"), ("cy", "f4"), ("minx", "f4"), ("maxx", "f4"), ("miny", "f4"), ("maxy", "f4"),
+                   ("bf", "f4"), ("cos_limit", "f4"), ("log_scale_factor", "f4"), ("n_levels", "i4")]
+FRUSTUM_FRAME_DTYPE = np.dtype(_FRUSTUM_FIELDS + [("level_ratio", "f4", 16)])
+ORC_FRUSTUM_FRAME_DTYPE = np.dtype(_FRUSTUM_FIELDS)
+assert FRUSTUM_FRAME_DTYPE.itemsize == 180 and ORC_FRUSTUM_FRAME_DTYPE.itemsize == 116
+
 assert SBP_FRAME_DTYPE.itemsize == 88 + 64 + 112
 assert NAVSTATE_DTYPE.itemsize == 22 * 8 and CAMERA_DTYPE.itemsize == 64 + 96

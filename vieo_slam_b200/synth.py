@@ -514,3 +514,99 @@ def make_sbp_problem(seed, n_frames=2, mode=SBP_LAST_FRAME, n_kp=1200, n_q=700, 
     for k, v_ in qs.items():
         out["q_" + k] = np.ascontiguousarray(np.concatenate(v_))
     return out
+
+
+# ---------------------------------------------------------------- Frame::isInFrustum / SearchLocalPoints problems
+from .layouts import FRUSTUM_FRAME_DTYPE  # noqa: E402
+
+
+def make_frustum_problem(seed, n_frames=2, n_kp=1200, n_q=1500, th=1.0, th_far=0.0, skip_frac=0.1, blocked_frac=0.0,
+                         cluster=False):
+    """A make_sbp_problem(LOCAL_MAP) batch plus what Frame::isInFrustum reads: per frame the float pose / intrinsics
+    record (`frustum`, FRUSTUM_FRAME_DTYPE), per candidate map point p_wP, p_normal, p_max_dist (mfMaxDistance),
+    p_min_dist (mfMinDistance), p_skip.  Points fall behind the camera, outside the image, outside the scale-invariance
+    range and beyond the 60-degree viewing cone in realistic proportions."""
+    pb = make_sbp_problem(seed, n_frames, mode=SBP_LOCAL_MAP, n_kp=n_kp, n_q=n_q, th=th, th_far=th_far,
+                          blocked_frac=blocked_frac, cluster=cluster)
+    r = np.random.default_rng(seed + 1000)
+    fr = pb["frames"]
+    ff = np.zeros(n_frames, FRUSTUM_FRAME_DTYPE)
+    nq = len(pb["q_level"])
+    wP = pb["q_Xw"].astype(np.float32)
+    Pn = np.zeros((nq, 3), np.float32); mx = np.zeros(nq, np.float32); mn = np.zeros(nq, np.float32)
+    sf = np.float32(1.2)
+    scale = sf ** np.arange(8, dtype=np.float32)
+    for f in range(n_frames):
+        F = fr[f]
+        b, m = int(F["q_begin"]), int(F["n_q"])
+        Rcw = R_from_quat(F["qcw"]); tcw = np.array(F["tcw"])
+        Ow = -Rcw.T @ tcw
+        G = ff[f]
+        G["q_begin"], G["n_q"] = b, m
+        G["Rcw"] = Rcw.astype(np.float32).ravel(); G["tcw"] = tcw.astype(np.float32); G["Ow"] = Ow.astype(np.float32)
+        for k in ("fx", "fy", "cx", "cy", "minx", "maxx", "miny", "maxy", "bf"):
+            G[k] = F[k]
+        G["cos_limit"] = 0.5
+        G["log_scale_factor"] = np.log(sf)     # float log of the float scale factor (src/FrameBase.cpp:288)
+        G["n_levels"] = 8
+        PO = wP[b:b + m].astype(np.float64) - Ow
+        d = np.linalg.norm(PO, axis=1)
+        # mean viewing direction: the ray perturbed by up to ~75 degrees, so a share of the points leaves the cone
+        ang = np.abs(r.normal(0, 0.6, m))
+        ax = np.cross(PO, r.normal(0, 1, (m, 3))); ax /= np.linalg.norm(ax, axis=1, keepdims=True) + 1e-300
+        dirn = PO / (d[:, None] + 1e-300)
+        nrm = dirn * np.cos(ang)[:, None] + ax * np.sin(ang)[:, None]
+        Pn[b:b + m] = (nrm * r.uniform(0.9, 1.0, (m, 1))).astype(np.float32)   # mNormalVector is a mean of unit vectors
+        lvl = r.integers(0, 8, m)
+        dref = d * r.uniform(0.5, 1.9, m)                                      # reference distance of the observation
+        mx[b:b + m] = (dref * scale[lvl]).astype(np.float32)
+        mn[b:b + m] = mx[b:b + m] / scale[7]
+    pb["frustum"] = ff
+    pb["p_wP"], pb["p_normal"], pb["p_max_dist"], pb["p_min_dist"] = wP, Pn, mx, mn
+    pb["p_skip"] = (r.random(nq) < skip_frac).astype(np.uint8)
+    return pb
+
+
+def make_distinctive_problem(seed, n_points=500, max_obs=30, long_lists=()):
+    """CSR batch for MapPoint::ComputeDistinctiveDescriptors: every map point owns n observations (0 .. max_obs, plus the
+    explicit lengths of `long_lists`) whose descriptors are noisy copies of a per-point prototype, addressed through a
+    shuffled row table into one descriptor pool.  -> dict(pool, rows, ptr)"""
+    r = np.random.default_rng(seed)
+    n_obs = np.concatenate([r.integers(0, max_obs + 1, n_points), np.asarray(long_lists, np.int64)]).astype(np.int64)
+    r.shuffle(n_obs)
+    ptr = np.zeros(len(n_obs) + 1, np.int32)
+    ptr[1:] = np.cumsum(n_obs)
+    total = int(ptr[-1])
+    proto = r.integers(0, 256, (len(n_obs), 32), dtype=np.uint8)
+    owner = np.repeat(np.arange(len(n_obs)), n_obs)
+    d = _flip_bits(proto[owner], r.integers(0, 60, total), r)
+    # coarse distances create many equal medians: the first-row-wins rule is exercised
+    perm = r.permutation(total + 17)[:total].astype(np.int32)
+    pool = r.integers(0, 256, (total + 17, 32), dtype=np.uint8)
+    pool[perm] = d
+    return dict(pool=pool, rows=perm, ptr=ptr)
+
+
+def make_gyro_bias_problem(seed, n_kf=20, kf_gap=4, bg_true=(0.02, -0.015, 0.01), noisy_imu=True):
+    """Keyframe chain for Optimizer::OptimizeInitialGyroBias: IMU samples carry the gyro bias bg_true, the keyframe
+    pre-integrations are linearised at zero bias.  -> dict(seq, kf_idx, Rwb (n_kf,3,3), samples, seg_ptr, ti_tj)"""
+    # kf_gap = (lo, hi): keyframe spacing drawn per pair, so the rotation covariances (the bInfo weights) differ
+    if np.ndim(kf_gap) == 0:
+        idx = np.arange(n_kf) * int(kf_gap)
+    else:
+        gaps = np.random.default_rng(seed + 5).integers(kf_gap[0], kf_gap[1] + 1, n_kf - 1)
+        idx = np.r_[0, np.cumsum(gaps)]
+    seq = vio_sequence(seed, int(idx[-1]) + 1, noisy_imu=noisy_imu)
+    seq["imu"][:, 4:7] += np.asarray(bg_true) - seq["bg"]
+    seq["truth"]["bg"] = 0.0
+    seq["truth"]["ba"] = seq["ba"]
+    Rwb = np.stack([R_from_quat(seq["truth"][i]["q"]) for i in idx])
+    imu, t = seq["imu"], seq["times"]
+    seg, tt, chunks = [0, 0], [(0.0, 0.0)], []
+    for k in range(1, n_kf):
+        ti, tj = t[idx[k - 1]], t[idx[k]]
+        lo = max(np.searchsorted(imu[:, 0], ti, "right") - 1, 0)
+        hi = min(np.searchsorted(imu[:, 0], tj, "left") + 1, len(imu))
+        chunks.append(imu[lo:hi]); seg.append(seg[-1] + hi - lo); tt.append((ti, tj))
+    return dict(seq=seq, kf_idx=idx, Rwb=Rwb, samples=np.vstack(chunks), seg_ptr=np.array(seg, np.int32),
+                ti_tj=np.array(tt), bg_true=np.asarray(bg_true, np.float64))
