@@ -533,7 +533,7 @@ def run_gpu(args, rank, world, local_rank):
     except Exception:
         pass
     # ---- CPU baseline: the oracle threaded like the reference, bounded sample
-    cpu_frames = args.cpu_frames - args.cpu_frames % LBA_EVERY
+    cpu_frames = max(LBA_EVERY, args.cpu_frames - args.cpu_frames % LBA_EVERY)   # whole LocalBA periods, at least one
     cpu_lbas = make_lba_windows(203, 1, oracle_preint_fn()) if not lbas else lbas
     cpu_v, cpu_dt = cpu_pipeline(host[0, :cpu_frames], trk, cpu_lbas, True)
     line = {

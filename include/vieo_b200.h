@@ -431,6 +431,45 @@ int vieo_search_local_points(const VieoFrustumFrame* frustum, const VieoSbpFrame
                              int32_t* q_dist, int32_t* n_matches, int device);
 
 /* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjectionBase (src/ORBmatcher.cc:26-227), the search half behind ORBmatcher::Fuse(KeyFrame*,
+ * vector<MapPoint*>, th) (:1152-1165, LocalMapping::SearchInNeighbors), Fuse(KeyFrame*, Scw, ...) (:1167-1220) and the
+ * Sim3 / keyframe projection searches: per map point the projection into the keyframe, IsInImage,
+ * the scale-invariance range, the 60-degree viewing cone (bCheckViewingAngle), PredictScale, GetFeaturesInArea(u, v,
+ * th_radius * scale[level]), level band [level - 1, level], the chi-square gate against the keypoint (stereo 7.8 / mono
+ * 5.99, only with pbf) and the strict-'<' Hamming arg-min.  What follows in the reference (bestDist <= th_bestdist,
+ * FuseMP / AddObservation / vpReplacePoint, the IsInKeyFrame skip) only edits map-point links and stays on the host.
+ * Single camera, usedistort_ == false.  One record per keyframe of the batch. */
+typedef struct VieoProjSearchFrame {
+  int32_t kp_begin, n_kp;       /* the keyframe's keypoints (mvKeysUn) in the keypoint arrays (<= VIEO_SBP_MAX_KEYPOINTS) */
+  int32_t q_begin, n_q;         /* the map points projected into it */
+  float Rcw[9], tcw[3], Ow[3];  /* Rcrw, tcrw, pKF->GetCameraCenter() cast to float */
+  float fx, fy, cx, cy;         /* mpCameras[0]->toK() cast to float */
+  float minx, maxx, miny, maxy; /* gridinfo_.minmax_xy_ */
+  float grid_winv, grid_hinv;   /* gridinfo_.fgrids_widthinv_ / fgrids_heightinv_ */
+  float bf;                     /* *pbf */
+  int32_t use_bf;               /* pbf != nullptr: chi-square gate on */
+  int32_t check_viewing_angle;  /* bCheckViewingAngle */
+  float th_radius;
+  int32_t n_levels;
+  float log_scale_factor;       /* scalepyrinfo_.flogscalefactor_ */
+  float scale[16];              /* scalepyrinfo_.vscalefactor_ */
+  float inv_level_sigma2[16];   /* scalepyrinfo_.vinvlevelsigma2_ */
+  float level_ratio[16];        /* vieo_frustum_level_table; filled by the host-buffer call, by the caller for _dev */
+} VieoProjSearchFrame;
+/* Per map point: wP / normal [n][3], max_dist / min_dist = mfMaxDistance / mfMinDistance, q_desc [n][32] =
+ * GetDescriptor(), q_skip (nullable) != 0: null / bad / already in the keyframe.  Outputs: best_idx = keyframe-relative
+ * keypoint (-1: none), best_dist (256: none), level = nPredictedLevel (-1: the point failed a geometric test). */
+int vieo_proj_search_batch(const VieoProjSearchFrame* frames, int n_frames, const VieoKeyPoint* kps, const float* uright,
+                           const uint8_t* desc, const float* wP, const float* normal, const float* max_dist,
+                           const float* min_dist, const uint8_t* q_desc, const uint8_t* q_skip, int32_t* best_idx,
+                           int32_t* best_dist, int32_t* level, int device);
+int vieo_proj_search_batch_dev(const VieoProjSearchFrame* frames_dev, int n_frames, const VieoKeyPoint* kps_dev,
+                               const float* uright_dev, const uint8_t* desc_dev, const float* wP_dev, const float* normal_dev,
+                               const float* max_dist_dev, const float* min_dist_dev, const uint8_t* q_desc_dev,
+                               const uint8_t* q_skip_dev, int32_t* best_idx_dev, int32_t* best_dist_dev, int32_t* level_dev,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stereo front-end over HOST buffers — the hot work of the Frame::Frame stereo constructor
  * (src/Frame.cc:218-316): ORBextractor::operator() for both cameras (:259-278) and the brute-force
  * left->right knnMatch(k=2) of ComputeStereoFishEyeMatches (:620-628), for a batch of frames, with the

@@ -114,6 +114,26 @@ typedef struct OrcFrustumFrame {
   float log_scale_factor;       /* scalepyrinfo_.flogscalefactor_ */
   int32_t n_levels;             /* scalepyrinfo_.vscalefactor_.size() */
 } OrcFrustumFrame;
+/* ORBmatcher::SearchByProjectionBase search half (sbp_oracle.cc).  One keyframe per call. */
+typedef struct OrcProjSearchFrame {
+  int32_t kp_begin, n_kp, q_begin, n_q;
+  float Rcw[9], tcw[3], Ow[3];  /* Rcrw, tcrw, pKF->GetCameraCenter() cast to float */
+  float fx, fy, cx, cy;
+  float minx, maxx, miny, maxy;
+  float grid_winv, grid_hinv;
+  float bf;                     /* *pbf */
+  int32_t use_bf;               /* pbf != nullptr: chi-square gate on */
+  int32_t check_viewing_angle;  /* bCheckViewingAngle */
+  float th_radius;
+  int32_t n_levels;
+  float log_scale_factor;
+  float scale[16];              /* vscalefactor_ */
+  float inv_level_sigma2[16];   /* vinvlevelsigma2_ */
+  float level_ratio[16];        /* device only (vieo_frustum_level_table); ignored by the oracle */
+} OrcProjSearchFrame;
+void orc_sbp_base(const OrcProjSearchFrame* f, const OrcKeyPoint* kps, const float* uright, const uint8_t* desc,
+                  const float* wP, const float* Pn, const float* max_dist, const float* min_dist, const uint8_t* q_desc,
+                  const uint8_t* q_skip, int32_t* best_idx, int32_t* best_dist, int32_t* level);
 int orc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);
 int orc_is_in_frustum(const OrcFrustumFrame* f, int n, const float* wP, const float* Pn, const float* max_dist,
                       const float* min_dist, uint8_t* inview, float* proj, int32_t* level, float* viewcos, float* depth);

@@ -304,3 +304,83 @@ extern "C" int orc_is_in_frustum(const OrcFrustumFrame* f, int n, const float* w
   }
   return n_in;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjectionBase (src/ORBmatcher.cc:26-227) — the search half shared by Fuse(KF, vpMapPoints, th)
+// (:1152-1165, LocalMapping::SearchInNeighbors), Fuse(KF, Scw, ...) (:1167-1220, loop closing) and the Sim3 / relocalisation
+// variants: per map point the projection into the keyframe, the image / scale-invariance / viewing-cone tests,
+// PredictScale, GetFeaturesInArea(u, v, th_radius * scale[level]), level band [level - 1, level], the chi-square gate
+// against the keypoint (stereo 7.8 / mono 5.99, only with pbf), and the strict-'<' Hamming arg-min.  Single camera,
+// usedistort_ == false.  What the reference then does with (bestIdx, bestDist) — threshold, FuseMP / AddObservation /
+// vpReplacePoint, the IsInKeyFrame skip — only touches map-point links, never keypoints or descriptors, so the search
+// result of a point does not depend on the points before it; that policy stays on the host.  q_skip != 0: the point is
+// null / bad / already in the keyframe (pvbAlreadyMatched1).  best_idx = -1, best_dist = 256: nothing found.
+extern "C" void orc_sbp_base(const OrcProjSearchFrame* f, const OrcKeyPoint* kps, const float* uright, const uint8_t* desc,
+                             const float* wP, const float* Pn, const float* max_dist, const float* min_dist,
+                             const uint8_t* q_desc, const uint8_t* q_skip, int32_t* best_idx, int32_t* best_dist,
+                             int32_t* level) {
+  OrcSbpFrame g{};  // the grid helpers only read the grid fields
+  g.n_kp = f->n_kp;
+  g.minx = f->minx; g.maxx = f->maxx; g.miny = f->miny; g.maxy = f->maxy;
+  g.grid_winv = f->grid_winv; g.grid_hinv = f->grid_hinv;
+  Grid grid(g, kps);
+  std::vector<int> cand;
+  for (int i = 0; i < f->n_q; ++i) {
+    best_idx[i] = -1;
+    best_dist[i] = 256;
+    level[i] = -1;
+    if (q_skip && q_skip[i]) continue;
+    const float* P = wP + 3 * i;
+    float Pc[3];
+    for (int r = 0; r < 3; ++r)
+      Pc[r] = sum3(f->Rcw[3 * r] * P[0], f->Rcw[3 * r + 1] * P[1], f->Rcw[3 * r + 2] * P[2]) + f->tcw[r];
+    if (Pc[2] <= 0.0) continue;
+    const float invz = 1 / Pc[2];
+    const float xn = Pc[0] * invz, yn = Pc[1] * invz;
+    const float u = sum3(f->fx * xn, 0.0f * yn, f->cx * 1.0f);
+    const float v = sum3(0.0f * xn, f->fy * yn, f->cy * 1.0f);
+    if (!(u >= f->minx && u < f->maxx && v >= f->miny && v < f->maxy)) continue;  // IsInImage (FrameBase.cpp:171-174)
+    const float PO[3] = {P[0] - f->Ow[0], P[1] - f->Ow[1], P[2] - f->Ow[2]};
+    const float dist3D = std::sqrt(sum3(PO[0] * PO[0], PO[1] * PO[1], PO[2] * PO[2]));
+    const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
+    if (dist3D < minDistance || dist3D > maxDistance) continue;
+    if (f->check_viewing_angle) {
+      const float dot = sum3(PO[0] * Pn[3 * i], PO[1] * Pn[3 * i + 1], PO[2] * Pn[3 * i + 2]);
+      if ((double)dot < 0.5 * (double)dist3D) continue;
+    }
+    const int nPredictedLevel = orc_predict_scale(max_dist[i], dist3D, f->log_scale_factor, f->n_levels);
+    level[i] = nPredictedLevel;
+    const float radius = f->th_radius * f->scale[nPredictedLevel];
+    features_in_area(g, grid, kps, u, v, radius, -1, -1, cand);
+    if (cand.empty()) continue;
+    int bestDist = INT32_MAX, bestIdx = -1;
+    for (int idx : cand) {
+      const OrcKeyPoint& kp = kps[idx];
+      const int kpLevel = kp.octave;
+      if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+      if (f->use_bf) {
+        const float kpr = uright[idx];
+        if (kpr >= 0) {
+          const float ex = u - kp.x, ey = v - kp.y;
+          const float ur = u - f->bf * invz;
+          const float er = ur - kpr;
+          const float e2 = ex * ex + ey * ey + er * er;
+          if ((double)(e2 * f->inv_level_sigma2[kpLevel]) > 7.8) continue;
+        } else {
+          const float ex = u - kp.x, ey = v - kp.y;
+          const float e2 = ex * ex + ey * ey;
+          if ((double)(e2 * f->inv_level_sigma2[kpLevel]) > 5.99) continue;
+        }
+      }
+      const int dist = descriptor_distance(q_desc + 32 * (size_t)i, desc + 32 * (size_t)idx);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx = idx;
+      }
+    }
+    if (bestIdx >= 0) {
+      best_idx[i] = bestIdx;
+      best_dist[i] = bestDist;
+    }
+  }
+}

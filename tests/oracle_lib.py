@@ -474,3 +474,26 @@ def gyro_bias_init(pre, Rwb, use_info=True):
     dbg = np.zeros(3)
     n = L.orc_gyro_bias_init(_p(pre), _p(Rwb), len(pre), int(use_info), _p(dbg))
     return n, dbg
+
+
+# ---- ORBmatcher::SearchByProjectionBase, search half (oracle/sbp_oracle.cc) -------------------------------------------------
+def proj_search(pb):
+    """Oracle over every keyframe of a synth.make_fuse_problem dict -> (best_idx, best_dist, level) per map point."""
+    L = lib()
+    L.orc_sbp_base.argtypes = [C.c_void_p] * 13
+    L.orc_sbp_base.restype = None
+    fr = pb["frames"]
+    nq = len(pb["p_max_dist"])
+    best = np.full(nq, -1, np.int32); dist = np.full(nq, -1, np.int32); lvl = np.full(nq, -1, np.int32)
+    vp = C.c_void_p
+
+    def at(a, i):
+        a = pb[a] if isinstance(a, str) else a
+        return vp(a.ctypes.data + i * a.strides[0])
+    for f in range(len(fr)):
+        kb, qb = int(fr[f]["kp_begin"]), int(fr[f]["q_begin"])
+        skip = at("p_skip", qb) if pb.get("p_skip") is not None else None
+        L.orc_sbp_base(vp(fr.ctypes.data + f * fr.strides[0]), at("kps", kb), at("uright", kb), at("desc", kb), at("p_wP", qb),
+                       at("p_normal", qb), at("p_max_dist", qb), at("p_min_dist", qb), at("q_desc", qb), skip, at(best, qb),
+                       at(dist, qb), at(lvl, qb))
+    return best, dist, lvl

@@ -138,3 +138,35 @@ def test_initial_gyro_bias_and_reintegration(use_info):
     # with exact rotations the step recovers the bias the gyro samples carry (first order)
     _, bg4, _ = imu.OptimizeInitialGyroBias(pre, g["Rwb"], np.zeros(3), bInfo=use_info)
     assert np.abs(bg4 - g["bg_true"]).max() < 3e-4
+
+
+@pytest.mark.parametrize("kw", [dict(n_frames=6, n_q=2000), dict(use_bf=False, check_viewing_angle=False, th_radius=4.0),
+                                dict(cluster=True, th_radius=6.0, n_kp=1500, n_q=800), dict(n_frames=1, n_q=9000, th_radius=2.5)])
+def test_search_by_projection_base_matches_oracle(kw):
+    """ORBmatcher::SearchByProjectionBase search half (Fuse / Sim3 / keyframe projection searches): bit-exact keypoint,
+    distance and predicted level per map point."""
+    import vieo_slam_b200.api as api
+    pb = synth.make_fuse_problem(81, **kw)
+    got = api.ORBmatcher().SearchByProjectionBase(pb)
+    ref = O.proj_search(pb)
+    for a, b, name in zip(got, ref, ("best_idx", "best_dist", "level")):
+        assert np.array_equal(a, b), (name, np.nonzero(a != b)[0][:10])
+    hit, nfused = api.ORBmatcher().Fuse(pb)
+    assert nfused.min() > 100 and (hit >= 0).sum() == nfused.sum()
+    assert ((ref[2] >= 0) & (ref[0] < 0)).sum() > 20
+
+
+def test_search_by_projection_base_edge_cases():
+    import vieo_slam_b200.api as api
+    pb = synth.make_fuse_problem(82, n_frames=3, n_q=300)
+    pb["frames"][1]["n_kp"] = 0      # keyframe without keypoints
+    pb["frames"][2]["n_q"] = 0       # nothing to project
+    pb["p_skip"] = None
+    got = api.ORBmatcher().SearchByProjectionBase(pb)
+    ref = O.proj_search(pb)
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    b1 = int(pb["frames"][1]["q_begin"])
+    assert (got[0][b1:b1 + 300] == -1).all()
+    big = synth.make_fuse_problem(83, n_frames=1, n_kp=4200, n_q=50)
+    with pytest.raises(api.VieoError):
+        api.ORBmatcher().SearchByProjectionBase(big)

@@ -190,3 +190,73 @@ def test_gyro_bias_oracle():
     assert O.gyro_bias_init(pre2, g["Rwb"], True)[0] == 14
     n, dbg = O.gyro_bias_init(pre[:1], g["Rwb"][:1], True)
     assert n == 0 and not dbg.any()
+
+
+def _naive_proj_search(pb, f, qs):
+    """src/ORBmatcher.cc:26-227 (single camera, default MatchMultiCam mode, search half) in numpy float32 scalars, with the
+    brute-force GetFeaturesInArea of tests/test_oracle_sbp.py."""
+    from test_oracle_sbp import hamming, naive_candidates
+    F = pb["frames"][f]
+    kb, n, qb = int(F["kp_begin"]), int(F["n_kp"]), int(F["q_begin"])
+    kps, ur, desc = pb["kps"][kb:kb + n], pb["uright"][kb:kb + n], pb["desc"][kb:kb + n]
+    R = F["Rcw"].reshape(3, 3)
+    out = {}
+    for qi in qs:
+        q = qb + qi
+        out[qi] = (-1, 256, -1)
+        if pb["p_skip"][q]:
+            continue
+        P, Pn = pb["p_wP"][q], pb["p_normal"][q]
+        Pc = [f32(_sum3(f32(R[r, 0] * P[0]), f32(R[r, 1] * P[1]), f32(R[r, 2] * P[2])) + F["tcw"][r]) for r in range(3)]
+        if Pc[2] <= 0:
+            continue
+        invz = f32(f32(1) / Pc[2])
+        u = _sum3(f32(F["fx"] * f32(Pc[0] * invz)), f32(f32(0) * f32(Pc[1] * invz)), F["cx"])
+        v = _sum3(f32(f32(0) * f32(Pc[0] * invz)), f32(F["fy"] * f32(Pc[1] * invz)), F["cy"])
+        if not (F["minx"] <= u < F["maxx"] and F["miny"] <= v < F["maxy"]):
+            continue
+        PO = [f32(P[k] - F["Ow"][k]) for k in range(3)]
+        dist = f32(np.sqrt(_sum3(f32(PO[0] * PO[0]), f32(PO[1] * PO[1]), f32(PO[2] * PO[2]))))
+        if dist < f32(f32(0.8) * pb["p_min_dist"][q]) or dist > f32(f32(1.2) * pb["p_max_dist"][q]):
+            continue
+        if F["check_viewing_angle"] and float(_sum3(f32(PO[0] * Pn[0]), f32(PO[1] * Pn[1]), f32(PO[2] * Pn[2]))) < 0.5 * float(dist):
+            continue
+        lvl = O.predict_scale(float(pb["p_max_dist"][q]), float(dist), float(F["log_scale_factor"]), int(F["n_levels"]))
+        radius = f32(F["th_radius"] * F["scale"][lvl])
+        best, bidx = 2 ** 31 - 1, -1
+        for j in naive_candidates(F, kps, u, v, radius, -1, -1):
+            kl = int(kps["octave"][j])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            if F["use_bf"]:
+                ex, ey = f32(u - kps["x"][j]), f32(v - kps["y"][j])
+                if ur[j] >= 0:
+                    er = f32(f32(u - f32(F["bf"] * invz)) - ur[j])
+                    e2 = f32(f32(f32(ex * ex) + f32(ey * ey)) + f32(er * er))
+                    if float(f32(e2 * F["inv_level_sigma2"][kl])) > 7.8:
+                        continue
+                else:
+                    e2 = f32(f32(ex * ex) + f32(ey * ey))
+                    if float(f32(e2 * F["inv_level_sigma2"][kl])) > 5.99:
+                        continue
+            d = hamming(pb["q_desc"][q], desc[j])
+            if d < best:
+                best, bidx = d, j
+        out[qi] = (bidx, best if bidx >= 0 else 256, lvl)
+    return out
+
+
+def test_proj_search_oracle_matches_naive_restatement():
+    for seed, kw in ((71, dict()), (72, dict(use_bf=False, check_viewing_angle=False, th_radius=4.0)),
+                     (73, dict(cluster=True, th_radius=6.0, n_kp=700))):
+        pb = synth.make_fuse_problem(seed, n_frames=2, n_q=260, **kw)
+        best, dist, lvl = O.proj_search(pb)
+        found = gated = 0
+        for f in range(2):
+            qb = int(pb["frames"][f]["q_begin"])
+            ref = _naive_proj_search(pb, f, range(int(pb["frames"][f]["n_q"])))
+            for qi, (b, d, l) in ref.items():
+                assert (best[qb + qi], dist[qb + qi], lvl[qb + qi]) == (b, d, l), (seed, f, qi)
+                found += b >= 0
+                gated += l >= 0 and b < 0
+        assert found > 60 and gated > 20     # both outcomes occur

@@ -4,7 +4,7 @@ TAG=${1:-v}
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_next.py tests/test_gpu_sbp.py tests/test_gpu_imu.py -q -m gpu > gpurun_out/${TAG}_pytest_next.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_next.log
 tail -25 gpurun_out/${TAG}_pytest_next.log
-timeout 240 python bench.py --steps 3 --warmup 3 --cpu-frames 4 > gpurun_out/${TAG}_bench_short.json 2> gpurun_out/${TAG}_bench_short.err; echo "bench rc=$?"
+timeout 240 python bench.py --steps 3 --warmup 3 --cpu-frames 8 > gpurun_out/${TAG}_bench_short.json 2> gpurun_out/${TAG}_bench_short.err; echo "bench rc=$?"
 tail -3 gpurun_out/${TAG}_bench_short.err
 python - <<'PY'
 import json

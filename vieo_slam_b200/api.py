@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvieo_b200.so")
 
-from .layouts import FRUSTUM_FRAME_DTYPE  # noqa: E402
+from .layouts import FRUSTUM_FRAME_DTYPE, PROJ_SEARCH_FRAME_DTYPE  # noqa: E402
 
 KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")])
 
@@ -72,6 +72,8 @@ def lib():
         L.vieo_frustum_batch.argtypes = [vp, i32] + [vp] * 11 + [i32]
         L.vieo_frustum_batch_dev.argtypes = [vp, i32] + [vp] * 12
         L.vieo_search_local_points.argtypes = [vp, vp, i32] + [vp] * 21 + [i32]
+        L.vieo_proj_search_batch.argtypes = [vp, i32] + [vp] * 12 + [i32]
+        L.vieo_proj_search_batch_dev.argtypes = [vp, i32] + [vp] * 13
         L.vieo_distinctive_descriptors.argtypes = [vp, i32, vp, vp, i32, vp, vp, i32]
         L.vieo_distinctive_descriptors_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp]
         L.vieo_imu_init_gyro_bias.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32]
@@ -398,6 +400,32 @@ class ORBmatcher:
                                               _p(out["level"]), _p(out["viewcos"]), _p(out["depth"]), _p(out["n_inview"]),
                                               _p(kp_match), _p(q_match), _p(q_dist), _p(nm), self.device))
         return out, kp_match, q_match, q_dist, nm
+
+    def SearchByProjectionBase(self, pb):
+        """The search half of ORBmatcher::SearchByProjectionBase (src/ORBmatcher.cc:26-227; Fuse, Sim3 and keyframe
+        projection searches) over the keyframes of a synth.make_fuse_problem dict.
+        -> (best_idx, best_dist, level) per map point; the caller applies th_bestdist and the FuseMP policy."""
+        fr = np.ascontiguousarray(pb["frames"], PROJ_SEARCH_FRAME_DTYPE)
+        a = {k: np.ascontiguousarray(pb[k], dt) for k, dt in (("kps", KP_DTYPE), ("uright", np.float32), ("desc", np.uint8),
+                                                               ("p_wP", np.float32), ("p_normal", np.float32),
+                                                               ("p_max_dist", np.float32), ("p_min_dist", np.float32),
+                                                               ("q_desc", np.uint8))}
+        skip = None if pb.get("p_skip") is None else np.ascontiguousarray(pb["p_skip"], np.uint8)
+        nq = len(a["p_max_dist"])
+        best = np.full(nq, -1, np.int32); dist = np.full(nq, -1, np.int32); lvl = np.full(nq, -1, np.int32)
+        _check(lib().vieo_proj_search_batch(_p(fr), len(fr), _p(a["kps"]), _p(a["uright"]), _p(a["desc"]), _p(a["p_wP"]),
+                                            _p(a["p_normal"]), _p(a["p_max_dist"]), _p(a["p_min_dist"]), _p(a["q_desc"]),
+                                            _p(skip), _p(best), _p(dist), _p(lvl), self.device))
+        return best, dist, lvl
+
+    def Fuse(self, pb, th_bestdist=None):
+        """ORBmatcher::Fuse(pKF, vpMapPoints, th) (:1152-1165) up to the map-point bookkeeping: per map point the keypoint
+        it would be fused into (bestDist <= TH_LOW), else -1; -> (keypoint index per point, nFused per keyframe)."""
+        th = self.TH_LOW if th_bestdist is None else th_bestdist
+        best, dist, _ = self.SearchByProjectionBase(pb)
+        hit = np.where((best >= 0) & (dist <= th), best, -1).astype(np.int32)
+        fr = pb["frames"]
+        return hit, np.array([int((hit[int(f["q_begin"]):int(f["q_begin"]) + int(f["n_q"])] >= 0).sum()) for f in fr], np.int32)
 
     def ComputeDistinctiveDescriptors(self, desc_pool, ptr, rows=None):
         """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:314-378) for a CSR batch of map points.

@@ -66,9 +66,25 @@ __device__ __forceinline__ void qrot(const double* q, const double* v, double* o
 // GetFeaturesInArea (src/FrameBase.cpp:95-142), warp-cooperative.  Lanes take the window's cells in the reference's
 // order (32 per pass); sink(pos, kp) is called for every candidate that passes the level / window / ur gates, pos = its
 // rank in the reference's candidate order.  Returns the number of candidates (warp-uniform).
-template <class Sink>
-__device__ __forceinline__ int enumerate(const VieoSbpFrame& F, const SbpShared& S, const VieoKeyPoint* __restrict__ kps,
-                                         const float* __restrict__ uright, const Cand& c, int lane, Sink&& sink) {
+struct GridGeom {  // gridinfo_: image bounds and inverse cell sizes
+  float minx, miny, grid_winv, grid_hinv;
+};
+// the stereo gate of the tracking searches (:1403-1408 / :292-297): |ur - uright[j]| <= r for keypoints with a right match
+struct UrGate {
+  const float* __restrict__ uright;
+  float ur, r;
+  __device__ __forceinline__ bool operator()(int j, const VieoKeyPoint&) const {
+    const float urj = uright[j];
+    if (urj > 0) {
+      const float er = fabsf(ur - urj);
+      if (er > r) return false;
+    }
+    return true;
+  }
+};
+template <class Gate, class Sink>
+__device__ __forceinline__ int enumerate_gated(const GridGeom& F, const SbpShared& S, const VieoKeyPoint* __restrict__ kps,
+                                               const Cand& c, int lane, const Gate& gate, Sink&& sink) {
   const int min_cellx = max(0, (int)floorf((c.x - F.minx - c.r) * F.grid_winv));
   if (min_cellx >= kCols) return 0;
   const int max_cellx = min(kCols - 1, (int)ceilf((c.x - F.minx + c.r) * F.grid_winv));
@@ -88,12 +104,7 @@ __device__ __forceinline__ int enumerate(const VieoSbpFrame& F, const SbpShared&
     }
     const float distx = kp.x - c.x, disty = kp.y - c.y;
     if (!(fabsf(distx) < c.r && fabsf(disty) < c.r)) return false;
-    const float urj = uright[j];
-    if (urj > 0) {
-      const float er = fabsf(c.ur - urj);
-      if (er > c.r) return false;
-    }
-    return true;
+    return gate(j, kp);
   };
   int base = 0;
   for (int c0 = 0; c0 < ncell; c0 += 32) {
@@ -116,6 +127,53 @@ __device__ __forceinline__ int enumerate(const VieoSbpFrame& F, const SbpShared&
     base += __shfl_sync(0xffffffffu, incl, 31);
   }
   return base;
+}
+template <class Sink>
+__device__ __forceinline__ int enumerate(const VieoSbpFrame& F, const SbpShared& S, const VieoKeyPoint* __restrict__ kps,
+                                         const float* __restrict__ uright, const Cand& c, int lane, Sink&& sink) {
+  return enumerate_gated(GridGeom{F.minx, F.miny, F.grid_winv, F.grid_hinv}, S, kps, c, lane, UrGate{uright, c.ur, c.r},
+                         static_cast<Sink&&>(sink));
+}
+
+// FrameBase::AssignFeaturesToGrid / PosInGrid (src/FrameBase.cpp:143-170) by the whole CTA: counting sort of the keypoints
+// into the cells, every cell's list ordered by keypoint index (= the reference's push_back order).  S.cnt must be zero on
+// entry (and the zeroing visible: __syncthreads before the call); ends with a __syncthreads.
+__device__ __forceinline__ void build_grid(SbpShared& S, const GridGeom& G, const VieoKeyPoint* __restrict__ kps, int N,
+                                           int tid, int T) {
+  for (int i = tid; i < N; i += T) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, G.minx), G.grid_winv));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, G.miny), G.grid_hinv));
+    if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
+    atomicAdd(&S.cnt[px * kRows + py], 1);
+  }
+  __syncthreads();
+  warp0_excl_scan(S.cnt, kCells, &S.total);
+  __syncthreads();
+  for (int i = tid; i < kCells; i += T) S.cell_start[i] = (uint16_t)S.cnt[i];
+  if (tid == 0) S.cell_start[kCells] = (uint16_t)S.total;
+  __syncthreads();
+  // fill (unordered inside a cell), then order every cell's few entries by keypoint index = push_back order
+  for (int i = tid; i < N; i += T) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, G.minx), G.grid_winv));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, G.miny), G.grid_hinv));
+    if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
+    const int slot = atomicAdd(&S.cnt[px * kRows + py], 1);
+    S.cell_items[slot] = (uint16_t)i;
+  }
+  __syncthreads();
+  for (int cidx = tid; cidx < kCells; cidx += T) {
+    const int s = S.cell_start[cidx], e = S.cell_start[cidx + 1];
+    for (int a = s + 1; a < e; ++a) {
+      const uint16_t v = S.cell_items[a];
+      int b = a - 1;
+      while (b >= s && S.cell_items[b] > v) {
+        S.cell_items[b + 1] = S.cell_items[b];
+        --b;
+      }
+      S.cell_items[b + 1] = v;
+    }
+  }
+  __syncthreads();
 }
 
 struct QueryIn {
@@ -189,13 +247,7 @@ __global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpF
   const uint8_t* desc = desc_all + 32 * (size_t)F.kp_begin;
   int32_t* kpm = kp_match + F.kp_begin;
   // ---- phase A: AssignFeaturesToGrid / PosInGrid (src/FrameBase.cpp:143-170) ------------------------------------------
-  for (int i = tid; i < N; i += T) {
-    kpm[i] = -1;
-    const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, F.minx), F.grid_winv));
-    const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, F.miny), F.grid_hinv));
-    if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
-    atomicAdd(&S.cnt[px * kRows + py], 1);
-  }
+  for (int i = tid; i < N; i += T) kpm[i] = -1;
   for (int i = tid; i < kMaxKp / 32; i += T) {
     uint32_t m = 0;
     if (kp_blocked)
@@ -205,34 +257,7 @@ __global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpF
       }
     S.blocked[i] = m;
   }
-  __syncthreads();
-  warp0_excl_scan(S.cnt, kCells, &S.total);
-  __syncthreads();
-  for (int i = tid; i < kCells; i += T) S.cell_start[i] = (uint16_t)S.cnt[i];
-  if (tid == 0) S.cell_start[kCells] = (uint16_t)S.total;
-  __syncthreads();
-  // fill (unordered inside a cell), then order every cell's few entries by keypoint index = push_back order
-  for (int i = tid; i < N; i += T) {
-    const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, F.minx), F.grid_winv));
-    const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, F.miny), F.grid_hinv));
-    if (px < 0 || px >= kCols || py < 0 || py >= kRows) continue;
-    const int slot = atomicAdd(&S.cnt[px * kRows + py], 1);
-    S.cell_items[slot] = (uint16_t)i;
-  }
-  __syncthreads();
-  for (int cidx = tid; cidx < kCells; cidx += T) {
-    const int s = S.cell_start[cidx], e = S.cell_start[cidx + 1];
-    for (int a = s + 1; a < e; ++a) {
-      const uint16_t v = S.cell_items[a];
-      int b = a - 1;
-      while (b >= s && S.cell_items[b] > v) {
-        S.cell_items[b + 1] = S.cell_items[b];
-        --b;
-      }
-      S.cell_items[b + 1] = v;
-    }
-  }
-  __syncthreads();
+  build_grid(S, GridGeom{F.minx, F.miny, F.grid_winv, F.grid_hinv}, kps, N, tid, T);
   // ---- frame constants ------------------------------------------------------------------------------------------------
   bool fwd = false, bwd = false;
   if (mode == VIEO_SBP_LAST_FRAME) {
@@ -392,6 +417,132 @@ __global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpF
   if (lane == 0) n_matches[f] = nmatches;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjectionBase (src/ORBmatcher.cc:26-227), search half: the projection of every map point into a
+// keyframe, IsInImage, scale-invariance range, viewing cone, PredictScale (threshold table, see frustum.cu),
+// GetFeaturesInArea(u, v, th_radius * scale[level]) with the level band [level - 1, level], the chi-square gate against the
+// keypoint (with pbf) and the strict-'<' Hamming arg-min.  Used by Fuse(KF, vpMapPoints, th) (LocalMapping::
+// SearchInNeighbors), Fuse(KF, Scw, ...) and the Sim3 / keyframe SearchByProjection variants.  The map-point link updates
+// that follow (FuseMP / AddObservation / vpReplacePoint) never change keypoints or descriptors, so every point is
+// independent: one CTA per keyframe builds the grid, one warp per map point searches; no claim pass.
+struct Chi2Gate {
+  const float* __restrict__ uright;
+  const float* inv_level_sigma2;
+  float u, v, ur;
+  int use_bf;
+  __device__ __forceinline__ bool operator()(int j, const VieoKeyPoint& kp) const {
+    if (!use_bf) return true;
+    const float kpr = uright[j];
+    const float ex = __fsub_rn(u, kp.x), ey = __fsub_rn(v, kp.y);
+    const float exy = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+    if (kpr >= 0) {
+      const float er = __fsub_rn(ur, kpr);
+      const float e2 = __fadd_rn(exy, __fmul_rn(er, er));
+      return !((double)__fmul_rn(e2, inv_level_sigma2[kp.octave]) > 7.8);   // chi2(0.05, 3)
+    }
+    return !((double)__fmul_rn(exy, inv_level_sigma2[kp.octave]) > 5.99);   // chi2(0.05, 2)
+  }
+};
+__device__ __forceinline__ float sum3f(float a0, float a1, float a2) { return __fadd_rn(a0, __fadd_rn(a1, a2)); }
+
+__global__ void __launch_bounds__(kSbpWarps * 32) k_proj_search(const VieoProjSearchFrame* __restrict__ frames,
+                                                                const VieoKeyPoint* __restrict__ kps_all,
+                                                                const float* __restrict__ ur_all,
+                                                                const uint8_t* __restrict__ desc_all,
+                                                                const float* __restrict__ wP, const float* __restrict__ Pn,
+                                                                const float* __restrict__ max_dist,
+                                                                const float* __restrict__ min_dist,
+                                                                const uint8_t* __restrict__ q_desc,
+                                                                const uint8_t* __restrict__ q_skip,
+                                                                int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist,
+                                                                int32_t* __restrict__ level_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SbpShared& S = *reinterpret_cast<SbpShared*>(smem_raw);
+  __shared__ VieoProjSearchFrame F;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
+  for (int i = tid; i < (int)(sizeof(VieoProjSearchFrame) / 4); i += T)
+    reinterpret_cast<uint32_t*>(&F)[i] = reinterpret_cast<const uint32_t*>(frames + f)[i];
+  for (int i = tid; i < kCells; i += T) S.cnt[i] = 0;
+  __syncthreads();
+  const int N = F.n_kp, nq = F.n_q;
+  if (N > kMaxKp || N < 0 || nq < 0 || F.n_levels < 1 || F.n_levels > 16) {
+    for (int qi = tid; qi < nq; qi += T) {  // reported per query: level -2
+      best_idx[F.q_begin + qi] = -1;
+      best_dist[F.q_begin + qi] = 256;
+      level_out[F.q_begin + qi] = -2;
+    }
+    return;
+  }
+  const VieoKeyPoint* kps = kps_all + F.kp_begin;
+  const float* uright = ur_all + F.kp_begin;
+  const uint8_t* desc = desc_all + 32 * (size_t)F.kp_begin;
+  const GridGeom G{F.minx, F.miny, F.grid_winv, F.grid_hinv};
+  build_grid(S, G, kps, N, tid, T);
+  for (int qi = warp; qi < nq; qi += kSbpWarps) {
+    const size_t q = (size_t)F.q_begin + qi;
+    int lvl = -1, bidx = -1, bdist = 256;
+    if (!(q_skip && q_skip[q])) {
+      const float X = wP[3 * q], Y = wP[3 * q + 1], Z = wP[3 * q + 2];
+      float Pc[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        Pc[r] = __fadd_rn(sum3f(__fmul_rn(F.Rcw[3 * r], X), __fmul_rn(F.Rcw[3 * r + 1], Y), __fmul_rn(F.Rcw[3 * r + 2], Z)),
+                          F.tcw[r]);
+      if (!(Pc[2] <= 0.0f)) {
+        const float invz = __fdiv_rn(1.0f, Pc[2]);
+        const float xn = __fmul_rn(Pc[0], invz), yn = __fmul_rn(Pc[1], invz);
+        const float u = sum3f(__fmul_rn(F.fx, xn), __fmul_rn(0.0f, yn), __fmul_rn(F.cx, 1.0f));
+        const float v = sum3f(__fmul_rn(0.0f, xn), __fmul_rn(F.fy, yn), __fmul_rn(F.cy, 1.0f));
+        if (u >= F.minx && u < F.maxx && v >= F.miny && v < F.maxy) {
+          const float ox = __fsub_rn(X, F.Ow[0]), oy = __fsub_rn(Y, F.Ow[1]), oz = __fsub_rn(Z, F.Ow[2]);
+          const float d3 = __fsqrt_rn(sum3f(__fmul_rn(ox, ox), __fmul_rn(oy, oy), __fmul_rn(oz, oz)));
+          const float mx = max_dist[q];
+          bool ok = !(d3 < __fmul_rn(0.8f, min_dist[q]) || d3 > __fmul_rn(1.2f, mx));
+          if (ok && F.check_viewing_angle) {
+            const float dot = sum3f(__fmul_rn(ox, Pn[3 * q]), __fmul_rn(oy, Pn[3 * q + 1]), __fmul_rn(oz, Pn[3 * q + 2]));
+            ok = !((double)dot < 0.5 * (double)d3);
+          }
+          if (ok) {
+            const float ratio = __fdiv_rn(mx, d3);
+            lvl = 0;
+            for (int k = 1; k < F.n_levels; ++k) lvl += ratio >= F.level_ratio[k] ? 1 : 0;
+            Cand c;
+            c.x = u; c.y = v;
+            c.r = __fmul_rn(F.th_radius, F.scale[lvl]);
+            c.minlevel = lvl - 1; c.maxlevel = lvl;
+            c.ur = 0;
+            const Chi2Gate gate{uright, F.inv_level_sigma2, u, v, __fsub_rn(u, __fmul_rn(F.bf, invz)), F.use_bf};
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(q_desc + 32 * q));
+            const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(q_desc + 32 * q) + 1);
+            uint32_t bkey = 0xffffffffu;
+            int bj = -1;
+            enumerate_gated(G, S, kps, c, lane, gate, [&](int pos, int j) {
+              const uint32_t key = ((uint32_t)hamming256(d0, d1, desc + 32 * (size_t)j) << 16) | (uint32_t)pos;
+              if (key < bkey) {
+                bkey = key;
+                bj = j;
+              }
+            });
+            // strict '<' in candidate order == lexicographic minimum of (distance, position)
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, bkey);
+            if (kmin != 0xffffffffu) {
+              const int src = __ffs(__ballot_sync(0xffffffffu, bkey == kmin)) - 1;
+              bidx = __shfl_sync(0xffffffffu, bj, src);
+              bdist = (int)(kmin >> 16);
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      best_idx[q] = bidx;
+      best_dist[q] = bdist;
+      level_out[q] = lvl;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -506,6 +657,95 @@ int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const Vie
   if (e != cudaSuccess) {
     set_error("vieo_sbp_batch: %s", cudaGetErrorString(e));
     return VIEO_E_CUDA;
+  }
+  return rc;
+}
+
+int vieo_proj_search_batch_dev(const VieoProjSearchFrame* frames_dev, int n_frames, const VieoKeyPoint* kps_dev,
+                               const float* uright_dev, const uint8_t* desc_dev, const float* wP_dev, const float* normal_dev,
+                               const float* max_dist_dev, const float* min_dist_dev, const uint8_t* q_desc_dev,
+                               const uint8_t* q_skip_dev, int32_t* best_idx_dev, int32_t* best_dist_dev, int32_t* level_dev,
+                               void* stream) {
+  VIEO_ARG(n_frames >= 0, "bad argument");
+  if (n_frames == 0) return VIEO_OK;
+  VIEO_ARG(frames_dev && kps_dev && uright_dev && desc_dev && wP_dev && normal_dev && max_dist_dev && min_dist_dev &&
+               q_desc_dev && best_idx_dev && best_dist_dev && level_dev, "null argument");
+  VIEO_ARG(((uintptr_t)desc_dev | (uintptr_t)q_desc_dev) % 16 == 0, "descriptors must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VIEO_CK(cudaFuncSetAttribute(k_proj_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SbpShared)));
+    attr_set = true;
+  }
+  k_proj_search<<<n_frames, kSbpWarps * 32, sizeof(SbpShared), (cudaStream_t)stream>>>(
+      frames_dev, kps_dev, uright_dev, desc_dev, wP_dev, normal_dev, max_dist_dev, min_dist_dev, q_desc_dev, q_skip_dev,
+      best_idx_dev, best_dist_dev, level_dev);
+  VIEO_CK(cudaGetLastError());
+  return VIEO_OK;
+}
+
+int vieo_proj_search_batch(const VieoProjSearchFrame* frames, int n_frames, const VieoKeyPoint* kps, const float* uright,
+                           const uint8_t* desc, const float* wP, const float* normal, const float* max_dist,
+                           const float* min_dist, const uint8_t* q_desc, const uint8_t* q_skip, int32_t* best_idx,
+                           int32_t* best_dist, int32_t* level, int device) {
+  VIEO_ARG(n_frames >= 0, "bad argument");
+  if (n_frames == 0) return VIEO_OK;
+  VIEO_ARG(frames, "null argument");
+  size_t nk = 0, nq = 0;
+  std::vector<VieoProjSearchFrame> fr(frames, frames + n_frames);
+  for (int f = 0; f < n_frames; ++f) {
+    VIEO_ARG(fr[f].n_kp >= 0 && fr[f].n_q >= 0 && fr[f].kp_begin >= 0 && fr[f].q_begin >= 0, "bad frame range");
+    if (fr[f].n_kp > kMaxKp) {
+      set_error("vieo_proj_search_batch: frame %d has %d keypoints (max %d)", f, fr[f].n_kp, kMaxKp);
+      return VIEO_E_CAPACITY;
+    }
+    int rc = vieo_frustum_level_table(fr[f].log_scale_factor, fr[f].n_levels, fr[f].level_ratio);
+    if (rc) return rc;
+    nk = std::max(nk, (size_t)fr[f].kp_begin + fr[f].n_kp);
+    nq = std::max(nq, (size_t)fr[f].q_begin + fr[f].n_q);
+  }
+  VIEO_ARG(nk == 0 || (kps && uright && desc), "null keypoint array");
+  VIEO_ARG(nq == 0 || (wP && normal && max_dist && min_dist && q_desc && best_idx && best_dist && level), "null query array");
+  int rc = use_device(device);
+  if (rc) return rc;
+  CallScratch* cs = call_scratch(device);
+  VIEO_ARG(cs, "no call scratch");
+  const size_t nk1 = std::max<size_t>(nk, 1), nq1 = std::max<size_t>(nq, 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) / 16 * 16; return o; };
+  const size_t o_fr = take(sizeof(VieoProjSearchFrame) * n_frames), o_kp = take(sizeof(VieoKeyPoint) * nk1), o_ur = take(4 * nk1),
+               o_de = take(32 * nk1), o_wp = take(12 * nq1), o_pn = take(12 * nq1), o_mx = take(4 * nq1), o_mn = take(4 * nq1),
+               o_qd = take(32 * nq1), o_sk = take(nq1);
+  const size_t in_bytes = off;
+  const size_t o_bi = take(4 * nq1), o_bd = take(4 * nq1), o_lv = take(4 * nq1);
+  const size_t io_bytes = off;
+  uint8_t* dbuf = (uint8_t*)cs->get(0, io_bytes);
+  uint8_t* hbuf = (uint8_t*)cs->get_pinned(io_bytes);
+  VIEO_ARG(dbuf && hbuf, "staging allocation failed");
+  auto put = [&](size_t o, const void* src, size_t bytes) { if (src && bytes) memcpy(hbuf + o, src, bytes); };
+  put(o_fr, fr.data(), sizeof(VieoProjSearchFrame) * n_frames);
+  put(o_kp, kps, sizeof(VieoKeyPoint) * nk); put(o_ur, uright, 4 * nk); put(o_de, desc, 32 * nk);
+  put(o_wp, wP, 12 * nq); put(o_pn, normal, 12 * nq); put(o_mx, max_dist, 4 * nq); put(o_mn, min_dist, 4 * nq);
+  put(o_qd, q_desc, 32 * nq); put(o_sk, q_skip, nq);
+  cudaError_t e = cudaMemcpyAsync(dbuf, hbuf, in_bytes, cudaMemcpyHostToDevice, cs->st);
+  // queries outside every frame's range read back as -1
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_bi, 0xff, io_bytes - o_bi, cs->st);
+  if (e == cudaSuccess) {
+    rc = vieo_proj_search_batch_dev((const VieoProjSearchFrame*)(dbuf + o_fr), n_frames, (const VieoKeyPoint*)(dbuf + o_kp),
+                                    (const float*)(dbuf + o_ur), dbuf + o_de, (const float*)(dbuf + o_wp),
+                                    (const float*)(dbuf + o_pn), (const float*)(dbuf + o_mx), (const float*)(dbuf + o_mn),
+                                    dbuf + o_qd, q_skip ? dbuf + o_sk : nullptr, (int32_t*)(dbuf + o_bi),
+                                    (int32_t*)(dbuf + o_bd), (int32_t*)(dbuf + o_lv), cs->st);
+    if (rc == VIEO_OK) {
+      e = cudaMemcpyAsync(hbuf + o_bi, dbuf + o_bi, io_bytes - o_bi, cudaMemcpyDeviceToHost, cs->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(cs->st);
+    }
+  }
+  if (e != cudaSuccess) {
+    set_error("vieo_proj_search_batch: %s", cudaGetErrorString(e));
+    return VIEO_E_CUDA;
+  }
+  if (rc == VIEO_OK && nq) {
+    memcpy(best_idx, hbuf + o_bi, 4 * nq); memcpy(best_dist, hbuf + o_bd, 4 * nq); memcpy(level, hbuf + o_lv, 4 * nq);
   }
   return rc;
 }

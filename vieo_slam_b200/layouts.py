@@ -48,5 +48,14 @@ FRUSTUM_FRAME_DTYPE = np.dtype(_FRUSTUM_FIELDS + [("level_ratio", "f4", 16)])
 ORC_FRUSTUM_FRAME_DTYPE = np.dtype(_FRUSTUM_FIELDS)
 assert FRUSTUM_FRAME_DTYPE.itemsize == 180 and ORC_FRUSTUM_FRAME_DTYPE.itemsize == 116
 
+# VieoProjSearchFrame (include/vieo_b200.h) == OrcProjSearchFrame: one keyframe of a SearchByProjectionBase batch
+PROJ_SEARCH_FRAME_DTYPE = np.dtype([("kp_begin", "i4"), ("n_kp", "i4"), ("q_begin", "i4"), ("n_q", "i4"), ("Rcw", "f4", 9),
+                                    ("tcw", "f4", 3), ("Ow", "f4", 3), ("fx", "f4"), ("fy", "f4"), ("cx", "f4"), ("cy", "f4"),
+                                    ("minx", "f4"), ("maxx", "f4"), ("miny", "f4"), ("maxy", "f4"), ("grid_winv", "f4"),
+                                    ("grid_hinv", "f4"), ("bf", "f4"), ("use_bf", "i4"), ("check_viewing_angle", "i4"),
+                                    ("th_radius", "f4"), ("n_levels", "i4"), ("log_scale_factor", "f4"), ("scale", "f4", 16),
+                                    ("inv_level_sigma2", "f4", 16), ("level_ratio", "f4", 16)])
+assert PROJ_SEARCH_FRAME_DTYPE.itemsize == 332
+
 assert SBP_FRAME_DTYPE.itemsize == 88 + 64 + 112
 assert NAVSTATE_DTYPE.itemsize == 22 * 8 and CAMERA_DTYPE.itemsize == 64 + 96

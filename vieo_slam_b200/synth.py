@@ -610,3 +610,39 @@ def make_gyro_bias_problem(seed, n_kf=20, kf_gap=4, bg_true=(0.02, -0.015, 0.01)
         chunks.append(imu[lo:hi]); seg.append(seg[-1] + hi - lo); tt.append((ti, tj))
     return dict(seq=seq, kf_idx=idx, Rwb=Rwb, samples=np.vstack(chunks), seg_ptr=np.array(seg, np.int32),
                 ti_tj=np.array(tt), bg_true=np.asarray(bg_true, np.float64))
+
+
+from .layouts import PROJ_SEARCH_FRAME_DTYPE  # noqa: E402
+
+
+def make_fuse_problem(seed, n_frames=3, n_kp=1200, n_q=1500, th_radius=3.0, use_bf=True, check_viewing_angle=True,
+                      skip_frac=0.1, cluster=False):
+    """Batch for ORBmatcher::SearchByProjectionBase / Fuse: keyframes with keypoints + map points to project into them
+    (make_frustum_problem geometry), predicted levels consistent with the keypoint octaves for the true matches so that the
+    level band and the chi-square gate both pass and reject in realistic proportions."""
+    pb = make_frustum_problem(seed, n_frames=n_frames, n_kp=n_kp, n_q=n_q, th=1.0, skip_frac=skip_frac, cluster=cluster)
+    r = np.random.default_rng(seed + 2000)
+    fr = np.zeros(n_frames, PROJ_SEARCH_FRAME_DTYPE)
+    inv_s2, scl = inv_level_sigma2()
+    for f in range(n_frames):
+        F, G, H = pb["frames"][f], pb["frustum"][f], fr[f]
+        for k in ("kp_begin", "n_kp", "q_begin", "n_q", "minx", "maxx", "miny", "maxy", "grid_winv", "grid_hinv", "bf", "fx",
+                  "fy", "cx", "cy"):
+            H[k] = F[k]
+        for k in ("Rcw", "tcw", "Ow", "log_scale_factor", "n_levels"):
+            H[k] = G[k]
+        H["use_bf"], H["check_viewing_angle"], H["th_radius"] = int(use_bf), int(check_viewing_angle), th_radius
+        H["scale"][:8] = scl; H["inv_level_sigma2"][:8] = inv_s2
+        # scale-invariance range such that PredictScale lands on (or next to) the query's level: mfMaxDistance =
+        # dist * 1.2^level * jitter
+        b, m = int(F["q_begin"]), int(F["n_q"])
+        d = np.linalg.norm(pb["p_wP"][b:b + m].astype(np.float64) - np.array(G["Ow"], np.float64), axis=1)
+        lv = pb["q_level"][b:b + m]
+        mx = d * 1.2 ** (lv - 0.5) * r.uniform(0.9, 1.1, m)
+        far = r.random(m) < 0.08                       # outside the invariance range
+        mx[far] *= r.choice([0.2, 6.0], int(far.sum()))
+        pb["p_max_dist"][b:b + m] = mx.astype(np.float32)
+        pb["p_min_dist"][b:b + m] = pb["p_max_dist"][b:b + m] / np.float32(scl[7])
+    pb["frames_sbp"] = pb["frames"]
+    pb["frames"] = fr
+    return pb
