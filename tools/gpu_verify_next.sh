@@ -6,8 +6,8 @@ timeout 300 python -m pytest tests/test_gpu_next.py tests/test_gpu_sbp.py tests/
 tail -25 gpurun_out/${TAG}_pytest_next.log
 timeout 240 python bench.py --steps 3 --warmup 3 --cpu-frames 8 > gpurun_out/${TAG}_bench_short.json 2> gpurun_out/${TAG}_bench_short.err; echo "bench rc=$?"
 tail -3 gpurun_out/${TAG}_bench_short.err
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/TAG_bench_short.json".replace("TAG", "'$TAG'")).read().strip().splitlines()[-1])
-print(d["value"], d["e2e"]["value"], d["roofline"]["stage_ms_per_step"], d["config"]["isolated_stage_ms"])
-PY
+python -c "
+import json,sys
+d = json.loads(open('gpurun_out/${TAG}_bench_short.json').read().strip().splitlines()[-1])
+print(d['value'], d['e2e']['value'], d['roofline']['stage_ms_per_step'], d['config']['isolated_stage_ms'])
+"

@@ -282,6 +282,8 @@ int vieo_search_local_points(const VieoFrustumFrame* frustum, const VieoSbpFrame
                              const uint8_t* desc, const uint8_t* kp_blocked, uint8_t* inview, float* proj, int32_t* level,
                              float* viewcos, float* depth, int32_t* n_inview, int32_t* kp_match, int32_t* q_match,
                              int32_t* q_dist, int32_t* n_matches, int device) {
+  VIEO_ARG(n_frames >= 0, "bad argument");
+  if (n_frames == 0) return VIEO_OK;
   VIEO_ARG(frames, "null argument");
   return frustum_host(frustum, frames, n_frames, wP, normal, max_dist, min_dist, skip, kps, uright, desc, q_desc, q_flags,
                       kp_blocked, inview, proj, level, viewcos, depth, n_inview, kp_match, q_match, q_dist, n_matches, device);

@@ -151,6 +151,61 @@ class ORBmatcher {
     for (int32_t n : n_matches) total += n;
     return total;
   }
+  // Tracking::SearchLocalPoints (src/Tracking.cc:2308-2368): Frame::isInFrustum(pMP, 0.5) for every candidate local map
+  // point, then SearchByProjection(F, vpMapPoints, th, th_far) over those in view; one call, one stream.  The caller
+  // copies inview / proj / level / viewcos / depth back into MapPoint::trackinfo_ only if it needs them (IncreaseVisible
+  // uses `inview`).  Returns nmatches summed over the frames.
+  int SearchLocalPoints(std::vector<VieoFrustumFrame>& frustum, std::vector<VieoSbpFrame>& frames, const float* wP,
+                        const float* normal, const float* max_dist, const float* min_dist, const uint8_t* skip,
+                        const uint8_t* q_desc, const uint8_t* q_flags, const VieoKeyPoint* keys_un, const float* vuright,
+                        const uint8_t* descriptors, const uint8_t* kp_blocked, std::vector<uint8_t>& inview,
+                        std::vector<float>& proj, std::vector<int32_t>& level, std::vector<float>& viewcos,
+                        std::vector<float>& depth, std::vector<int32_t>& n_inview, std::vector<int32_t>& kp_match,
+                        std::vector<int32_t>& q_match, std::vector<int32_t>& q_dist, std::vector<int32_t>& n_matches) const {
+    size_t nk = 0, nq = 0;
+    for (VieoSbpFrame& f : frames) {
+      f.nn_ratio = mfNNratio;
+      f.check_orientation = mbCheckOrientation ? 1 : 0;
+      nk = std::max(nk, (size_t)f.kp_begin + f.n_kp);
+      nq = std::max(nq, (size_t)f.q_begin + f.n_q);
+    }
+    inview.assign(nq, 0); proj.assign(3 * nq, 0.f); level.assign(nq, -1); viewcos.assign(nq, 0.f); depth.assign(nq, 0.f);
+    n_inview.assign(frames.size(), 0);
+    kp_match.assign(nk, -1); q_match.assign(nq, -1); q_dist.assign(nq, -1); n_matches.assign(frames.size(), 0);
+    vieo_check(vieo_search_local_points(frustum.data(), frames.data(), (int)frames.size(), wP, normal, max_dist, min_dist,
+                                        skip, q_desc, q_flags, keys_un, vuright, descriptors, kp_blocked, inview.data(),
+                                        proj.data(), level.data(), viewcos.data(), depth.data(), n_inview.data(),
+                                        kp_match.data(), q_match.data(), q_dist.data(), n_matches.data(), device_),
+               "vieo_search_local_points");
+    int total = 0;
+    for (int32_t n : n_matches) total += n;
+    return total;
+  }
+  // The search half of SearchByProjectionBase (src/ORBmatcher.cc:26-227) for a batch of keyframes — what Fuse(pKF,
+  // vpMapPoints, th) runs before FuseMP: best_idx[i] >= 0 && best_dist[i] <= TH_LOW are the points to fuse / add.
+  void SearchByProjectionBase(const std::vector<VieoProjSearchFrame>& kfs, const VieoKeyPoint* keys_un, const float* vuright,
+                              const uint8_t* descriptors, const float* wP, const float* normal, const float* max_dist,
+                              const float* min_dist, const uint8_t* q_desc, const uint8_t* q_skip,
+                              std::vector<int32_t>& best_idx, std::vector<int32_t>& best_dist,
+                              std::vector<int32_t>& level) const {
+    size_t nq = 0;
+    for (const VieoProjSearchFrame& f : kfs) nq = std::max(nq, (size_t)f.q_begin + f.n_q);
+    best_idx.assign(nq, -1); best_dist.assign(nq, 256); level.assign(nq, -1);
+    vieo_check(vieo_proj_search_batch(kfs.data(), (int)kfs.size(), keys_un, vuright, descriptors, wP, normal, max_dist,
+                                      min_dist, q_desc, q_skip, best_idx.data(), best_dist.data(), level.data(), device_),
+               "vieo_proj_search_batch");
+  }
+  // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:314-378) for every map point LocalMapping touched in one
+  // call: ptr / rows = CSR lists of the observed descriptor rows in desc_pool; best[p] indexes point p's list.
+  void ComputeDistinctiveDescriptors(const uint8_t* desc_pool, int n_pool, const std::vector<int32_t>& rows,
+                                     const std::vector<int32_t>& ptr, std::vector<int32_t>& best,
+                                     std::vector<int32_t>& median) const {
+    const int n = (int)ptr.size() - 1;
+    best.assign(std::max(n, 0), -1); median.assign(std::max(n, 0), -1);
+    if (n <= 0) return;
+    vieo_check(vieo_distinctive_descriptors(desc_pool, n_pool, rows.empty() ? nullptr : rows.data(), ptr.data(), n,
+                                            best.data(), median.data(), device_), "vieo_distinctive_descriptors");
+  }
   float mfNNratio;
   bool mbCheckOrientation;
 
@@ -214,6 +269,25 @@ struct Optimizer {
     return res.n_inliers;
   }
 };
+
+// Optimizer::OptimizeInitialGyroBias(vpKFInit, bg, bInfo) (include/Optimizer.h:819-892) followed by the re-integration
+// of every keyframe interval with the new bias (src/Odom/IMUInitialization.cpp:640-648).  pre[i] = vpKFInit[i]->
+// GetIMUPreInt() (entry 0 ignored), Rwb[i] = Rwc_i * Rcb row-major; with sample lists given, reint receives
+// ComputePreInt()'s results.  Returns num_equations.
+inline int OptimizeInitialGyroBias(const std::vector<VieoImuPreint>& pre, const std::vector<double>& Rwb, double bg[3],
+                                   bool bInfo = true, const std::vector<double>* samples = nullptr,
+                                   const std::vector<int32_t>* seg_ptr = nullptr, const std::vector<double>* ti_tj = nullptr,
+                                   const std::vector<double>* ba = nullptr, std::vector<VieoImuPreint>* reint = nullptr,
+                                   int device = 0) {
+  int neq = 0;
+  const int n = (int)pre.size();
+  if (reint) reint->resize(n);
+  vieo_check(vieo_imu_init_gyro_bias(pre.data(), Rwb.data(), n, bInfo ? 1 : 0, bg, &neq, samples ? samples->data() : nullptr,
+                                     seg_ptr ? seg_ptr->data() : nullptr, ti_tj ? ti_tj->data() : nullptr,
+                                     ba ? ba->data() : nullptr, &IMUPreintegrator::Noise(), reint ? reint->data() : nullptr,
+                                     device), "vieo_imu_init_gyro_bias");
+  return neq;
+}
 
 // LocalBundleAdjustmentNavStatePRV engine: long-lived (LocalMapping thread), reused across windows
 class LocalBA {
