@@ -1,15 +1,39 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, smoke, bench lines, ncu launch list, ncu --set full of the top kernels.
-# usage: bash tools/gpu_round.sh [tag]   (outputs under gpurun_out/<tag>_*)
+# Round evidence in two gpurun calls (each bounded; gpurun_out/ must stay under 64 MiB to travel back):
+#   bash tools/gpu_round.sh <tag> run      GPU parity tests, smoke, bench lines (ours / no-LBA / reference arm)
+#   bash tools/gpu_round.sh <tag> profile  ncu launch list of the bench command + ncu --set full of the top kernels
+# outputs under gpurun_out/<tag>_*
 TAG=${1:-r}
-set -x
+WHAT=${2:-run}
 mkdir -p gpurun_out
+T0=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" >> gpurun_out/${TAG}_${WHAT}_steps.log; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_nvsmi.txt
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
-timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err
-timeout 900 python bench.py --steps 20 --warmup 3 --lba 0 > gpurun_out/${TAG}_bench_nolba.json 2> gpurun_out/${TAG}_bench_nolba.err
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --cpu-frames 8 > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_fast_cells|k_orient_desc|k_quadtree|k_resize|k_stereo_match|k_sbp|k_pose_opt|k_imu_preint|k_ba_linearize|k_ba_schur|k_ba_chol' -s 60 -c 36 -o gpurun_out/${TAG}_prof python bench.py --steps 1 --warmup 3 --cpu-frames 8 --lba-workers 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
-ls -la gpurun_out
+if [ "$WHAT" = run ]; then
+  timeout 420 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
+  stamp pytest; tail -3 gpurun_out/${TAG}_pytest_gpu.log
+  timeout 120 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log
+  stamp smoke; tail -2 gpurun_out/${TAG}_smoke.log
+  timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err
+  stamp bench; cat gpurun_out/${TAG}_bench.json
+  timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
+  stamp bench_ref
+  timeout 200 python bench.py --steps 10 --warmup 3 --lba 0 --cpu-frames 8 > gpurun_out/${TAG}_bench_nolba.json 2> gpurun_out/${TAG}_bench_nolba.err
+  stamp bench_nolba
+else
+  timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --cpu-frames 8 > gpurun_out/${TAG}_ncu_bench.log 2>&1
+  stamp launches
+  timeout 330 ncu --set full --clock-control none --import-source on \
+    -k regex:'k_fast_cells|k_orient_desc|k_quadtree|k_resize|k_stereo_match|k_sbp|k_frustum|k_pose_opt|k_imu_preint|k_ba_linearize|k_ba_schur|k_ba_chol' \
+    -s 60 -c 36 -o gpurun_out/${TAG}_prof python bench.py --steps 1 --warmup 3 --cpu-frames 8 --lba-workers 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
+  stamp ncu_full
+  # the summaries are made on the box too, in case the report is too large to travel
+  python tools/ncu_summary.py full gpurun_out/${TAG}_prof.ncu-rep gpurun_out/${TAG}_ncu_full.csv > /dev/null 2>&1
+  python tools/ncu_summary.py launches gpurun_out/${TAG}_launches.csv gpurun_out/${TAG}_launches.md > /dev/null 2>&1
+  SZ=$(stat -c %s gpurun_out/${TAG}_prof.ncu-rep 2>/dev/null || echo 0)
+  if [ "$SZ" -gt 40000000 ]; then rm -f gpurun_out/${TAG}_prof.ncu-rep; echo "report ($SZ bytes) summarised on the box and dropped" >> gpurun_out/${TAG}_${WHAT}_steps.log; fi
+  stamp summaries; head -30 gpurun_out/${TAG}_launches.md
+fi
+cat gpurun_out/${TAG}_${WHAT}_steps.log
+du -sh gpurun_out

@@ -237,34 +237,26 @@ int vieo_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_
   if (nq == 0) return VIEO_OK;
   int rc = use_device(device);
   if (rc) return rc;
-  uint8_t *dq = nullptr, *dt = nullptr;
-  int *dn = nullptr, *di = nullptr, *dd = nullptr;
+  // per-thread staging (device buffers and stream reused across calls): a call costs copies + one kernel
+  CallScratch* cs = call_scratch(device);
+  if (!cs) return VIEO_E_CUDA;
+  uint8_t* dq = (uint8_t*)cs->get(0, (size_t)nq * 32);
+  uint8_t* dt = (uint8_t*)cs->get(1, (size_t)std::max(nt, 1) * 32);
+  int* dn = (int*)cs->get(2, 8);
+  int* dio = (int*)cs->get(3, (size_t)nq * 16);
+  if (!dq || !dt || !dn || !dio) return VIEO_E_CUDA;
+  cudaStream_t st = cs->st;
   const int hn[2] = {nq, nt};
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  step(cudaMalloc(&dq, (size_t)nq * 32));
-  step(cudaMalloc(&dt, (size_t)std::max(nt, 1) * 32));
-  step(cudaMalloc(&dn, 8));
-  step(cudaMalloc(&di, (size_t)nq * 8));
-  step(cudaMalloc(&dd, (size_t)nq * 8));
-  if (e == cudaSuccess) {
-    step(cudaMemcpy(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice));
-    if (nt) step(cudaMemcpy(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice));
-    step(cudaMemcpy(dn, hn, 8, cudaMemcpyHostToDevice));
-  }
-  if (e == cudaSuccess) {
-    rc = vieo_hamming_knn2_batch_dev(dq, 0, dn, nq, dt, 0, dn + 1, nt, 1, 1, di, dd, nullptr);
-    if (rc == VIEO_OK) {
-      step(cudaMemcpy(idx, di, (size_t)nq * 8, cudaMemcpyDeviceToHost));
-      step(cudaMemcpy(dist, dd, (size_t)nq * 8, cudaMemcpyDeviceToHost));
-    }
-  }
-  cudaFree(dq); cudaFree(dt); cudaFree(dn); cudaFree(di); cudaFree(dd);
-  if (e != cudaSuccess) {
-    set_error("vieo_hamming_knn2: %s", cudaGetErrorString(e));
-    return VIEO_E_CUDA;
-  }
-  return rc;
+  VIEO_CK(cudaMemcpyAsync(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
+  if (nt) VIEO_CK(cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaMemcpyAsync(dn, hn, 8, cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaStreamSynchronize(st));  // hn is a local; q / t may be pageable
+  rc = vieo_hamming_knn2_batch_dev(dq, 0, dn, nq, dt, 0, dn + 1, nt, 1, 1, dio, dio + 2 * (size_t)nq, st);
+  if (rc) return rc;
+  VIEO_CK(cudaMemcpyAsync(idx, dio, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaMemcpyAsync(dist, dio + 2 * (size_t)nq, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaStreamSynchronize(st));
+  return VIEO_OK;
 }
 
 int vieo_hamming_csr(const uint8_t* q, const uint8_t* t, int nt, const int32_t* row_ptr, const int32_t* cand,
@@ -277,34 +269,27 @@ int vieo_hamming_csr(const uint8_t* q, const uint8_t* t, int nt, const int32_t* 
   VIEO_ARG(ncand >= 0 && ncand < (1 << 22) && (ncand == 0 || (cand && t)), "candidate list too long or null");
   int rc = use_device(device);
   if (rc) return rc;
-  uint8_t *dq = nullptr, *dt = nullptr;
-  int *drp = nullptr, *dc = nullptr, *dout = nullptr;
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  step(cudaMalloc(&dq, (size_t)nrows * 32));
-  step(cudaMalloc(&dt, (size_t)std::max(nt, 1) * 32));
-  step(cudaMalloc(&drp, sizeof(int) * (nrows + 1)));
-  step(cudaMalloc(&dc, sizeof(int) * std::max(ncand, 1)));
-  step(cudaMalloc(&dout, sizeof(int) * 4 * nrows));
-  if (e == cudaSuccess) {
-    step(cudaMemcpy(dq, q, (size_t)nrows * 32, cudaMemcpyHostToDevice));
-    if (nt) step(cudaMemcpy(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice));
-    step(cudaMemcpy(drp, row_ptr, sizeof(int) * (nrows + 1), cudaMemcpyHostToDevice));
-    if (ncand) step(cudaMemcpy(dc, cand, sizeof(int) * ncand, cudaMemcpyHostToDevice));
-  }
-  if (e == cudaSuccess) {
-    k_csr<<<(nrows + 3) / 4, 128>>>(dq, dt, drp, dc, nrows, dout, dout + nrows, dout + 2 * nrows, dout + 3 * nrows);
-    step(cudaGetLastError());
-    step(cudaMemcpy(best_dist, dout, sizeof(int) * nrows, cudaMemcpyDeviceToHost));
-    step(cudaMemcpy(best_idx, dout + nrows, sizeof(int) * nrows, cudaMemcpyDeviceToHost));
-    step(cudaMemcpy(second_dist, dout + 2 * nrows, sizeof(int) * nrows, cudaMemcpyDeviceToHost));
-    step(cudaMemcpy(second_idx, dout + 3 * nrows, sizeof(int) * nrows, cudaMemcpyDeviceToHost));
-  }
-  cudaFree(dq); cudaFree(dt); cudaFree(drp); cudaFree(dc); cudaFree(dout);
-  if (e != cudaSuccess) {
-    set_error("vieo_hamming_csr: %s", cudaGetErrorString(e));
-    return VIEO_E_CUDA;
-  }
+  CallScratch* cs = call_scratch(device);
+  if (!cs) return VIEO_E_CUDA;
+  uint8_t* dq = (uint8_t*)cs->get(0, (size_t)nrows * 32);
+  uint8_t* dt = (uint8_t*)cs->get(1, (size_t)std::max(nt, 1) * 32);
+  int* drp = (int*)cs->get(2, sizeof(int) * ((size_t)nrows + 1));
+  int* dc = (int*)cs->get(3, sizeof(int) * (size_t)std::max(ncand, 1));
+  int* dout = (int*)cs->get(4, sizeof(int) * 4 * (size_t)nrows);
+  if (!dq || !dt || !drp || !dc || !dout) return VIEO_E_CUDA;
+  cudaStream_t st = cs->st;
+  VIEO_CK(cudaMemcpyAsync(dq, q, (size_t)nrows * 32, cudaMemcpyHostToDevice, st));
+  if (nt) VIEO_CK(cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+  VIEO_CK(cudaMemcpyAsync(drp, row_ptr, sizeof(int) * ((size_t)nrows + 1), cudaMemcpyHostToDevice, st));
+  if (ncand) VIEO_CK(cudaMemcpyAsync(dc, cand, sizeof(int) * (size_t)ncand, cudaMemcpyHostToDevice, st));
+  k_csr<<<(nrows + 3) / 4, 128, 0, st>>>(dq, dt, drp, dc, nrows, dout, dout + nrows, dout + 2 * (size_t)nrows,
+                                         dout + 3 * (size_t)nrows);
+  VIEO_CK(cudaGetLastError());
+  VIEO_CK(cudaMemcpyAsync(best_dist, dout, sizeof(int) * nrows, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaMemcpyAsync(best_idx, dout + nrows, sizeof(int) * nrows, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaMemcpyAsync(second_dist, dout + 2 * (size_t)nrows, sizeof(int) * nrows, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaMemcpyAsync(second_idx, dout + 3 * (size_t)nrows, sizeof(int) * nrows, cudaMemcpyDeviceToHost, st));
+  VIEO_CK(cudaStreamSynchronize(st));
   return VIEO_OK;
 }
 
