@@ -465,26 +465,29 @@ def run_gpu(args, rank, world, local_rank):
                             max_frames=F, device=local_rank)
     outs = fe.alloc_outputs(F, pinned=True)
     host_np = host_t.numpy()
-    trk_pool = ThreadPoolExecutor(1)
-    if part:
-        trk_pool.submit(part.bind, api.SM_FRONTEND).result()   # the tracking thread's staging stream
+    # the batch holds 128 independent frames (as many tracking threads' worth of work): its three host-buffer stages run
+    # on three host threads, each with its own staging stream, so their pinned-memory copies overlap
+    trk_pool = ThreadPoolExecutor(3, initializer=(lambda: part.bind(api.SM_FRONTEND)) if part else None)
     matcher = api.ORBmatcher(0.8, True, device=local_rank)
 
-    def tracking_host():
+    def trk_motion_model():
         pre_gpu.preintegrate_batch(*trk["imu"])
-        nm = 0
-        nm += int(matcher.SearchByProjection(trk["sbp"][0])[3][0])
-        nm += int(matcher.SearchLocalPoints(trk["sbp"][1])[4][0])
+        return int(matcher.SearchByProjection(trk["sbp"][0])[3][0])
+
+    def trk_local_map():
+        return int(matcher.SearchLocalPoints(trk["sbp"][1], want_tracking_info=False)[4][0])
+
+    def trk_pose_opt():
         r = api.Optimizer.PoseOptimizationBatch(trk["pbs"], trk["cam"], trk["Xw"], trk["obs"], trk["w"], trk["flags"],
                                                 device=local_rank)
-        return int(r[0]["n_inliers"][0]) + nm
+        return int(r[0]["n_inliers"][0])
 
     def e2e_step(i):
         futs = [lba_pool.submit(lba_job, wk, wk) for wk in range(n_workers)]
-        ft = trk_pool.submit(tracking_host)
+        fts = [trk_pool.submit(fn) for fn in (trk_motion_model, trk_local_map, trk_pose_opt)]
         res = fe.process(host_np[i % pool], outs)
         st = fe.stereo_rectified(F, BF, MINZ)
-        _ = int(res[2][0]) + ft.result() + int(st[2][0, 0])
+        _ = int(res[2][0]) + sum(ft.result() for ft in fts) + int(st[2][0, 0])
         for f in futs:
             f.result()
 
@@ -510,7 +513,7 @@ def run_gpu(args, rank, world, local_rank):
                "uright", "desc", "kp_blocked")
     sbp_in = (sum(int(v.nbytes) for v in trk["sbp"][0].values() if isinstance(v, np.ndarray)) +
               sum(int(trk["sbp"][1][k].nbytes) for k in lm_keys))
-    sbp_out = sum(4 * (len(pb["kps"]) + 2 * len(pb["q_level"]) + F) for pb in trk["sbp"]) + 25 * len(trk["sbp"][1]["q_level"]) + 4 * F
+    sbp_out = sum(4 * (len(pb["kps"]) + 2 * len(pb["q_level"]) + F) for pb in trk["sbp"]) + len(trk["sbp"][1]["q_level"]) + 4 * F   # + inview, n_inview
     h2d = F * 2 * H * W + trk_in + sbp_in + n_lba * lba_bytes
     d2h = (sum(int(o.nbytes) for o in outs) + 3 * F * cap * 4 + sbp_out + F * api.PREINT_DTYPE.itemsize + n_pb * api.POSEOPT_RESULT_DTYPE.itemsize
            + 9 * n_edges + n_lba * (64 * 176 + 2048 * 24 + 16384 * 9))

@@ -422,7 +422,8 @@ int vieo_frustum_batch(const VieoFrustumFrame* frames, int n_frames, const float
                        int32_t* level, float* viewcos, float* depth, int32_t* n_inview, int device);
 /* Visibility test + local-map guided search on one stream; frames[f] and frustum[f] share q_begin / n_q, the search
  * reads the tracking info the first kernel left in HBM.  Outputs of both halves as documented above / at
- * vieo_sbp_batch. */
+ * vieo_sbp_batch; proj / level / viewcos / depth may ALL be null (Tracking::SearchLocalPoints only needs inview and the
+ * matches): the tracking info then never leaves the device. */
 int vieo_search_local_points(const VieoFrustumFrame* frustum, const VieoSbpFrame* frames, int n_frames, const float* wP,
                              const float* normal, const float* max_dist, const float* min_dist, const uint8_t* skip,
                              const uint8_t* q_desc, const uint8_t* q_flags, const VieoKeyPoint* kps, const float* uright,

@@ -79,6 +79,10 @@ def test_search_local_points_matches_oracle(kw):
         assert np.array_equal(a, b), (name, np.nonzero(a != b)[0][:10])
     assert nm.min() > 20
     assert (q_match[fo["inview"] == 0] == -1).all()
+    # without the tracking info: same matches, same visibility flags
+    fo2, kp2, qm2, qd2, nm2 = api.ORBmatcher(0.8).SearchLocalPoints(pb, want_tracking_info=False)
+    assert np.array_equal(fo2["inview"], fo["inview"]) and np.array_equal(fo2["n_inview"], fo["n_inview"])
+    assert np.array_equal(kp2, kp_match) and np.array_equal(qm2, q_match) and np.array_equal(qd2, q_dist) and np.array_equal(nm2, nm)
     # the stand-alone search fed with the frustum outputs (level -1 = skipped query) gives the same answer
     q = dict(pb); q["mode"] = 1
     q["q_proj"], q["q_level"], q["q_viewcos"], q["q_depth"] = fo["proj"], fo["level"], fo["viewcos"], fo["depth"]

@@ -21,6 +21,10 @@ if [ "$WHAT" = run ]; then
   timeout 200 python bench.py --steps 10 --warmup 3 --lba 0 --cpu-frames 8 > gpurun_out/${TAG}_bench_nolba.json 2> gpurun_out/${TAG}_bench_nolba.err
   stamp bench_nolba
 else
+  timeout 200 python -m pytest tests/test_gpu_next.py tests/test_gpu_orb.py -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu2.log
+  stamp pytest2; tail -3 gpurun_out/${TAG}_pytest_gpu2.log
+  timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench2.json 2> gpurun_out/${TAG}_bench2.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench2.err
+  stamp bench2; cat gpurun_out/${TAG}_bench2.json
   timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --cpu-frames 8 > gpurun_out/${TAG}_ncu_bench.log 2>&1
   stamp launches

@@ -374,11 +374,12 @@ class ORBmatcher:
         _check(lib().vieo_hamming_csr(_p(q), _p(t), len(t), _p(row_ptr), _p(cand), n, *[_p(x) for x in o], self.device))
         return o
 
-    def SearchLocalPoints(self, pb):
+    def SearchLocalPoints(self, pb, want_tracking_info=True):
         """Tracking::SearchLocalPoints (src/Tracking.cc:2308-2368): Frame::isInFrustum over every candidate local map point
         followed by SearchByProjection(F, vpMapPoints, th, th_far) on the same stream (vieo_search_local_points).  `pb` is
         a synth.make_frustum_problem dict that also carries the guided-search arrays.
-        Returns (frustum outputs dict, kp_match, q_match, q_dist, n_matches)."""
+        Returns (frustum outputs dict, kp_match, q_match, q_dist, n_matches); want_tracking_info=False leaves the
+        projections / levels / cosines / depths on the device (only inview and n_inview are filled)."""
         fr = np.ascontiguousarray(pb["frames"]).copy()
         fr["nn_ratio"] = self.mfNNratio
         fr["check_orientation"] = int(self.mbCheckOrientation)
@@ -396,8 +397,9 @@ class ORBmatcher:
         nm = np.zeros(len(fr), np.int32)
         _check(lib().vieo_search_local_points(_p(ff), _p(fr), len(fr), _p(a["p_wP"]), _p(a["p_normal"]), _p(a["p_max_dist"]),
                                               _p(a["p_min_dist"]), _p(skip), _p(a["q_desc"]), _p(a["q_flags"]), _p(a["kps"]),
-                                              _p(a["uright"]), _p(a["desc"]), _p(blk), _p(out["inview"]), _p(out["proj"]),
-                                              _p(out["level"]), _p(out["viewcos"]), _p(out["depth"]), _p(out["n_inview"]),
+                                              _p(a["uright"]), _p(a["desc"]), _p(blk), _p(out["inview"]),
+                                              *[_p(out[k]) if want_tracking_info else None for k in ("proj", "level", "viewcos", "depth")],
+                                              _p(out["n_inview"]),
                                               _p(kp_match), _p(q_match), _p(q_dist), _p(nm), self.device))
         return out, kp_match, q_match, q_dist, nm
 

@@ -112,6 +112,13 @@ extern "C" {
 int vieo_frustum_level_table(float log_scale_factor, int n_levels, float table[16]) {
   VIEO_ARG(table && n_levels >= 1 && n_levels <= 16, "bad pyramid depth");
   VIEO_ARG(log_scale_factor > 0.0f && std::isfinite(log_scale_factor), "log scale factor must be positive");
+  // a batch repeats one pyramid: the last table is kept per thread (the bisection costs ~1100 logf calls)
+  thread_local float c_lsf = 0.0f, c_table[16];
+  thread_local int c_levels = 0;
+  if (c_levels == n_levels && c_lsf == log_scale_factor) {
+    memcpy(table, c_table, sizeof(c_table));
+    return VIEO_OK;
+  }
   for (int k = 0; k < 16; ++k) table[k] = INFINITY;
   table[0] = 0.0f;
   for (int k = 1; k < n_levels; ++k) {
@@ -137,6 +144,9 @@ int vieo_frustum_level_table(float log_scale_factor, int n_levels, float table[1
     }
     memcpy(&table[k], &lo, 4);
   }
+  memcpy(c_table, table, sizeof(c_table));
+  c_lsf = log_scale_factor;
+  c_levels = n_levels;
   return VIEO_OK;
 }
 
@@ -184,7 +194,11 @@ static int frustum_host(const VieoFrustumFrame* frames, const VieoSbpFrame* sbp,
       nk = std::max(nk, (size_t)sbp[f].kp_begin + sbp[f].n_kp);
     }
   }
-  VIEO_ARG(nq == 0 || (wP && normal && max_dist && min_dist && inview && proj && level && viewcos && depth), "null point array");
+  VIEO_ARG(nq == 0 || (wP && normal && max_dist && min_dist && inview), "null point array");
+  // the tracking info is optional for the fused call (Tracking only needs btrack_inview_ and the matches)
+  const bool want_info = proj || level || viewcos || depth;
+  VIEO_ARG(sbp || nq == 0 || (proj && level && viewcos && depth), "null point array");
+  VIEO_ARG(!want_info || nq == 0 || (proj && level && viewcos && depth), "tracking-info outputs must be given together");
   if (sbp) {
     VIEO_ARG(n_matches, "null argument");
     VIEO_ARG(nk == 0 || (kps && uright && desc && kp_match), "null keypoint array");
@@ -204,12 +218,12 @@ static int frustum_host(const VieoFrustumFrame* frames, const VieoSbpFrame* sbp,
                o_ur = take(sbp ? 4 * nk1 : 0), o_de = take(sbp ? 32 * nk1 : 0), o_bl = take(sbp ? nk1 : 0),
                o_qd = take(sbp ? 32 * nq1 : 0), o_fl = take(sbp ? nq1 : 0);
   const size_t in_bytes = off;
-  // outputs (one contiguous device->host copy)
-  const size_t o_iv = take(nq1), o_pr = take(12 * nq1), o_lv = take(4 * nq1), o_vc = take(4 * nq1), o_dp = take(4 * nq1),
-               o_ni = take(4 * nf);
+  // outputs: [inview | n_inview | matches] always come back, the tracking info behind them only when asked for
+  const size_t o_iv = take(nq1), o_ni = take(4 * nf);
   const size_t o_km = take(sbp ? 4 * nk1 : 0), o_qm = take(sbp ? 4 * nq1 : 0), o_qs = take(sbp ? 4 * nq1 : 0),
                o_nm = take(sbp ? 4 * nf : 0);
-  const size_t io_bytes = off;
+  const size_t o_pr = take(12 * nq1), o_lv = take(4 * nq1), o_vc = take(4 * nq1), o_dp = take(4 * nq1);
+  const size_t io_bytes = off, back_bytes = want_info ? io_bytes : o_pr;
   const size_t sc_bytes = sbp ? vieo_sbp_scratch_bytes((int)nq1) : 16;
   uint8_t* dbuf = (uint8_t*)cs->get(0, io_bytes);
   void* dsc = cs->get(1, sc_bytes);
@@ -226,10 +240,11 @@ static int frustum_host(const VieoFrustumFrame* frames, const VieoSbpFrame* sbp,
   }
   cudaError_t e = cudaMemcpyAsync(dbuf, hbuf, in_bytes, cudaMemcpyHostToDevice, cs->st);
   // points outside every frame's range read back as "not in view" (level -1) / unmatched
-  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_iv, 0, o_lv - o_iv, cs->st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_lv, 0xff, o_vc - o_lv, cs->st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_vc, 0, o_ni - o_vc, cs->st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_iv, 0, o_ni - o_iv, cs->st);
   if (e == cudaSuccess && sbp) e = cudaMemsetAsync(dbuf + o_km, 0xff, o_nm - o_km, cs->st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_pr, 0, o_lv - o_pr, cs->st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_lv, 0xff, o_vc - o_lv, cs->st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_vc, 0, io_bytes - o_vc, cs->st);
   if (e == cudaSuccess) {
     rc = vieo_frustum_batch_dev((const VieoFrustumFrame*)(dbuf + o_ff), n_frames, (const float*)(dbuf + o_wp),
                                 (const float*)(dbuf + o_pn), (const float*)(dbuf + o_mx), (const float*)(dbuf + o_mn),
@@ -246,7 +261,7 @@ static int frustum_host(const VieoFrustumFrame* frames, const VieoSbpFrame* sbp,
                               (int32_t*)(dbuf + o_nm), dsc, sc_bytes, cs->st);
     }
     if (rc == VIEO_OK) {
-      e = cudaMemcpyAsync(hbuf + o_iv, dbuf + o_iv, io_bytes - o_iv, cudaMemcpyDeviceToHost, cs->st);
+      e = cudaMemcpyAsync(hbuf + o_iv, dbuf + o_iv, back_bytes - o_iv, cudaMemcpyDeviceToHost, cs->st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(cs->st);
     }
   }
@@ -256,8 +271,11 @@ static int frustum_host(const VieoFrustumFrame* frames, const VieoSbpFrame* sbp,
   }
   if (rc != VIEO_OK) return rc;
   if (nq) {
-    memcpy(inview, hbuf + o_iv, nq); memcpy(proj, hbuf + o_pr, 12 * nq); memcpy(level, hbuf + o_lv, 4 * nq);
-    memcpy(viewcos, hbuf + o_vc, 4 * nq); memcpy(depth, hbuf + o_dp, 4 * nq);
+    memcpy(inview, hbuf + o_iv, nq);
+    if (want_info) {
+      memcpy(proj, hbuf + o_pr, 12 * nq); memcpy(level, hbuf + o_lv, 4 * nq);
+      memcpy(viewcos, hbuf + o_vc, 4 * nq); memcpy(depth, hbuf + o_dp, 4 * nq);
+    }
   }
   memcpy(n_inview, hbuf + o_ni, 4 * nf);
   if (sbp) {
