@@ -532,7 +532,8 @@ def run_gpu(args, rank, world, local_rank):
     achieved = alg_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        per_image = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["per_image"].get(dom)
+        traffic = None if per_image is None else int(per_image) * n_img   # per launch, like `achieved`
     except Exception:
         pass
     # ---- CPU baseline: the oracle threaded like the reference, bounded sample
