@@ -139,7 +139,7 @@ def main(out_path=None):
     cv_sum = rows[0][1] + rows[1][1] + rows[3][1]
     lines.append(f"\ncv2 pyramid + per-cell FAST + blur alone: {cv_sum:.1f} ms per image (no quadtree, orientation or descriptors). "
                  "The stand-alone `orc_fast_detect` timed above is the simple per-pixel pin of cv::FAST used by the golden tests; the "
-                 "oracle's extractor scores each level once and is faster than both:")
+                 "oracle's extractor scores each level once; its whole pipeline costs about what the three cv2 primitives cost alone:")
     lines.append(f"ORBextractor::operator() restated by the oracle (pyramid + FAST + quadtree + orientation + blur + descriptors), "
                  f"one image: {full:.1f} ms — the reference reports 35-43 ms per stereo FRAME for its whole front-end "
                  f"(README.md:60, i9-14900HX, one thread per camera).")
