@@ -884,6 +884,62 @@ void orc_navstate_oplus(OrcNavState* ns, int kind, const double* dx) {
   to_c(s, ns);
 }
 
+// EdgeReprojectPRS / PRSStereo (g2otypes.h:321-541, MODE_OPT_VAR = 1, NV = 3): the point vertex holds the UNSCALED
+// position Xh, Xw = scale * Xh; J_point = (Jproj Rcw) * scale, J_scale = (Jproj Rcw) * Xh (:517-521), the pose block is
+// the PR edge's at Xw.  Restated for the next round's device side (GlobalBundleAdjustmentNavStatePRV with bScaleOpt,
+// src/Optimizer.cc:843-851, 1132-1200); no device code uses it yet.
+void orc_edge_reproject_scale(const OrcCamera* cam, const OrcNavState* ns, const double Xh[3], double scale_est,
+                              const float obs[3], int stereo, double e[3], double* J_pose, double* J_point, double* J_scale) {
+  const double Xw[3] = {Xh[0] * scale_est, Xh[1] * scale_est, Xh[2] * scale_est};
+  double JX[9];
+  orc_edge_reproject(cam, ns, Xw, obs, stereo, e, J_pose, (J_point || J_scale) ? JX : nullptr, nullptr);
+  if (J_scale)
+    for (int r = 0; r < 3; ++r) J_scale[r] = JX[3 * r] * Xh[0] + JX[3 * r + 1] * Xh[1] + JX[3 * r + 2] * Xh[2];
+  if (J_point)
+    for (int k = 0; k < 9; ++k) J_point[k] = JX[k] * scale_est;
+}
+
+// VertexGThetaXYRwI (g2otypes.h:674-698): RwI such that gw = RwI * GI, GI = (0, 0, |gw|); 2-dim update on the right.
+void orc_gdir_init(const double gw[3], double q_wI[4]) {
+  const double n = std::sqrt(gw[0] * gw[0] + gw[1] * gw[1] + gw[2] * gw[2]);
+  const double g[3] = {gw[0] / n, gw[1] / n, gw[2] / n};
+  double a[3] = {-g[1], g[0], 0.0};  // (0,0,1) x g
+  const double na = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  const double th = std::acos(g[2]);
+  // Eigen 3.3 normalized() returns a zero vector unchanged: gw parallel OR anti-parallel to the z axis gives RwI = I
+  // (for the anti-parallel case RwI * GI = -gw: the reference's behaviour, reproduced)
+  const double inv = na > 0 ? 1.0 / na : 1.0;
+  const double w[3] = {a[0] * inv * th, a[1] * inv * th, a[2] * inv * th};
+  const Quat q = so3_exp_q(w);
+  q_wI[0] = q.w; q_wI[1] = q.x; q_wI[2] = q.y; q_wI[3] = q.z;
+}
+void orc_gdir_oplus(double q_wI[4], const double d[2]) {
+  const double w[3] = {d[0], d[1], 0.0};
+  const Quat q = qnormalized(qmul({q_wI[0], q_wI[1], q_wI[2], q_wI[3]}, so3_exp_q(w)));
+  q_wI[0] = q.w; q_wI[1] = q.x; q_wI[2] = q.y; q_wI[3] = q.z;
+}
+// EdgeNavStatePRVG (EdgeNavStateI<6>, g2otypes.h:725-884): the PRV edge with gw = RwI * GI and the extra 9x2 block
+// JG (:868-876): rows P = RiT dt^2/2 RwI GI^[:, 0:2], rows V = RiT dt RwI GI^[:, 0:2], rows R = 0.
+void orc_edge_navstate_g(const OrcNavState* nsi, const OrcNavState* nsj, const OrcImuPreint* pre, const double q_wI[4],
+                         const double GI[3], double e[9], double* Ji, double* Jj, double* Jb, double* JG) {
+  const M3 RwI = qmat({q_wI[0], q_wI[1], q_wI[2], q_wI[3]});
+  double gw[3];
+  mulv(RwI, GI, gw);
+  orc_edge_navstate(nsi, nsj, pre, gw, 1, e, Ji, Jj, Jb);
+  if (JG) {
+    const NS a = from_c(*nsi);
+    const M3 RiT = tr(qmat(a.q));
+    const M3 A = mul(RiT, mul(RwI, hat(GI)));  // 3x3, first two columns used
+    const double dt = pre->dt;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 2; ++c) {
+        JG[2 * r + c] = A.m[3 * r + c] * (dt * dt / 2.0);      // rows 0..2: P
+        JG[2 * (3 + r) + c] = 0.0;                             // rows 3..5: R
+        JG[2 * (6 + r) + c] = A.m[3 * r + c] * dt;             // rows 6..8: V
+      }
+  }
+}
+
 void orc_edge_prior_pvr(const OrcNavState* ns, const OrcNavState* prior, double e[15], double* Jpvr) {
   const NS s = from_c(*ns), p = from_c(*prior);
   prior_error(s, s, p, e);

@@ -129,6 +129,14 @@ void orc_edge_navstate(const OrcNavState* nsi, const OrcNavState* nsj, const Orc
                        int order, double e[9], double* Ji, double* Jj, double* Jb);
 /* NavState::IncSmall variants: kind 0 = PR(6), 1 = PVR(9), 2 = V(3), 3 = Bias(6) */
 void orc_navstate_oplus(OrcNavState* ns, int kind, const double* dx);
+/* Edges of the scale / gravity-direction variants of the global BA (restated ahead of their device side):
+ * EdgeReprojectPRS[Stereo] with a VertexScale, VertexGThetaXYRwI and EdgeNavStatePRVG.  J_scale [3], JG [9][2]. */
+void orc_edge_reproject_scale(const OrcCamera* cam, const OrcNavState* ns, const double Xh[3], double scale_est,
+                              const float obs[3], int stereo, double e[3], double* J_pose, double* J_point, double* J_scale);
+void orc_gdir_init(const double gw[3], double q_wI[4]);
+void orc_gdir_oplus(double q_wI[4], const double d[2]);
+void orc_edge_navstate_g(const OrcNavState* nsi, const OrcNavState* nsj, const OrcImuPreint* pre, const double q_wI[4],
+                         const double GI[3], double e[9], double* Ji, double* Jj, double* Jb, double* JG);
 void orc_edge_prior_pvr(const OrcNavState* ns, const OrcNavState* prior, double e[15], double* Jpvr /*15x9*/);
 int orc_inverse(const double* A, int n, double* Ainv);
 #ifdef __cplusplus

@@ -497,3 +497,49 @@ def proj_search(pb):
                        at("p_normal", qb), at("p_max_dist", qb), at("p_min_dist", qb), at("q_desc", qb), skip, at(best, qb),
                        at(dist, qb), at(lvl, qb))
     return best, dist, lvl
+
+
+# ---- scale / gravity-direction variants of the global-BA edges (oracle/ba_oracle.cc; restated ahead of the device side)
+def edge_reproject_scale(cam, ns, Xh, scale, obs, stereo):
+    """EdgeReprojectPRS[Stereo] -> (e, J_pose (3,6), J_point (3,3), J_scale (3,))"""
+    L = lib()
+    L.orc_edge_reproject_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.orc_edge_reproject_scale.restype = None
+    cam = np.ascontiguousarray(cam); ns = np.ascontiguousarray(ns)
+    Xh = np.ascontiguousarray(Xh, np.float64); obs = np.ascontiguousarray(obs, np.float32)
+    e = np.zeros(3); Jp = np.zeros((3, 6)); JX = np.zeros((3, 3)); Js = np.zeros(3)
+    L.orc_edge_reproject_scale(cam.ctypes.data, ns.ctypes.data, _p(Xh), float(scale), _p(obs), int(stereo), _p(e), _p(Jp),
+                               _p(JX), _p(Js))
+    return e, Jp, JX, Js
+
+
+def gdir_init(gw):
+    """VertexGThetaXYRwI::setToOriginImpl(gw) -> unit quaternion (w, x, y, z) of RwI"""
+    L = lib()
+    L.orc_gdir_init.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_gdir_init.restype = None
+    gw = np.ascontiguousarray(gw, np.float64); q = np.zeros(4)
+    L.orc_gdir_init(_p(gw), _p(q))
+    return q
+
+
+def gdir_oplus(q, d):
+    L = lib()
+    L.orc_gdir_oplus.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_gdir_oplus.restype = None
+    q = np.array(q, np.float64).copy(); d = np.ascontiguousarray(d, np.float64)
+    L.orc_gdir_oplus(_p(q), _p(d))
+    return q
+
+
+def edge_navstate_g(nsi, nsj, pre, q_wI, GI):
+    """EdgeNavStatePRVG -> (e, Ji, Jj, Jb, JG (9,2)); residual / column order P, R, V"""
+    L = lib()
+    L.orc_edge_navstate_g.argtypes = [C.c_void_p] * 10
+    L.orc_edge_navstate_g.restype = None
+    nsi = np.ascontiguousarray(nsi); nsj = np.ascontiguousarray(nsj); pre = np.ascontiguousarray(pre)
+    q_wI = np.ascontiguousarray(q_wI, np.float64); GI = np.ascontiguousarray(GI, np.float64)
+    e = np.zeros(9); Ji = np.zeros((9, 9)); Jj = np.zeros((9, 9)); Jb = np.zeros((9, 6)); JG = np.zeros((9, 2))
+    L.orc_edge_navstate_g(nsi.ctypes.data, nsj.ctypes.data, pre.ctypes.data, _p(q_wI), _p(GI), _p(e), _p(Ji), _p(Jj), _p(Jb),
+                          _p(JG))
+    return e, Ji, Jj, Jb, JG

@@ -401,3 +401,62 @@ def test_global_ba_robust_flag_changes_kernels():
     # global BA uses sqrt(5.99), not the local BA's sqrt(5.991f): a mono edge with chi2 between the two deltas^2 tells
     c = O.local_ba_prv(d, cam)
     assert c["res"]["err0"] != a["res"]["err0"]
+
+
+def test_scale_edge_jacobians_numeric():
+    """EdgeReprojectPRS[Stereo] (g2otypes.h:321-541, scale vertex of GlobalBundleAdjustmentNavStatePRV with bScaleOpt):
+    error at Xw = s * Xh, point block scaled by s, scale block = (Jproj Rcw) Xh — against central differences."""
+    cam = synth.euroc_camera()
+    r = np.random.default_rng(4)
+    ns = synth.vio_sequence(3, 4)["truth"][2]
+    X = synth.landmarks_in_view(cam, ns, 6, r)
+    obs = np.array([100, 200, 90], np.float32)
+    for i in range(6):
+        for stereo in (0, 1):
+            for s in (1.0, 0.93, 1.2):
+                Xh = X[i] / s                     # the same world point through a different scale estimate
+                e, Jp, JX, Js = O.edge_reproject_scale(cam, ns, Xh, s, obs, stereo)
+                e0, Jp0, JX0, _ = O.edge_reproject(cam, ns, X[i], obs, stereo)
+                assert np.allclose(e, e0, atol=1e-4) and np.allclose(Jp, Jp0, rtol=1e-6, atol=1e-6)   # float-rounded projection
+                assert np.allclose(JX, JX0 * s, rtol=1e-9, atol=1e-9)
+                d = 2e-3
+                Jsn = (O.edge_reproject_scale(cam, ns, Xh, s + d, obs, stereo)[0] -
+                       O.edge_reproject_scale(cam, ns, Xh, s - d, obs, stereo)[0]) / (2 * d)
+                JXn = np.zeros((3, 3))
+                for c in range(3):
+                    dx = np.zeros(3); dx[c] = d
+                    JXn[:, c] = (O.edge_reproject_scale(cam, ns, Xh + dx, s, obs, stereo)[0] -
+                                 O.edge_reproject_scale(cam, ns, Xh - dx, s, obs, stereo)[0]) / (2 * d)
+                rows = 3 if stereo else 2
+                assert np.allclose(Js[:rows], Jsn[:rows], rtol=3e-3, atol=0.3), (Js, Jsn)
+                assert np.allclose(JX[:rows], JXn[:rows], rtol=3e-3, atol=0.3)
+
+
+def test_gravity_direction_vertex_and_edge(seq):
+    """VertexGThetaXYRwI + EdgeNavStatePRVG (g2otypes.h:674-698, 725-884): RwI * GI reproduces gw, the edge equals the PRV
+    edge at that gravity, the 9x2 block matches central differences of the 2-dim right update, rows R are zero."""
+    r = np.random.default_rng(6)
+    G = 9.81
+    GI = np.array([0, 0, G])
+    # exactly (anti-)parallel to z: a_wI is the zero vector, Eigen's normalized() leaves it, RwI = I (reference behaviour)
+    assert np.allclose(O.gdir_init(np.array([0, 0, -G])), [1, 0, 0, 0]) and np.allclose(O.gdir_init(GI), [1, 0, 0, 0])
+    for gw in (np.array([0.02, -0.01, -9.81]), np.array([0.3, -0.2, -9.7]), np.array([1.0, 2.0, 9.5])):
+        gw = gw / np.linalg.norm(gw) * G
+        q = O.gdir_init(gw)
+        assert np.allclose(synth.R_from_quat(q) @ GI, gw, atol=1e-9)
+        i, j = 20, 21
+        nsi = synth.perturb_state(seq["truth"][i], r); nsj = synth.perturb_state(seq["truth"][j], r)
+        pre = seq["pre"][j]
+        e, Ji, Jj, Jb, JG = O.edge_navstate_g(nsi, nsj, pre, q, GI)
+        e0, Ji0, Jj0, Jb0 = O.edge_navstate(nsi, nsj, pre, gw, 1)
+        assert np.allclose(e, e0, atol=1e-12) and np.allclose(Ji, Ji0) and np.allclose(Jj, Jj0) and np.allclose(Jb, Jb0)
+        d = 1e-6
+        for c in range(2):
+            dx = np.zeros(2); dx[c] = d
+            num = (O.edge_navstate_g(nsi, nsj, pre, O.gdir_oplus(q, dx), GI)[0] -
+                   O.edge_navstate_g(nsi, nsj, pre, O.gdir_oplus(q, -dx), GI)[0]) / (2 * d)
+            assert np.allclose(JG[:, c], num, rtol=1e-5, atol=1e-7), (c, JG[:, c], num)
+        assert not JG[3:6].any() and np.abs(JG[6:9]).max() > 0.1 * pre["dt"] * G
+        # a rotation about the gravity axis itself (third component) is not a degree of freedom: the update ignores it
+        q2 = O.gdir_oplus(q, [0.0, 0.0])
+        assert np.allclose(q2, q, atol=1e-15)
