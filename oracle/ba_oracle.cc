@@ -438,8 +438,18 @@ struct Graph {
   int total_iters = 0;
   std::vector<NS> st_bak;
   std::vector<double> X_bak;
+  // VertexScale (g2otypes.h:294-311) of GlobalBundleAdjustmentNavStatePRV with bScaleOpt (src/Optimizer.cc:843-851): the
+  // visual edges become EdgeReprojectPRS[Stereo] (Xw = sc * X, :1132-1200).  One extra row / column of the reduced system
+  // after every keyframe vertex (id_scale = maxKFid + 1).  Off by default: nothing below changes the arithmetic then.
+  bool has_scale = false;
+  double sc = 1.0, sc_bak = 1.0;
+  int off_s = -1;
+  std::vector<double> Ws;  // per visual edge [3]: Js^T (w Omega) JX
 
   int d0() const { return pvr ? 9 : 6; }
+  void world_point(const VisEdge& e, double Xw[3]) const {
+    for (int k = 0; k < 3; ++k) Xw[k] = has_scale ? X[3 * e.p + k] * sc : X[3 * e.p + k];
+  }
 
   void initialize() {  // initializeOptimization(0) + buildIndexMapping
     const int K = (int)st.size();
@@ -452,11 +462,13 @@ struct Graph {
         off2[k] = np; np += 6;
       }
     }
+    off_s = -1;
+    if (has_scale) { off_s = np; np += 1; }
     vis_active.assign(vis.size(), 0);
     pt_active.assign(X.size() / 3, 0);
     for (size_t i = 0; i < vis.size(); ++i) {
       const VisEdge& e = vis[i];
-      const bool anyfree = off0[e.s] >= 0 || points_free;
+      const bool anyfree = off0[e.s] >= 0 || points_free || has_scale;
       vis_active[i] = e.level == 0 && anyfree;
       if (vis_active[i] && points_free) pt_active[e.p] = 1;
     }
@@ -471,14 +483,17 @@ struct Graph {
     }
   }
   void vis_error(VisEdge& e) {
-    reproj_error(cam, st[e.s], &X[3 * e.p], e.obs, e.stereo, e.err);
+    double Xw[3];
+    world_point(e, Xw);
+    reproj_error(cam, st[e.s], Xw, e.obs, e.stereo, e.err);
     double c = 0;
     for (int k = 0; k < (e.stereo ? 3 : 2); ++k) c += e.err[k] * (e.w * e.err[k]);
     e.chi2 = c;
   }
   double vis_depth(const VisEdge& e) {
-    double t[3];
-    return reproj_error(cam, st[e.s], &X[3 * e.p], e.obs, e.stereo, t);
+    double t[3], Xw[3];
+    world_point(e, Xw);
+    return reproj_error(cam, st[e.s], Xw, e.obs, e.stereo, t);
   }
   void den_error(DenseEdge& e) {
     if (e.type == 0) navstate_error(st[e.si], st[e.sj], *e.pre, gw, !pvr, e.err);
@@ -590,6 +605,7 @@ struct Graph {
       bl.assign((size_t)P * 3, 0.0);
       W.assign(vis.size() * (size_t)dv * 3, 0.0);
     }
+    if (has_scale) Ws.assign(vis.size() * (size_t)3, 0.0);
     double Ji[135], Jj[81], Jb[90];
     for (size_t i = 0; i < den.size(); ++i)
       if (den_active[i]) add_dense(den[i], dense_blocks(den[i], Ji, Jj, Jb));
@@ -597,8 +613,13 @@ struct Graph {
       if (!vis_active[i]) continue;
       const VisEdge& e = vis[i];
       const int DE = e.stereo ? 3 : 2;
-      double Jp[9], Jr[9], JX[9], r[2];
-      reproj_jac(cam, st[e.s], &X[3 * e.p], e.stereo, Jp, Jr, JX);
+      double Jp[9], Jr[9], JX[9], r[2], Xw[3], Js[3] = {0, 0, 0};
+      world_point(e, Xw);
+      reproj_jac(cam, st[e.s], Xw, e.stereo, Jp, Jr, JX);
+      if (has_scale) {  // J_scale = (Jproj Rcw) Xh, J_point = (Jproj Rcw) sc (g2otypes.h:517-521)
+        for (int k = 0; k < DE; ++k) Js[k] = JX[3 * k] * X[3 * e.p] + JX[3 * k + 1] * X[3 * e.p + 1] + JX[3 * k + 2] * X[3 * e.p + 2];
+        for (int k = 0; k < 9; ++k) JX[k] *= sc;
+      }
       e.rk.rho(e.chi2, r);
       const double w = r[1] * e.w;
       double J[3][9];  // pose Jacobian DE x dv: dp | (dv) | dphi
@@ -622,6 +643,28 @@ struct Graph {
             H[(size_t)(o + a) * np + o + c] += h;
           }
         }
+      }
+      if (has_scale) {
+        double sb = 0, sh = 0;
+        for (int k = 0; k < DE; ++k) {
+          sb += Js[k] * oe[k];
+          sh += (Js[k] * w) * Js[k];
+        }
+        b[off_s] += sb;
+        H[(size_t)off_s * np + off_s] += sh;
+        if (o >= 0)
+          for (int a = 0; a < dv; ++a) {
+            double h = 0;
+            for (int k = 0; k < DE; ++k) h += (J[k][a] * w) * Js[k];
+            H[(size_t)(o + a) * np + off_s] += h;
+            H[(size_t)off_s * np + o + a] += h;
+          }
+        if (points_free)
+          for (int c = 0; c < 3; ++c) {
+            double h = 0;
+            for (int k = 0; k < DE; ++k) h += (Js[k] * w) * JX[3 * k + c];
+            Ws[i * 3 + c] = h;
+          }
       }
       if (points_free) {
         double* Hl = &Hll[(size_t)9 * e.p];
@@ -701,6 +744,28 @@ struct Graph {
                   S[(size_t)(oa + r) * np + ob + c] -= WD[3 * r] * Wb[3 * c] + WD[3 * r + 1] * Wb[3 * c + 1] + WD[3 * r + 2] * Wb[3 * c + 2];
             }
           }
+          if (has_scale) {  // the scale row / column: every active edge of the point carries a 1x3 block Ws
+            for (size_t a = i0; a < i1; ++a) {
+              if (!vis_active[a]) continue;
+              const double* Wa = &Ws[a * 3];
+              double WD[3];
+              for (int c = 0; c < 3; ++c) WD[c] = Wa[0] * Di[c] + Wa[1] * Di[3 + c] + Wa[2] * Di[6 + c];
+              bs[off_s] -= Wa[0] * db[0] + Wa[1] * db[1] + Wa[2] * db[2];
+              for (size_t c2 = i0; c2 < i1; ++c2) {
+                if (!vis_active[c2]) continue;
+                const double* Wc = &Ws[c2 * 3];
+                S[(size_t)off_s * np + off_s] -= WD[0] * Wc[0] + WD[1] * Wc[1] + WD[2] * Wc[2];
+                const int ob = off0[vis[c2].s];
+                if (ob < 0) continue;
+                const double* Wb = &W[c2 * (size_t)dv * 3];
+                for (int c = 0; c < dv; ++c) {
+                  const double v = WD[0] * Wb[3 * c] + WD[1] * Wb[3 * c + 1] + WD[2] * Wb[3 * c + 2];
+                  S[(size_t)off_s * np + ob + c] -= v;
+                  S[(size_t)(ob + c) * np + off_s] -= v;
+                }
+              }
+            }
+          }
         }
         i0 = i1;
       }
@@ -725,6 +790,10 @@ struct Graph {
             for (int k = 0; k < 3; ++k)
               for (int r = 0; r < dv; ++r) c[k] -= Wa[3 * r + k] * x[oa + r];
           }
+          if (has_scale)
+            for (size_t a = i0; a < i1; ++a)
+              if (vis_active[a])
+                for (int k = 0; k < 3; ++k) c[k] -= Ws[a * 3 + k] * x[off_s];
           const double* Di = &Dinv[(size_t)9 * p];
           for (int a = 0; a < 3; ++a) xl[3 * p + a] = Di[3 * a] * c[0] + Di[3 * a + 1] * c[1] + Di[3 * a + 2] * c[2];
         }
@@ -746,6 +815,7 @@ struct Graph {
       for (size_t p = 0; p < pt_active.size(); ++p)
         if (pt_active[p])
           for (int k = 0; k < 3; ++k) X[3 * p + k] += xl[3 * p + k];
+    if (has_scale) sc += x[off_s];  // VertexScale::oplusImpl
   }
   double compute_scale() const {
     double s = 0;
@@ -774,6 +844,7 @@ struct Graph {
     do {
       st_bak = st;
       X_bak = X;
+      sc_bak = sc;
       const bool ok2 = solve_system();
       if ((int)x.size() != np) x.assign(np, 0.0);
       if (points_free && xl.size() != X.size()) xl.assign(X.size(), 0.0);
@@ -797,6 +868,7 @@ struct Graph {
         ni *= 2;
         st = st_bak;
         X = X_bak;
+        sc = sc_bak;
       }
       qmax++;
     } while (rho < 0 && qmax < 10 && !terminate());
@@ -1282,6 +1354,61 @@ int orc_global_ba_prv(const OrcBaProblem* pb_in, const OrcCamera* cam, int n_ite
   for (int k = 0; k < K; ++k) to_c(g.st[k], &states_out[k]);
   if (points_out) memcpy(points_out, g.X.data(), sizeof(double) * 3 * (size_t)P);
   return it;
+}
+
+// The same with bScaleOpt = true (System::FinalGBA, src/System.cc:28-29): VertexScale seeded with 1, visual edges
+// EdgeReprojectPRS[Stereo]; on return the points are multiplied by the recovered scale (src/Optimizer.cc:1258-1336).
+// Restated ahead of its device side; scale_out receives the vertex estimate.
+int orc_global_ba_prv_scale(const OrcBaProblem* pb_in, const OrcCamera* cam, int n_iterations, int robust,
+                            OrcNavState* states_out, double* points_out, double* edge_chi2, OrcBaResult* res,
+                            double* scale_out) {
+  const int K = pb_in->n_states, P = pb_in->n_points, E = pb_in->n_edges;
+  memset(res, 0, sizeof(*res));
+  *scale_out = 1.0;
+  for (int k = 0; k < K; ++k) states_out[k] = pb_in->states[k];
+  if (points_out) memcpy(points_out, pb_in->points, sizeof(double) * 3 * (size_t)P);
+  OrcBaProblem pb = *pb_in;
+  pb.global_ba = 1 | (robust ? 2 : 0);
+  pb.large = 0; pb.rec_init = 0;
+  Graph g;
+  int optit[2];
+  if (!build_lba_graph(&pb, cam, g, optit)) return 0;
+  g.has_scale = true;
+  g.sc = 1.0;
+  g.initialize();
+  g.compute_active_errors();
+  res->err0 = g.active_robust_chi2();
+  const int it = g.optimize(n_iterations);
+  res->iterations[0] = it;
+  g.compute_active_errors();
+  res->err_end = g.active_robust_chi2();
+  res->lambda_final = g.lambda;
+  res->accepted = 1;
+  *scale_out = g.sc;
+  if (edge_chi2)
+    for (int i = 0; i < E; ++i) edge_chi2[i] = g.vis[i].chi2;
+  for (int k = 0; k < K; ++k) to_c(g.st[k], &states_out[k]);
+  if (points_out)
+    for (size_t k = 0; k < (size_t)3 * P; ++k) points_out[k] = g.sc * g.X[k];
+  return it;
+}
+// One damped step of the LBA graph with a scale vertex at estimate scale0: x_pose [np] (the scale is the LAST entry).
+int orc_ba_debug_step_scale(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, double scale0, double* x_pose,
+                            double* x_points, double* chi2) {
+  Graph g;
+  int optit[2];
+  if (!build_lba_graph(pb, cam, g, optit)) return -1;
+  g.has_scale = true;
+  g.sc = scale0;
+  g.initialize();
+  g.compute_active_errors();
+  if (chi2) *chi2 = g.active_robust_chi2();
+  g.build_system();
+  g.lambda = lambda;
+  if (!g.solve_system()) return -2;
+  memcpy(x_pose, g.x.data(), sizeof(double) * g.np);
+  if (x_points) memcpy(x_points, g.xl.data(), sizeof(double) * g.xl.size());
+  return g.np;
 }
 
 // One damped Gauss-Newton step of the LBA graph at the input estimate (build + Schur solve with the given lambda):

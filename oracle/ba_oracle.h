@@ -109,6 +109,12 @@ int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* 
  * vertex set-up to before the write-back.  Returns the LM iterations run. */
 int orc_global_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, int n_iterations, int robust, OrcNavState* states_out,
                       double* points_out, double* edge_chi2, OrcBaResult* res);
+/* bScaleOpt = true (System::FinalGBA): VertexScale + EdgeReprojectPRS[Stereo]; points_out = scale * points. */
+int orc_global_ba_prv_scale(const OrcBaProblem* pb, const OrcCamera* cam, int n_iterations, int robust,
+                            OrcNavState* states_out, double* points_out, double* edge_chi2, OrcBaResult* res,
+                            double* scale_out);
+int orc_ba_debug_step_scale(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, double scale0, double* x_pose,
+                            double* x_points, double* chi2);
 
 /* One damped Gauss-Newton step (build + Schur solve at the given lambda) at the input estimate, for the tests'
  * cross-check against a dense solve of the full normal equations.  Returns the pose dimension np or < 0. */

@@ -543,3 +543,27 @@ def edge_navstate_g(nsi, nsj, pre, q_wI, GI):
     L.orc_edge_navstate_g(nsi.ctypes.data, nsj.ctypes.data, pre.ctypes.data, _p(q_wI), _p(GI), _p(e), _p(Ji), _p(Jj), _p(Jb),
                           _p(JG))
     return e, Ji, Jj, Jb, JG
+
+
+def global_ba_prv_scale(d, cam, n_iterations=10, robust=False):
+    """GlobalBundleAdjustmentNavStatePRV with bScaleOpt = true -> dict incl. `scale`; points are returned scaled."""
+    pb, keep = ba_problem_struct(d)
+    L = lib()
+    cam = np.ascontiguousarray(cam)
+    st = np.zeros(len(d["states"]), NAVSTATE_DTYPE); pts = np.zeros((len(d["points"]), 3))
+    chi2 = np.zeros(len(d["edge_state"])); res = np.zeros(1, BA_RESULT_DTYPE); sc = np.zeros(1)
+    L.orc_global_ba_prv_scale.argtypes = None
+    it = L.orc_global_ba_prv_scale(C.byref(pb), C.c_void_p(cam.ctypes.data), C.c_int(n_iterations), C.c_int(int(robust)), _p(st),
+                                   _p(pts), _p(chi2), _p(res), _p(sc))
+    return dict(states=st, points=pts, edge_chi2=chi2, res=res[0], iterations=it, scale=float(sc[0]))
+
+
+def ba_debug_step_scale(d, cam, lam, scale0, **kw):
+    L = lib()
+    L.orc_ba_debug_step_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    pb, keep = ba_problem_struct(d, **kw)
+    cam = np.ascontiguousarray(cam)
+    xp = np.zeros(15 * pb.n_states + 1); xl = np.zeros((pb.n_points, 3)); chi2 = np.zeros(1)
+    n = L.orc_ba_debug_step_scale(C.byref(pb), cam.ctypes.data, lam, scale0, _p(xp), _p(xl), _p(chi2))
+    assert n >= 0, n
+    return xp[:n], xl, chi2[0]

@@ -179,12 +179,9 @@ def _lba(seq, **kw):
     return cam, synth.make_lba_problem(seq, pre, kf, cam, n_local=8, n_fixed=6, n_points=300, seed=4, **kw)
 
 
-def test_schur_step_matches_dense_normal_equations(seq):
-    """F3: the oracle's Schur-complement solve equals a numpy solve of the full (poses + points) system assembled
-    independently from the per-edge Jacobians."""
-    cam, d = _lba(seq)
-    lam = 1.0
-    xp, xl, chi2 = O.ba_debug_step(d, cam, lam)
+def _dense_normal_equations(d, cam, scale=None):
+    """Full (poses [+ scale] + points) normal equations of the LBA graph assembled from the per-edge oracle functions,
+    independently of the oracle's Schur code.  Layout: [pose vertices (n) | scale (1, if given) | points (3P)]."""
     K, P = len(d["states"]), len(d["points"])
     off = {}; n = 0
     for k in range(K):
@@ -194,8 +191,8 @@ def test_schur_step_matches_dense_normal_equations(seq):
         if f & 2 and not f & 4:
             off[(k, 1)] = n; n += 3
             off[(k, 2)] = n; n += 6
-    assert n == len(xp)
-    N = n + 3 * P
+    ns = n + (1 if scale is not None else 0)
+    N = ns + 3 * P
     H = np.zeros((N, N)); b = np.zeros(N)
 
     def huber(c, delta):
@@ -205,13 +202,18 @@ def test_schur_step_matches_dense_normal_equations(seq):
     for i in range(len(d["edge_state"])):
         s, p = d["edge_state"][i], d["edge_point"][i]
         st = bool(d["edge_flags"][i] & EDGE_STEREO)
-        e, Jp, JX, _ = O.edge_reproject(cam, d["states"][s], d["points"][p], d["obs"][i], st)
+        if scale is None:
+            e, Jp, JX, _ = O.edge_reproject(cam, d["states"][s], d["points"][p], d["obs"][i], st)
+        else:
+            e, Jp, JX, Js = O.edge_reproject_scale(cam, d["states"][s], d["points"][p], scale, d["obs"][i], st)
         rows = 3 if st else 2
         w = float(d["inv_sigma2"][i]); c = w * (e[:rows] ** 2).sum()
         w *= huber(c, ds if st else dm)
-        blocks = [(n + 3 * p, JX[:rows])]
+        blocks = [(ns + 3 * p, JX[:rows])]
         if (s, 0) in off:
             blocks.append((off[(s, 0)], Jp[:rows]))
+        if scale is not None:
+            blocks.append((n, Js[:rows].reshape(rows, 1)))
         for oa, Ja in blocks:
             b[oa:oa + Ja.shape[1]] -= Ja.T @ (w * e[:rows])
             for ob, Jb_ in blocks:
@@ -239,9 +241,37 @@ def test_schur_step_matches_dense_normal_equations(seq):
             b[oa:oa + 6] -= Ja.T @ (wb * ib @ eb)
             for ob, Jb_ in blocks:
                 H[oa:oa + 6, ob:ob + 6] += Ja.T @ (wb * ib) @ Jb_
-    x = np.linalg.solve(H + lam * np.eye(N), b)
+    return H, b, ns
+
+
+def test_schur_step_matches_dense_normal_equations(seq):
+    """F3: the oracle's Schur-complement solve equals a numpy solve of the full (poses + points) system assembled
+    independently from the per-edge Jacobians."""
+    cam, d = _lba(seq)
+    lam = 1.0
+    xp, xl, chi2 = O.ba_debug_step(d, cam, lam)
+    H, b, n = _dense_normal_equations(d, cam)
+    assert n == len(xp)
+    x = np.linalg.solve(H + lam * np.eye(len(b)), b)
     assert np.allclose(xp, x[:n], rtol=1e-7, atol=1e-10)
     assert np.allclose(xl.ravel(), x[n:], rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("scale0", [1.0, 0.95])
+def test_schur_step_with_scale_vertex_matches_dense_normal_equations(seq, scale0):
+    """The scale row / column of the reduced camera system (VertexScale + EdgeReprojectPRS, bScaleOpt) against the dense
+    solve: pose-scale, scale-scale and scale-landmark blocks all enter the Schur complement."""
+    cam, d = _lba(seq)
+    d = dict(d)
+    d["points"] = d["points"] / scale0          # unscaled landmarks: the world points stay where they were
+    lam = 0.7
+    xp, xl, chi2 = O.ba_debug_step_scale(d, cam, lam, scale0)
+    H, b, n = _dense_normal_equations(d, cam, scale=scale0)
+    assert n == len(xp)
+    x = np.linalg.solve(H + lam * np.eye(len(b)), b)
+    assert np.allclose(xp, x[:n], rtol=1e-6, atol=1e-9), np.abs(xp - x[:n]).max()
+    assert np.allclose(xl.ravel(), x[n:], rtol=1e-6, atol=1e-9)
+    assert abs(xp[-1]) > 1e-9                   # the scale does move
 
 
 def test_local_ba_prv_converges(seq):
@@ -460,3 +490,24 @@ def test_gravity_direction_vertex_and_edge(seq):
         # a rotation about the gravity axis itself (third component) is not a degree of freedom: the update ignores it
         q2 = O.gdir_oplus(q, [0.0, 0.0])
         assert np.allclose(q2, q, atol=1e-15)
+
+
+def test_global_ba_with_scale_vertex(seq):
+    """GlobalBundleAdjustmentNavStatePRV with bScaleOpt (System::FinalGBA): same cost as the plain global BA on the same
+    map (the scale is a gauge direction of the free landmarks), landmarks stored at a wrong common scale are absorbed,
+    keyframe 0 stays fixed and the returned points are the scaled ones."""
+    cam = synth.euroc_camera()
+    kf = list(range(0, 60, 3))
+    pre = O.imu_preintegrate_frames(seq, kf, O.imu_noise())
+    g = synth.make_gba_problem(seq, pre, kf, cam, n_points=400, seed=3)
+    plain = O.global_ba_prv(g, cam, n_iterations=10, robust=False)
+    sc = O.global_ba_prv_scale(g, cam, n_iterations=10, robust=False)
+    assert sc["res"]["err_end"] < 1.05 * plain["res"]["err_end"] and sc["res"]["err_end"] < 0.2 * sc["res"]["err0"]
+    assert sc["states"][0]["p"].tobytes() == g["states"][0]["p"].tobytes()
+    assert abs(sc["scale"] - 1.0) < 0.05
+    assert np.median(np.linalg.norm(sc["points"] - plain["points"], axis=1)) < 0.02
+    # landmarks 8 % too small: with the metric scale pinned by the inertial edges the estimate s * X returns to the truth
+    g2 = dict(g); g2["points"] = g["points"] / 1.08
+    sc2 = O.global_ba_prv_scale(g2, cam, n_iterations=15, robust=False)
+    assert sc2["res"]["err_end"] < 1.2 * plain["res"]["err_end"]
+    assert np.median(np.linalg.norm(sc2["points"] - plain["points"], axis=1)) < 0.03
