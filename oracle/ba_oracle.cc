@@ -445,6 +445,21 @@ struct Graph {
   double sc = 1.0, sc_bak = 1.0;
   int off_s = -1;
   std::vector<double> Ws;  // per visual edge [3]: Js^T (w Omega) JX
+  // VertexGThetaXYRwI (g2otypes.h:674-698) of the IMU initialiser's call (pimu_initiator, src/Optimizer.cc:852-865): the
+  // inertial edges become EdgeNavStatePRVG with gw = RwI * GI; two more rows / columns after the scale (id_g =
+  // maxKFid + 2).  Off by default.
+  bool has_g = false;
+  Quat qwI{1, 0, 0, 0}, qwI_bak{1, 0, 0, 0};
+  double GI[3] = {0, 0, 0};
+  int off_g = -1;
+  double JGbuf[18];
+  void gravity(double g[3]) const {
+    if (!has_g) {
+      g[0] = gw[0]; g[1] = gw[1]; g[2] = gw[2];
+      return;
+    }
+    mulv(qmat(qwI), GI, g);
+  }
 
   int d0() const { return pvr ? 9 : 6; }
   void world_point(const VisEdge& e, double Xw[3]) const {
@@ -462,8 +477,9 @@ struct Graph {
         off2[k] = np; np += 6;
       }
     }
-    off_s = -1;
+    off_s = off_g = -1;
     if (has_scale) { off_s = np; np += 1; }
+    if (has_g) { off_g = np; np += 2; }
     vis_active.assign(vis.size(), 0);
     pt_active.assign(X.size() / 3, 0);
     for (size_t i = 0; i < vis.size(); ++i) {
@@ -476,7 +492,8 @@ struct Graph {
     for (size_t i = 0; i < den.size(); ++i) {
       const DenseEdge& e = den[i];
       bool anyfree = false;
-      if (e.type == 0) anyfree = off0[e.si] >= 0 || off0[e.sj] >= 0 || off1[e.si] >= 0 || off1[e.sj] >= 0 || off2[e.si] >= 0;
+      if (e.type == 0) anyfree = off0[e.si] >= 0 || off0[e.sj] >= 0 || off1[e.si] >= 0 || off1[e.sj] >= 0 || off2[e.si] >= 0 || has_g;
+      if (e.type == 3) anyfree = off2[e.si] >= 0;
       if (e.type == 1) anyfree = off2[e.si] >= 0 || off2[e.sj] >= 0;
       if (e.type == 2) anyfree = off0[e.si] >= 0 || off2[e.si] >= 0;
       den_active[i] = anyfree;
@@ -496,7 +513,16 @@ struct Graph {
     return reproj_error(cam, st[e.s], Xw, e.obs, e.stereo, t);
   }
   void den_error(DenseEdge& e) {
-    if (e.type == 0) navstate_error(st[e.si], st[e.sj], *e.pre, gw, !pvr, e.err);
+    if (e.type == 0) {
+      double g[3];
+      gravity(g);
+      navstate_error(st[e.si], st[e.sj], *e.pre, g, !pvr, e.err);
+    }
+    if (e.type == 3) {  // EdgeNavStateBias between the fixed prior-bias vertex (e.prior) and keyframe si's bias
+      const NS &a = e.prior, &c = st[e.si];
+      for (int k = 0; k < 3; ++k) e.err[k] = (c.bg[k] + c.dbg[k]) - (a.bg[k] + a.dbg[k]);
+      for (int k = 0; k < 3; ++k) e.err[3 + k] = (c.ba[k] + c.dba[k]) - (a.ba[k] + a.dba[k]);
+    }
     if (e.type == 1) {
       const NS &a = st[e.si], &c = st[e.sj];
       for (int k = 0; k < 3; ++k) e.err[k] = (c.bg[k] + c.dbg[k]) - (a.bg[k] + a.dbg[k]);
@@ -575,14 +601,34 @@ struct Graph {
   }
   std::vector<Blk> dense_blocks(const DenseEdge& e, double* Ji, double* Jj, double* Jb) {
     std::vector<Blk> blks;
+    if (e.type == 3) {
+      for (int i = 0; i < 36; ++i) Jj[i] = 0;
+      for (int i = 0; i < 6; ++i) Jj[7 * i] = 1;
+      blks = {{off2[e.si], 6, Jj, 6, 0}};
+      return blks;
+    }
     if (e.type == 0) {
-      navstate_jac(st[e.si], st[e.sj], *e.pre, gw, !pvr, e.err, Ji, Jj, Jb);
+      double g[3];
+      gravity(g);
+      navstate_jac(st[e.si], st[e.sj], *e.pre, g, !pvr, e.err, Ji, Jj, Jb);
+      if (has_g) {  // JG (g2otypes.h:868-876): P rows RiT dt^2/2 RwI GI^[:, 0:2], V rows RiT dt RwI GI^[:, 0:2], R rows 0
+        const M3 A = mul(tr(qmat(st[e.si].q)), mul(qmat(qwI), hat(GI)));
+        const double dt = e.pre->dt;
+        const int idR = pvr ? 6 : 3, idV = 9 - idR;
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 2; ++c) {
+            JGbuf[2 * r + c] = A.m[3 * r + c] * (dt * dt / 2.0);
+            JGbuf[2 * (idR + r) + c] = 0.0;
+            JGbuf[2 * (idV + r) + c] = A.m[3 * r + c] * dt;
+          }
+      }
       if (pvr) {
         blks = {{off0[e.si], 9, Ji, 9, 0}, {off0[e.sj], 9, Jj, 9, 0}, {off2[e.si], 6, Jb, 6, 0}};
       } else {
         blks = {{off0[e.si], 6, Ji, 9, 0}, {off0[e.sj], 6, Jj, 9, 0}, {off1[e.si], 3, Ji, 9, 6},
                 {off1[e.sj], 3, Jj, 9, 6}, {off2[e.si], 6, Jb, 6, 0}};
       }
+      if (has_g) blks.push_back({off_g, 2, JGbuf, 2, 0});
     } else if (e.type == 1) {
       for (int i = 0; i < 36; ++i) Ji[i] = Jj[i] = 0;
       for (int i = 0; i < 6; ++i) {
@@ -816,6 +862,10 @@ struct Graph {
         if (pt_active[p])
           for (int k = 0; k < 3; ++k) X[3 * p + k] += xl[3 * p + k];
     if (has_scale) sc += x[off_s];  // VertexScale::oplusImpl
+    if (has_g) {                    // VertexGThetaXYRwI::oplusImpl: RwI <- RwI Exp((dx, dy, 0))
+      const double w[3] = {x[off_g], x[off_g + 1], 0.0};
+      qwI = qnormalized(qmul(qwI, so3_exp_q(w)));
+    }
   }
   double compute_scale() const {
     double s = 0;
@@ -845,6 +895,7 @@ struct Graph {
       st_bak = st;
       X_bak = X;
       sc_bak = sc;
+      qwI_bak = qwI;
       const bool ok2 = solve_system();
       if ((int)x.size() != np) x.assign(np, 0.0);
       if (points_free && xl.size() != X.size()) xl.assign(X.size(), 0.0);
@@ -869,6 +920,7 @@ struct Graph {
         st = st_bak;
         X = X_bak;
         sc = sc_bak;
+        qwI = qwI_bak;
       }
       qmax++;
     } while (rho < 0 && qmax < 10 && !terminate());
@@ -1391,6 +1443,82 @@ int orc_global_ba_prv_scale(const OrcBaProblem* pb_in, const OrcCamera* cam, int
   if (points_out)
     for (size_t k = 0; k < (size_t)3 * P; ++k) points_out[k] = g.sc * g.X[k];
   return it;
+}
+// The IMU initialiser's call (pimu_initiator != nullptr, src/Odom/IMUInitialization.cpp:475: bRobust = false, bScaleOpt =
+// false): keyframe 0 keeps only PR fixed (V / Bias free, :825-831 — the caller's state_flags say so), gravity-direction
+// vertex seeded from gw (:852-865), EdgeNavStatePRVG on every pair (:955-957), one prior-bias edge from a fixed copy of the
+// earliest keyframe's bias with information invSigma / sum(dt) (:866-900, 1026-1054).  states[0] is the earliest keyframe.
+// gw_io: in = the initialiser's gravity, out = RwI * GI.
+int orc_global_ba_prv_init(const OrcBaProblem* pb_in, const OrcCamera* cam, int n_iterations, double gw_io[3],
+                           OrcNavState* states_out, double* points_out, double* edge_chi2, OrcBaResult* res) {
+  const int K = pb_in->n_states, P = pb_in->n_points, E = pb_in->n_edges;
+  memset(res, 0, sizeof(*res));
+  for (int k = 0; k < K; ++k) states_out[k] = pb_in->states[k];
+  if (points_out) memcpy(points_out, pb_in->points, sizeof(double) * 3 * (size_t)P);
+  OrcBaProblem pb = *pb_in;
+  pb.global_ba = 1;
+  pb.large = 0; pb.rec_init = 0;
+  memcpy(pb.gw, gw_io, 24);
+  Graph g;
+  int optit[2];
+  if (!build_lba_graph(&pb, cam, g, optit)) return 0;
+  g.has_g = true;
+  const double gn = std::sqrt(gw_io[0] * gw_io[0] + gw_io[1] * gw_io[1] + gw_io[2] * gw_io[2]);
+  g.GI[0] = 0; g.GI[1] = 0; g.GI[2] = gn;
+  double q[4];
+  orc_gdir_init(gw_io, q);
+  g.qwI = {q[0], q[1], q[2], q[3]};
+  // prior-bias edge on the earliest keyframe; sum_dt over every keyframe pair as the reference accumulates it (:940-947)
+  double sum_dt = 0;
+  for (int m = 0; m < pb.n_imu; ++m) {
+    double dtij = pb.preint[m].dt != 0 ? pb.preint[m].dt : pb.imu_dt_kf[m];
+    if (dtij <= (double)1e-6f) dtij = 15;
+    sum_dt += dtij;
+  }
+  if (K > 0 && g.has_vb[0]) {
+    DenseEdge e;
+    e.type = 3; e.si = 0; e.sj = 0; e.D = 6;
+    e.prior = g.st[0];
+    e.info.assign(36, 0.0);
+    for (int k = 0; k < 6; ++k) e.info[7 * k] = (k < 3 ? pb.inv_sigma_bg2 : pb.inv_sigma_ba2) / sum_dt;
+    g.den.push_back(e);
+  }
+  g.initialize();
+  g.compute_active_errors();
+  res->err0 = g.active_robust_chi2();
+  const int it = g.optimize(n_iterations);
+  res->iterations[0] = it;
+  g.compute_active_errors();
+  res->err_end = g.active_robust_chi2();
+  res->lambda_final = g.lambda;
+  res->accepted = 1;
+  g.gravity(gw_io);
+  if (edge_chi2)
+    for (int i = 0; i < E; ++i) edge_chi2[i] = g.vis[i].chi2;
+  for (int k = 0; k < K; ++k) to_c(g.st[k], &states_out[k]);
+  if (points_out) memcpy(points_out, g.X.data(), sizeof(double) * 3 * (size_t)P);
+  return it;
+}
+// One damped step of the LBA graph with a gravity-direction vertex seeded from gw: x_pose [np] (its two entries LAST).
+int orc_ba_debug_step_gdir(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, const double gw[3], double* x_pose,
+                           double* x_points, double* chi2) {
+  Graph g;
+  int optit[2];
+  if (!build_lba_graph(pb, cam, g, optit)) return -1;
+  g.has_g = true;
+  g.GI[0] = 0; g.GI[1] = 0; g.GI[2] = std::sqrt(gw[0] * gw[0] + gw[1] * gw[1] + gw[2] * gw[2]);
+  double q[4];
+  orc_gdir_init(gw, q);
+  g.qwI = {q[0], q[1], q[2], q[3]};
+  g.initialize();
+  g.compute_active_errors();
+  if (chi2) *chi2 = g.active_robust_chi2();
+  g.build_system();
+  g.lambda = lambda;
+  if (!g.solve_system()) return -2;
+  memcpy(x_pose, g.x.data(), sizeof(double) * g.np);
+  if (x_points) memcpy(x_points, g.xl.data(), sizeof(double) * g.xl.size());
+  return g.np;
 }
 // One damped step of the LBA graph with a scale vertex at estimate scale0: x_pose [np] (the scale is the LAST entry).
 int orc_ba_debug_step_scale(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, double scale0, double* x_pose,

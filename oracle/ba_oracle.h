@@ -113,6 +113,11 @@ int orc_global_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, int n_iterat
 int orc_global_ba_prv_scale(const OrcBaProblem* pb, const OrcCamera* cam, int n_iterations, int robust,
                             OrcNavState* states_out, double* points_out, double* edge_chi2, OrcBaResult* res,
                             double* scale_out);
+/* the IMU initialiser's call: gravity-direction vertex + EdgeNavStatePRVG + one prior-bias edge; gw_io in / out */
+int orc_global_ba_prv_init(const OrcBaProblem* pb, const OrcCamera* cam, int n_iterations, double gw_io[3],
+                           OrcNavState* states_out, double* points_out, double* edge_chi2, OrcBaResult* res);
+int orc_ba_debug_step_gdir(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, const double gw[3], double* x_pose,
+                           double* x_points, double* chi2);
 int orc_ba_debug_step_scale(const OrcBaProblem* pb, const OrcCamera* cam, double lambda, double scale0, double* x_pose,
                             double* x_points, double* chi2);
 

@@ -567,3 +567,27 @@ def ba_debug_step_scale(d, cam, lam, scale0, **kw):
     n = L.orc_ba_debug_step_scale(C.byref(pb), cam.ctypes.data, lam, scale0, _p(xp), _p(xl), _p(chi2))
     assert n >= 0, n
     return xp[:n], xl, chi2[0]
+
+
+def global_ba_prv_init(d, cam, n_iterations, gw):
+    """GlobalBundleAdjustmentNavStatePRV with an IMU initiator -> dict incl. the refined gravity `gw`."""
+    pb, keep = ba_problem_struct(d)
+    L = lib()
+    cam = np.ascontiguousarray(cam)
+    st = np.zeros(len(d["states"]), NAVSTATE_DTYPE); pts = np.zeros((len(d["points"]), 3))
+    chi2 = np.zeros(len(d["edge_state"])); res = np.zeros(1, BA_RESULT_DTYPE); g = np.array(gw, np.float64).copy()
+    L.orc_global_ba_prv_init.argtypes = None
+    it = L.orc_global_ba_prv_init(C.byref(pb), C.c_void_p(cam.ctypes.data), C.c_int(n_iterations), _p(g), _p(st), _p(pts), _p(chi2),
+                                  _p(res))
+    return dict(states=st, points=pts, edge_chi2=chi2, res=res[0], iterations=it, gw=g)
+
+
+def ba_debug_step_gdir(d, cam, lam, gw, **kw):
+    L = lib()
+    L.orc_ba_debug_step_gdir.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    pb, keep = ba_problem_struct(d, **kw)
+    cam = np.ascontiguousarray(cam); gw = np.ascontiguousarray(gw, np.float64)
+    xp = np.zeros(15 * pb.n_states + 2); xl = np.zeros((pb.n_points, 3)); chi2 = np.zeros(1)
+    n = L.orc_ba_debug_step_gdir(C.byref(pb), cam.ctypes.data, lam, _p(gw), _p(xp), _p(xl), _p(chi2))
+    assert n >= 0, n
+    return xp[:n], xl, chi2[0]

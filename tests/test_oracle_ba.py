@@ -179,7 +179,7 @@ def _lba(seq, **kw):
     return cam, synth.make_lba_problem(seq, pre, kf, cam, n_local=8, n_fixed=6, n_points=300, seed=4, **kw)
 
 
-def _dense_normal_equations(d, cam, scale=None):
+def _dense_normal_equations(d, cam, scale=None, gdir=None):
     """Full (poses [+ scale] + points) normal equations of the LBA graph assembled from the per-edge oracle functions,
     independently of the oracle's Schur code.  Layout: [pose vertices (n) | scale (1, if given) | points (3P)]."""
     K, P = len(d["states"]), len(d["points"])
@@ -191,7 +191,7 @@ def _dense_normal_equations(d, cam, scale=None):
         if f & 2 and not f & 4:
             off[(k, 1)] = n; n += 3
             off[(k, 2)] = n; n += 6
-    ns = n + (1 if scale is not None else 0)
+    ns = n + (1 if scale is not None else 0) + (2 if gdir is not None else 0)   # gdir = (q_wI, GI): two more columns
     N = ns + 3 * P
     H = np.zeros((N, N)); b = np.zeros(N)
 
@@ -222,12 +222,17 @@ def _dense_normal_equations(d, cam, scale=None):
         i, j = d["imu_i"][m], d["imu_j"][m]
         pre = d["preint"][m]
         fixed = bool(d["state_flags"][i] & 1)
-        e, Ji, Jj, Jb = O.edge_navstate(d["states"][i], d["states"][j], pre, d["gw"], 1)
+        if gdir is None:
+            e, Ji, Jj, Jb = O.edge_navstate(d["states"][i], d["states"][j], pre, d["gw"], 1)
+        else:
+            e, Ji, Jj, Jb, JG = O.edge_navstate_g(d["states"][i], d["states"][j], pre, gdir[0], gdir[1])
         info = np.linalg.inv(pre["SigmaPRV"]) * (1e-2 if fixed else 1.0)
         c = e @ info @ e
         wI = huber(c, float(np.float32(np.sqrt(16.919)))) if fixed else 1.0
         blocks = [((i, 0), Ji[:, :6]), ((j, 0), Jj[:, :6]), ((i, 1), Ji[:, 6:]), ((j, 1), Jj[:, 6:]), ((i, 2), Jb)]
         blocks = [(off[k], J) for k, J in blocks if k in off]
+        if gdir is not None:
+            blocks.append((ns - 2, JG))
         for oa, Ja in blocks:
             b[oa:oa + Ja.shape[1]] -= Ja.T @ (wI * info @ e)
             for ob, Jb_ in blocks:
@@ -511,3 +516,45 @@ def test_global_ba_with_scale_vertex(seq):
     sc2 = O.global_ba_prv_scale(g2, cam, n_iterations=15, robust=False)
     assert sc2["res"]["err_end"] < 1.2 * plain["res"]["err_end"]
     assert np.median(np.linalg.norm(sc2["points"] - plain["points"], axis=1)) < 0.03
+
+
+def test_schur_step_with_gravity_direction_vertex_matches_dense_normal_equations(seq):
+    """The two gravity-direction columns (VertexGThetaXYRwI + EdgeNavStatePRVG) of the reduced camera system against the
+    dense solve of the full normal equations."""
+    cam, d = _lba(seq)
+    gw = np.array([0.35, -0.25, -9.79]); gw *= 9.81 / np.linalg.norm(gw)     # a tilted estimate: the residuals see it
+    lam = 0.5
+    xp, xl, chi2 = O.ba_debug_step_gdir(d, cam, lam, gw)
+    H, b, n = _dense_normal_equations(d, cam, gdir=(O.gdir_init(gw), np.array([0, 0, 9.81])))
+    assert n == len(xp)
+    x = np.linalg.solve(H + lam * np.eye(len(b)), b)
+    assert np.allclose(xp, x[:n], rtol=1e-6, atol=1e-9), np.abs(xp - x[:n]).max()
+    assert np.allclose(xl.ravel(), x[n:], rtol=1e-6, atol=1e-9)
+    assert np.abs(xp[-2:]).max() > 1e-6
+
+
+def test_global_ba_of_the_imu_initialiser_refines_gravity(seq):
+    """GlobalBundleAdjustmentNavStatePRV as IMUInitialization calls it (gravity-direction vertex, keyframe 0 with free V /
+    Bias, prior-bias edge): a gravity estimate 2 degrees off is pulled back to the true direction, its norm is kept, the
+    cost falls and keyframe 0's pose stays fixed."""
+    cam = synth.euroc_camera()
+    kf = list(range(0, 60, 3))
+    pre = O.imu_preintegrate_frames(seq, kf, O.imu_noise())
+    g = dict(synth.make_gba_problem(seq, pre, kf, cam, n_points=400, seed=3))
+    flags = g["state_flags"].copy(); flags[0] = 1 | 2          # keyframe 0: PR fixed, V / Bias free (:825-831)
+    g["state_flags"] = flags
+    tilt = synth.so3_exp(np.array([np.deg2rad(2.0), np.deg2rad(-1.0), 0.0]))
+    gw0 = tilt @ synth.GRAVITY_W
+    out = O.global_ba_prv_init(g, cam, 15, gw0)
+
+    def ang(a, b):
+        return np.degrees(np.arccos(np.clip(a @ b / np.linalg.norm(a) / np.linalg.norm(b), -1, 1)))
+    assert ang(gw0, synth.GRAVITY_W) > 2.0
+    assert ang(out["gw"], synth.GRAVITY_W) < 0.3, ang(out["gw"], synth.GRAVITY_W)
+    assert abs(np.linalg.norm(out["gw"]) - np.linalg.norm(gw0)) < 1e-9
+    assert out["res"]["err_end"] < 0.2 * out["res"]["err0"]
+    assert out["states"][0]["p"].tobytes() == g["states"][0]["p"].tobytes()
+    assert out["states"][0]["q"].tobytes() == g["states"][0]["q"].tobytes()
+    assert not np.array_equal(out["states"][0]["v"], g["states"][0]["v"])      # free now
+    b0 = g["states"][0]["bg"] + g["states"][0]["dbg"]; b1 = out["states"][0]["bg"] + out["states"][0]["dbg"]
+    assert np.abs(b1 - b0).max() < 5e-3                                        # held by the prior-bias edge
