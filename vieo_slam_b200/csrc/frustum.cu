@@ -154,7 +154,7 @@ int vieo_frustum_batch_dev(const VieoFrustumFrame* frames_dev, int n_frames, con
                            const float* max_dist_dev, const float* min_dist_dev, const uint8_t* skip_dev,
                            uint8_t* inview_dev, float* proj_dev, int32_t* level_dev, float* viewcos_dev, float* depth_dev,
                            int32_t* n_inview_dev, void* stream) {
-  VIEO_ARG(n_frames >= 0, "bad argument");
+  VIEO_ARG(n_frames >= 0 && n_frames <= 65535, "bad argument (at most 65535 frames per call)");
   if (n_frames == 0) return VIEO_OK;
   VIEO_ARG(frames_dev && wP_dev && normal_dev && max_dist_dev && min_dist_dev && inview_dev && proj_dev && level_dev &&
                viewcos_dev && depth_dev && n_inview_dev, "null argument");
