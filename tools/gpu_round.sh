@@ -25,18 +25,23 @@ else
   stamp pytest2; tail -3 gpurun_out/${TAG}_pytest_gpu2.log
   timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench2.json 2> gpurun_out/${TAG}_bench2.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench2.err
   stamp bench2; cat gpurun_out/${TAG}_bench2.json
-  timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --cpu-frames 8 > gpurun_out/${TAG}_ncu_bench.log 2>&1
+  timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 1 --warmup 3 --cpu-frames 8 > gpurun_out/${TAG}_ncu_bench.log 2>&1
   stamp launches
-  timeout 330 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_fast_cells|k_orient_desc|k_quadtree|k_resize|k_stereo_match|k_sbp|k_frustum|k_pose_opt|k_imu_preint|k_ba_linearize|k_ba_schur|k_ba_chol' \
-    -s 60 -c 36 -o gpurun_out/${TAG}_prof python bench.py --steps 1 --warmup 3 --cpu-frames 8 --lba-workers 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
-  stamp ncu_full
-  # the summaries are made on the box too, in case the report is too large to travel
-  python tools/ncu_summary.py full gpurun_out/${TAG}_prof.ncu-rep gpurun_out/${TAG}_ncu_full.csv > /dev/null 2>&1
+  # ncu --set full in three short captures (one report each, summarised on the box; a report travels only if it is small):
+  # the front-end kernels of one step with source, the tracking kernels, a slice of one LocalBA window's chain
+  full() {  # name, kernel regex, skip, count, extra ncu flags, extra bench flags
+    timeout 200 ncu --set full --clock-control none $5 -k regex:"$2" -s $3 -c $4 -o gpurun_out/${TAG}_prof_$1 \
+      python bench.py --steps 1 --warmup 3 --cpu-frames 8 $6 > gpurun_out/${TAG}_ncu_full_$1.log 2>&1
+    python tools/ncu_summary.py full gpurun_out/${TAG}_prof_$1.ncu-rep gpurun_out/${TAG}_ncu_full_$1.csv > /dev/null 2>&1
+    SZ=$(stat -c %s gpurun_out/${TAG}_prof_$1.ncu-rep 2>/dev/null || echo 0)
+    if [ "$SZ" -gt 20000000 ]; then rm -f gpurun_out/${TAG}_prof_$1.ncu-rep; echo "report $1 ($SZ bytes) summarised on the box and dropped" >> gpurun_out/${TAG}_${WHAT}_steps.log; fi
+    stamp ncu_full_$1
+  }
+  full frontend 'k_fast_cells|k_resize|k_quadtree|k_orient_desc|k_stereo_match' 11 11 "--import-source on" "--lba 0"
+  full tracking 'k_sbp|k_frustum|k_pose_opt|k_imu_preint|k_knn2|k_proj_search|k_distinctive' 6 6 "" "--lba 0"
+  full lba 'k_ba_' 120 24 "" "--lba-workers 1"
   python tools/ncu_summary.py launches gpurun_out/${TAG}_launches.csv gpurun_out/${TAG}_launches.md > /dev/null 2>&1
-  SZ=$(stat -c %s gpurun_out/${TAG}_prof.ncu-rep 2>/dev/null || echo 0)
-  if [ "$SZ" -gt 40000000 ]; then rm -f gpurun_out/${TAG}_prof.ncu-rep; echo "report ($SZ bytes) summarised on the box and dropped" >> gpurun_out/${TAG}_${WHAT}_steps.log; fi
   stamp summaries; head -30 gpurun_out/${TAG}_launches.md
 fi
 cat gpurun_out/${TAG}_${WHAT}_steps.log
