@@ -133,6 +133,46 @@ def make_tracking_inputs(seed, F, preint_fn):
     return dict(imu=imu_in, pbs=pbs, cam=cam, Xw=arrays[0], obs=arrays[1], w=arrays[2], flags=arrays[3], seq=seq, sbp=sbp)
 
 
+def single_frame_latency(api, imgs1, trk, pre_gpu, matcher, device, reps=20):
+    """Median / minimum wall time of ONE stereo frame through the host-buffer API (copies included): front-end (two
+    extractions + rectified-stereo association), IMU pre-integration, the two guided searches with the visibility test,
+    two PoseOptimization calls.  imgs1: (1, 2, H, W) host images."""
+    from vieo_slam_b200 import synth
+    fe1 = api.StereoFrontend(EUROC["nfeatures"], EUROC["scale"], EUROC["nlevels"], EUROC["ini_th"], EUROC["min_th"], W, H,
+                             max_frames=1, device=device)
+    outs1 = fe1.alloc_outputs(1, pinned=True)
+    smp, seg, tt, bb = trk["imu"]
+    imu1 = (np.ascontiguousarray(smp[seg[0]:seg[1]]), np.array([0, seg[1] - seg[0]], np.int32), tt[:1], bb[:1])
+    sbp1 = synth.make_sbp_problem(91, n_frames=1, mode=synth.SBP_LAST_FRAME, n_kp=1200, n_q=SBP_QUERIES[0], th=7.0)
+    slp1 = synth.make_frustum_problem(92, n_frames=1, n_kp=1200, n_q=SBP_QUERIES[1], th=1.0, blocked_frac=0.3, skip_frac=0.1)
+    F = len(trk["pbs"]) // 2
+    pbs1 = np.ascontiguousarray(trk["pbs"][[0, F]])
+    bf = np.float32(EUROC["bf"]); minz = np.float32(bf / np.float32(EUROC["fx"]))
+    stages = {"front_end": [], "tracking": []}
+
+    def one():
+        t0 = time.perf_counter()
+        fe1.process(imgs1, outs1)
+        fe1.stereo_rectified(1, bf, minz)
+        t1 = time.perf_counter()
+        pre_gpu.preintegrate_batch(*imu1)
+        matcher.SearchByProjection(sbp1)
+        matcher.SearchLocalPoints(slp1, want_tracking_info=False)
+        api.Optimizer.PoseOptimizationBatch(pbs1, trk["cam"], trk["Xw"], trk["obs"], trk["w"], trk["flags"], device=device)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+    for _ in range(3):
+        one()
+    for _ in range(reps):
+        a, b = one()
+        stages["front_end"].append(1e3 * a); stages["tracking"].append(1e3 * b)
+    fe1.close()
+    tot = np.array(stages["front_end"]) + np.array(stages["tracking"])
+    return {"median": float(np.median(tot)), "min": float(tot.min()), "front_end_median": float(np.median(stages["front_end"])),
+            "tracking_median": float(np.median(stages["tracking"])), "reps": reps,
+            "what": "one stereo frame, host buffers in and out, tracking stages in sequence on one thread"}
+
+
 def make_lba_windows(seed, n, preint_fn):
     from vieo_slam_b200 import synth
     out = []
@@ -536,6 +576,13 @@ def run_gpu(args, rank, world, local_rank):
         traffic = None if per_image is None else int(per_image) * n_img   # per launch, like `achieved`
     except Exception:
         pass
+    # ---- single-frame latency (SURVEY.md 8d asks for both figures): ONE stereo frame through the same host-buffer calls,
+    # nothing batched; reported beside the throughput, never part of `value`.  Guarded: a failure here leaves null.
+    latency = None
+    try:
+        latency = single_frame_latency(api, host_np[0][:1], trk, pre_gpu, matcher, local_rank)
+    except Exception as ex:   # noqa: BLE001
+        print(f"single-frame latency not measured: {ex}", file=sys.stderr)
     # ---- CPU baseline: the oracle threaded like the reference, bounded sample
     cpu_frames = max(LBA_EVERY, args.cpu_frames - args.cpu_frames % LBA_EVERY)   # whole LocalBA periods, at least one
     cpu_lbas = make_lba_windows(203, 1, oracle_preint_fn()) if not lbas else lbas
@@ -553,6 +600,7 @@ def run_gpu(args, rank, world, local_rank):
                    "isolated_stage_ms": iso},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "single_frame_latency_ms": latency,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
