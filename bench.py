@@ -147,7 +147,7 @@ def single_frame_latency(api, imgs1, trk, pre_gpu, matcher, device, reps=20):
     slp1 = synth.make_frustum_problem(92, n_frames=1, n_kp=1200, n_q=SBP_QUERIES[1], th=1.0, blocked_frac=0.3, skip_frac=0.1)
     F = len(trk["pbs"]) // 2
     pbs1 = np.ascontiguousarray(trk["pbs"][[0, F]])
-    bf = np.float32(EUROC["bf"]); minz = np.float32(bf / np.float32(EUROC["fx"]))
+    bf = float(np.float32(EUROC["bf"])); minz = float(np.float32(EUROC["bf"]) / np.float32(EUROC["fx"]))
     stages = {"front_end": [], "tracking": []}
 
     def one():
