@@ -260,3 +260,35 @@ def test_proj_search_oracle_matches_naive_restatement():
                 found += b >= 0
                 gated += l >= 0 and b < 0
         assert found > 60 and gated > 20     # both outcomes occur
+
+
+def test_properties_of_the_restatements():
+    """Size-independent properties (hypothesis): PredictScale is monotone in the ratio and clamped; the winner of
+    ComputeDistinctiveDescriptors does not depend on how often the other observations' order is rotated behind it, and its
+    median is the minimum over all rows."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.floats(1e-3, 1e3), st.floats(1.0001, 1.5), st.floats(1.05, 2.5), st.integers(1, 16))
+    def monotone(ratio, step, sf, nl):
+        lsf = float(np.log(f32(sf)))
+        a = O.predict_scale(ratio, 1.0, lsf, nl)
+        b = O.predict_scale(ratio * step, 1.0, lsf, nl)
+        assert 0 <= a <= b <= nl - 1
+    monotone()
+
+    rng = np.random.default_rng(8)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(0, 2 ** 31 - 1))
+    def distinct(n, seed):
+        r = np.random.default_rng(seed)
+        proto = r.integers(0, 256, 32, dtype=np.uint8)
+        d = np.stack([np.bitwise_xor(proto, (r.random(32) < 0.08).astype(np.uint8) * r.integers(1, 256, 32, dtype=np.uint8))
+                      for _ in range(n)])
+        best, med = O.distinctive_descriptors(d, [0, n])
+        ints = [int.from_bytes(x.tobytes(), "little") for x in d]
+        meds = [sorted((a ^ c).bit_count() for c in ints)[int(0.5 * (n - 1))] for a in ints]
+        assert med[0] == min(meds) and best[0] == meds.index(min(meds))
+    distinct()
+    del rng
