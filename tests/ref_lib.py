@@ -1,0 +1,129 @@
+"""ctypes binding of oracle/_ref/libref.so — TEST INFRASTRUCTURE ONLY.
+
+libref.so is the REFERENCE's own src/ORBextractor.cc (whole unit) and two ORBmatcher member functions, compiled
+unchanged by oracle/ref_build/Makefile (needs /root/reference; the prebuilt .so travels to the GPU box).  It exists to
+pin the oracle restatement: tests assert oracle == _ref.  Nothing under vieo_slam_b200/ may load it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle_lib import KP_DTYPE, _p
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "_ref", "libref.so")
+REF_SRC = "/root/reference"
+
+
+def available():
+    """True when libref.so exists or can be built (the reference sources are present)."""
+    return os.path.exists(_SO) or os.path.isdir(os.path.join(REF_SRC, "src"))
+
+
+def build(force=False):
+    if os.path.isdir(os.path.join(REF_SRC, "src")):  # make decides whether anything is stale
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle", "ref_build")] + (["-B"] if force else []),
+                              stdout=subprocess.DEVNULL)
+    if not os.path.exists(_SO):
+        raise RuntimeError("oracle/_ref/libref.so missing and /root/reference absent: cannot build the compiled reference")
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = _lib = C.CDLL(build())
+        i32p = C.POINTER(C.c_int32)
+        L.ref_orb_create.restype = C.c_void_p
+        L.ref_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_orb_destroy.argtypes = [C.c_void_p]
+        L.ref_orb_tables.argtypes = [C.c_void_p] * 7
+        L.ref_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, i32p]
+        L.ref_orb_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
+        L.ref_orb_get_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_quadtree.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int]
+        L.ref_ic_angle.restype = C.c_float
+        L.ref_ic_angle.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.ref_orb_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                         C.c_void_p]
+        L.ref_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    return _lib
+
+
+class RefOrb:
+    """The reference's ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST), compiled here."""
+
+    def __init__(self, nfeatures=1200, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.h = lib().ref_orb_create(nfeatures, scale, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_orb_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sc, isc, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        q, um = np.empty(n, np.int32), np.empty(16, np.int32)
+        lib().ref_orb_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(q), _p(um))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, quota=q, umax=um)
+
+    def extract(self, img, lapping=None, cap=8192):
+        """operator(): returns (n, kps, desc, ret) like OrbOracle.extract (ret = monoIndex or -1)."""
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int32(0)
+        lap = None if lapping is None else np.asarray(lapping, np.int32)
+        if img is None or img.size == 0:
+            ret = lib().ref_orb_extract(self.h, None, 0, 0, 0, None, _p(kps), _p(desc), cap, C.byref(n))
+            return 0, kps[:0], desc[:0], ret
+        img = np.ascontiguousarray(img, np.uint8)
+        ret = lib().ref_orb_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0],
+                                    None if lap is None else _p(lap), _p(kps), _p(desc), cap, C.byref(n))
+        assert ret != -2, "capacity"
+        return n.value, kps[:n.value], desc[:n.value], ret
+
+    def level(self, l):
+        w, h = C.c_int32(), C.c_int32()
+        assert lib().ref_orb_level_size(self.h, l, C.byref(w), C.byref(h)) == 0
+        out = np.empty((h.value, w.value), np.uint8)
+        lib().ref_orb_get_level(self.h, l, _p(out))
+        return out
+
+    def quadtree(self, xyr, minX, maxX, minY, maxY, N, level=0):
+        xyr = np.ascontiguousarray(xyr, np.int32)
+        out = np.empty((max(len(xyr), 1), 3), np.int32)
+        n = lib().ref_quadtree(self.h, _p(xyr), len(xyr), minX, maxX, minY, maxY, N, level, _p(out), len(out))
+        assert n >= 0
+        return out[:n]
+
+    def ic_angle(self, img, x, y):
+        img = np.ascontiguousarray(img, np.uint8)
+        return lib().ref_ic_angle(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], float(x), float(y))
+
+
+def orb_descriptor(blurred, x, y, angle_deg):
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    d = np.empty(32, np.uint8)
+    lib().ref_orb_descriptor(_p(blurred), blurred.shape[1], blurred.shape[0], blurred.strides[0], float(x), float(y),
+                             float(angle_deg), _p(d))
+    return d
+
+
+def descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return lib().ref_descriptor_distance(_p(a), _p(b))
+
+
+def three_maxima(sizes):
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    out = np.empty(3, np.int32)
+    lib().ref_three_maxima(_p(sizes), len(sizes), _p(out))
+    return tuple(int(v) for v in out)

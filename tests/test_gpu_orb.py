@@ -44,6 +44,30 @@ def test_extract_matches_goldens_and_oracle(api, goldens):
         assert np.array_equal(orb.debug_candidates(0, l), g[f"A_cand{l}"].astype(np.int32))
 
 
+def test_extract_matches_compiled_reference(api):
+    """The CUDA extractor against the REFERENCE's own src/ORBextractor.cc compiled unchanged (oracle/_ref/libref.so, built
+    in the container from /root/reference and shipped prebuilt): keypoints, order, angles, descriptors, lapping split."""
+    import ref_lib as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    from vieo_slam_b200.synth import texture
+    for (nf, sc, nl), img, lap in [((1200, 1.2, 8), texture(480, 752, 7), None),
+                                   ((1200, 1.2, 8), texture(480, 752, 11, gain=0.35), None),
+                                   ((1000, 1.2, 8), texture(512, 512, 21), (0, 10000)),
+                                   ((1000, 1.2, 8), texture(512, 512, 22), (100, 200)),
+                                   ((187, 2.0, 4), texture(480, 640, 31), None)]:
+        h, w = img.shape
+        orb = api.ORBextractor(nf, sc, nl, 20, 7, w, h, max_batch=2)
+        ret, kps, desc = orb(img, pvLappingArea=None if lap is None else list(lap), want_pyramid=True)
+        ref = R.RefOrb(nf, sc, nl, 20, 7)
+        rn, rkps, rdesc, rret = ref.extract(img, lap)
+        assert len(kps) == rn and ret == rret
+        assert kps.tobytes() == rkps.tobytes() and np.array_equal(desc, rdesc)
+        for l in range(nl):
+            assert np.array_equal(orb.mvImagePyramid[l], ref.level(l))
+        orb.close()
+
+
 def test_extract_small_dark_and_scale2(api, goldens):
     g = goldens
     _same_extract(api, g["B_img"], 300, 1.2, 4)
