@@ -273,7 +273,11 @@ typedef struct VieoBaProblem {
   int32_t large;       /* bLarge */
   int32_t rec_init;    /* bRecInit */
   int32_t visual_only; /* Optimizer::LocalBundleAdjustment: PR vertices only, no inertial edges */
-  int32_t global_ba;   /* 0; vieo_global_ba_prv sets bit 0 (graph of GlobalBundleAdjustmentNavStatePRV) and bit 1 = bRobust */
+  int32_t global_ba;   /* 0; vieo_global_ba_prv[_ex] sets bit 0 (graph of GlobalBundleAdjustmentNavStatePRV), bit 1 = bRobust,
+                          bit 2 = VertexScale + EdgeReprojectPRS[Stereo] (bScaleOpt), bit 3 = VertexGThetaXYRwI +
+                          EdgeNavStatePRVG, bit 4 = the prior-bias edge on states[0] (pimu_initiator sets 3 and 4); bits
+                          2 - 4 need a handle from vieo_ba_create_global */
+  double scale_init;   /* estimate VertexScale starts from (bit 2); <= 0 means 1 (setEstimate(1.), src/Optimizer.cc:845) */
 } VieoBaProblem;
 typedef struct VieoBaResult {
   double err0, err_end; /* activeRobustChi2 before / after (src/Optimizer.cc:539, 652), rounded to float like the reference */
@@ -311,6 +315,27 @@ int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* c
 int vieo_global_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, int n_iterations, int robust,
                        const volatile uint8_t* stop, VieoNavState* states_out, double* points_out, double* edge_chi2,
                        VieoBaResult* res);
+/* The two other callers of GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342):
+ *   scale_opt  bScaleOpt = true — System::FinalGBA (src/System.cc:24-29): VertexScale (g2otypes.h:294-311, :843-851)
+ *              seeded with 1 as one more row / column of the reduced camera system, every reprojection edge an
+ *              EdgeReprojectPRS[Stereo] (:1132-1200; Xw = s X, J_scale = Jproj Rcw X, g2otypes.h:517-521); points_out are
+ *              multiplied by the recovered scale (:1311-1334), `scale` returns the vertex estimate;
+ *   imu_init   pimu_initiator != nullptr — IMUInitialization::Run (src/Odom/IMUInitialization.cpp:475; the caller passes
+ *              robust = 0 and state_flags 1|2 for keyframe 0: PR fixed, V / Bias free, :825-831): VertexGThetaXYRwI
+ *              (g2otypes.h:674-698, :852-865) seeded from `gw`, EdgeNavStatePRVG on every keyframe pair (:955-957), one
+ *              EdgeNavStateBias from a fixed copy of states[0]'s bias with information invSigma / sum(dt) (:866-900,
+ *              :1026-1054; states[0] must be the earliest keyframe); `gw` returns RwI * GI (:1262-1275).
+ * ex == NULL is vieo_global_ba_prv. */
+typedef struct VieoGbaExtra {
+  int32_t scale_opt, imu_init;
+  double scale; /* out */
+  double gw[3]; /* in (imu_init) / out */
+} VieoGbaExtra;
+int vieo_global_ba_prv_ex(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, int n_iterations, int robust,
+                          VieoGbaExtra* ex, const volatile uint8_t* stop, VieoNavState* states_out, double* points_out,
+                          double* edge_chi2, VieoBaResult* res);
+/* Estimates of the border vertices of the current problem: VertexScale (1 without it) and RwI * GI (gw without it). */
+int vieo_ba_get_border(vieo_ba_t* h, double* scale_out, double* gw_out /* nullable [3] */);
 /* Building blocks (what `optimizer.optimize(n)` and friends do), for callers that keep the policy on their side. */
 int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam);
 int vieo_ba_chi2_large_set_level(vieo_ba_t* h, float rat);           /* GraphOperator::Chi2LargeSetLevel */

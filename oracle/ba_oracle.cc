@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "so3_oracle.h"
@@ -340,17 +341,57 @@ void inv3(const double* D, double* I) {
   I[6] = c02 * id; I[7] = (D[1] * D[6] - D[0] * D[7]) * id; I[8] = (D[0] * D[4] - D[1] * D[3]) * id;
 }
 // Cholesky solve A x = b (A symmetric, full storage); false when a pivot is not positive (LDLT::isPositive)
+// Dense Cholesky (lower triangle, row-major) + two triangular solves.  Every entry is the scalar recurrence
+//   L[i][j] = (A[i][j] - sum_{k<j} L[i][k] L[j][k]) / L[j][j],  k ascending,
+// exactly as before; two things make map-sized systems (global BA, n ~ 6000) practical without changing one bit of it:
+//  * skyline: first[i] = first structurally non-zero column of row i (fill-in never moves it left), sums start at
+//    max(first[i], first[j]) — the skipped terms are products with exact zeros;
+//  * column blocks of 64: once the diagonal block is done, the rows below are independent and are spread over the host
+//    threads (each entry still sums in the same order).
 bool chol_solve(std::vector<double>& A, int n, const double* b, double* x) {
-  for (int j = 0; j < n; ++j) {
-    double d = A[j * n + j];
-    for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
-    if (!(d > 0) || !std::isfinite(d)) return false;
-    d = std::sqrt(d);
-    A[j * n + j] = d;
-    for (int i = j + 1; i < n; ++i) {
-      double s = A[i * n + j];
-      for (int k = 0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
-      A[i * n + j] = s / d;
+  const size_t N = (size_t)n;
+  std::vector<int> first(n);
+  for (int i = 0; i < n; ++i) {
+    int f = 0;
+    while (f < i && A[i * N + f] == 0.0) ++f;
+    first[i] = f;
+  }
+  auto entry = [&](int i, int j) {  // L[i][j] for i > j, given L[j][j]
+    double s = A[i * N + j];
+    const double* ri = &A[i * N];
+    const double* rj = &A[j * N];
+    for (int k = std::max(first[i], first[j]); k < j; ++k) s -= ri[k] * rj[k];
+    A[i * N + j] = s / rj[j];
+  };
+  const int NB = 64;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int j1 = std::min(j0 + NB, n);
+    for (int j = j0; j < j1; ++j) {  // diagonal block, serial
+      double d = A[j * N + j];
+      for (int k = first[j]; k < j; ++k) d -= A[j * N + k] * A[j * N + k];
+      if (!(d > 0) || !std::isfinite(d)) return false;
+      A[j * N + j] = std::sqrt(d);
+      for (int i = j + 1; i < j1; ++i)
+        if (first[i] <= j) entry(i, j);
+    }
+    const int rows = n - j1;
+    if (rows <= 0) continue;
+    auto work = [&](int r0, int r1) {
+      for (int i = r0; i < r1; ++i)
+        for (int j = std::max(j0, first[i]); j < j1; ++j) entry(i, j);
+    };
+    const int nt = (int)std::min<unsigned>(hw, (unsigned)std::max(1, rows / 64));
+    if (nt <= 1) {
+      work(j1, n);
+    } else {
+      std::vector<std::thread> th;
+      // interleaved chunks: the rows' costs grow with i
+      for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t] {
+          for (int c = j1 + 16 * t; c < n; c += 16 * nt) work(c, std::min(c + 16, n));
+        });
+      for (auto& q : th) q.join();
     }
   }
   std::vector<double> y(n);

@@ -258,3 +258,103 @@ def test_global_ba_config5_sized_properties(big_ba):
     assert 0.5 < out["res"]["err_end"] / (2.7 * len(d["edge_state"])) < 1.5
     again = big_ba.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=10, bRobust=False)
     assert again["states"].tobytes() == out["states"].tobytes() and again["points"].tobytes() == out["points"].tobytes()
+
+
+# ---------------------------------------------------------------- global BA: scale vertex and gravity-direction vertex
+def test_gba_scale_single_step_matches_oracle(big_ba):
+    """One damped step with VertexScale (EdgeReprojectPRS[Stereo]) as the border row / column of the reduced camera system:
+    pose increments, the scale increment (last entry) and the landmark back-substitution against the oracle."""
+    _, _, cam, d = _gba(15, 400)
+    for sc0 in (1.0, 1.03):
+        big_ba.set_problem(d, cam, global_ba=4, scale_init=sc0)
+        for lam in (1.0, 1e-3):
+            xp, xl, H, b = big_ba.debug_step(lam)
+            oxp, oxl, _ = O.ba_debug_step_scale(d, cam, lam, sc0)
+            assert len(xp) == len(oxp) == 14 * 15 + 1
+            assert np.abs(xp - oxp).max() <= 1e-8 * max(1.0, np.abs(oxp).max()), np.abs(xp - oxp).max()
+            assert np.abs(xl - oxl).max() <= 1e-8 * max(1.0, np.abs(oxl).max())
+
+
+def test_gba_gdir_single_step_matches_oracle(big_ba):
+    """One damped step with VertexGThetaXYRwI + EdgeNavStatePRVG (two border rows / columns) against the oracle."""
+    _, _, cam, d = _gba(15, 400)
+    gw = np.array(d["gw"], np.float64)
+    # a gravity estimate 2 degrees off, as the initialiser hands it over
+    a = np.deg2rad(2.0)
+    R = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    gw0 = R @ gw
+    d2 = dict(d)
+    d2["gw"] = gw0
+    big_ba.set_problem(d2, cam, global_ba=8)
+    for lam in (1.0, 1e-3):
+        xp, xl, H, b = big_ba.debug_step(lam)
+        oxp, oxl, _ = O.ba_debug_step_gdir(d2, cam, lam, gw0)
+        assert len(xp) == len(oxp) == 14 * 15 + 2
+        assert np.abs(xp - oxp).max() <= 1e-8 * max(1.0, np.abs(oxp).max()), np.abs(xp - oxp).max()
+        assert np.abs(xl - oxl).max() <= 1e-8 * max(1.0, np.abs(oxl).max())
+
+
+def _cmp_gba(out, ref, d):
+    assert out["iterations"] == ref["iterations"]
+    for k in ("err0", "err_end"):
+        assert abs(out["res"][k] - ref["res"][k]) <= 1e-6 * abs(ref["res"][k]), (k, out["res"][k], ref["res"][k])
+    for f in ("p", "q", "v", "dbg", "dba"):
+        assert np.abs(out["states"][f] - ref["states"][f]).max() < 1e-7, f
+    assert np.abs(out["points"] - ref["points"]).max() < 1e-6
+    sc = np.maximum(np.abs(ref["edge_chi2"]), 1.0)
+    assert (np.abs(out["edge_chi2"] - ref["edge_chi2"]) / sc).max() < 1e-6
+
+
+@pytest.mark.parametrize("robust,outl,map_scale", [(False, 0.0, 1.0), (False, 0.0, 1.04), (True, 0.05, 0.97)])
+def test_global_ba_scale_matches_oracle(big_ba, robust, outl, map_scale):
+    """GlobalBundleAdjustmentNavStatePRV with bScaleOpt = true (System::FinalGBA) at 40 keyframes against
+    orc_global_ba_prv_scale: chi2 1e-6, states, scaled points, the recovered scale; a map whose points are 1 / map_scale of
+    the metric ones ("unscaled Xw but scaled pwb") must come back with scale ~ map_scale."""
+    _, _, cam, d = _gba(40, 1500, seed=5, outlier_frac=outl)
+    d = dict(d)
+    if map_scale != 1.0:
+        d["points"] = d["points"] / map_scale
+    out = big_ba.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=10, bRobust=robust, bScaleOpt=True)
+    ref = O.global_ba_prv_scale(d, cam, n_iterations=10, robust=robust)
+    _cmp_gba(out, ref, d)
+    assert abs(out["scale"] - ref["scale"]) < 1e-8
+    assert out["states"][0].tobytes() == d["states"][0].tobytes()
+    if map_scale != 1.0:
+        assert abs(out["scale"] - map_scale) < 0.01, out["scale"]
+
+
+def test_global_ba_imu_init_matches_oracle(big_ba):
+    """The IMU initialiser's call (pimu_initiator != nullptr): keyframe 0 PR fixed / V, Bias free, gravity-direction vertex,
+    EdgeNavStatePRVG, prior-bias edge — against orc_global_ba_prv_init, and the 2-degree gravity error is removed."""
+    _, _, cam, d = _gba(30, 1000, seed=6)
+    d = dict(d)
+    fl = np.array(d["state_flags"], np.uint8).copy()
+    fl[0] = 1 | 2  # PR fixed, V / Bias free (src/Optimizer.cc:825-831)
+    d["state_flags"] = fl
+    gw = np.array(d["gw"], np.float64)
+    a = np.deg2rad(2.0)
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    gw0 = R @ gw
+    out = big_ba.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=10, bRobust=False, imu_init_gw=gw0)
+    ref = O.global_ba_prv_init(d, cam, 10, gw0)
+    _cmp_gba(out, ref, d)
+    assert np.abs(out["gw"] - ref["gw"]).max() < 1e-8
+    ang = np.degrees(np.arccos(np.clip(out["gw"] @ gw / (np.linalg.norm(out["gw"]) * np.linalg.norm(gw)), -1, 1)))
+    assert ang < 0.2, ang
+    assert abs(np.linalg.norm(out["gw"]) - np.linalg.norm(gw0)) < 1e-9  # only the direction is a variable
+
+
+def test_global_ba_config5_scale_matches_oracle_value(big_ba):
+    """BASELINE configs[4] AS SPECIFIED: 400 keyframes, ~25k points, ~320k observations, nIterations = 20, no robust
+    kernel, WITH the scale vertex (System::FinalGBA, src/System.cc:24-29) — compared against the oracle's value (its dense
+    Cholesky is skyline-blocked and threaded, bit-identical to the scalar recurrence, so 400 keyframes take ~30 s)."""
+    s, kf, cam, d = _gba(400, 25000, seed=8)
+    out = big_ba.GlobalBundleAdjustmentNavStatePRV(d, cam, nIterations=20, bRobust=False, bScaleOpt=True)
+    ref = O.global_ba_prv_scale(d, cam, n_iterations=20, robust=False)
+    assert out["iterations"] == ref["iterations"], (out["iterations"], ref["iterations"])
+    for k in ("err0", "err_end"):
+        assert abs(out["res"][k] - ref["res"][k]) <= 1e-6 * abs(ref["res"][k]), (k, out["res"][k], ref["res"][k])
+    assert abs(out["scale"] - ref["scale"]) < 1e-7
+    assert np.abs(out["states"]["p"] - ref["states"]["p"]).max() < 1e-6  # << 1 mm (north_star: 1 mm ATE)
+    assert np.abs(out["points"] - ref["points"]).max() < 1e-5
+    assert out["states"][0].tobytes() == d["states"][0].tobytes()

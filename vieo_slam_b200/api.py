@@ -102,6 +102,8 @@ def lib():
         L.vieo_ba_stream.restype = vp
         L.vieo_local_ba_prv.argtypes = [vp] * 9
         L.vieo_global_ba_prv.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+        L.vieo_global_ba_prv_ex.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+        L.vieo_ba_get_border.argtypes = [vp, vp, vp]
         L.vieo_ba_set_problem.argtypes = [vp, vp, vp]
         L.vieo_ba_chi2_large_set_level.argtypes = [vp, C.c_float]
         L.vieo_ba_active_robust_chi2.argtypes = [vp, i32, vp]
@@ -609,7 +611,12 @@ class VieoBaProblem(C.Structure):
                 ("edge_point", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p), ("edge_flags", C.c_void_p),
                 ("imu_i", C.c_void_p), ("imu_j", C.c_void_p), ("preint", C.c_void_p), ("imu_dt_kf", C.c_void_p),
                 ("gw", C.c_double * 3), ("inv_sigma_bg2", C.c_double), ("inv_sigma_ba2", C.c_double),
-                ("large", C.c_int32), ("rec_init", C.c_int32), ("visual_only", C.c_int32), ("global_ba", C.c_int32)]
+                ("large", C.c_int32), ("rec_init", C.c_int32), ("visual_only", C.c_int32), ("global_ba", C.c_int32),
+                ("scale_init", C.c_double)]
+
+
+class VieoGbaExtra(C.Structure):
+    _fields_ = [("scale_opt", C.c_int32), ("imu_init", C.c_int32), ("scale", C.c_double), ("gw", C.c_double * 3)]
 
 
 _BA_ARRAYS = (("states", NAVSTATE_DTYPE), ("state_flags", np.uint8), ("points", np.float64), ("edge_state", np.int32),
@@ -674,26 +681,47 @@ class BundleAdjuster:
         _check(lib().vieo_local_ba_prv(self._h, C.byref(pb), _p(cam), _p(stop), _p(st), _p(pts), _p(chi2), _p(erase), _p(res)))
         return dict(states=st, points=pts, edge_chi2=chi2, erase=erase, res=res[0])
 
-    def GlobalBundleAdjustmentNavStatePRV(self, d, cam, nIterations=5, bRobust=True, stop=None):
-        """Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342; bScaleOpt = false) on the flattened
-        map; the handle must have been created with global_ba=True."""
+    def GlobalBundleAdjustmentNavStatePRV(self, d, cam, nIterations=5, bRobust=True, stop=None, bScaleOpt=False,
+                                          imu_init_gw=None):
+        """Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342) on the flattened map; the handle must
+        have been created with global_ba=True.  bScaleOpt: the scale vertex of System::FinalGBA (result `scale`, points
+        returned scaled).  imu_init_gw: the IMU initialiser's call (pimu_initiator) with its gravity estimate (result
+        `gw` = refined gravity)."""
         pb, keep = ba_problem(d)
         cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
         st = np.zeros(pb.n_states, NAVSTATE_DTYPE); pts = np.zeros((pb.n_points, 3)); chi2 = np.zeros(pb.n_edges)
         res = np.zeros(1, BA_RESULT_DTYPE)
-        it = _check(lib().vieo_global_ba_prv(self._h, C.byref(pb), _p(cam), int(nIterations), int(bRobust), _p(stop), _p(st),
-                                             _p(pts), _p(chi2), _p(res)))
-        return dict(states=st, points=pts, edge_chi2=chi2, res=res[0], iterations=it)
+        if not bScaleOpt and imu_init_gw is None:
+            it = _check(lib().vieo_global_ba_prv(self._h, C.byref(pb), _p(cam), int(nIterations), int(bRobust), _p(stop),
+                                                 _p(st), _p(pts), _p(chi2), _p(res)))
+            return dict(states=st, points=pts, edge_chi2=chi2, res=res[0], iterations=it)
+        ex = VieoGbaExtra()
+        ex.scale_opt, ex.imu_init = int(bool(bScaleOpt)), int(imu_init_gw is not None)
+        if imu_init_gw is not None:
+            ex.gw = (C.c_double * 3)(*[float(v) for v in imu_init_gw])
+        it = _check(lib().vieo_global_ba_prv_ex(self._h, C.byref(pb), _p(cam), int(nIterations), int(bRobust), C.byref(ex),
+                                                _p(stop), _p(st), _p(pts), _p(chi2), _p(res)))
+        return dict(states=st, points=pts, edge_chi2=chi2, res=res[0], iterations=it, scale=float(ex.scale),
+                    gw=np.array(list(ex.gw)))
 
-    def set_problem(self, d, cam, **kw):
+    def set_problem(self, d, cam, global_ba=0, scale_init=0.0, **kw):
+        """global_ba: VieoBaProblem.global_ba bits (1 global graph, 2 robust, 4 scale vertex, 8 gravity-direction vertex)."""
         pb, keep = ba_problem(d, **kw)
+        pb.global_ba, pb.scale_init = int(global_ba), float(scale_init)
         cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
         _check(lib().vieo_ba_set_problem(self._h, C.byref(pb), _p(cam)))
         self._n = (pb.n_states, pb.n_points, pb.n_edges)
 
+    def get_border(self):
+        sc = C.c_double(0)
+        gw = np.zeros(3)
+        _check(lib().vieo_ba_get_border(self._h, C.byref(sc), _p(gw)))
+        return sc.value, gw
+
     def debug_step(self, lam):
         K, P, E = self._n
-        xp = np.zeros(15 * K); xl = np.zeros((P, 3)); H = np.zeros((15 * K) ** 2); b = np.zeros(15 * K)
+        n_ = 15 * K + 3
+        xp = np.zeros(n_); xl = np.zeros((P, 3)); H = np.zeros(n_ ** 2); b = np.zeros(n_)
         n = _check(lib().vieo_ba_debug_step(self._h, lam, _p(xp), _p(xl), _p(H), _p(b)))
         return xp[:n], xl, H[:n * n].reshape(n, n), b[:n]
 

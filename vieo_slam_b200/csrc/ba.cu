@@ -34,23 +34,68 @@ namespace vieo {
 constexpr int kBaWarps = 8;
 constexpr int kLinPts = 4, kLinLanes = 32 / kLinPts;  // k_ba_linearize: map points per warp / lanes per point
 
-struct BaDense {  // one inertial (EdgeNavStatePRV) or bias random-walk (EdgeNavStateBias) factor
-  int type;       // 0 IMU, 1 bias
+constexpr int kDJ = 26;  // columns of an inertial edge's Jacobian strip: 24 keyframe columns + 2 gravity-direction ones
+struct BaDense {  // one inertial (EdgeNavStatePRV[G]) or bias random-walk (EdgeNavStateBias) factor
+  int type;       // 0 IMU, 1 bias walk, 3 prior-bias edge of the IMU initialiser's global BA (src/Optimizer.cc:1026-1054):
+                  //   EdgeNavStateBias from a FIXED copy of keyframe si's bias (info[6..12) = its bg + dbg, ba + dba)
   int si, sj, pre;
   int color, pad_;  // big path: edges of one colour share no keyframe and are accumulated concurrently
   double delta;     // Huber delta, 0 = none
   double info[81];  // IMU: 9x9 information; bias: [0..6) diagonal
 };
 struct BaDenseWork {
-  double J[9 * 24];  // IMU: [Ji(PR) | Jj(PR) | Ji(V) | Jj(V) | Jb], 9 x 24 row-major
-  double AtO[216];   // J^T (rho' Omega), 24 x 9
+  double J[9 * kDJ];    // IMU: [Ji(PR) | Jj(PR) | Ji(V) | Jj(V) | Jb | JG], 9 x 26 row-major (JG: EdgeNavStatePRVG only)
+  double AtO[kDJ * 9];  // J^T (rho' Omega), 26 x 9
   double oe[9], err[9];
   double chi2, r1, rho0;
+  double gg[6];  // gravity-direction block of this edge: JG^T rho' Omega JG (2 x 2) | rhs (2); summed over edges in order
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident optimiser state.  Every kernel of the LM trial reads its sizes and the current linearisation set from
+// here, so the trial sequence has constant launch parameters and is replayed as ONE CUDA graph launch per trial; the
+// Levenberg-Marquardt bookkeeping (gain ratio, lambda schedule, accept / restore, stop criteria) runs in k_ba_control.
+struct BaParams {
+  int K, P, E, np, nfree, n_den, n_pblk, has_dup;
+  int n_colors;         // big path: colours of the inertial edges (see BaDense::color)
+  int rank, world;      // landmark sharding (1 = single GPU)
+  int big;              // global-BA sized handle: H is zeroed by a memset node, multi-CTA Schur / Cholesky kernels
+  int lambda_on_poses;  // sharded runs add lambda to the pose diagonal on rank 0 only
+  int cur;              // linearisation set (0/1) that belongs to the current estimate
+  int done;             // optimize() finished: trial kernels return immediately
+  int stop;             // host abort flag seen (pbStopFlag)
+  int iteration, iters_target, iters_done, qmax, nBad, ok;
+  int trials;           // LM trials run by the current optimize()
+  double lambda, ni, user_lambda;
+  double chi_cur, ini_chi;   // activeRobustChi2 of the current estimate / at the start of the iteration
+  double pair[2];            // [robust chi2 of the last linearisation, landmark part of computeScale] (all-reduced when sharded)
+  double pscale, chi_dense;  // pose part of computeScale; dense-edge chi2 of the last linearisation
+  CamK cam;                  // camera, gravity and Huber deltas of the problem
+  Vec3 gw;
+  double dm, ds;
+  // VertexScale (g2otypes.h:294-311; GlobalBundleAdjustmentNavStatePRV with bScaleOpt, src/Optimizer.cc:843-851) and
+  // VertexGThetaXYRwI (g2otypes.h:674-698; the IMU initialiser's call, :852-865): dense border rows / columns of the
+  // reduced camera system AFTER every keyframe vertex (ids maxKFid + 1 / + 2): np = keyframe dims + 1 + 2.
+  int has_scale, off_s, has_g, off_g;
+  double sc, sc_bak;          // VertexScale estimate (1 without the vertex: X * 1.0 is exact) and its push() copy
+  double qwI[4], qwI_bak[4];  // RwI (w, x, y, z)
+  double GI[3];               // (0, 0, |gw|)
+};
+// gravity in the world frame as the inertial edges see it: gw, or RwI * GI with the gravity-direction vertex
+__device__ __forceinline__ Vec3 ba_gravity(const BaParams& prm) {
+  if (!prm.has_g) return prm.gw;
+  return m3_mulv(q_matrix({prm.qwI[0], prm.qwI[1], prm.qwI[2], prm.qwI[3]}), {prm.GI[0], prm.GI[1], prm.GI[2]});
+}
 
 __global__ void k_ba_campose(CamK cam, const VieoNavState* __restrict__ st, int K, CamPose* __restrict__ cp) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < K) cp[k] = cam_pose(cam, ns_load(st[k]));
+}
+
+// world position of a map point as the visual edges see it: X, or sc * X with the scale vertex (EdgeReprojectPRS:
+// "unscaled Xw but scaled pwb", g2otypes.h:400-406 with MODE 1); sc == 1.0 without the vertex, and x * 1.0 == x exactly
+__device__ __forceinline__ Vec3 ba_world_point(const double* __restrict__ X, size_t p, double sc) {
+  return {X[3 * p] * sc, X[3 * p + 1] * sc, X[3 * p + 2] * sc};
 }
 
 __device__ __forceinline__ double edge_huber_delta(uint8_t flags, uint8_t lvl, double dm, double ds) {
@@ -66,8 +111,9 @@ __global__ void __launch_bounds__(256) k_ba_errors(CamK cam, const CamPose* __re
                                                    const uint8_t* __restrict__ flags, const uint8_t* __restrict__ lvl,
                                                    const uint8_t* __restrict__ sfix, int points_free, int E, int all,
                                                    double dm, double ds, double* __restrict__ chi2,
-                                                   double* __restrict__ partial) {
+                                                   double* __restrict__ partial, const BaParams* __restrict__ prmq) {
   __shared__ double s_w[8];
+  const double sc = prmq->sc;
   const int i = blockIdx.x * 256 + threadIdx.x;
   double r0 = 0;
   if (i < E) {
@@ -80,7 +126,7 @@ __global__ void __launch_bounds__(256) k_ba_errors(CamK cam, const CamPose* __re
     } else if (active || all) {
       const bool stereo = flags[i] & VIEO_EDGE_STEREO;
       double e[3];
-      reproj_error(cam, cp[es[i]], ld3(X + 3 * (size_t)ep[i]), obs + 3 * (size_t)i, stereo, e);
+      reproj_error(cam, cp[es[i]], ba_world_point(X, ep[i], sc), obs + 3 * (size_t)i, stereo, e);
       const double wi = (double)w[i];
       double c = 0;
       for (int k = 0; k < (stereo ? 3 : 2); ++k) c += e[k] * (wi * e[k]);
@@ -102,12 +148,23 @@ __global__ void __launch_bounds__(256) k_ba_errors(CamK cam, const CamPose* __re
   }
 }
 
+// EdgeNavStateBias between the fixed prior-bias vertex (values in d.info[6..12)) and keyframe si's bias vertex
+__device__ __forceinline__ void ba_prior_bias_error(const BaDense& d, const NavS& c, double* err) {
+  err[0] = (c.bg.x + c.dbg.x) - d.info[6];
+  err[1] = (c.bg.y + c.dbg.y) - d.info[7];
+  err[2] = (c.bg.z + c.dbg.z) - d.info[8];
+  err[3] = (c.ba.x + c.dba.x) - d.info[9];
+  err[4] = (c.ba.y + c.dba.y) - d.info[10];
+  err[5] = (c.ba.z + c.dba.z) - d.info[11];
+}
+
 // errors of the inertial / bias edges (one thread each) and the total robust chi2 (dense first, then the visual
 // partial sums in block order) -> *out.  Also sums the landmark part of the gain-ratio denominator when asked.
 __global__ void __launch_bounds__(128) k_ba_dense_errors(const BaDense* __restrict__ den, int n_den, const VieoNavState* __restrict__ st,
-                                  const VieoImuPreint* __restrict__ pre, Vec3 gw, BaDenseWork* __restrict__ wk,
+                                  const VieoImuPreint* __restrict__ pre, const BaParams* __restrict__ prmq, BaDenseWork* __restrict__ wk,
                                   const double* __restrict__ partial, int n_partial, double* __restrict__ out,
                                   const double* __restrict__ scale_part, int n_scale, double* __restrict__ scale_out) {
+  const Vec3 gw = ba_gravity(*prmq);
   const bool sum_only = n_scale < 0;  // keep the stored errors (activeRobustChi2 without computeActiveErrors)
   for (int m = threadIdx.x; m < n_den && !sum_only; m += blockDim.x) {
     const BaDense& d = den[m];
@@ -121,6 +178,9 @@ __global__ void __launch_bounds__(128) k_ba_dense_errors(const BaDense* __restri
         for (int j = 0; j < 9; ++j) t += d.info[i * 9 + j] * W.err[j];
         c += W.err[i] * t;
       }
+    } else if (d.type == 3) {
+      ba_prior_bias_error(d, a, W.err);
+      for (int i = 0; i < 6; ++i) c += W.err[i] * (d.info[i] * W.err[i]);
     } else {
       W.err[0] = (b.bg.x + b.dbg.x) - (a.bg.x + a.dbg.x);
       W.err[1] = (b.bg.y + b.dbg.y) - (a.bg.y + a.dbg.y);
@@ -152,66 +212,89 @@ __global__ void __launch_bounds__(128) k_ba_dense_errors(const BaDense* __restri
 // EdgeNavStatePRV Jacobians written straight into the edge's 9 x 24 strip [Ji(PR) | Jj(PR) | Ji(V) | Jj(V) | Jb]
 // (same arithmetic as navstate_jac with prv = true)
 template <class Pre>
-__device__ void navstate_jac24(const NavS& si, const NavS& sj, const Pre& m, const Vec3& gw, const double e[9], double* J) {
+__device__ void navstate_jac24(const NavS& si, const NavS& sj, const Pre& m, const Vec3& gw, const double e[9], double* J,
+                               const BaParams* gprm = nullptr) {
   const Mat3 RiT = m3_t(q_matrix(si.q)), Rj = q_matrix(sj.q);
   const double dt = m.dt;
-  for (int i = 0; i < 216; ++i) J[i] = 0;
+  for (int i = 0; i < 9 * kDJ; ++i) J[i] = 0;
   const Mat3 JgR = ld_m3(m.JgR);
   // column bases: Ji P 0, R 3, V 12; Jj P 6, R 9, V 15; Jb 18
   Vec3 a = {sj.p.x - si.p.x - si.v.x * dt - gw.x * (dt * dt / 2), sj.p.y - si.p.y - si.v.y * dt - gw.y * (dt * dt / 2),
             sj.p.z - si.p.z - si.v.z * dt - gw.z * (dt * dt / 2)};
   Vec3 b = m3_mulv(RiT, a);
-  setb(J, 24, 0, 3, m3_hat(b));
-  setb(J, 24, 0, 0, m3_scale(m3_identity(), -1.0));
-  setb(J, 24, 0, 12, m3_scale(m3_scale(RiT, -1.0), dt));
-  setb(J, 24, 0, 18, m3_scale(ld_m3(m.Jgp), -1.0));
-  setb(J, 24, 0, 21, m3_scale(ld_m3(m.Jap), -1.0));
-  setb(J, 24, 0, 6, m3_mul(RiT, Rj));
+  setb(J, kDJ, 0, 3, m3_hat(b));
+  setb(J, kDJ, 0, 0, m3_scale(m3_identity(), -1.0));
+  setb(J, kDJ, 0, 12, m3_scale(m3_scale(RiT, -1.0), dt));
+  setb(J, kDJ, 0, 18, m3_scale(ld_m3(m.Jgp), -1.0));
+  setb(J, kDJ, 0, 21, m3_scale(ld_m3(m.Jap), -1.0));
+  setb(J, kDJ, 0, 6, m3_mul(RiT, Rj));
   a = {sj.v.x - si.v.x - gw.x * dt, sj.v.y - si.v.y - gw.y * dt, sj.v.z - si.v.z - gw.z * dt};
   b = m3_mulv(RiT, a);
-  setb(J, 24, 6, 3, m3_hat(b));
-  setb(J, 24, 6, 12, m3_scale(RiT, -1.0));
-  setb(J, 24, 6, 18, m3_scale(ld_m3(m.Jgv), -1.0));
-  setb(J, 24, 6, 21, m3_scale(ld_m3(m.Jav), -1.0));
-  setb(J, 24, 6, 15, RiT);
+  setb(J, kDJ, 6, 3, m3_hat(b));
+  setb(J, kDJ, 6, 12, m3_scale(RiT, -1.0));
+  setb(J, kDJ, 6, 18, m3_scale(ld_m3(m.Jgv), -1.0));
+  setb(J, kDJ, 6, 21, m3_scale(ld_m3(m.Jav), -1.0));
+  setb(J, kDJ, 6, 15, RiT);
   const Vec3 eR = ld3(e + 3);
   const Mat3 Jrinv = so3_JrInv(eR);
   const Mat3 RjTRi = q_matrix(q_normalized(q_mul(q_conj(sj.q), si.q)));
-  setb(J, 24, 3, 3, m3_scale(m3_mul(Jrinv, RjTRi), -1.0));
+  setb(J, kDJ, 3, 3, m3_scale(m3_mul(Jrinv, RjTRi), -1.0));
   const Vec3 w = m3_mulv(JgR, si.dbg);
   const Mat3 Tm = m3_mul(m3_mul(m3_mul(m3_scale(Jrinv, -1.0), so3_Exp({-eR.x, -eR.y, -eR.z})), so3_Jr(w)), JgR);
-  setb(J, 24, 3, 18, Tm);
-  setb(J, 24, 3, 9, Jrinv);
+  setb(J, kDJ, 3, 18, Tm);
+  setb(J, kDJ, 3, 9, Jrinv);
+  if (gprm && gprm->has_g) {
+    // EdgeNavStatePRVG, JG (g2otypes.h:868-876): P rows RiT dt^2/2 RwI GI^[:, 0:2], V rows RiT dt RwI GI^[:, 0:2], R rows 0
+    const Mat3 RwI = q_matrix({gprm->qwI[0], gprm->qwI[1], gprm->qwI[2], gprm->qwI[3]});
+    const Mat3 A = m3_mul(RiT, m3_mul(RwI, m3_hat({gprm->GI[0], gprm->GI[1], gprm->GI[2]})));
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 2; ++c) {
+        J[r * kDJ + 24 + c] = A.m[3 * r + c] * (dt * dt / 2.0);
+        J[(6 + r) * kDJ + 24 + c] = A.m[3 * r + c] * dt;
+      }
+  }
 }
 
 // accumulate one inertial / bias edge's (J^T rho' Omega) J block into H / b with the threads [t0, t0 + tn) of the block
-__device__ __forceinline__ void ba_dense_add_edge(const BaDense& d, const BaDenseWork& W, const int* __restrict__ off0,
+// off_g >= 0 (gravity-direction vertex): its cross blocks with the edge's keyframes go to H like the others (edges of a
+// colour share no keyframe), its own 2 x 2 block and rhs — shared by EVERY inertial edge — into W.gg, summed afterwards.
+__device__ __forceinline__ void ba_dense_add_edge(const BaDense& d, BaDenseWork& W, const int* __restrict__ off0,
                                                   const int* __restrict__ off1, const int* __restrict__ off2, int np,
-                                                  double* __restrict__ H, double* __restrict__ b, int t0, int tn) {
+                                                  double* __restrict__ H, double* __restrict__ b, int t0, int tn,
+                                                  int off_g = -1) {
     const int tl = (int)threadIdx.x - t0;
     if (tl < 0 || tl >= tn) return;
     if (d.type == 0) {
-      const int offs[5] = {off0[d.si], off0[d.sj], off1[d.si], off1[d.sj], off2[d.si]};
-      const int base[6] = {0, 6, 12, 15, 18, 24};
+      const int offs[6] = {off0[d.si], off0[d.sj], off1[d.si], off1[d.sj], off2[d.si], off_g};
+      const int base[7] = {0, 6, 12, 15, 18, 24, 26};
       auto gcol = [&](int lc) {
-        int blk = lc < 6 ? 0 : lc < 12 ? 1 : lc < 15 ? 2 : lc < 18 ? 3 : 4;
+        int blk = lc < 6 ? 0 : lc < 12 ? 1 : lc < 15 ? 2 : lc < 18 ? 3 : lc < 24 ? 4 : 5;
         return offs[blk] < 0 ? -1 : offs[blk] + (lc - base[blk]);
       };
-      for (int t = tl; t < 24 * 25; t += tn) {
-        const int r = t / 25, c = t % 25;
+      const int nc = off_g >= 0 ? kDJ : 24;
+      for (int t = tl; t < nc * (nc + 1); t += tn) {
+        const int r = t / (nc + 1), c = t % (nc + 1);
         const int gr = gcol(r);
         if (gr < 0) continue;
-        if (c == 24) {
+        if (c == nc) {
           double sum = 0;
-          for (int i = 0; i < 9; ++i) sum += W.J[i * 24 + r] * W.oe[i];
-          b[gr] += sum;
+          for (int i = 0; i < 9; ++i) sum += W.J[i * kDJ + r] * W.oe[i];
+          if (r >= 24) W.gg[4 + r - 24] = sum;
+          else b[gr] += sum;
           continue;
         }
         const int gc = gcol(c);
         if (gc < 0) continue;
         double sum = 0;
-        for (int j = 0; j < 9; ++j) sum += W.AtO[r * 9 + j] * W.J[j * 24 + c];
-        H[(size_t)gr * np + gc] += sum;
+        for (int j = 0; j < 9; ++j) sum += W.AtO[r * 9 + j] * W.J[j * kDJ + c];
+        if (r >= 24 && c >= 24) W.gg[2 * (r - 24) + c - 24] = sum;
+        else H[(size_t)gr * np + gc] += sum;
+      }
+    } else if (d.type == 3) {
+      const int oi = off2[d.si];
+      if (tl < 6 && oi >= 0) {
+        H[(size_t)(oi + tl) * np + oi + tl] += W.r1 * d.info[tl];
+        b[oi + tl] += W.oe[tl];
       }
     } else {
       const int oi = off2[d.si], oj = off2[d.sj];
@@ -242,7 +325,7 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
                                const VieoImuPreint* __restrict__ pre, Vec3 gw, BaDenseWork* __restrict__ wk,
                                const int* __restrict__ off0, const int* __restrict__ off1, const int* __restrict__ off2,
                                int np, double* __restrict__ H, double* __restrict__ b, double* __restrict__ chi_dense,
-                               bool eval_only = false) {
+                               bool eval_only = false, const BaParams* gprm = nullptr) {
   const int T = blockDim.x;
   // the pre-integrations' fields the edges read (61 doubles each) staged in shared memory: the residual / Jacobian
   // code is one long dependent chain per thread, global-memory latency on every field would dominate it
@@ -271,11 +354,13 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
     if (d.type == 0) {
       if (m < kStage) {
         navstate_error(a, c, s_pre[m], gw, true, W.err);
-        navstate_jac24(a, c, s_pre[m], gw, W.err, W.J);
+        navstate_jac24(a, c, s_pre[m], gw, W.err, W.J, gprm);
       } else {
         navstate_error(a, c, pre[d.pre], gw, true, W.err);
-        navstate_jac24(a, c, pre[d.pre], gw, W.err, W.J);
+        navstate_jac24(a, c, pre[d.pre], gw, W.err, W.J, gprm);
       }
+    } else if (d.type == 3) {
+      ba_prior_bias_error(d, a, W.err);
     } else {
       W.err[0] = (c.bg.x + c.dbg.x) - (a.bg.x + a.dbg.x);
       W.err[1] = (c.bg.y + c.dbg.y) - (a.bg.y + a.dbg.y);
@@ -312,13 +397,13 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
   }
   __syncthreads();
   // AtO[a][j] = sum_i J[i][a] (r1 Omega[i][j]) for IMU edges; oe <- -(Omega e) r1
-  for (int t = threadIdx.x; t < n_den * 216; t += T) {
-    const int m = t / 216, e = t % 216, a = e / 9, j = e % 9;
+  for (int t = threadIdx.x; t < n_den * kDJ * 9; t += T) {
+    const int m = t / (kDJ * 9), e = t % (kDJ * 9), a = e / 9, j = e % 9;
     const BaDense& d = den[m];
     if (d.type != 0) continue;
     const BaDenseWork& W = wk[m];
     double q = 0;
-    for (int i = 0; i < 9; ++i) q += W.J[i * 24 + a] * (W.r1 * d.info[i * 9 + j]);
+    for (int i = 0; i < 9; ++i) q += W.J[i * kDJ + a] * (W.r1 * d.info[i * 9 + j]);
     wk[m].AtO[e] = q;
   }
   __syncthreads();
@@ -340,35 +425,16 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Device-resident optimiser state.  Every kernel of the LM trial reads its sizes and the current linearisation set from
-// here, so the trial sequence has constant launch parameters and is replayed as ONE CUDA graph launch per trial; the
-// Levenberg-Marquardt bookkeeping (gain ratio, lambda schedule, accept / restore, stop criteria) runs in k_ba_control.
-struct BaParams {
-  int K, P, E, np, nfree, n_den, n_pblk, has_dup;
-  int n_colors;         // big path: colours of the inertial edges (see BaDense::color)
-  int rank, world;      // landmark sharding (1 = single GPU)
-  int big;              // global-BA sized handle: H is zeroed by a memset node, multi-CTA Schur / Cholesky kernels
-  int lambda_on_poses;  // sharded runs add lambda to the pose diagonal on rank 0 only
-  int cur;              // linearisation set (0/1) that belongs to the current estimate
-  int done;             // optimize() finished: trial kernels return immediately
-  int stop;             // host abort flag seen (pbStopFlag)
-  int iteration, iters_target, iters_done, qmax, nBad, ok;
-  int trials;           // LM trials run by the current optimize()
-  double lambda, ni, user_lambda;
-  double chi_cur, ini_chi;   // activeRobustChi2 of the current estimate / at the start of the iteration
-  double pair[2];            // [robust chi2 of the last linearisation, landmark part of computeScale] (all-reduced when sharded)
-  double pscale, chi_dense;  // pose part of computeScale; dense-edge chi2 of the last linearisation
-  CamK cam;                  // camera, gravity and Huber deltas of the problem
-  Vec3 gw;
-  double dm, ds;
-};
 struct BaBuf {  // device pointers of one handle (constant for its lifetime)
   BaParams* prm;
   VieoNavState *st, *st_bak;
   CamPose* cp;
   double *X, *X_bak, *chi2, *A, *Dinv, *db, *S, *bs, *bsys, *x, *partial, *scale_part, *part;
   double *W[2], *Hll[2], *bl[2], *H[2], *b[2];
+  // scale vertex (global-BA handles only): per point wsp = sum of its edges' Js^T (w Omega) JX (the point's 1 x 3 block of
+  // the scale row, per linearisation set), up = Dinv wsp, sred = (wsp . up, wsp . db); per edge As = [Hps 6 | Hss | bs];
+  // spart: per linearize block partial sums of (Hss, bs)
+  double *wsp[2], *up, *sred, *As, *spart;
   uint8_t* pt_active[2];
   const int *es, *ep, *pt_ptr, *off0, *off1, *off2, *prcol, *free_state, *free_off, *ps_ptr, *ps_edges;
   const float *obs, *w;
@@ -382,8 +448,13 @@ struct BaBuf {  // device pointers of one handle (constant for its lifetime)
 // evaluates one reprojection edge (residual, chi2, Huber weight, Jacobians), the 3x3 Hll / bl are reduced with warp
 // shuffles, W (Hpl) and A (the edge's Hpp / b part) are stored per edge.  The extra last block does the inertial edges.
 // into_other: write the set that does NOT belong to the current estimate (speculative linearisation of a trial).
-__global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize(BaBuf B, int into_other) {
+// kScale: the visual edges are EdgeReprojectPRS[Stereo] (src/Optimizer.cc:1132-1200; g2otypes.h:517-521): Xw = sc * X,
+// J_point = (Jproj Rcw) sc, J_scale = (Jproj Rcw) X — a separate instantiation so that the local windows' kernel keeps
+// its register budget.
+template <bool kScale>
+__global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize_t(BaBuf B, int into_other) {
   __shared__ double s_chi[kBaWarps];
+  __shared__ double s_ss[kBaWarps][2];
   const BaParams& prm = *B.prm;
   if (prm.done) return;
   const int set = into_other ? 1 - prm.cur : prm.cur;
@@ -398,24 +469,32 @@ __global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize(BaBuf B, int 
   // so the blocks past ceil(P / 32) of the (warp-per-point sized) grid have nothing to do but report a zero chi2 part
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & (kLinLanes - 1);
   if ((int)blockIdx.x * kBaWarps * kLinPts >= prm.P) {
-    if (threadIdx.x == 0) B.partial[blockIdx.x] = 0;
+    if (threadIdx.x == 0) {
+      B.partial[blockIdx.x] = 0;
+      if (kScale) B.spart[2 * blockIdx.x] = B.spart[2 * blockIdx.x + 1] = 0;
+    }
     return;
   }
   const int p = (blockIdx.x * kBaWarps + warp) * kLinPts + lane / kLinLanes;
   double* Wb = B.W[set];
-  double acc[9], rsum = 0;
+  constexpr int kAcc = kScale ? 12 : 9;
+  double acc[kAcc], rsum = 0, hss = 0, bss = 0;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0;
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0;
+  const double sc = kScale ? prm.sc : 1.0;
   bool any = false;
   if (p < prm.P) {
     const int i0 = B.pt_ptr[p], i1 = B.pt_ptr[p + 1];
-    const Vec3 Xp = ld3(B.X + 3 * (size_t)p);
+    const Vec3 Xh = ld3(B.X + 3 * (size_t)p);
+    const Vec3 Xp = kScale ? Vec3{Xh.x * sc, Xh.y * sc, Xh.z * sc} : Xh;
     for (int i = i0 + sub; i < i1; i += kLinLanes) {
       double* Wi = Wb + 18 * (size_t)i;
       double* Ai = B.A + 27 * (size_t)i;
       if (B.lvl[i] & 1) {
         for (int k = 0; k < 18; ++k) Wi[k] = 0;
         for (int k = 0; k < 27; ++k) Ai[k] = 0;
+        if (kScale)
+          for (int k = 0; k < 8; ++k) B.As[8 * (size_t)i + k] = 0;
         continue;
       }
       any = true;
@@ -430,6 +509,12 @@ __global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize(BaBuf B, int 
       B.chi2[i] = c;
       Mat3 Jp, Jr, JX;
       reproj_jac(prm.cam, B.cp[s], Xp, stereo, Jp, Jr, JX);
+      double Js[3] = {0, 0, 0};
+      if (kScale) {
+        for (int k = 0; k < DE; ++k) Js[k] = JX.m[3 * k] * Xh.x + JX.m[3 * k + 1] * Xh.y + JX.m[3 * k + 2] * Xh.z;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) JX.m[k] *= sc;
+      }
       double r0, r1;
       huber_rho(edge_huber_delta(B.flags[i], B.lvl[i], prm.dm, prm.ds), c, r0, r1);
       rsum += r0;
@@ -456,6 +541,31 @@ __global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize(BaBuf B, int 
           double hh = 0;
           for (int k = 0; k < DE; ++k) hh += (JX.m[3 * k + r] * ww) * JX.m[3 * k + cc];
           acc[q++] += hh;
+        }
+      }
+      if (kScale) {
+        double* Asi = B.As + 8 * (size_t)i;
+        double sb = 0, sh = 0;
+        for (int k = 0; k < DE; ++k) {
+          sb += Js[k] * oe[k];
+          sh += (Js[k] * ww) * Js[k];
+        }
+        bss += sb;
+        hss += sh;
+        Asi[6] = sh;
+        Asi[7] = sb;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          double hh = 0;
+          for (int k = 0; k < DE; ++k) hh += (Js[k] * ww) * JX.m[3 * k + cc];
+          acc[9 + cc] += hh;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double hh = 0;
+          if (!B.sfix[s])
+            for (int k = 0; k < DE; ++k) hh += (J[k][r] * ww) * Js[k];
+          Asi[r] = hh;
         }
       }
       if (!B.sfix[s]) {
@@ -485,11 +595,22 @@ __global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize(BaBuf B, int 
     }
   }
 #pragma unroll
-  for (int k = 0; k < 9; ++k)
+  for (int k = 0; k < kAcc; ++k)
 #pragma unroll
     for (int o = kLinLanes / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+  if (kScale) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      hss += __shfl_xor_sync(0xffffffffu, hss, o);
+      bss += __shfl_xor_sync(0xffffffffu, bss, o);
+    }
+    if (lane == 0) {
+      s_ss[warp][0] = hss;
+      s_ss[warp][1] = bss;
+    }
+  }
   any = ((__ballot_sync(0xffffffffu, any) >> (lane & ~(kLinLanes - 1))) & ((1u << kLinLanes) - 1)) != 0;
   if (lane == 0) s_chi[warp] = rsum;
   if (sub == 0) {
@@ -501,6 +622,10 @@ __global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize(BaBuf B, int 
       double* bb = B.bl[set] + 3 * (size_t)p;
       bb[0] = acc[6]; bb[1] = acc[7]; bb[2] = acc[8];
       B.pt_active[set][p] = any;
+      if (kScale) {
+        double* ws = B.wsp[set] + 3 * (size_t)p;
+        ws[0] = acc[kAcc - 3]; ws[1] = acc[kAcc - 2]; ws[2] = acc[kAcc - 1];
+      }
     }
   }
   __syncthreads();
@@ -508,6 +633,15 @@ __global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize(BaBuf B, int 
     double t = 0;
     for (int k = 0; k < kBaWarps; ++k) t += s_chi[k];
     B.partial[blockIdx.x] = t;
+    if (kScale) {
+      double h = 0, b2 = 0;
+      for (int k = 0; k < kBaWarps; ++k) {
+        h += s_ss[k][0];
+        b2 += s_ss[k][1];
+      }
+      B.spart[2 * blockIdx.x] = h;
+      B.spart[2 * blockIdx.x + 1] = b2;
+    }
   }
 }
 
@@ -557,7 +691,49 @@ __global__ void __launch_bounds__(256) k_ba_pose_reduce(BaBuf B, int into_other)
       }
     }
   }
+  if (prm.has_scale) {  // the keyframe's 6 x 1 block of the scale column: fixed-order sum of its edges' Hps
+    __syncthreads();
+    double hp[6] = {0, 0, 0, 0, 0, 0};
+    for (int t = B.ps_ptr[f] + threadIdx.x; t < B.ps_ptr[f + 1]; t += 256) {
+      const double* Asi = B.As + 8 * (size_t)B.ps_edges[t];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) hp[q] += Asi[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) hp[q] += __shfl_xor_sync(0xffffffffu, hp[q], s);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s_w[threadIdx.x >> 5][q] = hp[q];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      double v = 0;
+      for (int w = 0; w < 8; ++w) v += s_w[w][threadIdx.x];
+      H[(size_t)(o + threadIdx.x) * np + prm.off_s] += v;
+      H[(size_t)prm.off_s * np + o + threadIdx.x] += v;
+    }
+  }
   if (f != 0) return;
+  if (threadIdx.x == 0 && prm.has_scale) {  // scale diagonal / rhs: the linearize blocks' partial sums in block order
+    double hs = 0, bs2 = 0;
+    for (int q = 0; q < prm.n_pblk; ++q) {
+      hs += B.spart[2 * q];
+      bs2 += B.spart[2 * q + 1];
+    }
+    H[(size_t)prm.off_s * np + prm.off_s] += hs;
+    b[prm.off_s] += bs2;
+  }
+  if (threadIdx.x == 32 && prm.has_g) {  // gravity-direction 2 x 2 block / rhs: the inertial edges' parts in edge order
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < prm.n_den; ++m)
+      if (B.den[m].type == 0)
+        for (int q = 0; q < 6; ++q) g[q] += B.wk[m].gg[q];
+    for (int r = 0; r < 2; ++r) {
+      for (int c = 0; c < 2; ++c) H[(size_t)(prm.off_g + r) * np + prm.off_g + c] += g[2 * r + c];
+      b[prm.off_g + r] += g[4 + r];
+    }
+  }
   double sc = 0;
   for (int t = threadIdx.x; t < prm.P; t += 256) sc += B.scale_part[t];
   s_s[threadIdx.x] = sc;
@@ -710,6 +886,10 @@ __global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode, cudaGraph
     double* sd = reinterpret_cast<double*>(B.st);
     for (int t = threadIdx.x; t < nS; t += 256) sd[t] = sb[t];
     for (int t = threadIdx.x; t < nX; t += 256) B.X[t] = B.X_bak[t];
+    if (threadIdx.x == 0) {
+      prm.sc = prm.sc_bak;
+      for (int q = 0; q < 4; ++q) prm.qwI[q] = prm.qwI_bak[q];
+    }
   }
 }
 
@@ -736,6 +916,10 @@ __global__ void k_ba_prep_solve(BaBuf B, double lambda_arg, int use_arg) {
   if (!B.pt_active[set][p]) {
     for (int k = 0; k < 9; ++k) I[k] = 0;
     B.db[3 * p] = B.db[3 * p + 1] = B.db[3 * p + 2] = 0;
+    if (prm.has_scale) {
+      B.up[3 * p] = B.up[3 * p + 1] = B.up[3 * p + 2] = 0;
+      B.sred[2 * p] = B.sred[2 * p + 1] = 0;
+    }
     return;
   }
   double D[9];
@@ -748,6 +932,14 @@ __global__ void k_ba_prep_solve(BaBuf B, double lambda_arg, int use_arg) {
   I[6] = c02 * id; I[7] = (D[1] * D[6] - D[0] * D[7]) * id; I[8] = (D[0] * D[4] - D[1] * D[3]) * id;
   const double* bb = B.bl[set] + 3 * p;
   for (int a = 0; a < 3; ++a) B.db[3 * p + a] = I[3 * a] * bb[0] + I[3 * a + 1] * bb[1] + I[3 * a + 2] * bb[2];
+  if (prm.has_scale) {  // the point's part of the scale row of the Schur complement: up = Dinv wsp
+    const double* ws = B.wsp[set] + 3 * p;
+    double u[3];
+    for (int a = 0; a < 3; ++a) u[a] = I[3 * a] * ws[0] + I[3 * a + 1] * ws[1] + I[3 * a + 2] * ws[2];
+    B.up[3 * p] = u[0]; B.up[3 * p + 1] = u[1]; B.up[3 * p + 2] = u[2];
+    B.sred[2 * p] = ws[0] * u[0] + ws[1] * u[1] + ws[2] * u[2];
+    B.sred[2 * p + 1] = ws[0] * B.db[3 * p] + ws[1] * B.db[3 * p + 1] + ws[2] * B.db[3 * p + 2];
+  }
 }
 
 // Schur complement.  Block (f, s): chunk s of free keyframe f's edge list.  Each warp walks its edges in order; for
@@ -989,9 +1181,35 @@ constexpr int kGbaSchurThreads = 512;
 __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int force) {
   extern __shared__ double s_tile[];  // [6][ld]
   const BaParams& prm = *B.prm;
-  if ((prm.done && !force) || (int)blockIdx.x >= prm.nfree || prm.E == 0) return;
-  const int nfree = prm.nfree, np = prm.np, ld = 6 * nfree + 1;
+  if ((prm.done && !force) || prm.E == 0) return;
+  const int nfree = prm.nfree, np = prm.np, ld = 6 * nfree + 2;  // columns: keyframe blocks | W db | W up (scale column)
   const int f = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
+  if (f == nfree) {
+    // extra block: diagonal / rhs of the scale row, S_ss -= sum_p wsp . up, bs_s -= sum_p wsp . db (fixed-order tree)
+    if (!prm.has_scale) return;
+    double a0 = 0, a1 = 0;
+    for (int p = tid; p < prm.P; p += T) {
+      a0 += B.sred[2 * (size_t)p];
+      a1 += B.sred[2 * (size_t)p + 1];
+    }
+    s_tile[tid] = a0;
+    s_tile[T + tid] = a1;
+    __syncthreads();
+    for (int o = T / 2; o > 0; o >>= 1) {
+      if (tid < o) {
+        s_tile[tid] += s_tile[tid + o];
+        s_tile[T + tid] += s_tile[T + tid + o];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      B.S[(size_t)prm.off_s * np + prm.off_s] -= s_tile[0];
+      B.bs[prm.off_s] -= s_tile[T];
+    }
+    return;
+  }
+  if (f > nfree) return;
+  const bool has_scale = prm.has_scale != 0;
   const double* Wb = B.W[prm.cur];
   for (int t = tid; t < 6 * ld; t += T) s_tile[t] = 0;
   __syncthreads();
@@ -1006,6 +1224,10 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
     if (tid < 6) {
       const double* d = B.db + 3 * (size_t)p;
       s_tile[tid * ld + 6 * nfree] += Wa[3 * tid] * d[0] + Wa[3 * tid + 1] * d[1] + Wa[3 * tid + 2] * d[2];
+    } else if (tid >= 32 && tid < 38 && has_scale) {
+      const int r = tid - 32;
+      const double* u = B.up + 3 * (size_t)p;
+      s_tile[r * ld + 6 * nfree + 1] += Wa[3 * r] * u[0] + Wa[3 * r + 1] * u[1] + Wa[3 * r + 2] * u[2];
     }
     if (!dup) {
       for (int e = tid; e < 36 * nc; e += T) {
@@ -1041,7 +1263,12 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
   for (int t = tid; t < 6 * ld; t += T) {
     const int r = t / ld, c = t % ld;
     if (c == 6 * nfree) B.bs[o + r] -= s_tile[t];
-    else B.S[(size_t)(o + r) * np + B.free_off[c / 6] + c % 6] -= s_tile[t];
+    else if (c == 6 * nfree + 1) {
+      if (has_scale) {
+        B.S[(size_t)(o + r) * np + prm.off_s] -= s_tile[t];
+        B.S[(size_t)prm.off_s * np + o + r] -= s_tile[t];
+      }
+    } else B.S[(size_t)(o + r) * np + B.free_off[c / 6] + c % 6] -= s_tile[t];
   }
 }
 
@@ -1332,8 +1559,8 @@ __global__ void __launch_bounds__(256) k_gba_dense_eval(BaBuf B, int into_other)
   if (prm.done) return;
   const int m0 = blockIdx.x * kGbaDenPerCta;
   if (m0 >= prm.n_den) return;
-  ba_dense_block(B.den + m0, min(kGbaDenPerCta, prm.n_den - m0), B.st, B.pre, prm.gw, B.wk + m0, B.off0, B.off1, B.off2, prm.np,
-                 nullptr, nullptr, nullptr, true);
+  ba_dense_block(B.den + m0, min(kGbaDenPerCta, prm.n_den - m0), B.st, B.pre, ba_gravity(prm), B.wk + m0, B.off0, B.off1,
+                 B.off2, prm.np, nullptr, nullptr, nullptr, true, &prm);
 }
 // ... then the accumulation, one colour per launch and one CTA per edge: edges of a colour share no keyframe, colours run
 // one after the other, so every entry of H / b is summed in a fixed order without atomics.
@@ -1349,7 +1576,7 @@ __global__ void __launch_bounds__(128) k_gba_dense_accum(BaBuf B, int into_other
     prm.chi_dense = tot;
   }
   if (B.den[m].color != color) return;
-  ba_dense_add_edge(B.den[m], B.wk[m], B.off0, B.off1, B.off2, prm.np, B.H[set], B.b[set], 0, 128);
+  ba_dense_add_edge(B.den[m], B.wk[m], B.off0, B.off1, B.off2, prm.np, B.H[set], B.b[set], 0, 128, prm.has_g ? prm.off_g : -1);
 }
 
 // One warp per point: xl = Dinv (bl - sum_a W_a^T xp), X += xl (apply != 0), landmark part of computeScale; the
@@ -1381,6 +1608,16 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_backsub(BaBuf B, int apply
         for (int j = 0; j < prm.np; ++j) s += B.x[j] * (lambda * B.x[j] + B.bsys[j]);
       prm.pscale = s;
     }
+    if (threadIdx.x == 32 && apply && (prm.has_scale || prm.has_g)) {  // push() + oplus of the two border vertices
+      prm.sc_bak = prm.sc;
+      for (int q = 0; q < 4; ++q) prm.qwI_bak[q] = prm.qwI[q];
+      if (ok && prm.has_scale) prm.sc += B.x[prm.off_s];  // VertexScale::oplusImpl
+      if (ok && prm.has_g) {  // VertexGThetaXYRwI::oplusImpl: RwI <- RwI Exp((dx, dy, 0))
+        const Quat q = q_normalized(q_mul({prm.qwI[0], prm.qwI[1], prm.qwI[2], prm.qwI[3]},
+                                          so3_exp_q({B.x[prm.off_g], B.x[prm.off_g + 1], 0.0})));
+        prm.qwI[0] = q.w; prm.qwI[1] = q.x; prm.qwI[2] = q.y; prm.qwI[3] = q.z;
+      }
+    }
     return;
   }
   if ((int)blockIdx.x >= prm.n_pblk) return;
@@ -1411,6 +1648,11 @@ __global__ void __launch_bounds__(kBaWarps * 32) k_ba_backsub(BaBuf B, int apply
     for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
   __syncwarp();  // the X_bak copy above read X before lane 0 updates it
   if (lane == 0) {
+    if (prm.has_scale) {  // the point's block of the scale column times the scale increment
+      const double xs = B.x[prm.off_s];
+      const double* ws = B.wsp[set] + 3 * (size_t)p;
+      c[0] += ws[0] * xs; c[1] += ws[1] * xs; c[2] += ws[2] * xs;
+    }
     const double* bb = B.bl[set] + 3 * (size_t)p;
     const double* Di = B.Dinv + 9 * (size_t)p;
     const double cc[3] = {bb[0] - c[0], bb[1] - c[1], bb[2] - c[2]};
@@ -1431,7 +1673,7 @@ __global__ void k_ba_classify(CamK cam, const CamPose* __restrict__ cp, const do
                               const int* __restrict__ es, const int* __restrict__ ep, const float* __restrict__ obs,
                               const uint8_t* __restrict__ flags, const double* __restrict__ chi2, int E, int mode, float rat,
                               int set_level, int remove_kernels, int use_close, uint8_t* __restrict__ lvl,
-                              uint8_t* __restrict__ bad_out) {
+                              uint8_t* __restrict__ bad_out, const BaParams* __restrict__ prmq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E) return;
   const bool stereo = flags[i] & VIEO_EDGE_STEREO;
@@ -1441,7 +1683,7 @@ __global__ void k_ba_classify(CamK cam, const CamPose* __restrict__ cp, const do
     bad = chi2[i] > (double)th;
   } else {
     double e[3];
-    const double depth = reproj_error(cam, cp[es[i]], ld3(X + 3 * (size_t)ep[i]), obs + 3 * (size_t)i, stereo, e);
+    const double depth = reproj_error(cam, cp[es[i]], ba_world_point(X, ep[i], prmq->sc), obs + 3 * (size_t)i, stereo, e);
     const float chi2Mono = 5.991f;
     if (stereo) bad = chi2[i] > 7.815 || !(depth > 0.);
     else if (!use_close) bad = chi2[i] > 5.991 || !(depth > 0.);  // visual LocalBundleAdjustment (src/Optimizer.cc:2198)
@@ -1465,6 +1707,7 @@ struct vieo_ba {
   int K = 0, P = 0, E = 0, M = 0, np = 0, nfree = 0, n_den = 0, n_part = 0, n_pblk = 0, n_colors = 1;
   bool points_free = true, has_dup = false, visual_only = false;
   bool big = false;  // global-BA sized handle (dense multi-CTA Schur / Cholesky path, no trial graph)
+  bool has_scale = false, has_g = false;  // border vertices of the current problem (global handles only)
   double* d_yv = nullptr;
   uint8_t* d_nz = nullptr;  // tile structure map of the dense Cholesky
   int rank = 0, world = 1;
@@ -1503,6 +1746,25 @@ namespace {
 template <class T>
 cudaError_t dalloc(T** p, size_t n) {
   return cudaMalloc((void**)p, sizeof(T) * std::max<size_t>(n, 1));
+}
+
+// SO3ex::exp -> normalised quaternion (w, x, y, z): host copy of so3_exp_q (so3.cuh) for the gravity-direction seed
+void host_so3_exp_q(double wx, double wy, double wz, double q[4]) {
+  const double theta = std::sqrt(wx * wx + wy * wy + wz * wz);
+  double imag, real;
+  if (theta < 1e-5) {
+    const double t2 = theta * theta;
+    imag = 0.5 - t2 / 48.;
+    real = 1.0 - t2 / 8.;
+  } else {
+    const double half = 0.5 * theta;
+    imag = std::sin(half) / theta;
+    real = std::cos(half);
+  }
+  q[0] = real; q[1] = imag * wx; q[2] = imag * wy; q[3] = imag * wz;
+  const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n > 0)
+    for (int k = 0; k < 4; ++k) q[k] /= n;
 }
 
 bool host_inverse(const double* A, int n, double* Ai) {
@@ -1548,7 +1810,9 @@ bool host_inverse(const double* A, int n, double* Ai) {
 
 constexpr int kNodesPerTrial = 8;  // kernels of one LM trial (ba_enqueue_trial)
 size_t schur_smem(int nfree) { return sizeof(double) * kBaWarps * 6 * (6 * (size_t)nfree + 1); }
-size_t gba_schur_smem(int nfree) { return sizeof(double) * 6 * (6 * (size_t)nfree + 1); }
+size_t gba_schur_smem(int nfree) {  // row tile [6][6 nfree + 2]; the extra block's two reduction arrays need 2 T doubles
+  return sizeof(double) * std::max<size_t>(6 * (6 * (size_t)nfree + 2), 2 * (size_t)kGbaSchurThreads);
+}
 
 int ba_campose(vieo_ba* h) {
   k_ba_campose<<<(h->K + 127) / 128, 128, 0, h->st>>>(h->cam, h->B.st, h->K, h->B.cp);
@@ -1562,10 +1826,10 @@ int ba_errors(vieo_ba* h, int all, double* d_out) {
   if (h->E > 0) {
     k_ba_errors<<<h->n_part, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_w, h->d_flags,
                                               h->d_lvl, h->d_sfix, h->points_free ? 1 : 0, h->E, all, h->dm, h->ds,
-                                              h->B.chi2, h->B.partial);
+                                              h->B.chi2, h->B.partial, h->B.prm);
     h->launches++;
   }
-  k_ba_dense_errors<<<1, 128, 0, h->st>>>(h->d_den, h->n_den, h->B.st, h->d_pre, h->gw, h->B.wk, h->B.partial,
+  k_ba_dense_errors<<<1, 128, 0, h->st>>>(h->d_den, h->n_den, h->B.st, h->d_pre, h->B.prm, h->B.wk, h->B.partial,
                                           h->E > 0 ? h->n_part : 0, d_out, nullptr, all == 2 ? -1 : 0, nullptr);
   h->launches++;
   BA_CK(cudaGetLastError());
@@ -1586,7 +1850,8 @@ int ba_enqueue_linearize(vieo_ba* h, int into_other, bool at_capacity) {
   const int pblk = at_capacity ? h->cap_pblk : h->n_pblk, nf = at_capacity ? h->cap_free : h->nfree;
   if (h->big) {  // one block cannot zero np^2 entries or walk hundreds of inertial factors: dedicated kernels
     k_gba_zero_h<<<1184, 256, 0, h->st>>>(h->B, into_other);
-    k_ba_linearize<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
+    if (h->has_scale) k_ba_linearize_t<true><<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
+    else k_ba_linearize_t<false><<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
     h->launches += 2;
     if (h->n_den > 0) {
       k_gba_dense_eval<<<(h->n_den + kGbaDenPerCta - 1) / kGbaDenPerCta, 256, 0, h->st>>>(h->B, into_other);
@@ -1597,7 +1862,7 @@ int ba_enqueue_linearize(vieo_ba* h, int into_other, bool at_capacity) {
     h->launches++;
     return VIEO_OK;
   }
-  k_ba_linearize<<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
+  k_ba_linearize_t<false><<<pblk + 1, kBaWarps * 32, 0, h->st>>>(h->B, into_other);
   k_ba_pose_reduce<<<std::max(nf, 1), 256, 0, h->st>>>(h->B, into_other);
   h->launches += 2;
   return VIEO_OK;
@@ -1612,7 +1877,7 @@ int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, dou
     const int n = h->np;
     const size_t nn = std::max<size_t>(std::max<size_t>((size_t)n * n, (size_t)n), std::max<size_t>(P, 1));
     k_ba_prep_solve<<<(unsigned)((nn + 255) / 256), 256, 0, h->st>>>(h->B, lambda, force);
-    k_gba_schur<<<std::max(nf, 1), kGbaSchurThreads, gba_schur_smem(h->nfree), h->st>>>(h->B, force);
+    k_gba_schur<<<nf + 1, kGbaSchurThreads, gba_schur_smem(h->nfree), h->st>>>(h->B, force);
     h->launches += 2;
     int rc = ba_allreduce(h, h->d_sys, h->sys_count());
     if (rc) return rc;
@@ -1674,7 +1939,7 @@ void ba_free(vieo_ba* h) {
   BaBuf& B = h->B;
   void* ptrs[] = {B.prm, B.st, B.st_bak, B.cp, B.X, B.X_bak, B.chi2, B.A, B.Dinv, B.db, B.x, B.partial, B.scale_part, B.part,
                   B.W[0], B.W[1], B.Hll[0], B.Hll[1], B.bl[0], B.bl[1], B.H[0], B.H[1], B.b[0], B.b[1], B.pt_active[0],
-                  B.pt_active[1], B.wk, h->d_nz, h->d_yv, h->d_sys, h->d_xl, h->d_ctl, h->d_lvl, h->d_bad, h->d_flags, h->d_sfix, h->d_es,
+                  B.pt_active[1], B.wk, B.wsp[0], B.wsp[1], B.up, B.sred, B.As, B.spart, h->d_nz, h->d_yv, h->d_sys, h->d_xl, h->d_ctl, h->d_lvl, h->d_bad, h->d_flags, h->d_sfix, h->d_es,
                   h->d_ep, h->d_pt_ptr, h->d_off0, h->d_off1, h->d_off2, h->d_prcol, h->d_free_state, h->d_free_off,
                   h->d_ps_ptr, h->d_ps_edges, h->d_obs, h->d_w, h->d_pre, h->d_den};
   for (void* p : ptrs)
@@ -1717,7 +1982,8 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
   h->cap_free = h->big ? max_states : std::min(max_states, kSchurMaxFree);
   const size_t K = max_states, P = max_points, E = max_edges, M = max_imu;
   // free keyframes (+ a few V/Bias-only) x 15; even so that double2 stores cover H exactly
-  const size_t NP = 15 * (size_t)(h->big ? max_states + (max_states & 1) : std::min(max_states, kSchurMaxFree + 8));
+  // (global handles: + 4 for the scale and gravity-direction border, count kept even)
+  const size_t NP = h->big ? 15 * (size_t)(max_states + (max_states & 1)) + 4 : 15 * (size_t)std::min(max_states, kSchurMaxFree + 8);
   BaBuf& B = h->B;
   cudaError_t e = cudaSuccess;
   auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
@@ -1736,6 +2002,9 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
   step(dalloc(&h->d_xl, 3 * P)); step(dalloc(&B.partial, std::max((E + 255) / 256, P / kBaWarps + 1) + 2));
   step(dalloc(&B.scale_part, P));
   if (h->big) {
+    for (int s = 0; s < 2; ++s) step(dalloc(&B.wsp[s], 3 * P));
+    step(dalloc(&B.up, 3 * P)); step(dalloc(&B.sred, 2 * P)); step(dalloc(&B.As, 8 * E));
+    step(dalloc(&B.spart, 2 * ((size_t)h->cap_pblk + 2)));
     step(dalloc(&B.part, 16));
     step(dalloc(&h->d_nz, (NP / kGNB + 1) * (NP / kGNB + 1)));
     step(dalloc(&h->d_yv, NP));
@@ -1747,7 +2016,7 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
   step(dalloc(&h->d_free_state, K)); step(dalloc(&h->d_free_off, K)); step(dalloc(&h->d_ps_ptr, K + 1));
   step(dalloc(&h->d_ps_edges, E)); step(dalloc(&h->d_obs, 3 * E)); step(dalloc(&h->d_w, E));
   step(dalloc(&h->d_flags, E)); step(dalloc(&h->d_lvl, E)); step(dalloc(&h->d_sfix, K));
-  step(dalloc(&h->d_bad, E)); step(dalloc(&h->d_pre, M)); step(dalloc(&h->d_den, 2 * M)); step(dalloc(&B.wk, 2 * M));
+  step(dalloc(&h->d_bad, E)); step(dalloc(&h->d_pre, M)); step(dalloc(&h->d_den, 2 * M + 1)); step(dalloc(&B.wk, 2 * M + 1));
   step(cudaMallocHost((void**)&h->h_ctl, sizeof(double) * 16));
   step(cudaMallocHost((void**)&h->h_prm, sizeof(BaParams)));
   h->stage_cap = K * (sizeof(VieoNavState) + 64) + P * 32 + E * 40 + M * (sizeof(VieoImuPreint) + 2 * sizeof(BaDense)) + 4096;
@@ -1891,6 +2160,14 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
       h->off2[k] = np; np += 6;
     }
   }
+  // border vertices after every keyframe vertex: VertexScale (id maxKFid + 1), VertexGThetaXYRwI (id maxKFid + 2)
+  const bool want_scale = pb->global_ba & 4, want_g = pb->global_ba & 8, want_prior_bias = pb->global_ba & 16;
+  VIEO_ARG(!(want_scale || want_g) || h->big, "the scale / gravity-direction vertices need a handle from vieo_ba_create_global");
+  h->has_scale = want_scale;
+  h->has_g = want_g;
+  int off_s = -1, off_g = -1;
+  if (want_scale) { off_s = np; np += 1; }
+  if (want_g) { off_g = np; np += 2; }
   h->np = np;
   h->nfree = (int)free_state.size();
   // point ranges + per-keyframe edge lists
@@ -1953,6 +2230,26 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
     if (kernel) d.delta = (double)thBias;
     den.push_back(d);
   }
+  // the IMU initialiser's prior-bias edge (src/Optimizer.cc:866-900, 1026-1054): EdgeNavStateBias from a fixed copy of the
+  // earliest keyframe's bias (states[0]) with information invSigma / sum(dt_ij) over every keyframe pair (:940-947)
+  if (want_prior_bias && M > 0 && (pb->state_flags[0] & 2)) {
+    double sum_dt = 0;
+    for (int m = 0; m < M; ++m) {
+      double dtij = pb->preint[m].dt != 0 ? pb->preint[m].dt : pb->imu_dt_kf[m];
+      if (dtij <= (double)1e-6f) dtij = 15;
+      sum_dt += dtij;
+    }
+    BaDense d;
+    memset(&d, 0, sizeof(d));
+    d.type = 3; d.si = 0; d.sj = 0; d.pre = 0;
+    for (int k = 0; k < 6; ++k) d.info[k] = (k < 3 ? pb->inv_sigma_bg2 : pb->inv_sigma_ba2) / sum_dt;
+    const VieoNavState& s0 = pb->states[0];
+    for (int k = 0; k < 3; ++k) {
+      d.info[6 + k] = s0.bg[k] + s0.dbg[k];
+      d.info[9 + k] = s0.ba[k] + s0.dba[k];
+    }
+    den.push_back(d);
+  }
   // greedy colouring of the inertial edges by shared keyframes (a chain needs two colours)
   int n_colors = 1;
   {
@@ -1973,7 +2270,7 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
     }
   }
   h->n_den = (int)den.size();
-  VIEO_ARG(h->n_den <= 2 * h->capM, "too many inertial edges");
+  VIEO_ARG(h->n_den <= 2 * h->capM + 1, "too many inertial edges");
   std::vector<uint8_t> lvl(std::max(E, 1));
   for (int i = 0; i < E; ++i)
     lvl[i] = ((pb->edge_flags[i] & VIEO_EDGE_LEVEL1) ? 1 : 0) | (((pb->edge_flags[i] & VIEO_EDGE_NOKERNEL) || (global && !g_robust)) ? 2 : 0);
@@ -2030,6 +2327,23 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   q.ok = 1;
   q.ni = 2;
   q.cam = h->cam; q.gw = h->gw; q.dm = h->dm; q.ds = h->ds;
+  q.has_scale = want_scale ? 1 : 0; q.off_s = off_s;
+  q.has_g = want_g ? 1 : 0; q.off_g = off_g;
+  q.sc = q.sc_bak = (want_scale && pb->scale_init > 0) ? pb->scale_init : 1.0;
+  q.qwI[0] = q.qwI_bak[0] = 1.0;
+  if (want_g) {
+    // VertexGThetaXYRwI::setToOriginImpl(gw) (g2otypes.h:682-690): RwI = Exp(normalized((0,0,1) x gw/|gw|) acos(gw_z/|gw|));
+    // Eigen's normalized() leaves a zero vector unchanged, so gw (anti-)parallel to z gives the identity
+    const double n = std::sqrt(pb->gw[0] * pb->gw[0] + pb->gw[1] * pb->gw[1] + pb->gw[2] * pb->gw[2]);
+    VIEO_ARG(n > 0, "zero gravity vector");
+    const double g[3] = {pb->gw[0] / n, pb->gw[1] / n, pb->gw[2] / n};
+    const double a[3] = {-g[1], g[0], 0.0};
+    const double na = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    const double th = std::acos(g[2]), inv = na > 0 ? 1.0 / na : 1.0;
+    host_so3_exp_q(a[0] * inv * th, a[1] * inv * th, a[2] * inv * th, q.qwI);
+    for (int k = 0; k < 4; ++k) q.qwI_bak[k] = q.qwI[k];
+    q.GI[0] = 0; q.GI[1] = 0; q.GI[2] = n;
+  }
   BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
   BA_CK(cudaStreamSynchronize(h->st));  // the host staging vectors die here
   return VIEO_OK;
@@ -2042,7 +2356,7 @@ int vieo_ba_chi2_large_set_level(vieo_ba_t* h, float rat) {
   if (rc) return rc;
   if (h->E > 0) {
     k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
-                                                         h->B.chi2, h->E, 0, rat, 1, 0, 1, h->d_lvl, nullptr);
+                                                         h->B.chi2, h->E, 0, rat, 1, 0, 1, h->d_lvl, nullptr, h->B.prm);
     h->launches++;
   }
   BA_CK(cudaGetLastError());
@@ -2145,7 +2459,7 @@ int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host) {
   ba_campose(h);
   k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
                                                        h->B.chi2, h->E, 1, 0.f, bad_host ? 0 : 1, remove_kernels, h->visual_only ? 0 : 1, h->d_lvl,
-                                                       h->d_bad);
+                                                       h->d_bad, h->B.prm);
   h->launches++;
   BA_CK(cudaGetLastError());
   if (bad_host) {
@@ -2182,6 +2496,29 @@ int vieo_ba_get(vieo_ba_t* h, VieoNavState* states_out, double* points_out, doub
   return VIEO_OK;
 }
 
+// estimates of the border vertices: VertexScale, and RwI * GI of VertexGThetaXYRwI (gw_out nullable)
+int vieo_ba_get_border(vieo_ba_t* h, double* scale_out, double* gw_out) {
+  VIEO_ARG(h, "null handle");
+  BA_CK(cudaSetDevice(h->device));
+  int rc = ba_read_prm(h);
+  if (rc) return rc;
+  const BaParams& q = *h->h_prm;
+  if (scale_out) *scale_out = q.has_scale ? q.sc : 1.0;
+  if (gw_out) {
+    if (!q.has_g) {
+      gw_out[0] = q.gw.x; gw_out[1] = q.gw.y; gw_out[2] = q.gw.z;
+    } else {  // q_matrix(qwI) * (0, 0, G): third column of the rotation matrix (so3.cuh q_matrix) times G
+      const double w = q.qwI[0], x = q.qwI[1], y = q.qwI[2], z = q.qwI[3];
+      const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+      const double twx = tx * w, twy = ty * w, txx = tx * x, txz = tz * x, tyy = ty * y, tyz = tz * y;
+      gw_out[0] = (txz + twy) * q.GI[2];
+      gw_out[1] = (tyz - twx) * q.GI[2];
+      gw_out[2] = (1 - (txx + tyy)) * q.GI[2];
+    }
+  }
+  return VIEO_OK;
+}
+
 int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_points, double* H_out, double* b_out) {
   VIEO_ARG(h && x_pose, "null argument");
   BA_CK(cudaSetDevice(h->device));
@@ -2208,20 +2545,28 @@ int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_po
   return h->np;
 }
 
-// Optimizer::GlobalBundleAdjustmentNavStatePRV, src/Optimizer.cc:771-1342 (bScaleOpt = false, no IMU initiator), on the
-// flattened problem: one optimize(nIterations) with g2o's own initial lambda, no outlier pass.
-int vieo_global_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb_in, const VieoCamera* cam, int n_iterations, int robust,
-                       const volatile uint8_t* stop, VieoNavState* states_out, double* points_out, double* edge_chi2,
-                       VieoBaResult* res) {
+// Optimizer::GlobalBundleAdjustmentNavStatePRV, src/Optimizer.cc:771-1342, on the flattened problem: one
+// optimize(nIterations) with g2o's own initial lambda, no outlier pass.  ex (nullable) selects the two variants:
+//   scale_opt (bScaleOpt, System::FinalGBA src/System.cc:24-29): VertexScale seeded with 1, EdgeReprojectPRS[Stereo]; on
+//     return the points are multiplied by the recovered scale (:1311-1334) and ex->scale holds the vertex estimate;
+//   imu_init (pimu_initiator, src/Odom/IMUInitialization.cpp:475): VertexGThetaXYRwI seeded from ex->gw,
+//     EdgeNavStatePRVG on every pair, the prior-bias edge on states[0]; ex->gw returns RwI * GI (:1262-1275).
+int vieo_global_ba_prv_ex(vieo_ba_t* h, const VieoBaProblem* pb_in, const VieoCamera* cam, int n_iterations, int robust,
+                          VieoGbaExtra* ex, const volatile uint8_t* stop, VieoNavState* states_out, double* points_out,
+                          double* edge_chi2, VieoBaResult* res) {
   VIEO_ARG(h && pb_in && cam && res && states_out, "null argument");
   VIEO_ARG(!pb_in->visual_only, "the global BA of the visual-only system is not implemented");
   VIEO_ARG(h->big, "vieo_global_ba_prv needs a handle from vieo_ba_create_global");
+  const bool scale_opt = ex && ex->scale_opt, imu_init = ex && ex->imu_init;
   memset(res, 0, sizeof(*res));
   memcpy(states_out, pb_in->states, sizeof(VieoNavState) * pb_in->n_states);
   if (points_out && pb_in->n_points) memcpy(points_out, pb_in->points, 24 * (size_t)pb_in->n_points);
   VieoBaProblem pb = *pb_in;
-  pb.global_ba = 1 | (robust ? 2 : 0);
+  pb.global_ba = 1 | (robust ? 2 : 0) | (scale_opt ? 4 : 0) | (imu_init ? 8 | 16 : 0);
   pb.large = 0; pb.rec_init = 0;
+  pb.scale_init = 1.0;
+  if (ex) ex->scale = 1.0;
+  if (imu_init) memcpy(pb.gw, ex->gw, 24);
   int rc = vieo_ba_set_problem(h, &pb, cam);
   if (rc) return rc;
   if (h->np == 0) return 0;  // bdimPoses == false (:1249)
@@ -2239,7 +2584,17 @@ int vieo_global_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb_in, const VieoCamer
   res->lambda_final = h->h_prm->lambda;
   res->accepted = 1;
   if ((rc = vieo_ba_get(h, states_out, points_out, edge_chi2))) return rc;
+  if (ex) {
+    if ((rc = vieo_ba_get_border(h, &ex->scale, imu_init ? ex->gw : nullptr))) return rc;
+    if (scale_opt && points_out)
+      for (size_t k = 0; k < 3 * (size_t)pb.n_points; ++k) points_out[k] = ex->scale * points_out[k];
+  }
   return it;
+}
+int vieo_global_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb_in, const VieoCamera* cam, int n_iterations, int robust,
+                       const volatile uint8_t* stop, VieoNavState* states_out, double* points_out, double* edge_chi2,
+                       VieoBaResult* res) {
+  return vieo_global_ba_prv_ex(h, pb_in, cam, n_iterations, robust, nullptr, stop, states_out, points_out, edge_chi2, res);
 }
 
 // Optimizer::LocalBundleAdjustmentNavStatePRV, src/Optimizer.cc:133-700, on the flattened problem
