@@ -289,7 +289,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = max(2 * cores, 2 * LBA_EVERY)
+    frames = args.frames  # the same batch per step as the GPU arm (same `config`)
     frames -= frames % LBA_EVERY
     imgs = stereo_stream(frames, 505, dark_every=16).reshape(frames, 2, H, W)
     pre = oracle_preint_fn()
@@ -306,8 +306,11 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
-            "config": {"workload": workload_name(frames), "frames_per_step": frames, "lba_every": LBA_EVERY,
-                       "note": "CPU oracle port of the reference path (the reference needs OpenCV/Eigen/Sophus: unbuildable offline)"},
+            "config": {"workload": workload_name(frames), "frames_per_step_per_gpu": frames, "image": f"{W}x{H}", "nfeatures": 1200,
+                       "levels": 8, "lba_every": LBA_EVERY, "lba_window": LBA_SHAPE, "pose_opt_points": list(POSE_POINTS),
+                       "sbp_queries": list(SBP_QUERIES),
+                       "note": "CPU oracle port of the reference path (the BA / matcher / IMU units need Eigen/Sophus/g2o: unbuildable "
+                               "offline; the extractor restatement is pinned to the compiled reference, oracle/_ref)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{frames} synthetic stereo frames per step (+{frames // LBA_EVERY} LocalBA windows), "
                                        "frames spread over one worker thread per core"},
@@ -630,14 +633,28 @@ def main():
     ap.add_argument("--lba-workers", type=int, default=16, help="host threads (one BA handle + stream each) running LocalBA windows")
     ap.add_argument("--lba-windows", type=int, default=3, help="distinct LocalBA problems generated")
     ap.add_argument("--ba-sms", type=int, default=0, help="SMs reserved for the LocalBA streams (CUDA green context); 0: no partition")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
+                    help="BASELINE.json configs index: 1 = the metric's workload (default, what the driver runs); 3 = 4-camera KB8 rig, "
+                         "per-camera ORB shard + pair matching (tools/bench_multicam.py); 4 = final GlobalBA with the scale vertex, "
+                         "landmark-sharded (tools/bench_gba.py)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config != 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        mod = __import__("bench_multicam" if args.config == 3 else "bench_gba")
+        if args.impl == "reference":
+            mod.run_reference(args, rank, world)
+        else:
+            mod.run_gpu(args, rank, world, local_rank, ClockSampler, peaks)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
+        if args.warmup < 3:  # timing rule: at least 3 warm-up steps; the JSON line reports the count actually run
+            print(f"bench.py: --warmup {args.warmup} raised to 3 (minimum for a valid measurement)", file=sys.stderr)
+            args.warmup = 3
         run_gpu(args, rank, world, local_rank)
 
 

@@ -118,6 +118,34 @@ int vieo_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_
 int vieo_hamming_knn2_batch_dev(const uint8_t* q_dev, size_t q_stride, const int32_t* nq_dev, int max_nq,
                                 const uint8_t* t_dev, size_t t_stride, const int32_t* nt_dev, int max_nt,
                                 int count_stride, int n_pairs, int32_t* idx_dev, int32_t* dist_dev, void* stream);
+/* ---- multi-camera frames (KB8 / distorted-stereo rigs; BASELINE configs[3]) ---------------------------------
+ * ORBextractor::operator()'s lapping-area ordering (src/ORBextractor.cc:1041-1057) on device-resident level-ordered
+ * outputs of vieo_orb_extract_batch_dev: per image, keypoints with lapping[0] <= pt.x <= lapping[1] are written from the
+ * BACK of the arrays in reverse visiting order, the others from the front; n_mono = monoIndex (the reference's return
+ * value).  lapping_dev = [n_img][2] int32 on the device, or NULL = pvLappingArea == nullptr: order kept and n_mono = 0
+ * (monoIndex is never advanced, :1003,1057 — every keypoint then takes part in the pair matching).  Out of place. */
+int vieo_lapping_split_dev(const VieoKeyPoint* kps_in_dev, const uint8_t* desc_in_dev, const int32_t* n_kp_dev, int n_img,
+                           int cap, const int32_t* lapping_dev, VieoKeyPoint* kps_out_dev, uint8_t* desc_out_dev,
+                           int32_t* n_mono_dev, void* stream);
+/* Frame::ComputeStereoFishEyeMatches, brute-force half (src/Frame.cc:613-663) for n_frames frames of n_cams cameras
+ * (image of (frame f, camera c) = f * frame_stride + c * cam_stride in the `cap`-slot arrays — [frame][camera] order is
+ * (n_cams, 1), the per-camera shards gathered from the GPUs of a rig [camera][frame] are (1, frames per shard) —
+ * lapping-ordered as above): for every camera pair i < j in the
+ * reference's order, BFMatcher(NORM_HAMMING).knnMatch(desc_i[num_mono_i:], desc_j[num_mono_j:], k = 2) — skipped (no
+ * matches) when either side has no in-area keypoint (:623) — and Lowe's ratio test `size >= 2 && (d0 < 0.7 d1 || (d0 < 75 &&
+ * d0 < 0.9 d1))` (:659-663).  Outputs [n_frames][n_pairs][cap]: idx / dist [..][2] (queryIdx row r <-> keypoint r +
+ * num_mono_i; trainIdx + num_mono_j is the keypoint of camera j; -1 / INT32_MAX = none), good = passed the ratio test
+ * (the matches FillMatchesFromPair is called on). */
+int vieo_fisheye_knn_dev(const uint8_t* desc_dev, const int32_t* n_kp_dev, const int32_t* n_mono_dev, int n_cams,
+                         int n_frames, int cap, int frame_stride, int cam_stride, int32_t* idx_dev, int32_t* dist_dev,
+                         uint8_t* good_dev, void* stream);
+/* Host-buffer form of both for a batch of frames: per-camera extraction (Frame::Frame, src/Frame.cc:259-278) with the
+ * camera's lapping area (lapping = [n_cams][2], NULL = none) + the pair matching above.  imgs: [n_frames][n_cams] images
+ * `img_stride` bytes apart; cap = vieo_orb_max_keypoints(h); n_frames * n_cams <= max_batch.
+ * kps / desc [n_img][cap], n_kp / n_mono [n_img], pair_* as above (may be NULL when n_cams == 1). */
+int vieo_multicam_frames(vieo_orb_t* h, int n_frames, int n_cams, const uint8_t* imgs, size_t img_stride, int row_stride,
+                         const int32_t* lapping, VieoKeyPoint* kps, uint8_t* desc, int32_t* n_kp, int32_t* n_mono,
+                         int32_t* pair_idx, int32_t* pair_dist, uint8_t* pair_good);
 /* Candidate-list search: row r compares q row r with t rows cand[row_ptr[r] .. row_ptr[r+1]) in list
  * order; strict '<' keeps the first of equal distances (the reference's loops).  Outputs per row: best
  * and second-best distance (256 when absent) and their train indices (-1 when absent). */
@@ -299,6 +327,18 @@ void vieo_ba_destroy(vieo_ba_t* h);
 typedef int (*vieo_allreduce_fn)(void* ctx, double* buf_dev, size_t count, void* stream);
 int vieo_ba_set_sharding(vieo_ba_t* h, int rank, int world, vieo_allreduce_fn allreduce, void* ctx);
 void* vieo_ba_stream(vieo_ba_t* h);
+/* The same exchange issued by the library itself: an NCCL communicator created from a 128-byte unique id (rank 0 makes it
+ * with vieo_comm_unique_id, the launcher hands it to the other ranks — torch.distributed broadcast, MPI, a file).  With
+ * vieo_ba_set_comm the handle calls ncclAllReduce(sum, fp64) on its own stream: no host callback in the data path, and
+ * the abort flag (pbStopFlag) is folded into the all-reduced trial record so that every rank stops at the same LM trial.
+ * libnccl.so.2 is resolved at run time (dlopen); single-GPU users never load it. */
+#define VIEO_COMM_ID_BYTES 128
+typedef struct vieo_comm vieo_comm_t;
+int vieo_comm_unique_id(uint8_t id[VIEO_COMM_ID_BYTES]);
+int vieo_comm_create(const uint8_t id[VIEO_COMM_ID_BYTES], int rank, int world, int device, vieo_comm_t** out);
+void vieo_comm_destroy(vieo_comm_t* c);
+int vieo_comm_allreduce_f64(vieo_comm_t* c, double* buf_dev, size_t count, void* stream);
+int vieo_ba_set_comm(vieo_ba_t* h, vieo_comm_t* comm /* NULL: single GPU */);
 /* The whole reference routine from "Setup optimizer" to the err/err_end guard on the flattened problem: Chi2LargeSetLevel,
  * optimize(optit[0]), inlier re-classification + kernel removal, optimize(optit[1]), outlier list.
  *   stop      pbStopFlag (mbAbortBA), polled before optimising and every LM iteration; may be NULL

@@ -213,3 +213,34 @@ extern "C" void orc_distinctive_descriptors(const uint8_t* desc_pool, const int3
     median[p] = BestMedian;
   }
 }
+
+// Frame::ComputeStereoFishEyeMatches, brute-force half (src/Frame.cc:613-663) for ONE frame of n_cams cameras whose
+// keypoints are already lapping-ordered by ORBextractor::operator() (in-area ones at rows >= num_mono): for every camera
+// pair i < j in the reference's loop order, knnMatch(desc_i[num_mono_i:], desc_j[num_mono_j:], k = 2) — the pair is
+// skipped (:623) when either side has no in-area row — then `size >= 2 && (d0 < d1 * 0.7 || (d0 < 75 && d0 < d1 * 0.9))`
+// with float distances against double constants (:659-663).  desc: n_cams blocks of `cap` rows.  Outputs [n_pairs][cap]:
+// idx / dist [..][2] (-1 / INT_MAX = none), good (0 / 1).
+extern "C" void orc_fisheye_matches(const uint8_t* desc, const int32_t* n_kp, const int32_t* n_mono, int n_cams, int cap,
+                                    int32_t* idx, int32_t* dist, uint8_t* good) {
+  const int thOrbDist = (100 + 50) / 2;  // (ORBmatcher::TH_HIGH + ORBmatcher::TH_LOW) / 2
+  int pair = 0;
+  for (int i = 0; i < n_cams - 1; ++i)
+    for (int j = i + 1; j < n_cams; ++j, ++pair) {
+      int32_t* pi = idx + (size_t)pair * cap * 2;
+      int32_t* pd = dist + (size_t)pair * cap * 2;
+      uint8_t* pg = good + (size_t)pair * cap;
+      for (int r = 0; r < cap; ++r) {
+        pi[2 * r] = pi[2 * r + 1] = -1;
+        pd[2 * r] = pd[2 * r + 1] = INT_MAX;
+        pg[r] = 0;
+      }
+      if (n_mono[i] >= n_kp[i] || n_mono[j] >= n_kp[j]) continue;
+      const int nq = n_kp[i] - n_mono[i], nt = n_kp[j] - n_mono[j];
+      orc_hamming_knn2(desc + ((size_t)i * cap + n_mono[i]) * 32, nq, desc + ((size_t)j * cap + n_mono[j]) * 32, nt, pi, pd);
+      for (int r = 0; r < nq; ++r) {
+        if (pi[2 * r + 1] < 0) continue;  // knnMatch returned fewer than 2 neighbours
+        const float d0 = (float)pd[2 * r], d1 = (float)pd[2 * r + 1];
+        pg[r] = (d0 < d1 * 0.7 || (d0 < thOrbDist && d0 < d1 * 0.9)) ? 1 : 0;
+      }
+    }
+}

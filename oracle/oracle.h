@@ -140,3 +140,13 @@ int orc_is_in_frustum(const OrcFrustumFrame* f, int n, const float* wP, const fl
 #ifdef __cplusplus
 }
 #endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* Frame::ComputeStereoFishEyeMatches brute-force half for one multi-camera frame (match_oracle.cc) */
+void orc_fisheye_matches(const uint8_t* desc, const int32_t* n_kp, const int32_t* n_mono, int n_cams, int cap, int32_t* idx,
+                         int32_t* dist, uint8_t* good);
+#ifdef __cplusplus
+}
+#endif

@@ -169,6 +169,22 @@ def hamming_knn2(q, t):
     return idx, dist
 
 
+def fisheye_matches(desc, n_kp, n_mono):
+    """Frame::ComputeStereoFishEyeMatches brute-force half for one frame: desc [n_cams][cap][32] -> idx, dist
+    [n_pairs][cap][2], good [n_pairs][cap]."""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n_cams, cap = desc.shape[0], desc.shape[1]
+    n_pairs = n_cams * (n_cams - 1) // 2
+    n_kp = np.ascontiguousarray(n_kp, np.int32); n_mono = np.ascontiguousarray(n_mono, np.int32)
+    idx = np.empty((n_pairs, cap, 2), np.int32); dist = np.empty((n_pairs, cap, 2), np.int32)
+    good = np.empty((n_pairs, cap), np.uint8)
+    L = lib()
+    L.orc_fisheye_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_fisheye_matches.restype = None
+    L.orc_fisheye_matches(_p(desc), _p(n_kp), _p(n_mono), n_cams, cap, _p(idx), _p(dist), _p(good))
+    return idx, dist, good
+
+
 def hamming_csr(q, t, row_ptr, cand):
     q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
     row_ptr = np.ascontiguousarray(row_ptr, np.int32); cand = np.ascontiguousarray(cand, np.int32)

@@ -142,3 +142,34 @@ def test_hamming_oracle(goldens):
     # empty rows
     bd, bi, sd, si = O.hamming_csr(q[:3], t, np.zeros(4, np.int32), np.zeros(0, np.int32))
     assert (bd == 256).all() and (bi == -1).all()
+
+
+def test_fisheye_matches_against_cv2_bfmatcher():
+    """Frame::ComputeStereoFishEyeMatches brute-force half: the oracle against cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2)
+    on the in-area slices of every camera pair + the ratio test evaluated in numpy float32 / float64."""
+    cv2 = pytest.importorskip("cv2")
+    r = np.random.default_rng(17)
+    n_cams, cap = 4, 96
+    desc = r.integers(0, 256, (n_cams, cap, 32), dtype=np.uint8)
+    desc[1, 30:60] = desc[0, 10:40] ^ (r.integers(0, 256, (30, 32)) < 20).astype(np.uint8)  # near copies
+    nk = np.array([90, 96, 50, 7], np.int32); nm = np.array([5, 20, 50, 0], np.int32)
+    idx, dist, good = O.fisheye_matches(desc, nk, nm)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    p = 0
+    for i in range(n_cams - 1):
+        for j in range(i + 1, n_cams):
+            if nm[i] >= nk[i] or nm[j] >= nk[j]:
+                assert (idx[p] == -1).all() and not good[p].any()
+                p += 1
+                continue
+            m = bf.knnMatch(desc[i, nm[i]:nk[i]], desc[j, nm[j]:nk[j]], k=2)
+            for q, mm in enumerate(m):
+                assert [x.trainIdx for x in mm] == [v for v in idx[p, q] if v >= 0]
+                assert [int(x.distance) for x in mm] == [int(v) for v, k in zip(dist[p, q], idx[p, q]) if k >= 0]
+                g = len(mm) >= 2 and (np.float64(np.float32(mm[0].distance)) < np.float64(np.float32(mm[1].distance)) * 0.7 or
+                                      (mm[0].distance < 75 and
+                                       np.float64(np.float32(mm[0].distance)) < np.float64(np.float32(mm[1].distance)) * 0.9))
+                assert bool(good[p, q]) == bool(g)
+            assert not good[p, len(m):].any()
+            p += 1
+    assert good.sum() > 10

@@ -42,7 +42,11 @@ def main():
     part = sharding.shard_lba_problem(d, rank, world)
     caps = dict(max_states=n_kf + 8, max_points=len(d["points"]) + 8, max_edges=len(d["edge_state"]) + 8, max_imu=n_kf + 8)
     ba = api.BundleAdjuster(device=local, global_ba=True, **caps)
-    sharding.install_allreduce(ba, rank, world)
+    comm = sharding.make_comm(rank, world, local)
+    if os.environ.get("VIEO_SHARD_CALLBACK") == "1":
+        sharding.install_allreduce(ba, rank, world)
+    else:
+        sharding.install_comm(ba, comm)
     ba.GlobalBundleAdjustmentNavStatePRV(part, cam, nIterations=2, bRobust=False)  # warm-up (NCCL channels, allocations)
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()

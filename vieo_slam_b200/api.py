@@ -93,11 +93,20 @@ def lib():
         L.vieo_imu_preint_batch_dev.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
         L.vieo_pose_opt_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32]
         L.vieo_pose_opt_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.vieo_multicam_frames.argtypes = [vp, i32, i32, vp, C.c_size_t, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.vieo_lapping_split_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+        L.vieo_fisheye_knn_dev.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
         L.vieo_ba_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
         L.vieo_ba_create_global.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
         L.vieo_ba_destroy.argtypes = [vp]
         L.vieo_ba_destroy.restype = None
         L.vieo_ba_set_sharding.argtypes = [vp, i32, i32, vp, vp]
+        L.vieo_comm_unique_id.argtypes = [vp]
+        L.vieo_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+        L.vieo_comm_destroy.argtypes = [vp]
+        L.vieo_comm_destroy.restype = None
+        L.vieo_comm_allreduce_f64.argtypes = [vp, vp, C.c_size_t, vp]
+        L.vieo_ba_set_comm.argtypes = [vp, vp]
         L.vieo_ba_stream.argtypes = [vp]
         L.vieo_ba_stream.restype = vp
         L.vieo_local_ba_prv.argtypes = [vp] * 9
@@ -238,6 +247,24 @@ class ORBextractor:
         _check(lib().vieo_orb_extract_batch(self._h, n, _p(images), images.strides[0], images.strides[1], _p(kps),
                                             _p(desc), self.cap, _p(nk)))
         return kps, desc, nk
+
+    def multicam_frames(self, images, n_cams, lapping=None):
+        """Multi-camera frames (KB8 rigs): images (n_frames * n_cams, H, W) u8 ordered [frame][camera]; lapping =
+        [n_cams][2] or None.  Per-camera ORBextractor::operator() with the lapping area (Frame::Frame, src/Frame.cc:259-278)
+        + the brute-force half of Frame::ComputeStereoFishEyeMatches (:613-663) for every camera pair.
+        -> dict(kps [n_img, cap], desc, n_kp, n_mono, pair_idx [n_frames, n_pairs, cap, 2], pair_dist, pair_good)."""
+        images = np.ascontiguousarray(images, np.uint8)
+        n_img = images.shape[0]
+        assert n_img % n_cams == 0
+        n_frames, n_pairs = n_img // n_cams, n_cams * (n_cams - 1) // 2
+        kps = np.empty((n_img, self.cap), KP_DTYPE); desc = np.empty((n_img, self.cap, 32), np.uint8)
+        nk = np.empty(n_img, np.int32); nm = np.empty(n_img, np.int32)
+        pi = np.empty((n_frames, n_pairs, self.cap, 2), np.int32); pd = np.empty((n_frames, n_pairs, self.cap, 2), np.int32)
+        pg = np.empty((n_frames, n_pairs, self.cap), np.uint8)
+        lap = None if lapping is None else np.ascontiguousarray(lapping, np.int32).reshape(n_cams, 2)
+        _check(lib().vieo_multicam_frames(self._h, n_frames, n_cams, _p(images), images.strides[0], images.strides[1],
+                                          _p(lap), _p(kps), _p(desc), _p(nk), _p(nm), _p(pi), _p(pd), _p(pg)))
+        return dict(kps=kps, desc=desc, n_kp=nk, n_mono=nm, pair_idx=pi, pair_dist=pd, pair_good=pg)
 
     def extract_batch_dev(self, imgs_ptr, n, img_stride, row_stride, kps_ptr, desc_ptr, cap, nkp_ptr, stream=0):
         """All pointers are device addresses (ints); asynchronous on `stream`."""
@@ -638,6 +665,35 @@ def ba_problem(d, large=False, rec_init=False, visual_only=False):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it; the launcher hands it to the other ranks)."""
+    buf = np.zeros(COMM_ID_BYTES, np.uint8)
+    _check(lib().vieo_comm_unique_id(_p(buf)))
+    return buf
+
+
+class Comm:
+    """Library-owned NCCL communicator (vieo_comm_*): the sharded bundle adjustment's all-reduce issued from C."""
+
+    def __init__(self, unique_id, rank, world, device=0):
+        self._h = C.c_void_p()
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert uid.size == COMM_ID_BYTES
+        _check(lib().vieo_comm_create(_p(uid), rank, world, device, C.byref(self._h)))
+        self.rank, self.world = rank, world
+
+    def allreduce_f64(self, ptr, count, stream=0):
+        _check(lib().vieo_comm_allreduce_f64(self._h, ptr, count, stream))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h and _lib is not None:
+            _lib.vieo_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 class BundleAdjuster:
@@ -672,6 +728,11 @@ class BundleAdjuster:
                 return 1
         self._cb = ALLREDUCE_FN(cb) if allreduce else None
         _check(lib().vieo_ba_set_sharding(self._h, rank, world, C.cast(self._cb, C.c_void_p) if self._cb else None, None))
+
+    def set_comm(self, comm):
+        """Sharding with the library's own NCCL communicator (no host callback); None: single GPU."""
+        self._comm = comm
+        _check(lib().vieo_ba_set_comm(self._h, comm._h if comm is not None else None))
 
     def LocalBundleAdjustmentNavStatePRV(self, d, cam, large=False, rec_init=False, visual_only=False, stop=None):
         pb, keep = ba_problem(d, large, rec_init, visual_only)
@@ -725,8 +786,8 @@ class BundleAdjuster:
         n = _check(lib().vieo_ba_debug_step(self._h, lam, _p(xp), _p(xl), _p(H), _p(b)))
         return xp[:n], xl, H[:n * n].reshape(n, n), b[:n]
 
-    def optimize(self, iterations, lambda_init=0.0):
-        return _check(lib().vieo_ba_optimize(self._h, iterations, lambda_init, None))
+    def optimize(self, iterations, lambda_init=0.0, stop=None):
+        return _check(lib().vieo_ba_optimize(self._h, iterations, lambda_init, _p(stop)))
 
     def active_robust_chi2(self, recompute=True):
         c = C.c_double(0)

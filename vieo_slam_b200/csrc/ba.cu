@@ -68,7 +68,8 @@ struct BaParams {
   int trials;           // LM trials run by the current optimize()
   double lambda, ni, user_lambda;
   double chi_cur, ini_chi;   // activeRobustChi2 of the current estimate / at the start of the iteration
-  double pair[2];            // [robust chi2 of the last linearisation, landmark part of computeScale] (all-reduced when sharded)
+  double pair[4];            // [robust chi2 of the last linearisation, landmark part of computeScale, abort flag seen by
+                             //  this rank, -] — all-reduced when sharded, so every rank sees the same sums
   double pscale, chi_dense;  // pose part of computeScale; dense-edge chi2 of the last linearisation
   CamK cam;                  // camera, gravity and Huber deltas of the problem
   Vec3 gw;
@@ -652,16 +653,20 @@ __global__ void __launch_bounds__(256) k_ba_pose_reduce(BaBuf B, int into_other)
   __shared__ double s_w[8][27];
   __shared__ double s_s[256];
   const BaParams& prm = *B.prm;
-  if (prm.done || (int)blockIdx.x >= prm.nfree) return;
+  if (prm.done) return;
+  const int f = blockIdx.x;
+  const bool have_kf = f < prm.nfree;  // block 0 also totals the step's scalars, free keyframes or not
+  if (!have_kf && f != 0) return;
   const int set = into_other ? 1 - prm.cur : prm.cur;
   const int np = prm.np;
   double* H = B.H[set];
   double* b = B.b[set];
-  const int f = blockIdx.x, k = B.free_state[f], o = B.off0[k];
+  const int o = have_kf ? B.off0[B.free_state[f]] : 0;
+  const int e0 = have_kf ? B.ps_ptr[f] : 0, e1 = have_kf ? B.ps_ptr[f + 1] : 0;
   double acc[27];
 #pragma unroll
   for (int q = 0; q < 27; ++q) acc[q] = 0;
-  for (int t = B.ps_ptr[f] + threadIdx.x; t < B.ps_ptr[f + 1]; t += 256) {
+  for (int t = e0 + threadIdx.x; t < e1; t += 256) {
     const double* Ai = B.A + 27 * (size_t)B.ps_edges[t];
 #pragma unroll
     for (int q = 0; q < 27; ++q) acc[q] += Ai[q];
@@ -680,7 +685,7 @@ __global__ void __launch_bounds__(256) k_ba_pose_reduce(BaBuf B, int into_other)
     s_w[0][threadIdx.x] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && have_kf) {
     int q = 0;
     for (int a = 0; a < 6; ++a) {
       b[o + a] += s_w[0][21 + a];
@@ -694,7 +699,7 @@ __global__ void __launch_bounds__(256) k_ba_pose_reduce(BaBuf B, int into_other)
   if (prm.has_scale) {  // the keyframe's 6 x 1 block of the scale column: fixed-order sum of its edges' Hps
     __syncthreads();
     double hp[6] = {0, 0, 0, 0, 0, 0};
-    for (int t = B.ps_ptr[f] + threadIdx.x; t < B.ps_ptr[f + 1]; t += 256) {
+    for (int t = e0 + threadIdx.x; t < e1; t += 256) {
       const double* Asi = B.As + 8 * (size_t)B.ps_edges[t];
 #pragma unroll
       for (int q = 0; q < 6; ++q) hp[q] += Asi[q];
@@ -707,7 +712,7 @@ __global__ void __launch_bounds__(256) k_ba_pose_reduce(BaBuf B, int into_other)
 #pragma unroll
       for (int q = 0; q < 6; ++q) s_w[threadIdx.x >> 5][q] = hp[q];
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if (threadIdx.x < 6 && have_kf) {
       double v = 0;
       for (int w = 0; w < 8; ++w) v += s_w[w][threadIdx.x];
       H[(size_t)(o + threadIdx.x) * np + prm.off_s] += v;
@@ -759,6 +764,7 @@ __global__ void __launch_bounds__(256) k_ba_pose_reduce(BaBuf B, int into_other)
   if (threadIdx.x == 0) {
     B.prm->pair[0] = tot;
     B.prm->pair[1] = scale_total;
+    B.prm->pair[2] = prm.stop ? 1.0 : 0.0;  // summed over ranks: the abort takes effect at the same trial everywhere
   }
 }
 
@@ -813,6 +819,9 @@ __global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode, cudaGraph
     if (cond && threadIdx.x == 0) cudaGraphSetConditional(cond, 0);
     return;
   }
+  // the caller's abort flag (pbStopFlag): this rank's copy, or — sharded — the all-reduced count of ranks that saw it, so
+  // that every rank stops enqueuing collectives at the same trial (ranks poll their host flags at different moments)
+  const bool stop_now = prm.world > 1 ? prm.pair[2] > 0.0 : prm.stop != 0;
   if (mode == 0) {
     double lam = prm.user_lambda;
     if (!(lam > 0) && prm.world > 1) {  // from the all-reduced k_ba_diag_pack buffer
@@ -834,7 +843,7 @@ __global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode, cudaGraph
       prm.iteration = 0;
       prm.iters_done = 0;
       prm.qmax = 0;
-      if (prm.iters_target <= 0 || prm.stop) prm.done = 1;
+      if (prm.iters_target <= 0 || stop_now) prm.done = 1;
     }
     return;
   }
@@ -860,7 +869,7 @@ __global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode, cudaGraph
     }
     prm.qmax++;
     prm.trials++;
-    const bool more_trials = rho < 0 && prm.qmax < 10 && !prm.stop;
+    const bool more_trials = rho < 0 && prm.qmax < 10 && !stop_now;
     if (!more_trials) {
       prm.iters_done++;
       bool terminate = prm.qmax == 10 || rho == 0;
@@ -870,7 +879,7 @@ __global__ void __launch_bounds__(256) k_ba_control(BaBuf B, int mode, cudaGraph
         if (prm.nBad >= 3) terminate = true;
       }
       prm.iteration++;
-      if (terminate || prm.iteration >= prm.iters_target || prm.stop) prm.done = 1;
+      if (terminate || prm.iteration >= prm.iters_target || stop_now) prm.done = 1;
       else {
         prm.ini_chi = prm.chi_cur;
         prm.qmax = 0;
@@ -1713,6 +1722,8 @@ struct vieo_ba {
   int rank = 0, world = 1;
   vieo_allreduce_fn allreduce = nullptr;
   void* ar_ctx = nullptr;
+  vieo_comm* comm = nullptr;  // library-owned NCCL communicator (vieo_ba_set_comm): the exchange without a host callback
+  bool sharded() const { return world > 1 && (allreduce || comm); }
   CamK cam;
   Vec3 gw;
   double dm = 0, ds = 0;
@@ -1817,6 +1828,27 @@ size_t gba_schur_smem(int nfree) {  // row tile [6][6 nfree + 2]; the extra bloc
 int ba_campose(vieo_ba* h) {
   k_ba_campose<<<(h->K + 127) / 128, 128, 0, h->st>>>(h->cam, h->B.st, h->K, h->B.cp);
   h->launches++;
+  BA_CK(cudaGetLastError());
+  return VIEO_OK;
+}
+
+int ba_allreduce(vieo_ba* h, double* buf, size_t n);
+
+// The caller's abort flag as ONE decision for all ranks of a sharded handle (max over ranks through the sum all-reduce);
+// a plain read on a single GPU.  Synchronises the stream when sharded.
+int ba_agree_stop(vieo_ba* h, const volatile uint8_t* stop, bool* out) {
+  const bool mine = stop && *stop;
+  if (!h->sharded()) {
+    *out = mine;
+    return VIEO_OK;
+  }
+  h->h_ctl[8] = mine ? 1.0 : 0.0;
+  BA_CK(cudaMemcpyAsync(h->d_ctl + 8, h->h_ctl + 8, 8, cudaMemcpyHostToDevice, h->st));
+  int rc = ba_allreduce(h, h->d_ctl + 8, 1);
+  if (rc) return rc;
+  BA_CK(cudaMemcpyAsync(h->h_ctl + 8, h->d_ctl + 8, 8, cudaMemcpyDeviceToHost, h->st));
+  BA_CK(cudaStreamSynchronize(h->st));
+  *out = h->h_ctl[8] > 0.0;
   return VIEO_OK;
 }
 
@@ -1837,7 +1869,8 @@ int ba_errors(vieo_ba* h, int all, double* d_out) {
 }
 
 int ba_allreduce(vieo_ba* h, double* buf, size_t n) {
-  if (!(h->allreduce && h->world > 1)) return VIEO_OK;
+  if (!h->sharded()) return VIEO_OK;
+  if (h->comm) return vieo::comm_allreduce_f64(h->comm, buf, n, h->st);
   if (h->allreduce(h->ar_ctx, buf, n, (void*)h->st)) {
     vieo::set_error("allreduce callback failed");
     return VIEO_E_CUDA;
@@ -1923,7 +1956,7 @@ int ba_enqueue_trial(vieo_ba* h, bool at_capacity, cudaGraphConditionalHandle co
   int rc;
   if ((rc = ba_enqueue_solve(h, at_capacity, 0, 0.0, nullptr))) return rc;
   if ((rc = ba_enqueue_linearize(h, 1, at_capacity))) return rc;
-  if (!at_capacity && (rc = ba_allreduce(h, h->B.prm->pair, 2))) return rc;
+  if (!at_capacity && (rc = ba_allreduce(h, h->B.prm->pair, 3))) return rc;
   k_ba_control<<<1, 256, 0, h->st>>>(h->B, 1, cond);
   h->launches++;
   return VIEO_OK;
@@ -2104,9 +2137,20 @@ void vieo_ba_destroy(vieo_ba_t* h) {
   delete h;
 }
 
+int vieo_ba_set_comm(vieo_ba_t* h, vieo_comm_t* comm) {
+  VIEO_ARG(h, "null handle");
+  h->comm = comm;
+  h->allreduce = nullptr;
+  h->ar_ctx = nullptr;
+  h->rank = 0;
+  h->world = 1;
+  if (comm) vieo::comm_info(comm, &h->rank, &h->world);
+  return VIEO_OK;
+}
 int vieo_ba_set_sharding(vieo_ba_t* h, int rank, int world, vieo_allreduce_fn allreduce, void* ctx) {
   VIEO_ARG(h && world >= 1 && rank >= 0 && rank < world, "bad argument");
   h->rank = rank; h->world = world; h->allreduce = allreduce; h->ar_ctx = ctx;
+  h->comm = nullptr;
   return VIEO_OK;
 }
 
@@ -2123,6 +2167,31 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   }
   VIEO_ARG(K > 0 && pb->states && pb->state_flags, "no states");
   VIEO_ARG(E == 0 || (pb->edge_state && pb->edge_point && pb->obs && pb->inv_sigma2 && pb->edge_flags && pb->points), "null edge array");
+  // the whole problem is validated BEFORE any handle state changes: a rejected problem leaves the previous one usable
+  for (int i = 0; i < E; ++i) {
+    VIEO_ARG(pb->edge_point[i] >= 0 && pb->edge_point[i] < P && pb->edge_state[i] >= 0 && pb->edge_state[i] < K, "edge index out of range");
+    VIEO_ARG(i == 0 || pb->edge_point[i - 1] <= pb->edge_point[i], "edges must be sorted by point");
+  }
+  VIEO_ARG(M == 0 || (pb->imu_i && pb->imu_j && pb->preint && pb->imu_dt_kf), "null inertial array");
+  for (int m = 0; m < M; ++m)
+    VIEO_ARG(pb->imu_i[m] >= 0 && pb->imu_i[m] < K && pb->imu_j[m] >= 0 && pb->imu_j[m] < K, "imu state index out of range");
+  VIEO_ARG(cam->model >= 0 && cam->model <= 2 && cam->num_k >= 0 && cam->num_k <= 6, "unsupported camera model");
+  VIEO_ARG(!(pb->global_ba & (4 | 8 | 16)) || h->big, "the scale / gravity-direction vertices need a handle from vieo_ba_create_global");
+  {
+    int nfree_ = 0;
+    size_t np_ = 0;
+    for (int k = 0; k < K; ++k) {
+      const uint8_t f = pb->state_flags[k];
+      if (!(f & 1)) { ++nfree_; np_ += 6; }
+      if ((f & 2) && !(f & 4) && !pb->visual_only) np_ += 9;
+    }
+    np_ += ((pb->global_ba & 4) ? 1 : 0) + ((pb->global_ba & 8) ? 2 : 0);
+    if (nfree_ > h->cap_free || np_ > h->cap_np) {
+      set_error("vieo_ba_set_problem: %d free keyframes / %zu pose dimensions exceed the engine's tile (%d / %zu)", nfree_, np_,
+                h->cap_free, h->cap_np);
+      return VIEO_E_CAPACITY;
+    }
+  }
   BA_CK(cudaSetDevice(h->device));
   h->K = K; h->P = P; h->E = E; h->M = M;
   h->launches = 0;
@@ -2321,7 +2390,7 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   q.n_colors = n_colors;
   h->n_colors = n_colors;
   q.rank = h->rank;
-  q.world = (h->allreduce && h->world > 1) ? h->world : 1;
+  q.world = h->sharded() ? h->world : 1;
   q.lambda_on_poses = h->rank == 0 ? 1 : 0;
   q.done = 1;
   q.ok = 1;
@@ -2375,8 +2444,10 @@ int vieo_ba_active_robust_chi2(vieo_ba_t* h, int recompute, double* chi2) {
     int rc = ba_errors(h, 2, h->d_ctl + 6);
     if (rc) return rc;
   }
-  if (h->allreduce && h->world > 1)
-    if (h->allreduce(h->ar_ctx, h->d_ctl + 6, 1, (void*)h->st)) return VIEO_E_CUDA;
+  {
+    int rc2 = ba_allreduce(h, h->d_ctl + 6, 1);
+    if (rc2) return rc2;
+  }
   BA_CK(cudaMemcpyAsync(h->h_ctl + 6, h->d_ctl + 6, 8, cudaMemcpyDeviceToHost, h->st));
   BA_CK(cudaStreamSynchronize(h->st));
   *chi2 = h->h_ctl[6];
@@ -2387,19 +2458,23 @@ int vieo_ba_optimize(vieo_ba_t* h, int iterations, double lambda_init, const vol
   VIEO_ARG(h && iterations >= 0, "bad argument");
   BA_CK(cudaSetDevice(h->device));
   if (h->np == 0 || iterations == 0) return 0;
-  if (stop && *stop) return 0;
-  const bool sharded = h->allreduce && h->world > 1;
+  const bool sharded = h->sharded();
+  // single GPU: nothing to do once the caller asked to stop.  Sharded: a rank must not leave before its peers do — its
+  // flag goes into the all-reduced trial record instead and k_ba_control ends the call on every rank at once.
+  if (!sharded && stop && *stop) return 0;
   // optimize() state machine on the device: reset, then a fresh linearisation at the current estimate (levels / kernels
   // may have changed since the last call)
   BaParams& q = *h->h_prm;
   q.cur = 0; q.done = 0; q.stop = 0; q.ok = 1;
   q.iteration = 0; q.iters_target = iterations; q.iters_done = 0; q.qmax = 0; q.nBad = 0; q.trials = 0;
   q.user_lambda = lambda_init;
+  if (sharded && stop && *stop) q.stop = 1;
   BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
   BA_CK(cudaMemsetAsync(h->B.x, 0, 8 * (size_t)h->np, h->st));
   int rc = ba_campose(h);
+  if (rc) return rc;
   if ((rc = ba_enqueue_linearize(h, 0, false))) return rc;
-  if ((rc = ba_allreduce(h, h->B.prm->pair, 2))) return rc;
+  if ((rc = ba_allreduce(h, h->B.prm->pair, 3))) return rc;
   if (sharded && !(lambda_init > 0)) {  // g2o's own initial lambda needs the global maximum of the diagonal
     k_ba_diag_pack<<<1, 256, 0, h->st>>>(h->B);
     h->launches++;
@@ -2456,7 +2531,10 @@ int vieo_ba_reclassify(vieo_ba_t* h, int remove_kernels, uint8_t* bad_host) {
   VIEO_ARG(h, "null handle");
   BA_CK(cudaSetDevice(h->device));
   if (h->E == 0) return VIEO_OK;
-  ba_campose(h);
+  {
+    int rc = ba_campose(h);
+    if (rc) return rc;
+  }
   k_ba_classify<<<(h->E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags,
                                                        h->B.chi2, h->E, 1, 0.f, bad_host ? 0 : 1, remove_kernels, h->visual_only ? 0 : 1, h->d_lvl,
                                                        h->d_bad, h->B.prm);
@@ -2526,6 +2604,7 @@ int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_po
   q.cur = 0; q.done = 0; q.stop = 0; q.ok = 1;
   BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
   int rc = ba_campose(h);
+  if (rc) return rc;
   if ((rc = ba_enqueue_linearize(h, 0, false))) return rc;
   if ((rc = ba_enqueue_solve(h, false, 1, lambda, h->d_xl))) return rc;
   BA_CK(cudaGetLastError());
@@ -2574,7 +2653,9 @@ int vieo_global_ba_prv_ex(vieo_ba_t* h, const VieoBaProblem* pb_in, const VieoCa
   if ((rc = vieo_ba_active_robust_chi2(h, 1, &chi))) return rc;
   res->err0 = chi;
   int it = 0;
-  if (!(stop && *stop)) {
+  bool stopped = false;
+  if ((rc = ba_agree_stop(h, stop, &stopped))) return rc;
+  if (!stopped) {
     it = vieo_ba_optimize(h, n_iterations, 0.0, stop);
     if (it < 0) return it;
   }
@@ -2615,7 +2696,9 @@ int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* c
   if (!anyfree) return VIEO_OK;  // if (!bdimPoses) return; (:178)
   int rc = vieo_ba_set_problem(h, pb, cam);
   if (rc) return rc;
-  if (stop && *stop) return VIEO_OK;  // "Aborted OLBA" (:524-528)
+  bool stopped = false;
+  if ((rc = ba_agree_stop(h, stop, &stopped))) return rc;
+  if (stopped) return VIEO_OK;  // "Aborted OLBA" (:524-528)
   if (!pb->visual_only && (rc = vieo_ba_chi2_large_set_level(h, 100.f))) return rc;  // PRV version only (:534-536)
   double chi = 0;
   if ((rc = vieo_ba_active_robust_chi2(h, 1, &chi))) return rc;
@@ -2625,7 +2708,8 @@ int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* c
   if (n < 0) return n;
   res->iterations[0] = n;
   bool bDoMore = true;
-  if (stop && *stop) bDoMore = false;
+  if ((rc = ba_agree_stop(h, stop, &stopped))) return rc;
+  if (stopped) bDoMore = false;
   if (bDoMore) {
     if ((rc = vieo_ba_reclassify(h, 1, nullptr))) return rc;
     n = vieo_ba_optimize(h, optit[1], lambda0, stop);

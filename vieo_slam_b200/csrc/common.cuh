@@ -80,9 +80,17 @@ __device__ __forceinline__ void warp0_excl_scan(int* a, int n, int* total) {
 
 }  // namespace vieo
 
+// internal cross-file hooks (comm.cu -> ba.cu)
+struct vieo_comm;
+namespace vieo {
+int comm_allreduce_f64(vieo_comm* c, double* buf, size_t count, cudaStream_t stream);
+void comm_info(const vieo_comm* c, int* rank, int* world);
+}  // namespace vieo
+
 // internal cross-file hooks (orb.cu -> frontend.cu)
 struct vieo_orb;
 namespace vieo {
 int orb_enqueue_host(vieo_orb* h, int n_img, const uint8_t* imgs, size_t img_stride, int row_stride);
+void orb_info(vieo_orb* h, int* device, int* max_batch);
 void orb_dev_outputs(vieo_orb* h, VieoKeyPoint** kps, uint8_t** desc, int** nkp, int* cap, cudaStream_t* st);
 }  // namespace vieo

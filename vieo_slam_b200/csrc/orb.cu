@@ -1111,6 +1111,10 @@ int orb_enqueue_host(vieo_orb* h, int n_img, const uint8_t* imgs, size_t img_str
                               h->cfg.width, h->cfg.height, cudaMemcpyHostToDevice, st));
   return orb_run(h, n_img, P.lvl[0], P.img_stride[0], P.pitch[0], h->d_kps, h->d_desc, h->cap_total, h->d_nkp, st);
 }
+void orb_info(vieo_orb* h, int* device, int* max_batch) {
+  *device = h->device;
+  *max_batch = h->cfg.max_batch;
+}
 void orb_dev_outputs(vieo_orb* h, VieoKeyPoint** kps, uint8_t** desc, int** nkp, int* cap, cudaStream_t* st) {
   *kps = h->d_kps;
   *desc = h->d_desc;

@@ -67,6 +67,25 @@ def install_allreduce(ba, rank, world, group=None):
     return allreduce
 
 
+def make_comm(rank, world, device, group=None):
+    """Library-owned NCCL communicator for a torch.distributed job: rank 0 creates the unique id, one broadcast hands it
+    to the others (the only use of torch.distributed: rendez-vous, never the data path)."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    uid = torch.from_numpy(api.comm_unique_id() if rank == 0 else np.zeros(api.COMM_ID_BYTES, np.uint8))
+    if dist.get_backend(group) == "nccl":
+        uid = uid.cuda(device)
+    dist.broadcast(uid, src=0, group=group)
+    return api.Comm(uid.cpu().numpy(), rank, world, device)
+
+
+def install_comm(ba, comm):
+    """Sharded BundleAdjuster with the all-reduce issued by the library (ncclAllReduce on the handle's stream)."""
+    ba.set_comm(comm)
+    return comm
+
+
 def _tensor_from_ptr(ptr, count):
     """Zero-copy float64 CUDA tensor over memory owned by the C library (via __cuda_array_interface__)."""
     import torch
