@@ -396,8 +396,8 @@ def run_gpu(args, rank, world, local_rank):
                 setattr(q, name, fr[name].data_ptr())
         sbp_dev.append((int(pb["mode"]), d, q, out, scr, fr))
 
-    def sbp_enqueue(stream):
-        for mode, d, q, out, scr, fr in sbp_dev:
+    def sbp_enqueue(stream, which=None):
+        for mode, d, q, out, scr, fr in (sbp_dev if which is None else sbp_dev[which:which + 1]):
             if fr is not None:
                 api.frustum_batch_dev(fr["frames"].data_ptr(), F, d["p_wP"].data_ptr(), d["p_normal"].data_ptr(),
                                       d["p_max_dist"].data_ptr(), d["p_min_dist"].data_ptr(), d["p_skip"].data_ptr(),
@@ -409,8 +409,10 @@ def run_gpu(args, rank, world, local_rank):
     n_workers = max(1, min(args.lba_workers, n_lba)) if n_lba else 0
     if part:
         part.bind(api.SM_BA)
+    # one engine (handle + stream) per LocalBA window of a step; each host worker thread drives its share of them through
+    # the asynchronous C ABI: every window is enqueued (device-side LM loops) before any is awaited
     bas = [api.BundleAdjuster(max_states=64, max_points=2048, max_edges=16384, max_imu=16, device=local_rank)
-           for _ in range(n_workers)]
+           for _ in range(n_lba)]
     lba_pool = ThreadPoolExecutor(n_workers) if n_workers else None
     torch.cuda.synchronize()
     if part:
@@ -422,26 +424,51 @@ def run_gpu(args, rank, world, local_rank):
         main = torch.cuda.current_stream()
         side = torch.cuda.Stream()
 
-    def lba_job(wk, i0):
-        for i in range(i0, n_lba, n_workers):
-            out = bas[wk].LocalBundleAdjustmentNavStatePRV(lbas[i % len(lbas)], trk["cam"])
+    def lba_job(wk, i0, on=False):
+        mine = list(range(i0, n_lba, n_workers))
+        for i in mine:
+            bas[i].begin(lbas[i % len(lbas)], trk["cam"])
+        n = 0
+        for i in mine:
+            out = bas[i].end()
             assert out["res"]["accepted"] == 1
-        return bas[wk].last_launches()
+            n += bas[i].last_launches()
+            if on:
+                lba_ms_acc.append((bas[i].last_ms(), int(out["res"]["iterations"].sum())))
+        return n
 
-    def step(i):
-        futs = [lba_pool.submit(lba_job, wk, wk) for wk in range(n_workers)]
+    # CUDA-event brackets around every kernel group of the step, recorded on the stream the group is launched on (the
+    # extractor's four stages are bracketed inside the library, vieo_orb_profile; a LocalBA window on its engine's stream,
+    # vieo_ba_last_ms).  Read only after the timed region: no synchronisation is added to it.
+    TIMED = ("stereo_match", "imu_preint", "search_by_projection_last_frame", "is_in_frustum+search_by_projection_local_map",
+             "pose_opt_x2")
+    evs = {k: [] for k in TIMED}
+    lba_ms_acc = []
+
+    def timed(name, stream, fn, on):
+        if not on:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        evs[name].append((a, b))
+
+    def step(i, on=False):
+        futs = [lba_pool.submit(lba_job, wk, wk, on) for wk in range(n_workers)]
         imgs = dev_imgs[i % pool]
         s = main.cuda_stream
         orb.extract_batch_dev(imgs.data_ptr(), n_img, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), s)
-        orb.stereo_match_dev(F, kps.data_ptr(), desc.data_ptr(), nkp.data_ptr(), cap, BF, MINZ, s_ur.data_ptr(),
-                             s_dp.data_ptr(), s_sad.data_ptr(), s)
+        timed("stereo_match", main, lambda: orb.stereo_match_dev(F, kps.data_ptr(), desc.data_ptr(), nkp.data_ptr(), cap, BF, MINZ,
+                                                                 s_ur.data_ptr(), s_dp.data_ptr(), s_sad.data_ptr(), s), on)
         s2 = side.cuda_stream
-        pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(), d_bb.data_ptr(), F,
-                                       d_pre.data_ptr(), s2)
-        sbp_enqueue(s2)
-        api.Optimizer.pose_opt_batch_dev(d_pbs.data_ptr(), n_pb, d_cam.data_ptr(), d_Xw.data_ptr(), d_obs.data_ptr(),
-                                         d_w.data_ptr(), d_fl.data_ptr(), d_res.data_ptr(), d_outl.data_ptr(),
-                                         d_chi.data_ptr(), s2)
+        timed("imu_preint", side, lambda: pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(),
+                                                                         d_bb.data_ptr(), F, d_pre.data_ptr(), s2), on)
+        timed("search_by_projection_last_frame", side, lambda: sbp_enqueue(s2, 0), on)
+        timed("is_in_frustum+search_by_projection_local_map", side, lambda: sbp_enqueue(s2, 1), on)
+        timed("pose_opt_x2", side, lambda: api.Optimizer.pose_opt_batch_dev(
+            d_pbs.data_ptr(), n_pb, d_cam.data_ptr(), d_Xw.data_ptr(), d_obs.data_ptr(), d_w.data_ptr(), d_fl.data_ptr(),
+            d_res.data_ptr(), d_outl.data_ptr(), d_chi.data_ptr(), s2), on)
         main.wait_stream(side)
         return sum(f.result() for f in futs)
 
@@ -462,7 +489,7 @@ def run_gpu(args, rank, world, local_rank):
     e0.record()
     side.wait_stream(main)
     for i in range(args.steps):
-        step(args.warmup + i)   # joins the LocalBA workers (their calls are synchronous) before returning
+        step(args.warmup + i, True)   # joins the LocalBA workers (they end their windows) before returning
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -565,18 +592,58 @@ def run_gpu(args, rank, world, local_rank):
         if dist_on:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (live CUDA-event stage times over the timed region)
+    # ---- roofline: every kernel group of the step with its ALGORITHMIC bytes per launch, timed live over the
+    # timed region; the dominant group = largest device time per step.  frac = achieved / measured HBM peak.
     peak, peak_src = peaks()
-    dom = max(stage_ms, key=stage_ms.get)
-    stage_bytes = {"fast_cells": FAST_BYTES_PER_IMAGE, "pyramid": LEVEL_PX, "orient_desc": 1200 * (43 * 43 + 56),
-                   "quadtree": 25000 * 6}
-    dom_ms = stage_ms[dom] / max(ncalls, 1)
-    alg_bytes = stage_bytes[dom] * n_img
-    achieved = alg_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
+    nc = max(ncalls, 1)
+    orb_ms = sum(stage_ms.values()) / nc
+    groups = {}
+
+    def add(name, ms_per_step, alg_bytes, launches, note):
+        groups[name] = {"ms_per_step": ms_per_step, "launches_per_step": launches, "alg_bytes_per_step": int(alg_bytes),
+                        "GBps": alg_bytes / (ms_per_step / 1e3) / 1e9 if ms_per_step > 0 else 0.0,
+                        "frac": (alg_bytes / (ms_per_step / 1e3) / 1e9 / peak) if ms_per_step > 0 else 0.0, "bytes": note}
+    add("orb_extract_x2", orb_ms, ORB_BYTES_PER_IMAGE * n_img, orb.last_launches(),
+        "SURVEY 8(d): 1,189,367 B per 752x480 1200-feature image (input + levels >= 1 + 60 B per keypoint) x images per step, "
+        "over the summed stage times of k_resize x7, k_fast_cells, k_quadtree, k_orient_desc")
+
+    def ev_ms(name):
+        v = [a.elapsed_time(b) for a, b in evs[name]]
+        return float(np.mean(v)) if v else 0.0
+    nL = EUROC["nfeatures"]
+    add("stereo_match", ev_ms("stereo_match"), F * ((24 + 32) * 2 * nL + (121 + 231) * nL + 12 * nL), 1,
+        "per stereo frame: keypoints + descriptors of both views (56 B x 2 x 1200), 11x11 left patch + 11x21 right window per left "
+        "keypoint, 12 B out per left keypoint")
+    add("imu_preint", ev_ms("imu_preint"), 56 * len(trk["imu"][0]) + 1792 * F, 1, "SURVEY 8(d): 56 B per sample + 1792 B out per interval")
+    for nm, pb in zip(("search_by_projection_last_frame", "is_in_frustum+search_by_projection_local_map"), trk["sbp"]):
+        nk_, nq_ = len(pb["kps"]), len(pb["q_level"])
+        add(nm, ev_ms(nm), 56 * nk_ + 77 * nq_ + 4 * nk_ + 8 * nq_ + (62 * nq_ if "frustum" in pb else 0), 2 if "frustum" in pb else 1,
+            "56 B per keypoint + 77 B per query read, 4 B per keypoint + 8 B per query written" +
+            (" (+ 33 B read + 29 B written per map point of the visibility test)" if "frustum" in pb else ""))
+    n_e = trk["pbs"]["edge_end"].astype(np.int64) - trk["pbs"]["edge_begin"].astype(np.int64)
+    add("pose_opt_x2", ev_ms("pose_opt_x2"), int((6376 + 50 * n_e).sum()), 1,
+        "per frame problem: 4192 B problem + 41 B per edge read once, 2184 B result + 9 B per edge written once (the 4 x 10 LM "
+        "iterations run out of shared memory)")
+    if lba_ms_acc:
+        d0 = lbas[0]
+        E_, P_, K_ = len(d0["edge_state"]), len(d0["points"]), len(d0["states"])
+        b_lin = 52 * E_ + 48 * P_ + 176 * K_ + 1600 * (len(d0["imu_i"]))
+        n_lin = float(np.mean([it for _, it in lba_ms_acc])) + 2   # one linearisation per LM iteration at least + one per stage
+        add("local_ba_prv_windows", float(np.mean([m for m, _ in lba_ms_acc])) * n_lba, n_lba * n_lin * b_lin, ba_launches,
+            "SURVEY 8(d): B_lin = 52 E + 48 P + 176 K + 1.6k (K - 1) per linearisation x (LM iterations + 2) per window x windows "
+            "per step; ms = sum of the windows' device times (they overlap on their own streams)")
+    dom = max(groups, key=lambda k: groups[k]["ms_per_step"])
+    tot_ms = sum(g["ms_per_step"] for g in groups.values())
+    for g in groups.values():
+        g["share_of_summed_group_time"] = g["ms_per_step"] / tot_ms if tot_ms > 0 else 0.0
+    traffic, traffic_over_alg = None, None
     try:
-        per_image = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["per_image"].get(dom)
-        traffic = None if per_image is None else int(per_image) * n_img   # per launch, like `achieved`
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = {"orb_extract_x2": "orb_total"}.get(dom, dom)
+        per_unit = tj["per_image"].get(key) if key == "orb_total" else tj.get("per_step_256_problems", {}).get(key)
+        if per_unit is not None:
+            traffic = int(per_unit) * (n_img if key == "orb_total" else 1)   # per launch, like `achieved`
+            traffic_over_alg = traffic / groups[dom]["alg_bytes_per_step"]
     except Exception:
         pass
     # ---- single-frame latency (SURVEY.md 8d asks for both figures): ONE stereo frame through the same host-buffer calls,
@@ -605,11 +672,15 @@ def run_gpu(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "single_frame_latency_ms": latency,
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "alg_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
-                     "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
-                     "orb_pipeline_GBps": ORB_BYTES_PER_IMAGE * n_img * ncalls / (sum(stage_ms.values()) / 1e3) / 1e9},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": groups[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                     "frac": groups[dom]["frac"], "traffic": traffic, "traffic_over_alg": traffic_over_alg, "peak_source": peak_src,
+                     "alg_bytes_per_launch": groups[dom]["alg_bytes_per_step"], "launch_ms": groups[dom]["ms_per_step"],
+                     "method": "SURVEY 8(d) algorithmic bytes of the group per step / its device time per step (CUDA events on its "
+                               "own stream inside the timed region); dominant = largest device time per step over ALL groups",
+                     "orb_stage_ms_per_step": {k: v / nc for k, v in stage_ms.items()},
+                     "all_groups": groups,
+                     "whole_step_GBps": sum(g["alg_bytes_per_step"] for g in groups.values()) / (ms_max / args.steps / 1e3) / 1e9,
+                     "whole_step_frac": sum(g["alg_bytes_per_step"] for g in groups.values()) / (ms_max / args.steps / 1e3) / 1e9 / peak},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 3, "kind": "port",
                          "sample": f"{cpu_frames} stereo frames of the same stream + {cpu_frames // LBA_EVERY} LocalBA windows; "
                                    f"one thread per camera (src/Frame.cc:259-278), one tracking thread, one LocalMapping thread "
@@ -630,7 +701,8 @@ def main():
     ap.add_argument("--pool", type=int, default=4, help="distinct input batches rotated through")
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--lba", type=int, default=1, help="0: leave LocalBA out of the step")
-    ap.add_argument("--lba-workers", type=int, default=16, help="host threads (one BA handle + stream each) running LocalBA windows")
+    ap.add_argument("--lba-workers", type=int, default=2,
+                    help="host threads driving the LocalBA windows of a step (one engine per window, enqueued asynchronously)")
     ap.add_argument("--lba-windows", type=int, default=3, help="distinct LocalBA problems generated")
     ap.add_argument("--ba-sms", type=int, default=0, help="SMs reserved for the LocalBA streams (CUDA green context); 0: no partition")
     ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],

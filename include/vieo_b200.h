@@ -345,6 +345,20 @@ int vieo_ba_set_comm(vieo_ba_t* h, vieo_comm_t* comm /* NULL: single GPU */);
  *   outputs   states_out [n_states], points_out [P][3], edge_chi2 [E], erase [E] (1 = ErasePairObs candidate) */
 int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, const volatile uint8_t* stop,
                       VieoNavState* states_out, double* points_out, double* edge_chi2, uint8_t* erase, VieoBaResult* res);
+/* Asynchronous form of the same routine: _begin uploads the problem and enqueues EVERYTHING on the handle's stream — both
+ * optimize() stages run as device-side Levenberg-Marquardt loops (CUDA graph with a WHILE node), the inlier
+ * re-classification between them and the outlier pass are kernels, the results land in pinned staging — and returns without
+ * waiting; _end waits (forwarding the abort flag to the device while it does), applies the "FAIL LOCAL-INERTIAL BA" guard and
+ * fills the outputs; _poll returns 1 once _end would not block.  pb's arrays may be released after _begin.  One host thread
+ * can keep many windows in flight (LocalMapping + several sessions): _batch begins all n, then ends all n.
+ * Sharded handles run synchronously inside _begin (their exchange decisions need the host). */
+int vieo_local_ba_prv_begin(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, const volatile uint8_t* stop);
+int vieo_local_ba_prv_poll(vieo_ba_t* h);
+int vieo_local_ba_prv_end(vieo_ba_t* h, VieoNavState* states_out, double* points_out, double* edge_chi2, uint8_t* erase,
+                          VieoBaResult* res);
+int vieo_local_ba_prv_batch(vieo_ba_t* const* hs, const VieoBaProblem* const* pbs, const VieoCamera* cam, int n,
+                            const volatile uint8_t* stop, VieoNavState* const* states_out, double* const* points_out,
+                            double* const* edge_chi2, uint8_t* const* erase, VieoBaResult* res);
 /* Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342; bScaleOpt = false, no IMU initiator): every
  * keyframe carries PR / V / Bias vertices (keyframe 0: state_flags 1|2|4, the others 2), IMU + bias-walk edges between
  * consecutive keyframes (information x 1e-2 where the previous bias vertex is fixed, :955-958, :979-983), reprojection
@@ -388,6 +402,10 @@ int vieo_ba_get(vieo_ba_t* h, VieoNavState* states_out, double* points_out, doub
  * (vieo_ba_get_hessian_blocks of SURVEY.md 8b). */
 int vieo_ba_debug_step(vieo_ba_t* h, double lambda, double* x_pose, double* x_points, double* H_out, double* b_out);
 int vieo_ba_last_launches(const vieo_ba_t* h);
+/* Device time (CUDA events on the handle's stream, upload to last download) of the last vieo_local_ba_prv[_begin/_end]
+ * call that took the asynchronous path, and the LM trials of its last optimize() stage — for bench.py's roofline. */
+double vieo_ba_last_ms(const vieo_ba_t* h);
+int vieo_ba_last_trials(const vieo_ba_t* h);
 
 /* ------------------------------------------------------------------------------------------------
  * SM partitions (CUDA green contexts).  The reference runs Tracking, LocalMapping and LoopClosing on separate CPU

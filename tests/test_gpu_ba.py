@@ -358,3 +358,42 @@ def test_global_ba_config5_scale_matches_oracle_value(big_ba):
     assert np.abs(out["states"]["p"] - ref["states"]["p"]).max() < 1e-6  # << 1 mm (north_star: 1 mm ATE)
     assert np.abs(out["points"] - ref["points"]).max() < 1e-5
     assert out["states"][0].tobytes() == d["states"][0].tobytes()
+
+
+# ---------------------------------------------------------------- asynchronous LocalBA (begin / end / batch)
+def test_local_ba_async_batch_equals_sync():
+    """Four windows enqueued from ONE host thread on four engines (vieo_local_ba_prv_begin ... _end) give bit for bit what
+    the synchronous call gives window by window; an engine refuses a second begin before its end."""
+    import vieo_slam_b200.api as api
+    probs = []
+    for i in range(4):
+        seq = synth.vio_sequence(300 + i, 110, speed=1.5, rot=1.0)
+        kf = list(range(0, 110, 4))
+        pre = O.imu_preintegrate_frames(seq, kf, O.imu_noise())
+        probs.append(synth.make_lba_problem(seq, pre, kf, synth.euroc_camera(), n_local=10, n_fixed=12, n_points=500 + 100 * i, seed=20 + i))
+    cam = synth.euroc_camera()
+    engines = [api.BundleAdjuster(max_states=64, max_points=2048, max_edges=16384, max_imu=16) for _ in range(4)]
+    sync = [engines[0].LocalBundleAdjustmentNavStatePRV(d, cam) for d in probs]
+    outs = api.local_ba_prv_batch(engines, probs, cam)
+    for a, b in zip(outs, sync):
+        assert a["states"].tobytes() == b["states"].tobytes() and a["points"].tobytes() == b["points"].tobytes()
+        assert a["edge_chi2"].tobytes() == b["edge_chi2"].tobytes() and np.array_equal(a["erase"], b["erase"])
+        assert a["res"].tobytes() == b["res"].tobytes()
+    # and against the oracle, like every other LocalBA test
+    ref = O.local_ba_prv(probs[2], cam)
+    assert abs(outs[2]["res"]["err_end"] - ref["res"]["err_end"]) <= 1e-6 * abs(ref["res"]["err_end"])
+    assert np.array_equal(outs[2]["erase"], ref["erase"])
+    engines[1].begin(probs[1], cam)
+    with pytest.raises(api.VieoError):
+        engines[1].begin(probs[1], cam)
+    assert engines[1].end()["states"].tobytes() == sync[1]["states"].tobytes()
+    # abort raised while the window is in flight: the call still ends, with a valid (possibly less converged) result
+    stop = np.zeros(1, np.uint8)
+    engines[3].begin(probs[3], cam, stop=stop)
+    stop[0] = 1
+    out = engines[3].end()
+    assert np.isfinite(out["res"]["err_end"]) and out["res"]["iterations"][0] <= 4 and out["res"]["iterations"][1] <= 6
+    stop[0] = 1
+    engines[3].begin(probs[3], cam, stop=stop)  # raised before the call: "Aborted OLBA", nothing changes
+    out = engines[3].end()
+    assert out["states"].tobytes() == np.ascontiguousarray(probs[3]["states"]).tobytes() and out["res"]["iterations"].sum() == 0

@@ -110,6 +110,10 @@ def lib():
         L.vieo_ba_stream.argtypes = [vp]
         L.vieo_ba_stream.restype = vp
         L.vieo_local_ba_prv.argtypes = [vp] * 9
+        L.vieo_local_ba_prv_begin.argtypes = [vp] * 4
+        L.vieo_local_ba_prv_poll.argtypes = [vp]
+        L.vieo_local_ba_prv_end.argtypes = [vp] * 6
+        L.vieo_local_ba_prv_batch.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         L.vieo_global_ba_prv.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
         L.vieo_global_ba_prv_ex.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
         L.vieo_ba_get_border.argtypes = [vp, vp, vp]
@@ -121,6 +125,9 @@ def lib():
         L.vieo_ba_get.argtypes = [vp, vp, vp, vp]
         L.vieo_ba_debug_step.argtypes = [vp, C.c_double, vp, vp, vp, vp]
         L.vieo_ba_last_launches.argtypes = [vp]
+        L.vieo_ba_last_ms.argtypes = [vp]
+        L.vieo_ba_last_ms.restype = C.c_double
+        L.vieo_ba_last_trials.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -664,6 +671,13 @@ def ba_problem(d, large=False, rec_init=False, visual_only=False):
     return pb, keep
 
 
+def local_ba_prv_batch(bas, problems, cam, **kw):
+    """n LocalBA windows on n handles from ONE host thread: every window is enqueued before any is awaited."""
+    for ba, d in zip(bas, problems):
+        ba.begin(d, cam, **kw)
+    return [ba.end() for ba in bas[:len(problems)]]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 COMM_ID_BYTES = 128
 
@@ -742,6 +756,24 @@ class BundleAdjuster:
         _check(lib().vieo_local_ba_prv(self._h, C.byref(pb), _p(cam), _p(stop), _p(st), _p(pts), _p(chi2), _p(erase), _p(res)))
         return dict(states=st, points=pts, edge_chi2=chi2, erase=erase, res=res[0])
 
+    def begin(self, d, cam, large=False, rec_init=False, visual_only=False, stop=None):
+        """vieo_local_ba_prv_begin: enqueue the whole LocalBA routine on the handle's stream and return."""
+        pb, keep = ba_problem(d, large, rec_init, visual_only)
+        cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
+        self._inflight = (pb.n_states, pb.n_points, pb.n_edges)
+        self._stop_keep = stop
+        _check(lib().vieo_local_ba_prv_begin(self._h, C.byref(pb), _p(cam), _p(stop)))
+
+    def poll(self):
+        return bool(lib().vieo_local_ba_prv_poll(self._h))
+
+    def end(self):
+        K, P, E = self._inflight
+        st = np.zeros(K, NAVSTATE_DTYPE); pts = np.zeros((P, 3)); chi2 = np.zeros(E)
+        erase = np.zeros(E, np.uint8); res = np.zeros(1, BA_RESULT_DTYPE)
+        _check(lib().vieo_local_ba_prv_end(self._h, _p(st), _p(pts), _p(chi2), _p(erase), _p(res)))
+        return dict(states=st, points=pts, edge_chi2=chi2, erase=erase, res=res[0])
+
     def GlobalBundleAdjustmentNavStatePRV(self, d, cam, nIterations=5, bRobust=True, stop=None, bScaleOpt=False,
                                           imu_init_gw=None):
         """Optimizer::GlobalBundleAdjustmentNavStatePRV (src/Optimizer.cc:771-1342) on the flattened map; the handle must
@@ -802,3 +834,6 @@ class BundleAdjuster:
 
     def last_launches(self):
         return lib().vieo_ba_last_launches(self._h)
+
+    def last_ms(self):
+        return lib().vieo_ba_last_ms(self._h)

@@ -66,6 +66,7 @@ struct BaParams {
   int stop;             // host abort flag seen (pbStopFlag)
   int iteration, iters_target, iters_done, qmax, nBad, ok;
   int trials;           // LM trials run by the current optimize()
+  int iters_hist[2];    // iterations of the earlier optimize() stages of an asynchronous LocalBA call (k_ba_begin)
   double lambda, ni, user_lambda;
   double chi_cur, ini_chi;   // activeRobustChi2 of the current estimate / at the start of the iteration
   double pair[4];            // [robust chi2 of the last linearisation, landmark part of computeScale, abort flag seen by
@@ -805,6 +806,19 @@ __global__ void __launch_bounds__(256) k_ba_diag_pack(BaBuf B) {
     __syncthreads();
   }
   for (int r = threadIdx.x; r < prm.world; r += 256) B.S[np + r] = r == prm.rank ? s[0] : 0.0;
+}
+
+// Start of an optimize() stage without a host round trip (asynchronous LocalBA): resets the device-side state machine.
+// stage > 0 keeps a raised abort flag (the reference skips the second stage once pbStopFlag is set, src/Optimizer.cc:589-593)
+// and files the previous stage's iteration count.
+__global__ void k_ba_begin(BaBuf B, int stage, int iterations, double lambda_init) {
+  BaParams& q = *B.prm;
+  if (stage > 0) q.iters_hist[stage - 1] = q.iters_done;
+  else q.stop = 0;
+  q.cur = 0; q.done = 0; q.ok = 1;
+  q.iteration = 0; q.iters_target = iterations; q.iters_done = 0; q.qmax = 0; q.nBad = 0; q.trials = 0;
+  q.user_lambda = lambda_init;
+  if (q.stop) q.iters_target = 0;  // k_ba_control (mode 0) ends the stage at once
 }
 
 // Levenberg-Marquardt bookkeeping on the device (OptimizationAlgorithmLevenberg::solve, :83-166; SparseOptimizer::
@@ -1682,9 +1696,10 @@ __global__ void k_ba_classify(CamK cam, const CamPose* __restrict__ cp, const do
                               const int* __restrict__ es, const int* __restrict__ ep, const float* __restrict__ obs,
                               const uint8_t* __restrict__ flags, const double* __restrict__ chi2, int E, int mode, float rat,
                               int set_level, int remove_kernels, int use_close, uint8_t* __restrict__ lvl,
-                              uint8_t* __restrict__ bad_out, const BaParams* __restrict__ prmq) {
+                              uint8_t* __restrict__ bad_out, const BaParams* __restrict__ prmq, int skip_if_stop = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E) return;
+  if (skip_if_stop && prmq->stop) return;  // aborted after the first stage: levels and kernels stay (bDoMore == false)
   const bool stereo = flags[i] & VIEO_EDGE_STEREO;
   bool bad;
   if (mode == 0) {
@@ -1717,6 +1732,21 @@ struct vieo_ba {
   bool points_free = true, has_dup = false, visual_only = false;
   bool big = false;  // global-BA sized handle (dense multi-CTA Schur / Cholesky path, no trial graph)
   bool has_scale = false, has_g = false;  // border vertices of the current problem (global handles only)
+  // asynchronous LocalBA (vieo_local_ba_prv_begin / _end): 0 idle, 1 nothing to do (no free keyframe), 2 aborted before
+  // optimising, 3 enqueued, 4 ran synchronously inside begin (sharded handle / no optimize graph)
+  int async_state = 0;
+  bool defer_sync = false;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // device time of the last asynchronous LocalBA call (vieo_ba_last_ms)
+  float last_ms = 0.f;
+  bool upload_direct = false;  // set_problem copied from caller memory (staging too small): it must synchronise
+  const volatile uint8_t* async_stop = nullptr;
+  VieoBaProblem async_pb;      // shallow copy (sizes / flags) of the problem in flight
+  std::vector<VieoNavState> async_states;
+  std::vector<double> async_points;
+  std::vector<uint8_t> sync_erase;
+  std::vector<double> sync_chi2;
+  VieoBaResult sync_res;
+  int sync_rc = 0;
   double* d_yv = nullptr;
   uint8_t* d_nz = nullptr;  // tile structure map of the dense Cholesky
   int rank = 0, world = 1;
@@ -1977,6 +2007,8 @@ void ba_free(vieo_ba* h) {
                   h->d_ps_ptr, h->d_ps_edges, h->d_obs, h->d_w, h->d_pre, h->d_den};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+  if (h->ev_end) cudaEventDestroy(h->ev_end);
   if (h->trial_graph) cudaGraphExecDestroy(h->trial_graph);
   if (h->opt_graph) cudaGraphExecDestroy(h->opt_graph);
   if (h->st_ctl) cudaStreamDestroy(h->st_ctl);
@@ -2050,6 +2082,7 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
   step(dalloc(&h->d_ps_edges, E)); step(dalloc(&h->d_obs, 3 * E)); step(dalloc(&h->d_w, E));
   step(dalloc(&h->d_flags, E)); step(dalloc(&h->d_lvl, E)); step(dalloc(&h->d_sfix, K));
   step(dalloc(&h->d_bad, E)); step(dalloc(&h->d_pre, M)); step(dalloc(&h->d_den, 2 * M + 1)); step(dalloc(&B.wk, 2 * M + 1));
+  step(cudaEventCreate(&h->ev_begin)); step(cudaEventCreate(&h->ev_end));
   step(cudaMallocHost((void**)&h->h_ctl, sizeof(double) * 16));
   step(cudaMallocHost((void**)&h->h_prm, sizeof(BaParams)));
   h->stage_cap = K * (sizeof(VieoNavState) + 64) + P * 32 + E * 40 + M * (sizeof(VieoImuPreint) + 2 * sizeof(BaDense)) + 4096;
@@ -2156,6 +2189,8 @@ int vieo_ba_set_sharding(vieo_ba_t* h, int rank, int world, vieo_allreduce_fn al
 
 void* vieo_ba_stream(vieo_ba_t* h) { return h ? (void*)h->st : nullptr; }
 int vieo_ba_last_launches(const vieo_ba_t* h) { return h ? h->launches : 0; }
+double vieo_ba_last_ms(const vieo_ba_t* h) { return h ? (double)h->last_ms : 0.0; }
+int vieo_ba_last_trials(const vieo_ba_t* h) { return h && h->h_prm ? h->h_prm->trials : 0; }
 
 int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam) {
   VIEO_ARG(h && pb && cam, "null argument");
@@ -2345,10 +2380,14 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
     lvl[i] = ((pb->edge_flags[i] & VIEO_EDGE_LEVEL1) ? 1 : 0) | (((pb->edge_flags[i] & VIEO_EDGE_NOKERNEL) || (global && !g_robust)) ? 2 : 0);
   // every array goes through the pinned staging buffer: asynchronous copies, no driver-side pageable staging
   h->stage_used = 0;
+  h->upload_direct = false;
   auto up = [&](void* d, const void* s, size_t n) {
     if (!n) return cudaSuccess;
     const size_t o = (h->stage_used + 15) & ~(size_t)15;
-    if (o + n > h->stage_cap) return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, h->st);
+    if (o + n > h->stage_cap) {
+      h->upload_direct = true;
+      return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, h->st);
+    }
     memcpy(h->h_stage + o, s, n);
     h->stage_used = o + n;
     return cudaMemcpyAsync(d, h->h_stage + o, n, cudaMemcpyHostToDevice, h->st);
@@ -2414,7 +2453,9 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
     q.GI[0] = 0; q.GI[1] = 0; q.GI[2] = n;
   }
   BA_CK(cudaMemcpyAsync(h->B.prm, &q, sizeof(q), cudaMemcpyHostToDevice, h->st));
-  BA_CK(cudaStreamSynchronize(h->st));  // the host staging vectors die here
+  // the host staging vectors die here: synchronise unless every array went through the pinned staging buffer and the
+  // caller (vieo_local_ba_prv_begin) keeps the handle's host mirrors untouched until its end call
+  if (h->upload_direct || !h->defer_sync) BA_CK(cudaStreamSynchronize(h->st));
   return VIEO_OK;
 }
 
@@ -2678,19 +2719,210 @@ int vieo_global_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb_in, const VieoCamer
   return vieo_global_ba_prv_ex(h, pb_in, cam, n_iterations, robust, nullptr, stop, states_out, points_out, edge_chi2, res);
 }
 
+int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, const volatile uint8_t* stop,
+                      VieoNavState* states_out, double* points_out, double* edge_chi2, uint8_t* erase, VieoBaResult* res);
+// ---- asynchronous form: begin enqueues the WHOLE routine on the handle's stream (problem upload, Chi2LargeSetLevel, both
+// optimize() stages as device-side LM loops, the re-classification between them, the outlier pass, the downloads into
+// pinned staging) and returns; end waits, forwards the abort flag while it waits, and applies the reference's accept /
+// reject policy.  One host thread can keep many windows in flight (vieo_local_ba_prv_batch).
+static void lba_iteration_plan(const VieoBaProblem* pb, int optit[2], double* lambda0) {
+  if (pb->visual_only) { optit[0] = 5; optit[1] = 10; *lambda0 = 0; }
+  else if (pb->large) { optit[0] = 2; optit[1] = 2; *lambda0 = 1e-2; }
+  else { optit[0] = 4; optit[1] = 6; *lambda0 = 1e0; }
+}
+
+static int lba_enqueue_stage(vieo_ba* h, int stage, int iterations, double lambda0) {
+  k_ba_begin<<<1, 1, 0, h->st>>>(h->B, stage, iterations, lambda0);
+  BA_CK(cudaMemsetAsync(h->B.x, 0, 8 * (size_t)h->np, h->st));
+  h->launches++;
+  int rc = ba_campose(h);
+  if (rc) return rc;
+  if ((rc = ba_enqueue_linearize(h, 0, false))) return rc;
+  k_ba_control<<<1, 256, 0, h->st>>>(h->B, 0, 0);
+  h->launches++;
+  BA_CK(cudaGraphLaunch(h->opt_graph, h->st));
+  h->launches += kNodesPerTrial;
+  return VIEO_OK;
+}
+
+int vieo_local_ba_prv_begin(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, const volatile uint8_t* stop) {
+  VIEO_ARG(h && pb && cam, "null argument");
+  VIEO_ARG(h->async_state == 0, "vieo_local_ba_prv_begin: the previous call on this handle was not ended");
+  h->async_pb = *pb;
+  h->async_stop = stop;
+  h->async_states.assign(pb->states, pb->states + pb->n_states);
+  h->async_points.assign(pb->points, pb->points + 3 * (size_t)pb->n_points);
+  bool anyfree = false;
+  for (int k = 0; k < pb->n_states; ++k) anyfree |= !(pb->state_flags[k] & 1);
+  if (!anyfree) {  // if (!bdimPoses) return; (:178)
+    h->async_state = 1;
+    return VIEO_OK;
+  }
+  if (h->sharded() || !h->opt_graph || h->big) {
+    // the exchange decisions of a sharded handle need host round trips: run the synchronous routine now
+    h->sync_erase.assign(std::max(pb->n_edges, 1), 0);
+    h->sync_chi2.assign(std::max(pb->n_edges, 1), 0.0);
+    h->async_state = 0;
+    h->sync_rc = vieo_local_ba_prv(h, pb, cam, stop, h->async_states.data(), h->async_points.data(), h->sync_chi2.data(),
+                                   h->sync_erase.data(), &h->sync_res);
+    h->async_state = 4;
+    return h->sync_rc;
+  }
+  int optit[2];
+  double lambda0;
+  lba_iteration_plan(pb, optit, &lambda0);
+  h->defer_sync = true;
+  BA_CK(cudaSetDevice(h->device));
+  BA_CK(cudaEventRecord(h->ev_begin, h->st));
+  int rc = vieo_ba_set_problem(h, pb, cam);
+  h->defer_sync = false;
+  if (rc) return rc;
+  if (stop && *stop) {  // "Aborted OLBA" (:524-528)
+    BA_CK(cudaStreamSynchronize(h->st));
+    h->async_state = 2;
+    return VIEO_OK;
+  }
+  const int K = h->K, P = h->P, E = h->E;
+  if (!pb->visual_only && (rc = vieo_ba_chi2_large_set_level(h, 100.f))) return rc;  // PRV version only (:534-536)
+  if ((rc = ba_errors(h, 0, h->d_ctl + 6))) return rc;                               // err (:539)
+  if ((rc = lba_enqueue_stage(h, 0, optit[0], lambda0))) return rc;
+  if (E > 0) {  // inlier re-classification + kernel removal (:597-633); skipped on the device once the abort flag is up
+    if ((rc = ba_campose(h))) return rc;
+    k_ba_classify<<<(E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags, h->B.chi2, E,
+                                                     1, 0.f, 1, 1, h->visual_only ? 0 : 1, h->d_lvl, h->d_bad, h->B.prm, 1);
+    h->launches++;
+  }
+  if ((rc = lba_enqueue_stage(h, 1, optit[1], lambda0))) return rc;
+  if ((rc = ba_errors(h, 2, h->d_ctl + 7))) return rc;  // err_end over the stored errors (:652)
+  if (E > 0) {  // outlier candidates (:668-700) — computed always, used only if the result is accepted
+    if ((rc = ba_campose(h))) return rc;
+    k_ba_classify<<<(E + 255) / 256, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags, h->B.chi2, E,
+                                                     1, 0.f, 0, 0, h->visual_only ? 0 : 1, h->d_lvl, h->d_bad, h->B.prm, 0);
+    h->launches++;
+  }
+  // downloads into the pinned staging buffer (the uploads that used it are ahead of them on the stream)
+  const size_t ns = sizeof(VieoNavState) * (size_t)K, nx = 24 * (size_t)P, nc = 8 * (size_t)E, nb = (size_t)E;
+  uint8_t* ps = h->h_stage;
+  uint8_t* px = ps + ((ns + 15) & ~(size_t)15);
+  uint8_t* pc = px + ((nx + 15) & ~(size_t)15);
+  uint8_t* pbad = pc + ((nc + 15) & ~(size_t)15);
+  VIEO_ARG((size_t)(pbad - ps) + nb <= h->stage_cap, "staging buffer too small for the asynchronous download");
+  BA_CK(cudaMemcpyAsync(ps, h->B.st, ns, cudaMemcpyDeviceToHost, h->st));
+  if (nx) BA_CK(cudaMemcpyAsync(px, h->B.X, nx, cudaMemcpyDeviceToHost, h->st));
+  if (nc) BA_CK(cudaMemcpyAsync(pc, h->B.chi2, nc, cudaMemcpyDeviceToHost, h->st));
+  if (nb) BA_CK(cudaMemcpyAsync(pbad, h->d_bad, nb, cudaMemcpyDeviceToHost, h->st));
+  BA_CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, 8 * 16, cudaMemcpyDeviceToHost, h->st));
+  BA_CK(cudaMemcpyAsync(h->h_prm, h->B.prm, sizeof(BaParams), cudaMemcpyDeviceToHost, h->st));
+  BA_CK(cudaEventRecord(h->ev_end, h->st));
+  BA_CK(cudaGetLastError());
+  h->async_state = 3;
+  return VIEO_OK;
+}
+
+// 1 when vieo_local_ba_prv_end would not block (or nothing is in flight); forwards the caller's abort flag to the device
+int vieo_local_ba_prv_poll(vieo_ba_t* h) {
+  if (!h || h->async_state != 3) return 1;
+  cudaSetDevice(h->device);
+  if (cudaStreamQuery(h->st) != cudaErrorNotReady) return 1;
+  if (h->async_stop && *h->async_stop) {
+    static const int one = 1;
+    cudaMemcpyAsync(&h->B.prm->stop, &one, sizeof(int), cudaMemcpyHostToDevice, h->st_ctl);
+    h->async_stop = nullptr;  // sent once
+  }
+  return 0;
+}
+
+int vieo_local_ba_prv_end(vieo_ba_t* h, VieoNavState* states_out, double* points_out, double* edge_chi2, uint8_t* erase,
+                          VieoBaResult* res) {
+  VIEO_ARG(h && res && states_out && erase, "null argument");
+  VIEO_ARG(h->async_state != 0, "vieo_local_ba_prv_end without a begin");
+  const VieoBaProblem& pb = h->async_pb;
+  const int state = h->async_state;
+  h->async_state = 0;
+  memset(res, 0, sizeof(*res));
+  memcpy(states_out, h->async_states.data(), sizeof(VieoNavState) * pb.n_states);
+  if (points_out && pb.n_points) memcpy(points_out, h->async_points.data(), 24 * (size_t)pb.n_points);
+  memset(erase, 0, pb.n_edges);
+  if (state == 1 || state == 2) return VIEO_OK;
+  if (state == 4) {
+    *res = h->sync_res;
+    if (edge_chi2 && pb.n_edges) memcpy(edge_chi2, h->sync_chi2.data(), 8 * (size_t)pb.n_edges);
+    memcpy(erase, h->sync_erase.data(), pb.n_edges);
+    return h->sync_rc;
+  }
+  BA_CK(cudaSetDevice(h->device));
+  h->async_state = 3;
+  while (!vieo_local_ba_prv_poll(h)) std::this_thread::sleep_for(std::chrono::microseconds(20));
+  h->async_state = 0;
+  BA_CK(cudaStreamSynchronize(h->st));
+  cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end);
+  const int K = h->K, P = h->P, E = h->E;
+  const size_t ns = sizeof(VieoNavState) * (size_t)K, nx = 24 * (size_t)P, nc = 8 * (size_t)E;
+  const uint8_t* ps = h->h_stage;
+  const uint8_t* px = ps + ((ns + 15) & ~(size_t)15);
+  const uint8_t* pc = px + ((nx + 15) & ~(size_t)15);
+  const uint8_t* pbad = pc + ((nc + 15) & ~(size_t)15);
+  const BaParams& q = *h->h_prm;
+  h->launches += kNodesPerTrial * std::max(q.trials - 1, 0);
+  const float err = (float)h->h_ctl[6], err_end = (float)h->h_ctl[7];
+  res->err0 = err;
+  res->err_end = err_end;
+  res->iterations[0] = q.iters_hist[0];
+  res->iterations[1] = q.iters_done;
+  res->lambda_final = q.lambda;
+  if (edge_chi2 && nc) memcpy(edge_chi2, pc, nc);
+  if (!pb.visual_only && (2 * err < err_end || std::isnan(err) || std::isnan(err_end)) && !pb.large) {
+    res->accepted = 0;  // "FAIL LOCAL-INERTIAL BA" (:663-666)
+    return VIEO_OK;
+  }
+  res->accepted = 1;
+  int ne = 0;
+  for (int i = 0; i < E; ++i) {
+    erase[i] = pbad[i];
+    ne += pbad[i];
+  }
+  res->n_erase = ne;
+  memcpy(states_out, ps, ns);
+  if (points_out && nx) memcpy(points_out, px, nx);
+  return VIEO_OK;
+}
+
+// n independent windows, one handle each, driven by the calling thread: everything is enqueued before anything is awaited
+int vieo_local_ba_prv_batch(vieo_ba_t* const* hs, const VieoBaProblem* const* pbs, const VieoCamera* cam, int n,
+                            const volatile uint8_t* stop, VieoNavState* const* states_out, double* const* points_out,
+                            double* const* edge_chi2, uint8_t* const* erase, VieoBaResult* res) {
+  VIEO_ARG(hs && pbs && cam && n >= 0 && states_out && erase && res, "null argument");
+  int first = VIEO_OK, begun = 0;
+  for (; begun < n; ++begun)
+    if ((first = vieo_local_ba_prv_begin(hs[begun], pbs[begun], cam, stop))) break;
+  for (int i = 0; i < begun; ++i) {
+    const int rc = vieo_local_ba_prv_end(hs[i], states_out[i], points_out ? points_out[i] : nullptr,
+                                         edge_chi2 ? edge_chi2[i] : nullptr, erase[i], &res[i]);
+    if (rc && !first) first = rc;
+  }
+  return first;
+}
+
 // Optimizer::LocalBundleAdjustmentNavStatePRV, src/Optimizer.cc:133-700, on the flattened problem
 int vieo_local_ba_prv(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera* cam, const volatile uint8_t* stop,
                       VieoNavState* states_out, double* points_out, double* edge_chi2, uint8_t* erase, VieoBaResult* res) {
   VIEO_ARG(h && pb && cam && res && states_out && erase, "null argument");
+  if (!h->sharded() && h->opt_graph && !h->big && h->async_state == 0) {
+    // single GPU: the whole routine is enqueued at once (device-side LM loops) and awaited with ONE synchronisation
+    int rc = vieo_local_ba_prv_begin(h, pb, cam, stop);
+    if (rc) {
+      h->async_state = 0;
+      return rc;
+    }
+    return vieo_local_ba_prv_end(h, states_out, points_out, edge_chi2, erase, res);
+  }
   memset(res, 0, sizeof(*res));
   memcpy(states_out, pb->states, sizeof(VieoNavState) * pb->n_states);
   if (points_out && pb->n_points) memcpy(points_out, pb->points, 24 * (size_t)pb->n_points);
   memset(erase, 0, pb->n_edges);
   int optit[2];
   double lambda0;
-  if (pb->visual_only) { optit[0] = 5; optit[1] = 10; lambda0 = 0; }
-  else if (pb->large) { optit[0] = 2; optit[1] = 2; lambda0 = 1e-2; }
-  else { optit[0] = 4; optit[1] = 6; lambda0 = 1e0; }
+  lba_iteration_plan(pb, optit, &lambda0);
   bool anyfree = false;
   for (int k = 0; k < pb->n_states; ++k) anyfree |= !(pb->state_flags[k] & 1);
   if (!anyfree) return VIEO_OK;  // if (!bdimPoses) return; (:178)
