@@ -418,11 +418,15 @@ def run_gpu(args, rank, world, local_rank):
     if part:
         part.bind(api.SM_FRONTEND)
         main = torch.cuda.ExternalStream(part.stream(api.SM_FRONTEND), device=dev)
-        side = torch.cuda.ExternalStream(part.stream(api.SM_FRONTEND), device=dev)
+        side, side_b, side_c = (torch.cuda.ExternalStream(part.stream(api.SM_FRONTEND), device=dev) for _ in range(3))
         torch.cuda.set_stream(main)
     else:
         main = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        side, side_b, side_c = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    # the batch holds 128 independent frames at different stages of Tracking::Track(): the extractor + stereo association
+    # (main), IMU + TrackWithMotionModel's search (side), SearchLocalPoints (side_b) and the PoseOptimization calls (side_c)
+    # are enqueued on four streams, the LocalBA windows on their engines' streams
+    sides = (side, side_b, side_c)
 
     def lba_job(wk, i0, on=False):
         mine = list(range(i0, n_lba, n_workers))
@@ -461,20 +465,22 @@ def run_gpu(args, rank, world, local_rank):
         orb.extract_batch_dev(imgs.data_ptr(), n_img, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), s)
         timed("stereo_match", main, lambda: orb.stereo_match_dev(F, kps.data_ptr(), desc.data_ptr(), nkp.data_ptr(), cap, BF, MINZ,
                                                                  s_ur.data_ptr(), s_dp.data_ptr(), s_sad.data_ptr(), s), on)
-        s2 = side.cuda_stream
+        s2, s3, s4 = side.cuda_stream, side_b.cuda_stream, side_c.cuda_stream
         timed("imu_preint", side, lambda: pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(),
                                                                          d_bb.data_ptr(), F, d_pre.data_ptr(), s2), on)
         timed("search_by_projection_last_frame", side, lambda: sbp_enqueue(s2, 0), on)
-        timed("is_in_frustum+search_by_projection_local_map", side, lambda: sbp_enqueue(s2, 1), on)
-        timed("pose_opt_x2", side, lambda: api.Optimizer.pose_opt_batch_dev(
+        timed("is_in_frustum+search_by_projection_local_map", side_b, lambda: sbp_enqueue(s3, 1), on)
+        timed("pose_opt_x2", side_c, lambda: api.Optimizer.pose_opt_batch_dev(
             d_pbs.data_ptr(), n_pb, d_cam.data_ptr(), d_Xw.data_ptr(), d_obs.data_ptr(), d_w.data_ptr(), d_fl.data_ptr(),
-            d_res.data_ptr(), d_outl.data_ptr(), d_chi.data_ptr(), s2), on)
-        main.wait_stream(side)
+            d_res.data_ptr(), d_outl.data_ptr(), d_chi.data_ptr(), s4), on)
+        for sd in sides:
+            main.wait_stream(sd)
         return sum(f.result() for f in futs)
 
     ba_launches = 0
     for i in range(args.warmup):
-        side.wait_stream(main)
+        for sd in sides:
+            sd.wait_stream(main)
         ba_launches = step(i)
     launches_per_step = orb.last_launches() + 1 + 2 + 2 + ba_launches  # extractor + stereo match + (imu, pose opt) + 2 guided searches + LocalBA
     torch.cuda.synchronize()
@@ -487,7 +493,8 @@ def run_gpu(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    side.wait_stream(main)
+    for sd in sides:
+        sd.wait_stream(main)
     for i in range(args.steps):
         step(args.warmup + i, True)   # joins the LocalBA workers (they end their windows) before returning
     e1.record()
@@ -701,7 +708,7 @@ def main():
     ap.add_argument("--pool", type=int, default=4, help="distinct input batches rotated through")
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--lba", type=int, default=1, help="0: leave LocalBA out of the step")
-    ap.add_argument("--lba-workers", type=int, default=2,
+    ap.add_argument("--lba-workers", type=int, default=1,
                     help="host threads driving the LocalBA windows of a step (one engine per window, enqueued asynchronously)")
     ap.add_argument("--lba-windows", type=int, default=3, help="distinct LocalBA problems generated")
     ap.add_argument("--ba-sms", type=int, default=0, help="SMs reserved for the LocalBA streams (CUDA green context); 0: no partition")

@@ -9,6 +9,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvieo_b200.so")
+if os.environ.get("VIEO_B200_LIB"):  # alternative build of the same library (profiling / kernel-variant experiments)
+    LIB_PATH = os.environ["VIEO_B200_LIB"]
 
 from .layouts import FRUSTUM_FRAME_DTYPE, PROJ_SEARCH_FRAME_DTYPE  # noqa: E402
 

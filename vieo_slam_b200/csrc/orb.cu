@@ -787,12 +787,16 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(OrbParams P, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// Rectified-stereo association, Frame::ComputeStereoMatches (src/Frame.cc:451-611).  One CTA per stereo frame (left
-// image 2f, right image 2f+1 of the batch).  A warp takes one left keypoint: lanes scan the right keypoints in index
-// order (row-band / octave / disparity-range predicate, 256-bit Hamming), the lexicographic (distance, index) minimum is
-// the reference's strict-'<' arg-min; matches under (TH_HIGH+TH_LOW)/2 are refined with the 11x11 L1 block search over
-// +-5 px in the keypoint's pyramid level (integer arithmetic, lanes over pixels) and the parabola fit.  The CTA then
-// applies the 1.5 * 1.4 * median(SAD) filter with a rank selection over the accepted matches.
+// Rectified-stereo association, Frame::ComputeStereoMatches (src/Frame.cc:451-611), two kernels.
+// k_stereo_match, grid (kStereoSplit, frames): a CTA takes one slice of the frame's left keypoints (left image 2f, right
+// image 2f+1 of the batch) after staging the right keypoints' search keys (x, row band, octave: 12 B each) in shared
+// memory.  A warp takes one left keypoint: lanes scan the right keypoints in index order (row-band / octave /
+// disparity-range predicate, 256-bit Hamming), the lexicographic (distance, index) minimum is the reference's strict-'<'
+// arg-min; matches under (TH_HIGH+TH_LOW)/2 are refined with the 11x11 L1 block search over +-5 px in the keypoint's
+// pyramid level (integer arithmetic, lanes over pixels) and the parabola fit.
+// k_stereo_filter, one CTA per frame — the only per-frame step: the 1.5 * 1.4 * median(SAD) filter with a rank selection
+// over the accepted matches.
+constexpr int kStereoSplit = 8;
 struct StereoLevels {
   const uint8_t* base[kMaxLevels];
   size_t img_stride[kMaxLevels];
@@ -803,9 +807,10 @@ __global__ void __launch_bounds__(256) k_stereo_match(StereoLevels Lv, const Vie
                                                       const uint8_t* __restrict__ desc, const int* __restrict__ nkp, int cap,
                                                       int n_rows, float bf, float minZ, float* __restrict__ uright,
                                                       float* __restrict__ depth, int* __restrict__ sad_out) {
-  extern __shared__ int s_sad[];  // [cap]
-  __shared__ int s_med;
-  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  extern __shared__ float s_rx[];                      // [cap] right keypoint x
+  int* s_band = reinterpret_cast<int*>(s_rx + cap);    // [cap] row band (minr << 16) | (maxr & 0xffff), both int16
+  int8_t* s_oct = reinterpret_cast<int8_t*>(s_band + cap);  // [cap]
+  const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iml = 2 * f, imr = 2 * f + 1;
   const int nl = min(nkp[iml], cap), nr = min(nkp[imr], cap);
   const VieoKeyPoint* KL = kps + (size_t)iml * cap;
@@ -816,15 +821,25 @@ __global__ void __launch_bounds__(256) k_stereo_match(StereoLevels Lv, const Vie
   float* DP = depth + (size_t)f * cap;
   int* SD = sad_out + (size_t)f * cap;
   const float minD = 0, maxD = bf / minZ;
-  for (int i = threadIdx.x; i < cap; i += 256) {
+  // this CTA's slice of the left keypoints; the last slice also clears the unused tail of the output rows
+  const int per = (nl + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int l0 = min((int)blockIdx.x * per, nl), l1 = min(l0 + per, nl);
+  const int c1 = blockIdx.x == gridDim.x - 1 ? cap : l1;
+  for (int i = l0 + threadIdx.x; i < c1; i += 256) {
     UR[i] = -1.0f;
     DP[i] = -1.0f;
     SD[i] = -1;
-    s_sad[i] = -1;
   }
-  if (threadIdx.x == 0) s_med = 0;
+  for (int i = threadIdx.x; i < nr; i += 256) {
+    const VieoKeyPoint k = KR[i];
+    const float r = 2.0f * Lv.scale[k.octave];
+    const int maxr = (int)ceilf(k.y + r), minr = (int)floorf(k.y - r);
+    s_rx[i] = k.x;
+    s_band[i] = (minr << 16) | (maxr & 0xffff);
+    s_oct[i] = (int8_t)k.octave;
+  }
   __syncthreads();
-  for (int iL = warp; iL < nl; iL += 8) {
+  for (int iL = l0 + warp; iL < l1; iL += 8) {
     const VieoKeyPoint kpL = KL[iL];
     const int levelL = kpL.octave;
     const float vL = kpL.y, uL = kpL.x;
@@ -836,16 +851,17 @@ __global__ void __launch_bounds__(256) k_stereo_match(StereoLevels Lv, const Vie
     for (int k = 0; k < 8; ++k) dl[k] = reinterpret_cast<const uint32_t*>(DL + 32 * (size_t)iL)[k];
     int best = 100, bestIdx = 0x7fffffff;  // TH_HIGH
     for (int iR = lane; iR < nr; iR += 32) {
-      const VieoKeyPoint kpR = KR[iR];
-      if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
-      const float r = 2.0f * Lv.scale[kpR.octave];
-      const int maxr = (int)ceilf(kpR.y + r), minr = (int)floorf(kpR.y - r);
+      const int oct = s_oct[iR];
+      if (oct < levelL - 1 || oct > levelL + 1) continue;
+      const int band = s_band[iR];
+      const int minr = band >> 16, maxr = (int)(short)(band & 0xffff);
       if (row < minr || row > maxr) continue;
-      if (!(kpR.x >= minU && kpR.x <= maxU)) continue;
-      const uint32_t* dr = reinterpret_cast<const uint32_t*>(DR + 32 * (size_t)iR);
-      int d = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) d += __popc(dl[k] ^ dr[k]);
+      const float xr = s_rx[iR];
+      if (!(xr >= minU && xr <= maxU)) continue;
+      const uint4* dr = reinterpret_cast<const uint4*>(DR + 32 * (size_t)iR);
+      const uint4 r0 = __ldg(dr), r1 = __ldg(dr + 1);
+      const int d = __popc(dl[0] ^ r0.x) + __popc(dl[1] ^ r0.y) + __popc(dl[2] ^ r0.z) + __popc(dl[3] ^ r0.w) +
+                    __popc(dl[4] ^ r1.x) + __popc(dl[5] ^ r1.y) + __popc(dl[6] ^ r1.z) + __popc(dl[7] ^ r1.w);
       if (d < best) {  // lanes see ascending indices: strict '<' keeps the first
         best = d;
         bestIdx = iR;
@@ -860,7 +876,7 @@ __global__ void __launch_bounds__(256) k_stereo_match(StereoLevels Lv, const Vie
       }
     }
     if (!(best < 75)) continue;  // thOrbDist = (TH_HIGH + TH_LOW) / 2
-    const float uR0 = KR[bestIdx].x;
+    const float uR0 = s_rx[bestIdx];
     const float sf = Lv.inv_scale[levelL];
     const float scaleduL = roundf(kpL.x * sf), scaledvL = roundf(kpL.y * sf), scaleduR0 = roundf(uR0 * sf);
     const int w = 5, L = 5;
@@ -914,18 +930,32 @@ __global__ void __launch_bounds__(256) k_stereo_match(StereoLevels Lv, const Vie
           }
           DP[iL] = bf / disparity;
           UR[iL] = bestuR;
-          SD[iL] = bestSad;
-          s_sad[iL] = bestSad;
+          SD[iL] = bestSad;  // >= 0 exactly for the accepted matches (k_stereo_filter's input)
         }
       }
     }
   }
-  __syncthreads();
-  // median of the accepted SADs = element n/2 of the sorted (sad, index) list: the value v with
-  // #(sad < v) <= n/2 < #(sad <= v)
-  int n_acc = 0;
-  for (int i = threadIdx.x; i < nl; i += 256) n_acc += s_sad[i] >= 0;
+}
+
+// median of the accepted SADs = element n/2 of the sorted (sad, index) list: the value v with
+// #(sad < v) <= n/2 < #(sad <= v); matches at or above 1.5 * 1.4 * median lose uright / depth (src/Frame.cc:599-610)
+__global__ void __launch_bounds__(256) k_stereo_filter(const int* __restrict__ nkp, int cap, float* __restrict__ uright,
+                                                       float* __restrict__ depth, const int* __restrict__ sad_out) {
+  extern __shared__ int s_sad[];  // [cap]
+  __shared__ int s_med;
   __shared__ int s_cnt[8];
+  const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nl = min(nkp[2 * f], cap);
+  float* UR = uright + (size_t)f * cap;
+  float* DP = depth + (size_t)f * cap;
+  const int* SD = sad_out + (size_t)f * cap;
+  int n_acc = 0;
+  for (int i = threadIdx.x; i < nl; i += 256) {
+    const int v = SD[i];
+    s_sad[i] = v;
+    n_acc += v >= 0;
+  }
+  if (threadIdx.x == 0) s_med = 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
   if (lane == 0) s_cnt[warp] = n_acc;
@@ -1520,15 +1550,13 @@ int vieo_orb_stereo_match_dev(vieo_orb_t* h, int n_frames, const VieoKeyPoint* k
     Lv.scale[l] = P.scale[l];
     Lv.inv_scale[l] = h->inv_scale[l];
   }
-  const size_t smem = sizeof(int) * (size_t)cap;
-  VIEO_ARG(smem <= 96 * 1024, "cap too large for the stereo kernel");
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    VIEO_CK(cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  k_stereo_match<<<n_frames, 256, smem, (cudaStream_t)stream>>>(Lv, kps_dev, desc_dev, n_kp_dev, cap, P.h[0], bf, min_z,
-                                                                uright_dev, depth_dev, sad_dev);
+  // shared memory: 9 B per right keypoint (match) / 4 B per left keypoint (filter); stays below the 48 KB default
+  const size_t smem = ((size_t)9 * cap + 15) & ~(size_t)15, smem_f = sizeof(int) * (size_t)cap;
+  VIEO_ARG(smem <= 48 * 1024, "cap too large for the stereo kernels (at most 5461 keypoints per image)");
+  VIEO_ARG(n_frames <= 65535, "too many frames per call");
+  k_stereo_match<<<dim3(kStereoSplit, n_frames), 256, smem, (cudaStream_t)stream>>>(Lv, kps_dev, desc_dev, n_kp_dev, cap, P.h[0],
+                                                                                    bf, min_z, uright_dev, depth_dev, sad_dev);
+  k_stereo_filter<<<n_frames, 256, smem_f, (cudaStream_t)stream>>>(n_kp_dev, cap, uright_dev, depth_dev, sad_dev);
   VIEO_CK(cudaGetLastError());
   return VIEO_OK;
 }

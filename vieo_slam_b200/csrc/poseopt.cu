@@ -32,9 +32,22 @@ __device__ long long g_po_prof[16];
 #define PO_ACC(slot, t0, t1)
 #endif
 
-constexpr int kPoThreads = 256;
+#ifndef VIEO_PO_THREADS
+#define VIEO_PO_THREADS 256
+#endif
+#ifndef VIEO_PO_MIN_CTAS
+// two resident CTAs per SM (128 registers, ~6 KB of L1-resident spills per thread in the single-lane inertial / prior
+// paths): measured on B200 for 256 problems — 3.37 ms at 254 registers / 1 CTA per SM, 3.08 ms here, 3.20 ms with 128
+// threads, 3.35 / 3.74 ms with 128 threads at 168 / 128 registers (profiles/r02e_poseopt_variants.txt) — the kernel is
+// bound by the latency of its serial fp64 chains, so the smaller footprint costs nothing and leaves half of every SM's
+// register file to the kernels of the other streams
+#define VIEO_PO_MIN_CTAS 2
+#endif
+constexpr int kPoThreads = VIEO_PO_THREADS;
 constexpr int kPoWarps = kPoThreads / 32;
-constexpr int kPoVisWarps = 6;    // warps 0..5: visual edges; warp 6: bias + prior edges; warp 7: inertial edge
+constexpr int kPoVisWarps = kPoWarps - 2;  // the first warps: visual edges; then one warp for the bias + prior edges and
+constexpr int kPoImuWarp = kPoWarps - 1;   // the last one for the inertial edge
+static_assert(kPoThreads >= 96 && kPoThreads % 32 == 0, "k_pose_opt needs at least one visual warp and 70 threads");
 constexpr int kPoN = 30;          // largest system: cur PVR 9 + bias 6 + last PVR 9 + bias 6
 constexpr int kPoMaxEdges = 4096; // per frame (the reference has N <= nfeatures + a few per camera)
 
@@ -269,7 +282,7 @@ __device__ void evaluate(const PoCtx& c, PoSmem& sm, int set) {
       }
     }
   } else if (c.imu_mode && lane == 0) {
-    if (warp == 7) {
+    if (warp == kPoImuWarp) {
       if (c.has_imu) {
         navstate_error(sm.st[1], sm.st[0], sm.pre, c.gw, false, sm.err_imu);
         navstate_jac_pvr24(sm.st[1], sm.st[0], sm.pre, c.gw, sm.err_imu, sm.Jimu);
@@ -284,8 +297,8 @@ __device__ void evaluate(const PoCtx& c, PoSmem& sm, int set) {
   }
   PO_T(t_b);
   if (threadIdx.x == 0) PO_ACC(0, t_a, t_b);        // visual edges, thread 0
-  if (threadIdx.x == 224) PO_ACC(1, t_a, t_b);      // inertial edge, warp 7 lane 0
-  if (threadIdx.x == 192) PO_ACC(2, t_a, t_b);      // bias + prior, warp 6 lane 0
+  if (threadIdx.x == 32 * kPoImuWarp) PO_ACC(1, t_a, t_b);      // inertial edge, last warp lane 0
+  if (threadIdx.x == 32 * (kPoImuWarp - 1)) PO_ACC(2, t_a, t_b);  // bias + prior, lane 0 of the warp before
   block_sum<28>(sm, acc, kPoVisWarps);  // its barriers also publish the dense residuals / Jacobians
   PO_T(t_c);
   if (threadIdx.x == 0) PO_ACC(3, t_b, t_c);        // wait + reduction
@@ -540,7 +553,7 @@ __device__ void optimize(const PoCtx& c, PoSmem& sm, int iterations) {
   }
 }
 
-__global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProblem* __restrict__ pbs,
+__global__ void __launch_bounds__(kPoThreads, VIEO_PO_MIN_CTAS) k_pose_opt(const VieoPoseOptProblem* __restrict__ pbs,
                                                          const VieoCamera* __restrict__ camp,
                                                          const double* __restrict__ Xw, const float* __restrict__ obs,
                                                          const float* __restrict__ inv_sigma2,
@@ -709,11 +722,11 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_opt(const VieoPoseOptProble
   __syncthreads();
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0 && warp == 7 && c.has_imu) {
+    if (lane == 0 && warp == kPoImuWarp && c.has_imu) {
       navstate_error(sm.st[1], sm.st[0], sm.pre, c.gw, false, sm.err_imu);
       navstate_jac_pvr24(sm.st[1], sm.st[0], sm.pre, c.gw, sm.err_imu, sm.Jimu);
     }
-    if (lane == 0 && warp == 6) {
+    if (lane == 0 && warp == kPoImuWarp - 1) {
       bias_error(sm);
       if (!c.fixed_last) {
         prior_error(sm.st[1], c.prior, sm.err_prior);

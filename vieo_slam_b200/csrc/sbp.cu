@@ -295,20 +295,34 @@ __global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpF
   // ---- phase C: the sequential claim pass ---------------------------------------------------------------------------------
   int nmatches = 0;
   const float factor = 1.0f / HISTO_LENGTH;
+  // The pass is sequential by definition (a claimed keypoint changes the next query's arg-min), so its cost is the latency
+  // of one iteration: the next query's candidate count and its two list entries per lane are loaded one iteration ahead
+  // (the list slots exist for every query, entries past the count are simply not used).
+  int n_next = nq > 0 ? fcnt[0] : 0;
+  uint32_t ea_next = nq > 0 ? flist[lane] : 0u, eb_next = nq > 0 ? flist[lane + 32] : 0u;
+  uint8_t fl_next = nq > 0 ? Q.flags[F.q_begin] : 0;
   for (int qi = 0; qi < nq; ++qi) {
     const int q = F.q_begin + qi;
-    const int n = fcnt[qi];
+    const int n = n_next;
+    const uint32_t ea = ea_next, eb = eb_next;
+    const uint8_t qflag = fl_next;
+    if (qi + 1 < nq) {
+      n_next = fcnt[qi + 1];
+      const uint32_t* Ln = flist + (size_t)(qi + 1) * kListCap;
+      ea_next = Ln[lane];
+      eb_next = Ln[lane + 32];
+      fl_next = Q.flags[q + 1];
+    }
     uint32_t best = 0xffffffffu, second = 0xffffffffu;  // lane-local two smallest keys (dist << 16 | pos)
     int idx_a = -1, idx_b = -1;                          // keypoints of the lane's two entries
     if (n > 0 && n <= kListCap) {
-      const uint32_t* L = flist + (size_t)qi * kListCap;
       if (lane < n) {
-        const uint32_t e = L[lane];
+        const uint32_t e = ea;
         idx_a = (int)(e & 0xffffu);
         if (!((S.blocked[idx_a >> 5] >> (idx_a & 31)) & 1u)) best = (e & 0xffff0000u) | (uint32_t)lane;
       }
       if (lane + 32 < n) {
-        const uint32_t e = L[lane + 32];
+        const uint32_t e = eb;
         idx_b = (int)(e & 0xffffu);
         if (!((S.blocked[idx_b >> 5] >> (idx_b & 31)) & 1u)) second = (e & 0xffff0000u) | (uint32_t)(lane + 32);
       }
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpF
       int bin = -1;
       if (take >= 0) {
         kpm[take] = qi;
-        if (Q.flags[q] & 1) S.blocked[take >> 5] |= 1u << (take & 31);
+        if (qflag & 1) S.blocked[take >> 5] |= 1u << (take & 31);
         if (mode == VIEO_SBP_LAST_FRAME && F.check_orientation) {
           float rot = __fsub_rn(Q.angle[q], kps[take].angle);
           if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
