@@ -408,6 +408,74 @@ double vieo_ba_last_ms(const vieo_ba_t* h);
 int vieo_ba_last_trials(const vieo_ba_t* h);
 
 /* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:896-1150; called by
+ * LocalMapping::CreateNewMapPoints for every neighbour keyframe, src/LocalMapping.cc:709) for single-pinhole keyframes
+ * (usedistort_ == false, one camera each): the DBoW2::FeatureVector walk over common vocabulary nodes (:964-1135), per
+ * unmatched keypoint of KF1 the Hamming arg-min (<= TH_LOW, equal distances: the later candidate wins) over the node's
+ * unmatched keypoints of KF2 that pass the mono-mono epipole-distance rule (:1031-1035) and
+ * GeometricCamera::epipolarConstrain (common/camera_models/camera_base.h:360-404), each KF2 keypoint matched at most once
+ * in the reference's visiting order (:1001-1002), the rotation histogram with ComputeThreeMaxima (:1137-1156).
+ * A batch of keyframe pairs, device resident, one CTA per pair.  Shared arrays: kps (mvKeysUn), uright (vuright_), desc
+ * (mDescriptors), has_mp (GetMapPoint(idx) != nullptr) per keypoint; the FeatureVectors flattened: fv_node = node ids in
+ * std::map order (ascending), fv_ptr = n_nodes + 1 offsets per vector (relative to its idx*_begin), fv_idx = keypoint
+ * indices in push order.  The shim forms F12 = K1^-T [t12]x R12 K2^-1 in double (Eigen inverse(), host side) and the
+ * epipole (ex, ey) of KF1's centre in KF2 (:908-927) per pair. */
+typedef struct VieoSftPair {
+  int32_t kp1_begin, n_kp1, kp2_begin, n_kp2;           /* keypoint ranges of the two keyframes (<= 8192 keypoints each) */
+  int32_t node1_begin, n_nodes1, node2_begin, n_nodes2; /* ranges in fv_node */
+  int32_t ptr1_begin, ptr2_begin;                       /* first of the n_nodes + 1 entries in fv_ptr */
+  int32_t idx1_begin, idx2_begin;                       /* ranges in fv_idx */
+  int32_t out_begin;                                    /* this pair's n_kp1 slots in match12 / pairs_out (prefix sum of n_kp1) */
+  int32_t nscr_begin;                                   /* prefix sum of n_nodes1 (scratch) */
+  int32_t only_stereo, check_orientation;               /* bOnlyStereo, mbCheckOrientation */
+  float ex, ey;                                         /* epipole in KF2 */
+  float scale_factor2[16];                              /* pKF2->scalepyrinfo_.vscalefactor_ */
+  float level_sigma2_2[16];                             /* pKF2->scalepyrinfo_.vlevelsigma2_ */
+  double F12[9];                                        /* row-major */
+} VieoSftPair;
+size_t vieo_sft_scratch_bytes(int n_out_total, int n_nodes1_total);
+/* match12 [n_out_total]: per KF1 keypoint of each pair the matched KF2 keypoint or -1 (after the rotation filter);
+ * pairs_out [n_out_total][2]: vMatchedPairs as (idx1, idx2) in the reference's creation order, n_matches[p] of them for
+ * pair p (its return value; -1: a size limit was exceeded). */
+int vieo_search_for_triangulation_dev(const VieoSftPair* pairs_dev, int n_pairs, const VieoKeyPoint* kps_dev,
+                                      const float* uright_dev, const uint8_t* desc_dev, const uint8_t* has_mp_dev,
+                                      const int32_t* fv_node_dev, const int32_t* fv_ptr_dev, const int32_t* fv_idx_dev,
+                                      int n_out_total, int n_nodes1_total, int32_t* match12_dev, int32_t* pairs_out_dev,
+                                      int32_t* n_matches_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+/* Host-buffer form (every range of every pair is validated against the array sizes given). */
+int vieo_search_for_triangulation(const VieoSftPair* pairs, int n_pairs, const VieoKeyPoint* kps, const float* uright,
+                                  const uint8_t* desc, const uint8_t* has_mp, const int32_t* fv_node, const int32_t* fv_ptr,
+                                  const int32_t* fv_idx, int n_kp_total, int n_node_total, int n_ptr_total, int n_idx_total,
+                                  int n_out_total, int n_nodes1_total, int32_t* match12, int32_t* pairs_out, int32_t* n_matches,
+                                  int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:344-505;
+ * Tracking::TrackReferenceKeyFrame, Relocalization, LoopClosing), single camera: FeatureVector walk, per keyframe keypoint
+ * with a live map point the best / second-best Hamming distance over the not-yet-matched frame keypoints of the same node,
+ * accepted when best <= TH_LOW and best < mfNNratio * second, rotation histogram.  Same flattened FeatureVector layout as
+ * VieoSftPair; keyframe = side 1, frame = side 2; mp_ok [keypoint] = GetMapPoint(idx) && !isBad() (keyframe side).
+ * One camera per keyframe means a map point sits on one keyframe keypoint (the (pMP, img_id) table of :363 never fires);
+ * the host-buffer form does not check that.  match_f [n_out_total]: per frame keypoint of each pair (out_begin = prefix sum
+ * of n_kp2) the keyframe keypoint whose map point it received, -1 none; n_matches [n_pairs] = the return value. */
+typedef struct VieoBowPair {
+  int32_t kp1_begin, n_kp1, kp2_begin, n_kp2;
+  int32_t node1_begin, n_nodes1, node2_begin, n_nodes2;
+  int32_t ptr1_begin, ptr2_begin, idx1_begin, idx2_begin;
+  int32_t out_begin;
+  int32_t check_orientation; /* mbCheckOrientation */
+  float nn_ratio;            /* mfNNratio */
+  int32_t pad_;
+} VieoBowPair;
+int vieo_search_by_bow_dev(const VieoBowPair* pairs_dev, int n_pairs, const VieoKeyPoint* kps_dev, const uint8_t* desc_dev,
+                           const uint8_t* mp_ok_dev, const int32_t* fv_node_dev, const int32_t* fv_ptr_dev,
+                           const int32_t* fv_idx_dev, int n_out_total, int32_t* match_f_dev, int32_t* n_matches_dev,
+                           void* scratch_dev /* >= n_out_total bytes */, size_t scratch_bytes, void* stream);
+int vieo_search_by_bow(const VieoBowPair* pairs, int n_pairs, const VieoKeyPoint* kps, const uint8_t* desc, const uint8_t* mp_ok,
+                       const int32_t* fv_node, const int32_t* fv_ptr, const int32_t* fv_idx, int n_kp_total, int n_node_total,
+                       int n_ptr_total, int n_idx_total, int n_out_total, int32_t* match_f, int32_t* n_matches, int device);
+
+/* ------------------------------------------------------------------------------------------------
  * SM partitions (CUDA green contexts).  The reference runs Tracking, LocalMapping and LoopClosing on separate CPU
  * threads (src/System.cc); here they share one device, and the BA engines' chains of tiny ordered kernels starve beside
  * the front-end's saturating ones unless they own a few SMs.  A partition splits the device into `ba_sms` SMs for the

@@ -150,3 +150,22 @@ void orc_fisheye_matches(const uint8_t* desc, const int32_t* n_kp, const int32_t
 #ifdef __cplusplus
 }
 #endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* ORBmatcher::SearchForTriangulation, single pinhole camera (sft_oracle.cc) */
+int orc_search_for_triangulation(const OrcKeyPoint* kp1, const float* ur1, const uint8_t* desc1, const uint8_t* has_mp1,
+                                 const int32_t* fv1_node, const int32_t* fv1_ptr, const int32_t* fv1_idx, int n_nodes1,
+                                 const OrcKeyPoint* kp2, const float* ur2, const uint8_t* desc2, const uint8_t* has_mp2,
+                                 const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int n_nodes2,
+                                 const double F12[9], float ex, float ey, const float* scale_factor2,
+                                 const float* level_sigma2_2, int only_stereo, int check_orientation, int32_t* pairs, int cap);
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...), single camera (sft_oracle.cc) */
+int orc_search_by_bow(const OrcKeyPoint* kp_kf, const uint8_t* desc_kf, const int32_t* mp_id, const int32_t* fv1_node,
+                      const int32_t* fv1_ptr, const int32_t* fv1_idx, int n_nodes1, const OrcKeyPoint* kp_f,
+                      const uint8_t* desc_f, int n_f, const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx,
+                      int n_nodes2, float nn_ratio, int check_orientation, int32_t* match_f);
+#ifdef __cplusplus
+}
+#endif

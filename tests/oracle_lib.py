@@ -607,3 +607,50 @@ def ba_debug_step_gdir(d, cam, lam, gw, **kw):
     n = L.orc_ba_debug_step_gdir(C.byref(pb), cam.ctypes.data, lam, _p(gw), _p(xp), _p(xl), _p(chi2))
     assert n >= 0, n
     return xp[:n], xl, chi2[0]
+
+
+def search_for_triangulation(pb, p):
+    """ORBmatcher::SearchForTriangulation for pair p of a synth.make_sft_problem dict -> (pairs [n, 2], nmatches)."""
+    P = pb["pairs"][p]
+    L = lib()
+    L.orc_search_for_triangulation.restype = C.c_int
+    L.orc_search_for_triangulation.argtypes = ([C.c_void_p] * 7 + [C.c_int]) * 2 + [C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                                                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+
+    def kf(kb, n, nb, nn, pb_, ib):
+        ptr = np.ascontiguousarray(pb["fv_ptr"][pb_:pb_ + nn + 1], np.int32)
+        return [np.ascontiguousarray(pb["kps"][kb:kb + n]), np.ascontiguousarray(pb["uright"][kb:kb + n], np.float32),
+                np.ascontiguousarray(pb["desc"][kb:kb + n], np.uint8), np.ascontiguousarray(pb["has_mp"][kb:kb + n], np.uint8),
+                np.ascontiguousarray(pb["fv_node"][nb:nb + nn], np.int32), ptr,
+                np.ascontiguousarray(pb["fv_idx"][ib:ib + ptr[-1]], np.int32)]
+    a = kf(P["kp1_begin"], P["n_kp1"], P["node1_begin"], P["n_nodes1"], P["ptr1_begin"], P["idx1_begin"])
+    b = kf(P["kp2_begin"], P["n_kp2"], P["node2_begin"], P["n_nodes2"], P["ptr2_begin"], P["idx2_begin"])
+    F = np.ascontiguousarray(P["F12"], np.float64); sf = np.ascontiguousarray(P["scale_factor2"], np.float32)
+    s2 = np.ascontiguousarray(P["level_sigma2_2"], np.float32)
+    cap = int(P["n_kp1"]) + 1
+    out = np.full((cap, 2), -1, np.int32)
+    n = L.orc_search_for_triangulation(*[_p(x) for x in a], int(P["n_nodes1"]), *[_p(x) for x in b], int(P["n_nodes2"]), _p(F),
+                                       float(P["ex"]), float(P["ey"]), _p(sf), _p(s2), int(P["only_stereo"]),
+                                       int(P["check_orientation"]), _p(out), cap)
+    return out[:n], n
+
+
+def search_by_bow(pb, p):
+    """ORBmatcher::SearchByBoW(KeyFrame, Frame) for pair p of a synth.make_bow_problem dict -> (match_f [n_kp2], nmatches)."""
+    P = pb["pairs"][p]
+    L = lib()
+    L.orc_search_by_bow.restype = C.c_int
+    L.orc_search_by_bow.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_float, C.c_int, C.c_void_p]
+
+    def fv(nb, nn, pb_, ib):
+        ptr = np.ascontiguousarray(pb["fv_ptr"][pb_:pb_ + nn + 1], np.int32)
+        return [np.ascontiguousarray(pb["fv_node"][nb:nb + nn], np.int32), ptr, np.ascontiguousarray(pb["fv_idx"][ib:ib + ptr[-1]], np.int32)]
+    k1 = slice(int(P["kp1_begin"]), int(P["kp1_begin"] + P["n_kp1"])); k2 = slice(int(P["kp2_begin"]), int(P["kp2_begin"] + P["n_kp2"]))
+    mp_id = np.where(pb["mp_ok"][k1] != 0, np.arange(int(P["n_kp1"])), -1).astype(np.int32)  # one camera: a map point per keypoint
+    a = fv(P["node1_begin"], P["n_nodes1"], P["ptr1_begin"], P["idx1_begin"]); b = fv(P["node2_begin"], P["n_nodes2"], P["ptr2_begin"], P["idx2_begin"])
+    kk1 = np.ascontiguousarray(pb["kps"][k1]); dd1 = np.ascontiguousarray(pb["desc"][k1], np.uint8)
+    kk2 = np.ascontiguousarray(pb["kps"][k2]); dd2 = np.ascontiguousarray(pb["desc"][k2], np.uint8)
+    mf = np.empty(max(int(P["n_kp2"]), 1), np.int32)
+    n = L.orc_search_by_bow(_p(kk1), _p(dd1), _p(mp_id), *[_p(x) for x in a], int(P["n_nodes1"]), _p(kk2), _p(dd2), int(P["n_kp2"]),
+                            *[_p(x) for x in b], int(P["n_nodes2"]), float(P["nn_ratio"]), int(P["check_orientation"]), _p(mf))
+    return mf[:int(P["n_kp2"])], n

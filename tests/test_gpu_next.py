@@ -174,3 +174,59 @@ def test_search_by_projection_base_edge_cases():
     big = synth.make_fuse_problem(83, n_frames=1, n_kp=4200, n_q=50)
     with pytest.raises(api.VieoError):
         api.ORBmatcher().SearchByProjectionBase(big)
+
+
+# ---------------------------------------------------------------- ORBmatcher::SearchForTriangulation
+@pytest.mark.parametrize("seed,n_kp,n_nodes,share", [(1, 1200, 90, True), (2, 300, 6, False), (3, 2000, 400, True)])
+def test_search_for_triangulation_matches_oracle(seed, n_kp, n_nodes, share):
+    """Keyframe pairs of LocalMapping::CreateNewMapPoints: matches, their creation order, the per-keypoint map and the
+    return value bit-exact against the oracle; few nodes -> long candidate lists (> 32 passing candidates: overflow path),
+    shared / separate first keyframes, bOnlyStereo and mbCheckOrientation on and off."""
+    import vieo_slam_b200.api as api
+    pb = synth.make_sft_problem(seed, n_pairs=5, n_kp=n_kp, n_nodes=n_nodes, share_kf1=share)
+    m12, po, nm = api.search_for_triangulation(pb)
+    tot = 0
+    for p in range(5):
+        P = pb["pairs"][p]
+        ref, n = O.search_for_triangulation(pb, p)
+        assert nm[p] == n, (p, nm[p], n)
+        ob = int(P["out_begin"])
+        assert np.array_equal(po[ob:ob + n], ref), p
+        want = np.full(int(P["n_kp1"]), -1, np.int32)
+        want[ref[:, 0]] = ref[:, 1]
+        assert np.array_equal(m12[ob:ob + int(P["n_kp1"])], want)
+        tot += n
+    assert tot > 50
+
+
+def test_search_for_triangulation_edge_cases():
+    import vieo_slam_b200.api as api
+    pb = synth.make_sft_problem(7, n_pairs=2, n_kp=200, n_nodes=10)
+    full = dict(pb); full["has_mp"] = np.ones_like(pb["has_mp"])
+    assert (api.search_for_triangulation(full)[2] == 0).all()
+    bad = dict(pb); bad["pairs"] = pb["pairs"].copy(); bad["pairs"]["n_kp2"][1] = 10 ** 6
+    with pytest.raises(api.VieoError):
+        api.search_for_triangulation(bad)
+    none = dict(pb); none["pairs"] = pb["pairs"][:0]
+    assert len(api.search_for_triangulation(none)[2]) == 0
+
+
+# ---------------------------------------------------------------- ORBmatcher::SearchByBoW(KeyFrame, Frame)
+@pytest.mark.parametrize("seed,n_kp,n_nodes", [(1, 1200, 90), (2, 400, 5), (3, 2500, 700)])
+def test_search_by_bow_matches_oracle(seed, n_kp, n_nodes):
+    """vpMapPointMatches (which keyframe keypoint's map point every frame keypoint received) and the return value bit-exact
+    against the oracle; few nodes -> long lists with many equal distances, ratios 0.7 / 0.9, orientation check on / off."""
+    import vieo_slam_b200.api as api
+    pb = synth.make_bow_problem(seed, n_pairs=6, n_kp=n_kp, n_nodes=n_nodes)
+    mf, nm = api.search_by_bow(pb)
+    tot = 0
+    for p in range(6):
+        P = pb["pairs"][p]
+        ref, n = O.search_by_bow(pb, p)
+        ob = int(P["out_begin"])
+        assert nm[p] == n, (p, nm[p], n)
+        assert np.array_equal(mf[ob:ob + int(P["n_kp2"])], ref), p
+        tot += n
+    assert tot > 100
+    none = dict(pb); none["mp_ok"] = np.zeros_like(pb["mp_ok"])
+    assert (api.search_by_bow(none)[1] == 0).all()

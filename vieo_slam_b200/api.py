@@ -98,6 +98,12 @@ def lib():
         L.vieo_multicam_frames.argtypes = [vp, i32, i32, vp, C.c_size_t, i32, vp, vp, vp, vp, vp, vp, vp, vp]
         L.vieo_lapping_split_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
         L.vieo_fisheye_knn_dev.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        L.vieo_sft_scratch_bytes.argtypes = [i32, i32]
+        L.vieo_sft_scratch_bytes.restype = sz
+        L.vieo_search_for_triangulation_dev.argtypes = [vp, i32] + [vp] * 7 + [i32, i32, vp, vp, vp, vp, sz, vp]
+        L.vieo_search_for_triangulation.argtypes = [vp, i32] + [vp] * 7 + [i32] * 6 + [vp, vp, vp, i32]
+        L.vieo_search_by_bow_dev.argtypes = [vp, i32] + [vp] * 6 + [i32, vp, vp, vp, sz, vp]
+        L.vieo_search_by_bow.argtypes = [vp, i32] + [vp] * 6 + [i32] * 5 + [vp, vp, i32]
         L.vieo_ba_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
         L.vieo_ba_create_global.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
         L.vieo_ba_destroy.argtypes = [vp]
@@ -671,6 +677,38 @@ def ba_problem(d, large=False, rec_init=False, visual_only=False):
     pb.inv_sigma_bg2, pb.inv_sigma_ba2 = d["inv_sigma_bg2"], d["inv_sigma_ba2"]
     pb.large, pb.rec_init, pb.visual_only = int(large), int(rec_init), int(visual_only)
     return pb, keep
+
+
+def search_for_triangulation(pb, device=0):
+    """ORBmatcher::SearchForTriangulation for a batch of keyframe pairs (synth.make_sft_problem layout, host arrays).
+    -> (match12 [n_out_total], pairs_out [n_out_total, 2], n_matches [n_pairs])."""
+    from .layouts import SFT_PAIR_DTYPE
+    pairs = np.ascontiguousarray(pb["pairs"], SFT_PAIR_DTYPE)
+    arrs = [np.ascontiguousarray(pb["kps"], KP_DTYPE), np.ascontiguousarray(pb["uright"], np.float32),
+            np.ascontiguousarray(pb["desc"], np.uint8), np.ascontiguousarray(pb["has_mp"], np.uint8),
+            np.ascontiguousarray(pb["fv_node"], np.int32), np.ascontiguousarray(pb["fv_ptr"], np.int32),
+            np.ascontiguousarray(pb["fv_idx"], np.int32)]
+    n_out = int(pb["n_out_total"])
+    m12 = np.empty(max(n_out, 1), np.int32); po = np.empty((max(n_out, 1), 2), np.int32); nm = np.empty(max(len(pairs), 1), np.int32)
+    _check(lib().vieo_search_for_triangulation(_p(pairs), len(pairs), *[_p(a) for a in arrs], len(arrs[0]), len(arrs[4]),
+                                               len(arrs[5]), len(arrs[6]), n_out, int(pb["n_nodes1_total"]), _p(m12), _p(po),
+                                               _p(nm), device))
+    return m12[:n_out], po[:n_out], nm[:len(pairs)]
+
+
+def search_by_bow(pb, device=0):
+    """ORBmatcher::SearchByBoW(KeyFrame, Frame) for a batch of pairs (synth.make_bow_problem layout).
+    -> (match_f [n_out_total], n_matches [n_pairs])."""
+    from .layouts import BOW_PAIR_DTYPE
+    pairs = np.ascontiguousarray(pb["pairs"], BOW_PAIR_DTYPE)
+    arrs = [np.ascontiguousarray(pb["kps"], KP_DTYPE), np.ascontiguousarray(pb["desc"], np.uint8),
+            np.ascontiguousarray(pb["mp_ok"], np.uint8), np.ascontiguousarray(pb["fv_node"], np.int32),
+            np.ascontiguousarray(pb["fv_ptr"], np.int32), np.ascontiguousarray(pb["fv_idx"], np.int32)]
+    n_out = int(pb["n_out_total"])
+    mf = np.empty(max(n_out, 1), np.int32); nm = np.empty(max(len(pairs), 1), np.int32)
+    _check(lib().vieo_search_by_bow(_p(pairs), len(pairs), *[_p(a) for a in arrs], len(arrs[0]), len(arrs[3]), len(arrs[4]),
+                                    len(arrs[5]), n_out, _p(mf), _p(nm), device))
+    return mf[:n_out], nm[:len(pairs)]
 
 
 def local_ba_prv_batch(bas, problems, cam, **kw):

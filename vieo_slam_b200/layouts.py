@@ -59,3 +59,18 @@ assert PROJ_SEARCH_FRAME_DTYPE.itemsize == 332
 
 assert SBP_FRAME_DTYPE.itemsize == 88 + 64 + 112
 assert NAVSTATE_DTYPE.itemsize == 22 * 8 and CAMERA_DTYPE.itemsize == 64 + 96
+
+# VieoSftPair (ORBmatcher::SearchForTriangulation, one keyframe pair)
+SFT_PAIR_DTYPE = np.dtype([("kp1_begin", "i4"), ("n_kp1", "i4"), ("kp2_begin", "i4"), ("n_kp2", "i4"), ("node1_begin", "i4"),
+                           ("n_nodes1", "i4"), ("node2_begin", "i4"), ("n_nodes2", "i4"), ("ptr1_begin", "i4"), ("ptr2_begin", "i4"),
+                           ("idx1_begin", "i4"), ("idx2_begin", "i4"), ("out_begin", "i4"), ("nscr_begin", "i4"),
+                           ("only_stereo", "i4"), ("check_orientation", "i4"), ("ex", "f4"), ("ey", "f4"),
+                           ("scale_factor2", "f4", 16), ("level_sigma2_2", "f4", 16), ("F12", "f8", 9)])
+assert SFT_PAIR_DTYPE.itemsize == 72 + 128 + 72
+
+# VieoBowPair (ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...), one (keyframe, frame) pair)
+BOW_PAIR_DTYPE = np.dtype([("kp1_begin", "i4"), ("n_kp1", "i4"), ("kp2_begin", "i4"), ("n_kp2", "i4"), ("node1_begin", "i4"),
+                           ("n_nodes1", "i4"), ("node2_begin", "i4"), ("n_nodes2", "i4"), ("ptr1_begin", "i4"), ("ptr2_begin", "i4"),
+                           ("idx1_begin", "i4"), ("idx2_begin", "i4"), ("out_begin", "i4"), ("check_orientation", "i4"),
+                           ("nn_ratio", "f4"), ("pad_", "i4")])
+assert BOW_PAIR_DTYPE.itemsize == 64

@@ -646,3 +646,146 @@ def make_fuse_problem(seed, n_frames=3, n_kp=1200, n_q=1500, th_radius=3.0, use_
     pb["frames_sbp"] = pb["frames"]
     pb["frames"] = fr
     return pb
+
+
+# ------------------------------------------------------------------------------------------------------------
+# SearchForTriangulation problems: keyframe pairs related by a known relative pose, keypoints of
+# KF2 = projections of KF1's back-projected keypoints (so the epipolar constraint holds for true matches) + distractors,
+# descriptors = near copies, DBoW2-like FeatureVectors (keypoints hashed into vocabulary nodes, true matches mostly in
+# the same node), existing map points, stereo / mono mix, rotation outliers.
+from .layouts import SFT_PAIR_DTYPE  # noqa: E402
+
+
+def _fundamental(K1, K2, R12, t12):
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    return np.linalg.inv(K1.T) @ tx @ R12 @ np.linalg.inv(K2)
+
+
+def make_sft_problem(seed, n_pairs=4, n_kp=1200, n_nodes=90, share_kf1=True):
+    """-> dict of flat arrays in the C-ABI layout of vieo_search_for_triangulation_dev (+ 'pairs' SFT_PAIR_DTYPE)."""
+    r = np.random.default_rng(seed)
+    fx, fy, cx, cy = (np.float32(EUROC[k]) for k in ("fx", "fy", "cx", "cy"))
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+    scale = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    sigma2 = (scale * scale).astype(np.float32)
+    kps, ur, desc, has_mp, fv_node, fv_ptr, fv_idx = [], [], [], [], [], [], []
+    kf = []  # per keyframe: (kp_begin, n_kp, node_begin, n_nodes, ptr_begin, idx_begin)
+
+    def add_kf(k, u, d, m, node_of_kp):
+        kb = sum(len(x) for x in kps)
+        ids = np.unique(node_of_kp)
+        lists = [np.nonzero(node_of_kp == i)[0] for i in ids]
+        for L in lists:
+            r.shuffle(L)  # push order inside a node is the keypoint loop order in DBoW2; any fixed order serves
+        ptr = np.concatenate([[0], np.cumsum([len(L) for L in lists])]).astype(np.int32)
+        rec = (kb, len(k), sum(len(x) for x in fv_node), len(ids), sum(len(x) for x in fv_ptr), sum(len(x) for x in fv_idx))
+        kps.append(k); ur.append(u); desc.append(d); has_mp.append(m)
+        fv_node.append(ids.astype(np.int32)); fv_ptr.append(ptr); fv_idx.append(np.concatenate(lists).astype(np.int32))
+        kf.append(rec)
+        return len(kf) - 1
+
+    def rand_kf(n):
+        k = np.zeros(n, KP_DTYPE)
+        k["x"] = r.uniform(20, EUROC["w"] - 20, n).astype(np.float32)
+        k["y"] = r.uniform(20, EUROC["h"] - 20, n).astype(np.float32)
+        k["octave"] = r.integers(0, 8, n)
+        k["angle"] = r.uniform(0, 360, n).astype(np.float32)
+        k["size"] = 31
+        return k
+
+    pairs = np.zeros(n_pairs, SFT_PAIR_DTYPE)
+    k1 = rand_kf(n_kp)
+    d1 = r.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    node1 = r.integers(0, n_nodes, n_kp) * 7 + 3  # sparse node ids
+    u1 = np.where(r.random(n_kp) < 0.5, k1["x"] - r.uniform(2, 40, n_kp), -1).astype(np.float32)
+    m1 = (r.random(n_kp) < 0.35).astype(np.uint8)
+    i_kf1 = add_kf(k1, u1, d1, m1, node1)
+    out_b = nscr_b = 0
+    for p in range(n_pairs):
+        if not share_kf1 and p > 0:
+            k1 = rand_kf(n_kp); d1 = r.integers(0, 256, (n_kp, 32), dtype=np.uint8); node1 = r.integers(0, n_nodes, n_kp) * 7 + 3
+            u1 = np.where(r.random(n_kp) < 0.5, k1["x"] - r.uniform(2, 40, n_kp), -1).astype(np.float32)
+            m1 = (r.random(n_kp) < 0.35).astype(np.uint8)
+            i_kf1 = add_kf(k1, u1, d1, m1, node1)
+        # relative pose 1 <- 2 and the second keyframe
+        a = r.normal(0, 0.05, 3); th = np.linalg.norm(a); ax = a / th
+        Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        R12 = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t12 = r.normal(0, 0.25, 3)
+        n2 = n_kp + int(r.integers(-100, 100))
+        k2 = rand_kf(n2)
+        d2 = r.integers(0, 256, (n2, 32), dtype=np.uint8)
+        node2 = r.integers(0, n_nodes + 10, n2) * 7 + 3
+        # true correspondences for ~60 % of KF1's keypoints: X1 = depth * K^-1 x1; x2 = K R21 (X1 - t12)
+        nm = int(0.6 * min(n_kp, n2))
+        src = r.permutation(n_kp)[:nm]; dst = r.permutation(n2)[:nm]
+        z = r.uniform(2, 15, nm)
+        X1 = (np.linalg.inv(K) @ np.stack([k1["x"][src], k1["y"][src], np.ones(nm)])) * z
+        X2 = R12.T @ (X1 - t12[:, None])
+        x2 = K @ (X2 / X2[2])
+        ok = (X2[2] > 0.5) & (x2[0] > 5) & (x2[0] < EUROC["w"] - 5) & (x2[1] > 5) & (x2[1] < EUROC["h"] - 5)
+        src, dst, x2 = src[ok], dst[ok], x2[:, ok]
+        noise = r.normal(0, 0.6, (2, len(src))) * scale[k1["octave"][src]]
+        k2["x"][dst] = (x2[0] + noise[0]).astype(np.float32); k2["y"][dst] = (x2[1] + noise[1]).astype(np.float32)
+        k2["octave"][dst] = np.clip(k1["octave"][src] + r.integers(-1, 2, len(src)), 0, 7)
+        rot_common = r.uniform(-20, 20)
+        k2["angle"][dst] = ((k1["angle"][src] - rot_common + r.normal(0, 3, len(src))) % 360).astype(np.float32)
+        bad_rot = r.random(len(src)) < 0.08
+        k2["angle"][dst[bad_rot]] = r.uniform(0, 360, int(bad_rot.sum())).astype(np.float32)
+        d2[dst] = d1[src]
+        nflip = r.integers(0, 60, len(src))  # some beyond TH_LOW
+        for j, f in zip(dst, nflip):
+            bits = r.choice(256, int(f), replace=False)
+            np.bitwise_xor.at(d2[j], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+        node2[dst] = node1[src]
+        stray = r.random(len(src)) < 0.1
+        node2[dst[stray]] = r.integers(0, n_nodes, int(stray.sum())) * 7 + 3
+        # decoys: duplicates of some matched descriptors in the same node (ties / competing claims)
+        nd = len(src) // 10
+        dec = r.permutation(n2)[:nd]; which = r.integers(0, len(src), nd)
+        d2[dec] = d2[dst[which]]; node2[dec] = node2[dst[which]]
+        k2["x"][dec] = k2["x"][dst[which]] + r.normal(0, 1.0, nd).astype(np.float32)
+        k2["y"][dec] = k2["y"][dst[which]] + r.normal(0, 1.0, nd).astype(np.float32)
+        k2["octave"][dec] = k2["octave"][dst[which]]
+        u2 = np.where(r.random(n2) < 0.5, k2["x"] - r.uniform(2, 40, n2), -1).astype(np.float32)
+        m2 = (r.random(n2) < 0.35).astype(np.uint8)
+        i_kf2 = add_kf(k2, u2, d2, m2, node2)
+        A, B = kf[i_kf1], kf[i_kf2]
+        P = pairs[p]
+        P["kp1_begin"], P["n_kp1"], P["node1_begin"], P["n_nodes1"], P["ptr1_begin"], P["idx1_begin"] = A
+        P["kp2_begin"], P["n_kp2"], P["node2_begin"], P["n_nodes2"], P["ptr2_begin"], P["idx2_begin"] = B
+        P["out_begin"], P["nscr_begin"] = out_b, nscr_b
+        out_b += A[1]; nscr_b += A[3]
+        P["only_stereo"] = int(p % 4 == 3)
+        P["check_orientation"] = int(p % 3 != 2)
+        C2 = R12.T @ (-t12)  # centre of camera 1 in camera 2
+        e = K.astype(np.float32) @ np.array([C2[0] / C2[2], C2[1] / C2[2], 1], np.float32)
+        P["ex"], P["ey"] = e[0], e[1]
+        P["scale_factor2"][:8] = scale; P["level_sigma2_2"][:8] = sigma2
+        P["F12"] = _fundamental(K, K, R12, t12).reshape(-1)
+    return dict(pairs=pairs, kps=np.concatenate(kps), uright=np.concatenate(ur), desc=np.concatenate(desc),
+                has_mp=np.concatenate(has_mp), fv_node=np.concatenate(fv_node), fv_ptr=np.concatenate(fv_ptr),
+                fv_idx=np.concatenate(fv_idx), n_out_total=out_b, n_nodes1_total=nscr_b)
+
+
+def make_bow_problem(seed, n_pairs=4, n_kp=1200, n_nodes=90, nn_ratio=0.7):
+    """SearchByBoW(KeyFrame, Frame) problems on the keyframe pairs of make_sft_problem: side 1 = keyframe (its keypoints WITH
+    a map point are the queries), side 2 = frame.  -> the same flat arrays + 'pairs' (BOW_PAIR_DTYPE), 'mp_ok'."""
+    from .layouts import BOW_PAIR_DTYPE
+    pb = make_sft_problem(seed, n_pairs=n_pairs, n_kp=n_kp, n_nodes=n_nodes, share_kf1=False)
+    bp = np.zeros(n_pairs, BOW_PAIR_DTYPE)
+    ob = 0
+    for p in range(n_pairs):
+        for k in ("kp1_begin", "n_kp1", "kp2_begin", "n_kp2", "node1_begin", "n_nodes1", "node2_begin", "n_nodes2", "ptr1_begin",
+                  "ptr2_begin", "idx1_begin", "idx2_begin"):
+            bp[k][p] = pb["pairs"][k][p]
+        bp["out_begin"][p] = ob
+        ob += int(bp["n_kp2"][p])
+        bp["check_orientation"][p] = int(p % 2 == 0)
+        bp["nn_ratio"][p] = nn_ratio if p % 3 else 0.9
+    r = np.random.default_rng(seed + 99)
+    out = dict(pb)
+    out["pairs"] = bp
+    out["mp_ok"] = (r.random(len(pb["has_mp"])) < 0.6).astype(np.uint8)
+    out["n_out_total"] = ob
+    return out
