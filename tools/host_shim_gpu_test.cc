@@ -1,0 +1,247 @@
+// The C++ boundary on the GPU: the reference-facing classes of vieo_slam_b200/host/vieo_shims.hpp and the flatten /
+// write-back templates of vieo_flatten.hpp driven with real data.  tests/test_gpu_shims.py writes the inputs as raw arrays
+// into a directory, runs this binary, and byte-compares what it writes back with the results of the ctypes path.
+//   host_shim_gpu_test <dir>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <string>
+
+#include "../vieo_slam_b200/host/vieo_flatten.hpp"
+
+using namespace VIEO_SLAM_B200;
+
+template <class T>
+std::vector<T> rd(const std::string& dir, const char* name) {
+  std::ifstream f(dir + "/" + name, std::ios::binary | std::ios::ate);
+  if (!f) { std::fprintf(stderr, "missing %s\n", name); std::exit(2); }
+  const size_t n = (size_t)f.tellg();
+  std::vector<T> v(n / sizeof(T));
+  f.seekg(0);
+  f.read((char*)v.data(), (std::streamsize)(v.size() * sizeof(T)));
+  return v;
+}
+template <class T>
+void wr(const std::string& dir, const char* name, const T* p, size_t n) {
+  std::ofstream f(dir + "/" + name, std::ios::binary);
+  f.write((const char*)p, (std::streamsize)(n * sizeof(T)));
+}
+
+// ---- minimal stand-ins with the reference's member names (see vieo_flatten.hpp) ---------------------------------------------
+struct NavState { VieoNavState s; };
+inline VieoNavState vieo_from_navstate(const NavState& n) { return n.s; }
+inline void vieo_to_navstate(const VieoNavState& v, NavState& n) { n.s = v; }
+struct KeyFrame;
+struct MapPoint {
+  double X[3];
+  int updated = 0;
+  std::vector<std::pair<KeyFrame*, size_t>> obs_;
+  const std::vector<std::pair<KeyFrame*, size_t>>& observations() const { return obs_; }
+  void UpdateNormalAndDepth() { ++updated; }
+};
+inline void vieo_get_world_pos(const MapPoint& m, double o[3]) { o[0] = m.X[0]; o[1] = m.X[1]; o[2] = m.X[2]; }
+inline void vieo_set_world_pos(MapPoint& m, const double* i) { m.X[0] = i[0]; m.X[1] = i[1]; m.X[2] = i[2]; }
+struct StereoInfo { std::vector<float> vuright_, vdepth_; };
+struct ScaleInfo { std::vector<float> vinvlevelsigma2_; };
+struct Frame {
+  int N = 0;
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<cv::KeyPoint> mvKeysUn;
+  StereoInfo stereoinfo_;
+  ScaleInfo scalepyrinfo_;
+  std::vector<bool> mvbOutlier;
+  NavState ns;
+  NavState GetNavState() const { return ns; }
+  void SetNavState(const NavState& n) { ns = n; }
+};
+
+struct KeyFrame {
+  std::vector<cv::KeyPoint> mvKeysUn;
+  StereoInfo stereoinfo_;
+  ScaleInfo scalepyrinfo_;
+  NavState ns;
+  KeyFrame* prev = nullptr;
+  double ftimestamp_ = 0;
+  int erased = 0;
+  NavState GetNavState() const { return ns; }
+  void SetNavState(const NavState& n) { ns = n; }
+  KeyFrame* GetPrevKeyFrame() const { return prev; }
+};
+inline void ErasePairObs(KeyFrame* kf, MapPoint*) { ++kf->erased; }
+
+// FlattenLocalWindow / WriteBackLocalWindow on a tiny hand-made window: ordering and bookkeeping only (no device call)
+static int window_templates_check() {
+  KeyFrame k[3];
+  MapPoint m[2];
+  for (int i = 0; i < 3; ++i) {
+    k[i].mvKeysUn.resize(4);
+    k[i].stereoinfo_.vuright_ = {-1.f, 10.f, -1.f, 3.f};
+    k[i].stereoinfo_.vdepth_ = {-1.f, 4.f, -1.f, 50.f};
+    k[i].scalepyrinfo_.vinvlevelsigma2_ = {1.f};
+    k[i].ftimestamp_ = 0.5 * i;
+    std::memset(&k[i].ns.s, 0, sizeof(VieoNavState));
+    k[i].ns.s.q[0] = 1;
+  }
+  k[1].prev = &k[0]; k[2].prev = &k[1];
+  m[0].X[0] = 1; m[0].X[1] = 2; m[0].X[2] = 3; m[0].obs_ = {{&k[0], 1}, {&k[2], 3}};
+  m[1].X[0] = 4; m[1].X[1] = 5; m[1].X[2] = 6; m[1].obs_ = {{&k[1], 0}, {&k[2], 1}, {&k[0], 2}};
+  std::vector<KeyFrame*> local = {&k[1], &k[2]}, fixed = {&k[0]};
+  std::vector<MapPoint*> mps = {&m[0], &m[1]};
+  auto W = FlattenLocalWindow<KeyFrame, MapPoint>(local, fixed, mps, 20.f, [](KeyFrame*) { return VieoImuPreint{}; });
+  if (W.kfs.size() != 3 || W.mps.size() != 2 || W.edge_state.size() != 5 || W.imu_i.size() != 2) return 1;
+  if (W.state_flags[0] != 2 || W.state_flags[2] != (1 | 2 | 4)) return 2;      // k[0] is fixed and carries V / Bias
+  if (W.edge_point[0] != 0 || W.edge_point[2] != 1 || W.edge_state[0] != 2 || W.edge_state[1] != 1) return 3;
+  if (!(W.edge_flags[0] & VIEO_EDGE_STEREO) || !(W.edge_flags[0] & VIEO_EDGE_CLOSE) || (W.edge_flags[1] & VIEO_EDGE_CLOSE)) return 4;
+  const double gw[3] = {0, 0, -9.81};
+  VieoBaProblem pb = W.problem(gw, 1.0, 1.0, false, false);
+  if (pb.n_states != 3 || pb.n_edges != 5 || pb.n_imu != 2) return 5;
+  VieoBaResult res{};
+  res.accepted = 1;
+  std::vector<VieoNavState> so(W.states);
+  so[0].p[0] = 7;
+  std::vector<double> po = {9, 9, 9, 8, 8, 8};
+  std::vector<uint8_t> er = {0, 1, 0, 0, 0};
+  WriteBackLocalWindow(W, 2, res, so, po, er);
+  if (k[1].ns.s.p[0] != 7 || m[0].X[0] != 9 || m[1].X[2] != 8 || m[0].updated != 1 || k[2].erased != 1) return 6;
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  const std::string dir = argv[1];
+  if (int rc = window_templates_check()) {
+    std::fprintf(stderr, "window templates check failed: %d\n", rc);
+    return 5;
+  }
+  if (std::string(argv[1]) == "--templates-only") {
+    std::printf("HOST_TEMPLATES_OK\n");
+    return 0;
+  }
+  try {
+    // 1. ORBextractor::operator() — keypoints, descriptors, monoIndex, public pyramid
+    {
+      auto meta = rd<int32_t>(dir, "orb_meta.i32");  // w, h, nfeatures, nlevels, lapping0, lapping1 (-1: none)
+      auto img = rd<uint8_t>(dir, "orb_img.u8");
+      ORBextractor ex(meta[2], 1.2f, meta[3], 20, 7);
+      cv::Mat image(meta[1], meta[0], img.data());
+      cv::Mat mask, desc;
+      std::vector<cv::KeyPoint> kps;
+      std::vector<int> lap = {meta[4], meta[5]};
+      const int mono = ex(image, mask, kps, desc, meta[4] >= 0 ? &lap : nullptr);
+      std::vector<float> flat;
+      for (const cv::KeyPoint& k : kps) {
+        flat.insert(flat.end(), {k.pt.x, k.pt.y, k.size, k.angle, k.response});
+        float oct;
+        std::memcpy(&oct, &k.octave, 4);
+        flat.push_back(oct);
+      }
+      wr(dir, "orb_kps.out", flat.data(), flat.size());
+      wr(dir, "orb_desc.out", desc.data, (size_t)desc.rows * 32);
+      const int32_t info[3] = {mono, (int32_t)kps.size(), ex.GetLevels()};
+      wr(dir, "orb_info.out", info, 3);
+      wr(dir, "orb_level3.out", ex.mvImagePyramid[3].data, (size_t)ex.mvImagePyramid[3].rows * ex.mvImagePyramid[3].cols);
+      cv::Mat empty;
+      if (ex(empty, mask, kps, desc) != -1) return 3;
+    }
+    // 2. IMUPreIntegratorBase::PreIntegration
+    {
+      auto smp = rd<double>(dir, "imu_samples.f64");  // n x 7 (t, a, w)
+      auto par = rd<double>(dir, "imu_par.f64");      // ti, tj, bg(3), ba(3), sigma2(4)
+      IMUPreintegrator::SetParam(&par[8], 1, 200.0);
+      std::list<IMUSample> data;
+      for (size_t i = 0; i + 6 < smp.size(); i += 7) data.push_back({smp[i], {smp[i + 1], smp[i + 2], smp[i + 3]}, {smp[i + 4], smp[i + 5], smp[i + 6]}});
+      IMUPreintegrator pre;
+      const int st = pre.PreIntegration(par[0], par[1], &par[2], &par[5], data.begin(), data.end());
+      std::vector<double> o;
+      o.insert(o.end(), pre.mRij, pre.mRij + 9); o.insert(o.end(), pre.mvij, pre.mvij + 3); o.insert(o.end(), pre.mpij, pre.mpij + 3);
+      o.insert(o.end(), pre.mSigmaijPRV, pre.mSigmaijPRV + 81); o.insert(o.end(), pre.mSigmaij, pre.mSigmaij + 81);
+      o.insert(o.end(), pre.mJgpij, pre.mJgpij + 9); o.insert(o.end(), pre.mJapij, pre.mJapij + 9);
+      o.insert(o.end(), pre.mJgvij, pre.mJgvij + 9); o.insert(o.end(), pre.mJavij, pre.mJavij + 9);
+      o.insert(o.end(), pre.mJgRij, pre.mJgRij + 9);
+      o.push_back(pre.mdeltatij); o.push_back((double)st);
+      wr(dir, "imu.out", o.data(), o.size());
+    }
+    // 3. Optimizer::PoseOptimization through the flatten template on a stand-in Frame
+    {
+      auto cam = rd<VieoCamera>(dir, "po_cam.bin");
+      auto ns = rd<VieoNavState>(dir, "po_state.bin");
+      auto X = rd<double>(dir, "po_Xw.f64");
+      auto ob = rd<float>(dir, "po_obs.f32");
+      auto w = rd<float>(dir, "po_w.f32");
+      auto fl = rd<uint8_t>(dir, "po_flags.u8");
+      const int E = (int)fl.size();
+      Frame F;
+      F.N = E + 5;  // a few keypoints without a map point
+      std::vector<MapPoint> mps(E);
+      F.mvpMapPoints.assign(F.N, nullptr); F.mvKeysUn.resize(F.N); F.stereoinfo_.vuright_.assign(F.N, -1.f);
+      F.mvbOutlier.assign(F.N, true);
+      F.scalepyrinfo_.vinvlevelsigma2_ = {1.f, 0.f};
+      // invSigma2 values are arbitrary floats in the dump: one table entry per edge keeps them exact
+      F.scalepyrinfo_.vinvlevelsigma2_.assign(w.begin(), w.end());
+      for (int e = 0; e < E; ++e) {
+        const int i = e + (e >= 3 ? 2 : 0) + (e >= 40 ? 3 : 0);  // holes at 3, 4 and three more from 42 on
+        mps[e].X[0] = X[3 * e]; mps[e].X[1] = X[3 * e + 1]; mps[e].X[2] = X[3 * e + 2];
+        F.mvpMapPoints[i] = &mps[e];
+        F.mvKeysUn[i].pt.x = ob[3 * e]; F.mvKeysUn[i].pt.y = ob[3 * e + 1]; F.mvKeysUn[i].octave = e;
+        F.stereoinfo_.vuright_[i] = (fl[e] & VIEO_EDGE_STEREO) ? ob[3 * e + 2] : -1.f;
+      }
+      F.ns.s = ns[0];
+      const int inl = PoseOptimizationVisual(&F, cam[0]);
+      std::vector<uint8_t> outl;
+      for (int i = 0; i < F.N; ++i)
+        if (F.mvpMapPoints[i]) outl.push_back(F.mvbOutlier[i] ? 1 : 0);
+      wr(dir, "po_outlier.out", outl.data(), outl.size());
+      wr(dir, "po_state.out", &F.ns.s, 1);
+      const int32_t r[1] = {inl};
+      wr(dir, "po_inliers.out", r, 1);
+    }
+    // 4. LocalBA::Run and the asynchronous Begin / End on the dumped window
+    {
+      auto cam = rd<VieoCamera>(dir, "ba_cam.bin");
+      auto st = rd<VieoNavState>(dir, "ba_states.bin");
+      auto sf = rd<uint8_t>(dir, "ba_state_flags.u8");
+      auto pts = rd<double>(dir, "ba_points.f64");
+      auto es = rd<int32_t>(dir, "ba_edge_state.i32");
+      auto ep = rd<int32_t>(dir, "ba_edge_point.i32");
+      auto ob = rd<float>(dir, "ba_obs.f32");
+      auto w = rd<float>(dir, "ba_w.f32");
+      auto ef = rd<uint8_t>(dir, "ba_edge_flags.u8");
+      auto ii = rd<int32_t>(dir, "ba_imu_i.i32");
+      auto ij = rd<int32_t>(dir, "ba_imu_j.i32");
+      auto pre = rd<VieoImuPreint>(dir, "ba_preint.bin");
+      auto dt = rd<double>(dir, "ba_dt.f64");
+      auto par = rd<double>(dir, "ba_par.f64");  // gw(3), inv_sigma_bg2, inv_sigma_ba2
+      VieoBaProblem pb{};
+      pb.n_states = (int)st.size(); pb.n_points = (int)pts.size() / 3; pb.n_edges = (int)es.size(); pb.n_imu = (int)ii.size();
+      pb.states = st.data(); pb.state_flags = sf.data(); pb.points = pts.data(); pb.edge_state = es.data(); pb.edge_point = ep.data();
+      pb.obs = ob.data(); pb.inv_sigma2 = w.data(); pb.edge_flags = ef.data(); pb.imu_i = ii.data(); pb.imu_j = ij.data();
+      pb.preint = pre.data(); pb.imu_dt_kf = dt.data();
+      pb.gw[0] = par[0]; pb.gw[1] = par[1]; pb.gw[2] = par[2]; pb.inv_sigma_bg2 = par[3]; pb.inv_sigma_ba2 = par[4];
+      LocalBA ba(64, 4096, 32768, 32);
+      std::vector<VieoNavState> so(st.size());
+      std::vector<double> po(pts.size()), chi(es.size());
+      std::vector<uint8_t> er(es.size());
+      VieoBaResult res{};
+      bool stop = false;
+      ba.Run(pb, cam[0], &stop, so.data(), po.data(), chi.data(), er.data(), res);
+      wr(dir, "ba_states.out", so.data(), so.size());
+      wr(dir, "ba_points.out", po.data(), po.size());
+      wr(dir, "ba_erase.out", er.data(), er.size());
+      wr(dir, "ba_res.out", &res, 1);
+      std::vector<VieoNavState> so2(st.size());
+      std::vector<double> po2(pts.size());
+      std::vector<uint8_t> er2(es.size());
+      VieoBaResult res2{};
+      ba.Begin(pb, cam[0], &stop);
+      ba.End(so2.data(), po2.data(), nullptr, er2.data(), res2);
+      if (std::memcmp(so.data(), so2.data(), sizeof(VieoNavState) * so.size()) || std::memcmp(po.data(), po2.data(), 8 * po.size()) ||
+          er != er2) return 4;
+    }
+    std::printf("HOST_SHIM_GPU_OK %s\n", vieo_version());
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "exception: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

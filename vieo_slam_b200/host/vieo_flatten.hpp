@@ -1,0 +1,170 @@
+// Graph collection and write-back for the optimiser entry points, as code: what the reference's Optimizer methods do
+// between "Set ... vertices / edges" and "Recover optimized ..." (src/Optimizer.cc:1611-1874 for the visual
+// PoseOptimization, :133-520 + :704-768 for LocalBundleAdjustmentNavStatePRV), written against the REFERENCE's member names
+// so that the bodies drop into src/Optimizer.cc unchanged.  Templates: the reference's Frame / KeyFrame / MapPoint types
+// need OpenCV, Eigen and Sophus, which this repository cannot include; tools/host_shim_gpu_test.cc instantiates them with
+// minimal stand-ins that carry the same member names, and the GPU test compares the results with the ctypes path.
+//
+// Customisation points the integrator supplies for its own types (two-line functions over NavState / Eigen vectors):
+//   VieoNavState vieo_from_navstate(const NavStateT&);   void vieo_to_navstate(const VieoNavState&, NavStateT&);
+//   void vieo_get_world_pos(const MapPointT&, double out[3]);   void vieo_set_world_pos(MapPointT&, const double in[3]);
+#pragma once
+#include <cmath>
+#include <vector>
+
+#include "vieo_shims.hpp"
+
+namespace VIEO_SLAM_B200 {
+
+// ---- Optimizer::PoseOptimization(Frame* pFrame, Frame* pLastF) (visual, src/Optimizer.cc:1611-1874) -----------------------
+// Collection (:1660-1760): every pFrame->mvpMapPoints[i] != nullptr gives one edge; mono when vuright_[i] < 0, else stereo;
+// information = vinvlevelsigma2_[kpUn.octave]; pFrame->mvbOutlier[i] = false.  Write-back (:1850-1872): mvbOutlier from the
+// last classification, pose from the optimised vertex.  Returns nInitialCorrespondences - nBad.
+template <class FrameT>
+int PoseOptimizationVisual(FrameT* pFrame, const VieoCamera& cam, int device = 0) {
+  std::vector<double> Xw;
+  std::vector<float> obs, w;
+  std::vector<uint8_t> flags;
+  std::vector<int> edge_kp;
+  const int N = pFrame->N;
+  for (int i = 0; i < N; i++) {
+    auto* pMP = pFrame->mvpMapPoints[i];
+    if (!pMP) continue;
+    pFrame->mvbOutlier[i] = false;
+    const auto& kpUn = pFrame->mvKeysUn[i];
+    const float ur = pFrame->stereoinfo_.vuright_[i];
+    double X[3];
+    vieo_get_world_pos(*pMP, X);
+    Xw.insert(Xw.end(), X, X + 3);
+    obs.push_back(kpUn.pt.x); obs.push_back(kpUn.pt.y); obs.push_back(ur < 0 ? 0.f : ur);
+    w.push_back(pFrame->scalepyrinfo_.vinvlevelsigma2_[kpUn.octave]);
+    flags.push_back(ur < 0 ? 0 : VIEO_EDGE_STEREO);
+    edge_kp.push_back(i);
+  }
+  if ((int)edge_kp.size() < 3) return 0;  // :1762-1763
+  VieoPoseOptProblem pb{};
+  pb.mode = 0;
+  pb.cur = vieo_from_navstate(pFrame->GetNavState());
+  VieoPoseOptResult res{};
+  std::vector<uint8_t> outlier;
+  const int inliers = Optimizer::PoseOptimization(pb, cam, Xw, obs, w, flags, res, outlier, device);
+  for (size_t e = 0; e < edge_kp.size(); ++e) pFrame->mvbOutlier[edge_kp[e]] = outlier[e] != 0;
+  auto ns = pFrame->GetNavState();
+  vieo_to_navstate(res.cur, ns);
+  pFrame->SetNavState(ns);  // also refreshes Tcw (UpdatePoseFromNS)
+  return inliers;
+}
+
+// ---- Optimizer::LocalBundleAdjustmentNavStatePRV (src/Optimizer.cc:21-769): flattening of an already collected window --------
+// lLocalKeyFrames (ascending id), lFixedCameras, lLocalMapPoints as the reference builds them (:52-131); observations()
+// returns the (KeyFrame*, idx) pairs of a map point.  Produces the arrays of VieoBaProblem (keyframes local-first, edges
+// sorted by point) and remembers which (KeyFrame*, MapPoint*) every edge was, for ErasePairObs in the write-back.
+template <class KeyFrameT, class MapPointT>
+struct LocalWindow {
+  std::vector<KeyFrameT*> kfs;       // local first, then fixed
+  std::vector<MapPointT*> mps;
+  std::vector<VieoNavState> states;
+  std::vector<uint8_t> state_flags;
+  std::vector<double> points;
+  std::vector<int32_t> edge_state, edge_point, imu_i, imu_j;
+  std::vector<float> obs, inv_sigma2;
+  std::vector<uint8_t> edge_flags;
+  std::vector<VieoImuPreint> preint;
+  std::vector<double> imu_dt_kf;
+
+  VieoBaProblem problem(const double gw[3], double inv_sigma_bg2, double inv_sigma_ba2, bool bLarge, bool bRecInit) const {
+    VieoBaProblem pb{};
+    pb.n_states = (int)states.size(); pb.n_points = (int)mps.size(); pb.n_edges = (int)edge_state.size(); pb.n_imu = (int)imu_i.size();
+    pb.states = states.data(); pb.state_flags = state_flags.data(); pb.points = points.data();
+    pb.edge_state = edge_state.data(); pb.edge_point = edge_point.data(); pb.obs = obs.data(); pb.inv_sigma2 = inv_sigma2.data();
+    pb.edge_flags = edge_flags.data(); pb.imu_i = imu_i.data(); pb.imu_j = imu_j.data(); pb.preint = preint.data();
+    pb.imu_dt_kf = imu_dt_kf.data();
+    pb.gw[0] = gw[0]; pb.gw[1] = gw[1]; pb.gw[2] = gw[2];
+    pb.inv_sigma_bg2 = inv_sigma_bg2; pb.inv_sigma_ba2 = inv_sigma_ba2;
+    pb.large = bLarge; pb.rec_init = bRecInit;
+    return pb;
+  }
+};
+
+template <class KeyFrameT, class MapPointT, class PreintOf>
+LocalWindow<KeyFrameT, MapPointT> FlattenLocalWindow(const std::vector<KeyFrameT*>& lLocalKeyFrames,
+                                                     const std::vector<KeyFrameT*>& lFixedCameras,
+                                                     const std::vector<MapPointT*>& lLocalMapPoints, float th_dist_far,
+                                                     PreintOf preint_of) {
+  LocalWindow<KeyFrameT, MapPointT> W;
+  auto index_of = [&](KeyFrameT* kf) {
+    for (size_t k = 0; k < W.kfs.size(); ++k)
+      if (W.kfs[k] == kf) return (int)k;
+    return -1;
+  };
+  for (KeyFrameT* kf : lLocalKeyFrames) {  // PR + V + Bias vertices (:141-176)
+    W.kfs.push_back(kf);
+    W.states.push_back(vieo_from_navstate(kf->GetNavState()));
+    W.state_flags.push_back(2);
+  }
+  for (KeyFrameT* kf : lFixedCameras) {  // fixed PR; the previous window's last keyframe also carries fixed V / Bias (:180-217)
+    W.kfs.push_back(kf);
+    W.states.push_back(vieo_from_navstate(kf->GetNavState()));
+    W.state_flags.push_back(1);
+  }
+  for (KeyFrameT* kf1 : lLocalKeyFrames) {  // inertial + bias-walk edges to the previous keyframe (:219-330)
+    KeyFrameT* kf0 = kf1->GetPrevKeyFrame();
+    if (!kf0) continue;
+    int i0 = index_of(kf0);
+    if (i0 < 0) continue;
+    if (W.state_flags[i0] == 1) W.state_flags[i0] = 1 | 2 | 4;  // fixed keyframe that takes part in an inertial edge
+    W.imu_i.push_back(i0);
+    W.imu_j.push_back(index_of(kf1));
+    W.preint.push_back(preint_of(kf1));
+    W.imu_dt_kf.push_back(kf1->ftimestamp_ - kf0->ftimestamp_);
+  }
+  const float chi_far = th_dist_far;
+  for (MapPointT* mp : lLocalMapPoints) {  // point vertices and reprojection edges, point by point (:367-520)
+    double X[3];
+    vieo_get_world_pos(*mp, X);
+    const int p = (int)W.mps.size();
+    bool any = false;
+    for (const auto& ob : mp->observations()) {
+      KeyFrameT* kf = ob.first;
+      const int s = index_of(kf);
+      if (s < 0) continue;
+      const size_t idx = ob.second;
+      const auto& kpUn = kf->mvKeysUn[idx];
+      const float ur = kf->stereoinfo_.vuright_[idx];
+      W.edge_state.push_back(s);
+      W.edge_point.push_back(p);
+      W.obs.push_back(kpUn.pt.x); W.obs.push_back(kpUn.pt.y); W.obs.push_back(ur < 0 ? 0.f : ur);
+      W.inv_sigma2.push_back(kf->scalepyrinfo_.vinvlevelsigma2_[kpUn.octave]);
+      uint8_t fl = ur < 0 ? 0 : VIEO_EDGE_STEREO;
+      if (!(kf->stereoinfo_.vdepth_[idx] > chi_far)) fl |= VIEO_EDGE_CLOSE;  // far-point guard (:393-396)
+      W.edge_flags.push_back(fl);
+      any = true;
+    }
+    if (!any) continue;
+    W.mps.push_back(mp);
+    W.points.insert(W.points.end(), X, X + 3);
+  }
+  return W;
+}
+
+// Write-back (:704-768): erase the outlier observations, SetNavState on the local keyframes, SetWorldPos +
+// UpdateNormalAndDepth on the points.  Nothing is written when the result was rejected (res.accepted == 0, :663-666).
+template <class KeyFrameT, class MapPointT>
+void WriteBackLocalWindow(LocalWindow<KeyFrameT, MapPointT>& W, size_t n_local, const VieoBaResult& res,
+                          const std::vector<VieoNavState>& states_out, const std::vector<double>& points_out,
+                          const std::vector<uint8_t>& erase) {
+  if (!res.accepted) return;
+  for (size_t e = 0; e < erase.size(); ++e)
+    if (erase[e]) ErasePairObs(W.kfs[W.edge_state[e]], W.mps[W.edge_point[e]]);
+  for (size_t k = 0; k < n_local; ++k) {
+    auto ns = W.kfs[k]->GetNavState();
+    vieo_to_navstate(states_out[k], ns);
+    W.kfs[k]->SetNavState(ns);
+  }
+  for (size_t p = 0; p < W.mps.size(); ++p) {
+    vieo_set_world_pos(*W.mps[p], &points_out[3 * p]);
+    W.mps[p]->UpdateNormalAndDepth();
+  }
+}
+
+}  // namespace VIEO_SLAM_B200

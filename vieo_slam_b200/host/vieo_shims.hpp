@@ -206,12 +206,99 @@ class ORBmatcher {
     vieo_check(vieo_distinctive_descriptors(desc_pool, n_pool, rows.empty() ? nullptr : rows.data(), ptr.data(), n,
                                             best.data(), median.data(), device_), "vieo_distinctive_descriptors");
   }
+  // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:896-1150) for a batch
+  // of keyframe pairs (LocalMapping::CreateNewMapPoints loops over the neighbours, src/LocalMapping.cc:680-709); the
+  // caller flattens mvKeysUn / vuright_ / mDescriptors / GetMapPoint() != nullptr and the two DBoW2::FeatureVectors per
+  // pair and forms F12 and the epipole.  pairs_out holds vMatchedPairs of pair p at
+  // [pairs[p].out_begin, + n_matches[p]) as (idx1, idx2); returns the sum of the return values.
+  int SearchForTriangulation(std::vector<VieoSftPair>& pairs, const std::vector<VieoKeyPoint>& keys_un,
+                             const std::vector<float>& vuright, const std::vector<uint8_t>& descriptors,
+                             const std::vector<uint8_t>& has_mp, const std::vector<int32_t>& fv_node,
+                             const std::vector<int32_t>& fv_ptr, const std::vector<int32_t>& fv_idx,
+                             std::vector<int32_t>& match12, std::vector<int32_t>& pairs_out, std::vector<int32_t>& n_matches,
+                             bool bOnlyStereo = false) const {
+    int n_out = 0, n_nodes1 = 0;
+    for (VieoSftPair& p : pairs) {
+      p.out_begin = n_out; p.nscr_begin = n_nodes1;
+      n_out += p.n_kp1; n_nodes1 += p.n_nodes1;
+      p.only_stereo = bOnlyStereo ? 1 : 0;
+      p.check_orientation = mbCheckOrientation ? 1 : 0;
+    }
+    match12.assign(std::max(n_out, 1), -1); pairs_out.assign((size_t)2 * std::max(n_out, 1), -1); n_matches.assign(pairs.size(), 0);
+    vieo_check(vieo_search_for_triangulation(pairs.data(), (int)pairs.size(), keys_un.data(), vuright.data(), descriptors.data(),
+                                             has_mp.data(), fv_node.data(), fv_ptr.data(), fv_idx.data(), (int)keys_un.size(),
+                                             (int)fv_node.size(), (int)fv_ptr.size(), (int)fv_idx.size(), n_out, n_nodes1,
+                                             match12.data(), pairs_out.data(), n_matches.data(), device_),
+               "vieo_search_for_triangulation");
+    int total = 0;
+    for (int32_t n : n_matches) total += n;
+    return total;
+  }
+  // ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:344-505) for a batch of (keyframe, frame) pairs:
+  // match_f[pairs[p].out_begin + i] = keyframe keypoint whose map point frame keypoint i received (-1: none).
+  int SearchByBoW(std::vector<VieoBowPair>& pairs, const std::vector<VieoKeyPoint>& keys, const std::vector<uint8_t>& descriptors,
+                  const std::vector<uint8_t>& mp_ok, const std::vector<int32_t>& fv_node, const std::vector<int32_t>& fv_ptr,
+                  const std::vector<int32_t>& fv_idx, std::vector<int32_t>& match_f, std::vector<int32_t>& n_matches) const {
+    int n_out = 0;
+    for (VieoBowPair& p : pairs) {
+      p.out_begin = n_out;
+      n_out += p.n_kp2;
+      p.nn_ratio = mfNNratio;
+      p.check_orientation = mbCheckOrientation ? 1 : 0;
+    }
+    match_f.assign(std::max(n_out, 1), -1); n_matches.assign(pairs.size(), 0);
+    vieo_check(vieo_search_by_bow(pairs.data(), (int)pairs.size(), keys.data(), descriptors.data(), mp_ok.data(), fv_node.data(),
+                                  fv_ptr.data(), fv_idx.data(), (int)keys.size(), (int)fv_node.size(), (int)fv_ptr.size(),
+                                  (int)fv_idx.size(), n_out, match_f.data(), n_matches.data(), device_), "vieo_search_by_bow");
+    int total = 0;
+    for (int32_t n : n_matches) total += n;
+    return total;
+  }
   float mfNNratio;
   bool mbCheckOrientation;
 
  private:
   int device_;
 };
+
+// Frame::Frame's per-camera extraction with the lapping area + the brute-force half of
+// Frame::ComputeStereoFishEyeMatches (src/Frame.cc:259-278, 613-663) for one multi-camera frame: n_cams images of the
+// extractor's size, lapping = n_cams x {x0, x1} (nullptr: none).  vvkeys / vdescriptors / num_mono as the reference's
+// members; allmatches[p] = knnMatch(k = 2) rows of camera pair p (i < j in the reference's order) with `good` = passed the
+// ratio test (:659-663).
+struct FisheyePairMatches {
+  std::vector<DMatch2> knn;
+  std::vector<uint8_t> good;
+};
+inline void ExtractAndMatchMultiCam(vieo_orb_t* extractor, int n_cams, const uint8_t* imgs, size_t img_stride, int row_stride,
+                                    const int32_t* lapping, std::vector<std::vector<VieoKeyPoint>>& vvkeys,
+                                    std::vector<std::vector<uint8_t>>& vdescriptors, std::vector<int>& num_mono,
+                                    std::vector<FisheyePairMatches>& allmatches) {
+  const int cap = vieo_orb_max_keypoints(extractor), n_pairs = n_cams * (n_cams - 1) / 2;
+  std::vector<VieoKeyPoint> k((size_t)n_cams * cap);
+  std::vector<uint8_t> d((size_t)n_cams * cap * 32), pg((size_t)std::max(n_pairs, 1) * cap);
+  std::vector<int32_t> nk(n_cams), nm(n_cams), pi((size_t)std::max(n_pairs, 1) * cap * 2), pd(pi.size());
+  vieo_check(vieo_multicam_frames(extractor, 1, n_cams, imgs, img_stride, row_stride, lapping, k.data(), d.data(), nk.data(),
+                                  nm.data(), pi.data(), pd.data(), pg.data()), "vieo_multicam_frames");
+  vvkeys.resize(n_cams); vdescriptors.resize(n_cams); num_mono.assign(nm.begin(), nm.end());
+  for (int c = 0; c < n_cams; ++c) {
+    vvkeys[c].assign(k.begin() + (size_t)c * cap, k.begin() + (size_t)c * cap + nk[c]);
+    vdescriptors[c].assign(d.begin() + (size_t)c * cap * 32, d.begin() + ((size_t)c * cap + nk[c]) * 32);
+  }
+  allmatches.assign(n_pairs, FisheyePairMatches());
+  int p = 0;
+  for (int i = 0; i < n_cams - 1; ++i)
+    for (int j = i + 1; j < n_cams; ++j, ++p) {
+      if (nm[i] >= nk[i] || nm[j] >= nk[j]) continue;  // the pair is skipped (:623)
+      const int nq = nk[i] - nm[i];
+      allmatches[p].knn.resize(nq); allmatches[p].good.resize(nq);
+      for (int r = 0; r < nq; ++r) {
+        const size_t o = ((size_t)p * cap + r);
+        allmatches[p].knn[r] = {{pi[2 * o], pi[2 * o + 1]}, {pd[2 * o], pd[2 * o + 1]}};
+        allmatches[p].good[r] = pg[o];
+      }
+    }
+}
 
 // IMUPreIntegratorBase<IMUDataBase> (src/Odom/OdomPreIntegrator.h:108-223): public members kept, PreIntegration on
 // the device.  Sample = {t, a, w}.
@@ -307,6 +394,15 @@ class LocalBA {
     vieo_check(rc, "vieo_local_ba_prv");
     return rc;
   }
+  // asynchronous form: Begin enqueues the whole routine on the engine's stream and returns (the LocalMapping thread can
+  // go on collecting the next window), End waits and fills the outputs
+  void Begin(const VieoBaProblem& pb, const VieoCamera& cam, const bool* pbStopFlag) {
+    vieo_check(vieo_local_ba_prv_begin(h_, &pb, &cam, reinterpret_cast<const volatile uint8_t*>(pbStopFlag)), "vieo_local_ba_prv_begin");
+  }
+  bool Ready() { return vieo_local_ba_prv_poll(h_) != 0; }
+  void End(VieoNavState* states_out, double* points_out, double* edge_chi2, uint8_t* erase, VieoBaResult& res) {
+    vieo_check(vieo_local_ba_prv_end(h_, states_out, points_out, edge_chi2, erase, &res), "vieo_local_ba_prv_end");
+  }
 
  private:
   vieo_ba_t* h_ = nullptr;
@@ -328,6 +424,21 @@ class GlobalBA {
     int rc = vieo_global_ba_prv(h_, &pb, &cam, nIterations, bRobust ? 1 : 0, reinterpret_cast<const volatile uint8_t*>(pbStopFlag),
                                 states_out, points_out, nullptr, &res);
     vieo_check(rc, "vieo_global_ba_prv");
+    return rc;
+  }
+  // bScaleOpt (System::FinalGBA): *scale receives the VertexScale estimate, points_out are already multiplied by it;
+  // gw_init (the IMU initialiser's call, pimu_initiator != nullptr): in = its gravity estimate, out = RwI * GI
+  int RunEx(const VieoBaProblem& pb, const VieoCamera& cam, int nIterations, bool bRobust, bool bScaleOpt, double* scale,
+            double* gw_init, const bool* pbStopFlag, VieoNavState* states_out, double* points_out, VieoBaResult& res) {
+    VieoGbaExtra ex{};
+    ex.scale_opt = bScaleOpt ? 1 : 0;
+    ex.imu_init = gw_init ? 1 : 0;
+    if (gw_init) std::memcpy(ex.gw, gw_init, 24);
+    int rc = vieo_global_ba_prv_ex(h_, &pb, &cam, nIterations, bRobust ? 1 : 0, &ex,
+                                   reinterpret_cast<const volatile uint8_t*>(pbStopFlag), states_out, points_out, nullptr, &res);
+    vieo_check(rc, "vieo_global_ba_prv_ex");
+    if (scale) *scale = ex.scale;
+    if (gw_init) std::memcpy(gw_init, ex.gw, 24);
     return rc;
   }
 
