@@ -1495,31 +1495,43 @@ __global__ void __launch_bounds__(256) k_gchol_syrk(BaBuf B, uint8_t* __restrict
     Bt[m][r] = (j0 + r < n && m < nb) ? B.S[(size_t)(j0 + r) * n + k0 + m] : 0.0;
   }
   __syncthreads();
-  const int ty = t / 16, tx = t % 16;
-  double acc[4][4];
+  // FP64 tensor cores: D(8x8) += A(8x4) B(4x8) with mma.sync.m8n8k4.f64 (SASS: DMMA).  The 64 x 64 tile is split over the 8
+  // warps as 16 rows x 32 columns each = 2 x 4 accumulator blocks; per k-step of 4 a lane loads two A and four B
+  // fragment entries.  Fragment layout (PTX ISA, m8n8k4 .f64): a = A[lane / 4][lane % 4], b = B[lane % 4][lane / 4],
+  // c/d = C[lane / 4][2 (lane % 4) + {0, 1}].  At / Bt are k-major with a row pitch of 68 doubles: the 16 lanes of a
+  // half-warp (k = 0..3, rows 0..3) hit 16 distinct 8-byte banks.
+  const int warp = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
+  const int r0 = 16 * (warp >> 1), c0 = 32 * (warp & 1);
+  double acc[2][4][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0;
-  for (int m = 0; m < nb; ++m) {
-    double av[4], bv[4];
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  for (int kk = 0; kk < kGNB; kk += 4) {  // rows of At / Bt beyond nb are zero
+    double af[2], bf[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) av[a] = At[m][4 * ty + a];
+    for (int a = 0; a < 2; ++a) af[a] = At[kk + q][r0 + 8 * a + g];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) bv[b] = Bt[m][4 * tx + b];
+    for (int b = 0; b < 4; ++b) bf[b] = Bt[kk + q][c0 + 8 * b + g];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+      for (int b = 0; b < 4; ++b)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                     : "+d"(acc[a][b][0]), "+d"(acc[a][b][1])
+                     : "d"(af[a]), "d"(bf[b]));
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int i = i0 + 4 * ty + a;
+  for (int a = 0; a < 2; ++a) {
+    const int i = i0 + r0 + 8 * a + g;
     if (i >= n) continue;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int j = j0 + 4 * tx + b;
-      if (j < n && j <= i) B.S[(size_t)i * n + j] -= acc[a][b];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = j0 + c0 + 8 * b + 2 * q + e;
+        if (j < n && j <= i) B.S[(size_t)i * n + j] -= acc[a][b][e];
+      }
     }
   }
 }
@@ -1592,35 +1604,60 @@ __global__ void __launch_bounds__(32) k_vb_factor(BaBuf B, int force) {
   BaParams& prm = *B.prm;
   if ((prm.done && !force) || !prm.vb_elim) return;
   const int lane = threadIdx.x, np = prm.np, Ky = prm.Ky;
-  const int r = lane / kVB, c = lane % kVB;  // lanes 0..26 cover three rows at a time
   bool good = true;
-  for (int m = 0; m < Ky; ++m) {
+  // the chain is sequential by definition: what can be hidden is the latency of the 2 x 81 scattered loads of a block,
+  // fetched one step ahead into registers (entries e = lane, lane + 32, lane + 64 of D_m and of E_{m-1})
+  double nd[3] = {0, 0, 0}, ne[3] = {0, 0, 0};
+  auto fetch = [&](int m) {
     const int* ym = B.ymap + kVB * m;
-    // D_m and E_{m-1} = S(y_m, y_{m-1})
-    for (int e = lane; e < kVB * kVB; e += 32) {
-      const int i = e / kVB, j = e % kVB;
-      sD[i][j] = B.S[(size_t)ym[i] * np + ym[j]];
-      sF[i][j] = m > 0 ? B.S[(size_t)ym[i] * np + B.ymap[kVB * (m - 1) + j]] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int e = lane + 32 * q;
+      if (e < kVB * kVB) {
+        const int i = e / kVB, j = e % kVB;
+        nd[q] = B.S[(size_t)ym[i] * np + ym[j]];
+        ne[q] = m > 0 ? B.S[(size_t)ym[i] * np + B.ymap[kVB * (m - 1) + j]] : 0.0;
+      }
     }
+  };
+  if (Ky > 0) fetch(0);
+  for (int m = 0; m < Ky; ++m) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int e = lane + 32 * q;
+      if (e < kVB * kVB) {
+        sD[e / kVB][e % kVB] = nd[q];
+        sF[e / kVB][e % kVB] = ne[q];
+      }
+    }
+    if (m + 1 < Ky) fetch(m + 1);
     __syncwarp();
     if (m > 0) {
       // F = E L_{m-1}^-T: row i of F solves F(i, :) L^T = E(i, :) by forward substitution over the columns (lane i < 9)
       if (lane < kVB) {
         double f[kVB];
+#pragma unroll
         for (int j = 0; j < kVB; ++j) {
           double v = sF[lane][j];
+#pragma unroll
           for (int k = 0; k < j; ++k) v -= f[k] * sL[j][k];
           f[j] = v / sL[j][j];
         }
+#pragma unroll
         for (int j = 0; j < kVB; ++j) sF[lane][j] = f[j];
       }
       __syncwarp();
-      for (int e = lane; e < kVB * kVB; e += 32) {
-        const int i = e / kVB, j = e % kVB;
-        double v = 0;
-        for (int k = 0; k < kVB; ++k) v += sF[i][k] * sF[j][k];
-        sD[i][j] -= v;
-        B.vbF[(size_t)(m - 1) * 81 + e] = sF[i][j];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int e = lane + 32 * q;
+        if (e < kVB * kVB) {
+          const int i = e / kVB, j = e % kVB;
+          double v = 0;
+#pragma unroll
+          for (int k = 0; k < kVB; ++k) v += sF[i][k] * sF[j][k];
+          sD[i][j] -= v;
+          B.vbF[(size_t)(m - 1) * 81 + e] = sF[i][j];
+        }
       }
       __syncwarp();
     }
@@ -1640,11 +1677,14 @@ __global__ void __launch_bounds__(32) k_vb_factor(BaBuf B, int force) {
       if (lane < j) sL[lane][j] = 0.0;
       __syncwarp();
     }
-    for (int e = lane; e < kVB * kVB; e += 32) B.vbL[(size_t)m * 81 + e] = sL[e / kVB][e % kVB];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int e = lane + 32 * q;
+      if (e < kVB * kVB) B.vbL[(size_t)m * 81 + e] = sL[e / kVB][e % kVB];
+    }
     __syncwarp();
   }
-  (void)r; (void)c;
-  if (lane == 0 && !good) prm.ok = 0;  // ok was set to 1 by the caller (k_vb_prepare) before this kernel
+  if (lane == 0 && !good) prm.ok = 0;  // ok was set to 1 by k_vb_prepare before this kernel
 }
 
 // marks the start of a solve for the eliminated form: prm.ok = 1 (k_gchol_diag's first panel would otherwise overwrite a
@@ -1655,56 +1695,93 @@ __global__ void k_vb_prepare(BaBuf B, int force) {
   prm.ok = 1;
 }
 
-__global__ void __launch_bounds__(128) k_vb_solve(BaBuf B, int force) {
+constexpr int kVbSolveThreads = 64, kVbChunk = 16;
+__global__ void __launch_bounds__(kVbSolveThreads) k_vb_solve(BaBuf B, int force) {
+  __shared__ double sLF[kVbChunk][2][81];  // the chain factors of a chunk of blocks, staged once per CTA
   const BaParams& prm = *B.prm;
   if ((prm.done && !force) || !prm.vb_elim) return;
   const int cn = prm.cn, np = prm.np, Ky = prm.Ky, ld = cn + 1;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > cn) return;
-  const bool rhs = c == cn;
-  const int pc = rhs ? 0 : B.pmap[c];
+  const int c = blockIdx.x * kVbSolveThreads + threadIdx.x;
+  const bool live = c <= cn, rhs = c == cn;
+  const int pc = (live && !rhs) ? B.pmap[c] : 0;
   double z[kVB];
+#pragma unroll
+  for (int i = 0; i < kVB; ++i) z[i] = 0;
   // forward: z_m = L_m^-1 (r_m - F_{m-1} z_{m-1})
-  for (int m = 0; m < Ky; ++m) {
-    const int* ym = B.ymap + kVB * m;
-    double v[kVB];
-    for (int i = 0; i < kVB; ++i) v[i] = rhs ? B.bs[ym[i]] : B.S[(size_t)ym[i] * np + pc];
-    if (m > 0) {
-      const double* F = B.vbF + (size_t)(m - 1) * 81;
+  for (int m0 = 0; m0 < Ky; m0 += kVbChunk) {
+    const int mc = min(kVbChunk, Ky - m0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < mc * 162; e += kVbSolveThreads) {
+      const int mm = e / 162, w = (e % 162) / 81, k = e % 81;
+      const int m = m0 + mm;
+      sLF[mm][w][k] = w == 0 ? B.vbL[(size_t)m * 81 + k] : (m > 0 ? B.vbF[(size_t)(m - 1) * 81 + k] : 0.0);
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int mm = 0; mm < mc; ++mm) {
+      const int m = m0 + mm;
+      const int* ym = B.ymap + kVB * m;
+      double v[kVB];
+#pragma unroll
+      for (int i = 0; i < kVB; ++i) v[i] = rhs ? B.bs[ym[i]] : __ldg(&B.S[(size_t)ym[i] * np + pc]);
+      const double* F = sLF[mm][1];
+#pragma unroll
       for (int i = 0; i < kVB; ++i) {
         double a = 0;
+#pragma unroll
         for (int k = 0; k < kVB; ++k) a += F[i * kVB + k] * z[k];
         v[i] -= a;
       }
+      const double* L = sLF[mm][0];
+#pragma unroll
+      for (int i = 0; i < kVB; ++i) {
+        double a = v[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) a -= L[i * kVB + k] * z[k];
+        z[i] = a / L[i * kVB + i];
+      }
+#pragma unroll
+      for (int i = 0; i < kVB; ++i) B.Z[(size_t)(kVB * m + i) * ld + c] = z[i];
     }
-    const double* L = B.vbL + (size_t)m * 81;
-    for (int i = 0; i < kVB; ++i) {
-      double a = v[i];
-      for (int k = 0; k < i; ++k) a -= L[i * kVB + k] * z[k];
-      z[i] = a / L[i * kVB + i];
-    }
-    for (int i = 0; i < kVB; ++i) B.Z[(size_t)(kVB * m + i) * ld + c] = z[i];
   }
   // backward: w_m = L_m^-T (z_m - F_m^T w_{m+1})
   double w[kVB];
-  for (int m = Ky - 1; m >= 0; --m) {
-    double v[kVB];
-    for (int i = 0; i < kVB; ++i) v[i] = B.Z[(size_t)(kVB * m + i) * ld + c];
-    if (m < Ky - 1) {
-      const double* F = B.vbF + (size_t)m * 81;
+#pragma unroll
+  for (int i = 0; i < kVB; ++i) w[i] = 0;
+  for (int m1 = Ky; m1 > 0; m1 -= kVbChunk) {
+    const int m0 = max(0, m1 - kVbChunk), mc = m1 - m0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < mc * 162; e += kVbSolveThreads) {
+      const int mm = e / 162, wh = (e % 162) / 81, k = e % 81;
+      const int m = m0 + mm;
+      sLF[mm][wh][k] = wh == 0 ? B.vbL[(size_t)m * 81 + k] : (m < Ky - 1 ? B.vbF[(size_t)m * 81 + k] : 0.0);
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int mm = mc - 1; mm >= 0; --mm) {
+      const int m = m0 + mm;
+      double v[kVB];
+#pragma unroll
+      for (int i = 0; i < kVB; ++i) v[i] = B.Z[(size_t)(kVB * m + i) * ld + c];
+      const double* F = sLF[mm][1];
+#pragma unroll
       for (int i = 0; i < kVB; ++i) {
         double a = 0;
+#pragma unroll
         for (int k = 0; k < kVB; ++k) a += F[k * kVB + i] * w[k];
         v[i] -= a;
       }
+      const double* L = sLF[mm][0];
+#pragma unroll
+      for (int i = kVB - 1; i >= 0; --i) {
+        double a = v[i];
+#pragma unroll
+        for (int k = i + 1; k < kVB; ++k) a -= L[k * kVB + i] * w[k];
+        w[i] = a / L[i * kVB + i];
+      }
+#pragma unroll
+      for (int i = 0; i < kVB; ++i) B.Z[(size_t)(kVB * m + i) * ld + c] = w[i];
     }
-    const double* L = B.vbL + (size_t)m * 81;
-    for (int i = kVB - 1; i >= 0; --i) {
-      double a = v[i];
-      for (int k = i + 1; k < kVB; ++k) a -= L[k * kVB + i] * w[k];
-      w[i] = a / L[i * kVB + i];
-    }
-    for (int i = 0; i < kVB; ++i) B.Z[(size_t)(kVB * m + i) * ld + c] = w[i];
   }
 }
 
@@ -1941,6 +2018,8 @@ struct vieo_ba {
   bool vb_elim = false;     // V / Bias chain eliminated before the dense factorisation (global handles)
   int cn = 0, Ky = 0;
   int *d_pmap = nullptr, *d_ymap = nullptr, *d_ylo = nullptr, *d_yhi = nullptr;
+  cudaStream_t st_aux = nullptr;  // the chain factorisation / solve runs beside the landmark Schur complement (single GPU)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int rank = 0, world = 1;
   vieo_allreduce_fn allreduce = nullptr;
   void* ar_ctx = nullptr;
@@ -2132,10 +2211,24 @@ int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, dou
     const int n = h->np;
     const size_t nn = std::max<size_t>(std::max<size_t>((size_t)n * n, (size_t)n), std::max<size_t>(P, 1));
     k_ba_prep_solve<<<(unsigned)((nn + 255) / 256), 256, 0, h->st>>>(h->B, lambda, force);
+    // The chain blocks (V / Bias rows of S) come from the inertial edges and the damping only — the landmark Schur
+    // complement never touches them — so on one GPU their factorisation and the Z solve run BESIDE k_gba_schur on a
+    // second stream; sharded, the inertial part lives on rank 0 until the all-reduce, so the chain waits for it.
+    const bool vb_side = h->vb_elim && !h->sharded();
+    if (vb_side) {
+      BA_CK(cudaEventRecord(h->ev_fork, h->st));
+      BA_CK(cudaStreamWaitEvent(h->st_aux, h->ev_fork, 0));
+      k_vb_prepare<<<1, 1, 0, h->st_aux>>>(h->B, force);
+      k_vb_factor<<<1, 32, 0, h->st_aux>>>(h->B, force);
+      k_vb_solve<<<(h->cn + 1 + kVbSolveThreads - 1) / kVbSolveThreads, kVbSolveThreads, 0, h->st_aux>>>(h->B, force);
+      BA_CK(cudaEventRecord(h->ev_join, h->st_aux));
+      h->launches += 3;
+    }
     k_gba_schur<<<nf + 1, kGbaSchurThreads, gba_schur_smem(h->nfree), h->st>>>(h->B, force);
     h->launches += 2;
     int rc = ba_allreduce(h, h->d_sys, h->sys_count());
     if (rc) return rc;
+    if (vb_side) BA_CK(cudaStreamWaitEvent(h->st, h->ev_join, 0));
     // the dense factorisation runs on the reduced camera system itself, or — V / Bias chain eliminated first — on the
     // compact PR system (BaBuf copy whose S / bschur / x point at the compact buffers)
     BaBuf Bc = h->B;
@@ -2143,11 +2236,14 @@ int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, dou
     if (h->vb_elim) {
       nc = h->cn;
       Bc.S = h->B.cS; Bc.bs = h->B.cbs; Bc.x = h->B.cx;
-      k_vb_prepare<<<1, 1, 0, h->st>>>(h->B, force);
-      k_vb_factor<<<1, 32, 0, h->st>>>(h->B, force);
-      k_vb_solve<<<(nc + 1 + 127) / 128, 128, 0, h->st>>>(h->B, force);
+      if (!vb_side) {
+        k_vb_prepare<<<1, 1, 0, h->st>>>(h->B, force);
+        k_vb_factor<<<1, 32, 0, h->st>>>(h->B, force);
+        k_vb_solve<<<(nc + 1 + kVbSolveThreads - 1) / kVbSolveThreads, kVbSolveThreads, 0, h->st>>>(h->B, force);
+        h->launches += 3;
+      }
       k_vb_reduce<<<dim3((nc + 1 + 127) / 128, nc), 128, 0, h->st>>>(h->B, force);
-      h->launches += 4;
+      h->launches++;
     }
     const int T = (nc + kGNB - 1) / kGNB;
     k_gchol_scan<<<dim3(T, T), 256, 0, h->st>>>(Bc, h->d_nz, T, force);
@@ -2217,6 +2313,9 @@ void ba_free(vieo_ba* h) {
                   h->d_ps_ptr, h->d_ps_edges, h->d_obs, h->d_w, h->d_pre, h->d_den};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->st_aux) cudaStreamDestroy(h->st_aux);
   if (h->ev_begin) cudaEventDestroy(h->ev_begin);
   if (h->ev_end) cudaEventDestroy(h->ev_end);
   if (h->trial_graph) cudaGraphExecDestroy(h->trial_graph);
@@ -2280,6 +2379,9 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
     for (int s = 0; s < 2; ++s) step(dalloc(&B.wsp[s], 3 * P));
     step(dalloc(&B.up, 3 * P)); step(dalloc(&B.sred, 2 * P)); step(dalloc(&B.As, 8 * E));
     step(dalloc(&B.spart, 2 * ((size_t)h->cap_pblk + 2)));
+    step(make_stream(&h->st_aux, true));
+    step(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    step(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     {
       const size_t CN = 6 * K + 4, NY = 9 * K;
       step(dalloc(&B.cS, CN * CN)); step(dalloc(&B.cbs, CN)); step(dalloc(&B.cx, CN));
