@@ -411,6 +411,8 @@ def run_gpu(args, rank, world, local_rank):
         part.bind(api.SM_BA)
     # one engine (handle + stream) per LocalBA window of a step; each host worker thread drives its share of them through
     # the asynchronous C ABI: every window is enqueued (device-side LM loops) before any is awaited
+    if args.prio:
+        api.lib().vieo_ba_stream_priority(0)
     bas = [api.BundleAdjuster(max_states=64, max_points=2048, max_edges=16384, max_imu=16, device=local_rank)
            for _ in range(n_lba)]
     lba_pool = ThreadPoolExecutor(n_workers) if n_workers else None
@@ -421,7 +423,10 @@ def run_gpu(args, rank, world, local_rank):
         side, side_b, side_c = (torch.cuda.ExternalStream(part.stream(api.SM_FRONTEND), device=dev) for _ in range(3))
         torch.cuda.set_stream(main)
     else:
-        main = torch.cuda.current_stream()
+        # the extractor + stereo chain is the step's critical path: it gets the high-priority stream, the tracking stages and
+        # the LocalBA engines (pipelined over a whole step) normal priority
+        main = torch.cuda.Stream(priority=-1) if args.prio else torch.cuda.current_stream()
+        torch.cuda.set_stream(main)
         side, side_b, side_c = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     # the batch holds 128 independent frames at different stages of Tracking::Track(): the extractor + stereo association
     # (main), IMU + TrackWithMotionModel's search (side), SearchLocalPoints (side_b) and the PoseOptimization calls (side_c)
@@ -585,19 +590,29 @@ def run_gpu(args, rank, world, local_rank):
 
     for i in range(max(3, args.warmup)):
         e2e_step(i)
-    if dist_on:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(args.warmup + i)
-    lba_drain()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist_on:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * F * args.steps / float(t.item())
+    # The host-side figure is wall clock over K steps of ~15 ms: one scheduling hiccup of the shared host moves it by tens
+    # of percent, so the K steps are timed three times back to back (max over ranks each) and the MEDIAN is reported; all
+    # three are in the line.  The collector is paused inside the timed regions.
+    import gc
+    e2e_runs = []
+    for rep_ in range(3):
+        lba_drain()
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        gc.disable()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(args.warmup + i)
+        lba_drain()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        gc.enable()
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if dist_on:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_runs.append(world * F * args.steps / float(t.item()))
+    e2e_value = float(np.median(e2e_runs))
     lba_bytes = sum(int(np.asarray(v).nbytes) for v in lbas[0].values() if hasattr(v, "nbytes")) if lbas else 0
     trk_in = sum(int(np.asarray(a).nbytes) for a in trk["imu"]) + sum(int(trk[k].nbytes) for k in ("pbs", "Xw", "obs", "w", "flags"))
     # bytes the two host-buffer search calls stage: the last-frame search copies every array of its problem; the fused
@@ -692,7 +707,8 @@ def run_gpu(args, rank, world, local_rank):
                    "sm_partition": {"ba": part.sms(api.SM_BA), "frontend_tracking": part.sms(api.SM_FRONTEND)} if part else None,
                    "isolated_stage_ms": iso},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "runs": e2e_runs, "how": "median of three back-to-back timings of the K steps (wall clock, max over ranks)"},
         "single_frame_latency_ms": latency,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": groups[dom]["GBps"], "peak": peak, "unit": "GB/s",
@@ -728,6 +744,7 @@ def main():
                     help="host threads driving the LocalBA windows of a step (one engine per window, enqueued asynchronously)")
     ap.add_argument("--lba-windows", type=int, default=3, help="distinct LocalBA problems generated")
     ap.add_argument("--ba-sms", type=int, default=0, help="SMs reserved for the LocalBA streams (CUDA green context); 0: no partition")
+    ap.add_argument("--prio", type=int, default=1, help="1: front-end stream at high priority, LocalBA engines at normal priority")
     ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
                     help="BASELINE.json configs index: 1 = the metric's workload (default, what the driver runs); 3 = 4-camera KB8 rig, "
                          "per-camera ORB shard + pair matching (tools/bench_multicam.py); 4 = final GlobalBA with the scale vertex, "

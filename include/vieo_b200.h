@@ -321,6 +321,10 @@ int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, i
  * free keyframes (local windows) and run an LM trial as one CUDA graph. */
 int vieo_ba_create_global(int max_states, int max_points, int max_edges, int max_imu, int device, vieo_ba_t** out);
 void vieo_ba_destroy(vieo_ba_t* h);
+/* Stream priority of the engines created AFTER the call (process-wide): 1 = highest (default: one LocalMapping thread
+ * waits for its window, its chain of small kernels must not queue behind the tracker's), 0 = normal (many windows kept in
+ * flight beside the front-end: the front-end is the critical path). */
+void vieo_ba_stream_priority(int high);
 /* Sharding over GPUs: each rank holds a subset of the points with all their edges, the keyframe states
  * replicated, the inertial edges on rank 0.  `allreduce` sums `count` doubles at device pointer `buf` in place over
  * all ranks, ordered on `stream` (the host wraps ncclAllReduce / torch.distributed.all_reduce).  NULL: single GPU. */

@@ -106,6 +106,8 @@ def lib():
         L.vieo_search_by_bow.argtypes = [vp, i32] + [vp] * 6 + [i32] * 5 + [vp, vp, i32]
         L.vieo_ba_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
         L.vieo_ba_create_global.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
+        L.vieo_ba_stream_priority.argtypes = [i32]
+        L.vieo_ba_stream_priority.restype = None
         L.vieo_ba_destroy.argtypes = [vp]
         L.vieo_ba_destroy.restype = None
         L.vieo_ba_set_sharding.argtypes = [vp, i32, i32, vp, vp]

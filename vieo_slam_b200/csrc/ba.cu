@@ -20,6 +20,7 @@
 // The LM accept/reject logic stays on the host (one 64-byte read-back per trial) because it must poll the caller's
 // abort flag (pbStopFlag, sparse_optimizer.cpp:376) anyway.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -2331,6 +2332,12 @@ void ba_free(vieo_ba* h) {
 
 extern "C" {
 
+// Stream priority of the engines created from now on (process-wide): high (default) when a LocalMapping thread waits for
+// its window and the chain of small kernels must not queue behind the tracker's; normal for throughput runs that keep many
+// windows in flight beside the front-end (bench.py), where the front-end is the critical path.
+static std::atomic<bool> g_ba_high_priority{true};
+void vieo_ba_stream_priority(int high) { g_ba_high_priority.store(high != 0); }
+
 static int ba_create_impl(int max_states, int max_points, int max_edges, int max_imu, int device, bool big, vieo_ba_t** out);
 int vieo_ba_create(int max_states, int max_points, int max_edges, int max_imu, int device, vieo_ba_t** out) {
   return ba_create_impl(max_states, max_points, max_edges, max_imu, device, false, out);
@@ -2363,7 +2370,7 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
   auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   // the engine's kernels are tiny and latency-critical: highest stream priority, and inside the calling thread's SM
   // partition when there is one (vieo_sm_partition_bind_thread)
-  step(make_stream(&h->st, true));
+  step(make_stream(&h->st, g_ba_high_priority.load()));
   step(dalloc(&B.prm, 1));
   step(dalloc(&B.st, K)); step(dalloc(&B.st_bak, K)); step(dalloc(&B.cp, K));
   step(dalloc(&B.X, 3 * P)); step(dalloc(&B.X_bak, 3 * P)); step(dalloc(&B.chi2, E));
