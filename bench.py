@@ -744,7 +744,7 @@ def main():
                     help="host threads driving the LocalBA windows of a step (one engine per window, enqueued asynchronously)")
     ap.add_argument("--lba-windows", type=int, default=3, help="distinct LocalBA problems generated")
     ap.add_argument("--ba-sms", type=int, default=0, help="SMs reserved for the LocalBA streams (CUDA green context); 0: no partition")
-    ap.add_argument("--prio", type=int, default=1, help="1: front-end stream at high priority, LocalBA engines at normal priority")
+    ap.add_argument("--prio", type=int, default=0, help="1: front-end stream at high priority, LocalBA engines at normal priority")
     ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
                     help="BASELINE.json configs index: 1 = the metric's workload (default, what the driver runs); 3 = 4-camera KB8 rig, "
                          "per-camera ORB shard + pair matching (tools/bench_multicam.py); 4 = final GlobalBA with the scale vertex, "

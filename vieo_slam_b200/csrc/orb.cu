@@ -69,6 +69,52 @@ __device__ const int8_t d_pattern[1024] = {
 
 // ------------------------------------------------------------------------------------------------
 // Pyramid: level l from level l-1, all images of the batch in one launch.  4 pixels per thread.
+// The whole pyramid of one image in ONE launch: level l is made from level l - 1 of the SAME image, so a CTA per image
+// walks the levels with a block barrier in between (its own writes, through L1 / L2, are visible to its own threads after
+// __syncthreads; plain loads, not the non-coherent path).  Same arithmetic as k_resize.  Seven dependent launches become
+// one: under load (tracking + LocalBA streams on the device) every launch boundary of the chain costs a scheduling round.
+struct PyrArgs {
+  const uint8_t* img0;
+  size_t img0_stride;
+  int img0_pitch, nlevels;
+  uint8_t* lvl[kMaxLevels];
+  size_t stride[kMaxLevels];
+  int pitch[kMaxLevels], w[kMaxLevels], h[kMaxLevels];
+  const int4* rx[kMaxLevels];
+  const int4* ry[kMaxLevels];
+};
+__global__ void __launch_bounds__(1024) k_pyramid(PyrArgs A) {
+  const int img = blockIdx.x;
+  for (int l = 1; l < A.nlevels; ++l) {
+    const uint8_t* s = l == 1 ? A.img0 + (size_t)img * A.img0_stride : A.lvl[l - 1] + (size_t)img * A.stride[l - 1];
+    const int sp = l == 1 ? A.img0_pitch : A.pitch[l - 1];
+    uint8_t* d = A.lvl[l] + (size_t)img * A.stride[l];
+    const int dw = A.w[l], dh = A.h[l], dp = A.pitch[l], nx4 = (dw + 3) >> 2;
+    const int4* rx = A.rx[l];
+    const int4* ry = A.ry[l];
+    for (int i = threadIdx.x; i < nx4 * dh; i += 1024) {
+      const int y = i / nx4, x4 = (i - y * nx4) << 2;
+      const int4 fy = __ldg(ry + y);
+      const uint8_t* r0 = s + (size_t)fy.x * sp;
+      const uint8_t* r1 = s + (size_t)fy.y * sp;
+      uint32_t out = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = x4 + k;
+        if (x < dw) {
+          const int4 fx = __ldg(rx + x);
+          const int h0 = r0[fx.x] * fx.z + r0[fx.y] * fx.w;
+          const int h1 = r1[fx.x] * fx.z + r1[fx.y] * fx.w;
+          const int v = (((fy.z * (h0 >> 4)) >> 16) + ((fy.w * (h1 >> 4)) >> 16) + 2) >> 2;
+          out |= (uint32_t)(v & 0xff) << (8 * k);
+        }
+      }
+      *reinterpret_cast<uint32_t*>(d + (size_t)y * dp + x4) = out;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src, size_t src_img_stride, int src_pitch,
                                                 uint8_t* __restrict__ dst, size_t dst_img_stride, int dst_pitch,
                                                 int dw, int dh, const int4* __restrict__ rx,
@@ -1085,6 +1131,17 @@ int orb_run(vieo_orb* h, int n_img, const uint8_t* img0, size_t img0_stride, int
     ev = h->prof_ev.data() + (size_t)5 * h->prof_calls++;
     VIEO_CK(cudaEventRecord(ev[0], st));
   }
+  static const bool pyr_multi = getenv("VIEO_ORB_PYR_MULTI") != nullptr;  // the seven-launch form, for comparison
+  if (!pyr_multi && P.nlevels > 1) {
+    PyrArgs A;
+    A.img0 = img0; A.img0_stride = img0_stride; A.img0_pitch = img0_pitch; A.nlevels = P.nlevels;
+    for (int l = 0; l < P.nlevels; ++l) {
+      A.lvl[l] = P.lvl[l]; A.stride[l] = P.img_stride[l]; A.pitch[l] = P.pitch[l]; A.w[l] = P.w[l]; A.h[l] = P.h[l];
+      A.rx[l] = P.rx[l]; A.ry[l] = P.ry[l];
+    }
+    k_pyramid<<<n_img, 1024, 0, st>>>(A);
+    ++launches;
+  } else
   for (int l = 1; l < P.nlevels; ++l) {
     const uint8_t* src = l == 1 ? img0 : P.lvl[l - 1];
     const size_t sstride = l == 1 ? img0_stride : P.img_stride[l - 1];
