@@ -38,8 +38,8 @@ else
     if [ "$SZ" -gt 20000000 ]; then rm -f gpurun_out/${TAG}_prof_$1.ncu-rep; echo "report $1 ($SZ bytes) summarised on the box and dropped" >> gpurun_out/${TAG}_${WHAT}_steps.log; fi
     stamp ncu_full_$1
   }
-  full frontend 'k_fast_cells|k_resize|k_quadtree|k_orient_desc|k_stereo_match' 11 11 "--import-source on" "--lba 0"
-  full tracking 'k_sbp|k_frustum|k_pose_opt|k_imu_preint|k_knn2|k_proj_search|k_distinctive' 6 6 "" "--lba 0"
+  full frontend 'k_fast_cells|k_pyramid|k_quadtree|k_orient_desc|k_stereo_match|k_stereo_filter' 6 6 "--import-source on" "--lba 0"
+  full tracking 'k_sbp|k_frustum|k_pose_opt|k_imu_preint' 6 6 "" "--lba 0"
   full lba 'k_ba_' 120 24 "" "--lba-workers 1"
   python tools/ncu_summary.py launches gpurun_out/${TAG}_launches.csv gpurun_out/${TAG}_launches.md > /dev/null 2>&1
   stamp summaries; head -30 gpurun_out/${TAG}_launches.md
