@@ -52,6 +52,22 @@ CallScratch* call_scratch(int device);
 // (vieo_sm_partition_bind_thread), else an ordinary stream.  high_priority: the device's highest stream priority.
 cudaError_t make_stream(cudaStream_t* st, bool high_priority);
 
+// Opt a kernel into `bytes` of dynamic shared memory once per DEVICE (function attributes are per device / context; the
+// C ABI serves several GPUs from one process).  `done` is the call site's own flag array; races only repeat the call.
+struct SmemOptIn {
+  bool done[64] = {};
+};
+template <class F>
+inline cudaError_t smem_opt_in(F kernel, size_t bytes, SmemOptIn& flags) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && flags.done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) flags.done[dev] = true;
+  return e;
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {

@@ -856,11 +856,8 @@ int vieo_pose_opt_batch_dev(const VieoPoseOptProblem* pbs_dev, int n, const Vieo
   VIEO_ARG(n >= 0, "bad argument");
   if (n == 0) return VIEO_OK;
   VIEO_ARG(pbs_dev && cam_dev && res_dev && outlier_dev && chi2_dev, "null argument");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VIEO_CK(cudaFuncSetAttribute(k_pose_opt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoSmem)));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;
+  VIEO_CK(smem_opt_in(k_pose_opt, sizeof(PoSmem), opt_in));
   k_pose_opt<<<n, kPoThreads, sizeof(PoSmem), (cudaStream_t)stream>>>(pbs_dev, cam_dev, Xw_dev, obs_dev, inv_sigma2_dev,
                                                                       flags_dev, res_dev, outlier_dev, chi2_dev);
   VIEO_CK(cudaGetLastError());

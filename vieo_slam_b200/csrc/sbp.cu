@@ -579,11 +579,8 @@ int vieo_sbp_batch_dev(int mode, const VieoSbpFrame* frames_dev, int n_frames, c
   else VIEO_ARG(q->proj && q->viewcos && q->depth, "null query array");
   VIEO_ARG(((uintptr_t)desc_dev | (uintptr_t)q->desc) % 16 == 0, "descriptors must be 16-byte aligned");
   VIEO_ARG(scratch_bytes >= (size_t)(kListCap + 1) * 4, "scratch too small");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VIEO_CK(cudaFuncSetAttribute(k_sbp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SbpShared)));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;
+  VIEO_CK(smem_opt_in(k_sbp, sizeof(SbpShared), opt_in));
   // scratch = [counts (n_q_total) | lists (n_q_total x kListCap)]; the caller sized it with vieo_sbp_scratch_bytes
   const size_t nq_total = scratch_bytes / ((size_t)(kListCap + 1) * 4);
   int32_t* counts = (int32_t*)scratch_dev;
@@ -685,11 +682,8 @@ int vieo_proj_search_batch_dev(const VieoProjSearchFrame* frames_dev, int n_fram
   VIEO_ARG(frames_dev && kps_dev && uright_dev && desc_dev && wP_dev && normal_dev && max_dist_dev && min_dist_dev &&
                q_desc_dev && best_idx_dev && best_dist_dev && level_dev, "null argument");
   VIEO_ARG(((uintptr_t)desc_dev | (uintptr_t)q_desc_dev) % 16 == 0, "descriptors must be 16-byte aligned");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VIEO_CK(cudaFuncSetAttribute(k_proj_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SbpShared)));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;
+  VIEO_CK(smem_opt_in(k_proj_search, sizeof(SbpShared), opt_in));
   k_proj_search<<<n_frames, kSbpWarps * 32, sizeof(SbpShared), (cudaStream_t)stream>>>(
       frames_dev, kps_dev, uright_dev, desc_dev, wP_dev, normal_dev, max_dist_dev, min_dist_dev, q_desc_dev, q_skip_dev,
       best_idx_dev, best_dist_dev, level_dev);
