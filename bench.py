@@ -475,21 +475,31 @@ def run_gpu(args, rank, world, local_rank):
         b.record(stream)
         evs[name].append((a, b))
 
+    # DIAGNOSTIC ONLY (never set by the driver): VIEO_BENCH_SKIP=orb,stereo,imu,sbp0,sbp1,po leaves kernel groups out of the
+    # step to read each group's marginal cost; the JSON line then carries "diagnostic_skip" and is not a bench value
+    skip = set(filter(None, os.environ.get("VIEO_BENCH_SKIP", "").split(",")))
+
     def step(i, on=False):
         futs = [lba_pool.submit(lba_job, wk, wk, on) for wk in range(n_workers)]
         imgs = dev_imgs[i % pool]
         s = main.cuda_stream
-        orb.extract_batch_dev(imgs.data_ptr(), n_img, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), s)
-        timed("stereo_match", main, lambda: orb.stereo_match_dev(F, kps.data_ptr(), desc.data_ptr(), nkp.data_ptr(), cap, BF, MINZ,
-                                                                 s_ur.data_ptr(), s_dp.data_ptr(), s_sad.data_ptr(), s), on)
+        if "orb" not in skip:
+            orb.extract_batch_dev(imgs.data_ptr(), n_img, H * W, W, kps.data_ptr(), desc.data_ptr(), cap, nkp.data_ptr(), s)
+        if "stereo" not in skip:
+            timed("stereo_match", main, lambda: orb.stereo_match_dev(F, kps.data_ptr(), desc.data_ptr(), nkp.data_ptr(), cap, BF, MINZ,
+                                                                     s_ur.data_ptr(), s_dp.data_ptr(), s_sad.data_ptr(), s), on)
         s2, s3, s4 = side.cuda_stream, side_b.cuda_stream, side_c.cuda_stream
-        timed("imu_preint", side, lambda: pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(),
-                                                                         d_bb.data_ptr(), F, d_pre.data_ptr(), s2), on)
-        timed("search_by_projection_last_frame", side, lambda: sbp_enqueue(s2, 0), on)
-        timed("is_in_frustum+search_by_projection_local_map", side_b, lambda: sbp_enqueue(s3, 1), on)
-        timed("pose_opt_x2", side_c, lambda: api.Optimizer.pose_opt_batch_dev(
-            d_pbs.data_ptr(), n_pb, d_cam.data_ptr(), d_Xw.data_ptr(), d_obs.data_ptr(), d_w.data_ptr(), d_fl.data_ptr(),
-            d_res.data_ptr(), d_outl.data_ptr(), d_chi.data_ptr(), s4), on)
+        if "imu" not in skip:
+            timed("imu_preint", side, lambda: pre_gpu.preintegrate_batch_dev(d_smp.data_ptr(), d_seg.data_ptr(), d_tt.data_ptr(),
+                                                                             d_bb.data_ptr(), F, d_pre.data_ptr(), s2), on)
+        if "sbp0" not in skip:
+            timed("search_by_projection_last_frame", side, lambda: sbp_enqueue(s2, 0), on)
+        if "sbp1" not in skip:
+            timed("is_in_frustum+search_by_projection_local_map", side_b, lambda: sbp_enqueue(s3, 1), on)
+        if "po" not in skip:
+            timed("pose_opt_x2", side_c, lambda: api.Optimizer.pose_opt_batch_dev(
+                d_pbs.data_ptr(), n_pb, d_cam.data_ptr(), d_Xw.data_ptr(), d_obs.data_ptr(), d_w.data_ptr(), d_fl.data_ptr(),
+                d_res.data_ptr(), d_outl.data_ptr(), d_chi.data_ptr(), s4), on)
         for sd in sides:
             main.wait_stream(sd)
         return sum(f.result() for f in futs)
@@ -711,6 +721,7 @@ def run_gpu(args, rank, world, local_rank):
                 "runs": e2e_runs, "how": "median of three back-to-back timings of the K steps (wall clock, max over ranks)"},
         "single_frame_latency_ms": latency,
         "gpu_launches": launches_per_step * args.steps,
+        **({"diagnostic_skip": sorted(skip), "invalid": "diagnostic run with kernel groups left out"} if skip else {}),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": groups[dom]["GBps"], "peak": peak, "unit": "GB/s",
                      "frac": groups[dom]["frac"], "traffic": traffic, "traffic_over_alg": traffic_over_alg, "peak_source": peak_src,
                      "alg_bytes_per_launch": groups[dom]["alg_bytes_per_step"], "launch_ms": groups[dom]["ms_per_step"],

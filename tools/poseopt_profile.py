@@ -35,7 +35,7 @@ if hasattr(L, "vieo_debug_po_prof"):
     v = list(buf)
     calls = max(v[7], 1)
     names = ["visual(thread0)", "imu(w7l0)", "bias+prior(w6l0)", "wait+reduce", "Oe/chi2/AtO", "H entries", "evaluate total", "calls",
-             "chol+solves", "oplus+campose"]
+             "chol+solves", "oplus+campose", "prologue", "reclassify", "marginalise", "kernel total"]
     print("block 0, cycles per evaluate call (calls = %d):" % calls)
     for k, nm in enumerate(names):
-        if k != 7: print(f"  {nm:20s} {v[k] / calls:10.0f}")
+        if k != 7: print(f"  {nm:20s} {v[k] / calls:10.0f}   total {v[k]:12d}")

@@ -72,8 +72,8 @@ struct PoSmem {
   NavS st[2], bak[2], ini[2];
   CamPose cp;
   VieoImuPreintLite pre;  // the frame's pre-integration staged once (the Sigma blocks are left out)
-  double lambda, ni;
-  int nBad, ok, total_iters, cur;
+  double lambda, ni, inv_d;
+  int nBad, ok, total_iters, cur, inv_piv;
   uint8_t eflag[kPoMaxEdges];  // bit0: level 1, bit1: kernel removed
 };
 
@@ -138,9 +138,9 @@ __device__ void navstate_jac_pvr24(const NavS& si, const NavS& sj, const Pre& m,
                                    double* J) {
   const Mat3 RiT = m3_t(q_matrix(si.q)), Rj = q_matrix(sj.q);
   const double dt = m.dt;
-  for (int i = 0; i < 216; ++i) J[i] = 0;
   const Mat3 JgR = ld_m3(m.JgR);
-  // rows / state columns in P, V, R order; column bases: Ji 0, Jj 9, Jb 18
+  // rows / state columns in P, V, R order; column bases: Ji 0, Jj 9, Jb 18.  The strip is zeroed ONCE per problem by the
+  // whole block (the blocks written here are always the same ones)
   Vec3 a = {sj.p.x - si.p.x - si.v.x * dt - gw.x * (dt * dt / 2), sj.p.y - si.p.y - si.v.y * dt - gw.y * (dt * dt / 2),
             sj.p.z - si.p.z - si.v.z * dt - gw.z * (dt * dt / 2)};
   Vec3 b = m3_mulv(RiT, a);
@@ -176,14 +176,58 @@ __device__ __forceinline__ void bias_error(PoSmem& sm) {
   sm.err_bias[4] = (d.ba.y + d.dba.y) - (a.ba.y + a.dba.y);
   sm.err_bias[5] = (d.ba.z + d.dba.z) - (a.ba.z + a.dba.z);
 }
-// [Jpvr 15x9 | Jb 15x6] of the prior edge (ld 15) at the current estimate; err_prior must be current
+// [Jpvr 15x9 | Jb 15x6] of the prior edge (ld 15) at the current estimate; err_prior must be current.  sm.Jpri is zeroed
+// once per problem by the whole block; only the five diagonal blocks are ever written
 __device__ __forceinline__ void prior_jac15(const PoCtx& c, PoSmem& sm) {
-  for (int i = 0; i < 225; ++i) sm.Jpri[i] = 0;
   setb(sm.Jpri, 15, 0, 0, m3_mul(m3_t(q_matrix(c.prior.q)), q_matrix(sm.st[1].q)));
   setb(sm.Jpri, 15, 3, 3, m3_identity());
   setb(sm.Jpri, 15, 6, 6, so3_JrInv(ld3(sm.err_prior + 6)));
   setb(sm.Jpri, 15, 9, 9, m3_identity());
   setb(sm.Jpri, 15, 12, 12, m3_identity());
+}
+
+// Gauss-Jordan inverse with partial pivoting by the whole block: the same operation sequence per entry as the
+// single-thread dense_inverse (ba_edges.cuh), so the result is bit-identical; 3 barriers per column instead of n^2
+// dependent shared-memory round trips on one lane.  M (n x n, shared) is destroyed, Ai (n x n, shared) receives the
+// inverse.  Columns of M already eliminated are left stale (nothing reads them again).  All threads call it; the return
+// value is uniform.
+__device__ bool block_inverse(PoSmem& sm, double* M, int n, double* Ai) {
+  const int t = threadIdx.x;
+  for (int i = t; i < n * n; i += kPoThreads) Ai[i] = (i / n == i % n) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int c = 0; c < n; ++c) {
+    if (t == 0) {
+      int piv = c;
+      for (int r = c + 1; r < n; ++r)
+        if (fabs(M[r * n + c]) > fabs(M[piv * n + c])) piv = r;
+      const double p = M[piv * n + c];
+      sm.inv_piv = p == 0 ? -1 : piv;
+      sm.inv_d = p == 0 ? 0.0 : 1.0 / p;
+    }
+    __syncthreads();
+    const int piv = sm.inv_piv;
+    if (piv < 0) return false;
+    const double d = sm.inv_d;
+    if (t < 2 * n) {  // swap rows piv and c of [M | Ai], scale the new row c
+      double* X = t < n ? M : Ai;
+      const int j = t < n ? t : t - n;
+      const double vp = X[piv * n + j], vc = X[c * n + j];
+      if (piv != c) X[piv * n + j] = vc;
+      X[c * n + j] = vp * d;
+    }
+    __syncthreads();
+    for (int i = t; i < n * 2 * n; i += kPoThreads) {
+      const int r = i / (2 * n), jj = i % (2 * n);
+      if (r == c || jj == c) continue;
+      const double f = M[r * n + c];
+      if (f == 0) continue;
+      double* X = jj < n ? M : Ai;
+      const int j = jj < n ? jj : jj - n;
+      X[r * n + j] -= f * X[c * n + j];
+    }
+    __syncthreads();
+  }
+  return true;
 }
 
 // Omega e, chi2 and Huber weights of the inertial / bias / prior edges from the residuals in shared memory.
@@ -404,55 +448,77 @@ __device__ void evaluate(const PoCtx& c, PoSmem& sm, int set) {
   }
 }
 
-// (H + lambda I) x = b by warp 0 (n <= 30 <= 32: lane i owns row i).  Column-oriented Cholesky and substitutions with
-// one reciprocal square root per column instead of divisions.  Sets sm.ok (LDLT::isPositive).  Other warps wait at
-// the caller's barrier.
-__device__ void solve_system(PoSmem& sm, const PoLin& L, int n) {
-  if (threadIdx.x >= 32) return;
+// (H + lambda I) x = b by warp 0 (N <= 30 <= 32).  Lane i keeps row i of the lower triangle in REGISTERS (fully
+// unrolled over the compile-time dimension, so every index is static): per column one broadcast of the pivot, one
+// reciprocal square root, and the rank-1 update of the trailing rows with the column entries exchanged by shuffles —
+// no shared-memory round trips and no __syncwarp inside the factorisation (the round-1 form kept A in shared memory:
+// 17 k cycles per solve at N = 30).  The arithmetic per entry is the same sequence as before (A[i][k] -= f_i * f_k in
+// increasing j), so the factor is bit-identical.  Sets sm.ok (LDLT::isPositive).  Other warps wait at the caller's barrier.
+template <int N>
+__device__ __forceinline__ void solve_system_n(PoSmem& sm, const PoLin& L) {
   const int i = threadIdx.x;
-  double* A = sm.S;
-  for (int t = i; t < n * n; t += 32) A[t] = L.H[t] + ((t / n == t % n) ? sm.lambda : 0.0);
-  __syncwarp();
+  double a[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) a[k] = (i < N && k <= i) ? L.H[i * N + k] + (k == i ? sm.lambda : 0.0) : 0.0;
   bool good = true;
-  for (int j = 0; j < n; ++j) {
-    const double d2 = A[j * n + j];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double d2 = __shfl_sync(0xffffffffu, a[j], j);
     if (!(d2 > 0) || !isfinite(d2)) {
       good = false;
       break;
     }
     const double rd = rsqrt(d2);
-    __syncwarp();
-    if (i == j) A[j * n + j] = d2 * rd;  // sqrt(d2)
     double f = 0;
-    if (i > j && i < n) {
-      f = A[i * n + j] * rd;
-      A[i * n + j] = f;
+    if (i == j) a[j] = d2 * rd;  // sqrt(d2)
+    else if (i > j && i < N) {
+      f = a[j] * rd;
+      a[j] = f;
     }
-    __syncwarp();
-    if (i > j && i < n)
-      for (int k = j + 1; k <= i; ++k) A[i * n + k] -= f * A[k * n + j];
-    __syncwarp();
+#pragma unroll
+    for (int k = j + 1; k < N; ++k) {
+      // unconditional: on lanes i < k this only touches a[k] above the diagonal, which nothing reads (a predicate here
+      // costs ptxas 3 KB of spill code under the 128-register cap)
+      a[k] -= f * __shfl_sync(0xffffffffu, f, k);
+    }
   }
   if (i == 0) sm.ok = good ? 1 : 0;
   if (!good) return;
-  // forward: L y = b; backward: L^T x = y.  Lane i carries entry i; the pivot entry is broadcast every step.
-  const double rdi = i < n ? 1.0 / A[i * n + i] : 0.0;
-  double yi = i < n ? L.b[i] : 0.0;
-  for (int j = 0; j < n; ++j) {
-    const double yj = __shfl_sync(0xffffffffu, yi * rdi, j);
+  // forward: L y = b with the row in registers; the pivot entry is broadcast every step
+  double dii = 1.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (k == i) dii = a[k];
+  const double rd_i = i < N ? 1.0 / dii : 0.0;
+  double yi = i < N ? L.b[i] : 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double yj = __shfl_sync(0xffffffffu, yi * rd_i, j);
     if (i == j) yi = yj;
-    else if (i > j && i < n) yi -= A[i * n + j] * yj;
+    else if (i > j && i < N) yi -= a[j] * yj;
   }
+  // backward: L^T x = y needs column i of L on lane i: the factor goes through shared memory once (sm.S, row-major)
+  double* A = sm.S;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (i < N && k <= i) A[i * N + k] = a[k];
+  __syncwarp();
   double xi = yi;
-  for (int j = n - 1; j >= 0; --j) {
-    const double xj = __shfl_sync(0xffffffffu, xi * rdi, j);
+  for (int j = N - 1; j >= 0; --j) {
+    const double xj = __shfl_sync(0xffffffffu, xi * rd_i, j);
     if (i == j) xi = xj;
-    else if (i < j) xi -= A[j * n + i] * xj;
+    else if (i < j) xi -= A[j * N + i] * xj;
   }
-  if (i < n) {
+  if (i < N) {
     sm.y[i] = yi;
     sm.x[i] = xi;
   }
+}
+__device__ void solve_system(PoSmem& sm, const PoLin& L, int n) {
+  if (threadIdx.x >= 32) return;
+  if (n == 30) solve_system_n<30>(sm, L);
+  else if (n == 15) solve_system_n<15>(sm, L);
+  else solve_system_n<6>(sm, L);
 }
 
 __device__ void apply_update(const PoCtx& c, PoSmem& sm) {
@@ -588,6 +654,7 @@ __global__ void __launch_bounds__(kPoThreads, VIEO_PO_MIN_CTAS) k_pose_opt(const
   c.gw = ld3(pb.gw);
   c.prior = ns_load(pb.prior);
   const int E = c.E;
+  PO_T(t_k0);
 
   for (int i = threadIdx.x; i < E; i += kPoThreads) {
     sm.eflag[i] = 0;
@@ -617,23 +684,32 @@ __global__ void __launch_bounds__(kPoThreads, VIEO_PO_MIN_CTAS) k_pose_opt(const
     sm.rho_imu = sm.rho_bias = sm.rho_prior = 0;
     sm.r1_imu = sm.r1_bias = sm.r1_prior = 1;
     if (c.imu_mode) {
-      if (c.has_imu) {  // GetProcessedInfoij = mSigmaij.inverse() (OdomPreIntegrator.h:129-138), x 1e-2 when last is fixed
-        for (int i = 0; i < 81; ++i) sm.S[i] = pb.preint.SigmaPVR[i];
-        if (!dense_inverse(sm.S, 9, sm.info_imu))
-          for (int i = 0; i < 81; ++i) sm.info_imu[i] = nan("");
-        if (c.fixed_last)
-          for (int i = 0; i < 81; ++i) sm.info_imu[i] *= 1e-2;
-      }
       const double dtij = pb.preint.dt != 0 ? pb.preint.dt : pb.dt_frames;
       for (int k = 0; k < 6; ++k) {
         const double w = (k < 3 ? pb.inv_sigma_bg2 : pb.inv_sigma_ba2) / dtij;
         sm.info_bias[k] = c.fixed_last ? w * 1e-2 : w;
       }
-      if (!c.fixed_last)
-        for (int i = 0; i < 225; ++i) sm.info_prior[i] = pb.prior_info[i];
+    }
+  }
+  if (c.imu_mode) {
+    for (int i = threadIdx.x; i < 216; i += kPoThreads) sm.Jimu[i] = 0;
+    for (int i = threadIdx.x; i < 225; i += kPoThreads) sm.Jpri[i] = 0;
+    if (!c.fixed_last)
+      for (int i = threadIdx.x; i < 225; i += kPoThreads) sm.info_prior[i] = pb.prior_info[i];
+    if (c.has_imu) {  // GetProcessedInfoij = mSigmaij.inverse() (OdomPreIntegrator.h:129-138), x 1e-2 when last is fixed
+      for (int i = threadIdx.x; i < 81; i += kPoThreads) sm.S[i] = pb.preint.SigmaPVR[i];
+      __syncthreads();
+      const bool inv_ok = block_inverse(sm, sm.S, 9, sm.info_imu);
+      for (int i = threadIdx.x; i < 81; i += kPoThreads) {
+        double v = inv_ok ? sm.info_imu[i] : nan("");
+        if (c.fixed_last) v *= 1e-2;
+        sm.info_imu[i] = v;
+      }
     }
   }
   __syncthreads();
+  PO_T(t_k1);
+  if (threadIdx.x == 0) PO_ACC(10, t_k0, t_k1);
   const int nInitial = pb.edge_end - pb.edge_begin;
   if (nInitial < 3 && !(c.imu_mode && pb.no_mps)) {  // src/Optimizer.cc:1787, include/Optimizer.h:499-503
     if (threadIdx.x == 0) {
@@ -658,6 +734,7 @@ __global__ void __launch_bounds__(kPoThreads, VIEO_PO_MIN_CTAS) k_pose_opt(const
     }
     __syncthreads();
     optimize(c, sm, 10);
+    PO_T(t_r0);
     double bad[1] = {0};
     for (int i = threadIdx.x; i < E; i += kPoThreads) {
       double e[3], depth = 1;
@@ -675,6 +752,8 @@ __global__ void __launch_bounds__(kPoThreads, VIEO_PO_MIN_CTAS) k_pose_opt(const
     }
     block_sum<1>(sm, bad, kPoWarps);
     nBad = (int)sm.tot[0];
+    PO_T(t_r1);
+    if (threadIdx.x == 0) PO_ACC(11, t_r0, t_r1);
     if (n_edges_total < 10) break;
   }
   if (c.imu_mode && nInitial - nBad < 30) {  // rescue pass (include/Optimizer.h:619-648)
@@ -719,6 +798,7 @@ __global__ void __launch_bounds__(kPoThreads, VIEO_PO_MIN_CTAS) k_pose_opt(const
   }
   // ---- marginal prior, exact_mode = kExactRobust (include/Optimizer.h:126-206, 671-728) ----------------------
   // errors of the inertial / bias / prior edges recomputed and every edge re-linearised at the final estimate
+  PO_T(t_m0);
   __syncthreads();
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -738,8 +818,6 @@ __global__ void __launch_bounds__(kPoThreads, VIEO_PO_MIN_CTAS) k_pose_opt(const
   __syncthreads();
   dense_chi2(c, sm);
   const double wI = sm.r1_imu, wB = sm.r1_bias, wP = sm.r1_prior;
-  for (int i = threadIdx.x; i < 225; i += kPoThreads) sm.C[i] = sm.CL[i] = sm.CCL[i] = 0;
-  __syncthreads();
   {
     double acc[21];
 #pragma unroll
@@ -773,63 +851,97 @@ __global__ void __launch_bounds__(kPoThreads, VIEO_PO_MIN_CTAS) k_pose_opt(const
     }
     block_sum<21>(sm, acc, kPoWarps);
   }
-  if (threadIdx.x == 0) {
-    const double* Ji = sm.Jimu;       // 9 x 24, columns 0..8
-    const double* Jj = sm.Jimu + 9;   // columns 9..17
-    const double* Jb = sm.Jimu + 18;  // columns 18..23
-    if (c.has_imu) jtoj(Jj, 24, 0, 9, sm.info_imu, 9, wI, Jj, 24, 0, 9, sm.C, 15, 0, 0, false);
-    for (int k = 0; k < 6; ++k) sm.C[(9 + k) * 15 + 9 + k] = wB * sm.info_bias[k];
-    int q = 0;
-    for (int a = 0; a < 6; ++a) {
-      const int ra = a < 3 ? a : 3 + a;
-      for (int cc = a; cc < 6; ++cc) {
-        const int rc = cc < 3 ? cc : 3 + cc;
-        const double h = sm.tot[q++];
-        sm.C[ra * 15 + rc] += h;
-        if (rc != ra) sm.C[rc * 15 + ra] += h;
-      }
+  // Every product below is formed by the whole block, one output entry per thread, with the summation order of the
+  // single-thread jtoj() it replaces (W = (w Omega) J first, then J^T W), so the entries are bit-identical:
+  //   G  (24 x 24) = Jimu^T (wI Omega_imu) Jimu     over the strip [Ji | Jj | Jb]
+  //   Gp (15 x 15) = Jpri^T (wP Omega_prior) Jpri
+  double* Wi = sm.AtOimu;        // 9 x 24
+  double* Wp = sm.AtOpri;        // 15 x 15
+  double* G = sm.lin[1].H;       // 576 of 900
+  double* Gp = sm.lin[1].H + 576;  // 225
+  for (int t = threadIdx.x; t < 216 + 225; t += kPoThreads) {
+    if (t < 216) {
+      const int i = t / 24, cc = t % 24;
+      double q = 0;
+      if (c.has_imu)
+        for (int j = 0; j < 9; ++j) q += (wI * sm.info_imu[i * 9 + j]) * sm.Jimu[j * 24 + cc];
+      Wi[t] = q;
+    } else if (!c.fixed_last) {
+      const int u = t - 216, i = u / 15, cc = u % 15;
+      double q = 0;
+      for (int j = 0; j < 15; ++j) q += (wP * sm.info_prior[i * 15 + j]) * sm.Jpri[j * 15 + cc];
+      Wp[u] = q;
     }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 576 + 225; t += kPoThreads) {
+    if (t < 576) {
+      const int a = t / 24, cc = t % 24;
+      double q = 0;
+      if (c.has_imu)
+        for (int i = 0; i < 9; ++i) q += sm.Jimu[i * 24 + a] * Wi[i * 24 + cc];
+      G[t] = q;
+    } else if (!c.fixed_last) {
+      const int u = t - 576, a = u / 15, cc = u % 15;
+      double q = 0;
+      for (int i = 0; i < 15; ++i) q += sm.Jpri[i * 15 + a] * Wp[i * 15 + cc];
+      Gp[u] = q;
+    }
+  }
+  __syncthreads();
+  // C: frame block; CL: last-frame block (inertial + bias walk + prior); CCL: coupling.  Strip columns: Ji 0.., Jj 9.., Jb 18..
+  if (threadIdx.x < 225) {
+    const int a = threadIdx.x / 15, cc = threadIdx.x % 15;
+    const double wb = (a >= 9 && a == cc) ? wB * sm.info_bias[a - 9] : 0.0;
+    double v = (a < 9 && cc < 9 && c.has_imu) ? G[(9 + a) * 24 + 9 + cc] : 0.0;
+    if (a >= 9 && a == cc) v = wb;
+    // visual 6 x 6 (dp, dphi) -> state rows {0, 1, 2, 6, 7, 8}, upper-triangle packing of block_sum<21>
+    const int va = a < 3 ? a : (a >= 6 && a < 9 ? a - 3 : -1), vc = cc < 3 ? cc : (cc >= 6 && cc < 9 ? cc - 3 : -1);
+    if (va >= 0 && vc >= 0) {
+      const int lo = min(va, vc), hi = max(va, vc);
+      v += sm.tot[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+    }
+    sm.C[threadIdx.x] = v;
     if (!c.fixed_last) {
-      if (c.has_imu) {
-        jtoj(Ji, 24, 0, 9, sm.info_imu, 9, wI, Ji, 24, 0, 9, sm.CL, 15, 0, 0, false);
-        jtoj(Ji, 24, 0, 9, sm.info_imu, 9, wI, Jb, 24, 0, 6, sm.CL, 15, 0, 9, false);
-        jtoj(Jb, 24, 0, 6, sm.info_imu, 9, wI, Jb, 24, 0, 6, sm.CL, 15, 9, 9, false);
-        for (int a = 0; a < 9; ++a)
-          for (int cc = 0; cc < 6; ++cc) sm.CL[(9 + cc) * 15 + a] = sm.CL[a * 15 + 9 + cc];
-        jtoj(Jj, 24, 0, 9, sm.info_imu, 9, wI, Ji, 24, 0, 9, sm.CCL, 15, 0, 0, false);
-        jtoj(Jj, 24, 0, 9, sm.info_imu, 9, wI, Jb, 24, 0, 6, sm.CCL, 15, 0, 9, false);
-      }
-      for (int k = 0; k < 6; ++k) {
-        sm.CL[(9 + k) * 15 + 9 + k] += wB * sm.info_bias[k];
-        sm.CCL[(9 + k) * 15 + 9 + k] = -(wB * sm.info_bias[k]);
-      }
-      const double* Jpp = sm.Jpri;      // 15 x 15, columns 0..8
-      const double* Jpb = sm.Jpri + 9;  // columns 9..14
-      jtoj(Jpp, 15, 0, 9, sm.info_prior, 15, wP, Jpp, 15, 0, 9, sm.CL, 15, 0, 0, true);
-      jtoj(Jpb, 15, 0, 6, sm.info_prior, 15, wP, Jpb, 15, 0, 6, sm.CL, 15, 9, 9, true);
-      jtoj(Jpp, 15, 0, 9, sm.info_prior, 15, wP, Jpb, 15, 0, 6, sm.CL, 15, 0, 9, true);
-      for (int a = 0; a < 9; ++a)
-        for (int cc = 0; cc < 6; ++cc) sm.CL[(9 + cc) * 15 + a] = sm.CL[a * 15 + 9 + cc];
-      // cov_inv -= E C^-1 E^T (JacobiSVD inverse without clamping in the reference, :709-728)
-      double* Cinv = sm.lin[0].H;  // 225 <= 900
-      double* T = sm.S;
-      if (!dense_inverse(sm.CL, 15, Cinv))
-        for (int i = 0; i < 225; ++i) Cinv[i] = nan("");
-      for (int a = 0; a < 15; ++a)
-        for (int cc = 0; cc < 15; ++cc) {
-          double s = 0;
-          for (int k = 0; k < 15; ++k) s += sm.CCL[a * 15 + k] * Cinv[k * 15 + cc];
-          T[a * 15 + cc] = s;
-        }
-      for (int a = 0; a < 15; ++a)
-        for (int cc = 0; cc < 15; ++cc) {
-          double s = 0;
-          for (int k = 0; k < 15; ++k) s += T[a * 15 + k] * sm.CCL[cc * 15 + k];
-          sm.C[a * 15 + cc] -= s;
-        }
+      // upper-right block first, the lower-left one is its mirror (as the reference fills it)
+      const int ua = (a >= 9 && cc < 9) ? cc : a, uc = (a >= 9 && cc < 9) ? a : cc;
+      double l = 0;
+      if (c.has_imu) l = G[(ua < 9 ? ua : 18 + ua - 9) * 24 + (uc < 9 ? uc : 18 + uc - 9)];
+      if (ua >= 9 && ua == uc) l += wB * sm.info_bias[ua - 9];
+      l += Gp[ua * 15 + uc];
+      sm.CL[threadIdx.x] = l;
+      double k = 0;
+      if (a < 9) k = c.has_imu ? G[(9 + a) * 24 + (cc < 9 ? cc : 18 + cc - 9)] : 0.0;
+      else if (a == cc) k = -wb;
+      sm.CCL[threadIdx.x] = k;
     }
-    for (int i = 0; i < 225; ++i) R.marg_cov_inv[i] = sm.C[i];
-    R.prior_set = 1;
+  }
+  __syncthreads();
+  if (!c.fixed_last) {
+    // cov_inv -= E C^-1 E^T (JacobiSVD inverse without clamping in the reference, :709-728)
+    double* Cinv = sm.lin[0].H;  // 225 <= 900
+    double* T = sm.S;
+    const bool inv_ok = block_inverse(sm, sm.CL, 15, Cinv);
+    if (threadIdx.x < 225) {
+      const int a = threadIdx.x / 15, cc = threadIdx.x % 15;
+      double q = 0;
+      for (int k = 0; k < 15; ++k) q += sm.CCL[a * 15 + k] * (inv_ok ? Cinv[k * 15 + cc] : nan(""));
+      T[threadIdx.x] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x < 225) {
+      const int a = threadIdx.x / 15, cc = threadIdx.x % 15;
+      double q = 0;
+      for (int k = 0; k < 15; ++k) q += T[a * 15 + k] * sm.CCL[cc * 15 + k];
+      sm.C[threadIdx.x] -= q;
+    }
+  }
+  if (threadIdx.x < 225) R.marg_cov_inv[threadIdx.x] = sm.C[threadIdx.x];
+  if (threadIdx.x == 0) R.prior_set = 1;
+  PO_T(t_m1);
+  if (threadIdx.x == 0) {
+    PO_ACC(12, t_m0, t_m1);
+    PO_ACC(13, t_k0, t_m1);
   }
 }
 

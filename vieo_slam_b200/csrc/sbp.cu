@@ -4,12 +4,12 @@
 //
 // The reference loop is sequential in the map points: a keypoint taken by an earlier point (with Observations() > 0) is
 // skipped by every later one.  Only that claim step is order dependent, so the work is split:
-//   phase A  (whole CTA, one CTA per frame)  AssignFeaturesToGrid: counting sort of the keypoints into the 64 x 48 cells,
+//   phase A  (whole CTA; 8 list CTAs per frame, each with its own copy)  AssignFeaturesToGrid: counting sort of the keypoints into the 64 x 48 cells,
 //            cell lists ordered by keypoint index like the reference's push_back order; lists live in shared memory.
-//   phase B  (16 warps, one query per warp at a time)  projection (LAST_FRAME), GetFeaturesInArea in the reference's
+//   phase B  (k_sbp_lists: 8 CTAs x 8 warps per frame, one query per warp at a time)  projection (LAST_FRAME), GetFeaturesInArea in the reference's
 //            candidate order (ix-major, iy, insertion order), level band, window and stereo-ur gates, 256-bit Hamming
 //            distance of every surviving candidate -> compact per-query list (dist << 16 | keypoint) in HBM scratch.
-//   phase C  (warp 0)  walks the queries in order: masks the candidates whose keypoint is already claimed (bitmap in
+//   phase C  (k_sbp_claim: one warp per frame)  walks the queries in order: masks the candidates whose keypoint is already claimed (bitmap in
 //            shared memory), arg-min / second-min by warp redux on (dist, position) keys (strict '<' of the reference ==
 //            lexicographic order), acceptance tests, claim.  Lists longer than kListCap fall back to a re-enumeration.
 //            LAST_FRAME then applies the rotation-histogram check.
@@ -222,44 +222,9 @@ __device__ __forceinline__ bool make_window(int mode, const VieoSbpFrame& F, con
   return true;
 }
 
-__global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpFrame* __restrict__ frames,
-                                                        const VieoKeyPoint* __restrict__ kps_all,
-                                                        const float* __restrict__ ur_all, const uint8_t* __restrict__ desc_all,
-                                                        QueryIn Q, const uint8_t* __restrict__ kp_blocked,
-                                                        int32_t* __restrict__ kp_match, int32_t* __restrict__ q_match,
-                                                        int32_t* __restrict__ q_dist, int32_t* __restrict__ n_matches,
-                                                        uint32_t* __restrict__ lists, int32_t* __restrict__ counts) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SbpShared& S = *reinterpret_cast<SbpShared*>(smem_raw);
-  __shared__ VieoSbpFrame F;
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
-  for (int i = tid; i < (int)(sizeof(VieoSbpFrame) / 4); i += T)
-    reinterpret_cast<uint32_t*>(&F)[i] = reinterpret_cast<const uint32_t*>(frames + f)[i];
-  for (int i = tid; i < kCells; i += T) S.cnt[i] = 0;
-  __syncthreads();
-  const int N = F.n_kp, nq = F.n_q;
-  if (N > kMaxKp || N < 0 || nq < 0) {
-    if (tid == 0) n_matches[f] = -1;
-    return;
-  }
-  const VieoKeyPoint* kps = kps_all + F.kp_begin;
-  const float* uright = ur_all + F.kp_begin;
-  const uint8_t* desc = desc_all + 32 * (size_t)F.kp_begin;
-  int32_t* kpm = kp_match + F.kp_begin;
-  // ---- phase A: AssignFeaturesToGrid / PosInGrid (src/FrameBase.cpp:143-170) ------------------------------------------
-  for (int i = tid; i < N; i += T) kpm[i] = -1;
-  for (int i = tid; i < kMaxKp / 32; i += T) {
-    uint32_t m = 0;
-    if (kp_blocked)
-      for (int b = 0; b < 32; ++b) {
-        const int k = 32 * i + b;
-        if (k < N && kp_blocked[F.kp_begin + k]) m |= 1u << b;
-      }
-    S.blocked[i] = m;
-  }
-  build_grid(S, GridGeom{F.minx, F.miny, F.grid_winv, F.grid_hinv}, kps, N, tid, T);
-  // ---- frame constants ------------------------------------------------------------------------------------------------
-  bool fwd = false, bwd = false;
+// frame constants of the LAST_FRAME search: forward / backward motion along the optical axis (:1314-1323)
+__device__ __forceinline__ void motion_flags(int mode, const VieoSbpFrame& F, bool& fwd, bool& bwd) {
+  fwd = bwd = false;
   if (mode == VIEO_SBP_LAST_FRAME) {
     // Tlrcr = Tlrw * Tcrw^-1: translation = Rl (-(Rc^-1 tc)) + tl (:1314-1319)
     const double qci[4] = {F.qcw[0], -F.qcw[1], -F.qcw[2], -F.qcw[3]};
@@ -271,10 +236,41 @@ __global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpF
     fwd = tz > (double)F.b && !F.mono;
     bwd = -tz > (double)F.b && !F.mono;
   }
+}
+
+// Phases A + B.  kListCtas CTAs per frame (grid = (kListCtas, frames)): each builds the frame's grid in its own shared
+// memory (a few microseconds) and lists the candidates of its share of the queries, one query per warp at a time.  Round 1
+// ran A, B and C in ONE 512-thread CTA per frame: 0.86 waves at 7 % of the warp slots, holding every register of 128 SMs for
+// the whole search, so nothing of the other streams could run beside it (profiles/r02k_marginal.txt: the two searches cost the
+// step 1.7 of their 2.0 ms).
+constexpr int kListCtas = 8, kListWarps = 8;
+__global__ void __launch_bounds__(kListWarps * 32) k_sbp_lists(int mode, const VieoSbpFrame* __restrict__ frames,
+                                                               const VieoKeyPoint* __restrict__ kps_all,
+                                                               const float* __restrict__ ur_all,
+                                                               const uint8_t* __restrict__ desc_all, QueryIn Q,
+                                                               uint32_t* __restrict__ lists, int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SbpShared& S = *reinterpret_cast<SbpShared*>(smem_raw);
+  __shared__ VieoSbpFrame F;
+  const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
+  for (int i = tid; i < (int)(sizeof(VieoSbpFrame) / 4); i += T)
+    reinterpret_cast<uint32_t*>(&F)[i] = reinterpret_cast<const uint32_t*>(frames + f)[i];
+  for (int i = tid; i < kCells; i += T) S.cnt[i] = 0;
+  __syncthreads();
+  const int N = F.n_kp, nq = F.n_q;
+  if (N > kMaxKp || N < 0 || nq < 0) return;  // reported by the claim kernel
+  if ((int)blockIdx.x * kListWarps >= nq) return;
+  const VieoKeyPoint* kps = kps_all + F.kp_begin;
+  const float* uright = ur_all + F.kp_begin;
+  const uint8_t* desc = desc_all + 32 * (size_t)F.kp_begin;
+  // ---- phase A: AssignFeaturesToGrid / PosInGrid (src/FrameBase.cpp:143-170) ------------------------------------------
+  build_grid(S, GridGeom{F.minx, F.miny, F.grid_winv, F.grid_hinv}, kps, N, tid, T);
+  bool fwd, bwd;
+  motion_flags(mode, F, fwd, bwd);
   uint32_t* flist = lists + (size_t)F.q_begin * kListCap;
   int32_t* fcnt = counts + F.q_begin;
   // ---- phase B: candidate lists -----------------------------------------------------------------------------------------
-  for (int qi = warp; qi < nq; qi += kSbpWarps) {
+  for (int qi = blockIdx.x * kListWarps + warp; qi < nq; qi += kListCtas * kListWarps) {
     const int q = F.q_begin + qi;
     Cand c;
     int n = 0;
@@ -290,9 +286,51 @@ __global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpF
     }
     if (lane == 0) fcnt[qi] = n;
   }
-  __syncthreads();
-  if (warp != 0) return;
-  // ---- phase C: the sequential claim pass ---------------------------------------------------------------------------------
+}
+
+// Phase C: the sequential claim pass, ONE WARP per frame (grid = frames, 32 threads): tiny footprint, so the pass — whose
+// cost is the latency of nq dependent iterations — runs beside the other streams' kernels.  The frame grid is only needed by
+// the overflow path (a list longer than kListCap is re-enumerated with the claim filter): it is built lazily, by this warp,
+// the first time such a query appears.
+__global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* __restrict__ frames,
+                                                  const VieoKeyPoint* __restrict__ kps_all, const float* __restrict__ ur_all,
+                                                  const uint8_t* __restrict__ desc_all, QueryIn Q,
+                                                  const uint8_t* __restrict__ kp_blocked, int32_t* __restrict__ kp_match,
+                                                  int32_t* __restrict__ q_match, int32_t* __restrict__ q_dist,
+                                                  int32_t* __restrict__ n_matches, const uint32_t* __restrict__ lists,
+                                                  int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SbpShared& S = *reinterpret_cast<SbpShared*>(smem_raw);
+  __shared__ VieoSbpFrame F;
+  const int f = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < (int)(sizeof(VieoSbpFrame) / 4); i += 32)
+    reinterpret_cast<uint32_t*>(&F)[i] = reinterpret_cast<const uint32_t*>(frames + f)[i];
+  __syncwarp();
+  const int N = F.n_kp, nq = F.n_q;
+  if (N > kMaxKp || N < 0 || nq < 0) {
+    if (lane == 0) n_matches[f] = -1;
+    return;
+  }
+  const VieoKeyPoint* kps = kps_all + F.kp_begin;
+  const float* uright = ur_all + F.kp_begin;
+  const uint8_t* desc = desc_all + 32 * (size_t)F.kp_begin;
+  int32_t* kpm = kp_match + F.kp_begin;
+  for (int i = lane; i < N; i += 32) kpm[i] = -1;
+  for (int i = lane; i < kMaxKp / 32; i += 32) {
+    uint32_t m = 0;
+    if (kp_blocked) {
+      const int k = 32 * i;
+      for (int b = 0; b < 32 && k + b < N; ++b)
+        if (kp_blocked[F.kp_begin + k + b]) m |= 1u << b;
+    }
+    S.blocked[i] = m;
+  }
+  __syncwarp();
+  bool fwd, bwd;
+  motion_flags(mode, F, fwd, bwd);
+  bool have_grid = false;
+  const uint32_t* flist = lists + (size_t)F.q_begin * kListCap;
+  int32_t* fcnt = counts + F.q_begin;
   int nmatches = 0;
   const float factor = 1.0f / HISTO_LENGTH;
   // The pass is sequential by definition (a claimed keypoint changes the next query's arg-min), so its cost is the latency
@@ -332,6 +370,12 @@ __global__ void __launch_bounds__(kSbpWarps * 32) k_sbp(int mode, const VieoSbpF
       }
     } else if (n > kListCap) {
       // overflow: re-enumerate with the claim filter (same order, same keys)
+      if (!have_grid) {  // warp-uniform; the CTA is this one warp, so build_grid's barriers are warp barriers
+        for (int i = lane; i < kCells; i += 32) S.cnt[i] = 0;
+        __syncthreads();
+        build_grid(S, GridGeom{F.minx, F.miny, F.grid_winv, F.grid_hinv}, kps, N, lane, 32);
+        have_grid = true;
+      }
       Cand c;
       make_window(mode, F, Q, q, fwd, bwd, c);
       const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q));
@@ -579,16 +623,22 @@ int vieo_sbp_batch_dev(int mode, const VieoSbpFrame* frames_dev, int n_frames, c
   else VIEO_ARG(q->proj && q->viewcos && q->depth, "null query array");
   VIEO_ARG(((uintptr_t)desc_dev | (uintptr_t)q->desc) % 16 == 0, "descriptors must be 16-byte aligned");
   VIEO_ARG(scratch_bytes >= (size_t)(kListCap + 1) * 4, "scratch too small");
-  static SmemOptIn opt_in;
-  VIEO_CK(smem_opt_in(k_sbp, sizeof(SbpShared), opt_in));
+  static SmemOptIn opt_in_lists, opt_in_claim;
+  VIEO_CK(smem_opt_in(k_sbp_lists, sizeof(SbpShared), opt_in_lists));
+  VIEO_CK(smem_opt_in(k_sbp_claim, sizeof(SbpShared), opt_in_claim));
   // scratch = [counts (n_q_total) | lists (n_q_total x kListCap)]; the caller sized it with vieo_sbp_scratch_bytes
   const size_t nq_total = scratch_bytes / ((size_t)(kListCap + 1) * 4);
   int32_t* counts = (int32_t*)scratch_dev;
   uint32_t* lists = (uint32_t*)scratch_dev + nq_total;
   QueryIn Q{q->Xw, q->level, q->angle, q->proj, q->viewcos, q->depth, q->desc, q->flags};
-  k_sbp<<<n_frames, kSbpWarps * 32, sizeof(SbpShared), (cudaStream_t)stream>>>(
-      mode, frames_dev, kps_dev, uright_dev, desc_dev, Q, kp_blocked_dev, kp_match_dev, q_match_dev, q_dist_dev, n_matches_dev,
-      lists, counts);
+  for (int f0 = 0; f0 < n_frames; f0 += 65535) {  // grid.y bound
+    const int nf = std::min(n_frames - f0, 65535);
+    k_sbp_lists<<<dim3(kListCtas, nf), kListWarps * 32, sizeof(SbpShared), (cudaStream_t)stream>>>(
+        mode, frames_dev + f0, kps_dev, uright_dev, desc_dev, Q, lists, counts);
+  }
+  k_sbp_claim<<<n_frames, 32, sizeof(SbpShared), (cudaStream_t)stream>>>(mode, frames_dev, kps_dev, uright_dev, desc_dev, Q,
+                                                                        kp_blocked_dev, kp_match_dev, q_match_dev, q_dist_dev,
+                                                                        n_matches_dev, lists, counts);
   VIEO_CK(cudaGetLastError());
   return VIEO_OK;
 }
