@@ -68,6 +68,10 @@ struct BaParams {
   int iteration, iters_target, iters_done, qmax, nBad, ok;
   int trials;           // LM trials run by the current optimize()
   int iters_hist[2];    // iterations of the earlier optimize() stages of an asynchronous LocalBA call (k_ba_begin)
+  // the LocalBA routine as ONE graph (vieo_local_ba_prv_begin): what the by-value launch arguments of the direct path carry
+  int visual_only;      // Optimizer::LocalBundleAdjustment (no inertial / bias edges, no Chi2LargeSetLevel pass)
+  int plan_it[2];       // iterations of the two optimize() stages
+  double plan_lambda0;  // their initial lambda (0: g2o's own)
   double lambda, ni, user_lambda;
   double chi_cur, ini_chi;   // activeRobustChi2 of the current estimate / at the start of the iteration
   double pair[4];            // [robust chi2 of the last linearisation, landmark part of computeScale, abort flag seen by
@@ -98,6 +102,12 @@ __global__ void k_ba_campose(CamK cam, const VieoNavState* __restrict__ st, int 
   if (k < K) cp[k] = cam_pose(cam, ns_load(st[k]));
 }
 
+// graph form: sizes and camera from the device-resident problem header (constant launch parameters, capacity grid)
+__global__ void k_ba_campose_p(const BaParams* __restrict__ prm, const VieoNavState* __restrict__ st, CamPose* __restrict__ cp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < prm->K) cp[k] = cam_pose(prm->cam, ns_load(st[k]));
+}
+
 // world position of a map point as the visual edges see it: X, or sc * X with the scale vertex (EdgeReprojectPRS:
 // "unscaled Xw but scaled pwb", g2otypes.h:400-406 with MODE 1); sc == 1.0 without the vertex, and x * 1.0 == x exactly
 __device__ __forceinline__ Vec3 ba_world_point(const double* __restrict__ X, size_t p, double sc) {
@@ -117,8 +127,17 @@ __global__ void __launch_bounds__(256) k_ba_errors(CamK cam, const CamPose* __re
                                                    const uint8_t* __restrict__ flags, const uint8_t* __restrict__ lvl,
                                                    const uint8_t* __restrict__ sfix, int points_free, int E, int all,
                                                    double dm, double ds, double* __restrict__ chi2,
-                                                   double* __restrict__ partial, const BaParams* __restrict__ prmq) {
+                                                   double* __restrict__ partial, const BaParams* __restrict__ prmq,
+                                                   int skip_if_visual = 0) {
   __shared__ double s_w[8];
+  if (E < 0) {  // graph form (capacity grid): sizes, camera and Huber deltas from the device-resident problem header
+    if (skip_if_visual && prmq->visual_only) return;
+    E = prmq->E;
+    cam = prmq->cam;
+    dm = prmq->dm;
+    ds = prmq->ds;
+    if ((int)blockIdx.x * 256 >= E) return;  // k_ba_dense_errors sums the first ceil(E / 256) partials only
+  }
   const double sc = prmq->sc;
   const int i = blockIdx.x * 256 + threadIdx.x;
   double r0 = 0;
@@ -169,7 +188,13 @@ __device__ __forceinline__ void ba_prior_bias_error(const BaDense& d, const NavS
 __global__ void __launch_bounds__(128) k_ba_dense_errors(const BaDense* __restrict__ den, int n_den, const VieoNavState* __restrict__ st,
                                   const VieoImuPreint* __restrict__ pre, const BaParams* __restrict__ prmq, BaDenseWork* __restrict__ wk,
                                   const double* __restrict__ partial, int n_partial, double* __restrict__ out,
-                                  const double* __restrict__ scale_part, int n_scale, double* __restrict__ scale_out) {
+                                  const double* __restrict__ scale_part, int n_scale, double* __restrict__ scale_out,
+                                  int skip_if_visual = 0) {
+  if (n_den < 0) {  // graph form: sizes from the device-resident problem header
+    if (skip_if_visual && prmq->visual_only) return;
+    n_den = prmq->n_den;
+    n_partial = (prmq->E + 255) / 256;
+  }
   const Vec3 gw = ba_gravity(*prmq);
   const bool sum_only = n_scale < 0;  // keep the stored errors (activeRobustChi2 without computeActiveErrors)
   for (int m = threadIdx.x; m < n_den && !sum_only; m += blockDim.x) {
@@ -821,6 +846,10 @@ __global__ void __launch_bounds__(256) k_ba_diag_pack(BaBuf B) {
 // and files the previous stage's iteration count.
 __global__ void k_ba_begin(BaBuf B, int stage, int iterations, double lambda_init) {
   BaParams& q = *B.prm;
+  if (iterations < 0) {  // graph form: the iteration plan travels in the problem header
+    iterations = q.plan_it[stage];
+    lambda_init = q.plan_lambda0;
+  }
   if (stage > 0) q.iters_hist[stage - 1] = q.iters_done;
   else q.stop = 0;
   q.cur = 0; q.done = 0; q.ok = 1;
@@ -1963,8 +1992,15 @@ __global__ void k_ba_classify(CamK cam, const CamPose* __restrict__ cp, const do
                               const int* __restrict__ es, const int* __restrict__ ep, const float* __restrict__ obs,
                               const uint8_t* __restrict__ flags, const double* __restrict__ chi2, int E, int mode, float rat,
                               int set_level, int remove_kernels, int use_close, uint8_t* __restrict__ lvl,
-                              uint8_t* __restrict__ bad_out, const BaParams* __restrict__ prmq, int skip_if_stop = 0) {
+                              uint8_t* __restrict__ bad_out, const BaParams* __restrict__ prmq, int skip_if_stop = 0,
+                              int skip_if_visual = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (E < 0) {  // graph form (capacity grid): sizes / camera / close-point gate from the device-resident problem header
+    if (skip_if_visual && prmq->visual_only) return;
+    E = prmq->E;
+    cam = prmq->cam;
+    use_close = prmq->visual_only ? 0 : 1;
+  }
   if (i >= E) return;
   if (skip_if_stop && prmq->stop) return;  // aborted after the first stage: levels and kernels stay (bDoMore == false)
   const bool stereo = flags[i] & VIEO_EDGE_STEREO;
@@ -2035,6 +2071,14 @@ struct vieo_ba {
   // a whole optimize() as ONE launch: a WHILE conditional node whose body is the LM trial; k_ba_control keeps the loop
   // alive until the device-side state machine is done (no host round trip per trial)
   cudaGraphExec_t opt_graph = nullptr;
+  // the whole LocalBA routine (everything vieo_local_ba_prv_begin enqueues after the problem upload) as ONE graph with
+  // constant launch parameters: capacity grids, sizes / camera / iteration plan read from the device-resident header,
+  // two WHILE nodes for the optimize() stages, the downloads as capacity-sized copies into the pinned staging buffer
+  cudaGraphExec_t win_graph = nullptr;
+  int win_nodes = 0;           // kernels of the graph outside the two WHILE bodies
+  int plan_it[2] = {0, 0};     // set by vieo_local_ba_prv_begin before set_problem fills the header
+  double plan_lambda0 = 0;
+  size_t dl_off[4] = {0, 0, 0, 0};  // states | points | chi2 | erase candidates in h_stage of the call in flight
   cudaStream_t st_ctl = nullptr;  // side stream for the abort flag while the optimize graph runs
   // buffers that are not part of BaBuf
   double *d_sys = nullptr, *d_xl = nullptr, *d_ctl = nullptr;
@@ -2321,11 +2365,137 @@ void ba_free(vieo_ba* h) {
   if (h->ev_end) cudaEventDestroy(h->ev_end);
   if (h->trial_graph) cudaGraphExecDestroy(h->trial_graph);
   if (h->opt_graph) cudaGraphExecDestroy(h->opt_graph);
+  if (h->win_graph) cudaGraphExecDestroy(h->win_graph);
   if (h->st_ctl) cudaStreamDestroy(h->st_ctl);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_prm) cudaFreeHost(h->h_prm);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->st) cudaStreamDestroy(h->st);
+}
+
+
+// download layout of a LocalBA call in the pinned staging buffer (16-byte aligned spans)
+void lba_dl_layout(size_t K, size_t P, size_t E, size_t off[4], size_t* total) {
+  const size_t ns = sizeof(VieoNavState) * K, nx = 24 * P, nc = 8 * E;
+  off[0] = 0;
+  off[1] = (ns + 15) & ~(size_t)15;
+  off[2] = off[1] + ((nx + 15) & ~(size_t)15);
+  off[3] = off[2] + ((nc + 15) & ~(size_t)15);
+  *total = off[3] + E;
+}
+
+// The LocalBA routine of vieo_local_ba_prv_begin captured once per handle.  The two optimize() stages are WHILE nodes
+// spliced into the capture (cudaStreamGetCaptureInfo -> cudaGraphAddNode -> cudaStreamUpdateCaptureDependencies); their
+// bodies are captured on a second stream.  Every launch parameter is a capacity or a constant: the same executable graph
+// serves every window the handle ever sees, so begin() costs the upload + ONE launch instead of ~45 driver calls
+// (tools/lba_async_probe.py: 0.31 ms of host time per window, 16 windows per bench step from one thread).
+bool lba_build_window_graph(vieo_ba* h) {
+  cudaStream_t side = nullptr;
+  if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return false;
+  const int capE = h->capE, gridE = std::max((capE + 255) / 256, 1), gridK = (h->capK + 127) / 128;
+  int nodes = 0;
+  bool ok = cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  bool capturing = ok;
+  auto campose = [&]() {
+    k_ba_campose_p<<<gridK, 128, 0, h->st>>>(h->B.prm, h->B.st, h->B.cp);
+    ++nodes;
+  };
+  auto errors = [&](int all, double* d_out, int skipvis) {
+    campose();
+    k_ba_errors<<<gridE, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_w, h->d_flags, h->d_lvl,
+                                          h->d_sfix, 1, -1, all, 0.0, 0.0, h->B.chi2, h->B.partial, h->B.prm, skipvis);
+    k_ba_dense_errors<<<1, 128, 0, h->st>>>(h->d_den, -1, h->B.st, h->d_pre, h->B.prm, h->B.wk, h->B.partial, 0, d_out, nullptr,
+                                            all == 2 ? -1 : 0, nullptr, skipvis);
+    nodes += 2;
+  };
+  auto classify = [&](int mode, float rat, int set_level, int remove_kernels, uint8_t* bad, int skip_if_stop, int skipvis) {
+    k_ba_classify<<<gridE, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_flags, h->B.chi2, -1, mode,
+                                            rat, set_level, remove_kernels, -1, h->d_lvl, bad, h->B.prm, skip_if_stop, skipvis);
+    ++nodes;
+  };
+  auto stage = [&](int st_idx) {
+    k_ba_begin<<<1, 1, 0, h->st>>>(h->B, st_idx, -1, 0.0);
+    ok = ok && cudaMemsetAsync(h->B.x, 0, 8 * h->cap_np, h->st) == cudaSuccess;
+    campose();
+    ba_enqueue_linearize(h, 0, true);
+    k_ba_control<<<1, 256, 0, h->st>>>(h->B, 0, 0);
+    nodes += 4;
+    // WHILE node after everything captured so far
+    cudaStreamCaptureStatus status;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    ok = ok && cudaStreamGetCaptureInfo_v2(h->st, &status, nullptr, &g, &deps, &ndeps) == cudaSuccess &&
+         status == cudaStreamCaptureStatusActive;
+    cudaGraphConditionalHandle hc = 0;
+    ok = ok && cudaGraphConditionalHandleCreate(&hc, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    cudaGraphNode_t node = nullptr;
+    cudaGraph_t body = nullptr, tmp = nullptr;
+    if (ok) {
+      cudaGraphNodeParams np_ = {};
+      np_.type = cudaGraphNodeTypeConditional;
+      np_.conditional.handle = hc;
+      np_.conditional.type = cudaGraphCondTypeWhile;
+      np_.conditional.size = 1;
+      ok = cudaGraphAddNode(&node, g, deps, ndeps, &np_) == cudaSuccess;
+      if (ok) body = np_.conditional.phGraph_out[0];
+    }
+    if (ok) {
+      cudaStream_t keep = h->st;
+      h->st = side;
+      ok = cudaStreamBeginCaptureToGraph(side, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        ba_enqueue_trial(h, true, hc);
+        ok = cudaStreamEndCapture(side, &tmp) == cudaSuccess;
+      }
+      h->st = keep;
+    }
+    ok = ok && cudaStreamUpdateCaptureDependencies(h->st, &node, 1, cudaStreamSetCaptureDependencies) == cudaSuccess;
+  };
+  if (ok) {
+    // Chi2LargeSetLevel(100) of the PRV version only (:534-536): the three kernels return at once for a visual-only problem
+    errors(1, h->d_ctl + 5, 1);
+    classify(0, 100.f, 1, 0, nullptr, 0, 1);
+    errors(0, h->d_ctl + 6, 0);  // err (:539)
+    stage(0);
+    if (ok) {
+      campose();  // inlier re-classification + kernel removal (:597-633); skipped once the abort flag is up
+      classify(1, 0.f, 1, 1, h->d_bad, 1, 0);
+      stage(1);
+    }
+    if (ok) {
+      errors(2, h->d_ctl + 7, 0);  // err_end over the stored errors (:652)
+      campose();                   // outlier candidates (:668-700)
+      classify(1, 0.f, 0, 0, h->d_bad, 0, 0);
+      size_t off[4], total;
+      lba_dl_layout((size_t)h->capK, (size_t)h->capP, (size_t)capE, off, &total);
+      ok = total <= h->stage_cap;
+      uint8_t* hs = h->h_stage;
+      ok = ok && cudaMemcpyAsync(hs + off[0], h->B.st, sizeof(VieoNavState) * (size_t)h->capK, cudaMemcpyDeviceToHost, h->st) == cudaSuccess;
+      if (h->capP) ok = ok && cudaMemcpyAsync(hs + off[1], h->B.X, 24 * (size_t)h->capP, cudaMemcpyDeviceToHost, h->st) == cudaSuccess;
+      if (capE) {
+        ok = ok && cudaMemcpyAsync(hs + off[2], h->B.chi2, 8 * (size_t)capE, cudaMemcpyDeviceToHost, h->st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(hs + off[3], h->d_bad, (size_t)capE, cudaMemcpyDeviceToHost, h->st) == cudaSuccess;
+      }
+      ok = ok && cudaMemcpyAsync(h->h_ctl, h->d_ctl, 8 * 16, cudaMemcpyDeviceToHost, h->st) == cudaSuccess;
+      ok = ok && cudaMemcpyAsync(h->h_prm, h->B.prm, sizeof(BaParams), cudaMemcpyDeviceToHost, h->st) == cudaSuccess;
+    }
+  }
+  cudaGraph_t g = nullptr;
+  if (capturing) {
+    const bool ended = cudaStreamEndCapture(h->st, &g) == cudaSuccess;
+    ok = ok && ended;
+  }
+  if (ok) ok = cudaGraphInstantiate(&h->win_graph, g, 0) == cudaSuccess;
+  if (!ok) {
+    h->win_graph = nullptr;
+    cudaGetLastError();
+  }
+  if (g) cudaGraphDestroy(g);
+  cudaStreamDestroy(side);
+  h->win_nodes = nodes;
+  h->launches = 0;
+  return ok;
 }
 
 }  // namespace
@@ -2476,6 +2646,8 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
         cudaGraphExecDestroy(h->opt_graph);
         h->opt_graph = nullptr;
       }
+      // the whole-routine graph; a failure leaves the kernel-by-kernel enqueue of vieo_local_ba_prv_begin in charge
+      if (ok && !getenv("VIEO_BA_NO_WINDOW_GRAPH")) lba_build_window_graph(h);
     }
     h->launches = 0;
   }
@@ -2819,6 +2991,8 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   q.ok = 1;
   q.ni = 2;
   q.cam = h->cam; q.gw = h->gw; q.dm = h->dm; q.ds = h->ds;
+  q.visual_only = h->visual_only ? 1 : 0;
+  q.plan_it[0] = h->plan_it[0]; q.plan_it[1] = h->plan_it[1]; q.plan_lambda0 = h->plan_lambda0;
   q.vb_elim = h->vb_elim ? 1 : 0; q.cn = h->cn; q.Ky = h->Ky;
   q.has_scale = want_scale ? 1 : 0; q.off_s = off_s;
   q.has_g = want_g ? 1 : 0; q.off_g = off_g;
@@ -3156,6 +3330,7 @@ int vieo_local_ba_prv_begin(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCam
   int optit[2];
   double lambda0;
   lba_iteration_plan(pb, optit, &lambda0);
+  h->plan_it[0] = optit[0]; h->plan_it[1] = optit[1]; h->plan_lambda0 = lambda0;  // into the device-resident header
   h->defer_sync = true;
   BA_CK(cudaSetDevice(h->device));
   BA_CK(cudaEventRecord(h->ev_begin, h->st));
@@ -3168,6 +3343,17 @@ int vieo_local_ba_prv_begin(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCam
     return VIEO_OK;
   }
   const int K = h->K, P = h->P, E = h->E;
+  if (h->win_graph && !h->upload_direct) {
+    // ONE launch: Chi2LargeSetLevel, err, both optimize() stages (WHILE nodes), the re-classification between them, err_end,
+    // the outlier pass and the (capacity-sized) downloads
+    size_t total;
+    lba_dl_layout((size_t)h->capK, (size_t)h->capP, (size_t)h->capE, h->dl_off, &total);
+    BA_CK(cudaGraphLaunch(h->win_graph, h->st));
+    h->launches += h->win_nodes + 2 * kNodesPerTrial;
+    BA_CK(cudaEventRecord(h->ev_end, h->st));
+    h->async_state = 3;
+    return VIEO_OK;
+  }
   if (!pb->visual_only && (rc = vieo_ba_chi2_large_set_level(h, 100.f))) return rc;  // PRV version only (:534-536)
   if ((rc = ba_errors(h, 0, h->d_ctl + 6))) return rc;                               // err (:539)
   if ((rc = lba_enqueue_stage(h, 0, optit[0], lambda0))) return rc;
@@ -3187,11 +3373,13 @@ int vieo_local_ba_prv_begin(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCam
   }
   // downloads into the pinned staging buffer (the uploads that used it are ahead of them on the stream)
   const size_t ns = sizeof(VieoNavState) * (size_t)K, nx = 24 * (size_t)P, nc = 8 * (size_t)E, nb = (size_t)E;
-  uint8_t* ps = h->h_stage;
-  uint8_t* px = ps + ((ns + 15) & ~(size_t)15);
-  uint8_t* pc = px + ((nx + 15) & ~(size_t)15);
-  uint8_t* pbad = pc + ((nc + 15) & ~(size_t)15);
-  VIEO_ARG((size_t)(pbad - ps) + nb <= h->stage_cap, "staging buffer too small for the asynchronous download");
+  size_t dl_total;
+  lba_dl_layout((size_t)K, (size_t)P, (size_t)E, h->dl_off, &dl_total);
+  uint8_t* ps = h->h_stage + h->dl_off[0];
+  uint8_t* px = h->h_stage + h->dl_off[1];
+  uint8_t* pc = h->h_stage + h->dl_off[2];
+  uint8_t* pbad = h->h_stage + h->dl_off[3];
+  VIEO_ARG(dl_total <= h->stage_cap, "staging buffer too small for the asynchronous download");
   BA_CK(cudaMemcpyAsync(ps, h->B.st, ns, cudaMemcpyDeviceToHost, h->st));
   if (nx) BA_CK(cudaMemcpyAsync(px, h->B.X, nx, cudaMemcpyDeviceToHost, h->st));
   if (nc) BA_CK(cudaMemcpyAsync(pc, h->B.chi2, nc, cudaMemcpyDeviceToHost, h->st));
@@ -3243,10 +3431,10 @@ int vieo_local_ba_prv_end(vieo_ba_t* h, VieoNavState* states_out, double* points
   cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end);
   const int K = h->K, P = h->P, E = h->E;
   const size_t ns = sizeof(VieoNavState) * (size_t)K, nx = 24 * (size_t)P, nc = 8 * (size_t)E;
-  const uint8_t* ps = h->h_stage;
-  const uint8_t* px = ps + ((ns + 15) & ~(size_t)15);
-  const uint8_t* pc = px + ((nx + 15) & ~(size_t)15);
-  const uint8_t* pbad = pc + ((nc + 15) & ~(size_t)15);
+  const uint8_t* ps = h->h_stage + h->dl_off[0];
+  const uint8_t* px = h->h_stage + h->dl_off[1];
+  const uint8_t* pc = h->h_stage + h->dl_off[2];
+  const uint8_t* pbad = h->h_stage + h->dl_off[3];
   const BaParams& q = *h->h_prm;
   h->launches += kNodesPerTrial * std::max(q.trials - 1, 0);
   const float err = (float)h->h_ctl[6], err_end = (float)h->h_ctl[7];
