@@ -278,6 +278,41 @@ int vieo_pose_opt_batch_dev(const VieoPoseOptProblem* pbs_dev, int n, const Vieo
                             const float* obs_dev, const float* inv_sigma2_dev, const uint8_t* flags_dev,
                             VieoPoseOptResult* res_dev, uint8_t* outlier_dev, double* chi2_dev, void* stream);
 
+/* ---- Optimizer::OptimizeSim3 (src/Optimizer.cc:2689-2920): the loop closer's Sim3 refinement of candidate keyframe pairs ----
+ * One free VertexNavStatePR (S12 as a NavState: mRwb = R12^-1, mpwb = -(mRwb t12), :2717-2722) + VertexScale (fixed iff
+ * bFixScale) + fixed points; per match i an EdgeReprojectPRS (kpUn1 <- S12 P3D2c) and an EdgeReprojectPRSInv
+ * (kpUn2 <- S12^-1 P3D1c) (src/Odom/g2otypes.h:321-549), Huber sqrt(th2), information invSigma2(octave) I; optimize(5), pairs
+ * with a chi2 > th2 removed, optimize(10 if any was removed else 5).  Replaces the g2o graph of the routine; the caller
+ * (LoopClosing::ComputeSim3, src/LoopClosing.cc) keeps the candidate policy and converts S12 <-> NavState. */
+typedef struct VieoSim3Problem {
+  VieoNavState ns;        /* only p, q are read */
+  double scale;           /* g2oS12.scale() */
+  float th2;              /* chi2 gate (10 in LoopClosing); Huber delta = sqrtf(th2) */
+  int32_t fix_scale;      /* bFixScale (stereo / RGB-D / VIO with known scale) */
+  int32_t m_begin, m_end; /* this candidate's range in the shared match arrays */
+} VieoSim3Problem;
+typedef struct VieoSim3Result {
+  VieoNavState ns;    /* optimised vertex (the input when n_inliers == 0: the reference returns before the write-back) */
+  double scale;
+  double chi2_final;  /* robust chi2 of the pairs still in the graph after the last optimize() */
+  double lambda_final;
+  int32_t n_inliers;  /* the reference's return value nIn */
+  int32_t n_corr;     /* nCorrespondences */
+  int32_t n_bad;      /* pairs removed after the first stage */
+  int32_t iterations; /* LM iterations run in total */
+} VieoSim3Result;
+/* A batch of candidates, one thread block each.  Per match of the shared arrays: Xc1 / Xc2 [M][3] f64 = P3D1c / P3D2c (the
+ * float products of :2771-2783, cast to double), obs1 / obs2 [M][2] f32 (kpUn.pt), inv_sigma2_1 / _2 [M] f32.  Outputs: res
+ * [n], keep [M] u8 (0: vpMatches1[i] = nullptr), chi2_12 / chi2_21 [M] f64 (last e->chi2() of the pair; may be NULL in the
+ * host-buffer form).  _dev: scratch_dev [M] bytes. */
+int vieo_optimize_sim3_batch(const VieoSim3Problem* pbs, int n, const VieoCamera* cam, const double* Xc1, const double* Xc2,
+                             const float* obs1, const float* obs2, const float* inv_sigma2_1, const float* inv_sigma2_2,
+                             int n_matches, VieoSim3Result* res, uint8_t* keep, double* chi2_12, double* chi2_21, int device);
+int vieo_optimize_sim3_batch_dev(const VieoSim3Problem* pbs_dev, int n, const VieoCamera* cam_dev, const double* Xc1_dev,
+                                 const double* Xc2_dev, const float* obs1_dev, const float* obs2_dev,
+                                 const float* inv_sigma2_1_dev, const float* inv_sigma2_2_dev, VieoSim3Result* res_dev,
+                                 uint8_t* keep_dev, double* chi2_12_dev, double* chi2_21_dev, uint8_t* scratch_dev, void* stream);
+
 /* ---- local bundle adjustment: PR-V-Bias vertices per keyframe, marginalised map points --------------------
  * The flattened graph of Optimizer::LocalBundleAdjustmentNavStatePRV (src/Optimizer.cc:133-520).  Keyframes
  * ("states") come local-first in ascending id (the reference's vertex ids 3k, 3k+1, 3k+2), then the fixed ones.

@@ -1679,3 +1679,262 @@ int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* 
 }
 
 }  // extern "C"
+
+// ================================================================================================================
+// Optimizer::OptimizeSim3 (src/Optimizer.cc:2689-2920): EdgeReproject<2, 6, 3, MODE> with MODE 1 (PRS) / 2 (PRSInv)
+// (src/Odom/g2otypes.h:346-399 GetTcw_wX, :400-406 computeError, :439-541 linearizeOplus; USE_P_PLUS_RDP defined)
+namespace {
+struct Sim3Edge {
+  double e[2], Jp[12], Js[2];  // J_pose 2 x 6 (dp | dphi), J_scale 2 x 1
+};
+void sim3_edge(const Cam& c, const NS& ns, double sc, const double Xh[3], const float obs[2], bool inverse, bool jac, Sim3Edge& o) {
+  M3 Rwb = qmat(ns.q);
+  double twb[3] = {ns.p[0], ns.p[1], ns.p[2]};
+  const M3 Rbw_var = Rwb;  // "*pRbw = ns.getRwb()" (:361): the un-transposed rotation
+  double sfac = sc;
+  if (inverse) {
+    sfac = 1. / sfac;
+    Rwb = tr(Rwb);
+    double t[3];
+    mulv(Rwb, twb, t);
+    for (int i = 0; i < 3; ++i) twb[i] = -t[i];
+  }
+  const M3 Rcw = mul(c.Rcb, tr(Rwb));
+  double tcw[3];
+  mulv(Rcw, twb, tcw);
+  for (int i = 0; i < 3; ++i) tcw[i] = -tcw[i] + c.tcb[i];
+  if (inverse)
+    for (int i = 0; i < 3; ++i) tcw[i] *= sfac;
+  const double Xw[3] = {Xh[0] * sfac, Xh[1] * sfac, Xh[2] * sfac};
+  double Pc[3];
+  mulv(Rcw, Xw, Pc);
+  for (int i = 0; i < 3; ++i) Pc[i] += tcw[i];
+  float u, v;
+  double Jc[6];
+  cam_project(c, Pc, &u, &v, jac ? Jc : nullptr);
+  o.e[0] = (double)obs[0] - (double)u;
+  o.e[1] = (double)obs[1] - (double)v;
+  if (!jac) return;
+  M3 Jproj = {{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+  for (int i = 0; i < 6; ++i) Jproj.m[i] = -Jc[i];
+  M3 JdP = mul(Jproj, scale(c.Rcb, -1.0));
+  M3 JdR;
+  if (!inverse) {
+    const double d[3] = {Xw[0] - ns.p[0], Xw[1] - ns.p[1], Xw[2] - ns.p[2]};
+    double Paux[3];
+    mulv(tr(qmat(ns.q)), d, Paux);
+    JdR = mul(mul(Jproj, c.Rcb), hat(Paux));
+  } else {
+    JdR = mul(mul(Jproj, scale(Rcw, -1.0)), hat(Xw));
+  }
+  const M3 JX = mul(Jproj, Rcw);  // _jacobianOplus[0] before the chain factors
+  double Js[2];
+  for (int r = 0; r < 2; ++r) Js[r] = JX.m[3 * r] * Xh[0] + JX.m[3 * r + 1] * Xh[1] + JX.m[3 * r + 2] * Xh[2];
+  if (inverse) {
+    JdP = mul(JdP, scale(Rbw_var, -1.0));  // J_twb_tbw (:524)
+    for (int r = 0; r < 2; ++r) {
+      const double jt = Jproj.m[3 * r] * tcw[0] + Jproj.m[3 * r + 1] * tcw[1] + Jproj.m[3 * r + 2] * tcw[2];
+      Js[r] = (Js[r] + jt) * (-sfac * sfac);  // (:538-539)
+    }
+  }
+  for (int r = 0; r < 2; ++r) {
+    for (int k = 0; k < 3; ++k) {
+      o.Jp[6 * r + k] = JdP.m[3 * r + k];
+      o.Jp[6 * r + 3 + k] = JdR.m[3 * r + k];
+    }
+    o.Js[r] = Js[r];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+void orc_edge_sim3(const OrcCamera* cam, const OrcNavState* ns, double scale, const double Xh[3], const float obs[2],
+                   int inverse, double e[2], double* J_pose, double* J_scale) {
+  Sim3Edge o;
+  sim3_edge(cam_from_c(*cam), from_c(*ns), scale, Xh, obs, inverse != 0, J_pose || J_scale, o);
+  e[0] = o.e[0];
+  e[1] = o.e[1];
+  if (J_pose) memcpy(J_pose, o.Jp, sizeof(o.Jp));
+  if (J_scale) memcpy(J_scale, o.Js, sizeof(o.Js));
+}
+
+int orc_optimize_sim3(const OrcSim3Problem* pb, const OrcCamera* cam_c, const double* Xc1, const double* Xc2, const float* obs1,
+                      const float* obs2, const float* inv_sigma2_1, const float* inv_sigma2_2, OrcSim3Result* res,
+                      uint8_t* keep, double* chi2_12, double* chi2_21) {
+  memset(res, 0, sizeof(*res));
+  res->ns = pb->ns;
+  res->scale = pb->scale;
+  const Cam cam = cam_from_c(*cam_c);
+  const int M = pb->m_end - pb->m_begin, b0 = pb->m_begin;
+  const int n = pb->fix_scale ? 6 : 7;
+  NS ns = from_c(pb->ns);
+  double sc = pb->scale;
+  Huber rk;
+  rk.set((double)std::sqrt(pb->th2));  // const float deltaHuber = sqrt(th2) (:2752)
+  const double th2 = (double)pb->th2;
+  std::vector<uint8_t> active(M, 1);
+  std::vector<double> c12(M, 0.0), c21(M, 0.0);
+  for (int i = 0; i < M; ++i) keep[b0 + i] = 1;
+  res->n_corr = M;
+  double lambda = 0, ni = 2;
+  int total_iters = 0;
+  auto errors = [&]() {  // computeActiveErrors + activeRobustChi2
+    double tot = 0;
+    for (int i = 0; i < M; ++i) {
+      if (!active[i]) continue;
+      const int g = b0 + i;
+      Sim3Edge o;
+      double r[2];
+      sim3_edge(cam, ns, sc, Xc2 + 3 * g, obs1 + 2 * g, false, false, o);
+      const double w1 = (double)inv_sigma2_1[g];
+      c12[i] = o.e[0] * (w1 * o.e[0]) + o.e[1] * (w1 * o.e[1]);
+      rk.rho(c12[i], r);
+      tot += r[0];
+      sim3_edge(cam, ns, sc, Xc1 + 3 * g, obs2 + 2 * g, true, false, o);
+      const double w2 = (double)inv_sigma2_2[g];
+      c21[i] = o.e[0] * (w2 * o.e[0]) + o.e[1] * (w2 * o.e[1]);
+      rk.rho(c21[i], r);
+      tot += r[0];
+    }
+    return tot;
+  };
+  std::vector<double> H(49), bvec(7), x(7);
+  auto add_edge = [&](const Sim3Edge& o, double w, double chi) {
+    double r[2];
+    rk.rho(chi, r);
+    double J[2][7];
+    for (int k = 0; k < 2; ++k) {
+      for (int a = 0; a < 6; ++a) J[k][a] = o.Jp[6 * k + a];
+      J[k][6] = o.Js[k];
+    }
+    const double ww = r[1] * w;
+    for (int a = 0; a < n; ++a) {
+      double sb = 0;
+      for (int k = 0; k < 2; ++k) sb += J[k][a] * (-(w * o.e[k]) * r[1]);
+      bvec[a] += sb;
+      for (int cc = 0; cc < n; ++cc) {
+        double h = 0;
+        for (int k = 0; k < 2; ++k) h += (J[k][a] * ww) * J[k][cc];
+        H[a * n + cc] += h;
+      }
+    }
+  };
+  auto build = [&]() {  // linearizeOplus + constructQuadraticForm at the current estimate (errors must be current)
+    std::fill(H.begin(), H.end(), 0.0);
+    std::fill(bvec.begin(), bvec.end(), 0.0);
+    for (int i = 0; i < M; ++i) {
+      if (!active[i]) continue;
+      const int g = b0 + i;
+      Sim3Edge o;
+      sim3_edge(cam, ns, sc, Xc2 + 3 * g, obs1 + 2 * g, false, true, o);
+      add_edge(o, (double)inv_sigma2_1[g], c12[i]);
+      sim3_edge(cam, ns, sc, Xc1 + 3 * g, obs2 + 2 * g, true, true, o);
+      add_edge(o, (double)inv_sigma2_2[g], c21[i]);
+    }
+  };
+  auto optimize = [&](int iterations) {  // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve
+    int nBad = 0;
+    bool ok = true;
+    std::fill(x.begin(), x.end(), 0.0);
+    for (int it = 0; it < iterations && ok; ++it) {
+      double currentChi = errors();
+      double tempChi = currentChi;
+      const double iniChi = currentChi;
+      build();
+      if (it == 0) {
+        double mx = 0;
+        for (int j = 0; j < n; ++j) mx = std::max(std::fabs(H[j * n + j]), mx);
+        lambda = 1e-5 * mx;
+        ni = 2;
+        nBad = 0;
+      }
+      double rho = 0;
+      int qmax = 0;
+      do {
+        const NS ns_bak = ns;
+        const double sc_bak = sc;
+        std::vector<double> A(H.begin(), H.begin() + n * n);
+        for (int j = 0; j < n; ++j) A[j * n + j] += lambda;
+        const bool ok2 = chol_solve(A, n, bvec.data(), x.data());
+        if (ok2) {
+          inc_pr(ns, x.data());
+          if (n == 7) sc += x[6];
+        }
+        tempChi = errors();
+        if (!ok2) tempChi = std::numeric_limits<double>::max();
+        rho = currentChi - tempChi;
+        double scale = 0;
+        for (int j = 0; j < n; ++j) scale += x[j] * (lambda * x[j] + bvec[j]);
+        scale += 1e-3;
+        rho /= scale;
+        if (rho > 0 && std::isfinite(tempChi)) {
+          double alpha = 1. - std::pow((2 * rho - 1), 3);
+          alpha = std::min(alpha, 2. / 3.);
+          lambda *= std::max(1. / 3., alpha);
+          ni = 2;
+          currentChi = tempChi;
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          ns = ns_bak;
+          sc = sc_bak;
+        }
+        qmax++;
+      } while (rho < 0 && qmax < 10);
+      ++total_iters;
+      if (qmax == 10 || rho == 0) { ok = false; break; }
+      if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+      else nBad = 0;
+      if (nBad >= 3) ok = false;
+    }
+  };
+  optimize(5);
+  int nBad = 0;
+  for (int i = 0; i < M; ++i)
+    if (c12[i] > th2 || c21[i] > th2) {  // (:2858-2868)
+      keep[b0 + i] = 0;
+      active[i] = 0;
+      nBad++;
+    }
+  res->n_bad = nBad;
+  const int nMore = nBad > 0 ? 10 : 5;
+  auto store_chi = [&]() {
+    for (int i = 0; i < M; ++i) {
+      if (chi2_12) chi2_12[b0 + i] = c12[i];
+      if (chi2_21) chi2_21[b0 + i] = c21[i];
+    }
+  };
+  res->iterations = total_iters;
+  res->lambda_final = lambda;
+  if (M - nBad < 10) {  // (:2878) the Sim3 estimate is NOT written back
+    store_chi();
+    res->n_inliers = 0;
+    return 0;
+  }
+  optimize(nMore);
+  int nIn = 0;
+  for (int i = 0; i < M; ++i) {
+    if (!active[i]) continue;
+    if (c12[i] > th2 || c21[i] > th2) keep[b0 + i] = 0;
+    else nIn++;
+  }
+  store_chi();
+  {
+    double tot = 0, r[2];
+    for (int i = 0; i < M; ++i)
+      if (active[i]) {
+        rk.rho(c12[i], r); tot += r[0];
+        rk.rho(c21[i], r); tot += r[0];
+      }
+    res->chi2_final = tot;
+  }
+  to_c(ns, &res->ns);
+  res->scale = sc;
+  res->n_inliers = nIn;
+  res->iterations = total_iters;
+  res->lambda_final = lambda;
+  return nIn;
+}
+
+}  // extern "C"

@@ -149,6 +149,35 @@ void orc_gdir_oplus(double q_wI[4], const double d[2]);
 void orc_edge_navstate_g(const OrcNavState* nsi, const OrcNavState* nsj, const OrcImuPreint* pre, const double q_wI[4],
                          const double GI[3], double e[9], double* Ji, double* Jj, double* Jb, double* JG);
 void orc_edge_prior_pvr(const OrcNavState* ns, const OrcNavState* prior, double e[15], double* Jpvr /*15x9*/);
+
+/* ---- Optimizer::OptimizeSim3 (src/Optimizer.cc:2689-2920) ---------------------------------------------------------
+ * One free VertexNavStatePR (S12 as a NavState: mRwb = R12^-1, mpwb = -(mRwb t12), :2717-2722) + VertexScale (fixed iff
+ * bFixScale) + FIXED points; per match an EdgeReprojectPRS (x1 = pi(S12 X2c), g2otypes.h MODE 1) and an
+ * EdgeReprojectPRSInv (x2 = pi(S12^-1 X1c), MODE 2), Huber sqrt(th2); optimize(5), outlier pairs removed, optimize(5 | 10). */
+typedef struct OrcSim3Problem {
+  OrcNavState ns;   /* only p, q are read */
+  double scale;     /* g2oS12.scale() */
+  float th2;        /* chi2 gate; Huber delta = sqrtf(th2) */
+  int32_t fix_scale;
+  int32_t m_begin, m_end; /* this candidate's range in the shared match arrays */
+} OrcSim3Problem;
+typedef struct OrcSim3Result {
+  OrcNavState ns;   /* optimised (input when the call returned 0 before the second stage) */
+  double scale;
+  double chi2_final, lambda_final;
+  int32_t n_inliers;  /* return value nIn (0: fewer than 10 inlier pairs after the first stage) */
+  int32_t n_corr;     /* nCorrespondences */
+  int32_t n_bad;      /* pairs removed after the first stage */
+  int32_t iterations; /* LM iterations run in total */
+} OrcSim3Result;
+/* Xc1 / Xc2 [M][3]: P3D1c / P3D2c (float arithmetic of :2771-2783 done by the caller, cast to double); obs1 / obs2 [M][2];
+ * inv_sigma2_1 / _2 [M].  keep [M]: 1 = vpMatches1 entry kept.  chi2_12 / chi2_21 [M]: last e->chi2() of the pair. */
+int orc_optimize_sim3(const OrcSim3Problem* pb, const OrcCamera* cam, const double* Xc1, const double* Xc2, const float* obs1,
+                      const float* obs2, const float* inv_sigma2_1, const float* inv_sigma2_2, OrcSim3Result* res,
+                      uint8_t* keep, double* chi2_12, double* chi2_21);
+/* the two edges alone: inverse = 0 EdgeReprojectPRS, 1 EdgeReprojectPRSInv.  e[2], J_pose[2][6] (dp, dphi), J_scale[2] */
+void orc_edge_sim3(const OrcCamera* cam, const OrcNavState* ns, double scale, const double Xh[3], const float obs[2],
+                   int inverse, double e[2], double* J_pose, double* J_scale);
 int orc_inverse(const double* A, int n, double* Ainv);
 #ifdef __cplusplus
 }

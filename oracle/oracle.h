@@ -103,6 +103,14 @@ int orc_sbp_local_map(const OrcSbpFrame* f, const OrcKeyPoint* kps, const float*
                       const float* q_proj, const int32_t* q_level, const float* q_viewcos, const float* q_depth,
                       const uint8_t* q_desc, const uint8_t* q_flags, const uint8_t* kp_blocked, int32_t* kp_match,
                       int32_t* q_match, int32_t* q_dist);
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist, th_far_pts)
+ * (src/ORBmatcher.cc:1471-1606), the relocalisation search.  Queries = pKF's map points that are good and not in
+ * sAlreadyFound, in keypoint order; q_angle = pKF->mvKeys[i].angle; q_max_dist / q_min_dist = mfMaxDistance / mfMinDistance
+ * (the 1.2 / 0.8 factors are applied inside); kp_blocked: keypoints of the current frame that hold a map point. */
+int orc_sbp_reloc(const OrcSbpFrame* f, int orb_dist, float log_scale_factor, const OrcKeyPoint* kps, const uint8_t* desc,
+                  const double* q_Xw, const float* q_angle, const float* q_max_dist, const float* q_min_dist,
+                  const uint8_t* q_desc, const uint8_t* kp_blocked, int32_t* kp_match, int32_t* q_match, int32_t* q_dist,
+                  int32_t* q_level);
 /* Frame::isInFrustum + MapPoint::PredictScale (sbp_oracle.cc), single camera, usedistort_ == false. */
 typedef struct OrcFrustumFrame {
   int32_t q_begin, n_q;         /* this frame's candidate map points in the point arrays */

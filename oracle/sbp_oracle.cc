@@ -384,3 +384,94 @@ extern "C" void orc_sbp_base(const OrcProjSearchFrame* f, const OrcKeyPoint* kps
     }
   }
 }
+
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist,
+// th_far_pts) (src/ORBmatcher.cc:1471-1606) — Tracking::Relocalization's guided search after the PnP pose.  Single camera,
+// usedistort_ == false.  Differences to the last-frame search restated above: no "invzc < 0" skip, the level comes from
+// MapPoint::PredictScale of the camera-centre distance (with the 0.8 / 1.2 invariance gate), the band is always
+// [level - 1, level + 1], no stereo ur gate, EVERY accepted match claims its keypoint (AddMapPoint makes
+// CurrentFrame.GetMapPointMatches()[i2] non-null, :1553-1554), the acceptance threshold is the caller's ORBdist.
+// q_level (nullable): the predicted level of each query (-1: failed a geometric test), for the tests.
+extern "C" int orc_sbp_reloc(const OrcSbpFrame* f, int orb_dist, float log_scale_factor, const OrcKeyPoint* kps,
+                             const uint8_t* desc, const double* q_Xw, const float* q_angle, const float* q_max_dist,
+                             const float* q_min_dist, const uint8_t* q_desc, const uint8_t* kp_blocked, int32_t* kp_match,
+                             int32_t* q_match, int32_t* q_dist, int32_t* q_level) {
+  int nmatches = 0;
+  Grid grid(*f, kps);
+  std::vector<uint8_t> blocked(f->n_kp, 0);
+  for (int i = 0; i < f->n_kp; ++i) {
+    kp_match[i] = -1;
+    if (kp_blocked) blocked[i] = kp_blocked[i];
+  }
+  std::vector<std::vector<int>> rotHist(HISTO_LENGTH);
+  const float factor = 1.0f / HISTO_LENGTH;
+  // Twcr = Tcrw.inverse(): translation = Rc^-1 * (tc * -1) (Sophus SE3::inverse)
+  double twc[3];
+  {
+    const double qci[4] = {f->qcw[0], -f->qcw[1], -f->qcw[2], -f->qcw[3]};
+    const double nt[3] = {f->tcw[0] * -1.0, f->tcw[1] * -1.0, f->tcw[2] * -1.0};
+    qrot(qci, nt, twc);
+  }
+  std::vector<int> cand;
+  for (int i = 0; i < f->n_q; ++i) {
+    q_match[i] = -1;
+    q_dist[i] = 256;
+    if (q_level) q_level[i] = -1;
+    const double* Xw = q_Xw + 3 * (size_t)i;
+    double x3Dcr[3];
+    qrot(f->qcw, Xw, x3Dcr);
+    for (int k = 0; k < 3; ++k) x3Dcr[k] += f->tcw[k];
+    if (f->th_far > 0 && x3Dcr[2] > (double)f->th_far) continue;
+    const float invzc = (float)(1.0 / x3Dcr[2]);
+    const float xc = (float)x3Dcr[0], yc = (float)x3Dcr[1];
+    const float xn = xc * invzc, yn = yc * invzc;
+    const float u = (f->fx * xn + 0.f * yn) + f->cx * 1.f;
+    const float v = (0.f * xn + f->fy * yn) + f->cy * 1.f;
+    if (!(u >= f->minx && u < f->maxx && v >= f->miny && v < f->maxy)) continue;
+    const double PO[3] = {Xw[0] - twc[0], Xw[1] - twc[1], Xw[2] - twc[2]};
+    const float dist3D = (float)std::sqrt(PO[0] * PO[0] + PO[1] * PO[1] + PO[2] * PO[2]);
+    const float maxDistance = 1.2f * q_max_dist[i], minDistance = 0.8f * q_min_dist[i];
+    if (dist3D < minDistance || dist3D > maxDistance) continue;
+    const int nPredictedLevel = orc_predict_scale(q_max_dist[i], dist3D, log_scale_factor, f->n_levels);
+    if (q_level) q_level[i] = nPredictedLevel;
+    const float radius = f->th * f->scale[nPredictedLevel];
+    features_in_area(*f, grid, kps, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (blocked[i2]) continue;
+      const int dist = descriptor_distance(q_desc + 32 * (size_t)i, desc + 32 * (size_t)i2);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx2 = i2;
+      }
+    }
+    if (bestDist <= orb_dist) {
+      kp_match[bestIdx2] = i;
+      blocked[bestIdx2] = 1;
+      q_match[i] = bestIdx2;
+      q_dist[i] = bestDist;
+      nmatches++;
+      if (f->check_orientation) {
+        float rot = q_angle[i] - kps[bestIdx2].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(bestIdx2);
+      }
+    }
+  }
+  if (f->check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1, cnt[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; ++i) cnt[i] = (int)rotHist[i].size();
+    three_maxima(cnt, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int k : rotHist[i]) {
+          kp_match[k] = -1;
+          nmatches--;
+        }
+  }
+  return nmatches;
+}

@@ -654,3 +654,32 @@ def search_by_bow(pb, p):
     n = L.orc_search_by_bow(_p(kk1), _p(dd1), _p(mp_id), *[_p(x) for x in a], int(P["n_nodes1"]), _p(kk2), _p(dd2), int(P["n_kp2"]),
                             *[_p(x) for x in b], int(P["n_nodes2"]), float(P["nn_ratio"]), int(P["check_orientation"]), _p(mf))
     return mf[:int(P["n_kp2"])], n
+
+
+def edge_sim3(cam, ns, scale, Xh, obs, inverse):
+    """orc_edge_sim3: EdgeReprojectPRS (inverse = 0) / EdgeReprojectPRSInv (1) -> (e[2], J_pose[2][6], J_scale[2])"""
+    L = lib()
+    L.orc_edge_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_edge_sim3.restype = None
+    cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1); ns = np.ascontiguousarray(ns, NAVSTATE_DTYPE).reshape(1)
+    Xh = np.ascontiguousarray(Xh, np.float64); obs = np.ascontiguousarray(obs, np.float32)
+    e = np.zeros(2); Jp = np.zeros((2, 6)); Js = np.zeros(2)
+    L.orc_edge_sim3(_p(cam), _p(ns), float(scale), _p(Xh), _p(obs), int(inverse), _p(e), _p(Jp), _p(Js))
+    return e, Jp, Js
+
+
+def optimize_sim3(pbs, cam, Xc1, Xc2, obs1, obs2, w1, w2):
+    """orc_optimize_sim3 on every problem -> (results, keep u8[M], chi2_12[M], chi2_21[M])"""
+    from vieo_slam_b200.layouts import SIM3_PROBLEM_DTYPE, SIM3_RESULT_DTYPE
+    L = lib()
+    L.orc_optimize_sim3.argtypes = [C.c_void_p] * 12
+    pbs = np.ascontiguousarray(pbs, SIM3_PROBLEM_DTYPE); cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
+    Xc1 = np.ascontiguousarray(Xc1, np.float64); Xc2 = np.ascontiguousarray(Xc2, np.float64)
+    obs1 = np.ascontiguousarray(obs1, np.float32); obs2 = np.ascontiguousarray(obs2, np.float32)
+    w1 = np.ascontiguousarray(w1, np.float32); w2 = np.ascontiguousarray(w2, np.float32)
+    M = len(Xc1)
+    res = np.zeros(len(pbs), SIM3_RESULT_DTYPE); keep = np.zeros(M, np.uint8); c12 = np.zeros(M); c21 = np.zeros(M)
+    for k in range(len(pbs)):
+        L.orc_optimize_sim3(pbs[k:k + 1].ctypes.data, _p(cam), _p(Xc1), _p(Xc2), _p(obs1), _p(obs2), _p(w1), _p(w2),
+                            res[k:k + 1].ctypes.data, _p(keep), _p(c12), _p(c21))
+    return res, keep, c12, c21

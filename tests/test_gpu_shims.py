@@ -69,6 +69,26 @@ def test_cpp_shims_equal_ctypes_on_gpu(tmp_path):
     w("ba_obs.f32", lba["obs"]); w("ba_w.f32", lba["inv_sigma2"]); w("ba_edge_flags.u8", lba["edge_flags"])
     w("ba_imu_i.i32", lba["imu_i"]); w("ba_imu_j.i32", lba["imu_j"]); w("ba_preint.bin", lba["preint"]); w("ba_dt.f64", lba["imu_dt_kf"])
     w("ba_par.f64", np.r_[lba["gw"], lba["inv_sigma_bg2"], lba["inv_sigma_ba2"]])
+    # 5. OptimizeSim3
+    from vieo_slam_b200.layouts import SIM3_PROBLEM_DTYPE
+    cam3 = synth.euroc_camera()
+    cam3["Rcb"] = np.eye(3); cam3["tcb"] = 0
+    s3 = synth.make_sim3_problems(cam3, n_candidates=1, n_matches=90, seed=13, fix_scale=True)
+    spb, sX1, sX2, so1, so2, sw1, sw2, _ = s3
+    inv_s2, _scl = synth.inv_level_sigma2()
+    oct_of = lambda wv: np.array([int(np.argmin(np.abs(inv_s2 - v))) for v in wv], np.int32)
+    q_ns = spb["ns"]["q"][0]; p_ns = spb["ns"]["p"][0]
+    q12 = np.array([q_ns[0], -q_ns[1], -q_ns[2], -q_ns[3]])
+
+    def rot(q):  # the template's quaternion -> matrix formula, same operation order
+        w_, x, y, z = (float(v) for v in q)
+        return [1 - 2 * (y * y + z * z), 2 * (x * y - w_ * z), 2 * (x * z + w_ * y), 2 * (x * y + w_ * z), 1 - 2 * (x * x + z * z),
+                2 * (y * z - w_ * x), 2 * (x * z - w_ * y), 2 * (y * z + w_ * x), 1 - 2 * (x * x + y * y)]
+    R12 = rot(q12)
+    t12 = np.array([-(R12[3 * r] * float(p_ns[0]) + R12[3 * r + 1] * float(p_ns[1]) + R12[3 * r + 2] * float(p_ns[2])) for r in range(3)])
+    w("s3_cam.bin", np.asarray(cam3).reshape(1)); w("s3_X1.f64", sX1); w("s3_X2.f64", sX2); w("s3_obs1.f32", so1); w("s3_obs2.f32", so2)
+    w("s3_oct1.i32", oct_of(sw1)); w("s3_oct2.i32", oct_of(sw2)); w("s3_invsigma2.f32", inv_s2)
+    w("s3_par.f64", np.r_[q12, t12, float(spb["scale"][0]), 10.0, 1.0])
     out = subprocess.run([str(_build(tmp_path)), str(d)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "HOST_SHIM_GPU_OK" in out.stdout, out.stdout + out.stderr
     r = lambda name, dt: np.fromfile(str(d / name), dt)
@@ -101,3 +121,18 @@ def test_cpp_shims_equal_ctypes_on_gpu(tmp_path):
     assert r("ba_points.out", np.uint8).tobytes() == ref["points"].tobytes()
     assert r("ba_erase.out", np.uint8).tobytes() == ref["erase"].tobytes()
     assert r("ba_res.out", np.uint8).tobytes() == ref["res"].tobytes()
+    # 5: the template rebuilds the vertex from (q12, t12) with the same formulas
+    Rq = rot(q_ns)
+    one3 = np.zeros(1, SIM3_PROBLEM_DTYPE)
+    one3["ns"]["q"] = q_ns
+    one3["ns"]["p"] = [-(Rq[3 * r_] * float(t12[0]) + Rq[3 * r_ + 1] * float(t12[1]) + Rq[3 * r_ + 2] * float(t12[2])) for r_ in range(3)]
+    one3["scale"] = spb["scale"][0]; one3["th2"] = 10.0; one3["fix_scale"] = 1; one3["m_end"] = 90
+    r3, keep3, _, _ = api.Optimizer.OptimizeSim3Batch(one3, cam3, sX1.astype(np.float32).astype(np.float64),
+                                                      sX2.astype(np.float32).astype(np.float64), so1, so2, sw1, sw2)
+    got3 = r("s3.out", np.float64)
+    assert int(got3[0]) == int(r3["n_inliers"][0]) > 50
+    assert r("s3_keep.out", np.uint8).tobytes() == keep3.tobytes()
+    qo = r3["ns"]["q"][0]; po = r3["ns"]["p"][0]
+    q12o = np.array([qo[0], -qo[1], -qo[2], -qo[3]]); Ro = rot(q12o)
+    t12o = [-(Ro[3 * r_] * float(po[0]) + Ro[3 * r_ + 1] * float(po[1]) + Ro[3 * r_ + 2] * float(po[2])) for r_ in range(3)]
+    assert got3[1:5].tobytes() == q12o.tobytes() and got3[5:8].tobytes() == np.array(t12o).tobytes() and got3[8] == r3["scale"][0]

@@ -39,6 +39,8 @@ struct MapPoint {
   std::vector<std::pair<KeyFrame*, size_t>> obs_;
   const std::vector<std::pair<KeyFrame*, size_t>>& observations() const { return obs_; }
   void UpdateNormalAndDepth() { ++updated; }
+  bool bad = false;
+  bool isBad() const { return bad; }
 };
 inline void vieo_get_world_pos(const MapPoint& m, double o[3]) { o[0] = m.X[0]; o[1] = m.X[1]; o[2] = m.X[2]; }
 inline void vieo_set_world_pos(MapPoint& m, const double* i) { m.X[0] = i[0]; m.X[1] = i[1]; m.X[2] = i[2]; }
@@ -67,6 +69,8 @@ struct KeyFrame {
   NavState GetNavState() const { return ns; }
   void SetNavState(const NavState& n) { ns = n; }
   KeyFrame* GetPrevKeyFrame() const { return prev; }
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<MapPoint*> GetMapPointMatches() const { return mvpMapPoints; }
 };
 inline void ErasePairObs(KeyFrame* kf, MapPoint*) { ++kf->erased; }
 
@@ -237,6 +241,48 @@ int main(int argc, char** argv) {
       ba.End(so2.data(), po2.data(), nullptr, er2.data(), res2);
       if (std::memcmp(so.data(), so2.data(), sizeof(VieoNavState) * so.size()) || std::memcmp(po.data(), po2.data(), 8 * po.size()) ||
           er != er2) return 4;
+    }
+    // 5. Optimizer::OptimizeSim3 through the collection / write-back template on stand-in keyframes.  Keyframe 1 holds
+    //    map point i at keypoint i, the match is a second map point observed in keyframe 2 at keypoint i; both keyframes'
+    //    camera poses are the identity, so the dumped camera-frame positions are the map points' world positions.  One
+    //    matched map point is bad and one match is empty: neither may reach the optimiser.
+    {
+      auto cam = rd<VieoCamera>(dir, "s3_cam.bin");
+      auto X1 = rd<double>(dir, "s3_X1.f64");
+      auto X2 = rd<double>(dir, "s3_X2.f64");
+      auto o1 = rd<float>(dir, "s3_obs1.f32");
+      auto o2 = rd<float>(dir, "s3_obs2.f32");
+      auto oc1 = rd<int32_t>(dir, "s3_oct1.i32");
+      auto oc2 = rd<int32_t>(dir, "s3_oct2.i32");
+      auto isig = rd<float>(dir, "s3_invsigma2.f32");
+      auto par = rd<double>(dir, "s3_par.f64");  // q12(4), t12(3), s12, th2, bFixScale
+      const int M = (int)oc1.size();
+      KeyFrame k1, k2;
+      std::vector<MapPoint> m1(M + 2), m2(M + 2);
+      std::vector<MapPoint*> vpMatches1(M + 2, nullptr);
+      k1.scalepyrinfo_.vinvlevelsigma2_ = isig; k2.scalepyrinfo_.vinvlevelsigma2_ = isig;
+      k1.mvKeysUn.resize(M + 2); k2.mvKeysUn.resize(M + 2); k1.mvpMapPoints.resize(M + 2);
+      for (int i = 0; i < M + 2; ++i) {
+        const int j = std::min(i, M - 1);
+        for (int c = 0; c < 3; ++c) { m1[i].X[c] = X1[3 * j + c]; m2[i].X[c] = X2[3 * j + c]; }
+        k1.mvKeysUn[i].pt.x = o1[2 * j]; k1.mvKeysUn[i].pt.y = o1[2 * j + 1]; k1.mvKeysUn[i].octave = oc1[j];
+        k2.mvKeysUn[i].pt.x = o2[2 * j]; k2.mvKeysUn[i].pt.y = o2[2 * j + 1]; k2.mvKeysUn[i].octave = oc2[j];
+        k1.mvpMapPoints[i] = &m1[i];
+        vpMatches1[i] = &m2[i];
+      }
+      m2[M].bad = true;             // a bad matched point: skipped (:2767)
+      vpMatches1[M + 1] = nullptr;  // no match: skipped (:2754)
+      const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, z3[3] = {0, 0, 0};
+      double q12[4] = {par[0], par[1], par[2], par[3]}, t12[3] = {par[4], par[5], par[6]}, s12 = par[7];
+      MapPoint* base = m2.data();
+      const int nIn = OptimizeSim3<KeyFrame, MapPoint>(&k1, &k2, vpMatches1, I3, z3, I3, z3, q12, t12, s12, (float)par[8], par[9] != 0,
+                                                       cam[0], [&](MapPoint* p) { return (int)(p - base); });
+      std::vector<uint8_t> kept(M + 2);
+      for (int i = 0; i < M + 2; ++i) kept[i] = vpMatches1[i] != nullptr;
+      if (!kept[M]) return 6;  // the skipped bad match is not touched by the write-back
+      const double o[9] = {(double)nIn, q12[0], q12[1], q12[2], q12[3], t12[0], t12[1], t12[2], s12};
+      wr(dir, "s3.out", o, 9);
+      wr(dir, "s3_keep.out", kept.data(), (size_t)M);
     }
     std::printf("HOST_SHIM_GPU_OK %s\n", vieo_version());
   } catch (const std::exception& e) {

@@ -644,6 +644,29 @@ class Optimizer:
         return res, outlier, chi2
 
     @staticmethod
+    def OptimizeSim3Batch(pbs, cam, Xc1, Xc2, obs1, obs2, inv_sigma2_1, inv_sigma2_2, device=0):
+        """A batch of Optimizer::OptimizeSim3 calls (src/Optimizer.cc:2689-2920), one candidate keyframe pair per problem.
+        -> (results SIM3_RESULT_DTYPE[n], keep u8[M] (0: vpMatches1[i] = nullptr), chi2_12 f64[M], chi2_21 f64[M])"""
+        from .layouts import SIM3_PROBLEM_DTYPE, SIM3_RESULT_DTYPE
+        pbs = np.ascontiguousarray(pbs, SIM3_PROBLEM_DTYPE)
+        cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1)
+        Xc1 = np.ascontiguousarray(Xc1, np.float64).reshape(-1, 3)
+        Xc2 = np.ascontiguousarray(Xc2, np.float64).reshape(-1, 3)
+        obs1 = np.ascontiguousarray(obs1, np.float32).reshape(-1, 2)
+        obs2 = np.ascontiguousarray(obs2, np.float32).reshape(-1, 2)
+        w1 = np.ascontiguousarray(inv_sigma2_1, np.float32)
+        w2 = np.ascontiguousarray(inv_sigma2_2, np.float32)
+        M = len(Xc1)
+        assert len(Xc2) == M and len(obs1) == M and len(obs2) == M and len(w1) == M and len(w2) == M
+        res = np.zeros(len(pbs), SIM3_RESULT_DTYPE)
+        keep = np.zeros(M, np.uint8)
+        c12 = np.zeros(M, np.float64)
+        c21 = np.zeros(M, np.float64)
+        _check(lib().vieo_optimize_sim3_batch(_p(pbs), len(pbs), _p(cam), _p(Xc1), _p(Xc2), _p(obs1), _p(obs2), _p(w1), _p(w2), M,
+                                              _p(res), _p(keep), _p(c12), _p(c21), device))
+        return res, keep, c12, c21
+
+    @staticmethod
     def pose_opt_batch_dev(pbs_ptr, n, cam_ptr, Xw_ptr, obs_ptr, w_ptr, flags_ptr, res_ptr, outlier_ptr, chi2_ptr, stream=0):
         _check(lib().vieo_pose_opt_batch_dev(pbs_ptr, n, cam_ptr, Xw_ptr, obs_ptr, w_ptr, flags_ptr, res_ptr, outlier_ptr,
                                              chi2_ptr, stream))

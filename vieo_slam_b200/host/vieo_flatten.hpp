@@ -167,4 +167,71 @@ void WriteBackLocalWindow(LocalWindow<KeyFrameT, MapPointT>& W, size_t n_local, 
   }
 }
 
+// ---- Optimizer::OptimizeSim3 (src/Optimizer.cc:2689-2920): collection and write-back ------------------------------------------
+// Collection (:2753-2845): for every i with vpMatches1[i], pMP1 = pKF1->GetMapPointMatches()[i], pMP2 = vpMatches1[i], both
+// good and pMP2 observed in pKF2 at i2: P3D1c = R1w * P3D1w + t1w and P3D2c = R2w * P3D2w + t2w in FLOAT (:2771-2783), the
+// undistorted keypoints kpUn1 = pKF1->mvKeysUn[i], kpUn2 = pKF2->mvKeysUn[i2] and their level informations.  R1w / t1w /
+// R2w / t2w: row-major float[9] / float[3] of pKF1->GetRotation() ... (:2711-2714).  q12 (w, x, y, z), t12, s12: g2oS12 in
+// and out.  index_in_kf2(pMP2) returns i2 or -1.  Write-back (:2858-2868, 2894-2905): vpMatches1[i] = nullptr for dropped
+// pairs; g2oS12 only when the call did not return 0 before the second stage.  Returns nIn.
+template <class KeyFrameT, class MapPointT, class IndexInKF2>
+int OptimizeSim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches1, const float R1w[9], const float t1w[3],
+                 const float R2w[9], const float t2w[3], double q12[4], double t12[3], double& s12, float th2, bool bFixScale,
+                 const VieoCamera& cam, IndexInKF2 index_in_kf2, int device = 0) {
+  const int N = (int)vpMatches1.size();
+  const auto vpMapPoints1 = pKF1->GetMapPointMatches();
+  std::vector<double> Xc1, Xc2;
+  std::vector<float> obs1, obs2, w1, w2;
+  std::vector<int> vnIndexEdge;
+  auto to_cam = [](const float R[9], const float t[3], const double Xw[3], std::vector<double>& out) {
+    const float x = (float)Xw[0], y = (float)Xw[1], z = (float)Xw[2];
+    for (int r = 0; r < 3; ++r) out.push_back((double)(R[3 * r] * x + R[3 * r + 1] * y + R[3 * r + 2] * z + t[r]));
+  };
+  for (int i = 0; i < N; i++) {
+    if (!vpMatches1[i]) continue;
+    MapPointT* pMP1 = vpMapPoints1[i];
+    MapPointT* pMP2 = vpMatches1[i];
+    if (!pMP1 || !pMP2) continue;
+    const int i2 = index_in_kf2(pMP2);
+    if (pMP1->isBad() || pMP2->isBad() || i2 < 0) continue;
+    double X1[3], X2[3];
+    vieo_get_world_pos(*pMP1, X1);
+    vieo_get_world_pos(*pMP2, X2);
+    to_cam(R1w, t1w, X1, Xc1);
+    to_cam(R2w, t2w, X2, Xc2);
+    const auto& kpUn1 = pKF1->mvKeysUn[i];
+    const auto& kpUn2 = pKF2->mvKeysUn[i2];
+    obs1.push_back(kpUn1.pt.x); obs1.push_back(kpUn1.pt.y);
+    obs2.push_back(kpUn2.pt.x); obs2.push_back(kpUn2.pt.y);
+    w1.push_back(pKF1->scalepyrinfo_.vinvlevelsigma2_[kpUn1.octave]);
+    w2.push_back(pKF2->scalepyrinfo_.vinvlevelsigma2_[kpUn2.octave]);
+    vnIndexEdge.push_back(i);
+  }
+  // the vertex: ns.mRwb = R12^-1, ns.mpwb = -(mRwb * t12) (:2717-2722)
+  VieoSim3Problem pb{};
+  const double w = q12[0], x = -q12[1], y = -q12[2], z = -q12[3];  // conjugate = inverse rotation
+  pb.ns.q[0] = w; pb.ns.q[1] = x; pb.ns.q[2] = y; pb.ns.q[3] = z;
+  const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z),
+                       2 * (y * z - w * x),     2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+  for (int r = 0; r < 3; ++r) pb.ns.p[r] = -(R[3 * r] * t12[0] + R[3 * r + 1] * t12[1] + R[3 * r + 2] * t12[2]);
+  pb.scale = s12;
+  pb.th2 = th2;
+  pb.fix_scale = bFixScale ? 1 : 0;
+  VieoSim3Result res{};
+  std::vector<uint8_t> keep;
+  const int nIn = Optimizer::OptimizeSim3(pb, cam, Xc1, Xc2, obs1, obs2, w1, w2, res, keep, device);
+  for (size_t e = 0; e < vnIndexEdge.size(); ++e)
+    if (!keep[e]) vpMatches1[vnIndexEdge[e]] = nullptr;
+  if (res.n_corr - res.n_bad >= 10) {  // not the early "return 0" (:2878): "Recover optimized Sim3" (:2907-2917): R12 = mRwb^-1, t12 = -(R12 * mpwb)
+    const double qw = res.ns.q[0], qx = -res.ns.q[1], qy = -res.ns.q[2], qz = -res.ns.q[3];
+    q12[0] = qw; q12[1] = qx; q12[2] = qy; q12[3] = qz;
+    const double Q[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qw * qz), 2 * (qx * qz + qw * qy), 2 * (qx * qy + qw * qz),
+                         1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qw * qx), 2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx),
+                         1 - 2 * (qx * qx + qy * qy)};
+    for (int r = 0; r < 3; ++r) t12[r] = -(Q[3 * r] * res.ns.p[0] + Q[3 * r + 1] * res.ns.p[1] + Q[3 * r + 2] * res.ns.p[2]);
+    s12 = res.scale;
+  }
+  return nIn;
+}
+
 }  // namespace VIEO_SLAM_B200

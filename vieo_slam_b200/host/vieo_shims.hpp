@@ -355,6 +355,21 @@ struct Optimizer {
                                    mvbOutlier.data(), chi2.data(), device), "vieo_pose_opt_batch");
     return res.n_inliers;
   }
+  // OptimizeSim3(pKF1, pKF2, vpMatches1, g2oS12, th2, bFixScale) (src/Optimizer.cc:2689-2920) on flattened matches: pb.ns /
+  // pb.scale carry g2oS12 in and res.ns / res.scale carry it out; keep[i] == 0 means vpMatches1[idx_of_match[i]] = nullptr
+  static int OptimizeSim3(VieoSim3Problem& pb, const VieoCamera& cam, const std::vector<double>& Xc1,
+                          const std::vector<double>& Xc2, const std::vector<float>& obs1, const std::vector<float>& obs2,
+                          const std::vector<float>& inv_sigma2_1, const std::vector<float>& inv_sigma2_2, VieoSim3Result& res,
+                          std::vector<uint8_t>& keep, int device = 0) {
+    const int M = (int)inv_sigma2_1.size();
+    pb.m_begin = 0;
+    pb.m_end = M;
+    keep.assign(M, 0);
+    vieo_check(vieo_optimize_sim3_batch(&pb, 1, &cam, Xc1.data(), Xc2.data(), obs1.data(), obs2.data(), inv_sigma2_1.data(),
+                                        inv_sigma2_2.data(), M, &res, keep.data(), nullptr, nullptr, device),
+               "vieo_optimize_sim3_batch");
+    return res.n_inliers;
+  }
 };
 
 // Optimizer::OptimizeInitialGyroBias(vpKFInit, bg, bInfo) (include/Optimizer.h:819-892) followed by the re-integration

@@ -28,6 +28,13 @@ POSEOPT_RESULT_DTYPE = np.dtype([("cur", NAVSTATE_DTYPE), ("last", NAVSTATE_DTYP
                                  ("chi2_final", "f8"), ("lambda_final", "f8"), ("n_inliers", "i4"), ("n_initial", "i4"),
                                  ("iterations", "i4"), ("prior_set", "i4")])
 
+# VieoSim3Problem / VieoSim3Result (Optimizer::OptimizeSim3); the oracle's OrcSim3* are byte-identical
+SIM3_PROBLEM_DTYPE = np.dtype([("ns", NAVSTATE_DTYPE), ("scale", "f8"), ("th2", "f4"), ("fix_scale", "i4"), ("m_begin", "i4"),
+                               ("m_end", "i4")])
+SIM3_RESULT_DTYPE = np.dtype([("ns", NAVSTATE_DTYPE), ("scale", "f8"), ("chi2_final", "f8"), ("lambda_final", "f8"),
+                              ("n_inliers", "i4"), ("n_corr", "i4"), ("n_bad", "i4"), ("iterations", "i4")])
+assert SIM3_PROBLEM_DTYPE.itemsize == 200 and SIM3_RESULT_DTYPE.itemsize == 216
+
 BA_RESULT_DTYPE = np.dtype([("err0", "f8"), ("err_end", "f8"), ("lambda_final", "f8"), ("iterations", "i4", 2),
                             ("accepted", "i4"), ("n_erase", "i4")])
 

@@ -789,3 +789,52 @@ def make_bow_problem(seed, n_pairs=4, n_kp=1200, n_nodes=90, nn_ratio=0.7):
     out["mp_ok"] = (r.random(len(pb["has_mp"])) < 0.6).astype(np.uint8)
     out["n_out_total"] = ob
     return out
+
+
+def make_sim3_problems(cam, n_candidates=4, n_matches=120, seed=0, fix_scale=False, outlier_frac=0.15, th2=10.0,
+                       few_matches_every=0):
+    """Loop-closing candidates for Optimizer::OptimizeSim3 (src/Optimizer.cc:2689-2920): two keyframes looking at the same
+    landmarks whose camera frames are related by a similarity S12 (x1 = s R12 x2 + t12, the drift the loop closer corrects).
+    Per match: the landmark in both camera frames (float products like :2771-2783), its keypoints in both images with
+    octave-dependent noise, some outliers.  The initial estimate is the true S12 perturbed.  few_matches_every = k: every
+    k-th candidate has 12 matches most of which are outliers (the "fewer than 10 inliers" exit).
+    -> (problems SIM3_PROBLEM_DTYPE, Xc1, Xc2, obs1, obs2, w1, w2, truth list of (R12, t12, s))"""
+    from .layouts import SIM3_PROBLEM_DTYPE
+    r = np.random.default_rng(seed + 7000)
+    inv_s2, scl = inv_level_sigma2()
+    pbs = np.zeros(n_candidates, SIM3_PROBLEM_DTYPE)
+    X1s, X2s, O1, O2, W1, W2, truth = [], [], [], [], [], [], []
+    m0 = 0
+    fx, fy, cx, cy = (float(cam[k]) for k in ("fx", "fy", "cx", "cy"))
+    for c in range(n_candidates):
+        few = few_matches_every and (c % few_matches_every == few_matches_every - 1)
+        M = 12 if few else n_matches
+        s = 1.0 if fix_scale else float(r.uniform(0.85, 1.2))
+        R12 = so3_exp(r.normal(0, 0.15, 3))
+        t12 = r.normal(0, 0.4, 3)
+        # landmarks in camera-2 coordinates, in front of both cameras
+        u2 = r.uniform(40, EUROC["w"] - 40, M); v2 = r.uniform(40, EUROC["h"] - 40, M); z2 = r.uniform(2.0, 9.0, M)
+        X2 = np.stack([(u2 - cx) / fx * z2, (v2 - cy) / fy * z2, z2], 1)
+        X1 = s * X2 @ R12.T + t12
+        X1f = X1.astype(np.float32).astype(np.float64)
+        X2f = X2.astype(np.float32).astype(np.float64)
+        oct1 = r.integers(0, 8, M); oct2 = r.integers(0, 8, M)
+        o1 = np.stack([fx * X1[:, 0] / X1[:, 2] + cx, fy * X1[:, 1] / X1[:, 2] + cy], 1) + r.normal(0, 1, (M, 2)) * scl[oct1][:, None]
+        o2 = np.stack([u2, v2], 1) + r.normal(0, 1, (M, 2)) * scl[oct2][:, None]
+        out = r.random(M) < (0.7 if few else outlier_frac)
+        o1[out] += r.uniform(-25, 25, (int(out.sum()), 2))
+        pb = pbs[c]
+        # the vertex: mRwb = R12^-1, mpwb = -(mRwb t12) (:2717-2722), started off the truth
+        Rp = R12 @ so3_exp(r.normal(0, np.deg2rad(1.0), 3))
+        tp = t12 + r.normal(0, 0.03, 3)
+        pb["ns"]["q"] = quat_from_R(Rp.T)
+        pb["ns"]["p"] = -(Rp.T @ tp)
+        pb["scale"] = 1.0 if fix_scale else s * float(r.uniform(0.97, 1.03))
+        pb["th2"] = th2
+        pb["fix_scale"] = int(fix_scale)
+        pb["m_begin"], pb["m_end"] = m0, m0 + M
+        m0 += M
+        X1s.append(X1f); X2s.append(X2f); O1.append(o1.astype(np.float32)); O2.append(o2.astype(np.float32))
+        W1.append(inv_s2[oct1]); W2.append(inv_s2[oct2]); truth.append((R12, t12, s))
+    return (pbs, np.concatenate(X1s), np.concatenate(X2s), np.concatenate(O1), np.concatenate(O2), np.concatenate(W1),
+            np.concatenate(W2), truth)
