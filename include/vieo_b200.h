@@ -579,6 +579,34 @@ int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const Vie
                    const uint8_t* desc, const VieoSbpQueries* q, const uint8_t* kp_blocked, int32_t* kp_match,
                    int32_t* q_match, int32_t* q_dist, int32_t* n_matches, int device);
 
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist,
+ * th_far_pts) (src/ORBmatcher.cc:1471-1606): Tracking::Relocalization's guided search after the PnP pose, on the same two
+ * kernels (third window rule: level = MapPoint::PredictScale of the camera-centre distance inside the 0.8 / 1.2 invariance
+ * range, band [level - 1, level + 1], no stereo gate, every accepted match claims its keypoint, acceptance bestDist <=
+ * ORBdist, rotation histogram with pKF->mvKeys[i].angle).  frames[f]: keypoint / query ranges, image bounds, grid, fx..cy,
+ * th, th_far, check_orientation, n_levels, scale[], qcw / tcw = CurrentFrame.GetTcwCst(); the other fields are unused.
+ * Queries = pKF's map points that are good and not in sAlreadyFound (the host filters, :1487-1489), in keypoint order:
+ * q_Xw [n][3] f64, q_angle = pKF->mvKeys[i].angle, q_max_dist / q_min_dist = mfMaxDistance / mfMinDistance, q_desc [n][32].
+ * kp_blocked: keypoints of CurrentFrame that hold a map point on entry.  Outputs as vieo_sbp_batch, plus q_level
+ * (nullable) = nPredictedLevel (-1: the point failed a geometric test).  Single camera, usedistort_ == false. */
+#define VIEO_SBP_RELOC 2
+typedef struct VieoSbpReloc {
+  int32_t orb_dist;       /* ORBdist (< 256) */
+  float log_scale_factor; /* CurrentFrame.scalepyrinfo_.flogscalefactor_ */
+  float level_ratio[16];  /* vieo_frustum_level_table(log_scale_factor, n_levels): filled by the host-buffer call, by the
+                             caller for _dev */
+} VieoSbpReloc;
+int vieo_sbp_reloc_batch(const VieoSbpFrame* frames, const VieoSbpReloc* reloc, int n_frames, const VieoKeyPoint* kps,
+                         const uint8_t* desc, const double* q_Xw, const float* q_angle, const float* q_max_dist,
+                         const float* q_min_dist, const uint8_t* q_desc, const uint8_t* kp_blocked, int32_t* kp_match,
+                         int32_t* q_match, int32_t* q_dist, int32_t* q_level, int32_t* n_matches, int device);
+int vieo_sbp_reloc_batch_dev(const VieoSbpFrame* frames_dev, const VieoSbpReloc* reloc_dev, int n_frames,
+                             const VieoKeyPoint* kps_dev, const uint8_t* desc_dev, const double* q_Xw_dev,
+                             const float* q_angle_dev, const float* q_max_dist_dev, const float* q_min_dist_dev,
+                             const uint8_t* q_desc_dev, const uint8_t* kp_blocked_dev, int32_t* kp_match_dev,
+                             int32_t* q_match_dev, int32_t* q_dist_dev, int32_t* q_level_dev, int32_t* n_matches_dev,
+                             void* scratch_dev, size_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Frame::isInFrustum (src/Frame.cc:335-416) with MapPoint::PredictScale (src/MapPoint.cc:491-509) for every candidate map
  * point of a batch of frames, and Tracking::SearchLocalPoints' pair "visibility test -> SearchByProjection(F,

@@ -683,3 +683,27 @@ def optimize_sim3(pbs, cam, Xc1, Xc2, obs1, obs2, w1, w2):
         L.orc_optimize_sim3(pbs[k:k + 1].ctypes.data, _p(cam), _p(Xc1), _p(Xc2), _p(obs1), _p(obs2), _p(w1), _p(w2),
                             res[k:k + 1].ctypes.data, _p(keep), _p(c12), _p(c21))
     return res, keep, c12, c21
+
+
+def sbp_reloc(pb, frames=None):
+    """orc_sbp_reloc over every frame of a synth.make_reloc_problem batch -> (kp_match, q_match, q_dist, q_level, n_matches)"""
+    L = lib()
+    L.orc_sbp_reloc.restype = C.c_int
+    L.orc_sbp_reloc.argtypes = [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 12
+    fr = pb["frames"]
+    nq = len(pb["q_angle"])
+    kp_match = np.full(len(pb["kps"]), -1, np.int32)
+    q_match = np.full(nq, -1, np.int32); q_dist = np.full(nq, -1, np.int32); q_level = np.full(nq, -1, np.int32)
+    nm = np.zeros(len(fr), np.int32)
+
+    def at(a, i):
+        a = pb[a] if isinstance(a, str) else a
+        return a.ctypes.data + i * a.strides[0]
+    for f in (range(len(fr)) if frames is None else frames):
+        kb, qb = int(fr[f]["kp_begin"]), int(fr[f]["q_begin"])
+        blk = at("kp_blocked", kb) if pb.get("kp_blocked") is not None else None
+        nm[f] = L.orc_sbp_reloc(fr.ctypes.data + f * fr.strides[0], int(pb["reloc"][f]["orb_dist"]),
+                                float(pb["reloc"][f]["log_scale_factor"]), at("kps", kb), at("desc", kb), at("q_Xw", qb),
+                                at("q_angle", qb), at("q_max_dist", qb), at("q_min_dist", qb), at("q_desc", qb), blk,
+                                at(kp_match, kb), at(q_match, qb), at(q_dist, qb), at(q_level, qb))
+    return kp_match, q_match, q_dist, q_level, nm

@@ -62,3 +62,34 @@ def test_search_by_projection_deterministic():
     a = _run(pb)
     b = _run(pb)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+# ---- the relocalisation search: ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist, th_far_pts) ----
+RELOC_CASES = [dict(th=10.0, orb_dist=100), dict(th=3.0, orb_dist=64, blocked_frac=0.3), dict(th=15.0, orb_dist=100, th_far=7.0),
+               dict(th=30.0, orb_dist=100, cluster=True, n_kp=1500, n_q=500)]   # > 64 candidates: the re-enumeration path
+
+
+@pytest.mark.parametrize("kw", RELOC_CASES)
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_reloc_search_matches_oracle(kw, check_ori):
+    import vieo_slam_b200.api as api
+    pb = synth.make_reloc_problem(31, n_frames=5, **kw)
+    pb["frames"]["check_orientation"] = int(check_ori)
+    out = api.ORBmatcher(0.9, check_ori).SearchByProjectionReloc(pb)
+    ref = O.sbp_reloc(pb)
+    for a, b, name in zip(out, ref, ("kp_match", "q_match", "q_dist", "q_level", "n_matches")):
+        assert np.array_equal(a, b), (name, np.nonzero(a != b)[0][:10])
+    assert out[4].min() > 30 and (out[3] == -1).sum() > 10
+
+
+def test_reloc_search_edge_cases():
+    import vieo_slam_b200.api as api
+    pb = synth.make_reloc_problem(32, n_frames=3)
+    pb["frames"][1]["n_q"] = 0
+    pb["frames"][2]["n_kp"] = 0
+    out = api.ORBmatcher(0.9, True).SearchByProjectionReloc(pb)
+    ref = O.sbp_reloc(pb)
+    assert all(np.array_equal(a, b) for a, b in zip(out, ref)) and out[4][1] == 0 and out[4][2] == 0
+    pb["reloc"]["orb_dist"] = 256
+    with pytest.raises(api.VieoError):
+        api.ORBmatcher().SearchByProjectionReloc(pb)

@@ -400,6 +400,28 @@ class ORBmatcher:
                                     self.device))
         return kp_match, q_match, q_dist, nm
 
+    def SearchByProjectionReloc(self, pb):
+        """Batched ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist, th_far_pts)
+        (src/ORBmatcher.cc:1471-1606) over the frames of a synth.make_reloc_problem dict.
+        Returns (kp_match, q_match, q_dist, q_level, n_matches)."""
+        from .layouts import SBP_RELOC_DTYPE
+        fr = np.ascontiguousarray(pb["frames"]).copy()
+        fr["check_orientation"] = int(self.mbCheckOrientation)
+        rl = np.ascontiguousarray(pb["reloc"], SBP_RELOC_DTYPE)
+        a = {k: np.ascontiguousarray(pb[k], dt) for k, dt in (("kps", KP_DTYPE), ("desc", np.uint8), ("q_Xw", np.float64),
+                                                               ("q_angle", np.float32), ("q_max_dist", np.float32),
+                                                               ("q_min_dist", np.float32), ("q_desc", np.uint8))}
+        blk = None if pb.get("kp_blocked") is None else np.ascontiguousarray(pb["kp_blocked"], np.uint8)
+        nq = len(a["q_angle"])
+        kp_match = np.full(len(a["kps"]), -1, np.int32)
+        q_match = np.full(nq, -1, np.int32); q_dist = np.full(nq, -1, np.int32); q_level = np.full(nq, -1, np.int32)
+        nm = np.zeros(len(fr), np.int32)
+        _check(lib().vieo_sbp_reloc_batch(_p(fr), _p(rl), len(fr), _p(a["kps"]), _p(a["desc"]), _p(a["q_Xw"]), _p(a["q_angle"]),
+                                          _p(a["q_max_dist"]), _p(a["q_min_dist"]), _p(a["q_desc"]),
+                                          _p(blk) if blk is not None else None, _p(kp_match), _p(q_match), _p(q_dist),
+                                          _p(q_level), _p(nm), self.device))
+        return kp_match, q_match, q_dist, q_level, nm
+
     def knnMatch2(self, q, t):
         """cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) -> (idx[nq,2], dist[nq,2])."""
         q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)

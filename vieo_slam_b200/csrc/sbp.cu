@@ -43,7 +43,8 @@ struct SbpShared {
 struct Cand {  // one query's search window
   float x, y, r;
   int minlevel, maxlevel;
-  float ur;  // predicted right coordinate for the stereo gate
+  float ur;  // predicted right coordinate for the stereo gate (NaN-free sentinel: use_ur == 0 switches the gate off)
+  int use_ur;
 };
 
 __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint8_t* __restrict__ b) {
@@ -73,7 +74,9 @@ struct GridGeom {  // gridinfo_: image bounds and inverse cell sizes
 struct UrGate {
   const float* __restrict__ uright;
   float ur, r;
+  int on;
   __device__ __forceinline__ bool operator()(int j, const VieoKeyPoint&) const {
+    if (!on) return true;  // the relocalisation search has no stereo gate
     const float urj = uright[j];
     if (urj > 0) {
       const float er = fabsf(ur - urj);
@@ -131,7 +134,7 @@ __device__ __forceinline__ int enumerate_gated(const GridGeom& F, const SbpShare
 template <class Sink>
 __device__ __forceinline__ int enumerate(const VieoSbpFrame& F, const SbpShared& S, const VieoKeyPoint* __restrict__ kps,
                                          const float* __restrict__ uright, const Cand& c, int lane, Sink&& sink) {
-  return enumerate_gated(GridGeom{F.minx, F.miny, F.grid_winv, F.grid_hinv}, S, kps, c, lane, UrGate{uright, c.ur, c.r},
+  return enumerate_gated(GridGeom{F.minx, F.miny, F.grid_winv, F.grid_hinv}, S, kps, c, lane, UrGate{uright, c.ur, c.r, c.use_ur},
                          static_cast<Sink&&>(sink));
 }
 
@@ -185,11 +188,45 @@ struct QueryIn {
   const float* depth;
   const uint8_t* desc;
   const uint8_t* flags;
+  // RELOC: mfMaxDistance / mfMinDistance per query, one VieoSbpReloc per frame, predicted level out (nullable)
+  const float* max_dist;
+  const float* min_dist;
+  const VieoSbpReloc* reloc;
+  int32_t* level_out;
 };
 
 // window of query q (frame-relative qi = q - F.q_begin); false: the query is skipped before the search
 __device__ __forceinline__ bool make_window(int mode, const VieoSbpFrame& F, const QueryIn& Q, int q, bool fwd, bool bwd,
-                                            Cand& c) {
+                                            Cand& c, const VieoSbpReloc* R = nullptr, const double* twc = nullptr) {
+  c.use_ur = 1;
+  if (mode == VIEO_SBP_RELOC) {
+    // SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist, th_far_pts) (src/ORBmatcher.cc:1490-1536)
+    const double* Xw = Q.Xw + 3 * (size_t)q;
+    double x3Dcr[3];
+    qrot(F.qcw, Xw, x3Dcr);
+    x3Dcr[0] += F.tcw[0]; x3Dcr[1] += F.tcw[1]; x3Dcr[2] += F.tcw[2];
+    if (F.th_far > 0 && x3Dcr[2] > (double)F.th_far) return false;
+    const float invzc = (float)(1.0 / x3Dcr[2]);  // no "invzc < 0" skip in this routine
+    const float xn = __fmul_rn((float)x3Dcr[0], invzc), yn = __fmul_rn((float)x3Dcr[1], invzc);
+    const float u = __fadd_rn(__fmul_rn(F.fx, xn), F.cx), v = __fadd_rn(__fmul_rn(F.fy, yn), F.cy);
+    if (!(u >= F.minx && u < F.maxx && v >= F.miny && v < F.maxy)) return false;
+    const double POx = Xw[0] - twc[0], POy = Xw[1] - twc[1], POz = Xw[2] - twc[2];
+    const float dist3D = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(POx, POx), __dmul_rn(POy, POy)), __dmul_rn(POz, POz)));
+    const float maxD = Q.max_dist[q];
+    if (dist3D < __fmul_rn(0.8f, Q.min_dist[q]) || dist3D > __fmul_rn(1.2f, maxD)) return false;
+    // MapPoint::PredictScale by counting thresholds (vieo_frustum_level_table): ratio = mfMaxDistance / dist3D
+    const float ratio = __fdiv_rn(maxD, dist3D);
+    int lvl = 0;
+    for (int k = 1; k < F.n_levels; ++k) lvl += ratio >= R->level_ratio[k] ? 1 : 0;
+    if (ratio != ratio) lvl = 0;
+    if (Q.level_out) Q.level_out[q] = lvl;
+    c.x = u; c.y = v;
+    c.r = __fmul_rn(F.th, F.scale[lvl]);
+    c.minlevel = lvl - 1; c.maxlevel = lvl + 1;
+    c.ur = 0.f;
+    c.use_ur = 0;
+    return true;
+  }
   if (mode == VIEO_SBP_LAST_FRAME) {
     double x3Dr[3];
     qrot(F.qcw, Q.Xw + 3 * (size_t)q, x3Dr);
@@ -220,6 +257,13 @@ __device__ __forceinline__ bool make_window(int mode, const VieoSbpFrame& F, con
   c.minlevel = lvl - 1; c.maxlevel = lvl;
   c.ur = Q.proj[3 * (size_t)q + 2];
   return true;
+}
+
+// Twcr = Tcrw.inverse() (Sophus SE3::inverse): translation = Rc^-1 * (tc * -1) — the camera centre of the RELOC search (:1476-1478)
+__device__ __forceinline__ void camera_centre(const VieoSbpFrame& F, double twc[3]) {
+  const double qci[4] = {F.qcw[0], -F.qcw[1], -F.qcw[2], -F.qcw[3]};
+  const double nt[3] = {F.tcw[0] * -1.0, F.tcw[1] * -1.0, F.tcw[2] * -1.0};
+  qrot(qci, nt, twc);
 }
 
 // frame constants of the LAST_FRAME search: forward / backward motion along the optical axis (:1314-1323)
@@ -267,6 +311,9 @@ __global__ void __launch_bounds__(kListWarps * 32) k_sbp_lists(int mode, const V
   build_grid(S, GridGeom{F.minx, F.miny, F.grid_winv, F.grid_hinv}, kps, N, tid, T);
   bool fwd, bwd;
   motion_flags(mode, F, fwd, bwd);
+  double twc[3] = {0, 0, 0};
+  const VieoSbpReloc* R = mode == VIEO_SBP_RELOC ? Q.reloc + f : nullptr;
+  if (mode == VIEO_SBP_RELOC) camera_centre(F, twc);
   uint32_t* flist = lists + (size_t)F.q_begin * kListCap;
   int32_t* fcnt = counts + F.q_begin;
   // ---- phase B: candidate lists -----------------------------------------------------------------------------------------
@@ -274,7 +321,7 @@ __global__ void __launch_bounds__(kListWarps * 32) k_sbp_lists(int mode, const V
     const int q = F.q_begin + qi;
     Cand c;
     int n = 0;
-    if (make_window(mode, F, Q, q, fwd, bwd, c)) {
+    if (make_window(mode, F, Q, q, fwd, bwd, c, R, twc)) {
       const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q));
       const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q) + 1);
       uint32_t* L = flist + (size_t)qi * kListCap;
@@ -328,6 +375,11 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
   __syncwarp();
   bool fwd, bwd;
   motion_flags(mode, F, fwd, bwd);
+  double twc[3] = {0, 0, 0};
+  const VieoSbpReloc* R = mode == VIEO_SBP_RELOC ? Q.reloc + f : nullptr;
+  if (mode == VIEO_SBP_RELOC) camera_centre(F, twc);
+  const int th_accept = mode == VIEO_SBP_RELOC ? R->orb_dist : TH_HIGH;  // bestDist <= ORBdist (:1551) / TH_HIGH
+  const bool rot_check = (mode == VIEO_SBP_LAST_FRAME || mode == VIEO_SBP_RELOC) && F.check_orientation;
   bool have_grid = false;
   const uint32_t* flist = lists + (size_t)F.q_begin * kListCap;
   int32_t* fcnt = counts + F.q_begin;
@@ -338,7 +390,7 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
   // (the list slots exist for every query, entries past the count are simply not used).
   int n_next = nq > 0 ? fcnt[0] : 0;
   uint32_t ea_next = nq > 0 ? flist[lane] : 0u, eb_next = nq > 0 ? flist[lane + 32] : 0u;
-  uint8_t fl_next = nq > 0 ? Q.flags[F.q_begin] : 0;
+  uint8_t fl_next = (nq > 0 && Q.flags) ? Q.flags[F.q_begin] : 0;
   for (int qi = 0; qi < nq; ++qi) {
     const int q = F.q_begin + qi;
     const int n = n_next;
@@ -349,7 +401,7 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
       const uint32_t* Ln = flist + (size_t)(qi + 1) * kListCap;
       ea_next = Ln[lane];
       eb_next = Ln[lane + 32];
-      fl_next = Q.flags[q + 1];
+      fl_next = Q.flags ? Q.flags[q + 1] : 0;
     }
     uint32_t best = 0xffffffffu, second = 0xffffffffu;  // lane-local two smallest keys (dist << 16 | pos)
     int idx_a = -1, idx_b = -1;                          // keypoints of the lane's two entries
@@ -377,7 +429,7 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
         have_grid = true;
       }
       Cand c;
-      make_window(mode, F, Q, q, fwd, bwd, c);
+      make_window(mode, F, Q, q, fwd, bwd, c, R, twc);
       const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q));
       const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(Q.desc + 32 * (size_t)q) + 1);
       enumerate(F, S, kps, uright, c, lane, [&](int pos, int j) {
@@ -397,7 +449,7 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
       if (m1 != 0xffffffffu) {
         const int bestDist = (int)(m1 >> 16);
         const int bestIdx = __reduce_max_sync(0xffffffffu, best == m1 ? idx_a : -1);
-        if (bestDist <= TH_HIGH) {
+        if (bestDist <= th_accept) {
           bool ok = true;
           if (mode == VIEO_SBP_LOCAL_MAP) {
             const uint32_t c2 = best == m1 ? second : best;
@@ -421,8 +473,9 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
       int bin = -1;
       if (take >= 0) {
         kpm[take] = qi;
-        if (qflag & 1) S.blocked[take >> 5] |= 1u << (take & 31);
-        if (mode == VIEO_SBP_LAST_FRAME && F.check_orientation) {
+        // RELOC: AddMapPoint makes the keypoint's slot non-null for every later query (:1541-1543, 1553)
+        if ((qflag & 1) || mode == VIEO_SBP_RELOC) S.blocked[take >> 5] |= 1u << (take & 31);
+        if (rot_check) {
           float rot = __fsub_rn(Q.angle[q], kps[take].angle);
           if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
           bin = (int)roundf(__fmul_rn(rot, factor));
@@ -435,7 +488,7 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
     __syncwarp();
   }
   // ---- rotation consistency (:1445-1464) ---------------------------------------------------------------------------------
-  if (mode == VIEO_SBP_LAST_FRAME && F.check_orientation) {
+  if (rot_check) {
     int h = 0;  // lane b < 30 counts bin b
     for (int qi = 0; qi < nq; ++qi) h += (fcnt[qi] == lane) ? 1 : 0;
     if (lane < HISTO_LENGTH) S.hist[lane] = h;
@@ -609,6 +662,33 @@ size_t vieo_sbp_scratch_bytes(int n_queries_total) {
   return (size_t)std::max(n_queries_total, 1) * (kListCap + 1) * 4;
 }
 
+static int sbp_launch(int mode, const VieoSbpFrame* frames_dev, int n_frames, const VieoKeyPoint* kps_dev,
+                      const float* uright_dev, const uint8_t* desc_dev, const QueryIn& Q, const uint8_t* kp_blocked_dev,
+                      int32_t* kp_match_dev, int32_t* q_match_dev, int32_t* q_dist_dev, int32_t* n_matches_dev,
+                      void* scratch_dev, size_t scratch_bytes, void* stream) {
+  VIEO_ARG(((uintptr_t)desc_dev | (uintptr_t)Q.desc) % 16 == 0, "descriptors must be 16-byte aligned");
+  VIEO_ARG(scratch_bytes >= (size_t)(kListCap + 1) * 4, "scratch too small");
+  static SmemOptIn opt_in_lists, opt_in_claim;
+  VIEO_CK(smem_opt_in(k_sbp_lists, sizeof(SbpShared), opt_in_lists));
+  VIEO_CK(smem_opt_in(k_sbp_claim, sizeof(SbpShared), opt_in_claim));
+  // scratch = [counts (n_q_total) | lists (n_q_total x kListCap)]; the caller sized it with vieo_sbp_scratch_bytes
+  const size_t nq_total = scratch_bytes / ((size_t)(kListCap + 1) * 4);
+  int32_t* counts = (int32_t*)scratch_dev;
+  uint32_t* lists = (uint32_t*)scratch_dev + nq_total;
+  for (int f0 = 0; f0 < n_frames; f0 += 65535) {  // grid.y bound
+    const int nf = std::min(n_frames - f0, 65535);
+    QueryIn Qc = Q;
+    if (Qc.reloc) Qc.reloc += f0;
+    k_sbp_lists<<<dim3(kListCtas, nf), kListWarps * 32, sizeof(SbpShared), (cudaStream_t)stream>>>(
+        mode, frames_dev + f0, kps_dev, uright_dev, desc_dev, Qc, lists, counts);
+  }
+  k_sbp_claim<<<n_frames, 32, sizeof(SbpShared), (cudaStream_t)stream>>>(mode, frames_dev, kps_dev, uright_dev, desc_dev, Q,
+                                                                        kp_blocked_dev, kp_match_dev, q_match_dev, q_dist_dev,
+                                                                        n_matches_dev, lists, counts);
+  VIEO_CK(cudaGetLastError());
+  return VIEO_OK;
+}
+
 int vieo_sbp_batch_dev(int mode, const VieoSbpFrame* frames_dev, int n_frames, const VieoKeyPoint* kps_dev,
                        const float* uright_dev, const uint8_t* desc_dev, const VieoSbpQueries* q, const uint8_t* kp_blocked_dev,
                        int32_t* kp_match_dev, int32_t* q_match_dev, int32_t* q_dist_dev, int32_t* n_matches_dev,
@@ -621,26 +701,102 @@ int vieo_sbp_batch_dev(int mode, const VieoSbpFrame* frames_dev, int n_frames, c
   VIEO_ARG(q->desc && q->flags && q->level, "null query array");
   if (mode == VIEO_SBP_LAST_FRAME) VIEO_ARG(q->Xw && q->angle, "null query array");
   else VIEO_ARG(q->proj && q->viewcos && q->depth, "null query array");
-  VIEO_ARG(((uintptr_t)desc_dev | (uintptr_t)q->desc) % 16 == 0, "descriptors must be 16-byte aligned");
-  VIEO_ARG(scratch_bytes >= (size_t)(kListCap + 1) * 4, "scratch too small");
-  static SmemOptIn opt_in_lists, opt_in_claim;
-  VIEO_CK(smem_opt_in(k_sbp_lists, sizeof(SbpShared), opt_in_lists));
-  VIEO_CK(smem_opt_in(k_sbp_claim, sizeof(SbpShared), opt_in_claim));
-  // scratch = [counts (n_q_total) | lists (n_q_total x kListCap)]; the caller sized it with vieo_sbp_scratch_bytes
-  const size_t nq_total = scratch_bytes / ((size_t)(kListCap + 1) * 4);
-  int32_t* counts = (int32_t*)scratch_dev;
-  uint32_t* lists = (uint32_t*)scratch_dev + nq_total;
-  QueryIn Q{q->Xw, q->level, q->angle, q->proj, q->viewcos, q->depth, q->desc, q->flags};
-  for (int f0 = 0; f0 < n_frames; f0 += 65535) {  // grid.y bound
-    const int nf = std::min(n_frames - f0, 65535);
-    k_sbp_lists<<<dim3(kListCtas, nf), kListWarps * 32, sizeof(SbpShared), (cudaStream_t)stream>>>(
-        mode, frames_dev + f0, kps_dev, uright_dev, desc_dev, Q, lists, counts);
+  QueryIn Q{q->Xw, q->level, q->angle, q->proj, q->viewcos, q->depth, q->desc, q->flags, nullptr, nullptr, nullptr, nullptr};
+  return sbp_launch(mode, frames_dev, n_frames, kps_dev, uright_dev, desc_dev, Q, kp_blocked_dev, kp_match_dev, q_match_dev,
+                    q_dist_dev, n_matches_dev, scratch_dev, scratch_bytes, stream);
+}
+
+// ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist, th_far_pts) (src/ORBmatcher.cc:1471-1606)
+int vieo_sbp_reloc_batch_dev(const VieoSbpFrame* frames_dev, const VieoSbpReloc* reloc_dev, int n_frames,
+                             const VieoKeyPoint* kps_dev, const uint8_t* desc_dev, const double* q_Xw_dev,
+                             const float* q_angle_dev, const float* q_max_dist_dev, const float* q_min_dist_dev,
+                             const uint8_t* q_desc_dev, const uint8_t* kp_blocked_dev, int32_t* kp_match_dev,
+                             int32_t* q_match_dev, int32_t* q_dist_dev, int32_t* q_level_dev, int32_t* n_matches_dev,
+                             void* scratch_dev, size_t scratch_bytes, void* stream) {
+  VIEO_ARG(n_frames >= 0, "bad argument");
+  if (n_frames == 0) return VIEO_OK;
+  VIEO_ARG(frames_dev && reloc_dev && kps_dev && desc_dev && q_Xw_dev && q_angle_dev && q_max_dist_dev && q_min_dist_dev &&
+               q_desc_dev && kp_match_dev && q_match_dev && q_dist_dev && n_matches_dev && scratch_dev, "null argument");
+  QueryIn Q{q_Xw_dev, nullptr, q_angle_dev, nullptr, nullptr, nullptr, q_desc_dev, nullptr, q_max_dist_dev, q_min_dist_dev,
+            reloc_dev, q_level_dev};
+  return sbp_launch(VIEO_SBP_RELOC, frames_dev, n_frames, kps_dev, nullptr, desc_dev, Q, kp_blocked_dev, kp_match_dev,
+                    q_match_dev, q_dist_dev, n_matches_dev, scratch_dev, scratch_bytes, stream);
+}
+
+int vieo_sbp_reloc_batch(const VieoSbpFrame* frames, const VieoSbpReloc* reloc, int n_frames, const VieoKeyPoint* kps,
+                         const uint8_t* desc, const double* q_Xw, const float* q_angle, const float* q_max_dist,
+                         const float* q_min_dist, const uint8_t* q_desc, const uint8_t* kp_blocked, int32_t* kp_match,
+                         int32_t* q_match, int32_t* q_dist, int32_t* q_level, int32_t* n_matches, int device) {
+  VIEO_ARG(n_frames >= 0, "bad argument");
+  if (n_frames == 0) return VIEO_OK;
+  VIEO_ARG(frames && reloc && n_matches, "null argument");
+  size_t nk = 0, nq = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    VIEO_ARG(frames[f].n_kp >= 0 && frames[f].n_q >= 0 && frames[f].kp_begin >= 0 && frames[f].q_begin >= 0, "bad frame range");
+    if (frames[f].n_kp > kMaxKp) {
+      set_error("vieo_sbp_reloc_batch: frame %d has %d keypoints (max %d)", f, frames[f].n_kp, kMaxKp);
+      return VIEO_E_CAPACITY;
+    }
+    VIEO_ARG(frames[f].n_levels >= 1 && frames[f].n_levels <= 16, "bad pyramid depth");
+    VIEO_ARG(reloc[f].orb_dist >= 0 && reloc[f].orb_dist < 256, "ORBdist must be below 256");
+    nk = std::max(nk, (size_t)frames[f].kp_begin + frames[f].n_kp);
+    nq = std::max(nq, (size_t)frames[f].q_begin + frames[f].n_q);
   }
-  k_sbp_claim<<<n_frames, 32, sizeof(SbpShared), (cudaStream_t)stream>>>(mode, frames_dev, kps_dev, uright_dev, desc_dev, Q,
-                                                                        kp_blocked_dev, kp_match_dev, q_match_dev, q_dist_dev,
-                                                                        n_matches_dev, lists, counts);
-  VIEO_CK(cudaGetLastError());
-  return VIEO_OK;
+  VIEO_ARG(nk == 0 || (kps && desc && kp_match), "null keypoint array");
+  VIEO_ARG(nq == 0 || (q_Xw && q_angle && q_max_dist && q_min_dist && q_desc && q_match && q_dist), "null query array");
+  int rc = use_device(device);
+  if (rc) return rc;
+  CallScratch* cs = call_scratch(device);
+  VIEO_ARG(cs, "no call scratch");
+  std::vector<VieoSbpReloc> rl(reloc, reloc + n_frames);
+  for (int f = 0; f < n_frames; ++f)
+    if ((rc = vieo_frustum_level_table(rl[f].log_scale_factor, frames[f].n_levels, rl[f].level_ratio))) return rc;
+  const size_t nk1 = std::max<size_t>(nk, 1), nq1 = std::max<size_t>(nq, 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) / 16 * 16; return o; };
+  const size_t o_fr = take(sizeof(VieoSbpFrame) * n_frames), o_rl = take(sizeof(VieoSbpReloc) * n_frames),
+               o_kp = take(sizeof(VieoKeyPoint) * nk1), o_de = take(32 * nk1), o_bl = take(nk1), o_xw = take(24 * nq1),
+               o_an = take(4 * nq1), o_mx = take(4 * nq1), o_mn = take(4 * nq1), o_qd = take(32 * nq1);
+  const size_t in_bytes = off;
+  const size_t o_km = take(4 * nk1), o_qm = take(4 * nq1), o_qs = take(4 * nq1), o_ql = take(4 * nq1), o_nm = take(4 * (size_t)n_frames);
+  const size_t io_bytes = off;
+  const size_t sc_bytes = vieo_sbp_scratch_bytes((int)nq1);
+  uint8_t* dbuf = (uint8_t*)cs->get(0, io_bytes);
+  void* dsc = cs->get(1, sc_bytes);
+  uint8_t* hbuf = (uint8_t*)cs->get_pinned(io_bytes);
+  VIEO_ARG(dbuf && dsc && hbuf, "staging allocation failed");
+  auto put = [&](size_t o, const void* src, size_t bytes) { if (src && bytes) memcpy(hbuf + o, src, bytes); };
+  put(o_fr, frames, sizeof(VieoSbpFrame) * n_frames); put(o_rl, rl.data(), sizeof(VieoSbpReloc) * n_frames);
+  put(o_kp, kps, sizeof(VieoKeyPoint) * nk); put(o_de, desc, 32 * nk); put(o_bl, kp_blocked, nk);
+  put(o_xw, q_Xw, 24 * nq); put(o_an, q_angle, 4 * nq); put(o_mx, q_max_dist, 4 * nq); put(o_mn, q_min_dist, 4 * nq);
+  put(o_qd, q_desc, 32 * nq);
+  cudaError_t e = cudaMemcpyAsync(dbuf, hbuf, in_bytes, cudaMemcpyHostToDevice, cs->st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_km, 0xff, o_nm - o_km, cs->st);  // outside every frame's range: -1
+  if (e == cudaSuccess) {
+    rc = vieo_sbp_reloc_batch_dev((const VieoSbpFrame*)(dbuf + o_fr), (const VieoSbpReloc*)(dbuf + o_rl), n_frames,
+                                  (const VieoKeyPoint*)(dbuf + o_kp), dbuf + o_de, (const double*)(dbuf + o_xw),
+                                  (const float*)(dbuf + o_an), (const float*)(dbuf + o_mx), (const float*)(dbuf + o_mn), dbuf + o_qd,
+                                  kp_blocked ? dbuf + o_bl : nullptr, (int32_t*)(dbuf + o_km), (int32_t*)(dbuf + o_qm),
+                                  (int32_t*)(dbuf + o_qs), (int32_t*)(dbuf + o_ql), (int32_t*)(dbuf + o_nm), dsc, sc_bytes, cs->st);
+    if (rc == VIEO_OK) {
+      e = cudaMemcpyAsync(hbuf + o_km, dbuf + o_km, io_bytes - o_km, cudaMemcpyDeviceToHost, cs->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(cs->st);
+    }
+  }
+  if (e == cudaSuccess && rc == VIEO_OK) {
+    if (nk) memcpy(kp_match, hbuf + o_km, 4 * nk);
+    if (nq) {
+      memcpy(q_match, hbuf + o_qm, 4 * nq);
+      memcpy(q_dist, hbuf + o_qs, 4 * nq);
+      if (q_level) memcpy(q_level, hbuf + o_ql, 4 * nq);
+    }
+    memcpy(n_matches, hbuf + o_nm, 4 * (size_t)n_frames);
+  }
+  if (e != cudaSuccess) {
+    set_error("vieo_sbp_reloc_batch: %s", cudaGetErrorString(e));
+    return VIEO_E_CUDA;
+  }
+  return rc;
 }
 
 int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const VieoKeyPoint* kps, const float* uright,
@@ -665,8 +821,9 @@ int vieo_sbp_batch(int mode, const VieoSbpFrame* frames, int n_frames, const Vie
   VIEO_ARG(nq == 0 || (q->desc && q->flags && q->level && q_match && q_dist), "null query array");
   if (mode == VIEO_SBP_LAST_FRAME) VIEO_ARG(nq == 0 || (q->Xw && q->angle), "null query array");
   else VIEO_ARG(nq == 0 || (q->proj && q->viewcos && q->depth), "null query array");
-  for (size_t i = 0; i < nq; ++i)
-    VIEO_ARG(q->level[i] >= (mode == VIEO_SBP_LOCAL_MAP ? -1 : 0) && q->level[i] < 16, "query level out of range");
+  for (int f = 0; f < n_frames; ++f)  // against the frame's OWN pyramid depth: a level past it would index an unset scale[]
+    for (int i = frames[f].q_begin; i < frames[f].q_begin + frames[f].n_q; ++i)
+      VIEO_ARG(q->level[i] >= (mode == VIEO_SBP_LOCAL_MAP ? -1 : 0) && q->level[i] < frames[f].n_levels, "query level out of range");
   int rc = use_device(device);
   if (rc) return rc;
   CallScratch* cs = call_scratch(device);

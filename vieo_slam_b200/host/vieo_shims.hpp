@@ -129,6 +129,29 @@ class ORBmatcher {
     vieo_check(vieo_hamming_csr(q.data, t.data, t.rows, row_ptr.data(), cand.data(), n, best.data(), best_idx.data(),
                                 second.data(), second_idx.data(), device_), "vieo_hamming_csr");
   }
+  // SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist, th_far_pts) (src/ORBmatcher.cc:
+  // 1471-1606), Tracking::Relocalization's guided search, one record per (candidate keyframe, current-frame copy) pair.
+  // Queries = pKF's map points that are good and not in sAlreadyFound, in keypoint order.  th goes into
+  // frames[f].th, ORBdist into reloc[f].orb_dist.  Returns nmatches summed over the records.
+  int SearchByProjectionReloc(std::vector<VieoSbpFrame>& frames, const std::vector<VieoSbpReloc>& reloc, const VieoKeyPoint* keys_un,
+                              const uint8_t* descriptors, const double* q_Xw, const float* q_angle, const float* q_max_dist,
+                              const float* q_min_dist, const uint8_t* q_desc, const uint8_t* kp_blocked,
+                              std::vector<int32_t>& kp_match, std::vector<int32_t>& q_match, std::vector<int32_t>& q_dist,
+                              std::vector<int32_t>& n_matches) const {
+    size_t nk = 0, nq = 0;
+    for (VieoSbpFrame& f : frames) {
+      f.check_orientation = mbCheckOrientation ? 1 : 0;
+      nk = std::max(nk, (size_t)f.kp_begin + f.n_kp);
+      nq = std::max(nq, (size_t)f.q_begin + f.n_q);
+    }
+    kp_match.assign(nk, -1); q_match.assign(nq, -1); q_dist.assign(nq, -1); n_matches.assign(frames.size(), 0);
+    vieo_check(vieo_sbp_reloc_batch(frames.data(), reloc.data(), (int)frames.size(), keys_un, descriptors, q_Xw, q_angle, q_max_dist,
+                                    q_min_dist, q_desc, kp_blocked, kp_match.data(), q_match.data(), q_dist.data(), nullptr,
+                                    n_matches.data(), device_), "vieo_sbp_reloc_batch");
+    int total = 0;
+    for (int v : n_matches) total += v;
+    return total;
+  }
   // The tracking thread's SearchByProjection overloads on the flattened frame(s) (src/ORBmatcher.cc:230-335,
   // 1303-1467; INTEGRATION.md 2b shows how Frame / MapPoint fields map onto the arrays).  mode = VIEO_SBP_LAST_FRAME or
   // VIEO_SBP_LOCAL_MAP; the matcher's mfNNratio / mbCheckOrientation are written into every frame record.

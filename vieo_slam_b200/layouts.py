@@ -44,7 +44,10 @@ SBP_FRAME_DTYPE = np.dtype([("kp_begin", "i4"), ("n_kp", "i4"), ("q_begin", "i4"
                             ("fx", "f4"), ("fy", "f4"), ("cx", "f4"), ("cy", "f4"), ("th", "f4"), ("th_far", "f4"),
                             ("nn_ratio", "f4"), ("mono", "i4"), ("check_orientation", "i4"), ("n_levels", "i4"),
                             ("scale", "f4", 16), ("qcw", "f8", 4), ("tcw", "f8", 3), ("qlw", "f8", 4), ("tlw", "f8", 3)])
-SBP_LAST_FRAME, SBP_LOCAL_MAP = 0, 1
+SBP_LAST_FRAME, SBP_LOCAL_MAP, SBP_RELOC = 0, 1, 2
+# VieoSbpReloc: per-frame record of the relocalisation search (ORBmatcher::SearchByProjection(Frame&, KeyFrame*, ...))
+SBP_RELOC_DTYPE = np.dtype([("orb_dist", "i4"), ("log_scale_factor", "f4"), ("level_ratio", "f4", 16)])
+assert SBP_RELOC_DTYPE.itemsize == 72
 
 # VieoFrustumFrame (include/vieo_b200.h): one current frame of a Frame::isInFrustum batch; the oracle's OrcFrustumFrame is
 # the same record without the trailing level_ratio table

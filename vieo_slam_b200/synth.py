@@ -516,6 +516,39 @@ def make_sbp_problem(seed, n_frames=2, mode=SBP_LAST_FRAME, n_kp=1200, n_q=700, 
     return out
 
 
+def make_reloc_problem(seed, n_frames=3, n_kp=1200, n_q=600, th=10.0, orb_dist=100, th_far=0.0, blocked_frac=0.1, cluster=False):
+    """Tracking::Relocalization's guided search (ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist,
+    th_far_pts), src/ORBmatcher.cc:1471-1606): the frames / keypoints / queries of make_sbp_problem plus, per query, the map
+    point's scale-invariance range chosen so that MapPoint::PredictScale lands near the source keypoint's octave (some
+    queries fall outside the 0.8 / 1.2 gate), and the per-frame VieoSbpReloc record."""
+    from .layouts import SBP_RELOC_DTYPE
+    pb = make_sbp_problem(seed, n_frames=n_frames, mode=SBP_LAST_FRAME, n_kp=n_kp, n_q=n_q, th=th, th_far=th_far,
+                          blocked_frac=blocked_frac, cluster=cluster)
+    r = np.random.default_rng(seed + 4242)
+    _, scl = inv_level_sigma2()
+    fr = pb["frames"]
+    mx = np.zeros(len(pb["q_level"]), np.float32); mn = np.zeros(len(pb["q_level"]), np.float32)
+    for f in range(len(fr)):
+        Rcw = R_from_quat(fr[f]["qcw"]); tcw = fr[f]["tcw"]
+        Ow = -Rcw.T @ tcw
+        q0, nq = int(fr[f]["q_begin"]), int(fr[f]["n_q"])
+        d = np.linalg.norm(pb["q_Xw"][q0:q0 + nq] - Ow, axis=1)
+        lvl = pb["q_level"][q0:q0 + nq]
+        mxd = d * scl[lvl] * r.uniform(0.93, 1.07, nq)          # PredictScale = ceil(log(max / d) / log 1.2) ~ lvl
+        mnd = mxd / scl[7]
+        far = r.random(nq) < 0.06
+        mxd[far] *= 0.5                                          # beyond 1.2 x max: dropped
+        near = r.random(nq) < 0.04
+        mnd[near] = d[near] * 1.5                                # closer than 0.8 x min: dropped
+        mx[q0:q0 + nq] = mxd; mn[q0:q0 + nq] = mnd
+    rl = np.zeros(len(fr), SBP_RELOC_DTYPE)
+    rl["orb_dist"] = orb_dist
+    rl["log_scale_factor"] = np.float32(np.log(np.float32(1.2)))
+    pb["q_max_dist"], pb["q_min_dist"], pb["reloc"] = mx, mn, rl
+    pb["mode"] = 2
+    return pb
+
+
 # ---------------------------------------------------------------- Frame::isInFrustum / SearchLocalPoints problems
 from .layouts import FRUSTUM_FRAME_DTYPE  # noqa: E402
 
