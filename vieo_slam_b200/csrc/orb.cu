@@ -25,9 +25,9 @@ constexpr int kQtThreads = 512;
 constexpr int kDescWarps = 4;
 constexpr int kPR = 21;           // raw patch radius: 18 (rotated pattern reach) + 3 (7-tap blur)
 constexpr int kPW = 2 * kPR + 1;  // 43
-constexpr int kPWp = 44;          // padded row of the raw patch
+constexpr int kPWp = 52;          // row of the staged raw patch in bytes: 13 words, the patch starts at byte xoff (0..3) of it
 constexpr int kBW = 37;           // blurred window (+-18)
-constexpr int kBWp = 38;
+constexpr int kBWp = 40;          // 20 words: four outputs = two aligned word stores
 constexpr int kProfRing = 1024;    // profiled calls kept between vieo_orb_profile_read()s
 
 struct Cell {
@@ -751,13 +751,25 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(OrbParams P, co
   const int W = P.w[level], H = P.h[level];
   uint8_t* raw = s_raw[warp];
   uint16_t* hb = s_hb[warp];
-  // rows of the patch, lanes along the row (two turns for the 43 columns); the reflection only exists at the image edge
-  if (kx >= kPR && kx + kPR < W && ky >= kPR && ky + kPR < H) {
-    const uint8_t* src = base + (size_t)(ky - kPR) * pitch + (kx - kPR);
+  // The kernel is bound by the shared-memory pipe (one instruction per clock per SM), so the patch moves as 32-bit words:
+  // interior keypoints of a 4-byte-pitched image copy each row's 12 aligned words (the patch then starts at byte xoff of
+  // the staged row); keypoints near the image edge (REFLECT_101, only there) and odd pitches take the byte path.
+  int xoff = 0;
+  const uint8_t* first = base + (size_t)(ky - kPR) * pitch + (kx - kPR);
+  if ((pitch & 3) == 0 && kx >= kPR + 3 && kx + kPR + 3 < W && ky >= kPR && ky + kPR < H) {
+    xoff = (int)((uintptr_t)first & 3);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(first - xoff);
+    const int pw = pitch >> 2;
+    uint32_t* raw32 = reinterpret_cast<uint32_t*>(raw);
+    for (int it = lane; it < kPW * 12; it += 32) {
+      const int r = it / 12, w = it - 12 * r;
+      raw32[r * (kPWp / 4) + w] = __ldg(src + (size_t)r * pw + w);
+    }
+  } else if (kx >= kPR && kx + kPR < W && ky >= kPR && ky + kPR < H) {
 #pragma unroll 4
     for (int r = 0; r < kPW; ++r) {
-      raw[r * kPWp + lane] = __ldg(src + (size_t)r * pitch + lane);
-      if (lane + 32 < kPW) raw[r * kPWp + lane + 32] = __ldg(src + (size_t)r * pitch + lane + 32);
+      raw[r * kPWp + lane] = __ldg(first + (size_t)r * pitch + lane);
+      if (lane + 32 < kPW) raw[r * kPWp + lane + 32] = __ldg(first + (size_t)r * pitch + lane + 32);
     }
   } else {
     const int gx0 = reflect101(kx - kPR + lane, W), gx1 = reflect101(kx - kPR + min(lane + 32, kPW - 1), W);
@@ -773,7 +785,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(OrbParams P, co
   if (lane < 2 * kHalfPatch + 1) {
     const int v = lane - kHalfPatch;
     const int d = c_umax[v < 0 ? -v : v];
-    const uint8_t* row = raw + (kPR + v) * kPWp + kPR;
+    const uint8_t* row = raw + (kPR + v) * kPWp + xoff + kPR;
     int rs = 0;
     for (int u = -d; u <= d; ++u) {
       const int val = row[u];
@@ -788,14 +800,29 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(OrbParams P, co
     m01 += __shfl_xor_sync(0xffffffffu, m01, o);
   }
   const float angle = fast_atan2_deg((float)m01, (float)m10);
-  // horizontal pass, 8-fractional-bit kernel {18,34,48,56,48,34,18} (sum 256): exact in 16 bits
-#pragma unroll 4
-  for (int r = 0; r < kPW; ++r) {
-    const uint8_t* s = raw + r * kPWp + lane;
-    hb[r * kBWp + lane] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
-    if (lane + 32 < kBW) {
-      s += 32;
-      hb[r * kBWp + lane + 32] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+  // Horizontal pass, 8-fractional-bit kernel {18,34,48,56,48,34,18} (sum 256): exact in 16 bits.  A work item is four
+  // consecutive outputs of one row: four aligned word loads, realigned by xoff with funnel shifts, then the 7 taps on PACKED
+  // pairs — (b[k], b[k+2]) as two 16-bit halves of one register, so one integer multiply-add serves two outputs (each half
+  // stays below 65536: no carry crosses) — and two aligned word stores.  Same integer sums as the byte form: bit-exact.
+  {
+    const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(raw);
+    uint32_t* hb32 = reinterpret_cast<uint32_t*>(hb);
+    const int sh = 8 * xoff;
+    for (int it = lane; it < kPW * 10; it += 32) {
+      const int r = it / 10, g = it - 10 * r;
+      const uint32_t* w = raw32 + r * (kPWp / 4) + g;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+      const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+      const uint32_t E0 = v0 & 0x00ff00ffu, O0 = (v0 >> 8) & 0x00ff00ffu;  // (b0, b2), (b1, b3)
+      const uint32_t E1 = v1 & 0x00ff00ffu, O1 = (v1 >> 8) & 0x00ff00ffu;  // (b4, b6), (b5, b7)
+      const uint32_t E2 = v2 & 0x00ff00ffu, O2 = (v2 >> 8) & 0x00ff00ffu;  // (b8, b10), (b9, b11)
+      const uint32_t P2 = __byte_perm(E0, E1, 0x5432), P3 = __byte_perm(O0, O1, 0x5432);  // (b2, b4), (b3, b5)
+      const uint32_t P6 = __byte_perm(E1, E2, 0x5432), P7 = __byte_perm(O1, O2, 0x5432);  // (b6, b8), (b7, b9)
+      // (o0, o2): taps P0..P6 = E0, O0, P2, P3, E1, O1, P6;  (o1, o3): taps P1..P7
+      const uint32_t A = 18u * (E0 + P6) + 34u * (O0 + O1) + 48u * (P2 + E1) + 56u * P3;
+      const uint32_t B = 18u * (O0 + P7) + 34u * (P2 + P6) + 48u * (P3 + O1) + 56u * E1;
+      hb32[r * (kBWp / 2) + 2 * g] = __byte_perm(A, B, 0x5410);      // (o0, o1)
+      hb32[r * (kBWp / 2) + 2 * g + 1] = __byte_perm(A, B, 0x7632);  // (o2, o3)
     }
   }
   __syncwarp();
