@@ -38,6 +38,7 @@ struct SbpShared {
   int cnt[kCells];  // phase A counters (reused as scan input)
   int total;
   int hist[HISTO_LENGTH];
+  uint8_t oct[kMaxKp];  // claim kernel: keypoint octaves staged once (the ratio test reads two per accepted query)
 };
 
 struct Cand {  // one query's search window
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(kListWarps * 32) k_sbp_lists(int mode, const V
 // cost is the latency of nq dependent iterations — runs beside the other streams' kernels.  The frame grid is only needed by
 // the overflow path (a list longer than kListCap is re-enumerated with the claim filter): it is built lazily, by this warp,
 // the first time such a query appears.
-__global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* __restrict__ frames,
+__global__ void __launch_bounds__(32, 1) k_sbp_claim(int mode, const VieoSbpFrame* __restrict__ frames,
                                                   const VieoKeyPoint* __restrict__ kps_all, const float* __restrict__ ur_all,
                                                   const uint8_t* __restrict__ desc_all, QueryIn Q,
                                                   const uint8_t* __restrict__ kp_blocked, int32_t* __restrict__ kp_match,
@@ -362,7 +363,10 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
   const float* uright = ur_all + F.kp_begin;
   const uint8_t* desc = desc_all + 32 * (size_t)F.kp_begin;
   int32_t* kpm = kp_match + F.kp_begin;
-  for (int i = lane; i < N; i += 32) kpm[i] = -1;
+  for (int i = lane; i < N; i += 32) {
+    kpm[i] = -1;
+    S.oct[i] = (uint8_t)kps[i].octave;
+  }
   for (int i = lane; i < kMaxKp / 32; i += 32) {
     uint32_t m = 0;
     if (kp_blocked) {
@@ -386,22 +390,40 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
   int nmatches = 0;
   const float factor = 1.0f / HISTO_LENGTH;
   // The pass is sequential by definition (a claimed keypoint changes the next query's arg-min), so its cost is the latency
-  // of one iteration: the next query's candidate count and its two list entries per lane are loaded one iteration ahead
-  // (the list slots exist for every query, entries past the count are simply not used).
-  int n_next = nq > 0 ? fcnt[0] : 0;
-  uint32_t ea_next = nq > 0 ? flist[lane] : 0u, eb_next = nq > 0 ? flist[lane + 32] : 0u;
-  uint8_t fl_next = (nq > 0 && Q.flags) ? Q.flags[F.q_begin] : 0;
-  for (int qi = 0; qi < nq; ++qi) {
+  // of one iteration (~150 cycles of warp reductions and shared-memory reads) — as long as no iteration waits for HBM / L2
+  // (~700 cycles): the candidate counts and flags of 32 queries are loaded at once (lane l keeps query chunk + l, broadcast
+  // by shuffle), the two list entries per lane are loaded kAhead iterations ahead into a small register ring (the list
+  // slots exist for every query, entries past the count are simply not used).
+  constexpr int kAhead = 4;
+  uint32_t ea_r[kAhead], eb_r[kAhead];
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) {
+    const bool in = k < nq;
+    ea_r[k] = in ? flist[(size_t)k * kListCap + lane] : 0u;
+    eb_r[k] = in ? flist[(size_t)k * kListCap + lane + 32] : 0u;
+  }
+  int n_chunk = 0, fl_chunk = 0, my_take = -1, my_dist = 256;
+  // kAhead iterations per trip with the ring slot a COMPILE-TIME index: a slot is consumed and refilled in place, never
+  // moved, so no iteration touches a register whose load is still in flight (rotating the ring would wait for the newest
+  // load every iteration: the pass then ran at one L2 round trip per query)
+  for (int qb = 0; qb < nq; qb += kAhead) {
+#pragma unroll
+  for (int kk = 0; kk < kAhead; ++kk) {
+    const int qi = qb + kk;
+    if (qi >= nq) break;
     const int q = F.q_begin + qi;
-    const int n = n_next;
-    const uint32_t ea = ea_next, eb = eb_next;
-    const uint8_t qflag = fl_next;
-    if (qi + 1 < nq) {
-      n_next = fcnt[qi + 1];
-      const uint32_t* Ln = flist + (size_t)(qi + 1) * kListCap;
-      ea_next = Ln[lane];
-      eb_next = Ln[lane + 32];
-      fl_next = Q.flags ? Q.flags[q + 1] : 0;
+    if ((qi & 31) == 0) {  // fcnt[qi' >= qi] still holds the candidate counts: the pass overwrites entries behind it only
+      const int qq = qi + lane;
+      n_chunk = qq < nq ? fcnt[qq] : 0;
+      fl_chunk = (qq < nq && Q.flags) ? Q.flags[F.q_begin + qq] : 0;
+    }
+    const int n = __shfl_sync(0xffffffffu, n_chunk, qi & 31);
+    const uint8_t qflag = (uint8_t)__shfl_sync(0xffffffffu, fl_chunk, qi & 31);
+    const uint32_t ea = ea_r[kk], eb = eb_r[kk];
+    if (qi + kAhead < nq) {
+      const uint32_t* Ln = flist + (size_t)(qi + kAhead) * kListCap;
+      ea_r[kk] = Ln[lane];
+      eb_r[kk] = Ln[lane + 32];
     }
     uint32_t best = 0xffffffffu, second = 0xffffffffu;  // lane-local two smallest keys (dist << 16 | pos)
     int idx_a = -1, idx_b = -1;                          // keypoints of the lane's two entries
@@ -457,7 +479,7 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
             if (m2 != 0xffffffffu) {
               const int i2 = __reduce_max_sync(0xffffffffu, c2 == m2 ? (best == m1 ? idx_b : idx_a) : -1);
               const int bestDist2 = (int)(m2 >> 16);
-              if (kps[bestIdx].octave == kps[i2].octave && (float)bestDist > __fmul_rn(F.nn_ratio, (float)bestDist2)) ok = false;
+              if (S.oct[bestIdx] == S.oct[i2] && (float)bestDist > __fmul_rn(F.nn_ratio, (float)bestDist2)) ok = false;
             }
           }
           if (ok) {
@@ -467,24 +489,45 @@ __global__ void __launch_bounds__(32) k_sbp_claim(int mode, const VieoSbpFrame* 
         }
       }
     }
-    if (lane == 0) {
-      q_match[q] = take;
-      q_dist[q] = take_dist;
+    // No global store inside the pass: __syncwarp orders memory for the warp and would wait for the store's round trip to
+    // L2 every iteration (measured: ~1100 cycles per query with the stores, the pass was 0.56 / 1.42 ms for 700 / 2500
+    // queries).  Lane (qi & 31) keeps query qi's result; every 32 queries the lanes write theirs with coalesced stores.
+    if (lane == (qi & 31)) {
+      my_take = take;
+      my_dist = take_dist;
+    }
+    // RELOC: AddMapPoint makes the keypoint's slot non-null for every later query (:1541-1543, 1553)
+    if (lane == 0 && take >= 0 && ((qflag & 1) || mode == VIEO_SBP_RELOC)) S.blocked[take >> 5] |= 1u << (take & 31);
+    nmatches += take >= 0;
+    __syncwarp();
+    if ((qi & 31) == 31 || qi == nq - 1) {
+      const int qq = (qi & ~31) + lane;
+      if (qq <= qi) {
+        q_match[F.q_begin + qq] = my_take;
+        q_dist[F.q_begin + qq] = my_dist;
+        fcnt[qq] = my_take;  // reused: the keypoint an accepted query took (-1 none); the rotation bins follow after the pass
+        // AddMapPoint: the LAST query that took a keypoint owns it (an earlier taker with Observations() == 0 did not
+        // block it); queries are flushed out of order across lanes, the maximum is the last one
+        if (my_take >= 0) atomicMax(&kpm[my_take], qq);
+      }
+    }
+  }
+  }
+  __syncwarp();
+  // rotation bins of the accepted queries, lanes over queries (kept out of the sequential pass: the keypoint's angle is a
+  // dependent global load)
+  if (rot_check) {
+    for (int qi = lane; qi < nq; qi += 32) {
+      const int take = fcnt[qi];
       int bin = -1;
       if (take >= 0) {
-        kpm[take] = qi;
-        // RELOC: AddMapPoint makes the keypoint's slot non-null for every later query (:1541-1543, 1553)
-        if ((qflag & 1) || mode == VIEO_SBP_RELOC) S.blocked[take >> 5] |= 1u << (take & 31);
-        if (rot_check) {
-          float rot = __fsub_rn(Q.angle[q], kps[take].angle);
-          if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-          bin = (int)roundf(__fmul_rn(rot, factor));
-          if (bin == HISTO_LENGTH) bin = 0;
-        }
+        float rot = __fsub_rn(Q.angle[F.q_begin + qi], kps[take].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == HISTO_LENGTH) bin = 0;
       }
-      fcnt[qi] = bin;  // reused: rotation bin of an accepted query (-1 none)
+      fcnt[qi] = bin;
     }
-    nmatches += take >= 0;
     __syncwarp();
   }
   // ---- rotation consistency (:1445-1464) ---------------------------------------------------------------------------------
