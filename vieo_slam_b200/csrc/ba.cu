@@ -2899,8 +2899,18 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
     ylo.assign(pmap.size(), 1 << 30);
     yhi.assign(pmap.size(), 0);
     bool chain = Ky > 0;
-    for (const BaDense& d : den) {
-      if (d.type == 3) continue;
+    // The structure comes from the PROBLEM's inertial topology, not from this rank's edge list: a sharded handle keeps the
+    // inertial edges on rank 0 only, but after the all-reduce every rank eliminates the same chain with the same PR <-> V /
+    // Bias coupling ranges (a rank that derived them from its empty list solved a different system: states off by 1e-2)
+    struct Topo { int type, si, sj; };
+    std::vector<Topo> topo;
+    if (!pb->visual_only && pb->imu_i && pb->imu_j && pb->preint)
+      for (int m = 0; m < pb->n_imu; ++m) {
+        VIEO_ARG(pb->imu_i[m] >= 0 && pb->imu_i[m] < K && pb->imu_j[m] >= 0 && pb->imu_j[m] < K, "imu state index out of range");
+        if (pb->preint[m].dt != 0) topo.push_back({0, pb->imu_i[m], pb->imu_j[m]});
+        topo.push_back({1, pb->imu_i[m], pb->imu_j[m]});
+      }
+    for (const Topo& d : topo) {
       const int a = yblk[d.si], b = yblk[d.sj];
       if (a >= 0 && b >= 0 && std::abs(a - b) != 1) chain = false;
       if (d.type != 0) continue;

@@ -22,6 +22,7 @@ constexpr int kBorder = 16;      // EDGE_THRESHOLD - 3
 constexpr int kHalfPatch = 15;
 constexpr int kFastThreads = 256;
 constexpr int kQtThreads = 512;
+constexpr int kQtKnodeSmem = 12288;  // keys whose node index lives in shared memory (u16 each); more keys: the HBM scratch
 constexpr int kDescWarps = 4;
 constexpr int kPR = 21;           // raw patch radius: 18 (rotated pattern reach) + 3 (7-tap blur)
 constexpr int kPW = 2 * kPR + 1;  // 43
@@ -58,6 +59,7 @@ struct OrbParams {  // passed by value to kernels
   int* cell_cnt;               // [img][n_cells]
   uint32_t* keys;              // [img][key_begin[nlevels]]
   uint16_t* knode;             // same shape
+  int qt_knode_off;            // byte offset of the shared-memory node-index array in k_quadtree's dynamic region
   uint32_t* lvl_kp;            // [img][slot_begin[nlevels]] packed keypoints after the quadtree (list order)
   int* lvl_cnt;                // [img][nlevels]
 };
@@ -411,13 +413,16 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(OrbParams P) {
     S.ta = (int*)take(4 * MAXN);
     S.tb = (int*)take(4 * MAXN);
   }
+  // the node index of every key is rewritten in every split round: in shared memory when the level's keys fit (they do for
+  // every level of a 752 x 480 image), instead of a read-modify-write of HBM scratch per round (209 MB written per 256 images)
+  uint16_t* s_knode = reinterpret_cast<uint16_t*>(smem + P.qt_knode_off);
   __shared__ int s_total, s_total2, s_nk, s_cut;
   __shared__ int s_celloff[512];  // per-level cell count <= 512 (checked at create)
 
   const int ncell = P.cell_begin[level + 1] - P.cell_begin[level];
   const int* ccnt = P.cell_cnt + (size_t)img * P.n_cells + P.cell_begin[level];
   uint32_t* keys = P.keys + (size_t)img * P.key_begin[P.nlevels] + P.key_begin[level];
-  uint16_t* knode = P.knode + (size_t)img * P.key_begin[P.nlevels] + P.key_begin[level];
+  uint16_t* knode = P.knode + (size_t)img * P.key_begin[P.nlevels] + P.key_begin[level];  // re-pointed once nk is known
   uint32_t* out_kp = P.lvl_kp + (size_t)img * P.slot_begin[P.nlevels] + P.slot_begin[level];
   int* out_cnt = P.lvl_cnt + (size_t)img * P.nlevels + level;
 
@@ -431,6 +436,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(OrbParams P) {
     if (tid == 0) *out_cnt = 0;
     return;
   }
+  if (nk <= kQtKnodeSmem) knode = s_knode;
   {
     const uint32_t* cand = P.cand + ((size_t)img * P.n_cells + P.cell_begin[level]) * P.cell_cap;
     const int wid = tid >> 5, lane = tid & 31;
@@ -1378,6 +1384,8 @@ int vieo_orb_create(const VieoOrbConfig* cfg, int device, vieo_orb_t** out) {
   h->tm0_ptr = nullptr; h->tm0_stride = 0; h->tm0_pitch = 0; h->tm0_n = 0;
   h->fast_smem = (((size_t)2 * P.tile_pitch * P.tile_h + 15) & ~(size_t)15) + 16 + 4 * (kFastThreads / 32);
   h->qt_smem = (size_t)max_maxn * (2 * (4 + 4 + 2 * 4 + 1) + 16 + 16 + 5 * 4) + 16 * 32;
+  P.qt_knode_off = (int)((h->qt_smem + 15) & ~(size_t)15);
+  h->qt_smem = (size_t)P.qt_knode_off + 2 * (size_t)kQtKnodeSmem;
   if (h->qt_smem > 200 * 1024) {
     set_error("per-level feature quota %d needs %zu B of shared memory for the quadtree (limit 200 KiB)", max_maxn,
               h->qt_smem);

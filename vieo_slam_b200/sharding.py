@@ -1,6 +1,6 @@
 """Host-side sharding helpers.  Units that shard without any exchange (cameras, frames,
 PoseOptimization problems) are split by `shard_range`; LocalBA is landmark-partitioned: every rank keeps all keyframe
-states, a subset of the map points with ALL their edges, and only rank 0 keeps the inertial edges; the reduced camera
+states, a subset of the map points with ALL their edges, and only rank 0 evaluates the inertial edges; the reduced camera
 system is summed with one all-reduce per LM trial through the callback installed by `install_allreduce`."""
 import numpy as np
 
@@ -39,11 +39,22 @@ def shard_lba_problem(d, rank, world):
     for k in ("edge_state", "obs", "inv_sigma2", "edge_flags"):
         out[k] = d[k][sel]
     out["edge_point"] = remap[d["edge_point"][sel]].astype(np.int32)  # stays sorted: remap is monotone on `mine`
-    if rank != 0:  # inertial / bias-walk edges live on rank 0 only
-        for k in ("imu_i", "imu_j", "preint", "imu_dt_kf"):
-            out[k] = d[k][:0]
+    # The inertial / bias-walk edges are EVALUATED on rank 0 only (the library drops them on the other ranks of a sharded
+    # handle), but their arrays travel to every rank: the global BA derives the V / Bias chain it eliminates before the dense
+    # factorisation from this topology, and every rank must eliminate the same chain after the all-reduce.
     out["point_ids"] = mine
     out["edge_ids"] = np.nonzero(sel)[0]
+    return out
+
+
+def evaluated_edges(part, rank):
+    """The edges a rank actually evaluates: its visual edges, plus the inertial / bias-walk edges on rank 0 only — what the
+    library does with a sharded handle, for code (the CPU oracle in the tests) that has no notion of ranks."""
+    if rank == 0:
+        return part
+    out = dict(part)
+    for k in ("imu_i", "imu_j", "preint", "imu_dt_kf"):
+        out[k] = part[k][:0]
     return out
 
 
