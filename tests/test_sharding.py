@@ -95,3 +95,18 @@ def test_sharded_local_ba_matches_single_gpu():
                           "--master-addr", "127.0.0.1", "--master-port", "29631",
                           os.path.join(ROOT, "tools", "sharded_lba_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "SHARDED_LBA_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_sharded_global_ba_matches_single_gpu():
+    """2 ranks / 2 GPUs over NCCL: the landmark-sharded global BA (V / Bias chain eliminated on every rank after the
+    all-reduce) reproduces the single-GPU states to 1e-7 and chi2 to 1e-6."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29633",
+                          os.path.join(ROOT, "tools", "sharded_gba_check.py"), "60", "3000", "6"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "SHARDED_GBA_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
