@@ -313,6 +313,49 @@ int vieo_optimize_sim3_batch_dev(const VieoSim3Problem* pbs_dev, int n, const Vi
                                  const float* inv_sigma2_1_dev, const float* inv_sigma2_2_dev, VieoSim3Result* res_dev,
                                  uint8_t* keep_dev, double* chi2_12_dev, double* chi2_21_dev, uint8_t* scratch_dev, void* stream);
 
+/* ---- Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:2309-2688): the loop closer's pose-graph optimisation ----------
+ * Replaces the g2o graph of the routine (BlockSolver_7_3 + LinearSolverEigen + Levenberg, setUserLambdaInit(1e-16),
+ * optimize(20), :2316-2334, :2618-2620): VertexSim3Expmap per keyframe (types_seven_dof_expmap.h:22-66, estimate = vScw,
+ * _fix_scale = bFixScale, the loop keyframe fixed), EdgeSim3 per collected edge (error log(Sji Siw Sjw^-1), :101-129; its
+ * Jacobians are g2o's central differences with delta 1e-9, core/base_binary_edge.hpp:123-187), 7x7 information per edge
+ * (identity except the reduced pure-odometry edges, :2507-2541).  The caller keeps the edge-collection policy (loop
+ * connections, spanning tree, earlier loop edges, covisibility >= 100: :2396-2615; template
+ * VIEO_SLAM_B200::flatten::OptimizeEssentialGraph in vieo_flatten.hpp) and the write-back under mMutexMapUpdate.
+ * g2o::Sim3 (types/sim3.h:40-57): rotation in Eigen's coefficient order (x, y, z, w), translation, scale. */
+typedef struct VieoSim3 {
+  double q[4];
+  double t[3];
+  double s;
+} VieoSim3;
+typedef struct VieoPoseGraphStats {
+  double chi2_initial; /* activeChi2 before the first iteration */
+  double chi2_final;   /* after the last accepted step */
+  double lambda_final;
+  int32_t iterations;  /* LM iterations run (<= the argument: g2o stops after 3 iterations gaining < 0.1 %) */
+  int32_t trials;      /* damped solves in total */
+  int32_t n_free;      /* free vertices with at least one active edge */
+  int32_t ok;          /* 0: a factorisation met a non-positive pivot (the trial was rejected, like LDLT failing) */
+} VieoPoseGraphStats;
+/* Scw [n_vertices]: initial estimates; fixed [n_vertices] u8; edge_i / edge_j [n_edges]: vertex 0 / vertex 1 of the EdgeSim3;
+ * Sji [n_edges]: measurements; info: [n_edges][49] row-major or NULL (identity for every edge); lambda_init <= 0: g2o's
+ * 1e-5 * max diag(H).  Outputs: Scw_out [n_vertices] (vertices without an active edge and fixed ones are copied), Tcw_out
+ * [n_vertices][12] row-major 3x4 [R | t / s] (the "SE3 Pose Recovering" of :2624-2642; may be NULL), stats.
+ * The whole Levenberg-Marquardt loop is ONE cooperative kernel launch (device-wide barriers between the phases). */
+int vieo_essential_graph_optimize(int n_vertices, const VieoSim3* Scw, const uint8_t* fixed, int fix_scale, int n_edges,
+                                  const int32_t* edge_i, const int32_t* edge_j, const VieoSim3* Sji, const double* info,
+                                  int iterations, double lambda_init, VieoSim3* Scw_out, double* Tcw_out,
+                                  VieoPoseGraphStats* stats, int device);
+/* Test hook: builds the system at the initial estimate, applies ONE damped step with `lambda` and returns; H_out [n][n] /
+ * b_out [n] (n = 7 * stats->n_free, free vertices in ascending index; may be NULL) receive the undamped system. */
+int vieo_essential_graph_debug_step(int n_vertices, const VieoSim3* Scw, const uint8_t* fixed, int fix_scale, int n_edges,
+                                    const int32_t* edge_i, const int32_t* edge_j, const VieoSim3* Sji, const double* info,
+                                    double lambda, VieoSim3* Scw_out, VieoPoseGraphStats* stats, double* H_out,
+                                    double* b_out, int device);
+/* "Correct points" (:2645-2676): Pw_out[i] = (Scw_after[ref[i]]^-1).map(Scw_before[ref[i]].map(Pw[i])), positions are float
+ * (MapPoint::Tdata), arithmetic in double.  ref[i] = mnCorrectedReference or the reference keyframe's index (:2655-2664). */
+int vieo_essential_graph_correct_points(int n_points, const float* Pw, const int32_t* ref, int n_vertices,
+                                        const VieoSim3* Scw_before, const VieoSim3* Scw_after, float* Pw_out, int device);
+
 /* ---- local bundle adjustment: PR-V-Bias vertices per keyframe, marginalised map points --------------------
  * The flattened graph of Optimizer::LocalBundleAdjustmentNavStatePRV (src/Optimizer.cc:133-520).  Keyframes
  * ("states") come local-first in ascending id (the reference's vertex ids 3k, 3k+1, 3k+2), then the fixed ones.

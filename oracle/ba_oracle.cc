@@ -1010,6 +1010,9 @@ void jtoj(const double* Ja, int lda, int ca, int na, const double* Om, int D, do
 
 }  // namespace
 
+// the skyline Cholesky above, for the other oracle translation units (posegraph_oracle.cc)
+bool orc_chol_solve_skyline(std::vector<double>& A, int n, const double* b, double* x) { return chol_solve(A, n, b, x); }
+
 extern "C" {
 
 int orc_inverse(const double* A, int n, double* Ainv) { return inverse(A, n, Ainv) ? 0 : -1; }

@@ -179,6 +179,27 @@ int orc_optimize_sim3(const OrcSim3Problem* pb, const OrcCamera* cam, const doub
 void orc_edge_sim3(const OrcCamera* cam, const OrcNavState* ns, double scale, const double Xh[3], const float obs[2],
                    int inverse, double e[2], double* J_pose, double* J_scale);
 int orc_inverse(const double* A, int n, double* Ainv);
+
+/* ---- Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:2309-2688), posegraph_oracle.cc --------------------------------
+ * g2o::Sim3 (types/sim3.h): r as Eigen coefficient order (x, y, z, w), t, s. */
+typedef struct OrcSim3 {
+  double q[4];
+  double t[3];
+  double s;
+} OrcSim3;
+void orc_sim3_exp(const double u[7], OrcSim3* out);
+void orc_sim3_log(const OrcSim3* S, double out[7]);
+void orc_sim3_mul(const OrcSim3* a, const OrcSim3* b, OrcSim3* out);
+void orc_sim3_inv(const OrcSim3* a, OrcSim3* out);
+void orc_sim3_from_Rt(const double R[9], const double t[3], double s, OrcSim3* out);
+void orc_edge_sim3_graph(const OrcSim3* meas, const OrcSim3* v0, const OrcSim3* v1, int fix0, int fix1, int fix_scale, double e[7],
+                         double Ji[49], double Jj[49]);
+int orc_essential_graph(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix_scale, int E, const int32_t* ei, const int32_t* ej,
+                        const OrcSim3* meas, const double* info, int iterations, double lambda_init, int single_step, OrcSim3* out,
+                        double* stats, double* H_out, double* b_out);
+void orc_essential_graph_recover_se3(int K, const OrcSim3* S, double* Tcw);
+void orc_essential_graph_correct_points(int n, const float* Pw, const int32_t* ref, const OrcSim3* Scw_before, const OrcSim3* Scw_after,
+                                        float* out);
 #ifdef __cplusplus
 }
 #endif

@@ -707,3 +707,111 @@ def sbp_reloc(pb, frames=None):
                                 at("q_angle", qb), at("q_max_dist", qb), at("q_min_dist", qb), at("q_desc", qb), blk,
                                 at(kp_match, kb), at(q_match, qb), at(q_dist, qb), at(q_level, qb))
     return kp_match, q_match, q_dist, q_level, nm
+
+
+# ---- Optimizer::OptimizeEssentialGraph (oracle/posegraph_oracle.cc) ---------------------------------------------------------
+def _pg():
+    L = lib()
+    if not getattr(L, "_pg_ready", False):
+        for f, n in (("orc_sim3_exp", 2), ("orc_sim3_log", 2), ("orc_sim3_mul", 3), ("orc_sim3_inv", 2)):
+            getattr(L, f).argtypes = [C.c_void_p] * n
+            getattr(L, f).restype = None
+        L.orc_essential_graph_recover_se3.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_essential_graph_recover_se3.restype = None
+        L.orc_essential_graph_correct_points.argtypes = [C.c_int] + [C.c_void_p] * 5
+        L.orc_essential_graph_correct_points.restype = None
+        L._pg_ready = True
+    return L
+
+
+def _sim3(a):
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    return np.ascontiguousarray(a, SIM3_DTYPE)
+
+
+def sim3_exp(u):
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    out = np.zeros(1, SIM3_DTYPE); u = np.ascontiguousarray(u, np.float64)
+    _pg().orc_sim3_exp(_p(u), _p(out))
+    return out[0]
+
+
+def sim3_log(S):
+    S = _sim3(S).reshape(1); out = np.zeros(7)
+    _pg().orc_sim3_log(_p(S), _p(out))
+    return out
+
+
+def sim3_mul(a, b):
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    a = _sim3(a).reshape(1); b = _sim3(b).reshape(1); out = np.zeros(1, SIM3_DTYPE)
+    _pg().orc_sim3_mul(_p(a), _p(b), _p(out))
+    return out[0]
+
+
+def sim3_inv(a):
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    a = _sim3(a).reshape(1); out = np.zeros(1, SIM3_DTYPE)
+    _pg().orc_sim3_inv(_p(a), _p(out))
+    return out[0]
+
+
+def sim3_from_Rt(R, t, s=1.0):
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    R = np.ascontiguousarray(R, np.float64); t = np.ascontiguousarray(t, np.float64); out = np.zeros(1, SIM3_DTYPE)
+    L = lib()
+    L.orc_sim3_from_Rt.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.orc_sim3_from_Rt(_p(R), _p(t), float(s), _p(out))
+    return out[0]
+
+
+def edge_sim3_graph(meas, v0, v1, fix0=False, fix1=False, fix_scale=False, jac=True):
+    """EdgeSim3::computeError (+ the numeric Jacobians of BaseBinaryEdge::linearizeOplus) -> (e[7], Ji[7][7], Jj[7][7])"""
+    L = lib()
+    L.orc_edge_sim3_graph.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 3
+    L.orc_edge_sim3_graph.restype = None
+    meas = _sim3(meas).reshape(1); v0 = _sim3(v0).reshape(1); v1 = _sim3(v1).reshape(1)
+    e = np.zeros(7); Ji = np.zeros((7, 7)); Jj = np.zeros((7, 7))
+    L.orc_edge_sim3_graph(_p(meas), _p(v0), _p(v1), int(fix0), int(fix1), int(fix_scale), _p(e), _p(Ji) if jac else None,
+                          _p(Jj) if jac else None)
+    return e, Ji, Jj
+
+
+def essential_graph(pb, iterations=20, lambda_init=1e-16, single_step=False, want_system=False):
+    """orc_essential_graph on a synth.make_essential_graph problem -> (Scw_out SIM3_DTYPE[K], stats dict[, H, b])"""
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    L = lib()
+    L.orc_essential_graph.restype = C.c_int
+    L.orc_essential_graph.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    S = _sim3(pb["Scw"]); fixed = np.ascontiguousarray(pb["fixed"], np.uint8)
+    ei = np.ascontiguousarray(pb["ei"], np.int32); ej = np.ascontiguousarray(pb["ej"], np.int32); meas = _sim3(pb["meas"])
+    info = None if pb.get("info") is None else np.ascontiguousarray(pb["info"], np.float64)
+    out = np.zeros(len(S), SIM3_DTYPE); stats = np.zeros(5)
+    K = len(S)
+    nfree = 7 * K
+    H = np.zeros((nfree, nfree)) if want_system else None
+    b = np.zeros(nfree) if want_system else None
+    n = L.orc_essential_graph(K, _p(S), _p(fixed), int(pb["fix_scale"]), len(ei), _p(ei), _p(ej), _p(meas), None if info is None else _p(info),
+                              int(iterations), float(lambda_init), int(single_step), _p(out), _p(stats), None if H is None else _p(H),
+                              None if b is None else _p(b))
+    assert n >= 0, n
+    st = dict(chi2_initial=stats[0], chi2_final=stats[1], iterations=int(stats[2]), lambda_final=stats[3], trials=int(stats[4]), n=n)
+    if want_system:
+        Hn = H.reshape(-1)[:n * n].reshape(n, n).copy()
+        return out, st, Hn, b[:n].copy()
+    return out, st
+
+
+def essential_graph_recover_se3(S):
+    S = _sim3(S); T = np.zeros((len(S), 3, 4))
+    _pg().orc_essential_graph_recover_se3(len(S), _p(S), _p(T))
+    return T
+
+
+def essential_graph_correct_points(Pw, ref, S_before, S_after):
+    Pw = np.ascontiguousarray(Pw, np.float32); ref = np.ascontiguousarray(ref, np.int32)
+    out = np.zeros_like(Pw)
+    _pg().orc_essential_graph_correct_points(len(Pw), _p(Pw), _p(ref), _p(_sim3(S_before)),
+                                             _p(_sim3(S_after)), _p(out))
+    return out

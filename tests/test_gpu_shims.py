@@ -136,3 +136,16 @@ def test_cpp_shims_equal_ctypes_on_gpu(tmp_path):
     q12o = np.array([qo[0], -qo[1], -qo[2], -qo[3]]); Ro = rot(q12o)
     t12o = [-(Ro[3 * r_] * float(po[0]) + Ro[3 * r_ + 1] * float(po[1]) + Ro[3 * r_ + 2] * float(po[2])) for r_ in range(3)]
     assert got3[1:5].tobytes() == q12o.tobytes() and got3[5:8].tobytes() == np.array(t12o).tobytes() and got3[8] == r3["scale"][0]
+    # 6: the essential graph collected by the template, optimised and written back in C++, against the ctypes path on the same arrays
+    from vieo_slam_b200.layouts import SIM3_DTYPE, POSEGRAPH_STATS_DTYPE
+    pg = dict(Scw=r("pg_Scw.bin", SIM3_DTYPE), fixed=r("pg_fixed.u8", np.uint8), fix_scale=1, ei=r("pg_ei.i32", np.int32),
+              ej=r("pg_ej.i32", np.int32), meas=r("pg_meas.bin", SIM3_DTYPE), info=r("pg_info.f64", np.float64).reshape(-1, 49))
+    assert len(pg["Scw"]) == 24 and len(pg["ei"]) > 40
+    out6, T6, st6 = api.Optimizer.OptimizeEssentialGraph(pg)
+    assert r("pg_Scw.out", np.uint8).tobytes() == out6.tobytes()
+    assert r("pg_stats.out", np.uint8).tobytes() == st6.tobytes() and st6["chi2_final"] < st6["chi2_initial"]
+    Tc = r("pg_Tcw.out", np.float64).reshape(24, 3, 4)
+    keep = np.arange(24) != 9  # the bad keyframe's pose is not written
+    assert Tc[keep].tobytes() == T6[keep].tobytes()
+    P6 = api.Optimizer.essential_graph_correct_points(r("pg_Pw.f32", np.float32), r("pg_ref.i32", np.int32), pg["Scw"], out6)
+    assert r("pg_Pw.out", np.uint8).tobytes() == P6.tobytes()

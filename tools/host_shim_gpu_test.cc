@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <cmath>
 #include <map>
+#include <set>
 #include <string>
 
 #include "../vieo_slam_b200/host/vieo_flatten.hpp"
@@ -74,6 +76,136 @@ struct KeyFrame {
 };
 inline void ErasePairObs(KeyFrame* kf, MapPoint*) { ++kf->erased; }
 
+// ---- stand-ins for the essential-graph templates (member names of include/KeyFrame.h / MapPoint.h / Map.h) -----------------------
+struct PgKeyFrame {
+  unsigned long nid_ = 0;
+  bool bad = false;
+  char state = 2;  // Tracking::OK
+  PgKeyFrame* parent = nullptr;
+  PgKeyFrame* prev = nullptr;
+  std::set<PgKeyFrame*> children, loop_edges;
+  std::map<PgKeyFrame*, int> weights;
+  double Rcw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tcw[3] = {0, 0, 0};
+  double sig_phi = 0, sig_p = 0;  // odometry sigmas of this keyframe's pre-integration (0: none)
+  int pose_sets = 0;
+  bool isBad() const { return bad; }
+  char getState() const { return state; }
+  PgKeyFrame* GetParent() const { return parent; }
+  PgKeyFrame* GetPrevKeyFrame() const { return prev; }
+  int GetWeight(PgKeyFrame* o) const { auto it = weights.find(o); return it == weights.end() ? 0 : it->second; }
+  std::set<PgKeyFrame*> GetLoopEdges() const { return loop_edges; }
+  bool hasChild(PgKeyFrame* o) const { return children.count(o) != 0; }
+  std::vector<PgKeyFrame*> GetCovisiblesByWeight(int w) const {
+    std::vector<PgKeyFrame*> v;
+    for (auto& kv : weights) if (kv.second >= w) v.push_back(kv.first);
+    return v;
+  }
+};
+inline void vieo_get_Tcw(const PgKeyFrame& k, double R[9], double t[3]) { std::memcpy(R, k.Rcw, sizeof(k.Rcw)); std::memcpy(t, k.tcw, sizeof(k.tcw)); }
+inline void vieo_set_Tcw(PgKeyFrame& k, const double T[12]) {
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) k.Rcw[3 * r + c] = T[4 * r + c]; k.tcw[r] = T[4 * r + 3]; }
+  ++k.pose_sets;
+}
+inline bool vieo_odom_sigma(const PgKeyFrame& k, double& a, double& b) { a = k.sig_phi; b = k.sig_p; return k.sig_phi > 0; }
+struct PgMapPoint {
+  float X[3];
+  bool bad = false;
+  unsigned long mnCorrectedByKF = 0, mnCorrectedReference = 0;
+  PgKeyFrame* ref = nullptr;
+  int updated = 0;
+  bool isBad() const { return bad; }
+  PgKeyFrame* GetReferenceKeyFrame() const { return ref; }
+  void UpdateNormalAndDepth() { ++updated; }
+};
+inline void vieo_get_world_pos_f(const PgMapPoint& m, float o[3]) { o[0] = m.X[0]; o[1] = m.X[1]; o[2] = m.X[2]; }
+inline void vieo_set_world_pos_f(PgMapPoint& m, const float* i) { m.X[0] = i[0]; m.X[1] = i[1]; m.X[2] = i[2]; }
+struct PgMap {
+  std::vector<PgKeyFrame*> kfs;
+  std::vector<PgMapPoint*> mps;
+  std::vector<PgKeyFrame*> GetAllKeyFrames() const { return kfs; }
+  std::vector<PgMapPoint*> GetAllMapPoints() const { return mps; }
+  unsigned int GetMaxKFid() const { unsigned int m = 0; for (auto* k : kfs) m = std::max<unsigned int>(m, (unsigned int)k->nid_); return m; }
+};
+
+// A hand-made map for the essential-graph templates: 24 keyframes on a circle, drifting heading, keyframe 23 closes the loop on
+// keyframe 2.  Keyframe 9 is bad, keyframe 14 was tracked by odometry only (pure-odometry spanning-tree edge with reduced
+// information), (17, 5) is an earlier loop edge, covisibility >= 100 links i -> i - 2.
+struct PgWorld {
+  std::vector<PgKeyFrame> kf;
+  std::vector<PgMapPoint> mp;
+  PgMap map;
+  std::map<PgKeyFrame*, VieoSim3> NonCorrected, Corrected;
+  std::map<PgKeyFrame*, std::set<PgKeyFrame*>> LoopConnections;
+  PgWorld() : kf(24), mp(40) {
+    for (int i = 0; i < 24; ++i) {
+      PgKeyFrame& k = kf[i];
+      k.nid_ = i;
+      const double a = 0.26 * i + 0.004 * i * i * 0.1, c = std::cos(a), s_ = std::sin(a);  // Rwc = Rz(a) with drift; Rcw = Rz(-a)
+      const double Rcw[9] = {c, s_, 0, -s_, c, 0, 0, 0, 1};
+      const double pw[3] = {5 * std::cos(0.26 * i) + 0.01 * i, 5 * std::sin(0.26 * i), 0.02 * i};
+      std::memcpy(k.Rcw, Rcw, sizeof(Rcw));
+      for (int r = 0; r < 3; ++r) k.tcw[r] = -(Rcw[3 * r] * pw[0] + Rcw[3 * r + 1] * pw[1] + Rcw[3 * r + 2] * pw[2]);
+      if (i > 0) { k.parent = &kf[i - 1]; k.prev = &kf[i - 1]; kf[i - 1].children.insert(&k); k.weights[&kf[i - 1]] = 150; kf[i - 1].weights[&k] = 150; }
+      if (i > 1) { k.weights[&kf[i - 2]] = 120; kf[i - 2].weights[&k] = 120; }
+      if (i > 2) { k.weights[&kf[i - 3]] = 60; kf[i - 3].weights[&k] = 60; }
+      map.kfs.push_back(&k);
+    }
+    kf[9].bad = true;
+    kf[10].parent = &kf[8]; kf[9].children.erase(&kf[10]); kf[8].children.insert(&kf[10]);  // the spanning tree skips the bad keyframe
+    kf[14].state = 1; kf[14].weights[&kf[13]] = 20; kf[13].weights[&kf[14]] = 20; kf[14].sig_phi = 0.02; kf[14].sig_p = 0.05;
+    kf[17].loop_edges.insert(&kf[5]); kf[5].loop_edges.insert(&kf[17]);
+    // the loop: keyframes 21..23 get corrected Sim3s (a small rotation about z and a shift towards keyframe 2's neighbourhood)
+    for (int i = 21; i < 24; ++i) {
+      NonCorrected[&kf[i]] = vieo_sim3_from_Rt(kf[i].Rcw, kf[i].tcw, 1.0);
+      const double d = -0.05, c = std::cos(d), s_ = std::sin(d);
+      const double dR[9] = {c, -s_, 0, s_, c, 0, 0, 0, 1}, dt[3] = {0.08, -0.05, 0.01};
+      Corrected[&kf[i]] = vieo_sim3_mul(NonCorrected[&kf[i]], vieo_sim3_from_Rt(dR, dt, 1.0));
+      for (int j = 1; j <= 3; ++j) { LoopConnections[&kf[i]].insert(&kf[j]); kf[i].weights[&kf[j]] = (i == 23 && j == 2) ? 40 : (j == 3 ? 80 : 130); }
+    }
+    for (int m = 0; m < 40; ++m) {
+      mp[m].X[0] = 0.3f * m - 4.f; mp[m].X[1] = 0.11f * m; mp[m].X[2] = 1.f + 0.05f * m;
+      mp[m].ref = &kf[(m * 7) % 24 == 9 ? 10 : (m * 7) % 24];
+      if (m % 5 == 0) { mp[m].mnCorrectedByKF = 23; mp[m].mnCorrectedReference = 22; }
+      if (m == 13) mp[m].bad = true;
+      map.mps.push_back(&mp[m]);
+    }
+  }
+};
+
+static int essential_graph_templates_check() {
+  PgWorld W;
+  auto G = CollectEssentialGraph(&W.map, &W.kf[2], &W.kf[23], W.NonCorrected, W.Corrected, W.LoopConnections, (char)2);
+  if (G.vScw.size() != 24 || G.kf_of[9] != nullptr || !G.fixed[2] || G.fixed[3]) return 1;
+  std::set<std::pair<int, int>> e;
+  for (size_t k = 0; k < G.edge_i.size(); ++k) {
+    if (G.edge_i[k] == 9 || G.edge_j[k] == 9) return 2;  // nothing touches the bad keyframe
+    e.insert({G.edge_i[k], G.edge_j[k]});
+  }
+  // loop connections: weight >= 100 or the (cur, loop) pair itself (:2409)
+  if (!e.count({23, 2}) || !e.count({23, 1}) || e.count({23, 3}) || !e.count({21, 2}) || e.count({22, 3})) return 3;
+  // spanning tree incl. the re-parented keyframe, earlier loop edge, covisibility i -> i - 2 but not the weak i - 3 link,
+  // and no covisibility duplicate of a parent / child pair
+  if (!e.count({10, 8}) || !e.count({17, 5}) || !e.count({12, 10}) || e.count({12, 9}) || e.count({8, 5}) || !e.count({1, 0})) return 4;
+  size_t n_10_8 = 0;
+  for (size_t k = 0; k < G.edge_i.size(); ++k) n_10_8 += G.edge_i[k] == 10 && G.edge_j[k] == 8;
+  if (n_10_8 != 1) return 5;  // parent edge only: GetCovisiblesByWeight's (10, 8) is skipped (pKFn != pParentKF)
+  // the pure-odometry edge (14 -> 13) carries diag(a I3, b I3, 1) with a = b = 1 here (the only such edge defines fOdomBase)
+  if (!G.any_odom_info || G.info.size() != 49 * G.edge_i.size()) return 6;
+  for (size_t k = 0; k < G.edge_i.size(); ++k) {
+    const double* om = &G.info[49 * k];
+    const bool odom = G.edge_i[k] == 14 && G.edge_j[k] == 13;
+    if (odom && !(om[0] == 1.0 && om[24] == 1.0 && om[48] == 1.0)) return 7;
+    if (!odom) for (int q = 0; q < 49; ++q) if (om[q] != (q % 8 == 0 ? 1.0 : 0.0)) return 8;
+  }
+  // a measurement is Sjw * Swi of the non-corrected poses for normal edges: (1, 0) from the keyframes' own poses
+  for (size_t k = 0; k < G.edge_i.size(); ++k)
+    if (G.edge_i[k] == 1 && G.edge_j[k] == 0) {
+      const VieoSim3 want = vieo_sim3_mul(vieo_sim3_from_Rt(W.kf[0].Rcw, W.kf[0].tcw, 1.0), vieo_sim3_inv(vieo_sim3_from_Rt(W.kf[1].Rcw, W.kf[1].tcw, 1.0)));
+      if (std::memcmp(&want, &G.Sji[k], sizeof(want))) return 9;
+    }
+  return 0;
+}
+
 // FlattenLocalWindow / WriteBackLocalWindow on a tiny hand-made window: ordering and bookkeeping only (no device call)
 static int window_templates_check() {
   KeyFrame k[3];
@@ -116,6 +248,10 @@ int main(int argc, char** argv) {
   const std::string dir = argv[1];
   if (int rc = window_templates_check()) {
     std::fprintf(stderr, "window templates check failed: %d\n", rc);
+    return 5;
+  }
+  if (int rc = essential_graph_templates_check()) {
+    std::fprintf(stderr, "essential-graph templates check failed: %d\n", rc);
     return 5;
   }
   if (std::string(argv[1]) == "--templates-only") {
@@ -283,6 +419,38 @@ int main(int argc, char** argv) {
       const double o[9] = {(double)nIn, q12[0], q12[1], q12[2], q12[3], t12[0], t12[1], t12[2], s12};
       wr(dir, "s3.out", o, 9);
       wr(dir, "s3_keep.out", kept.data(), (size_t)M);
+    }
+    // 6. Optimizer::OptimizeEssentialGraph through the collection / write-back templates on the hand-made map: the flattened
+    //    graph and the results are written out; the test feeds the same arrays to the ctypes path and compares the bytes.
+    {
+      PgWorld W;
+      auto G = CollectEssentialGraph(&W.map, &W.kf[2], &W.kf[23], W.NonCorrected, W.Corrected, W.LoopConnections, (char)2);
+      wr(dir, "pg_Scw.bin", G.vScw.data(), G.vScw.size());
+      wr(dir, "pg_fixed.u8", G.fixed.data(), G.fixed.size());
+      wr(dir, "pg_ei.i32", G.edge_i.data(), G.edge_i.size());
+      wr(dir, "pg_ej.i32", G.edge_j.data(), G.edge_j.size());
+      wr(dir, "pg_meas.bin", G.Sji.data(), G.Sji.size());
+      wr(dir, "pg_info.f64", G.info.data(), G.info.size());
+      std::vector<float> Pw;
+      std::vector<int32_t> ref;
+      for (auto& m : W.mp) {
+        if (m.bad) continue;
+        Pw.insert(Pw.end(), m.X, m.X + 3);
+        ref.push_back(m.mnCorrectedByKF == 23 ? (int)m.mnCorrectedReference : (int)m.ref->nid_);
+      }
+      wr(dir, "pg_Pw.f32", Pw.data(), Pw.size());
+      wr(dir, "pg_ref.i32", ref.data(), ref.size());
+      VieoPoseGraphStats st{};
+      const int its = OptimizeAndWriteBackEssentialGraph(&W.map, G, &W.kf[23], true, st);
+      if (its < 1 || W.kf[9].pose_sets != 0 || W.kf[3].pose_sets != 1 || W.mp[13].updated != 0 || W.mp[12].updated != 1) return 7;
+      wr(dir, "pg_Scw.out", G.vScw.data(), G.vScw.size());
+      std::vector<double> T;
+      for (auto& k : W.kf) { for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T.push_back(k.Rcw[3 * r + c]); T.push_back(k.tcw[r]); } }
+      wr(dir, "pg_Tcw.out", T.data(), T.size());
+      std::vector<float> Po;
+      for (auto& m : W.mp) if (!m.bad) Po.insert(Po.end(), m.X, m.X + 3);
+      wr(dir, "pg_Pw.out", Po.data(), Po.size());
+      wr(dir, "pg_stats.out", &st, 1);
     }
     std::printf("HOST_SHIM_GPU_OK %s\n", vieo_version());
   } catch (const std::exception& e) {

@@ -689,6 +689,58 @@ class Optimizer:
         return res, keep, c12, c21
 
     @staticmethod
+    def OptimizeEssentialGraph(pb, iterations=20, lambda_init=1e-16, device=0, want_Tcw=True):
+        """The g2o part of Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:2309-2688) on a flattened graph (dict of
+        synth.make_essential_graph: Scw, fixed, fix_scale, ei, ej, meas, info) -> (Scw_out SIM3_DTYPE[K], Tcw [K][3][4] or None,
+        stats POSEGRAPH_STATS_DTYPE record).  One cooperative kernel launch runs the whole optimize(20)."""
+        from .layouts import SIM3_DTYPE, POSEGRAPH_STATS_DTYPE
+        S = np.ascontiguousarray(pb["Scw"], SIM3_DTYPE); fixed = np.ascontiguousarray(pb["fixed"], np.uint8)
+        ei = np.ascontiguousarray(pb["ei"], np.int32); ej = np.ascontiguousarray(pb["ej"], np.int32)
+        meas = np.ascontiguousarray(pb["meas"], SIM3_DTYPE)
+        info = None if pb.get("info") is None else np.ascontiguousarray(pb["info"], np.float64).reshape(len(ei), 49)
+        assert len(fixed) == len(S) and len(ej) == len(ei) and len(meas) == len(ei)
+        out = np.zeros(len(S), SIM3_DTYPE); T = np.zeros((len(S), 3, 4)) if want_Tcw else None
+        st = np.zeros(1, POSEGRAPH_STATS_DTYPE)
+        L = lib()
+        L.vieo_essential_graph_optimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _check(L.vieo_essential_graph_optimize(len(S), _p(S), _p(fixed), int(pb["fix_scale"]), len(ei), _p(ei), _p(ej), _p(meas),
+                                               None if info is None else _p(info), int(iterations), float(lambda_init), _p(out),
+                                               None if T is None else _p(T), _p(st), device))
+        return out, T, st[0]
+
+    @staticmethod
+    def essential_graph_debug_step(pb, lam, device=0):
+        """vieo_essential_graph_debug_step -> (Scw_out, stats, H [n][n], b [n]) with n = 7 * stats["n_free"]"""
+        from .layouts import SIM3_DTYPE, POSEGRAPH_STATS_DTYPE
+        S = np.ascontiguousarray(pb["Scw"], SIM3_DTYPE); fixed = np.ascontiguousarray(pb["fixed"], np.uint8)
+        ei = np.ascontiguousarray(pb["ei"], np.int32); ej = np.ascontiguousarray(pb["ej"], np.int32)
+        meas = np.ascontiguousarray(pb["meas"], SIM3_DTYPE)
+        info = None if pb.get("info") is None else np.ascontiguousarray(pb["info"], np.float64).reshape(len(ei), 49)
+        nmax = 7 * len(S)
+        out = np.zeros(len(S), SIM3_DTYPE); st = np.zeros(1, POSEGRAPH_STATS_DTYPE); H = np.zeros(nmax * nmax); b = np.zeros(nmax)
+        L = lib()
+        L.vieo_essential_graph_debug_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _check(L.vieo_essential_graph_debug_step(len(S), _p(S), _p(fixed), int(pb["fix_scale"]), len(ei), _p(ei), _p(ej), _p(meas),
+                                                 None if info is None else _p(info), float(lam), _p(out), _p(st), _p(H), _p(b), device))
+        n = 7 * int(st[0]["n_free"])
+        return out, st[0], H[:n * n].reshape(n, n).copy(), b[:n].copy()
+
+    @staticmethod
+    def essential_graph_correct_points(Pw, ref, Scw_before, Scw_after, device=0):
+        """The "Correct points" loop of Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:2645-2676) -> float32 [n][3]"""
+        from .layouts import SIM3_DTYPE
+        Pw = np.ascontiguousarray(Pw, np.float32).reshape(-1, 3); ref = np.ascontiguousarray(ref, np.int32)
+        a = np.ascontiguousarray(Scw_before, SIM3_DTYPE); b = np.ascontiguousarray(Scw_after, SIM3_DTYPE)
+        assert len(a) == len(b) and len(ref) == len(Pw)
+        out = np.zeros_like(Pw)
+        L = lib()
+        L.vieo_essential_graph_correct_points.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _check(L.vieo_essential_graph_correct_points(len(Pw), _p(Pw), _p(ref), len(a), _p(a), _p(b), _p(out), device))
+        return out
+
+    @staticmethod
     def pose_opt_batch_dev(pbs_ptr, n, cam_ptr, Xw_ptr, obs_ptr, w_ptr, flags_ptr, res_ptr, outlier_ptr, chi2_ptr, stream=0):
         _check(lib().vieo_pose_opt_batch_dev(pbs_ptr, n, cam_ptr, Xw_ptr, obs_ptr, w_ptr, flags_ptr, res_ptr, outlier_ptr,
                                              chi2_ptr, stream))

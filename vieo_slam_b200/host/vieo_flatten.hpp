@@ -12,6 +12,10 @@
 #include <cmath>
 #include <vector>
 
+#include <map>
+#include <set>
+
+#include "../csrc/sim3.cuh"  // g2o::Sim3 product / inverse as plain host functions (the header is host-compilable)
 #include "vieo_shims.hpp"
 
 namespace VIEO_SLAM_B200 {
@@ -232,6 +236,191 @@ int OptimizeSim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMa
     s12 = res.scale;
   }
   return nIn;
+}
+
+// ---- Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:2309-2688): collection and write-back -------------------------------
+// Vertices are indexed by nid_ (0 .. GetMaxKFid()), as the reference's vScw / vCorrectedSwc are; a bad keyframe keeps its
+// slot but gets no vertex (:2351) - here: no edge may name it, its slot is copied through.
+// Customisation points: void vieo_get_Tcw(const KeyFrameT&, double Rcw[9], double tcw[3]) (GetRotation / GetTranslation),
+// void vieo_set_Tcw(KeyFrameT&, const double Tcw[12]) (SetPose + UpdateNavStatePVRFromTcw, :2638-2641),
+// bool vieo_odom_sigma(const KeyFrameT& kf, double& sigma_phi, double& sigma_p): the two norms of :2454-2463 / :2525-2538
+// taken from kf's encoder / IMU pre-integrations (false: the keyframe has none), void vieo_get_world_pos_f(const MapPointT&,
+// float[3]) / vieo_set_world_pos_f(MapPointT&, const float[3]).  Sim3From: the caller's g2o::Sim3 -> VieoSim3 is
+// {r.coeffs(), t, s} member for member.
+inline VieoSim3 vieo_sim3_from_Rt(const double R[9], const double t[3], double s) {  // Sim3(Matrix3d, Vector3d, double), sim3.h:59
+  vieo::Sim3d o;
+  vieo::s3_R2q(R, o.q);
+  o.t[0] = t[0]; o.t[1] = t[1]; o.t[2] = t[2];
+  o.s = s;
+  VieoSim3 v;
+  std::memcpy(&v, &o, sizeof(v));
+  return v;
+}
+inline VieoSim3 vieo_sim3_mul(const VieoSim3& a, const VieoSim3& b) {
+  vieo::Sim3d x, y;
+  std::memcpy(&x, &a, sizeof(x));
+  std::memcpy(&y, &b, sizeof(y));
+  const vieo::Sim3d r = vieo::s3_mul(x, y);
+  VieoSim3 v;
+  std::memcpy(&v, &r, sizeof(v));
+  return v;
+}
+inline VieoSim3 vieo_sim3_inv(const VieoSim3& a) {
+  vieo::Sim3d x;
+  std::memcpy(&x, &a, sizeof(x));
+  const vieo::Sim3d r = vieo::s3_inv(x);
+  VieoSim3 v;
+  std::memcpy(&v, &r, sizeof(v));
+  return v;
+}
+
+template <class KeyFrameT>
+struct EssentialGraph {
+  std::vector<KeyFrameT*> kf_of;  // vertex index (nid_) -> keyframe (nullptr: bad / absent)
+  std::vector<VieoSim3> vScw;
+  std::vector<uint8_t> fixed;
+  std::vector<int32_t> edge_i, edge_j;
+  std::vector<VieoSim3> Sji;
+  std::vector<double> info;  // [E][49]; empty while every edge carries the identity
+  bool any_odom_info = false;
+  void add_edge(int i, int j, const VieoSim3& S, const double* om49) {
+    edge_i.push_back(i);
+    edge_j.push_back(j);
+    Sji.push_back(S);
+    for (int k = 0; k < 49; ++k) info.push_back(om49 ? om49[k] : (k % 8 == 0 ? 1.0 : 0.0));
+    if (om49) any_odom_info = true;
+  }
+};
+
+template <class MapT, class KeyFrameT, class Sim3Map, class ConnMap>
+EssentialGraph<KeyFrameT> CollectEssentialGraph(MapT* pMap, KeyFrameT* pLoopKF, KeyFrameT* pCurKF, const Sim3Map& NonCorrectedSim3,
+                                                const Sim3Map& CorrectedSim3, const ConnMap& LoopConnections, char tracking_ok_state) {
+  EssentialGraph<KeyFrameT> G;
+  const std::vector<KeyFrameT*> vpKFs = pMap->GetAllKeyFrames();
+  const unsigned int nMaxKFid = pMap->GetMaxKFid();
+  const int minFeat = 100;  // (:2345)
+  G.kf_of.assign(nMaxKFid + 1, nullptr);
+  G.fixed.assign(nMaxKFid + 1, 0);
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, z3[3] = {0, 0, 0};
+  G.vScw.assign(nMaxKFid + 1, vieo_sim3_from_Rt(I3, z3, 1.0));
+  for (KeyFrameT* pKF : vpKFs) {  // "Set KeyFrame vertices" (:2348-2385)
+    if (pKF->isBad()) continue;
+    const int nIDi = (int)pKF->nid_;
+    auto it = CorrectedSim3.find(pKF);
+    if (it != CorrectedSim3.end()) G.vScw[nIDi] = it->second;
+    else {
+      double Rcw[9], tcw[3];
+      vieo_get_Tcw(*pKF, Rcw, tcw);
+      G.vScw[nIDi] = vieo_sim3_from_Rt(Rcw, tcw, 1.0);
+    }
+    if (pKF == pLoopKF) G.fixed[nIDi] = 1;
+    G.kf_of[nIDi] = pKF;
+  }
+  std::set<std::pair<long unsigned int, long unsigned int>> sInsertedEdges;
+  for (const auto& mit : LoopConnections) {  // "Set Loop edges" (:2396-2430)
+    KeyFrameT* pKF = mit.first;
+    const long unsigned int nIDi = pKF->nid_;
+    const VieoSim3 Swi = vieo_sim3_inv(G.vScw[nIDi]);
+    for (KeyFrameT* pKFj : mit.second) {
+      const long unsigned int nIDj = pKFj->nid_;
+      if ((nIDi != pCurKF->nid_ || nIDj != pLoopKF->nid_) && pKF->GetWeight(pKFj) < minFeat) continue;
+      if (!G.kf_of[nIDi] || !G.kf_of[nIDj]) continue;  // g2o refuses an edge to a missing vertex
+      G.add_edge((int)nIDi, (int)nIDj, vieo_sim3_mul(G.vScw[nIDj], Swi), nullptr);
+      sInsertedEdges.insert(std::make_pair(std::min(nIDi, nIDj), std::max(nIDi, nIDj)));
+    }
+  }
+  auto pure_odom_pair = [&](KeyFrameT* pKF, KeyFrameT* pParentKF) {  // (:2449-2450, :2503-2504)
+    return (pKF->getState() != tracking_ok_state && pKF->GetPrevKeyFrame() == pParentKF) ||
+           (pParentKF->getState() != tracking_ok_state && pParentKF->GetPrevKeyFrame() == pKF);
+  };
+  float fOdomBase[2] = {1, 1};  // (:2444-2469): the smallest odometry sigmas over the pure-odometry spanning-tree edges
+  for (KeyFrameT* pKF : vpKFs) {
+    KeyFrameT* pParentKF = pKF->GetParent();
+    if (pParentKF && pKF->GetWeight(pParentKF) < minFeat && pure_odom_pair(pKF, pParentKF)) {
+      double sphi = 0, sp = 0;
+      if (vieo_odom_sigma(pKF->getState() != tracking_ok_state ? *pKF : *pParentKF, sphi, sp)) {
+        if (fOdomBase[0] > sphi) fOdomBase[0] = (float)sphi;
+        if (fOdomBase[1] > sp) fOdomBase[1] = (float)sp;
+      }
+    }
+  }
+  auto nc = [&](KeyFrameT* kf) -> VieoSim3 {  // the pose before this loop correction
+    auto it = NonCorrectedSim3.find(kf);
+    return it != NonCorrectedSim3.end() ? it->second : G.vScw[kf->nid_];
+  };
+  for (KeyFrameT* pKF : vpKFs) {  // "Set normal edges" (:2472-2616)
+    const int nIDi = (int)pKF->nid_;
+    if (!G.kf_of[nIDi]) continue;
+    const VieoSim3 Swi = vieo_sim3_inv(nc(pKF));
+    KeyFrameT* pParentKF = pKF->GetParent();
+    if (pParentKF && G.kf_of[pParentKF->nid_]) {  // spanning-tree edge (:2490-2549)
+      const VieoSim3 Sji = vieo_sim3_mul(nc(pParentKF), Swi);
+      double om[49];
+      const double* use = nullptr;
+      if (pKF->GetWeight(pParentKF) < minFeat && pure_odom_pair(pKF, pParentKF)) {
+        double sphi = 0, sp = 0;
+        if (vieo_odom_sigma(pKF->GetPrevKeyFrame() == pParentKF ? *pKF : *pParentKF, sphi, sp)) {
+          for (int k = 0; k < 49; ++k) om[k] = k % 8 == 0 ? 1.0 : 0.0;
+          const float EPS_MAX_INFO = 1e6f;
+          float elemInfo = fOdomBase[0] / (float)sphi;
+          if (!(!elemInfo || elemInfo > EPS_MAX_INFO)) om[0] = om[8] = om[16] = elemInfo;
+          elemInfo = fOdomBase[1] / (float)sp;
+          if (!(!elemInfo || elemInfo > EPS_MAX_INFO)) om[24] = om[32] = om[40] = elemInfo;
+          use = om;
+        }
+      }
+      G.add_edge(nIDi, (int)pParentKF->nid_, Sji, use);
+    }
+    const std::set<KeyFrameT*> sLoopEdges = pKF->GetLoopEdges();  // earlier loop edges (:2551-2577)
+    for (KeyFrameT* pLKF : sLoopEdges)
+      if (pLKF->nid_ < pKF->nid_ && G.kf_of[pLKF->nid_]) G.add_edge(nIDi, (int)pLKF->nid_, vieo_sim3_mul(nc(pLKF), Swi), nullptr);
+    const std::vector<KeyFrameT*> vpConnectedKFs = pKF->GetCovisiblesByWeight(minFeat);  // covisibility edges (:2579-2615)
+    for (KeyFrameT* pKFn : vpConnectedKFs) {
+      if (pKFn && pKFn != pParentKF && !pKF->hasChild(pKFn) && !sLoopEdges.count(pKFn)) {
+        if (!pKFn->isBad() && pKFn->nid_ < pKF->nid_) {
+          if (sInsertedEdges.count(std::make_pair(std::min(pKF->nid_, pKFn->nid_), std::max(pKF->nid_, pKFn->nid_)))) continue;
+          G.add_edge(nIDi, (int)pKFn->nid_, vieo_sim3_mul(nc(pKFn), Swi), nullptr);
+        }
+      }
+    }
+  }
+  if (!G.any_odom_info) G.info.clear();
+  return G;
+}
+
+// Optimise + write-back (:2618-2682): SetPose from [R | t / s], then every good map point through its reference keyframe's
+// pose before / after; the caller holds pMap->mMutexMapUpdate around this call and calls pMap->InformNewBigChange() after.
+template <class MapT, class KeyFrameT>
+int OptimizeAndWriteBackEssentialGraph(MapT* pMap, EssentialGraph<KeyFrameT>& G, KeyFrameT* pCurKF, bool bFixScale,
+                                       VieoPoseGraphStats& stats, int device = 0) {
+  std::vector<VieoSim3> Scw_out;
+  std::vector<double> Tcw;
+  const int its = Optimizer::OptimizeEssentialGraph(G.vScw, G.fixed, bFixScale, G.edge_i, G.edge_j, G.Sji, G.info, Scw_out, Tcw, stats, device);
+  for (size_t k = 0; k < G.kf_of.size(); ++k)
+    if (G.kf_of[k]) vieo_set_Tcw(*G.kf_of[k], &Tcw[12 * k]);
+  const auto vpMPs = pMap->GetAllMapPoints();
+  std::vector<float> Pw, Pw_out;
+  std::vector<int32_t> ref;
+  std::vector<size_t> which;
+  for (size_t i = 0; i < vpMPs.size(); ++i) {
+    auto* pMP = vpMPs[i];
+    if (pMP->isBad()) continue;
+    const int nIDr = pMP->mnCorrectedByKF == pCurKF->nid_ ? (int)pMP->mnCorrectedReference : (int)pMP->GetReferenceKeyFrame()->nid_;
+    float X[3];
+    vieo_get_world_pos_f(*pMP, X);
+    Pw.insert(Pw.end(), X, X + 3);
+    ref.push_back(nIDr);
+    which.push_back(i);
+  }
+  Pw_out.resize(Pw.size());
+  vieo_check(vieo_essential_graph_correct_points((int)ref.size(), Pw.data(), ref.data(), (int)G.vScw.size(), G.vScw.data(), Scw_out.data(),
+                                                 Pw_out.data(), device), "vieo_essential_graph_correct_points");
+  for (size_t e = 0; e < which.size(); ++e) {
+    vieo_set_world_pos_f(*vpMPs[which[e]], &Pw_out[3 * e]);
+    vpMPs[which[e]]->UpdateNormalAndDepth();
+  }
+  G.vScw = Scw_out;
+  return its;
 }
 
 }  // namespace VIEO_SLAM_B200

@@ -378,6 +378,22 @@ struct Optimizer {
                                    mvbOutlier.data(), chi2.data(), device), "vieo_pose_opt_batch");
     return res.n_inliers;
   }
+  // The g2o part of OptimizeEssentialGraph(pMap, pLoopKF, pCurKF, NonCorrectedSim3, CorrectedSim3, LoopConnections, bFixScale)
+  // (src/Optimizer.cc:2309-2688) on a collected graph (vieo_flatten.hpp: CollectEssentialGraph): setUserLambdaInit(1e-16),
+  // optimize(20).  Scw_out[k] / Tcw_out[12 k] per vertex; returns the number of LM iterations run.
+  static int OptimizeEssentialGraph(const std::vector<VieoSim3>& vScw, const std::vector<uint8_t>& fixed, bool bFixScale,
+                                    const std::vector<int32_t>& edge_i, const std::vector<int32_t>& edge_j,
+                                    const std::vector<VieoSim3>& Sji, const std::vector<double>& info /* empty: identity */,
+                                    std::vector<VieoSim3>& Scw_out, std::vector<double>& Tcw_out, VieoPoseGraphStats& stats,
+                                    int device = 0) {
+    const int K = (int)vScw.size(), E = (int)edge_i.size();
+    Scw_out.assign(K, VieoSim3{});
+    Tcw_out.assign(12 * (size_t)K, 0.0);
+    vieo_check(vieo_essential_graph_optimize(K, vScw.data(), fixed.data(), bFixScale ? 1 : 0, E, edge_i.data(), edge_j.data(), Sji.data(),
+                                             info.empty() ? nullptr : info.data(), 20, 1e-16, Scw_out.data(), Tcw_out.data(), &stats,
+                                             device), "vieo_essential_graph_optimize");
+    return stats.iterations;
+  }
   // OptimizeSim3(pKF1, pKF2, vpMatches1, g2oS12, th2, bFixScale) (src/Optimizer.cc:2689-2920) on flattened matches: pb.ns /
   // pb.scale carry g2oS12 in and res.ns / res.scale carry it out; keep[i] == 0 means vpMatches1[idx_of_match[i]] = nullptr
   static int OptimizeSim3(VieoSim3Problem& pb, const VieoCamera& cam, const std::vector<double>& Xc1,

@@ -84,3 +84,10 @@ BOW_PAIR_DTYPE = np.dtype([("kp1_begin", "i4"), ("n_kp1", "i4"), ("kp2_begin", "
                            ("idx1_begin", "i4"), ("idx2_begin", "i4"), ("out_begin", "i4"), ("check_orientation", "i4"),
                            ("nn_ratio", "f4"), ("pad_", "i4")])
 assert BOW_PAIR_DTYPE.itemsize == 64
+
+# VieoSim3 (g2o::Sim3, optimizer/g2o/g2o/types/sim3.h): r in Eigen coefficient order (x, y, z, w), t, s; OrcSim3 is identical
+SIM3_DTYPE = np.dtype([("q", "f8", 4), ("t", "f8", 3), ("s", "f8")])
+# VieoPoseGraphStats (Optimizer::OptimizeEssentialGraph)
+POSEGRAPH_STATS_DTYPE = np.dtype([("chi2_initial", "f8"), ("chi2_final", "f8"), ("lambda_final", "f8"), ("iterations", "i4"),
+                                  ("trials", "i4"), ("n_free", "i4"), ("ok", "i4")])
+assert SIM3_DTYPE.itemsize == 64 and POSEGRAPH_STATS_DTYPE.itemsize == 40

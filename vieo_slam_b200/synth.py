@@ -871,3 +871,123 @@ def make_sim3_problems(cam, n_candidates=4, n_matches=120, seed=0, fix_scale=Fal
         W1.append(inv_s2[oct1]); W2.append(inv_s2[oct2]); truth.append((R12, t12, s))
     return (pbs, np.concatenate(X1s), np.concatenate(X2s), np.concatenate(O1), np.concatenate(O2), np.concatenate(W1),
             np.concatenate(W2), truth)
+
+
+# ---- Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:2309-2688) ----------------------------------------------------------
+def _s3(R, t, s=1.0):
+    return (np.asarray(R, float), np.asarray(t, float), float(s))
+
+
+def _s3_mul(a, b):
+    return (a[0] @ b[0], a[2] * (a[0] @ b[1]) + a[1], a[2] * b[2])
+
+
+def _s3_inv(a):
+    return (a[0].T, -(a[0].T @ a[1]) / a[2], 1.0 / a[2])
+
+
+def _s3_rec(S):
+    from .layouts import SIM3_DTYPE
+    o = np.zeros((), SIM3_DTYPE)
+    q = quat_from_R(S[0])  # (w, x, y, z)
+    o["q"] = [q[1], q[2], q[3], q[0]]
+    o["t"] = S[1]
+    o["s"] = S[2]
+    return o
+
+
+def make_essential_graph(K=60, seed=0, fix_scale=True, n_neighbors=5, odom_info_every=0, n_points=0, extra_loops=2,
+                         drift_rot_deg=0.15, drift_trans=0.01, drift_scale=0.004):
+    """The graph Optimizer::OptimizeEssentialGraph hands to g2o, as LoopClosing::CorrectLoop produces it: K keyframes on a closed
+    circuit whose map poses carry accumulated odometry drift (rotation, translation and, when !fix_scale, scale); the last keyframe
+    re-observes keyframe `loop` (2) and it and its n_neighbors predecessors carry a corrected Sim3 (CorrectedSim3, propagated through the
+    non-corrected relative poses, src/LoopClosing.cc CorrectLoop).  Vertices start from vScw (corrected where available, :2357-2371), the
+    loop keyframe is fixed (:2373).  Edges (vertex 0 = i, vertex 1 = j, measurement Sji):
+      * new loop connections (:2396-2430): corrected-set keyframe i -> keyframes j around the loop keyframe, Sji = vScw[j] * vScw[i]^-1;
+      * spanning tree (:2490-2549): parent i-1 (every 7th keyframe: i-2), Sji from the NON-corrected poses; with odom_info_every = k every
+        k-th of them carries the reduced odometry information matrix diag(a I3, b I3, 1) of :2507-2541;
+      * earlier loop edges (:2551-2577) and covisibility >= 100 edges (:2579-2615), both with j < i, non-corrected.
+    n_points > 0 adds map points (float positions, reference keyframe index) for the correction step (:2645-2676).
+    -> dict(Scw, fixed, fix_scale, ei, ej, meas, info (None or [E][49]), truth (Scw of the drift-free circuit), Pw, ref)"""
+    from .layouts import SIM3_DTYPE
+    r = np.random.default_rng(seed + 9100)
+    # drift-free circuit: camera centres on a circle of radius 6 m with some height variation, looking along the tangent
+    ang = np.linspace(0, 2 * np.pi, K, endpoint=False) * (K - 1) / K * 0.98
+    Twc = []
+    for a in ang:
+        Rwc = so3_exp(np.array([0.0, 0.0, a])) @ so3_exp(np.array([0.03 * np.sin(3 * a), 0.02 * np.cos(2 * a), 0.0]))
+        pw = np.array([6 * np.cos(a), 6 * np.sin(a), 0.4 * np.sin(2 * a)])
+        Twc.append((Rwc, pw))
+    true_cw = [_s3(Rwc.T, -(Rwc.T @ pw)) for Rwc, pw in Twc]
+    # the map: relative motions integrated with drift
+    map_cw = [true_cw[0]]
+    sc = 1.0
+    for k in range(1, K):
+        rel = _s3_mul(true_cw[k], _s3_inv(true_cw[k - 1]))  # S_k,k-1
+        dR = so3_exp(r.normal(0, np.deg2rad(drift_rot_deg), 3))
+        if not fix_scale:
+            sc *= 1.0 + r.normal(0, drift_scale)
+        rel_d = _s3(dR @ rel[0], rel[1] * sc + r.normal(0, drift_trans, 3))
+        map_cw.append(_s3_mul(rel_d, map_cw[-1]))
+    loop, cur = 2, K - 1
+    # corrected Sim3 of the current keyframe: measured S_cur,loop (near the truth, with the scale the drift accumulated) * S_loop,w
+    rel_cl = _s3_mul(true_cw[cur], _s3_inv(true_cw[loop]))
+    s_cl = 1.0 if fix_scale else 1.0 / sc * (1.0 + r.normal(0, 0.002))
+    meas_cl = _s3(so3_exp(r.normal(0, np.deg2rad(0.05), 3)) @ rel_cl[0], rel_cl[1] + r.normal(0, 0.005, 3), s_cl)
+    corr_cur = _s3_mul(meas_cl, map_cw[loop])
+    corrected = {}
+    non_corrected = {}
+    for i in range(cur - n_neighbors, cur + 1):
+        Sic = _s3_mul(map_cw[i], _s3_inv(map_cw[cur]))
+        corrected[i] = _s3_mul(Sic, corr_cur)
+        non_corrected[i] = map_cw[i]
+    vScw = [corrected.get(k, map_cw[k]) for k in range(K)]
+    nc = lambda k: non_corrected.get(k, vScw[k])  # noqa: E731  (:2470-2476)
+    ei, ej, meas, info = [], [], [], []
+    I7 = np.eye(7)
+
+    def add(i, j, Sji, om=I7):
+        ei.append(i); ej.append(j); meas.append(_s3_rec(Sji)); info.append(om.reshape(-1))
+    inserted = set()
+    for i in sorted(corrected):  # new loop connections
+        for j in range(max(loop - 2, 0), loop + 3):
+            if r.random() < 0.75 or (i == cur and j == loop):
+                add(i, j, _s3_mul(vScw[j], _s3_inv(vScw[i])))
+                inserted.add((min(i, j), max(i, j)))
+    prev_loops = set()
+    for _ in range(extra_loops if K >= 24 else 0):
+        a = int(r.integers(K // 2, K - n_neighbors - 2)); b = int(r.integers(4, K // 3))
+        prev_loops.add((a, b))
+    for i in range(K):
+        Swi = _s3_inv(nc(i))
+        par = None
+        if i > 0:
+            par = i - 2 if (i % 7 == 0 and i >= 2) else i - 1
+            om = I7
+            if odom_info_every and i % odom_info_every == 0:
+                om = np.diag([*(3 * [float(r.uniform(0.05, 0.9))]), *(3 * [float(r.uniform(0.05, 0.9))]), 1.0])
+            add(i, par, _s3_mul(nc(par), Swi), om)
+        for (a, b) in sorted(prev_loops):
+            if a == i:
+                add(i, b, _s3_mul(nc(b), Swi))
+        for d in (2, 3, 4):
+            j = i - d
+            if j < 0 or j == par or (min(i, j), max(i, j)) in inserted or (i, j) in prev_loops:
+                continue
+            if r.random() < (0.8 if d == 2 else 0.4):
+                add(i, j, _s3_mul(nc(j), Swi))
+    fixed = np.zeros(K, np.uint8)
+    fixed[loop] = 1
+    out = dict(Scw=np.array([_s3_rec(S) for S in vScw], SIM3_DTYPE), fixed=fixed, fix_scale=int(fix_scale),
+               ei=np.array(ei, np.int32), ej=np.array(ej, np.int32), meas=np.array(meas, SIM3_DTYPE),
+               info=np.array(info) if odom_info_every else None, truth=np.array([_s3_rec(S) for S in true_cw], SIM3_DTYPE),
+               loop=loop, cur=cur)
+    if n_points:
+        ref = r.integers(0, K, n_points).astype(np.int32)
+        Pw = np.zeros((n_points, 3), np.float32)
+        for i in range(n_points):
+            S = _s3_inv(vScw[ref[i]])
+            Pc = np.array([r.uniform(-2, 2), r.uniform(-1.5, 1.5), r.uniform(1.5, 9.0)])
+            Pw[i] = S[2] * (S[0] @ Pc) + S[1]
+        out["Pw"], out["ref"] = Pw, ref
+    return out
