@@ -1391,7 +1391,7 @@ __global__ void __launch_bounds__(256) k_gchol_diag(BaBuf B, double* __restrict_
       for (int j = 0; j < kGSub; ++j) {
         const double d = A[c0 + j][c0 + j];
         if (lane == 0 && !(d > 0)) s_good = 0;
-        const double sq = sqrt(d), rs = 1.0 / sq;
+        const double rs = rsqrt(d), sq = d * rs;  // no division or square root on the dependent path
         __syncwarp();
         double l = 0;
         if (lane == j) {
@@ -1481,20 +1481,37 @@ __global__ void __launch_bounds__(128) k_gchol_trsm(BaBuf B, const uint8_t* __re
     rd[t] = t < nb ? 1.0 / B.S[(size_t)(k0 + t) * n + k0 + t] : 1.0;
   }
   __syncthreads();
+  // Blocked substitution over four 16-column blocks: the part of a block that depends on the finished columns to its left is a
+  // small matrix product spread over the whole CTA (8 outputs per thread); only the 16 x 16 triangular solve of the block is
+  // sequential per row (136 instead of 2016 dependent multiply-adds per row).  Padding rows / columns are zeros / identity.
+  for (int cb = 0; cb < kGNB; cb += kGSub) {
+    if (cb > 0) {
+      const int r = t & 63, cg = cb + (t >> 6) * 8;
+      double acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+      for (int m = 0; m < cb; ++m) {
+        const double a = As[r][m];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fma(-a, Ls[cg + q][m], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) As[r][cg + q] += acc[q];
+      __syncthreads();
+    }
+    if (t < kGNB) {
+#pragma unroll 4
+      for (int j = cb; j < cb + kGSub; ++j) {
+        double acc = As[t][j];
+        for (int m = cb; m < j; ++m) acc = fma(-As[t][m], Ls[j][m], acc);
+        As[t][j] = acc * rd[j];
+      }
+    }
+    __syncthreads();
+  }
   if (t < nr) {
     double dy = 0;
-    for (int j = 0; j < nb; ++j) {
-      double acc = As[t][j], acc2 = 0;
-      int m = 0;
-      for (; m + 1 < j; m += 2) {
-        acc = fma(-As[t][m], Ls[j][m], acc);
-        acc2 = fma(-As[t][m + 1], Ls[j][m + 1], acc2);
-      }
-      if (m < j) acc = fma(-As[t][m], Ls[j][m], acc);
-      acc = (acc + acc2) * rd[j];
-      As[t][j] = acc;
-      dy = fma(acc, sy[j], dy);
-    }
+    for (int j = 0; j < nb; ++j) dy = fma(As[t][j], sy[j], dy);
     yv[i0 + t] -= dy;
   }
   __syncthreads();
@@ -1629,14 +1646,18 @@ __global__ void __launch_bounds__(256) k_gchol_back(BaBuf B, const uint8_t* __re
 //   k_vb_back    y = Z(:, cn) - Z(:, 0:cn) xp, and the scatter of (xp, y) back into the interleaved order of B.x
 constexpr int kVB = 9;
 
+constexpr int kVbLS = 90;  // stride of a chain block in vbL: the 9 x 9 factor, then the reciprocals of its diagonal
+
 __global__ void __launch_bounds__(32) k_vb_factor(BaBuf B, int force) {
-  __shared__ double sL[kVB][kVB + 1], sF[kVB][kVB + 1], sD[kVB][kVB + 1];
+  __shared__ double sL[kVB][kVB + 1], sF[kVB][kVB + 1], sD[kVB][kVB + 1], sR[kVB];
   BaParams& prm = *B.prm;
   if ((prm.done && !force) || !prm.vb_elim) return;
   const int lane = threadIdx.x, np = prm.np, Ky = prm.Ky;
   bool good = true;
   // the chain is sequential by definition: what can be hidden is the latency of the 2 x 81 scattered loads of a block,
-  // fetched one step ahead into registers (entries e = lane, lane + 32, lane + 64 of D_m and of E_{m-1})
+  // fetched one step ahead into registers (entries e = lane, lane + 32, lane + 64 of D_m and of E_{m-1}); what can be
+  // shortened is the dependent arithmetic of a step: no fp64 division or square root on the path (rsqrt of the pivot gives
+  // both L_jj = d rs and 1 / L_jj = rs; the reciprocals are kept for the substitutions here and in k_vb_solve)
   double nd[3] = {0, 0, 0}, ne[3] = {0, 0, 0};
   auto fetch = [&](int m) {
     const int* ym = B.ymap + kVB * m;
@@ -1671,7 +1692,7 @@ __global__ void __launch_bounds__(32) k_vb_factor(BaBuf B, int force) {
           double v = sF[lane][j];
 #pragma unroll
           for (int k = 0; k < j; ++k) v -= f[k] * sL[j][k];
-          f[j] = v / sL[j][j];
+          f[j] = v * sR[j];
         }
 #pragma unroll
         for (int j = 0; j < kVB; ++j) sF[lane][j] = f[j];
@@ -1691,27 +1712,34 @@ __global__ void __launch_bounds__(32) k_vb_factor(BaBuf B, int force) {
       }
       __syncwarp();
     }
-    // L_m = chol(D): column by column, lanes over rows
-    for (int j = 0; j < kVB; ++j) {
-      double d = sD[j][j];
-      for (int k = 0; k < j; ++k) d -= sL[j][k] * sL[j][k];
-      if (!(d > 0) || !isfinite(d)) good = false;
-      const double dj = sqrt(d);
-      __syncwarp();
-      if (lane == j) sL[j][j] = dj;
-      if (lane > j && lane < kVB) {
-        double v = sD[lane][j];
-        for (int k = 0; k < j; ++k) v -= sL[lane][k] * sL[j][k];
-        sL[lane][j] = v / dj;
+    // L_m = chol(D), right-looking on a register-resident row per lane (lane i < 9 owns row i of D): per column one rsqrt and
+    // one broadcast of the finished column through shared memory
+    {
+      double row[kVB];
+#pragma unroll
+      for (int c = 0; c < kVB; ++c) row[c] = lane < kVB ? sD[lane][c] : 0.0;
+#pragma unroll
+      for (int j = 0; j < kVB; ++j) {
+        const double d = __shfl_sync(0xffffffffu, row[j], j);
+        if (!(d > 0) || !isfinite(d)) good = false;
+        const double rs = rsqrt(d);
+        const double lij = lane == j ? d * rs : (lane > j ? row[j] * rs : 0.0);
+        row[j] = lij;
+        if (lane < kVB) sL[lane][j] = lij;
+        if (lane == j) sR[j] = rs;
+        __syncwarp();
+#pragma unroll
+        for (int c = j + 1; c < kVB; ++c)
+          if (lane >= c && lane < kVB) row[c] -= lij * sL[c][j];
       }
-      if (lane < j) sL[lane][j] = 0.0;
-      __syncwarp();
     }
+    __syncwarp();
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       const int e = lane + 32 * q;
-      if (e < kVB * kVB) B.vbL[(size_t)m * 81 + e] = sL[e / kVB][e % kVB];
+      if (e < kVB * kVB) B.vbL[(size_t)m * kVbLS + e] = sL[e / kVB][e % kVB];
     }
+    if (lane < kVB) B.vbL[(size_t)m * kVbLS + 81 + lane] = sR[lane];
     __syncwarp();
   }
   if (lane == 0 && !good) prm.ok = 0;  // ok was set to 1 by k_vb_prepare before this kernel
@@ -1725,35 +1753,59 @@ __global__ void k_vb_prepare(BaBuf B, int force) {
   prm.ok = 1;
 }
 
-constexpr int kVbSolveThreads = 64, kVbChunk = 16;
+constexpr int kVbSolveThreads = 32, kVbChunk = 16;
+// Thread per right-hand side (column c of Syp, or by): the dependent chain of a step is what the kernel costs, so a step holds
+// no division (reciprocal diagonals from k_vb_factor), no dependent index load (the chunk's ymap rows are staged with its
+// factors) and no load of a structural zero: column c of Syp is non-zero only in the chain blocks [ylo[c], yhi[c]) (one or two
+// inertial edges touch a keyframe), so the forward sweep starts at ylo[c] with z = 0 and reads S only inside that range; the
+// backward sweep prefetches its Z rows one step ahead.  32-thread CTAs: 76 of them at 400 keyframes, one warp per SM.
 __global__ void __launch_bounds__(kVbSolveThreads) k_vb_solve(BaBuf B, int force) {
   __shared__ double sLF[kVbChunk][2][81];  // the chain factors of a chunk of blocks, staged once per CTA
+  __shared__ double sRc[kVbChunk][kVB];
+  __shared__ int sYm[kVbChunk][kVB];
   const BaParams& prm = *B.prm;
   if ((prm.done && !force) || !prm.vb_elim) return;
   const int cn = prm.cn, np = prm.np, Ky = prm.Ky, ld = cn + 1;
   const int c = blockIdx.x * kVbSolveThreads + threadIdx.x;
   const bool live = c <= cn, rhs = c == cn;
   const int pc = (live && !rhs) ? B.pmap[c] : 0;
+  const int lo = !live ? Ky : (rhs ? 0 : B.ylo[c]), hi = rhs ? Ky : (live ? B.yhi[c] : 0);
   double z[kVB];
 #pragma unroll
   for (int i = 0; i < kVB; ++i) z[i] = 0;
-  // forward: z_m = L_m^-1 (r_m - F_{m-1} z_{m-1})
-  for (int m0 = 0; m0 < Ky; m0 += kVbChunk) {
-    const int mc = min(kVbChunk, Ky - m0);
+  auto stage = [&](int m0, int mc, bool backward) {
     __syncthreads();
     for (int e = threadIdx.x; e < mc * 162; e += kVbSolveThreads) {
       const int mm = e / 162, w = (e % 162) / 81, k = e % 81;
       const int m = m0 + mm;
-      sLF[mm][w][k] = w == 0 ? B.vbL[(size_t)m * 81 + k] : (m > 0 ? B.vbF[(size_t)(m - 1) * 81 + k] : 0.0);
+      double v;
+      if (w == 0) v = B.vbL[(size_t)m * kVbLS + k];
+      else if (!backward) v = m > 0 ? B.vbF[(size_t)(m - 1) * 81 + k] : 0.0;
+      else v = m < Ky - 1 ? B.vbF[(size_t)m * 81 + k] : 0.0;
+      sLF[mm][w][k] = v;
+    }
+    for (int e = threadIdx.x; e < mc * kVB; e += kVbSolveThreads) {
+      sRc[e / kVB][e % kVB] = B.vbL[(size_t)(m0 + e / kVB) * kVbLS + 81 + e % kVB];
+      sYm[e / kVB][e % kVB] = B.ymap[kVB * (m0 + e / kVB) + e % kVB];
     }
     __syncthreads();
-    if (!live) continue;
+  };
+  // forward: z_m = L_m^-1 (r_m - F_{m-1} z_{m-1})
+  for (int m0 = 0; m0 < Ky; m0 += kVbChunk) {
+    const int mc = min(kVbChunk, Ky - m0);
+    if (__syncthreads_and(m0 + mc <= lo)) continue;  // the whole CTA is still before its first block
+    stage(m0, mc, false);
     for (int mm = 0; mm < mc; ++mm) {
       const int m = m0 + mm;
-      const int* ym = B.ymap + kVB * m;
+      if (m < lo) continue;
       double v[kVB];
+      if (m < hi) {
 #pragma unroll
-      for (int i = 0; i < kVB; ++i) v[i] = rhs ? B.bs[ym[i]] : __ldg(&B.S[(size_t)ym[i] * np + pc]);
+        for (int i = 0; i < kVB; ++i) v[i] = rhs ? B.bs[sYm[mm][i]] : __ldg(&B.S[(size_t)sYm[mm][i] * np + pc]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kVB; ++i) v[i] = 0.0;
+      }
       const double* F = sLF[mm][1];
 #pragma unroll
       for (int i = 0; i < kVB; ++i) {
@@ -1768,31 +1820,31 @@ __global__ void __launch_bounds__(kVbSolveThreads) k_vb_solve(BaBuf B, int force
         double a = v[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) a -= L[i * kVB + k] * z[k];
-        z[i] = a / L[i * kVB + i];
+        z[i] = a * sRc[mm][i];
       }
 #pragma unroll
       for (int i = 0; i < kVB; ++i) B.Z[(size_t)(kVB * m + i) * ld + c] = z[i];
     }
   }
-  // backward: w_m = L_m^-T (z_m - F_m^T w_{m+1})
-  double w[kVB];
+  // backward: w_m = L_m^-T (z_m - F_m^T w_{m+1}); blocks before lo hold z_m = 0 (never written by the forward sweep)
+  double w[kVB], nx[kVB];
 #pragma unroll
   for (int i = 0; i < kVB; ++i) w[i] = 0;
+  auto fetch_z = [&](int m) {
+#pragma unroll
+    for (int i = 0; i < kVB; ++i) nx[i] = (live && m >= lo) ? B.Z[(size_t)(kVB * m + i) * ld + c] : 0.0;
+  };
+  if (Ky > 0) fetch_z(Ky - 1);
   for (int m1 = Ky; m1 > 0; m1 -= kVbChunk) {
     const int m0 = max(0, m1 - kVbChunk), mc = m1 - m0;
-    __syncthreads();
-    for (int e = threadIdx.x; e < mc * 162; e += kVbSolveThreads) {
-      const int mm = e / 162, wh = (e % 162) / 81, k = e % 81;
-      const int m = m0 + mm;
-      sLF[mm][wh][k] = wh == 0 ? B.vbL[(size_t)m * 81 + k] : (m < Ky - 1 ? B.vbF[(size_t)m * 81 + k] : 0.0);
-    }
-    __syncthreads();
+    stage(m0, mc, true);
     if (!live) continue;
     for (int mm = mc - 1; mm >= 0; --mm) {
       const int m = m0 + mm;
       double v[kVB];
 #pragma unroll
-      for (int i = 0; i < kVB; ++i) v[i] = B.Z[(size_t)(kVB * m + i) * ld + c];
+      for (int i = 0; i < kVB; ++i) v[i] = nx[i];
+      if (m > 0) fetch_z(m - 1);
       const double* F = sLF[mm][1];
 #pragma unroll
       for (int i = 0; i < kVB; ++i) {
@@ -1807,7 +1859,7 @@ __global__ void __launch_bounds__(kVbSolveThreads) k_vb_solve(BaBuf B, int force
         double a = v[i];
 #pragma unroll
         for (int k = i + 1; k < kVB; ++k) a -= L[k * kVB + i] * w[k];
-        w[i] = a / L[i * kVB + i];
+        w[i] = a * sRc[mm][i];
       }
 #pragma unroll
       for (int i = 0; i < kVB; ++i) B.Z[(size_t)(kVB * m + i) * ld + c] = w[i];
@@ -2562,7 +2614,7 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
     {
       const size_t CN = 6 * K + 4, NY = 9 * K;
       step(dalloc(&B.cS, CN * CN)); step(dalloc(&B.cbs, CN)); step(dalloc(&B.cx, CN));
-      step(dalloc(&B.vbL, 81 * K)); step(dalloc(&B.vbF, 81 * K)); step(dalloc(&B.Z, NY * (CN + 1)));
+      step(dalloc(&B.vbL, kVbLS * K)); step(dalloc(&B.vbF, 81 * K)); step(dalloc(&B.Z, NY * (CN + 1)));
       step(dalloc(&h->d_pmap, CN)); step(dalloc(&h->d_ymap, NY)); step(dalloc(&h->d_ylo, CN)); step(dalloc(&h->d_yhi, CN));
     }
     step(dalloc(&B.part, 16));
