@@ -28,6 +28,11 @@ extern "C" {
 const char* vieo_last_error(void); /* thread-local text of the last failure */
 int vieo_device_count(void);
 const char* vieo_version(void);
+/* How host threads wait for the device in this process (cudaSetDeviceFlags on `device`): 0 the driver's heuristic (spins
+ * while there are more logical CPUs than contexts), 1 spin, 2 yield between polls, 3 block on an interrupt.  The reference
+ * runs Tracking / LocalMapping / LoopClosing threads beside the per-camera extractor threads: several processes of that
+ * shape on one host (one per GPU) oversubscribe the cores with spinning waiters, mode 2 keeps the launching threads running. */
+int vieo_set_host_sync(int device, int mode);
 
 /* ------------------------------------------------------------------------------------------------
  * ORB extractor — replaces ORBextractor (include/ORBextractor.h:27-80, src/ORBextractor.cc:391-1081).

@@ -643,6 +643,11 @@ from .layouts import (BA_RESULT_DTYPE, CAMERA_DTYPE, NAVSTATE_DTYPE, POSEOPT_PRO
                       POSEOPT_RESULT_DTYPE)
 
 
+def set_host_sync(mode, device=0):
+    """vieo_set_host_sync: 0 auto, 1 spin, 2 yield, 3 blocking (how host threads wait for the device)"""
+    _check(lib().vieo_set_host_sync(int(device), int(mode)))
+
+
 class Optimizer:
     """Static surface of the reference's Optimizer (include/Optimizer.h:46-121) over flattened problems."""
 

@@ -356,7 +356,7 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
                                const VieoImuPreint* __restrict__ pre, Vec3 gw, BaDenseWork* __restrict__ wk,
                                const int* __restrict__ off0, const int* __restrict__ off1, const int* __restrict__ off2,
                                int np, double* __restrict__ H, double* __restrict__ b, double* __restrict__ chi_dense,
-                               bool eval_only = false, const BaParams* gprm = nullptr) {
+                               bool eval_only = false, const BaParams* gprm = nullptr, int n_colors = 0) {
   const int T = blockDim.x;
   // the pre-integrations' fields the edges read (61 doubles each) staged in shared memory: the residual / Jacobian
   // code is one long dependent chain per thread, global-memory latency on every field would dominate it
@@ -444,10 +444,21 @@ __device__ void ba_dense_block(const BaDense* __restrict__ den, int n_den, const
   }
   __syncthreads();
   if (eval_only) return;  // global BA: accumulation by k_gba_dense_accum, one colour of edges per launch
-  // local windows: the block walks the edges in the oracle's order
-  for (int m = 0; m < n_den; ++m) {
-    ba_dense_add_edge(den[m], wk[m], off0, off1, off2, np, H, b, 0, T);
-    __syncthreads();
+  // local windows: edges of one colour share no keyframe (set_problem's greedy colouring, two colours for the inertial chain
+  // and two for its bias-walk edges), so a colour's edges are added back to back by the whole block without a barrier between
+  // them and only the colours are separated: 4 barriers instead of one per edge.  An entry shared by two edges now sums them in colour order, not
+  // edge order (a last-bit difference, inside the 1e-6 chi2 tolerance the local BA is held to).
+  if (n_colors > 0) {
+    for (int c = 0; c < n_colors; ++c) {
+      for (int m = 0; m < n_den; ++m)
+        if (den[m].color == c) ba_dense_add_edge(den[m], wk[m], off0, off1, off2, np, H, b, 0, T);  // no barrier inside a colour
+      __syncthreads();
+    }
+  } else {
+    for (int m = 0; m < n_den; ++m) {
+      ba_dense_add_edge(den[m], wk[m], off0, off1, off2, np, H, b, 0, T);
+      __syncthreads();
+    }
   }
   if (threadIdx.x == 0) {
     double tot = 0;
@@ -496,7 +507,7 @@ __global__ void __launch_bounds__(kBaWarps * 32, 2) k_ba_linearize_t(BaBuf B, in
   if (blockIdx.x == gridDim.x - 1) {
     if (!prm.big)
       ba_dense_block(B.den, prm.n_den, B.st, B.pre, prm.gw, B.wk, B.off0, B.off1, B.off2, prm.np, B.H[set], B.b[set],
-                     &B.prm->chi_dense);
+                     &B.prm->chi_dense, false, nullptr, prm.n_colors);
     return;
   }
   if ((int)blockIdx.x >= prm.n_pblk) return;
@@ -1386,26 +1397,31 @@ __global__ void __launch_bounds__(256) k_gchol_diag(BaBuf B, double* __restrict_
   __syncthreads();
   if (t < kGNB) sy[t] = t < nb ? yv[k0 + t] : 0.0;
   for (int c0 = 0; c0 < kGNB; c0 += kGSub) {
-    // (1) the 16 x 16 diagonal sub-block, by warp 0 (lane = row)
+    // (1) the 16 x 16 diagonal sub-block, by warp 0: lane i < 16 keeps row i in registers, a finished column travels by
+    // shuffle; one rsqrt per pivot (L_jj = d rs, 1 / L_jj = rs), no shared-memory round trip inside the 16 dependent steps
     if (warp == 0) {
+      double row[kGSub];
+#pragma unroll
+      for (int c = 0; c < kGSub; ++c) row[c] = lane < kGSub ? A[c0 + lane][c0 + c] : 0.0;
+#pragma unroll
       for (int j = 0; j < kGSub; ++j) {
-        const double d = A[c0 + j][c0 + j];
+        const double d = __shfl_sync(0xffffffffu, row[j], j);
         if (lane == 0 && !(d > 0)) s_good = 0;
-        const double rs = rsqrt(d), sq = d * rs;  // no division or square root on the dependent path
-        __syncwarp();
-        double l = 0;
-        if (lane == j) {
-          A[c0 + j][c0 + j] = sq;
-          rd[c0 + j] = rs;
+        const double rs = rsqrt(d);
+        const double lij = lane == j ? d * rs : (lane > j ? row[j] * rs : 0.0);
+        row[j] = lij;
+        if (lane == j) rd[c0 + j] = rs;
+#pragma unroll
+        for (int c = 1; c < kGSub; ++c) {  // constant bounds: both loops unroll and row[] stays in registers
+          if (c <= j) continue;
+          const double lc = __shfl_sync(0xffffffffu, lij, c);
+          if (lane >= c) row[c] = fma(-lij, lc, row[c]);
         }
-        if (lane > j && lane < kGSub) {
-          l = A[c0 + lane][c0 + j] * rs;
-          A[c0 + lane][c0 + j] = l;
-        }
-        __syncwarp();
-        if (lane > j && lane < kGSub)
-          for (int k = j + 1; k <= lane; ++k) A[c0 + lane][c0 + k] = fma(-l, A[c0 + k][c0 + j], A[c0 + lane][c0 + k]);
-        __syncwarp();
+      }
+      if (lane < kGSub) {
+#pragma unroll
+        for (int c = 0; c < kGSub; ++c)
+          if (c <= lane) A[c0 + lane][c0 + c] = row[c];
       }
     }
     __syncthreads();

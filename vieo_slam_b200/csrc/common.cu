@@ -250,4 +250,13 @@ int vieo_device_count(void) {
   return n;
 }
 const char* vieo_version(void) { return "vieo_b200 0.1.0 (sm_100a)"; }
+
+int vieo_set_host_sync(int device, int mode) {
+  VIEO_ARG(mode >= 0 && mode <= 3, "mode must be 0 (auto), 1 (spin), 2 (yield) or 3 (blocking)");
+  int rc = vieo::use_device(device);
+  if (rc) return rc;
+  const unsigned flags[4] = {cudaDeviceScheduleAuto, cudaDeviceScheduleSpin, cudaDeviceScheduleYield, cudaDeviceScheduleBlockingSync};
+  VIEO_CK(cudaSetDeviceFlags(flags[mode]));
+  return VIEO_OK;
+}
 }
