@@ -629,6 +629,24 @@ def run_gpu(args, rank, world, local_rank):
             f.result()
 
     e2e_run(0, max(8, args.warmup))  # every pool thread has run every stage once (thread-local staging is allocated on first use)
+    # ... which a fixed count does not guarantee: the pools hand a stage to whichever thread is free, and a thread that meets a
+    # larger stage for the first time grows its pinned staging (cudaHostAlloc, slow and device-synchronising; slower still when
+    # 8 ranks do it at once).  Untimed chunks of K steps are repeated until two consecutive ones agree within 10 % (at most 6).
+    prev_chunk = None
+    for _ in range(6):
+        lba_drain()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_run(0, args.steps)
+        lba_drain()
+        torch.cuda.synchronize()
+        chunk = time.perf_counter() - t0
+        flag = torch.tensor([1.0 if (prev_chunk is not None and abs(chunk - prev_chunk) <= 0.1 * prev_chunk) else 0.0], device=dev)
+        if dist_on:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # every rank leaves the warm-up in the same round
+        prev_chunk = chunk
+        if float(flag.item()) > 0:
+            break
     # The host-side figure is wall clock over K steps of ~10 ms: one scheduling hiccup of the shared host moves it by tens
     # of percent, so the K steps are timed three times back to back (max over ranks each) and the MEDIAN is reported; all
     # three are in the line.  The collector is paused inside the timed regions.

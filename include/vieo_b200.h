@@ -686,6 +686,42 @@ int vieo_frustum_batch_dev(const VieoFrustumFrame* frames_dev, int n_frames, con
 int vieo_frustum_batch(const VieoFrustumFrame* frames, int n_frames, const float* wP, const float* normal,
                        const float* max_dist, const float* min_dist, const uint8_t* skip, uint8_t* inview, float* proj,
                        int32_t* level, float* viewcos, float* depth, int32_t* n_inview, int device);
+/* ---- Frame::isInFrustum with a camera rig (mpCameras.size() > 1, KB8 / multi-camera configs; src/Frame.cc:351-411) ----
+ * Per camera cami: Pc = mpCameras[cami]->GetTcr() * Pcr (Sophus::SE3f: the float quaternion rotation of
+ * common/so3_extra.h:102-104 + translation), twc = mOw + Rcrw^T GetTrc().translation(), the pixel by K * p_normalize in float
+ * (usedistort_ == false: model 0) or by the camera's own Project evaluated in double and rounded to float (usedistort_: model 1
+ * PinholeCamera, 2 KB8Camera, common/camera_models/camera_{pinhole,kb8}.h), per-camera bounds gridinfo_.minmax_xy_[cami];
+ * distance / viewing-angle / PredictScale tests as in the single-camera form.  Every float operation in the reference's
+ * order; the KB8 angle uses the device's fp64 atan2 (<= 2 ulp from the host's): the float pixel can differ in its last bit
+ * when the double lands within 1e-16 relative of a float rounding boundary (about once in 1e8 projections). */
+typedef struct VieoFrustumCam {
+  float q_cr[4];                /* GetTcr().unit_quaternion() coefficients (x, y, z, w) */
+  float t_cr[3];                /* GetTcr().translation() */
+  float t_rc[3];                /* GetTrc().translation() */
+  float fx, fy, cx, cy;
+  float k[4];                   /* KB8 k1..k4 (model 2) */
+  float minx, maxx, miny, maxy; /* gridinfo_.minmax_xy_[cami] */
+  int32_t model;                /* 0, 1 or 2 (see above) */
+  int32_t pad_;
+} VieoFrustumCam;
+typedef struct VieoFrustumRigFrame {
+  int32_t q_begin, n_q;         /* this frame's candidate map points in the point arrays */
+  float Rcw[9], tcw[3], Ow[3];  /* Tcw_ rotation (row-major), mtcw, mOw cast to float (the rig's reference frame) */
+  float bf, cos_limit, log_scale_factor;
+  int32_t n_levels, n_cams;     /* n_cams <= 4 */
+  float level_ratio[16];        /* vieo_frustum_level_table: filled by the host-buffer call, by the caller for _dev */
+  VieoFrustumCam cam[4];
+} VieoFrustumRigFrame;
+/* Outputs per point: inview = btrack_inview_; cam_mask bit c set = camera c pushed an entry into vtrack_* (the shim appends the
+ * set slots in camera order: vtrack_cami_); per camera slot proj [n][4][3] = (u, v, ur), level [n][4] (-1 when not set),
+ * viewcos [n][4]; depth [n] = track_depth_ (mean dist3D over the set cameras); n_inview [n_frames]. */
+int vieo_frustum_rig_batch_dev(const VieoFrustumRigFrame* frames_dev, int n_frames, const float* wP_dev, const float* normal_dev,
+                               const float* max_dist_dev, const float* min_dist_dev, const uint8_t* skip_dev, uint8_t* inview_dev,
+                               uint8_t* cam_mask_dev, float* proj_dev, int32_t* level_dev, float* viewcos_dev, float* depth_dev,
+                               int32_t* n_inview_dev, void* stream);
+int vieo_frustum_rig_batch(const VieoFrustumRigFrame* frames, int n_frames, const float* wP, const float* normal,
+                           const float* max_dist, const float* min_dist, const uint8_t* skip, uint8_t* inview, uint8_t* cam_mask,
+                           float* proj, int32_t* level, float* viewcos, float* depth, int32_t* n_inview, int device);
 /* Visibility test + local-map guided search on one stream; frames[f] and frustum[f] share q_begin / n_q, the search
  * reads the tracking info the first kernel left in HBM.  Outputs of both halves as documented above / at
  * vieo_sbp_batch; proj / level / viewcos / depth may ALL be null (Tracking::SearchLocalPoints only needs inview and the

@@ -142,6 +142,33 @@ typedef struct OrcProjSearchFrame {
 void orc_sbp_base(const OrcProjSearchFrame* f, const OrcKeyPoint* kps, const float* uright, const uint8_t* desc,
                   const float* wP, const float* Pn, const float* max_dist, const float* min_dist, const uint8_t* q_desc,
                   const uint8_t* q_skip, int32_t* best_idx, int32_t* best_dist, int32_t* level);
+/* Frame::isInFrustum with a camera rig (mpCameras.size() > 1, src/Frame.cc:335-416): per camera Pc = GetTcr() * Pcr
+ * (Sophus::SE3f: Eigen's float _transformVector + translation), twc = mOw + Rcrw^T GetTrc().translation(), projection by
+ * K (usedistort_ == false, model 0) or by the camera's own Project in double (usedistort_: 1 pinhole, 2 KB8,
+ * common/camera_models/camera_{pinhole,kb8}.h), per-camera image bounds. */
+typedef struct OrcFrustumCam {
+  float q_cr[4];                /* GetTcr().unit_quaternion() (x, y, z, w) */
+  float t_cr[3];                /* GetTcr().translation() */
+  float t_rc[3];                /* GetTrc().translation() */
+  float fx, fy, cx, cy;         /* parameters_[0..3] */
+  float k[4];                   /* KB8 k1..k4 */
+  float minx, maxx, miny, maxy; /* gridinfo_.minmax_xy_[cami] */
+  int32_t model;                /* 0: K * p_normalize in float; 1: PinholeCamera::Project; 2: KB8Camera::Project */
+  int32_t pad_;
+} OrcFrustumCam;
+typedef struct OrcFrustumRigFrame {
+  int32_t q_begin, n_q;
+  float Rcw[9], tcw[3], Ow[3];
+  float bf, cos_limit, log_scale_factor;
+  int32_t n_levels, n_cams;     /* n_cams <= 4 */
+  float level_ratio[16];        /* device only */
+  OrcFrustumCam cam[4];
+} OrcFrustumRigFrame;
+/* Outputs per point: inview = btrack_inview_, cam_mask bit c = camera c pushed an entry (vtrack_cami_), per camera slot
+ * proj [n][4][3] = (u, v, ur), level [n][4] (-1), viewcos [n][4]; depth [n] = track_depth_ (mean over the cameras in view). */
+int orc_is_in_frustum_rig(const OrcFrustumRigFrame* f, int n, const float* wP, const float* Pn, const float* max_dist,
+                          const float* min_dist, uint8_t* inview, uint8_t* cam_mask, float* proj, int32_t* level, float* viewcos,
+                          float* depth);
 int orc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);
 int orc_is_in_frustum(const OrcFrustumFrame* f, int n, const float* wP, const float* Pn, const float* max_dist,
                       const float* min_dist, uint8_t* inview, float* proj, int32_t* level, float* viewcos, float* depth);

@@ -305,6 +305,112 @@ extern "C" int orc_is_in_frustum(const OrcFrustumFrame* f, int n, const float* w
   return n_in;
 }
 
+// Frame::isInFrustum for a camera rig (src/Frame.cc:351-411 with mpCameras.size() > 1): the single-camera restatement above
+// with the per-camera steps the reference adds.  Sophus::SE3f * Vector3f = unit_quaternion()._transformVector(p) +
+// translation() (common/so3_extra.h:102-104; Eigen: uv = q.vec x p; uv += uv; p + w uv + q.vec x uv), all float.  With
+// usedistort_ the pixel comes from the camera's Project in double, rounded to float (camera_pinhole.h:70-83,
+// camera_kb8.h:68-106: atan2, the k4..k1 Horner chain as written, then the base class' projection of (mx, my, 1)).
+namespace {
+inline void cross3f(const float a[3], const float b[3], float o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline void project_double(const OrcFrustumCam& c, const float Pc[3], float& u, float& v) {
+  const double x = (double)Pc[0], y = (double)Pc[1];
+  if (c.model == 2) {
+    const double x2 = x * x, y2 = y * y, r2 = x2 + y2, r = std::sqrt(r2);
+    const float precision_r = 1e-5f;
+    if (r > precision_r) {
+      const double z = (double)Pc[2];
+      const double theta = std::atan2(r, z), theta2 = theta * theta;
+      double thetad = c.k[3] * theta2;
+      thetad += c.k[2];
+      thetad *= theta2;
+      thetad += c.k[1];
+      thetad *= theta2;
+      thetad += c.k[0];
+      thetad *= theta2;
+      thetad += 1;
+      thetad *= theta;
+      const double mx = x * thetad / r, my = y * thetad / r;
+      const double invz = 1. / 1.;
+      u = (float)((double)c.fx * mx * invz + c.cx);
+      v = (float)((double)c.fy * my * invz + c.cy);
+      return;
+    }
+  }
+  const double z = (double)Pc[2], invz = 1. / z;
+  u = (float)((double)c.fx * x * invz + c.cx);
+  v = (float)((double)c.fy * y * invz + c.cy);
+}
+}  // namespace
+extern "C" int orc_is_in_frustum_rig(const OrcFrustumRigFrame* f, int n, const float* wP, const float* Pn, const float* max_dist,
+                                     const float* min_dist, uint8_t* inview, uint8_t* cam_mask, float* proj, int32_t* level,
+                                     float* viewcos, float* depth) {
+  int n_in = 0;
+  for (int i = 0; i < n; ++i) {
+    inview[i] = 0;
+    cam_mask[i] = 0;
+    depth[i] = 0;
+    for (int c = 0; c < 4; ++c) {
+      level[4 * i + c] = -1;
+      viewcos[4 * i + c] = 0;
+      proj[12 * i + 3 * c] = proj[12 * i + 3 * c + 1] = proj[12 * i + 3 * c + 2] = 0;
+    }
+    const float* P = wP + 3 * i;
+    const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
+    float Pcr[3];
+    for (int r = 0; r < 3; ++r)
+      Pcr[r] = sum3(f->Rcw[3 * r] * P[0], f->Rcw[3 * r + 1] * P[1], f->Rcw[3 * r + 2] * P[2]) + f->tcw[r];
+    float sum_depth = 0;
+    int count = 0;
+    for (int ci = 0; ci < f->n_cams; ++ci) {
+      const OrcFrustumCam& c = f->cam[ci];
+      float uv[3], cr[3], Pc[3];
+      cross3f(c.q_cr, Pcr, uv);
+      for (int k = 0; k < 3; ++k) uv[k] += uv[k];
+      cross3f(c.q_cr, uv, cr);
+      for (int k = 0; k < 3; ++k) Pc[k] = ((Pcr[k] + c.q_cr[3] * uv[k]) + cr[k]) + c.t_cr[k];
+      float twc[3];
+      for (int k = 0; k < 3; ++k)  // Rcrw^T t: column k of Rcrw dotted with t
+        twc[k] = f->Ow[k] + sum3(f->Rcw[k] * c.t_rc[0], f->Rcw[3 + k] * c.t_rc[1], f->Rcw[6 + k] * c.t_rc[2]);
+      const float PcZ = Pc[2];
+      if (PcZ < 0.0f) continue;
+      const float invz = 1.0f / PcZ;
+      float u, v;
+      if (c.model == 0) {
+        const float xn = Pc[0] * invz, yn = Pc[1] * invz;
+        u = sum3(c.fx * xn, 0.0f * yn, c.cx * 1.0f);
+        v = sum3(0.0f * xn, c.fy * yn, c.cy * 1.0f);
+      } else {
+        project_double(c, Pc, u, v);
+      }
+      if (u < c.minx || u > c.maxx) continue;
+      if (v < c.miny || v > c.maxy) continue;
+      const float PO[3] = {P[0] - twc[0], P[1] - twc[1], P[2] - twc[2]};
+      const float dist3D = std::sqrt(sum3(PO[0] * PO[0], PO[1] * PO[1], PO[2] * PO[2]));
+      if (dist3D < minDistance || dist3D > maxDistance) continue;
+      const float vc = sum3(PO[0] * Pn[3 * i], PO[1] * Pn[3 * i + 1], PO[2] * Pn[3 * i + 2]) / dist3D;
+      if (vc < f->cos_limit) continue;
+      level[4 * i + ci] = orc_predict_scale(max_dist[i], dist3D, f->log_scale_factor, f->n_levels);
+      proj[12 * i + 3 * ci] = u;
+      proj[12 * i + 3 * ci + 1] = v;
+      proj[12 * i + 3 * ci + 2] = u - f->bf * invz;
+      viewcos[4 * i + ci] = vc;
+      cam_mask[i] |= (uint8_t)(1u << ci);
+      sum_depth += dist3D;
+      ++count;
+    }
+    if (count) {
+      depth[i] = sum_depth / (float)count;
+      inview[i] = 1;
+      ++n_in;
+    }
+  }
+  return n_in;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // ORBmatcher::SearchByProjectionBase (src/ORBmatcher.cc:26-227) — the search half shared by Fuse(KF, vpMapPoints, th)
 // (:1152-1165, LocalMapping::SearchInNeighbors), Fuse(KF, Scw, ...) (:1167-1220, loop closing) and the Sim3 / relocalisation

@@ -815,3 +815,33 @@ def essential_graph_correct_points(Pw, ref, S_before, S_after):
     _pg().orc_essential_graph_correct_points(len(Pw), _p(Pw), _p(ref), _p(_sim3(S_before)),
                                              _p(_sim3(S_after)), _p(out))
     return out
+
+
+def is_in_frustum_rig(pb):
+    """orc_is_in_frustum_rig over every frame of a synth.make_frustum_rig_problem dict -> dict(inview, cam_mask, proj [n][4][3],
+    level [n][4], viewcos [n][4], depth, n_inview); points with p_skip set stay "not in view"."""
+    L = lib()
+    L.orc_is_in_frustum_rig.restype = C.c_int
+    L.orc_is_in_frustum_rig.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 10
+    rig = pb["rig"]
+    n = len(pb["p_max_dist"])
+    out = dict(inview=np.zeros(n, np.uint8), cam_mask=np.zeros(n, np.uint8), proj=np.zeros((n, 4, 3), np.float32),
+               level=np.full((n, 4), -1, np.int32), viewcos=np.zeros((n, 4), np.float32), depth=np.zeros(n, np.float32),
+               n_inview=np.zeros(len(rig), np.int32))
+    skip = pb.get("p_skip")
+    for f in range(len(rig)):
+        b, m = int(rig[f]["q_begin"]), int(rig[f]["n_q"])
+        idx = np.arange(b, b + m)
+        if skip is not None:
+            idx = idx[skip[b:b + m] == 0]
+        if len(idx) == 0:
+            continue
+        a = [np.ascontiguousarray(pb[k][idx], np.float32) for k in ("p_wP", "p_normal", "p_max_dist", "p_min_dist")]
+        k = len(idx)
+        o = [np.zeros(k, np.uint8), np.zeros(k, np.uint8), np.zeros((k, 4, 3), np.float32), np.zeros((k, 4), np.int32),
+             np.zeros((k, 4), np.float32), np.zeros(k, np.float32)]
+        one = np.ascontiguousarray(rig[f:f + 1])
+        out["n_inview"][f] = L.orc_is_in_frustum_rig(_p(one), k, *[_p(x) for x in a], *[_p(x) for x in o])
+        for key, arr in zip(("inview", "cam_mask", "proj", "level", "viewcos", "depth"), o):
+            out[key][idx] = arr
+    return out

@@ -230,3 +230,54 @@ def test_search_by_bow_matches_oracle(seed, n_kp, n_nodes):
     assert tot > 100
     none = dict(pb); none["mp_ok"] = np.zeros_like(pb["mp_ok"])
     assert (api.search_by_bow(none)[1] == 0).all()
+
+
+# ---- Frame::isInFrustum with a camera rig (vieo_frustum_rig_batch, csrc/frustum.cu k_frustum_rig) -------------------------------
+@pytest.mark.parametrize("model,n_cams,n_frames,n_q", [(2, 4, 3, 2500), (0, 2, 2, 900), (1, 3, 2, 900), (2, 1, 1, 300)])
+def test_is_in_frustum_rig_matches_oracle(model, n_cams, n_frames, n_q):
+    """Bit-exact floats, levels, camera masks and mean depths for every camera model.  The KB8 form evaluates atan2 in double on
+    the device (<= 2 ulp from glibc's): a float pixel could differ in its last bit once in ~1e8 projections, so the few thousand of
+    this test are compared exactly."""
+    import vieo_slam_b200.api as api
+    pb = synth.make_frustum_rig_problem(40 + model + n_cams, n_frames=n_frames, n_q=n_q, n_cams=n_cams, model=model)
+    ref = O.is_in_frustum_rig(pb)
+    got = api.frustum_rig_batch(pb)
+    for k in ("inview", "cam_mask", "level", "n_inview"):
+        assert np.array_equal(got[k], ref[k]), k
+    for k in ("proj", "viewcos", "depth"):
+        assert got[k].tobytes() == ref[k].tobytes(), k
+    assert ref["n_inview"].sum() > 0.1 * n_q * n_frames / 2
+    if n_cams >= 3:
+        assert (np.bitwise_count(ref["cam_mask"]) > 1).sum() > 10
+
+
+def test_is_in_frustum_rig_edge_cases():
+    import vieo_slam_b200.api as api
+    pb = synth.make_frustum_rig_problem(77, n_frames=2, n_q=400, n_cams=4, model=2, skip_frac=0.5)
+    # a point on the optical axis of camera 0 (r <= 1e-5: the pinhole branch of KB8Camera::Project), NaN / inf positions, an empty frame
+    G = pb["rig"][0]
+    R = G["Rcw"].reshape(3, 3).astype(np.float64)
+    from vieo_slam_b200.synth import R_from_quat
+    C = G["cam"][0]
+    Rcr = R_from_quat(np.array([C["q_cr"][3], C["q_cr"][0], C["q_cr"][1], C["q_cr"][2]], np.float64))
+    Pc = np.array([0.0, 0.0, 3.0])
+    Pcr = Rcr.T @ (Pc - C["t_cr"].astype(np.float64))
+    Pw = R.T @ (Pcr - G["tcw"].astype(np.float64))
+    b = int(G["q_begin"])
+    pb["p_wP"][b] = Pw.astype(np.float32); pb["p_skip"][b] = 0
+    pb["p_max_dist"][b] = 30.0; pb["p_min_dist"][b] = 0.1
+    pb["p_normal"][b] = (Pw - G["Ow"]) / np.linalg.norm(Pw - G["Ow"])
+    pb["p_wP"][b + 1] = [np.nan, 0, 1]; pb["p_skip"][b + 1] = 0
+    pb["p_wP"][b + 2] = [np.inf, 1, 1]; pb["p_skip"][b + 2] = 0
+    pb["rig"][1]["n_q"] = 0
+    ref = O.is_in_frustum_rig(pb)
+    got = api.frustum_rig_batch(pb)
+    assert ref["inview"][b] == 1 and ref["cam_mask"][b] & 1
+    for k in ("inview", "cam_mask", "level", "n_inview"):
+        assert np.array_equal(got[k], ref[k]), k
+    for k in ("proj", "viewcos", "depth"):
+        assert got[k].tobytes() == ref[k].tobytes(), k
+    assert got["n_inview"][1] == 0
+    bad = dict(pb); bad["rig"] = pb["rig"].copy(); bad["rig"]["n_cams"] = 5
+    with pytest.raises(Exception):
+        api.frustum_rig_batch(bad)

@@ -292,3 +292,88 @@ def test_properties_of_the_restatements():
         assert med[0] == min(meds) and best[0] == meds.index(min(meds))
     distinct()
     del rng
+
+
+# ---- Frame::isInFrustum with a camera rig (src/Frame.cc:351-411, mpCameras.size() > 1) ------------------------------------------
+def _cross32(a, b):
+    return [f32(f32(a[1] * b[2]) - f32(a[2] * b[1])), f32(f32(a[2] * b[0]) - f32(a[0] * b[2])), f32(f32(a[0] * b[1]) - f32(a[1] * b[0]))]
+
+
+def _naive_rig_point(G, wP, Pn, mx, mn):
+    """src/Frame.cc:351-411 line by line in numpy float32 scalars; the distorted projection through python floats (doubles) and
+    math.atan2 — the libm the reference calls — written straight from camera_kb8.h:68-106 / camera_pinhole.h:70-83."""
+    import math
+    R = G["Rcw"].reshape(3, 3)
+    Pcr = [f32(_sum3(f32(R[r, 0] * wP[0]), f32(R[r, 1] * wP[1]), f32(R[r, 2] * wP[2])) + G["tcw"][r]) for r in range(3)]
+    res, sum_depth = [], f32(0)
+    for ci in range(int(G["n_cams"])):
+        C = G["cam"][ci]
+        qv, w = C["q_cr"][:3], C["q_cr"][3]
+        uv = _cross32(qv, Pcr)
+        uv = [f32(x + x) for x in uv]
+        cr = _cross32(qv, uv)
+        Pc = [f32(f32(f32(Pcr[k] + f32(w * uv[k])) + cr[k]) + C["t_cr"][k]) for k in range(3)]
+        twc = [f32(G["Ow"][k] + _sum3(f32(R[0, k] * C["t_rc"][0]), f32(R[1, k] * C["t_rc"][1]), f32(R[2, k] * C["t_rc"][2]))) for k in range(3)]
+        if Pc[2] < f32(0):
+            continue
+        with np.errstate(all="ignore"):
+            invz = f32(f32(1) / Pc[2])
+        if int(C["model"]) == 0:
+            xn, yn = f32(Pc[0] * invz), f32(Pc[1] * invz)
+            u = _sum3(f32(C["fx"] * xn), f32(f32(0) * yn), C["cx"])
+            v = _sum3(f32(f32(0) * xn), f32(C["fy"] * yn), C["cy"])
+        else:
+            x, y, z = float(Pc[0]), float(Pc[1]), float(Pc[2])
+            r = math.sqrt(x * x + y * y)
+            if int(C["model"]) == 2 and r > float(f32(1e-5)):
+                th = math.atan2(r, z); th2 = th * th
+                td = float(C["k"][3]) * th2
+                td += float(C["k"][2]); td *= th2
+                td += float(C["k"][1]); td *= th2
+                td += float(C["k"][0]); td *= th2
+                td += 1; td *= th
+                u = f32(float(C["fx"]) * (x * td / r) * 1.0 + float(C["cx"]))
+                v = f32(float(C["fy"]) * (y * td / r) * 1.0 + float(C["cy"]))
+            else:
+                iz = 1.0 / z if z != 0 else math.inf
+                u = f32(float(C["fx"]) * x * iz + float(C["cx"]))
+                v = f32(float(C["fy"]) * y * iz + float(C["cy"]))
+        if u < C["minx"] or u > C["maxx"] or v < C["miny"] or v > C["maxy"]:
+            continue
+        PO = [f32(wP[k] - twc[k]) for k in range(3)]
+        dist = f32(np.sqrt(_sum3(f32(PO[0] * PO[0]), f32(PO[1] * PO[1]), f32(PO[2] * PO[2]))))
+        if dist < f32(f32(0.8) * mn) or dist > f32(f32(1.2) * mx):
+            continue
+        vc = f32(_sum3(f32(PO[0] * Pn[0]), f32(PO[1] * Pn[1]), f32(PO[2] * Pn[2])) / dist)
+        if vc < G["cos_limit"]:
+            continue
+        lvl = O.predict_scale(float(mx), float(dist), float(G["log_scale_factor"]), int(G["n_levels"]))
+        res.append((ci, u, v, f32(u - f32(G["bf"] * invz)), lvl, vc))
+        sum_depth = f32(sum_depth + dist)
+    return res, (f32(sum_depth / f32(len(res))) if res else f32(0))
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("model,n_cams", [(2, 4), (0, 2), (1, 3)])
+def test_frustum_rig_oracle_matches_naive_restatement(model, n_cams):
+    pb = synth.make_frustum_rig_problem(21 + model, n_frames=2, n_q=500, n_cams=n_cams, model=model, skip_frac=0.0)
+    out = O.is_in_frustum_rig(pb)
+    n_in, n_multi = 0, 0
+    for f, G in enumerate(pb["rig"]):
+        for q in range(int(G["q_begin"]), int(G["q_begin"]) + int(G["n_q"])):
+            res, depth = _naive_rig_point(G, pb["p_wP"][q], pb["p_normal"][q], pb["p_max_dist"][q], pb["p_min_dist"][q])
+            assert bool(out["inview"][q]) == bool(res), q
+            assert int(out["cam_mask"][q]) == sum(1 << r[0] for r in res), q
+            assert out["depth"][q] == depth, q
+            for ci, u, v, ur, lvl, vc in res:
+                assert out["proj"][q, ci].tobytes() == np.array([u, v, ur], f32).tobytes(), (q, ci)
+                assert out["level"][q, ci] == lvl and out["viewcos"][q, ci] == vc
+            for ci in range(4):
+                if not (int(out["cam_mask"][q]) >> ci) & 1:
+                    assert out["level"][q, ci] == -1 and not out["proj"][q, ci].any()
+            n_in += bool(res); n_multi += len(res) > 1
+    assert n_in == out["n_inview"].sum() and n_in > 50
+    if n_cams >= 3:
+        assert n_multi > 10   # points seen by several cameras of the rig: track_depth_ is a mean

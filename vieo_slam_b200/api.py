@@ -643,6 +643,26 @@ from .layouts import (BA_RESULT_DTYPE, CAMERA_DTYPE, NAVSTATE_DTYPE, POSEOPT_PRO
                       POSEOPT_RESULT_DTYPE)
 
 
+def frustum_rig_batch(pb, device=0):
+    """Frame::isInFrustum with a camera rig (vieo_frustum_rig_batch) over a synth.make_frustum_rig_problem dict ->
+    dict(inview, cam_mask, proj [n][4][3], level [n][4], viewcos [n][4], depth, n_inview)"""
+    from .layouts import FRUSTUM_RIG_FRAME_DTYPE
+    rig = np.ascontiguousarray(pb["rig"], FRUSTUM_RIG_FRAME_DTYPE)
+    wP = np.ascontiguousarray(pb["p_wP"], np.float32); Pn = np.ascontiguousarray(pb["p_normal"], np.float32)
+    mx = np.ascontiguousarray(pb["p_max_dist"], np.float32); mn = np.ascontiguousarray(pb["p_min_dist"], np.float32)
+    skip = None if pb.get("p_skip") is None else np.ascontiguousarray(pb["p_skip"], np.uint8)
+    n = len(mx)
+    out = dict(inview=np.zeros(n, np.uint8), cam_mask=np.zeros(n, np.uint8), proj=np.zeros((n, 4, 3), np.float32),
+               level=np.full((n, 4), -1, np.int32), viewcos=np.zeros((n, 4), np.float32), depth=np.zeros(n, np.float32),
+               n_inview=np.zeros(len(rig), np.int32))
+    L = lib()
+    L.vieo_frustum_rig_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 12 + [C.c_int]
+    _check(L.vieo_frustum_rig_batch(_p(rig), len(rig), _p(wP), _p(Pn), _p(mx), _p(mn), None if skip is None else _p(skip),
+                                    _p(out["inview"]), _p(out["cam_mask"]), _p(out["proj"]), _p(out["level"]), _p(out["viewcos"]),
+                                    _p(out["depth"]), _p(out["n_inview"]), device))
+    return out
+
+
 def set_host_sync(mode, device=0):
     """vieo_set_host_sync: 0 auto, 1 spin, 2 yield, 3 blocking (how host threads wait for the device)"""
     _check(lib().vieo_set_host_sync(int(device), int(mode)))

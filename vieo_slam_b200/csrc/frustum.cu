@@ -96,6 +96,149 @@ __global__ void __launch_bounds__(kFrThreads) k_frustum(const VieoFrustumFrame* 
   if (tid == 0 && s_cnt) atomicAdd(n_inview + f, s_cnt);
 }
 
+// Rig form (mpCameras.size() > 1): the same thread-per-point kernel, with the per-camera steps of src/Frame.cc:351-411 in a
+// loop over <= 4 cameras.  Float operations are explicit round-to-nearest intrinsics in the reference's order (Eigen's
+// _transformVector: uv = q.vec x p; uv += uv; p + w uv + q.vec x uv); with usedistort_ the camera's Project runs in double
+// as written in common/camera_models (library compiled with -fmad=false).  112 B written per point (4 camera slots).
+__device__ __forceinline__ void cross3f(const float a[3], const float b[3], float o[3]) {
+  o[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
+  o[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
+  o[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+}
+__device__ __forceinline__ void rig_project_double(const VieoFrustumCam& c, const float Pc[3], float& u, float& v) {
+  const double x = (double)Pc[0], y = (double)Pc[1];
+  if (c.model == 2) {
+    const double x2 = x * x, y2 = y * y, r2 = x2 + y2, r = sqrt(r2);
+    const float precision_r = 1e-5f;
+    if (r > (double)precision_r) {
+      const double z = (double)Pc[2];
+      const double theta = atan2(r, z), theta2 = theta * theta;
+      double thetad = (double)c.k[3] * theta2;
+      thetad += (double)c.k[2];
+      thetad *= theta2;
+      thetad += (double)c.k[1];
+      thetad *= theta2;
+      thetad += (double)c.k[0];
+      thetad *= theta2;
+      thetad += 1;
+      thetad *= theta;
+      const double mx = x * thetad / r, my = y * thetad / r;
+      const double invz = 1. / 1.;
+      u = (float)((double)c.fx * mx * invz + (double)c.cx);
+      v = (float)((double)c.fy * my * invz + (double)c.cy);
+      return;
+    }
+  }
+  const double z = (double)Pc[2], invz = 1. / z;
+  u = (float)((double)c.fx * x * invz + (double)c.cx);
+  v = (float)((double)c.fy * y * invz + (double)c.cy);
+}
+
+__global__ void __launch_bounds__(kFrThreads) k_frustum_rig(const VieoFrustumRigFrame* __restrict__ frames,
+                                                            const float* __restrict__ wP, const float* __restrict__ Pn,
+                                                            const float* __restrict__ max_dist,
+                                                            const float* __restrict__ min_dist,
+                                                            const uint8_t* __restrict__ skip, uint8_t* __restrict__ inview,
+                                                            uint8_t* __restrict__ cam_mask, float* __restrict__ proj,
+                                                            int32_t* __restrict__ level, float* __restrict__ viewcos,
+                                                            float* __restrict__ depth, int32_t* __restrict__ n_inview) {
+  __shared__ VieoFrustumRigFrame F;
+  __shared__ int s_cnt;
+  const int f = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < (int)(sizeof(VieoFrustumRigFrame) / 4); i += kFrThreads)
+    reinterpret_cast<uint32_t*>(&F)[i] = reinterpret_cast<const uint32_t*>(frames + f)[i];
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int qi = blockIdx.x * kFrThreads + tid; qi < F.n_q; qi += gridDim.x * kFrThreads) {
+    const size_t q = (size_t)F.q_begin + qi;
+    float o_proj[12], o_vc[4];
+    int o_lvl[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      o_lvl[c] = -1;
+      o_vc[c] = 0.0f;
+      o_proj[3 * c] = o_proj[3 * c + 1] = o_proj[3 * c + 2] = 0.0f;
+    }
+    unsigned mask = 0;
+    float sum_depth = 0.0f;
+    int count = 0;
+    if (!(skip && skip[q])) {
+      const float X = wP[3 * q], Y = wP[3 * q + 1], Z = wP[3 * q + 2];
+      const float mx = max_dist[q];
+      const float maxD = __fmul_rn(1.2f, mx), minD = __fmul_rn(0.8f, min_dist[q]);
+      float Pcr[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        Pcr[r] = __fadd_rn(sum3(__fmul_rn(F.Rcw[3 * r], X), __fmul_rn(F.Rcw[3 * r + 1], Y), __fmul_rn(F.Rcw[3 * r + 2], Z)),
+                           F.tcw[r]);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        if (ci >= F.n_cams) continue;
+        const VieoFrustumCam& C = F.cam[ci];
+        const float qv[3] = {C.q_cr[0], C.q_cr[1], C.q_cr[2]};
+        float uv[3], cr[3], Pc[3], twc[3];
+        cross3f(qv, Pcr, uv);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) uv[k] = __fadd_rn(uv[k], uv[k]);
+        cross3f(qv, uv, cr);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          Pc[k] = __fadd_rn(__fadd_rn(__fadd_rn(Pcr[k], __fmul_rn(C.q_cr[3], uv[k])), cr[k]), C.t_cr[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          twc[k] = __fadd_rn(F.Ow[k], sum3(__fmul_rn(F.Rcw[k], C.t_rc[0]), __fmul_rn(F.Rcw[3 + k], C.t_rc[1]),
+                                           __fmul_rn(F.Rcw[6 + k], C.t_rc[2])));
+        const float PcZ = Pc[2];
+        if (PcZ < 0.0f) continue;
+        const float invz = __fdiv_rn(1.0f, PcZ);
+        float u, v;
+        if (C.model == 0) {
+          const float xn = __fmul_rn(Pc[0], invz), yn = __fmul_rn(Pc[1], invz);
+          u = sum3(__fmul_rn(C.fx, xn), __fmul_rn(0.0f, yn), __fmul_rn(C.cx, 1.0f));
+          v = sum3(__fmul_rn(0.0f, xn), __fmul_rn(C.fy, yn), __fmul_rn(C.cy, 1.0f));
+        } else {
+          rig_project_double(C, Pc, u, v);
+        }
+        if (u < C.minx || u > C.maxx) continue;
+        if (v < C.miny || v > C.maxy) continue;
+        const float ox = __fsub_rn(X, twc[0]), oy = __fsub_rn(Y, twc[1]), oz = __fsub_rn(Z, twc[2]);
+        const float d3 = __fsqrt_rn(sum3(__fmul_rn(ox, ox), __fmul_rn(oy, oy), __fmul_rn(oz, oz)));
+        if (d3 < minD || d3 > maxD) continue;
+        const float vc = __fdiv_rn(sum3(__fmul_rn(ox, Pn[3 * q]), __fmul_rn(oy, Pn[3 * q + 1]), __fmul_rn(oz, Pn[3 * q + 2])), d3);
+        if (vc < F.cos_limit) continue;
+        const float ratio = __fdiv_rn(mx, d3);
+        int lvl = 0;
+        for (int k = 1; k < F.n_levels; ++k) lvl += ratio >= F.level_ratio[k] ? 1 : 0;
+        o_lvl[ci] = lvl;
+        o_vc[ci] = vc;
+        o_proj[3 * ci] = u;
+        o_proj[3 * ci + 1] = v;
+        o_proj[3 * ci + 2] = __fsub_rn(u, __fmul_rn(F.bf, invz));
+        mask |= 1u << ci;
+        sum_depth = __fadd_rn(sum_depth, d3);
+        ++count;
+      }
+    }
+    const bool in = count > 0;
+    inview[q] = in ? 1 : 0;
+    cam_mask[q] = (uint8_t)mask;
+    depth[q] = in ? __fdiv_rn(sum_depth, (float)count) : 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      level[4 * q + c] = o_lvl[c];
+      viewcos[4 * q + c] = o_vc[c];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) proj[12 * q + k] = o_proj[k];
+    mine += in ? 1 : 0;
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((tid & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (tid == 0 && s_cnt) atomicAdd(n_inview + f, s_cnt);
+}
+
 // ceil(logf(ratio) / lsf) >= k, evaluated as the reference does (float log, float divide, ceil)
 inline bool level_reached(float ratio, float lsf, int k) {
   const float x = std::ceil(std::log(ratio) / lsf);
@@ -283,6 +426,87 @@ static int frustum_host(const VieoFrustumFrame* frames, const VieoSbpFrame* sbp,
     if (nq) { memcpy(q_match, hbuf + o_qm, 4 * nq); memcpy(q_dist, hbuf + o_qs, 4 * nq); }
     memcpy(n_matches, hbuf + o_nm, 4 * nf);
   }
+  return VIEO_OK;
+}
+
+int vieo_frustum_rig_batch_dev(const VieoFrustumRigFrame* frames_dev, int n_frames, const float* wP_dev, const float* normal_dev,
+                               const float* max_dist_dev, const float* min_dist_dev, const uint8_t* skip_dev, uint8_t* inview_dev,
+                               uint8_t* cam_mask_dev, float* proj_dev, int32_t* level_dev, float* viewcos_dev, float* depth_dev,
+                               int32_t* n_inview_dev, void* stream) {
+  VIEO_ARG(n_frames >= 0 && n_frames <= 65535, "bad argument (at most 65535 frames per call)");
+  if (n_frames == 0) return VIEO_OK;
+  VIEO_ARG(frames_dev && wP_dev && normal_dev && max_dist_dev && min_dist_dev && inview_dev && cam_mask_dev && proj_dev &&
+               level_dev && viewcos_dev && depth_dev && n_inview_dev, "null argument");
+  VIEO_CK(cudaMemsetAsync(n_inview_dev, 0, 4 * (size_t)n_frames, (cudaStream_t)stream));
+  k_frustum_rig<<<dim3(kFrBlocksPerFrame, n_frames), kFrThreads, 0, (cudaStream_t)stream>>>(
+      frames_dev, wP_dev, normal_dev, max_dist_dev, min_dist_dev, skip_dev, inview_dev, cam_mask_dev, proj_dev, level_dev,
+      viewcos_dev, depth_dev, n_inview_dev);
+  VIEO_CK(cudaGetLastError());
+  return VIEO_OK;
+}
+
+int vieo_frustum_rig_batch(const VieoFrustumRigFrame* frames, int n_frames, const float* wP, const float* normal,
+                           const float* max_dist, const float* min_dist, const uint8_t* skip, uint8_t* inview, uint8_t* cam_mask,
+                           float* proj, int32_t* level, float* viewcos, float* depth, int32_t* n_inview, int device) {
+  VIEO_ARG(n_frames >= 0, "bad argument");
+  if (n_frames == 0) return VIEO_OK;
+  VIEO_ARG(frames && n_inview, "null argument");
+  size_t nq = 0;
+  std::vector<VieoFrustumRigFrame> fr(frames, frames + n_frames);
+  for (int f = 0; f < n_frames; ++f) {
+    VIEO_ARG(fr[f].q_begin >= 0 && fr[f].n_q >= 0, "bad frame range");
+    VIEO_ARG(fr[f].n_cams >= 1 && fr[f].n_cams <= 4, "a rig has 1 to 4 cameras");
+    for (int c = 0; c < fr[f].n_cams; ++c) VIEO_ARG(fr[f].cam[c].model >= 0 && fr[f].cam[c].model <= 2, "camera model must be 0, 1 or 2");
+    int rc = vieo_frustum_level_table(fr[f].log_scale_factor, fr[f].n_levels, fr[f].level_ratio);
+    if (rc) return rc;
+    nq = std::max(nq, (size_t)fr[f].q_begin + fr[f].n_q);
+  }
+  VIEO_ARG(nq == 0 || (wP && normal && max_dist && min_dist && inview && cam_mask && proj && level && viewcos && depth), "null point array");
+  int rc = use_device(device);
+  if (rc) return rc;
+  CallScratch* cs = call_scratch(device);
+  VIEO_ARG(cs, "no call scratch");
+  const size_t nq1 = std::max<size_t>(nq, 1), nf = (size_t)n_frames;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) / 16 * 16; return o; };
+  const size_t o_ff = take(sizeof(VieoFrustumRigFrame) * nf), o_wp = take(12 * nq1), o_pn = take(12 * nq1), o_mx = take(4 * nq1),
+               o_mn = take(4 * nq1), o_sk = take(nq1);
+  const size_t in_bytes = off;
+  const size_t o_iv = take(nq1), o_cm = take(nq1), o_ni = take(4 * nf), o_dp = take(4 * nq1), o_vc = take(16 * nq1), o_pr = take(48 * nq1),
+               o_lv = take(16 * nq1);
+  const size_t io_bytes = off;
+  uint8_t* dbuf = (uint8_t*)cs->get(0, io_bytes);
+  uint8_t* hbuf = (uint8_t*)cs->get_pinned(io_bytes);
+  VIEO_ARG(dbuf && hbuf, "staging allocation failed");
+  auto put = [&](size_t o, const void* src, size_t bytes) { if (src && bytes) memcpy(hbuf + o, src, bytes); };
+  put(o_ff, fr.data(), sizeof(VieoFrustumRigFrame) * nf);
+  put(o_wp, wP, 12 * nq); put(o_pn, normal, 12 * nq); put(o_mx, max_dist, 4 * nq); put(o_mn, min_dist, 4 * nq);
+  put(o_sk, skip, nq);
+  cudaError_t e = cudaMemcpyAsync(dbuf, hbuf, in_bytes, cudaMemcpyHostToDevice, cs->st);
+  // points outside every frame's range read back as "not in view" (level -1)
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_iv, 0, o_lv - o_iv, cs->st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbuf + o_lv, 0xff, io_bytes - o_lv, cs->st);
+  if (e == cudaSuccess) {
+    rc = vieo_frustum_rig_batch_dev((const VieoFrustumRigFrame*)(dbuf + o_ff), n_frames, (const float*)(dbuf + o_wp),
+                                    (const float*)(dbuf + o_pn), (const float*)(dbuf + o_mx), (const float*)(dbuf + o_mn),
+                                    skip ? dbuf + o_sk : nullptr, dbuf + o_iv, dbuf + o_cm, (float*)(dbuf + o_pr),
+                                    (int32_t*)(dbuf + o_lv), (float*)(dbuf + o_vc), (float*)(dbuf + o_dp), (int32_t*)(dbuf + o_ni),
+                                    cs->st);
+    if (rc == VIEO_OK) {
+      e = cudaMemcpyAsync(hbuf + o_iv, dbuf + o_iv, io_bytes - o_iv, cudaMemcpyDeviceToHost, cs->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(cs->st);
+    }
+  }
+  if (e != cudaSuccess) {
+    set_error("vieo_frustum_rig: %s", cudaGetErrorString(e));
+    return VIEO_E_CUDA;
+  }
+  if (rc != VIEO_OK) return rc;
+  if (nq) {
+    memcpy(inview, hbuf + o_iv, nq); memcpy(cam_mask, hbuf + o_cm, nq); memcpy(depth, hbuf + o_dp, 4 * nq);
+    memcpy(viewcos, hbuf + o_vc, 16 * nq); memcpy(proj, hbuf + o_pr, 48 * nq); memcpy(level, hbuf + o_lv, 16 * nq);
+  }
+  memcpy(n_inview, hbuf + o_ni, 4 * nf);
   return VIEO_OK;
 }
 

@@ -91,3 +91,12 @@ SIM3_DTYPE = np.dtype([("q", "f8", 4), ("t", "f8", 3), ("s", "f8")])
 POSEGRAPH_STATS_DTYPE = np.dtype([("chi2_initial", "f8"), ("chi2_final", "f8"), ("lambda_final", "f8"), ("iterations", "i4"),
                                   ("trials", "i4"), ("n_free", "i4"), ("ok", "i4")])
 assert SIM3_DTYPE.itemsize == 64 and POSEGRAPH_STATS_DTYPE.itemsize == 40
+
+# VieoFrustumCam / VieoFrustumRigFrame (Frame::isInFrustum with a camera rig); OrcFrustumCam / OrcFrustumRigFrame are identical
+FRUSTUM_CAM_DTYPE = np.dtype([("q_cr", "f4", 4), ("t_cr", "f4", 3), ("t_rc", "f4", 3), ("fx", "f4"), ("fy", "f4"), ("cx", "f4"),
+                              ("cy", "f4"), ("k", "f4", 4), ("minx", "f4"), ("maxx", "f4"), ("miny", "f4"), ("maxy", "f4"),
+                              ("model", "i4"), ("pad_", "i4")])
+FRUSTUM_RIG_FRAME_DTYPE = np.dtype([("q_begin", "i4"), ("n_q", "i4"), ("Rcw", "f4", 9), ("tcw", "f4", 3), ("Ow", "f4", 3), ("bf", "f4"),
+                                    ("cos_limit", "f4"), ("log_scale_factor", "f4"), ("n_levels", "i4"), ("n_cams", "i4"),
+                                    ("level_ratio", "f4", 16), ("cam", FRUSTUM_CAM_DTYPE, 4)])
+assert FRUSTUM_CAM_DTYPE.itemsize == 96 and FRUSTUM_RIG_FRAME_DTYPE.itemsize == 8 + 60 + 20 + 64 + 4 * 96

@@ -991,3 +991,41 @@ def make_essential_graph(K=60, seed=0, fix_scale=True, n_neighbors=5, odom_info_
             Pw[i] = S[2] * (S[0] @ Pc) + S[1]
         out["Pw"], out["ref"] = Pw, ref
     return out
+
+
+def make_frustum_rig_problem(seed, n_frames=2, n_q=1200, n_cams=4, model=2, skip_frac=0.05):
+    """Frame::isInFrustum with a camera rig (src/Frame.cc:351-411, mpCameras.size() > 1): the map points, normals and distance
+    ranges of make_frustum_problem, and per frame a rig of n_cams cameras looking left / right / up-left / up-right of the
+    reference frame (TUM-VI-like 512 x 512 KB8 cameras when model == 2; model 0 = undistorted K multiply, 1 = PinholeCamera::Project
+    in double), each with its own extrinsics Trc, intrinsics and image bounds.  -> dict(rig FRUSTUM_RIG_FRAME_DTYPE[n_frames],
+    p_wP, p_normal, p_max_dist, p_min_dist, p_skip)"""
+    from .layouts import FRUSTUM_RIG_FRAME_DTYPE
+    pb = make_frustum_problem(seed, n_frames=n_frames, n_q=n_q, skip_frac=skip_frac)
+    r = np.random.default_rng(seed + 4100)
+    rig = np.zeros(n_frames, FRUSTUM_RIG_FRAME_DTYPE)
+    yaw = [0.35, -0.35, 0.9, -0.9]
+    for f in range(n_frames):
+        G, S = rig[f], pb["frustum"][f]
+        for k in ("q_begin", "n_q", "Rcw", "tcw", "Ow", "bf", "cos_limit", "log_scale_factor", "n_levels"):
+            G[k] = S[k]
+        G["n_cams"] = n_cams
+        for c in range(n_cams):
+            C = G["cam"][c]
+            Rrc = so3_exp(np.array([0.05 * r.normal(), yaw[c] + 0.02 * r.normal(), 0.03 * r.normal()]))  # camera c in the reference frame
+            trc = np.array([0.05 * (c - 1.5), 0.01 * r.normal(), 0.02 * r.normal()])
+            Rcr = Rrc.T
+            tcr = -Rcr @ trc
+            q = quat_from_R(Rcr)  # (w, x, y, z)
+            C["q_cr"] = np.array([q[1], q[2], q[3], q[0]], np.float32)
+            C["t_cr"] = tcr.astype(np.float32)
+            C["t_rc"] = trc.astype(np.float32)
+            if model == 2:
+                C["fx"], C["fy"], C["cx"], C["cy"] = 190.98 + c, 190.97 - c, 254.93 + 2 * c, 256.9 - c
+                C["k"] = np.array([0.0034823894, 0.0007150348, -0.0020532361, 0.00020293673]) * (1 + 0.05 * c)
+                C["minx"], C["maxx"], C["miny"], C["maxy"] = 0.0, 512.0, 0.0, 512.0
+            else:
+                C["fx"], C["fy"], C["cx"], C["cy"] = S["fx"] + c, S["fy"] - c, S["cx"] + 2 * c, S["cy"] - c
+                C["minx"], C["maxx"], C["miny"], C["maxy"] = S["minx"], S["maxx"], S["miny"], S["maxy"]
+            C["model"] = model
+    pb["rig"] = rig
+    return pb
