@@ -43,6 +43,16 @@ def workload_name(frames):
             "+ 2x PoseOptimization (PVR) per frame, "
             "LocalBundleAdjustmentNavStatePRV every 8th frame")
 
+def workload_config(frames, pool, with_lba):
+    """The `config` object of the JSON line: the workload only, so that both arms print the same bytes."""
+    return {"workload": workload_name(frames), "frames_per_step_per_gpu": frames, "image": f"{W}x{H}", "nfeatures": 1200, "levels": 8,
+            "cache": f"inputs rotate over {pool} batches ({pool * frames * 2 * H * W / 1e6:.0f} MB > 126 MB L2)",
+            "stages": ["orb_extract_x2", "stereo_matches_rectified", "imu_preint", "search_by_projection_last_frame",
+                       "is_in_frustum+search_by_projection_local_map", "pose_opt_x2"] + (["local_ba_prv"] if with_lba else []),
+            "pose_opt_points": list(POSE_POINTS), "sbp_queries": list(SBP_QUERIES), "lba_every": LBA_EVERY if with_lba else 0,
+            "lba_window": LBA_SHAPE}
+
+
 
 def peaks():
     try:
@@ -306,11 +316,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
-            "config": {"workload": workload_name(frames), "frames_per_step_per_gpu": frames, "image": f"{W}x{H}", "nfeatures": 1200,
-                       "levels": 8, "lba_every": LBA_EVERY, "lba_window": LBA_SHAPE, "pose_opt_points": list(POSE_POINTS),
-                       "sbp_queries": list(SBP_QUERIES),
-                       "note": "CPU oracle port of the reference path (the BA / matcher / IMU units need Eigen/Sophus/g2o: unbuildable "
-                               "offline; the extractor restatement is pinned to the compiled reference, oracle/_ref)"},
+            "config": workload_config(frames, args.pool, True),
+            "run_info": {"note": "CPU oracle port of the reference path (the BA / matcher / IMU units need Eigen/Sophus/g2o: unbuildable "
+                                 "offline; the extractor restatement is pinned to the compiled reference, oracle/_ref)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{frames} synthetic stereo frames per step (+{frames // LBA_EVERY} LocalBA windows), "
                                        "frames spread over one worker thread per core"},
@@ -755,13 +763,12 @@ def run_gpu(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8+f64", "data": "synthetic",
-        "config": {"workload": workload_name(F), "frames_per_step_per_gpu": F, "image": f"{W}x{H}", "nfeatures": 1200,
-                   "levels": 8, "cache": f"inputs rotate over {pool} batches ({pool * F * 2 * H * W / 1e6:.0f} MB > 126 MB L2)",
-                   "stages": ["orb_extract_x2", "stereo_matches_rectified", "imu_preint", "search_by_projection_last_frame", "is_in_frustum+search_by_projection_local_map", "pose_opt_x2"] + (["local_ba_prv"] if n_lba else []),
-                   "pose_opt_points": list(POSE_POINTS), "sbp_queries": list(SBP_QUERIES), "lba_every": LBA_EVERY if n_lba else 0, "lba_window": LBA_SHAPE,
-                   "lba_workers": n_workers, "host_sync": host_sync, "host_cores_allowed": cores_allowed,
-                   "sm_partition": {"ba": part.sms(api.SM_BA), "frontend_tracking": part.sms(api.SM_FRONTEND)} if part else None,
-                   "isolated_stage_ms": iso},
+        # `config` describes the WORKLOAD and is byte-identical in both arms (same frames per step, stages, sizes); what is
+        # specific to this run of this arm (threads, host, isolated stage timings) sits in `run_info`
+        "config": workload_config(F, pool, bool(n_lba)),
+        "run_info": {"lba_workers": n_workers, "host_sync": host_sync, "host_cores_allowed": cores_allowed,
+                     "sm_partition": {"ba": part.sms(api.SM_BA), "frontend_tracking": part.sms(api.SM_FRONTEND)} if part else None,
+                     "isolated_stage_ms": iso},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "runs": e2e_runs, "batches_in_flight": 2,

@@ -9,7 +9,7 @@ python - <<PY
 import json
 try:
     d=json.loads(open("gpurun_out/${TAG}_bench.json").read().strip().splitlines()[-1])
-    print("value",round(d["value"]),"ms/step",round(d["ms_per_step"],2),"e2e",round(d["e2e"]["value"]),"lat",d.get("single_frame_latency_ms",{}).get("median"),"lba_window_ms",d["config"]["isolated_stage_ms"])
+    print("value",round(d["value"]),"ms/step",round(d["ms_per_step"],2),"e2e",round(d["e2e"]["value"]),"lat",d.get("single_frame_latency_ms",{}).get("median"),"lba_window_ms",d["run_info"]["isolated_stage_ms"])
     print({k:round(v["ms_per_step"],2) for k,v in d["roofline"]["all_groups"].items()})
 except Exception as e: print("bench parse failed",e); print(open("gpurun_out/${TAG}_bench.err").read()[-1500:])
 PY

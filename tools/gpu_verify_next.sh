@@ -9,5 +9,5 @@ tail -3 gpurun_out/${TAG}_bench_short.err
 python -c "
 import json,sys
 d = json.loads(open('gpurun_out/${TAG}_bench_short.json').read().strip().splitlines()[-1])
-print(d['value'], d['e2e']['value'], d['roofline']['stage_ms_per_step'], d['config']['isolated_stage_ms'])
+print(d['value'], d['e2e']['value'], d['roofline']['stage_ms_per_step'], d['run_info']['isolated_stage_ms'])
 "
