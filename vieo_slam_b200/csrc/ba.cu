@@ -2268,7 +2268,10 @@ int ba_agree_stop(vieo_ba* h, const volatile uint8_t* stop, bool* out) {
 
 // stand-alone computeActiveErrors (+ every edge when all) and the robust chi2 into *d_out (used outside the LM loop)
 int ba_errors(vieo_ba* h, int all, double* d_out) {
-  ba_campose(h);
+  {
+    const int rc = ba_campose(h);
+    if (rc) return rc;
+  }
   if (h->E > 0) {
     k_ba_errors<<<h->n_part, 256, 0, h->st>>>(h->cam, h->B.cp, h->B.X, h->d_es, h->d_ep, h->d_obs, h->d_w, h->d_flags,
                                               h->d_lvl, h->d_sfix, h->points_free ? 1 : 0, h->E, all, h->dm, h->ds,

@@ -80,6 +80,15 @@ void* CallScratch::get(int slot, size_t bytes) {
   return buf[slot];
 }
 
+CallScratch::~CallScratch() {
+  if (device < 0) return;
+  if (st) cudaStreamSynchronize(st);
+  for (int k = 0; k < 12; ++k)
+    if (buf[k]) cudaFree(buf[k]);
+  if (hbuf) cudaFreeHost(hbuf);
+  if (st) cudaStreamDestroy(st);
+}
+
 void* CallScratch::get_pinned(size_t bytes) {
   if (bytes == 0) bytes = 1;
   if (hcap >= bytes) return hbuf;
@@ -106,6 +115,9 @@ void* CallScratch::get_pinned(size_t bytes) {
 // and the front-end / tracking streams the remaining ones.  Driver entry points are resolved through the runtime
 // (cudaGetDriverEntryPoint): no link-time dependency on libcuda.
 #include <cuda.h>
+
+#include <mutex>
+#include <set>
 struct vieo_sm_partition {
   int device = 0;
   CUgreenCtx ctx[2] = {nullptr, nullptr};  // [VIEO_SM_FRONTEND, VIEO_SM_BA]
@@ -140,6 +152,14 @@ const DriverApi& driver_api() {
 }
 thread_local vieo_sm_partition* t_part = nullptr;
 thread_local int t_which = 0;
+// Partitions that exist: a thread's binding (t_part) is only a key into this set, so a thread that is still bound when another
+// thread destroys the partition falls back to ordinary streams instead of dereferencing a freed object.
+std::mutex g_part_mu;
+std::set<vieo_sm_partition*> g_parts;
+bool partition_alive(vieo_sm_partition* p) {
+  std::lock_guard<std::mutex> lk(g_part_mu);
+  return p && g_parts.count(p) != 0;
+}
 }  // namespace
 
 namespace vieo {
@@ -147,6 +167,7 @@ cudaError_t make_stream(cudaStream_t* st, bool high_priority) {
   int lo = 0, hi = 0;
   cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
   if (e != cudaSuccess) return e;
+  if (t_part && !partition_alive(t_part)) t_part = nullptr;  // destroyed by another thread since this one was bound
   if (t_part && t_part->ctx[t_which]) {
     CUstream s = nullptr;
     if (driver_api().GreenCtxStreamCreate(&s, t_part->ctx[t_which], CU_STREAM_NON_BLOCKING, high_priority ? hi : 0) != CUDA_SUCCESS)
@@ -195,12 +216,23 @@ int vieo_sm_partition_create(int device, int ba_sms, vieo_sm_partition_t** out) 
     }
     p->sms[w] = (int)res[w]->sm.smCount;
   }
+  {
+    std::lock_guard<std::mutex> lk(g_part_mu);
+    g_parts.insert(p);
+  }
   *out = p;
   return VIEO_OK;
 }
 void vieo_sm_partition_destroy(vieo_sm_partition_t* p) {
   if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_part_mu);
+    g_parts.erase(p);  // other threads still bound to p see it gone at their next make_stream
+  }
   if (t_part == p) t_part = nullptr;
+  // Streams created inside the partition belong to handles / per-thread staging that the caller destroys first (documented in
+  // the header); the device is drained so that no kernel of such a stream is in flight when the green contexts go away.
+  cudaDeviceSynchronize();
   for (int w = 0; w < 2; ++w)
     if (p->ctx[w]) driver_api().GreenCtxDestroy(p->ctx[w]);
   delete p;
@@ -209,6 +241,7 @@ int vieo_sm_partition_sms(const vieo_sm_partition_t* p, int which) { return p &&
 int vieo_sm_partition_bind_thread(vieo_sm_partition_t* p, int which) {
   using namespace vieo;
   VIEO_ARG(which == VIEO_SM_FRONTEND || which == VIEO_SM_BA, "bad partition index");
+  VIEO_ARG(p == nullptr || partition_alive(p), "the partition was destroyed");
   t_part = p;
   t_which = which;
   return VIEO_OK;

@@ -45,6 +45,9 @@ struct CallScratch {
   void* hbuf = nullptr;
   size_t hcap = 0;
   void* get_pinned(size_t bytes);
+  // a host thread that used a host-buffer entry point gives its stream and staging back when it exits (thread-local
+  // destructors of the main thread run before the runtime's own teardown)
+  ~CallScratch();
 };
 CallScratch* call_scratch(int device);
 
