@@ -1286,7 +1286,44 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
   __syncthreads();
   const int t0 = B.ps_ptr[f], t1 = B.ps_ptr[f + 1];
   const int dup = prm.has_dup;
-  for (int t = t0; t < t1; ++t) {
+  if (!dup) {
+    // Owner-computes, no barrier inside the walk: thread (g = tid / 36, r, cc) owns the tile entries (r, 6 col + cc) of the
+    // columns col % 14 == g, so two edges never race on an entry and the warps drift apart over the keyframe's edges, hiding
+    // each other's index-chain latency (ps_edges -> ep -> pt_ptr -> es -> prcol -> W: the barrier-per-edge form paid that chain
+    // 800 times per keyframe, 2.5 ms per trial).  Every entry still receives its edges in the same order with the same
+    // arithmetic: bit-identical to the barrier form.  Threads 504..509 carry the rhs and scale columns of row tid - 504.
+    constexpr int kGroups = kGbaSchurThreads / 36;
+    const int g = tid / 36, e36 = tid - 36 * g, r = e36 / 6, cc = e36 - 6 * r;
+    const int xr = tid - 36 * kGroups;  // 0..7 for the spare threads
+    for (int t = t0; t < t1; ++t) {
+      const int a = B.ps_edges[t];
+      const int p = B.ep[a];
+      const int c0 = B.pt_ptr[p], c1 = B.pt_ptr[p + 1];
+      const double* Di = B.Dinv + 9 * (size_t)p;
+      const double* Wa = Wb + 18 * (size_t)a;
+      if (g < kGroups) {
+        const double w0 = Wa[3 * r], w1 = Wa[3 * r + 1], w2 = Wa[3 * r + 2];
+        const double d0 = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
+        const double d1 = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
+        const double d2 = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
+        for (int c = c0; c < c1; ++c) {
+          const int col = B.prcol[B.es[c]];
+          if (col < 0 || col % kGroups != g) continue;
+          const double* Wc = Wb + 18 * (size_t)c + 3 * cc;
+          s_tile[r * ld + 6 * col + cc] += d0 * Wc[0] + d1 * Wc[1] + d2 * Wc[2];
+        }
+      } else if (xr < 6) {
+        const double* d = B.db + 3 * (size_t)p;
+        s_tile[xr * ld + 6 * nfree] += Wa[3 * xr] * d[0] + Wa[3 * xr + 1] * d[1] + Wa[3 * xr + 2] * d[2];
+        if (has_scale) {
+          const double* u = B.up + 3 * (size_t)p;
+          s_tile[xr * ld + 6 * nfree + 1] += Wa[3 * xr] * u[0] + Wa[3 * xr + 1] * u[1] + Wa[3 * xr + 2] * u[2];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int t = t0; dup && t < t1; ++t) {
     const int a = B.ps_edges[t];
     const int p = B.ep[a];
     const int c0 = B.pt_ptr[p], nc = B.pt_ptr[p + 1] - c0;
@@ -1769,117 +1806,97 @@ __global__ void k_vb_prepare(BaBuf B, int force) {
   prm.ok = 1;
 }
 
-constexpr int kVbSolveThreads = 32, kVbChunk = 16;
-// Thread per right-hand side (column c of Syp, or by): the dependent chain of a step is what the kernel costs, so a step holds
-// no division (reciprocal diagonals from k_vb_factor), no dependent index load (the chunk's ymap rows are staged with its
-// factors) and no load of a structural zero: column c of Syp is non-zero only in the chain blocks [ylo[c], yhi[c]) (one or two
-// inertial edges touch a keyframe), so the forward sweep starts at ylo[c] with z = 0 and reads S only inside that range; the
-// backward sweep prefetches its Z rows one step ahead.  32-thread CTAs: 76 of them at 400 keyframes, one warp per SM.
+// Nine lanes per right-hand side (column c of Syp, or by), lane i = row i of the 9-dimensional chain block, three columns per
+// warp: a step is a 9 x 9 matrix-vector product and a 9 x 9 triangular solve whose operands a single thread had to pull
+// through 117 shared-memory loads with nothing to hide their latency behind (one warp per SM: 1.9 us per step).  Here a lane
+// keeps ITS row of F and L in registers (prefetched one step ahead straight from L2 / L1: every warp reads the same factors),
+// the vector travels by shuffles, and the dependent chain of a step is 9 multiply-adds + 9 (multiply, shuffle, multiply-add).
+// No division (reciprocal diagonals from k_vb_factor), no load of a structural zero: column c of Syp is non-zero only in the
+// chain blocks [ylo[c], yhi[c]), the forward sweep starts at the warp's first such block with z = 0.
+constexpr int kVbCols = 3, kVbSolveWarps = 4, kVbSolveThreads = 32 * kVbSolveWarps;
 __global__ void __launch_bounds__(kVbSolveThreads) k_vb_solve(BaBuf B, int force) {
-  __shared__ double sLF[kVbChunk][2][81];  // the chain factors of a chunk of blocks, staged once per CTA
-  __shared__ double sRc[kVbChunk][kVB];
-  __shared__ int sYm[kVbChunk][kVB];
   const BaParams& prm = *B.prm;
   if ((prm.done && !force) || !prm.vb_elim) return;
   const int cn = prm.cn, np = prm.np, Ky = prm.Ky, ld = cn + 1;
-  const int c = blockIdx.x * kVbSolveThreads + threadIdx.x;
-  const bool live = c <= cn, rhs = c == cn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / kVB, i = lane - kVB * g, base = kVB * g;  // lanes 27..31 idle (they shuffle along, never store)
+  const int c = (blockIdx.x * kVbSolveWarps + warp) * kVbCols + g;
+  const bool live = g < kVbCols && c <= cn, rhs = c == cn;
   const int pc = (live && !rhs) ? B.pmap[c] : 0;
   const int lo = !live ? Ky : (rhs ? 0 : B.ylo[c]), hi = rhs ? Ky : (live ? B.yhi[c] : 0);
-  double z[kVB];
+  constexpr unsigned kFull = 0xffffffffu;
+  const int m_start = __reduce_min_sync(kFull, lo);
+  // ---- forward: z_m = L_m^-1 (r_m - F_{m-1} z_{m-1}) ----
+  double Fi[kVB], Li[kVB], ri = 1.0, z = 0.0;
+  int ymi = 0;
+  auto fetch_fwd = [&](int m, double (&F)[kVB], double (&L)[kVB], double& r, int& ym) {
 #pragma unroll
-  for (int i = 0; i < kVB; ++i) z[i] = 0;
-  auto stage = [&](int m0, int mc, bool backward) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < mc * 162; e += kVbSolveThreads) {
-      const int mm = e / 162, w = (e % 162) / 81, k = e % 81;
-      const int m = m0 + mm;
-      double v;
-      if (w == 0) v = B.vbL[(size_t)m * kVbLS + k];
-      else if (!backward) v = m > 0 ? B.vbF[(size_t)(m - 1) * 81 + k] : 0.0;
-      else v = m < Ky - 1 ? B.vbF[(size_t)m * 81 + k] : 0.0;
-      sLF[mm][w][k] = v;
+    for (int k = 0; k < kVB; ++k) {
+      F[k] = m > 0 ? B.vbF[(size_t)(m - 1) * 81 + i * kVB + k] : 0.0;
+      L[k] = B.vbL[(size_t)m * kVbLS + i * kVB + k];
     }
-    for (int e = threadIdx.x; e < mc * kVB; e += kVbSolveThreads) {
-      sRc[e / kVB][e % kVB] = B.vbL[(size_t)(m0 + e / kVB) * kVbLS + 81 + e % kVB];
-      sYm[e / kVB][e % kVB] = B.ymap[kVB * (m0 + e / kVB) + e % kVB];
-    }
-    __syncthreads();
+    r = B.vbL[(size_t)m * kVbLS + 81 + i];
+    ym = B.ymap[kVB * m + i];
   };
-  // forward: z_m = L_m^-1 (r_m - F_{m-1} z_{m-1})
-  for (int m0 = 0; m0 < Ky; m0 += kVbChunk) {
-    const int mc = min(kVbChunk, Ky - m0);
-    if (__syncthreads_and(m0 + mc <= lo)) continue;  // the whole CTA is still before its first block
-    stage(m0, mc, false);
-    for (int mm = 0; mm < mc; ++mm) {
-      const int m = m0 + mm;
-      if (m < lo) continue;
-      double v[kVB];
-      if (m < hi) {
+  if (m_start < Ky) fetch_fwd(m_start, Fi, Li, ri, ymi);
+  for (int m = m_start; m < Ky; ++m) {
+    double nF[kVB], nL[kVB], nr = 1.0;
+    int nym = 0;
+    if (m + 1 < Ky) fetch_fwd(m + 1, nF, nL, nr, nym);
+    double v = 0.0;
+    if (live && m >= lo && m < hi) v = rhs ? B.bs[ymi] : __ldg(&B.S[(size_t)ymi * np + pc]);
+    double a = 0.0;
 #pragma unroll
-        for (int i = 0; i < kVB; ++i) v[i] = rhs ? B.bs[sYm[mm][i]] : __ldg(&B.S[(size_t)sYm[mm][i] * np + pc]);
-      } else {
+    for (int k = 0; k < kVB; ++k) a += Fi[k] * __shfl_sync(kFull, z, base + k);
+    v -= a;
 #pragma unroll
-        for (int i = 0; i < kVB; ++i) v[i] = 0.0;
-      }
-      const double* F = sLF[mm][1];
-#pragma unroll
-      for (int i = 0; i < kVB; ++i) {
-        double a = 0;
-#pragma unroll
-        for (int k = 0; k < kVB; ++k) a += F[i * kVB + k] * z[k];
-        v[i] -= a;
-      }
-      const double* L = sLF[mm][0];
-#pragma unroll
-      for (int i = 0; i < kVB; ++i) {
-        double a = v[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) a -= L[i * kVB + k] * z[k];
-        z[i] = a * sRc[mm][i];
-      }
-#pragma unroll
-      for (int i = 0; i < kVB; ++i) B.Z[(size_t)(kVB * m + i) * ld + c] = z[i];
+    for (int j = 0; j < kVB; ++j) {
+      const double zj = __shfl_sync(kFull, v * ri, base + j);
+      if (i == j) z = zj;
+      else if (i > j) v -= Li[j] * zj;
     }
+    if (live && m >= lo) B.Z[(size_t)(kVB * m + i) * ld + c] = z;
+#pragma unroll
+    for (int k = 0; k < kVB; ++k) {
+      Fi[k] = nF[k];
+      Li[k] = nL[k];
+    }
+    ri = nr;
+    ymi = nym;
   }
-  // backward: w_m = L_m^-T (z_m - F_m^T w_{m+1}); blocks before lo hold z_m = 0 (never written by the forward sweep)
-  double w[kVB], nx[kVB];
+  // ---- backward: w_m = L_m^-T (z_m - F_m^T w_{m+1}); blocks before lo hold z_m = 0 (the forward sweep never wrote them) ----
+  double w = 0.0, nx = 0.0;
+  auto fetch_bwd = [&](int m, double (&F)[kVB], double (&L)[kVB], double& r, double& zin) {
 #pragma unroll
-  for (int i = 0; i < kVB; ++i) w[i] = 0;
-  auto fetch_z = [&](int m) {
-#pragma unroll
-    for (int i = 0; i < kVB; ++i) nx[i] = (live && m >= lo) ? B.Z[(size_t)(kVB * m + i) * ld + c] : 0.0;
-  };
-  if (Ky > 0) fetch_z(Ky - 1);
-  for (int m1 = Ky; m1 > 0; m1 -= kVbChunk) {
-    const int m0 = max(0, m1 - kVbChunk), mc = m1 - m0;
-    stage(m0, mc, true);
-    if (!live) continue;
-    for (int mm = mc - 1; mm >= 0; --mm) {
-      const int m = m0 + mm;
-      double v[kVB];
-#pragma unroll
-      for (int i = 0; i < kVB; ++i) v[i] = nx[i];
-      if (m > 0) fetch_z(m - 1);
-      const double* F = sLF[mm][1];
-#pragma unroll
-      for (int i = 0; i < kVB; ++i) {
-        double a = 0;
-#pragma unroll
-        for (int k = 0; k < kVB; ++k) a += F[k * kVB + i] * w[k];
-        v[i] -= a;
-      }
-      const double* L = sLF[mm][0];
-#pragma unroll
-      for (int i = kVB - 1; i >= 0; --i) {
-        double a = v[i];
-#pragma unroll
-        for (int k = i + 1; k < kVB; ++k) a -= L[k * kVB + i] * w[k];
-        w[i] = a * sRc[mm][i];
-      }
-#pragma unroll
-      for (int i = 0; i < kVB; ++i) B.Z[(size_t)(kVB * m + i) * ld + c] = w[i];
+    for (int k = 0; k < kVB; ++k) {
+      F[k] = m < Ky - 1 ? B.vbF[(size_t)m * 81 + k * kVB + i] : 0.0;   // column i of F_m
+      L[k] = B.vbL[(size_t)m * kVbLS + k * kVB + i];                   // column i of L_m
     }
+    r = B.vbL[(size_t)m * kVbLS + 81 + i];
+    zin = (live && m >= lo) ? B.Z[(size_t)(kVB * m + i) * ld + c] : 0.0;
+  };
+  if (Ky > 0) fetch_bwd(Ky - 1, Fi, Li, ri, nx);
+  for (int m = Ky - 1; m >= 0; --m) {
+    double nF[kVB], nL[kVB], nr = 1.0, nz = 0.0;
+    if (m > 0) fetch_bwd(m - 1, nF, nL, nr, nz);
+    double v = nx, a = 0.0;
+#pragma unroll
+    for (int k = 0; k < kVB; ++k) a += Fi[k] * __shfl_sync(kFull, w, base + k);
+    v -= a;
+#pragma unroll
+    for (int j = kVB - 1; j >= 0; --j) {
+      const double wj = __shfl_sync(kFull, v * ri, base + j);
+      if (i == j) w = wj;
+      else if (i < j) v -= Li[j] * wj;
+    }
+    if (live) B.Z[(size_t)(kVB * m + i) * ld + c] = w;
+#pragma unroll
+    for (int k = 0; k < kVB; ++k) {
+      Fi[k] = nF[k];
+      Li[k] = nL[k];
+    }
+    ri = nr;
+    nx = nz;
   }
 }
 
@@ -2336,7 +2353,7 @@ int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, dou
       BA_CK(cudaStreamWaitEvent(h->st_aux, h->ev_fork, 0));
       k_vb_prepare<<<1, 1, 0, h->st_aux>>>(h->B, force);
       k_vb_factor<<<1, 32, 0, h->st_aux>>>(h->B, force);
-      k_vb_solve<<<(h->cn + 1 + kVbSolveThreads - 1) / kVbSolveThreads, kVbSolveThreads, 0, h->st_aux>>>(h->B, force);
+      k_vb_solve<<<(h->cn + 1 + kVbCols * kVbSolveWarps - 1) / (kVbCols * kVbSolveWarps), kVbSolveThreads, 0, h->st_aux>>>(h->B, force);
       BA_CK(cudaEventRecord(h->ev_join, h->st_aux));
       h->launches += 3;
     }
@@ -2355,7 +2372,7 @@ int ba_enqueue_solve(vieo_ba* h, bool at_capacity, int force, double lambda, dou
       if (!vb_side) {
         k_vb_prepare<<<1, 1, 0, h->st>>>(h->B, force);
         k_vb_factor<<<1, 32, 0, h->st>>>(h->B, force);
-        k_vb_solve<<<(nc + 1 + kVbSolveThreads - 1) / kVbSolveThreads, kVbSolveThreads, 0, h->st>>>(h->B, force);
+        k_vb_solve<<<(nc + 1 + kVbCols * kVbSolveWarps - 1) / (kVbCols * kVbSolveWarps), kVbSolveThreads, 0, h->st>>>(h->B, force);
         h->launches += 3;
       }
       k_vb_reduce<<<dim3((nc + 1 + 127) / 128, nc), 128, 0, h->st>>>(h->B, force);
