@@ -483,6 +483,7 @@ struct BaBuf {  // device pointers of one handle (constant for its lifetime)
   const int *pmap, *ymap, *ylo, *yhi;
   uint8_t* pt_active[2];
   const int *es, *ep, *pt_ptr, *off0, *off1, *off2, *prcol, *free_state, *free_off, *ps_ptr, *ps_edges;
+  const int* ecol;  // per edge: prcol[es[edge]] (the free-keyframe column of the edge's keyframe, -1 when fixed)
   const float *obs, *w;
   const uint8_t *flags, *lvl, *sfix;
   const VieoImuPreint* pre;
@@ -1287,41 +1288,83 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
   const int t0 = B.ps_ptr[f], t1 = B.ps_ptr[f + 1];
   const int dup = prm.has_dup;
   if (!dup) {
-    // Owner-computes, no barrier inside the walk: thread (g = tid / 36, r, cc) owns the tile entries (r, 6 col + cc) of the
-    // columns col % 14 == g, so two edges never race on an entry and the warps drift apart over the keyframe's edges, hiding
-    // each other's index-chain latency (ps_edges -> ep -> pt_ptr -> es -> prcol -> W: the barrier-per-edge form paid that chain
-    // 800 times per keyframe, 2.5 ms per trial).  Every entry still receives its edges in the same order with the same
-    // arithmetic: bit-identical to the barrier form.  Threads 504..509 carry the rhs and scale columns of row tid - 504.
-    constexpr int kGroups = kGbaSchurThreads / 36;
-    const int g = tid / 36, e36 = tid - 36 * g, r = e36 / 6, cc = e36 - 6 * r;
-    const int xr = tid - 36 * kGroups;  // 0..7 for the spare threads
-    for (int t = t0; t < t1; ++t) {
-      const int a = B.ps_edges[t];
-      const int p = B.ep[a];
-      const int c0 = B.pt_ptr[p], c1 = B.pt_ptr[p + 1];
-      const double* Di = B.Dinv + 9 * (size_t)p;
+    // The walk over the keyframe's edges, one edge per barrier (two edges of a keyframe may meet in a column, so the order is
+    // fixed) — but with NOTHING of an edge's five-deep index chain (ps_edges -> ep -> pt_ptr -> column -> W) left on the step:
+    // the chain is a register pipeline four edges deep (edge index t + 4, its point t + 3, the point's edge range t + 2, this
+    // thread's operands t + 1), so an iteration issues next edges' loads, then works from registers: 12 multiply-adds, one
+    // shared-memory add, the barrier.  (The un-pipelined form paid ~2300 cycles of load latency per edge, 2.5 ms per trial.)
+    // Thread e = tid handles entry (co-observation e / 36, row (e % 36) / 6, column e % 6) of the point's first 14
+    // co-observations; a point with more takes the rare extra passes with plain loads.  Same sums in the same order as before.
+    const int sub = tid / 36, e36 = tid - 36 * sub, r = e36 / 6, cc = e36 - 6 * r;
+    struct Ops {
+      double w[3], d[9], wc[3], xd[3], xu[3];
+      int col;
+    };
+    auto clampt = [&](int t) { return t < t1 ? t : t1 - 1; };
+    auto load_ops = [&](int a, int p, int c0, int c1, Ops& o) {
       const double* Wa = Wb + 18 * (size_t)a;
-      if (g < kGroups) {
-        const double w0 = Wa[3 * r], w1 = Wa[3 * r + 1], w2 = Wa[3 * r + 2];
-        const double d0 = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
-        const double d1 = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
-        const double d2 = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
-        for (int c = c0; c < c1; ++c) {
-          const int col = B.prcol[B.es[c]];
-          if (col < 0 || col % kGroups != g) continue;
-          const double* Wc = Wb + 18 * (size_t)c + 3 * cc;
-          s_tile[r * ld + 6 * col + cc] += d0 * Wc[0] + d1 * Wc[1] + d2 * Wc[2];
-        }
-      } else if (xr < 6) {
-        const double* d = B.db + 3 * (size_t)p;
-        s_tile[xr * ld + 6 * nfree] += Wa[3 * xr] * d[0] + Wa[3 * xr + 1] * d[1] + Wa[3 * xr + 2] * d[2];
-        if (has_scale) {
-          const double* u = B.up + 3 * (size_t)p;
-          s_tile[xr * ld + 6 * nfree + 1] += Wa[3 * xr] * u[0] + Wa[3 * xr + 1] * u[1] + Wa[3 * xr + 2] * u[2];
+      const double* Di = B.Dinv + 9 * (size_t)p;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o.w[k] = Wa[3 * r + k];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o.d[k] = Di[k];
+      const int c = c0 + sub;
+      o.col = c < c1 ? B.ecol[c] : -1;
+      const double* Wc = Wb + 18 * (size_t)(c < c1 ? c : c0) + 3 * cc;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o.wc[k] = Wc[k];
+      if (tid < 6 || (tid >= 32 && tid < 38)) {  // rhs column (tid < 6) and scale column (32 <= tid < 38) of row tid % 32
+        const double* x = (tid < 6 ? B.db : B.up) + 3 * (size_t)p;
+        const int rr = tid & 31;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          o.xd[k] = Wa[3 * rr + k];
+          o.xu[k] = (tid < 6 || has_scale) ? x[k] : 0.0;
         }
       }
+    };
+    if (t0 < t1) {
+      int a1 = B.ps_edges[clampt(t0 + 1)], a2 = B.ps_edges[clampt(t0 + 2)], a3 = B.ps_edges[clampt(t0 + 3)];
+      int a0 = B.ps_edges[t0];
+      int p0 = B.ep[a0], p1 = B.ep[a1], p2 = B.ep[a2];
+      int c00 = B.pt_ptr[p0], c01 = B.pt_ptr[p0 + 1], c10 = B.pt_ptr[p1], c11 = B.pt_ptr[p1 + 1];
+      Ops cur, nxt;
+      load_ops(a0, p0, c00, c01, cur);
+      for (int t = t0; t < t1; ++t) {
+        // ---- issue the loads of the following edges ----
+        const int a4 = B.ps_edges[clampt(t + 4)];
+        const int p3 = B.ep[a3];
+        const int c20 = B.pt_ptr[p2], c21 = B.pt_ptr[p2 + 1];
+        load_ops(a1, p1, c10, c11, nxt);
+        // ---- edge t from registers ----
+        if (tid < 6) s_tile[tid * ld + 6 * nfree] += cur.xd[0] * cur.xu[0] + cur.xd[1] * cur.xu[1] + cur.xd[2] * cur.xu[2];
+        else if (tid >= 32 && tid < 38 && has_scale)
+          s_tile[(tid - 32) * ld + 6 * nfree + 1] += cur.xd[0] * cur.xu[0] + cur.xd[1] * cur.xu[1] + cur.xd[2] * cur.xu[2];
+        const double d0 = cur.w[0] * cur.d[0] + cur.w[1] * cur.d[3] + cur.w[2] * cur.d[6];
+        const double d1 = cur.w[0] * cur.d[1] + cur.w[1] * cur.d[4] + cur.w[2] * cur.d[7];
+        const double d2 = cur.w[0] * cur.d[2] + cur.w[1] * cur.d[5] + cur.w[2] * cur.d[8];
+        if (cur.col >= 0) s_tile[r * ld + 6 * cur.col + cc] += d0 * cur.wc[0] + d1 * cur.wc[1] + d2 * cur.wc[2];
+        const int nc = c01 - c00;
+        for (int e = tid + T; e < 36 * nc; e += T) {  // co-observations 15, 16, ... of a long track
+          const int c = c00 + e / 36, r2 = (e % 36) / 6, cc2 = e % 6;
+          const int col = B.ecol[c];
+          if (col < 0) continue;
+          const double* Wa = Wb + 18 * (size_t)a0;
+          const double w0 = Wa[3 * r2], w1 = Wa[3 * r2 + 1], w2 = Wa[3 * r2 + 2];
+          const double e0 = w0 * cur.d[0] + w1 * cur.d[3] + w2 * cur.d[6];
+          const double e1 = w0 * cur.d[1] + w1 * cur.d[4] + w2 * cur.d[7];
+          const double e2 = w0 * cur.d[2] + w1 * cur.d[5] + w2 * cur.d[8];
+          const double* Wc = Wb + 18 * (size_t)c + 3 * cc2;
+          s_tile[r2 * ld + 6 * col + cc2] += e0 * Wc[0] + e1 * Wc[1] + e2 * Wc[2];
+        }
+        __syncthreads();
+        // ---- rotate the pipeline ----
+        a0 = a1; a1 = a2; a2 = a3; a3 = a4;
+        p0 = p1; p1 = p2; p2 = p3;
+        c00 = c10; c01 = c11; c10 = c20; c11 = c21;
+        cur = nxt;
+      }
     }
-    __syncthreads();
   }
   for (int t = t0; dup && t < t1; ++t) {
     const int a = B.ps_edges[t];
@@ -2169,7 +2212,7 @@ struct vieo_ba {
   double *d_sys = nullptr, *d_xl = nullptr, *d_ctl = nullptr;
   uint8_t *d_lvl = nullptr, *d_bad = nullptr, *d_flags = nullptr, *d_sfix = nullptr;
   int *d_es = nullptr, *d_ep = nullptr, *d_pt_ptr = nullptr, *d_off0 = nullptr, *d_off1 = nullptr, *d_off2 = nullptr,
-      *d_prcol = nullptr, *d_free_state = nullptr, *d_free_off = nullptr, *d_ps_ptr = nullptr, *d_ps_edges = nullptr;
+      *d_prcol = nullptr, *d_free_state = nullptr, *d_free_off = nullptr, *d_ps_ptr = nullptr, *d_ps_edges = nullptr, *d_ecol = nullptr;
   float *d_obs = nullptr, *d_w = nullptr;
   VieoImuPreint* d_pre = nullptr;
   BaDense* d_den = nullptr;
@@ -2443,7 +2486,7 @@ void ba_free(vieo_ba* h) {
                   B.pt_active[1], B.wk, B.wsp[0], B.wsp[1], B.up, B.sred, B.As, B.spart, B.cS, B.cbs, B.cx, B.vbL, B.vbF, B.Z,
                   h->d_pmap, h->d_ymap, h->d_ylo, h->d_yhi, h->d_nz, h->d_yv, h->d_sys, h->d_xl, h->d_ctl, h->d_lvl, h->d_bad, h->d_flags, h->d_sfix, h->d_es,
                   h->d_ep, h->d_pt_ptr, h->d_off0, h->d_off1, h->d_off2, h->d_prcol, h->d_free_state, h->d_free_off,
-                  h->d_ps_ptr, h->d_ps_edges, h->d_obs, h->d_w, h->d_pre, h->d_den};
+                  h->d_ps_ptr, h->d_ps_edges, h->d_obs, h->d_w, h->d_pre, h->d_den, h->d_ecol};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -2663,6 +2706,7 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
   step(dalloc(&h->d_off0, K)); step(dalloc(&h->d_off1, K)); step(dalloc(&h->d_off2, K)); step(dalloc(&h->d_prcol, K));
   step(dalloc(&h->d_free_state, K)); step(dalloc(&h->d_free_off, K)); step(dalloc(&h->d_ps_ptr, K + 1));
   step(dalloc(&h->d_ps_edges, E)); step(dalloc(&h->d_obs, 3 * E)); step(dalloc(&h->d_w, E));
+  step(dalloc(&h->d_ecol, E));
   step(dalloc(&h->d_flags, E)); step(dalloc(&h->d_lvl, E)); step(dalloc(&h->d_sfix, K));
   step(dalloc(&h->d_bad, E)); step(dalloc(&h->d_pre, M)); step(dalloc(&h->d_den, 2 * M + 1)); step(dalloc(&B.wk, 2 * M + 1));
   step(cudaEventCreate(&h->ev_begin)); step(cudaEventCreate(&h->ev_end));
@@ -2673,6 +2717,7 @@ static int ba_create_impl(int max_states, int max_points, int max_edges, int max
   if (e == cudaSuccess) {
     h->cap_np = NP;
     B.bs = h->d_sys; B.bsys = h->d_sys + NP; B.S = h->d_sys + 2 * NP;
+    B.ecol = h->d_ecol;
     B.es = h->d_es; B.ep = h->d_ep; B.pt_ptr = h->d_pt_ptr; B.off0 = h->d_off0; B.off1 = h->d_off1; B.off2 = h->d_off2;
     B.prcol = h->d_prcol; B.free_state = h->d_free_state; B.free_off = h->d_free_off; B.ps_ptr = h->d_ps_ptr;
     B.ps_edges = h->d_ps_edges; B.obs = h->d_obs; B.w = h->d_w; B.flags = h->d_flags; B.lvl = h->d_lvl; B.sfix = h->d_sfix;
@@ -3054,6 +3099,11 @@ int vieo_ba_set_problem(vieo_ba_t* h, const VieoBaProblem* pb, const VieoCamera*
   BA_CK(up(h->d_off1, h->off1.data(), 4 * (size_t)K));
   BA_CK(up(h->d_off2, h->off2.data(), 4 * (size_t)K));
   BA_CK(up(h->d_prcol, prcol.data(), 4 * (size_t)K));
+  {
+    std::vector<int> ecol((size_t)std::max(E, 1));
+    for (int i = 0; i < E; ++i) ecol[i] = prcol[pb->edge_state[i]];
+    BA_CK(up(h->d_ecol, ecol.data(), 4 * (size_t)E));
+  }
   BA_CK(up(h->d_free_state, free_state.data(), 4 * (size_t)h->nfree));
   BA_CK(up(h->d_free_off, free_off.data(), 4 * (size_t)h->nfree));
   BA_CK(up(h->d_ps_ptr, ps_ptr.data(), 4 * (size_t)(h->nfree + 1)));
