@@ -1249,6 +1249,54 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_chol(BaBuf B, int force) {
 // Schur complement, one CTA per free keyframe row: the CTA owns the 6 x (6 nfree + 1) row tile in shared memory and
 // walks the keyframe's edges in order; for edge a the whole CTA adds the (W_a Dinv) W_c^T blocks of the point's other
 // observations c (one thread per entry, distinct columns, no atomics), then the tile is subtracted from S / bschur.
+// ---- shared-memory pipeline primitives of k_gba_schur (mbarrier, TMA 1-D bulk copy, cp.async) --------------------------------
+constexpr int kSchurRing = 4, kSchurChunk = 32;
+struct __align__(128) SchurSlot {
+  double Wc[kSchurChunk * 18];  // the point's co-observation W blocks (bulk copy destination, 16-byte aligned)
+  double Wa[18];                // the edge's own W block (bulk copy destination)
+  double Di[9], db[3], up[3];   // the point's inverse Hll, Hll^-1 bl, Hll^-1 wsp
+  int cols[kSchurChunk];        // free-keyframe column of every co-observation (-1: fixed keyframe)
+  int n, flags;                 // co-observations in this slot; 1 = first slot of its edge, 2 = last slot of the walk
+};
+__host__ __device__ inline size_t schur_ring_offset(int nfree) {
+  const size_t tile = sizeof(double) * (6 * (6 * (size_t)nfree + 2));
+  return (tile + 127) / 128 * 128;
+}
+__device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "VIEO_SW_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra VIEO_SD_%=;\n"
+      "bra VIEO_SW_%=;\n"
+      "VIEO_SD_%=:\n"
+      "}\n" ::"r"(sm_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm_addr(dst)),
+               "l"(src), "r"(bytes), "r"(sm_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sm_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sm_addr(bar)) : "memory");
+}
+
 constexpr int kGbaSchurThreads = 512;
 __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int force) {
   extern __shared__ double s_tile[];  // [6][ld]
@@ -1287,84 +1335,114 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
   __syncthreads();
   const int t0 = B.ps_ptr[f], t1 = B.ps_ptr[f + 1];
   const int dup = prm.has_dup;
-  if (!dup) {
-    // The walk over the keyframe's edges, one edge per barrier (two edges of a keyframe may meet in a column, so the order is
-    // fixed) — but with NOTHING of an edge's five-deep index chain (ps_edges -> ep -> pt_ptr -> column -> W) left on the step:
-    // the chain is a register pipeline four edges deep (edge index t + 4, its point t + 3, the point's edge range t + 2, this
-    // thread's operands t + 1), so an iteration issues next edges' loads, then works from registers: 12 multiply-adds, one
-    // shared-memory add, the barrier.  (The un-pipelined form paid ~2300 cycles of load latency per edge, 2.5 ms per trial.)
-    // Thread e = tid handles entry (co-observation e / 36, row (e % 36) / 6, column e % 6) of the point's first 14
-    // co-observations; a point with more takes the rare extra passes with plain loads.  Same sums in the same order as before.
-    const int sub = tid / 36, e36 = tid - 36 * sub, r = e36 / 6, cc = e36 - 6 * r;
-    struct Ops {
-      double w[3], d[9], wc[3], xd[3], xu[3];
-      int col;
-    };
-    auto clampt = [&](int t) { return t < t1 ? t : t1 - 1; };
-    auto load_ops = [&](int a, int p, int c0, int c1, Ops& o) {
-      const double* Wa = Wb + 18 * (size_t)a;
-      const double* Di = B.Dinv + 9 * (size_t)p;
+  if (!dup && t0 < t1) {
+    // The walk over the keyframe's edges as a PRODUCER / CONSUMER pipeline through shared memory (two edges of a keyframe may
+    // meet in a column, so the edges are consumed strictly in order, one consumer barrier per step):
+    //  * warp 15 produces: it resolves the index chain of 32 edges at a time, one edge per lane (ps_edges -> ep -> pt_ptr and
+    //    the point's Dinv / db / up: the five-deep dependent chain that cost the un-pipelined walk ~2300 cycles per edge is
+    //    paid once per 32 edges), then fills a ring of kSchurRing slots per edge: the edge's own W block and the point's
+    //    CONTIGUOUS run of co-observation W blocks (edges are sorted by point) by two bulk async copies (TMA 1-D,
+    //    cp.async.bulk ... mbarrier::complete_tx), the co-observations' columns by 4-byte cp.async, the 15 doubles of the
+    //    point from the owning lane's registers; a `full` mbarrier per slot collects the byte count and the lanes' arrivals;
+    //  * warps 0..14 consume: wait for the slot, 12 multiply-adds per entry from shared memory into the row tile (thread e
+    //    handles co-observation e / 36, row (e % 36) / 6, column e % 6), a named barrier of the 480 consumers, and one
+    //    arrival on the slot's `empty` mbarrier.  A point with more than 32 co-observations takes several slots.
+    // Every tile entry receives its edges in the same order with the same arithmetic as the one-barrier-per-edge form.
+    SchurSlot* ring = reinterpret_cast<SchurSlot*>(reinterpret_cast<uint8_t*>(s_tile) + schur_ring_offset(nfree));
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kSchurRing);
+    uint64_t* empty = full + kSchurRing;
+    if (tid == 0) {
+      for (int k = 0; k < kSchurRing; ++k) {
+        mbar_init(&full[k], 33);  // 32 lanes' cp.async arrivals + lane 0's arrive.expect_tx
+        mbar_init(&empty[k], 1);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    constexpr int kConsumers = kGbaSchurThreads - 32;
+    if (tid >= kConsumers) {
+      // ---------------- producer warp ----------------
+      const int lane = tid - kConsumers;
+      int fill = 0;
+      for (int tb = t0; tb < t1; tb += 32) {
+        const int t = tb + lane;
+        const bool valid = t < t1;
+        const int a = valid ? B.ps_edges[t] : 0;
+        const int p = valid ? B.ep[a] : 0;
+        const int c0 = valid ? B.pt_ptr[p] : 0, c1 = valid ? B.pt_ptr[p + 1] : 0;
+        double pt[15];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) o.w[k] = Wa[3 * r + k];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) o.d[k] = Di[k];
-      const int c = c0 + sub;
-      o.col = c < c1 ? B.ecol[c] : -1;
-      const double* Wc = Wb + 18 * (size_t)(c < c1 ? c : c0) + 3 * cc;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) o.wc[k] = Wc[k];
-      if (tid < 6 || (tid >= 32 && tid < 38)) {  // rhs column (tid < 6) and scale column (32 <= tid < 38) of row tid % 32
-        const double* x = (tid < 6 ? B.db : B.up) + 3 * (size_t)p;
-        const int rr = tid & 31;
+        for (int k = 0; k < 9; ++k) pt[k] = valid ? B.Dinv[9 * (size_t)p + k] : 0.0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          o.xd[k] = Wa[3 * rr + k];
-          o.xu[k] = (tid < 6 || has_scale) ? x[k] : 0.0;
+          pt[9 + k] = valid ? B.db[3 * (size_t)p + k] : 0.0;
+          pt[12 + k] = (valid && has_scale) ? B.up[3 * (size_t)p + k] : 0.0;
+        }
+        const int n_here = min(32, t1 - tb);
+        for (int l = 0; l < n_here; ++l) {
+          const int a_l = __shfl_sync(0xffffffffu, a, l), c0_l = __shfl_sync(0xffffffffu, c0, l), c1_l = __shfl_sync(0xffffffffu, c1, l);
+          const bool last_edge = tb + l == t1 - 1;
+          int cs = c0_l;
+          do {  // at least one slot per edge, so the consumers always meet the walk's last slot
+            const int n = max(0, min(kSchurChunk, c1_l - cs));
+            const int slot = fill % kSchurRing;
+            mbar_wait(&empty[slot], ((fill / kSchurRing) & 1) ^ 1);
+            SchurSlot& S = ring[slot];
+            if (lane == l) {
+#pragma unroll
+              for (int k = 0; k < 9; ++k) S.Di[k] = pt[k];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                S.db[k] = pt[9 + k];
+                S.up[k] = pt[12 + k];
+              }
+              S.n = n;
+              S.flags = (cs == c0_l ? 1 : 0) | ((last_edge && cs + kSchurChunk >= c1_l) ? 2 : 0);  // (an empty range: one slot, both flags)
+            }
+            if (lane < n) cp_async4(&S.cols[lane], B.ecol + cs + lane);
+            cp_async_mbar_arrive(&full[slot]);
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_expect_tx(&full[slot], 144u * (unsigned)(n + 1));
+              bulk_g2s(S.Wa, Wb + 18 * (size_t)a_l, 144u, &full[slot]);
+              if (n > 0) bulk_g2s(S.Wc, Wb + 18 * (size_t)cs, 144u * (unsigned)n, &full[slot]);
+            }
+            ++fill;
+            cs += kSchurChunk;
+          } while (cs < c1_l);
         }
       }
-    };
-    if (t0 < t1) {
-      int a1 = B.ps_edges[clampt(t0 + 1)], a2 = B.ps_edges[clampt(t0 + 2)], a3 = B.ps_edges[clampt(t0 + 3)];
-      int a0 = B.ps_edges[t0];
-      int p0 = B.ep[a0], p1 = B.ep[a1], p2 = B.ep[a2];
-      int c00 = B.pt_ptr[p0], c01 = B.pt_ptr[p0 + 1], c10 = B.pt_ptr[p1], c11 = B.pt_ptr[p1 + 1];
-      Ops cur, nxt;
-      load_ops(a0, p0, c00, c01, cur);
-      for (int t = t0; t < t1; ++t) {
-        // ---- issue the loads of the following edges ----
-        const int a4 = B.ps_edges[clampt(t + 4)];
-        const int p3 = B.ep[a3];
-        const int c20 = B.pt_ptr[p2], c21 = B.pt_ptr[p2 + 1];
-        load_ops(a1, p1, c10, c11, nxt);
-        // ---- edge t from registers ----
-        if (tid < 6) s_tile[tid * ld + 6 * nfree] += cur.xd[0] * cur.xu[0] + cur.xd[1] * cur.xu[1] + cur.xd[2] * cur.xu[2];
-        else if (tid >= 32 && tid < 38 && has_scale)
-          s_tile[(tid - 32) * ld + 6 * nfree + 1] += cur.xd[0] * cur.xu[0] + cur.xd[1] * cur.xu[1] + cur.xd[2] * cur.xu[2];
-        const double d0 = cur.w[0] * cur.d[0] + cur.w[1] * cur.d[3] + cur.w[2] * cur.d[6];
-        const double d1 = cur.w[0] * cur.d[1] + cur.w[1] * cur.d[4] + cur.w[2] * cur.d[7];
-        const double d2 = cur.w[0] * cur.d[2] + cur.w[1] * cur.d[5] + cur.w[2] * cur.d[8];
-        if (cur.col >= 0) s_tile[r * ld + 6 * cur.col + cc] += d0 * cur.wc[0] + d1 * cur.wc[1] + d2 * cur.wc[2];
-        const int nc = c01 - c00;
-        for (int e = tid + T; e < 36 * nc; e += T) {  // co-observations 15, 16, ... of a long track
-          const int c = c00 + e / 36, r2 = (e % 36) / 6, cc2 = e % 6;
-          const int col = B.ecol[c];
-          if (col < 0) continue;
-          const double* Wa = Wb + 18 * (size_t)a0;
-          const double w0 = Wa[3 * r2], w1 = Wa[3 * r2 + 1], w2 = Wa[3 * r2 + 2];
-          const double e0 = w0 * cur.d[0] + w1 * cur.d[3] + w2 * cur.d[6];
-          const double e1 = w0 * cur.d[1] + w1 * cur.d[4] + w2 * cur.d[7];
-          const double e2 = w0 * cur.d[2] + w1 * cur.d[5] + w2 * cur.d[8];
-          const double* Wc = Wb + 18 * (size_t)c + 3 * cc2;
-          s_tile[r2 * ld + 6 * col + cc2] += e0 * Wc[0] + e1 * Wc[1] + e2 * Wc[2];
+    } else {
+      // ---------------- consumers ----------------
+      for (int k = 0;; ++k) {
+        const int slot = k % kSchurRing;
+        mbar_wait(&full[slot], (k / kSchurRing) & 1);
+        const SchurSlot& S = ring[slot];
+        const int n = S.n, fl = S.flags;
+        if (fl & 1) {
+          if (tid < 6) s_tile[tid * ld + 6 * nfree] += S.Wa[3 * tid] * S.db[0] + S.Wa[3 * tid + 1] * S.db[1] + S.Wa[3 * tid + 2] * S.db[2];
+          else if (tid >= 32 && tid < 38 && has_scale) {
+            const int r = tid - 32;
+            s_tile[r * ld + 6 * nfree + 1] += S.Wa[3 * r] * S.up[0] + S.Wa[3 * r + 1] * S.up[1] + S.Wa[3 * r + 2] * S.up[2];
+          }
         }
-        __syncthreads();
-        // ---- rotate the pipeline ----
-        a0 = a1; a1 = a2; a2 = a3; a3 = a4;
-        p0 = p1; p1 = p2; p2 = p3;
-        c00 = c10; c01 = c11; c10 = c20; c11 = c21;
-        cur = nxt;
+        for (int e = tid; e < 36 * n; e += kConsumers) {
+          const int j = e / 36, e36 = e - 36 * j, r = e36 / 6, cc = e36 - 6 * r;
+          const int col = S.cols[j];
+          if (col < 0) continue;
+          const double w0 = S.Wa[3 * r], w1 = S.Wa[3 * r + 1], w2 = S.Wa[3 * r + 2];
+          const double d0 = w0 * S.Di[0] + w1 * S.Di[3] + w2 * S.Di[6];
+          const double d1 = w0 * S.Di[1] + w1 * S.Di[4] + w2 * S.Di[7];
+          const double d2 = w0 * S.Di[2] + w1 * S.Di[5] + w2 * S.Di[8];
+          const double* Wc = S.Wc + 18 * j + 3 * cc;
+          s_tile[r * ld + 6 * col + cc] += d0 * Wc[0] + d1 * Wc[1] + d2 * Wc[2];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+        if (tid == 0) mbar_arrive(&empty[slot]);
+        if (fl & 2) break;
       }
     }
+    __syncthreads();
   }
   for (int t = t0; dup && t < t1; ++t) {
     const int a = B.ps_edges[t];
@@ -2296,7 +2374,9 @@ bool host_inverse(const double* A, int n, double* Ai) {
 constexpr int kNodesPerTrial = 8;  // kernels of one LM trial (ba_enqueue_trial)
 size_t schur_smem(int nfree) { return sizeof(double) * kBaWarps * 6 * (6 * (size_t)nfree + 1); }
 size_t gba_schur_smem(int nfree) {  // row tile [6][6 nfree + 2]; the extra block's two reduction arrays need 2 T doubles
-  return sizeof(double) * std::max<size_t>(6 * (6 * (size_t)nfree + 2), 2 * (size_t)kGbaSchurThreads);
+  const size_t tile = sizeof(double) * std::max<size_t>(6 * (6 * (size_t)nfree + 2), 2 * (size_t)kGbaSchurThreads);
+  // + the producer / consumer ring behind the tile and its 2 x kSchurRing mbarriers
+  return std::max(tile, schur_ring_offset(nfree) + kSchurRing * sizeof(SchurSlot) + 2 * kSchurRing * sizeof(uint64_t));
 }
 
 int ba_campose(vieo_ba* h) {
