@@ -1250,7 +1250,7 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_chol(BaBuf B, int force) {
 // walks the keyframe's edges in order; for edge a the whole CTA adds the (W_a Dinv) W_c^T blocks of the point's other
 // observations c (one thread per entry, distinct columns, no atomics), then the tile is subtracted from S / bschur.
 // ---- shared-memory pipeline primitives of k_gba_schur (mbarrier, TMA 1-D bulk copy, cp.async) --------------------------------
-constexpr int kSchurRing = 4, kSchurChunk = 32;
+constexpr int kSchurRingMax = 16, kSchurChunk = 32;  // ring depth: as many slots as fit beside the row tile, at most 16
 struct __align__(128) SchurSlot {
   double Wc[kSchurChunk * 18];  // the point's co-observation W blocks (bulk copy destination, 16-byte aligned)
   double Wa[18];                // the edge's own W block (bulk copy destination)
@@ -1261,6 +1261,14 @@ struct __align__(128) SchurSlot {
 __host__ __device__ inline size_t schur_ring_offset(int nfree) {
   const size_t tile = sizeof(double) * (6 * (6 * (size_t)nfree + 2));
   return (tile + 127) / 128 * 128;
+}
+// slots that fit into the 227 KB of a CTA behind the row tile (the bulk copies of a slot take ~1.5 us to land: with 4 slots
+// the consumers waited for every one of them; 16 slots keep ~10 edges in flight)
+__host__ __device__ inline int schur_ring_depth(int nfree) {
+  const size_t left = 227 * 1024 - 256 - schur_ring_offset(nfree);
+  const size_t per = sizeof(SchurSlot) + 16;
+  const int d = (int)(left / per);
+  return d < 2 ? 2 : (d > kSchurRingMax ? kSchurRingMax : d);
 }
 __device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -1340,7 +1348,7 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
     // meet in a column, so the edges are consumed strictly in order, one consumer barrier per step):
     //  * warp 15 produces: it resolves the index chain of 32 edges at a time, one edge per lane (ps_edges -> ep -> pt_ptr and
     //    the point's Dinv / db / up: the five-deep dependent chain that cost the un-pipelined walk ~2300 cycles per edge is
-    //    paid once per 32 edges), then fills a ring of kSchurRing slots per edge: the edge's own W block and the point's
+    //    paid once per 32 edges), then fills a ring of up to 16 slots, one per edge: the edge's own W block and the point's
     //    CONTIGUOUS run of co-observation W blocks (edges are sorted by point) by two bulk async copies (TMA 1-D,
     //    cp.async.bulk ... mbarrier::complete_tx), the co-observations' columns by 4-byte cp.async, the 15 doubles of the
     //    point from the owning lane's registers; a `full` mbarrier per slot collects the byte count and the lanes' arrivals;
@@ -1349,6 +1357,7 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
     //    arrival on the slot's `empty` mbarrier.  A point with more than 32 co-observations takes several slots.
     // Every tile entry receives its edges in the same order with the same arithmetic as the one-barrier-per-edge form.
     SchurSlot* ring = reinterpret_cast<SchurSlot*>(reinterpret_cast<uint8_t*>(s_tile) + schur_ring_offset(nfree));
+    const int kSchurRing = schur_ring_depth(nfree);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + kSchurRing);
     uint64_t* empty = full + kSchurRing;
     if (tid == 0) {
@@ -2376,7 +2385,8 @@ size_t schur_smem(int nfree) { return sizeof(double) * kBaWarps * 6 * (6 * (size
 size_t gba_schur_smem(int nfree) {  // row tile [6][6 nfree + 2]; the extra block's two reduction arrays need 2 T doubles
   const size_t tile = sizeof(double) * std::max<size_t>(6 * (6 * (size_t)nfree + 2), 2 * (size_t)kGbaSchurThreads);
   // + the producer / consumer ring behind the tile and its 2 x kSchurRing mbarriers
-  return std::max(tile, schur_ring_offset(nfree) + kSchurRing * sizeof(SchurSlot) + 2 * kSchurRing * sizeof(uint64_t));
+  const size_t R = (size_t)schur_ring_depth(nfree);
+  return std::max(tile, schur_ring_offset(nfree) + R * sizeof(SchurSlot) + 2 * R * sizeof(uint64_t));
 }
 
 int ba_campose(vieo_ba* h) {
