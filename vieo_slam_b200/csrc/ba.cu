@@ -1250,7 +1250,7 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_chol(BaBuf B, int force) {
 // walks the keyframe's edges in order; for edge a the whole CTA adds the (W_a Dinv) W_c^T blocks of the point's other
 // observations c (one thread per entry, distinct columns, no atomics), then the tile is subtracted from S / bschur.
 // ---- shared-memory pipeline primitives of k_gba_schur (mbarrier, TMA 1-D bulk copy, cp.async) --------------------------------
-constexpr int kSchurRingMax = 16, kSchurChunk = 32;  // ring depth: as many slots as fit beside the row tile, at most 16
+constexpr int kSchurRingMax = 4, kSchurChunk = 32;  // ring depth (measured: 16 slots are no faster than 4 — the walk is bound by the per-edge issue cost of producer and TMA unit, not by copy latency)
 struct __align__(128) SchurSlot {
   double Wc[kSchurChunk * 18];  // the point's co-observation W blocks (bulk copy destination, 16-byte aligned)
   double Wa[18];                // the edge's own W block (bulk copy destination)
@@ -1262,8 +1262,7 @@ __host__ __device__ inline size_t schur_ring_offset(int nfree) {
   const size_t tile = sizeof(double) * (6 * (6 * (size_t)nfree + 2));
   return (tile + 127) / 128 * 128;
 }
-// slots that fit into the 227 KB of a CTA behind the row tile (the bulk copies of a slot take ~1.5 us to land: with 4 slots
-// the consumers waited for every one of them; 16 slots keep ~10 edges in flight)
+// slots behind the row tile, bounded by what is left of the CTA's 227 KB
 __host__ __device__ inline int schur_ring_depth(int nfree) {
   const size_t left = 227 * 1024 - 256 - schur_ring_offset(nfree);
   const size_t per = sizeof(SchurSlot) + 16;
@@ -1348,7 +1347,7 @@ __global__ void __launch_bounds__(kGbaSchurThreads) k_gba_schur(BaBuf B, int for
     // meet in a column, so the edges are consumed strictly in order, one consumer barrier per step):
     //  * warp 15 produces: it resolves the index chain of 32 edges at a time, one edge per lane (ps_edges -> ep -> pt_ptr and
     //    the point's Dinv / db / up: the five-deep dependent chain that cost the un-pipelined walk ~2300 cycles per edge is
-    //    paid once per 32 edges), then fills a ring of up to 16 slots, one per edge: the edge's own W block and the point's
+    //    paid once per 32 edges), then fills a ring of kSchurRingMax slots, one per edge: the edge's own W block and the point's
     //    CONTIGUOUS run of co-observation W blocks (edges are sorted by point) by two bulk async copies (TMA 1-D,
     //    cp.async.bulk ... mbarrier::complete_tx), the co-observations' columns by 4-byte cp.async, the 15 doubles of the
     //    point from the owning lane's registers; a `full` mbarrier per slot collects the byte count and the lanes' arrivals;
