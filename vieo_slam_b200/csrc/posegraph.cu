@@ -734,7 +734,19 @@ int pg_run(int K, const VieoSim3* Scw, const uint8_t* fixed, int fix_scale, int 
   P.stats = (VieoPoseGraphStats*)d_stats.p;
   P.Tcw = (double*)d_tcw.p;
   void* args[] = {&P};
-  VIEO_CK(cudaLaunchCooperativeKernel((const void*)k_posegraph, dim3(G), dim3(kPgThreads), args, kPgSmem, st));
+  {
+    // a thread bound to an SM partition (green context) owns fewer SMs than the device reports: a cooperative grid that does
+    // not fit is refused, not queued — halve it until it is accepted (the kernel is written for any grid size >= 1)
+    int g_try = G;
+    cudaError_t le;
+    for (;;) {
+      le = cudaLaunchCooperativeKernel((const void*)k_posegraph, dim3(g_try), dim3(kPgThreads), args, kPgSmem, st);
+      if (le != cudaErrorCooperativeLaunchTooLarge || g_try == 1) break;
+      (void)cudaGetLastError();
+      g_try = std::max(1, g_try / 2);
+    }
+    VIEO_CK(le);
+  }
   VIEO_CK(cudaMemcpyAsync(Scw_out, ds, sizeof(Sim3d) * (size_t)K, cudaMemcpyDeviceToHost, st));
   VIEO_CK(cudaMemcpyAsync(stats, d_stats.p, sizeof(*stats), cudaMemcpyDeviceToHost, st));
   if (Tcw_out) VIEO_CK(cudaMemcpyAsync(Tcw_out, d_tcw.p, sizeof(double) * 12 * (size_t)K, cudaMemcpyDeviceToHost, st));
