@@ -62,6 +62,18 @@ def compute():
     tilt = synth.so3_exp(np.array([0.03, -0.02, 0.0])) @ synth.GRAVITY_W
     go = O.global_ba_prv_init(gi, cam, 8, tilt)
     out["gbai_gw"], out["gbai_err"] = go["gw"], np.array([go["res"]["err_end"]])
+    # loop closing: Sim3 refinement, essential graph (single damped step: no accept / reject decisions on numeric-Jacobian noise),
+    # point correction; the rig form of the visibility test
+    eg = synth.make_essential_graph(K=30, seed=5, fix_scale=False, odom_info_every=4, n_points=200)
+    so, st, H, b = O.essential_graph(eg, lambda_init=1e-3, single_step=True, want_system=True)
+    out["eg_t"], out["eg_s"], out["eg_chi"], out["eg_Hdiag"], out["eg_b"] = so["t"], so["s"], np.array([st["chi2_initial"], st["chi2_final"]]), np.diag(H).copy(), b
+    full, stf = O.essential_graph(eg)
+    out["eg_full_chi"] = np.array([stf["chi2_final"]])
+    out["eg_points"] = O.essential_graph_correct_points(eg["Pw"], eg["ref"], eg["Scw"], so)
+    rp = synth.make_frustum_rig_problem(19, n_frames=2, n_q=800, n_cams=4, model=2)
+    ro = O.is_in_frustum_rig(rp)
+    for k in ("inview", "cam_mask", "level", "proj", "viewcos", "depth", "n_inview"):
+        out["rig_" + k] = ro[k]
     return {k: np.asarray(v) for k, v in out.items()}
 
 
