@@ -1769,7 +1769,7 @@ __global__ void __launch_bounds__(256) k_gchol_back(BaBuf B, const uint8_t* __re
                                                     int k0, int force) {
   extern __shared__ double s_gchol[];
   double (*Ls)[kGNB + 1] = reinterpret_cast<double (*)[kGNB + 1]>(s_gchol);
-  __shared__ double sx[kGNB];
+  __shared__ double sx[kGNB], rdb[kGNB];  // rdb = 1 / L_jj, taken off the 64-step dependent chain below
   const BaParams& prm = *B.prm;
   if (prm.done && !force) return;
   const int n = prm.vb_elim ? prm.cn : prm.np;  // the compact system when the V / Bias chain is eliminated first
@@ -1787,10 +1787,12 @@ __global__ void __launch_bounds__(256) k_gchol_back(BaBuf B, const uint8_t* __re
     Ls[i][j] = (i < nb && j <= i) ? B.S[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
   }
   __syncthreads();
+  if (t < kGNB) rdb[t] = 1.0 / Ls[t][t];
+  __syncthreads();
   if (t < 32) {  // x_k = L_kk^-T y_k by back substitution (lane holds rows lane and lane + 32)
     double x0 = lane < nb ? yv[k0 + lane] : 0.0, x1 = lane + 32 < nb ? yv[k0 + lane + 32] : 0.0;
     for (int j = kGNB - 1; j >= 0; --j) {
-      const double xj = __shfl_sync(0xffffffffu, j < 32 ? x0 : x1, j & 31) * (1.0 / Ls[j][j]);
+      const double xj = __shfl_sync(0xffffffffu, j < 32 ? x0 : x1, j & 31) * rdb[j];
       if (lane == j) x0 = xj;
       if (lane + 32 == j) x1 = xj;
       if (lane < j) x0 = fma(-Ls[j][lane], xj, x0);
