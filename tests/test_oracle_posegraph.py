@@ -129,3 +129,32 @@ def test_loop_closure_distributes_the_drift(fix_scale):
         Rk = T[k][:, :3]
         np.testing.assert_allclose(Rk @ Rk.T, np.eye(3), atol=1e-9)
         np.testing.assert_allclose(T[k][:, 3] * out[k]["s"], out[k]["t"], atol=1e-12)
+
+
+# ---- property tests (hypothesis) of the Sim3 restatement ---------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_vec7 = st.tuples(*([st.floats(-1.2, 1.2)] * 3 + [st.floats(-5, 5)] * 3 + [st.floats(-0.4, 0.4)]))
+
+
+@settings(max_examples=150, deadline=None)
+@given(_vec7, _vec7, _vec7)
+def test_sim3_group_properties(u, v, w):
+    a, b, c = O.sim3_exp(np.array(u)), O.sim3_exp(np.array(v)), O.sim3_exp(np.array(w))
+    # associativity, inverse, log(exp) on the principal branch, exp(0) = identity
+    np.testing.assert_allclose(_mat(O.sim3_mul(O.sim3_mul(a, b), c)), _mat(O.sim3_mul(a, O.sim3_mul(b, c))), atol=1e-9)
+    np.testing.assert_allclose(_mat(O.sim3_mul(a, O.sim3_inv(a))), np.eye(4), atol=1e-10)
+    uu = np.array(u)
+    if 1e-4 < np.linalg.norm(uu[:3]) < 3.0 and abs(uu[6]) > 1e-4:   # away from the reference's own small-angle approximations
+        np.testing.assert_allclose(O.sim3_log(a), uu, atol=1e-8)
+    ident = O.sim3_exp(np.zeros(7))
+    assert ident["s"] == 1.0 and np.array_equal(ident["t"], np.zeros(3)) and np.array_equal(ident["q"], [0, 0, 0, 1])
+
+
+@settings(max_examples=60, deadline=None)
+@given(_vec7, _vec7)
+def test_edge_error_vanishes_on_its_own_measurement(u, v):
+    v0, v1 = O.sim3_exp(np.array(u)), O.sim3_exp(np.array(v))
+    meas = O.sim3_mul(v1, O.sim3_inv(v0))      # Sji = Sjw Siw^-1
+    e, _, _ = O.edge_sim3_graph(meas, v0, v1, jac=False)
+    assert np.abs(e).max() < 1e-8
