@@ -13,6 +13,7 @@
 #include "ba_oracle.h"
 
 #include <algorithm>
+#include <functional>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -455,6 +456,9 @@ struct VisEdge {
   double err[3];
   double chi2 = 0;
 };
+
+// LM driver used by Graph::optimize (nullptr: orc_lm_optimize); a test hook, see orc_set_lm_driver
+OrcLmDriver g_lm_driver = nullptr;
 
 struct Graph {
   bool pvr;  // slot 0 is PVR(9) (pose optimisation) instead of PR(6)
@@ -918,68 +922,77 @@ struct Graph {
     return s;
   }
   bool terminate() const { return stop && *stop; }
-  // OptimizationAlgorithmLevenberg::solve: 0 OK, 1 Terminate
-  int lm_iteration(int iteration) {
-    compute_active_errors();
-    double currentChi = active_robust_chi2();
-    double tempChi = currentChi;
-    const double iniChi = currentChi;
-    build_system();
-    if (iteration == 0) {
-      lambda = lambda_init();
-      ni = 2;
-      nBad = 0;
-    }
-    double rho = 0;
-    int qmax = 0;
-    do {
-      st_bak = st;
-      X_bak = X;
-      sc_bak = sc;
-      qwI_bak = qwI;
-      const bool ok2 = solve_system();
-      if ((int)x.size() != np) x.assign(np, 0.0);
-      if (points_free && xl.size() != X.size()) xl.assign(X.size(), 0.0);
-      apply_update();
-      compute_active_errors();
-      tempChi = active_robust_chi2();
-      if (!ok2) tempChi = std::numeric_limits<double>::max();
-      rho = currentChi - tempChi;
-      double scale = compute_scale();
-      scale += 1e-3;
-      rho /= scale;
-      if (rho > 0 && std::isfinite(tempChi)) {
-        double alpha = 1. - std::pow((2 * rho - 1), 3);
-        alpha = std::min(alpha, 2. / 3.);
-        const double sf = std::max(1. / 3., alpha);
-        lambda *= sf;
-        ni = 2;
-        currentChi = tempChi;
-      } else {
-        lambda *= ni;
-        ni *= 2;
-        st = st_bak;
-        X = X_bak;
-        sc = sc_bak;
-        qwI = qwI_bak;
-      }
-      qmax++;
-    } while (rho < 0 && qmax < 10 && !terminate());
-    if (qmax == 10 || rho == 0) return 1;
-    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
-    else nBad = 0;
-    if (nBad >= 3) return 1;
-    return 0;
-  }
+  // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve: the control flow lives in ONE place, the callback driver of
+  // lm_oracle.cc (orc_lm_optimize) — or the driver a test installs with orc_set_lm_driver, i.e. the REFERENCE's own solve() /
+  // optimize() compiled unchanged in oracle/_ref (tests/test_oracle_ref.py runs every BA driver both ways, bit for bit).  The
+  // callbacks are this graph's operations; g2o's solution vector is [poses | free landmarks], which is what x() / b() /
+  // hessian_diag() present to computeScale / computeLambdaInit.
+  std::vector<int> lm_pts;
+  std::vector<double> lm_x, lm_b;
   int optimize(int iterations) {
-    int n = 0;
-    bool ok = true;
     x.assign(np, 0.0);
-    for (int i = 0; i < iterations && !terminate() && ok; ++i) {
-      ok = lm_iteration(i) == 0;
-      ++n;
-      ++total_iters;
-    }
+    lm_pts.clear();
+    if (points_free)
+      for (size_t p = 0; p < pt_active.size(); ++p)
+        if (pt_active[p]) lm_pts.push_back((int)p);
+    OrcLmCallbacks cb;
+    cb.ctx = this;
+    cb.n = np + 3 * (int)lm_pts.size();
+    cb.errors = [](void* c) {
+      Graph* g = (Graph*)c;
+      g->compute_active_errors();
+      return g->active_robust_chi2();
+    };
+    cb.build = [](void* c) { ((Graph*)c)->build_system(); };
+    cb.solve = [](void* c, double l) {
+      Graph* g = (Graph*)c;
+      g->lambda = l;
+      const bool ok2 = g->solve_system();
+      if ((int)g->x.size() != g->np) g->x.assign(g->np, 0.0);
+      if (g->points_free && g->xl.size() != g->X.size()) g->xl.assign(g->X.size(), 0.0);
+      return ok2 ? 1 : 0;
+    };
+    cb.update = [](void* c) { ((Graph*)c)->apply_update(); };
+    cb.push = [](void* c) {
+      Graph* g = (Graph*)c;
+      g->st_bak = g->st;
+      g->X_bak = g->X;
+      g->sc_bak = g->sc;
+      g->qwI_bak = g->qwI;
+    };
+    cb.pop = [](void* c) {
+      Graph* g = (Graph*)c;
+      g->st = g->st_bak;
+      g->X = g->X_bak;
+      g->sc = g->sc_bak;
+      g->qwI = g->qwI_bak;
+    };
+    cb.discard_top = [](void*) {};
+    cb.x = [](void* c) {
+      Graph* g = (Graph*)c;
+      g->lm_x.assign(g->x.begin(), g->x.begin() + g->np);
+      for (int p : g->lm_pts)
+        for (int k = 0; k < 3; ++k) g->lm_x.push_back(g->xl[3 * (size_t)p + k]);
+      return (const double*)g->lm_x.data();
+    };
+    cb.b = [](void* c) {
+      Graph* g = (Graph*)c;
+      g->lm_b.assign(g->b.begin(), g->b.begin() + g->np);
+      for (int p : g->lm_pts)
+        for (int k = 0; k < 3; ++k) g->lm_b.push_back(g->bl[3 * (size_t)p + k]);
+      return (const double*)g->lm_b.data();
+    };
+    cb.hessian_diag = [](void* c, int j) {
+      Graph* g = (Graph*)c;
+      if (j < g->np) return g->H[(size_t)j * g->np + j];
+      const int q = j - g->np;
+      return g->Hll[9 * (size_t)g->lm_pts[q / 3] + 4 * (q % 3)];
+    };
+    cb.terminate = [](void* c) { return ((Graph*)c)->terminate() ? 1 : 0; };
+    double st5[5] = {0, 0, 0, 0, 0};
+    const int n = (g_lm_driver ? g_lm_driver : orc_lm_optimize)(&cb, iterations, user_lambda, st5);
+    if (n > 0) lambda = st5[3];
+    total_iters += n;
     return n;
   }
 };
@@ -1009,6 +1022,15 @@ void jtoj(const double* Ja, int lda, int ca, int na, const double* Om, int D, do
 }
 
 }  // namespace
+
+// test hook: run every BA driver of this file (pose optimisation, local / global BA) through another LM driver with the
+// OrcLmDriver signature — oracle/_ref's ref_lm_optimize, the reference's own solve() / optimize() compiled unchanged
+extern "C" void orc_set_lm_driver(OrcLmDriver d) { g_lm_driver = d; }
+
+// camera Project() alone (pinned against the reference's own function text compiled in oracle/_ref, tests/test_oracle_ref.py)
+extern "C" void orc_cam_project(const OrcCamera* cam, const double P[3], float uv[2], double* J /* 2x3 or NULL */) {
+  cam_project(cam_from_c(*cam), P, &uv[0], &uv[1], J);
+}
 
 // the skyline Cholesky above, for the other oracle translation units (posegraph_oracle.cc)
 bool orc_chol_solve_skyline(std::vector<double>& A, int n, const double* b, double* x) { return chol_solve(A, n, b, x); }
@@ -1780,7 +1802,7 @@ int orc_optimize_sim3(const OrcSim3Problem* pb, const OrcCamera* cam_c, const do
   std::vector<double> c12(M, 0.0), c21(M, 0.0);
   for (int i = 0; i < M; ++i) keep[b0 + i] = 1;
   res->n_corr = M;
-  double lambda = 0, ni = 2;
+  double lambda = 0;
   int total_iters = 0;
   auto errors = [&]() {  // computeActiveErrors + activeRobustChi2
     double tot = 0;
@@ -1836,61 +1858,50 @@ int orc_optimize_sim3(const OrcSim3Problem* pb, const OrcCamera* cam_c, const do
       add_edge(o, (double)inv_sigma2_2[g], c21[i]);
     }
   };
-  auto optimize = [&](int iterations) {  // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve
-    int nBad = 0;
-    bool ok = true;
+  // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve through the callback driver (lm_oracle.cc / the test hook)
+  struct Ctx {
+    std::function<double()> errors;
+    std::function<void()> build, update;
+    std::function<bool(double)> solve;
+    NS* ns;
+    double* sc;
+    NS ns_bak;
+    double sc_bak;
+    std::vector<double>*H, *bvec, *x;
+    int n;
+  } ctx;
+  ctx.errors = errors;
+  ctx.build = build;
+  ctx.update = [&]() {
+    inc_pr(ns, x.data());
+    if (n == 7) sc += x[6];
+  };
+  ctx.solve = [&](double lam) {
+    std::vector<double> A(H.begin(), H.begin() + n * n);
+    for (int j = 0; j < n; ++j) A[j * n + j] += lam;
+    return chol_solve(A, n, bvec.data(), x.data());
+  };
+  ctx.ns = &ns; ctx.sc = &sc; ctx.H = &H; ctx.bvec = &bvec; ctx.x = &x; ctx.n = n;
+  OrcLmCallbacks cb;
+  cb.ctx = &ctx;
+  cb.n = n;
+  cb.errors = [](void* c) { return ((Ctx*)c)->errors(); };
+  cb.build = [](void* c) { ((Ctx*)c)->build(); };
+  cb.solve = [](void* c, double l) { return ((Ctx*)c)->solve(l) ? 1 : 0; };
+  cb.update = [](void* c) { ((Ctx*)c)->update(); };
+  cb.push = [](void* c) { ((Ctx*)c)->ns_bak = *((Ctx*)c)->ns; ((Ctx*)c)->sc_bak = *((Ctx*)c)->sc; };
+  cb.pop = [](void* c) { *((Ctx*)c)->ns = ((Ctx*)c)->ns_bak; *((Ctx*)c)->sc = ((Ctx*)c)->sc_bak; };
+  cb.discard_top = [](void*) {};
+  cb.x = [](void* c) { return (const double*)((Ctx*)c)->x->data(); };
+  cb.b = [](void* c) { return (const double*)((Ctx*)c)->bvec->data(); };
+  cb.hessian_diag = [](void* c, int j) { return (*((Ctx*)c)->H)[j * ((Ctx*)c)->n + j]; };
+  cb.terminate = nullptr;
+  auto optimize = [&](int iterations) {
     std::fill(x.begin(), x.end(), 0.0);
-    for (int it = 0; it < iterations && ok; ++it) {
-      double currentChi = errors();
-      double tempChi = currentChi;
-      const double iniChi = currentChi;
-      build();
-      if (it == 0) {
-        double mx = 0;
-        for (int j = 0; j < n; ++j) mx = std::max(std::fabs(H[j * n + j]), mx);
-        lambda = 1e-5 * mx;
-        ni = 2;
-        nBad = 0;
-      }
-      double rho = 0;
-      int qmax = 0;
-      do {
-        const NS ns_bak = ns;
-        const double sc_bak = sc;
-        std::vector<double> A(H.begin(), H.begin() + n * n);
-        for (int j = 0; j < n; ++j) A[j * n + j] += lambda;
-        const bool ok2 = chol_solve(A, n, bvec.data(), x.data());
-        if (ok2) {
-          inc_pr(ns, x.data());
-          if (n == 7) sc += x[6];
-        }
-        tempChi = errors();
-        if (!ok2) tempChi = std::numeric_limits<double>::max();
-        rho = currentChi - tempChi;
-        double scale = 0;
-        for (int j = 0; j < n; ++j) scale += x[j] * (lambda * x[j] + bvec[j]);
-        scale += 1e-3;
-        rho /= scale;
-        if (rho > 0 && std::isfinite(tempChi)) {
-          double alpha = 1. - std::pow((2 * rho - 1), 3);
-          alpha = std::min(alpha, 2. / 3.);
-          lambda *= std::max(1. / 3., alpha);
-          ni = 2;
-          currentChi = tempChi;
-        } else {
-          lambda *= ni;
-          ni *= 2;
-          ns = ns_bak;
-          sc = sc_bak;
-        }
-        qmax++;
-      } while (rho < 0 && qmax < 10);
-      ++total_iters;
-      if (qmax == 10 || rho == 0) { ok = false; break; }
-      if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
-      else nBad = 0;
-      if (nBad >= 3) ok = false;
-    }
+    double st5[5] = {0, 0, 0, 0, 0};
+    const int its = (g_lm_driver ? g_lm_driver : orc_lm_optimize)(&cb, iterations, 0.0, st5);
+    if (its > 0) lambda = st5[3];
+    total_iters += its;
   };
   optimize(5);
   int nBad = 0;

@@ -179,6 +179,34 @@ int orc_optimize_sim3(const OrcSim3Problem* pb, const OrcCamera* cam, const doub
 void orc_edge_sim3(const OrcCamera* cam, const OrcNavState* ns, double scale, const double Xh[3], const float obs[2],
                    int inverse, double e[2], double* J_pose, double* J_scale);
 int orc_inverse(const double* A, int n, double* Ainv);
+/* ---- g2o's Levenberg-Marquardt control flow over callbacks (lm_oracle.cc) ---------------------------------------------------
+ * SparseOptimizer::optimize (sparse_optimizer.cpp:354-419) around OptimizationAlgorithmLevenberg::solve
+ * (optimization_algorithm_levenberg.cpp:61-189).  The problem is whatever the callbacks say; the oracle's essential-graph
+ * optimisation runs through this driver, and oracle/_ref compiles the REFERENCE's own two functions against the same callbacks
+ * (ref_lm_optimize), so the control flow — lambda schedule, accept / reject, the three stop rules — is pinned by the reference's
+ * text on identical arithmetic. */
+typedef struct OrcLmCallbacks {
+  void* ctx;
+  int n;                                   /* dimension of the system (solver->vectorSize()) */
+  double (*errors)(void* ctx);             /* computeActiveErrors() then activeRobustChi2() */
+  void (*build)(void* ctx);                /* solver->buildSystem() */
+  int (*solve)(void* ctx, double lambda);  /* setLambda(lambda, true); solve(); restoreDiagonal() -> 1 when the solve succeeded */
+  void (*update)(void* ctx);               /* optimizer->update(solver->x()) */
+  void (*push)(void* ctx);
+  void (*pop)(void* ctx);
+  void (*discard_top)(void* ctx);
+  const double* (*x)(void* ctx);           /* solver->x() */
+  const double* (*b)(void* ctx);           /* solver->b() */
+  double (*hessian_diag)(void* ctx, int j); /* H(j, j) of the last buildSystem (computeLambdaInit) */
+  int (*terminate)(void* ctx);             /* the force-stop flag; may be NULL */
+} OrcLmCallbacks;
+/* stats = {chi2 at the first iteration's start, chi2 after the last accepted step, iterations run, final lambda, trials} */
+typedef int (*OrcLmDriver)(const OrcLmCallbacks* cb, int iterations, double user_lambda_init, double* stats);
+int orc_lm_optimize(const OrcLmCallbacks* cb, int iterations, double user_lambda_init, double* stats);
+/* test hook: the LM driver behind every BA driver of ba_oracle.cc (NULL restores orc_lm_optimize) */
+void orc_set_lm_driver(OrcLmDriver d);
+/* camm::{Pinhole,Radtan,KB8}Camera::Project: float pixel + d(img)/d(p3d) (2x3 row-major, may be NULL) */
+void orc_cam_project(const OrcCamera* cam, const double P[3], float uv[2], double* J);
 
 /* ---- Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:2309-2688), posegraph_oracle.cc --------------------------------
  * g2o::Sim3 (types/sim3.h): r as Eigen coefficient order (x, y, z, w), t, s. */
@@ -197,6 +225,10 @@ void orc_edge_sim3_graph(const OrcSim3* meas, const OrcSim3* v0, const OrcSim3* 
 int orc_essential_graph(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix_scale, int E, const int32_t* ei, const int32_t* ej,
                         const OrcSim3* meas, const double* info, int iterations, double lambda_init, int single_step, OrcSim3* out,
                         double* stats, double* H_out, double* b_out);
+/* orc_essential_graph with an explicit LM driver (NULL: orc_lm_optimize); tests pass oracle/_ref's ref_lm_optimize */
+int orc_essential_graph_lm(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix_scale, int E, const int32_t* ei, const int32_t* ej,
+                           const OrcSim3* meas, const double* info, int iterations, double lambda_init, OrcLmDriver lm, OrcSim3* out,
+                           double* stats);
 void orc_essential_graph_recover_se3(int K, const OrcSim3* S, double* Tcw);
 void orc_essential_graph_correct_points(int n, const float* Pw, const int32_t* ref, const OrcSim3* Scw_before, const OrcSim3* Scw_after,
                                         float* out);

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <vector>
 
@@ -316,9 +317,9 @@ void orc_edge_sim3_graph(const OrcSim3* meas, const OrcSim3* v0, const OrcSim3* 
 // the user's initial lambda (<= 0: g2o's 1e-5 max diag).  single_step != 0: build the system at the initial estimate, apply ONE
 // damped step with lambda_init and return (test hook; H / b copied out when given).  stats = {chi2 before, chi2 after,
 // iterations run, final lambda, LM trials}.
-int orc_essential_graph(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix_scale, int E, const int32_t* ei, const int32_t* ej,
-                        const OrcSim3* meas_c, const double* info, int iterations, double lambda_init, int single_step, OrcSim3* out,
-                        double* stats, double* H_out, double* b_out) {
+static int essential_graph_impl(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix_scale, int E, const int32_t* ei,
+                                const int32_t* ej, const OrcSim3* meas_c, const double* info, int iterations, double lambda_init,
+                                int single_step, OrcLmDriver lm, OrcSim3* out, double* stats, double* H_out, double* b_out) {
   std::vector<S3> est(K), meas(E);
   for (int k = 0; k < K; ++k) est[k] = from_c(Scw[k]);
   for (int e = 0; e < E; ++e) meas[e] = from_c(meas_c[e]);
@@ -432,10 +433,7 @@ int orc_essential_graph(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix
     for (int k = 0; k < K; ++k)
       if (hidx[k] >= 0) est[k] = oplus(est[k], &x[7 * hidx[k]], fs);
   };
-  double lambda = 0, ni = 2;
-  int nBad = 0, total_iters = 0, trials = 0;
   double chi_first = 0, chi_last = 0;
-  bool ok = true;
   if (single_step) {
     chi_first = errors();
     build();
@@ -452,63 +450,58 @@ int orc_essential_graph(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix
     }
     return ok2 ? n : -2;
   }
-  for (int it = 0; it < iterations && ok; ++it) {
-    double currentChi = errors();
-    double tempChi = currentChi;
-    const double iniChi = currentChi;
-    if (it == 0) chi_first = currentChi;
-    build();
-    if (it == 0) {
-      if (lambda_init > 0) lambda = lambda_init;
-      else {
-        double mx = 0;
-        for (int j = 0; j < n; ++j) mx = std::max(std::fabs(H[(size_t)j * n + j]), mx);
-        lambda = 1e-5 * mx;
-      }
-      ni = 2;
-      nBad = 0;
-    }
-    double rho = 0;
-    int qmax = 0;
-    do {
-      const std::vector<S3> bak(est);
-      std::vector<double> A(H);
-      for (int j = 0; j < n; ++j) A[(size_t)j * n + j] += lambda;
-      const bool ok2 = orc_chol_solve_skyline(A, n, b.data(), x.data());
-      if (ok2) update();
-      tempChi = errors();
-      if (!ok2) tempChi = std::numeric_limits<double>::max();
-      rho = currentChi - tempChi;
-      double scale = 0;
-      for (int j = 0; j < n; ++j) scale += x[j] * (lambda * x[j] + b[j]);
-      scale += 1e-3;
-      rho /= scale;
-      if (rho > 0 && std::isfinite(tempChi)) {
-        double alpha = 1. - std::pow((2 * rho - 1), 3);
-        alpha = std::min(alpha, 2. / 3.);
-        lambda *= std::max(1. / 3., alpha);
-        ni = 2;
-        currentChi = tempChi;
-      } else {
-        lambda *= ni;
-        ni *= 2;
-        est = bak;
-      }
-      qmax++;
-      trials++;
-    } while (rho < 0 && qmax < 10);
-    ++total_iters;
-    chi_last = currentChi;
-    if (qmax == 10 || rho == 0) { ok = false; break; }
-    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
-    else nBad = 0;
-    if (nBad >= 3) ok = false;
-  }
+  // optimize(iterations): g2o's Levenberg-Marquardt through the callback driver (lm_oracle.cc, or the reference's own compiled
+  // solve() when the caller passes oracle/_ref's driver)
+  struct Ctx {
+    std::function<double()> errors;
+    std::function<void()> build, update;
+    std::function<bool(double)> solve;
+    std::vector<std::vector<S3>> stack;
+    std::vector<S3>* est;
+    std::vector<double>*H, *b, *x;
+    int n;
+  } ctx;
+  ctx.errors = errors;
+  ctx.build = build;
+  ctx.update = update;
+  ctx.solve = [&](double lambda) {
+    std::vector<double> A(H);
+    for (int j = 0; j < n; ++j) A[(size_t)j * n + j] += lambda;
+    return orc_chol_solve_skyline(A, n, b.data(), x.data());
+  };
+  ctx.est = &est; ctx.H = &H; ctx.b = &b; ctx.x = &x; ctx.n = n;
+  OrcLmCallbacks cb;
+  cb.ctx = &ctx;
+  cb.n = n;
+  cb.errors = [](void* c) { return ((Ctx*)c)->errors(); };
+  cb.build = [](void* c) { ((Ctx*)c)->build(); };
+  cb.solve = [](void* c, double lambda) { return ((Ctx*)c)->solve(lambda) ? 1 : 0; };
+  cb.update = [](void* c) { ((Ctx*)c)->update(); };
+  cb.push = [](void* c) { ((Ctx*)c)->stack.push_back(*((Ctx*)c)->est); };
+  cb.pop = [](void* c) { *((Ctx*)c)->est = ((Ctx*)c)->stack.back(); ((Ctx*)c)->stack.pop_back(); };
+  cb.discard_top = [](void* c) { ((Ctx*)c)->stack.pop_back(); };
+  cb.x = [](void* c) { return (const double*)((Ctx*)c)->x->data(); };
+  cb.b = [](void* c) { return (const double*)((Ctx*)c)->b->data(); };
+  cb.hessian_diag = [](void* c, int j) { return (*((Ctx*)c)->H)[(size_t)j * ((Ctx*)c)->n + j]; };
+  cb.terminate = nullptr;
+  double st5[5] = {0, 0, 0, 0, 0};
+  (lm ? lm : orc_lm_optimize)(&cb, iterations, lambda_init, st5);
   for (int k = 0; k < K; ++k) to_c(est[k], out + k);
-  if (stats) {
-    stats[0] = chi_first; stats[1] = chi_last; stats[2] = total_iters; stats[3] = lambda; stats[4] = trials;
-  }
+  if (stats) std::copy(st5, st5 + 5, stats);
   return n;
+}
+
+int orc_essential_graph(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix_scale, int E, const int32_t* ei, const int32_t* ej,
+                        const OrcSim3* meas_c, const double* info, int iterations, double lambda_init, int single_step, OrcSim3* out,
+                        double* stats, double* H_out, double* b_out) {
+  return essential_graph_impl(K, Scw, fixed, fix_scale, E, ei, ej, meas_c, info, iterations, lambda_init, single_step, nullptr, out,
+                              stats, H_out, b_out);
+}
+int orc_essential_graph_lm(int K, const OrcSim3* Scw, const uint8_t* fixed, int fix_scale, int E, const int32_t* ei, const int32_t* ej,
+                           const OrcSim3* meas_c, const double* info, int iterations, double lambda_init, OrcLmDriver lm, OrcSim3* out,
+                           double* stats) {
+  return essential_graph_impl(K, Scw, fixed, fix_scale, E, ei, ej, meas_c, info, iterations, lambda_init, 0, lm, out, stats, nullptr,
+                              nullptr);
 }
 
 // "SE3 Pose Recovering" (src/Optimizer.cc:2624-2642): Tiw = [R | t / s] of the optimised Siw -> Tcw[12] row-major 3x4

@@ -845,3 +845,74 @@ def is_in_frustum_rig(pb):
         for key, arr in zip(("inview", "cam_mask", "proj", "level", "viewcos", "depth"), o):
             out[key][idx] = arr
     return out
+
+
+def cam_project(cam, P, want_jac=True):
+    """orc_cam_project: the oracle's camera Project() -> (uv f32[2], J f64[2][3] | None)"""
+    L = lib()
+    L.orc_cam_project.argtypes = [C.c_void_p] * 4
+    L.orc_cam_project.restype = None
+    cam = np.ascontiguousarray(cam, CAMERA_DTYPE).reshape(1); P = np.ascontiguousarray(P, np.float64)
+    uv = np.zeros(2, np.float32); J = np.zeros((2, 3)) if want_jac else None
+    L.orc_cam_project(_p(cam), _p(P), _p(uv), None if J is None else _p(J))
+    return uv, J
+
+
+# ---- g2o's Levenberg-Marquardt control flow over callbacks (oracle/lm_oracle.cc; oracle/_ref compiles the reference's own) -----
+class OrcLmCallbacks(C.Structure):
+    _F = {"d_v": C.CFUNCTYPE(C.c_double, C.c_void_p), "v_v": C.CFUNCTYPE(None, C.c_void_p), "i_vd": C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double),
+          "p_v": C.CFUNCTYPE(C.c_void_p, C.c_void_p), "d_vi": C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int), "i_v": C.CFUNCTYPE(C.c_int, C.c_void_p)}
+    _fields_ = [("ctx", C.c_void_p), ("n", C.c_int), ("errors", _F["d_v"]), ("build", _F["v_v"]), ("solve", _F["i_vd"]), ("update", _F["v_v"]),
+                ("push", _F["v_v"]), ("pop", _F["v_v"]), ("discard_top", _F["v_v"]), ("x", _F["p_v"]), ("b", _F["p_v"]),
+                ("hessian_diag", _F["d_vi"]), ("terminate", _F["i_v"])]
+
+
+def lm_callbacks(problem):
+    """Wrap a python problem object (methods errors / build / solve / update / push / pop / discard_top / hessian_diag / terminate,
+    persistent float64 arrays x and b, attribute n) into an OrcLmCallbacks struct; keep the returned object alive during the call."""
+    F = OrcLmCallbacks._F
+    cb = OrcLmCallbacks()
+    cb.ctx = None
+    cb.n = int(problem.n)
+    cb.errors = F["d_v"](lambda c: float(problem.errors()))
+    cb.build = F["v_v"](lambda c: problem.build())
+    cb.solve = F["i_vd"](lambda c, lam: int(bool(problem.solve(lam))))
+    cb.update = F["v_v"](lambda c: problem.update())
+    cb.push = F["v_v"](lambda c: problem.push())
+    cb.pop = F["v_v"](lambda c: problem.pop())
+    cb.discard_top = F["v_v"](lambda c: problem.discard_top())
+    cb.x = F["p_v"](lambda c: problem.x.ctypes.data)
+    cb.b = F["p_v"](lambda c: problem.b.ctypes.data)
+    cb.hessian_diag = F["d_vi"](lambda c, j: float(problem.hessian_diag(j)))
+    cb.terminate = F["i_v"](lambda c: int(bool(problem.terminate())))
+    return cb
+
+
+def lm_optimize(problem, iterations, user_lambda_init=0.0, driver=None):
+    """orc_lm_optimize (or another driver with the same signature, e.g. ref_lib.lib().ref_lm_optimize) -> stats[5]"""
+    cb = lm_callbacks(problem)
+    stats = np.zeros(5)
+    fn = driver
+    if fn is None:
+        fn = lib().orc_lm_optimize
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        fn.restype = C.c_int
+    fn(C.byref(cb), int(iterations), float(user_lambda_init), _p(stats))
+    return stats
+
+
+def essential_graph_lm(pb, driver_ptr, iterations=20, lambda_init=1e-16):
+    """orc_essential_graph_lm with an explicit LM driver (a C function pointer as an int / c_void_p; None: the oracle's own)"""
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    L = lib()
+    L.orc_essential_graph_lm.restype = C.c_int
+    L.orc_essential_graph_lm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    S = _sim3(pb["Scw"]); fixed = np.ascontiguousarray(pb["fixed"], np.uint8)
+    ei = np.ascontiguousarray(pb["ei"], np.int32); ej = np.ascontiguousarray(pb["ej"], np.int32); meas = _sim3(pb["meas"])
+    info = None if pb.get("info") is None else np.ascontiguousarray(pb["info"], np.float64)
+    out = np.zeros(len(S), SIM3_DTYPE); stats = np.zeros(5)
+    n = L.orc_essential_graph_lm(len(S), _p(S), _p(fixed), int(pb["fix_scale"]), len(ei), _p(ei), _p(ej), _p(meas),
+                                 None if info is None else _p(info), int(iterations), float(lambda_init), driver_ptr, _p(out), _p(stats))
+    assert n >= 0
+    return out, stats

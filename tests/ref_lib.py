@@ -53,6 +53,12 @@ def lib():
                                          C.c_void_p]
         L.ref_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_cam_project.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_cam_project.restype = None
+        L.ref_predict_scale.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
+        L.ref_predict_scale.restype = C.c_int
+        L.ref_lm_optimize.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.ref_lm_optimize.restype = C.c_int
     return _lib
 
 
@@ -127,3 +133,16 @@ def three_maxima(sizes):
     out = np.empty(3, np.int32)
     lib().ref_three_maxima(_p(sizes), len(sizes), _p(out))
     return tuple(int(v) for v in out)
+
+
+def cam_project(model, params, P, want_jac=True):
+    """camm::{Pinhole (0), Radtan (1), KB8 (2)}Camera::Project of the reference, compiled unchanged -> (uv f32[2], J f64[2][3] | None)"""
+    params = np.ascontiguousarray(params, np.float32); P = np.ascontiguousarray(P, np.float64)
+    uv = np.zeros(2, np.float32); J = np.zeros((2, 3)) if want_jac else None
+    lib().ref_cam_project(int(model), _p(params), len(params), _p(P), _p(uv), None if J is None else _p(J), None)
+    return uv, J
+
+
+def predict_scale(max_distance, current_dist, log_scale_factor, n_levels):
+    """MapPoint::PredictScale of the reference, compiled unchanged"""
+    return int(lib().ref_predict_scale(float(max_distance), float(current_dist), float(log_scale_factor), int(n_levels)))

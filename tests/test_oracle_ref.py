@@ -146,3 +146,247 @@ def test_three_maxima_equal_reference():
     for _ in range(300):
         s = r.integers(0, r.integers(1, 60), 30).astype(np.int32)
         assert R.three_maxima(s) == py(s)
+
+
+# ---- camera models: camm::{Pinhole,Radtan,KB8}Camera::Project compiled unchanged -----------------------------
+def _cam_params(cam):
+    m = int(cam["model"])
+    p = [cam["fx"], cam["fy"], cam["cx"], cam["cy"]]
+    if m == 1:
+        p += list(cam["dist"][:int(cam["num_k"]) + 2])
+    elif m == 2:
+        p += list(cam["dist"][:4])
+    return m, np.array(p, np.float32)
+
+
+@pytest.mark.parametrize("model", ["pinhole", "radtan", "radtan3", "kb8"])
+def test_camera_project_equal_reference(model):
+    """The oracle's Project() (float pixel and d(img)/d(p3d)) against the reference's own function bodies, bit for bit: 2000 random
+    camera-frame points incl. points behind the principal plane of the fisheye, on the optical axis (KB8's r <= 1e-5 branch) and
+    far off-axis."""
+    from vieo_slam_b200 import synth
+    cam = {"pinhole": synth.euroc_camera(), "radtan": synth.radtan_camera(), "radtan3": synth.radtan_camera(k=(-0.28, 0.074, -0.01)),
+           "kb8": synth.kb8_camera(k=(-0.0135, 0.021, -0.03, 0.012))}[model]
+    m, params = _cam_params(cam)
+    r = np.random.default_rng(17)
+    P = np.concatenate([r.normal(0, 1.5, (1990, 3)) + [0, 0, 3.0],
+                        [[0, 0, 2.0], [1e-7, -2e-7, 1.0], [3e-6, 0, 5.0], [5.0, -4.0, 0.5], [0.3, 0.2, -1.0], [1e-3, 1e-3, 1e-3],
+                         [2.0, 0.0, 1e-9], [-1.0, 2.0, 8.0], [0.0, 1e-5, 1.0], [7e-6, 7e-6, 1.0]]])
+    if model != "kb8":
+        P = P[np.abs(P[:, 2]) > 1e-6]      # 1 / z of the plane models
+    n_axis = 0
+    for p in P:
+        uo, Jo = O.cam_project(cam, p)
+        ur, Jr = R.cam_project(m, params, p)
+        assert uo.tobytes() == ur.tobytes(), (model, p, uo, ur)
+        assert np.array_equal(Jo, Jr, equal_nan=True) and (Jo[np.isfinite(Jr)].tobytes() == Jr[np.isfinite(Jr)].tobytes()), (model, p)
+        n_axis += np.hypot(p[0], p[1]) <= 1e-5
+    assert n_axis >= 3
+
+
+def test_rig_frustum_projection_equal_reference():
+    """The rig visibility test's own double-precision projection (oracle/sbp_oracle.cc project_double) against the compiled reference:
+    a rig whose reference frame and camera extrinsics are identities sees the map point at Pc = wP exactly."""
+    from vieo_slam_b200 import synth
+    for model in (1, 2):
+        pb = synth.make_frustum_rig_problem(5, n_frames=1, n_q=400, n_cams=1, model=model, skip_frac=0.0)
+        G = pb["rig"][0]
+        G["Rcw"] = np.eye(3, dtype=np.float32).ravel(); G["tcw"] = 0; G["Ow"] = 0
+        C = G["cam"][0]
+        C["q_cr"] = [0, 0, 0, 1]; C["t_cr"] = 0; C["t_rc"] = 0
+        C["minx"], C["maxx"], C["miny"], C["maxy"] = -1e9, 1e9, -1e9, 1e9
+        G["cos_limit"] = -2.0
+        r = np.random.default_rng(3)
+        pb["p_wP"][:] = (r.normal(0, 1.0, (400, 3)) + [0, 0, 2.5]).astype(np.float32)
+        pb["p_max_dist"][:] = 1e6; pb["p_min_dist"][:] = 0.0
+        out = O.is_in_frustum_rig(pb)
+        params = np.array([C["fx"], C["fy"], C["cx"], C["cy"], *C["k"]], np.float32)[:8 if model == 2 else 4]
+        seen = 0
+        for q in range(400):
+            if not out["inview"][q]:
+                continue
+            uv, _ = R.cam_project(2 if model == 2 else 0, params, pb["p_wP"][q].astype(np.float64), want_jac=False)
+            assert out["proj"][q, 0, :2].tobytes() == uv.tobytes(), (model, q)
+            seen += 1
+        assert seen > 300
+
+
+def test_predict_scale_equal_reference():
+    """MapPoint::PredictScale (src/MapPoint.cc:491-509) compiled unchanged against the oracle's restatement: random ratios, the float
+    neighbourhood of every level boundary 1.2^k, both pyramid shapes of the configs."""
+    r = np.random.default_rng(9)
+    for sf, nl in ((1.2, 8), (2.0, 4)):
+        lsf = float(np.log(np.float32(sf)))
+        cases = [(float(np.float32(mx)), float(np.float32(d))) for mx, d in zip(r.uniform(0.5, 60, 3000), r.uniform(0.2, 40, 3000))]
+        for k in range(-2, nl + 2):
+            b = np.float32(sf) ** np.float32(k)
+            for ulp in range(-6, 7):
+                x = b
+                for _ in range(abs(ulp)):
+                    x = np.nextafter(x, np.float32(np.inf if ulp > 0 else -np.inf), dtype=np.float32)
+                cases.append((float(x), 1.0))
+        for mx, d in cases:
+            assert O.predict_scale(mx, d, lsf, nl) == R.predict_scale(mx, d, lsf, nl), (mx, d, sf)
+
+
+# ---- g2o's Levenberg-Marquardt control flow: the reference's own solve() / optimize() compiled unchanged (SURVEY 8a row F2) ------
+class _Lsq:
+    """A nonlinear least-squares problem behind the LM callbacks: residual r(theta), Jacobian J(theta); records every lambda the
+    driver asks a solve for and every push / pop / discard, so two drivers can be compared event by event."""
+
+    def __init__(self, res, jac, theta0, fail_below=None, stop_after_solves=None):
+        self.res, self.jac = res, jac
+        self.theta = np.array(theta0, np.float64)
+        self.n = len(self.theta)
+        self.x = np.zeros(self.n); self.b = np.zeros(self.n); self.H = np.zeros((self.n, self.n))
+        self.stack, self.log = [], []
+        self.fail_below, self.stop_after = fail_below, stop_after_solves
+        self.n_solves = 0
+
+    def errors(self):
+        r = self.res(self.theta)
+        v = float(r @ r)
+        self.log.append(("chi", v))
+        return v
+
+    def build(self):
+        J, r = self.jac(self.theta), self.res(self.theta)
+        self.H[:] = J.T @ J
+        self.b[:] = -(J.T @ r)
+
+    def solve(self, lam):
+        self.log.append(("lambda", lam))
+        self.n_solves += 1
+        if self.fail_below is not None and lam < self.fail_below:
+            return False          # like LDLT meeting a non-positive pivot: x keeps its previous content
+        try:
+            c = np.linalg.cholesky(self.H + lam * np.eye(self.n))
+        except np.linalg.LinAlgError:
+            return False
+        self.x[:] = np.linalg.solve(c.T, np.linalg.solve(c, self.b))
+        return True
+
+    def update(self):
+        self.theta = self.theta + self.x
+
+    def push(self):
+        self.stack.append(self.theta.copy()); self.log.append(("push",))
+
+    def pop(self):
+        self.theta = self.stack.pop(); self.log.append(("pop",))
+
+    def discard_top(self):
+        self.stack.pop(); self.log.append(("discard",))
+
+    def hessian_diag(self, j):
+        return self.H[j, j]
+
+    def terminate(self):
+        return self.stop_after is not None and self.n_solves >= self.stop_after
+
+
+def _lm_cases():
+    r = np.random.default_rng(4)
+    A = r.normal(0, 1, (12, 4)); y = r.normal(0, 1, 12)
+    t = np.linspace(0, 2, 25); yexp = 2.0 * np.exp(-1.3 * t) + 0.5 + 0.01 * r.normal(0, 1, 25)
+    rosen = (lambda th: np.array([10 * (th[1] - th[0] ** 2), 1 - th[0]]), lambda th: np.array([[-20 * th[0], 10.0], [-1.0, 0.0]]))
+    expfit = (lambda th: th[0] * np.exp(th[1] * t) + th[2] - yexp,
+              lambda th: np.stack([np.exp(th[1] * t), th[0] * t * np.exp(th[1] * t), np.ones_like(t)], 1))
+    # rank-deficient: the second parameter never enters the residual -> H singular, solvable only through the damping
+    deficient = (lambda th: np.array([th[0] - 1.0, 2 * th[0] - 2.0]), lambda th: np.array([[1.0, 0.0], [2.0, 0.0]]))
+    # a residual that grows when the step is taken (tan blows up): rejections, lambda *= ni, ni *= 2
+    wild = (lambda th: np.array([np.tan(th[0]) - 0.3, 0.1 * th[0]]), lambda th: np.array([[1 / np.cos(th[0]) ** 2], [0.1]]))
+    return {
+        "linear": (dict(res=lambda th: A @ th - y, jac=lambda th: A, theta0=np.zeros(4)), 10, 0.0),
+        "linear_user_lambda": (dict(res=lambda th: A @ th - y, jac=lambda th: A, theta0=np.ones(4)), 10, 1e-16),
+        "rosenbrock": (dict(res=rosen[0], jac=rosen[1], theta0=[-1.2, 1.0]), 20, 0.0),
+        "expfit": (dict(res=expfit[0], jac=expfit[1], theta0=[1.0, -0.5, 0.0]), 15, 0.0),
+        "rank_deficient": (dict(res=deficient[0], jac=deficient[1], theta0=[5.0, 3.0]), 8, 1e-300),
+        "solver_fails_until_damped": (dict(res=rosen[0], jac=rosen[1], theta0=[-1.2, 1.0], fail_below=5e-2), 12, 1e-6),
+        "ten_failures_terminate": (dict(res=rosen[0], jac=rosen[1], theta0=[-1.2, 1.0], fail_below=1e300), 5, 1e-3),
+        "wild": (dict(res=wild[0], jac=wild[1], theta0=[1.4]), 12, 1e-9),
+        "terminate_flag": (dict(res=expfit[0], jac=expfit[1], theta0=[1.0, -0.5, 0.0], stop_after_solves=3), 15, 0.0),
+        "zero_iterations": (dict(res=rosen[0], jac=rosen[1], theta0=[-1.2, 1.0]), 0, 0.0),
+    }
+
+
+@pytest.mark.parametrize("name", list(_lm_cases()))
+def test_lm_control_flow_equal_reference(name):
+    """The oracle's LM driver against OptimizationAlgorithmLevenberg::solve + SparseOptimizer::optimize of the reference, compiled
+    unchanged, on the same callbacks: every lambda handed to the solver, every push / pop / discard, every chi2 evaluation, the
+    iteration and trial counts, the final lambda and the final state are identical (the arithmetic is the callbacks', the control
+    flow — gain ratio, lambda schedule, the three stop rules, the failed-solve path — is what is compared)."""
+    kw, iters, lam0 = _lm_cases()[name]
+    a, b = _Lsq(**kw), _Lsq(**kw)
+    with np.errstate(all="ignore"):
+        sa = O.lm_optimize(a, iters, lam0)
+        sb = O.lm_optimize(b, iters, lam0, driver=R.lib().ref_lm_optimize)
+    assert a.log == b.log, name   # every chi2 evaluation, lambda, push / pop / discard in the same order with the same values
+    assert a.theta.tobytes() == b.theta.tobytes(), name
+    assert sa[2] == sb[2] and sa[4] == sb[4], (name, sa, sb)            # iterations, trials
+    assert sa[0] == sb[0] and sa[3] == sb[3], (name, sa, sb)            # first chi2, final lambda
+    assert sa[1] == sb[1] or (np.isnan(sa[1]) and np.isnan(sb[1])), (name, sa, sb)   # chi2 after the last accepted step
+    if name == "ten_failures_terminate":
+        assert sa[4] == 10 and sa[2] == 1
+    if name == "terminate_flag":
+        assert a.n_solves == 3
+
+
+def test_essential_graph_through_the_reference_lm():
+    """The whole essential-graph optimisation of the oracle driven by the reference's compiled LM functions: bit-identical vertices and
+    statistics to the oracle's own driver (graphs with accepted-only steps and with rejections at the optimum)."""
+    import ctypes as C
+    from vieo_slam_b200 import synth
+    drv = C.cast(R.lib().ref_lm_optimize, C.c_void_p)
+    for K, seed, fs, odom in ((12, 12, True, 0), (40, 3, False, 4), (80, 7, True, 6)):
+        pb = synth.make_essential_graph(K=K, seed=seed, fix_scale=fs, odom_info_every=odom, n_neighbors=min(5, K - 5))
+        oa, sa = O.essential_graph_lm(pb, None)
+        ob, sb = O.essential_graph_lm(pb, drv)
+        assert oa.tobytes() == ob.tobytes(), K
+        assert sa[0] == sb[0] and sa[2] == sb[2] and sa[3] == sb[3] and sa[4] == sb[4], (K, sa, sb)
+        assert sa[1] == sb[1]
+
+
+def test_ba_drivers_through_the_reference_lm():
+    """Every bundle-adjustment driver of the oracle — PoseOptimization (visual and IMU, 4 x optimize(10) with re-classification),
+    LocalBundleAdjustmentNavStatePRV (two stages, outlier erasure), GlobalBundleAdjustmentNavStatePRV (plain and with the scale vertex),
+    OptimizeSim3 — run with its Levenberg-Marquardt control flow supplied by the REFERENCE's compiled solve() / optimize() (orc_set_lm_driver):
+    states, points, outlier / erase sets, chi2 and iteration counts bit-identical to the oracle's own driver."""
+    import ctypes as C
+    from vieo_slam_b200 import synth
+    L = O.lib()
+    L.orc_set_lm_driver.argtypes = [C.c_void_p]
+    L.orc_set_lm_driver.restype = None
+    nz = O.imu_noise()
+    seq = synth.vio_sequence(15, 48)
+    cam = synth.euroc_camera()
+    pre_all = O.imu_preintegrate_frames(seq, list(range(48)), nz)
+    pbs, X, obs, w, fl = synth.make_pose_problems(seq, pre_all, cam, n_points=250, seed=2)
+    pbs_v = synth.make_pose_problems(seq, pre_all, cam, n_points=250, seed=2, mode=0)
+    kf = list(range(0, 48, 3))
+    pre_kf = O.imu_preintegrate_frames(seq, kf, nz)
+    dl = synth.make_lba_problem(seq, pre_kf, kf, cam, n_local=6, n_fixed=5, n_points=250, seed=6)
+    gb = synth.make_gba_problem(seq, pre_kf, kf, cam, n_points=300, seed=5, outlier_frac=0.05)
+    cam3 = synth.euroc_camera(); cam3["Rcb"] = np.eye(3); cam3["tcb"] = 0
+    s3p = synth.make_sim3_problems(cam3, n_candidates=4, n_matches=100, seed=8, fix_scale=False, few_matches_every=3)
+    s3 = (s3p[0], cam3) + tuple(s3p[1:7])
+
+    def run_all():
+        a = O.pose_optimization(pbs[:5], cam, X, obs, w, fl)
+        b = O.pose_optimization(pbs_v[0][:3], cam, *pbs_v[1:5])
+        c = O.local_ba_prv(dl, cam)
+        d = O.global_ba_prv(gb, cam, n_iterations=7, robust=True)
+        e = O.global_ba_prv_scale(gb, cam, n_iterations=6, robust=False)
+        f = O.optimize_sim3(*s3)
+        return [f[0].tobytes(), f[1].tobytes(), f[2].tobytes(), f[3].tobytes(), a[0].tobytes(), a[1].tobytes(), a[2].tobytes(), b[0].tobytes(), b[1].tobytes(),
+                c["states"].tobytes(), c["points"].tobytes(), c["erase"].tobytes(), c["res"].tobytes(),
+                d["states"].tobytes(), d["points"].tobytes(), d["res"].tobytes(),
+                e["states"].tobytes(), e["points"].tobytes(), np.float64(e["scale"]).tobytes(), e["res"].tobytes()]
+    own = run_all()
+    L.orc_set_lm_driver(C.cast(R.lib().ref_lm_optimize, C.c_void_p))
+    try:
+        ref = run_all()
+    finally:
+        L.orc_set_lm_driver(None)
+    assert [x == y for x, y in zip(own, ref)] == [True] * len(own)
+    assert own == run_all()   # the hook is off again
