@@ -1023,6 +1023,13 @@ void jtoj(const double* Ja, int lda, int ca, int na, const double* Om, int D, do
 
 }  // namespace
 
+// RobustKernelHuber as the edges use it (delta^2 kept in float): rho(e) and rho'(e)
+extern "C" void orc_huber(double delta, double e, double rho[2]) {
+  Huber k;
+  k.set(delta);
+  k.rho(e, rho);
+}
+
 // test hook: run every BA driver of this file (pose optimisation, local / global BA) through another LM driver with the
 // OrcLmDriver signature — oracle/_ref's ref_lm_optimize, the reference's own solve() / optimize() compiled unchanged
 extern "C" void orc_set_lm_driver(OrcLmDriver d) { g_lm_driver = d; }

@@ -203,6 +203,8 @@ typedef struct OrcLmCallbacks {
 /* stats = {chi2 at the first iteration's start, chi2 after the last accepted step, iterations run, final lambda, trials} */
 typedef int (*OrcLmDriver)(const OrcLmCallbacks* cb, int iterations, double user_lambda_init, double* stats);
 int orc_lm_optimize(const OrcLmCallbacks* cb, int iterations, double user_lambda_init, double* stats);
+/* g2o::RobustKernelHuber::robustify with setDelta(delta): rho[0] = rho(e), rho[1] = rho'(e) */
+void orc_huber(double delta, double e, double rho[2]);
 /* test hook: the LM driver behind every BA driver of ba_oracle.cc (NULL restores orc_lm_optimize) */
 void orc_set_lm_driver(OrcLmDriver d);
 /* camm::{Pinhole,Radtan,KB8}Camera::Project: float pixel + d(img)/d(p3d) (2x3 row-major, may be NULL) */

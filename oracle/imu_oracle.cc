@@ -4,6 +4,7 @@
 // Eigen / Sophus are absent here ("parity unpinned" for their rounding): quaternion<->matrix conversions
 // follow Eigen 3.3.7's published formulas; the tests pin this file with closed-form constant-rate answers.
 #include <cmath>
+#include <vector>
 #include <cstring>
 
 #include "oracle.h"
@@ -51,7 +52,16 @@ void propagate(double* S, const double* A, const double* Bg, const double* Ba, d
 }
 
 // IMUPreIntegratorBase::update (OdomPreIntegrator.h:432-506)
+// test hook: when set, every update() call of this thread records its arguments (omega, acc, dt) — the sample selection /
+// interpolation of PreIntegration is pinned against the reference's own function through this trace (tests/test_oracle_ref.py)
+thread_local std::vector<double>* g_update_trace = nullptr;
+
 void update(Preint& s, const double omega[3], const double acc[3], double dt, const OrcImuNoise& nz) {
+  if (g_update_trace) {
+    g_update_trace->insert(g_update_trace->end(), omega, omega + 3);
+    g_update_trace->insert(g_update_trace->end(), acc, acc + 3);
+    g_update_trace->push_back(dt);
+  }
   const double dt2div2 = dt * dt / 2;
   const double wdt[3] = {omega[0] * dt, omega[1] * dt, omega[2] * dt};
   const M3 dR = so3_Exp(wdt), Jr = so3_Jr(wdt), skewa = hat(acc);
@@ -258,6 +268,22 @@ int orc_imu_preintegrate(const double* smp, int n, double ti, double tj, const d
   out->dt = s.dt;
   out->status = status;
   return status;
+}
+
+// PreIntegration's update() calls alone: trace [cap][7] = (omega, acc, dt) per call; returns the status, *n_updates the call count
+int orc_imu_preintegrate_trace(const double* smp, int n, double ti, double tj, const double bg[3], const double ba[3], double* trace,
+                               int cap, int* n_updates) {
+  std::vector<double> tr;
+  OrcImuNoise nz;
+  const double s2[4] = {1e-4, 1e-2, 1e-6, 1e-4};
+  orc_imu_set_param(&nz, s2, 1, 200.0);
+  OrcImuPreint out;
+  g_update_trace = &tr;
+  const int rc = orc_imu_preintegrate(smp, n, ti, tj, bg, ba, &nz, &out);
+  g_update_trace = nullptr;
+  *n_updates = (int)(tr.size() / 7);
+  for (size_t k = 0; k < tr.size() && k < (size_t)cap * 7; ++k) trace[k] = tr[k];
+  return rc;
 }
 
 // Optimizer::OptimizeInitialGyroBias (include/Optimizer.h:819-892) with EdgeGyrBias (src/Odom/g2otypes.h:940-973): one

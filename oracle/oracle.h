@@ -71,6 +71,9 @@ typedef struct OrcImuPreint { /* public members of IMUPreIntegratorBase (OdomPre
 void orc_imu_set_param(OrcImuNoise* nz, const double sigma2[4], int dt_cov_noise_fixed, double freq_ref);
 int orc_imu_preintegrate(const double* smp, int n, double ti, double tj, const double bg[3], const double ba[3],
                          const OrcImuNoise* nz, OrcImuPreint* out);
+/* the update() calls of the same routine alone: trace [cap][7] = (omega, acc, dt) per call (test hook) */
+int orc_imu_preintegrate_trace(const double* smp, int n, double ti, double tj, const double bg[3], const double ba[3], double* trace,
+                               int cap, int* n_updates);
 /* Optimizer::OptimizeInitialGyroBias: pre [n_kf] (entry 0 ignored), Rwb [n_kf][9] -> dbg, returns num_equations */
 int orc_gyro_bias_init(const OrcImuPreint* pre, const double* Rwb, int n_kf, int use_info, double dbg[3]);
 #ifdef __cplusplus

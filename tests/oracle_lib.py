@@ -916,3 +916,15 @@ def essential_graph_lm(pb, driver_ptr, iterations=20, lambda_init=1e-16):
                                  None if info is None else _p(info), int(iterations), float(lambda_init), driver_ptr, _p(out), _p(stats))
     assert n >= 0
     return out, stats
+
+
+def imu_preintegrate_trace(samples, ti, tj, bg, ba, cap=4096):
+    """orc_imu_preintegrate_trace: the update() calls of the oracle's PreIntegration -> (status, trace [n][7])"""
+    L = lib()
+    L.orc_imu_preintegrate_trace.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    L.orc_imu_preintegrate_trace.restype = C.c_int
+    smp = np.ascontiguousarray(samples, np.float64).reshape(-1, 7)
+    bg = np.ascontiguousarray(bg, np.float64); ba = np.ascontiguousarray(ba, np.float64)
+    tr = np.zeros((cap, 7)); n = C.c_int(0)
+    rc = L.orc_imu_preintegrate_trace(_p(smp), len(smp), float(ti), float(tj), _p(bg), _p(ba), _p(tr), cap, C.byref(n))
+    return rc, tr[:n.value].copy()

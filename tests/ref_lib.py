@@ -59,6 +59,8 @@ def lib():
         L.ref_predict_scale.restype = C.c_int
         L.ref_lm_optimize.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.ref_lm_optimize.restype = C.c_int
+        L.ref_imu_preintegrate_trace.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_imu_preintegrate_trace.restype = C.c_int
     return _lib
 
 
@@ -146,3 +148,13 @@ def cam_project(model, params, P, want_jac=True):
 def predict_scale(max_distance, current_dist, log_scale_factor, n_levels):
     """MapPoint::PredictScale of the reference, compiled unchanged"""
     return int(lib().ref_predict_scale(float(max_distance), float(current_dist), float(log_scale_factor), int(n_levels)))
+
+
+def imu_preintegrate_trace(samples, ti, tj, bg, ba, cap=4096):
+    """IMUPreIntegratorBase::PreIntegration of the reference, compiled unchanged, with a recording update() ->
+    (status, trace [n][7] = (omega, acc, dt) per update() call, mdeltatij after the call started from 123)"""
+    smp = np.ascontiguousarray(samples, np.float64).reshape(-1, 7)
+    bg = np.ascontiguousarray(bg, np.float64); ba = np.ascontiguousarray(ba, np.float64)
+    tr = np.zeros((cap, 7)); n = C.c_int(0); dtj = C.c_double(0)
+    rc = lib().ref_imu_preintegrate_trace(_p(smp), len(smp), float(ti), float(tj), _p(bg), _p(ba), _p(tr), cap, C.byref(n), C.byref(dtj))
+    return rc, tr[:n.value].copy(), dtj.value

@@ -390,3 +390,57 @@ def test_ba_drivers_through_the_reference_lm():
         L.orc_set_lm_driver(None)
     assert [x == y for x, y in zip(own, ref)] == [True] * len(own)
     assert own == run_all()   # the hook is off again
+
+
+def test_imu_preintegration_sample_selection_equal_reference():
+    """IMUPreIntegratorBase::PreIntegration (src/Odom/OdomPreIntegrator.h:227-430) compiled unchanged with a recording update(): the
+    oracle issues the same update(omega, acc, dt) calls, bit for bit — forward and reversed time, frame stamps between / on / before /
+    after the samples, duplicated samples (dt == 0), a single sample, a > 1.5 s gap (status -1), an empty list."""
+    r = np.random.default_rng(12)
+    bg, ba = r.normal(0, 0.01, 3), r.normal(0, 0.1, 3)
+    n_cases = n_nonempty = n_abort = n_back = 0
+    for trial in range(400):
+        n = int(r.integers(1, 40))
+        t = np.cumsum(r.uniform(0.002, 0.012, n)) + 10.0
+        if trial % 7 == 0 and n > 3:
+            t[n // 2] = t[n // 2 - 1]                      # a duplicated stamp
+        if trial % 11 == 0 and n > 4:
+            t[n // 3:] += r.choice([1.2, 1.8, 2.5])         # a gap around the 1.5 s gate
+        smp = np.concatenate([t[:, None], r.normal(0, 1, (n, 3)) + [0, 0, 9.8], r.normal(0, 0.3, (n, 3))], 1)
+        choices = np.concatenate([t, t + 0.001, t - 0.001, [t[0] - 0.05, t[-1] + 0.05, t[0] - 3.0, t[-1] + 3.0]])
+        for _ in range(6):
+            ti, tj = (float(x) for x in r.choice(choices, 2))
+            so, to = O.imu_preintegrate_trace(smp, ti, tj, bg, ba)
+            sr, tr, dtj = R.imu_preintegrate_trace(smp, ti, tj, bg, ba)
+            assert so == sr, (trial, ti, tj)
+            assert to.shape == tr.shape and to.tobytes() == tr.tobytes(), (trial, ti, tj, to, tr)
+            n_cases += 1; n_nonempty += len(to) > 0; n_abort += sr == -1; n_back += ti > tj
+            if sr == -1:
+                assert dtj == 0.0
+    assert n_cases == 2400 and n_nonempty > 1500 and n_abort > 20 and n_back > 800
+    # the empty list leaves everything untouched
+    so, to = O.imu_preintegrate_trace(np.zeros((0, 7)), 1.0, 2.0, bg, ba)
+    sr, tr, dtj = R.imu_preintegrate_trace(np.zeros((0, 7)), 1.0, 2.0, bg, ba)
+    assert so == sr == 0 and len(to) == len(tr) == 0 and dtj == 123.0
+
+
+def test_huber_kernel_equal_reference():
+    """g2o::RobustKernelHuber (setDelta + robustify, delta^2 held in a float member in this fork) compiled unchanged against the
+    oracle's kernel: rho and rho' bit for bit for the deltas the drivers use and random ones, incl. the e == float(delta^2) boundary."""
+    import ctypes as C
+    Lo, Lr = O.lib(), R.lib()
+    Lo.orc_huber.argtypes = [C.c_double, C.c_double, C.c_void_p]; Lo.orc_huber.restype = None
+    Lr.ref_huber.argtypes = [C.c_double, C.c_double, C.c_void_p]; Lr.ref_huber.restype = None
+    r = np.random.default_rng(2)
+    deltas = [np.sqrt(5.991), np.sqrt(7.815), np.sqrt(16.919), np.sqrt(12.592), 5.0, float(np.sqrt(np.float32(10.0)))] + list(r.uniform(0.1, 9, 40))
+    n_out = 0
+    for d in deltas:
+        ds = float(np.float32(d * d))
+        es = list(r.uniform(0, 4 * d * d, 60)) + [ds, np.nextafter(ds, 0), np.nextafter(ds, 1e9), 0.0, 1e-300, 1e12]
+        for e in es:
+            a = np.zeros(2); b = np.zeros(3)
+            Lo.orc_huber(float(d), float(e), a.ctypes.data)
+            Lr.ref_huber(float(d), float(e), b.ctypes.data)
+            assert a.tobytes() == b[:2].tobytes(), (d, e, a, b)
+            n_out += b[1] != 1.0
+    assert n_out > 500
