@@ -158,3 +158,24 @@ def imu_preintegrate_trace(samples, ti, tj, bg, ba, cap=4096):
     tr = np.zeros((cap, 7)); n = C.c_int(0); dtj = C.c_double(0)
     rc = lib().ref_imu_preintegrate_trace(_p(smp), len(smp), float(ti), float(tj), _p(bg), _p(ba), _p(tr), cap, C.byref(n), C.byref(dtj))
     return rc, tr[:n.value].copy(), dtj.value
+
+
+def stereo_matches(orbL, kl, dl, orbR, kr, dr, bf, minZ):
+    """Frame::ComputeStereoMatches of the reference, compiled unchanged, on the pyramids of two ORACLE extractor instances (the same
+    inputs as oracle_lib.stereo_matches) -> (uright f32[nl], depth f32[nl], kept)"""
+    L = lib()
+    L.ref_stereo_matches.restype = C.c_int
+    L.ref_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    n = orbL.nlevels
+    lvL = [np.ascontiguousarray(orbL.level(l)) for l in range(n)]
+    lvR = [np.ascontiguousarray(orbR.level(l)) for l in range(n)]
+    pl = (C.c_void_p * n)(*[a.ctypes.data for a in lvL]); pr = (C.c_void_p * n)(*[a.ctypes.data for a in lvR])
+    lw = np.array([a.shape[1] for a in lvL], np.int32); lh = np.array([a.shape[0] for a in lvL], np.int32)
+    tb = orbL.tables()
+    kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    ur = np.empty(len(kl), np.float32); dp = np.empty(len(kl), np.float32)
+    kept = L.ref_stereo_matches(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), pl, pr, _p(lw), _p(lh), n, _p(tb["scale"]),
+                                _p(tb["inv_scale"]), float(bf), float(minZ), _p(ur), _p(dp))
+    return ur, dp, kept

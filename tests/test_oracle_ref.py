@@ -444,3 +444,20 @@ def test_huber_kernel_equal_reference():
             assert a.tobytes() == b[:2].tobytes(), (d, e, a, b)
             n_out += b[1] != 1.0
     assert n_out > 500
+
+
+def test_compute_stereo_matches_equal_reference():
+    """Frame::ComputeStereoMatches (src/Frame.cc:451-611) compiled unchanged against the oracle's restatement on rectified stereo pairs
+    (bright, dark and 512 x 512 frames, different disparities): uright and depth of every left keypoint bit for bit."""
+    from vieo_slam_b200.synth import EUROC, stereo_stream
+    bf = np.float32(EUROC["bf"]); minZ = np.float32(bf / np.float32(EUROC["fx"]))
+    imgs = stereo_stream(4, 31, dark_every=2).reshape(4, 2, 480, 752)
+    total = 0
+    for f in range(4):
+        oL, oR = O.OrbOracle(1200, 1.2, 8, 20, 7), O.OrbOracle(1200, 1.2, 8, 20, 7)
+        nl, kl, dl, _ = oL.extract(imgs[f, 0]); nr, kr, dr, _ = oR.extract(imgs[f, 1])
+        ur, dp, sad, kept = O.stereo_matches(oL, kl, dl, oR, kr, dr, bf, minZ)
+        ur2, dp2, kept2 = R.stereo_matches(oL, kl, dl, oR, kr, dr, bf, minZ)
+        assert kept == kept2 and ur.tobytes() == ur2.tobytes() and dp.tobytes() == dp2.tobytes(), f
+        total += kept
+    assert total > 1000
