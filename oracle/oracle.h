@@ -172,6 +172,10 @@ typedef struct OrcFrustumRigFrame {
 int orc_is_in_frustum_rig(const OrcFrustumRigFrame* f, int n, const float* wP, const float* Pn, const float* max_dist,
                           const float* min_dist, uint8_t* inview, uint8_t* cam_mask, float* proj, int32_t* level, float* viewcos,
                           float* depth);
+/* the frame grid alone (test hook): candidate lists of n_q windows (x, y, r | minlevel, maxlevel) in the reference's walk order */
+int orc_features_in_area(const OrcKeyPoint* kps, int n_kp, float minx, float maxx, float miny, float maxy, float winv, float hinv,
+                         const float* q_xyr, const int32_t* q_levels, int n_q, int32_t* out_ptr, int32_t* out_idx, int cap,
+                         uint8_t* in_image);
 int orc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);
 int orc_is_in_frustum(const OrcFrustumFrame* f, int n, const float* wP, const float* Pn, const float* max_dist,
                       const float* min_dist, uint8_t* inview, float* proj, int32_t* level, float* viewcos, float* depth);

@@ -581,3 +581,32 @@ extern "C" int orc_sbp_reloc(const OrcSbpFrame* f, int orb_dist, float log_scale
   }
   return nmatches;
 }
+
+
+// Test hook: the grid alone — AssignFeaturesToGrid over one frame's keypoints, then GetFeaturesInArea / IsInImage per query
+// (x, y, r, minlevel, maxlevel); the candidate lists in walk order.  Pinned against the reference's own four functions compiled
+// unchanged (oracle/_ref, tests/test_oracle_ref.py).
+extern "C" int orc_features_in_area(const OrcKeyPoint* kps, int n_kp, float minx, float maxx, float miny, float maxy, float winv,
+                                    float hinv, const float* q_xyr, const int32_t* q_levels, int n_q, int32_t* out_ptr,
+                                    int32_t* out_idx, int cap, uint8_t* in_image) {
+  OrcSbpFrame f;
+  memset(&f, 0, sizeof(f));
+  f.n_kp = n_kp;
+  f.minx = minx; f.maxx = maxx; f.miny = miny; f.maxy = maxy;
+  f.grid_winv = winv; f.grid_hinv = hinv;
+  const Grid grid(f, kps);
+  std::vector<int> cand;
+  int total = 0;
+  out_ptr[0] = 0;
+  for (int q = 0; q < n_q; ++q) {
+    const float x = q_xyr[3 * q], y = q_xyr[3 * q + 1];
+    features_in_area(f, grid, kps, x, y, q_xyr[3 * q + 2], q_levels[2 * q], q_levels[2 * q + 1], cand);
+    for (int j : cand) {
+      if (total < cap) out_idx[total] = j;
+      ++total;
+    }
+    out_ptr[q + 1] = total;
+    if (in_image) in_image[q] = (x >= f.minx && x < f.maxx && y >= f.miny && y < f.maxy) ? 1 : 0;
+  }
+  return total;
+}

@@ -461,3 +461,51 @@ def test_compute_stereo_matches_equal_reference():
         assert kept == kept2 and ur.tobytes() == ur2.tobytes() and dp.tobytes() == dp2.tobytes(), f
         total += kept
     assert total > 1000
+
+
+def test_frame_grid_equal_reference():
+    """FrameBase::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea / IsInImage (src/FrameBase.cpp:95-174) compiled unchanged: the
+    oracle returns the same candidate lists IN THE SAME ORDER for random windows — windows that leave the image on every side, radii
+    from sub-pixel to half the image, every level-band form the searches use (forward, backward, +-1, [l - 1, l], none), keypoints
+    outside the undistorted bounds, clustered keypoints (long cell lists)."""
+    import ctypes as C
+    from oracle_lib import KP_DTYPE
+    Lo, Lr = O.lib(), R.lib()
+    sig = [C.c_void_p, C.c_int] + [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    for fn in (Lo.orc_features_in_area, Lr.ref_features_in_area):
+        fn.argtypes = sig; fn.restype = C.c_int
+    r = np.random.default_rng(23)
+    n_total = 0
+    for case in range(12):
+        w, h = (752, 480) if case % 2 == 0 else (512, 512)
+        minx, maxx, miny, maxy = (np.float32(v) for v in ((-3.7, w + 4.2, -2.1, h + 1.6) if case % 3 else (0, w, 0, h)))
+        winv = np.float32(64) / np.float32(maxx - minx); hinv = np.float32(48) / np.float32(maxy - miny)
+        n_kp = int(r.integers(50, 2000))
+        kps = np.zeros(n_kp, KP_DTYPE)
+        if case % 4 == 3:   # clustered
+            c = r.uniform([50, 50], [w - 50, h - 50], (8, 2))
+            p = c[r.integers(0, 8, n_kp)] + r.normal(0, 6, (n_kp, 2))
+        else:
+            p = r.uniform([minx - 5, miny - 5], [maxx + 5, maxy + 5], (n_kp, 2))
+        kps["x"], kps["y"] = p[:, 0].astype(np.float32), p[:, 1].astype(np.float32)
+        kps["octave"] = r.integers(0, 8, n_kp)
+        n_q = 600
+        q = np.zeros((n_q, 3), np.float32)
+        q[:, 0] = r.uniform(minx - 40, maxx + 40, n_q); q[:, 1] = r.uniform(miny - 40, maxy + 40, n_q)
+        q[:, 2] = r.choice([0.4, 3.0, 7.0, 15.0, 40.0, 250.0], n_q) * r.uniform(0.5, 1.5, n_q)
+        q[:50, :2] = p[r.integers(0, n_kp, 50)].astype(np.float32)      # windows centred on keypoints
+        lv = r.integers(0, 8, n_q)
+        form = r.integers(0, 5, n_q)
+        ql = np.stack([np.where(form == 0, 0, np.where(form == 1, lv, np.where(form == 2, lv - 1, np.where(form == 3, lv - 1, -1)))),
+                       np.where(form == 0, lv, np.where(form == 1, -1, np.where(form == 2, lv + 1, np.where(form == 3, lv, -1))))], 1).astype(np.int32)
+        outs = []
+        for fn in (Lo.orc_features_in_area, Lr.ref_features_in_area):
+            ptr = np.zeros(n_q + 1, np.int32); idx = np.zeros(400000, np.int32); inim = np.zeros(n_q, np.uint8)
+            tot = fn(kps.ctypes.data, n_kp, float(minx), float(maxx), float(miny), float(maxy), float(winv), float(hinv), q.ctypes.data,
+                     ql.ctypes.data, n_q, ptr.ctypes.data, idx.ctypes.data, len(idx), inim.ctypes.data)
+            assert tot <= len(idx)
+            outs.append((tot, ptr.copy(), idx[:tot].copy(), inim.copy()))
+        assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2]), case
+        assert np.array_equal(outs[0][3], outs[1][3])
+        n_total += outs[0][0]
+    assert n_total > 50000
