@@ -1,0 +1,330 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, th_far_pts) (src/ORBmatcher.cc:1303-1467)
+// and ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th, th_far_pts) (:230-335) + RadiusByViewingCos (:337-342) of
+// the REFERENCE compiled UNCHANGED, on top of the reference's own grid functions (FrameBase::GetFeaturesInArea / AssignFeaturesToGrid
+// / PosInGrid / IsInImage) and ORBmatcher::DescriptorDistance / ComputeThreeMaxima, all cut out of the sources by name at build time.
+// What is pinned: the control flow of the two tracking searches — forward / backward / +-1 level bands, the th_far and depth gates,
+// the stereo ur gate, the "keypoint already holds an observed map point" rule, best / second-best with the same-level ratio test,
+// the claim order, the rotation histogram and its three maxima.  What this file supplies (stand-ins, stated for what they are):
+// the members of Frame / MapPoint / Camera the bodies touch, a TU-local cv::Mat / KeyPoint (`#define cv cvst`), three-element
+// vectors, a 3 x 3 float matrix-vector product, and an SE3 (unit quaternion + translation) whose product / inverse / action are
+// Sophus' formulas (so3 * p = Eigen's _transformVector; T1 * T2 = (q1 q2, t1 + q1 * t2); T^-1 = (q*, q* * (-t))) — the same
+// formulas the oracle restates, so for these few lines the comparison is between two copies of one formula.
+#include <limits.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <array>
+#include <cassert>
+#include <cmath>
+#include <list>
+#include <memory>
+#include <set>
+#include <tuple>
+#include <vector>
+using namespace std;
+
+#define PRINT_DEBUG_FILE_MUTEX(...)
+#define PRINT_DEBUG_FILE(...)
+
+namespace cvst {
+struct Point2f {
+  float x, y;
+};
+struct KeyPoint {
+  Point2f pt;
+  float size, angle, response;
+  int octave, class_id;
+};
+class Mat {  // descriptor rows only
+ public:
+  const uint8_t* data = nullptr;
+  int rows = 0;
+  Mat() {}
+  Mat(const uint8_t* d, int r) : data(d), rows(r) {}
+  Mat row(int r) const { return Mat(data + 32 * (size_t)r, 1); }
+  template <class T> const T* ptr() const { return (const T*)data; }
+};
+}  // namespace cvst
+#define cv cvst
+
+namespace Eigen {
+template <class T>
+struct Vec3 {
+  T v[3];
+  Vec3() : v{0, 0, 0} {}
+  Vec3(T a, T b, T c) : v{a, b, c} {}
+  T& operator()(int i) { return v[i]; }
+  const T& operator()(int i) const { return v[i]; }
+  T& operator[](int i) { return v[i]; }
+  const T& operator[](int i) const { return v[i]; }
+  template <class U> Vec3<U> cast() const { return Vec3<U>((U)v[0], (U)v[1], (U)v[2]); }
+};
+using Vector3d = Vec3<double>;
+using Vector3f = Vec3<float>;
+struct Matrix3f {
+  float m[9];
+  template <class U> Matrix3f cast() const { return *this; }
+};
+inline Vector3f operator*(const Matrix3f& K, const Vector3f& p) {
+  Vector3f o;
+  for (int r = 0; r < 3; ++r) o.v[r] = (K.m[3 * r] * p.v[0] + K.m[3 * r + 1] * p.v[1]) + K.m[3 * r + 2] * p.v[2];
+  return o;
+}
+}  // namespace Eigen
+using Eigen::Vector3d;
+using Eigen::Vector3f;
+
+namespace Sophus {
+struct SE3d {  // unit quaternion (w, x, y, z) + translation
+  double q[4] = {1, 0, 0, 0}, t[3] = {0, 0, 0};
+  static void rot(const double q[4], const double v[3], double o[3]) {  // Eigen::QuaternionBase::_transformVector
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    double uv[3] = {y * v[2] - z * v[1], z * v[0] - x * v[2], x * v[1] - y * v[0]};
+    for (int i = 0; i < 3; ++i) uv[i] += uv[i];
+    const double c[3] = {y * uv[2] - z * uv[1], z * uv[0] - x * uv[2], x * uv[1] - y * uv[0]};
+    for (int i = 0; i < 3; ++i) o[i] = v[i] + w * uv[i] + c[i];
+  }
+  SE3d inverse() const {
+    SE3d o;
+    o.q[0] = q[0]; o.q[1] = -q[1]; o.q[2] = -q[2]; o.q[3] = -q[3];
+    const double nt[3] = {t[0] * -1.0, t[1] * -1.0, t[2] * -1.0};
+    rot(o.q, nt, o.t);
+    return o;
+  }
+  SE3d operator*(const SE3d& b) const {
+    SE3d o;
+    o.q[0] = q[0] * b.q[0] - q[1] * b.q[1] - q[2] * b.q[2] - q[3] * b.q[3];
+    o.q[1] = q[0] * b.q[1] + q[1] * b.q[0] + q[2] * b.q[3] - q[3] * b.q[2];
+    o.q[2] = q[0] * b.q[2] + q[2] * b.q[0] + q[3] * b.q[1] - q[1] * b.q[3];
+    o.q[3] = q[0] * b.q[3] + q[3] * b.q[0] + q[1] * b.q[2] - q[2] * b.q[1];
+    double r[3];
+    rot(q, b.t, r);
+    for (int i = 0; i < 3; ++i) o.t[i] = t[i] + r[i];
+    return o;
+  }
+  Vector3d operator*(const Vector3d& p) const {
+    double r[3];
+    rot(q, p.v, r);
+    return Vector3d(r[0] + t[0], r[1] + t[1], r[2] + t[2]);
+  }
+  Vector3d translation() const { return Vector3d(t[0], t[1], t[2]); }
+  template <class U> SE3d cast() const { return *this; }
+};
+}  // namespace Sophus
+
+namespace VIEO_SLAM_SBP {
+struct Vector2img {
+  float v[2];
+  float& operator[](int i) { return v[i]; }
+};
+namespace camm {
+struct Camera {
+  using Tio = double;
+  using Ptr = std::shared_ptr<Camera>;
+  Sophus::SE3d Tcr;
+  Eigen::Matrix3f K;
+  const Sophus::SE3d& GetTcr() const { return Tcr; }
+  Eigen::Matrix3f toK() const { return K; }
+  void Project(const Vector3d&, Vector2img*) const {}  // usedistort_ is false in this wrapper
+};
+}  // namespace camm
+
+class MapPoint {
+ public:
+  Vector3f pos;
+  const uint8_t* desc = nullptr;
+  int obs = 0;
+  long unsigned int mnId = 0;
+  // the tracking info Frame::isInFrustum leaves (include/MapPoint.h _TrackFastMatchInfo): what the local-map search reads
+  struct TrackInfo {
+    static const int NUM_PROJ = 3;
+    bool btrack_inview_ = false;
+    list<float> vtrack_proj_[NUM_PROJ];
+    list<int> vtrack_scalelevel_;
+    list<float> vtrack_viewcos_;
+    list<size_t> vtrack_cami_;
+    float track_depth_ = 0;
+  } trackinfo;
+  bool bad = false;
+  Vector3f GetWorldPos() { return pos; }
+  cv::Mat GetDescriptor() { return cv::Mat(desc, 1); }
+  int Observations() { return obs; }
+  bool isBad() { return bad; }
+  TrackInfo& GetTrackInfoRef() { return trackinfo; }
+};
+
+class FrameBase {  // as in ref_grid_wrap.cc
+ public:
+  typedef struct _GridInfo {
+    vector<float> fgrids_widthinv_;
+    vector<float> fgrids_heightinv_;
+    const int FRAME_GRID_ROWS = 48;
+    const int FRAME_GRID_COLS = 64;
+    vector<array<float, 4>> minmax_xy_;
+  } GridInfo;
+  GridInfo gridinfo_;
+  vector<vector<vector<size_t>>> vgrids_;
+  int N = 0;
+  static bool usedistort_;
+  vector<camm::Camera::Ptr> mpCameras;
+  vector<cv::KeyPoint> mvKeys, mvKeysUn;
+  vector<pair<size_t, size_t>> mapn2in_;
+  vector<size_t> GetFeaturesInArea(uint8_t cami, const float& x, const float& y, const float& r, const int minlevel = -1,
+                                   const int maxlevel = -1) const;
+  void AssignFeaturesToGrid();
+  bool PosInGrid(uint8_t cami, const cv::KeyPoint& kp, int& posX, int& posY);
+  bool IsInImage(uint8_t cami, const float& x, const float& y) const;
+};
+bool FrameBase::usedistort_ = false;
+#include "grid_fns.inc"
+
+class Frame : public FrameBase {
+ public:
+  Sophus::SE3d Tcw;
+  const Sophus::SE3d GetTcwCst() const { return Tcw; }
+  struct {
+    float baseline_bf_[2];
+    vector<float> vuright_;
+  } stereoinfo_;
+  struct {
+    vector<float> vscalefactor_;
+  } scalepyrinfo_;
+  vector<MapPoint*> mvpMapPoints;
+  vector<bool> mvbOutlier;
+  cv::Mat mDescriptors;
+  const vector<MapPoint*>& GetMapPointMatches() const { return mvpMapPoints; }
+  void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
+  void EraseMapPointMatch(const size_t& idx) { mvpMapPoints[idx] = nullptr; }
+};
+
+class ORBmatcher {
+ public:
+  ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+  static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
+  static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+  void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+  int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono, const float th_far_pts = 0);
+  int SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th = 3, const float th_far_pts = 0);
+  float RadiusByViewingCos(const float& viewCos);
+  float mfNNratio;
+  bool mbCheckOrientation;
+};
+const int ORBmatcher::TH_HIGH = 100;  // src/ORBmatcher.cc:20-22
+const int ORBmatcher::TH_LOW = 50;
+const int ORBmatcher::HISTO_LENGTH = 30;
+#include "orbmatcher_fns.inc"
+#include "sbp_fns.inc"
+}  // namespace VIEO_SLAM_SBP
+#undef cv
+
+struct RefKp {
+  float x, y, size, angle, response;
+  int32_t octave;
+};
+struct RefSbpFrame {  // == OrcSbpFrame
+  int32_t kp_begin, n_kp, q_begin, n_q;
+  float minx, maxx, miny, maxy, grid_winv, grid_hinv, bf, b, fx, fy, cx, cy, th, th_far, nn_ratio;
+  int32_t mono, check_orientation, n_levels;
+  float scale[16];
+  double qcw[4], tcw[3], qlw[4], tlw[3];
+};
+static void fill_frame(VIEO_SLAM_SBP::Frame& F, const RefSbpFrame* f, const RefKp* kps, const float* uright, const uint8_t* desc) {
+  using namespace VIEO_SLAM_SBP;
+  auto cam = std::make_shared<camm::Camera>();
+  const float K[9] = {f->fx, 0.f, f->cx, 0.f, f->fy, f->cy, 0.f, 0.f, 1.f};
+  for (int i = 0; i < 9; ++i) cam->K.m[i] = K[i];
+  F.mpCameras.push_back(cam);
+  F.gridinfo_.fgrids_widthinv_ = {f->grid_winv};
+  F.gridinfo_.fgrids_heightinv_ = {f->grid_hinv};
+  F.gridinfo_.minmax_xy_.push_back({f->minx, f->maxx, f->miny, f->maxy});
+  F.N = f->n_kp;
+  F.mvKeysUn.resize(f->n_kp);
+  for (int i = 0; i < f->n_kp; ++i) {
+    F.mvKeysUn[i].pt.x = kps[i].x; F.mvKeysUn[i].pt.y = kps[i].y; F.mvKeysUn[i].octave = kps[i].octave; F.mvKeysUn[i].angle = kps[i].angle;
+  }
+  F.mvKeys = F.mvKeysUn;
+  F.AssignFeaturesToGrid();
+  F.stereoinfo_.baseline_bf_[0] = f->b;
+  F.stereoinfo_.baseline_bf_[1] = f->bf;
+  F.stereoinfo_.vuright_.assign(uright, uright + f->n_kp);
+  F.scalepyrinfo_.vscalefactor_.assign(f->scale, f->scale + f->n_levels);
+  F.mvpMapPoints.assign(f->n_kp, nullptr);
+  F.mDescriptors = cvst::Mat(desc, f->n_kp);
+  for (int k = 0; k < 4; ++k) F.Tcw.q[k] = f->qcw[k];
+  for (int k = 0; k < 3; ++k) F.Tcw.t[k] = f->tcw[k];
+}
+
+// same arguments as orc_sbp_last_frame; kp_match[k] = the query that ended up in CurrentFrame.mvpMapPoints[k] (-1 none)
+extern "C" int ref_sbp_last_frame(const RefSbpFrame* f, const RefKp* kps, const float* uright, const uint8_t* desc, const double* q_Xw,
+                                  const int32_t* q_octave, const float* q_angle, const uint8_t* q_desc, const uint8_t* q_flags,
+                                  const uint8_t* kp_blocked, int32_t* kp_match) {
+  using namespace VIEO_SLAM_SBP;
+  Frame cur, last;
+  fill_frame(cur, f, kps, uright, desc);
+  MapPoint blocker;
+  blocker.obs = 1;
+  if (kp_blocked)
+    for (int k = 0; k < f->n_kp; ++k)
+      if (kp_blocked[k]) cur.mvpMapPoints[k] = &blocker;
+  std::vector<MapPoint> mps(f->n_q);
+  last.N = f->n_q;
+  last.mvKeys.resize(f->n_q);
+  last.mvpMapPoints.resize(f->n_q);
+  last.mvbOutlier.assign(f->n_q, false);
+  for (int i = 0; i < f->n_q; ++i) {
+    // GetWorldPos() is float in the reference (MapPoint::Vector3data) and cast back to double: the caller passes float-valued doubles
+    mps[i].pos = Vector3f((float)q_Xw[3 * i], (float)q_Xw[3 * i + 1], (float)q_Xw[3 * i + 2]);
+    mps[i].desc = q_desc + 32 * (size_t)i;
+    mps[i].obs = (q_flags[i] & 1) ? 1 : 0;
+    mps[i].mnId = i;
+    last.mvpMapPoints[i] = &mps[i];
+    last.mvKeys[i].octave = q_octave[i];
+    last.mvKeys[i].angle = q_angle[i];
+  }
+  for (int k = 0; k < 4; ++k) last.Tcw.q[k] = f->qlw[k];
+  for (int k = 0; k < 3; ++k) last.Tcw.t[k] = f->tlw[k];
+  ORBmatcher m(f->nn_ratio, f->check_orientation != 0);
+  const int n = m.SearchByProjection(cur, last, f->th, f->mono != 0, f->th_far);
+  for (int k = 0; k < f->n_kp; ++k) {
+    MapPoint* p = cur.mvpMapPoints[k];
+    kp_match[k] = (p && p != &blocker) ? (int32_t)(p - mps.data()) : -1;
+  }
+  return n;
+}
+
+// same arguments as orc_sbp_local_map: queries = the local map points in view with the tracking info Frame::isInFrustum left
+extern "C" int ref_sbp_local_map(const RefSbpFrame* f, const RefKp* kps, const float* uright, const uint8_t* desc, const float* q_proj,
+                                 const int32_t* q_level, const float* q_viewcos, const float* q_depth, const uint8_t* q_desc,
+                                 const uint8_t* q_flags, const uint8_t* kp_blocked, int32_t* kp_match) {
+  using namespace VIEO_SLAM_SBP;
+  Frame cur;
+  fill_frame(cur, f, kps, uright, desc);
+  MapPoint blocker;
+  blocker.obs = 1;
+  if (kp_blocked)
+    for (int k = 0; k < f->n_kp; ++k)
+      if (kp_blocked[k]) cur.mvpMapPoints[k] = &blocker;
+  std::vector<MapPoint> mps(f->n_q);
+  std::vector<MapPoint*> vp(f->n_q);
+  for (int i = 0; i < f->n_q; ++i) {
+    MapPoint& m = mps[i];
+    m.desc = q_desc + 32 * (size_t)i;
+    m.obs = (q_flags[i] & 1) ? 1 : 0;
+    m.mnId = i;
+    m.trackinfo.btrack_inview_ = true;
+    for (int k = 0; k < 3; ++k) m.trackinfo.vtrack_proj_[k].push_back(q_proj[3 * i + k]);
+    m.trackinfo.vtrack_scalelevel_.push_back(q_level[i]);
+    m.trackinfo.vtrack_viewcos_.push_back(q_viewcos[i]);
+    m.trackinfo.vtrack_cami_.push_back(0);
+    m.trackinfo.track_depth_ = q_depth[i];
+    vp[i] = &m;
+  }
+  ORBmatcher m(f->nn_ratio, f->check_orientation != 0);
+  const int n = m.SearchByProjection(cur, vp, f->th, f->th_far);
+  for (int k = 0; k < f->n_kp; ++k) {
+    MapPoint* p = cur.mvpMapPoints[k];
+    kp_match[k] = (p && p != &blocker) ? (int32_t)(p - mps.data()) : -1;
+  }
+  return n;
+}

@@ -179,3 +179,49 @@ def stereo_matches(orbL, kl, dl, orbR, kr, dr, bf, minZ):
     kept = L.ref_stereo_matches(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), pl, pr, _p(lw), _p(lh), n, _p(tb["scale"]),
                                 _p(tb["inv_scale"]), float(bf), float(minZ), _p(ur), _p(dp))
     return ur, dp, kept
+
+
+def search_by_projection_last_frame(pb):
+    """ORBmatcher::SearchByProjection(Frame&, const Frame& last, ...) of the reference, compiled unchanged, over every frame of a
+    synth.make_sbp_problem(mode = SBP_LAST_FRAME) batch -> (kp_match, n_matches)"""
+    L = lib()
+    L.ref_sbp_last_frame.argtypes = None
+    L.ref_sbp_last_frame.restype = C.c_int
+    fr = pb["frames"]
+    kp_match = np.full(len(pb["kps"]), -1, np.int32)
+    nm = np.zeros(len(fr), np.int32)
+    vp = C.c_void_p
+
+    def at(a, i):
+        a = pb[a]
+        return vp(a.ctypes.data + i * a.strides[0])
+    for f in range(len(fr)):
+        kb, qb = int(fr[f]["kp_begin"]), int(fr[f]["q_begin"])
+        blk = at("kp_blocked", kb) if pb.get("kp_blocked") is not None else None
+        nm[f] = L.ref_sbp_last_frame(vp(fr.ctypes.data + f * fr.strides[0]), at("kps", kb), at("uright", kb), at("desc", kb), at("q_Xw", qb),
+                                     at("q_level", qb), at("q_angle", qb), at("q_desc", qb), at("q_flags", qb), blk,
+                                     vp(kp_match.ctypes.data + 4 * kb))
+    return kp_match, nm
+
+
+def search_by_projection_local_map(pb):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, th_far_pts) of the reference, compiled unchanged, over
+    every frame of a synth.make_sbp_problem(mode = SBP_LOCAL_MAP) batch -> (kp_match, n_matches)"""
+    L = lib()
+    L.ref_sbp_local_map.argtypes = None
+    L.ref_sbp_local_map.restype = C.c_int
+    fr = pb["frames"]
+    kp_match = np.full(len(pb["kps"]), -1, np.int32)
+    nm = np.zeros(len(fr), np.int32)
+    vp = C.c_void_p
+
+    def at(a, i):
+        a = pb[a]
+        return vp(a.ctypes.data + i * a.strides[0])
+    for f in range(len(fr)):
+        kb, qb = int(fr[f]["kp_begin"]), int(fr[f]["q_begin"])
+        blk = at("kp_blocked", kb) if pb.get("kp_blocked") is not None else None
+        nm[f] = L.ref_sbp_local_map(vp(fr.ctypes.data + f * fr.strides[0]), at("kps", kb), at("uright", kb), at("desc", kb), at("q_proj", qb),
+                                    at("q_level", qb), at("q_viewcos", qb), at("q_depth", qb), at("q_desc", qb), at("q_flags", qb), blk,
+                                    vp(kp_match.ctypes.data + 4 * kb))
+    return kp_match, nm

@@ -509,3 +509,41 @@ def test_frame_grid_equal_reference():
         assert np.array_equal(outs[0][3], outs[1][3])
         n_total += outs[0][0]
     assert n_total > 50000
+
+
+@pytest.mark.parametrize("kw", [dict(seed=5, th=15.0), dict(seed=6, th=7.0, mono=True), dict(seed=7, th=15.0, motion="forward"),
+                                dict(seed=8, th=15.0, motion="backward"), dict(seed=9, th=30.0, cluster=True, blocked_frac=0.3),
+                                dict(seed=10, th=15.0, th_far=6.0)])
+def test_search_by_projection_last_frame_equal_reference(kw):
+    """ORBmatcher::SearchByProjection(Frame&, const Frame& last, th, bMono, th_far_pts) (src/ORBmatcher.cc:1303-1467) compiled
+    unchanged over the reference's own grid functions: the oracle assigns the same map point to the same keypoint and returns the
+    same match count — level bands for forward / backward / uncertain motion, monocular frames, the th_far gate, blocked keypoints,
+    clustered keypoints with many candidates per window, the rotation histogram."""
+    from vieo_slam_b200 import synth
+    import inspect
+    args = {k: v for k, v in kw.items() if k in inspect.signature(synth.make_sbp_problem).parameters}
+    pb = synth.make_sbp_problem(kw["seed"], 3, mode=synth.SBP_LAST_FRAME, **{k: v for k, v in args.items() if k != "seed"})
+    pb["q_Xw"] = np.ascontiguousarray(pb["q_Xw"].astype(np.float32).astype(np.float64))   # MapPoint positions are float in the reference
+    kp_o, q_o, d_o, n_o = O.search_by_projection(pb)
+    kp_r, n_r = R.search_by_projection_last_frame(pb)
+    assert np.array_equal(n_o, n_r), (n_o, n_r)
+    assert np.array_equal(kp_o, kp_r)
+    assert n_o.sum() > 100
+
+
+@pytest.mark.parametrize("kw", [dict(seed=15, th=1.0), dict(seed=16, th=3.0), dict(seed=17, th=1.0, cluster=True, blocked_frac=0.3),
+                                dict(seed=18, th=5.0, th_far=6.0), dict(seed=19, th=1.0, mono=True)])
+def test_search_by_projection_local_map_equal_reference(kw):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, th_far_pts) + RadiusByViewingCos (src/ORBmatcher.cc:230-342)
+    compiled unchanged over the reference's own grid functions: same keypoint -> map point assignment and match count as the oracle
+    — the 2.5 / 4.0 window by viewing cosine, the [l - 1, l] level band, the ur gate, best / second-best with the same-level ratio
+    test, blocked keypoints, the th_far gate on track_depth_."""
+    from vieo_slam_b200 import synth
+    pb = synth.make_sbp_problem(kw["seed"], 3, mode=synth.SBP_LOCAL_MAP, n_q=1800, **{k: v for k, v in kw.items() if k != "seed"})
+    for ratio in (0.8, 0.6):
+        pb["frames"]["nn_ratio"] = ratio
+        kp_o, q_o, d_o, n_o = O.search_by_projection(pb)
+        kp_r, n_r = R.search_by_projection_local_map(pb)
+        assert np.array_equal(n_o, n_r), (n_o, n_r)
+        assert np.array_equal(kp_o, kp_r)
+        assert n_o.sum() > 100
