@@ -1030,6 +1030,33 @@ extern "C" void orc_huber(double delta, double e, double rho[2]) {
   k.rho(e, rho);
 }
 
+// the SO3 helpers of so3_oracle.h for the tests (oracle/_ref compiles common/so3_extra.h itself): op 0 exp(w) -> unit quaternion
+// (w, x, y, z); 1 Exp(w) -> R; 2 log of a quaternion; 3 Log(R); 4 JacobianR(w); 5 JacobianRInv(w); 6 normalizeRotationM(R)
+extern "C" void orc_so3(int op, const double* in, double* out) {
+  auto put = [&](const M3& m) {
+    for (int k = 0; k < 9; ++k) out[k] = m.m[k];
+  };
+  M3 R;
+  if (op == 3 || op == 6)
+    for (int k = 0; k < 9; ++k) R.m[k] = in[k];
+  if (op == 0) {
+    const Quat q = so3_exp_q(in);
+    out[0] = q.w, out[1] = q.x, out[2] = q.y, out[3] = q.z;
+  } else if (op == 1) {
+    put(so3_Exp(in));
+  } else if (op == 2) {
+    so3_log_q(qnormalized({in[0], in[1], in[2], in[3]}), out);
+  } else if (op == 3) {
+    so3_log_q(qnormalized(mquat(R)), out);
+  } else if (op == 4) {
+    put(so3_Jr(in));
+  } else if (op == 5) {
+    put(so3_JrInv(in));
+  } else if (op == 6) {
+    put(normalize_rot(R));
+  }
+}
+
 // test hook: run every BA driver of this file (pose optimisation, local / global BA) through another LM driver with the
 // OrcLmDriver signature — oracle/_ref's ref_lm_optimize, the reference's own solve() / optimize() compiled unchanged
 extern "C" void orc_set_lm_driver(OrcLmDriver d) { g_lm_driver = d; }

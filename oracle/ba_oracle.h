@@ -205,6 +205,9 @@ typedef int (*OrcLmDriver)(const OrcLmCallbacks* cb, int iterations, double user
 int orc_lm_optimize(const OrcLmCallbacks* cb, int iterations, double user_lambda_init, double* stats);
 /* g2o::RobustKernelHuber::robustify with setDelta(delta): rho[0] = rho(e), rho[1] = rho'(e) */
 void orc_huber(double delta, double e, double rho[2]);
+/* SO3ex helpers (common/so3_extra.h) as restated in so3_oracle.h: op 0 exp -> quaternion, 1 Exp -> R, 2 log(q), 3 Log(R),
+ * 4 JacobianR, 5 JacobianRInv, 6 normalizeRotationM; matrices row-major */
+void orc_so3(int op, const double* in, double* out);
 /* test hook: the LM driver behind every BA driver of ba_oracle.cc (NULL restores orc_lm_optimize) */
 void orc_set_lm_driver(OrcLmDriver d);
 /* camm::{Pinhole,Radtan,KB8}Camera::Project: float pixel + d(img)/d(p3d) (2x3 row-major, may be NULL) */

@@ -1,0 +1,418 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// The inertial arithmetic of the REFERENCE compiled UNCHANGED against a minimal stand-in for Eigen / Sophus::SO3 (eigstub/, both are
+// third-party dependencies absent from this image):
+//   * common/so3_extra.h, whole, from where it lies (SO3ex::exp / log / Log / Exp / JacobianR / JacobianRInv / normalizeRotationM);
+//   * src/Odom/NavState.h, whole (the state and its IncSmall updates = the vertices' oplus);
+//   * IMUPreIntegratorBase::update (src/Odom/OdomPreIntegrator.h:431-506): the covariance / bias-Jacobian / delta recurrence, cut out
+//     by name at build time into oracle/_ref/gen/inertial_*.inc, like the vertex and edge classes below;
+//   * VertexNavState<D>, VertexNavStateBias, VertexGThetaXYRwI and the edges EdgeNavStateI<NV> (PVR, PRV, PRVG), EdgeNavStateBias,
+//     EdgeNavStatePriorPRVBias, EdgeNavStatePriorPVRBias, EdgeGyrBias (src/Odom/g2otypes.h, g2otypes.cpp): class definitions and
+//     computeError / linearizeOplus bodies.
+// What is declared here by hand is only what those texts name from g2o (vertex / edge base classes holding _estimate, _vertices,
+// _error, _measurement and the Jacobian slots) and the data members of IMUDataBase / IMUPreIntegratorBase that update() touches.
+// The C entry points mirror the oracle's (orc_edge_navstate, orc_navstate_oplus, ...) with the same struct layouts.
+#include <math.h>
+#include <stdlib.h>
+#include <cassert>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "common/so3_extra.h"    // the reference's, unchanged
+#include "src/Odom/NavState.h"   // the reference's, unchanged
+
+#include "../ba_oracle.h"  // struct layouts only (OrcNavState, OrcImuPreint, OrcImuNoise)
+
+namespace VIEO_SLAM_INERTIAL {  // own namespaces: other wrappers of this library declare stand-ins under the reference's names
+using namespace VIEO_SLAM;
+typedef Eigen::Matrix<double, 9, 9> Matrix9d;
+typedef NavState NavStated;
+
+struct IMUDataBase {  // src/Odom/OdomData.h:22-36: the statics update() reads
+  static Matrix3d mSigmag, mSigmaa;
+  static int mdt_cov_noise_fixed;
+  static double mFreqRef;
+};
+Matrix3d IMUDataBase::mSigmag, IMUDataBase::mSigmaa;
+int IMUDataBase::mdt_cov_noise_fixed = 0;
+double IMUDataBase::mFreqRef = 0;
+
+template <class IMUDataBase>
+class IMUPreIntegratorBase {  // data members of OdomPreIntegrator.h:105-150
+ public:
+  typedef double Tcalc;
+  using SO3calc = Sophus::SO3ex<Tcalc>;
+  double mdeltatij = 0;
+  Matrix3d mRij;
+  Vector3d mvij, mpij;
+  Matrix9d mSigmaijPRV, mSigmaij;
+  Matrix3d mJgpij, mJapij, mJgvij, mJavij, mJgRij;
+  IMUPreIntegratorBase() { mRij.setIdentity(); }
+  void update(const Vector3d& omega, const Vector3d& acc, const double& dt);
+};
+template <class IMUDataBase>
+#include "inertial_update.inc"
+
+typedef IMUPreIntegratorBase<IMUDataBase> IMUPreintegrator;
+}  // namespace VIEO_SLAM_INERTIAL
+
+namespace G2O_INERTIAL {
+using namespace VIEO_SLAM_INERTIAL;
+using namespace Eigen;
+
+struct OptimizableGraph {
+  struct Vertex {
+    virtual ~Vertex() {}
+  };
+};
+template <int D, class T>
+class BaseVertex : public OptimizableGraph::Vertex {
+ public:
+  static const int Dimension = D;
+  const T& estimate() const { return _estimate; }
+  void setEstimate(const T& e) { _estimate = e; }
+
+ protected:
+  T _estimate;
+};
+class VertexSBAPointXYZ : public BaseVertex<3, Vector3d> {};
+
+struct JacSlot {  // one _jacobianOplus[i] of a multi edge (a dynamic-size map in g2o)
+  int rows = 0, cols = 0;
+  std::vector<double> v;  // row-major
+  template <class O>
+  JacSlot& operator=(const Eigen::MatrixBase<O>& o) {
+    rows = O::Rows, cols = O::Cols;
+    v.resize((size_t)rows * cols);
+    for (int i = 0; i < rows; ++i)
+      for (int j = 0; j < cols; ++j) v[(size_t)i * cols + j] = o.coeff(i, j);
+    return *this;
+  }
+};
+template <int D, class E>
+class BaseMultiEdge {
+ public:
+  virtual ~BaseMultiEdge() {}
+  void resize(size_t n) {
+    _vertices.assign(n, nullptr);
+    _jacobianOplus.resize(n);
+  }
+  virtual void computeError() = 0;
+  virtual void linearizeOplus() = 0;
+  std::vector<OptimizableGraph::Vertex*> _vertices;
+  Matrix<double, D, 1> _error;
+  E _measurement;
+  std::vector<JacSlot> _jacobianOplus;
+};
+template <int D, class E>
+using BaseMultiEdgeEx = BaseMultiEdge<D, E>;
+template <int D, class E, class Xi, class Xj>
+class BaseBinaryEdge {
+ public:
+  virtual ~BaseBinaryEdge() {}
+  virtual void computeError() = 0;
+  virtual void linearizeOplus() = 0;
+  OptimizableGraph::Vertex* _vertices[2] = {nullptr, nullptr};
+  Matrix<double, D, 1> _error;
+  E _measurement;
+  Matrix<double, D, Xi::Dimension> _jacobianOplusXi;
+  Matrix<double, D, Xj::Dimension> _jacobianOplusXj;
+};
+template <int D, class E, class Xi, class Xj>
+using BaseBinaryEdgeEx = BaseBinaryEdge<D, E, Xi, Xj>;
+template <int D, class E, class Xi>
+class BaseUnaryEdge {
+ public:
+  virtual ~BaseUnaryEdge() {}
+  virtual void computeError() = 0;
+  virtual void linearizeOplus() = 0;
+  const E& measurement() const { return _measurement; }
+  Matrix<double, D, D>& information() { return _information; }
+  const Matrix<double, D, D>& information() const { return _information; }
+  OptimizableGraph::Vertex* _vertices[1] = {nullptr};
+  Matrix<double, D, 1> _error;
+  E _measurement;
+  Matrix<double, D, D> _information;
+  Matrix<double, D, Xi::Dimension> _jacobianOplusXi;
+};
+template <int D, class M, class I>
+bool readEdge(std::istream&, M&, I&) {
+  return true;
+}
+template <int D, class M, class I>
+bool writeEdge(std::ostream&, const M&, const I&) {
+  return true;
+}
+
+// class definitions and member bodies of the reference, in the order of its header
+template <int D>
+#include "inertial_vertex_navstate.inc"
+typedef VertexNavState<6> VertexNavStatePR;
+typedef VertexNavState<3> VertexNavStateV;
+typedef VertexNavState<9> VertexNavStatePVR;
+#include "inertial_vertex_bias.inc"
+#include "inertial_vertex_gtheta.inc"
+template <int NV>
+#include "inertial_edge_navstate_class.inc"
+template <int NV>
+#include "inertial_edge_navstate_error.inc"
+template <int NV>
+#include "inertial_edge_navstate_jac.inc"
+typedef EdgeNavStateI<5> EdgeNavStatePRV;
+typedef EdgeNavStateI<6> EdgeNavStatePRVG;
+typedef EdgeNavStateI<3> EdgeNavStatePVR;
+#include "inertial_edge_classes.inc"
+typedef VertexSBAPointXYZ VertexGyrBias;
+#include "inertial_edge_gyrbias_class.inc"
+#include "inertial_edge_fns.inc"
+}  // namespace G2O_INERTIAL
+
+namespace g2o = G2O_INERTIAL;
+namespace {
+using namespace VIEO_SLAM_INERTIAL;
+using Eigen::Matrix;
+using Eigen::Quaterniond;
+using Sophus::SO3exd;
+
+NavState to_ns(const OrcNavState& s) {
+  NavState n;
+  n.mpwb = Vector3d(s.p);
+  n.mRwb = SO3exd(Quaterniond(s.q[0], s.q[1], s.q[2], s.q[3]));
+  n.mvwb = Vector3d(s.v);
+  n.mbg = Vector3d(s.bg), n.mba = Vector3d(s.ba), n.mdbg = Vector3d(s.dbg), n.mdba = Vector3d(s.dba);
+  return n;
+}
+void from_ns(const NavState& n, OrcNavState* s) {
+  const Quaterniond& q = n.mRwb.unit_quaternion();
+  s->q[0] = q.w(), s->q[1] = q.x(), s->q[2] = q.y(), s->q[3] = q.z();
+  for (int k = 0; k < 3; ++k) {
+    s->p[k] = n.mpwb(k), s->v[k] = n.mvwb(k);
+    s->bg[k] = n.mbg(k), s->ba[k] = n.mba(k), s->dbg[k] = n.mdbg(k), s->dba[k] = n.mdba(k);
+  }
+}
+template <int R, int C>
+Matrix<double, R, C> from_rm(const double* p) {
+  Matrix<double, R, C> m;
+  for (int i = 0; i < R; ++i)
+    for (int j = 0; j < C; ++j) m(i, j) = p[i * C + j];
+  return m;
+}
+template <class M>
+void to_rm(const Eigen::MatrixBase<M>& m, double* p) {
+  for (int i = 0; i < (int)M::Rows; ++i)
+    for (int j = 0; j < (int)M::Cols; ++j) p[i * (int)M::Cols + j] = m.coeff(i, j);
+}
+IMUPreintegrator to_pre(const OrcImuPreint& o) {
+  IMUPreintegrator p;
+  p.mRij = from_rm<3, 3>(o.Rij);
+  p.mvij = Vector3d(o.vij), p.mpij = Vector3d(o.pij);
+  p.mSigmaijPRV = from_rm<9, 9>(o.SigmaPRV), p.mSigmaij = from_rm<9, 9>(o.SigmaPVR);
+  p.mJgpij = from_rm<3, 3>(o.Jgp), p.mJapij = from_rm<3, 3>(o.Jap), p.mJgvij = from_rm<3, 3>(o.Jgv);
+  p.mJavij = from_rm<3, 3>(o.Jav), p.mJgRij = from_rm<3, 3>(o.JgR);
+  p.mdeltatij = o.dt;
+  return p;
+}
+// copies block (rows x cols, row-major slot) into dst [rows][ld] at column c0
+void put_cols(const g2o::JacSlot& s, double* dst, int ld, int c0) {
+  for (int i = 0; i < s.rows; ++i)
+    for (int j = 0; j < s.cols; ++j) dst[i * ld + c0 + j] = s.v[(size_t)i * s.cols + j];
+}
+}  // namespace
+
+// op: 0 exp(w) -> quaternion (w, x, y, z); 1 Exp(w) -> R; 2 SO3ex(q).log(); 3 Log(R); 4 JacobianR(w); 5 JacobianRInv(w);
+//     6 normalizeRotationM(R); 7 the Sophus base class' log() of q (what a product of two SO3ex yields in this build)
+extern "C" void ref_so3(int op, const double* in, double* out) {
+  if (op == 0) {
+    const Quaterniond q = SO3exd::exp(Vector3d(in)).unit_quaternion();
+    out[0] = q.w(), out[1] = q.x(), out[2] = q.y(), out[3] = q.z();
+  } else if (op == 1) {
+    to_rm(SO3exd::Exp(Vector3d(in)), out);
+  } else if (op == 2) {
+    to_rm(SO3exd(Quaterniond(in[0], in[1], in[2], in[3])).log(), out);
+  } else if (op == 3) {
+    to_rm(SO3exd::Log(from_rm<3, 3>(in)), out);
+  } else if (op == 4) {
+    to_rm(SO3exd::JacobianR(Vector3d(in)), out);
+  } else if (op == 5) {
+    to_rm(SO3exd::JacobianRInv(Vector3d(in)), out);
+  } else if (op == 6) {
+    to_rm(SO3exd::normalizeRotationM(from_rm<3, 3>(in)), out);
+  } else if (op == 7) {
+    const Sophus::SO3<double> s = SO3exd(Quaterniond(in[0], in[1], in[2], in[3])) * SO3exd();
+    to_rm(s.log(), out);
+  }
+}
+
+// reset state, then update(omega, acc, dt) for every row of trace [n][7]
+extern "C" void ref_imu_update_sequence(const OrcImuNoise* nz, const double* trace, int n, OrcImuPreint* out) {
+  IMUDataBase::mSigmag = Matrix3d::Identity() * nz->sigma_g;
+  IMUDataBase::mSigmaa = Matrix3d::Identity() * nz->sigma_a;
+  IMUDataBase::mdt_cov_noise_fixed = nz->dt_cov_noise_fixed;
+  IMUDataBase::mFreqRef = nz->freq_ref;
+  IMUPreintegrator p;
+  for (int i = 0; i < n; ++i) p.update(Vector3d(trace + 7 * i), Vector3d(trace + 7 * i + 3), trace[7 * i + 6]);
+  std::memset(out, 0, sizeof(*out));
+  to_rm(p.mRij, out->Rij), to_rm(p.mvij, out->vij), to_rm(p.mpij, out->pij);
+  to_rm(p.mSigmaijPRV, out->SigmaPRV), to_rm(p.mSigmaij, out->SigmaPVR);
+  to_rm(p.mJgpij, out->Jgp), to_rm(p.mJapij, out->Jap), to_rm(p.mJgvij, out->Jgv), to_rm(p.mJavij, out->Jav), to_rm(p.mJgRij, out->JgR);
+  out->dt = p.mdeltatij;
+}
+
+// EdgeNavStateI<3> (order 0, PVR), <5> (order 1, PRV) or <6> (q_wI != nullptr: PRVG with gw = GI): e [9], Ji / Jj [9][9] with
+// the state columns in the residual's order, Jb [9][6], JG [9][2]
+extern "C" void ref_edge_navstate(const OrcNavState* nsi, const OrcNavState* nsj, const OrcImuPreint* pre, const double gw[3], int order,
+                                  const double* q_wI, double e[9], double* Ji, double* Jj, double* Jb, double* JG) {
+  using namespace g2o;
+  const NavState a = to_ns(*nsi), b = to_ns(*nsj);
+  VertexNavStateBias vb;
+  vb.setEstimate(a);
+  if (order == 0) {
+    VertexNavStatePVR vi, vj;
+    vi.setEstimate(a), vj.setEstimate(b);
+    EdgeNavStatePVR ed;
+    ed._vertices[0] = &vi, ed._vertices[1] = &vj, ed._vertices[2] = &vb;
+    ed._measurement = to_pre(*pre);
+    ed.SetParams(Vector3d(gw));
+    ed.computeError();
+    to_rm(ed._error, e);
+    if (Ji) {
+      ed.linearizeOplus();
+      put_cols(ed._jacobianOplus[0], Ji, 9, 0), put_cols(ed._jacobianOplus[1], Jj, 9, 0), put_cols(ed._jacobianOplus[2], Jb, 6, 0);
+    }
+    return;
+  }
+  VertexNavStatePR pi, pj;
+  VertexNavStateV wi, wj;
+  pi.setEstimate(a), pj.setEstimate(b), wi.setEstimate(a), wj.setEstimate(b);
+  auto run = [&](auto& ed) {
+    ed._vertices[0] = &pi, ed._vertices[1] = &pj, ed._vertices[2] = &wi, ed._vertices[3] = &wj, ed._vertices[4] = &vb;
+    ed._measurement = to_pre(*pre);
+    ed.SetParams(Vector3d(gw));
+    ed.computeError();
+    to_rm(ed._error, e);
+    if (Ji) {
+      ed.linearizeOplus();
+      put_cols(ed._jacobianOplus[0], Ji, 9, 0), put_cols(ed._jacobianOplus[2], Ji, 9, 6);
+      put_cols(ed._jacobianOplus[1], Jj, 9, 0), put_cols(ed._jacobianOplus[3], Jj, 9, 6);
+      put_cols(ed._jacobianOplus[4], Jb, 6, 0);
+    }
+  };
+  if (!q_wI) {
+    EdgeNavStatePRV ed;
+    run(ed);
+  } else {
+    VertexGThetaXYRwI vg;
+    vg.setEstimate(SO3exd(Quaterniond(q_wI[0], q_wI[1], q_wI[2], q_wI[3])));
+    EdgeNavStatePRVG ed;
+    ed._vertices[5] = &vg;
+    run(ed);
+    if (Ji && JG) put_cols(ed._jacobianOplus[5], JG, 2, 0);
+  }
+}
+
+// kind 0 = PR (6), 1 = PVR (9), 2 = V (3), 3 = Bias (6): the vertices' oplusImpl
+extern "C" void ref_navstate_oplus(OrcNavState* ns, int kind, const double* dx) {
+  using namespace g2o;
+  auto run = [&](auto& v) {
+    v.setEstimate(to_ns(*ns));
+    v.oplusImpl(dx);
+    from_ns(v.estimate(), ns);
+  };
+  if (kind == 0) {
+    VertexNavStatePR v;
+    run(v);
+  } else if (kind == 1) {
+    VertexNavStatePVR v;
+    run(v);
+  } else if (kind == 2) {
+    VertexNavStateV v;
+    run(v);
+  } else {
+    VertexNavStateBias v;
+    run(v);
+  }
+}
+
+// VertexGThetaXYRwI::setToOriginImpl(gw) / oplusImpl
+extern "C" void ref_gdir(int op, const double* in, double q_wI[4]) {
+  g2o::VertexGThetaXYRwI v;
+  if (op == 0) {
+    Vector3d gw(in);
+    v.setToOriginImpl(gw);
+  } else {
+    v.setEstimate(SO3exd(Quaterniond(q_wI[0], q_wI[1], q_wI[2], q_wI[3])));
+    v.oplusImpl(in);
+  }
+  const Quaterniond& q = v.estimate().unit_quaternion();
+  q_wI[0] = q.w(), q_wI[1] = q.x(), q_wI[2] = q.y(), q_wI[3] = q.z();
+}
+
+// EdgeNavStatePriorPVRBias (form 0: e [15], Jpvr [15][9], Jbias [15][6]) / EdgeNavStatePriorPRVBias (form 1: Jpvr holds
+// [PR | V] = 15 x 9 in P R V order)
+extern "C" void ref_edge_prior(int form, const OrcNavState* ns, const OrcNavState* prior, double e[15], double* Jpvr, double* Jbias) {
+  using namespace g2o;
+  const NavState s = to_ns(*ns);
+  VertexNavStateBias vb;
+  vb.setEstimate(s);
+  if (form == 0) {
+    VertexNavStatePVR v;
+    v.setEstimate(s);
+    EdgeNavStatePriorPVRBias ed;
+    ed._vertices[0] = &v, ed._vertices[1] = &vb;
+    ed._measurement = to_ns(*prior);
+    ed.computeError();
+    to_rm(ed._error, e);
+    if (Jpvr) {
+      ed.linearizeOplus();
+      to_rm(ed._jacobianOplusXi, Jpvr);
+      if (Jbias) to_rm(ed._jacobianOplusXj, Jbias);
+    }
+  } else {
+    VertexNavStatePR vp;
+    VertexNavStateV vv;
+    vp.setEstimate(s), vv.setEstimate(s);
+    EdgeNavStatePriorPRVBias ed;
+    ed._vertices[0] = &vp, ed._vertices[1] = &vv, ed._vertices[2] = &vb;
+    ed._measurement = to_ns(*prior);
+    ed.computeError();
+    to_rm(ed._error, e);
+    if (Jpvr) {
+      ed.linearizeOplus();
+      put_cols(ed._jacobianOplus[0], Jpvr, 9, 0), put_cols(ed._jacobianOplus[1], Jpvr, 9, 6);
+      if (Jbias) put_cols(ed._jacobianOplus[2], Jbias, 6, 0);
+    }
+  }
+}
+
+// EdgeNavStateBias: e [6] = (bg_j + dbg_j) - (bg_i + dbg_i), same for ba; Ji / Jj [6][6]
+extern "C" void ref_edge_bias(const OrcNavState* nsi, const OrcNavState* nsj, double e[6], double* Ji, double* Jj) {
+  using namespace g2o;
+  VertexNavStateBias vi, vj;
+  vi.setEstimate(to_ns(*nsi)), vj.setEstimate(to_ns(*nsj));
+  EdgeNavStateBias ed;
+  ed._vertices[0] = &vi, ed._vertices[1] = &vj;
+  ed.computeError();
+  to_rm(ed._error, e);
+  if (Ji) {
+    ed.linearizeOplus();
+    to_rm(ed._jacobianOplusXi, Ji), to_rm(ed._jacobianOplusXj, Jj);
+  }
+}
+
+// EdgeGyrBias (Optimizer::OptimizeInitialGyroBias' edge): matrices row-major
+extern "C" void ref_edge_gyr_bias(const double* dRij, const double* JgRij, const double* Rwbi, const double* Rwbj, const double bg[3],
+                                  double e[3], double* J) {
+  using namespace g2o;
+  VertexGyrBias v;
+  v.setEstimate(Vector3d(bg));
+  EdgeGyrBias ed;
+  ed._vertices[0] = &v;
+  ed.deltaRij = from_rm<3, 3>(dRij), ed.JgRij = from_rm<3, 3>(JgRij), ed.Rwbi = from_rm<3, 3>(Rwbi), ed.Rwbj = from_rm<3, 3>(Rwbj);
+  ed.computeError();
+  to_rm(ed._error, e);
+  if (J) {
+    ed.linearizeOplus();
+    to_rm(ed._jacobianOplusXi, J);
+  }
+}

@@ -928,3 +928,13 @@ def imu_preintegrate_trace(samples, ti, tj, bg, ba, cap=4096):
     tr = np.zeros((cap, 7)); n = C.c_int(0)
     rc = L.orc_imu_preintegrate_trace(_p(smp), len(smp), float(ti), float(tj), _p(bg), _p(ba), _p(tr), cap, C.byref(n))
     return rc, tr[:n.value].copy()
+
+
+def so3(op, x):
+    """orc_so3: op 0 exp -> q (w,x,y,z), 1 Exp -> R, 2 log(q), 3 Log(R), 4 JacobianR, 5 JacobianRInv, 6 normalizeRotationM"""
+    L = lib()
+    L.orc_so3.argtypes = [C.c_int, C.c_void_p, C.c_void_p]; L.orc_so3.restype = None
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros({0: 4, 2: 3, 3: 3}.get(op, 9))
+    L.orc_so3(op, _p(x), _p(out))
+    return out.reshape(3, 3) if out.size == 9 else out

@@ -225,3 +225,92 @@ def search_by_projection_local_map(pb):
                                     at("q_level", qb), at("q_viewcos", qb), at("q_depth", qb), at("q_desc", qb), at("q_flags", qb), blk,
                                     vp(kp_match.ctypes.data + 4 * kb))
     return kp_match, nm
+
+
+# ---- the inertial arithmetic (oracle/ref_build/ref_inertial_wrap.cc): so3_extra.h, NavState.h, IMUPreIntegratorBase::update and the
+# inertial vertices / edges of g2otypes compiled unchanged against the Eigen / Sophus stand-in
+def so3(op, x):
+    """op 0 exp -> q (w,x,y,z), 1 Exp -> R, 2 SO3ex(q).log(), 3 Log(R), 4 JacobianR, 5 JacobianRInv, 6 normalizeRotationM,
+    7 Sophus' base-class log() of q"""
+    L = lib()
+    L.ref_so3.argtypes = [C.c_int, C.c_void_p, C.c_void_p]; L.ref_so3.restype = None
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros({0: 4, 2: 3, 3: 3, 7: 3}.get(op, 9))
+    L.ref_so3(op, x.ctypes.data, out.ctypes.data)
+    return out.reshape(3, 3) if out.size == 9 else out
+
+
+def imu_update_sequence(nz, trace, preint_dtype):
+    """reset state + IMUPreIntegratorBase::update per row of trace [n][7] = (omega, acc, dt) -> PREINT record"""
+    L = lib()
+    L.ref_imu_update_sequence.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]; L.ref_imu_update_sequence.restype = None
+    tr = np.ascontiguousarray(trace, np.float64).reshape(-1, 7)
+    out = np.zeros(1, preint_dtype)
+    L.ref_imu_update_sequence(C.byref(nz), tr.ctypes.data, len(tr), out.ctypes.data)
+    return out[0]
+
+
+def edge_navstate(nsi, nsj, pre, gw, order, q_wI=None):
+    """EdgeNavStateI<3 | 5 | 6>: -> (e, Ji, Jj, Jb[, JG]); with q_wI, gw is GI and the edge is EdgeNavStatePRVG"""
+    L = lib()
+    L.ref_edge_navstate.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 6; L.ref_edge_navstate.restype = None
+    nsi = np.ascontiguousarray(nsi); nsj = np.ascontiguousarray(nsj); pre = np.ascontiguousarray(pre)
+    gw = np.ascontiguousarray(gw, np.float64)
+    e = np.zeros(9); Ji = np.zeros((9, 9)); Jj = np.zeros((9, 9)); Jb = np.zeros((9, 6)); JG = np.zeros((9, 2))
+    q = None if q_wI is None else np.ascontiguousarray(q_wI, np.float64)
+    L.ref_edge_navstate(nsi.ctypes.data, nsj.ctypes.data, pre.ctypes.data, gw.ctypes.data, int(order), None if q is None else q.ctypes.data,
+                        e.ctypes.data, Ji.ctypes.data, Jj.ctypes.data, Jb.ctypes.data, JG.ctypes.data)
+    return (e, Ji, Jj, Jb) if q is None else (e, Ji, Jj, Jb, JG)
+
+
+def navstate_oplus(ns, kind, dx):
+    L = lib()
+    L.ref_navstate_oplus.argtypes = [C.c_void_p, C.c_int, C.c_void_p]; L.ref_navstate_oplus.restype = None
+    out = np.array(ns).reshape(1).copy()
+    dx = np.ascontiguousarray(dx, np.float64)
+    L.ref_navstate_oplus(out.ctypes.data, int(kind), dx.ctypes.data)
+    return out[0]
+
+
+def gdir_init(gw):
+    L = lib()
+    L.ref_gdir.argtypes = [C.c_int, C.c_void_p, C.c_void_p]; L.ref_gdir.restype = None
+    gw = np.ascontiguousarray(gw, np.float64); q = np.zeros(4)
+    L.ref_gdir(0, gw.ctypes.data, q.ctypes.data)
+    return q
+
+
+def gdir_oplus(q, d):
+    L = lib()
+    L.ref_gdir.argtypes = [C.c_int, C.c_void_p, C.c_void_p]; L.ref_gdir.restype = None
+    q = np.array(q, np.float64).copy(); d = np.ascontiguousarray(d, np.float64)
+    L.ref_gdir(1, d.ctypes.data, q.ctypes.data)
+    return q
+
+
+def edge_prior(form, ns, prior):
+    """form 0 EdgeNavStatePriorPVRBias, 1 EdgeNavStatePriorPRVBias -> (e [15], J_state [15][9], J_bias [15][6])"""
+    L = lib()
+    L.ref_edge_prior.argtypes = [C.c_int] + [C.c_void_p] * 5; L.ref_edge_prior.restype = None
+    ns = np.ascontiguousarray(ns); prior = np.ascontiguousarray(prior)
+    e = np.zeros(15); J = np.zeros((15, 9)); Jb = np.zeros((15, 6))
+    L.ref_edge_prior(int(form), ns.ctypes.data, prior.ctypes.data, e.ctypes.data, J.ctypes.data, Jb.ctypes.data)
+    return e, J, Jb
+
+
+def edge_bias(nsi, nsj):
+    L = lib()
+    L.ref_edge_bias.argtypes = [C.c_void_p] * 5; L.ref_edge_bias.restype = None
+    nsi = np.ascontiguousarray(nsi); nsj = np.ascontiguousarray(nsj)
+    e = np.zeros(6); Ji = np.zeros((6, 6)); Jj = np.zeros((6, 6))
+    L.ref_edge_bias(nsi.ctypes.data, nsj.ctypes.data, e.ctypes.data, Ji.ctypes.data, Jj.ctypes.data)
+    return e, Ji, Jj
+
+
+def edge_gyr_bias(dRij, JgRij, Rwbi, Rwbj, bg):
+    L = lib()
+    L.ref_edge_gyr_bias.argtypes = [C.c_void_p] * 7; L.ref_edge_gyr_bias.restype = None
+    a = [np.ascontiguousarray(x, np.float64) for x in (dRij, JgRij, Rwbi, Rwbj, bg)]
+    e = np.zeros(3); J = np.zeros((3, 3))
+    L.ref_edge_gyr_bias(*[x.ctypes.data for x in a], e.ctypes.data, J.ctypes.data)
+    return e, J

@@ -547,3 +547,170 @@ def test_search_by_projection_local_map_equal_reference(kw):
         assert np.array_equal(n_o, n_r), (n_o, n_r)
         assert np.array_equal(kp_o, kp_r)
         assert n_o.sum() > 100
+
+
+# ---- the inertial arithmetic, compiled unchanged against the Eigen / Sophus stand-in (oracle/ref_build/eigstub) ------------------------
+# These comparisons carry a relative tolerance instead of bit equality: the stand-in evaluates Eigen's expressions eagerly, and the
+# order in which a dot product's terms are added is Eigen's own business (it depends on its version, vectorisation and -march).
+def _close(a, b, tol=1e-12):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and bool(np.all(np.abs(a - b) <= tol * (1.0 + np.maximum(np.abs(a), np.abs(b)))))
+
+
+def test_so3_helpers_equal_reference():
+    """common/so3_extra.h compiled whole: SO3ex::exp / Exp / log / Log / JacobianR / JacobianRInv / normalizeRotationM against
+    so3_oracle.h over the small-angle branch (|w| < 1e-5), ordinary angles and angles next to pi; Sophus' own log() (what a product of
+    two SO3ex yields in the USE_SOPHUS_NEWEST build, used by EdgeNavStateI's rotation residual) equals SO3ex::log away from pi."""
+    r = np.random.default_rng(1)
+    for s in [0.0, 1e-12, 1e-8, 9.9e-6, 1.01e-5, 1e-4, 1e-2, 0.3, 1.0, 2.0, 3.0, np.pi - 1e-3, np.pi - 1e-7]:
+        for _ in range(20):
+            w = r.normal(0, 1, 3); w *= s / np.linalg.norm(w)
+            for op in (0, 1, 4, 5):
+                assert _close(O.so3(op, w), R.so3(op, w), 1e-14), (op, s, w)
+            q = R.so3(0, w)
+            assert _close(O.so3(2, q), R.so3(2, q), 1e-14) and _close(O.so3(2, -q), R.so3(2, -q), 1e-14)
+            Rm = R.so3(1, w)
+            assert _close(O.so3(3, Rm), R.so3(3, Rm), 1e-13), (s, w)
+            noisy = Rm + r.normal(0, 1e-9, (3, 3))
+            assert _close(O.so3(6, noisy), R.so3(6, noisy), 1e-14)
+            if s < 3.1:
+                assert _close(R.so3(7, q), R.so3(2, q), 1e-12), (s, w)
+            # round trip and the Jacobians' defining property Jr * Jr^-1 = I
+            if 0 < s < 3.1:
+                assert np.allclose(R.so3(2, q), w, rtol=1e-9, atol=1e-15)
+                assert np.allclose(R.so3(4, w) @ R.so3(5, w), np.eye(3), atol=1e-9)
+
+
+def test_imu_update_recurrence_equal_reference():
+    """IMUPreIntegratorBase::update (src/Odom/OdomPreIntegrator.h:431-506) compiled unchanged: delta R / v / p, the five bias Jacobians
+    and both 9x9 covariances (PRV and PVR order) after feeding it the update() calls the sample selection issues — which the recording
+    test above shows to be the reference's — equal the oracle's whole pre-integration; all three noise forms (discrete sigma, sigma / dt,
+    sigma * freq_ref for long steps)."""
+    s = synth_mod().vio_sequence(21, 40)
+    imu, t = s["imu"], s["times"]
+    n_checked = 0
+    for fixed, freq in ((1, 200.0), (0, 0.0), (0, 200.0), (0, 1000.0)):
+        nz = O.imu_noise(dt_cov_noise_fixed=fixed, freq_ref=freq)
+        for k in range(1, 40, 3):
+            for (ti, tj) in ((t[k - 1], t[k]), (t[k], t[k - 1]), (t[max(k - 3, 0)], t[k])):
+                lo = max(np.searchsorted(imu[:, 0], min(ti, tj), "right") - 1, 0)
+                hi = min(np.searchsorted(imu[:, 0], max(ti, tj), "left") + 1, len(imu))
+                bg, ba = s["truth"][k]["bg"], s["truth"][k]["ba"]
+                want = O.imu_preintegrate(imu[lo:hi], ti, tj, bg, ba, nz)
+                rc, tr = O.imu_preintegrate_trace(imu[lo:hi], ti, tj, bg, ba)
+                assert rc == 0 and len(tr) > 0
+                got = R.imu_update_sequence(nz, tr, O.PREINT_DTYPE)
+                for f in ("Rij", "vij", "pij", "Jgp", "Jap", "Jgv", "Jav", "JgR", "dt"):
+                    assert _close(want[f], got[f], 1e-12), (f, fixed, freq, k)
+                for f in ("SigmaPRV", "SigmaPVR"):
+                    sc = np.abs(want[f]).max()
+                    assert sc > 0 and np.abs(want[f] - got[f]).max() <= 1e-11 * sc, (f, fixed, freq, k)
+                n_checked += 1
+    assert n_checked == 4 * 13 * 3
+
+
+def synth_mod():
+    from vieo_slam_b200 import synth
+    return synth
+
+
+@pytest.fixture(scope="module")
+def inertial_seq():
+    s = synth_mod().vio_sequence(5, 40)
+    s["pre"] = O.imu_preintegrate_frames(s, list(range(40)), O.imu_noise())
+    return s
+
+
+def test_inertial_edges_equal_reference(inertial_seq):
+    """EdgeNavStateI<3> (PVR), <5> (PRV) and <6> (PRVG, with VertexGThetaXYRwI) of src/Odom/g2otypes.h:725-884 compiled unchanged — class
+    definitions, computeError and linearizeOplus — over the reference's own NavState / SO3ex: residuals and every Jacobian block equal
+    the oracle's, incl. large bias corrections and rotation residuals of tens of degrees."""
+    synth = synth_mod()
+    seq = inertial_seq
+    r = np.random.default_rng(4)
+    G = 9.81
+    for trial in range(60):
+        j = int(r.integers(1, 40)); i = j - 1
+        big = trial % 3 == 2
+        nsi = synth.perturb_state(seq["truth"][i], r, drot=np.deg2rad(20 if big else 0.3), dp=0.3 if big else 0.01)
+        nsj = synth.perturb_state(seq["truth"][j], r, drot=np.deg2rad(20 if big else 0.3))
+        nsi["dbg"] = r.normal(0, 2e-2 if big else 1e-3, 3); nsi["dba"] = r.normal(0, 1e-1 if big else 1e-2, 3)
+        pre = seq["pre"][j]
+        gw = synth.GRAVITY_W if trial % 2 else r.normal(0, 1, 3) * 5
+        for order in (0, 1):
+            a = O.edge_navstate(nsi, nsj, pre, gw, order)
+            b = R.edge_navstate(nsi, nsj, pre, gw, order)
+            for x, y, name in zip(a, b, ("e", "Ji", "Jj", "Jb")):
+                assert _close(x, y, 1e-11), (trial, order, name, np.abs(x - y).max())
+        gdir = gw / np.linalg.norm(gw) * G
+        qo, qr = O.gdir_init(gdir), R.gdir_init(gdir)
+        assert _close(qo, qr, 1e-14)
+        d2 = r.normal(0, 0.05, 2)
+        assert _close(O.gdir_oplus(qo, d2), R.gdir_oplus(qo, d2), 1e-14)
+        GI = np.array([0.0, 0.0, G])
+        a = O.edge_navstate_g(nsi, nsj, pre, qo, GI)
+        b = R.edge_navstate(nsi, nsj, pre, GI, 1, q_wI=qo)
+        for x, y, name in zip(a, b, ("e", "Ji", "Jj", "Jb", "JG")):
+            assert _close(x, y, 1e-11), (trial, name, np.abs(x - y).max())
+    # gravity (anti-)parallel to the z axis: normalized() of the zero cross product, RwI = I on both sides
+    for gz in ([0, 0, G], [0, 0, -G]):
+        assert _close(O.gdir_init(np.array(gz, float)), R.gdir_init(np.array(gz, float)), 1e-15)
+
+
+def test_vertex_updates_and_prior_edges_equal_reference(inertial_seq):
+    """NavState::IncSmall / IncSmallBias through VertexNavState<6 | 9 | 3>::oplusImpl and VertexNavStateBias::oplusImpl (src/Odom/NavState.h
+    whole, g2otypes.h:270-285, 553-567), EdgeNavStatePriorPVRBias (g2otypes.cpp:84-124) and EdgeNavStateBias (:14-35), compiled unchanged."""
+    synth = synth_mod()
+    seq = inertial_seq
+    r = np.random.default_rng(8)
+    for trial in range(80):
+        ns = synth.perturb_state(seq["truth"][int(r.integers(0, 40))], r, drot=np.deg2rad(30))
+        ns["dbg"] = r.normal(0, 1e-3, 3); ns["dba"] = r.normal(0, 1e-2, 3)
+        scale = [1e-9, 1e-3, 0.3][trial % 3]
+        for kind, n in ((0, 6), (1, 9), (2, 3), (3, 6)):
+            dx = r.normal(0, scale, n)
+            a, b = O.navstate_oplus(ns, kind, dx), R.navstate_oplus(ns, kind, dx)
+            for f in ("p", "q", "v", "bg", "ba", "dbg", "dba"):
+                assert _close(a[f], b[f], 1e-14), (trial, kind, f)
+        prior = synth.perturb_state(ns, r, drot=np.deg2rad([0.3, 15][trial % 2]), dp=0.2)
+        prior["dbg"] = r.normal(0, 1e-3, 3); prior["dba"] = r.normal(0, 1e-2, 3)
+        eo, Jo = O.edge_prior_pvr(ns, prior)
+        er, Jr, Jbr = R.edge_prior(0, ns, prior)
+        assert _close(eo, er, 1e-12) and _close(Jo, Jr, 1e-12), trial
+        assert np.array_equal(Jbr[9:], np.eye(6)) and not Jbr[:9].any()
+        # the PRV form holds the same quantities in P R V order (the LocalBA / GlobalBA engines use the PVR form's values re-ordered)
+        e1, J1, Jb1 = R.edge_prior(1, ns, prior)
+        perm = [0, 1, 2, 6, 7, 8, 3, 4, 5]
+        assert _close(e1[:9], er[perm], 1e-12) and _close(e1[9:], er[9:], 1e-15)
+        assert _close(J1[:9][:, :9], Jr[perm][:, perm], 1e-12)
+        eb, Ji, Jj = R.edge_bias(ns, prior)
+        want = np.r_[(prior["bg"] + prior["dbg"]) - (ns["bg"] + ns["dbg"]), (prior["ba"] + prior["dba"]) - (ns["ba"] + ns["dba"])]
+        assert np.array_equal(eb, want) and np.array_equal(Ji, -np.eye(6)) and np.array_equal(Jj, np.eye(6))
+
+
+def test_initial_gyro_bias_edge_equal_reference():
+    """EdgeGyrBias (src/Odom/g2otypes.h:940-973, the edge of Optimizer::OptimizeInitialGyroBias) compiled unchanged: one Gauss-Newton
+    step assembled from the REFERENCE's residuals and Jacobians (H = sum J^T W J, b = -sum J^T W e at bg = 0, W the inverse rotation
+    block of the PRV covariance) gives the oracle's estimate; the edge also agrees at a non-zero bias."""
+    synth = synth_mod()
+    g = synth.make_gyro_bias_problem(31, n_kf=16, kf_gap=(1, 12))
+    pre = O.imu_preintegrate_frames(g["seq"], g["kf_idx"], O.imu_noise())
+    rng = np.random.default_rng(3)
+    Rwb = np.stack([Rm @ synth.so3_exp(rng.normal(0, 2e-3, 3)) for Rm in g["Rwb"]])
+    for use_info in (True, False):
+        H = np.zeros((3, 3)); b = np.zeros(3)
+        for i in range(1, len(pre)):
+            e, J = R.edge_gyr_bias(pre[i]["Rij"], pre[i]["JgR"], Rwb[i - 1], Rwb[i], np.zeros(3))
+            W = np.linalg.inv(pre[i]["SigmaPRV"][3:6, 3:6]) if use_info else np.eye(3)
+            H += J.T @ W @ J; b -= J.T @ W @ e
+        n, dbg = O.gyro_bias_init(pre, Rwb, use_info)
+        want = np.linalg.solve(H, b)
+        assert n == 15 and np.abs(dbg - want).max() <= 1e-9 * np.abs(want).max(), (dbg, want)
+    # the residual at a non-zero bias is the rotation part of the PRV inertial edge with that bias correction
+    i = 4
+    bg = np.array([2e-3, -1e-3, 3e-3])
+    e, J = R.edge_gyr_bias(pre[i]["Rij"], pre[i]["JgR"], Rwb[i - 1], Rwb[i], bg)
+    nsi = np.zeros(1, O.NAVSTATE_DTYPE)[0]; nsj = nsi.copy()
+    nsi["q"] = synth.quat_from_R(Rwb[i - 1]); nsj["q"] = synth.quat_from_R(Rwb[i]); nsi["dbg"] = bg
+    e9, Ji, Jj, Jb = O.edge_navstate(nsi, nsj, pre[i], np.zeros(3), 1)
+    assert np.allclose(e, e9[3:6], rtol=0, atol=1e-12) and np.allclose(J, Jb[3:6, :3], rtol=0, atol=1e-10)
