@@ -8,8 +8,10 @@
 //   drivers     Optimizer::PoseOptimization visual (src/Optimizer.cc:1611-1874) and IMU/PVR incl. the kExactRobust
 //               marginal prior (include/Optimizer.h:126-816), LocalBundleAdjustmentNavStatePRV (src/Optimizer.cc:21-769)
 // Eigen is absent here: LDLT / inverse() / JacobiSVD are restated as Cholesky / Gauss-Jordan ("parity unpinned" for
-// their rounding; the tests pin this file with numeric Jacobians, a scipy solve of the full normal equations and
-// closed-form cases).
+// their last-bit rounding).  Pinned by the reference itself where it compiles (oracle/_ref, tests/test_oracle_ref.py): every edge
+// and vertex class of g2otypes compiled unchanged against an Eigen / Sophus stand-in (residuals, Jacobians, updates to 1e-10), the
+// camera models' Project() and the Huber kernel bit for bit, and g2o's own Levenberg-Marquardt solve() / optimize() driving every
+// driver of this file bit-identically; plus numeric Jacobians, a scipy solve of the full normal equations and closed-form cases.
 #include "ba_oracle.h"
 
 #include <algorithm>

@@ -1,8 +1,10 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see orb_oracle.cc header).  CPU restatement of the on-manifold IMU
 // pre-integrator: IMUPreIntegratorBase::PreIntegration / update (src/Odom/OdomPreIntegrator.h:227-506),
 // the SO(3) helpers of common/so3_extra.h:121-288 and IMUDataBase::SetParam (src/Odom/OdomData.h:41-56).
-// Eigen / Sophus are absent here ("parity unpinned" for their rounding): quaternion<->matrix conversions
-// follow Eigen 3.3.7's published formulas; the tests pin this file with closed-form constant-rate answers.
+// Eigen / Sophus are absent here ("parity unpinned" for their last-bit rounding): quaternion<->matrix conversions
+// follow Eigen 3.3.7's published formulas.  Pinned by the reference's own PreIntegration / update() / so3_extra.h compiled unchanged
+// against a stand-in for the two libraries (oracle/_ref, tests/test_oracle_ref.py: same update() calls bit for bit, recurrence to
+// 1e-12) and by closed-form constant-rate answers.
 #include <cmath>
 #include <vector>
 #include <cstring>

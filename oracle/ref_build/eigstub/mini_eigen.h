@@ -49,6 +49,7 @@ class MatrixBase {
   int rows() const { return Rows; }
   int cols() const { return Cols; }
   int size() const { return Rows * Cols; }
+  const D& matrix() const { return derived(); }
   Matrix<Scalar, Cols, Rows> transpose() const {
     Matrix<Scalar, Cols, Rows> t;
     for (int i = 0; i < Rows; ++i)
@@ -178,6 +179,14 @@ class Writable : public MatrixBase<D> {
       for (int j = 0; j < Cols; ++j) derived().coeffRef(i, j) *= s;
     return derived();
   }
+  template <class O>
+  D& operator*=(const MatrixBase<O>& o) {
+    return assign(derived() * o);
+  }
+  D& transposeInPlace() {
+    static_assert((int)Rows == (int)Cols, "square");
+    return assign(this->transpose());
+  }
   D& operator/=(Scalar s) {
     for (int i = 0; i < Rows; ++i)
       for (int j = 0; j < Cols; ++j) derived().coeffRef(i, j) /= s;
@@ -244,6 +253,11 @@ class Matrix : public Writable<Matrix<S, R, C>> {
     assert(i >= 0 && i < R && j >= 0 && j < C);
     return m_[j * R + i];
   }
+  // a 1 x 1 result (an inner product written as a matrix product) converts to its scalar
+  template <class T, class = typename std::enable_if<std::is_same<T, S>::value && R == 1 && C == 1>::type>
+  operator T() const {
+    return m_[0];
+  }
   S* data() { return m_; }
   const S* data() const { return m_; }
   static Matrix Zero() { return Matrix(); }
@@ -271,6 +285,7 @@ class Block : public Writable<Block<P, R, C>> {
     return this->assign(o);
   }
   Block& operator=(const Block& o) { return this->assign(o); }
+  Block& operator=(const Matrix<Scalar, R, C>& o) { return this->assign(o); }
 };
 
 // read-only view of a raw array (the only form the reference's vertex updates use)
@@ -346,6 +361,16 @@ Matrix<typename traits<A>::Scalar, traits<A>::Rows, traits<A>::Cols> operator/(c
   for (int i = 0; i < (int)traits<A>::Rows; ++i)
     for (int j = 0; j < (int)traits<A>::Cols; ++j) r(i, j) = a.coeff(i, j) / s;
   return r;
+}
+
+// 1 x 1 results used as scalars
+template <class S>
+S operator+(const Matrix<S, 1, 1>& a, typename std::common_type<S>::type b) {
+  return a.coeff(0, 0) + b;
+}
+template <class S>
+S operator+(typename std::common_type<S>::type a, const Matrix<S, 1, 1>& b) {
+  return a + b.coeff(0, 0);
 }
 
 typedef Matrix<double, 2, 1> Vector2d;

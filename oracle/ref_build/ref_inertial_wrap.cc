@@ -24,6 +24,20 @@
 
 #include "../ba_oracle.h"  // struct layouts only (OrcNavState, OrcImuPreint, OrcImuNoise)
 
+extern "C" void ref_cam_project(int model, const float* params, int n_params, const double P[3], float uv[2], double* J, double* Jp);
+
+namespace G2O_INERTIAL {
+template <int D>
+struct JacDyn;
+}
+namespace Eigen {
+template <int D>
+struct traits<G2O_INERTIAL::JacDyn<D>> {
+  typedef double Scalar;
+  enum { Rows = D, Cols = 15 };
+};
+}  // namespace Eigen
+
 namespace VIEO_SLAM_INERTIAL {  // own namespaces: other wrappers of this library declare stand-ins under the reference's names
 using namespace VIEO_SLAM;
 typedef Eigen::Matrix<double, 9, 9> Matrix9d;
@@ -55,6 +69,35 @@ template <class IMUDataBase>
 #include "inertial_update.inc"
 
 typedef IMUPreIntegratorBase<IMUDataBase> IMUPreintegrator;
+
+// what EdgeReproject names from common/camera_models: a camera whose Project() is the reference's own (the three models' Project
+// bodies are compiled unchanged in ref_camera_wrap.cc of this library) and a camera-to-reference-camera transform (identity here)
+typedef float FLT_CAMM;
+namespace camm {
+struct SE3Standin {
+  Eigen::Matrix<FLT_CAMM, 3, 3> R = Eigen::Matrix<FLT_CAMM, 3, 3>::Identity();
+  Eigen::Matrix<FLT_CAMM, 3, 1> t;
+  const Eigen::Matrix<FLT_CAMM, 3, 3>& rotationMatrix() const { return R; }
+  const Eigen::Matrix<FLT_CAMM, 3, 1>& translation() const { return t; }
+};
+class Camera {
+ public:
+  int model = 0;
+  std::vector<float> params;
+  SE3Standin Tcr;
+  const SE3Standin& GetTcr() const { return Tcr; }
+  void Project(const Vector3d& p, Eigen::Matrix<FLT_CAMM, 2, 1>* img, Eigen::Matrix<double, 2, 3>* J = nullptr) const {
+    float uv[2];
+    double j[6];
+    const double P[3] = {p(0), p(1), p(2)};
+    ref_cam_project(model, params.data(), (int)params.size(), P, uv, J ? j : nullptr, nullptr);
+    if (img) (*img)(0) = uv[0], (*img)(1) = uv[1];
+    if (J)
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) (*J)(r, c) = j[3 * r + c];
+  }
+};
+}  // namespace camm
 }  // namespace VIEO_SLAM_INERTIAL
 
 namespace G2O_INERTIAL {
@@ -78,18 +121,54 @@ class BaseVertex : public OptimizableGraph::Vertex {
 };
 class VertexSBAPointXYZ : public BaseVertex<3, Vector3d> {};
 
-struct JacSlot {  // one _jacobianOplus[i] of a multi edge (a dynamic-size map in g2o)
-  int rows = 0, cols = 0;
-  std::vector<double> v;  // row-major
+// one _jacobianOplus[i] of a multi edge (g2o: a map with D rows and as many columns as the vertex has dimensions), with the
+// handful of operations EdgeReproject::linearizeOplus applies to it
+template <int D>
+struct JacDyn {
+  int cols = 0;
+  double v[D * 15] = {};  // column-major
+  double coeff(int i, int j) const { return v[j * D + i]; }
+  double& coeffRef(int i, int j) { return v[j * D + i]; }
   template <class O>
-  JacSlot& operator=(const Eigen::MatrixBase<O>& o) {
-    rows = O::Rows, cols = O::Cols;
-    v.resize((size_t)rows * cols);
-    for (int i = 0; i < rows; ++i)
-      for (int j = 0; j < cols; ++j) v[(size_t)i * cols + j] = o.coeff(i, j);
+  JacDyn& operator=(const Eigen::MatrixBase<O>& o) {
+    static_assert((int)O::Rows == D, "rows");
+    cols = O::Cols;
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < cols; ++j) coeffRef(i, j) = o.coeff(i, j);
+    return *this;
+  }
+  template <int C>
+  operator Matrix<double, D, C>() const {
+    assert(cols == C);
+    Matrix<double, D, C> m;
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < C; ++j) m(i, j) = coeff(i, j);
+    return m;
+  }
+  template <int BR, int BC>
+  Eigen::Block<JacDyn, BR, BC> block(int i, int j) {
+    assert(j + BC <= cols);
+    return Eigen::Block<JacDyn, BR, BC>(*this, i, j);
+  }
+  template <class B>
+  JacDyn& operator*=(const Eigen::MatrixBase<B>& b) {
+    static_assert((int)B::Rows == (int)B::Cols, "square");
+    const Matrix<double, D, B::Cols> r = static_cast<Matrix<double, D, B::Rows>>(*this) * b;
+    return *this = r;
+  }
+  JacDyn& operator*=(double s) {
+    for (int k = 0; k < D * cols; ++k) v[k] *= s;
     return *this;
   }
 };
+template <int D, class B>
+Matrix<double, D, Eigen::traits<B>::Cols> operator*(const JacDyn<D>& a, const Eigen::MatrixBase<B>& b) {
+  return static_cast<Matrix<double, D, Eigen::traits<B>::Rows>>(a) * b;
+}
+template <int D, class B>
+Matrix<double, D, Eigen::traits<B>::Cols> operator+(const JacDyn<D>& a, const Eigen::MatrixBase<B>& b) {
+  return static_cast<Matrix<double, D, Eigen::traits<B>::Cols>>(a) + b;
+}
 template <int D, class E>
 class BaseMultiEdge {
  public:
@@ -103,7 +182,7 @@ class BaseMultiEdge {
   std::vector<OptimizableGraph::Vertex*> _vertices;
   Matrix<double, D, 1> _error;
   E _measurement;
-  std::vector<JacSlot> _jacobianOplus;
+  std::vector<JacDyn<D>> _jacobianOplus;
 };
 template <int D, class E>
 using BaseMultiEdgeEx = BaseMultiEdge<D, E>;
@@ -166,6 +245,14 @@ typedef EdgeNavStateI<3> EdgeNavStatePVR;
 typedef VertexSBAPointXYZ VertexGyrBias;
 #include "inertial_edge_gyrbias_class.inc"
 #include "inertial_edge_fns.inc"
+
+// the visual edge: VertexScale, EdgeReproject<DE, DV, NV, MODE_OPT_VAR> (class with GetTcw_wX / computeError) and its linearizeOplus
+using Vector2img = Eigen::Matrix<FLT_CAMM, 2, 1>;
+#include "visual_vertex_scale.inc"
+template <int DE, int DV, int NV, int MODE_OPT_VAR = 0>
+#include "visual_edge_reproject_class.inc"
+template <int DE, int DV, int NV, int MODE_OPT_VAR>
+#include "visual_edge_reproject_jac.inc"
 }  // namespace G2O_INERTIAL
 
 namespace g2o = G2O_INERTIAL;
@@ -213,10 +300,11 @@ IMUPreintegrator to_pre(const OrcImuPreint& o) {
   p.mdeltatij = o.dt;
   return p;
 }
-// copies block (rows x cols, row-major slot) into dst [rows][ld] at column c0
-void put_cols(const g2o::JacSlot& s, double* dst, int ld, int c0) {
-  for (int i = 0; i < s.rows; ++i)
-    for (int j = 0; j < s.cols; ++j) dst[i * ld + c0 + j] = s.v[(size_t)i * s.cols + j];
+// copies a slot (rows x cols) into dst [rows][ld] at column c0
+template <int D>
+void put_cols(const g2o::JacDyn<D>& s, double* dst, int ld, int c0) {
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < s.cols; ++j) dst[i * ld + c0 + j] = s.coeff(i, j);
 }
 }  // namespace
 
@@ -415,4 +503,54 @@ extern "C" void ref_edge_gyr_bias(const double* dRij, const double* JgRij, const
     ed.linearizeOplus();
     to_rm(ed._jacobianOplusXi, J);
   }
+}
+
+// EdgeReproject<DE, DV, NV, MODE>: form 0 PR (2,6,2), 1 PRStereo (3,6,2), 2 PVR (2,9,2), 3 PVRStereo (3,9,2), 4 PRS (2,6,3,1),
+// 5 PRSStereo (3,6,3,1), 6 PRSInv (2,6,3,2).  X = the point vertex' estimate, scale = the VertexScale estimate (forms >= 4).
+// e [DE], J_pose [DE][DV], J_point [DE][3], J_scale [DE] (forms >= 4), depth = GetDepth()
+namespace {
+template <int DE, int DV, int NV, int MODE>
+void run_reproject(const OrcCamera* cam, const OrcNavState* ns, const double X[3], const float* obs, double scale, double* e,
+                   double* J_pose, double* J_point, double* J_scale, double* depth) {
+  using namespace g2o;
+  camm::Camera c;
+  c.model = cam->model;
+  c.params = {cam->fx, cam->fy, cam->cx, cam->cy};
+  const int nd = cam->model == 1 ? cam->num_k + 2 : cam->model == 2 ? 4 : 0;
+  for (int k = 0; k < nd; ++k) c.params.push_back(cam->dist[k]);
+  VertexSBAPointXYZ vx;
+  vx.setEstimate(Vector3d(X));
+  VertexNavState<DV> vn;
+  vn.setEstimate(to_ns(*ns));
+  VertexScale vs;
+  vs.setEstimate(scale);
+  EdgeReproject<DE, DV, NV, MODE> edge;
+  BaseMultiEdge<DE, Matrix<double, DE, 1>>& ed = edge;  // the class re-declares the base members protected
+  ed._vertices[0] = &vx, ed._vertices[1] = &vn;
+  if (NV > 2) ed._vertices[2] = &vs;
+  ed._jacobianOplus[0].cols = 3, ed._jacobianOplus[1].cols = DV;
+  if (NV > 2) ed._jacobianOplus[2].cols = 1;
+  const float bf = cam->bf;
+  edge.SetParams(&c, from_rm<3, 3>(cam->Rcb), Vector3d(cam->tcb), &bf);
+  for (int k = 0; k < DE; ++k) ed._measurement(k) = (double)obs[k];
+  ed.computeError();
+  to_rm(ed._error, e);
+  if (depth) *depth = edge.GetDepth();
+  if (J_pose) {
+    ed.linearizeOplus();
+    put_cols(ed._jacobianOplus[1], J_pose, DV, 0);
+    put_cols(ed._jacobianOplus[0], J_point, 3, 0);
+    if (NV > 2) put_cols(ed._jacobianOplus[2], J_scale, 1, 0);
+  }
+}
+}  // namespace
+extern "C" void ref_edge_reproject(int form, const OrcCamera* cam, const OrcNavState* ns, const double X[3], const float* obs, double scale,
+                                   double* e, double* J_pose, double* J_point, double* J_scale, double* depth) {
+  if (form == 0) run_reproject<2, 6, 2, 0>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
+  if (form == 1) run_reproject<3, 6, 2, 0>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
+  if (form == 2) run_reproject<2, 9, 2, 0>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
+  if (form == 3) run_reproject<3, 9, 2, 0>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
+  if (form == 4) run_reproject<2, 6, 3, 1>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
+  if (form == 5) run_reproject<3, 6, 3, 1>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
+  if (form == 6) run_reproject<2, 6, 3, 2>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
 }

@@ -2,7 +2,8 @@
 // searches: ORBmatcher::SearchByProjection(Frame&, const Frame& last, ...) (src/ORBmatcher.cc:1303-1467) and
 // ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>, ...) (:230-335) on top of FrameBase::AssignFeaturesToGrid /
 // GetFeaturesInArea / PosInGrid / IsInImage (src/FrameBase.cpp:95-174).  Single pinhole camera (rectified stereo /
-// monocular, usedistort_ == false).  parity unpinned by reference tests (there are none); pinned by brute-force
+// monocular, usedistort_ == false).  The reference's tests hold no vectors for this path; pinned by the reference's own
+// functions compiled unchanged (oracle/_ref: both overloads and the grid functions, tests/test_oracle_ref.py) and by brute-force
 // restatements in tests/test_oracle_sbp.py.
 #include <cmath>
 #include <cstdint>

@@ -1,7 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see orb_oracle.cc header).  Fixed-size fp64 algebra and the SO(3) helpers of
 // common/so3_extra.h:121-288 (quaternion exp / log, Jr, Jr^-1, normalizeRotationM) shared by imu_oracle.cc and
-// ba_oracle.cc.  Eigen / Sophus are absent here ("parity unpinned" for their rounding): quaternion<->matrix
-// conversions follow Eigen 3.3.7's published formulas.
+// ba_oracle.cc.  Eigen / Sophus are absent here ("parity unpinned" for their last-bit rounding): quaternion<->matrix
+// conversions follow Eigen 3.3.7's published formulas.  common/so3_extra.h itself, compiled unchanged against a stand-in for the
+// two libraries, agrees with these helpers to 1 ulp (oracle/_ref, tests/test_oracle_ref.py::test_so3_helpers_equal_reference).
 #pragma once
 #include <cmath>
 #include <cstring>

@@ -314,3 +314,18 @@ def edge_gyr_bias(dRij, JgRij, Rwbi, Rwbj, bg):
     e = np.zeros(3); J = np.zeros((3, 3))
     L.ref_edge_gyr_bias(*[x.ctypes.data for x in a], e.ctypes.data, J.ctypes.data)
     return e, J
+
+
+def edge_reproject(form, cam, ns, X, obs, scale=1.0):
+    """EdgeReproject<DE, DV, NV, MODE> of the reference compiled unchanged over its own Project(): form 0 PR, 1 PRStereo, 2 PVR, 3 PVRStereo,
+    4 PRS, 5 PRSStereo, 6 PRSInv -> (e [DE], J_pose [DE][DV], J_point [DE][3], J_scale [DE], depth)"""
+    L = lib()
+    L.ref_edge_reproject.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 5; L.ref_edge_reproject.restype = None
+    DE = 3 if form in (1, 3, 5) else 2
+    DV = 9 if form in (2, 3) else 6
+    cam = np.ascontiguousarray(cam).reshape(1); ns = np.ascontiguousarray(ns).reshape(1)
+    X = np.ascontiguousarray(X, np.float64); obs = np.ascontiguousarray(obs, np.float32)
+    e = np.zeros(DE); Jp = np.zeros((DE, DV)); JX = np.zeros((DE, 3)); Js = np.zeros(DE); d = np.zeros(1)
+    L.ref_edge_reproject(int(form), cam.ctypes.data, ns.ctypes.data, X.ctypes.data, obs.ctypes.data, float(scale), e.ctypes.data,
+                         Jp.ctypes.data, JX.ctypes.data, Js.ctypes.data, d.ctypes.data)
+    return e, Jp, JX, Js, d[0]

@@ -714,3 +714,49 @@ def test_initial_gyro_bias_edge_equal_reference():
     nsi["q"] = synth.quat_from_R(Rwb[i - 1]); nsj["q"] = synth.quat_from_R(Rwb[i]); nsi["dbg"] = bg
     e9, Ji, Jj, Jb = O.edge_navstate(nsi, nsj, pre[i], np.zeros(3), 1)
     assert np.allclose(e, e9[3:6], rtol=0, atol=1e-12) and np.allclose(J, Jb[3:6, :3], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("model", ["pinhole", "radtan", "kb8"])
+def test_visual_edges_equal_reference(model, inertial_seq):
+    """EdgeReproject<DE, DV, NV, MODE_OPT_VAR> (src/Odom/g2otypes.h:321-541) compiled unchanged — GetTcw_wX, cam_project, computeError,
+    GetDepth, linearizeOplus — over the reference's own compiled Project() of the three camera models: the monocular / stereo PR edge of
+    PoseOptimization / LocalBA / GlobalBA, the scale-vertex forms PRS / PRSStereo of the final GlobalBA and the PRS / PRSInv pair of
+    OptimizeSim3 equal the oracle's residuals, Jacobian blocks and depths."""
+    synth = synth_mod()
+    cam = {"pinhole": synth.euroc_camera, "radtan": synth.radtan_camera, "kb8": synth.kb8_camera}[model]()
+    r = np.random.default_rng(17)
+    n = 0
+    for trial in range(60):
+        ns = synth.perturb_state(inertial_seq["truth"][int(r.integers(0, 40))], r, drot=np.deg2rad(10), dp=0.2)
+        Rwb = synth.R_from_quat(ns["q"])
+        Rcb = np.asarray(cam["Rcb"]).reshape(3, 3); tcb = np.asarray(cam["tcb"])
+        Pc = np.array([r.uniform(-1.5, 1.5), r.uniform(-1.0, 1.0), 1.0]) * r.uniform(0.8, 25.0)
+        Xw = Rwb @ (Rcb.T @ (Pc - tcb)) + ns["p"]
+        obs = np.array([r.uniform(0, 752), r.uniform(0, 480), r.uniform(0, 752)], np.float32)
+        for stereo in (0, 1):
+            eo, Jpo, JXo, do = O.edge_reproject(cam, ns, Xw, obs, stereo)
+            rows = 3 if stereo else 2
+            er, Jpr, JXr, _, dr = R.edge_reproject(stereo, cam, ns, Xw, obs)
+            assert _close(eo[:rows], er, 1e-12) and _close(Jpo[:rows], Jpr, 1e-11) and _close(JXo[:rows], JXr, 1e-11), (trial, stereo)
+            assert _close(do, dr, 1e-13)
+            # the PVR forms hold the same blocks with zero velocity columns in between
+            e9, J9, JX9, _, _ = R.edge_reproject(2 + stereo, cam, ns, Xw, obs)
+            assert np.array_equal(e9, er) and np.array_equal(J9[:, :3], Jpr[:, :3]) and np.array_equal(J9[:, 6:], Jpr[:, 3:])
+            assert not J9[:, 3:6].any() and np.array_equal(JX9, JXr)
+            # scale vertex (final GlobalBA): X = s * Xh
+            s = float(r.uniform(0.7, 1.4))
+            eo, Jpo, JXo, Jso = O.edge_reproject_scale(cam, ns, Xw / s, s, obs, stereo)
+            er, Jpr, JXr, Jsr, _ = R.edge_reproject(4 + stereo, cam, ns, Xw / s, obs, scale=s)
+            assert _close(eo[:rows], er, 1e-11) and _close(Jpo[:rows], Jpr, 1e-10) and _close(JXo[:rows], JXr, 1e-10), (trial, stereo)
+            assert _close(Jso[:rows], Jsr, 1e-10)
+            n += 1
+        # OptimizeSim3's pair: S12 as a NavState, points in the other camera's frame, Rcb = I, tcb = 0
+        cam_i = cam.copy(); cam_i["Rcb"] = np.eye(3).reshape(cam["Rcb"].shape); cam_i["tcb"] = 0
+        s12 = np.zeros(1, O.NAVSTATE_DTYPE)[0]
+        s12["q"] = synth.quat_from_R(synth.so3_exp(r.normal(0, 0.2, 3))); s12["p"] = r.normal(0, 0.3, 3)
+        s = float(r.uniform(0.8, 1.25))
+        for inverse in (0, 1):
+            eo, Jpo, Jso = O.edge_sim3(cam_i, s12, s, Pc, obs[:2], inverse)
+            er, Jpr, _, Jsr, _ = R.edge_reproject(6 if inverse else 4, cam_i, s12, Pc, obs[:2], scale=s)
+            assert _close(eo, er, 1e-11) and _close(Jpo, Jpr, 1e-10) and _close(Jso, Jsr, 1e-10), (trial, inverse)
+    assert n == 120
