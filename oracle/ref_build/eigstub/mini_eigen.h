@@ -11,7 +11,9 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdlib>
+#include <utility>
 #include <list>
+#include <ostream>
 #include <type_traits>
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
@@ -89,6 +91,47 @@ class MatrixBase {
       for (int j = 0; j < Cols; ++j) r(i, j) = (T)coeff(i, j);
     return r;
   }
+  struct PartialPivLU {  // Gaussian elimination with row pivoting on the largest magnitude (what Eigen's lu() of a fixed-size matrix is)
+    Plain lu;
+    int perm[Rows];
+    template <class B>
+    Matrix<Scalar, Rows, traits<B>::Cols> solve(const MatrixBase<B>& b) const {
+      Matrix<Scalar, Rows, traits<B>::Cols> x;
+      for (int c = 0; c < (int)traits<B>::Cols; ++c) {
+        for (int i = 0; i < Rows; ++i) {
+          Scalar v = b.coeff(perm[i], c);
+          for (int k = 0; k < i; ++k) v -= lu.coeff(i, k) * x(k, c);
+          x(i, c) = v;
+        }
+        for (int i = Rows - 1; i >= 0; --i) {
+          Scalar v = x(i, c);
+          for (int k = i + 1; k < Rows; ++k) v -= lu.coeff(i, k) * x(k, c);
+          x(i, c) = v / lu.coeff(i, i);
+        }
+      }
+      return x;
+    }
+  };
+  PartialPivLU lu() const {
+    static_assert((int)Rows == (int)Cols, "square");
+    PartialPivLU f;
+    f.lu = *this;
+    for (int i = 0; i < Rows; ++i) f.perm[i] = i;
+    for (int k = 0; k < Rows; ++k) {
+      int piv = k;
+      for (int i = k + 1; i < Rows; ++i)
+        if (std::abs(f.lu.coeff(i, k)) > std::abs(f.lu.coeff(piv, k))) piv = i;
+      if (piv != k) {
+        for (int j = 0; j < Cols; ++j) std::swap(f.lu.coeffRef(k, j), f.lu.coeffRef(piv, j));
+        std::swap(f.perm[k], f.perm[piv]);
+      }
+      for (int i = k + 1; i < Rows; ++i) {
+        const Scalar m = f.lu.coeffRef(i, k) /= f.lu.coeff(k, k);
+        for (int j = k + 1; j < Cols; ++j) f.lu.coeffRef(i, j) -= m * f.lu.coeff(k, j);
+      }
+    }
+    return f;
+  }
   // read-only sub-blocks are copies
   template <int N>
   Matrix<Scalar, N, 1> segment(int i) const {
@@ -161,6 +204,12 @@ class Writable : public MatrixBase<D> {
       for (int j = 0; j < Cols; ++j) derived().coeffRef(i, j) = Scalar(0);
     return derived();
   }
+  D& fill(Scalar v) {
+    for (int i = 0; i < Rows; ++i)
+      for (int j = 0; j < Cols; ++j) derived().coeffRef(i, j) = v;
+    return derived();
+  }
+  Block<D, Rows, 1> col(int j) { return Block<D, Rows, 1>(derived(), 0, j); }
   D& setIdentity() {
     for (int i = 0; i < Rows; ++i)
       for (int j = 0; j < Cols; ++j) derived().coeffRef(i, j) = Scalar(i == j);
@@ -304,6 +353,30 @@ class Map<const Matrix<S, R, C>> : public MatrixBase<Map<const Matrix<S, R, C>>>
   explicit Map(const S* p) : p_(p) {}
   S coeff(int i, int j) const { return p_[j * R + i]; }
 };
+
+template <class S, int R, int C>
+struct traits<Map<Matrix<S, R, C>>> {
+  typedef S Scalar;
+  enum { Rows = R, Cols = C };
+};
+template <class S, int R, int C>
+class Map<Matrix<S, R, C>> : public Writable<Map<Matrix<S, R, C>>> {
+  S* p_;
+
+ public:
+  explicit Map(S* p) : p_(p) {}
+  S coeff(int i, int j) const { return p_[j * R + i]; }
+  S& coeffRef(int i, int j) { return p_[j * R + i]; }
+};
+
+template <class D>
+std::ostream& operator<<(std::ostream& os, const MatrixBase<D>& m) {
+  for (int i = 0; i < (int)traits<D>::Rows; ++i) {
+    for (int j = 0; j < (int)traits<D>::Cols; ++j) os << (j ? " " : "") << m.coeff(i, j);
+    if (i + 1 < (int)traits<D>::Rows) os << "\n";
+  }
+  return os;
+}
 
 // ---- arithmetic (eager) ------------------------------------------------------------------------------------------------------
 template <class A, class B>

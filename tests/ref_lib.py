@@ -329,3 +329,35 @@ def edge_reproject(form, cam, ns, X, obs, scale=1.0):
     L.ref_edge_reproject(int(form), cam.ctypes.data, ns.ctypes.data, X.ctypes.data, obs.ctypes.data, float(scale), e.ctypes.data,
                          Jp.ctypes.data, JX.ctypes.data, Js.ctypes.data, d.ctypes.data)
     return e, Jp, JX, Js, d[0]
+
+
+# ---- g2o's Sim3 / VertexSim3Expmap / EdgeSim3 + the numeric-Jacobian linearizeOplus (oracle/ref_build/ref_sim3_wrap.cc)
+def _sim3_rec(a):
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    return np.ascontiguousarray(a, SIM3_DTYPE).reshape(1)
+
+
+def sim3(op, a=None, b=None, u=None):
+    """op 0 exp(u) -> S, 1 log(a) -> u, 2 a * b, 3 a^-1, 4 VertexSim3Expmap::oplusImpl(u) on a (b truthy: _fix_scale)"""
+    from vieo_slam_b200.layouts import SIM3_DTYPE
+    L = lib()
+    L.ref_sim3.argtypes = [C.c_int] + [C.c_void_p] * 4; L.ref_sim3.restype = None
+    out = np.zeros(1, SIM3_DTYPE)
+    uu = np.zeros(7) if u is None else np.array(u, np.float64).copy()
+    ar = None if a is None else _sim3_rec(a)
+    if op == 4:
+        br = np.zeros(1, SIM3_DTYPE); br["s"] = 1.0 if b else 0.0
+    else:
+        br = None if b is None else _sim3_rec(b)
+    L.ref_sim3(int(op), None if ar is None else ar.ctypes.data, None if br is None else br.ctypes.data, uu.ctypes.data, out.ctypes.data)
+    return uu if op == 1 else out[0]
+
+
+def edge_sim3_graph(meas, v0, v1, fix0=False, fix1=False, fix_scale=False):
+    L = lib()
+    L.ref_edge_sim3_graph.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 3; L.ref_edge_sim3_graph.restype = None
+    m, a, b = _sim3_rec(meas), _sim3_rec(v0), _sim3_rec(v1)
+    e = np.zeros(7); Ji = np.zeros((7, 7)); Jj = np.zeros((7, 7))
+    L.ref_edge_sim3_graph(m.ctypes.data, a.ctypes.data, b.ctypes.data, int(fix0), int(fix1), int(fix_scale), e.ctypes.data, Ji.ctypes.data,
+                          Jj.ctypes.data)
+    return e, Ji, Jj

@@ -760,3 +760,57 @@ def test_visual_edges_equal_reference(model, inertial_seq):
             er, Jpr, _, Jsr, _ = R.edge_reproject(6 if inverse else 4, cam_i, s12, Pc, obs[:2], scale=s)
             assert _close(eo, er, 1e-11) and _close(Jpo, Jpr, 1e-10) and _close(Jso, Jsr, 1e-10), (trial, inverse)
     assert n == 120
+
+
+def test_sim3_equal_reference():
+    """optimizer/g2o/g2o/types/sim3.h compiled whole against the Eigen stand-in: the Vector7d constructor (exp), log(), inverse(),
+    operator* and VertexSim3Expmap::oplusImpl equal the oracle's restatement in every branch (|sigma| and theta below / above 1e-5,
+    rotations up to ~pi)."""
+    r = np.random.default_rng(23)
+    n = 0
+    for th in (0.0, 1e-7, 9e-6, 1.1e-5, 1e-3, 0.5, 2.0, 3.0):
+        for sg in (0.0, 1e-7, 9e-6, 1.1e-5, 1e-2, 0.4, -0.7):
+            for _ in range(6):
+                w = r.normal(0, 1, 3); w *= th / np.linalg.norm(w)
+                u = np.r_[w, r.normal(0, 2, 3), sg]
+                So, Sr = O.sim3_exp(u), R.sim3(0, u=u)
+                for f in ("q", "t", "s"):
+                    assert _close(So[f], Sr[f], 1e-13), (th, sg, f, So[f], Sr[f])
+                lo, lr = O.sim3_log(So), R.sim3(1, a=So)
+                assert _close(lo, lr, 1e-9 if th < 1e-4 else 1e-11), (th, sg, lo, lr)
+                io, ir = O.sim3_inv(So), R.sim3(3, a=So)
+                T = O.sim3_exp(np.r_[r.normal(0, 0.3, 3), r.normal(0, 1, 3), r.normal(0, 0.2)])
+                mo, mr = O.sim3_mul(So, T), R.sim3(2, a=So, b=T)
+                for f in ("q", "t", "s"):
+                    assert _close(io[f], ir[f], 1e-13) and _close(mo[f], mr[f], 1e-13)
+                for fix in (False, True):                      # oplus: S <- exp(update) * S, sigma forced to 0 when the scale is fixed
+                    upd = np.r_[r.normal(0, 1e-2, 6), 0.03]
+                    want = O.sim3_mul(O.sim3_exp(np.r_[upd[:6], 0.0 if fix else upd[6]]), So)
+                    got = R.sim3(4, a=So, b=fix, u=upd)
+                    for f in ("q", "t", "s"):
+                        assert _close(want[f], got[f], 1e-13)
+                n += 1
+    assert n == 8 * 7 * 6
+
+
+def test_essential_graph_edge_equal_reference():
+    """EdgeSim3::computeError (types_seven_dof_expmap.h) and g2o's numeric-Jacobian BaseBinaryEdge::linearizeOplus
+    (core/base_binary_edge.hpp:131-203: delta 1e-9, central differences through push / oplus / pop, fixed vertices skipped) compiled
+    unchanged: residual to 1e-11; the Jacobians are differences of 1e-9 steps, so they agree to the noise of that quotient."""
+    r = np.random.default_rng(29)
+    for trial in range(40):
+        def rnd(scale_sigma=0.1):
+            return O.sim3_exp(np.r_[r.normal(0, 0.5, 3), r.normal(0, 2, 3), r.normal(0, scale_sigma)])
+        v0, v1 = rnd(), rnd()
+        meas = O.sim3_mul(O.sim3_mul(v1, O.sim3_inv(v0)), O.sim3_exp(np.r_[r.normal(0, 0.02, 3), r.normal(0, 0.05, 3), r.normal(0, 0.01)]))
+        fix0, fix1, fs = trial % 5 == 0, trial % 7 == 0, trial % 2 == 0
+        eo, Jio, Jjo = O.edge_sim3_graph(meas, v0, v1, fix0, fix1, fs)
+        er, Jir, Jjr = R.edge_sim3_graph(meas, v0, v1, fix0, fix1, fs)
+        assert _close(eo, er, 1e-11), (trial, eo, er)
+        if fix0 and fix1:
+            continue
+        sc = max(np.abs(Jir).max(), np.abs(Jjr).max(), 1.0)
+        assert np.abs(Jio - Jir).max() <= 2e-6 * sc and np.abs(Jjo - Jjr).max() <= 2e-6 * sc, (trial, np.abs(Jio - Jir).max())
+        assert (not Jir.any()) == bool(fix0) and (not Jjr.any()) == bool(fix1)
+        if fs:
+            assert not Jir[:, 6].any() and not Jjr[:, 6].any()
