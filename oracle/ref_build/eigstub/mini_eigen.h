@@ -3,8 +3,9 @@
 // bodies of IMUPreIntegratorBase::update and of the inertial edges of src/Odom/g2otypes.h / g2otypes.cpp).  Eigen itself is a
 // third-party dependency of the reference that is absent from this image (no network); this header lets those reference sources
 // compile UNCHANGED so the oracle's restatement of them can be checked against the reference's own text.  Fixed-size, column-major,
-// every expression evaluated eagerly into a temporary (Eigen's expression templates produce the same values up to the order in which
-// a dot product's terms are added, so comparisons made through this header carry a 1e-12 relative tolerance, not bit equality).
+// every expression evaluated eagerly into a temporary.  Reductions (dot products, norms, product coefficients) add their terms in the
+// order of Eigen's unrolled scalar reduction; where Eigen would vectorise or call its GEMM kernels instead (the 9 x 9 covariance
+// products, quaternion norms) the order is Eigen's own business, so comparisons in double carry a 1e-12 relative tolerance.
 // Quaternion <-> matrix conversions, the quaternion product and _transformVector restate Eigen 3.3's published formulas.
 #pragma once
 #include <cassert>
@@ -29,6 +30,16 @@ template <class P, int R, int C>
 class Block;
 template <class D>
 struct traits;
+
+// Eigen's fully unrolled scalar reduction (redux_novec_unroller): the terms [start, start + len) are summed as
+// sum(first half) + sum(second half), e.g. t0 + (t1 + t2) for three terms — the order of sum(), dot(), squaredNorm() and of the
+// coefficients of a small fixed-size product
+template <class F>
+auto redux_halves(const F& term, int start, int len) -> decltype(term(0)) {
+  if (len == 1) return term(start);
+  const int h = len / 2;
+  return redux_halves(term, start, h) + redux_halves(term, start + h, len - h);
+}
 
 template <class D>
 class MatrixBase {
@@ -59,10 +70,7 @@ class MatrixBase {
     return t;
   }
   Scalar squaredNorm() const {
-    Scalar s = 0;
-    for (int j = 0; j < Cols; ++j)
-      for (int i = 0; i < Rows; ++i) s += coeff(i, j) * coeff(i, j);
-    return s;
+    return redux_halves([this](int k) { return coeff(k % Rows, k / Rows) * coeff(k % Rows, k / Rows); }, 0, Rows * Cols);
   }
   Scalar norm() const { return std::sqrt(squaredNorm()); }
   Plain normalized() const {  // Eigen 3.3: a zero vector is returned unchanged
@@ -76,9 +84,7 @@ class MatrixBase {
   }
   template <class O>
   Scalar dot(const MatrixBase<O>& o) const {
-    Scalar s = 0;
-    for (int k = 0; k < Rows * Cols; ++k) s += (*this)(k) * o(k);
-    return s;
+    return redux_halves([this, &o](int k) { return (*this)(k) * o(k); }, 0, Rows * Cols);
   }
   template <class O>
   Matrix<Scalar, 3, 1> cross(const MatrixBase<O>& o) const {
@@ -408,9 +414,7 @@ Matrix<typename traits<A>::Scalar, traits<A>::Rows, traits<B>::Cols> operator*(c
   Matrix<typename traits<A>::Scalar, traits<A>::Rows, traits<B>::Cols> r;
   for (int i = 0; i < (int)traits<A>::Rows; ++i)
     for (int j = 0; j < (int)traits<B>::Cols; ++j) {
-      typename traits<A>::Scalar s = a.coeff(i, 0) * b.coeff(0, j);
-      for (int k = 1; k < (int)traits<A>::Cols; ++k) s += a.coeff(i, k) * b.coeff(k, j);
-      r(i, j) = s;
+      r(i, j) = redux_halves([&a, &b, i, j](int k) { return a.coeff(i, k) * b.coeff(k, j); }, 0, (int)traits<A>::Cols);
     }
   return r;
 }

@@ -361,3 +361,33 @@ def edge_sim3_graph(meas, v0, v1, fix0=False, fix1=False, fix_scale=False):
     L.ref_edge_sim3_graph(m.ctypes.data, a.ctypes.data, b.ctypes.data, int(fix0), int(fix1), int(fix_scale), e.ctypes.data, Ji.ctypes.data,
                           Jj.ctypes.data)
     return e, Ji, Jj
+
+
+def is_in_frustum_rig(pb):
+    """Frame::isInFrustum of the reference, compiled unchanged, over every frame of a synth.make_frustum_rig_problem dict; same outputs
+    as oracle_lib.is_in_frustum_rig"""
+    L = lib()
+    L.ref_is_in_frustum_rig.restype = C.c_int
+    L.ref_is_in_frustum_rig.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 10
+    rig = pb["rig"]
+    n = len(pb["p_max_dist"])
+    out = dict(inview=np.zeros(n, np.uint8), cam_mask=np.zeros(n, np.uint8), proj=np.zeros((n, 4, 3), np.float32),
+               level=np.full((n, 4), -1, np.int32), viewcos=np.zeros((n, 4), np.float32), depth=np.zeros(n, np.float32),
+               n_inview=np.zeros(len(rig), np.int32))
+    skip = pb.get("p_skip")
+    for f in range(len(rig)):
+        b, m = int(rig[f]["q_begin"]), int(rig[f]["n_q"])
+        idx = np.arange(b, b + m)
+        if skip is not None:
+            idx = idx[skip[b:b + m] == 0]
+        if len(idx) == 0:
+            continue
+        a = [np.ascontiguousarray(pb[k][idx], np.float32) for k in ("p_wP", "p_normal", "p_max_dist", "p_min_dist")]
+        k = len(idx)
+        o = [np.zeros(k, np.uint8), np.zeros(k, np.uint8), np.zeros((k, 4, 3), np.float32), np.zeros((k, 4), np.int32),
+             np.zeros((k, 4), np.float32), np.zeros(k, np.float32)]
+        one = np.ascontiguousarray(rig[f:f + 1])
+        out["n_inview"][f] = L.ref_is_in_frustum_rig(_p(one), k, *[_p(x) for x in a], *[_p(x) for x in o])
+        for key, arr in zip(("inview", "cam_mask", "proj", "level", "viewcos", "depth"), o):
+            out[key][idx] = arr
+    return out

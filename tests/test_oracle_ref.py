@@ -814,3 +814,28 @@ def test_essential_graph_edge_equal_reference():
         assert (not Jir.any()) == bool(fix0) and (not Jjr.any()) == bool(fix1)
         if fs:
             assert not Jir[:, 6].any() and not Jjr[:, 6].any()
+
+
+@pytest.mark.parametrize("model", [0, 1, 2])
+@pytest.mark.parametrize("n_cams", [1, 2, 4])
+def test_is_in_frustum_equal_reference(model, n_cams):
+    """Frame::isInFrustum (src/Frame.cc:335-416) compiled unchanged — per camera of the rig: GetTcr() * Pcr, the depth sign test, K *
+    p_normalize in float or the camera's own Project() (usedistort_), the per-camera image bounds, the scale-invariance distance band
+    (MapPoint::GetMin / MaxDistanceInvariance cut out with it), the viewing cosine, PredictScale, the tracking-info lists and the mean
+    depth — against the oracle: every output bit for bit (float reductions in the order of Eigen's unrolled redux, which the stand-in
+    restates: t0 + (t1 + t2))."""
+    synth = synth_mod()
+    pb = synth.make_frustum_rig_problem(40 + model, n_frames=3, n_q=1500, n_cams=n_cams, model=model)
+    # some points exactly on the decision boundaries: behind / on the camera plane, at the distance band's ends
+    G = pb["rig"][0]
+    Rcw = np.asarray(G["Rcw"], np.float32).reshape(3, 3); Ow = np.asarray(G["Ow"], np.float32)
+    for k in range(8):
+        pb["p_wP"][k] = Ow + Rcw.T @ np.array([0.1 * k, -0.05 * k, [0.0, -1.0, 1e-6, 2.0][k % 4]], np.float32)
+    d = np.linalg.norm(pb["p_wP"][8:16] - Ow, axis=1).astype(np.float32)
+    pb["p_max_dist"][8:12] = d[:4] / np.float32(1.2); pb["p_min_dist"][12:16] = d[4:] / np.float32(0.8)
+    a, b = O.is_in_frustum_rig(pb), R.is_in_frustum_rig(pb)
+    assert a["n_inview"].sum() > 1500 and np.array_equal(a["n_inview"], b["n_inview"])
+    for k in ("inview", "cam_mask", "level", "proj", "viewcos", "depth"):
+        assert a[k].tobytes() == b[k].tobytes(), (k, int((a[k] != b[k]).sum()))
+    if n_cams > 1:
+        assert len(np.unique(a["cam_mask"])) > 3      # points seen by different camera subsets
