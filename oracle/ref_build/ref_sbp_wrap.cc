@@ -18,6 +18,7 @@
 #include <cassert>
 #include <cmath>
 #include <list>
+#include <map>
 #include <memory>
 #include <set>
 #include <tuple>
@@ -26,6 +27,7 @@ using namespace std;
 
 #define PRINT_DEBUG_FILE_MUTEX(...)
 #define PRINT_DEBUG_FILE(...)
+#define CV_Assert(x) assert(x)
 
 namespace cvst {
 struct Point2f {
@@ -113,6 +115,10 @@ struct SE3d {  // unit quaternion (w, x, y, z) + translation
 };
 }  // namespace Sophus
 
+namespace DBoW2 {
+typedef std::map<unsigned int, std::vector<unsigned int>> FeatureVector;  // DBoW2/FeatureVector.h: node id -> feature indices
+}
+
 namespace VIEO_SLAM_SBP {
 struct Vector2img {
   float v[2];
@@ -193,13 +199,24 @@ class Frame : public FrameBase {
   vector<MapPoint*> mvpMapPoints;
   vector<bool> mvbOutlier;
   cv::Mat mDescriptors;
+  DBoW2::FeatureVector mFeatVec;
   const vector<MapPoint*>& GetMapPointMatches() const { return mvpMapPoints; }
   void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
   void EraseMapPointMatch(const size_t& idx) { mvpMapPoints[idx] = nullptr; }
 };
 
+class KeyFrame {  // the members SearchByBoW(KeyFrame*, Frame&, ...) reads
+ public:
+  vector<MapPoint*> mvpMapPoints;
+  vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  DBoW2::FeatureVector mFeatVec;
+  cv::Mat mDescriptors;
+  vector<cv::KeyPoint> mvKeys;
+};
+
 class ORBmatcher {
  public:
+  int SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches);
   ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
   static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
   static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
@@ -215,6 +232,7 @@ const int ORBmatcher::TH_LOW = 50;
 const int ORBmatcher::HISTO_LENGTH = 30;
 #include "orbmatcher_fns.inc"
 #include "sbp_fns.inc"
+#include "bow_fns.inc"
 }  // namespace VIEO_SLAM_SBP
 #undef cv
 
@@ -326,5 +344,40 @@ extern "C" int ref_sbp_local_map(const RefSbpFrame* f, const RefKp* kps, const f
     MapPoint* p = cur.mvpMapPoints[k];
     kp_match[k] = (p && p != &blocker) ? (int32_t)(p - mps.data()) : -1;
   }
+  return n;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:344-505), same arguments as orc_search_by_bow:
+// match_f[k] = id of the keyframe map point assigned to frame keypoint k, or -1
+extern "C" int ref_search_by_bow(const RefKp* kp_kf, const uint8_t* desc_kf, const int32_t* mp_id, const int32_t* fv1_node,
+                                 const int32_t* fv1_ptr, const int32_t* fv1_idx, int n_nodes1, const RefKp* kp_f, const uint8_t* desc_f,
+                                 int n_f, const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int n_nodes2,
+                                 float nn_ratio, int check_orientation, int32_t* match_f) {
+  using namespace VIEO_SLAM_SBP;
+  int n_kf = 0, max_id = -1;
+  for (int k = 0; k < fv1_ptr[n_nodes1]; ++k) n_kf = std::max(n_kf, fv1_idx[k] + 1);
+  for (int k = 0; k < n_kf; ++k) max_id = std::max(max_id, mp_id[k]);
+  std::vector<MapPoint> mps(max_id + 1);
+  for (int k = 0; k <= max_id; ++k) mps[k].mnId = k;
+  KeyFrame kf;
+  kf.mvpMapPoints.assign(n_kf, nullptr);
+  kf.mvKeys.resize(n_kf);
+  for (int k = 0; k < n_kf; ++k) {
+    if (mp_id[k] >= 0) kf.mvpMapPoints[k] = &mps[mp_id[k]];
+    kf.mvKeys[k].angle = kp_kf[k].angle;
+  }
+  kf.mDescriptors = cvst::Mat(desc_kf, n_kf);
+  for (int a = 0; a < n_nodes1; ++a)
+    kf.mFeatVec[(unsigned)fv1_node[a]].assign(fv1_idx + fv1_ptr[a], fv1_idx + fv1_ptr[a + 1]);
+  Frame F;
+  F.N = n_f;
+  F.mvKeys.resize(n_f);
+  for (int k = 0; k < n_f; ++k) F.mvKeys[k].angle = kp_f[k].angle;
+  F.mDescriptors = cvst::Mat(desc_f, n_f);
+  for (int a = 0; a < n_nodes2; ++a) F.mFeatVec[(unsigned)fv2_node[a]].assign(fv2_idx + fv2_ptr[a], fv2_idx + fv2_ptr[a + 1]);
+  ORBmatcher m(nn_ratio, check_orientation != 0);
+  std::vector<MapPoint*> out;
+  const int n = m.SearchByBoW(&kf, F, out);
+  for (int k = 0; k < n_f; ++k) match_f[k] = out[k] ? (int32_t)out[k]->mnId : -1;
   return n;
 }

@@ -635,7 +635,7 @@ def search_for_triangulation(pb, p):
     return out[:n], n
 
 
-def search_by_bow(pb, p):
+def search_by_bow(pb, p, mp_id=None):
     """ORBmatcher::SearchByBoW(KeyFrame, Frame) for pair p of a synth.make_bow_problem dict -> (match_f [n_kp2], nmatches)."""
     P = pb["pairs"][p]
     L = lib()
@@ -646,7 +646,8 @@ def search_by_bow(pb, p):
         ptr = np.ascontiguousarray(pb["fv_ptr"][pb_:pb_ + nn + 1], np.int32)
         return [np.ascontiguousarray(pb["fv_node"][nb:nb + nn], np.int32), ptr, np.ascontiguousarray(pb["fv_idx"][ib:ib + ptr[-1]], np.int32)]
     k1 = slice(int(P["kp1_begin"]), int(P["kp1_begin"] + P["n_kp1"])); k2 = slice(int(P["kp2_begin"]), int(P["kp2_begin"] + P["n_kp2"]))
-    mp_id = np.where(pb["mp_ok"][k1] != 0, np.arange(int(P["n_kp1"])), -1).astype(np.int32)  # one camera: a map point per keypoint
+    mp_id_default = np.where(pb["mp_ok"][k1] != 0, np.arange(int(P["n_kp1"])), -1).astype(np.int32)  # one camera: a map point per keypoint
+    mp_id = mp_id_default if mp_id is None else np.ascontiguousarray(mp_id, np.int32)
     a = fv(P["node1_begin"], P["n_nodes1"], P["ptr1_begin"], P["idx1_begin"]); b = fv(P["node2_begin"], P["n_nodes2"], P["ptr2_begin"], P["idx2_begin"])
     kk1 = np.ascontiguousarray(pb["kps"][k1]); dd1 = np.ascontiguousarray(pb["desc"][k1], np.uint8)
     kk2 = np.ascontiguousarray(pb["kps"][k2]); dd2 = np.ascontiguousarray(pb["desc"][k2], np.uint8)

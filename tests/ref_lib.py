@@ -391,3 +391,26 @@ def is_in_frustum_rig(pb):
         for key, arr in zip(("inview", "cam_mask", "proj", "level", "viewcos", "depth"), o):
             out[key][idx] = arr
     return out
+
+
+def search_by_bow(pb, p, mp_id=None):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) of the reference, compiled unchanged, for pair p of a synth.make_bow_problem dict
+    -> (match_f [n_kp2], nmatches); same inputs as oracle_lib.search_by_bow"""
+    P = pb["pairs"][p]
+    L = lib()
+    L.ref_search_by_bow.restype = C.c_int
+    L.ref_search_by_bow.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_float, C.c_int, C.c_void_p]
+
+    def fv(nb, nn, pb_, ib):
+        ptr = np.ascontiguousarray(pb["fv_ptr"][pb_:pb_ + nn + 1], np.int32)
+        return [np.ascontiguousarray(pb["fv_node"][nb:nb + nn], np.int32), ptr, np.ascontiguousarray(pb["fv_idx"][ib:ib + ptr[-1]], np.int32)]
+    k1 = slice(int(P["kp1_begin"]), int(P["kp1_begin"] + P["n_kp1"])); k2 = slice(int(P["kp2_begin"]), int(P["kp2_begin"] + P["n_kp2"]))
+    mp_id_default = np.where(pb["mp_ok"][k1] != 0, np.arange(int(P["n_kp1"])), -1).astype(np.int32)
+    mp_id = mp_id_default if mp_id is None else np.ascontiguousarray(mp_id, np.int32)
+    a = fv(P["node1_begin"], P["n_nodes1"], P["ptr1_begin"], P["idx1_begin"]); b = fv(P["node2_begin"], P["n_nodes2"], P["ptr2_begin"], P["idx2_begin"])
+    kk1 = np.ascontiguousarray(pb["kps"][k1]); dd1 = np.ascontiguousarray(pb["desc"][k1], np.uint8)
+    kk2 = np.ascontiguousarray(pb["kps"][k2]); dd2 = np.ascontiguousarray(pb["desc"][k2], np.uint8)
+    mf = np.empty(max(int(P["n_kp2"]), 1), np.int32)
+    n = L.ref_search_by_bow(_p(kk1), _p(dd1), _p(mp_id), *[_p(x) for x in a], int(P["n_nodes1"]), _p(kk2), _p(dd2), int(P["n_kp2"]),
+                            *[_p(x) for x in b], int(P["n_nodes2"]), float(P["nn_ratio"]), int(P["check_orientation"]), _p(mf))
+    return mf[:int(P["n_kp2"])], n

@@ -839,3 +839,48 @@ def test_is_in_frustum_equal_reference(model, n_cams):
         assert a[k].tobytes() == b[k].tobytes(), (k, int((a[k] != b[k]).sum()))
     if n_cams > 1:
         assert len(np.unique(a["cam_mask"])) > 3      # points seen by different camera subsets
+
+
+@pytest.mark.parametrize("seed", [3, 4, 5])
+def test_search_by_bow_equal_reference(seed):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:344-505) compiled unchanged over a std::map
+    FeatureVector (what DBoW2's is): the node merge with lower_bound jumps, best / second-best per keyframe map point over the frame
+    keypoints of the node not yet taken, TH_LOW and the ratio test, the rotation histogram with its three maxima — same assignment of
+    keyframe map points to frame keypoints and the same count as the oracle, with and without the orientation check."""
+    synth = synth_mod()
+    for ratio in (0.7, 0.9):
+        pb = synth.make_bow_problem(seed, n_pairs=4, n_kp=1000, n_nodes=70, nn_ratio=ratio)
+        tot = 0
+        for p in range(4):
+            for chk in (0, 1):
+                pb["pairs"]["check_orientation"][p] = chk
+                mo, no = O.search_by_bow(pb, p)
+                mr, nr = R.search_by_bow(pb, p)
+                assert no == nr and np.array_equal(mo, mr), (seed, p, chk, no, nr)
+                assert no == int((mo >= 0).sum())
+                tot += no
+        assert tot > 300
+
+
+def test_search_by_bow_shared_map_points_equal_reference():
+    """The same search when several keyframe keypoints hold the SAME map point (rigs: one point seen by more than one camera): the
+    second, closer match replaces the first one, frees its frame keypoint and removes its rotation-histogram entry
+    (src/ORBmatcher.cc:424-441, 485-492)."""
+    synth = synth_mod()
+    r = np.random.default_rng(31)
+    replaced = 0
+    for seed in (6, 7, 8):
+        pb = synth.make_bow_problem(seed, n_pairs=3, n_kp=900, n_nodes=40, nn_ratio=0.9)
+        for p in range(3):
+            n1 = int(pb["pairs"]["n_kp1"][p])
+            k1 = slice(int(pb["pairs"]["kp1_begin"][p]), int(pb["pairs"]["kp1_begin"][p]) + n1)
+            mp = np.where(pb["mp_ok"][k1] != 0, r.integers(0, n1 // 3, n1), -1).astype(np.int32)   # ~3 keypoints per map point
+            for chk in (0, 1):
+                pb["pairs"]["check_orientation"][p] = chk
+                mo, no = O.search_by_bow(pb, p, mp_id=mp)
+                mr, nr = R.search_by_bow(pb, p, mp_id=mp)
+                ids_o = np.where(mo >= 0, mp[np.maximum(mo, 0)], -1)      # the oracle reports the keyframe keypoint, the reference its map point
+                assert no == nr and np.array_equal(ids_o, mr), (seed, p, chk, no, nr)
+                m1, n1_ = O.search_by_bow(pb, p)
+                replaced += int(no < n1_)
+    assert replaced > 6
