@@ -1,5 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
-// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, th_far_pts) (src/ORBmatcher.cc:1303-1467)
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, th_far_pts) (src/ORBmatcher.cc:1303-1467),
+// SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist, th_far_pts) (:1471-1606), SearchByBoW(KeyFrame*, Frame&, ...) (:344-505)
 // and ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th, th_far_pts) (:230-335) + RadiusByViewingCos (:337-342) of
 // the REFERENCE compiled UNCHANGED, on top of the reference's own grid functions (FrameBase::GetFeaturesInArea / AssignFeaturesToGrid
 // / PosInGrid / IsInImage) and ORBmatcher::DescriptorDistance / ComputeThreeMaxima, all cut out of the sources by name at build time.
@@ -61,6 +62,12 @@ struct Vec3 {
   T& operator[](int i) { return v[i]; }
   const T& operator[](int i) const { return v[i]; }
   template <class U> Vec3<U> cast() const { return Vec3<U>((U)v[0], (U)v[1], (U)v[2]); }
+  Vec3& operator+=(const Vec3& o) {
+    for (int i = 0; i < 3; ++i) v[i] += o.v[i];
+    return *this;
+  }
+  Vec3 operator-(const Vec3& o) const { return Vec3(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+  T norm() const { return std::sqrt(v[0] * v[0] + (v[1] * v[1] + v[2] * v[2])); }  // Eigen's unrolled redux: t0 + (t1 + t2)
 };
 using Vector3d = Vec3<double>;
 using Vector3f = Vec3<float>;
@@ -71,6 +78,14 @@ struct Matrix3f {
 inline Vector3f operator*(const Matrix3f& K, const Vector3f& p) {
   Vector3f o;
   for (int r = 0; r < 3; ++r) o.v[r] = (K.m[3 * r] * p.v[0] + K.m[3 * r + 1] * p.v[1]) + K.m[3 * r + 2] * p.v[2];
+  return o;
+}
+struct Matrix3d {
+  double m[9];
+};
+inline Vector3d operator*(const Matrix3d& R, const Vector3d& p) {
+  Vector3d o;
+  for (int r = 0; r < 3; ++r) o.v[r] = R.m[3 * r] * p.v[0] + (R.m[3 * r + 1] * p.v[1] + R.m[3 * r + 2] * p.v[2]);
   return o;
 }
 }  // namespace Eigen
@@ -111,6 +126,12 @@ struct SE3d {  // unit quaternion (w, x, y, z) + translation
     return Vector3d(r[0] + t[0], r[1] + t[1], r[2] + t[2]);
   }
   Vector3d translation() const { return Vector3d(t[0], t[1], t[2]); }
+  Eigen::Matrix3d rotationMatrix() const {  // Eigen::QuaternionBase::toRotationMatrix
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x,
+                 tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    return Eigen::Matrix3d{{1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)}};
+  }
   template <class U> SE3d cast() const { return *this; }
 };
 }  // namespace Sophus
@@ -128,9 +149,10 @@ namespace camm {
 struct Camera {
   using Tio = double;
   using Ptr = std::shared_ptr<Camera>;
-  Sophus::SE3d Tcr;
+  Sophus::SE3d Tcr, Trc;
   Eigen::Matrix3f K;
   const Sophus::SE3d& GetTcr() const { return Tcr; }
+  const Sophus::SE3d& GetTrc() const { return Trc; }
   Eigen::Matrix3f toK() const { return K; }
   void Project(const Vector3d&, Vector2img*) const {}  // usedistort_ is false in this wrapper
 };
@@ -153,6 +175,10 @@ class MapPoint {
     float track_depth_ = 0;
   } trackinfo;
   bool bad = false;
+  float mfMaxDistance = 0, mfMinDistance = 0;
+  float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }  // src/MapPoint.cc:481-489 (compiled themselves in ref_frustum_wrap.cc)
+  float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
+  int PredictScale(const float& currentDist, class Frame* pF);
   Vector3f GetWorldPos() { return pos; }
   cv::Mat GetDescriptor() { return cv::Mat(desc, 1); }
   int Observations() { return obs; }
@@ -195,6 +221,7 @@ class Frame : public FrameBase {
   } stereoinfo_;
   struct {
     vector<float> vscalefactor_;
+    float flogscalefactor_ = 0;
   } scalepyrinfo_;
   vector<MapPoint*> mvpMapPoints;
   vector<bool> mvbOutlier;
@@ -205,7 +232,14 @@ class Frame : public FrameBase {
   void EraseMapPointMatch(const size_t& idx) { mvpMapPoints[idx] = nullptr; }
 };
 
-class KeyFrame {  // the members SearchByBoW(KeyFrame*, Frame&, ...) reads
+extern "C" int ref_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);  // ref_mappoint_wrap.cc
+}  // namespace VIEO_SLAM_SBP
+namespace VIEO_SLAM_SBP {
+int MapPoint::PredictScale(const float& currentDist, Frame* pF) {
+  return ref_predict_scale(mfMaxDistance, currentDist, pF->scalepyrinfo_.flogscalefactor_, (int)pF->scalepyrinfo_.vscalefactor_.size());
+}
+
+class KeyFrame {  // the members SearchByBoW(KeyFrame*, Frame&, ...) and the relocalisation search read
  public:
   vector<MapPoint*> mvpMapPoints;
   vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
@@ -217,6 +251,8 @@ class KeyFrame {  // the members SearchByBoW(KeyFrame*, Frame&, ...) reads
 class ORBmatcher {
  public:
   int SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches);
+  int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist,
+                         const float th_far_pts = 0);
   ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
   static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
   static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
@@ -233,6 +269,7 @@ const int ORBmatcher::HISTO_LENGTH = 30;
 #include "orbmatcher_fns.inc"
 #include "sbp_fns.inc"
 #include "bow_fns.inc"
+#include "reloc_fns.inc"
 }  // namespace VIEO_SLAM_SBP
 #undef cv
 
@@ -379,5 +416,39 @@ extern "C" int ref_search_by_bow(const RefKp* kp_kf, const uint8_t* desc_kf, con
   std::vector<MapPoint*> out;
   const int n = m.SearchByBoW(&kf, F, out);
   for (int k = 0; k < n_f; ++k) match_f[k] = out[k] ? (int32_t)out[k]->mnId : -1;
+  return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist, th_far_pts) (src/ORBmatcher.cc:1471-1606),
+// same inputs as orc_sbp_reloc: the queries are the keyframe's map points (already-found ones are simply not passed)
+extern "C" int ref_sbp_reloc(const RefSbpFrame* f, int orb_dist, float log_scale_factor, const RefKp* kps, const uint8_t* desc,
+                             const double* q_Xw, const float* q_angle, const float* q_max_dist, const float* q_min_dist,
+                             const uint8_t* q_desc, const uint8_t* kp_blocked, int32_t* kp_match) {
+  using namespace VIEO_SLAM_SBP;
+  Frame cur;
+  std::vector<float> no_right(f->n_kp, -1.0f);
+  fill_frame(cur, f, kps, no_right.data(), desc);
+  cur.scalepyrinfo_.flogscalefactor_ = log_scale_factor;
+  MapPoint blocker;
+  if (kp_blocked)
+    for (int k = 0; k < f->n_kp; ++k)
+      if (kp_blocked[k]) cur.mvpMapPoints[k] = &blocker;
+  std::vector<MapPoint> mps(f->n_q);
+  KeyFrame kf;
+  kf.mvKeys.resize(f->n_q);
+  for (int i = 0; i < f->n_q; ++i) {
+    mps[i].pos = Vector3f((float)q_Xw[3 * i], (float)q_Xw[3 * i + 1], (float)q_Xw[3 * i + 2]);
+    mps[i].desc = q_desc + 32 * (size_t)i;
+    mps[i].mnId = i;
+    mps[i].mfMaxDistance = q_max_dist[i], mps[i].mfMinDistance = q_min_dist[i];
+    kf.mvpMapPoints.push_back(&mps[i]);
+    kf.mvKeys[i].angle = q_angle[i];
+  }
+  ORBmatcher m(f->nn_ratio, f->check_orientation != 0);
+  const int n = m.SearchByProjection(cur, &kf, std::set<MapPoint*>(), f->th, orb_dist, f->th_far);
+  for (int k = 0; k < f->n_kp; ++k) {
+    MapPoint* p = cur.mvpMapPoints[k];
+    kp_match[k] = (p && p != &blocker) ? (int32_t)(p - mps.data()) : -1;
+  }
   return n;
 }

@@ -414,3 +414,25 @@ def search_by_bow(pb, p, mp_id=None):
     n = L.ref_search_by_bow(_p(kk1), _p(dd1), _p(mp_id), *[_p(x) for x in a], int(P["n_nodes1"]), _p(kk2), _p(dd2), int(P["n_kp2"]),
                             *[_p(x) for x in b], int(P["n_nodes2"]), float(P["nn_ratio"]), int(P["check_orientation"]), _p(mf))
     return mf[:int(P["n_kp2"])], n
+
+
+def sbp_reloc(pb):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist, th_far_pts) of the reference, compiled unchanged,
+    over every frame of a synth.make_reloc_problem batch -> (kp_match, n_matches)"""
+    L = lib()
+    L.ref_sbp_reloc.restype = C.c_int
+    L.ref_sbp_reloc.argtypes = [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 9
+    fr = pb["frames"]
+    kp_match = np.full(len(pb["kps"]), -1, np.int32)
+    nm = np.zeros(len(fr), np.int32)
+
+    def at(a, i):
+        a = pb[a] if isinstance(a, str) else a
+        return a.ctypes.data + i * a.strides[0]
+    for f in range(len(fr)):
+        kb, qb = int(fr[f]["kp_begin"]), int(fr[f]["q_begin"])
+        blk = at("kp_blocked", kb) if pb.get("kp_blocked") is not None else None
+        nm[f] = L.ref_sbp_reloc(fr.ctypes.data + f * fr.strides[0], int(pb["reloc"][f]["orb_dist"]), float(pb["reloc"][f]["log_scale_factor"]),
+                                at("kps", kb), at("desc", kb), at("q_Xw", qb), at("q_angle", qb), at("q_max_dist", qb), at("q_min_dist", qb),
+                                at("q_desc", qb), blk, at(kp_match, kb))
+    return kp_match, nm

@@ -884,3 +884,21 @@ def test_search_by_bow_shared_map_points_equal_reference():
                 m1, n1_ = O.search_by_bow(pb, p)
                 replaced += int(no < n1_)
     assert replaced > 6
+
+
+@pytest.mark.parametrize("kw", [dict(seed=51), dict(seed=52, th=15.0, orb_dist=64), dict(seed=53, th_far=8.0, cluster=True),
+                                dict(seed=54, blocked_frac=0.4, orb_dist=80)])
+def test_search_by_projection_reloc_equal_reference(kw):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist, th_far_pts) (src/ORBmatcher.cc:1471-1606,
+    Tracking::Relocalization's guided search) compiled unchanged over the compiled grid functions and PredictScale: the th_far gate,
+    the projection, the 0.8 / 1.2 scale-invariance gate on the camera-centre distance, the [l - 1, l + 1] band, claimed keypoints,
+    the caller's ORBdist, the rotation histogram — same keypoint assignments and counts as the oracle."""
+    synth = synth_mod()
+    pb = synth.make_reloc_problem(kw["seed"], n_frames=3, **{k: v for k, v in kw.items() if k != "seed"})
+    for chk in (0, 1):
+        pb["frames"]["check_orientation"] = chk
+        kp_o, q_o, d_o, l_o, n_o = O.sbp_reloc(pb)
+        kp_r, n_r = R.sbp_reloc(pb)
+        assert np.array_equal(n_o, n_r), (n_o, n_r)
+        assert np.array_equal(kp_o, kp_r)
+        assert n_o.sum() > 150
