@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
 // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, th_far_pts) (src/ORBmatcher.cc:1303-1467),
-// SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist, th_far_pts) (:1471-1606), SearchByBoW(KeyFrame*, Frame&, ...) (:344-505)
-// and ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th, th_far_pts) (:230-335) + RadiusByViewingCos (:337-342) of
+// SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist, th_far_pts) (:1471-1606), SearchByBoW(KeyFrame*, Frame&, ...) (:344-505),
+// SearchByProjectionBase (:26-227) and ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th, th_far_pts) (:230-335) + RadiusByViewingCos (:337-342) of
 // the REFERENCE compiled UNCHANGED, on top of the reference's own grid functions (FrameBase::GetFeaturesInArea / AssignFeaturesToGrid
 // / PosInGrid / IsInImage) and ORBmatcher::DescriptorDistance / ComputeThreeMaxima, all cut out of the sources by name at build time.
 // What is pinned: the control flow of the two tracking searches — forward / backward / +-1 level bands, the th_far and depth gates,
@@ -39,10 +39,11 @@ struct KeyPoint {
   float size, angle, response;
   int octave, class_id;
 };
-class Mat {  // descriptor rows only
+class Mat {  // descriptor rows, or (SearchByProjectionBase's Rcrw / tcrw / camera centre) a float rotation / vector read through Converter
  public:
   const uint8_t* data = nullptr;
   int rows = 0;
+  float poseR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, poset[3] = {0, 0, 0};
   Mat() {}
   Mat(const uint8_t* d, int r) : data(d), rows(r) {}
   Mat row(int r) const { return Mat(data + 32 * (size_t)r, 1); }
@@ -67,6 +68,8 @@ struct Vec3 {
     return *this;
   }
   Vec3 operator-(const Vec3& o) const { return Vec3(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+  Vec3 operator+(const Vec3& o) const { return Vec3(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
+  T dot(const Vec3& o) const { return v[0] * o.v[0] + (v[1] * o.v[1] + v[2] * o.v[2]); }
   T norm() const { return std::sqrt(v[0] * v[0] + (v[1] * v[1] + v[2] * v[2])); }  // Eigen's unrolled redux: t0 + (t1 + t2)
 };
 using Vector3d = Vec3<double>;
@@ -74,12 +77,14 @@ using Vector3f = Vec3<float>;
 struct Matrix3f {
   float m[9];
   template <class U> Matrix3f cast() const { return *this; }
+  Matrix3f transpose() const { return Matrix3f{{m[0], m[3], m[6], m[1], m[4], m[7], m[2], m[5], m[8]}}; }
 };
-inline Vector3f operator*(const Matrix3f& K, const Vector3f& p) {
+inline Vector3f operator*(const Matrix3f& K, const Vector3f& p) {  // coefficients in the order of Eigen's unrolled redux: t0 + (t1 + t2)
   Vector3f o;
-  for (int r = 0; r < 3; ++r) o.v[r] = (K.m[3 * r] * p.v[0] + K.m[3 * r + 1] * p.v[1]) + K.m[3 * r + 2] * p.v[2];
+  for (int r = 0; r < 3; ++r) o.v[r] = K.m[3 * r] * p.v[0] + (K.m[3 * r + 1] * p.v[1] + K.m[3 * r + 2] * p.v[2]);
   return o;
 }
+inline Vector3f operator*(const Matrix3f& R, const Vec3<double>& p) { return R * p.cast<float>(); }  // float rig offsets kept as doubles here
 struct Matrix3d {
   double m[9];
 };
@@ -124,6 +129,13 @@ struct SE3d {  // unit quaternion (w, x, y, z) + translation
     double r[3];
     rot(q, p.v, r);
     return Vector3d(r[0] + t[0], r[1] + t[1], r[2] + t[2]);
+  }
+  Vector3f operator*(const Vector3f& p) const {  // the rig transform is an SE3f in the reference: same formula in float
+    const float w = (float)q[0], x = (float)q[1], y = (float)q[2], z = (float)q[3];
+    float uv[3] = {y * p.v[2] - z * p.v[1], z * p.v[0] - x * p.v[2], x * p.v[1] - y * p.v[0]};
+    for (int i = 0; i < 3; ++i) uv[i] += uv[i];
+    const float c[3] = {y * uv[2] - z * uv[1], z * uv[0] - x * uv[2], x * uv[1] - y * uv[0]};
+    return Vector3f(((p.v[0] + w * uv[0]) + c[0]) + (float)t[0], ((p.v[1] + w * uv[1]) + c[1]) + (float)t[1], ((p.v[2] + w * uv[2]) + c[2]) + (float)t[2]);
   }
   Vector3d translation() const { return Vector3d(t[0], t[1], t[2]); }
   Eigen::Matrix3d rotationMatrix() const {  // Eigen::QuaternionBase::toRotationMatrix
@@ -179,6 +191,12 @@ class MapPoint {
   float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }  // src/MapPoint.cc:481-489 (compiled themselves in ref_frustum_wrap.cc)
   float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
   int PredictScale(const float& currentDist, class Frame* pF);
+  int PredictScale(const float& currentDist, class KeyFrame* pKF);
+  using Vector3data = Vector3f;
+  Vector3f normal;
+  Vector3f GetNormal() { return normal; }
+  bool IsInKeyFrame(class KeyFrame*) { return false; }
+  set<size_t> GetIndexInKeyFrame(class KeyFrame*) { return set<size_t>(); }
   Vector3f GetWorldPos() { return pos; }
   cv::Mat GetDescriptor() { return cv::Mat(desc, 1); }
   int Observations() { return obs; }
@@ -239,17 +257,47 @@ int MapPoint::PredictScale(const float& currentDist, Frame* pF) {
   return ref_predict_scale(mfMaxDistance, currentDist, pF->scalepyrinfo_.flogscalefactor_, (int)pF->scalepyrinfo_.vscalefactor_.size());
 }
 
-class KeyFrame {  // the members SearchByBoW(KeyFrame*, Frame&, ...) and the relocalisation search read
+struct Mat3Holder {
+  Eigen::Matrix3f m;
+  template <class U> Eigen::Matrix3f cast() const { return m; }
+};
+struct Converter {
+  static Mat3Holder toMatrix3d(const cv::Mat& p) {
+    Mat3Holder h;
+    for (int i = 0; i < 9; ++i) h.m.m[i] = p.poseR[i];
+    return h;
+  }
+  static Vector3d toVector3d(const cv::Mat& p) { return Vector3d(p.poset[0], p.poset[1], p.poset[2]); }
+};
+class KeyFrame : public FrameBase {  // the members SearchByBoW(KeyFrame*, Frame&, ...), the relocalisation search and SearchByProjectionBase read
  public:
   vector<MapPoint*> mvpMapPoints;
   vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+  void FuseMP(size_t, MapPoint*) {}
   DBoW2::FeatureVector mFeatVec;
   cv::Mat mDescriptors;
-  vector<cv::KeyPoint> mvKeys;
+  cv::Mat Ow;
+  cv::Mat GetCameraCenter() { return Ow; }
+  struct {
+    vector<float> vuright_;
+  } stereoinfo_;
+  struct {
+    vector<float> vscalefactor_, vinvlevelsigma2_;
+    float flogscalefactor_ = 0;
+  } scalepyrinfo_;
 };
+int MapPoint::PredictScale(const float& currentDist, KeyFrame* pKF) {
+  return ref_predict_scale(mfMaxDistance, currentDist, pKF->scalepyrinfo_.flogscalefactor_, (int)pKF->scalepyrinfo_.vscalefactor_.size());
+}
 
 class ORBmatcher {
  public:
+  enum ModeSBP { SBPFuseLater = 0x1, SBPMatchMultiCam = 0x2 };  // include/ORBmatcher.h:27
+  void SearchByProjectionBase(const vector<MapPoint*>& vpMapPoints1, cv::Mat Rcrw_cv, cv::Mat tcrw_cv, KeyFrame* pKF, const float th_radius,
+                              const float th_bestdist, bool bCheckViewingAngle = false, const float* pbf = nullptr, int* pnfused = nullptr,
+                              char mode = (char)SBPMatchMultiCam, vector<vector<bool>>* pvbAlreadyMatched1 = nullptr,
+                              vector<set<int>>* pvnMatch1 = nullptr);
   int SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches);
   int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist,
                          const float th_far_pts = 0);
@@ -270,6 +318,7 @@ const int ORBmatcher::HISTO_LENGTH = 30;
 #include "sbp_fns.inc"
 #include "bow_fns.inc"
 #include "reloc_fns.inc"
+#include "sbpbase_fns.inc"
 }  // namespace VIEO_SLAM_SBP
 #undef cv
 
@@ -451,4 +500,66 @@ extern "C" int ref_sbp_reloc(const RefSbpFrame* f, int orb_dist, float log_scale
     kp_match[k] = (p && p != &blocker) ? (int32_t)(p - mps.data()) : -1;
   }
   return n;
+}
+
+// ORBmatcher::SearchByProjectionBase (src/ORBmatcher.cc:26-227), the search half behind Fuse / SearchBySim3: same inputs as orc_sbp_base.
+// Run in the MatchMultiCam | FuseLater mode with th_bestdist = 256 so that pvnMatch1 reports the arg-min keypoint of every map point
+// that found one; best_dist is the Hamming distance to it.
+struct RefProjSearchFrame {  // == OrcProjSearchFrame
+  int32_t kp_begin, n_kp, q_begin, n_q;
+  float Rcw[9], tcw[3], Ow[3];
+  float fx, fy, cx, cy, minx, maxx, miny, maxy, grid_winv, grid_hinv, bf;
+  int32_t use_bf, check_viewing_angle;
+  float th_radius;
+  int32_t n_levels;
+  float log_scale_factor, scale[16], inv_level_sigma2[16], level_ratio[16];
+};
+extern "C" void ref_sbp_base(const RefProjSearchFrame* f, const RefKp* kps, const float* uright, const uint8_t* desc, const float* wP,
+                             const float* Pn, const float* max_dist, const float* min_dist, const uint8_t* q_desc, const uint8_t* q_skip,
+                             int32_t* best_idx, int32_t* best_dist) {
+  using namespace VIEO_SLAM_SBP;
+  KeyFrame kf;
+  auto cam = std::make_shared<camm::Camera>();
+  const float K[9] = {f->fx, 0.f, f->cx, 0.f, f->fy, f->cy, 0.f, 0.f, 1.f};
+  for (int i = 0; i < 9; ++i) cam->K.m[i] = K[i];
+  kf.mpCameras.push_back(cam);
+  kf.gridinfo_.fgrids_widthinv_ = {f->grid_winv};
+  kf.gridinfo_.fgrids_heightinv_ = {f->grid_hinv};
+  kf.gridinfo_.minmax_xy_.push_back({f->minx, f->maxx, f->miny, f->maxy});
+  kf.N = f->n_kp;
+  kf.mvKeysUn.resize(f->n_kp);
+  for (int i = 0; i < f->n_kp; ++i) kf.mvKeysUn[i].pt.x = kps[i].x, kf.mvKeysUn[i].pt.y = kps[i].y, kf.mvKeysUn[i].octave = kps[i].octave;
+  kf.mvKeys = kf.mvKeysUn;
+  kf.AssignFeaturesToGrid();
+  kf.stereoinfo_.vuright_.assign(uright, uright + f->n_kp);
+  kf.scalepyrinfo_.vscalefactor_.assign(f->scale, f->scale + f->n_levels);
+  kf.scalepyrinfo_.vinvlevelsigma2_.assign(f->inv_level_sigma2, f->inv_level_sigma2 + f->n_levels);
+  kf.scalepyrinfo_.flogscalefactor_ = f->log_scale_factor;
+  kf.mvpMapPoints.assign(f->n_kp, nullptr);
+  kf.mDescriptors = cvst::Mat(desc, f->n_kp);
+  cvst::Mat Rm, tm;
+  for (int i = 0; i < 9; ++i) Rm.poseR[i] = f->Rcw[i];
+  for (int i = 0; i < 3; ++i) tm.poset[i] = f->tcw[i], kf.Ow.poset[i] = f->Ow[i];
+  std::vector<MapPoint> mps(f->n_q);
+  std::vector<MapPoint*> vp(f->n_q, nullptr);
+  for (int i = 0; i < f->n_q; ++i) {
+    best_idx[i] = -1, best_dist[i] = 256;
+    if (q_skip && q_skip[i]) continue;
+    MapPoint& m = mps[i];
+    m.pos = Vector3f(wP[3 * i], wP[3 * i + 1], wP[3 * i + 2]);
+    m.normal = Vector3f(Pn[3 * i], Pn[3 * i + 1], Pn[3 * i + 2]);
+    m.mfMaxDistance = max_dist[i], m.mfMinDistance = min_dist[i];
+    m.desc = q_desc + 32 * (size_t)i;
+    vp[i] = &m;
+  }
+  ORBmatcher matcher(0.6f, true);
+  std::vector<std::set<int>> found;
+  const float bf = f->bf;
+  matcher.SearchByProjectionBase(vp, Rm, tm, &kf, f->th_radius, 256.0f, f->check_viewing_angle != 0, f->use_bf ? &bf : nullptr, nullptr,
+                                 (char)(ORBmatcher::SBPMatchMultiCam | ORBmatcher::SBPFuseLater), nullptr, &found);
+  for (int i = 0; i < f->n_q; ++i)
+    if (!found[i].empty() && *found[i].begin() >= 0) {
+      best_idx[i] = *found[i].begin();
+      best_dist[i] = ORBmatcher::DescriptorDistance(cvst::Mat(q_desc + 32 * (size_t)i, 1), cvst::Mat(desc + 32 * (size_t)best_idx[i], 1));
+    }
 }

@@ -436,3 +436,25 @@ def sbp_reloc(pb):
                                 at("kps", kb), at("desc", kb), at("q_Xw", qb), at("q_angle", qb), at("q_max_dist", qb), at("q_min_dist", qb),
                                 at("q_desc", qb), blk, at(kp_match, kb))
     return kp_match, nm
+
+
+def proj_search(pb):
+    """ORBmatcher::SearchByProjectionBase of the reference, compiled unchanged, over every keyframe of a synth.make_fuse_problem dict
+    -> (best_idx, best_dist) per map point (same inputs as oracle_lib.proj_search)"""
+    L = lib()
+    L.ref_sbp_base.argtypes = [C.c_void_p] * 12
+    L.ref_sbp_base.restype = None
+    fr = pb["frames"]
+    nq = len(pb["p_max_dist"])
+    best = np.full(nq, -1, np.int32); dist = np.full(nq, -1, np.int32)
+    vp = C.c_void_p
+
+    def at(a, i):
+        a = pb[a] if isinstance(a, str) else a
+        return vp(a.ctypes.data + i * a.strides[0])
+    for f in range(len(fr)):
+        kb, qb = int(fr[f]["kp_begin"]), int(fr[f]["q_begin"])
+        skip = at("p_skip", qb) if pb.get("p_skip") is not None else None
+        L.ref_sbp_base(vp(fr.ctypes.data + f * fr.strides[0]), at("kps", kb), at("uright", kb), at("desc", kb), at("p_wP", qb),
+                       at("p_normal", qb), at("p_max_dist", qb), at("p_min_dist", qb), at("q_desc", qb), skip, at(best, qb), at(dist, qb))
+    return best, dist

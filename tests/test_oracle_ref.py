@@ -902,3 +902,19 @@ def test_search_by_projection_reloc_equal_reference(kw):
         assert np.array_equal(n_o, n_r), (n_o, n_r)
         assert np.array_equal(kp_o, kp_r)
         assert n_o.sum() > 150
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(use_bf=False), dict(check_viewing_angle=False, th_radius=4.0), dict(cluster=True, skip_frac=0.3)])
+def test_search_by_projection_base_equal_reference(kw):
+    """ORBmatcher::SearchByProjectionBase (src/ORBmatcher.cc:26-227), the search half behind Fuse and SearchBySim3, compiled unchanged
+    over the compiled grid functions and PredictScale: projection, image / scale-invariance / viewing-cone tests, the window
+    th_radius * scale[level], the [l - 1, l] band, the stereo 7.8 / mono 5.99 chi-square gate, the strict-'<' Hamming arg-min — the
+    keypoint found for every map point (read from pvnMatch1 in the FuseLater mode with no distance threshold) and its distance equal
+    the oracle's."""
+    synth = synth_mod()
+    pb = synth.make_fuse_problem(61, **kw)
+    bo, do, lo = O.proj_search(pb)
+    br, dr = R.proj_search(pb)
+    assert (bo >= 0).sum() > 1500
+    assert np.array_equal(bo, br)
+    assert np.array_equal(do[bo >= 0], dr[bo >= 0])
