@@ -1032,6 +1032,14 @@ extern "C" void orc_huber(double delta, double e, double rho[2]) {
   k.rho(e, rho);
 }
 
+// GraphOperator::Chi2LargeSetLevel's decision (optimizer/optimizer_ba/g2o_graph_operator.h:13-31): the edge goes to level 1 when its
+// chi2 exceeds rat_th_chi2 * chi2_sig5_[dim_freedom], a FLOAT product of the 5 % chi-square table compared against the double chi2
+extern "C" int orc_chi2_large_level(double chi2, int dim_freedom, float rat_th_chi2) {
+  static const float chi2_sig5[16] = {0,       3.841f,  5.991f,  7.815f,  9.488f,  11.070f, 12.592f, 14.067f,
+                                      15.507f, 16.919f, 18.307f, 19.675f, 21.026f, 22.362f, 23.685f, 24.996f};
+  return chi2 > rat_th_chi2 * chi2_sig5[dim_freedom] ? 1 : 0;
+}
+
 // the SO3 helpers of so3_oracle.h for the tests (oracle/_ref compiles common/so3_extra.h itself): op 0 exp(w) -> unit quaternion
 // (w, x, y, z); 1 Exp(w) -> R; 2 log of a quaternion; 3 Log(R); 4 JacobianR(w); 5 JacobianRInv(w); 6 normalizeRotationM(R)
 extern "C" void orc_so3(int op, const double* in, double* out) {
@@ -1693,11 +1701,10 @@ int orc_local_ba_prv(const OrcBaProblem* pb, const OrcCamera* cam, OrcNavState* 
   const float chi2Mono = 5.991f;
   const bool vo = pb->visual_only != 0;  // Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1876-2307)
   // GraphOperator::Chi2LargeSetLevel (g2o_graph_operator.h:23-40), rat 100 — PRV version only (src/Optimizer.cc:534-536)
-  static const float chi2_sig5[4] = {0, 3.841f, 5.991f, 7.815f};
   if (!vo)
     for (VisEdge& e : g.vis) {
       g.vis_error(e);
-      if (e.chi2 > (double)(100.f * chi2_sig5[e.stereo ? 3 : 2])) e.level = 1;
+      if (orc_chi2_large_level(e.chi2, e.stereo ? 3 : 2, 100.f)) e.level = 1;
     }
   g.initialize();
   g.compute_active_errors();

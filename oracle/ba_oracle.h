@@ -205,6 +205,8 @@ typedef int (*OrcLmDriver)(const OrcLmCallbacks* cb, int iterations, double user
 int orc_lm_optimize(const OrcLmCallbacks* cb, int iterations, double user_lambda_init, double* stats);
 /* g2o::RobustKernelHuber::robustify with setDelta(delta): rho[0] = rho(e), rho[1] = rho'(e) */
 void orc_huber(double delta, double e, double rho[2]);
+/* GraphOperator::Chi2LargeSetLevel's per-edge decision: 1 = setLevel(1) */
+int orc_chi2_large_level(double chi2, int dim_freedom, float rat_th_chi2);
 /* SO3ex helpers (common/so3_extra.h) as restated in so3_oracle.h: op 0 exp -> quaternion, 1 Exp -> R, 2 log(q), 3 Log(R),
  * 4 JacobianR, 5 JacobianRInv, 6 normalizeRotationM; matrices row-major */
 void orc_so3(int op, const double* in, double* out);

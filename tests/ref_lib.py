@@ -458,3 +458,16 @@ def proj_search(pb):
         L.ref_sbp_base(vp(fr.ctypes.data + f * fr.strides[0]), at("kps", kb), at("uright", kb), at("desc", kb), at("p_wP", qb),
                        at("p_normal", qb), at("p_max_dist", qb), at("p_min_dist", qb), at("q_desc", qb), skip, at(best, qb), at(dist, qb))
     return best, dist
+
+
+def distinctive_descriptors(desc_pool, ptr, rows=None):
+    """MapPoint::ComputeDistinctiveDescriptors of the reference, compiled unchanged, per CSR point -> best (position in the point's list)"""
+    L = lib()
+    L.ref_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_distinctive_descriptors.restype = None
+    pool = np.ascontiguousarray(desc_pool, np.uint8).reshape(-1, 32)
+    ptr = np.ascontiguousarray(ptr, np.int32)
+    rows = None if rows is None else np.ascontiguousarray(rows, np.int32)
+    best = np.empty(len(ptr) - 1, np.int32)
+    L.ref_distinctive_descriptors(_p(pool), None if rows is None else _p(rows), _p(ptr), len(ptr) - 1, _p(best))
+    return best

@@ -918,3 +918,50 @@ def test_search_by_projection_base_equal_reference(kw):
     assert (bo >= 0).sum() > 1500
     assert np.array_equal(bo, br)
     assert np.array_equal(do[bo >= 0], dr[bo >= 0])
+
+
+def test_distinctive_descriptors_equal_reference():
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:314-378) compiled unchanged: all-pairs Hamming distances, the sorted
+    row's entry at int(0.5 (N - 1)), the first row with the least median — the same row as the oracle for 1 ... 40 observations,
+    near-duplicate descriptors (many equal medians) and points without observations."""
+    r = np.random.default_rng(37)
+    sizes = np.r_[0, 1, 2, 3, r.integers(1, 41, 300), 0]
+    ptr = np.r_[0, np.cumsum(sizes)].astype(np.int32)
+    pool = r.integers(0, 256, (int(ptr[-1]), 32), dtype=np.uint8)
+    for p in range(0, len(sizes), 3):                       # clusters of near-identical rows: ties between medians
+        b, e = ptr[p], ptr[p + 1]
+        if e - b > 2:
+            pool[b:e] = pool[b]
+            flips = r.integers(0, 256, e - b)
+            for i in range(b + 1, e):
+                pool[i, flips[i - b] // 8] ^= 1 << (flips[i - b] % 8)
+    bo, mo = O.distinctive_descriptors(pool, ptr)
+    br = R.distinctive_descriptors(pool, ptr)
+    assert np.array_equal(bo, br)
+    assert (bo == -1).sum() == 2 and (bo > 0).sum() > 100
+    rows = r.permutation(int(ptr[-1])).astype(np.int32)     # through a row list
+    bo, _ = O.distinctive_descriptors(pool, ptr, rows)
+    assert np.array_equal(bo, R.distinctive_descriptors(pool, ptr, rows))
+
+
+def test_chi2_large_set_level_equal_reference():
+    """g2o::GraphOperator (optimizer/optimizer_ba/g2o_graph_operator.h): the 5 % chi-square table and Chi2LargeSetLevel's decision
+    `chi2 > rat_th_chi2 * chi2_sig5_[dim]` — a float product against the edge's double chi2 — compiled unchanged against the oracle's,
+    on the float neighbourhood of every threshold the local BA uses (rat 100, dims 2 and 3) and random ones."""
+    import ctypes as C
+    Lo, Lr = O.lib(), R.lib()
+    for L, f in ((Lo, "orc_chi2_large_level"), (Lr, "ref_chi2_large_level")):
+        getattr(L, f).argtypes = [C.c_double, C.c_int, C.c_float]; getattr(L, f).restype = C.c_int
+    table = np.array([0, 3.841, 5.991, 7.815, 9.488, 11.070, 12.592, 14.067, 15.507, 16.919, 18.307, 19.675, 21.026, 22.362, 23.685, 24.996], np.float32)
+    r = np.random.default_rng(41)
+    n1 = 0
+    for dim in range(16):
+        for rat in [np.float32(100.0), np.float32(1.0)] + list(r.uniform(0.5, 200, 4).astype(np.float32)):
+            th = np.float32(rat * table[dim])
+            for c in [float(th), float(np.nextafter(th, np.float32(np.inf))), float(np.nextafter(th, np.float32(-np.inf))),
+                      float(np.nextafter(float(th), np.inf)), float(np.nextafter(float(th), -np.inf)), float(rat) * float(table[dim])] + \
+                     list(r.uniform(0, 2.5 * max(float(th), 1.0), 10)):
+                a, b = Lo.orc_chi2_large_level(c, dim, rat), Lr.ref_chi2_large_level(c, dim, rat)
+                assert a == b, (dim, rat, c)
+                n1 += a
+    assert n1 > 300
