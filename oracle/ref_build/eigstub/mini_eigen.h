@@ -97,6 +97,28 @@ class MatrixBase {
       for (int j = 0; j < Cols; ++j) r(i, j) = (T)coeff(i, j);
     return r;
   }
+  bool allFinite() const {
+    for (int i = 0; i < Rows; ++i)
+      for (int j = 0; j < Cols; ++j)
+        if (!std::isfinite(coeff(i, j))) return false;
+    return true;
+  }
+  // fixed-size 3 x 3 inverse the way Eigen computes it (cofactors of the first column -> determinant -> adjugate * 1 / det)
+  Plain inverse() const {
+    static_assert((int)Rows == 3 && (int)Cols == 3, "only the 3 x 3 inverse is restated");
+    auto cof = [this](int i, int j) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      return coeff(i1, j1) * coeff(i2, j2) - coeff(i1, j2) * coeff(i2, j1);
+    };
+    const Scalar c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    const Scalar det = c0 * coeff(0, 0) + (c1 * coeff(1, 0) + c2 * coeff(2, 0));
+    const Scalar invdet = Scalar(1) / det;
+    Plain r;
+    r(0, 0) = c0 * invdet; r(0, 1) = c1 * invdet; r(0, 2) = c2 * invdet;
+    r(1, 0) = cof(0, 1) * invdet; r(1, 1) = cof(1, 1) * invdet; r(1, 2) = cof(2, 1) * invdet;
+    r(2, 0) = cof(0, 2) * invdet; r(2, 1) = cof(1, 2) * invdet; r(2, 2) = cof(2, 2) * invdet;
+    return r;
+  }
   struct PartialPivLU {  // Gaussian elimination with row pivoting on the largest magnitude (what Eigen's lu() of a fixed-size matrix is)
     Plain lu;
     int perm[Rows];
@@ -172,6 +194,7 @@ class CommaInit {
     put(v);
     return *this;
   }
+  D finished() const { return m_; }
 };
 
 template <class D>
@@ -455,6 +478,7 @@ typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<double, 2, 2> Matrix2d;
 typedef Matrix<double, 3, 3> Matrix3d;
+typedef Matrix<float, 2, 1> Vector2f;
 typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<float, 3, 3> Matrix3f;
 

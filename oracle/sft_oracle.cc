@@ -2,8 +2,10 @@
 // (/root/reference/src/ORBmatcher.cc:896-1150) for the single-pinhole case (usedistort_ == false, one camera per
 // keyframe: vn_cams = {1, 1}, mapn2in_ empty, USE_STRATEGY_MIN_DIST as common/config.h:12 defines it), and of the
 // FeatureVector walk + best-match loop of ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (:344-505).
-// Each step cites the lines it follows.  "Parity unpinned" against a compiled reference (the unit needs Eigen / DBoW2 /
-// KeyFrame); pinned instead by a deliberately naive python restatement and known answers (tests/test_oracle_sft.py).
+// Each step cites the lines it follows.  Pinned by the reference itself: both functions are compiled UNCHANGED in oracle/_ref
+// (ref_sft_wrap.cc: SearchForTriangulation with GeometricCamera::epipolarConstrain / FillMatchesFromPair; ref_sbp_wrap.cc:
+// SearchByBoW) and tests/test_oracle_ref.py asserts the same match lists in the same order; tests/test_oracle_sft.py adds a
+// deliberately naive python restatement and known answers.
 #include <algorithm>
 #include <climits>
 #include <cmath>

@@ -471,3 +471,57 @@ def distinctive_descriptors(desc_pool, ptr, rows=None):
     best = np.empty(len(ptr) - 1, np.int32)
     L.ref_distinctive_descriptors(_p(pool), None if rows is None else _p(rows), _p(ptr), len(ptr) - 1, _p(best))
     return best
+
+
+def _quat_wxyz(R):
+    """unit quaternion (w, x, y, z) of a rotation matrix"""
+    from scipy.spatial.transform import Rotation
+    x, y, z, w = Rotation.from_matrix(R).as_quat()
+    return np.array([w, x, y, z], np.float64)
+
+
+def sft_poses(pb, p, seed=0):
+    """World poses (q_cw wxyz, t_cw) of the two keyframes of pair p such that Tc1w * Twc2 = (rel_R12, rel_t12): keyframe 1 gets a
+    random pose, keyframe 2 follows."""
+    from scipy.spatial.transform import Rotation
+    r = np.random.default_rng(1000 + seed)
+    R1 = Rotation.from_rotvec(r.normal(0, 0.4, 3)).as_matrix(); t1 = r.normal(0, 2.0, 3)
+    R12, t12 = pb["rel_R12"][p], pb["rel_t12"][p]
+    R2 = R12.T @ R1; t2 = R12.T @ (t1 - t12)          # Tc2w = T21 * Tc1w
+    return _quat_wxyz(R1), t1.astype(np.float64), _quat_wxyz(R2), t2.astype(np.float64)
+
+
+def sft_geometry(K4, q1, t1, q2, t2):
+    """(ex, ey, F12 [9]) formed from the poses with the stand-in's operations in the reference's order (ref_sft_wrap.cc)"""
+    L = lib()
+    L.ref_sft_geometry.restype = None
+    L.ref_sft_geometry.argtypes = [C.c_void_p] * 9
+    K4 = np.ascontiguousarray(K4, np.float32); ex = np.zeros(1, np.float32); ey = np.zeros(1, np.float32); F = np.zeros(9)
+    L.ref_sft_geometry(_p(K4), _p(q1), _p(t1), _p(K4), _p(q2), _p(t2), _p(ex), _p(ey), _p(F))
+    return float(ex[0]), float(ey[0]), F
+
+
+def search_for_triangulation(pb, p, K4, q1, t1, q2, t2):
+    """ORBmatcher::SearchForTriangulation of the reference, compiled unchanged (with GeometricCamera::epipolarConstrain and
+    FillMatchesFromPair), for pair p of a synth.make_sft_problem dict and keyframe poses -> (pairs [n, 2], nmatches)"""
+    P = pb["pairs"][p]
+    L = lib()
+    L.ref_search_for_triangulation.restype = C.c_int
+    side = [C.c_void_p] * 7 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int]
+    L.ref_search_for_triangulation.argtypes = side * 2 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+
+    def kf(kb, n, nb, nn, pb_, ib):
+        ptr = np.ascontiguousarray(pb["fv_ptr"][pb_:pb_ + nn + 1], np.int32)
+        return ([np.ascontiguousarray(pb["kps"][kb:kb + n]), np.ascontiguousarray(pb["uright"][kb:kb + n], np.float32),
+                 np.ascontiguousarray(pb["desc"][kb:kb + n], np.uint8), np.ascontiguousarray(pb["has_mp"][kb:kb + n], np.uint8)], int(n),
+                [np.ascontiguousarray(pb["fv_node"][nb:nb + nn], np.int32), ptr, np.ascontiguousarray(pb["fv_idx"][ib:ib + ptr[-1]], np.int32)], int(nn))
+    a, na, fa, nna = kf(P["kp1_begin"], P["n_kp1"], P["node1_begin"], P["n_nodes1"], P["ptr1_begin"], P["idx1_begin"])
+    b, nb_, fb, nnb = kf(P["kp2_begin"], P["n_kp2"], P["node2_begin"], P["n_nodes2"], P["ptr2_begin"], P["idx2_begin"])
+    K4 = np.ascontiguousarray(K4, np.float32)
+    sf = np.ascontiguousarray(P["scale_factor2"][:8], np.float32); s2 = np.ascontiguousarray(P["level_sigma2_2"][:8], np.float32)
+    cap = int(P["n_kp1"]) + 1
+    out = np.full((cap, 2), -1, np.int32); npairs = np.zeros(1, np.int32)
+    n = L.ref_search_for_triangulation(_p(K4), _p(q1), _p(t1), *[_p(x) for x in a], na, *[_p(x) for x in fa], nna,
+                                       _p(K4), _p(q2), _p(t2), *[_p(x) for x in b], nb_, *[_p(x) for x in fb], nnb,
+                                       _p(sf), _p(s2), 8, int(P["only_stereo"]), int(P["check_orientation"]), _p(out), cap, _p(npairs))
+    return out[:int(npairs[0])], n

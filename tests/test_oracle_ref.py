@@ -965,3 +965,65 @@ def test_chi2_large_set_level_equal_reference():
                 assert a == b, (dim, rat, c)
                 n1 += a
     assert n1 > 300
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_search_for_triangulation_equal_reference(seed):
+    """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:896-1150) compiled unchanged, with GeometricCamera::epipolarConstrain
+    (camera_base.h:287-406, the fundamental-matrix branch) and FillMatchesFromPair (:408-585, USE_STRATEGY_MIN_DIST) cut out of the
+    camera header: the FeatureVector walk, the map-point / only-stereo / injection skips, the epipole gate of monocular pairs, the
+    float / double mix of the epipolar distance, the match bookkeeping, the rotation histogram — the same (idx1, idx2) list in the
+    same order and the same count as the oracle.  The reference starts from keyframe POSES (T12 rounded to float), the oracle and
+    the C ABI from the caller's F12 / epipole: both are formed from the poses by ref_sft_geometry with the stand-in's operations."""
+    synth = synth_mod()
+    from vieo_slam_b200.synth import EUROC
+    K4 = np.array([EUROC[k] for k in ("fx", "fy", "cx", "cy")], np.float32)
+    pb = synth.make_sft_problem(seed, n_pairs=4, n_kp=900, n_nodes=60, share_kf1=(seed % 2 == 0))
+    tot = rejected = 0
+    for p in range(4):
+        q1, t1, q2, t2 = R.sft_poses(pb, p, seed)
+        ex, ey, F = R.sft_geometry(K4, q1, t1, q2, t2)
+        # the float-rounded T12 gives the generator's double F12 up to scale and ~1e-6
+        F0 = np.asarray(pb["pairs"][p]["F12"], np.float64)
+        assert np.allclose(F / np.linalg.norm(F), F0 / np.linalg.norm(F0), atol=2e-5)
+        assert abs(ex - float(pb["pairs"][p]["ex"])) < 0.05 * (1 + abs(ex)) and abs(ey - float(pb["pairs"][p]["ey"])) < 0.05 * (1 + abs(ey))
+        pb["pairs"]["F12"][p] = F; pb["pairs"]["ex"][p] = ex; pb["pairs"]["ey"][p] = ey
+        for only_stereo in (0, 1):
+            n_chk = []
+            for chk in (0, 1):
+                pb["pairs"]["only_stereo"][p] = only_stereo; pb["pairs"]["check_orientation"][p] = chk
+                po, no = O.search_for_triangulation(pb, p)
+                pr, nr = R.search_for_triangulation(pb, p, K4, q1, t1, q2, t2)
+                assert no == nr and np.array_equal(po, pr), (seed, p, only_stereo, chk, no, nr)
+                assert no == len(po)
+                tot += no; n_chk.append(no)
+            rejected += int(n_chk[1] < n_chk[0])                                        # the histogram dropped outliers
+    assert tot > 400 and rejected > 0
+
+
+def test_search_for_triangulation_epipole_gate_equal_reference():
+    """Monocular pairs near the epipole (src/ORBmatcher.cc:1031-1035): keyframe 2 moved straight ahead, so the epipole lies inside the
+    image and the 100 * scale gate decides; no stereo coordinates at all."""
+    synth = synth_mod()
+    from vieo_slam_b200.synth import EUROC
+    K4 = np.array([EUROC[k] for k in ("fx", "fy", "cx", "cy")], np.float32)
+    pb = synth.make_sft_problem(21, n_pairs=2, n_kp=700, n_nodes=12)
+    pb["uright"][:] = -1
+    for p in range(2):
+        pb["rel_R12"][p] = np.eye(3); pb["rel_t12"][p] = np.array([0.01, -0.02, 0.6])
+        P = pb["pairs"][p]
+        k2 = slice(int(P["kp2_begin"]), int(P["kp2_begin"] + P["n_kp2"]))
+        q1, t1, q2, t2 = R.sft_poses(pb, p, 5)
+        ex, ey, F = R.sft_geometry(K4, q1, t1, q2, t2)
+        assert 0 < ex < EUROC["w"] and 0 < ey < EUROC["h"]
+        r = np.random.default_rng(p)
+        near = r.random(int(P["n_kp2"])) < 0.5                                      # half of keyframe 2's keypoints around the epipole
+        pb["kps"]["x"][k2] = np.where(near, ex + r.normal(0, 12, near.size), pb["kps"]["x"][k2]).astype(np.float32)
+        pb["kps"]["y"][k2] = np.where(near, ey + r.normal(0, 12, near.size), pb["kps"]["y"][k2]).astype(np.float32)
+        pb["pairs"]["F12"][p] = F; pb["pairs"]["ex"][p] = ex; pb["pairs"]["ey"][p] = ey
+        pb["pairs"]["only_stereo"][p] = 0
+        for chk in (0, 1):
+            pb["pairs"]["check_orientation"][p] = chk
+            po, no = O.search_for_triangulation(pb, p)
+            pr, nr = R.search_for_triangulation(pb, p, K4, q1, t1, q2, t2)
+            assert no == nr and np.array_equal(po, pr), (p, chk, no, nr)

@@ -727,6 +727,7 @@ def make_sft_problem(seed, n_pairs=4, n_kp=1200, n_nodes=90, share_kf1=True):
         return k
 
     pairs = np.zeros(n_pairs, SFT_PAIR_DTYPE)
+    rel_R12, rel_t12 = [], []  # the relative poses the geometry was made with (for callers that start from poses, not from F12)
     k1 = rand_kf(n_kp)
     d1 = r.integers(0, 256, (n_kp, 32), dtype=np.uint8)
     node1 = r.integers(0, n_nodes, n_kp) * 7 + 3  # sparse node ids
@@ -796,7 +797,8 @@ def make_sft_problem(seed, n_pairs=4, n_kp=1200, n_nodes=90, share_kf1=True):
         P["ex"], P["ey"] = e[0], e[1]
         P["scale_factor2"][:8] = scale; P["level_sigma2_2"][:8] = sigma2
         P["F12"] = _fundamental(K, K, R12, t12).reshape(-1)
-    return dict(pairs=pairs, kps=np.concatenate(kps), uright=np.concatenate(ur), desc=np.concatenate(desc),
+        rel_R12.append(R12); rel_t12.append(t12)
+    return dict(rel_R12=np.array(rel_R12), rel_t12=np.array(rel_t12), pairs=pairs, kps=np.concatenate(kps), uright=np.concatenate(ur), desc=np.concatenate(desc),
                 has_mp=np.concatenate(has_mp), fv_node=np.concatenate(fv_node), fv_ptr=np.concatenate(fv_ptr),
                 fv_idx=np.concatenate(fv_idx), n_out_total=out_b, n_nodes1_total=nscr_b)
 
