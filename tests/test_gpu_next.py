@@ -199,6 +199,34 @@ def test_search_for_triangulation_matches_oracle(seed, n_kp, n_nodes, share):
     assert tot > 50
 
 
+def test_search_for_triangulation_matches_compiled_reference():
+    """The CUDA path against the REFERENCE's own ORBmatcher::SearchForTriangulation (+ GeometricCamera::epipolarConstrain /
+    FillMatchesFromPair) compiled unchanged (oracle/_ref/libref.so, built in the container and shipped prebuilt): the reference
+    starts from keyframe poses, the C ABI from the F12 / epipole the caller forms from them (ref_sft_geometry)."""
+    import ref_lib as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    import vieo_slam_b200.api as api
+    from vieo_slam_b200.synth import EUROC
+    K4 = np.array([EUROC[k] for k in ("fx", "fy", "cx", "cy")], np.float32)
+    pb = synth.make_sft_problem(41, n_pairs=6, n_kp=1200, n_nodes=80, share_kf1=False)
+    poses = []
+    for p in range(6):
+        q1, t1, q2, t2 = R.sft_poses(pb, p, 41)
+        ex, ey, F = R.sft_geometry(K4, q1, t1, q2, t2)
+        pb["pairs"]["F12"][p] = F; pb["pairs"]["ex"][p] = ex; pb["pairs"]["ey"][p] = ey
+        pb["pairs"]["only_stereo"][p] = p % 2; pb["pairs"]["check_orientation"][p] = (p // 2) % 2
+        poses.append((q1, t1, q2, t2))
+    m12, po, nm = api.search_for_triangulation(pb)
+    tot = 0
+    for p in range(6):
+        ref, n = R.search_for_triangulation(pb, p, K4, *poses[p])
+        ob = int(pb["pairs"][p]["out_begin"])
+        assert nm[p] == n and np.array_equal(po[ob:ob + n], ref), (p, nm[p], n)
+        tot += n
+    assert tot > 300
+
+
 def test_search_for_triangulation_edge_cases():
     import vieo_slam_b200.api as api
     pb = synth.make_sft_problem(7, n_pairs=2, n_kp=200, n_nodes=10)
