@@ -3,7 +3,7 @@
 // UNCHANGED: the 64 x 48 cell grid behind every guided search — which cells a window touches, the column-major cell walk, the level
 // band, the |dx| < r && |dy| < r box — i.e. the ORDER in which candidates reach the Hamming arg-min, which decides ties.  The four
 // member-function definitions are cut out of the source by name at build time (oracle/_ref/gen/grid_fns.inc); this file supplies
-// the members of FrameBase they read (include/FrameBase.h:105-233) and a TU-local cv::KeyPoint (`#define cv cvst`).
+// the members of FrameBase they read (include/FrameBase.h:105-233) and a TU-local cv::KeyPoint (`#define cv cvst_grid`).
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -14,7 +14,7 @@
 #include <vector>
 using namespace std;
 
-namespace cvst {
+namespace cvst_grid {
 struct Point2f {
   float x, y;
 };
@@ -23,8 +23,8 @@ struct KeyPoint {
   float size, angle, response;
   int octave, class_id;
 };
-}  // namespace cvst
-#define cv cvst
+}  // namespace cvst_grid
+#define cv cvst_grid
 namespace VIEO_SLAM_GRID {
 class FrameBase {
  public:

@@ -7,7 +7,7 @@
 // What is pinned: the control flow of the two tracking searches — forward / backward / +-1 level bands, the th_far and depth gates,
 // the stereo ur gate, the "keypoint already holds an observed map point" rule, best / second-best with the same-level ratio test,
 // the claim order, the rotation histogram and its three maxima.  What this file supplies (stand-ins, stated for what they are):
-// the members of Frame / MapPoint / Camera the bodies touch, a TU-local cv::Mat / KeyPoint (`#define cv cvst`), three-element
+// the members of Frame / MapPoint / Camera the bodies touch, a TU-local cv::Mat / KeyPoint (`#define cv cvst_sbp`), three-element
 // vectors, a 3 x 3 float matrix-vector product, and an SE3 (unit quaternion + translation) whose product / inverse / action are
 // Sophus' formulas (so3 * p = Eigen's _transformVector; T1 * T2 = (q1 q2, t1 + q1 * t2); T^-1 = (q*, q* * (-t))) — the same
 // formulas the oracle restates, so for these few lines the comparison is between two copies of one formula.
@@ -30,7 +30,7 @@ using namespace std;
 #define PRINT_DEBUG_FILE(...)
 #define CV_Assert(x) assert(x)
 
-namespace cvst {
+namespace cvst_sbp {
 struct Point2f {
   float x, y;
 };
@@ -49,8 +49,8 @@ class Mat {  // descriptor rows, or (SearchByProjectionBase's Rcrw / tcrw / came
   Mat row(int r) const { return Mat(data + 32 * (size_t)r, 1); }
   template <class T> const T* ptr() const { return (const T*)data; }
 };
-}  // namespace cvst
-#define cv cvst
+}  // namespace cvst_sbp
+#define cv cvst_sbp
 
 namespace Eigen {
 template <class T>
@@ -354,7 +354,7 @@ static void fill_frame(VIEO_SLAM_SBP::Frame& F, const RefSbpFrame* f, const RefK
   F.stereoinfo_.vuright_.assign(uright, uright + f->n_kp);
   F.scalepyrinfo_.vscalefactor_.assign(f->scale, f->scale + f->n_levels);
   F.mvpMapPoints.assign(f->n_kp, nullptr);
-  F.mDescriptors = cvst::Mat(desc, f->n_kp);
+  F.mDescriptors = cvst_sbp::Mat(desc, f->n_kp);
   for (int k = 0; k < 4; ++k) F.Tcw.q[k] = f->qcw[k];
   for (int k = 0; k < 3; ++k) F.Tcw.t[k] = f->tcw[k];
 }
@@ -452,14 +452,14 @@ extern "C" int ref_search_by_bow(const RefKp* kp_kf, const uint8_t* desc_kf, con
     if (mp_id[k] >= 0) kf.mvpMapPoints[k] = &mps[mp_id[k]];
     kf.mvKeys[k].angle = kp_kf[k].angle;
   }
-  kf.mDescriptors = cvst::Mat(desc_kf, n_kf);
+  kf.mDescriptors = cvst_sbp::Mat(desc_kf, n_kf);
   for (int a = 0; a < n_nodes1; ++a)
     kf.mFeatVec[(unsigned)fv1_node[a]].assign(fv1_idx + fv1_ptr[a], fv1_idx + fv1_ptr[a + 1]);
   Frame F;
   F.N = n_f;
   F.mvKeys.resize(n_f);
   for (int k = 0; k < n_f; ++k) F.mvKeys[k].angle = kp_f[k].angle;
-  F.mDescriptors = cvst::Mat(desc_f, n_f);
+  F.mDescriptors = cvst_sbp::Mat(desc_f, n_f);
   for (int a = 0; a < n_nodes2; ++a) F.mFeatVec[(unsigned)fv2_node[a]].assign(fv2_idx + fv2_ptr[a], fv2_idx + fv2_ptr[a + 1]);
   ORBmatcher m(nn_ratio, check_orientation != 0);
   std::vector<MapPoint*> out;
@@ -536,8 +536,8 @@ extern "C" void ref_sbp_base(const RefProjSearchFrame* f, const RefKp* kps, cons
   kf.scalepyrinfo_.vinvlevelsigma2_.assign(f->inv_level_sigma2, f->inv_level_sigma2 + f->n_levels);
   kf.scalepyrinfo_.flogscalefactor_ = f->log_scale_factor;
   kf.mvpMapPoints.assign(f->n_kp, nullptr);
-  kf.mDescriptors = cvst::Mat(desc, f->n_kp);
-  cvst::Mat Rm, tm;
+  kf.mDescriptors = cvst_sbp::Mat(desc, f->n_kp);
+  cvst_sbp::Mat Rm, tm;
   for (int i = 0; i < 9; ++i) Rm.poseR[i] = f->Rcw[i];
   for (int i = 0; i < 3; ++i) tm.poset[i] = f->tcw[i], kf.Ow.poset[i] = f->Ow[i];
   std::vector<MapPoint> mps(f->n_q);
@@ -560,6 +560,6 @@ extern "C" void ref_sbp_base(const RefProjSearchFrame* f, const RefKp* kps, cons
   for (int i = 0; i < f->n_q; ++i)
     if (!found[i].empty() && *found[i].begin() >= 0) {
       best_idx[i] = *found[i].begin();
-      best_dist[i] = ORBmatcher::DescriptorDistance(cvst::Mat(q_desc + 32 * (size_t)i, 1), cvst::Mat(desc + 32 * (size_t)best_idx[i], 1));
+      best_dist[i] = ORBmatcher::DescriptorDistance(cvst_sbp::Mat(q_desc + 32 * (size_t)i, 1), cvst_sbp::Mat(desc + 32 * (size_t)best_idx[i], 1));
     }
 }

@@ -8,7 +8,7 @@
 // per-image best distance, the epipole gate for monocular pairs, the float / double mix of the epipolar test, the bookkeeping of
 // vidxs_matches / goodmatches / mapcamidx2idxs / lastdists, the rotation histogram and the final pair list in creation order.
 // What this file supplies (stand-ins, stated for what they are): the members of KeyFrame / camera classes the bodies touch, a TU-local
-// cv::Mat / KeyPoint (`#define cv cvst`), a Sophus::SE3 over the SO3 stand-in (product / inverse / cast as Sophus defines them), and
+// cv::Mat / KeyPoint (`#define cv cvst_sft`), a Sophus::SE3 over the SO3 stand-in (product / inverse / cast as Sophus defines them), and
 // the Eigen stand-in of eigstub/ (3 x 3 inverse by cofactors like Eigen's fixed-size path).
 #include <math.h>
 #include <stdint.h>
@@ -24,7 +24,7 @@
 #include <vector>
 
 #include "mini_eigen.h"
-#include "sophus/so3.hpp"
+#include "sophus/se3.hpp"
 #include "common/so3_extra.h"       // the reference's, unchanged
 #include "common/unordered_hash.h"  // the reference's, unchanged
 
@@ -42,36 +42,7 @@ template <class T>
 using aligned_vector = std::vector<T>;  // common/eigen_utils.h: std::vector with Eigen's aligned allocator
 }
 
-namespace Sophus {
-template <class T>
-class SE3 {  // sophus/se3.hpp: (SO3, translation); T1 * T2 = (R1 R2, t1 + R1 t2); T^-1 = (R^-1, R^-1 * (t * -1))
- public:
-  SO3<T> so3_;
-  Eigen::Matrix<T, 3, 1> t_;
-  SE3() {
-    for (int i = 0; i < 3; ++i) t_(i) = T(0);
-  }
-  SE3(const SO3<T>& r, const Eigen::Matrix<T, 3, 1>& t) : so3_(r), t_(t) {}
-  SE3 inverse() const {
-    const SO3<T> inv = so3_.inverse();
-    const Eigen::Matrix<T, 3, 1> nt = t_ * T(-1);
-    return SE3(inv, inv * nt);
-  }
-  SE3 operator*(const SE3& o) const {
-    const Eigen::Matrix<T, 3, 1> rt = so3_ * o.t_;
-    return SE3(so3_ * o.so3_, t_ + rt);
-  }
-  template <class U>
-  SE3<U> cast() const {
-    return SE3<U>(so3_.template cast<U>(), t_.template cast<U>());
-  }
-  Eigen::Matrix<T, 3, 3> rotationMatrix() const { return so3_.matrix(); }
-  const Eigen::Matrix<T, 3, 1>& translation() const { return t_; }
-};
-typedef SE3<double> SE3d;
-}  // namespace Sophus
-
-namespace cvst {
+namespace cvst_sft {
 struct Point2f {
   float x, y;
 };
@@ -112,8 +83,8 @@ class Mat {
     return o;
   }
 };
-}  // namespace cvst
-#define cv cvst
+}  // namespace cvst_sft
+#define cv cvst_sft
 
 namespace DBoW2 {
 typedef std::map<unsigned int, std::vector<unsigned int>> FeatureVector;  // DBoW2/FeatureVector.h: node id -> feature indices
@@ -274,7 +245,7 @@ void fill_kf(KeyFrame& kf, MapPoint* some_mp, const float K[4], const double q_c
   kf.mvpMapPoints.assign(n_kp, nullptr);
   for (int i = 0; i < n_kp; ++i)
     if (has_mp[i]) kf.mvpMapPoints[i] = some_mp;
-  kf.mDescriptors = cvst::Mat(desc, n_kp);
+  kf.mDescriptors = cvst_sft::Mat(desc, n_kp);
   for (int a = 0; a < n_nodes; ++a) {
     auto& v = kf.mFeatVec[(unsigned)fv_node[a]];
     for (int i = fv_ptr[a]; i < fv_ptr[a + 1]; ++i) v.push_back((unsigned)fv_idx[i]);

@@ -3,7 +3,7 @@
 // with the octave band and the [uL - maxD, uL] gate, the 11 x 11 L1 search over +-5 px in the pyramid level, the parabola fit, the
 // disparity tests and the 1.5 * 1.4 * median filter.  The member-function definition is cut out of the source by name at build
 // time (oracle/_ref/gen/stereo_fns.inc) together with ORBmatcher::DescriptorDistance (orbmatcher_fns.inc); this file supplies the
-// members of Frame the body reads and a TU-local image type (namespace cvst, `#define cv cvst` around the cut text: the cvstub
+// members of Frame the body reads and a TU-local image type (namespace cvst_st, `#define cv cvst_st` around the cut text: the cvstub
 // header of the extractor build is u8-only) with the handful of cv::Mat operations the body uses: ROI headers, convertTo(CV_32F),
 // at<float>, Mat::ones, scalar * Mat, Mat - Mat, norm(NORM_L1).  All float values in the correlation are small integers, so every
 // one of those operations is exact in any evaluation order.
@@ -20,7 +20,7 @@ using namespace std;
 
 #define CV_8U 0
 #define CV_32F 5
-namespace cvst {
+namespace cvst_st {
 struct Point2f {
   float x, y;
 };
@@ -85,9 +85,9 @@ inline double norm(const Mat& a, const Mat& b, int /*NORM_L1*/) {
     for (int c = 0; c < a.cols; ++c) s += std::fabs((double)a.at<float>(r, c) - (double)b.at<float>(r, c));
   return s;
 }
-}  // namespace cvst
+}  // namespace cvst_st
 
-#define cv cvst
+#define cv cvst_st
 namespace VIEO_SLAM_STEREO {  // (a namespace of its own: ORBmatcher::ComputeThreeMaxima is also compiled in ref_match_wrap.cc)
 class ORBmatcher {  // declaration subset of include/ORBmatcher.h
  public:
@@ -134,12 +134,12 @@ extern "C" int ref_stereo_matches(const RefKp* kl, const uint8_t* dl, int nl, co
   Frame F;
   ORBextractor eL, eR;
   for (int l = 0; l < n_levels; ++l) {
-    eL.mvImagePyramid.push_back(cvst::Mat(lh[l], lw[l], CV_8U, (void*)pyrL[l], (size_t)lw[l]));
-    eR.mvImagePyramid.push_back(cvst::Mat(lh[l], lw[l], CV_8U, (void*)pyrR[l], (size_t)lw[l]));
+    eL.mvImagePyramid.push_back(cvst_st::Mat(lh[l], lw[l], CV_8U, (void*)pyrL[l], (size_t)lw[l]));
+    eR.mvImagePyramid.push_back(cvst_st::Mat(lh[l], lw[l], CV_8U, (void*)pyrR[l], (size_t)lw[l]));
   }
   F.mpORBextractors = {&eL, &eR};
   F.vvkeys_.resize(2);
-  auto fill = [](const RefKp* k, int n, std::vector<cvst::KeyPoint>& out) {
+  auto fill = [](const RefKp* k, int n, std::vector<cvst_st::KeyPoint>& out) {
     out.resize(n);
     for (int i = 0; i < n; ++i) {
       out[i].pt.x = k[i].x; out[i].pt.y = k[i].y; out[i].size = k[i].size; out[i].angle = k[i].angle;
@@ -149,10 +149,10 @@ extern "C" int ref_stereo_matches(const RefKp* kl, const uint8_t* dl, int nl, co
   fill(kl, nl, F.vvkeys_[0]);
   fill(kr, nr, F.vvkeys_[1]);
   F.N = nl;
-  F.mDescriptors = cvst::Mat(nl, 32, CV_8U, (void*)dl, 32);
+  F.mDescriptors = cvst_st::Mat(nl, 32, CV_8U, (void*)dl, 32);
   F.vdescriptors_.resize(2);
   F.vdescriptors_[0] = F.mDescriptors;
-  F.vdescriptors_[1] = cvst::Mat(nr, 32, CV_8U, (void*)dr, 32);
+  F.vdescriptors_[1] = cvst_st::Mat(nr, 32, CV_8U, (void*)dr, 32);
   F.scalepyrinfo_.vscalefactor_.assign(scale, scale + n_levels);
   F.mvInvScaleFactors.assign(inv_scale, inv_scale + n_levels);
   F.stereoinfo_.baseline_bf_[0] = minZ;  // the body reads [0] as minZ (:476) and [1] as bf

@@ -525,3 +525,24 @@ def search_for_triangulation(pb, p, K4, q1, t1, q2, t2):
                                        _p(K4), _p(q2), _p(t2), *[_p(x) for x in b], nb_, *[_p(x) for x in fb], nnb,
                                        _p(sf), _p(s2), 8, int(P["only_stereo"]), int(P["check_orientation"]), _p(out), cap, _p(npairs))
     return out[:int(npairs[0])], n
+
+
+def fisheye_matches(desc, n_kp, n_mono, octave=None, th_far_pts=0.0):
+    """Frame::ComputeStereoFishEyeMatches of the reference, compiled unchanged, for one frame: desc [n_cams][cap][32] ->
+    (rec [n, 5] = (cami, idxi, camj, idxj, dist) handed to FillMatchesFromPair in call order, N, mapn2in_ [N, 2], mDescriptors [N, 32])"""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n_cams, cap = desc.shape[0], desc.shape[1]
+    n_kp = np.ascontiguousarray(n_kp, np.int32); n_mono = np.ascontiguousarray(n_mono, np.int32)
+    octave = np.zeros((n_cams, cap), np.int32) if octave is None else np.ascontiguousarray(octave, np.int32)
+    rec_cap = 2 * n_cams * n_cams * cap + 1
+    rec = np.zeros((rec_cap, 5), np.int32); n_out = np.zeros(1, np.int32)
+    tot = int(n_kp.sum())
+    mc = np.zeros(max(tot, 1), np.int32); mi = np.zeros(max(tot, 1), np.int32); dout = np.zeros((max(tot, 1), 32), np.uint8)
+    L = lib()
+    L.ref_fisheye_matches.restype = C.c_int
+    L.ref_fisheye_matches.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    n = L.ref_fisheye_matches(_p(desc), _p(octave), _p(n_kp), _p(n_mono), n_cams, cap, float(th_far_pts), _p(rec), rec_cap, _p(n_out),
+                              _p(mc), _p(mi), _p(dout))
+    assert n <= rec_cap
+    N = int(n_out[0])
+    return rec[:n], N, np.stack([mc[:N], mi[:N]], 1), dout[:N]

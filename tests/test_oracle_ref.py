@@ -1027,3 +1027,91 @@ def test_search_for_triangulation_epipole_gate_equal_reference():
             po, no = O.search_for_triangulation(pb, p)
             pr, nr = R.search_for_triangulation(pb, p, K4, q1, t1, q2, t2)
             assert no == nr and np.array_equal(po, pr), (p, chk, no, nr)
+
+
+def _fisheye_frame(r, n_cams, cap, n_kp, n_mono, dup_frac=0.5, max_flip=40):
+    """random descriptors; in-area rows of camera j > i partly copied from camera i's in-area rows with 0 ... max_flip bits flipped"""
+    desc = r.integers(0, 256, (n_cams, cap, 32), dtype=np.uint8)
+    for i in range(n_cams - 1):
+        for j in range(i + 1, n_cams):
+            ni, nj = n_kp[i] - n_mono[i], n_kp[j] - n_mono[j]
+            if ni <= 0 or nj <= 0:
+                continue
+            m = int(dup_frac * min(ni, nj) / (n_cams - 1))
+            src = n_mono[i] + r.permutation(ni)[:m]; dst = n_mono[j] + r.permutation(nj)[:m]
+            desc[j, dst] = desc[i, src]
+            for d in dst:
+                bits = r.choice(256, int(r.integers(0, max_flip + 1)), replace=False)
+                np.bitwise_xor.at(desc[j, d], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    return desc
+
+
+def _expected_fisheye_calls(desc, n_kp, n_mono):
+    oi, od, og = O.fisheye_matches(desc, n_kp, n_mono)
+    n_cams = desc.shape[0]
+    rows, pair = [], 0
+    for i in range(n_cams - 1):
+        for j in range(i + 1, n_cams):
+            for q in np.nonzero(og[pair])[0]:
+                rows.append((i, q + n_mono[i], j, oi[pair, q, 0] + n_mono[j], od[pair, q, 0]))
+            pair += 1
+    return np.array(rows, np.int32).reshape(-1, 5)
+
+
+@pytest.mark.parametrize("n_cams", [2, 3, 4])
+def test_fisheye_matches_equal_reference(n_cams):
+    """Frame::ComputeStereoFishEyeMatches (src/Frame.cc:613-779) compiled unchanged (knnMatch forwarding to the cv2-pinned restatement, a
+    recording FillMatchesFromPair): the (camera, keypoint, camera, keypoint, distance) tuples it hands on — pair order, in-area slices,
+    the skipped pairs, the ratio test in its float / double mix, the num_mono offsets — equal the accepted matches of the oracle's
+    brute-force half, in order; the concatenated frame (N, mapn2in_, mDescriptors) is camera-major."""
+    r = np.random.default_rng(70 + n_cams)
+    cap, tot, passes2 = 400, 0, 0
+    for case in range(8):
+        n_kp = r.integers(150, cap + 1, n_cams).astype(np.int32)
+        n_mono = (n_kp * r.uniform(0.2, 0.7, n_cams)).astype(np.int32)
+        if case == 1:
+            n_mono[0] = n_kp[0]                      # no in-area row: every pair with camera 0 is skipped (:623)
+        if case == 2:
+            n_mono[-1] = n_kp[-1] - 1                # a train set of ONE row: knnMatch returns one neighbour, size() < 2
+        if case == 3:
+            n_kp[:] = r.integers(8, 14, n_cams); n_mono[:] = n_kp // 2     # fewer than 30 accepted matches: the second pass
+        desc = _fisheye_frame(r, n_cams, cap, n_kp, n_mono, max_flip=40 if case != 4 else 90)
+        rec, N, m2in, dall = R.fisheye_matches(desc, n_kp, n_mono, octave=r.integers(0, 8, (n_cams, cap)))
+        want = _expected_fisheye_calls(desc, n_kp, n_mono)
+        if len(want) < 30:                           # thresh_cosdisparity[0] != [1] and nMatches < 30: the pair loop runs twice (:648-690)
+            want = np.concatenate([want, want]); passes2 += 1
+        assert np.array_equal(rec, want), (n_cams, case, len(rec), len(want))
+        tot += len(want)
+        assert N == int(n_kp.sum())
+        assert np.array_equal(m2in, np.concatenate([np.stack([np.full(n, c), np.arange(n)], 1) for c, n in enumerate(n_kp)]))
+        assert np.array_equal(dall, np.concatenate([desc[c, :n] for c, n in enumerate(n_kp)]))
+    assert tot > 200 and passes2 >= 1
+
+
+def test_fisheye_ratio_boundaries_equal_reference():
+    """The ratio test on its boundaries: d0 == 0.7 * d1 and 0.9 * d1 in exact arithmetic (d1 = 10, 20, ... -> d0 = 7, 14 / 9, 18, ...),
+    d0 around thOrbDist = 75 — float distances against double constants (src/Frame.cc:659-663)."""
+    cases = [(7, 10), (14, 20), (63, 90), (9, 10), (18, 20), (72, 80), (74, 83), (75, 84), (76, 85), (70, 100), (69, 100), (0, 0), (0, 1),
+             (27, 30), (26, 30), (21, 30), (20, 30), (81, 90), (74, 82), (75, 83)]
+    n = len(cases)
+    desc = np.zeros((2, 2 * n + 2, 32), np.uint8)
+    # query q of camera 0 = block q of a 256-bit code space: train rows 2q / 2q + 1 differ from it in d0 / d1 bits, others are far
+    r = np.random.default_rng(5)
+    base = r.integers(0, 256, (n, 32), dtype=np.uint8)
+    for q, (d0, d1) in enumerate(cases):
+        desc[0, q] = base[q]
+        for k, d in enumerate((d0, d1)):
+            row = base[q].copy()
+            bits = r.choice(256, d, replace=False)
+            np.bitwise_xor.at(row, bits // 8, (1 << (bits % 8)).astype(np.uint8))
+            desc[1, 2 * q + k] = row
+    n_kp = np.array([n, 2 * n], np.int32); n_mono = np.zeros(2, np.int32)
+    oi, od, og = O.fisheye_matches(desc, n_kp, n_mono)
+    assert all(od[0, q, 0] == d0 and od[0, q, 1] == d1 for q, (d0, d1) in enumerate(cases))      # the planted neighbours are the two nearest
+    rec, N, _, _ = R.fisheye_matches(desc, n_kp, n_mono)
+    want = _expected_fisheye_calls(desc, n_kp, n_mono)
+    if len(want) < 30:
+        want = np.concatenate([want, want])
+    assert np.array_equal(rec, want)
+    good = og[0, :n].astype(bool)
+    assert good.sum() >= 6 and (~good).sum() >= 6
