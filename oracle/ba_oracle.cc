@@ -461,6 +461,7 @@ struct VisEdge {
 
 // LM driver used by Graph::optimize (nullptr: orc_lm_optimize); a test hook, see orc_set_lm_driver
 OrcLmDriver g_lm_driver = nullptr;
+OrcMargDump* g_marg_dump = nullptr;  // test hook, see orc_set_marg_dump
 
 struct Graph {
   bool pvr;  // slot 0 is PVR(9) (pose optimisation) instead of PR(6)
@@ -1070,6 +1071,7 @@ extern "C" void orc_so3(int op, const double* in, double* out) {
 // test hook: run every BA driver of this file (pose optimisation, local / global BA) through another LM driver with the
 // OrcLmDriver signature — oracle/_ref's ref_lm_optimize, the reference's own solve() / optimize() compiled unchanged
 extern "C" void orc_set_lm_driver(OrcLmDriver d) { g_lm_driver = d; }
+extern "C" void orc_set_marg_dump(OrcMargDump* d) { g_marg_dump = d; }
 
 // camera Project() alone (pinned against the reference's own function text compiled in oracle/_ref, tests/test_oracle_ref.py)
 extern "C" void orc_cam_project(const OrcCamera* cam, const double P[3], float uv[2], double* J /* 2x3 or NULL */) {
@@ -1360,6 +1362,23 @@ int orc_pose_optimization(const OrcPoseOptProblem* pb, const OrcCamera* cam, con
           C[a * 15 + c] += s;
         }
     }
+    OrcMargDump* dump = g_marg_dump;
+    if (dump) {
+      dump->filled = 1;
+      dump->has_imu = eI ? 1 : 0;
+      dump->fixed_last = fixed_last ? 1 : 0;
+      dump->n_vis = E;
+      if (eI) memcpy(dump->info_imu, eI->info.data(), sizeof(dump->info_imu));
+      dump->delta_imu = eI && eI->rk.on ? eI->rk.delta : -1.0;
+      memcpy(dump->info_bias, eB.info.data(), sizeof(dump->info_bias));
+      dump->delta_bias = eB.rk.on ? eB.rk.delta : -1.0;
+      dump->delta_prior = -1.0;
+      for (int i = 0; i < E && i < dump->cap; ++i) {
+        dump->level[i] = g.vis[i].level;
+        dump->delta[i] = g.vis[i].rk.on ? g.vis[i].rk.delta : -1.0;
+      }
+      memcpy(dump->C, C, sizeof(C));
+    }
     if (!fixed_last) {
       DenseEdge& eP = g.den[i_prior];
       g.den_error(eP);
@@ -1388,6 +1407,12 @@ int orc_pose_optimization(const OrcPoseOptProblem* pb, const OrcCamera* cam, con
         jtoj(Jj, 9, 0, 9, eI->info.data(), 9, wI, Jb, 6, 0, 6, CCL, 15, 0, 9, false);
       }
       for (int k = 0; k < 6; ++k) CCL[(9 + k) * 15 + 9 + k] = -(wB * eB.info[7 * k]);  // Xj^T (w Omega) Xi = -w Omega
+      if (dump) {
+        memcpy(dump->info_prior, eP.info.data(), sizeof(dump->info_prior));
+        dump->delta_prior = eP.rk.on ? eP.rk.delta : -1.0;
+        memcpy(dump->CL, CL, sizeof(CL));
+        memcpy(dump->CCL, CCL, sizeof(CCL));
+      }
       double Cinv[225], T[225];
       if (!inverse(CL, 15, Cinv))
         for (double& v : Cinv) v = std::numeric_limits<double>::quiet_NaN();

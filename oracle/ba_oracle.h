@@ -67,6 +67,20 @@ int orc_pose_optimization(const OrcPoseOptProblem* pb, const OrcCamera* cam, con
                           const float* inv_sigma2, const uint8_t* flags, OrcPoseOptResult* res, uint8_t* outlier,
                           double* chi2);
 
+/* Test hook: when set, the next orc_pose_optimization with compute_marg also records what Optimizer::FillCovInv
+ * (include/Optimizer.h:126-206) sees and yields — the information matrices and Huber deltas (< 0: no kernel) of the inertial /
+ * bias / prior edges and of every visual edge at that moment, the visual edges' levels, and the three blocks it assembles
+ * (schur_bec 0 / 2 / 1) BEFORE the Schur complement — so that tests can hand the same edges to the reference's compiled function. */
+typedef struct OrcMargDump {
+  int32_t filled, has_imu, fixed_last, n_vis, cap, pad_;
+  double info_imu[81], info_bias[36], info_prior[225];
+  double delta_imu, delta_bias, delta_prior;
+  double C[225], CL[225], CCL[225];
+  int32_t* level; /* [cap] */
+  double* delta;  /* [cap] */
+} OrcMargDump;
+void orc_set_marg_dump(OrcMargDump* d);
+
 /* ---- local / global BA (PR-V-Bias vertices per keyframe, marginalised points) ------------------------------- */
 typedef struct OrcBaProblem {
   int32_t n_states;  /* keyframes: local first (ascending id), then fixed */

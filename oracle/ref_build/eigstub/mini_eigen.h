@@ -197,9 +197,25 @@ class CommaInit {
   D finished() const { return m_; }
 };
 
+// a run-time-sized right-hand side (what Eigen::MatrixXd is to the reference's getHessian() members): any type deriving from this tag
+// with rows(), cols(), coeff(i, j) can be assigned / added to a fixed-size matrix or block of the same size
+struct DynamicRhsTag {};
+
 template <class D>
 class Writable : public MatrixBase<D> {
  public:
+  template <class X, class = typename std::enable_if<std::is_base_of<DynamicRhsTag, X>::value>::type>
+  D& assignDyn(const X& m, bool add) {
+    assert(m.rows() == (int)MatrixBase<D>::Rows && m.cols() == (int)MatrixBase<D>::Cols);
+    for (int i = 0; i < (int)MatrixBase<D>::Rows; ++i)
+      for (int j = 0; j < (int)MatrixBase<D>::Cols; ++j)
+        this->derived().coeffRef(i, j) = add ? this->derived().coeff(i, j) + m.coeff(i, j) : m.coeff(i, j);
+    return this->derived();
+  }
+  template <class X, class = typename std::enable_if<std::is_base_of<DynamicRhsTag, X>::value>::type>
+  D& operator+=(const X& m) {
+    return assignDyn(m, true);
+  }
   typedef MatrixBase<D> Base;
   typedef typename Base::Scalar Scalar;
   using Base::coeff;
@@ -364,6 +380,10 @@ class Block : public Writable<Block<P, R, C>> {
   }
   Block& operator=(const Block& o) { return this->assign(o); }
   Block& operator=(const Matrix<Scalar, R, C>& o) { return this->assign(o); }
+  template <class X, class = typename std::enable_if<std::is_base_of<DynamicRhsTag, X>::value>::type>
+  Block& operator=(const X& m) {
+    return this->assignDyn(m, false);
+  }
 };
 
 // read-only view of a raw array (the only form the reference's vertex updates use)

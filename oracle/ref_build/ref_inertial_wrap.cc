@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstring>
 #include <iostream>
+#include <memory>
 #include <vector>
 
 #include "common/so3_extra.h"    // the reference's, unchanged
@@ -121,6 +122,45 @@ class BaseVertex : public OptimizableGraph::Vertex {
 };
 class VertexSBAPointXYZ : public BaseVertex<3, Vector3d> {};
 
+// what the fork's getHessian() members return for a multi edge (Eigen::MatrixXd there): a small row-major dynamic matrix with the
+// three products `jac.transpose() * rinfo * jac` needs, every sum in index order
+struct DynMat : Eigen::DynamicRhsTag {
+  int r = 0, c = 0;
+  std::vector<double> v;
+  DynMat() {}
+  DynMat(int r_, int c_) : r(r_), c(c_), v((size_t)r_ * c_, 0.0) {}
+  template <class O>
+  DynMat(const Eigen::MatrixBase<O>& o) : r(O::Rows), c(O::Cols), v((size_t)O::Rows * O::Cols) {
+    for (int i = 0; i < r; ++i)
+      for (int j = 0; j < c; ++j) v[(size_t)i * c + j] = o.coeff(i, j);
+  }
+  int rows() const { return r; }
+  int cols() const { return c; }
+  double coeff(int i, int j) const { return v[(size_t)i * c + j]; }
+  double& coeffRef(int i, int j) { return v[(size_t)i * c + j]; }
+  DynMat transpose() const {
+    DynMat t(c, r);
+    for (int i = 0; i < r; ++i)
+      for (int j = 0; j < c; ++j) t.coeffRef(j, i) = coeff(i, j);
+    return t;
+  }
+};
+template <class B>
+DynMat operator*(const DynMat& a, const Eigen::MatrixBase<B>& b) {
+  assert(a.c == (int)B::Rows);
+  DynMat o(a.r, (int)B::Cols);
+  for (int i = 0; i < a.r; ++i)
+    for (int j = 0; j < (int)B::Cols; ++j) {
+      double s = 0;
+      for (int k = 0; k < a.c; ++k) s += a.coeff(i, k) * b.coeff(k, j);
+      o.coeffRef(i, j) = s;
+    }
+  return o;
+}
+template <int D>
+struct JacDyn;
+template <int D>
+DynMat operator*(const DynMat& a, const JacDyn<D>& b);
 // one _jacobianOplus[i] of a multi edge (g2o: a map with D rows and as many columns as the vertex has dimensions), with the
 // handful of operations EdgeReproject::linearizeOplus applies to it
 template <int D>
@@ -160,7 +200,25 @@ struct JacDyn {
     for (int k = 0; k < D * cols; ++k) v[k] *= s;
     return *this;
   }
+  DynMat transpose() const {
+    DynMat t(cols, D);
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < cols; ++j) t.coeffRef(j, i) = coeff(i, j);
+    return t;
+  }
 };
+template <int D>
+DynMat operator*(const DynMat& a, const JacDyn<D>& b) {
+  assert(a.c == D);
+  DynMat o(a.r, b.cols);
+  for (int i = 0; i < a.r; ++i)
+    for (int j = 0; j < b.cols; ++j) {
+      double s = 0;
+      for (int k = 0; k < D; ++k) s += a.coeff(i, k) * b.coeff(k, j);
+      o.coeffRef(i, j) = s;
+    }
+  return o;
+}
 template <int D, class B>
 Matrix<double, D, Eigen::traits<B>::Cols> operator*(const JacDyn<D>& a, const Eigen::MatrixBase<B>& b) {
   return static_cast<Matrix<double, D, Eigen::traits<B>::Rows>>(a) * b;
@@ -169,52 +227,105 @@ template <int D, class B>
 Matrix<double, D, Eigen::traits<B>::Cols> operator+(const JacDyn<D>& a, const Eigen::MatrixBase<B>& b) {
   return static_cast<Matrix<double, D, Eigen::traits<B>::Cols>>(a) + b;
 }
-template <int D, class E>
-class BaseMultiEdge {
+// g2o's robust kernel interface and this fork's Huber kernel (core/robust_kernel_impl.cpp, cut out by name like in ref_kernel_wrap.cc)
+class RobustKernel {
  public:
-  virtual ~BaseMultiEdge() {}
+  virtual ~RobustKernel() {}
+  virtual void robustify(double e2, Vector3d& rho) const = 0;
+  double _delta = 1.;
+};
+class RobustKernelHuber : public RobustKernel {
+ public:
+  virtual void setDelta(double delta);
+  virtual void setDeltaSqr(const double& delta, const double& deltaSqr);
+  virtual void robustify(double e2, Vector3d& rho) const;
+  float dsqr;
+};
+#include "kernel_fns.inc"
+namespace internal {
+inline int computeUpperTriangleIndex(int i, int j) { return j * (j - 1) / 2 + i; }  // core/base_multi_edge.h
+}
+// what g2o's BaseEdge gives every edge: error, information, chi2() = e^T Omega e, the robust kernel, the level
+template <int D>
+class EdgeCommon {
+ public:
+  typedef Matrix<double, D, D> InformationType;
+  virtual ~EdgeCommon() {}
+  const InformationType& information() const { return _information; }
+  InformationType& information() { return _information; }
+  void setInformation(const InformationType& i) { _information = i; }
+  double chi2() const { return _error.dot(_information * _error); }
+  RobustKernel* robustKernel() const { return _robustKernel; }
+  void setRobustKernel(RobustKernel* k) { _robustKernel = k; }
+  InformationType robustInformation(const Vector3d& rho) { return rho[1] * _information; }
+  int level() const { return _level; }
+  void setLevel(int l) { _level = l; }
+  Matrix<double, D, 1> _error;
+  InformationType _information = InformationType::Identity();
+  RobustKernel* _robustKernel = nullptr;
+  int _level = 0;
+};
+template <int D, class E>
+class BaseMultiEdge : public EdgeCommon<D> {
+ public:
+  typedef JacDyn<D> JacobianType;
+  struct HessianHelper {
+    DynMat matrix;
+    bool transposed = false;
+  };
   void resize(size_t n) {
     _vertices.assign(n, nullptr);
     _jacobianOplus.resize(n);
   }
   virtual void computeError() = 0;
   virtual void linearizeOplus() = 0;
+  std::vector<OptimizableGraph::Vertex*>& vertices() { return _vertices; }
   std::vector<OptimizableGraph::Vertex*> _vertices;
-  Matrix<double, D, 1> _error;
+  using EdgeCommon<D>::_error;
   E _measurement;
   std::vector<JacDyn<D>> _jacobianOplus;
+  std::vector<HessianHelper> _hessian;
 };
-template <int D, class E>
-using BaseMultiEdgeEx = BaseMultiEdge<D, E>;
 template <int D, class E, class Xi, class Xj>
-class BaseBinaryEdge {
+class BaseBinaryEdge : public EdgeCommon<D> {
  public:
-  virtual ~BaseBinaryEdge() {}
+  typedef Matrix<double, D, Xi::Dimension> JacobianXiOplusType;
+  typedef Matrix<double, D, Xj::Dimension> JacobianXjOplusType;
+  typedef Matrix<double, Xi::Dimension, Xj::Dimension> HessianBlockType;
+  typedef Matrix<double, Xj::Dimension, Xi::Dimension> HessianBlockTransposedType;
   virtual void computeError() = 0;
   virtual void linearizeOplus() = 0;
   OptimizableGraph::Vertex* _vertices[2] = {nullptr, nullptr};
-  Matrix<double, D, 1> _error;
+  using EdgeCommon<D>::_error;
   E _measurement;
-  Matrix<double, D, Xi::Dimension> _jacobianOplusXi;
-  Matrix<double, D, Xj::Dimension> _jacobianOplusXj;
+  JacobianXiOplusType _jacobianOplusXi;
+  JacobianXjOplusType _jacobianOplusXj;
+  HessianBlockType _hessian;
+  HessianBlockTransposedType _hessianTransposed;
+  bool _hessianRowMajor = false;
 };
-template <int D, class E, class Xi, class Xj>
-using BaseBinaryEdgeEx = BaseBinaryEdge<D, E, Xi, Xj>;
 template <int D, class E, class Xi>
-class BaseUnaryEdge {
+class BaseUnaryEdge : public EdgeCommon<D> {
  public:
-  virtual ~BaseUnaryEdge() {}
+  typedef Matrix<double, D, Xi::Dimension> JacobianXiOplusType;
   virtual void computeError() = 0;
   virtual void linearizeOplus() = 0;
   const E& measurement() const { return _measurement; }
-  Matrix<double, D, D>& information() { return _information; }
-  const Matrix<double, D, D>& information() const { return _information; }
+  OptimizableGraph::Vertex** vertices() { return _vertices; }
   OptimizableGraph::Vertex* _vertices[1] = {nullptr};
-  Matrix<double, D, 1> _error;
+  using EdgeCommon<D>::_error;
   E _measurement;
-  Matrix<double, D, D> _information;
-  Matrix<double, D, Xi::Dimension> _jacobianOplusXi;
+  JacobianXiOplusType _jacobianOplusXi;
 };
+// the fork's extension of the three edge bases (src/Odom/g2otypes.h:33-254: getRho, getHessian*), cut out by name
+typedef DynMat MatrixXd;
+typedef enum HessianExactMode { kExactNoRobust, kExactRobust, kNotExact } eHessianExactMode;  // g2otypes.h:34
+template <int D, typename E, typename VertexXi>
+#include "inertial_base_unary_ex.inc"
+template <int D, typename E, typename VertexXi, typename VertexXj>
+#include "inertial_base_binary_ex.inc"
+template <int D, typename E>
+#include "inertial_base_multi_ex.inc"
 template <int D, class M, class I>
 bool readEdge(std::istream&, M&, I&) {
   return true;
@@ -253,9 +364,33 @@ template <int DE, int DV, int NV, int MODE_OPT_VAR = 0>
 #include "visual_edge_reproject_class.inc"
 template <int DE, int DV, int NV, int MODE_OPT_VAR>
 #include "visual_edge_reproject_jac.inc"
+typedef EdgeReproject<2, 9, 2> EdgeReprojectPVR;  // g2otypes.h:546-547
+typedef EdgeReproject<3, 9, 2> EdgeReprojectPVRStereo;
+struct EdgeEncNavStatePVR {  // the wheel-encoder edge: never present on this path (FillCovInv receives nullptr)
+  void linearizeOplus() {}
+  Matrix<double, 9, 9> getHessianXi(bool = true) const { return Matrix<double, 9, 9>(); }
+  Matrix<double, 9, 9> getHessianXj(bool = true) const { return Matrix<double, 9, 9>(); }
+  Matrix<double, 9, 9> getHessianXji(int8_t = 0) const { return Matrix<double, 9, 9>(); }
+};
 }  // namespace G2O_INERTIAL
 
 namespace g2o = G2O_INERTIAL;
+// Optimizer::FillCovInv (include/Optimizer.h:126-206), the explicit J^T (rho' Omega) J assembly of PoseOptimization's marginal, cut
+// out by name
+namespace VIEO_SLAM_INERTIAL {
+using namespace Eigen;
+using std::vector;
+class Optimizer {
+ public:
+  template <class MatrixNVd>
+  static void FillCovInv(g2o::EdgeNavStatePVR* eNSPVR, g2o::EdgeNavStateBias* eNSBias, g2o::EdgeEncNavStatePVR* eEnc, const int8_t schur_bec,
+                         const vector<g2o::EdgeReprojectPVR*>* pvpEdgesMono, const vector<g2o::EdgeReprojectPVRStereo*>* pvpEdgesStereo,
+                         MatrixNVd& cov_inv, g2o::EdgeNavStatePriorPVRBias* eNSPrior = nullptr,
+                         const int8_t exact_mode = (int8_t)g2o::kExactRobust);
+};
+template <class MatrixNVd>
+#include "fill_cov_inv.inc"
+}  // namespace VIEO_SLAM_INERTIAL
 namespace {
 using namespace VIEO_SLAM_INERTIAL;
 using Eigen::Matrix;
@@ -299,6 +434,19 @@ IMUPreintegrator to_pre(const OrcImuPreint& o) {
   p.mJavij = from_rm<3, 3>(o.Jav), p.mJgRij = from_rm<3, 3>(o.JgR);
   p.mdeltatij = o.dt;
   return p;
+}
+// the fork's *EdgeEx classes re-declare the Jacobian members protected: read them through the (stand-in) g2o base
+template <int D, class E>
+g2o::BaseMultiEdge<D, E>& base_of(g2o::BaseMultiEdge<D, E>& e) {
+  return e;
+}
+template <int D, class E, class Xi, class Xj>
+g2o::BaseBinaryEdge<D, E, Xi, Xj>& base_of(g2o::BaseBinaryEdge<D, E, Xi, Xj>& e) {
+  return e;
+}
+template <int D, class E, class Xi>
+g2o::BaseUnaryEdge<D, E, Xi>& base_of(g2o::BaseUnaryEdge<D, E, Xi>& e) {
+  return e;
 }
 // copies a slot (rows x cols) into dst [rows][ld] at column c0
 template <int D>
@@ -366,7 +514,7 @@ extern "C" void ref_edge_navstate(const OrcNavState* nsi, const OrcNavState* nsj
     to_rm(ed._error, e);
     if (Ji) {
       ed.linearizeOplus();
-      put_cols(ed._jacobianOplus[0], Ji, 9, 0), put_cols(ed._jacobianOplus[1], Jj, 9, 0), put_cols(ed._jacobianOplus[2], Jb, 6, 0);
+      put_cols(base_of(ed)._jacobianOplus[0], Ji, 9, 0), put_cols(base_of(ed)._jacobianOplus[1], Jj, 9, 0), put_cols(base_of(ed)._jacobianOplus[2], Jb, 6, 0);
     }
     return;
   }
@@ -381,9 +529,9 @@ extern "C" void ref_edge_navstate(const OrcNavState* nsi, const OrcNavState* nsj
     to_rm(ed._error, e);
     if (Ji) {
       ed.linearizeOplus();
-      put_cols(ed._jacobianOplus[0], Ji, 9, 0), put_cols(ed._jacobianOplus[2], Ji, 9, 6);
-      put_cols(ed._jacobianOplus[1], Jj, 9, 0), put_cols(ed._jacobianOplus[3], Jj, 9, 6);
-      put_cols(ed._jacobianOplus[4], Jb, 6, 0);
+      put_cols(base_of(ed)._jacobianOplus[0], Ji, 9, 0), put_cols(base_of(ed)._jacobianOplus[2], Ji, 9, 6);
+      put_cols(base_of(ed)._jacobianOplus[1], Jj, 9, 0), put_cols(base_of(ed)._jacobianOplus[3], Jj, 9, 6);
+      put_cols(base_of(ed)._jacobianOplus[4], Jb, 6, 0);
     }
   };
   if (!q_wI) {
@@ -395,7 +543,7 @@ extern "C" void ref_edge_navstate(const OrcNavState* nsi, const OrcNavState* nsj
     EdgeNavStatePRVG ed;
     ed._vertices[5] = &vg;
     run(ed);
-    if (Ji && JG) put_cols(ed._jacobianOplus[5], JG, 2, 0);
+    if (Ji && JG) put_cols(base_of(ed)._jacobianOplus[5], JG, 2, 0);
   }
 }
 
@@ -453,8 +601,8 @@ extern "C" void ref_edge_prior(int form, const OrcNavState* ns, const OrcNavStat
     to_rm(ed._error, e);
     if (Jpvr) {
       ed.linearizeOplus();
-      to_rm(ed._jacobianOplusXi, Jpvr);
-      if (Jbias) to_rm(ed._jacobianOplusXj, Jbias);
+      to_rm(base_of(ed)._jacobianOplusXi, Jpvr);
+      if (Jbias) to_rm(base_of(ed)._jacobianOplusXj, Jbias);
     }
   } else {
     VertexNavStatePR vp;
@@ -484,7 +632,7 @@ extern "C" void ref_edge_bias(const OrcNavState* nsi, const OrcNavState* nsj, do
   to_rm(ed._error, e);
   if (Ji) {
     ed.linearizeOplus();
-    to_rm(ed._jacobianOplusXi, Ji), to_rm(ed._jacobianOplusXj, Jj);
+    to_rm(base_of(ed)._jacobianOplusXi, Ji), to_rm(base_of(ed)._jacobianOplusXj, Jj);
   }
 }
 
@@ -553,4 +701,108 @@ extern "C" void ref_edge_reproject(int form, const OrcCamera* cam, const OrcNavS
   if (form == 4) run_reproject<2, 6, 3, 1>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
   if (form == 5) run_reproject<3, 6, 3, 1>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
   if (form == 6) run_reproject<2, 6, 3, 2>(cam, ns, X, obs, scale, e, J_pose, J_point, J_scale, depth);
+}
+
+// Optimizer::FillCovInv on the edges of an inertial PoseOptimization at its final estimate: the inertial edge (last PVR, current PVR,
+// last bias), the bias random-walk edge, the prior edge of the last keyframe (when it is free) and the visual PVR edges with their
+// levels, information matrices and Huber kernels as given (delta < 0: no kernel).  Errors are computed first, as the caller does
+// (include/Optimizer.h:671-676).  C / CL / CCL [15][15] row-major = cov_inv for schur_bec 0 / 2 / 1 (CL, CCL only when prior != NULL).
+extern "C" void ref_fill_cov_inv(const OrcCamera* cam, const OrcNavState* cur, const OrcNavState* last, const OrcImuPreint* pre,
+                                 const double gw[3], const double* info_imu, double delta_imu, const double* info_bias, double delta_bias,
+                                 const OrcNavState* prior, const double* info_prior, double delta_prior, int n_vis, const double* X,
+                                 const float* obs, const uint8_t* stereo, const double* w, const int32_t* level, const double* delta,
+                                 double* C, double* CL, double* CCL) {
+  using namespace g2o;
+  camm::Camera c;
+  c.model = cam->model;
+  c.params = {cam->fx, cam->fy, cam->cx, cam->cy};
+  const int nd = cam->model == 1 ? cam->num_k + 2 : cam->model == 2 ? 4 : 0;
+  for (int k = 0; k < nd; ++k) c.params.push_back(cam->dist[k]);
+  const float bf = cam->bf;
+  VertexNavStatePVR vCur, vLast;
+  VertexNavStateBias vbCur, vbLast;
+  vCur.setEstimate(to_ns(*cur)), vbCur.setEstimate(to_ns(*cur));
+  vLast.setEstimate(to_ns(*last)), vbLast.setEstimate(to_ns(*last));
+  std::vector<std::unique_ptr<RobustKernelHuber>> kernels;
+  auto kernel = [&](double d) -> RobustKernel* {
+    if (d < 0) return nullptr;
+    kernels.emplace_back(new RobustKernelHuber);
+    kernels.back()->setDelta(d);
+    return kernels.back().get();
+  };
+  std::unique_ptr<EdgeNavStatePVR> eI;
+  if (pre) {
+    eI.reset(new EdgeNavStatePVR);
+    auto& b = base_of(*eI);
+    b._vertices[0] = &vLast, b._vertices[1] = &vCur, b._vertices[2] = &vbLast;
+    b._measurement = to_pre(*pre);
+    eI->SetParams(Vector3d(gw));
+    b.setInformation(from_rm<9, 9>(info_imu));
+    b.setRobustKernel(kernel(delta_imu));
+    b.computeError();
+  }
+  EdgeNavStateBias eB;
+  {
+    auto& b = base_of(eB);
+    b._vertices[0] = &vbLast, b._vertices[1] = &vbCur;
+    b.setInformation(from_rm<6, 6>(info_bias));
+    b.setRobustKernel(kernel(delta_bias));
+    b.computeError();
+  }
+  std::unique_ptr<EdgeNavStatePriorPVRBias> eP;
+  if (prior) {
+    eP.reset(new EdgeNavStatePriorPVRBias);
+    auto& b = base_of(*eP);
+    b._vertices[0] = &vLast, b._vertices[1] = &vbLast;
+    b._measurement = to_ns(*prior);
+    b.setInformation(from_rm<15, 15>(info_prior));
+    b.setRobustKernel(kernel(delta_prior));
+    b.computeError();
+  }
+  std::vector<VertexSBAPointXYZ> pts(n_vis);
+  std::vector<std::unique_ptr<EdgeReprojectPVR>> mono_own;
+  std::vector<std::unique_ptr<EdgeReprojectPVRStereo>> stereo_own;
+  std::vector<EdgeReprojectPVR*> mono;
+  std::vector<EdgeReprojectPVRStereo*> ster;
+  const Matrix3d Rcb = from_rm<3, 3>(cam->Rcb);
+  const Vector3d tcb(cam->tcb);
+  for (int i = 0; i < n_vis; ++i) {
+    pts[i].setEstimate(Vector3d(X + 3 * i));
+    if (stereo[i]) {
+      stereo_own.emplace_back(new EdgeReprojectPVRStereo);
+      auto& e = *stereo_own.back();
+      auto& b = base_of(e);
+      b._vertices[0] = &pts[i], b._vertices[1] = &vCur;
+      b._jacobianOplus[0].cols = 3, b._jacobianOplus[1].cols = 9;
+      e.SetParams(&c, Rcb, tcb, &bf);
+      for (int k = 0; k < 3; ++k) b._measurement(k) = (double)obs[3 * i + k];
+      b.setInformation(Matrix<double, 3, 3>::Identity() * w[i]);
+      b.setRobustKernel(kernel(delta[i]));
+      b.setLevel(level[i]);
+      b.computeError();
+      ster.push_back(&e);
+    } else {
+      mono_own.emplace_back(new EdgeReprojectPVR);
+      auto& e = *mono_own.back();
+      auto& b = base_of(e);
+      b._vertices[0] = &pts[i], b._vertices[1] = &vCur;
+      b._jacobianOplus[0].cols = 3, b._jacobianOplus[1].cols = 9;
+      e.SetParams(&c, Rcb, tcb, &bf);
+      for (int k = 0; k < 2; ++k) b._measurement(k) = (double)obs[3 * i + k];
+      b.setInformation(Matrix<double, 2, 2>::Identity() * w[i]);
+      b.setRobustKernel(kernel(delta[i]));
+      b.setLevel(level[i]);
+      b.computeError();
+      mono.push_back(&e);
+    }
+  }
+  typedef Matrix<double, 15, 15> Matrix15d;
+  Matrix15d c0, cl, ccl;
+  Optimizer::FillCovInv(eI.get(), &eB, (EdgeEncNavStatePVR*)nullptr, 0, &mono, &ster, c0, (EdgeNavStatePriorPVRBias*)nullptr, (int8_t)kExactRobust);
+  to_rm(c0, C);
+  if (prior) {
+    Optimizer::FillCovInv(eI.get(), &eB, (EdgeEncNavStatePVR*)nullptr, 2, &mono, &ster, cl, eP.get(), (int8_t)kExactRobust);
+    Optimizer::FillCovInv(eI.get(), &eB, (EdgeEncNavStatePVR*)nullptr, 1, &mono, &ster, ccl, (EdgeNavStatePriorPVRBias*)nullptr, (int8_t)kExactRobust);
+    to_rm(cl, CL), to_rm(ccl, CCL);
+  }
 }

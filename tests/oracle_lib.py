@@ -939,3 +939,34 @@ def so3(op, x):
     out = np.zeros({0: 4, 2: 3, 3: 3}.get(op, 9))
     L.orc_so3(op, _p(x), _p(out))
     return out.reshape(3, 3) if out.size == 9 else out
+
+
+class MargDump(C.Structure):
+    """OrcMargDump (oracle/ba_oracle.h): what Optimizer::FillCovInv sees and yields inside orc_pose_optimization"""
+    _fields_ = [("filled", C.c_int32), ("has_imu", C.c_int32), ("fixed_last", C.c_int32), ("n_vis", C.c_int32), ("cap", C.c_int32),
+                ("pad_", C.c_int32), ("info_imu", C.c_double * 81), ("info_bias", C.c_double * 36), ("info_prior", C.c_double * 225),
+                ("delta_imu", C.c_double), ("delta_bias", C.c_double), ("delta_prior", C.c_double),
+                ("C", C.c_double * 225), ("CL", C.c_double * 225), ("CCL", C.c_double * 225),
+                ("level", C.c_void_p), ("delta", C.c_void_p)]
+
+
+def pose_optimization_marg_dump(pb, cam, Xw, obs, inv_sigma2, flags):
+    """orc_pose_optimization on ONE problem with the marginal dump hook set -> (result, dump dict)"""
+    L = lib()
+    L.orc_set_marg_dump.argtypes = [C.c_void_p]
+    L.orc_set_marg_dump.restype = None
+    E = int(pb["edge_end"][0] - pb["edge_begin"][0])
+    level = np.zeros(max(E, 1), np.int32); delta = np.zeros(max(E, 1), np.float64)
+    d = MargDump()
+    d.cap = E; d.level = level.ctypes.data; d.delta = delta.ctypes.data
+    L.orc_set_marg_dump(C.addressof(d))
+    try:
+        res, outl, chi2 = pose_optimization(pb, cam, Xw, obs, inv_sigma2, flags)
+    finally:
+        L.orc_set_marg_dump(None)
+    out = dict(filled=int(d.filled), has_imu=int(d.has_imu), fixed_last=int(d.fixed_last), n_vis=int(d.n_vis),
+               info_imu=np.array(d.info_imu).reshape(9, 9), info_bias=np.array(d.info_bias).reshape(6, 6),
+               info_prior=np.array(d.info_prior).reshape(15, 15), delta_imu=float(d.delta_imu), delta_bias=float(d.delta_bias),
+               delta_prior=float(d.delta_prior), C=np.array(d.C).reshape(15, 15), CL=np.array(d.CL).reshape(15, 15),
+               CCL=np.array(d.CCL).reshape(15, 15), level=level[:E].copy(), delta=delta[:E].copy())
+    return res[0], out

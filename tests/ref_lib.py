@@ -546,3 +546,25 @@ def fisheye_matches(desc, n_kp, n_mono, octave=None, th_far_pts=0.0):
     assert n <= rec_cap
     N = int(n_out[0])
     return rec[:n], N, np.stack([mc[:N], mi[:N]], 1), dout[:N]
+
+
+def fill_cov_inv(cam, cur, last, pre, gw, info_imu, delta_imu, info_bias, delta_bias, prior, info_prior, delta_prior, X, obs, stereo, w,
+                 level, delta):
+    """Optimizer::FillCovInv of the reference (include/Optimizer.h:126-206), compiled unchanged over the compiled edge classes and the
+    fork's getHessian() members -> (C, CL, CCL) [15, 15] for schur_bec 0 / 2 / 1 (CL, CCL zero when prior is None)"""
+    L = lib()
+    L.ref_fill_cov_inv.restype = None
+    L.ref_fill_cov_inv.argtypes = ([C.c_void_p] * 6 + [C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_int]
+                                   + [C.c_void_p] * 9)
+    cam = np.ascontiguousarray(cam).reshape(1); cur = np.ascontiguousarray(cur).reshape(1); last = np.ascontiguousarray(last).reshape(1)
+    pre_a = None if pre is None else np.ascontiguousarray(pre).reshape(1)
+    prior_a = None if prior is None else np.ascontiguousarray(prior).reshape(1)
+    gw = np.ascontiguousarray(gw, np.float64)
+    ii = np.ascontiguousarray(info_imu, np.float64); ib = np.ascontiguousarray(info_bias, np.float64); ip = np.ascontiguousarray(info_prior, np.float64)
+    X = np.ascontiguousarray(X, np.float64); obs = np.ascontiguousarray(obs, np.float32); stereo = np.ascontiguousarray(stereo, np.uint8)
+    w = np.ascontiguousarray(w, np.float64); level = np.ascontiguousarray(level, np.int32); delta = np.ascontiguousarray(delta, np.float64)
+    Cm = np.zeros((15, 15)); CL = np.zeros((15, 15)); CCL = np.zeros((15, 15))
+    L.ref_fill_cov_inv(_p(cam), _p(cur), _p(last), None if pre_a is None else _p(pre_a), _p(gw), _p(ii), float(delta_imu), _p(ib),
+                       float(delta_bias), None if prior_a is None else _p(prior_a), _p(ip), float(delta_prior), len(X), _p(X), _p(obs),
+                       _p(stereo), _p(w), _p(level), _p(delta), _p(Cm), _p(CL), _p(CCL))
+    return Cm, CL, CCL

@@ -1115,3 +1115,40 @@ def test_fisheye_ratio_boundaries_equal_reference():
     assert np.array_equal(rec, want)
     good = og[0, :n].astype(bool)
     assert good.sum() >= 6 and (~good).sum() >= 6
+
+
+@pytest.mark.parametrize("chain_prior", [False, True])
+def test_fill_cov_inv_equal_reference(inertial_seq, chain_prior):
+    """Optimizer::FillCovInv (include/Optimizer.h:126-206) compiled unchanged, over the fork's getRho / getHessian / getHessianij /
+    getHessianXi / Xj / Xij / Xji members (src/Odom/g2otypes.h:36-254, the three *EdgeEx classes cut out by name), the compiled edge
+    classes and the compiled Huber kernel: the explicit J^T (rho' Omega) J assembly of PoseOptimization's marginal — which blocks of
+    which edges go where for schur_bec 0 / 2 / 1, level-0 visual edges only, the robust weights — equals the three blocks the oracle
+    forms before its Schur complement (row D6).  Tolerance, not bit equality: the reference adds the mono edges, then the stereo ones."""
+    synth = synth_mod()
+    seq = inertial_seq
+    cam = synth.euroc_camera()
+    n_pts = 350
+    pbs, X, obs, w, fl = synth.make_pose_problems(seq, seq["pre"], cam, n_points=n_pts, seed=3, chain_prior=chain_prior)
+    checked = 0
+    for k in ([1, 2] if chain_prior else [0, 3, 5]):
+        pb = pbs[k:k + 1]
+        res, d = O.pose_optimization_marg_dump(pb, cam, X, obs, w, fl)
+        assert d["filled"] == 1 and d["n_vis"] == n_pts and d["has_imu"] == 1
+        assert d["fixed_last"] == (0 if pb["last_has_prior"][0] else 1)
+        b, e = int(pb["edge_begin"][0]), int(pb["edge_end"][0])
+        free_last = not d["fixed_last"]
+        Cm, CL, CCL = R.fill_cov_inv(cam, res["cur"], res["last"], pb["preint"][0], pb["gw"][0], d["info_imu"], d["delta_imu"], d["info_bias"],
+                                     d["delta_bias"], pb["prior"][0] if free_last else None, d["info_prior"], d["delta_prior"], X[b:e], obs[b:e],
+                                     (fl[b:e] & 1).astype(np.uint8), w[b:e].astype(np.float64), d["level"], d["delta"])
+        sc = np.abs(d["C"]).max()
+        assert np.abs(Cm - d["C"]).max() <= 1e-13 * sc, (k, np.abs(Cm - d["C"]).max() / sc)
+        assert (d["level"] != 0).sum() > 10 and (d["level"] == 0).sum() > 100      # outliers were left out, inliers summed
+        if free_last:
+            for a, bb, nm in ((CL, d["CL"], "CL"), (CCL, d["CCL"], "CCL")):
+                s2 = np.abs(bb).max()
+                assert s2 > 0 and np.abs(a - bb).max() <= 1e-13 * s2, (k, nm, np.abs(a - bb).max() / s2)
+            assert np.abs(d["CL"][:9, 9:]).max() > 0 and d["delta_prior"] > 0
+        else:
+            assert np.all(Cm[:9, 9:] == 0) and np.all(Cm[9:, :9] == 0)
+        checked += 1
+    assert checked >= 2
