@@ -274,13 +274,17 @@ class KeyFrame : public FrameBase {  // the members SearchByBoW(KeyFrame*, Frame
   vector<MapPoint*> mvpMapPoints;
   vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
   MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
-  void FuseMP(size_t, MapPoint*) {}
+  std::vector<std::pair<size_t, MapPoint*>> fused;  // what Fuse hands to the map bookkeeping, recorded
+  void FuseMP(size_t idx, MapPoint* pMP) { fused.emplace_back(idx, pMP); }
   DBoW2::FeatureVector mFeatVec;
   cv::Mat mDescriptors;
-  cv::Mat Ow;
+  cv::Mat Ow, Rcw_m, tcw_m;
   cv::Mat GetCameraCenter() { return Ow; }
+  cv::Mat GetRotation() { return Rcw_m; }
+  cv::Mat GetTranslation() { return tcw_m; }
   struct {
     vector<float> vuright_;
+    float baseline_bf_[2] = {0, 0};
   } stereoinfo_;
   struct {
     vector<float> vscalefactor_, vinvlevelsigma2_;
@@ -298,6 +302,7 @@ class ORBmatcher {
                               const float th_bestdist, bool bCheckViewingAngle = false, const float* pbf = nullptr, int* pnfused = nullptr,
                               char mode = (char)SBPMatchMultiCam, vector<vector<bool>>* pvbAlreadyMatched1 = nullptr,
                               vector<set<int>>* pvnMatch1 = nullptr);
+  int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0);
   int SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches);
   int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist,
                          const float th_far_pts = 0);
@@ -319,6 +324,7 @@ const int ORBmatcher::HISTO_LENGTH = 30;
 #include "bow_fns.inc"
 #include "reloc_fns.inc"
 #include "sbpbase_fns.inc"
+#include "fuse_fns.inc"
 }  // namespace VIEO_SLAM_SBP
 #undef cv
 
@@ -562,4 +568,51 @@ extern "C" void ref_sbp_base(const RefProjSearchFrame* f, const RefKp* kps, cons
       best_idx[i] = *found[i].begin();
       best_dist[i] = ORBmatcher::DescriptorDistance(cvst_sbp::Mat(q_desc + 32 * (size_t)i, 1), cvst_sbp::Mat(desc + 32 * (size_t)best_idx[i], 1));
     }
+}
+
+// ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:1152-1165) compiled unchanged over the compiled
+// SearchByProjectionBase: same inputs as ref_sbp_base (the viewing-cone test and the stereo gate are what Fuse itself passes: on, with
+// the keyframe's bf).  fused_idx [n_q] = the keypoint KeyFrame::FuseMP was called with for each map point (-1: none); returns nFused.
+extern "C" int ref_fuse(const RefProjSearchFrame* f, const RefKp* kps, const float* uright, const uint8_t* desc, const float* wP,
+                        const float* Pn, const float* max_dist, const float* min_dist, const uint8_t* q_desc, const uint8_t* q_skip,
+                        int32_t* fused_idx) {
+  using namespace VIEO_SLAM_SBP;
+  KeyFrame kf;
+  auto cam = std::make_shared<camm::Camera>();
+  const float K[9] = {f->fx, 0.f, f->cx, 0.f, f->fy, f->cy, 0.f, 0.f, 1.f};
+  for (int i = 0; i < 9; ++i) cam->K.m[i] = K[i];
+  kf.mpCameras.push_back(cam);
+  kf.gridinfo_.fgrids_widthinv_ = {f->grid_winv};
+  kf.gridinfo_.fgrids_heightinv_ = {f->grid_hinv};
+  kf.gridinfo_.minmax_xy_.push_back({f->minx, f->maxx, f->miny, f->maxy});
+  kf.N = f->n_kp;
+  kf.mvKeysUn.resize(f->n_kp);
+  for (int i = 0; i < f->n_kp; ++i) kf.mvKeysUn[i].pt.x = kps[i].x, kf.mvKeysUn[i].pt.y = kps[i].y, kf.mvKeysUn[i].octave = kps[i].octave;
+  kf.mvKeys = kf.mvKeysUn;
+  kf.AssignFeaturesToGrid();
+  kf.stereoinfo_.vuright_.assign(uright, uright + f->n_kp);
+  kf.stereoinfo_.baseline_bf_[1] = f->bf;
+  kf.scalepyrinfo_.vscalefactor_.assign(f->scale, f->scale + f->n_levels);
+  kf.scalepyrinfo_.vinvlevelsigma2_.assign(f->inv_level_sigma2, f->inv_level_sigma2 + f->n_levels);
+  kf.scalepyrinfo_.flogscalefactor_ = f->log_scale_factor;
+  kf.mvpMapPoints.assign(f->n_kp, nullptr);
+  kf.mDescriptors = cvst_sbp::Mat(desc, f->n_kp);
+  for (int i = 0; i < 9; ++i) kf.Rcw_m.poseR[i] = f->Rcw[i];
+  for (int i = 0; i < 3; ++i) kf.tcw_m.poset[i] = f->tcw[i], kf.Ow.poset[i] = f->Ow[i];
+  std::vector<MapPoint> mps(f->n_q);
+  std::vector<MapPoint*> vp(f->n_q, nullptr);
+  for (int i = 0; i < f->n_q; ++i) {
+    fused_idx[i] = -1;
+    if (q_skip && q_skip[i]) continue;
+    MapPoint& m = mps[i];
+    m.pos = Vector3f(wP[3 * i], wP[3 * i + 1], wP[3 * i + 2]);
+    m.normal = Vector3f(Pn[3 * i], Pn[3 * i + 1], Pn[3 * i + 2]);
+    m.mfMaxDistance = max_dist[i], m.mfMinDistance = min_dist[i];
+    m.desc = q_desc + 32 * (size_t)i;
+    vp[i] = &m;
+  }
+  ORBmatcher matcher(0.6f, true);
+  const int n = matcher.Fuse(&kf, vp, f->th_radius);
+  for (auto& pr : kf.fused) fused_idx[pr.second - mps.data()] = (int32_t)pr.first;
+  return n;
 }

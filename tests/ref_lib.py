@@ -568,3 +568,26 @@ def fill_cov_inv(cam, cur, last, pre, gw, info_imu, delta_imu, info_bias, delta_
                        float(delta_bias), None if prior_a is None else _p(prior_a), _p(ip), float(delta_prior), len(X), _p(X), _p(obs),
                        _p(stereo), _p(w), _p(level), _p(delta), _p(Cm), _p(CL), _p(CCL))
     return Cm, CL, CCL
+
+
+def fuse(pb):
+    """ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) of the reference, compiled unchanged over the compiled
+    SearchByProjectionBase, for every keyframe of a synth.make_fuse_problem dict -> (keypoint FuseMP received per map point or -1,
+    nFused per keyframe)"""
+    L = lib()
+    L.ref_fuse.argtypes = [C.c_void_p] * 11
+    L.ref_fuse.restype = C.c_int
+    fr = pb["frames"]
+    nq = len(pb["p_max_dist"])
+    hit = np.full(nq, -1, np.int32); nf = np.zeros(len(fr), np.int32)
+    vp = C.c_void_p
+
+    def at(a, i):
+        a = pb[a] if isinstance(a, str) else a
+        return vp(a.ctypes.data + i * a.strides[0])
+    for f in range(len(fr)):
+        kb, qb = int(fr[f]["kp_begin"]), int(fr[f]["q_begin"])
+        skip = at("p_skip", qb) if pb.get("p_skip") is not None else None
+        nf[f] = L.ref_fuse(vp(fr.ctypes.data + f * fr.strides[0]), at("kps", kb), at("uright", kb), at("desc", kb), at("p_wP", qb),
+                           at("p_normal", qb), at("p_max_dist", qb), at("p_min_dist", qb), at("q_desc", qb), skip, at(hit, qb))
+    return hit, nf

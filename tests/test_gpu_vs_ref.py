@@ -77,6 +77,17 @@ def test_search_by_projection_base(api, kw):
     assert np.array_equal(dd[bd >= 0], dr[bd >= 0])
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(cluster=True, skip_frac=0.3), dict(th_radius=4.0)])
+def test_fuse(api, kw):
+    """ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:1152-1165): the keypoint each map point is fused into
+    (what KeyFrame::FuseMP receives) and nFused"""
+    pb = synth.make_fuse_problem(71, **kw)
+    hit, nf = api.ORBmatcher().Fuse(pb)
+    hr, nr = R.fuse(pb)
+    assert np.array_equal(hit, hr) and np.array_equal(nf, nr)
+    assert nr.sum() > 500
+
+
 @pytest.mark.parametrize("seed", [3, 4])
 def test_search_by_bow(api, seed):
     """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:344-505)"""

@@ -1152,3 +1152,20 @@ def test_fill_cov_inv_equal_reference(inertial_seq, chain_prior):
             assert np.all(Cm[:9, 9:] == 0) and np.all(Cm[9:, :9] == 0)
         checked += 1
     assert checked >= 2
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(cluster=True, skip_frac=0.3), dict(th_radius=4.0)])
+def test_fuse_equal_reference(kw):
+    """ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:1152-1165) compiled unchanged over the compiled
+    SearchByProjectionBase, KeyFrame::FuseMP recording: viewing-cone test on, the keyframe's bf for the stereo gate, `bestDist <=
+    TH_LOW` — the keypoint every map point is fused into and nFused equal the rule the host mirror applies to the search output
+    (vieo_slam_b200/api.py ORBmatcher.Fuse: best >= 0 and dist <= 50)."""
+    synth = synth_mod()
+    pb = synth.make_fuse_problem(71, **kw)          # defaults: use_bf, check_viewing_angle — what Fuse itself passes
+    bo, do, _ = O.proj_search(pb)
+    want = np.where((bo >= 0) & (do <= 50), bo, -1).astype(np.int32)
+    hit, nf = R.fuse(pb)
+    assert np.array_equal(hit, want)
+    fr = pb["frames"]
+    assert np.array_equal(nf, [int((want[int(f["q_begin"]):int(f["q_begin"]) + int(f["n_q"])] >= 0).sum()) for f in fr])
+    assert (want >= 0).sum() > 500 and ((bo >= 0) & (do > 50)).sum() > 20      # some found keypoints are too far in Hamming distance
