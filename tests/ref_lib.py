@@ -1,8 +1,13 @@
 """ctypes binding of oracle/_ref/libref.so — TEST INFRASTRUCTURE ONLY.
 
-libref.so is the REFERENCE's own src/ORBextractor.cc (whole unit) and two ORBmatcher member functions, compiled
-unchanged by oracle/ref_build/Makefile (needs /root/reference; the prebuilt .so travels to the GPU box).  It exists to
-pin the oracle restatement: tests assert oracle == _ref.  Nothing under vieo_slam_b200/ may load it."""
+libref.so is the REFERENCE compiled here where it compiles, unchanged from where it lies, by oracle/ref_build/Makefile (needs
+/root/reference; the prebuilt .so travels to the GPU box): src/ORBextractor.cc whole, and — cut out by name at build time — the
+matchers (every SearchByProjection overload, SearchByProjectionBase, Fuse, SearchByBoW, SearchForTriangulation with the cameras'
+epipolarConstrain / FillMatchesFromPair), the frame grid, ComputeStereoMatches, ComputeStereoFishEyeMatches, isInFrustum, the camera
+models' Project(), the IMU pre-integrator, NavState / so3_extra, every vertex / edge class of g2otypes with the fork's getHessian*
+members, Optimizer::FillCovInv, g2o's Levenberg-Marquardt control flow, Huber kernel and Sim3 (DESIGN.md section 2 lists what each
+wrapper pins and which stand-ins it declares).  It exists to pin the oracle restatement (tests/test_oracle_ref.py asserts
+oracle == _ref) and to be the checker of tests/test_gpu_vs_ref.py.  Nothing under vieo_slam_b200/ may load it."""
 import ctypes as C
 import os
 import subprocess
