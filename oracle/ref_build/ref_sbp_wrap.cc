@@ -48,6 +48,46 @@ class Mat {  // descriptor rows, or (SearchByProjectionBase's Rcrw / tcrw / came
   Mat(const uint8_t* d, int r) : data(d), rows(r) {}
   Mat row(int r) const { return Mat(data + 32 * (size_t)r, 1); }
   template <class T> const T* ptr() const { return (const T*)data; }
+  // the CV_32F pose algebra of SearchBySim3 (a 3 x 3 block in poseR or, is_t, a 3 x 1 block in poset): scaling through a double like
+  // cv::Mat::convertTo, products with a double accumulator rounded to float like OpenCV's gemm for CV_32F, sums in float
+  bool is_t = false;
+  Mat t() const {
+    Mat o = *this;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) o.poseR[3 * i + j] = poseR[3 * j + i];
+    return o;
+  }
+  friend Mat operator*(double s, const Mat& m) {
+    Mat o = m;
+    for (int i = 0; i < 9; ++i) o.poseR[i] = (float)(s * (double)m.poseR[i]);
+    for (int i = 0; i < 3; ++i) o.poset[i] = (float)(s * (double)m.poset[i]);
+    return o;
+  }
+  friend Mat operator-(const Mat& m) { return -1.0 * m; }
+  friend Mat operator*(const Mat& a, const Mat& b) {
+    Mat o;
+    o.is_t = b.is_t;
+    if (b.is_t) {
+      for (int i = 0; i < 3; ++i) {
+        double acc = 0;
+        for (int k = 0; k < 3; ++k) acc += (double)a.poseR[3 * i + k] * (double)b.poset[k];
+        o.poset[i] = (float)acc;
+      }
+    } else {
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double acc = 0;
+          for (int k = 0; k < 3; ++k) acc += (double)a.poseR[3 * i + k] * (double)b.poseR[3 * k + j];
+          o.poseR[3 * i + j] = (float)acc;
+        }
+    }
+    return o;
+  }
+  friend Mat operator+(const Mat& a, const Mat& b) {
+    Mat o = a;
+    for (int i = 0; i < 3; ++i) o.poset[i] = a.poset[i] + b.poset[i];
+    return o;
+  }
 };
 }  // namespace cvst_sbp
 #define cv cvst_sbp
@@ -196,7 +236,9 @@ class MapPoint {
   Vector3f normal;
   Vector3f GetNormal() { return normal; }
   bool IsInKeyFrame(class KeyFrame*) { return false; }
-  set<size_t> GetIndexInKeyFrame(class KeyFrame*) { return set<size_t>(); }
+  class KeyFrame* in_kf = nullptr;  // the keyframe observing this point and the keypoints it is observed at (SearchBySim3)
+  set<size_t> in_idx;
+  set<size_t> GetIndexInKeyFrame(class KeyFrame* pKF) { return pKF == in_kf ? in_idx : set<size_t>(); }
   Vector3f GetWorldPos() { return pos; }
   cv::Mat GetDescriptor() { return cv::Mat(desc, 1); }
   int Observations() { return obs; }
@@ -303,6 +345,8 @@ class ORBmatcher {
                               char mode = (char)SBPMatchMultiCam, vector<vector<bool>>* pvbAlreadyMatched1 = nullptr,
                               vector<set<int>>* pvnMatch1 = nullptr);
   int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0);
+  int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12,
+                   const float th);
   int SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches);
   int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist,
                          const float th_far_pts = 0);
@@ -325,6 +369,7 @@ const int ORBmatcher::HISTO_LENGTH = 30;
 #include "reloc_fns.inc"
 #include "sbpbase_fns.inc"
 #include "fuse_fns.inc"
+#include "sim3search_fns.inc"
 }  // namespace VIEO_SLAM_SBP
 #undef cv
 
@@ -614,5 +659,86 @@ extern "C" int ref_fuse(const RefProjSearchFrame* f, const RefKp* kps, const flo
   ORBmatcher matcher(0.6f, true);
   const int n = matcher.Fuse(&kf, vp, f->th_radius);
   for (auto& pr : kf.fused) fused_idx[pr.second - mps.data()] = (int32_t)pr.first;
+  return n;
+}
+
+// ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1222-1302, LoopClosing::ComputeSim3) compiled unchanged over the compiled
+// SearchByProjectionBase: two keyframes (f1 / f2: camera, grid, keypoints; their own map point per keypoint in the q arrays, q_skip =
+// the keypoint holds none; Rcw / tcw / Ow = the keyframe's pose), the similarity (s12, R12 row-major, t12), the search radius th and
+// prior12 [n_kp1] (-1 or the keyframe-2 keypoint already matched).  match12 [n_kp1] = keyframe-2 keypoint whose map point
+// vpMatches12[i1] holds afterwards (-1 none); returns nFound.  pose21 / pose12 [15] = (R | t | unused) the two searches ran with
+// (sR21 R1w, sR21 t1w + t21) and (sR12 R2w, sR12 t2w + t12): what the caller of the flat interface hands over as the frames' poses.
+namespace {
+struct Sim3Side {
+  VIEO_SLAM_SBP::KeyFrame kf;
+  std::vector<VIEO_SLAM_SBP::MapPoint> mps;
+};
+void fill_sim3_side(Sim3Side& S, const RefProjSearchFrame* f, const RefKp* kps, const float* uright, const uint8_t* desc, const float* wP,
+                    const float* Pn, const float* max_dist, const float* min_dist, const uint8_t* q_desc, const uint8_t* q_skip) {
+  using namespace VIEO_SLAM_SBP;
+  KeyFrame& kf = S.kf;
+  auto cam = std::make_shared<camm::Camera>();
+  const float K[9] = {f->fx, 0.f, f->cx, 0.f, f->fy, f->cy, 0.f, 0.f, 1.f};
+  for (int i = 0; i < 9; ++i) cam->K.m[i] = K[i];
+  kf.mpCameras.push_back(cam);
+  kf.gridinfo_.fgrids_widthinv_ = {f->grid_winv};
+  kf.gridinfo_.fgrids_heightinv_ = {f->grid_hinv};
+  kf.gridinfo_.minmax_xy_.push_back({f->minx, f->maxx, f->miny, f->maxy});
+  kf.N = f->n_kp;
+  kf.mvKeysUn.resize(f->n_kp);
+  for (int i = 0; i < f->n_kp; ++i) kf.mvKeysUn[i].pt.x = kps[i].x, kf.mvKeysUn[i].pt.y = kps[i].y, kf.mvKeysUn[i].octave = kps[i].octave;
+  kf.mvKeys = kf.mvKeysUn;
+  kf.AssignFeaturesToGrid();
+  kf.stereoinfo_.vuright_.assign(uright, uright + f->n_kp);
+  kf.stereoinfo_.baseline_bf_[1] = f->bf;
+  kf.scalepyrinfo_.vscalefactor_.assign(f->scale, f->scale + f->n_levels);
+  kf.scalepyrinfo_.vinvlevelsigma2_.assign(f->inv_level_sigma2, f->inv_level_sigma2 + f->n_levels);
+  kf.scalepyrinfo_.flogscalefactor_ = f->log_scale_factor;
+  kf.mDescriptors = cvst_sbp::Mat(desc, f->n_kp);
+  for (int i = 0; i < 9; ++i) kf.Rcw_m.poseR[i] = f->Rcw[i];
+  kf.tcw_m.is_t = true;
+  kf.Ow.is_t = true;
+  for (int i = 0; i < 3; ++i) kf.tcw_m.poset[i] = f->tcw[i], kf.Ow.poset[i] = f->Ow[i];
+  S.mps.resize(f->n_kp);
+  kf.mvpMapPoints.assign(f->n_kp, nullptr);
+  for (int i = 0; i < f->n_kp; ++i) {
+    if (q_skip[i]) continue;
+    MapPoint& m = S.mps[i];
+    m.pos = Vector3f(wP[3 * i], wP[3 * i + 1], wP[3 * i + 2]);
+    m.normal = Vector3f(Pn[3 * i], Pn[3 * i + 1], Pn[3 * i + 2]);
+    m.mfMaxDistance = max_dist[i], m.mfMinDistance = min_dist[i];
+    m.desc = q_desc + 32 * (size_t)i;
+    m.in_kf = &kf;
+    m.in_idx = {(size_t)i};
+    kf.mvpMapPoints[i] = &m;
+  }
+}
+}  // namespace
+extern "C" int ref_search_by_sim3(const RefProjSearchFrame* f1, const RefKp* kps1, const float* ur1, const uint8_t* desc1, const float* wP1,
+                                  const float* Pn1, const float* maxd1, const float* mind1, const uint8_t* qdesc1, const uint8_t* skip1,
+                                  const RefProjSearchFrame* f2, const RefKp* kps2, const float* ur2, const uint8_t* desc2, const float* wP2,
+                                  const float* Pn2, const float* maxd2, const float* mind2, const uint8_t* qdesc2, const uint8_t* skip2,
+                                  float s12, const float* R12, const float* t12, float th, const int32_t* prior12, int32_t* match12,
+                                  float* pose21, float* pose12) {
+  using namespace VIEO_SLAM_SBP;
+  Sim3Side A, B;
+  fill_sim3_side(A, f1, kps1, ur1, desc1, wP1, Pn1, maxd1, mind1, qdesc1, skip1);
+  fill_sim3_side(B, f2, kps2, ur2, desc2, wP2, Pn2, maxd2, mind2, qdesc2, skip2);
+  cvst_sbp::Mat Rm, tm;
+  tm.is_t = true;
+  for (int i = 0; i < 9; ++i) Rm.poseR[i] = R12[i];
+  for (int i = 0; i < 3; ++i) tm.poset[i] = t12[i];
+  std::vector<MapPoint*> m12(f1->n_kp, nullptr);
+  for (int i = 0; i < f1->n_kp; ++i)
+    if (prior12 && prior12[i] >= 0) m12[i] = B.kf.mvpMapPoints[prior12[i]];
+  ORBmatcher matcher(0.75f, true);
+  const int n = matcher.SearchBySim3(&A.kf, &B.kf, m12, s12, Rm, tm, th);
+  for (int i = 0; i < f1->n_kp; ++i) match12[i] = m12[i] ? (int32_t)(m12[i] - B.mps.data()) : -1;
+  {  // the same expressions as :1233-1238, 1264, 1274 for the flat interface's frame poses
+    const cvst_sbp::Mat sR12 = s12 * Rm, sR21 = (1.0 / s12) * Rm.t(), t21 = -sR21 * tm;
+    const cvst_sbp::Mat Ra = sR21 * A.kf.Rcw_m, ta = sR21 * A.kf.tcw_m + t21, Rb = sR12 * B.kf.Rcw_m, tb = sR12 * B.kf.tcw_m + tm;
+    for (int i = 0; i < 9; ++i) pose21[i] = Ra.poseR[i], pose12[i] = Rb.poseR[i];
+    for (int i = 0; i < 3; ++i) pose21[9 + i] = ta.poset[i], pose12[9 + i] = tb.poset[i];
+  }
   return n;
 }

@@ -596,3 +596,27 @@ def fuse(pb):
         nf[f] = L.ref_fuse(vp(fr.ctypes.data + f * fr.strides[0]), at("kps", kb), at("uright", kb), at("desc", kb), at("p_wP", qb),
                            at("p_normal", qb), at("p_max_dist", qb), at("p_min_dist", qb), at("q_desc", qb), skip, at(hit, qb))
     return hit, nf
+
+
+def search_by_sim3(side1, side2, sim3, th, prior12):
+    """ORBmatcher::SearchBySim3 of the reference, compiled unchanged over the compiled SearchByProjectionBase (sides / sim3 / prior12 as
+    tests/sim3_search_data.make returns them) -> (match12 [n_kp1], nFound, pose21 [12], pose12 [12])"""
+    L = lib()
+    L.ref_search_by_sim3.restype = C.c_int
+    L.ref_search_by_sim3.argtypes = [C.c_void_p] * 20 + [C.c_float, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 4
+    keep = []
+
+    def side(S):
+        a = [np.ascontiguousarray(S["frame"]).reshape(1), np.ascontiguousarray(S["kps"]), np.ascontiguousarray(S["uright"], np.float32),
+             np.ascontiguousarray(S["desc"], np.uint8), np.ascontiguousarray(S["wP"], np.float32), np.ascontiguousarray(S["Pn"], np.float32),
+             np.ascontiguousarray(S["maxd"], np.float32), np.ascontiguousarray(S["mind"], np.float32),
+             np.ascontiguousarray(S["qdesc"], np.uint8), np.ascontiguousarray(S["skip"], np.uint8)]
+        keep.extend(a)
+        return [_p(x) for x in a]
+    s12, R12, t12 = sim3
+    R12 = np.ascontiguousarray(R12, np.float32); t12 = np.ascontiguousarray(t12, np.float32)
+    prior12 = np.ascontiguousarray(prior12, np.int32)
+    n1 = len(side1["kps"])
+    m12 = np.full(n1, -1, np.int32); p21 = np.zeros(15, np.float32); p12 = np.zeros(15, np.float32)
+    n = L.ref_search_by_sim3(*side(side1), *side(side2), float(s12), _p(R12), _p(t12), float(th), _p(prior12), _p(m12), _p(p21), _p(p12))
+    return m12, n, p21[:12].copy(), p12[:12].copy()

@@ -88,6 +88,17 @@ def test_fuse(api, kw):
     assert nr.sum() > 500
 
 
+@pytest.mark.parametrize("seed,th", [(3, 7.5), (5, 4.0)])
+def test_search_by_sim3(api, seed, th):
+    """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1222-1302): vpMatches12 and nFound (one two-frame device search + the host agreement)"""
+    import sim3_search_data as D
+    s1, s2, sim3, prior = D.make(seed, th=th)
+    m12, n, p21, p12 = R.search_by_sim3(s1, s2, sim3, th, prior)
+    got, nf = api.ORBmatcher().SearchBySim3(D.flat_problem(s1, s2, p21, p12, prior, th))
+    assert nf == n and np.array_equal(got, m12)
+    assert n > 200
+
+
 @pytest.mark.parametrize("seed", [3, 4])
 def test_search_by_bow(api, seed):
     """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:344-505)"""

@@ -1169,3 +1169,26 @@ def test_fuse_equal_reference(kw):
     fr = pb["frames"]
     assert np.array_equal(nf, [int((want[int(f["q_begin"]):int(f["q_begin"]) + int(f["n_q"])] >= 0).sum()) for f in fr])
     assert (want >= 0).sum() > 500 and ((bo >= 0) & (do > 50)).sum() > 20      # some found keypoints are too far in Hamming distance
+
+
+@pytest.mark.parametrize("seed,th", [(3, 7.5), (4, 7.5), (5, 4.0)])
+def test_search_by_sim3_equal_reference(seed, th):
+    """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1222-1302) compiled unchanged over the compiled SearchByProjectionBase: the similarity
+    algebra that forms the two search poses, the already-matched masks, the two searches in the one-match mode (the arg-min keypoint
+    must hold a map point, bestDist <= TH_HIGH), the agreement check — vpMatches12 and nFound equal the oracle's two-frame search
+    followed by the host mirror's agreement rule (vieo_slam_b200/api.py ORBmatcher.sim3_agreement, plain numpy)."""
+    import sim3_search_data as D
+    import vieo_slam_b200.api as api
+    s1, s2, sim3, prior = D.make(seed, th=th)
+    m12, n, p21, p12 = R.search_by_sim3(s1, s2, sim3, th, prior)
+    assert np.abs(p21[:9] - s2["frame"]["Rcw"]).max() < 1e-5 and np.abs(p12[9:] - s1["frame"]["tcw"]).max() < 1e-4   # S12 is consistent
+    pb = D.flat_problem(s1, s2, p21, p12, prior, th)
+    best, dist, _ = O.proj_search(pb)
+    N1, N2 = len(s1["kps"]), len(s2["kps"])
+    want, nf = api.ORBmatcher.sim3_agreement(best, dist, pb["has_mp"], N2, N1, prior)
+    assert nf == n and np.array_equal(want, m12), (seed, nf, n)
+    assert n > 200 and (prior >= 0).sum() > 10 and np.array_equal(m12[prior >= 0], prior[prior >= 0])
+    bA, dA = best[:N1], dist[:N1]
+    assert ((bA >= 0) & (dA <= 100) & ~pb["has_mp"][:N2][np.maximum(bA, 0)]).sum() > 10     # arg-min keypoints without a map point: no match
+    one_way = (bA >= 0) & (dA <= 100) & pb["has_mp"][:N2][np.maximum(bA, 0)] & (m12 < 0)
+    assert one_way.sum() > 0                                                                   # found one way only: rejected by the agreement

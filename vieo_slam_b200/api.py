@@ -497,6 +497,35 @@ class ORBmatcher:
         fr = pb["frames"]
         return hit, np.array([int((hit[int(f["q_begin"]):int(f["q_begin"]) + int(f["n_q"])] >= 0).sum()) for f in fr], np.int32)
 
+    @staticmethod
+    def sim3_agreement(best, dist, has_mp, n_kp2, n_kp1, prior12=None, th_bestdist=100):
+        """The host half of ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1222-1302) over the output of its two searches run as ONE
+        two-frame SearchByProjectionBase batch — frame 0: keyframe 1's n_kp1 map points into keyframe 2 (keypoints 0 .. n_kp2), frame
+        1: keyframe 2's n_kp2 map points into keyframe 1 (keypoints n_kp2 ..).  The searches run in the one-match mode (mode =
+        ~SBPMatchMultiCam): the arg-min keypoint counts only if it holds a map point of its keyframe (has_mp, keypoint order of the
+        batch) and bestDist <= TH_HIGH (:205-222); a pair is accepted when both directions agree (:1281-1297).  prior12: matches
+        known before the call (their points were skipped by the searches, :1245-1258) — kept, not counted.
+        -> (match12 [n_kp1]: keyframe-2 keypoint whose map point vpMatches12[i1] holds, -1 none; nFound)."""
+        best = np.asarray(best); dist = np.asarray(dist); has_mp = np.asarray(has_mp).astype(bool)
+        bA, dA, bB, dB = best[:n_kp1], dist[:n_kp1], best[n_kp1:n_kp1 + n_kp2], dist[n_kp1:n_kp1 + n_kp2]
+        hasA, hasB = has_mp[:n_kp2], has_mp[n_kp2:n_kp2 + n_kp1]
+        mA = np.where((bA >= 0) & (dA <= th_bestdist) & hasA[np.maximum(bA, 0)], bA, -1)
+        mB = np.where((bB >= 0) & (dB <= th_bestdist) & hasB[np.maximum(bB, 0)], bB, -1)
+        match12 = np.full(n_kp1, -1, np.int32) if prior12 is None else np.array(prior12, np.int32)
+        agree = (mA >= 0) & (mB[np.maximum(mA, 0)] == np.arange(n_kp1))
+        match12[agree] = mA[agree]
+        return match12, int(agree.sum())
+
+    def SearchBySim3(self, pb):
+        """ORBmatcher::SearchBySim3 (LoopClosing::ComputeSim3): pb = the two-frame batch described in sim3_agreement (the caller forms
+        the frames' poses sR21 R1w, sR21 t1w + t21 and sR12 R2w, sR12 t2w + t12, th_radius = th, no bf gate, no viewing-cone test; skips
+        points without a map point or already matched) + 'has_mp' per keypoint and optionally 'prior12'."""
+        fr = pb["frames"]
+        if len(fr) != 2 or int(fr[0]["n_q"]) != int(fr[1]["n_kp"]) or int(fr[1]["n_q"]) != int(fr[0]["n_kp"]):
+            raise VieoError("SearchBySim3 needs the two mutual searches as frames 0 and 1")
+        best, dist, _ = self.SearchByProjectionBase(pb)
+        return self.sim3_agreement(best, dist, pb["has_mp"], int(fr[0]["n_kp"]), int(fr[1]["n_kp"]), pb.get("prior12"), self.TH_HIGH)
+
     def ComputeDistinctiveDescriptors(self, desc_pool, ptr, rows=None):
         """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:314-378) for a CSR batch of map points.
         -> (best index into each point's observation list or -1, that row's median distance)."""
