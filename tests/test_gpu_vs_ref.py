@@ -77,28 +77,6 @@ def test_search_by_projection_base(api, kw):
     assert np.array_equal(dd[bd >= 0], dr[bd >= 0])
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(cluster=True, skip_frac=0.3), dict(th_radius=4.0)])
-def test_fuse(api, kw):
-    """ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:1152-1165): the keypoint each map point is fused into
-    (what KeyFrame::FuseMP receives) and nFused"""
-    pb = synth.make_fuse_problem(71, **kw)
-    hit, nf = api.ORBmatcher().Fuse(pb)
-    hr, nr = R.fuse(pb)
-    assert np.array_equal(hit, hr) and np.array_equal(nf, nr)
-    assert nr.sum() > 500
-
-
-@pytest.mark.parametrize("seed,th", [(3, 7.5), (5, 4.0)])
-def test_search_by_sim3(api, seed, th):
-    """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1222-1302): vpMatches12 and nFound (one two-frame device search + the host agreement)"""
-    import sim3_search_data as D
-    s1, s2, sim3, prior = D.make(seed, th=th)
-    m12, n, p21, p12 = R.search_by_sim3(s1, s2, sim3, th, prior)
-    got, nf = api.ORBmatcher().SearchBySim3(D.flat_problem(s1, s2, p21, p12, prior, th))
-    assert nf == n and np.array_equal(got, m12)
-    assert n > 200
-
-
 @pytest.mark.parametrize("seed", [3, 4])
 def test_search_by_bow(api, seed):
     """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:344-505)"""
@@ -123,3 +101,26 @@ def test_is_in_frustum_rig(api, model, n_cams):
     assert ref["n_inview"].sum() > 1500 and np.array_equal(got["n_inview"], ref["n_inview"])
     for k in ("inview", "cam_mask", "level", "proj", "viewcos", "depth"):
         assert np.asarray(got[k]).tobytes() == np.asarray(ref[k]).tobytes(), (k, int((got[k] != ref[k]).sum()))
+
+
+# ---- added after the round's GPU budget was spent: run so far with the oracle standing in for the device search (kept last) ----
+@pytest.mark.parametrize("kw", [dict(), dict(cluster=True, skip_frac=0.3), dict(th_radius=4.0)])
+def test_fuse(api, kw):
+    """ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:1152-1165): the keypoint each map point is fused into
+    (what KeyFrame::FuseMP receives) and nFused"""
+    pb = synth.make_fuse_problem(71, **kw)
+    hit, nf = api.ORBmatcher().Fuse(pb)
+    hr, nr = R.fuse(pb)
+    assert np.array_equal(hit, hr) and np.array_equal(nf, nr)
+    assert nr.sum() > 500
+
+
+@pytest.mark.parametrize("seed,th", [(3, 7.5), (5, 4.0)])
+def test_search_by_sim3(api, seed, th):
+    """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1222-1302): vpMatches12 and nFound (one two-frame device search + the host agreement)"""
+    import sim3_search_data as D
+    s1, s2, sim3, prior = D.make(seed, th=th)
+    m12, n, p21, p12 = R.search_by_sim3(s1, s2, sim3, th, prior)
+    got, nf = api.ORBmatcher().SearchBySim3(D.flat_problem(s1, s2, p21, p12, prior, th))
+    assert nf == n and np.array_equal(got, m12)
+    assert n > 200
